@@ -1,0 +1,157 @@
+// Host launcher for the tcgen05 GEMM family (see gemm_sm100.cuh).  C ABI, called from Python via ctypes.
+#include "gemm_sm100.cuh"
+#include "runtime/driver.h"
+
+using namespace td;
+using namespace td::gemm;
+
+// Every field is 8 bytes wide so the ctypes mirror (triton_dist/_C.py: GemmArgs) cannot get padding wrong.
+struct TdGemmArgs {
+  long long mode;            // 0 plain, 1 AG, 2 RS
+  long long is_bf16;         // 1 bf16, 0 fp16
+  long long bn;              // 32 / 64 / 128 / 256
+  long long cta_group;       // 1 or 2
+  long long group_m;
+  long long n_comm_ctas;
+  long long use_tma_store;
+  long long num_sms;         // CTAs to launch (0 = all SMs)
+  long long M, N, K;
+  long long m_rot;
+  const void* A; long long a_rows; long long lda; long long a_nbuf; long long a_buf_stride_bytes;
+  const void* B; long long ldb;
+  void* C; long long c_rows; long long ldc;
+  // symmetric context
+  long long rank, world; unsigned long long symm_base, symm_stride, mc_base;
+  void* phase;
+  // AG
+  long long ag_rows_per_rank, ag_copy_local, ag_skip_wait;
+  const void* ag_a_local; void* ag_ws; long long ag_ws_buf_bytes; void* ag_flags; void* ag_ready;
+  // RS
+  long long rs_rows_per_rank; void* rs_stage; long long rs_stage_buf_bytes; void* rs_flags; void* rs_out; long long rs_ldo;
+};
+
+static int encode_tmap(CUtensorMap* out, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                       const cuuint32_t* box, bool is_bf16) {
+  auto enc = drv::cuTensorMapEncodeTiled_fn();
+  if (!enc) { drv::set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return -1; }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(out, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank,
+                   const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { drv::set_error("cuTensorMapEncodeTiled failed: %s", drv::err_str(r)); return -1; }
+  return 0;
+}
+
+template <int kMode, int BN, int kCtaGroup>
+static int launch_cfg(const Params& p, int grid, cudaStream_t stream) {
+  // deepest pipeline that fits in 227 KB next to the 32 KB epilogue staging
+  constexpr int kStageBytes = BM * BK * 2 + (BN / kCtaGroup) * BK * 2;
+  constexpr int kMaxStages = (232448 - 1024 - 2 * kCBlockBytes - 256) / kStageBytes;
+  constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
+  using L = SmemLayout<BN, kStages, kCtaGroup>;
+  auto kern = gemm_kernel<kMode, BN, kStages, kCtaGroup>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = L::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = kCtaGroup;
+  attrs[0].val.clusterDim.y = 1;
+  attrs[0].val.clusterDim.z = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 1;
+  TD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
+  return 0;
+}
+
+template <int kMode>
+static int dispatch(const Params& p, int bn, int cg, int grid, cudaStream_t s) {
+#define TD_CASE(BN_, CG_) if (bn == BN_ && cg == CG_) return launch_cfg<kMode, BN_, CG_>(p, grid, s);
+  TD_CASE(256, 2) TD_CASE(256, 1) TD_CASE(128, 2) TD_CASE(128, 1)
+  TD_CASE(64, 2) TD_CASE(64, 1) TD_CASE(32, 2) TD_CASE(32, 1)
+#undef TD_CASE
+  drv::set_error("unsupported tile config (bn must be 32/64/128/256, cta_group 1/2)");
+  return -1;
+}
+
+TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int cg = static_cast<int>(a->cta_group), bn = static_cast<int>(a->bn);
+  const bool bf16 = a->is_bf16 != 0;
+  if (a->K % 8 != 0 || a->lda % 8 != 0 || a->ldb % 8 != 0) { drv::set_error("K/lda/ldb must be multiples of 8 elements (16 B)"); return -1; }
+  Params p;
+  memset(&p, 0, sizeof(p));
+  {  // A: {K, rows, nbuf}
+    cuuint64_t dims[3] = {(cuuint64_t)a->K, (cuuint64_t)a->a_rows, (cuuint64_t)(a->a_nbuf > 0 ? a->a_nbuf : 1)};
+    cuuint64_t strides[2] = {(cuuint64_t)a->lda * 2, (cuuint64_t)(a->a_nbuf > 1 ? a->a_buf_stride_bytes : a->a_rows * a->lda * 2)};
+    cuuint32_t box[3] = {BK, BM, 1};
+    if (encode_tmap(&p.tmap_a, a->A, 3, dims, strides, box, bf16)) return -1;
+  }
+  {  // B: {K, N}
+    cuuint64_t dims[2] = {(cuuint64_t)a->K, (cuuint64_t)a->N};
+    cuuint64_t strides[1] = {(cuuint64_t)a->ldb * 2};
+    cuuint32_t box[2] = {BK, (cuuint32_t)(bn / cg)};
+    if (encode_tmap(&p.tmap_b, a->B, 2, dims, strides, box, bf16)) return -1;
+  }
+  p.use_tma_store = (a->use_tma_store && bn >= 64 && a->mode != kRS && a->ldc % 8 == 0) ? 1 : 0;
+  if (p.use_tma_store) {  // C: {N, rows}
+    cuuint64_t dims[2] = {(cuuint64_t)a->N, (cuuint64_t)a->c_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)a->ldc * 2};
+    cuuint32_t box[2] = {kCBlockCols, BM};
+    if (encode_tmap(&p.tmap_c, a->C, 2, dims, strides, box, bf16)) return -1;
+  }
+  const int TM = BM * cg;
+  p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K;
+  p.num_m = (p.M + TM - 1) / TM;
+  p.num_n = (p.N + bn - 1) / bn;
+  p.num_k = (p.K + BK - 1) / BK;
+  p.group_m = (int)(a->group_m > 0 ? a->group_m : 1);
+  if (p.group_m > p.num_m) p.group_m = p.num_m;
+  p.m_rot = (int)(((a->m_rot % p.num_m) + p.num_m) % p.num_m);
+  p.in_is_bf16 = bf16 ? 1 : 0;
+  p.n_comm_ctas = (int)a->n_comm_ctas;
+  p.C = a->C; p.ldc = a->ldc;
+  p.symm.rank = (int)a->rank; p.symm.world = (int)a->world;
+  p.symm.base = a->symm_base; p.symm.stride = a->symm_stride; p.symm.mc_base = a->mc_base;
+  p.phase = reinterpret_cast<uint32_t*>(a->phase);
+  p.ag_rows_per_rank = (int)a->ag_rows_per_rank; p.ag_copy_local = (int)a->ag_copy_local; p.ag_skip_wait = (int)a->ag_skip_wait;
+  p.ag_a_local = a->ag_a_local; p.ag_ws = reinterpret_cast<char*>(a->ag_ws); p.ag_ws_buf_bytes = a->ag_ws_buf_bytes;
+  p.ag_flags = reinterpret_cast<uint32_t*>(a->ag_flags); p.ag_ready = reinterpret_cast<uint32_t*>(a->ag_ready);
+  p.rs_rows_per_rank = (int)a->rs_rows_per_rank; p.rs_stage = reinterpret_cast<char*>(a->rs_stage);
+  p.rs_stage_buf_bytes = a->rs_stage_buf_bytes; p.rs_flags = reinterpret_cast<uint32_t*>(a->rs_flags);
+  p.rs_out = a->rs_out; p.rs_ldo = a->rs_ldo;
+
+  int dev = 0, sms = 0;
+  TD_CUDA_CHECK(cudaGetDevice(&dev));
+  TD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int grid = (a->num_sms > 0 && a->num_sms < sms) ? (int)a->num_sms : sms;
+  grid -= grid % cg;
+  if (p.n_comm_ctas % cg) p.n_comm_ctas += cg - p.n_comm_ctas % cg;
+  const int tiles = p.num_m * p.num_n;
+  // never launch more GEMM clusters than tiles (idle CTAs would only spin up TMEM)
+  int gemm_ctas = grid - p.n_comm_ctas;
+  if (gemm_ctas < cg) { drv::set_error("no CTAs left for the GEMM (n_comm_ctas too large)"); return -1; }
+  if (gemm_ctas / cg > tiles) gemm_ctas = tiles * cg;
+  grid = gemm_ctas + p.n_comm_ctas;
+
+  if (a->mode == kRS) {
+    if (p.rs_rows_per_rank % TM != 0) { drv::set_error("gemm_rs ring path needs (M / world) %% (128 * cta_group) == 0"); return -1; }
+    if (p.N % 8 != 0) { drv::set_error("N must be a multiple of 8"); return -1; }
+  }
+  if (!p.use_tma_store && (a->ldc % 8 != 0 || p.N % 8 != 0)) { drv::set_error("N/ldc must be multiples of 8 elements"); return -1; }
+  switch (a->mode) {
+    case kPlain: return dispatch<kPlain>(p, bn, cg, grid, stream);
+    case kAG: return dispatch<kAG>(p, bn, cg, grid, stream);
+    case kRS: return dispatch<kRS>(p, bn, cg, grid, stream);
+    default: drv::set_error("bad mode"); return -1;
+  }
+}
+
+TD_API const char* td_last_error() { return td::drv::g_last_error; }

@@ -1,0 +1,609 @@
+// tcgen05 / TMEM / TMA persistent GEMM for sm_100a with in-kernel collectives.
+//
+//   C[M,N] = A[M,K] * B[N,K]^T      (both operands K-major, bf16 or fp16 in, fp32 accumulate in TMEM)
+//
+// One kernel template covers the family the reference implements as separate Triton kernels plus host
+// copy-engine orchestration:
+//   kPlain : local GEMM                     (ref: python/triton_dist/kernels/nvidia/gemm.py:396-875,
+//                                                 python/little_kernel/benchmark/gemm_sm100/gemm_level9.py)
+//   kAG    : AllGather(A) fused with GEMM   (ref: kernels/nvidia/allgather_gemm.py:200-306 + allgather.py:100-124)
+//   kRS    : GEMM fused with ReduceScatter  (ref: kernels/nvidia/gemm_reduce_scatter.py:218-332 + reduce_scatter.py)
+//
+// B200-first design (not a translation of the reference):
+//   * warp-specialised CTA: warp0 = TMA producer, warp1 = single-thread tcgen05.mma issuer, warp2 = TMEM
+//     allocator, warps4-7 = epilogue (tcgen05.ld -> 16-bit -> swizzled smem -> TMA store or coalesced st.global).
+//   * optional CTA pairs (cta_group::2, UMMA 256 x BN x 16) with the B tile split across the pair.
+//   * double-buffered TMEM accumulators: the epilogue of tile i overlaps the mainloop of tile i+1.
+//   * kAG: "comm CTAs" of the same grid pull the peers' A shards over NVLink with TMA bulk copies
+//     (peer HBM -> smem ring -> local symmetric workspace) and bump per-(source, 128-row chunk) arrival
+//     counters; the TMA producer warp of a GEMM CTA acquires the counters of the rows it is about to load.
+//     The reference signals once per source rank from the host copy engine (allgather.py:100-124).
+//   * kRS: the reduce-scatter is a ring fused into the epilogue: the tile for owner o is computed by rank
+//     o-1 first, pushed (coalesced 16-byte stores over NVLink) into rank o-2's staging buffer, which adds
+//     its own TMEM accumulator and forwards, ... until rank o adds the last partial and writes the output.
+//     No separate reduction pass, no comm SMs; the reference needs scatter + barrier + ring_reduce kernel
+//     (reduce_scatter.py:551-707).
+//   * all flags carry monotonically increasing phase numbers kept in device memory: no flag reset, no
+//     host barrier between calls, and a captured CUDA graph replays correctly.
+#pragma once
+#include "td/primitives.cuh"
+
+namespace td {
+namespace gemm {
+
+constexpr int BM = 128;       // rows of C per CTA (UMMA M = 128 * cta_group)
+constexpr int BK = 64;        // 64 x 2 B = one 128-byte swizzle row
+constexpr int UMMA_K = 16;    // bf16/fp16
+constexpr int kThreads = 256;
+constexpr int kEpiWarp0 = 4;  // warps 4..7: TMEM lane quadrant == warp_idx % 4
+constexpr int kEpiThreads = 128;
+constexpr int kCBlockCols = 64;                       // epilogue staging block: 128 rows x 64 cols (16-bit) = 16 KB
+constexpr int kCBlockBytes = BM * kCBlockCols * 2;
+constexpr int kAGRowsPerChunk = 128;                  // AG arrival-flag granularity (rows of a source shard)
+constexpr int kAGSubPieces = 8;                       // each chunk is pulled as 8 independently flagged sub-pieces
+constexpr int kCommPieceBytes = 16 * 1024;            // one TMA bulk copy
+constexpr int kCommRingSlots = 12;                    // 192 KB smem ring in a comm CTA
+constexpr int kCommStoreDepth = 4;                    // bulk stores allowed to be reading smem concurrently
+
+enum Mode : int { kPlain = 0, kAG = 1, kRS = 2 };
+
+struct Params {
+  CUtensorMap tmap_a;   // dims {K, rows_a, nbuf}, box {64, 128, 1}, SWIZZLE_128B
+  CUtensorMap tmap_b;   // dims {K, N},            box {64, BN / cta_group}
+  CUtensorMap tmap_c;   // dims {N, rows_c},       box {64, 128}, SWIZZLE_128B (only if use_tma_store)
+  int M, N, K;
+  int num_m, num_n, num_k;   // tile counts; num_m is in units of BM * cta_group rows
+  int group_m;               // L2 swizzle band height (in m tiles)
+  int m_rot;                 // rotate the m-tile order by this many tiles (rank-dependent arrival order)
+  int in_is_bf16;            // 1 = bf16, 0 = fp16 (inputs and 16-bit outputs)
+  int use_tma_store;
+  int n_comm_ctas;           // CTAs [gridDim.x - n_comm_ctas, gridDim.x) run the collective
+  int pad0;
+  void* C;                   // output base (row-major)
+  long long ldc;             // leading dimension of C in elements
+  SymmCtx symm;
+  // ---- phase bookkeeping (device resident so a captured graph replays correctly) ----
+  // [0] = number of completed calls on this context, [1] = CTA exit counter, [2] = AG local-copy counter
+  uint32_t* phase;
+  // ---- AG ----
+  int ag_rows_per_rank;      // rows of A owned by each rank
+  int ag_copy_local;         // 1: comm CTAs copy a_local -> workspace; 0: caller already wrote the workspace
+  int ag_skip_wait;          // GEMM-only twin: never wait (measures exposed communication)
+  int pad1;
+  const void* ag_a_local;    // my shard [rows_per_rank, K]
+  char* ag_ws;               // my workspace: 2 buffers of [world * rows_per_rank, K] (symmetric)
+  long long ag_ws_buf_bytes; // bytes of one buffer
+  uint32_t* ag_flags;        // [2][world][chunks_per_rank] arrival counters (local)
+  uint32_t* ag_ready;        // [world]: ag_ready[s] >= p  <=>  rank s has its phase-p shard in ITS workspace (symmetric)
+  // ---- RS (ring) ----
+  int rs_rows_per_rank;      // M / world, multiple of BM * cta_group
+  int pad2;
+  char* rs_stage;            // symmetric: 2 buffers of [M, N] 16-bit running partial sums, written by rank+1
+  long long rs_stage_buf_bytes;
+  uint32_t* rs_flags;        // symmetric: [2][num_m * num_n], written by rank+1 with the phase number
+  void* rs_out;              // [rows_per_rank, N] final output (local)
+  long long rs_ldo;
+};
+
+// -------------------------------------------------------------------------------------------------
+// shared-memory carve-up (GEMM CTAs)
+// -------------------------------------------------------------------------------------------------
+template <int BN, int kStages, int kCtaGroup>
+struct SmemLayout {
+  static constexpr int kABytes = BM * BK * 2;                 // 16 KB
+  static constexpr int kBBytes = (BN / kCtaGroup) * BK * 2;   // this CTA's share of the B tile
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kCOff = kStages * kStageBytes;
+  static constexpr int kBarOff = kCOff + 2 * kCBlockBytes;
+  // barriers: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]; then the TMEM base pointer
+  static constexpr int kNumBars = 2 * kStages + 4;
+  static constexpr int kGemmBytes = kBarOff + kNumBars * 8 + 16;
+  static constexpr int kCommBytes = kCommRingSlots * kCommPieceBytes + kCommRingSlots * (8 + 8 + 8 + 8) + 64;
+  static constexpr int kTotal = (kGemmBytes > kCommBytes ? kGemmBytes : kCommBytes) + 1024;  // + alignment slack
+  static_assert(kStageBytes % 1024 == 0, "stage must keep 1024 B alignment for SWIZZLE_128B");
+  static_assert(kTotal <= 232448, "exceeds 227 KB of shared memory");
+};
+
+__host__ __device__ constexpr int tmem_cols_for(int bn) {
+  return 2 * bn <= 32 ? 32 : 2 * bn <= 64 ? 64 : 2 * bn <= 128 ? 128 : 2 * bn <= 256 ? 256 : 512;
+}
+
+// tile index -> (m tile, n tile); band-swizzled (m fastest inside a band of group_m tiles), then rotated
+TD_DEVICE void tile_coords(const Params& p, int t, int& m_tile, int& n_tile) {
+  const int per_band = p.group_m * p.num_n;
+  const int band = t / per_band;
+  const int first_m = band * p.group_m;
+  const int band_m = min(p.num_m - first_m, p.group_m);
+  const int r = t - band * per_band;
+  n_tile = r / band_m;
+  m_tile = first_m + r % band_m + p.m_rot;
+  if (m_tile >= p.num_m) m_tile -= p.num_m;
+}
+
+// -------------------------------------------------------------------------------------------------
+// AG consumer side: wait until rows [row0, row1) of the gathered A are resident in my workspace
+// -------------------------------------------------------------------------------------------------
+TD_DEVICE void ag_wait_rows(const Params& p, uint32_t ph, int row0, int row1) {
+  const int Ms = p.ag_rows_per_rank;
+  const int cpr = (Ms + kAGRowsPerChunk - 1) / kAGRowsPerChunk;
+  const uint32_t* flags = p.ag_flags + (ph & 1u) * p.symm.world * cpr;
+  const uint32_t target = ((ph + 1) >> 1) * kAGSubPieces;   // this buffer is used every second call
+  int r = row0;
+  while (r < row1) {
+    const int s = r / Ms;
+    const int b = (r - s * Ms) / kAGRowsPerChunk;
+    wait_ge<false>(flags + s * cpr + b, target);
+    r = min(s * Ms + (b + 1) * kAGRowsPerChunk, (s + 1) * Ms);
+  }
+  // the rows were written through the async proxy (bulk copies) of another CTA: order them before my TMA reads
+  ptx::fence_proxy_async();
+}
+
+// -------------------------------------------------------------------------------------------------
+// AG producer side (comm CTA): one thread drives a software-pipelined chain of TMA bulk copies
+//     source HBM (peer over NVLink, or my own shard) -> smem ring -> my workspace
+// Work items = (source s, chunk b, sub-piece u), enumerated in arrival order (own shard, rank+1, ...),
+// dealt round-robin to the comm CTAs so that all of them pull from the SAME peer at the same time and
+// every rank's NVLink egress serves exactly one puller at a time.
+// -------------------------------------------------------------------------------------------------
+struct AgPiece {
+  const char* src;
+  char* dst;
+  uint32_t bytes;
+  uint32_t* flag;        // non-null: this piece completes a sub-piece -> bump *flag after the store is complete
+  int local_done;        // 1: the sub-piece belongs to my own shard (counts towards publishing "ready")
+};
+
+struct AgCursor {
+  const Params& p;
+  uint32_t ph;
+  int comm_idx;
+  int W, me, Ms, cpr;
+  size_t row_bytes;
+  char* ws;
+  uint32_t* flags;
+  // iteration state
+  int j, b, u, item;
+  size_t off, end;       // byte range [off, end) of the current sub-piece still to be emitted
+  bool in_sub;
+  const char* src_base;
+  char* dst_base;
+  size_t sub_base;       // byte offset of the chunk inside the shard
+
+  TD_DEVICE AgCursor(const Params& p_, uint32_t ph_, int comm_idx_)
+      : p(p_), ph(ph_), comm_idx(comm_idx_) {
+    W = p.symm.world; me = p.symm.rank; Ms = p.ag_rows_per_rank;
+    cpr = (Ms + kAGRowsPerChunk - 1) / kAGRowsPerChunk;
+    row_bytes = static_cast<size_t>(p.K) * 2;
+    ws = p.ag_ws + (ph & 1u) * p.ag_ws_buf_bytes;
+    flags = p.ag_flags + (ph & 1u) * W * cpr;
+    j = p.ag_copy_local ? 0 : 1; b = 0; u = -1; item = -1;
+    off = end = 0; in_sub = false; src_base = nullptr; dst_base = nullptr; sub_base = 0;
+  }
+  // advance to my next sub-piece; returns false when exhausted
+  TD_DEVICE bool next_sub() {
+    while (true) {
+      ++u; ++item;
+      if (u == kAGSubPieces) { u = 0; ++b; }
+      if (b == cpr) { b = 0; ++j; }
+      if (j >= W) return false;
+      if (item % p.n_comm_ctas != comm_idx) continue;
+      const int s = (me + j) % W;
+      const int r0 = b * kAGRowsPerChunk, r1 = min(Ms, r0 + kAGRowsPerChunk);
+      const size_t cbytes = static_cast<size_t>(r1 - r0) * row_bytes;
+      const size_t sub = ((cbytes + kAGSubPieces - 1) / kAGSubPieces + 127) & ~static_cast<size_t>(127);
+      const size_t o0 = min(cbytes, sub * u), o1 = min(cbytes, sub * (u + 1));
+      const size_t shard_off = static_cast<size_t>(s) * Ms * row_bytes;
+      if (s == me) {
+        src_base = reinterpret_cast<const char*>(p.ag_a_local);
+      } else {
+        wait_ge<true>(p.ag_ready + s, ph);   // peer s has written its phase-ph shard into ITS workspace
+        src_base = symm_at(p.symm, ws, s) + shard_off;
+      }
+      dst_base = ws + shard_off;
+      sub_base = static_cast<size_t>(r0) * row_bytes;
+      off = o0; end = o1; in_sub = true;
+      return true;
+    }
+  }
+  // emit the next <=16 KB piece; returns false when there is no more work for this CTA
+  TD_DEVICE bool next(AgPiece& out) {
+    while (!in_sub) {
+      if (!next_sub()) return false;
+      if (off >= end) {   // empty sub-piece (tiny chunk): flag only
+        const int s = (me + j) % W;
+        out.src = nullptr; out.dst = nullptr; out.bytes = 0;
+        out.flag = flags + s * cpr + b;
+        out.local_done = (s == me);
+        in_sub = false;
+        return true;
+      }
+    }
+    const int s = (me + j) % W;
+    const uint32_t n = static_cast<uint32_t>(min(static_cast<size_t>(kCommPieceBytes), end - off));
+    out.src = src_base + sub_base + off;
+    out.dst = dst_base + sub_base + off;
+    out.bytes = n;
+    off += n;
+    const bool last = off >= end;
+    out.flag = last ? flags + s * cpr + b : nullptr;
+    out.local_done = (s == me);
+    if (last) in_sub = false;
+    return true;
+  }
+};
+
+TD_DEVICE void ag_publish_ready(const Params& p, uint32_t ph) {
+  ptx::fence_acq_rel_sys();
+  for (int q = 0; q < p.symm.world; ++q)
+    if (q != p.symm.rank) ptx::st_release_sys(symm_at(p.symm, p.ag_ready + p.symm.rank, q), ph);
+}
+
+TD_DEVICE void ag_comm_cta(const Params& p, uint32_t ph, int comm_idx, uint8_t* smem) {
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kCommRingSlots * kCommPieceBytes);
+  char** q_dst = reinterpret_cast<char**>(full + kCommRingSlots);
+  uint32_t** q_flag = reinterpret_cast<uint32_t**>(q_dst + kCommRingSlots);
+  uint64_t* q_meta = reinterpret_cast<uint64_t*>(q_flag + kCommRingSlots);   // bytes | local_done << 32
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kCommRingSlots; ++i) ptx::mbar_init(full + i, 1);
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;   // a single thread drives this SM's TMA unit
+
+  if (!p.ag_copy_local && comm_idx == 0) ag_publish_ready(p, ph);   // zero-copy: shard already in my workspace
+
+  const int cpr = (p.ag_rows_per_rank + kAGRowsPerChunk - 1) / kAGRowsPerChunk;
+  AgCursor cur(p, ph, comm_idx);
+  uint32_t loads = 0, stores = 0, retired = 0;   // pieces loaded / stored / whose smem slot is reusable
+  uint32_t parity_bits = 0;
+  bool more = true;
+  while (true) {
+    // 1. keep the load side of the ring full
+    while (more && loads - retired < kCommRingSlots) {
+      AgPiece pc;
+      more = cur.next(pc);
+      if (!more) break;
+      const uint32_t slot = loads % kCommRingSlots;
+      q_dst[slot] = pc.dst; q_flag[slot] = pc.flag;
+      q_meta[slot] = static_cast<uint64_t>(pc.bytes) | (static_cast<uint64_t>(pc.local_done) << 32);
+      if (pc.bytes) {
+        ptx::mbar_arrive_expect_tx(full + slot, pc.bytes);
+        ptx::bulk_g2s(smem + slot * kCommPieceBytes, pc.src, pc.bytes, full + slot);
+      }
+      ++loads;
+    }
+    if (stores == loads) break;
+    // 2. forward the oldest loaded piece to the workspace
+    const uint32_t slot = stores % kCommRingSlots;
+    const uint32_t bytes = static_cast<uint32_t>(q_meta[slot]);
+    if (bytes) {
+      ptx::mbar_wait(full + slot, (parity_bits >> slot) & 1u);
+      parity_bits ^= (1u << slot);
+      ptx::bulk_s2g(q_dst[slot], smem + slot * kCommPieceBytes, bytes);
+    }
+    ptx::bulk_commit();
+    ++stores;
+    if (q_flag[slot] != nullptr) {
+      // a sub-piece is complete once all its stores are COMPLETE (not merely read from smem)
+      ptx::bulk_wait<0>();
+      retired = stores;
+      ptx::fence_proxy_async();
+      ptx::red_release_gpu_add(q_flag[slot], 1u);
+      if ((q_meta[slot] >> 32) && p.ag_copy_local) {
+        const uint32_t done = ptx::atom_add_acq_rel_gpu(p.phase + 2, 1u) + 1u;
+        if (done == static_cast<uint32_t>(cpr * kAGSubPieces)) {   // my whole shard is in my workspace
+          p.phase[2] = 0;
+          ag_publish_ready(p, ph);
+        }
+      }
+    } else if (stores - retired > kCommStoreDepth) {
+      ptx::bulk_wait_read<kCommStoreDepth>();
+      retired = stores - kCommStoreDepth;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// the kernel
+// -------------------------------------------------------------------------------------------------
+template <int kMode, int BN, int kStages, int kCtaGroup>
+__global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant__ Params p) {
+  using L = SmemLayout<BN, kStages, kCtaGroup>;
+  constexpr int TM = BM * kCtaGroup;                     // rows of C per cluster tile
+  constexpr int kTmemCols = tmem_cols_for(BN);
+  constexpr int kNumCBlocks = (BN + kCBlockCols - 1) / kCBlockCols;
+  constexpr int kColsPerBlock = BN < kCBlockCols ? BN : kCBlockCols;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (kCtaGroup == 2) ? ptx::cluster_ctarank() : 0u;
+  const bool is_leader = cta_rank == 0;
+  const uint32_t ph = (kMode == kPlain) ? 0u : (p.phase[0] + 1u);
+
+  const int n_gemm_ctas = static_cast<int>(gridDim.x) - p.n_comm_ctas;
+  const bool is_comm = static_cast<int>(blockIdx.x) >= n_gemm_ctas;
+
+  if (is_comm) {
+    if constexpr (kMode == kAG) ag_comm_cta(p, ph, static_cast<int>(blockIdx.x) - n_gemm_ctas, smem);
+  } else {
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tmem_full = empty_bar + kStages;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    if (warp == 0 && lane == 0) {
+      ptx::prefetch_tensormap(&p.tmap_a);
+      ptx::prefetch_tensormap(&p.tmap_b);
+      if (p.use_tma_store) ptx::prefetch_tensormap(&p.tmap_c);
+    }
+    if (warp == 1 && lane == 0) {
+      for (int i = 0; i < kStages; ++i) {
+        ptx::mbar_init(full_bar + i, kCtaGroup);      // one producer arrival per CTA of the pair (+ tx bytes)
+        ptx::mbar_init(empty_bar + i, 1);             // one tcgen05.commit
+      }
+      for (int i = 0; i < 2; ++i) {
+        ptx::mbar_init(tmem_full + i, 1);                       // one tcgen05.commit
+        ptx::mbar_init(tmem_empty + i, 4 * kCtaGroup);          // one arrival per epilogue warp of the pair
+      }
+      ptx::fence_barrier_init();
+    }
+    if (warp == 2) {
+      ptx::tmem_alloc<kCtaGroup>(tmem_ptr_smem, kTmemCols);
+      ptx::tmem_relinquish<kCtaGroup>();
+    }
+    ptx::tc_fence_before();
+    if constexpr (kCtaGroup == 2) ptx::cluster_sync(); else __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int n_workers = n_gemm_ctas / kCtaGroup;                 // clusters that run GEMM tiles
+    const int worker = static_cast<int>(blockIdx.x) / kCtaGroup;
+    const int total_tiles = p.num_m * p.num_n;
+
+    if (warp == 0) {
+      // ================================ TMA producer ================================
+      if (lane == 0) {
+        int stage = 0; uint32_t phase = 0;
+        for (int t = worker; t < total_tiles; t += n_workers) {
+          int m_tile, n_tile;
+          tile_coords(p, t, m_tile, n_tile);
+          const int row0 = m_tile * TM + static_cast<int>(cta_rank) * BM;       // my 128 rows of A
+          const int brow0 = n_tile * BN + static_cast<int>(cta_rank) * (BN / kCtaGroup);
+          if constexpr (kMode == kAG) {
+            if (!p.ag_skip_wait && row0 < p.M) ag_wait_rows(p, ph, row0, min(p.M, row0 + BM));
+          }
+          const int abuf = (kMode == kAG) ? static_cast<int>(ph & 1u) : 0;
+          for (int kb = 0; kb < p.num_k; ++kb) {
+            ptx::mbar_wait(empty_bar + stage, phase ^ 1u);
+            uint8_t* sa = smem + stage * L::kStageBytes;
+            uint8_t* sb = sa + L::kABytes;
+            if constexpr (kCtaGroup == 1) {
+              ptx::mbar_arrive_expect_tx(full_bar + stage, L::kStageBytes);
+              ptx::tma_load_3d(&p.tmap_a, full_bar + stage, sa, kb * BK, row0, abuf);
+              ptx::tma_load_2d(&p.tmap_b, full_bar + stage, sb, kb * BK, brow0, ptx::kEvictLast);
+            } else {
+              // both CTAs land their bytes on the LEADER's barrier; the leader expects both halves
+              if (is_leader) ptx::mbar_arrive_expect_tx(full_bar + stage, 2 * L::kStageBytes);
+              else ptx::mbar_arrive_cluster(full_bar + stage, 0);
+              ptx::tma_load_3d_2sm(&p.tmap_a, full_bar + stage, sa, kb * BK, row0, abuf);
+              ptx::tma_load_2d_2sm(&p.tmap_b, full_bar + stage, sb, kb * BK, brow0, ptx::kEvictLast);
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      // ================================ MMA issuer (leader CTA, one thread) ================================
+      if (is_leader && lane == 0) {
+        const uint32_t idesc = ptx::make_idesc(p.in_is_bf16 ? 1u : 0u, p.in_is_bf16 ? 1u : 0u, TM, BN);
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int t = worker; t < total_tiles; t += n_workers) {
+          ptx::mbar_wait(tmem_empty + acc, acc_phase ^ 1u);        // epilogue has drained this accumulator
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+          for (int kb = 0; kb < p.num_k; ++kb) {
+            ptx::mbar_wait(full_bar + stage, phase);
+            ptx::tc_fence_after();
+            const uint32_t sa = ptx::smem_u32(smem + stage * L::kStageBytes);
+            const uint64_t adesc = ptx::make_smem_desc_k128(sa);
+            const uint64_t bdesc = ptx::make_smem_desc_k128(sa + L::kABytes);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // advance 32 B (= 16 bf16) along K inside the 128-byte swizzle atom: +2 in the 16-byte address field
+              ptx::mma_f16<kCtaGroup>(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            if constexpr (kCtaGroup == 1) ptx::mma_commit(empty_bar + stage);
+            else ptx::mma_commit_2sm(empty_bar + stage, 0b11);
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+          if constexpr (kCtaGroup == 1) ptx::mma_commit(tmem_full + acc);
+          else ptx::mma_commit_2sm(tmem_full + acc, 0b11);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+      }
+      __syncwarp();
+    } else if (warp >= kEpiWarp0) {
+      // ================================ epilogue ================================
+      const int ew = warp - kEpiWarp0;               // == warp % 4 == TMEM lane quadrant
+      const int et = threadIdx.x - kEpiWarp0 * 32;   // 0..127
+      const int my_row = ew * 32 + lane;             // row of the 128-row CTA tile held by this thread
+      uint8_t* smem_c = smem + L::kCOff;
+      int acc = 0; uint32_t acc_phase = 0;
+      uint32_t blk_iter = 0;                         // staging buffer = blk_iter & 1
+      for (int t = worker; t < total_tiles; t += n_workers) {
+        int m_tile, n_tile;
+        tile_coords(p, t, m_tile, n_tile);
+        const int row_base = m_tile * TM + static_cast<int>(cta_rank) * BM;   // global row of tile row 0
+        const int col_base = n_tile * BN;
+
+        // ---- RS ring bookkeeping for this tile ----
+        int rs_step = 0; bool rs_final = false;
+        const char* rs_in = nullptr;                 // running partial received from rank+1 (local memory)
+        char* dst_base = reinterpret_cast<char*>(p.C);
+        long long dst_ld = p.ldc;
+        int dst_row_off = 0;                         // subtract from the global row for the destination
+        if constexpr (kMode == kRS) {
+          const int W = p.symm.world, me = p.symm.rank;
+          const int owner = (m_tile * TM) / p.rs_rows_per_rank;
+          rs_step = (owner - me - 1 + 2 * W) % W;
+          rs_final = (rs_step == W - 1);
+          char* stage_buf = p.rs_stage + (ph & 1u) * p.rs_stage_buf_bytes;
+          if (rs_step > 0) {
+            rs_in = stage_buf;
+            if (et == 0) wait_ge<true>(p.rs_flags + (ph & 1u) * total_tiles + m_tile * p.num_n + n_tile, ph);
+            __syncwarp();
+          }
+          if (rs_final) {
+            dst_base = reinterpret_cast<char*>(p.rs_out); dst_ld = p.rs_ldo; dst_row_off = owner * p.rs_rows_per_rank;
+          } else {
+            dst_base = symm_at(p.symm, stage_buf, (me - 1 + W) % W); dst_ld = p.N; dst_row_off = 0;
+          }
+        }
+
+        ptx::mbar_wait(tmem_full + acc, acc_phase);
+        ptx::tc_fence_after();
+        if constexpr (kMode == kRS) { if (rs_step > 0) ptx::named_bar_sync(2, kEpiThreads); }  // flag acquired by et==0
+
+#pragma unroll 1
+        for (int cb = 0; cb < kNumCBlocks; ++cb, ++blk_iter) {
+          uint8_t* cbuf = smem_c + (blk_iter & 1u) * kCBlockBytes;
+          const uint32_t cbuf_u32 = ptx::smem_u32(cbuf);
+          if (p.use_tma_store) {       // the TMA store that last used this buffer must have finished reading it
+            if (et == 0) ptx::bulk_wait_read<1>();
+            __syncwarp();
+            ptx::named_bar_sync(1, kEpiThreads);
+          }
+          // ---- TMEM -> registers -> 16-bit -> swizzled smem ----
+#pragma unroll
+          for (int h = 0; h < kColsPerBlock / 32; ++h) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
+                                   static_cast<uint32_t>(acc * BN + cb * kCBlockCols + h * 32);
+            ptx::tmem_ld_32x32b_x32(taddr, v);
+            ptx::tmem_ld_wait();
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+            if constexpr (kMode == kRS) {
+              if (rs_step > 0) {   // add the running partial pushed by rank+1 (same global coordinates)
+                const int grow = row_base + my_row;
+                const int gcol = col_base + cb * kCBlockCols + h * 32;
+                if (grow < p.M) {
+                  const char* src = rs_in + (static_cast<size_t>(grow) * p.N + gcol) * 2;
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    if (gcol + q * 8 < p.N) {
+                      const uint4 x = ptx::ld_relaxed_sys_v4(src + q * 16);
+                      const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                      for (int e = 0; e < 4; ++e) {
+                        if (p.in_is_bf16) {
+                          f[q * 8 + 2 * e] += ptx::bf16_lo(w[e]);
+                          f[q * 8 + 2 * e + 1] += ptx::bf16_hi(w[e]);
+                        } else {
+                          const __half2 hh = *reinterpret_cast<const __half2*>(&w[e]);
+                          f[q * 8 + 2 * e] += __low2float(hh);
+                          f[q * 8 + 2 * e + 1] += __high2float(hh);
+                        }
+                      }
+                    }
+                  }
+                }
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 o;
+              if (p.in_is_bf16) {
+                o.x = ptx::pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]); o.y = ptx::pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
+                o.z = ptx::pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]); o.w = ptx::pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
+              } else {
+                o.x = ptx::pack_f16x2(f[q * 8 + 0], f[q * 8 + 1]); o.y = ptx::pack_f16x2(f[q * 8 + 2], f[q * 8 + 3]);
+                o.z = ptx::pack_f16x2(f[q * 8 + 4], f[q * 8 + 5]); o.w = ptx::pack_f16x2(f[q * 8 + 6], f[q * 8 + 7]);
+              }
+              const int chunk = h * 4 + q;                                   // 16-byte chunk inside the 128-byte row
+              ptx::st_shared_v4(cbuf_u32 + my_row * 128 + ((chunk ^ (my_row & 7)) << 4), o);
+            }
+          }
+          if (cb == kNumCBlocks - 1) {
+            // accumulator fully read: hand the TMEM stage back to the MMA issuer (on the leader CTA)
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (kCtaGroup == 1) ptx::mbar_arrive(tmem_empty + acc);
+              else ptx::mbar_arrive_cluster(tmem_empty + acc, 0);
+            }
+          }
+          if (p.use_tma_store) ptx::fence_proxy_async_smem();
+          ptx::named_bar_sync(1, kEpiThreads);
+          // ---- smem -> global ----
+          const int gcol0 = col_base + cb * kCBlockCols;
+          if (p.use_tma_store) {
+            if (et == 0 && gcol0 < p.N && row_base < p.M) {
+              ptx::tma_store_2d(&p.tmap_c, cbuf, gcol0, row_base);
+              ptx::bulk_commit();
+            }
+            __syncwarp();
+          } else {
+            // 8 lanes cover one 128-byte row: fully coalesced 16-byte stores (NVLink-friendly for peer pointers)
+            constexpr int kChunks = kColsPerBlock / 8;            // 16-byte chunks per row that carry data
+            const int chunk = et & 7;
+#pragma unroll
+            for (int r = et >> 3; r < BM; r += kEpiThreads / 8) {
+              const int grow = row_base + r;
+              const int gcol = gcol0 + chunk * 8;
+              if (chunk < kChunks && grow < p.M && gcol < p.N) {
+                const uint4 o = ptx::ld_shared_v4(cbuf_u32 + r * 128 + ((chunk ^ (r & 7)) << 4));
+                ptx::st_v4(dst_base + (static_cast<size_t>(grow - dst_row_off) * dst_ld + gcol) * 2, o);
+              }
+            }
+          }
+        }
+        if constexpr (kMode == kRS) {
+          if (!rs_final) {
+            // all epilogue threads' stores for this tile are issued -> one thread publishes the tile to rank-1
+            ptx::named_bar_sync(2, kEpiThreads);
+            if (et == 0) {
+              const int W = p.symm.world, me = p.symm.rank;
+              uint32_t* f = p.rs_flags + (ph & 1u) * total_tiles + m_tile * p.num_n + n_tile;
+              ptx::fence_acq_rel_sys();
+              ptx::st_release_sys(symm_at(p.symm, f, (me - 1 + W) % W), ph);
+            }
+            __syncwarp();
+          }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+      if (p.use_tma_store && et == 0) ptx::bulk_wait<0>();
+      __syncwarp();
+    }
+
+    // ---- teardown ----
+    ptx::tc_fence_before();
+    if constexpr (kCtaGroup == 2) ptx::cluster_sync(); else __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc<kCtaGroup>(tmem_base, kTmemCols);
+  }
+
+  // ---- phase bookkeeping: the last CTA to leave advances the call counter ----
+  if constexpr (kMode != kPlain) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(p.phase + 1, 1u) == gridDim.x - 1) {
+        p.phase[1] = 0;
+        __threadfence();
+        p.phase[0] = ph;
+      }
+    }
+  }
+}
+
+}  // namespace gemm
+}  // namespace td

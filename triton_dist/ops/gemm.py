@@ -1,0 +1,89 @@
+"""Local GEMM on the tcgen05/TMEM/TMA kernel (csrc/gemm_sm100.cuh) -- ``C = A @ B.T``.
+
+Reference counterparts: ``matmul*`` in /root/reference/python/triton_dist/kernels/nvidia/gemm.py:396-875
+(Triton tl.dot, per-device config tables with no B200 entry) and little_kernel's gemm_sm100 ladder
+(/root/reference/python/little_kernel/benchmark/gemm_sm100/gemm_level9.py: 2-CTA 256x256x64, 4 stages).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from .. import _C
+
+
+@dataclass(frozen=True)
+class GemmConfig:
+    """Tile configuration of the sm_100a GEMM.  ``bn``: 32/64/128/256, ``cta_group``: 1 or 2 (CTA pair)."""
+    bn: int = 256
+    cta_group: int = 2
+    group_m: int = 8
+    use_tma_store: bool = True
+    num_sms: int = 0          # 0 = all SMs
+    n_comm_ctas: int = 0      # fused ops only
+
+    def key(self):
+        return (self.bn, self.cta_group, self.group_m, int(self.use_tma_store), self.num_sms, self.n_comm_ctas)
+
+
+def default_config(M: int, N: int, K: int, num_sms: int = 148) -> GemmConfig:
+    """Shape heuristic (stands in for the reference's per-device config tables, gemm.py:184-393)."""
+    if M <= 128:
+        # skinny (decode): stream the weights with as many CTAs as possible
+        for bn in (32, 64, 128):
+            if (N + bn - 1) // bn <= num_sms or bn == 128:
+                return GemmConfig(bn=bn, cta_group=1, group_m=1)
+    tiles_256 = ((M + 255) // 256) * ((N + 255) // 256)
+    if tiles_256 >= num_sms // 2:
+        return GemmConfig(bn=256, cta_group=2, group_m=8)
+    tiles_128 = ((M + 255) // 256) * ((N + 127) // 128)
+    if tiles_128 >= num_sms // 2:
+        return GemmConfig(bn=128, cta_group=2, group_m=8)
+    return GemmConfig(bn=128, cta_group=1, group_m=8)
+
+
+def _check_operand(x: torch.Tensor, name: str):
+    if x.dim() != 2 or x.stride(1) != 1:
+        raise ValueError(f"{name} must be 2-D and K-major (row-major [rows, K])")
+    if x.dtype not in (torch.bfloat16, torch.float16):
+        raise ValueError(f"{name}: only bf16/fp16 supported by this entry point, got {x.dtype}")
+    if x.data_ptr() % 16 or x.stride(0) % 8:
+        raise ValueError(f"{name} must be 16-byte aligned with a leading dimension that is a multiple of 8")
+
+
+def fill_common(args: _C.GemmArgs, a_rows: int, A_ptr: int, lda: int, B: torch.Tensor, C_ptr: int, c_rows: int, ldc: int,
+                M: int, N: int, K: int, cfg: GemmConfig, is_bf16: bool):
+    args.is_bf16 = 1 if is_bf16 else 0
+    args.bn, args.cta_group, args.group_m = cfg.bn, cfg.cta_group, cfg.group_m
+    args.n_comm_ctas, args.use_tma_store, args.num_sms = cfg.n_comm_ctas, int(cfg.use_tma_store), cfg.num_sms
+    args.M, args.N, args.K = M, N, K
+    args.A, args.a_rows, args.lda, args.a_nbuf, args.a_buf_stride_bytes = A_ptr, a_rows, lda, 1, 0
+    args.B, args.ldb = B.data_ptr(), B.stride(0)
+    args.C, args.c_rows, args.ldc = C_ptr, c_rows, ldc
+    args.world = 1
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None,
+         config: Optional[GemmConfig] = None) -> torch.Tensor:
+    """``out[M,N] = a[M,K] @ b[N,K].T`` with fp32 accumulation in TMEM.  ``b`` is an ``nn.Linear`` weight."""
+    if not a.is_cuda:
+        raise RuntimeError("triton_dist.ops.gemm needs CUDA tensors (sm_100a kernel); the CPU path is emulation-only")
+    _check_operand(a, "a")
+    _check_operand(b, "b")
+    M, K = a.shape
+    N, Kb = b.shape
+    if K != Kb or a.dtype != b.dtype:
+        raise ValueError("shape/dtype mismatch")
+    if out is None:
+        out = torch.empty((M, N), dtype=a.dtype, device=a.device)
+    cfg = config or default_config(M, N, K)
+    args = _C.GemmArgs()
+    args.mode = 0
+    fill_common(args, M, a.data_ptr(), a.stride(0), b, out.data_ptr(), M, out.stride(0), M, N, K, cfg,
+                a.dtype == torch.bfloat16)
+    lib = _C.cuda_lib()
+    _C.check(lib.td_gemm_launch(C.byref(args), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "td_gemm_launch")
+    return out
