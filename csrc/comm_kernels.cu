@@ -1,0 +1,377 @@
+// Communication kernels over the symmetric heap: cross-rank barrier, fast AllReduce (one-shot / two-shot,
+// P2P and NVLS multimem), AllGather (pull / push / LL), and small memory ops.
+//
+// Reference counterparts (Triton + NVSHMEM): kernels/nvidia/allreduce.py:216-683 (7 methods),
+// kernels/nvidia/low_latency_allgather.py:48-700, kernels/nvidia/common_ops.py:154-224 (barriers),
+// kernels/nvidia/memory_ops.py.  Differences by design:
+//   * no grid-wide or cooperative launch: CTA b of every rank owns the same slice of the message, so a
+//     *per-CTA* cross-GPU barrier (flag-flip over NVLink, 32-bit monotone epochs) is all the ordering needed;
+//   * symmetric staging is double buffered by call parity and epochs are device resident, so there is no
+//     exit barrier, no flag reset and every kernel here can be captured in a CUDA graph;
+//   * NVLS paths use multimem.ld_reduce (in-switch reduction) / multimem.st (in-switch broadcast) directly.
+#include "td/primitives.cuh"
+#include "runtime/driver.h"
+
+using namespace td;
+
+namespace {
+
+constexpr int kCommThreads = 512;
+
+struct TdSymmArgs { long long rank, world; unsigned long long base, stride, mc_base; };
+
+inline SymmCtx make_ctx(const TdSymmArgs& s) {
+  SymmCtx c; c.rank = (int)s.rank; c.world = (int)s.world; c.base = s.base; c.stride = s.stride; c.mc_base = s.mc_base;
+  return c;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// barrier
+// ---------------------------------------------------------------------------------------------------------
+__global__ void barrier_all_kernel(SymmCtx c, uint32_t* slots, uint32_t* epoch_ctr) {
+  const uint32_t epoch = epoch_ctr[0] + 1;
+  barrier_all_block(c, slots, epoch);
+  if (threadIdx.x == 0) epoch_ctr[0] = epoch;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// element-wise helpers on 16-byte vectors
+// ---------------------------------------------------------------------------------------------------------
+enum DType : int { kBF16 = 0, kF16 = 1, kF32 = 2 };
+
+template <int kDType>
+TD_DEVICE void accum(float (&acc)[8], const uint4& v) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  if constexpr (kDType == kBF16) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { acc[2 * i] += ptx::bf16_lo(w[i]); acc[2 * i + 1] += ptx::bf16_hi(w[i]); }
+  } else if constexpr (kDType == kF16) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
+      acc[2 * i] += __low2float(h); acc[2 * i + 1] += __high2float(h);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] += __uint_as_float(w[i]);
+  }
+}
+template <int kDType>
+TD_DEVICE uint4 pack(const float (&acc)[8]) {
+  uint4 o;
+  if constexpr (kDType == kBF16) {
+    o.x = ptx::pack_bf16x2(acc[0], acc[1]); o.y = ptx::pack_bf16x2(acc[2], acc[3]);
+    o.z = ptx::pack_bf16x2(acc[4], acc[5]); o.w = ptx::pack_bf16x2(acc[6], acc[7]);
+  } else if constexpr (kDType == kF16) {
+    o.x = ptx::pack_f16x2(acc[0], acc[1]); o.y = ptx::pack_f16x2(acc[2], acc[3]);
+    o.z = ptx::pack_f16x2(acc[4], acc[5]); o.w = ptx::pack_f16x2(acc[6], acc[7]);
+  } else {
+    o.x = __float_as_uint(acc[0]); o.y = __float_as_uint(acc[1]); o.z = __float_as_uint(acc[2]); o.w = __float_as_uint(acc[3]);
+  }
+  return o;
+}
+template <int kDType>
+TD_DEVICE uint4 mc_ld_reduce(const void* mc) {
+  if constexpr (kDType == kBF16) return ptx::multimem_ld_reduce_bf16x8(mc);
+  else if constexpr (kDType == kF16) return ptx::multimem_ld_reduce_f16x8(mc);
+  else return ptx::multimem_ld_reduce_f32x4(mc);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// AllReduce
+// ---------------------------------------------------------------------------------------------------------
+enum ARMethod : int { kOneShot = 0, kTwoShot = 1, kOneShotMultimem = 2, kTwoShotMultimem = 3 };
+
+struct ARParams {
+  SymmCtx symm;
+  const uint4* in;        // user input (may alias the staging buffer when in_symm)
+  uint4* out;             // user output (local)
+  char* stage;            // symmetric: [2][stage_bytes]   input staging, double buffered by call parity
+  char* stage2;           // symmetric: [2][stage_bytes]   two-shot result staging
+  long long stage_bytes;
+  long long nvec;         // number of 16-byte vectors
+  uint32_t* slots;        // symmetric: [grid][2][world] per-CTA barrier slots
+  uint32_t* phase;        // local: [0] completed calls, [1] exit counter
+  int in_symm;            // input already lives in stage[parity] (zero-copy producer wrote it)
+};
+
+template <int kDType, int kMethod>
+__global__ void __launch_bounds__(kCommThreads, 1) allreduce_kernel(const ARParams p) {
+  const SymmCtx& c = p.symm;
+  const int W = c.world;
+  const uint32_t ph = p.phase[0] + 1;
+  const uint32_t par = ph & 1u;
+  uint32_t* my_slots = p.slots + blockIdx.x * 2 * W;
+  uint4* stage = reinterpret_cast<uint4*>(p.stage + par * p.stage_bytes);
+  uint4* stage2 = reinterpret_cast<uint4*>(p.stage2 + par * p.stage_bytes);
+
+  // this CTA's slice [v0, v1) of the message -- the SAME slice on every rank
+  const long long per = (p.nvec + gridDim.x - 1) / gridDim.x;
+  const long long v0 = min(p.nvec, per * blockIdx.x), v1 = min(p.nvec, v0 + per);
+
+  // 1. stage my input
+  if (!p.in_symm) {
+    for (long long v = v0 + threadIdx.x; v < v1; v += kCommThreads) stage[v] = p.in[v];
+  }
+  // 2. everyone's slice b is staged
+  barrier_all_block(c, my_slots, 2 * ph);
+
+  if constexpr (kMethod == kOneShot) {
+    for (long long v = v0 + threadIdx.x; v < v1; v += kCommThreads) {
+      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 1
+      for (int r0 = 0; r0 < W; r0 += 4) {
+        uint4 x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (r0 + u < W) x[u] = ptx::ld_relaxed_sys_v4(symm_at(c, stage + v, (c.rank + r0 + u) % W));
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (r0 + u < W) accum<kDType>(acc, x[u]);
+      }
+      p.out[v] = pack<kDType>(acc);
+    }
+  } else if constexpr (kMethod == kOneShotMultimem) {
+    const uint4* mc = symm_mc(c, stage);
+    for (long long v = v0 + threadIdx.x; v < v1; v += kCommThreads) p.out[v] = mc_ld_reduce<kDType>(mc + v);
+  } else {
+    // two-shot: inside my CTA slice, rank r reduces the r-th sub-slice and broadcasts it
+    const long long sper = ((v1 - v0) + W - 1) / W;
+    const long long s0 = min(v1, v0 + sper * c.rank), s1 = min(v1, s0 + sper);
+    if constexpr (kMethod == kTwoShot) {
+      for (long long v = s0 + threadIdx.x; v < s1; v += kCommThreads) {
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 1
+        for (int r0 = 0; r0 < W; r0 += 4) {
+          uint4 x[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (r0 + u < W) x[u] = ptx::ld_relaxed_sys_v4(symm_at(c, stage + v, (c.rank + r0 + u) % W));
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (r0 + u < W) accum<kDType>(acc, x[u]);
+        }
+        const uint4 o = pack<kDType>(acc);
+        for (int r = 0; r < W; ++r) ptx::st_v4(symm_at(c, stage2 + v, (c.rank + r) % W), o);
+      }
+    } else {
+      const uint4* mc_in = symm_mc(c, stage);
+      uint4* mc_out = symm_mc(c, stage2);
+      for (long long v = s0 + threadIdx.x; v < s1; v += kCommThreads)
+        ptx::multimem_st_v4(mc_out + v, mc_ld_reduce<kDType>(mc_in + v));
+    }
+    // 3. every rank's sub-slice has been broadcast into my stage2
+    barrier_all_block(c, my_slots, 2 * ph + 1);
+    for (long long v = v0 + threadIdx.x; v < v1; v += kCommThreads) p.out[v] = ptx::ld_relaxed_sys_v4(stage2 + v);
+  }
+
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(p.phase + 1, 1u) == gridDim.x - 1) { p.phase[1] = 0; __threadfence(); p.phase[0] = ph; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// AllGather (small / medium messages; the bulk AG of ag_gemm lives in gemm_sm100.cuh)
+//   mode 0 pull : barrier, then read every peer's shard
+//   mode 1 push : write my shard into every peer, then barrier
+//   mode 2 push-LL : 8-byte atoms {4 B data, 4 B flag = call id}; receiver spins on the flags, no barrier
+// ---------------------------------------------------------------------------------------------------------
+struct AGParams {
+  SymmCtx symm;
+  const uint4* in;        // my shard
+  uint4* out;             // [world * shard] gathered result (local; may be the symmetric buffer itself)
+  char* buf;              // symmetric: [2][world * shard_bytes]  (LL: [2][world * 2 * shard_bytes])
+  long long buf_bytes;    // bytes of one parity buffer
+  long long nvec;         // shard size in 16-byte vectors (LL: in 4-byte words)
+  uint32_t* slots;
+  uint32_t* phase;
+};
+
+template <int kMode>
+__global__ void __launch_bounds__(kCommThreads, 1) allgather_kernel(const AGParams p) {
+  const SymmCtx& c = p.symm;
+  const int W = c.world;
+  const uint32_t ph = p.phase[0] + 1;
+  const uint32_t par = ph & 1u;
+  uint32_t* my_slots = p.slots + blockIdx.x * 2 * W;
+  const long long per = (p.nvec + gridDim.x - 1) / gridDim.x;
+  const long long v0 = min(p.nvec, per * blockIdx.x), v1 = min(p.nvec, v0 + per);
+
+  if constexpr (kMode == 2) {
+    // LL: shard is an array of 32-bit words; atom = {word, flag}
+    uint2* buf = reinterpret_cast<uint2*>(p.buf + par * p.buf_bytes);
+    const uint32_t* in32 = reinterpret_cast<const uint32_t*>(p.in);
+    uint32_t* out32 = reinterpret_cast<uint32_t*>(p.out);
+    for (long long v = v0 + threadIdx.x; v < v1; v += kCommThreads) {
+      const uint2 atom = make_uint2(in32[v], ph);
+      for (int r = 0; r < W; ++r) {
+        uint2* dst = symm_at(c, buf + c.rank * p.nvec + v, (c.rank + r) % W);
+        asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(atom.x), "r"(atom.y) : "memory");
+      }
+    }
+    for (int s = 0; s < W; ++s) {
+      for (long long v = v0 + threadIdx.x; v < v1; v += kCommThreads) {
+        const uint2* src = buf + s * p.nvec + v;
+        uint32_t d, f;
+        do {
+          asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(d), "=r"(f) : "l"(src) : "memory");
+        } while (f != ph);
+        out32[s * p.nvec + v] = d;
+      }
+    }
+  } else {
+    uint4* buf = reinterpret_cast<uint4*>(p.buf + par * p.buf_bytes);
+    if constexpr (kMode == 1) {
+      for (long long v = v0 + threadIdx.x; v < v1; v += kCommThreads) {
+        const uint4 x = p.in[v];
+        for (int r = 0; r < W; ++r) ptx::st_v4(symm_at(c, buf + c.rank * p.nvec + v, (c.rank + r) % W), x);
+      }
+      barrier_all_block(c, my_slots, ph);
+      if (reinterpret_cast<uint4*>(p.out) != buf)
+        for (int s = 0; s < W; ++s)
+          for (long long v = v0 + threadIdx.x; v < v1; v += kCommThreads)
+            p.out[s * p.nvec + v] = ptx::ld_relaxed_sys_v4(buf + s * p.nvec + v);
+    } else {
+      for (long long v = v0 + threadIdx.x; v < v1; v += kCommThreads) buf[c.rank * p.nvec + v] = p.in[v];
+      barrier_all_block(c, my_slots, ph);
+      for (int r = 0; r < W; ++r) {
+        const int s = (c.rank + r) % W;
+        for (long long v = v0 + threadIdx.x; v < v1; v += kCommThreads)
+          p.out[s * p.nvec + v] = ptx::ld_relaxed_sys_v4(symm_at(c, buf + s * p.nvec + v, s));
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(p.phase + 1, 1u) == gridDim.x - 1) { p.phase[1] = 0; __threadfence(); p.phase[0] = ph; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// memory ops (reference: kernels/nvidia/memory_ops.py copy_tensor / fill_tensor / reduce_tensor)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void copy_kernel(uint4* dst, const uint4* src, long long nvec) {
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvec; v += (long long)gridDim.x * blockDim.x)
+    dst[v] = src[v];
+}
+__global__ void fill_kernel(uint32_t* dst, uint32_t value, long long n) {
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < n; v += (long long)gridDim.x * blockDim.x)
+    dst[v] = value;
+}
+// out[v] = sum_s in[s][v]  over `nsrc` contiguous slabs (fp32 accumulate)
+template <int kDType>
+__global__ void reduce_slabs_kernel(uint4* out, const uint4* in, long long nvec, int nsrc) {
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvec; v += (long long)gridDim.x * blockDim.x) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int s = 0; s < nsrc; ++s) accum<kDType>(acc, in[s * nvec + v]);
+    out[v] = pack<kDType>(acc);
+  }
+}
+
+template <int kDType>
+int launch_ar(int method, const ARParams& p, int grid, cudaStream_t s) {
+  switch (method) {
+    case kOneShot: allreduce_kernel<kDType, kOneShot><<<grid, kCommThreads, 0, s>>>(p); break;
+    case kTwoShot: allreduce_kernel<kDType, kTwoShot><<<grid, kCommThreads, 0, s>>>(p); break;
+    case kOneShotMultimem: allreduce_kernel<kDType, kOneShotMultimem><<<grid, kCommThreads, 0, s>>>(p); break;
+    case kTwoShotMultimem: allreduce_kernel<kDType, kTwoShotMultimem><<<grid, kCommThreads, 0, s>>>(p); break;
+    default: td::drv::set_error("bad allreduce method"); return -1;
+  }
+  TD_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+TD_API int td_barrier_all(const TdSymmArgs* s, void* slots, void* epoch_ctr, void* stream) {
+  SymmCtx c = make_ctx(*s);
+  barrier_all_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(c, reinterpret_cast<uint32_t*>(slots),
+                                                                           reinterpret_cast<uint32_t*>(epoch_ctr));
+  TD_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+struct TdARArgs {
+  TdSymmArgs symm;
+  long long method, dtype, grid, in_symm;
+  const void* in; void* out; void* stage; void* stage2; long long stage_bytes; long long nbytes;
+  void* slots; void* phase;
+};
+
+TD_API int td_allreduce(const TdARArgs* a, void* stream) {
+  if (a->nbytes % 16) { td::drv::set_error("allreduce: nbytes must be a multiple of 16"); return -1; }
+  if (a->nbytes > a->stage_bytes) { td::drv::set_error("allreduce: message larger than the staging buffer"); return -1; }
+  ARParams p;
+  p.symm = make_ctx(a->symm);
+  p.in = reinterpret_cast<const uint4*>(a->in); p.out = reinterpret_cast<uint4*>(a->out);
+  p.stage = reinterpret_cast<char*>(a->stage); p.stage2 = reinterpret_cast<char*>(a->stage2);
+  p.stage_bytes = a->stage_bytes; p.nvec = a->nbytes / 16;
+  p.slots = reinterpret_cast<uint32_t*>(a->slots); p.phase = reinterpret_cast<uint32_t*>(a->phase);
+  p.in_symm = (int)a->in_symm;
+  if ((a->method == kOneShotMultimem || a->method == kTwoShotMultimem) && p.symm.mc_base == 0) {
+    td::drv::set_error("allreduce: multimem method requested but no multicast mapping"); return -1;
+  }
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = (int)a->grid;
+  switch (a->dtype) {
+    case kBF16: return launch_ar<kBF16>((int)a->method, p, grid, s);
+    case kF16: return launch_ar<kF16>((int)a->method, p, grid, s);
+    case kF32: return launch_ar<kF32>((int)a->method, p, grid, s);
+    default: td::drv::set_error("allreduce: unsupported dtype"); return -1;
+  }
+}
+
+struct TdAGArgs {
+  TdSymmArgs symm;
+  long long mode, grid;
+  const void* in; void* out; void* buf; long long buf_bytes; long long shard_bytes;
+  void* slots; void* phase;
+};
+
+TD_API int td_allgather(const TdAGArgs* a, void* stream) {
+  AGParams p;
+  p.symm = make_ctx(a->symm);
+  p.in = reinterpret_cast<const uint4*>(a->in); p.out = reinterpret_cast<uint4*>(a->out);
+  p.buf = reinterpret_cast<char*>(a->buf); p.buf_bytes = a->buf_bytes;
+  p.slots = reinterpret_cast<uint32_t*>(a->slots); p.phase = reinterpret_cast<uint32_t*>(a->phase);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = (int)a->grid;
+  if (a->mode == 2) {
+    if (a->shard_bytes % 4) { td::drv::set_error("allgather LL: shard must be a multiple of 4 bytes"); return -1; }
+    p.nvec = a->shard_bytes / 4;
+    allgather_kernel<2><<<grid, kCommThreads, 0, s>>>(p);
+  } else {
+    if (a->shard_bytes % 16) { td::drv::set_error("allgather: shard must be a multiple of 16 bytes"); return -1; }
+    p.nvec = a->shard_bytes / 16;
+    if (a->mode == 1) allgather_kernel<1><<<grid, kCommThreads, 0, s>>>(p);
+    else allgather_kernel<0><<<grid, kCommThreads, 0, s>>>(p);
+  }
+  TD_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+TD_API int td_copy(void* dst, const void* src, long long nbytes, int grid, void* stream) {
+  if (nbytes % 16) { td::drv::set_error("td_copy: nbytes must be a multiple of 16"); return -1; }
+  copy_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<uint4*>(dst),
+                                                                         reinterpret_cast<const uint4*>(src), nbytes / 16);
+  TD_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+TD_API int td_fill32(void* dst, unsigned int value, long long n, int grid, void* stream) {
+  fill_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<uint32_t*>(dst), value, n);
+  TD_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+TD_API int td_reduce_slabs(void* out, const void* in, long long nbytes, int nsrc, int dtype, int grid, void* stream) {
+  if (nbytes % 16) { td::drv::set_error("td_reduce_slabs: nbytes must be a multiple of 16"); return -1; }
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  uint4* o = reinterpret_cast<uint4*>(out); const uint4* i = reinterpret_cast<const uint4*>(in);
+  if (dtype == kBF16) reduce_slabs_kernel<kBF16><<<grid, 256, 0, s>>>(o, i, nbytes / 16, nsrc);
+  else if (dtype == kF16) reduce_slabs_kernel<kF16><<<grid, 256, 0, s>>>(o, i, nbytes / 16, nsrc);
+  else reduce_slabs_kernel<kF32><<<grid, 256, 0, s>>>(o, i, nbytes / 16, nsrc);
+  TD_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
