@@ -375,3 +375,32 @@ TD_API int td_reduce_slabs(void* out, const void* in, long long nbytes, int nsrc
   TD_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// host-callable mirrors of the device primitives (td::notify / td::wait): one tiny kernel each, so that
+// Python-level protocols (tutorials, tests, pipeline-parallel send/recv) are stream ordered like the
+// reference's p2p_set_signal / p2p_wait_signal kernels (kernels/nvidia/p2p.py:33-60).
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void signal_kernel(uint32_t* addr, uint32_t value, int op) {
+  ptx::fence_acq_rel_sys();
+  if (op == 2) ptx::red_release_sys_add(addr, value);
+  else ptx::st_release_sys(addr, value);
+}
+__global__ void wait_kernel(const uint32_t* addr, int n, uint32_t value, int geq) {
+  if (geq) td::wait<true, true>(addr, n, value);
+  else td::wait<false, true>(addr, n, value);
+}
+}  // namespace
+
+TD_API int td_signal(void* addr, unsigned int value, int op, void* stream) {
+  signal_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<uint32_t*>(addr), value, op);
+  TD_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+TD_API int td_wait(const void* addr, int n, unsigned int value, int geq, void* stream) {
+  if (n < 1 || n > 32) { td::drv::set_error("td_wait: 1 <= n <= 32"); return -1; }
+  wait_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const uint32_t*>(addr), n, value, geq);
+  TD_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

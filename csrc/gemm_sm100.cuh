@@ -73,7 +73,7 @@ struct Params {
   const void* ag_a_local;    // my shard [rows_per_rank, K]
   char* ag_ws;               // my workspace: 2 buffers of [world * rows_per_rank, K] (symmetric)
   long long ag_ws_buf_bytes; // bytes of one buffer
-  uint32_t* ag_flags;        // [2][world][chunks_per_rank] arrival counters (local)
+  uint32_t* ag_flags;        // [2][world][chunks_per_rank][kAGSubPieces] = phase of the call that filled it (local)
   uint32_t* ag_ready;        // [world]: ag_ready[s] >= p  <=>  rank s has its phase-p shard in ITS workspace (symmetric)
   // ---- RS (ring) ----
   int rs_rows_per_rank;      // M / world, multiple of BM * cta_group
@@ -126,13 +126,16 @@ TD_DEVICE void tile_coords(const Params& p, int t, int& m_tile, int& n_tile) {
 TD_DEVICE void ag_wait_rows(const Params& p, uint32_t ph, int row0, int row1) {
   const int Ms = p.ag_rows_per_rank;
   const int cpr = (Ms + kAGRowsPerChunk - 1) / kAGRowsPerChunk;
-  const uint32_t* flags = p.ag_flags + (ph & 1u) * p.symm.world * cpr;
-  const uint32_t target = ((ph + 1) >> 1) * kAGSubPieces;   // this buffer is used every second call
+  // one flag per (source, chunk, sub-piece); a flag holds the phase number of the call that last filled it,
+  // so stale values from earlier calls (or other shapes) are simply "< ph" and nothing is ever reset
+  const uint32_t* flags = p.ag_flags + (ph & 1u) * p.symm.world * cpr * kAGSubPieces;
   int r = row0;
   while (r < row1) {
     const int s = r / Ms;
     const int b = (r - s * Ms) / kAGRowsPerChunk;
-    wait_ge<false>(flags + s * cpr + b, target);
+    const uint32_t* f = flags + (s * cpr + b) * kAGSubPieces;
+#pragma unroll 1
+    for (int u = 0; u < kAGSubPieces; ++u) wait_ge<false>(f + u, ph);
     r = min(s * Ms + (b + 1) * kAGRowsPerChunk, (s + 1) * Ms);
   }
   // the rows were written through the async proxy (bulk copies) of another CTA: order them before my TMA reads
@@ -176,7 +179,7 @@ struct AgCursor {
     cpr = (Ms + kAGRowsPerChunk - 1) / kAGRowsPerChunk;
     row_bytes = static_cast<size_t>(p.K) * 2;
     ws = p.ag_ws + (ph & 1u) * p.ag_ws_buf_bytes;
-    flags = p.ag_flags + (ph & 1u) * W * cpr;
+    flags = p.ag_flags + (ph & 1u) * W * cpr * kAGSubPieces;
     j = p.ag_copy_local ? 0 : 1; b = 0; u = -1; item = -1;
     off = end = 0; in_sub = false; src_base = nullptr; dst_base = nullptr; sub_base = 0;
   }
@@ -213,7 +216,7 @@ struct AgCursor {
       if (off >= end) {   // empty sub-piece (tiny chunk): flag only
         const int s = (me + j) % W;
         out.src = nullptr; out.dst = nullptr; out.bytes = 0;
-        out.flag = flags + s * cpr + b;
+        out.flag = flags + (s * cpr + b) * kAGSubPieces + u;
         out.local_done = (s == me);
         in_sub = false;
         return true;
@@ -226,7 +229,7 @@ struct AgCursor {
     out.bytes = n;
     off += n;
     const bool last = off >= end;
-    out.flag = last ? flags + s * cpr + b : nullptr;
+    out.flag = last ? flags + (s * cpr + b) * kAGSubPieces + u : nullptr;
     out.local_done = (s == me);
     if (last) in_sub = false;
     return true;
@@ -289,7 +292,7 @@ TD_DEVICE void ag_comm_cta(const Params& p, uint32_t ph, int comm_idx, uint8_t* 
       ptx::bulk_wait<0>();
       retired = stores;
       ptx::fence_proxy_async();
-      ptx::red_release_gpu_add(q_flag[slot], 1u);
+      ptx::st_release_gpu(q_flag[slot], ph);
       if ((q_meta[slot] >> 32) && p.ag_copy_local) {
         const uint32_t done = ptx::atom_add_acq_rel_gpu(p.phase + 2, 1u) + 1u;
         if (done == static_cast<uint32_t>(cpr * kAGSubPieces)) {   // my whole shard is in my workspace

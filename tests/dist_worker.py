@@ -1,0 +1,180 @@
+"""Multi-process test worker (launched by torchrun from tests/test_dist_*.py, on CPU/gloo or on GPUs).
+
+Pattern taken from the reference's test strategy: fresh random inputs every iteration,
+poisoned workspaces, golden = torch.distributed collective + matmul, per-rank asserts, straggler injection.
+Usage: torchrun ... tests/dist_worker.py <case> [args]
+"""
+import os
+import sys
+import time
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import triton_dist.utils as U  # noqa: E402
+
+
+def _assert_close(a, b, atol, rtol, what):
+    a, b = a.float().cpu(), b.float().cpu()
+    if not torch.allclose(a, b, atol=atol, rtol=rtol):
+        err = (a - b).abs()
+        raise AssertionError(f"[rank {U.rank()}] {what}: max abs err {err.max().item():.4g} at {err.argmax().item()} "
+                             f"(ref max {b.abs().max().item():.4g})")
+
+
+def case_primitives():
+    """notify/wait ring + symm_at + barrier (BASELINE config #1; reference tutorials/01, test_notify.py)."""
+    import ctypes
+    from triton_dist import language as dl
+    heap = U.get_heap()
+    W, me = U.world_size(), U.rank()
+    data = U.nvshmem_create_tensor((64,), torch.float32)
+    sig = U.nvshmem_create_tensor((8,), torch.int32)
+    U.barrier_all_on_stream()
+    nxt = (me + 1) % W
+    for rnd in range(1, 6):
+        payload = torch.full((64,), float(me * 100 + rnd), dtype=torch.float32, device=data.device)
+        # producer: data into the next rank's buffer, then the flag (release)
+        U.symm_at(data, nxt).copy_(payload)
+        dl.notify(sig[0:1], nxt, signal=rnd, sig_op="set", comm_scope="intra_node")
+        # consumer: wait for my predecessor's flag (acquire), then read
+        tok = dl.wait(sig[0:1], 1, "sys", "acquire", wait_value=rnd)
+        got = dl.consume_token(data, tok).clone()
+        prev = (me - 1 + W) % W
+        assert torch.all(got == float(prev * 100 + rnd)), (me, rnd, got[:4])
+        U.barrier_all_on_stream()
+    # ADD signal from every rank onto rank 0 (test_notify.py:57-69)
+    dl.notify(sig[1:2], 0, signal=1, sig_op="add")
+    U.barrier_all_on_stream()
+    if me == 0:
+        if data.is_cuda:
+            torch.cuda.synchronize()
+        assert int(sig[1].item()) == W, sig
+    U.barrier_all_on_stream()
+    U.nvshmem_free_tensor_sync(sig)
+    U.nvshmem_free_tensor_sync(data)
+
+
+def case_allgather():
+    from triton_dist.ops import comm
+    W, me = U.world_size(), U.rank()
+    dev = U.current_device()
+    ctx = comm.create_fast_allgather_context(1 << 20)
+    modes = ["pull", "push", "push_2d_ll"] if dev.type == "cuda" else ["push"]
+    for it in range(4):
+        for mode in modes:
+            for n in (16, 1000, 65536):
+                x = torch.randn(n, device=dev).to(torch.bfloat16 if n % 8 == 0 else torch.float32)
+                out = comm.fast_allgather(x, ctx, mode=mode)
+                ref = torch.empty(W * x.numel(), dtype=x.dtype, device=dev)
+                dist.all_gather_into_tensor(ref, x, group=U.get_triton_dist_world())
+                assert torch.equal(out.cpu().view(-1), ref.cpu()), (mode, n, it)
+    # intra-node copy-engine allgather (reference contract: allgather.py:100-124)
+    from triton_dist.ops.allgather import cp_engine_producer_all_gather_intra_node, create_allgather_buffers
+    bufs, flags = create_allgather_buffers(64 * W, 32, torch.float32)
+    for it in range(1, 4):
+        local = torch.randn(64, 32, device=dev)
+        cp_engine_producer_all_gather_intra_node(me, W, local, bufs, flags, signal_value=it)
+        U.barrier_all_on_stream()
+        ref = torch.empty(64 * W * 32, device=dev)
+        dist.all_gather_into_tensor(ref, local.view(-1), group=U.get_triton_dist_world())
+        assert torch.equal(bufs[me].cpu().view(-1), ref.cpu())
+        assert torch.all(flags[me][:W].cpu() == it)
+        U.barrier_all_on_stream()
+    ctx.finalize()
+
+
+def case_allreduce():
+    from triton_dist.ops import comm
+    dev = U.current_device()
+    ctx = comm.create_allreduce_ctx(4 << 20, U.rank(), U.world_size(), U.world_size())
+    methods = [comm.AllReduceMethod.OneShot, comm.AllReduceMethod.TwoShot]
+    if U.is_nvshmem_multimem_supported():
+        methods += [comm.AllReduceMethod.OneShot_Multimem, comm.AllReduceMethod.TwoShot_Multimem]
+    if dev.type != "cuda":
+        methods = [comm.AllReduceMethod.OneShot]
+    U.dist_print(f"allreduce methods: {[m.name for m in methods]} multimem={U.is_nvshmem_multimem_supported()}", allowed_ranks=[0])
+    gen = torch.Generator().manual_seed(1234)
+    for it in range(6):
+        for dtype in (torch.bfloat16, torch.float32, torch.float16):
+            n = int(torch.randint(1, 300000, (1,), generator=gen).item()) * 8
+            if it == 0:
+                n = 8
+            if it == 5:
+                n = (6 << 20) // 2     # larger than the workspace -> chunked
+            for m in methods:
+                x = (torch.randn(n, device=dev) * 0.5).to(dtype)
+                ref = x.clone()
+                dist.all_reduce(ref, group=U.get_triton_dist_world())
+                straggler = (it % U.world_size(), 2_000_000) if (dev.type == "cuda" and it in (2, 3)) else None
+                out = comm.all_reduce(x, m, ctx, straggler_option=straggler)
+                tol = 2e-2 if dtype != torch.float32 else 1e-4
+                _assert_close(out, ref, tol * 4, tol, f"allreduce {m.name} {dtype} n={n}")
+    ctx.finalize()
+
+
+def case_ag_gemm():
+    from triton_dist.ops.ag_gemm import ag_gemm, create_ag_gemm_context
+    dev = U.current_device()
+    W, me = U.world_size(), U.rank()
+    big = dev.type == "cuda"
+    shapes = [(512 * W, 512, 1024), (256 * W, 256, 512), (384 * W, 768, 256), (100 * W, 264, 520)] if big else \
+             [(16 * W, 24, 32), (5 * W, 8, 16)]
+    dtype = torch.bfloat16 if big else torch.float32
+    for (M, N, K) in shapes:
+        ctx = create_ag_gemm_context(M, N, K, dtype)
+        if big:
+            ctx.workspace.view(torch.int16).fill_(0x7FC0)      # poison (bf16 NaN pattern)
+        for it in range(5):
+            A = (torch.randn(M // W, K, device=dev) * 0.5).to(dtype)
+            Wt = (torch.randn(N, K, device=dev) * 0.5).to(dtype)
+            straggler = (it % W, 3_000_000) if (big and it in (1, 3)) else None
+            C = ag_gemm(A, Wt.t(), ctx, straggler_option=straggler)
+            full = torch.empty(M * K, device=dev, dtype=dtype)
+            dist.all_gather_into_tensor(full, A.view(-1), group=U.get_triton_dist_world())
+            ref = full.view(M, K).float() @ Wt.float().t()
+            _assert_close(C, ref, 0.5 if big else 1e-3, 2e-2 if big else 1e-4, f"ag_gemm {M}x{N}x{K} it{it}")
+        U.barrier_all_host()
+        ctx.finalize()
+
+
+def case_gemm_rs():
+    from triton_dist.ops.gemm_rs import create_gemm_rs_context, gemm_rs
+    dev = U.current_device()
+    W, me = U.world_size(), U.rank()
+    big = dev.type == "cuda"
+    shapes = [(256 * W, 512, 512), (128 * W, 256, 1024), (512 * W, 1024, 256), (128 * W, 264, 136), (40 * W, 256, 128)] if big else \
+             [(8 * W, 16, 24), (3 * W, 8, 8)]
+    dtype = torch.bfloat16 if big else torch.float32
+    for (M, N, K) in shapes:
+        ctx = create_gemm_rs_context(M, N, output_dtype=dtype)
+        for it in range(5):
+            A = (torch.randn(M, K, device=dev) * 0.5).to(dtype)
+            Wt = (torch.randn(N, K, device=dev) * 0.5).to(dtype)
+            straggler = (it % W, 3_000_000) if (big and it in (1, 3)) else None
+            C = gemm_rs(A, Wt.t(), ctx, straggler_option=straggler)
+            full = (A.float() @ Wt.float().t())
+            if dev.type == "cuda":
+                ref = torch.empty(M // W, N, device=dev, dtype=torch.float32)
+                dist.reduce_scatter_tensor(ref, full, group=U.get_triton_dist_world())
+            else:   # gloo has no reduce_scatter_tensor
+                dist.all_reduce(full, group=U.get_triton_dist_world())
+                ref = full[me * (M // W):(me + 1) * (M // W)]
+            _assert_close(C, ref, 1.0 if big else 1e-3, 3e-2 if big else 1e-4, f"gemm_rs {M}x{N}x{K} it{it}")
+        U.barrier_all_host()
+        ctx.finalize()
+
+
+CASES = {k[5:]: v for k, v in list(globals().items()) if k.startswith("case_")}
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(CASES)
+    U.initialize_distributed(seed=1 + int(os.environ.get("RANK", 0)))
+    t0 = time.time()
+    for name in names:
+        CASES[name]()
+        U.barrier_all_host()
+        U.dist_print(f"CASE {name} OK ({time.time() - t0:.1f}s)", allowed_ranks=[0])
+    U.finalize_distributed()

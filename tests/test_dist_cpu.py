@@ -1,0 +1,15 @@
+"""Protocol tests on the shared-memory emulation backend: gloo, world_size=2, no GPU (BASELINE config #1)."""
+import pytest
+
+from _launch import run_dist
+
+CPU_ENV = {"TD_FORCE_HOST_BACKEND": "1", "CUDA_VISIBLE_DEVICES": ""}
+
+
+@pytest.mark.parametrize("case", ["primitives", "allgather", "allreduce", "ag_gemm", "gemm_rs"])
+def test_cpu_world2(case):
+    run_dist([case], nproc=2, env_extra=CPU_ENV)
+
+
+def test_cpu_world3_ring():
+    run_dist(["gemm_rs", "ag_gemm"], nproc=3, env_extra=CPU_ENV)

@@ -1,0 +1,72 @@
+"""Host-side mirror of the device language.
+
+In the reference these are Triton builtins lowered through an MLIR dialect
+(/root/reference/python/triton_dist/language/distributed_ops.py:53-107).  In this framework the real primitives
+are C++ ``__device__`` functions (csrc/td/primitives.cuh: ``td::wait / notify / symm_at / rank / num_ranks``) used
+inside the hand-written kernels.  This module offers the same vocabulary at Python level -- stream-ordered one-thread
+kernels on the GPU, atomics on the shared-memory heap without one -- for tutorials, tests and host-driven protocols
+(pipeline-parallel hand-off, copy-engine producers).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from .. import _C
+from .. import utils as U
+
+_C.register("td_signal", C.c_int, [C.c_void_p, C.c_uint, C.c_int, C.c_void_p])
+_C.register("td_wait", C.c_int, [C.c_void_p, C.c_int, C.c_uint, C.c_int, C.c_void_p])
+
+SIGNAL_OP = {"set": 1, "add": 2}
+COMM_SCOPE = {"gpu": 1, "intra_node": 2, "inter_node": 3}
+
+
+def rank(axis: int = -1) -> int:
+    return U.rank()
+
+
+def num_ranks(axis: int = -1) -> int:
+    return U.world_size()
+
+
+def symm_at(t: torch.Tensor, peer: int) -> torch.Tensor:
+    return U.symm_at(t, peer)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def notify(ptr: torch.Tensor, peer: int, signal: int = 1, sig_op: str = "set", comm_scope: str = "intra_node"):
+    """Write/add ``signal`` into element 0 of ``ptr`` on rank ``peer`` with release semantics: everything this
+    stream (GPU) / thread (host) wrote before is visible to whoever acquires the flag."""
+    if comm_scope == "inter_node":
+        raise NotImplementedError("single NVSwitch domain only (SURVEY.md 5.8)")
+    heap = U.get_heap()
+    addr = heap.peer_ptr(ptr, peer) if peer != heap.rank else ptr.data_ptr()
+    if ptr.is_cuda:
+        _C.check(_C.cuda_lib().td_signal(C.c_void_p(addr), int(signal) & 0xFFFFFFFF, SIGNAL_OP[sig_op], _stream()), "td_signal")
+    else:
+        _C.host_lib().tdh_notify32(C.c_void_p(addr), int(signal) & 0xFFFFFFFF, SIGNAL_OP[sig_op])
+
+
+def wait(barrier_ptrs: torch.Tensor, num_barriers: int = 1, scope: str = "sys", semantic: str = "acquire",
+         wait_value: int = 1, geq: bool = False) -> int:
+    """Block (the stream / the thread) until ``num_barriers`` consecutive flags equal ``wait_value``.  Returns a
+    token for :func:`consume_token`, as in the reference."""
+    if barrier_ptrs.is_cuda:
+        _C.check(_C.cuda_lib().td_wait(C.c_void_p(barrier_ptrs.data_ptr()), num_barriers, int(wait_value) & 0xFFFFFFFF,
+                                       int(geq), _stream()), "td_wait")
+    else:
+        rc = _C.host_lib().tdh_wait32_n(C.c_void_p(barrier_ptrs.data_ptr()), num_barriers, int(wait_value) & 0xFFFFFFFF,
+                                        1 if geq else 0, U.get_int_env("TD_HOST_TIMEOUT_US", 60_000_000))
+        if rc:
+            raise TimeoutError("dl.wait timed out (hang detected)")
+    return int(wait_value)
+
+
+def consume_token(value, token):
+    """Identity; keeps the data dependence explicit in protocol code (DistributedOpToLLVM.cpp:231-241)."""
+    return value

@@ -1,0 +1,205 @@
+"""AllGather + GEMM in one kernel:  ``C[M, N/W] = allgather(A[M/W, K]) @ B[K, N/W]``.
+
+Reference: ``create_ag_gemm_context`` / ``ag_gemm`` (/root/reference/python/triton_dist/kernels/nvidia/
+allgather_gemm.py:511-619) -- there the all-gather is W-1 host-issued ``cudaMemcpyAsync`` + one
+``cuStreamWriteValue`` flag per source rank (allgather.py:100-124) around a Triton persistent GEMM.
+
+Here (csrc/gemm_sm100.cuh, mode kAG) the gather runs INSIDE the GEMM kernel: ``n_comm_ctas`` CTAs pull the peers'
+shards over NVLink with TMA bulk copies and publish per-(source, 128-row chunk, sub-piece) flags; the tcgen05 GEMM
+CTAs start on the local rows (tile order rotated by rank) and consume remote rows as they land.  No host barrier:
+workspaces are double buffered by call parity and flags carry monotone phase numbers kept on the device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional
+
+import torch
+
+from .. import _C
+from .. import utils as U
+from .gemm import GemmConfig, fill_common
+
+_CHUNK_ROWS = 128
+_SUB = 8
+
+
+@dataclass
+class AllGatherGEMMTensorParallelContext:
+    max_M: int
+    N_per_rank: int
+    K: int
+    dtype: torch.dtype
+    rank: int
+    num_ranks: int
+    num_local_ranks: int
+    workspace: torch.Tensor = None     # symmetric [2, max_M, K]
+    flags: torch.Tensor = None         # local int32 [2, W, chunks, 8]
+    ready: torch.Tensor = None         # symmetric int32 [W]
+    phase: torch.Tensor = None         # local int32 [4]
+    n_comm_ctas: int = 16
+    host_phase: int = 0                # emulation backend / bookkeeping mirror
+    _twin: "AllGatherGEMMTensorParallelContext" = None
+
+    @property
+    def symm_workspace(self):
+        return self.workspace
+
+    def local_input_buffer(self, rows: int) -> torch.Tensor:
+        """Zero-copy entry: where the NEXT call expects my shard ([rows, K] inside the workspace).  A producer
+        (e.g. the previous layer's epilogue) may write there directly and pass it as ``A``."""
+        ph = self._phase_value() + 1
+        buf = self.workspace[ph & 1]
+        return buf[self.rank * rows:(self.rank + 1) * rows]
+
+    def _phase_value(self) -> int:
+        return self.host_phase
+
+    def finalize(self):
+        heap = U.get_heap()
+        for t in (self.workspace, self.ready):
+            if t is not None:
+                heap.free_tensor(t)
+        self.workspace = self.ready = None
+
+
+def create_ag_gemm_context(max_M: int, N: int, K: int, dtype: torch.dtype, rank: Optional[int] = None,
+                           num_ranks: Optional[int] = None, num_local_ranks: Optional[int] = None,
+                           n_comm_ctas: int = 16, **_unused) -> AllGatherGEMMTensorParallelContext:
+    """``max_M`` = largest gathered M (rows of all ranks together); ``N`` = this rank's N shard."""
+    heap = U.get_heap()
+    rank = heap.rank if rank is None else rank
+    num_ranks = heap.world if num_ranks is None else num_ranks
+    ctx = AllGatherGEMMTensorParallelContext(max_M, N, K, dtype, rank, num_ranks, num_local_ranks or num_ranks,
+                                             n_comm_ctas=n_comm_ctas)
+    ctx.workspace = heap.tensor((2, max_M, K), dtype)
+    ctx.ready = heap.tensor((max(num_ranks, 4),), torch.int32)
+    max_ms = (max_M + num_ranks - 1) // num_ranks
+    chunks = (max_ms + _CHUNK_ROWS - 1) // _CHUNK_ROWS
+    ctx.flags = torch.zeros((2, num_ranks, chunks + 1, _SUB), dtype=torch.int32, device=heap.device)
+    ctx.phase = torch.zeros(4, dtype=torch.int32, device=heap.device)
+    U.barrier_all_host()
+    return ctx
+
+
+_WEIGHT_T_CACHE = {}
+
+
+def _as_nk(B: torch.Tensor) -> torch.Tensor:
+    """Return the operand as a K-major ``[N, K]`` matrix.  ``B`` is ``[K, N]``: normally the ``.t()`` view of an
+    ``nn.Linear`` weight (free); a genuinely N-major B is transposed once and cached (weights are static)."""
+    if B.stride(0) == 1:
+        return B.t()
+    key = (B.data_ptr(), tuple(B.shape), B._version)
+    w = _WEIGHT_T_CACHE.get(key)
+    if w is None:
+        w = B.t().contiguous()
+        _WEIGHT_T_CACHE.clear()
+        _WEIGHT_T_CACHE[key] = w
+    return w
+
+
+def default_ag_config(M: int, N: int, K: int, world: int) -> GemmConfig:
+    rows = M // max(world, 1)
+    if rows % 256 == 0 and N >= 256:
+        return GemmConfig(bn=256, cta_group=2, group_m=1, use_tma_store=True, n_comm_ctas=16 if world > 1 else 0)
+    if N >= 256:
+        return GemmConfig(bn=256, cta_group=1, group_m=1, use_tma_store=True, n_comm_ctas=16 if world > 1 else 0)
+    return GemmConfig(bn=128, cta_group=1, group_m=1, use_tma_store=True, n_comm_ctas=16 if world > 1 else 0)
+
+
+def ag_gemm(A: torch.Tensor, B: torch.Tensor, ctx: AllGatherGEMMTensorParallelContext,
+            gemm_config: Optional[GemmConfig] = None, straggler_option=None, debug: bool = False,
+            out: Optional[torch.Tensor] = None, skip_wait: bool = False, **_unused) -> torch.Tensor:
+    """A: ``[M/W, K]`` local shard, B: ``[K, N/W]`` -> ``[M, N/W]``.  ``skip_wait`` runs the GEMM-only twin
+    (flags ignored) used to measure exposed communication, like the reference's ``fake_barrier`` path."""
+    W = ctx.num_ranks
+    Ms, K = A.shape
+    Bnk = _as_nk(B)
+    N = Bnk.shape[0]
+    M = Ms * W
+    assert K == ctx.K and Bnk.shape[1] == K and M <= ctx.max_M and A.dtype == ctx.dtype == Bnk.dtype
+    if not A.is_cuda:
+        return _ag_gemm_host(A, Bnk, ctx, out)
+    if out is None:
+        out = torch.empty((M, N), dtype=A.dtype, device=A.device)
+    cfg = gemm_config or default_ag_config(M, N, K, W)
+    if W == 1:
+        from .gemm import gemm
+        return gemm(A, Bnk, out=out, config=GemmConfig(cfg.bn, cfg.cta_group, 8, cfg.use_tma_store, cfg.num_sms, 0))
+    if straggler_option and straggler_option[0] == ctx.rank:
+        torch.cuda._sleep(int(straggler_option[1]))
+    heap = U.get_heap()
+    A = A.contiguous()
+    ph = ctx.host_phase + 1
+    zero_copy = heap.contains(A) and A.data_ptr() == ctx.workspace[ph & 1][ctx.rank * Ms:].data_ptr()
+    args = _C.GemmArgs()
+    args.mode = 1
+    ws_buf_bytes = ctx.max_M * K * A.element_size()
+    fill_common(args, M, ctx.workspace.data_ptr(), K, Bnk, out.data_ptr(), M, out.stride(0), M, N, K, cfg,
+                A.dtype == torch.bfloat16)
+    args.a_nbuf, args.a_buf_stride_bytes = 2, ws_buf_bytes
+    tm = 128 * cfg.cta_group
+    args.m_rot = (ctx.rank * Ms) // tm
+    r, w, base, stride, mc = U.symm_ctx_fields()
+    args.rank, args.world, args.symm_base, args.symm_stride, args.mc_base = r, w, base, stride, mc
+    args.phase = ctx.phase.data_ptr()
+    args.ag_rows_per_rank, args.ag_copy_local, args.ag_skip_wait = Ms, 0 if zero_copy else 1, int(skip_wait)
+    args.ag_a_local, args.ag_ws, args.ag_ws_buf_bytes = A.data_ptr(), ctx.workspace.data_ptr(), ws_buf_bytes
+    args.ag_flags, args.ag_ready = ctx.flags.data_ptr(), ctx.ready.data_ptr()
+    if skip_wait:
+        args.n_comm_ctas = 0
+    _C.check(_C.cuda_lib().td_gemm_launch(C.byref(args), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+             "td_gemm_launch(ag)")
+    ctx.host_phase = ph
+    return out
+
+
+def gemm_only(A_full: torch.Tensor, B: torch.Tensor, out: Optional[torch.Tensor] = None,
+              gemm_config: Optional[GemmConfig] = None) -> torch.Tensor:
+    """The local GEMM on already-gathered rows (what the fused kernel must hide the all-gather behind)."""
+    from .gemm import gemm
+    return gemm(A_full, _as_nk(B), out=out, config=gemm_config)
+
+
+# reference names (allgather_gemm.py:725-800)
+def gemm_persistent(A, B, out=None, **_):
+    return gemm_only(A, B, out)
+
+
+gemm_non_persistent = gemm_persistent
+
+
+# ------------------------------------------------------------------------------------------------------------
+# emulation (no GPU): same protocol on the shared-memory heap
+# ------------------------------------------------------------------------------------------------------------
+def _ag_gemm_host(A, Bnk, ctx, out):
+    import ctypes
+    heap = U.get_heap()
+    lib = _C.host_lib()
+    W, me = ctx.num_ranks, ctx.rank
+    Ms, K = A.shape
+    ctx.host_phase += 1
+    ph = ctx.host_phase
+    ws = ctx.workspace[ph & 1]
+    timeout = U.get_int_env("TD_HOST_TIMEOUT_US", 60_000_000)
+    # 1. my shard into my workspace, publish "ready" on every peer
+    ws[me * Ms:(me + 1) * Ms].copy_(A)
+    for q in range(W):
+        if q != me:
+            lib.tdh_notify32(ctypes.c_void_p(heap.peer_ptr(ctx.ready.data_ptr() + 4 * me, q)), ph, 1)
+    # 2. pull peers in arrival order, GEMM per source block as it lands
+    N = Bnk.shape[0]
+    if out is None:
+        out = torch.empty((Ms * W, N), dtype=A.dtype)
+    bt = Bnk.float().t()
+    for j in range(W):
+        s = (me + j) % W
+        if s != me:
+            if lib.tdh_wait32(ctypes.c_void_p(ctx.ready.data_ptr() + 4 * s), ph, 1, timeout):
+                raise TimeoutError(f"ag_gemm: rank {s} never published phase {ph}")
+            peer_ws = heap.peer_view(ctx.workspace, s)[ph & 1]
+            ws[s * Ms:(s + 1) * Ms].copy_(peer_ws[s * Ms:(s + 1) * Ms])
+        out[s * Ms:(s + 1) * Ms] = (ws[s * Ms:(s + 1) * Ms].float() @ bt).to(A.dtype)
+    return out

@@ -216,22 +216,26 @@ def all_reduce(x: torch.Tensor, method=AllReduceMethod.Unknown, ctx: AllReduceCo
 
 
 def _all_reduce_host(x, ctx: AllReduceContext, output):
-    """Emulation: stage -> flag-flip barrier -> sum over peer views (one-shot protocol)."""
+    """Emulation: stage -> flag-flip barrier -> sum over peer views (one-shot protocol, chunked like the GPU path)."""
     heap = U.get_heap()
-    ctx.host_calls += 1
-    par = ctx.host_calls & 1
-    nbytes = x.numel() * x.element_size()
-    assert nbytes <= ctx.workspace_nbytes
-    st = ctx.stage[par * ctx.workspace_nbytes: par * ctx.workspace_nbytes + nbytes]
-    st.copy_(x.view(torch.uint8).view(-1))
     lib = _C.host_lib()
-    rc = lib.tdh_barrier_all(heap._handle, heap.offset_of(ctx.slots), 2 * ctx.host_calls, 60_000_000)
-    if rc:
-        raise TimeoutError(lib.tdh_last_error().decode())
-    acc = torch.zeros(x.shape, dtype=torch.float32)
-    for r in range(heap.world):
-        acc += heap.peer_view(st, (heap.rank + r) % heap.world).view(x.dtype).view(x.shape).float()
-    output.copy_(acc.to(x.dtype))
+    xb, ob = x.view(torch.uint8).view(-1), output.view(torch.uint8).view(-1)
+    total = xb.numel()
+    off = 0
+    while off < total:
+        n = min(ctx.workspace_nbytes, total - off)
+        ctx.host_calls += 1
+        par = ctx.host_calls & 1
+        st = ctx.stage[par * ctx.workspace_nbytes: par * ctx.workspace_nbytes + n]
+        st.copy_(xb[off:off + n])
+        rc = lib.tdh_barrier_all(heap._handle, heap.offset_of(ctx.slots), 2 * ctx.host_calls, 60_000_000)
+        if rc:
+            raise TimeoutError(lib.tdh_last_error().decode())
+        acc = torch.zeros(n // x.element_size(), dtype=torch.float32)
+        for r in range(heap.world):
+            acc += heap.peer_view(st, (heap.rank + r) % heap.world).view(x.dtype).float()
+        ob[off:off + n].copy_(acc.to(x.dtype).view(torch.uint8))
+        off += n
     return output
 
 

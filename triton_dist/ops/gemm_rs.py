@@ -1,0 +1,177 @@
+"""GEMM + ReduceScatter in one kernel:  ``C[M/W, N] = reduce_scatter(A[M, K/W] @ B[K/W, N])``.
+
+Reference: ``create_gemm_rs_context`` / ``gemm_rs`` (/root/reference/python/triton_dist/kernels/nvidia/
+gemm_reduce_scatter.py:71, :727-741) = Triton GEMM writing a symmetric buffer + per-segment counters ->
+copy-engine scatter -> barrier -> separate ``ring_reduce`` kernel (reduce_scatter.py:551-707).
+
+Here (csrc/gemm_sm100.cuh, mode kRS) the reduce-scatter is a ring fused into the tcgen05 epilogue: rank ``o-1``
+computes owner ``o``'s tile first and pushes it (coalesced 16-byte NVLink stores) into rank ``o-2``'s staging
+buffer; every rank adds its TMEM accumulator to the running partial it received and forwards it; rank ``o`` adds
+the last contribution and writes the final rows.  All SMs run GEMM tiles, there is no reduction pass and no
+barrier: staging is double buffered by call parity, per-tile flags carry monotone phase numbers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from .. import _C
+from .. import utils as U
+from .gemm import GemmConfig, fill_common, gemm
+from .ag_gemm import _as_nk
+
+
+@dataclass
+class GEMMReduceScatterTensorParallelContext:
+    max_M: int
+    N: int
+    rank: int
+    world_size: int
+    local_world_size: int
+    output_dtype: torch.dtype
+    stage: torch.Tensor = None      # symmetric [2, max_M, N]
+    flags: torch.Tensor = None      # symmetric int32 [2, max_tiles]
+    phase: torch.Tensor = None      # local int32 [4]
+    scratch: torch.Tensor = None    # symmetric [max_M, N] (fallback path only, lazily allocated)
+    host_phase: int = 0
+
+    def finalize(self):
+        heap = U.get_heap()
+        for t in (self.stage, self.flags, self.scratch):
+            if t is not None:
+                heap.free_tensor(t)
+        self.stage = self.flags = self.scratch = None
+
+
+def create_gemm_rs_context(max_M: int, N: int, rank: Optional[int] = None, world_size: Optional[int] = None,
+                           local_world_size: Optional[int] = None, output_dtype: torch.dtype = torch.bfloat16,
+                           rs_stream=None, reduce_st: bool = False, **_unused) -> GEMMReduceScatterTensorParallelContext:
+    heap = U.get_heap()
+    rank = heap.rank if rank is None else rank
+    world_size = heap.world if world_size is None else world_size
+    ctx = GEMMReduceScatterTensorParallelContext(max_M, N, rank, world_size, local_world_size or world_size, output_dtype)
+    ctx.stage = heap.tensor((2, max_M, N), output_dtype)
+    max_tiles = max(((max_M + 127) // 128) * ((N + 31) // 32), world_size, 8)
+    ctx.flags = heap.tensor((2, max_tiles), torch.int32)
+    ctx.phase = torch.zeros(4, dtype=torch.int32, device=heap.device)
+    U.barrier_all_host()
+    return ctx
+
+
+def default_rs_config(M: int, N: int, K: int, world: int) -> GemmConfig:
+    mr = M // max(world, 1)
+    if mr % 256 == 0 and N >= 256:
+        return GemmConfig(bn=256, cta_group=2, group_m=1, use_tma_store=False)
+    if mr % 128 == 0 and N >= 256:
+        return GemmConfig(bn=256, cta_group=1, group_m=1, use_tma_store=False)
+    if mr % 128 == 0:
+        return GemmConfig(bn=128 if N >= 128 else 64, cta_group=1, group_m=1, use_tma_store=False)
+    return GemmConfig(bn=128, cta_group=1, group_m=1, use_tma_store=False)
+
+
+def gemm_rs(A: torch.Tensor, B: torch.Tensor, ctx: GEMMReduceScatterTensorParallelContext,
+            gemm_config: Optional[GemmConfig] = None, persistent: bool = True, fuse_scatter: bool = True,
+            reduce_st: bool = False, out: Optional[torch.Tensor] = None, straggler_option=None, **_unused) -> torch.Tensor:
+    """A: ``[M, K/W]``, B: ``[K/W, N]`` (``.t()`` view of a ``[N, K/W]`` weight) -> ``[M/W, N]``."""
+    W = ctx.world_size
+    M, K = A.shape
+    Bnk = _as_nk(B)
+    N = Bnk.shape[0]
+    assert M % W == 0 and M <= ctx.max_M and N == ctx.N and Bnk.shape[1] == K
+    Mr = M // W
+    if not A.is_cuda:
+        return _gemm_rs_host(A, Bnk, ctx, out)
+    if out is None:
+        out = torch.empty((Mr, N), dtype=A.dtype, device=A.device)
+    cfg = gemm_config or default_rs_config(M, N, K, W)
+    if W == 1:
+        return gemm(A, Bnk, out=out, config=GemmConfig(cfg.bn, cfg.cta_group, 8, True, cfg.num_sms, 0))
+    if straggler_option and straggler_option[0] == ctx.rank:
+        torch.cuda._sleep(int(straggler_option[1]))
+    tm = 128 * cfg.cta_group
+    if Mr % tm != 0:
+        if Mr % 128 == 0:
+            cfg = GemmConfig(cfg.bn, 1, 1, False, cfg.num_sms, 0)
+            tm = 128
+        else:
+            return _gemm_rs_fallback(A, Bnk, ctx, out)
+    A = A.contiguous()
+    args = _C.GemmArgs()
+    args.mode = 2
+    fill_common(args, M, A.data_ptr(), A.stride(0), Bnk, out.data_ptr(), Mr, out.stride(0), M, N, K,
+                GemmConfig(cfg.bn, cfg.cta_group, cfg.group_m, False, cfg.num_sms, 0), A.dtype == torch.bfloat16)
+    # first the tiles owned by rank+1 (the chain for owner o starts at rank o-1 and ends at o)
+    args.m_rot = (((ctx.rank + 1) % W) * Mr) // tm
+    r, w, base, stride, mc = U.symm_ctx_fields()
+    args.rank, args.world, args.symm_base, args.symm_stride, args.mc_base = r, w, base, stride, mc
+    args.phase = ctx.phase.data_ptr()
+    args.rs_rows_per_rank = Mr
+    args.rs_stage, args.rs_stage_buf_bytes = ctx.stage.data_ptr(), ctx.max_M * N * A.element_size()
+    args.rs_flags, args.rs_out, args.rs_ldo = ctx.flags.data_ptr(), out.data_ptr(), out.stride(0)
+    _C.check(_C.cuda_lib().td_gemm_launch(C.byref(args), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+             "td_gemm_launch(rs)")
+    ctx.host_phase += 1
+    return out
+
+
+def _gemm_rs_fallback(A, Bnk, ctx, out):
+    """Shapes the ring cannot tile (M/W not a multiple of 128): local GEMM into a symmetric buffer, barrier,
+    then every rank pulls and sums its rows from all peers (P2P loads)."""
+    heap = U.get_heap()
+    W, me = ctx.world_size, ctx.rank
+    M, N = A.shape[0], Bnk.shape[0]
+    Mr = M // W
+    if ctx.scratch is None:
+        ctx.scratch = heap.tensor((ctx.max_M, ctx.N), ctx.output_dtype)
+        U.barrier_all_host()
+    U.barrier_all_on_stream()                      # peers finished reading the previous call's scratch
+    gemm(A, Bnk, out=ctx.scratch[:M])
+    U.barrier_all_on_stream()
+    acc = torch.zeros((Mr, N), dtype=torch.float32, device=A.device)
+    for j in range(W):
+        p = (me + j) % W
+        acc += heap.peer_view(ctx.scratch, p)[me * Mr:(me + 1) * Mr].float()
+    out.copy_(acc.to(out.dtype))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# emulation (no GPU): the same ring, flags and double buffering on the shared-memory heap
+# ------------------------------------------------------------------------------------------------------------
+def _gemm_rs_host(A, Bnk, ctx, out):
+    import ctypes
+    heap = U.get_heap()
+    lib = _C.host_lib()
+    W, me = ctx.world_size, ctx.rank
+    M, K = A.shape
+    N = Bnk.shape[0]
+    Mr = M // W
+    ctx.host_phase += 1
+    ph = ctx.host_phase
+    par = ph & 1
+    timeout = U.get_int_env("TD_HOST_TIMEOUT_US", 60_000_000)
+    if out is None:
+        out = torch.empty((Mr, N), dtype=A.dtype)
+    bt = Bnk.float().t()
+    stage = ctx.stage[par]
+    prev = (me - 1 + W) % W
+    prev_stage = heap.peer_view(ctx.stage, prev)[par]
+    for step in range(W):
+        owner = (me + 1 + step) % W              # step 0: rank+1's rows ... step W-1: my own rows
+        rows = slice(owner * Mr, (owner + 1) * Mr)
+        part = A[rows].float() @ bt
+        if step > 0:
+            # running partial pushed by rank+1 (which computed these rows one step earlier)
+            if lib.tdh_wait32(ctypes.c_void_p(ctx.flags.data_ptr() + 4 * (par * ctx.flags.shape[1] + owner)), ph, 1, timeout):
+                raise TimeoutError(f"gemm_rs: partial for owner {owner} never arrived (phase {ph})")
+            part = part + stage[rows].float()
+        if step == W - 1:
+            out.copy_(part.to(A.dtype))
+        else:
+            prev_stage[rows].copy_(part.to(A.dtype))
+            flag = heap.peer_ptr(ctx.flags.data_ptr() + 4 * (par * ctx.flags.shape[1] + owner), prev)
+            lib.tdh_notify32(ctypes.c_void_p(flag), ph, 1)
+    return out
