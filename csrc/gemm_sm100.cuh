@@ -153,9 +153,11 @@ struct AgPiece {
   const char* src;
   char* dst;
   uint32_t bytes;
-  uint32_t* flag;        // non-null: this piece completes a sub-piece -> bump *flag after the store is complete
+  uint32_t* flag;        // non-null: this piece completes a sub-piece -> publish *flag after the store is complete
   int local_done;        // 1: the sub-piece belongs to my own shard (counts towards publishing "ready")
 };
+
+enum AgNext : int { kAgPiece = 0, kAgNotReady = 1, kAgDone = 2 };
 
 struct AgCursor {
   const Params& p;
@@ -165,62 +167,61 @@ struct AgCursor {
   size_t row_bytes;
   char* ws;
   uint32_t* flags;
-  // iteration state
+  // enumeration state: (j, b, u) = (source distance, chunk, sub-piece) of the item under the cursor
   int j, b, u, item;
-  size_t off, end;       // byte range [off, end) of the current sub-piece still to be emitted
-  bool in_sub;
+  bool have_item;        // (j,b,u) is an item of mine that has not been opened yet
+  bool in_sub;           // a sub-piece is open: [off, end) still to be emitted
+  size_t off, end;
   const char* src_base;
   char* dst_base;
   size_t sub_base;       // byte offset of the chunk inside the shard
 
-  TD_DEVICE AgCursor(const Params& p_, uint32_t ph_, int comm_idx_)
-      : p(p_), ph(ph_), comm_idx(comm_idx_) {
+  TD_DEVICE AgCursor(const Params& p_, uint32_t ph_, int comm_idx_) : p(p_), ph(ph_), comm_idx(comm_idx_) {
     W = p.symm.world; me = p.symm.rank; Ms = p.ag_rows_per_rank;
     cpr = (Ms + kAGRowsPerChunk - 1) / kAGRowsPerChunk;
     row_bytes = static_cast<size_t>(p.K) * 2;
     ws = p.ag_ws + (ph & 1u) * p.ag_ws_buf_bytes;
     flags = p.ag_flags + (ph & 1u) * W * cpr * kAGSubPieces;
     j = p.ag_copy_local ? 0 : 1; b = 0; u = -1; item = -1;
-    off = end = 0; in_sub = false; src_base = nullptr; dst_base = nullptr; sub_base = 0;
+    have_item = false; in_sub = false; off = end = 0; src_base = nullptr; dst_base = nullptr; sub_base = 0;
   }
-  // advance to my next sub-piece; returns false when exhausted
-  TD_DEVICE bool next_sub() {
+  // move (j,b,u) to my next item; false when the enumeration is exhausted
+  TD_DEVICE bool advance() {
     while (true) {
       ++u; ++item;
       if (u == kAGSubPieces) { u = 0; ++b; }
       if (b == cpr) { b = 0; ++j; }
       if (j >= W) return false;
-      if (item % p.n_comm_ctas != comm_idx) continue;
+      if (item % p.n_comm_ctas == comm_idx) return true;
+    }
+  }
+  // Emit the next <= 16 KB piece.  NEVER blocks: if the next source has not published its shard yet the
+  // caller gets kAgNotReady and keeps draining its store queue (a blocking wait here deadlocks: the peers'
+  // "ready" depends on THEIR stores, which would be stuck behind the same wait).
+  TD_DEVICE AgNext next(AgPiece& out) {
+    if (!in_sub) {
+      if (!have_item) {
+        if (!advance()) return kAgDone;
+        have_item = true;
+      }
       const int s = (me + j) % W;
+      if (s != me && static_cast<int32_t>(ptx::ld_acquire_sys(p.ag_ready + s) - ph) < 0) return kAgNotReady;
+      have_item = false;
       const int r0 = b * kAGRowsPerChunk, r1 = min(Ms, r0 + kAGRowsPerChunk);
       const size_t cbytes = static_cast<size_t>(r1 - r0) * row_bytes;
       const size_t sub = ((cbytes + kAGSubPieces - 1) / kAGSubPieces + 127) & ~static_cast<size_t>(127);
-      const size_t o0 = min(cbytes, sub * u), o1 = min(cbytes, sub * (u + 1));
       const size_t shard_off = static_cast<size_t>(s) * Ms * row_bytes;
-      if (s == me) {
-        src_base = reinterpret_cast<const char*>(p.ag_a_local);
-      } else {
-        wait_ge<true>(p.ag_ready + s, ph);   // peer s has written its phase-ph shard into ITS workspace
-        src_base = symm_at(p.symm, ws, s) + shard_off;
-      }
+      src_base = (s == me) ? reinterpret_cast<const char*>(p.ag_a_local) : symm_at(p.symm, ws, s) + shard_off;
       dst_base = ws + shard_off;
       sub_base = static_cast<size_t>(r0) * row_bytes;
-      off = o0; end = o1; in_sub = true;
-      return true;
-    }
-  }
-  // emit the next <=16 KB piece; returns false when there is no more work for this CTA
-  TD_DEVICE bool next(AgPiece& out) {
-    while (!in_sub) {
-      if (!next_sub()) return false;
+      off = min(cbytes, sub * u); end = min(cbytes, sub * (u + 1));
       if (off >= end) {   // empty sub-piece (tiny chunk): flag only
-        const int s = (me + j) % W;
         out.src = nullptr; out.dst = nullptr; out.bytes = 0;
         out.flag = flags + (s * cpr + b) * kAGSubPieces + u;
         out.local_done = (s == me);
-        in_sub = false;
-        return true;
+        return kAgPiece;
       }
+      in_sub = true;
     }
     const int s = (me + j) % W;
     const uint32_t n = static_cast<uint32_t>(min(static_cast<size_t>(kCommPieceBytes), end - off));
@@ -232,7 +233,7 @@ struct AgCursor {
     out.flag = last ? flags + (s * cpr + b) * kAGSubPieces + u : nullptr;
     out.local_done = (s == me);
     if (last) in_sub = false;
-    return true;
+    return kAgPiece;
   }
 };
 
@@ -262,11 +263,12 @@ TD_DEVICE void ag_comm_cta(const Params& p, uint32_t ph, int comm_idx, uint8_t* 
   uint32_t parity_bits = 0;
   bool more = true;
   while (true) {
-    // 1. keep the load side of the ring full
+    // 1. keep the load side of the ring full (without ever blocking on a peer)
     while (more && loads - retired < kCommRingSlots) {
       AgPiece pc;
-      more = cur.next(pc);
-      if (!more) break;
+      const AgNext st = cur.next(pc);
+      if (st == kAgDone) { more = false; break; }
+      if (st == kAgNotReady) break;
       const uint32_t slot = loads % kCommRingSlots;
       q_dst[slot] = pc.dst; q_flag[slot] = pc.flag;
       q_meta[slot] = static_cast<uint64_t>(pc.bytes) | (static_cast<uint64_t>(pc.local_done) << 32);
@@ -276,7 +278,10 @@ TD_DEVICE void ag_comm_cta(const Params& p, uint32_t ph, int comm_idx, uint8_t* 
       }
       ++loads;
     }
-    if (stores == loads) break;
+    if (stores == loads) {
+      if (!more) break;
+      continue;                                  // nothing in flight: poll the peer's "ready" again
+    }
     // 2. forward the oldest loaded piece to the workspace
     const uint32_t slot = stores % kCommRingSlots;
     const uint32_t bytes = static_cast<uint32_t>(q_meta[slot]);
@@ -288,7 +293,7 @@ TD_DEVICE void ag_comm_cta(const Params& p, uint32_t ph, int comm_idx, uint8_t* 
     ptx::bulk_commit();
     ++stores;
     if (q_flag[slot] != nullptr) {
-      // a sub-piece is complete once all its stores are COMPLETE (not merely read from smem)
+      // a sub-piece is resident once all its stores are COMPLETE (not merely read from smem)
       ptx::bulk_wait<0>();
       retired = stores;
       ptx::fence_proxy_async();

@@ -44,11 +44,28 @@ def _nvcc() -> str:
 
 
 def _digest(paths, extra: str) -> str:
-    h = hashlib.sha256(extra.encode())
+    """Content hash that does not depend on where the repo is checked out (the GPU box uses a scratch path)."""
+    h = hashlib.sha256(extra.replace(str(ROOT), "<root>").encode())
     for p in sorted(paths):
-        h.update(str(p).encode())
+        h.update(str(Path(p).resolve().relative_to(ROOT)).encode())
         h.update(Path(p).read_bytes())
     return h.hexdigest()[:16]
+
+
+class _BuildLock:
+    """Inter-process lock: ranks launched together must not compile the same objects concurrently."""
+
+    def __enter__(self):
+        import fcntl
+        LIBDIR.mkdir(parents=True, exist_ok=True)
+        self.f = open(LIBDIR / ".build.lock", "w")
+        fcntl.flock(self.f, fcntl.LOCK_EX)
+        return self
+
+    def __exit__(self, *exc):
+        import fcntl
+        fcntl.flock(self.f, fcntl.LOCK_UN)
+        self.f.close()
 
 
 def _headers():
@@ -86,7 +103,12 @@ def _compile_objects(sources, compiler_cmd, tag, verbose):
 
 
 def build_cuda(verbose: bool = False, force: bool = False) -> Path:
-    """Compile every ``csrc/*.cu`` + ``csrc/runtime/*.cpp`` into ``libtd_b200.so`` (sm_100a only)."""
+    """Compile every ``csrc/*.cu`` + ``csrc/runtime/*.cu`` into ``libtd_b200.so`` (sm_100a only)."""
+    with _BuildLock():
+        return _build_cuda_locked(verbose, force)
+
+
+def _build_cuda_locked(verbose: bool, force: bool) -> Path:
     LIBDIR.mkdir(parents=True, exist_ok=True)
     out = LIBDIR / "libtd_b200.so"
     cu = sorted(CSRC.glob("*.cu")) + sorted((CSRC / "runtime").glob("*.cu"))
@@ -106,6 +128,11 @@ def build_cuda(verbose: bool = False, force: bool = False) -> Path:
 
 def build_host(verbose: bool = False, force: bool = False) -> Path:
     """Compile ``csrc/host/*.cpp`` into ``libtd_host.so`` (no CUDA dependency; runs on CPU-only boxes)."""
+    with _BuildLock():
+        return _build_host_locked(verbose, force)
+
+
+def _build_host_locked(verbose: bool, force: bool) -> Path:
     LIBDIR.mkdir(parents=True, exist_ok=True)
     out = LIBDIR / "libtd_host.so"
     srcs = sorted((CSRC / "host").glob("*.cpp"))
