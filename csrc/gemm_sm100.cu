@@ -19,7 +19,7 @@ struct TdGemmArgs {
   long long m_rot;
   const void* A; long long a_rows; long long lda; long long a_nbuf; long long a_buf_stride_bytes;
   const void* B; long long ldb;
-  void* C; long long c_rows; long long ldc;
+  void* C; long long c_rows; long long ldc; const void* c_phase; long long c_nbuf; long long c_buf_stride_bytes;
   // symmetric context
   long long rank, world; unsigned long long symm_base, symm_stride, mc_base;
   void* phase;
@@ -101,12 +101,14 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
     if (encode_tmap(&p.tmap_b, a->B, 2, dims, strides, box, bf16)) return -1;
   }
   p.use_tma_store = (a->use_tma_store && bn >= 64 && a->mode != kRS && a->ldc % 8 == 0) ? 1 : 0;
-  if (p.use_tma_store) {  // C: {N, rows}
-    cuuint64_t dims[2] = {(cuuint64_t)a->N, (cuuint64_t)a->c_rows};
-    cuuint64_t strides[1] = {(cuuint64_t)a->ldc * 2};
-    cuuint32_t box[2] = {kCBlockCols, BM};
-    if (encode_tmap(&p.tmap_c, a->C, 2, dims, strides, box, bf16)) return -1;
+  if (p.use_tma_store) {  // C: {N, rows, nbuf}
+    cuuint64_t dims[3] = {(cuuint64_t)a->N, (cuuint64_t)a->c_rows, (cuuint64_t)(a->c_nbuf > 0 ? a->c_nbuf : 1)};
+    cuuint64_t strides[2] = {(cuuint64_t)a->ldc * 2, (cuuint64_t)(a->c_nbuf > 1 ? a->c_buf_stride_bytes : a->c_rows * a->ldc * 2)};
+    cuuint32_t box[3] = {kCBlockCols, BM, 1};
+    if (encode_tmap(&p.tmap_c, a->C, 3, dims, strides, box, bf16)) return -1;
   }
+  p.c_phase = (a->c_nbuf > 1) ? reinterpret_cast<const uint32_t*>(a->c_phase) : nullptr;
+  p.c_buf_stride_bytes = a->c_buf_stride_bytes;
   const int TM = BM * cg;
   p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K;
   p.num_m = (p.M + TM - 1) / TM;

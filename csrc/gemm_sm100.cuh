@@ -50,7 +50,7 @@ enum Mode : int { kPlain = 0, kAG = 1, kRS = 2 };
 struct Params {
   CUtensorMap tmap_a;   // dims {K, rows_a, nbuf}, box {64, 128, 1}, SWIZZLE_128B
   CUtensorMap tmap_b;   // dims {K, N},            box {64, BN / cta_group}
-  CUtensorMap tmap_c;   // dims {N, rows_c},       box {64, 128}, SWIZZLE_128B (only if use_tma_store)
+  CUtensorMap tmap_c;   // dims {N, rows_c, nbuf}, box {64, 128, 1}, SWIZZLE_128B (only if use_tma_store)
   int M, N, K;
   int num_m, num_n, num_k;   // tile counts; num_m is in units of BM * cta_group rows
   int group_m;               // L2 swizzle band height (in m tiles)
@@ -61,6 +61,10 @@ struct Params {
   int pad0;
   void* C;                   // output base (row-major)
   long long ldc;             // leading dimension of C in elements
+  // optional device-selected output half: C += ((*c_phase + 1) & 1) * c_buf_stride_bytes.  Lets the GEMM write
+  // straight into the parity-double-buffered staging of a following collective inside a replayed CUDA graph.
+  const uint32_t* c_phase;
+  long long c_buf_stride_bytes;
   SymmCtx symm;
   // ---- phase bookkeeping (device resident so a captured graph replays correctly) ----
   // [0] = number of completed calls on this context, [1] = CTA exit counter, [2] = AG local-copy counter
@@ -331,6 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
   const uint32_t cta_rank = (kCtaGroup == 2) ? ptx::cluster_ctarank() : 0u;
   const bool is_leader = cta_rank == 0;
   const uint32_t ph = (kMode == kPlain) ? 0u : (p.phase[0] + 1u);
+  const int cbuf = p.c_phase ? static_cast<int>((p.c_phase[0] + 1u) & 1u) : 0;
 
   const int n_gemm_ctas = static_cast<int>(gridDim.x) - p.n_comm_ctas;
   const bool is_comm = static_cast<int>(blockIdx.x) >= n_gemm_ctas;
@@ -454,7 +459,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         // ---- RS ring bookkeeping for this tile ----
         int rs_step = 0; bool rs_final = false;
         const char* rs_in = nullptr;                 // running partial received from rank+1 (local memory)
-        char* dst_base = reinterpret_cast<char*>(p.C);
+        char* dst_base = reinterpret_cast<char*>(p.C) + cbuf * p.c_buf_stride_bytes;
         long long dst_ld = p.ldc;
         int dst_row_off = 0;                         // subtract from the global row for the destination
         if constexpr (kMode == kRS) {
@@ -481,8 +486,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
 
 #pragma unroll 1
         for (int cb = 0; cb < kNumCBlocks; ++cb, ++blk_iter) {
-          uint8_t* cbuf = smem_c + (blk_iter & 1u) * kCBlockBytes;
-          const uint32_t cbuf_u32 = ptx::smem_u32(cbuf);
+          uint8_t* cstage = smem_c + (blk_iter & 1u) * kCBlockBytes;
+          const uint32_t cbuf_u32 = ptx::smem_u32(cstage);
           if (p.use_tma_store) {       // the TMA store that last used this buffer must have finished reading it
             if (et == 0) ptx::bulk_wait_read<1>();
             __syncwarp();
@@ -555,7 +560,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
           const int gcol0 = col_base + cb * kCBlockCols;
           if (p.use_tma_store) {
             if (et == 0 && gcol0 < p.N && row_base < p.M) {
-              ptx::tma_store_2d(&p.tmap_c, cbuf, gcol0, row_base);
+              ptx::tma_store_3d(&p.tmap_c, cstage, gcol0, row_base, cbuf);
               ptx::bulk_commit();
             }
             __syncwarp();

@@ -1,0 +1,18 @@
+"""Multi-GPU checks (torchrun over NCCL + our symmetric heap).  Skipped when fewer than 2 GPUs are visible."""
+import pytest
+import torch
+
+from _launch import run_dist
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpu():
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.parametrize("case", ["primitives", "allgather", "allreduce", "ag_gemm", "gemm_rs"])
+def test_gpu_world2(case):
+    if _ngpu() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    run_dist([case], nproc=2, timeout=300)

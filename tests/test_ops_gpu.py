@@ -1,0 +1,99 @@
+"""Numerics of the glue kernels and flash-decode vs plain PyTorch fp32 references (real B200)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("H", [128, 4096, 5120])
+def test_rmsnorm(dtype, H):
+    from triton_dist.ops.elementwise import rmsnorm
+    x = torch.randn(37, H, device="cuda", dtype=dtype)
+    r = torch.randn(37, H, device="cuda", dtype=dtype)
+    w = (1 + 0.1 * torch.randn(H, device="cuda")).to(dtype)
+    y = rmsnorm(x, w, 1e-6)
+    ref = (x.float() * torch.rsqrt(x.float().pow(2).mean(-1, keepdim=True) + 1e-6)) * w.float()
+    torch.testing.assert_close(y.float(), ref, atol=3e-2, rtol=3e-2)
+    y2, h = rmsnorm(x, w, 1e-6, residual=r)
+    hh = (x + r)
+    torch.testing.assert_close(h.float(), hh.float(), atol=1e-2, rtol=1e-2)
+    ref2 = (hh.float() * torch.rsqrt(hh.float().pow(2).mean(-1, keepdim=True) + 1e-6)) * w.float()
+    torch.testing.assert_close(y2.float(), ref2, atol=5e-2, rtol=5e-2)
+
+
+def test_silu_mul():
+    from triton_dist.ops.elementwise import silu_mul
+    x = torch.randn(77, 2 * 1536, device="cuda", dtype=torch.bfloat16)
+    y = silu_mul(x)
+    ref = torch.nn.functional.silu(x[:, :1536].float()) * x[:, 1536:].float()
+    torch.testing.assert_close(y.float(), ref, atol=3e-2, rtol=3e-2)
+
+
+@pytest.mark.parametrize("qk_norm", [True, False])
+def test_qk_norm_rope_kv(qk_norm):
+    from triton_dist.ops.elementwise import qk_norm_rope_kv, rope_reference
+    B, S, Hq, Hkv, D, L = 2, 5, 4, 1, 128, 64
+    T = B * S
+    qkv = torch.randn(T, (Hq + 2 * Hkv) * D, device="cuda", dtype=torch.bfloat16)
+    kc = torch.zeros(B, L, Hkv, D, device="cuda", dtype=torch.bfloat16)
+    vc = torch.zeros_like(kc)
+    pos = (torch.arange(S, device="cuda") + 7).repeat(B).to(torch.int32)
+    bidx = torch.arange(B, device="cuda", dtype=torch.int32).repeat_interleave(S)
+    qw = (1 + 0.1 * torch.randn(D, device="cuda")).to(torch.bfloat16) if qk_norm else None
+    kw = (1 + 0.1 * torch.randn(D, device="cuda")).to(torch.bfloat16) if qk_norm else None
+    q = qk_norm_rope_kv(qkv, kc, vc, pos, bidx, Hq, Hkv, qw, kw, 1e-6, 1e6)
+    x = qkv.view(T, Hq + 2 * Hkv, D)
+    qr, kr, vr = x[:, :Hq], x[:, Hq:Hq + Hkv], x[:, Hq + Hkv:]
+    if qk_norm:
+        n = lambda t, w: ((t.float() * torch.rsqrt(t.float().pow(2).mean(-1, keepdim=True) + 1e-6)) * w.float()).to(torch.bfloat16)
+        qr, kr = n(qr, qw), n(kr, kw)
+    qr, kr = rope_reference(qr, pos, 1e6), rope_reference(kr, pos, 1e6)
+    torch.testing.assert_close(q.float(), qr.float(), atol=3e-2, rtol=3e-2)
+    torch.testing.assert_close(kc[bidx.long(), pos.long()].float(), kr.float(), atol=3e-2, rtol=3e-2)
+    assert torch.equal(vc[bidx.long(), pos.long()], vr)
+
+
+@pytest.mark.parametrize("Hq,Hkv", [(4, 1), (8, 2), (8, 8), (8, 1)])
+@pytest.mark.parametrize("paged", [False, True])
+def test_flash_decode(Hq, Hkv, paged):
+    from triton_dist.ops.flash_decode import _decode_reference, gqa_fwd_batch_decode, gqa_fwd_batch_decode_partial
+    torch.manual_seed(0)
+    B, D, L = 3, 128, 700
+    q = torch.randn(B, Hq, D, device="cuda", dtype=torch.bfloat16)
+    lens = torch.tensor([700, 1, 333], device="cuda", dtype=torch.int32)
+    if paged:
+        page, npages = 64, 40
+        kc = torch.randn(npages, page, Hkv, D, device="cuda", dtype=torch.bfloat16)
+        vc = torch.randn(npages, page, Hkv, D, device="cuda", dtype=torch.bfloat16)
+        bt = torch.stack([torch.randperm(npages, device="cuda")[:12] for _ in range(B)]).to(torch.int32)
+        o = gqa_fwd_batch_decode(q, kc, vc, lens, block_table=bt)
+        ref, _ = _decode_reference(q, kc, vc, lens, 1 / math.sqrt(D), bt, page)
+    else:
+        kc = torch.randn(B, L, Hkv, D, device="cuda", dtype=torch.bfloat16)
+        vc = torch.randn(B, L, Hkv, D, device="cuda", dtype=torch.bfloat16)
+        o = gqa_fwd_batch_decode(q, kc, vc, lens)
+        ref, lse_ref = _decode_reference(q, kc, vc, lens, 1 / math.sqrt(D))
+        _, lse = gqa_fwd_batch_decode_partial(q, kc, vc, lens, num_splits=5)
+        torch.testing.assert_close(lse, lse_ref, atol=2e-2, rtol=2e-2)
+    torch.testing.assert_close(o.float(), ref, atol=3e-2, rtol=3e-2)
+
+
+def test_engine_single_gpu_backends_agree():
+    import triton_dist.utils as U
+    from triton_dist.models import Engine, ModelConfig
+    U.initialize_distributed(seed=0)
+    cfg = ModelConfig(model_name="tiny-dense", max_length=64, dtype=torch.bfloat16, rank=0, world_size=1)
+    eng = Engine(cfg, temperature=0.0)
+    ids = torch.randint(0, 1000, (4, 6), device="cuda")
+    ref = eng.serve(ids, 5, backend="torch", use_cuda_graph=False)
+    for be in ("triton_dist_AR", "triton_dist_gemm_ar", "triton_dist"):
+        out = eng.serve(ids, 5, backend=be, use_cuda_graph=True)
+        # bf16 argmax can flip on near-ties; the first generated tokens come from the shared torch prefill
+        assert torch.equal(out[:, 0], ref[:, 0])
+        agree = (out == ref).float().mean().item()
+        assert agree >= 0.7, (be, agree, out, ref)
+    from triton_dist import _C
+    assert any("libtd_b200" in p for p in _C.loaded_libraries())

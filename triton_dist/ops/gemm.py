@@ -67,8 +67,11 @@ def fill_common(args: _C.GemmArgs, a_rows: int, A_ptr: int, lda: int, B: torch.T
 
 
 def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None,
-         config: Optional[GemmConfig] = None) -> torch.Tensor:
-    """``out[M,N] = a[M,K] @ b[N,K].T`` with fp32 accumulation in TMEM.  ``b`` is an ``nn.Linear`` weight."""
+         config: Optional[GemmConfig] = None, out_parity=None) -> torch.Tensor:
+    """``out[M,N] = a[M,K] @ b[N,K].T`` with fp32 accumulation in TMEM.  ``b`` is an ``nn.Linear`` weight.
+
+    ``out_parity=(phase_tensor, stride_bytes)``: ``out`` is half 0 of a parity-double-buffered staging area; the
+    kernel writes half ``(phase_tensor[0] + 1) & 1`` chosen ON THE DEVICE (CUDA-graph replay safe)."""
     if not a.is_cuda:
         raise RuntimeError("triton_dist.ops.gemm needs CUDA tensors (sm_100a kernel); the CPU path is emulation-only")
     _check_operand(a, "a")
@@ -84,6 +87,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None,
     args.mode = 0
     fill_common(args, M, a.data_ptr(), a.stride(0), b, out.data_ptr(), M, out.stride(0), M, N, K, cfg,
                 a.dtype == torch.bfloat16)
+    if out_parity is not None:
+        args.c_phase, args.c_nbuf, args.c_buf_stride_bytes = out_parity[0].data_ptr(), 2, int(out_parity[1])
     lib = _C.cuda_lib()
     _C.check(lib.td_gemm_launch(C.byref(args), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "td_gemm_launch")
     return out
