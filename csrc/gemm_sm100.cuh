@@ -77,7 +77,7 @@ struct Params {
   const void* ag_a_local;    // my shard [rows_per_rank, K]
   char* ag_ws;               // my workspace: 2 buffers of [world * rows_per_rank, K] (symmetric)
   long long ag_ws_buf_bytes; // bytes of one buffer
-  uint32_t* ag_flags;        // [2][world][chunks_per_rank][kAGSubPieces] = phase of the call that filled it (local)
+  uint32_t* ag_flags;        // symmetric: [2][world(src)][chunks_per_rank][kAGSubPieces] = phase of the call that filled it
   uint32_t* ag_ready;        // [world]: ag_ready[s] >= p  <=>  rank s has its phase-p shard in ITS workspace (symmetric)
   // ---- RS (ring) ----
   int rs_rows_per_rank;      // M / world, multiple of BM * cta_group
@@ -102,7 +102,7 @@ struct SmemLayout {
   // barriers: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]; then the TMEM base pointer
   static constexpr int kNumBars = 2 * kStages + 4;
   static constexpr int kGemmBytes = kBarOff + kNumBars * 8 + 16;
-  static constexpr int kCommBytes = kCommRingSlots * kCommPieceBytes + kCommRingSlots * (8 + 8 + 8 + 8) + 64;
+  static constexpr int kCommBytes = kCommRingSlots * kCommPieceBytes + kCommRingSlots * (8 + 8 + 8 + 8) + 64;  // ring + mbarriers + queues
   static constexpr int kTotal = (kGemmBytes > kCommBytes ? kGemmBytes : kCommBytes) + 1024;  // + alignment slack
   static_assert(kStageBytes % 1024 == 0, "stage must keep 1024 B alignment for SWIZZLE_128B");
   static_assert(kTotal <= 232448, "exceeds 227 KB of shared memory");
@@ -130,128 +130,44 @@ TD_DEVICE void tile_coords(const Params& p, int t, int& m_tile, int& n_tile) {
 TD_DEVICE void ag_wait_rows(const Params& p, uint32_t ph, int row0, int row1) {
   const int Ms = p.ag_rows_per_rank;
   const int cpr = (Ms + kAGRowsPerChunk - 1) / kAGRowsPerChunk;
-  // one flag per (source, chunk, sub-piece); a flag holds the phase number of the call that last filled it,
-  // so stale values from earlier calls (or other shapes) are simply "< ph" and nothing is ever reset
+  // one flag per (source, chunk, sub-piece), written by the SOURCE rank's comm CTA over NVLink after its
+  // pushed bytes are complete.  A flag holds the phase number of the call that last filled it, so stale
+  // values from earlier calls (or other shapes) are simply "< ph" and nothing is ever reset.
   const uint32_t* flags = p.ag_flags + (ph & 1u) * p.symm.world * cpr * kAGSubPieces;
   int r = row0;
   while (r < row1) {
     const int s = r / Ms;
     const int b = (r - s * Ms) / kAGRowsPerChunk;
-    const uint32_t* f = flags + (s * cpr + b) * kAGSubPieces;
+    if (s != p.symm.rank || p.ag_copy_local) {
+      const uint32_t* f = flags + (s * cpr + b) * kAGSubPieces;
 #pragma unroll 1
-    for (int u = 0; u < kAGSubPieces; ++u) wait_ge<false>(f + u, ph);
+      for (int u = 0; u < kAGSubPieces; ++u) wait_ge<true>(f + u, ph);
+    }
     r = min(s * Ms + (b + 1) * kAGRowsPerChunk, (s + 1) * Ms);
   }
-  // the rows were written through the async proxy (bulk copies) of another CTA: order them before my TMA reads
+  // the rows were written through the async proxy (bulk copies): order them before my TMA reads
   ptx::fence_proxy_async();
 }
 
 // -------------------------------------------------------------------------------------------------
-// AG producer side (comm CTA): one thread drives a software-pipelined chain of TMA bulk copies
-//     source HBM (peer over NVLink, or my own shard) -> smem ring -> my workspace
-// Work items = (source s, chunk b, sub-piece u), enumerated in arrival order (own shard, rank+1, ...),
-// dealt round-robin to the comm CTAs so that all of them pull from the SAME peer at the same time and
-// every rank's NVLink egress serves exactly one puller at a time.
+// AG producer side (comm CTA): PUSH my shard into every rank's workspace.
+//
+// Measured on 8xB200: a *pull* design (TMA bulk loads from peer HBM) tops out at ~7 GB/s per SM -- remote
+// reads are round trips and each SM only keeps a few KB of them in flight -- so 32 SMs reached 220 GB/s.
+// Remote *writes* are posted: one thread streams  local HBM -> smem ring -> peer HBM  with TMA bulk copies
+// and keeps kCommLag x 16 KB of stores un-acknowledged per SM.
+// Destinations are served one after the other in the order the consumers need the data (rank-1 first,
+// it starts with my rows right after its own), and at any moment every rank pushes to a different peer,
+// so each NVLink port carries exactly one stream in each direction.
 // -------------------------------------------------------------------------------------------------
-struct AgPiece {
-  const char* src;
-  char* dst;
-  uint32_t bytes;
-  uint32_t* flag;        // non-null: this piece completes a sub-piece -> publish *flag after the store is complete
-  int local_done;        // 1: the sub-piece belongs to my own shard (counts towards publishing "ready")
-};
-
-enum AgNext : int { kAgPiece = 0, kAgNotReady = 1, kAgDone = 2 };
-
-struct AgCursor {
-  const Params& p;
-  uint32_t ph;
-  int comm_idx;
-  int W, me, Ms, cpr;
-  size_t row_bytes;
-  char* ws;
-  uint32_t* flags;
-  // enumeration state: (j, b, u) = (source distance, chunk, sub-piece) of the item under the cursor
-  int j, b, u, item;
-  bool have_item;        // (j,b,u) is an item of mine that has not been opened yet
-  bool in_sub;           // a sub-piece is open: [off, end) still to be emitted
-  size_t off, end;
-  const char* src_base;
-  char* dst_base;
-  size_t sub_base;       // byte offset of the chunk inside the shard
-
-  TD_DEVICE AgCursor(const Params& p_, uint32_t ph_, int comm_idx_) : p(p_), ph(ph_), comm_idx(comm_idx_) {
-    W = p.symm.world; me = p.symm.rank; Ms = p.ag_rows_per_rank;
-    cpr = (Ms + kAGRowsPerChunk - 1) / kAGRowsPerChunk;
-    row_bytes = static_cast<size_t>(p.K) * 2;
-    ws = p.ag_ws + (ph & 1u) * p.ag_ws_buf_bytes;
-    flags = p.ag_flags + (ph & 1u) * W * cpr * kAGSubPieces;
-    j = p.ag_copy_local ? 0 : 1; b = 0; u = -1; item = -1;
-    have_item = false; in_sub = false; off = end = 0; src_base = nullptr; dst_base = nullptr; sub_base = 0;
-  }
-  // move (j,b,u) to my next item; false when the enumeration is exhausted
-  TD_DEVICE bool advance() {
-    while (true) {
-      ++u; ++item;
-      if (u == kAGSubPieces) { u = 0; ++b; }
-      if (b == cpr) { b = 0; ++j; }
-      if (j >= W) return false;
-      if (item % p.n_comm_ctas == comm_idx) return true;
-    }
-  }
-  // Emit the next <= 16 KB piece.  NEVER blocks: if the next source has not published its shard yet the
-  // caller gets kAgNotReady and keeps draining its store queue (a blocking wait here deadlocks: the peers'
-  // "ready" depends on THEIR stores, which would be stuck behind the same wait).
-  TD_DEVICE AgNext next(AgPiece& out) {
-    if (!in_sub) {
-      if (!have_item) {
-        if (!advance()) return kAgDone;
-        have_item = true;
-      }
-      const int s = (me + j) % W;
-      if (s != me && static_cast<int32_t>(ptx::ld_acquire_sys(p.ag_ready + s) - ph) < 0) return kAgNotReady;
-      have_item = false;
-      const int r0 = b * kAGRowsPerChunk, r1 = min(Ms, r0 + kAGRowsPerChunk);
-      const size_t cbytes = static_cast<size_t>(r1 - r0) * row_bytes;
-      const size_t sub = ((cbytes + kAGSubPieces - 1) / kAGSubPieces + 127) & ~static_cast<size_t>(127);
-      const size_t shard_off = static_cast<size_t>(s) * Ms * row_bytes;
-      src_base = (s == me) ? reinterpret_cast<const char*>(p.ag_a_local) : symm_at(p.symm, ws, s) + shard_off;
-      dst_base = ws + shard_off;
-      sub_base = static_cast<size_t>(r0) * row_bytes;
-      off = min(cbytes, sub * u); end = min(cbytes, sub * (u + 1));
-      if (off >= end) {   // empty sub-piece (tiny chunk): flag only
-        out.src = nullptr; out.dst = nullptr; out.bytes = 0;
-        out.flag = flags + (s * cpr + b) * kAGSubPieces + u;
-        out.local_done = (s == me);
-        return kAgPiece;
-      }
-      in_sub = true;
-    }
-    const int s = (me + j) % W;
-    const uint32_t n = static_cast<uint32_t>(min(static_cast<size_t>(kCommPieceBytes), end - off));
-    out.src = src_base + sub_base + off;
-    out.dst = dst_base + sub_base + off;
-    out.bytes = n;
-    off += n;
-    const bool last = off >= end;
-    out.flag = last ? flags + (s * cpr + b) * kAGSubPieces + u : nullptr;
-    out.local_done = (s == me);
-    if (last) in_sub = false;
-    return kAgPiece;
-  }
-};
-
-TD_DEVICE void ag_publish_ready(const Params& p, uint32_t ph) {
-  ptx::fence_acq_rel_sys();
-  for (int q = 0; q < p.symm.world; ++q)
-    if (q != p.symm.rank) ptx::st_release_sys(symm_at(p.symm, p.ag_ready + p.symm.rank, q), ph);
-}
+constexpr int kCommLag = 8;        // pushed pieces allowed to be incomplete before the oldest is awaited
+constexpr int kCommLoadAhead = 3;  // local loads issued ahead of the store stream
 
 TD_DEVICE void ag_comm_cta(const Params& p, uint32_t ph, int comm_idx, uint8_t* smem) {
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kCommRingSlots * kCommPieceBytes);
-  char** q_dst = reinterpret_cast<char**>(full + kCommRingSlots);
-  uint32_t** q_flag = reinterpret_cast<uint32_t**>(q_dst + kCommRingSlots);
-  uint64_t* q_meta = reinterpret_cast<uint64_t*>(q_flag + kCommRingSlots);   // bytes | local_done << 32
+  uint32_t** q_flag = reinterpret_cast<uint32_t**>(full + kCommRingSlots);   // flag to publish when the piece completes
+  char** q_dst = reinterpret_cast<char**>(q_flag + kCommRingSlots);
+  uint32_t* q_n = reinterpret_cast<uint32_t*>(q_dst + kCommRingSlots);
   if (threadIdx.x == 0) {
     for (int i = 0; i < kCommRingSlots; ++i) ptx::mbar_init(full + i, 1);
     ptx::fence_barrier_init();
@@ -259,61 +175,82 @@ TD_DEVICE void ag_comm_cta(const Params& p, uint32_t ph, int comm_idx, uint8_t* 
   __syncthreads();
   if (threadIdx.x != 0) return;   // a single thread drives this SM's TMA unit
 
-  if (!p.ag_copy_local && comm_idx == 0) ag_publish_ready(p, ph);   // zero-copy: shard already in my workspace
+  const int W = p.symm.world, me = p.symm.rank, Ms = p.ag_rows_per_rank;
+  const int cpr = (Ms + kAGRowsPerChunk - 1) / kAGRowsPerChunk;
+  const size_t row_bytes = static_cast<size_t>(p.K) * 2;
+  char* ws = p.ag_ws + (ph & 1u) * p.ag_ws_buf_bytes;
+  const size_t shard_off = static_cast<size_t>(me) * Ms * row_bytes;
+  const char* src_base = p.ag_copy_local ? reinterpret_cast<const char*>(p.ag_a_local) : ws + shard_off;
+  uint32_t* my_flags = p.ag_flags + (ph & 1u) * W * cpr * kAGSubPieces + me * cpr * kAGSubPieces;
 
-  const int cpr = (p.ag_rows_per_rank + kAGRowsPerChunk - 1) / kAGRowsPerChunk;
-  AgCursor cur(p, ph, comm_idx);
-  uint32_t loads = 0, stores = 0, retired = 0;   // pieces loaded / stored / whose smem slot is reusable
+  // piece counters: loaded >= issued (store issued) >= retired (store complete, flag published, slot reusable)
+  uint32_t loaded = 0, issued = 0, retired = 0;
   uint32_t parity_bits = 0;
-  bool more = true;
-  while (true) {
-    // 1. keep the load side of the ring full (without ever blocking on a peer)
-    while (more && loads - retired < kCommRingSlots) {
-      AgPiece pc;
-      const AgNext st = cur.next(pc);
-      if (st == kAgDone) { more = false; break; }
-      if (st == kAgNotReady) break;
-      const uint32_t slot = loads % kCommRingSlots;
-      q_dst[slot] = pc.dst; q_flag[slot] = pc.flag;
-      q_meta[slot] = static_cast<uint64_t>(pc.bytes) | (static_cast<uint64_t>(pc.local_done) << 32);
-      if (pc.bytes) {
-        ptx::mbar_arrive_expect_tx(full + slot, pc.bytes);
-        ptx::bulk_g2s(smem + slot * kCommPieceBytes, pc.src, pc.bytes, full + slot);
+  auto retire_to = [&](uint32_t upto) {
+    for (; retired < upto; ++retired) {
+      uint32_t* f = q_flag[retired % kCommRingSlots];
+      if (f != nullptr) {
+        ptx::fence_proxy_async();
+        ptx::fence_acq_rel_sys();
+        ptx::st_release_sys(f, ph);
       }
-      ++loads;
     }
-    if (stores == loads) {
-      if (!more) break;
-      continue;                                  // nothing in flight: poll the peer's "ready" again
-    }
-    // 2. forward the oldest loaded piece to the workspace
-    const uint32_t slot = stores % kCommRingSlots;
-    const uint32_t bytes = static_cast<uint32_t>(q_meta[slot]);
-    if (bytes) {
+  };
+  auto store_oldest = [&]() {            // forward the oldest loaded piece:  smem -> (peer) HBM, posted
+    const uint32_t slot = issued % kCommRingSlots;
+    if (q_n[slot]) {
       ptx::mbar_wait(full + slot, (parity_bits >> slot) & 1u);
       parity_bits ^= (1u << slot);
-      ptx::bulk_s2g(q_dst[slot], smem + slot * kCommPieceBytes, bytes);
+      ptx::bulk_s2g(q_dst[slot], smem + slot * kCommPieceBytes, q_n[slot]);
     }
     ptx::bulk_commit();
-    ++stores;
-    if (q_flag[slot] != nullptr) {
-      // a sub-piece is resident once all its stores are COMPLETE (not merely read from smem)
-      ptx::bulk_wait<0>();
-      retired = stores;
-      ptx::fence_proxy_async();
-      ptx::st_release_gpu(q_flag[slot], ph);
-      if ((q_meta[slot] >> 32) && p.ag_copy_local) {
-        const uint32_t done = ptx::atom_add_acq_rel_gpu(p.phase + 2, 1u) + 1u;
-        if (done == static_cast<uint32_t>(cpr * kAGSubPieces)) {   // my whole shard is in my workspace
-          p.phase[2] = 0;
-          ag_publish_ready(p, ph);
+    ++issued;
+    if (issued - retired > kCommLag) {
+      ptx::bulk_wait<kCommLag>();
+      retire_to(issued - kCommLag);
+    }
+  };
+  auto load_piece = [&](const char* src, char* dst, uint32_t n, uint32_t* flag) {
+    while (loaded - retired >= kCommRingSlots) {           // ring full: make progress on the store side
+      if (issued < loaded) store_oldest();
+      else { ptx::bulk_wait<0>(); retire_to(issued); }
+    }
+    const uint32_t slot = loaded % kCommRingSlots;
+    q_dst[slot] = dst; q_n[slot] = n; q_flag[slot] = flag;
+    if (n) {
+      ptx::mbar_arrive_expect_tx(full + slot, n);
+      ptx::bulk_g2s(smem + slot * kCommPieceBytes, src, n, full + slot);   // local HBM/L2 -> smem
+    }
+    ++loaded;
+    if (loaded - issued > kCommLoadAhead) store_oldest();
+  };
+
+  int item = 0;
+  for (int dist = p.ag_copy_local ? 0 : 1; dist < W; ++dist) {
+    const int d = (me - dist + W) % W;                       // destination rank
+    char* dst_base = symm_at(p.symm, ws, d) + shard_off;
+    uint32_t* dst_flags = symm_at(p.symm, my_flags, d);
+    for (int b = 0; b < cpr; ++b) {
+      const int r0 = b * kAGRowsPerChunk, r1 = min(Ms, r0 + kAGRowsPerChunk);
+      const size_t cbytes = static_cast<size_t>(r1 - r0) * row_bytes;
+      const size_t sub = ((cbytes + kAGSubPieces - 1) / kAGSubPieces + 127) & ~static_cast<size_t>(127);
+      for (int u = 0; u < kAGSubPieces; ++u, ++item) {
+        if (item % p.n_comm_ctas != comm_idx) continue;
+        size_t off = static_cast<size_t>(r0) * row_bytes + min(cbytes, sub * u);
+        const size_t end = static_cast<size_t>(r0) * row_bytes + min(cbytes, sub * (u + 1));
+        uint32_t* flag = dst_flags + b * kAGSubPieces + u;
+        if (off >= end) { load_piece(nullptr, nullptr, 0, flag); continue; }   // empty sub-piece: flag only
+        while (off < end) {
+          const uint32_t n = static_cast<uint32_t>(min(static_cast<size_t>(kCommPieceBytes), end - off));
+          load_piece(src_base + off, dst_base + off, n, (off + n >= end) ? flag : nullptr);
+          off += n;
         }
       }
-    } else if (stores - retired > kCommStoreDepth) {
-      ptx::bulk_wait_read<kCommStoreDepth>();
-      retired = stores - kCommStoreDepth;
     }
   }
+  while (issued < loaded) store_oldest();
+  ptx::bulk_wait<0>();
+  retire_to(issued);
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -4,10 +4,11 @@ Reference: ``create_ag_gemm_context`` / ``ag_gemm`` (/root/reference/python/trit
 allgather_gemm.py:511-619) -- there the all-gather is W-1 host-issued ``cudaMemcpyAsync`` + one
 ``cuStreamWriteValue`` flag per source rank (allgather.py:100-124) around a Triton persistent GEMM.
 
-Here (csrc/gemm_sm100.cuh, mode kAG) the gather runs INSIDE the GEMM kernel: ``n_comm_ctas`` CTAs pull the peers'
-shards over NVLink with TMA bulk copies and publish per-(source, 128-row chunk, sub-piece) flags; the tcgen05 GEMM
-CTAs start on the local rows (tile order rotated by rank) and consume remote rows as they land.  No host barrier:
-workspaces are double buffered by call parity and flags carry monotone phase numbers kept on the device.
+Here (csrc/gemm_sm100.cuh, mode kAG) the gather runs INSIDE the GEMM kernel: ``n_comm_ctas`` CTAs PUSH this rank's
+shard into every peer's workspace over NVLink with TMA bulk copies (posted writes; a pull design measured only
+~7 GB/s per SM on 8xB200) and publish per-(source, 128-row chunk, sub-piece) flags on the destination; the tcgen05
+GEMM CTAs start on the local rows (tile order rotated by rank) and consume remote rows as they land.  No host
+barrier: workspaces are double buffered by call parity and flags carry monotone phase numbers kept on the device.
 """
 from __future__ import annotations
 
@@ -35,7 +36,7 @@ class AllGatherGEMMTensorParallelContext:
     num_ranks: int
     num_local_ranks: int
     workspace: torch.Tensor = None     # symmetric [2, max_M, K]
-    flags: torch.Tensor = None         # local int32 [2, W, chunks, 8]
+    flags: torch.Tensor = None         # symmetric int32 [2, W, chunks, 8]
     ready: torch.Tensor = None         # symmetric int32 [W]
     phase: torch.Tensor = None         # local int32 [4]
     n_comm_ctas: int = 16
@@ -58,10 +59,10 @@ class AllGatherGEMMTensorParallelContext:
 
     def finalize(self):
         heap = U.get_heap()
-        for t in (self.workspace, self.ready):
+        for t in (self.workspace, self.ready, self.flags):
             if t is not None:
                 heap.free_tensor(t)
-        self.workspace = self.ready = None
+        self.workspace = self.ready = self.flags = None
 
 
 def create_ag_gemm_context(max_M: int, N: int, K: int, dtype: torch.dtype, rank: Optional[int] = None,
@@ -77,7 +78,7 @@ def create_ag_gemm_context(max_M: int, N: int, K: int, dtype: torch.dtype, rank:
     ctx.ready = heap.tensor((max(num_ranks, 4),), torch.int32)
     max_ms = (max_M + num_ranks - 1) // num_ranks
     chunks = (max_ms + _CHUNK_ROWS - 1) // _CHUNK_ROWS
-    ctx.flags = torch.zeros((2, num_ranks, chunks + 1, _SUB), dtype=torch.int32, device=heap.device)
+    ctx.flags = heap.tensor((2, num_ranks, chunks + 1, _SUB), torch.int32)      # written remotely by the sources
     ctx.phase = torch.zeros(4, dtype=torch.int32, device=heap.device)
     U.barrier_all_host()
     return ctx
@@ -101,12 +102,16 @@ def _as_nk(B: torch.Tensor) -> torch.Tensor:
 
 
 def default_ag_config(M: int, N: int, K: int, world: int) -> GemmConfig:
+    """Tiles of one source rank form one L2 band (``group_m`` = m-tiles per source), so the arrival order of the
+    shards is respected while B tiles are re-read once per source rather than once per m-tile."""
     rows = M // max(world, 1)
+    nc = 16 if world > 1 else 0
     if rows % 256 == 0 and N >= 256:
-        return GemmConfig(bn=256, cta_group=2, group_m=1, use_tma_store=True, n_comm_ctas=16 if world > 1 else 0)
+        return GemmConfig(bn=256, cta_group=2, group_m=max(1, rows // 256), use_tma_store=True, n_comm_ctas=nc)
+    gm = max(1, rows // 128) if rows % 128 == 0 else 1
     if N >= 256:
-        return GemmConfig(bn=256, cta_group=1, group_m=1, use_tma_store=True, n_comm_ctas=16 if world > 1 else 0)
-    return GemmConfig(bn=128, cta_group=1, group_m=1, use_tma_store=True, n_comm_ctas=16 if world > 1 else 0)
+        return GemmConfig(bn=256, cta_group=1, group_m=gm, use_tma_store=True, n_comm_ctas=nc)
+    return GemmConfig(bn=128, cta_group=1, group_m=gm, use_tma_store=True, n_comm_ctas=nc)
 
 
 def ag_gemm(A: torch.Tensor, B: torch.Tensor, ctx: AllGatherGEMMTensorParallelContext,
@@ -175,6 +180,9 @@ gemm_non_persistent = gemm_persistent
 # emulation (no GPU): same protocol on the shared-memory heap
 # ------------------------------------------------------------------------------------------------------------
 def _ag_gemm_host(A, Bnk, ctx, out):
+    """Same push protocol as the device kernel: my shard goes into EVERY rank's workspace (nearest consumer first),
+    each arrival is published with a release flag carrying the phase number; the GEMM consumes sources in arrival
+    order after acquiring their flags.  Workspaces are double buffered by call parity, nothing is reset."""
     import ctypes
     heap = U.get_heap()
     lib = _C.host_lib()
@@ -182,24 +190,24 @@ def _ag_gemm_host(A, Bnk, ctx, out):
     Ms, K = A.shape
     ctx.host_phase += 1
     ph = ctx.host_phase
-    ws = ctx.workspace[ph & 1]
+    par = ph & 1
     timeout = U.get_int_env("TD_HOST_TIMEOUT_US", 60_000_000)
-    # 1. my shard into my workspace, publish "ready" on every peer
-    ws[me * Ms:(me + 1) * Ms].copy_(A)
-    for q in range(W):
-        if q != me:
-            lib.tdh_notify32(ctypes.c_void_p(heap.peer_ptr(ctx.ready.data_ptr() + 4 * me, q)), ph, 1)
-    # 2. pull peers in arrival order, GEMM per source block as it lands
+    flag_off = lambda src: ctx.flags[par, src, 0, 0:1].data_ptr()
+    # 1. push (producer role)
+    for dist_ in range(W):
+        d = (me - dist_ + W) % W
+        dst_ws = heap.peer_view(ctx.workspace, d)[par]
+        dst_ws[me * Ms:(me + 1) * Ms].copy_(A)
+        lib.tdh_notify32(ctypes.c_void_p(heap.peer_ptr(flag_off(me), d)), ph, 1)
+    # 2. consume in arrival order
     N = Bnk.shape[0]
     if out is None:
         out = torch.empty((Ms * W, N), dtype=A.dtype)
     bt = Bnk.float().t()
+    ws = ctx.workspace[par]
     for j in range(W):
         s = (me + j) % W
-        if s != me:
-            if lib.tdh_wait32(ctypes.c_void_p(ctx.ready.data_ptr() + 4 * s), ph, 1, timeout):
-                raise TimeoutError(f"ag_gemm: rank {s} never published phase {ph}")
-            peer_ws = heap.peer_view(ctx.workspace, s)[ph & 1]
-            ws[s * Ms:(s + 1) * Ms].copy_(peer_ws[s * Ms:(s + 1) * Ms])
+        if lib.tdh_wait32(ctypes.c_void_p(flag_off(s)), ph, 1, timeout):
+            raise TimeoutError(f"ag_gemm: shard of rank {s} never arrived (phase {ph})")
         out[s * Ms:(s + 1) * Ms] = (ws[s * Ms:(s + 1) * Ms].float() @ bt).to(A.dtype)
     return out
