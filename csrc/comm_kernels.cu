@@ -80,7 +80,7 @@ TD_DEVICE uint4 mc_ld_reduce(const void* mc) {
 // ---------------------------------------------------------------------------------------------------------
 // AllReduce
 // ---------------------------------------------------------------------------------------------------------
-enum ARMethod : int { kOneShot = 0, kTwoShot = 1, kOneShotMultimem = 2, kTwoShotMultimem = 3 };
+enum ARMethod : int { kOneShot = 0, kTwoShot = 1, kOneShotMultimem = 2, kTwoShotMultimem = 3, kReduceScatter = 4, kReduceScatterMultimem = 5, kStageOnly = 6 };
 
 struct ARParams {
   SymmCtx symm;
@@ -105,6 +105,48 @@ __global__ void __launch_bounds__(kCommThreads, 1) allreduce_kernel(const ARPara
   uint4* stage = reinterpret_cast<uint4*>(p.stage + par * p.stage_bytes);
   uint4* stage2 = reinterpret_cast<uint4*>(p.stage2 + par * p.stage_bytes);
 
+  if constexpr (kMethod == kStageOnly) {
+    // copy the input into the staging half the NEXT collective launch on this context will use (same device-side
+    // parity, phase not advanced): a separate launch so that "kernel started" implies "staging complete"
+    const long long per_s = (p.nvec + gridDim.x - 1) / gridDim.x;
+    const long long s0 = min(p.nvec, per_s * blockIdx.x), s1 = min(p.nvec, s0 + per_s);
+    for (long long v = s0 + threadIdx.x; v < s1; v += kCommThreads) stage[v] = p.in[v];
+    return;
+  }
+  if constexpr (kMethod == kReduceScatter || kMethod == kReduceScatterMultimem) {
+    // ReduceScatter: the whole message was staged by an EARLIER launch on this stream (producer kernel or
+    // memcpy), so "peer CTA b reached this barrier" implies the peer's entire staging buffer is complete.
+    barrier_all_block(c, my_slots, 2 * ph);
+    const long long slice = p.nvec / W;                       // vectors owned by each rank
+    const long long base = slice * c.rank;
+    const long long per_rs = (slice + gridDim.x - 1) / gridDim.x;
+    const long long r0 = min(slice, per_rs * blockIdx.x), r1 = min(slice, r0 + per_rs);
+    if constexpr (kMethod == kReduceScatterMultimem) {
+      const uint4* mc = symm_mc(c, stage);
+      for (long long v = r0 + threadIdx.x; v < r1; v += kCommThreads) p.out[v] = mc_ld_reduce<kDType>(mc + base + v);
+    } else {
+      for (long long v = r0 + threadIdx.x; v < r1; v += kCommThreads) {
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 1
+        for (int q0 = 0; q0 < W; q0 += 4) {
+          uint4 x[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (q0 + u < W) x[u] = ptx::ld_relaxed_sys_v4(symm_at(c, stage + base + v, (c.rank + q0 + u) % W));
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (q0 + u < W) accum<kDType>(acc, x[u]);
+        }
+        p.out[v] = pack<kDType>(acc);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(p.phase + 1, 1u) == gridDim.x - 1) { p.phase[1] = 0; __threadfence(); p.phase[0] = ph; }
+    }
+    return;
+  }
   // this CTA's slice [v0, v1) of the message -- the SAME slice on every rank
   const long long per = (p.nvec + gridDim.x - 1) / gridDim.x;
   const long long v0 = min(p.nvec, per * blockIdx.x), v1 = min(p.nvec, v0 + per);
@@ -278,6 +320,9 @@ int launch_ar(int method, const ARParams& p, int grid, cudaStream_t s) {
     case kTwoShot: allreduce_kernel<kDType, kTwoShot><<<grid, kCommThreads, 0, s>>>(p); break;
     case kOneShotMultimem: allreduce_kernel<kDType, kOneShotMultimem><<<grid, kCommThreads, 0, s>>>(p); break;
     case kTwoShotMultimem: allreduce_kernel<kDType, kTwoShotMultimem><<<grid, kCommThreads, 0, s>>>(p); break;
+    case kStageOnly: allreduce_kernel<kDType, kStageOnly><<<grid, kCommThreads, 0, s>>>(p); break;
+    case kReduceScatter: allreduce_kernel<kDType, kReduceScatter><<<grid, kCommThreads, 0, s>>>(p); break;
+    case kReduceScatterMultimem: allreduce_kernel<kDType, kReduceScatterMultimem><<<grid, kCommThreads, 0, s>>>(p); break;
     default: td::drv::set_error("bad allreduce method"); return -1;
   }
   TD_CUDA_CHECK(cudaGetLastError());
@@ -311,7 +356,7 @@ TD_API int td_allreduce(const TdARArgs* a, void* stream) {
   p.stage_bytes = a->stage_bytes; p.nvec = a->nbytes / 16;
   p.slots = reinterpret_cast<uint32_t*>(a->slots); p.phase = reinterpret_cast<uint32_t*>(a->phase);
   p.in_symm = (int)a->in_symm;
-  if ((a->method == kOneShotMultimem || a->method == kTwoShotMultimem) && p.symm.mc_base == 0) {
+  if ((a->method == kOneShotMultimem || a->method == kTwoShotMultimem || a->method == kReduceScatterMultimem) && p.symm.mc_base == 0) {
     td::drv::set_error("allreduce: multimem method requested but no multicast mapping"); return -1;
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);

@@ -20,6 +20,7 @@ struct TdGemmArgs {
   const void* A; long long a_rows; long long lda; long long a_nbuf; long long a_buf_stride_bytes;
   const void* B; long long ldb;
   void* C; long long c_rows; long long ldc; const void* c_phase; long long c_nbuf; long long c_buf_stride_bytes;
+  const void* tile_expert; long long num_experts;   // grouped (MoE) mode: B is [num_experts * N, K]
   // symmetric context
   long long rank, world; unsigned long long symm_base, symm_stride, mc_base;
   void* phase;
@@ -46,9 +47,10 @@ template <int kMode, int BN, int kCtaGroup>
 static int launch_cfg(const Params& p, int grid, cudaStream_t stream) {
   // deepest pipeline that fits in 227 KB next to the 32 KB epilogue staging
   constexpr int kStageBytes = BM * BK * 2 + (BN / kCtaGroup) * BK * 2;
-  constexpr int kMaxStages = (232448 - 1024 - 2 * kCBlockBytes - 256) / kStageBytes;
+  constexpr int kExtra = (kMode == kAG) ? kAgInBytes : 0;     // AG: room for the in-CTA push ring
+  constexpr int kMaxStages = (232448 - 1024 - 2 * kCBlockBytes - 384 - kExtra) / kStageBytes;
   constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
-  using L = SmemLayout<BN, kStages, kCtaGroup>;
+  using L = SmemLayout<BN, kStages, kCtaGroup, kExtra>;
   auto kern = gemm_kernel<kMode, BN, kStages, kCtaGroup>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -95,7 +97,7 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
     if (encode_tmap(&p.tmap_a, a->A, 3, dims, strides, box, bf16)) return -1;
   }
   {  // B: {K, N}
-    cuuint64_t dims[2] = {(cuuint64_t)a->K, (cuuint64_t)a->N};
+    cuuint64_t dims[2] = {(cuuint64_t)a->K, (cuuint64_t)(a->N * (a->tile_expert ? a->num_experts : 1))};
     cuuint64_t strides[1] = {(cuuint64_t)a->ldb * 2};
     cuuint32_t box[2] = {BK, (cuuint32_t)(bn / cg)};
     if (encode_tmap(&p.tmap_b, a->B, 2, dims, strides, box, bf16)) return -1;
@@ -109,6 +111,8 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
   }
   p.c_phase = (a->c_nbuf > 1) ? reinterpret_cast<const uint32_t*>(a->c_phase) : nullptr;
   p.c_buf_stride_bytes = a->c_buf_stride_bytes;
+  p.tile_expert = reinterpret_cast<const int*>(a->tile_expert);
+  p.expert_rows = (int)a->N;
   const int TM = BM * cg;
   p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K;
   p.num_m = (p.M + TM - 1) / TM;
@@ -141,6 +145,12 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
   int gemm_ctas = grid - p.n_comm_ctas;
   if (gemm_ctas < cg) { drv::set_error("no CTAs left for the GEMM (n_comm_ctas too large)"); return -1; }
   if (gemm_ctas / cg > tiles) gemm_ctas = tiles * cg;
+  if (a->tile_expert && a->group_m > 1) p.group_m = 1;   // grouped: keep experts' tiles together (n fastest)
+  if (a->mode == kAG && a->world > 1 && !a->ag_skip_wait) {
+    // the all-gather is pushed by EVERY CTA (GEMM CTAs use their spare warp); SMs without tiles become
+    // dedicated comm CTAs so the whole chip feeds the NVLink port
+    p.n_comm_ctas = grid - gemm_ctas;
+  }
   grid = gemm_ctas + p.n_comm_ctas;
 
   if (a->mode == kRS) {

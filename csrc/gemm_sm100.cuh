@@ -43,7 +43,8 @@ constexpr int kAGRowsPerChunk = 128;                  // AG arrival-flag granula
 constexpr int kAGSubPieces = 8;                       // each chunk is pulled as 8 independently flagged sub-pieces
 constexpr int kCommPieceBytes = 16 * 1024;            // one TMA bulk copy
 constexpr int kCommRingSlots = 12;                    // 192 KB smem ring in a comm CTA
-constexpr int kCommStoreDepth = 4;                    // bulk stores allowed to be reading smem concurrently
+constexpr int kCommLag = 8;                           // pushed pieces allowed to be incomplete before the oldest is awaited
+constexpr int kCommLoadAhead = 3;                     // local loads issued ahead of the store stream
 
 enum Mode : int { kPlain = 0, kAG = 1, kRS = 2 };
 
@@ -65,6 +66,13 @@ struct Params {
   // straight into the parity-double-buffered staging of a following collective inside a replayed CUDA graph.
   const uint32_t* c_phase;
   long long c_buf_stride_bytes;
+  // optional grouped (MoE) mode: m-tile t multiplies with expert tile_expert[t]'s weight B[e] (rows
+  // [e * expert_rows, (e+1) * expert_rows) of the stacked B); tile_expert[t] < 0 marks an unused padded tile.
+  // The token rows are pre-sorted by expert and every expert segment is padded to a multiple of the tile height
+  // (csrc/moe_kernels.cu: moe_align_sort), so one m-tile never mixes experts.
+  const int* tile_expert;
+  int expert_rows;
+  int pad3;
   SymmCtx symm;
   // ---- phase bookkeeping (device resident so a captured graph replays correctly) ----
   // [0] = number of completed calls on this context, [1] = CTA exit counter, [2] = AG local-copy counter
@@ -92,7 +100,7 @@ struct Params {
 // -------------------------------------------------------------------------------------------------
 // shared-memory carve-up (GEMM CTAs)
 // -------------------------------------------------------------------------------------------------
-template <int BN, int kStages, int kCtaGroup>
+template <int BN, int kStages, int kCtaGroup, int kExtra = 0>
 struct SmemLayout {
   static constexpr int kABytes = BM * BK * 2;                 // 16 KB
   static constexpr int kBBytes = (BN / kCtaGroup) * BK * 2;   // this CTA's share of the B tile
@@ -101,7 +109,8 @@ struct SmemLayout {
   static constexpr int kBarOff = kCOff + 2 * kCBlockBytes;
   // barriers: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]; then the TMEM base pointer
   static constexpr int kNumBars = 2 * kStages + 4;
-  static constexpr int kGemmBytes = kBarOff + kNumBars * 8 + 16;
+  static constexpr int kExtraOff = ((kBarOff + kNumBars * 8 + 16 + 127) / 128) * 128;   // optional comm ring (AG mode)
+  static constexpr int kGemmBytes = kExtraOff + kExtra;
   static constexpr int kCommBytes = kCommRingSlots * kCommPieceBytes + kCommRingSlots * (8 + 8 + 8 + 8) + 64;  // ring + mbarriers + queues
   static constexpr int kTotal = (kGemmBytes > kCommBytes ? kGemmBytes : kCommBytes) + 1024;  // + alignment slack
   static_assert(kStageBytes % 1024 == 0, "stage must keep 1024 B alignment for SWIZZLE_128B");
@@ -160,20 +169,20 @@ TD_DEVICE void ag_wait_rows(const Params& p, uint32_t ph, int row0, int row1) {
 // it starts with my rows right after its own), and at any moment every rank pushes to a different peer,
 // so each NVLink port carries exactly one stream in each direction.
 // -------------------------------------------------------------------------------------------------
-constexpr int kCommLag = 8;        // pushed pieces allowed to be incomplete before the oldest is awaited
-constexpr int kCommLoadAhead = 3;  // local loads issued ahead of the store stream
-
-TD_DEVICE void ag_comm_cta(const Params& p, uint32_t ph, int comm_idx, uint8_t* smem) {
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kCommRingSlots * kCommPieceBytes);
-  uint32_t** q_flag = reinterpret_cast<uint32_t**>(full + kCommRingSlots);   // flag to publish when the piece completes
-  char** q_dst = reinterpret_cast<char**>(q_flag + kCommRingSlots);
-  uint32_t* q_n = reinterpret_cast<uint32_t*>(q_dst + kCommRingSlots);
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < kCommRingSlots; ++i) ptx::mbar_init(full + i, 1);
-    ptx::fence_barrier_init();
-  }
-  __syncthreads();
-  if (threadIdx.x != 0) return;   // a single thread drives this SM's TMA unit
+// One thread runs this loop.  kSlots x kPiece bytes of shared memory at `ring` (+ kSlots mbarriers and the
+// piece queues at `meta`) are private to it.  Dedicated comm CTAs use a deep ring (12 x 16 KB); the spare
+// warp of every GEMM CTA runs the same loop on a 4 x 8 KB ring carved out of one pipeline stage, because the
+// measured per-SM NVLink rate (~6-10 GB/s, reads and posted writes alike) means saturating the port takes
+// (nearly) all SMs, not a handful of "comm SMs".
+template <int kSlots, int kPiece, int kLag, int kAhead>
+TD_DEVICE void ag_push_loop(const Params& p, uint32_t ph, int comm_idx, int n_comm, uint8_t* ring, uint8_t* meta) {
+  uint64_t* full = reinterpret_cast<uint64_t*>(meta);
+  uint32_t** q_flag = reinterpret_cast<uint32_t**>(full + kSlots);   // flag to publish when the piece completes
+  char** q_dst = reinterpret_cast<char**>(q_flag + kSlots);
+  uint32_t* q_n = reinterpret_cast<uint32_t*>(q_dst + kSlots);
+  for (int i = 0; i < kSlots; ++i) ptx::mbar_init(full + i, 1);
+  ptx::fence_barrier_init();
+  ptx::fence_proxy_async();
 
   const int W = p.symm.world, me = p.symm.rank, Ms = p.ag_rows_per_rank;
   const int cpr = (Ms + kAGRowsPerChunk - 1) / kAGRowsPerChunk;
@@ -188,7 +197,7 @@ TD_DEVICE void ag_comm_cta(const Params& p, uint32_t ph, int comm_idx, uint8_t* 
   uint32_t parity_bits = 0;
   auto retire_to = [&](uint32_t upto) {
     for (; retired < upto; ++retired) {
-      uint32_t* f = q_flag[retired % kCommRingSlots];
+      uint32_t* f = q_flag[retired % kSlots];
       if (f != nullptr) {
         ptx::fence_proxy_async();
         ptx::fence_acq_rel_sys();
@@ -197,32 +206,32 @@ TD_DEVICE void ag_comm_cta(const Params& p, uint32_t ph, int comm_idx, uint8_t* 
     }
   };
   auto store_oldest = [&]() {            // forward the oldest loaded piece:  smem -> (peer) HBM, posted
-    const uint32_t slot = issued % kCommRingSlots;
+    const uint32_t slot = issued % kSlots;
     if (q_n[slot]) {
       ptx::mbar_wait(full + slot, (parity_bits >> slot) & 1u);
       parity_bits ^= (1u << slot);
-      ptx::bulk_s2g(q_dst[slot], smem + slot * kCommPieceBytes, q_n[slot]);
+      ptx::bulk_s2g(q_dst[slot], ring + slot * kPiece, q_n[slot]);
     }
     ptx::bulk_commit();
     ++issued;
-    if (issued - retired > kCommLag) {
-      ptx::bulk_wait<kCommLag>();
-      retire_to(issued - kCommLag);
+    if (issued - retired > kLag) {
+      ptx::bulk_wait<kLag>();
+      retire_to(issued - kLag);
     }
   };
   auto load_piece = [&](const char* src, char* dst, uint32_t n, uint32_t* flag) {
-    while (loaded - retired >= kCommRingSlots) {           // ring full: make progress on the store side
+    while (loaded - retired >= kSlots) {                   // ring full: make progress on the store side
       if (issued < loaded) store_oldest();
       else { ptx::bulk_wait<0>(); retire_to(issued); }
     }
-    const uint32_t slot = loaded % kCommRingSlots;
+    const uint32_t slot = loaded % kSlots;
     q_dst[slot] = dst; q_n[slot] = n; q_flag[slot] = flag;
     if (n) {
       ptx::mbar_arrive_expect_tx(full + slot, n);
-      ptx::bulk_g2s(smem + slot * kCommPieceBytes, src, n, full + slot);   // local HBM/L2 -> smem
+      ptx::bulk_g2s(ring + slot * kPiece, src, n, full + slot);   // local HBM/L2 -> smem
     }
     ++loaded;
-    if (loaded - issued > kCommLoadAhead) store_oldest();
+    if (loaded - issued > kAhead) store_oldest();
   };
 
   int item = 0;
@@ -235,13 +244,13 @@ TD_DEVICE void ag_comm_cta(const Params& p, uint32_t ph, int comm_idx, uint8_t* 
       const size_t cbytes = static_cast<size_t>(r1 - r0) * row_bytes;
       const size_t sub = ((cbytes + kAGSubPieces - 1) / kAGSubPieces + 127) & ~static_cast<size_t>(127);
       for (int u = 0; u < kAGSubPieces; ++u, ++item) {
-        if (item % p.n_comm_ctas != comm_idx) continue;
+        if (item % n_comm != comm_idx) continue;
         size_t off = static_cast<size_t>(r0) * row_bytes + min(cbytes, sub * u);
         const size_t end = static_cast<size_t>(r0) * row_bytes + min(cbytes, sub * (u + 1));
         uint32_t* flag = dst_flags + b * kAGSubPieces + u;
         if (off >= end) { load_piece(nullptr, nullptr, 0, flag); continue; }   // empty sub-piece: flag only
         while (off < end) {
-          const uint32_t n = static_cast<uint32_t>(min(static_cast<size_t>(kCommPieceBytes), end - off));
+          const uint32_t n = static_cast<uint32_t>(min(static_cast<size_t>(kPiece), end - off));
           load_piece(src_base + off, dst_base + off, n, (off + n >= end) ? flag : nullptr);
           off += n;
         }
@@ -253,12 +262,16 @@ TD_DEVICE void ag_comm_cta(const Params& p, uint32_t ph, int comm_idx, uint8_t* 
   retire_to(issued);
 }
 
+// ring of the spare warp inside a GEMM CTA (carved from the space of one pipeline stage)
+constexpr int kAgInSlots = 4, kAgInPiece = 8 * 1024, kAgInMeta = 256;
+constexpr int kAgInBytes = kAgInSlots * kAgInPiece + kAgInMeta;
+
 // -------------------------------------------------------------------------------------------------
 // the kernel
 // -------------------------------------------------------------------------------------------------
 template <int kMode, int BN, int kStages, int kCtaGroup>
 __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant__ Params p) {
-  using L = SmemLayout<BN, kStages, kCtaGroup>;
+  using L = SmemLayout<BN, kStages, kCtaGroup, (kMode == kAG ? kAgInBytes : 0)>;
   constexpr int TM = BM * kCtaGroup;                     // rows of C per cluster tile
   constexpr int kTmemCols = tmem_cols_for(BN);
   constexpr int kNumCBlocks = (BN + kCBlockCols - 1) / kCBlockCols;
@@ -278,7 +291,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
   const bool is_comm = static_cast<int>(blockIdx.x) >= n_gemm_ctas;
 
   if (is_comm) {
-    if constexpr (kMode == kAG) ag_comm_cta(p, ph, static_cast<int>(blockIdx.x) - n_gemm_ctas, smem);
+    // dedicated comm CTA (fills the SMs the GEMM has no tiles for): deep ring, one driving thread
+    if constexpr (kMode == kAG) {
+      if (threadIdx.x == 0)
+        ag_push_loop<kCommRingSlots, kCommPieceBytes, kCommLag, kCommLoadAhead>(
+            p, ph, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), smem, smem + kCommRingSlots * kCommPieceBytes);
+      __syncwarp();
+    }
   } else {
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
     uint64_t* empty_bar = full_bar + kStages;
@@ -322,8 +341,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         for (int t = worker; t < total_tiles; t += n_workers) {
           int m_tile, n_tile;
           tile_coords(p, t, m_tile, n_tile);
+          int expert = 0;
+          if (p.tile_expert) { expert = p.tile_expert[m_tile]; if (expert < 0) continue; }
           const int row0 = m_tile * TM + static_cast<int>(cta_rank) * BM;       // my 128 rows of A
-          const int brow0 = n_tile * BN + static_cast<int>(cta_rank) * (BN / kCtaGroup);
+          const int brow0 = expert * p.expert_rows + n_tile * BN + static_cast<int>(cta_rank) * (BN / kCtaGroup);
           if constexpr (kMode == kAG) {
             if (!p.ag_skip_wait && row0 < p.M) ag_wait_rows(p, ph, row0, min(p.M, row0 + BM));
           }
@@ -355,6 +376,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
         for (int t = worker; t < total_tiles; t += n_workers) {
+          if (p.tile_expert) {
+            int m_tile, n_tile;
+            tile_coords(p, t, m_tile, n_tile);
+            if (p.tile_expert[m_tile] < 0) continue;
+          }
           ptx::mbar_wait(tmem_empty + acc, acc_phase ^ 1u);        // epilogue has drained this accumulator
           ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
@@ -379,6 +405,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         }
       }
       __syncwarp();
+    } else if (warp == 3) {
+      // ================================ AG: every CTA also pushes its share of my shard ================================
+      if constexpr (kMode == kAG) {
+        if (lane == 0 && p.symm.world > 1 && !p.ag_skip_wait)
+          ag_push_loop<kAgInSlots, kAgInPiece, 2, 1>(p, ph, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x),
+                                                     smem + L::kExtraOff, smem + L::kExtraOff + kAgInSlots * kAgInPiece);
+        __syncwarp();
+      }
     } else if (warp >= kEpiWarp0) {
       // ================================ epilogue ================================
       const int ew = warp - kEpiWarp0;               // == warp % 4 == TMEM lane quadrant
@@ -390,6 +424,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
       for (int t = worker; t < total_tiles; t += n_workers) {
         int m_tile, n_tile;
         tile_coords(p, t, m_tile, n_tile);
+        if (p.tile_expert && p.tile_expert[m_tile] < 0) continue;
         const int row_base = m_tile * TM + static_cast<int>(cta_rank) * BM;   // global row of tile row 0
         const int col_base = n_tile * BN;
 

@@ -1,0 +1,209 @@
+// MoE routing / permutation kernels:
+//   * moe_align_sort  : (expert-major, block-aligned) token sort -- sorted_token_ids, per-m-tile expert ids,
+//                       per-expert offsets, padded total.  One CTA; counting sort in shared memory.
+//   * gather_rows     : x_sorted[i] = x[sorted_token_ids[i] / topk_div]   (pad rows -> zeros)
+//   * scatter_rows    : y[sorted_token_ids[i]] = y_sorted[i]
+//   * topk_reduce     : out[t] = sum_j w[t, j] * y[t * topk + j]          (fp32 accumulate)
+//   * bincount        : per-expert histogram
+//
+// Reference: csrc/lib/moe_utils.cu:65-315 (legacy, not compiled there), kernels/nvidia/moe_utils.py:145-508
+// (calc_gather_scatter_index, reduce_topk), allgather_group_gemm.py:86-166 (calc_sorted_gather_index_kernel),
+// threadblock_swizzle_ag_moe*.{py,cu} (tile order by arrival stage -- see `stage_of_rank` below).
+#include "td/ptx.cuh"
+#include "runtime/driver.h"
+
+using namespace td;
+
+namespace {
+
+// sorted layout: for each expert e, its (token,k) pairs in increasing flat index order (optionally grouped by the
+// all-gather arrival stage of the token's source rank first), padded with `pad_id` up to a multiple of block_m.
+//   topk_ids        : [n] flat (token * topk + k) -> expert
+//   sorted_ids      : [capacity]  flat pair index or pad_id
+//   tile_expert     : [capacity / block_m] expert of each m-tile (or -1 for unused tail tiles)
+//   expert_offsets  : [E + 1] start of each expert's padded segment
+//   total_padded    : [1]
+//   tokens_per_rank > 0: pairs of an expert are ordered by stage = (src_rank - my_rank) mod world  (AG arrival order)
+__global__ void __launch_bounds__(1024) moe_align_sort_kernel(const int* __restrict__ topk_ids, int n, int E, int block_m,
+                                                               int capacity, int pad_id, int* __restrict__ sorted_ids,
+                                                               int* __restrict__ tile_expert, int* __restrict__ expert_offsets,
+                                                               int* __restrict__ total_padded, int topk, int tokens_per_rank,
+                                                               int my_rank, int world) {
+  extern __shared__ int sm[];
+  int* counts = sm;                 // [E * stages]
+  int* starts = sm + E * max(world, 1);   // [E * stages]
+  const int stages = tokens_per_rank > 0 ? world : 1;
+  for (int i = threadIdx.x; i < E * stages; i += blockDim.x) counts[i] = 0;
+  __syncthreads();
+  auto stage_of = [&](int flat) -> int {
+    if (tokens_per_rank <= 0) return 0;
+    const int src = (flat / topk) / tokens_per_rank;
+    return (src - my_rank + world) % world;
+  };
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int e = topk_ids[i];
+    if (e >= 0 && e < E) atomicAdd(&counts[e * stages + stage_of(i)], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int off = 0;
+    for (int e = 0; e < E; ++e) {
+      expert_offsets[e] = off;
+      int c = 0;
+      for (int s = 0; s < stages; ++s) { starts[e * stages + s] = off + c; c += counts[e * stages + s]; }
+      const int padded = (c + block_m - 1) / block_m * block_m;
+      for (int t = off / block_m; t < (off + padded) / block_m; ++t) tile_expert[t] = e;
+      off += padded;
+    }
+    expert_offsets[E] = off;
+    total_padded[0] = off;
+    for (int t = off / block_m; t < capacity / block_m; ++t) tile_expert[t] = -1;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < capacity; i += blockDim.x) sorted_ids[i] = pad_id;
+  __syncthreads();
+  // stable placement: thread-serial per (expert, stage) bucket would be slow; instead each thread places its own
+  // elements with an atomic cursor, then each bucket is sorted by flat index to make the layout deterministic.
+  for (int i = threadIdx.x; i < E * stages; i += blockDim.x) counts[i] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int e = topk_ids[i];
+    if (e < 0 || e >= E) continue;
+    const int b = e * stages + stage_of(i);
+    const int pos = atomicAdd(&counts[b], 1);
+    sorted_ids[starts[b] + pos] = i;
+  }
+  __syncthreads();
+  // deterministic order inside each bucket: odd-even transposition by one thread-group per bucket is overkill for
+  // routing sizes; a simple insertion sort per bucket (buckets are small: n * topk / (E * stages) on average)
+  for (int b = threadIdx.x; b < E * stages; b += blockDim.x) {
+    int* a = sorted_ids + starts[b];
+    const int m = counts[b];
+    for (int i = 1; i < m; ++i) {
+      const int v = a[i];
+      int j = i - 1;
+      while (j >= 0 && a[j] > v) { a[j + 1] = a[j]; --j; }
+      a[j + 1] = v;
+    }
+  }
+}
+
+// dst[i, :] = (ids[i] == pad) ? 0 : src[ids[i] / div, :]    (rows of `row_bytes`, multiple of 16)
+__global__ void gather_rows_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, const int* __restrict__ ids,
+                                   const int* __restrict__ n_rows_ptr, int n_rows_max, int vec_per_row, int div, int pad_id) {
+  const int n_rows = n_rows_ptr ? min(*n_rows_ptr, n_rows_max) : n_rows_max;
+  const long long total = static_cast<long long>(n_rows) * vec_per_row;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int r = static_cast<int>(t / vec_per_row), v = static_cast<int>(t % vec_per_row);
+    const int id = ids[r];
+    dst[t] = (id == pad_id) ? make_uint4(0, 0, 0, 0) : src[static_cast<long long>(id / div) * vec_per_row + v];
+  }
+}
+// dst[ids[i], :] = src[i, :]   for ids[i] != pad
+__global__ void scatter_rows_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, const int* __restrict__ ids,
+                                    const int* __restrict__ n_rows_ptr, int n_rows_max, int vec_per_row, int pad_id) {
+  const int n_rows = n_rows_ptr ? min(*n_rows_ptr, n_rows_max) : n_rows_max;
+  const long long total = static_cast<long long>(n_rows) * vec_per_row;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int r = static_cast<int>(t / vec_per_row), v = static_cast<int>(t % vec_per_row);
+    const int id = ids[r];
+    if (id != pad_id) dst[static_cast<long long>(id) * vec_per_row + v] = src[t];
+  }
+}
+
+template <bool kBF16>
+__global__ void topk_reduce_kernel(uint4* __restrict__ out, const uint4* __restrict__ y, const float* __restrict__ w, int T,
+                                   int topk, int vec_per_row) {
+  const long long total = static_cast<long long>(T) * vec_per_row;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int tok = static_cast<int>(t / vec_per_row), v = static_cast<int>(t % vec_per_row);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int j = 0; j < topk; ++j) {
+      const uint4 x = y[(static_cast<long long>(tok) * topk + j) * vec_per_row + v];
+      const float wj = w ? w[tok * topk + j] : 1.f;
+      const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if constexpr (kBF16) { acc[2 * i] += wj * ptx::bf16_lo(xs[i]); acc[2 * i + 1] += wj * ptx::bf16_hi(xs[i]); }
+        else { const __half2 h = *reinterpret_cast<const __half2*>(&xs[i]); acc[2 * i] += wj * __low2float(h); acc[2 * i + 1] += wj * __high2float(h); }
+      }
+    }
+    uint4 o;
+    if constexpr (kBF16) { o.x = ptx::pack_bf16x2(acc[0], acc[1]); o.y = ptx::pack_bf16x2(acc[2], acc[3]); o.z = ptx::pack_bf16x2(acc[4], acc[5]); o.w = ptx::pack_bf16x2(acc[6], acc[7]); }
+    else { o.x = ptx::pack_f16x2(acc[0], acc[1]); o.y = ptx::pack_f16x2(acc[2], acc[3]); o.z = ptx::pack_f16x2(acc[4], acc[5]); o.w = ptx::pack_f16x2(acc[6], acc[7]); }
+    out[t] = o;
+  }
+}
+
+__global__ void bincount_kernel(const int* __restrict__ ids, int n, int* __restrict__ counts, int E) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int e = ids[i];
+    if (e >= 0 && e < E) atomicAdd(counts + e, 1);
+  }
+}
+
+}  // namespace
+
+TD_API int td_moe_align_sort(const void* topk_ids, int n, int E, int block_m, int capacity, int pad_id, void* sorted_ids,
+                             void* tile_expert, void* expert_offsets, void* total_padded, int topk, int tokens_per_rank,
+                             int my_rank, int world, void* stream) {
+  if (capacity % block_m) { td::drv::set_error("moe_align_sort: capacity must be a multiple of block_m"); return -1; }
+  const int stages = tokens_per_rank > 0 ? world : 1;
+  const size_t smem = sizeof(int) * 2 * E * (world > 1 ? world : 1);
+  if (smem > 200 * 1024) { td::drv::set_error("moe_align_sort: too many experts x ranks for shared memory"); return -1; }
+  (void)stages;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(moe_align_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+  moe_align_sort_kernel<<<1, 1024, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      (const int*)topk_ids, n, E, block_m, capacity, pad_id, (int*)sorted_ids, (int*)tile_expert, (int*)expert_offsets,
+      (int*)total_padded, topk, tokens_per_rank, my_rank, world);
+  TD_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+TD_API int td_gather_rows(void* dst, const void* src, const void* ids, const void* n_rows_ptr, int n_rows_max, long long row_bytes,
+                          int div, int pad_id, void* stream) {
+  if (row_bytes % 16) { td::drv::set_error("gather_rows: row size must be a multiple of 16 bytes"); return -1; }
+  if (n_rows_max == 0) return 0;
+  const int vpr = (int)(row_bytes / 16);
+  const long long total = (long long)n_rows_max * vpr;
+  const int grid = (int)min((long long)148 * 8, (total + 255) / 256);
+  gather_rows_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>((uint4*)dst, (const uint4*)src, (const int*)ids,
+                                                                                (const int*)n_rows_ptr, n_rows_max, vpr, div, pad_id);
+  TD_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+TD_API int td_scatter_rows(void* dst, const void* src, const void* ids, const void* n_rows_ptr, int n_rows_max, long long row_bytes,
+                           int pad_id, void* stream) {
+  if (row_bytes % 16) { td::drv::set_error("scatter_rows: row size must be a multiple of 16 bytes"); return -1; }
+  if (n_rows_max == 0) return 0;
+  const int vpr = (int)(row_bytes / 16);
+  const long long total = (long long)n_rows_max * vpr;
+  const int grid = (int)min((long long)148 * 8, (total + 255) / 256);
+  scatter_rows_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>((uint4*)dst, (const uint4*)src, (const int*)ids,
+                                                                                 (const int*)n_rows_ptr, n_rows_max, vpr, pad_id);
+  TD_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+TD_API int td_topk_reduce(void* out, const void* y, const void* w, int T, int topk, int H, int is_bf16, void* stream) {
+  if (H % 8) { td::drv::set_error("topk_reduce: H must be a multiple of 8"); return -1; }
+  if (T == 0) return 0;
+  const int vpr = H / 8;
+  const long long total = (long long)T * vpr;
+  const int grid = (int)min((long long)148 * 8, (total + 255) / 256);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (is_bf16) topk_reduce_kernel<true><<<grid, 256, 0, s>>>((uint4*)out, (const uint4*)y, (const float*)w, T, topk, vpr);
+  else topk_reduce_kernel<false><<<grid, 256, 0, s>>>((uint4*)out, (const uint4*)y, (const float*)w, T, topk, vpr);
+  TD_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+TD_API int td_bincount(const void* ids, int n, void* counts, int E, void* stream) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  TD_CUDA_CHECK(cudaMemsetAsync(counts, 0, sizeof(int) * E, s));
+  if (n) bincount_kernel<<<min(148, (n + 255) / 256), 256, 0, s>>>((const int*)ids, n, (int*)counts, E);
+  TD_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

@@ -167,6 +167,59 @@ def case_gemm_rs():
         ctx.finalize()
 
 
+def case_moe():
+    """ag_group_gemm + run_moe_reduce_rs vs the masked-matmul golden (reference: test_ag_moe.py, test_moe_reduce_rs.py)."""
+    from triton_dist.ops import moe as M
+    dev = U.current_device()
+    W, me = U.world_size(), U.rank()
+    big = dev.type == "cuda"
+    dtype = torch.bfloat16 if big else torch.float32
+    T, H, I, E, topk = (256 * W, 512, 1024, 8, 2) if big else (8 * W, 16, 32, 4, 2)
+    ag = M.create_ag_group_gemm_context(T, I // W, H, E, topk, dtype)
+    rs = M.create_moe_rs_context(me, W, W, T * topk, H, E, topk, dtype)
+    grp = U.get_triton_dist_world()
+    for it in range(3):
+        g = torch.Generator(device="cpu").manual_seed(100 + it)          # same routing on all ranks
+        ids = torch.stack([torch.randperm(E, generator=g)[:topk] for _ in range(T)]).to(torch.int32).to(dev)
+        wts = torch.softmax(torch.randn(T, topk, generator=g), -1).to(dev)
+        x = (torch.randn(T // W, H, device=dev) * 0.5).to(dtype)
+        w_up = (torch.randn(E, I // W, H, device=dev) * 0.2).to(dtype)
+        w_dn = (torch.randn(E, H, I // W, device=dev) * 0.2).to(dtype)
+        c = M.ag_group_gemm(x, w_up, ag, ids)
+        xf = torch.empty(T * H, device=dev, dtype=dtype)
+        dist.all_gather_into_tensor(xf, x.view(-1), group=grp)
+        xf = xf.view(T, H)
+        ref = torch.stack([xf[t].float() @ w_up[int(ids[t, j])].float().t() for t in range(T) for j in range(topk)])
+        _assert_close(c, ref, 0.3 if big else 1e-3, 3e-2 if big else 1e-4, f"ag_group_gemm it{it}")
+        h = (torch.randn(T * topk, I // W, device=dev) * 0.5).to(dtype)
+        out = M.run_moe_reduce_rs(h, w_dn, ids, wts, rs)
+        gold = M.moe_reduce_rs_torch(h, w_dn.transpose(1, 2), ids, wts, grp, W, me)
+        _assert_close(out, gold, 0.5 if big else 1e-3, 3e-2 if big else 1e-4, f"moe_reduce_rs it{it}")
+    U.barrier_all_host()
+    ag.finalize(); rs.finalize()
+
+
+def case_tp_e2e():
+    """TP inference demo: every backend must reproduce the torch (NCCL) backend's greedy tokens (test_tp_e2e.py --check)."""
+    from triton_dist.models import Engine, ModelConfig
+    dev = U.current_device()
+    W, me = U.world_size(), U.rank()
+    big = dev.type == "cuda"
+    for name in ("tiny-dense", "tiny-moe"):
+        cfg = ModelConfig(model_name=name, max_length=64, dtype=torch.bfloat16 if big else torch.float32, rank=me, world_size=W)
+        eng = Engine(cfg, temperature=0.0)
+        g = torch.Generator().manual_seed(7)
+        ids = torch.randint(0, 1000, (2 * W, 6), generator=g)
+        ref = eng.serve(ids, 5, backend="torch", use_cuda_graph=False)
+        backends = ("triton_dist", "triton_dist_AR", "triton_dist_gemm_ar") if name == "tiny-dense" else ("triton_dist", "triton_dist_AR")
+        for be in backends:
+            out = eng.serve(ids, 5, backend=be, use_cuda_graph=big)
+            agree = (out == ref).float().mean().item()
+            assert agree >= (0.7 if big else 1.0), (name, be, agree, out.tolist(), ref.tolist())
+            eng.model.finalize()
+        U.barrier_all_host()
+
+
 CASES = {k[5:]: v for k, v in list(globals().items()) if k.startswith("case_")}
 
 if __name__ == "__main__":

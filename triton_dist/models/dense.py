@@ -91,7 +91,8 @@ class DenseLLM:
         self.group = group
         self.dtype = model_config.dtype
         self.device = U.current_device()
-        self.layers = [DenseLLMLayer(i, group, self.rank, self.world_size) for i in range(self.arch.num_hidden_layers)]
+        layer_cls = getattr(self, "_layer_cls", DenseLLMLayer)
+        self.layers = [layer_cls(i, group, self.rank, self.world_size) for i in range(self.arch.num_hidden_layers)]
         self.embed_tokens = self.lm_head = self.norm_w = None
         self.mode = "torch"
         self.num_layers = self.arch.num_hidden_layers

@@ -215,6 +215,54 @@ def all_reduce(x: torch.Tensor, method=AllReduceMethod.Unknown, ctx: AllReduceCo
     return output
 
 
+def reduce_scatter(x: torch.Tensor, ctx: AllReduceContext, output: Optional[torch.Tensor] = None, max_sm: int = -1,
+                   stream=None) -> torch.Tensor:
+    """SUM reduce-scatter along dim 0: every rank contributes ``x`` ([W * n, ...]) and receives its ``n`` rows.
+    Staging (zero-copy if ``x`` is ``ctx.symm_input``) -> per-CTA flag barrier -> each rank pulls and reduces only
+    its own slice (NVLS ``multimem.ld_reduce`` when available, P2P loads otherwise)."""
+    W = ctx.world_size
+    assert x.is_contiguous() and x.shape[0] % W == 0
+    rows = x.shape[0] // W
+    if output is None:
+        output = torch.empty((rows,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    nbytes = x.numel() * x.element_size()
+    if nbytes > ctx.workspace_nbytes:
+        raise ValueError("reduce_scatter: message larger than the context workspace")
+    if not x.is_cuda:
+        full = _all_reduce_host(x, ctx, torch.empty_like(x))
+        output.copy_(full[ctx.rank * rows:(ctx.rank + 1) * rows])
+        return output
+    if (nbytes // W) % 16:
+        raise ValueError("reduce_scatter: per-rank slice must be a multiple of 16 bytes")
+    heap = U.get_heap()
+    xb = x.view(torch.uint8).view(-1)
+    in_stage = heap.contains(xb) and ctx.stage.data_ptr() <= xb.data_ptr() < ctx.stage.data_ptr() + 2 * ctx.workspace_nbytes
+    def mk(method, grid, inp):
+        a = _ARArgs()
+        a.symm = symm_args()
+        a.method, a.dtype, a.grid, a.in_symm = method, _DT[x.dtype], grid, 1
+        a.inp, a.out = inp, output.data_ptr()
+        a.stage, a.stage2, a.stage_bytes, a.nbytes = ctx.stage.data_ptr(), ctx.stage2.data_ptr(), ctx.workspace_nbytes, nbytes
+        a.slots, a.phase = ctx.slots.data_ptr(), ctx.phase.data_ptr()
+        return a
+    if not in_stage:
+        # stage with a SEPARATE launch (method 6): the reduce kernel's barrier relies on "staging finished before this
+        # kernel started"; the staging kernel picks the half from the same device-side parity (graph-replay safe)
+        st = mk(6, _ar_grid(nbytes, max_sm, ctx.grid_max), xb.data_ptr())
+        _C.check(_C.cuda_lib().td_allreduce(C.byref(st), _stream(stream)), "td_allreduce(stage)")
+    a = _ARArgs()
+    a.symm = symm_args()
+    a.method = 5 if U.is_nvshmem_multimem_supported() else 4
+    a.dtype = _DT[x.dtype]
+    a.grid = _ar_grid(nbytes // W, max_sm, ctx.grid_max)
+    a.in_symm = 1
+    a.inp, a.out = ctx.stage.data_ptr(), output.data_ptr()
+    a.stage, a.stage2, a.stage_bytes, a.nbytes = ctx.stage.data_ptr(), ctx.stage2.data_ptr(), ctx.workspace_nbytes, nbytes
+    a.slots, a.phase = ctx.slots.data_ptr(), ctx.phase.data_ptr()
+    _C.check(_C.cuda_lib().td_allreduce(C.byref(a), _stream(stream)), "td_allreduce(reduce_scatter)")
+    return output
+
+
 def _all_reduce_host(x, ctx: AllReduceContext, output):
     """Emulation: stage -> flag-flip barrier -> sum over peer views (one-shot protocol, chunked like the GPU path)."""
     heap = U.get_heap()

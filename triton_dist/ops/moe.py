@@ -1,0 +1,335 @@
+"""MoE building blocks: routing sort/align, grouped GEMM on tcgen05, top-k reduce, and the two TP-MoE fused ops.
+
+Reference:
+  * ``calc_gather_scatter_index`` / ``reduce_topk`` -- kernels/nvidia/moe_utils.py:145-508
+  * ``moe_grouped_gemm`` -- kernels/nvidia/group_gemm.py:251
+  * ``create_ag_group_gemm_context`` / ``ag_group_gemm`` -- kernels/nvidia/allgather_group_gemm.py:338-609
+  * ``create_moe_rs_context`` / ``run_moe_reduce_rs`` -- kernels/nvidia/moe_reduce_rs.py:88, 872-961
+  * ``create_moe_ar_context`` / ``run_moe_reduce_ar`` -- kernels/nvidia/moe_reduce_ar.py:645
+
+B200 design: tokens are sorted by expert once on the device (one CTA counting sort, segments padded to the tile
+height so an m-tile never mixes experts), gathered into expert-contiguous rows, and the *same* tcgen05 GEMM kernel
+runs with a per-m-tile expert id that offsets the B (weight) TMA coordinate -- no separate grouped-GEMM kernel and
+no host sync: the padded row count stays on the device and unused tiles are skipped by their ``-1`` expert id.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from .. import _C
+from .. import utils as U
+from . import comm
+from .gemm import GemmConfig, fill_common
+
+c_void_p, c_int, c_ll = C.c_void_p, C.c_int, C.c_longlong
+_C.register("td_moe_align_sort", c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_int, c_int, c_int, c_int, c_void_p])
+_C.register("td_gather_rows", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_void_p])
+_C.register("td_scatter_rows", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p])
+_C.register("td_topk_reduce", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p])
+_C.register("td_bincount", c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p])
+
+
+def _s():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# routing
+# ------------------------------------------------------------------------------------------------------------
+@dataclass
+class SortedRouting:
+    sorted_ids: torch.Tensor      # [capacity] flat (token * topk + k) index, or pad_id
+    tile_expert: torch.Tensor     # [capacity / block_m]
+    expert_offsets: torch.Tensor  # [E + 1]
+    total_padded: torch.Tensor    # [1] (device)
+    capacity: int
+    block_m: int
+    pad_id: int
+
+
+def padded_capacity(n_pairs: int, E: int, block_m: int) -> int:
+    """Upper bound of the padded row count: every expert wastes < block_m rows."""
+    return (n_pairs + E * (block_m - 1) + block_m - 1) // block_m * block_m
+
+
+def moe_align_sort(topk_ids: torch.Tensor, num_experts: int, block_m: int = 128, tokens_per_rank: int = 0,
+                   rank: int = 0, world: int = 1) -> SortedRouting:
+    """Sort the flat (token, k) pairs by expert, pad each expert segment to ``block_m`` rows.  With
+    ``tokens_per_rank`` the pairs of each expert are additionally ordered by all-gather arrival stage of their source
+    rank (the reference's threadblock_swizzle_ag_moe: tiles whose tokens arrive first run first)."""
+    ids = topk_ids.reshape(-1).to(torch.int32).contiguous()
+    n = ids.numel()
+    topk = topk_ids.shape[-1] if topk_ids.dim() > 1 else 1
+    cap = padded_capacity(n, num_experts, block_m)
+    dev = ids.device
+    pad_id = n
+    if not ids.is_cuda:
+        stage = ((torch.arange(n) // topk) // tokens_per_rank - rank) % world if tokens_per_rank > 0 else torch.zeros(n, dtype=torch.long)
+        key = ids.long() * (world + 1) * (n + 1) + stage * (n + 1) + torch.arange(n)
+        order = torch.argsort(key)
+        counts = torch.bincount(ids.long(), minlength=num_experts)
+        padded = (counts + block_m - 1) // block_m * block_m
+        offs = torch.zeros(num_experts + 1, dtype=torch.int64)
+        offs[1:] = torch.cumsum(padded, 0)
+        sorted_ids = torch.full((cap,), pad_id, dtype=torch.int32)
+        tile_expert = torch.full((cap // block_m,), -1, dtype=torch.int32)
+        src = 0
+        for e in range(num_experts):
+            c = int(counts[e])
+            sorted_ids[int(offs[e]):int(offs[e]) + c] = order[src:src + c].to(torch.int32)
+            tile_expert[int(offs[e]) // block_m:int(offs[e + 1]) // block_m] = e
+            src += c
+        return SortedRouting(sorted_ids, tile_expert, offs.to(torch.int32), offs[-1:].to(torch.int32), cap, block_m, pad_id)
+    sorted_ids = torch.empty(cap, dtype=torch.int32, device=dev)
+    tile_expert = torch.empty(cap // block_m, dtype=torch.int32, device=dev)
+    offs = torch.empty(num_experts + 1, dtype=torch.int32, device=dev)
+    total = torch.empty(1, dtype=torch.int32, device=dev)
+    _C.check(_C.cuda_lib().td_moe_align_sort(ids.data_ptr(), n, num_experts, block_m, cap, pad_id, sorted_ids.data_ptr(),
+                                             tile_expert.data_ptr(), offs.data_ptr(), total.data_ptr(), topk, tokens_per_rank,
+                                             rank, world, _s()), "td_moe_align_sort")
+    return SortedRouting(sorted_ids, tile_expert, offs, total, cap, block_m, pad_id)
+
+
+def gather_rows(src: torch.Tensor, routing: SortedRouting, div: int = 1, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``out[i] = src[sorted_ids[i] // div]`` (zeros for pad rows)."""
+    H = src.shape[-1]
+    out = torch.empty((routing.capacity, H), dtype=src.dtype, device=src.device) if out is None else out
+    if not src.is_cuda:
+        ids = routing.sorted_ids.long()
+        valid = ids != routing.pad_id
+        out.zero_()
+        out[valid] = src[ids[valid] // div]
+        return out
+    _C.check(_C.cuda_lib().td_gather_rows(out.data_ptr(), src.contiguous().data_ptr(), routing.sorted_ids.data_ptr(), None,
+                                          routing.capacity, H * src.element_size(), div, routing.pad_id, _s()), "td_gather_rows")
+    return out
+
+
+def scatter_rows(src_sorted: torch.Tensor, routing: SortedRouting, n_rows: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``out[sorted_ids[i]] = src_sorted[i]`` -- back to flat (token, k) order."""
+    H = src_sorted.shape[-1]
+    out = torch.empty((n_rows, H), dtype=src_sorted.dtype, device=src_sorted.device) if out is None else out
+    if not src_sorted.is_cuda:
+        ids = routing.sorted_ids.long()
+        valid = ids != routing.pad_id
+        out[ids[valid]] = src_sorted[valid]
+        return out
+    _C.check(_C.cuda_lib().td_scatter_rows(out.data_ptr(), src_sorted.data_ptr(), routing.sorted_ids.data_ptr(), None,
+                                           routing.capacity, H * src_sorted.element_size(), routing.pad_id, _s()), "td_scatter_rows")
+    return out
+
+
+def reduce_topk(y: torch.Tensor, weights: Optional[torch.Tensor], topk: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``out[t] = sum_j weights[t, j] * y[t * topk + j]`` with fp32 accumulation (moe_utils.py:reduce_topk_*)."""
+    T = y.shape[0] // topk
+    H = y.shape[1]
+    out = torch.empty((T, H), dtype=y.dtype, device=y.device) if out is None else out
+    if not y.is_cuda or H % 8 or y.dtype not in (torch.bfloat16, torch.float16):
+        w = weights.float().reshape(T, topk, 1) if weights is not None else 1.0
+        out.copy_((y.float().view(T, topk, H) * w).sum(1).to(y.dtype))
+        return out
+    wf = weights.float().contiguous() if weights is not None else None
+    _C.check(_C.cuda_lib().td_topk_reduce(out.data_ptr(), y.contiguous().data_ptr(), wf.data_ptr() if wf is not None else None,
+                                          T, topk, H, int(y.dtype == torch.bfloat16), _s()), "td_topk_reduce")
+    return out
+
+
+def histogram_by_expert(topk_ids: torch.Tensor, num_experts: int) -> torch.Tensor:
+    ids = topk_ids.reshape(-1).to(torch.int32).contiguous()
+    if not ids.is_cuda:
+        return torch.bincount(ids.long(), minlength=num_experts).to(torch.int32)
+    out = torch.empty(num_experts, dtype=torch.int32, device=ids.device)
+    _C.check(_C.cuda_lib().td_bincount(ids.data_ptr(), ids.numel(), out.data_ptr(), num_experts, _s()), "td_bincount")
+    return out
+
+
+bincount = histogram_by_expert
+
+
+# ------------------------------------------------------------------------------------------------------------
+# grouped GEMM
+# ------------------------------------------------------------------------------------------------------------
+def moe_grouped_gemm(x_sorted: torch.Tensor, w: torch.Tensor, routing: SortedRouting, out: Optional[torch.Tensor] = None,
+                     config: Optional[GemmConfig] = None) -> torch.Tensor:
+    """``y_sorted[i] = x_sorted[i] @ w[expert_of_row(i)].T``;  x_sorted: [capacity, K] (expert-sorted, padded),
+    w: [E, N, K] (K-major per expert).  Rows of unused padded tiles are left untouched."""
+    cap, K = x_sorted.shape
+    E, N, Kw = w.shape
+    assert Kw == K and cap == routing.capacity
+    out = torch.empty((cap, N), dtype=x_sorted.dtype, device=x_sorted.device) if out is None else out
+    if not x_sorted.is_cuda:
+        te = routing.tile_expert
+        bm = routing.block_m
+        for t in range(te.numel()):
+            e = int(te[t])
+            if e >= 0:
+                out[t * bm:(t + 1) * bm] = (x_sorted[t * bm:(t + 1) * bm].float() @ w[e].float().t()).to(out.dtype)
+        return out
+    cfg = config or GemmConfig(bn=256 if N >= 256 else 128, cta_group=1, group_m=1, use_tma_store=True)
+    assert routing.block_m == 128 * cfg.cta_group, "routing block_m must equal the GEMM tile height"
+    w2 = w.reshape(E * N, K)
+    args = _C.GemmArgs()
+    args.mode = 0
+    fill_common(args, cap, x_sorted.data_ptr(), x_sorted.stride(0), w2, out.data_ptr(), cap, out.stride(0), cap, N, K, cfg,
+                x_sorted.dtype == torch.bfloat16)
+    args.tile_expert, args.num_experts = routing.tile_expert.data_ptr(), E
+    _C.check(_C.cuda_lib().td_gemm_launch(C.byref(args), _s()), "td_gemm_launch(grouped)")
+    return out
+
+
+def moe_forward_local(x: torch.Tensor, w: torch.Tensor, topk_ids: torch.Tensor, num_experts: Optional[int] = None) -> torch.Tensor:
+    """``c[t * topk + j] = x[t] @ w[ids[t, j]].T`` for local tokens (no communication)."""
+    E = w.shape[0] if num_experts is None else num_experts
+    topk = topk_ids.shape[1]
+    r = moe_align_sort(topk_ids, E, 128)
+    xs = gather_rows(x, r, div=topk)
+    ys = moe_grouped_gemm(xs, w, r)
+    return scatter_rows(ys, r, topk_ids.numel())
+
+
+# ------------------------------------------------------------------------------------------------------------
+# AG + grouped GEMM (TP-MoE up projection)
+# ------------------------------------------------------------------------------------------------------------
+@dataclass
+class MoEAllGatherGroupGEMMContext:
+    max_ntokens: int
+    N_per_rank: int
+    K: int
+    num_experts: int
+    topk: int
+    dtype: torch.dtype
+    rank: int
+    world_size: int
+    ag_ctx: comm.FastAllGatherContext = None
+
+    def finalize(self):
+        if self.ag_ctx is not None:
+            self.ag_ctx.finalize()
+            self.ag_ctx = None
+
+
+def create_ag_group_gemm_context(max_ntokens: int, N_per_rank: int, K: int, num_experts: int, topk: int, dtype: torch.dtype,
+                                 rank: Optional[int] = None, world_size: Optional[int] = None, local_world_size=None,
+                                 **_unused) -> MoEAllGatherGroupGEMMContext:
+    heap = U.get_heap()
+    rank = heap.rank if rank is None else rank
+    world_size = heap.world if world_size is None else world_size
+    ctx = MoEAllGatherGroupGEMMContext(max_ntokens, N_per_rank, K, num_experts, topk, dtype, rank, world_size)
+    shard_bytes = (max_ntokens // world_size) * K * torch.empty(0, dtype=dtype).element_size()
+    ctx.ag_ctx = comm.create_fast_allgather_context(max(shard_bytes, 1024), rank, world_size, grid_max=64)
+    return ctx
+
+
+def ag_group_gemm(a: torch.Tensor, b: torch.Tensor, ctx: MoEAllGatherGroupGEMMContext, full_topk_ids: torch.Tensor,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """a: ``[T/W, K]`` local tokens, b: ``[E, N/W, K]`` (K-major expert weights; the reference passes ``[E, K, N/W]`` --
+    a ``transpose(1, 2)`` view of this layout is accepted), full_topk_ids: ``[T, topk]`` (already all-gathered)
+    -> ``c[T * topk, N/W]`` with row ``t * topk + j = a_full[t] @ b[ids[t, j]]``."""
+    W = ctx.world_size
+    if b.shape[1] == a.shape[1] and b.shape[2] != a.shape[1]:
+        b = b.transpose(1, 2)                      # [E, K, N] -> [E, N, K] view
+    if b.stride(2) != 1:
+        b = b.contiguous()
+    T = full_topk_ids.shape[0]
+    tpr = a.shape[0]
+    assert tpr * W == T
+    # 1. all-gather the tokens (push over NVLink; consumers sorted by arrival stage below)
+    if W > 1:
+        a_full = comm.fast_allgather(a.contiguous(), ctx.ag_ctx, mode="push").view(T, a.shape[1])
+    else:
+        a_full = a
+    # 2. route: expert-major, and within an expert by arrival stage of the source rank
+    r = moe_align_sort(full_topk_ids, ctx.num_experts, 128, tokens_per_rank=tpr, rank=ctx.rank, world=W)
+    xs = gather_rows(a_full, r, div=ctx.topk)
+    ys = moe_grouped_gemm(xs, b, r)
+    return scatter_rows(ys, r, T * ctx.topk, out=out)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# grouped GEMM + top-k reduce + ReduceScatter / AllReduce (TP-MoE down projection)
+# ------------------------------------------------------------------------------------------------------------
+@dataclass
+class MoEReduceRSContext:
+    rank: int
+    world_size: int
+    max_token_num: int       # T * topk
+    hidden_dim: int
+    num_experts: int
+    topk: int
+    dtype: torch.dtype
+    ar_ctx: comm.AllReduceContext = None
+
+    def finalize(self):
+        if self.ar_ctx is not None:
+            self.ar_ctx.finalize()
+            self.ar_ctx = None
+
+
+def create_moe_rs_context(rank: Optional[int], world_size: Optional[int], local_world_size, max_token_num: int,
+                          hidden_dim: int, num_experts: int, topk: int, dtype: torch.dtype, n_chunks_max: int = 8,
+                          **_unused) -> MoEReduceRSContext:
+    heap = U.get_heap()
+    rank = heap.rank if rank is None else rank
+    world_size = heap.world if world_size is None else world_size
+    ctx = MoEReduceRSContext(rank, world_size, max_token_num, hidden_dim, num_experts, topk, dtype)
+    T = max_token_num // topk
+    ctx.ar_ctx = comm.create_allreduce_ctx(max(T * hidden_dim * torch.empty(0, dtype=dtype).element_size(), 1024), rank,
+                                           world_size, world_size)
+    return ctx
+
+
+create_moe_ar_context = create_moe_rs_context
+
+
+def _moe_down_partial(x, w, chosen_experts, expert_weight, ctx):
+    """Local part: grouped GEMM over this rank's K-shard + weighted top-k reduction -> partial ``[T, N]``."""
+    if w.shape[1] == x.shape[1] and w.shape[2] != x.shape[1]:
+        w = w.transpose(1, 2)                      # [E, K/W, N] -> [E, N, K/W]
+    if w.stride(2) != 1:
+        w = w.contiguous()
+    r = moe_align_sort(chosen_experts, ctx.num_experts, 128)
+    xs = gather_rows(x, r, div=1)                  # rows of x are already (token, k) pairs
+    ys = moe_grouped_gemm(xs, w, r)
+    y = scatter_rows(ys, r, chosen_experts.numel())
+    return reduce_topk(y, expert_weight, ctx.topk)
+
+
+def run_moe_reduce_rs(x: torch.Tensor, w: torch.Tensor, chosen_experts: torch.Tensor, expert_weight: torch.Tensor,
+                      ctx: MoEReduceRSContext, n_chunks: int = 2, **_unused) -> torch.Tensor:
+    """x: ``[T*topk, K/W]``, w: ``[E, K/W, N]`` (or K-major ``[E, N, K/W]``), chosen_experts/expert_weight: ``[T, topk]``
+    -> ``[T/W, N]`` = reduce_scatter_ranks( sum_j weight[t,j] * (x[t*topk+j] @ w[e_tj]) )."""
+    part = _moe_down_partial(x, w, chosen_experts, expert_weight, ctx)
+    W = ctx.world_size
+    if W == 1:
+        return part
+    return comm.reduce_scatter(part.contiguous(), ctx.ar_ctx)
+
+
+def run_moe_reduce_ar(x, w, chosen_experts, expert_weight, ctx: MoEReduceRSContext, **_unused) -> torch.Tensor:
+    part = _moe_down_partial(x, w, chosen_experts, expert_weight, ctx)
+    if ctx.world_size == 1:
+        return part
+    return comm.all_reduce(part, None if part.is_cuda else comm.AllReduceMethod.OneShot, ctx.ar_ctx)
+
+
+def moe_reduce_rs_torch(x, w, chosen_experts, expert_weight, group, world_size, rank):
+    """Golden (reference test: test_moe_reduce_rs.py:88-107): masked per-expert matmul, weighted sum, reduce_scatter."""
+    if w.shape[1] != x.shape[1]:
+        w = w.transpose(1, 2)
+    T, topk = chosen_experts.shape
+    ids = chosen_experts.reshape(-1).long()
+    y = torch.zeros((T * topk, w.shape[2]), dtype=torch.float32, device=x.device)
+    for e in range(w.shape[0]):
+        m = ids == e
+        if m.any():
+            y[m] = x[m].float() @ w[e].float()
+    part = (y.view(T, topk, -1) * expert_weight.float()[..., None]).sum(1)
+    if world_size > 1:
+        dist.all_reduce(part, group=group)
+    return part[rank * (T // world_size):(rank + 1) * (T // world_size)]
