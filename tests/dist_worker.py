@@ -220,6 +220,59 @@ def case_tp_e2e():
         U.barrier_all_host()
 
 
+def case_ep_ll():
+    """EP low-latency dispatch + combine vs a gathered golden (reference: test_ep_ll_a2a.py)."""
+    from triton_dist.ops import ep_a2a as EP
+    dev = U.current_device()
+    W, me = U.world_size(), U.rank()
+    big = dev.type == "cuda"
+    T, H, topk, E = (96, 1024, 4, 8 * W) if big else (6, 128, 2, 2 * W)
+    epr = E // W
+    grp = U.get_triton_dist_world()
+    variants = [False, True] if big else [False]
+    for fp8 in variants:
+        ctx = EP.create_ep_ll_a2a_ctx(T, H, topk, E, online_quant_fp8=fp8, dtype=torch.bfloat16)
+        for it in range(4):
+            g = torch.Generator().manual_seed(1000 * it + me)
+            x = (torch.randn(T, H, generator=g) * 0.5).to(torch.bfloat16).to(dev)
+            idx = torch.stack([torch.randperm(E, generator=g)[:topk] for _ in range(T)]).to(torch.int32).to(dev)
+            if it == 2:
+                idx[0, 0] = -1                                   # an unrouted slot
+            wts = torch.softmax(torch.randn(T, topk, generator=g), -1).to(dev)
+            rx, rs, cnt, meta = EP.ep_ll_dispatch(ctx, x, idx)
+            # golden: gather everybody's tokens / routing
+            xs = torch.empty(W * T * H, dtype=torch.bfloat16, device=dev)
+            dist.all_gather_into_tensor(xs, x.view(-1), group=grp)
+            ids = torch.empty(W * T * topk, dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(ids, idx.view(-1), group=grp)
+            xs, ids = xs.view(W, T, H), ids.view(W, T, topk)
+            cnts, starts = meta.counts_and_starts()
+            dense = EP.dequant_fp8(rx, rs) if fp8 else rx
+            for le in range(epr):
+                e = me * epr + le
+                total = 0
+                for src in range(W):
+                    want = (ids[src] == e).nonzero()                       # [n, 2] (token, k)
+                    c, s = int(cnts[le, src]), int(starts[le, src])
+                    assert c == want.shape[0], (le, src, c, want.shape[0])
+                    total += c
+                    got_flat = meta.recv_token_source_indices[le, s:s + c].long()
+                    assert sorted(got_flat.tolist()) == sorted((want[:, 0] * topk + want[:, 1]).tolist())
+                    ref_rows = xs[src][got_flat // topk].float()
+                    _assert_close(dense[le, s:s + c], ref_rows, 0.08 if fp8 else 0.0, 0.08 if fp8 else 0.0, f"dispatch payload fp8={fp8}")
+                assert int(cnt[le]) == total
+            # experts = identity * (1 + local expert id): combine must return sum_k w * (1 + le) * x
+            y = torch.zeros((epr, W * T, H), dtype=torch.bfloat16, device=dev)
+            for le in range(epr):
+                n = int(cnt[le])
+                y[le, :n] = (dense[le, :n].float() * (1 + me * epr + le)).to(torch.bfloat16)
+            out = EP.ep_ll_combine(ctx, y, idx, wts, meta)
+            scale = ((idx.clamp(min=0).float() + 1) * wts * (idx >= 0)).sum(-1, keepdim=True)
+            _assert_close(out, x.float() * scale, 0.35 if fp8 else 0.1, 0.1 if fp8 else 3e-2, f"combine fp8={fp8} it{it}")
+        U.barrier_all_host()
+        ctx.finalize()
+
+
 CASES = {k[5:]: v for k, v in list(globals().items()) if k.startswith("case_")}
 
 if __name__ == "__main__":
