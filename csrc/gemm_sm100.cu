@@ -21,6 +21,7 @@ struct TdGemmArgs {
   const void* B; long long ldb;
   void* C; long long c_rows; long long ldc; const void* c_phase; long long c_nbuf; long long c_buf_stride_bytes;
   const void* tile_expert; long long num_experts;   // grouped (MoE) mode: B is [num_experts * N, K]
+  void* prof_buf; long long prof_cap; long long prof_slots;   // intra-kernel profiler (optional)
   // symmetric context
   long long rank, world; unsigned long long symm_base, symm_stride, mc_base;
   void* phase;
@@ -47,7 +48,7 @@ template <int kMode, int BN, int kCtaGroup>
 static int launch_cfg(const Params& p, int grid, cudaStream_t stream) {
   // deepest pipeline that fits in 227 KB next to the 32 KB epilogue staging
   constexpr int kStageBytes = BM * BK * 2 + (BN / kCtaGroup) * BK * 2;
-  constexpr int kExtra = (kMode == kAG) ? kAgInBytes : 0;     // AG: room for the in-CTA push ring
+  constexpr int kExtra = 0;
   constexpr int kMaxStages = (232448 - 1024 - 2 * kCBlockBytes - 384 - kExtra) / kStageBytes;
   constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
   using L = SmemLayout<BN, kStages, kCtaGroup, kExtra>;
@@ -113,6 +114,7 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
   p.c_buf_stride_bytes = a->c_buf_stride_bytes;
   p.tile_expert = reinterpret_cast<const int*>(a->tile_expert);
   p.expert_rows = (int)a->N;
+  p.prof.buf = reinterpret_cast<unsigned long long*>(a->prof_buf); p.prof.cap = (int)a->prof_cap; p.prof.num_slots = (int)a->prof_slots;
   const int TM = BM * cg;
   p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K;
   p.num_m = (p.M + TM - 1) / TM;
@@ -147,9 +149,8 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
   if (gemm_ctas / cg > tiles) gemm_ctas = tiles * cg;
   if (a->tile_expert && a->group_m > 1) p.group_m = 1;   // grouped: keep experts' tiles together (n fastest)
   if (a->mode == kAG && a->world > 1 && !a->ag_skip_wait) {
-    // the all-gather is pushed by EVERY CTA (GEMM CTAs use their spare warp); SMs without tiles become
-    // dedicated comm CTAs so the whole chip feeds the NVLink port
-    p.n_comm_ctas = grid - gemm_ctas;
+    if (p.n_comm_ctas < cg) p.n_comm_ctas = 16;
+    if (p.n_comm_ctas > kAGMaxSlices) p.n_comm_ctas = kAGMaxSlices;
   }
   grid = gemm_ctas + p.n_comm_ctas;
 

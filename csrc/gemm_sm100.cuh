@@ -27,6 +27,7 @@
 //     host barrier between calls, and a captured CUDA graph replays correctly.
 #pragma once
 #include "td/primitives.cuh"
+#include "td/profiler.cuh"
 
 namespace td {
 namespace gemm {
@@ -40,7 +41,7 @@ constexpr int kEpiThreads = 128;
 constexpr int kCBlockCols = 64;                       // epilogue staging block: 128 rows x 64 cols (16-bit) = 16 KB
 constexpr int kCBlockBytes = BM * kCBlockCols * 2;
 constexpr int kAGRowsPerChunk = 128;                  // AG arrival-flag granularity (rows of a source shard)
-constexpr int kAGSubPieces = 8;                       // each chunk is pulled as 8 independently flagged sub-pieces
+constexpr int kAGMaxSlices = 64;                      // max comm CTAs (= arrival flags per source rank)
 constexpr int kCommPieceBytes = 16 * 1024;            // one TMA bulk copy
 constexpr int kCommRingSlots = 12;                    // 192 KB smem ring in a comm CTA
 constexpr int kCommLag = 8;                           // pushed pieces allowed to be incomplete before the oldest is awaited
@@ -73,6 +74,8 @@ struct Params {
   const int* tile_expert;
   int expert_rows;
   int pad3;
+  // optional intra-kernel profiler (null = off): slot = blockIdx.x * 8 + warp
+  ProfBuf prof;
   SymmCtx symm;
   // ---- phase bookkeeping (device resident so a captured graph replays correctly) ----
   // [0] = number of completed calls on this context, [1] = CTA exit counter, [2] = AG local-copy counter
@@ -85,7 +88,7 @@ struct Params {
   const void* ag_a_local;    // my shard [rows_per_rank, K]
   char* ag_ws;               // my workspace: 2 buffers of [world * rows_per_rank, K] (symmetric)
   long long ag_ws_buf_bytes; // bytes of one buffer
-  uint32_t* ag_flags;        // symmetric: [2][world(src)][chunks_per_rank][kAGSubPieces] = phase of the call that filled it
+  uint32_t* ag_flags;        // symmetric: [2][world(src)][kAGMaxSlices] = phase of the call that pushed that slice
   uint32_t* ag_ready;        // [world]: ag_ready[s] >= p  <=>  rank s has its phase-p shard in ITS workspace (symmetric)
   // ---- RS (ring) ----
   int rs_rows_per_rank;      // M / world, multiple of BM * cta_group
@@ -111,7 +114,7 @@ struct SmemLayout {
   static constexpr int kNumBars = 2 * kStages + 4;
   static constexpr int kExtraOff = ((kBarOff + kNumBars * 8 + 16 + 127) / 128) * 128;   // optional comm ring (AG mode)
   static constexpr int kGemmBytes = kExtraOff + kExtra;
-  static constexpr int kCommBytes = kCommRingSlots * kCommPieceBytes + kCommRingSlots * (8 + 8 + 8 + 8) + 64;  // ring + mbarriers + queues
+  static constexpr int kCommBytes = kCommRingSlots * kCommPieceBytes + 256;   // comm CTA: kCommStreams x 2 x 16 KB rings + mbarriers
   static constexpr int kTotal = (kGemmBytes > kCommBytes ? kGemmBytes : kCommBytes) + 1024;  // + alignment slack
   static_assert(kStageBytes % 1024 == 0, "stage must keep 1024 B alignment for SWIZZLE_128B");
   static_assert(kTotal <= 232448, "exceeds 227 KB of shared memory");
@@ -119,6 +122,12 @@ struct SmemLayout {
 
 __host__ __device__ constexpr int tmem_cols_for(int bn) {
   return 2 * bn <= 32 ? 32 : 2 * bn <= 64 ? 64 : 2 * bn <= 128 ? 128 : 2 * bn <= 256 ? 256 : 512;
+}
+
+// bytes of my shard pushed by one comm CTA (128-byte aligned slices)
+__host__ __device__ inline size_t ag_slice_bytes(size_t shard_bytes, int n_comm) {
+  const size_t n = n_comm > 0 ? n_comm : 1;
+  return ((shard_bytes + n - 1) / n + 127) & ~static_cast<size_t>(127);
 }
 
 // tile index -> (m tile, n tile); band-swizzled (m fastest inside a band of group_m tiles), then rotated
@@ -137,141 +146,72 @@ TD_DEVICE void tile_coords(const Params& p, int t, int& m_tile, int& n_tile) {
 // AG consumer side: wait until rows [row0, row1) of the gathered A are resident in my workspace
 // -------------------------------------------------------------------------------------------------
 TD_DEVICE void ag_wait_rows(const Params& p, uint32_t ph, int row0, int row1) {
+  // The source rank's comm CTA c pushes byte slice c of its shard and then publishes flag[src][c] = phase on the
+  // destination.  A flag holds the phase number of the call that last filled it, so stale values from earlier
+  // calls (or other shapes) are simply "< ph" and nothing is ever reset.
   const int Ms = p.ag_rows_per_rank;
-  const int cpr = (Ms + kAGRowsPerChunk - 1) / kAGRowsPerChunk;
-  // one flag per (source, chunk, sub-piece), written by the SOURCE rank's comm CTA over NVLink after its
-  // pushed bytes are complete.  A flag holds the phase number of the call that last filled it, so stale
-  // values from earlier calls (or other shapes) are simply "< ph" and nothing is ever reset.
-  const uint32_t* flags = p.ag_flags + (ph & 1u) * p.symm.world * cpr * kAGSubPieces;
+  const size_t row_bytes = static_cast<size_t>(p.K) * 2;
+  const size_t shard_bytes = static_cast<size_t>(Ms) * row_bytes;
+  const size_t slice = ag_slice_bytes(shard_bytes, p.n_comm_ctas);
+  const uint32_t* flags = p.ag_flags + (ph & 1u) * p.symm.world * kAGMaxSlices;
   int r = row0;
   while (r < row1) {
     const int s = r / Ms;
-    const int b = (r - s * Ms) / kAGRowsPerChunk;
+    const int r_end = min(row1, (s + 1) * Ms);
     if (s != p.symm.rank || p.ag_copy_local) {
-      const uint32_t* f = flags + (s * cpr + b) * kAGSubPieces;
-#pragma unroll 1
-      for (int u = 0; u < kAGSubPieces; ++u) wait_ge<true>(f + u, ph);
+      const size_t b0 = static_cast<size_t>(r - s * Ms) * row_bytes, b1 = static_cast<size_t>(r_end - s * Ms) * row_bytes;
+      for (int c = static_cast<int>(b0 / slice); c <= static_cast<int>((b1 - 1) / slice); ++c)
+        wait_ge<true>(flags + s * kAGMaxSlices + c, ph);
     }
-    r = min(s * Ms + (b + 1) * kAGRowsPerChunk, (s + 1) * Ms);
+    r = r_end;
   }
-  // the rows were written through the async proxy (bulk copies): order them before my TMA reads
+  // rows were written by (remote) generic-proxy stores and are about to be read by TMA (async proxy)
   ptx::fence_proxy_async();
 }
 
 // -------------------------------------------------------------------------------------------------
-// AG producer side (comm CTA): PUSH my shard into every rank's workspace.
+// AG producer side (comm CTA c): PUSH byte slice c of my shard into every rank's workspace, nearest consumer
+// first (rank-1 starts with my rows right after its own; at any moment every rank pushes to a different peer,
+// so each NVLink port carries one stream per direction).
 //
-// Measured on 8xB200: a *pull* design (TMA bulk loads from peer HBM) tops out at ~7 GB/s per SM -- remote
-// reads are round trips and each SM only keeps a few KB of them in flight -- so 32 SMs reached 220 GB/s.
-// Remote *writes* are posted: one thread streams  local HBM -> smem ring -> peer HBM  with TMA bulk copies
-// and keeps kCommLag x 16 KB of stores un-acknowledged per SM.
-// Destinations are served one after the other in the order the consumers need the data (rank-1 first,
-// it starts with my rows right after its own), and at any moment every rank pushes to a different peer,
-// so each NVLink port carries exactly one stream in each direction.
+// Mechanism chosen from measurements on B200 (profiles/p2p_mechanisms_2xB200.json and the intra-kernel
+// profiles in profiles/): coalesced 16-byte generic stores from all 256 threads move ~42 GB/s per SM and
+// 16-32 SMs fill the port; the arrival flag needs a system-scope release AFTER the data (a relaxed flag store
+// following cp.async.bulk completion was observed to overtake the data), and that fence is expensive while
+// the SM has NVLink writes in flight -- so it is issued once per (CTA, destination), after a whole slice.
 // -------------------------------------------------------------------------------------------------
-// One thread runs this loop.  kSlots x kPiece bytes of shared memory at `ring` (+ kSlots mbarriers and the
-// piece queues at `meta`) are private to it.  Dedicated comm CTAs use a deep ring (12 x 16 KB); the spare
-// warp of every GEMM CTA runs the same loop on a 4 x 8 KB ring carved out of one pipeline stage, because the
-// measured per-SM NVLink rate (~6-10 GB/s, reads and posted writes alike) means saturating the port takes
-// (nearly) all SMs, not a handful of "comm SMs".
-template <int kSlots, int kPiece, int kLag, int kAhead>
-TD_DEVICE void ag_push_loop(const Params& p, uint32_t ph, int comm_idx, int n_comm, uint8_t* ring, uint8_t* meta) {
-  uint64_t* full = reinterpret_cast<uint64_t*>(meta);
-  uint32_t** q_flag = reinterpret_cast<uint32_t**>(full + kSlots);   // flag to publish when the piece completes
-  char** q_dst = reinterpret_cast<char**>(q_flag + kSlots);
-  uint32_t* q_n = reinterpret_cast<uint32_t*>(q_dst + kSlots);
-  for (int i = 0; i < kSlots; ++i) ptx::mbar_init(full + i, 1);
-  ptx::fence_barrier_init();
-  ptx::fence_proxy_async();
-
+TD_DEVICE void ag_comm_cta(const Params& p, uint32_t ph, int comm_idx) {
   const int W = p.symm.world, me = p.symm.rank, Ms = p.ag_rows_per_rank;
-  const int cpr = (Ms + kAGRowsPerChunk - 1) / kAGRowsPerChunk;
   const size_t row_bytes = static_cast<size_t>(p.K) * 2;
+  const size_t shard_bytes = static_cast<size_t>(Ms) * row_bytes;
+  const size_t slice = ag_slice_bytes(shard_bytes, p.n_comm_ctas);
+  const size_t b0 = min(shard_bytes, slice * comm_idx), b1 = min(shard_bytes, b0 + slice);
   char* ws = p.ag_ws + (ph & 1u) * p.ag_ws_buf_bytes;
   const size_t shard_off = static_cast<size_t>(me) * Ms * row_bytes;
-  const char* src_base = p.ag_copy_local ? reinterpret_cast<const char*>(p.ag_a_local) : ws + shard_off;
-  uint32_t* my_flags = p.ag_flags + (ph & 1u) * W * cpr * kAGSubPieces + me * cpr * kAGSubPieces;
-
-  // piece counters: loaded >= issued (store issued) >= retired (store complete, flag published, slot reusable)
-  uint32_t loaded = 0, issued = 0, retired = 0;
-  uint32_t parity_bits = 0;
-  auto retire_to = [&](uint32_t upto) {
-    for (; retired < upto; ++retired) {
-      uint32_t* f = q_flag[retired % kSlots];
-      if (f != nullptr) {
-        ptx::fence_proxy_async();
-        ptx::fence_acq_rel_sys();
-        ptx::st_release_sys(f, ph);
-      }
-    }
-  };
-  auto store_oldest = [&]() {            // forward the oldest loaded piece:  smem -> (peer) HBM, posted
-    const uint32_t slot = issued % kSlots;
-    if (q_n[slot]) {
-      ptx::mbar_wait(full + slot, (parity_bits >> slot) & 1u);
-      parity_bits ^= (1u << slot);
-      ptx::bulk_s2g(q_dst[slot], ring + slot * kPiece, q_n[slot]);
-    }
-    ptx::bulk_commit();
-    ++issued;
-    if (issued - retired > kLag) {
-      ptx::bulk_wait<kLag>();
-      retire_to(issued - kLag);
-    }
-  };
-  auto load_piece = [&](const char* src, char* dst, uint32_t n, uint32_t* flag) {
-    while (loaded - retired >= kSlots) {                   // ring full: make progress on the store side
-      if (issued < loaded) store_oldest();
-      else { ptx::bulk_wait<0>(); retire_to(issued); }
-    }
-    const uint32_t slot = loaded % kSlots;
-    q_dst[slot] = dst; q_n[slot] = n; q_flag[slot] = flag;
-    if (n) {
-      ptx::mbar_arrive_expect_tx(full + slot, n);
-      ptx::bulk_g2s(ring + slot * kPiece, src, n, full + slot);   // local HBM/L2 -> smem
-    }
-    ++loaded;
-    if (loaded - issued > kAhead) store_oldest();
-  };
-
-  int item = 0;
+  const char* src = (p.ag_copy_local ? reinterpret_cast<const char*>(p.ag_a_local) : ws + shard_off) + b0;
+  uint32_t* my_flag = p.ag_flags + (ph & 1u) * W * kAGMaxSlices + me * kAGMaxSlices + comm_idx;
+  const int pslot = static_cast<int>(blockIdx.x) * 8;
   for (int dist = p.ag_copy_local ? 0 : 1; dist < W; ++dist) {
-    const int d = (me - dist + W) % W;                       // destination rank
-    char* dst_base = symm_at(p.symm, ws, d) + shard_off;
-    uint32_t* dst_flags = symm_at(p.symm, my_flags, d);
-    for (int b = 0; b < cpr; ++b) {
-      const int r0 = b * kAGRowsPerChunk, r1 = min(Ms, r0 + kAGRowsPerChunk);
-      const size_t cbytes = static_cast<size_t>(r1 - r0) * row_bytes;
-      const size_t sub = ((cbytes + kAGSubPieces - 1) / kAGSubPieces + 127) & ~static_cast<size_t>(127);
-      for (int u = 0; u < kAGSubPieces; ++u, ++item) {
-        if (item % n_comm != comm_idx) continue;
-        size_t off = static_cast<size_t>(r0) * row_bytes + min(cbytes, sub * u);
-        const size_t end = static_cast<size_t>(r0) * row_bytes + min(cbytes, sub * (u + 1));
-        uint32_t* flag = dst_flags + b * kAGSubPieces + u;
-        if (off >= end) { load_piece(nullptr, nullptr, 0, flag); continue; }   // empty sub-piece: flag only
-        while (off < end) {
-          const uint32_t n = static_cast<uint32_t>(min(static_cast<size_t>(kPiece), end - off));
-          load_piece(src_base + off, dst_base + off, n, (off + n >= end) ? flag : nullptr);
-          off += n;
-        }
-      }
+    const int d = (me - dist + W) % W;
+    if (threadIdx.x == 0) prof_record(p.prof, pslot, 1, true);
+    if (b1 > b0) copy16_strided(symm_at(p.symm, ws, d) + shard_off + b0, src, b1 - b0, threadIdx.x, kThreads);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      prof_record(p.prof, pslot, 1, false);
+      prof_record(p.prof, pslot, 6, true);
+      ptx::fence_acq_rel_sys();
+      ptx::st_relaxed_sys(symm_at(p.symm, my_flag, d), ph);
+      prof_record(p.prof, pslot, 6, false);
     }
   }
-  while (issued < loaded) store_oldest();
-  ptx::bulk_wait<0>();
-  retire_to(issued);
 }
-
-// ring of the spare warp inside a GEMM CTA (carved from the space of one pipeline stage)
-constexpr int kAgInSlots = 4, kAgInPiece = 8 * 1024, kAgInMeta = 256;
-constexpr int kAgInBytes = kAgInSlots * kAgInPiece + kAgInMeta;
 
 // -------------------------------------------------------------------------------------------------
 // the kernel
 // -------------------------------------------------------------------------------------------------
 template <int kMode, int BN, int kStages, int kCtaGroup>
 __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant__ Params p) {
-  using L = SmemLayout<BN, kStages, kCtaGroup, (kMode == kAG ? kAgInBytes : 0)>;
+  using L = SmemLayout<BN, kStages, kCtaGroup>;
   constexpr int TM = BM * kCtaGroup;                     // rows of C per cluster tile
   constexpr int kTmemCols = tmem_cols_for(BN);
   constexpr int kNumCBlocks = (BN + kCBlockCols - 1) / kCBlockCols;
@@ -293,10 +233,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
   if (is_comm) {
     // dedicated comm CTA (fills the SMs the GEMM has no tiles for): deep ring, one driving thread
     if constexpr (kMode == kAG) {
-      if (threadIdx.x == 0)
-        ag_push_loop<kCommRingSlots, kCommPieceBytes, kCommLag, kCommLoadAhead>(
-            p, ph, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), smem, smem + kCommRingSlots * kCommPieceBytes);
-      __syncwarp();
+      ag_comm_cta(p, ph, static_cast<int>(blockIdx.x) - n_gemm_ctas);
     }
   } else {
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
@@ -346,7 +283,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
           const int row0 = m_tile * TM + static_cast<int>(cta_rank) * BM;       // my 128 rows of A
           const int brow0 = expert * p.expert_rows + n_tile * BN + static_cast<int>(cta_rank) * (BN / kCtaGroup);
           if constexpr (kMode == kAG) {
+            prof_record(p.prof, static_cast<int>(blockIdx.x) * 8, 3, true);
             if (!p.ag_skip_wait && row0 < p.M) ag_wait_rows(p, ph, row0, min(p.M, row0 + BM));
+            prof_record(p.prof, static_cast<int>(blockIdx.x) * 8, 3, false);
           }
           const int abuf = (kMode == kAG) ? static_cast<int>(ph & 1u) : 0;
           for (int kb = 0; kb < p.num_k; ++kb) {
@@ -383,6 +322,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
           }
           ptx::mbar_wait(tmem_empty + acc, acc_phase ^ 1u);        // epilogue has drained this accumulator
           ptx::tc_fence_after();
+          prof_record(p.prof, static_cast<int>(blockIdx.x) * 8 + 1, 4, true);
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
           for (int kb = 0; kb < p.num_k; ++kb) {
             ptx::mbar_wait(full_bar + stage, phase);
@@ -401,18 +341,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
           }
           if constexpr (kCtaGroup == 1) ptx::mma_commit(tmem_full + acc);
           else ptx::mma_commit_2sm(tmem_full + acc, 0b11);
+          prof_record(p.prof, static_cast<int>(blockIdx.x) * 8 + 1, 4, false);
           if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
       }
       __syncwarp();
-    } else if (warp == 3) {
-      // ================================ AG: every CTA also pushes its share of my shard ================================
-      if constexpr (kMode == kAG) {
-        if (lane == 0 && p.symm.world > 1 && !p.ag_skip_wait)
-          ag_push_loop<kAgInSlots, kAgInPiece, 2, 1>(p, ph, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x),
-                                                     smem + L::kExtraOff, smem + L::kExtraOff + kAgInSlots * kAgInPiece);
-        __syncwarp();
-      }
     } else if (warp >= kEpiWarp0) {
       // ================================ epilogue ================================
       const int ew = warp - kEpiWarp0;               // == warp % 4 == TMEM lane quadrant
@@ -454,6 +387,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
 
         ptx::mbar_wait(tmem_full + acc, acc_phase);
         ptx::tc_fence_after();
+        if (lane == 0) prof_record(p.prof, static_cast<int>(blockIdx.x) * 8 + warp, 5, true);
         if constexpr (kMode == kRS) { if (rs_step > 0) ptx::named_bar_sync(2, kEpiThreads); }  // flag acquired by et==0
 
 #pragma unroll 1
@@ -564,6 +498,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             __syncwarp();
           }
         }
+        if (lane == 0) prof_record(p.prof, static_cast<int>(blockIdx.x) * 8 + warp, 5, false);
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
       if (p.use_tma_store && et == 0) ptx::bulk_wait<0>();

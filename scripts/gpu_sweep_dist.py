@@ -56,7 +56,7 @@ for (M, N, K) in AG_SHAPES:
         for bn in (256,):
             if Nl < bn: continue
             t_twin = timed(lambda: gemm(full, B, out=out, config=GemmConfig(bn=bn, cta_group=cg, group_m=8)))
-            for nc in (16,):
+            for nc in (8, 16, 32):
                 cfg = GemmConfig(bn=bn, cta_group=cg, group_m=max(1, (M // W) // (128 * cg)), use_tma_store=True, n_comm_ctas=nc)
                 try:
                     c = ag_gemm(A, B.t(), ctx, gemm_config=cfg, out=out)

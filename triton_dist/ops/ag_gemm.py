@@ -36,7 +36,7 @@ class AllGatherGEMMTensorParallelContext:
     num_ranks: int
     num_local_ranks: int
     workspace: torch.Tensor = None     # symmetric [2, max_M, K]
-    flags: torch.Tensor = None         # symmetric int32 [2, W, chunks, 8]
+    flags: torch.Tensor = None         # symmetric int32 [2, W, 64]
     ready: torch.Tensor = None         # symmetric int32 [W]
     phase: torch.Tensor = None         # local int32 [4]
     n_comm_ctas: int = 16
@@ -78,7 +78,7 @@ def create_ag_gemm_context(max_M: int, N: int, K: int, dtype: torch.dtype, rank:
     ctx.ready = heap.tensor((max(num_ranks, 4),), torch.int32)
     max_ms = (max_M + num_ranks - 1) // num_ranks
     chunks = (max_ms + _CHUNK_ROWS - 1) // _CHUNK_ROWS
-    ctx.flags = heap.tensor((2, num_ranks, chunks + 1, _SUB), torch.int32)      # written remotely by the sources
+    ctx.flags = heap.tensor((2, num_ranks, 64), torch.int32)      # [parity][src][slice], written remotely by the sources
     ctx.phase = torch.zeros(4, dtype=torch.int32, device=heap.device)
     U.barrier_all_host()
     return ctx
@@ -116,7 +116,7 @@ def default_ag_config(M: int, N: int, K: int, world: int) -> GemmConfig:
 
 def ag_gemm(A: torch.Tensor, B: torch.Tensor, ctx: AllGatherGEMMTensorParallelContext,
             gemm_config: Optional[GemmConfig] = None, straggler_option=None, debug: bool = False,
-            out: Optional[torch.Tensor] = None, skip_wait: bool = False, **_unused) -> torch.Tensor:
+            out: Optional[torch.Tensor] = None, skip_wait: bool = False, profiler=None, **_unused) -> torch.Tensor:
     """A: ``[M/W, K]`` local shard, B: ``[K, N/W]`` -> ``[M, N/W]``.  ``skip_wait`` runs the GEMM-only twin
     (flags ignored) used to measure exposed communication, like the reference's ``fake_barrier`` path."""
     W = ctx.num_ranks
@@ -155,6 +155,8 @@ def ag_gemm(A: torch.Tensor, B: torch.Tensor, ctx: AllGatherGEMMTensorParallelCo
     args.ag_flags, args.ag_ready = ctx.flags.data_ptr(), ctx.ready.data_ptr()
     if skip_wait:
         args.n_comm_ctas = 0
+    if profiler is not None:
+        profiler.attach(args)
     _C.check(_C.cuda_lib().td_gemm_launch(C.byref(args), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
              "td_gemm_launch(ag)")
     ctx.host_phase = ph
@@ -192,7 +194,7 @@ def _ag_gemm_host(A, Bnk, ctx, out):
     ph = ctx.host_phase
     par = ph & 1
     timeout = U.get_int_env("TD_HOST_TIMEOUT_US", 60_000_000)
-    flag_off = lambda src: ctx.flags[par, src, 0, 0:1].data_ptr()
+    flag_off = lambda src: ctx.flags[par, src, 0:1].data_ptr()
     # 1. push (producer role)
     for dist_ in range(W):
         d = (me - dist_ + W) % W
