@@ -42,8 +42,8 @@ _C.register("td_ep_dispatch", c_int, [C.POINTER(_DispArgs), c_void_p])
 _C.register("td_ep_combine", c_int, [C.POINTER(_CombArgs), c_void_p])
 
 
-def _msg_bytes(H: int, fp8: bool) -> int:
-    payload = H + (H // 128) * 4 if fp8 else H * 2
+def _msg_bytes(H: int, fp8: bool, esize: int = 2) -> int:
+    payload = H + (H // 128) * 4 if fp8 else H * esize
     return (16 + payload + 15) // 16 * 16
 
 
@@ -99,7 +99,9 @@ def create_ep_ll_a2a_ctx(max_m: int, hidden: int, topk: int, num_experts: int, o
     assert fp8_gsize == 128 and num_experts % world_size == 0 and hidden % 128 == 0
     ctx = EPLowLatencyContext(max_m, hidden, topk, num_experts, online_quant_fp8, dtype, world_size, rank)
     epr = num_experts // world_size
-    msg = _msg_bytes(hidden, online_quant_fp8)
+    esize = torch.empty(0, dtype=dtype).element_size()
+    assert esize == 2 or heap.device.type != "cuda", "the CUDA kernels move 16-bit tokens"
+    msg = _msg_bytes(hidden, online_quant_fp8, esize)
     ctx.staging = heap.tensor((2, epr, world_size, max_m, msg), torch.uint8)
     ctx.recv_flag = heap.tensor((2, epr, world_size), torch.int64)
     ctx.comb = heap.tensor((2, max_m * topk, hidden), dtype)
@@ -198,7 +200,7 @@ def _dispatch_host(ctx, x, topk_idx):
         counts[e] += 1
         m = heap.peer_view(ctx.staging, dst)[par, le, me, slot]
         m[:4] = torch.tensor([pair], dtype=torch.int32).view(torch.uint8)
-        m[16:16 + H * 2] = xb[pair // ctx.topk]
+        m[16:16 + xb.shape[1]] = xb[pair // ctx.topk]
     for e in range(ctx.num_experts):
         dst, le = e // epr, e % epr
         f = heap.peer_ptr(ctx.recv_flag[par, le, me:me + 1].data_ptr(), dst)
@@ -221,7 +223,7 @@ def _dispatch_host(ctx, x, topk_idx):
             for i in range(cnt):
                 m = ctx.staging[par, le, src, i]
                 src_info[le, start + i] = int(m[:4].view(torch.int32)[0])
-                recv_x[le, start + i] = m[16:16 + H * 2].view(ctx.dtype)
+                recv_x[le, start + i] = m[16:16 + H * xb.element_size() * 0 + xb.shape[1]].view(ctx.dtype)
     return recv_x, None, recv_count, DispatchMetaInfo(src_info, recv_range)
 
 

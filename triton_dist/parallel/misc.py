@@ -1,0 +1,45 @@
+"""Small layer wrappers kept for API parity: ``GemmARLayer`` (layers/nvidia/gemm_allreduce_layer.py:143) and
+``AllGatherLayer`` (layers/nvidia/low_latency_allgather_layer.py:197)."""
+from __future__ import annotations
+
+import torch
+
+from .. import utils as U
+from ..ops import comm
+from ..ops.gemm_ar import create_gemm_ar_context, gemm_allreduce_op
+
+
+class GemmARLayer:
+    def __init__(self, tp_group, max_M: int, N: int, K: int, input_dtype: torch.dtype, output_dtype: torch.dtype,
+                 local_world_size: int, persistent: bool = True, use_ll_kernel: bool = False, copy_to_local: bool = True,
+                 NUM_COMM_SMS: int = 16):
+        heap = U.get_heap()
+        self.ctx = create_gemm_ar_context(None, heap.rank, heap.world, local_world_size, max_M, N, output_dtype)
+
+    def forward(self, x: torch.Tensor, weight: torch.Tensor, bias=None, scale_a=None, scale_b=None) -> torch.Tensor:
+        out = gemm_allreduce_op(self.ctx, x, weight)
+        return out if bias is None else out + bias
+
+    __call__ = forward
+
+    def finalize(self):
+        self.ctx.finalize()
+
+
+class AllGatherLayer:
+    def __init__(self, max_shard_bytes: int, stages: int = 2):
+        self.ctx = comm.create_fast_allgather_context(max_shard_bytes)
+
+    def _fwd(self, x, mode):
+        return comm.fast_allgather(x, self.ctx, mode=mode)
+
+    def forward_pull(self, x): return self._fwd(x, "pull")
+    def forward_push_2d(self, x): return self._fwd(x, "push")
+    def forward_push_3d(self, x): return self._fwd(x, "push")
+    def forward_push_2d_ll(self, x): return self._fwd(x, "push_2d_ll")
+    def forward_push_numa_2d(self, x): return self._fwd(x, "push")
+    def forward_push_numa_2d_ll(self, x): return self._fwd(x, "push_2d_ll")
+    def forward_push_2d_ll_multimem(self, x): return self._fwd(x, "push_2d_ll")
+
+    def finalize(self):
+        self.ctx.finalize()
