@@ -8,7 +8,7 @@ using namespace td::gemm;
 // Every field is 8 bytes wide so the ctypes mirror (triton_dist/_C.py: GemmArgs) cannot get padding wrong.
 struct TdGemmArgs {
   long long mode;            // 0 plain, 1 AG, 2 RS
-  long long is_bf16;         // 1 bf16, 0 fp16
+  long long is_bf16;         // 1 bf16, 0 fp16, 2 = MXFP8 inputs (e4m3 + UE8M0 scales per 32 K-elements), bf16 output
   long long bn;              // 32 / 64 / 128 / 256
   long long cta_group;       // 1 or 2
   long long group_m;
@@ -22,6 +22,7 @@ struct TdGemmArgs {
   void* C; long long c_rows; long long ldc; const void* c_phase; long long c_nbuf; long long c_buf_stride_bytes;
   const void* tile_expert; long long num_experts;   // grouped (MoE) mode: B is [num_experts * N, K]
   void* prof_buf; long long prof_cap; long long prof_slots;   // intra-kernel profiler (optional)
+  const void* sfa; const void* sfb; long long sfa_chunks; long long sfb_chunks;   // MXFP8: tiled scale factors (512 B chunks)
   // symmetric context
   long long rank, world; unsigned long long symm_base, symm_stride, mc_base;
   void* phase;
@@ -33,26 +34,28 @@ struct TdGemmArgs {
 };
 
 static int encode_tmap(CUtensorMap* out, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                       const cuuint32_t* box, bool is_bf16) {
+                       const cuuint32_t* box, int dtype /*0 fp16, 1 bf16, 2 u8, 3 u32 (no swizzle)*/) {
   auto enc = drv::cuTensorMapEncodeTiled_fn();
   if (!enc) { drv::set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return -1; }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(out, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank,
+  const CUtensorMapDataType dt = dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                 : dtype == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_UINT32;
+  CUresult r = enc(out, dt, rank,
                    const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   dtype == 3 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { drv::set_error("cuTensorMapEncodeTiled failed: %s", drv::err_str(r)); return -1; }
   return 0;
 }
 
-template <int kMode, int BN, int kCtaGroup>
+template <int kMode, int BN, int kCtaGroup, bool kFP8 = false>
 static int launch_cfg(const Params& p, int grid, cudaStream_t stream) {
   // deepest pipeline that fits in 227 KB next to the 32 KB epilogue staging
-  constexpr int kStageBytes = BM * BK * 2 + (BN / kCtaGroup) * BK * 2;
-  constexpr int kExtra = 0;
-  constexpr int kMaxStages = (232448 - 1024 - 2 * kCBlockBytes - 384 - kExtra) / kStageBytes;
+  constexpr int kStageBytes = SmemLayout<BN, 1, kCtaGroup, 0, kFP8>::kStageBytes;
+  constexpr int kMaxStages = (232448 - 1024 - 2 * kCBlockBytes - 384) / kStageBytes;
   constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
-  using L = SmemLayout<BN, kStages, kCtaGroup, kExtra>;
-  auto kern = gemm_kernel<kMode, BN, kStages, kCtaGroup>;
+  using L = SmemLayout<BN, kStages, kCtaGroup, 0, kFP8>;
+  auto kern = gemm_kernel<kMode, BN, kStages, kCtaGroup, kFP8>;
   static bool attr_set = false;
   if (!attr_set) {
     TD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -75,6 +78,14 @@ static int launch_cfg(const Params& p, int grid, cudaStream_t stream) {
 }
 
 template <int kMode>
+static int dispatch_fp8(const Params& p, int bn, int cg, int grid, cudaStream_t s) {
+  if (bn == 128 && cg == 2) return launch_cfg<kMode, 128, 2, true>(p, grid, s);
+  if (bn == 128 && cg == 1) return launch_cfg<kMode, 128, 1, true>(p, grid, s);
+  drv::set_error("MXFP8 path supports bn = 128 (cta_group 1 or 2)");
+  return -1;
+}
+
+template <int kMode>
 static int dispatch(const Params& p, int bn, int cg, int grid, cudaStream_t s) {
 #define TD_CASE(BN_, CG_) if (bn == BN_ && cg == CG_) return launch_cfg<kMode, BN_, CG_>(p, grid, s);
   TD_CASE(256, 2) TD_CASE(256, 1) TD_CASE(128, 2) TD_CASE(128, 1)
@@ -87,20 +98,25 @@ static int dispatch(const Params& p, int bn, int cg, int grid, cudaStream_t s) {
 TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int cg = static_cast<int>(a->cta_group), bn = static_cast<int>(a->bn);
-  const bool bf16 = a->is_bf16 != 0;
-  if (a->K % 8 != 0 || a->lda % 8 != 0 || a->ldb % 8 != 0) { drv::set_error("K/lda/ldb must be multiples of 8 elements (16 B)"); return -1; }
+  const bool fp8 = a->is_bf16 == 2;
+  const int bf16 = fp8 ? 2 : (a->is_bf16 != 0 ? 1 : 0);      // tensor-map dtype code of A / B
+  const int esz = fp8 ? 1 : 2;
+  if (a->K % (fp8 ? 128 : 8) != 0 || (a->lda * esz) % 16 != 0 || (a->ldb * esz) % 16 != 0) {
+    drv::set_error("K must be a multiple of 8 (16-bit) / 128 (MXFP8) and rows 16-byte aligned"); return -1;
+  }
+  const int bk_elems = fp8 ? 128 : BK;
   Params p;
   memset(&p, 0, sizeof(p));
   {  // A: {K, rows, nbuf}
     cuuint64_t dims[3] = {(cuuint64_t)a->K, (cuuint64_t)a->a_rows, (cuuint64_t)(a->a_nbuf > 0 ? a->a_nbuf : 1)};
-    cuuint64_t strides[2] = {(cuuint64_t)a->lda * 2, (cuuint64_t)(a->a_nbuf > 1 ? a->a_buf_stride_bytes : a->a_rows * a->lda * 2)};
-    cuuint32_t box[3] = {BK, BM, 1};
+    cuuint64_t strides[2] = {(cuuint64_t)a->lda * esz, (cuuint64_t)(a->a_nbuf > 1 ? a->a_buf_stride_bytes : a->a_rows * a->lda * esz)};
+    cuuint32_t box[3] = {(cuuint32_t)bk_elems, BM, 1};
     if (encode_tmap(&p.tmap_a, a->A, 3, dims, strides, box, bf16)) return -1;
   }
   {  // B: {K, N}
     cuuint64_t dims[2] = {(cuuint64_t)a->K, (cuuint64_t)(a->N * (a->tile_expert ? a->num_experts : 1))};
-    cuuint64_t strides[1] = {(cuuint64_t)a->ldb * 2};
-    cuuint32_t box[2] = {BK, (cuuint32_t)(bn / cg)};
+    cuuint64_t strides[1] = {(cuuint64_t)a->ldb * esz};
+    cuuint32_t box[2] = {(cuuint32_t)bk_elems, (cuuint32_t)(bn / cg)};
     if (encode_tmap(&p.tmap_b, a->B, 2, dims, strides, box, bf16)) return -1;
   }
   p.use_tma_store = (a->use_tma_store && bn >= 64 && a->mode != kRS && a->ldc % 8 == 0) ? 1 : 0;
@@ -108,7 +124,7 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
     cuuint64_t dims[3] = {(cuuint64_t)a->N, (cuuint64_t)a->c_rows, (cuuint64_t)(a->c_nbuf > 0 ? a->c_nbuf : 1)};
     cuuint64_t strides[2] = {(cuuint64_t)a->ldc * 2, (cuuint64_t)(a->c_nbuf > 1 ? a->c_buf_stride_bytes : a->c_rows * a->ldc * 2)};
     cuuint32_t box[3] = {kCBlockCols, BM, 1};
-    if (encode_tmap(&p.tmap_c, a->C, 3, dims, strides, box, bf16)) return -1;
+    if (encode_tmap(&p.tmap_c, a->C, 3, dims, strides, box, fp8 ? 1 : bf16)) return -1;
   }
   p.c_phase = (a->c_nbuf > 1) ? reinterpret_cast<const uint32_t*>(a->c_phase) : nullptr;
   p.c_buf_stride_bytes = a->c_buf_stride_bytes;
@@ -119,11 +135,19 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
   p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K;
   p.num_m = (p.M + TM - 1) / TM;
   p.num_n = (p.N + bn - 1) / bn;
-  p.num_k = (p.K + BK - 1) / BK;
+  p.num_k = (p.K + bk_elems - 1) / bk_elems;
+  if (fp8) {
+    cuuint64_t da[2] = {128, (cuuint64_t)a->sfa_chunks}, db[2] = {128, (cuuint64_t)a->sfb_chunks};
+    cuuint64_t st[1] = {512};
+    cuuint32_t bx[2] = {128, 1};
+    if (encode_tmap(&p.tmap_sfa, a->sfa, 2, da, st, bx, 3)) return -1;
+    if (encode_tmap(&p.tmap_sfb, a->sfb, 2, db, st, bx, 3)) return -1;
+    if (a->tile_expert) { drv::set_error("MXFP8 grouped GEMM is not wired yet"); return -1; }
+  }
   p.group_m = (int)(a->group_m > 0 ? a->group_m : 1);
   if (p.group_m > p.num_m) p.group_m = p.num_m;
   p.m_rot = (int)(((a->m_rot % p.num_m) + p.num_m) % p.num_m);
-  p.in_is_bf16 = bf16 ? 1 : 0;
+  p.in_is_bf16 = (a->is_bf16 != 0) ? 1 : 0;      // 16-bit outputs / partial sums are bf16 unless fp16 inputs
   p.n_comm_ctas = (int)a->n_comm_ctas;
   p.C = a->C; p.ldc = a->ldc;
   p.symm.rank = (int)a->rank; p.symm.world = (int)a->world;
@@ -159,6 +183,14 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
     if (p.N % 8 != 0) { drv::set_error("N must be a multiple of 8"); return -1; }
   }
   if (!p.use_tma_store && (a->ldc % 8 != 0 || p.N % 8 != 0)) { drv::set_error("N/ldc must be multiples of 8 elements"); return -1; }
+  if (fp8) {
+    switch (a->mode) {
+      case kPlain: return dispatch_fp8<kPlain>(p, bn, cg, grid, stream);
+      case kAG: return dispatch_fp8<kAG>(p, bn, cg, grid, stream);
+      case kRS: return dispatch_fp8<kRS>(p, bn, cg, grid, stream);
+      default: drv::set_error("bad mode"); return -1;
+    }
+  }
   switch (a->mode) {
     case kPlain: return dispatch<kPlain>(p, bn, cg, grid, stream);
     case kAG: return dispatch<kAG>(p, bn, cg, grid, stream);

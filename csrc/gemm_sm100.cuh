@@ -53,6 +53,8 @@ struct Params {
   CUtensorMap tmap_a;   // dims {K, rows_a, nbuf}, box {64, 128, 1}, SWIZZLE_128B
   CUtensorMap tmap_b;   // dims {K, N},            box {64, BN / cta_group}
   CUtensorMap tmap_c;   // dims {N, rows_c, nbuf}, box {64, 128, 1}, SWIZZLE_128B (only if use_tma_store)
+  CUtensorMap tmap_sfa; // MXFP8 only: dims {128 (uint32), m_tiles128 * k_blocks}: one 512-byte scale chunk per (128 rows, K=128)
+  CUtensorMap tmap_sfb; // MXFP8 only: same for B (n_tiles128 * k_blocks)
   int M, N, K;
   int num_m, num_n, num_k;   // tile counts; num_m is in units of BM * cta_group rows
   int group_m;               // L2 swizzle band height (in m tiles)
@@ -103,11 +105,17 @@ struct Params {
 // -------------------------------------------------------------------------------------------------
 // shared-memory carve-up (GEMM CTAs)
 // -------------------------------------------------------------------------------------------------
-template <int BN, int kStages, int kCtaGroup, int kExtra = 0>
+constexpr int kSFChunk = 512;   // UE8M0 scales of 128 rows x (K = 128): [32 lanes][4 row groups][4 k-blocks of 32]
+
+template <int BN, int kStages, int kCtaGroup, int kExtra = 0, bool kFP8 = false>
 struct SmemLayout {
-  static constexpr int kABytes = BM * BK * 2;                 // 16 KB
+  static constexpr int kABytes = BM * BK * 2;                 // 16 KB (128 rows x 128 B: 64 bf16 or 128 fp8 along K)
   static constexpr int kBBytes = (BN / kCtaGroup) * BK * 2;   // this CTA's share of the B tile
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kSFABytes = kFP8 ? kSFChunk : 0;                           // my 128 rows of A
+  static constexpr int kSFBBytes = kFP8 ? ((BN + 127) / 128) * kSFChunk : 0;      // ALL BN columns (needed by both CTAs)
+  static constexpr int kSFPad = kFP8 ? (1024 - (kSFABytes + kSFBBytes) % 1024) % 1024 : 0;
+  static constexpr int kStageBytes = kABytes + kBBytes + kSFABytes + kSFBBytes + kSFPad;
+  static constexpr int kTxBytes = kABytes + kBBytes + kSFABytes + kSFBBytes;      // bytes one CTA lands per stage
   static constexpr int kCOff = kStages * kStageBytes;
   static constexpr int kBarOff = kCOff + 2 * kCBlockBytes;
   // barriers: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]; then the TMEM base pointer
@@ -209,11 +217,15 @@ TD_DEVICE void ag_comm_cta(const Params& p, uint32_t ph, int comm_idx) {
 // -------------------------------------------------------------------------------------------------
 // the kernel
 // -------------------------------------------------------------------------------------------------
-template <int kMode, int BN, int kStages, int kCtaGroup>
+template <int kMode, int BN, int kStages, int kCtaGroup, bool kFP8 = false>
 __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant__ Params p) {
-  using L = SmemLayout<BN, kStages, kCtaGroup>;
+  using L = SmemLayout<BN, kStages, kCtaGroup, 0, kFP8>;
+  constexpr int kBKElems = kFP8 ? 128 : BK;              // K elements per 128-byte smem row
+  constexpr int kSFCols = 4 + 4 * ((BN + 127) / 128);    // TMEM columns of scale factors per pipeline stage (A + B)
+  constexpr int kSFBase = 2 * BN;                        // scale factors live after the two accumulator stages
+  static_assert(!kFP8 || (2 * BN + kStages * kSFCols <= 512), "TMEM: accumulators + scale-factor ring exceed 512 columns");
   constexpr int TM = BM * kCtaGroup;                     // rows of C per cluster tile
-  constexpr int kTmemCols = tmem_cols_for(BN);
+  constexpr int kTmemCols = kFP8 ? 512 : tmem_cols_for(BN);
   constexpr int kNumCBlocks = (BN + kCBlockCols - 1) / kCBlockCols;
   constexpr int kColsPerBlock = BN < kCBlockCols ? BN : kCBlockCols;
 
@@ -292,16 +304,30 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             ptx::mbar_wait(empty_bar + stage, phase ^ 1u);
             uint8_t* sa = smem + stage * L::kStageBytes;
             uint8_t* sb = sa + L::kABytes;
+            uint8_t* ssfa = sb + L::kBBytes;
+            uint8_t* ssfb = ssfa + L::kSFABytes;
             if constexpr (kCtaGroup == 1) {
-              ptx::mbar_arrive_expect_tx(full_bar + stage, L::kStageBytes);
-              ptx::tma_load_3d(&p.tmap_a, full_bar + stage, sa, kb * BK, row0, abuf);
-              ptx::tma_load_2d(&p.tmap_b, full_bar + stage, sb, kb * BK, brow0, ptx::kEvictLast);
+              ptx::mbar_arrive_expect_tx(full_bar + stage, L::kTxBytes);
+              ptx::tma_load_3d(&p.tmap_a, full_bar + stage, sa, kb * kBKElems, row0, abuf);
+              ptx::tma_load_2d(&p.tmap_b, full_bar + stage, sb, kb * kBKElems, brow0, ptx::kEvictLast);
+              if constexpr (kFP8) {
+                ptx::tma_load_2d(&p.tmap_sfa, full_bar + stage, ssfa, 0, (row0 / 128) * p.num_k + kb);
+#pragma unroll
+                for (int g = 0; g < (BN + 127) / 128; ++g)
+                  ptx::tma_load_2d(&p.tmap_sfb, full_bar + stage, ssfb + g * kSFChunk, 0, ((n_tile * BN) / 128 + g) * p.num_k + kb);
+              }
             } else {
               // both CTAs land their bytes on the LEADER's barrier; the leader expects both halves
-              if (is_leader) ptx::mbar_arrive_expect_tx(full_bar + stage, 2 * L::kStageBytes);
+              if (is_leader) ptx::mbar_arrive_expect_tx(full_bar + stage, 2 * L::kTxBytes);
               else ptx::mbar_arrive_cluster(full_bar + stage, 0);
-              ptx::tma_load_3d_2sm(&p.tmap_a, full_bar + stage, sa, kb * BK, row0, abuf);
-              ptx::tma_load_2d_2sm(&p.tmap_b, full_bar + stage, sb, kb * BK, brow0, ptx::kEvictLast);
+              ptx::tma_load_3d_2sm(&p.tmap_a, full_bar + stage, sa, kb * kBKElems, row0, abuf);
+              ptx::tma_load_2d_2sm(&p.tmap_b, full_bar + stage, sb, kb * kBKElems, brow0, ptx::kEvictLast);
+              if constexpr (kFP8) {
+                ptx::tma_load_2d_2sm(&p.tmap_sfa, full_bar + stage, ssfa, 0, (row0 / 128) * p.num_k + kb);
+#pragma unroll
+                for (int g = 0; g < (BN + 127) / 128; ++g)
+                  ptx::tma_load_2d_2sm(&p.tmap_sfb, full_bar + stage, ssfb + g * kSFChunk, 0, ((n_tile * BN) / 128 + g) * p.num_k + kb);
+              }
             }
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
@@ -312,6 +338,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
       // ================================ MMA issuer (leader CTA, one thread) ================================
       if (is_leader && lane == 0) {
         const uint32_t idesc = ptx::make_idesc(p.in_is_bf16 ? 1u : 0u, p.in_is_bf16 ? 1u : 0u, TM, BN);
+        (void)idesc;
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
         for (int t = worker; t < total_tiles; t += n_workers) {
@@ -330,10 +357,29 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             const uint32_t sa = ptx::smem_u32(smem + stage * L::kStageBytes);
             const uint64_t adesc = ptx::make_smem_desc_k128(sa);
             const uint64_t bdesc = ptx::make_smem_desc_k128(sa + L::kABytes);
+            if constexpr (!kFP8) {
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              // advance 32 B (= 16 bf16) along K inside the 128-byte swizzle atom: +2 in the 16-byte address field
-              ptx::mma_f16<kCtaGroup>(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                // advance 32 B (= 16 bf16) along K inside the 128-byte swizzle atom: +2 in the 16-byte address field
+                ptx::mma_f16<kCtaGroup>(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              }
+            } else {
+              // MXFP8: stage the UE8M0 scale factors of this k-block into TMEM (smem -> TMEM, 32 lanes x 16 B, replicated
+              // to the four lane quadrants), then 4 block-scaled MMAs of K = 32; sf_id selects the byte of each 32-bit
+              // scale word that belongs to the K-chunk.  tcgen05.cp and tcgen05.mma execute in issue order, so the
+              // TMEM slot of this smem stage is free again by the time it is reused kStages k-blocks later.
+              const uint32_t sf_tmem = tmem_base + static_cast<uint32_t>(kSFBase + stage * kSFCols);
+              const uint32_t ssfa = sa + L::kABytes + L::kBBytes;
+              ptx::tmem_cp_32x128b_warpx4<kCtaGroup>(sf_tmem, ptx::make_smem_desc_noswizzle(ssfa, 0, 128));
+#pragma unroll
+              for (int g = 0; g < (BN + 127) / 128; ++g)
+                ptx::tmem_cp_32x128b_warpx4<kCtaGroup>(sf_tmem + 4 + 4 * g,
+                                                        ptx::make_smem_desc_noswizzle(ssfa + L::kSFABytes + g * kSFChunk, 0, 128));
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t idm = ptx::make_idesc_mx(0u, 0u, TM, BN, static_cast<uint32_t>(k), static_cast<uint32_t>(k));
+                ptx::mma_mxf8<kCtaGroup>(d_tmem, adesc + 2u * k, bdesc + 2u * k, idm, (kb | k) != 0 ? 1u : 0u, sf_tmem, sf_tmem + 4);
+              }
             }
             if constexpr (kCtaGroup == 1) ptx::mma_commit(empty_bar + stage);
             else ptx::mma_commit_2sm(empty_bar + stage, 0b11);

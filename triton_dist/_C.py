@@ -45,6 +45,7 @@ class GemmArgs(C.Structure):
         ("C", c_void_p), ("c_rows", c_ll), ("ldc", c_ll), ("c_phase", c_void_p), ("c_nbuf", c_ll),
         ("c_buf_stride_bytes", c_ll), ("tile_expert", c_void_p), ("num_experts", c_ll),
         ("prof_buf", c_void_p), ("prof_cap", c_ll), ("prof_slots", c_ll),
+        ("sfa", c_void_p), ("sfb", c_void_p), ("sfa_chunks", c_ll), ("sfb_chunks", c_ll),
         ("rank", c_ll), ("world", c_ll), ("symm_base", c_ull), ("symm_stride", c_ull), ("mc_base", c_ull),
         ("phase", c_void_p),
         ("ag_rows_per_rank", c_ll), ("ag_copy_local", c_ll), ("ag_skip_wait", c_ll),

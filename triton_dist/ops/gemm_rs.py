@@ -178,3 +178,40 @@ def _gemm_rs_host(A, Bnk, ctx, out):
             flag = heap.peer_ptr(ctx.flags.data_ptr() + 4 * (par * ctx.flags.shape[1] + owner), prev)
             lib.tdh_notify32(ctypes.c_void_p(flag), ph, 1)
     return out
+
+
+def gemm_rs_mxfp8(a, b, ctx: GEMMReduceScatterTensorParallelContext, out: Optional[torch.Tensor] = None,
+                  gemm_config: Optional[GemmConfig] = None) -> torch.Tensor:
+    """Block-scaled fp8 GEMM + ring ReduceScatter (BASELINE config #3).  ``a``/``b``: :class:`triton_dist.ops.fp8.MXFP8Tensor`
+    of this rank's K-shard (``[M, K/W]`` and ``[N, K/W]``); partial sums travel in bf16 through the same fused-epilogue ring."""
+    from .fp8 import dequantize_mxfp8, fill_fp8, gemm_mxfp8
+    W = ctx.world_size
+    M, K = a.shape
+    N = b.shape[0]
+    assert M % W == 0 and M <= ctx.max_M and N == ctx.N
+    Mr = M // W
+    if not a.q.is_cuda:
+        return _gemm_rs_host(dequantize_mxfp8(a).to(ctx.output_dtype), dequantize_mxfp8(b).to(ctx.output_dtype), ctx, out)
+    if out is None:
+        out = torch.empty((Mr, N), dtype=torch.bfloat16, device=a.q.device)
+    if W == 1:
+        return gemm_mxfp8(a, b, out=out, config=gemm_config)
+    cg = 2 if Mr % 256 == 0 else 1
+    assert Mr % (128 * cg) == 0, "fp8 gemm_rs needs (M / world) % 128 == 0"
+    cfg = gemm_config or GemmConfig(bn=128, cta_group=cg, group_m=max(1, Mr // (128 * cg)), use_tma_store=False)
+    tm = 128 * cfg.cta_group
+    args = _C.GemmArgs()
+    args.mode = 2
+    fill_common(args, M, a.q.data_ptr(), a.q.stride(0), b.q, out.data_ptr(), Mr, out.stride(0), M, N, K,
+                GemmConfig(cfg.bn, cfg.cta_group, cfg.group_m, False, cfg.num_sms, 0), True)
+    fill_fp8(args, a, b)
+    args.m_rot = (((ctx.rank + 1) % W) * Mr) // tm
+    r, w, base, stride, mc = U.symm_ctx_fields()
+    args.rank, args.world, args.symm_base, args.symm_stride, args.mc_base = r, w, base, stride, mc
+    args.phase = ctx.phase.data_ptr()
+    args.rs_rows_per_rank = Mr
+    args.rs_stage, args.rs_stage_buf_bytes = ctx.stage.data_ptr(), ctx.max_M * N * 2
+    args.rs_flags, args.rs_out, args.rs_ldo = ctx.flags.data_ptr(), out.data_ptr(), out.stride(0)
+    _C.check(_C.cuda_lib().td_gemm_launch(C.byref(args), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "td_gemm_launch(rs, mxfp8)")
+    ctx.host_phase += 1
+    return out
