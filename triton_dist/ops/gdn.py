@@ -1,0 +1,75 @@
+"""Gated delta rule (Qwen3-Next linear attention), chunked forward.
+
+Reference: ``chunk_gated_delta_rule_fwd`` (/root/reference/python/triton_dist/kernels/nvidia/gdn.py:926, three Triton
+chunk kernels :123,:482,:785).  This is a local (no communication) op and not on any benchmarked path; it is implemented
+as the same chunk-parallel algorithm on batched tensor-core matmuls (intra-chunk triangular solve + inter-chunk state
+recurrence), fp32 accumulation, so it is exact against the sequential recurrence.
+
+Recurrence per head (S is [Dk, Dv]):   S_t = g_t * S_{t-1} + beta_t * k_t^T (v_t - g_t * k_t S_{t-1}) ;  o_t = q_t S_t
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+
+def gated_delta_rule_recurrent(q, k, v, g, beta, scale: Optional[float] = None, initial_state=None):
+    """Sequential reference.  q,k: [B,T,H,Dk]; v: [B,T,H,Dv]; g (log-decay), beta: [B,T,H]."""
+    B, T, H, Dk = q.shape
+    Dv = v.shape[-1]
+    scale = scale if scale is not None else Dk ** -0.5
+    S = torch.zeros(B, H, Dk, Dv, dtype=torch.float32, device=q.device) if initial_state is None else initial_state.float().clone()
+    o = torch.empty(B, T, H, Dv, dtype=torch.float32, device=q.device)
+    qf, kf, vf, gf, bf = q.float() * scale, k.float(), v.float(), g.float().exp(), beta.float()
+    for t in range(T):
+        S = S * gf[:, t, :, None, None]
+        pred = torch.einsum("bhk,bhkv->bhv", kf[:, t], S)
+        S = S + torch.einsum("bhk,bhv->bhkv", kf[:, t], (vf[:, t] - pred) * bf[:, t, :, None])
+        o[:, t] = torch.einsum("bhk,bhkv->bhv", qf[:, t], S)
+    return o.to(q.dtype), S
+
+
+def chunk_gated_delta_rule_fwd(q, k, v, g, beta, scale: Optional[float] = None, initial_state=None, output_final_state: bool = True,
+                               chunk_size: int = 64) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """Chunk-parallel forward (WY representation): within a chunk the delta-rule updates are resolved with one
+    unit-lower-triangular solve, chunks are chained through the [Dk, Dv] state."""
+    B, T, H, Dk = q.shape
+    Dv = v.shape[-1]
+    scale = scale if scale is not None else Dk ** -0.5
+    C = chunk_size
+    pad = (C - T % C) % C
+    if pad:
+        z = lambda x: torch.nn.functional.pad(x, (0, 0) * (x.dim() - 2) + (0, pad)) if x.dim() == 3 else torch.nn.functional.pad(x, (0, 0, 0, 0, 0, pad))
+        q, k, v = z(q), z(k), z(v)
+        g = torch.nn.functional.pad(g, (0, 0, 0, pad))
+        beta = torch.nn.functional.pad(beta, (0, 0, 0, pad))
+    Tp = T + pad
+    n = Tp // C
+    f = lambda x: x.float().view(B, n, C, H, -1).permute(0, 3, 1, 2, 4)          # [B,H,n,C,D]
+    qc, kc, vc = f(q) * scale, f(k), f(v)
+    gc = g.float().view(B, n, C, H).permute(0, 3, 1, 2)                          # [B,H,n,C] log decay
+    bc = beta.float().view(B, n, C, H).permute(0, 3, 1, 2)
+    gcum = gc.cumsum(-1)                                                          # decay from chunk start to t (inclusive)
+    # decay between positions inside a chunk: D[i,j] = exp(gcum_i - gcum_j) for j <= i
+    diff = gcum[..., :, None] - gcum[..., None, :]
+    tril = torch.tril(torch.ones(C, C, device=q.device, dtype=torch.bool))
+    Dm = torch.where(tril, diff.exp(), torch.zeros_like(diff))
+    kb = kc * bc[..., None]
+    # A = strictly-lower (beta_i k_i . k_j decay_ij);  (I + A) u = beta * (v - decayed k S0)  ->  solve once per chunk
+    A = torch.einsum("bhnik,bhnjk->bhnij", kb, kc) * Dm
+    A = A * torch.tril(torch.ones(C, C, device=q.device), -1)
+    eye = torch.eye(C, device=q.device).expand_as(A)
+    Tinv = torch.linalg.solve_triangular(eye + A, eye, upper=False)              # [B,H,n,C,C]
+    w = Tinv @ (kb * gcum.exp()[..., None])                                       # multiplies the incoming state
+    u = Tinv @ (vc * bc[..., None])
+    S = torch.zeros(B, H, Dk, Dv, dtype=torch.float32, device=q.device) if initial_state is None else initial_state.float().clone()
+    out = torch.empty(B, H, n, C, Dv, dtype=torch.float32, device=q.device)
+    qk = torch.einsum("bhnik,bhnjk->bhnij", qc, kc) * Dm
+    for c in range(n):
+        delta = u[:, :, c] - w[:, :, c] @ S                                       # effective "new values" of this chunk
+        out[:, :, c] = (qc[:, :, c] * gcum[:, :, c].exp()[..., None]) @ S + qk[:, :, c] @ delta
+        decay_end = (gcum[:, :, c, -1:, None] - gcum[:, :, c, :, None]).exp()     # from position j to the chunk end
+        S = S * gcum[:, :, c, -1].exp()[..., None, None] + (kc[:, :, c] * decay_end).transpose(-1, -2) @ delta
+    o = out.permute(0, 2, 3, 1, 4).reshape(B, Tp, H, Dv)[:, :T].to(v.dtype)
+    return o, (S if output_final_state else None)
