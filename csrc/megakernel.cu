@@ -1,0 +1,386 @@
+// Whole-model persistent decode kernel ("megakernel") for small batches: one launch runs every layer of a
+// tensor-parallel dense LLM decode step as a stream of tile-level TASKS pulled from per-CTA static queues and
+// ordered by a scoreboard of monotone counters.
+//
+// Reference: python/triton_dist/mega_triton_kernel/** -- ModelBuilder records ops, ops are tiled into tasks
+// (core/task_base.py:162-257), a scheduler fills per-SM queues (core/scheduler.py:103-168), a generated Triton kernel
+// loops {fetch task -> scoreboard.wait_deps -> run tile -> release} (core/code_generator.py:101-180).
+// Here the interpreter is one hand-written CUDA kernel; the builder/scheduler is native Python+C (triton_dist/mega_kernel).
+//
+// Design points:
+//   * decode with B <= 8 tokens is HBM-bound: linears are weight-streaming GEMVs on CUDA cores (tensor cores cannot
+//     help at M <= 8), 16-byte loads, 4 rows of W in flight per warp;
+//   * scoreboard counters are never reset: task k waits for  sb[dep] >= epoch * dep_count  where `epoch` is a
+//     device-resident step counter (CUDA-graph replayable, no memset);
+//   * the tensor-parallel all-reduce is a task too: one-shot over NVLink (multimem.ld_reduce when the heap has a
+//     multicast mapping, P2P loads otherwise) with per-(op, slice) epoch flags, fused with the residual add.
+#include "td/primitives.cuh"
+#include "runtime/driver.h"
+
+using namespace td;
+
+namespace {
+
+constexpr int kMKThreads = 256;
+constexpr int kMaxB = 8;
+
+enum TaskType : int { T_RMSNORM = 1, T_LINEAR = 2, T_QKROPE = 3, T_ATTN = 4, T_ALLREDUCE = 5, T_COPY = 6 };
+
+struct Task {            // 16 x int32
+  int type, dep_idx, dep_count, sig_idx;
+  int a[12];
+};
+
+struct MKParams {
+  const Task* tasks;           // all tasks, grouped by CTA
+  const int* queue_off;        // [grid + 1] range of each CTA's queue
+  void* const* ptrs;           // pointer table referenced by the tasks
+  uint32_t* sb;                // scoreboard counters (monotone)
+  uint32_t* epoch;             // [0] completed steps, [1] exit counter
+  SymmCtx symm;
+  int B;
+};
+
+TD_DEVICE float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+TD_DEVICE void unpack8(const uint4& v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { f[2 * i] = ptx::bf16_lo(w[i]); f[2 * i + 1] = ptx::bf16_hi(w[i]); }
+}
+TD_DEVICE uint4 pack8(const float (&f)[8]) {
+  uint4 o;
+  o.x = ptx::pack_bf16x2(f[0], f[1]); o.y = ptx::pack_bf16x2(f[2], f[3]); o.z = ptx::pack_bf16x2(f[4], f[5]); o.w = ptx::pack_bf16x2(f[6], f[7]);
+  return o;
+}
+
+// ---- RMSNORM: out = rmsnorm(in + res) * w ; res_out = in + res.  a: in, res(-1), w, out, res_out(-1), H, eps_bits ----
+TD_DEVICE void task_rmsnorm(const MKParams& p, const Task& t, float* red) {
+  const uint4* in = (const uint4*)p.ptrs[t.a[0]];
+  const uint4* res = t.a[1] >= 0 ? (const uint4*)p.ptrs[t.a[1]] : nullptr;
+  const uint4* w = (const uint4*)p.ptrs[t.a[2]];
+  uint4* out = (uint4*)p.ptrs[t.a[3]];
+  uint4* res_out = t.a[4] >= 0 ? (uint4*)p.ptrs[t.a[4]] : nullptr;
+  const int H = t.a[5], nvec = H / 8;
+  const float eps = __int_as_float(t.a[6]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int b = 0; b < p.B; ++b) {
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < nvec; i += kMKThreads) {
+      float f[8];
+      unpack8(in[b * nvec + i], f);
+      if (res) {
+        float r[8];
+        unpack8(res[b * nvec + i], r);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] += r[e];
+        const uint4 pk = pack8(f);
+        if (res_out) res_out[b * nvec + i] = pk;
+        unpack8(pk, f);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ss += f[e] * f[e];
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) red[warp] = ss;
+    __syncthreads();
+    float tot = 0.f;
+    for (int i = 0; i < kMKThreads / 32; ++i) tot += red[i];
+    const float inv = rsqrtf(tot / H + eps);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nvec; i += kMKThreads) {
+      float f[8], g[8];
+      if (res) { if (res_out) unpack8(res_out[b * nvec + i], f); else { float r[8]; unpack8(in[b * nvec + i], f); unpack8(res[b * nvec + i], r); for (int e = 0; e < 8; ++e) f[e] += r[e]; } }
+      else unpack8(in[b * nvec + i], f);
+      unpack8(w[i], g);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = f[e] * inv * g[e];
+      out[b * nvec + i] = pack8(f);
+    }
+  }
+}
+
+// ---- LINEAR (GEMV tile): out[b, n0 + j] = sum_k act(x)[b, k] * W[n0 + j, k].  a: x, w, out, K, ldo, n0, n_cnt, act, ldx ----
+TD_DEVICE void task_linear(const MKParams& p, const Task& t, uint8_t* smem) {
+  const uint4* x = (const uint4*)p.ptrs[t.a[0]];
+  const uint4* W = (const uint4*)p.ptrs[t.a[1]];
+  __nv_bfloat16* out = (__nv_bfloat16*)p.ptrs[t.a[2]];
+  const int K = t.a[3], ldo = t.a[4], n0 = t.a[5], n_cnt = t.a[6], act = t.a[7], ldx = t.a[8];
+  const int kvec = K / 8;
+  const int B = p.B;
+  // stage act(x) [B, K] in shared memory as fp32?  bf16 is enough: 16 B vectors
+  uint4* xs = reinterpret_cast<uint4*>(smem);
+  for (int i = threadIdx.x; i < B * kvec; i += kMKThreads) {
+    const int b = i / kvec, kv = i % kvec;
+    if (act == 0) xs[i] = x[b * (ldx / 8) + kv];
+    else {
+      float g[8], u[8];
+      unpack8(x[b * (ldx / 8) + kv], g);
+      unpack8(x[b * (ldx / 8) + kvec + kv], u);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) g[e] = g[e] / (1.f + __expf(-g[e])) * u[e];
+      xs[i] = pack8(g);
+    }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int R = 4;      // W rows in flight per warp
+  for (int j0 = warp * R; j0 < n_cnt; j0 += (kMKThreads / 32) * R) {
+    float acc[R][kMaxB];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int b = 0; b < kMaxB; ++b) acc[r][b] = 0.f;
+    for (int kv = lane; kv < kvec; kv += 32) {
+      uint4 wv[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        wv[r] = (j0 + r < n_cnt) ? ptx::ld_nc_v4(W + static_cast<size_t>(n0 + j0 + r) * kvec + kv) : make_uint4(0, 0, 0, 0);
+      float wf[R][8];
+#pragma unroll
+      for (int r = 0; r < R; ++r) unpack8(wv[r], wf[r]);
+#pragma unroll
+      for (int b = 0; b < kMaxB; ++b) {
+        if (b < B) {
+          float xf[8];
+          unpack8(xs[b * kvec + kv], xf);
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[r][b] += wf[r][e] * xf[e];
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int b = 0; b < kMaxB; ++b)
+        if (b < B) {
+          const float v = warp_sum(acc[r][b]);
+          if (lane == 0 && j0 + r < n_cnt) out[static_cast<size_t>(b) * ldo + n0 + j0 + r] = __float2bfloat16(v);
+        }
+  }
+}
+
+// ---- QKROPE: q/k RMSNorm + RoPE + KV append.  a: qkv, q_out, kcache, vcache, qn(-1), kn(-1), pos, Hq, Hkv, max_len, eps, theta ----
+TD_DEVICE void task_qkrope(const MKParams& p, const Task& t) {
+  const uint2* qkv = (const uint2*)p.ptrs[t.a[0]];
+  uint2* q_out = (uint2*)p.ptrs[t.a[1]];
+  uint2* kc = (uint2*)p.ptrs[t.a[2]];
+  uint2* vc = (uint2*)p.ptrs[t.a[3]];
+  const uint2* qn = t.a[4] >= 0 ? (const uint2*)p.ptrs[t.a[4]] : nullptr;
+  const uint2* kn = t.a[5] >= 0 ? (const uint2*)p.ptrs[t.a[5]] : nullptr;
+  const int* pos = (const int*)p.ptrs[t.a[6]];
+  const int Hq = t.a[7], Hkv = t.a[8], max_len = t.a[9];
+  const float eps = __int_as_float(t.a[10]), theta = __int_as_float(t.a[11]);
+  const int heads = Hq + 2 * Hkv;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int wi = warp; wi < p.B * heads; wi += kMKThreads / 32) {
+    const int b = wi / heads, h = wi % heads;
+    const uint2 raw = qkv[(static_cast<size_t>(b) * heads + h) * 32 + lane];
+    float f[4] = {ptx::bf16_lo(raw.x), ptx::bf16_hi(raw.x), ptx::bf16_lo(raw.y), ptx::bf16_hi(raw.y)};
+    const int ps = pos[b];
+    const bool is_v = h >= Hq + Hkv;
+    if (!is_v) {
+      const uint2* nw = (h < Hq) ? qn : kn;
+      if (nw) {
+        float ss = warp_sum(f[0] * f[0] + f[1] * f[1] + f[2] * f[2] + f[3] * f[3]);
+        const float inv = rsqrtf(ss / 128.f + eps);
+        const uint2 wr = nw[lane];
+        const float g[4] = {ptx::bf16_lo(wr.x), ptx::bf16_hi(wr.x), ptx::bf16_lo(wr.y), ptx::bf16_hi(wr.y)};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) f[e] = __bfloat162float(__float2bfloat16(f[e] * inv * g[e]));
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float other = __shfl_xor_sync(0xffffffffu, f[e], 16);
+        const int d = (lane & 15) * 4 + e;
+        float sn, cs;
+        sincosf(static_cast<float>(ps) * powf(theta, -static_cast<float>(2 * d) / 128.f), &sn, &cs);
+        f[e] = (lane < 16) ? (f[e] * cs - other * sn) : (f[e] * cs + other * sn);
+      }
+    }
+    uint2 o;
+    o.x = ptx::pack_bf16x2(f[0], f[1]); o.y = ptx::pack_bf16x2(f[2], f[3]);
+    if (h < Hq) q_out[(static_cast<size_t>(b) * Hq + h) * 32 + lane] = o;
+    else {
+      const int kvh = is_v ? h - Hq - Hkv : h - Hq;
+      (is_v ? vc : kc)[((static_cast<size_t>(b) * max_len + ps) * Hkv + kvh) * 32 + lane] = o;
+    }
+  }
+}
+
+// ---- ATTN: GQA decode for (b, kv head) over the whole context.  a: q, kcache, vcache, pos, out, b, kvh, Hq, Hkv, max_len, scale ----
+TD_DEVICE void task_attn(const MKParams& p, const Task& t, uint8_t* smem) {
+  const uint2* q = (const uint2*)p.ptrs[t.a[0]];
+  const uint2* kc = (const uint2*)p.ptrs[t.a[1]];
+  const uint2* vc = (const uint2*)p.ptrs[t.a[2]];
+  const int* pos = (const int*)p.ptrs[t.a[3]];
+  uint2* out = (uint2*)p.ptrs[t.a[4]];
+  const int b = t.a[5], kvh = t.a[6], Hq = t.a[7], Hkv = t.a[8], max_len = t.a[9];
+  const float scale = __int_as_float(t.a[10]);
+  const int G = Hq / Hkv;                       // <= 8
+  const int len = pos[b] + 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int NW = kMKThreads / 32;
+  float qf[8][4], m[8], l[8], o[8][4];
+  for (int g = 0; g < 8; ++g) {
+    m[g] = -INFINITY; l[g] = 0.f; o[g][0] = o[g][1] = o[g][2] = o[g][3] = 0.f;
+    if (g < G) {
+      const uint2 r = q[(static_cast<size_t>(b) * Hq + kvh * G + g) * 32 + lane];
+      qf[g][0] = ptx::bf16_lo(r.x) * scale; qf[g][1] = ptx::bf16_hi(r.x) * scale; qf[g][2] = ptx::bf16_lo(r.y) * scale; qf[g][3] = ptx::bf16_hi(r.y) * scale;
+    }
+  }
+  for (int j = warp; j < len; j += NW) {
+    const size_t row = ((static_cast<size_t>(b) * max_len + j) * Hkv + kvh) * 32 + lane;
+    const uint2 kr = kc[row], vr = vc[row];
+    const float kf[4] = {ptx::bf16_lo(kr.x), ptx::bf16_hi(kr.x), ptx::bf16_lo(kr.y), ptx::bf16_hi(kr.y)};
+    const float vf[4] = {ptx::bf16_lo(vr.x), ptx::bf16_hi(vr.x), ptx::bf16_lo(vr.y), ptx::bf16_hi(vr.y)};
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      if (g < G) {
+        const float s = warp_sum(qf[g][0] * kf[0] + qf[g][1] * kf[1] + qf[g][2] * kf[2] + qf[g][3] * kf[3]);
+        const float mn = fmaxf(m[g], s);
+        const float corr = __expf(m[g] - mn), pj = __expf(s - mn);
+        l[g] = l[g] * corr + pj;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[g][e] = o[g][e] * corr + pj * vf[e];
+        m[g] = mn;
+      }
+    }
+  }
+  float* sm_m = reinterpret_cast<float*>(smem);             // [NW][8]
+  float* sm_l = sm_m + NW * 8;                              // [NW][8]
+  float* sm_o = sm_l + NW * 8;                              // [NW][8][128]
+  for (int g = 0; g < G; ++g) {
+    if (lane == 0) { sm_m[warp * 8 + g] = m[g]; sm_l[warp * 8 + g] = l[g]; }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) sm_o[(warp * 8 + g) * 128 + lane * 4 + e] = o[g][e];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < G * 64; idx += kMKThreads) {    // two output elements per thread
+    const int g = idx / 64, d2 = idx % 64;
+    float mm = -INFINITY;
+    for (int w = 0; w < NW; ++w) mm = fmaxf(mm, sm_m[w * 8 + g]);
+    float ll = 0.f, o0 = 0.f, o1 = 0.f;
+    for (int w = 0; w < NW; ++w) {
+      const float c = (sm_m[w * 8 + g] == -INFINITY) ? 0.f : __expf(sm_m[w * 8 + g] - mm);
+      ll += sm_l[w * 8 + g] * c; o0 += sm_o[(w * 8 + g) * 128 + 2 * d2] * c; o1 += sm_o[(w * 8 + g) * 128 + 2 * d2 + 1] * c;
+    }
+    const float inv = ll > 0.f ? 1.f / ll : 0.f;
+    reinterpret_cast<uint32_t*>(out)[(static_cast<size_t>(b) * Hq + kvh * G + g) * 64 + d2] = ptx::pack_bf16x2(o0 * inv, o1 * inv);
+  }
+}
+
+// ---- ALLREDUCE slice (+ residual):  res_out[v] = res[v] + sum_r part_r[v].  a: part(symm), flags(symm), res, res_out, v0, v1, op_id, n_slices, slice ----
+TD_DEVICE void task_allreduce(const MKParams& p, const Task& t, uint32_t epoch) {
+  uint4* part = (uint4*)p.ptrs[t.a[0]];
+  uint32_t* flags = (uint32_t*)p.ptrs[t.a[1]];
+  const uint4* res = (const uint4*)p.ptrs[t.a[2]];
+  uint4* res_out = (uint4*)p.ptrs[t.a[3]];
+  const int v0 = t.a[4], v1 = t.a[5], slice = t.a[8];
+  const SymmCtx& c = p.symm;
+  const int W = c.world;
+  uint32_t* my_flags = flags + slice * W;                     // [W] one word per source rank
+  if (W > 1) {
+    // my partial slice is complete (scoreboard dependency) -> tell every rank, then wait for theirs
+    if (threadIdx.x < W) {
+      ptx::fence_acq_rel_sys();
+      ptx::st_release_sys(symm_at(c, my_flags + c.rank, threadIdx.x), epoch);
+      uint32_t v;
+      do { v = ptx::ld_acquire_sys(my_flags + threadIdx.x); } while (static_cast<int32_t>(v - epoch) < 0);
+    }
+    __syncthreads();
+  }
+  for (int v = v0 + threadIdx.x; v < v1; v += kMKThreads) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (W > 1 && c.mc_base) {
+      float f[8];
+      unpack8(ptx::multimem_ld_reduce_bf16x8(symm_mc(c, part) + v), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = f[e];
+    } else {
+      for (int r = 0; r < W; ++r) {
+        float f[8];
+        unpack8(ptx::ld_relaxed_sys_v4(symm_at(c, part + v, (c.rank + r) % W)), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += f[e];
+      }
+    }
+    if (res) {
+      float r[8];
+      unpack8(res[v], r);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += r[e];
+    }
+    res_out[v] = pack8(acc);
+  }
+}
+
+__global__ void __launch_bounds__(kMKThreads, 1) mega_kernel(const MKParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ float red[32];
+  const uint32_t epoch = p.epoch[0] + 1;
+  const int q0 = p.queue_off[blockIdx.x], q1 = p.queue_off[blockIdx.x + 1];
+  for (int qi = q0; qi < q1; ++qi) {
+    const Task& t = p.tasks[qi];
+    if (t.dep_idx >= 0) {
+      if (threadIdx.x == 0) {
+        const uint32_t target = epoch * static_cast<uint32_t>(t.dep_count);
+        while (static_cast<int32_t>(ptx::ld_acquire_gpu(p.sb + t.dep_idx) - target) < 0) {
+        }
+      }
+      __syncthreads();
+    }
+    switch (t.type) {
+      case T_RMSNORM: task_rmsnorm(p, t, red); break;
+      case T_LINEAR: task_linear(p, t, smem); break;
+      case T_QKROPE: task_qkrope(p, t); break;
+      case T_ATTN: task_attn(p, t, smem); break;
+      case T_ALLREDUCE: task_allreduce(p, t, epoch); break;
+      default: break;
+    }
+    __syncthreads();
+    if (t.sig_idx >= 0 && threadIdx.x == 0) {
+      __threadfence();
+      ptx::red_release_gpu_add(p.sb + t.sig_idx, 1u);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(p.epoch + 1, 1u) == gridDim.x - 1) { p.epoch[1] = 0; __threadfence(); p.epoch[0] = epoch; }
+  }
+}
+
+struct TdSymmArgs { long long rank, world; unsigned long long base, stride, mc_base; };
+
+}  // namespace
+
+struct TdMegaArgs {
+  TdSymmArgs symm;
+  const void* tasks; const void* queue_off; const void* ptrs; void* sb; void* epoch;
+  long long B, grid, smem_bytes;
+};
+
+TD_API int td_mega_task_size() { return (int)sizeof(Task); }
+
+TD_API int td_mega_launch(const TdMegaArgs* a, void* stream) {
+  if (a->B < 1 || a->B > kMaxB) { td::drv::set_error("megakernel: batch must be 1..8"); return -1; }
+  MKParams p;
+  p.tasks = (const Task*)a->tasks; p.queue_off = (const int*)a->queue_off; p.ptrs = (void* const*)a->ptrs;
+  p.sb = (uint32_t*)a->sb; p.epoch = (uint32_t*)a->epoch;
+  p.symm.rank = (int)a->symm.rank; p.symm.world = (int)a->symm.world; p.symm.base = a->symm.base; p.symm.stride = a->symm.stride; p.symm.mc_base = a->symm.mc_base;
+  p.B = (int)a->B;
+  static long long smem_set = 0;
+  if (a->smem_bytes > smem_set) {
+    TD_CUDA_CHECK(cudaFuncSetAttribute(mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a->smem_bytes));
+    smem_set = a->smem_bytes;
+  }
+  mega_kernel<<<(int)a->grid, kMKThreads, (size_t)a->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  TD_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

@@ -379,6 +379,36 @@ def case_ep_moe():
     moe.finalize()
 
 
+def case_mega():
+    """Megakernel decode step (task graph + scoreboard + in-kernel all-reduce) vs the layer-by-layer TP model."""
+    from triton_dist.models import AutoLLM, KV_Cache, ModelConfig
+    from triton_dist.mega_kernel import MegaDenseModel
+    dev = U.current_device()
+    W, me = U.world_size(), U.rank()
+    big = dev.type == "cuda"
+    dtype = torch.bfloat16 if big else torch.float32
+    cfg = ModelConfig(model_name="tiny-dense", max_length=64, dtype=dtype, rank=me, world_size=W)
+    m = AutoLLM.from_pretrained(cfg, U.get_triton_dist_world())
+    B = 2
+    mk = lambda: KV_Cache(m.num_layers, B, 64, m.num_key_value_heads, m.head_dim, dtype, W, dev)
+    kv, kv2 = mk(), mk()
+    g = torch.Generator(device="cpu").manual_seed(3 + me)
+    kv.k_cache.copy_((torch.randn(kv.k_cache.shape, generator=g) * 0.5).to(dtype)); kv.v_cache.copy_((torch.randn(kv.v_cache.shape, generator=g) * 0.5).to(dtype))
+    kv.kv_offset.fill_(9)
+    kv2.k_cache.copy_(kv.k_cache); kv2.v_cache.copy_(kv.v_cache); kv2.kv_offset.copy_(kv.kv_offset)
+    mega = MegaDenseModel(m, B, kv2)
+    for step in range(3):
+        ids = torch.randint(0, 1000, (B, 1), generator=torch.Generator().manual_seed(40 + step)).to(dev)
+        pos = kv.kv_offset.to(torch.int64)[:, None]
+        m.set_fwd("torch")
+        ref = m.inference(ids, pos, kv)
+        out = mega.mega_forward(ids)
+        _assert_close(out, ref, 6e-2 if big else 1e-4, 6e-2 if big else 1e-4, f"megakernel logits step {step}")
+        kv.inc_offset(1); kv2.inc_offset(1)
+    U.barrier_all_host()
+    mega.finalize()
+
+
 CASES = {k[5:]: v for k, v in list(globals().items()) if k.startswith("case_")}
 
 if __name__ == "__main__":

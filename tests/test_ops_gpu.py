@@ -97,3 +97,26 @@ def test_engine_single_gpu_backends_agree():
         assert agree >= 0.7, (be, agree, out, ref)
     from triton_dist import _C
     assert any("libtd_b200" in p for p in _C.loaded_libraries())
+
+
+def test_megakernel_single_gpu():
+    """One persistent kernel for the whole decode step vs the per-op model (same weights, same KV cache)."""
+    import triton_dist.utils as U
+    from triton_dist.mega_kernel import MegaDenseModel
+    from triton_dist.models import AutoLLM, KV_Cache, ModelConfig
+    U.initialize_distributed(seed=0)
+    cfg = ModelConfig(model_name="tiny-dense", max_length=64, dtype=torch.bfloat16, rank=0, world_size=1)
+    m = AutoLLM.from_pretrained(cfg)
+    B = 4
+    mk = lambda: KV_Cache(m.num_layers, B, 64, m.num_key_value_heads, m.head_dim, torch.bfloat16, 1, "cuda")
+    kv, kv2 = mk(), mk()
+    kv.rand_fill_kv_cache(17)
+    kv2.k_cache.copy_(kv.k_cache); kv2.v_cache.copy_(kv.v_cache); kv2.kv_offset.copy_(kv.kv_offset)
+    mega = MegaDenseModel(m, B, kv2)
+    for step in range(3):
+        ids = torch.randint(0, 1000, (B, 1), device="cuda")
+        ref = m.inference(ids, kv.kv_offset.to(torch.int64)[:, None], kv)
+        out = mega.mega_forward(ids)
+        torch.cuda.synchronize()
+        torch.testing.assert_close(out, ref, atol=6e-2, rtol=6e-2)
+        kv.inc_offset(1); kv2.inc_offset(1)

@@ -1,0 +1,259 @@
+"""MegaKernel: the whole decode step of a tensor-parallel dense LLM as ONE persistent CUDA kernel.
+
+Reference: /root/reference/python/triton_dist/mega_triton_kernel/** (``ModelBuilder.make_*`` -> task graph ->
+scheduler -> generated Triton kernel -> ``run()``; ``DenseModel.mega_forwrad``).  Here: ``ModelBuilder`` records ops
+and tiles them into tasks with scoreboard dependencies, ``schedule()`` deals them to per-CTA queues (round-robin or
+zig-zag, as core/scheduler.py:103-168), and the interpreter is the hand-written kernel in csrc/megakernel.cu.
+On the emulation backend ``run()`` interprets the same task list with PyTorch ops (same order, same buffers).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import struct
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import torch
+
+from .. import _C
+from .. import utils as U
+from ..ops.comm import SymmArgs, symm_args
+
+T_RMSNORM, T_LINEAR, T_QKROPE, T_ATTN, T_ALLREDUCE = 1, 2, 3, 4, 5
+TASK_NAMES = {1: "rms_norm", 2: "linear", 3: "qk_norm_rope_update_kvcache", 4: "flash_decode", 5: "allreduce"}
+
+
+class _MegaArgs(C.Structure):
+    _fields_ = [("symm", SymmArgs), ("tasks", C.c_void_p), ("queue_off", C.c_void_p), ("ptrs", C.c_void_p), ("sb", C.c_void_p),
+                ("epoch", C.c_void_p), ("B", C.c_longlong), ("grid", C.c_longlong), ("smem_bytes", C.c_longlong)]
+
+
+_C.register("td_mega_launch", C.c_int, [C.POINTER(_MegaArgs), C.c_void_p])
+_C.register("td_mega_task_size", C.c_int, [])
+
+
+def _fbits(x: float) -> int:
+    return struct.unpack("i", struct.pack("f", x))[0]
+
+
+@dataclass
+class Task:
+    type: int
+    dep_idx: int
+    dep_count: int
+    sig_idx: int
+    args: List[int]
+    layer: int = 0
+
+    def pack(self) -> List[int]:
+        a = list(self.args) + [0] * (12 - len(self.args))
+        return [self.type, self.dep_idx, self.dep_count, self.sig_idx] + a
+
+
+class ModelBuilder:
+    """Records ops of one decode step, tiles them into tasks, schedules them, launches the persistent kernel."""
+
+    def __init__(self, batch: int, num_sms: Optional[int] = None, schedule: str = "round_robin"):
+        assert 1 <= batch <= 8
+        self.B = batch
+        self.device = U.current_device()
+        self.is_cuda = self.device.type == "cuda"
+        self.num_sms = num_sms or (torch.cuda.get_device_properties(self.device).multi_processor_count if self.is_cuda else 8)
+        self.schedule_policy = schedule
+        self.tasks: List[Task] = []
+        self.ptrs: List[torch.Tensor] = []
+        self._ptr_idx: Dict[int, int] = {}
+        self.n_counters = 0
+        self.max_smem = 8 * 8 * 130 * 4 + 1024
+        self.compiled = False
+        self.cur_layer = 0
+        self.metrics: Dict[str, int] = {}
+
+    # ---- bookkeeping ----
+    def ptr(self, t: Optional[torch.Tensor]) -> int:
+        if t is None:
+            return -1
+        key = t.data_ptr()
+        if key not in self._ptr_idx:
+            self._ptr_idx[key] = len(self.ptrs)
+            self.ptrs.append(t)
+        return self._ptr_idx[key]
+
+    def counter(self) -> int:
+        self.n_counters += 1
+        return self.n_counters - 1
+
+    def _add(self, t: Task):
+        t.layer = self.cur_layer
+        self.tasks.append(t)
+        self.metrics[TASK_NAMES[t.type]] = self.metrics.get(TASK_NAMES[t.type], 0) + 1
+
+    # ---- ops (each returns (counter, count) that consumers wait on) ----
+    def make_rms_norm(self, x, weight, out, eps: float, dep=None, residual=None, residual_out=None):
+        sig = self.counter()
+        d = dep or (-1, 0)
+        self._add(Task(T_RMSNORM, d[0], d[1], sig, [self.ptr(x), self.ptr(residual), self.ptr(weight), self.ptr(out),
+                                                     self.ptr(residual_out), x.shape[-1], _fbits(eps)]))
+        return sig, 1
+
+    def make_linear(self, x, weight, out, dep, act_silu_mul: bool = False, tile_n: Optional[int] = None):
+        """out[B, N] = act(x) @ weight[N, K]^T (GEMV tiles).  ``act_silu_mul``: x is [B, 2K] = (gate | up)."""
+        N, K = weight.shape
+        tn = tile_n or max(8, ((N + self.num_sms - 1) // self.num_sms + 7) // 8 * 8)
+        sig = self.counter()
+        n_tiles = 0
+        for n0 in range(0, N, tn):
+            self._add(Task(T_LINEAR, dep[0], dep[1], sig, [self.ptr(x), self.ptr(weight), self.ptr(out), K, out.shape[-1], n0,
+                                                           min(tn, N - n0), int(act_silu_mul), x.shape[-1]]))
+            n_tiles += 1
+        self.max_smem = max(self.max_smem, self.B * K * 2 + 256)
+        return sig, n_tiles
+
+    make_qkv_proj = make_o_proj = make_fc1 = make_fc2 = make_linear
+
+    def make_qk_norm_rope_update_kvcache(self, qkv, q_out, k_cache, v_cache, q_norm_w, k_norm_w, positions, Hq, Hkv, eps, theta, dep):
+        sig = self.counter()
+        self._add(Task(T_QKROPE, dep[0], dep[1], sig, [self.ptr(qkv), self.ptr(q_out), self.ptr(k_cache), self.ptr(v_cache),
+                                                       self.ptr(q_norm_w), self.ptr(k_norm_w), self.ptr(positions), Hq, Hkv,
+                                                       k_cache.shape[1], _fbits(eps), _fbits(theta)]))
+        return sig, 1
+
+    def make_flash_decode(self, q, k_cache, v_cache, positions, out, Hq, Hkv, sm_scale, dep):
+        sig = self.counter()
+        n = 0
+        for b in range(self.B):
+            for kvh in range(Hkv):
+                self._add(Task(T_ATTN, dep[0], dep[1], sig, [self.ptr(q), self.ptr(k_cache), self.ptr(v_cache), self.ptr(positions),
+                                                             self.ptr(out), b, kvh, Hq, Hkv, k_cache.shape[1], _fbits(sm_scale)]))
+                n += 1
+        return sig, n
+
+    make_flash_attn = make_flash_decode
+
+    def make_allreduce(self, part_symm, flags_symm, residual, residual_out, dep, n_slices: int = 4):
+        """residual_out = residual + sum over ranks of part (one-shot over NVLink; fused residual add)."""
+        nvec = part_symm.numel() // 8
+        n_slices = max(1, min(n_slices, nvec))
+        per = (nvec + n_slices - 1) // n_slices
+        sig = self.counter()
+        for s in range(n_slices):
+            self._add(Task(T_ALLREDUCE, dep[0], dep[1], sig, [self.ptr(part_symm), self.ptr(flags_symm), self.ptr(residual),
+                                                              self.ptr(residual_out), s * per, min(nvec, (s + 1) * per), 0, n_slices, s]))
+        return sig, n_slices
+
+    def make_barrier_all_intra_node(self, *a, **k):
+        return None   # not needed: the all-reduce tasks carry their own epoch flags
+
+    # ---- scheduling + compile ----
+    def schedule(self) -> List[List[Task]]:
+        """Static per-CTA queues.  round_robin: task i -> CTA i % n;  zig_zag: alternate direction every sweep."""
+        n = self.num_sms
+        queues: List[List[Task]] = [[] for _ in range(n)]
+        for i, t in enumerate(self.tasks):
+            sweep, pos = divmod(i, n)
+            cta = pos if (self.schedule_policy == "round_robin" or sweep % 2 == 0) else n - 1 - pos
+            queues[cta].append(t)
+        return queues
+
+    def compile(self):
+        queues = self.schedule()
+        flat, off = [], [0]
+        for q in queues:
+            for t in q:
+                flat.extend(t.pack())
+            off.append(off[-1] + len(q))
+        self.order = [t for q in queues for t in q]
+        self.task_tensor = torch.tensor(flat, dtype=torch.int32, device=self.device).view(-1, 16)
+        self.queue_off = torch.tensor(off, dtype=torch.int32, device=self.device)
+        self.ptr_tensor = torch.tensor([t.data_ptr() for t in self.ptrs], dtype=torch.int64, device=self.device)
+        self.sb = torch.zeros(max(self.n_counters, 1), dtype=torch.int32, device=self.device)
+        self.epoch = torch.zeros(4, dtype=torch.int32, device=self.device)
+        self.compiled = True
+        return self
+
+    def get_sm_activity(self) -> Dict[str, int]:
+        return dict(self.metrics, tasks=len(self.tasks), counters=self.n_counters, ctas=self.num_sms)
+
+    # ---- run ----
+    def run(self, stream=None):
+        assert self.compiled
+        if not self.is_cuda:
+            return self._run_host()
+        a = _MegaArgs()
+        a.symm = symm_args()
+        a.tasks, a.queue_off, a.ptrs = self.task_tensor.data_ptr(), self.queue_off.data_ptr(), self.ptr_tensor.data_ptr()
+        a.sb, a.epoch = self.sb.data_ptr(), self.epoch.data_ptr()
+        a.B, a.grid, a.smem_bytes = self.B, self.num_sms, self.max_smem
+        _C.check(_C.cuda_lib().td_mega_launch(C.byref(a), C.c_void_p((stream or torch.cuda.current_stream()).cuda_stream)), "td_mega_launch")
+
+    # emulation: interpret the task list in program order with torch ops on the same buffers
+    def _run_host(self):
+        from ..ops.elementwise import rope_reference
+        import ctypes
+        heap = U.get_heap()
+        lib = _C.host_lib()
+        self.host_epoch = getattr(self, "host_epoch", 0) + 1
+        P = self.ptrs
+        B = self.B
+        for t in self.tasks:
+            a = t.args
+            if t.type == T_RMSNORM:
+                x = P[a[0]].view(B, -1).float()
+                if a[1] >= 0:
+                    x = x + P[a[1]].view(B, -1).float()
+                    if a[4] >= 0:
+                        P[a[4]].view(B, -1).copy_(x.to(P[a[4]].dtype))
+                eps = struct.unpack("f", struct.pack("i", a[6]))[0]
+                y = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps) * P[a[2]].float()
+                P[a[3]].view(B, -1).copy_(y.to(P[a[3]].dtype))
+            elif t.type == T_LINEAR:
+                K, n0, nc, act = a[3], a[5], a[6], a[7]
+                x = P[a[0]].view(B, -1).float()
+                if act:
+                    x = torch.nn.functional.silu(x[:, :K]) * x[:, K:2 * K]
+                else:
+                    x = x[:, :K]
+                P[a[2]].view(B, -1)[:, n0:n0 + nc] = (x @ P[a[1]][n0:n0 + nc].float().t()).to(P[a[2]].dtype)
+            elif t.type == T_QKROPE:
+                Hq, Hkv = a[7], a[8]
+                eps = struct.unpack("f", struct.pack("i", a[10]))[0]
+                theta = struct.unpack("f", struct.pack("i", a[11]))[0]
+                qkv = P[a[0]].view(B, Hq + 2 * Hkv, -1)
+                q, k, v = qkv[:, :Hq], qkv[:, Hq:Hq + Hkv], qkv[:, Hq + Hkv:]
+                nrm = lambda z, w: ((z.float() * torch.rsqrt(z.float().pow(2).mean(-1, keepdim=True) + eps)) * w.float()).to(z.dtype)
+                if a[4] >= 0:
+                    q, k = nrm(q, P[a[4]]), nrm(k, P[a[5]])
+                pos = P[a[6]].view(-1)[:B]
+                q, k = rope_reference(q, pos, theta), rope_reference(k, pos, theta)
+                P[a[1]].view(B, Hq, -1).copy_(q)
+                for b in range(B):
+                    P[a[2]][b, int(pos[b])] = k[b]
+                    P[a[3]][b, int(pos[b])] = v[b]
+            elif t.type == T_ATTN:
+                b, kvh, Hq, Hkv = a[5], a[6], a[7], a[8]
+                G = Hq // Hkv
+                scale = struct.unpack("f", struct.pack("i", a[10]))[0]
+                L = int(P[a[3]].view(-1)[b]) + 1
+                q = P[a[0]].view(B, Hq, -1)[b, kvh * G:(kvh + 1) * G].float()
+                k, v = P[a[1]][b, :L, kvh].float(), P[a[2]][b, :L, kvh].float()
+                pr = torch.softmax(q @ k.t() * scale, -1)
+                P[a[4]].view(B, Hq, -1)[b, kvh * G:(kvh + 1) * G] = (pr @ v).to(P[a[4]].dtype)
+            elif t.type == T_ALLREDUCE:
+                part, flags = P[a[0]], P[a[1]]
+                v0, v1, sl = a[4] * 8, a[5] * 8, a[8]
+                W, me = heap.world, heap.rank
+                fl = flags.view(-1)[sl * W:(sl + 1) * W]
+                for r in range(W):
+                    lib.tdh_notify32(ctypes.c_void_p(heap.peer_ptr(fl[me:me + 1].data_ptr(), r)), self.host_epoch, 1)
+                if lib.tdh_wait32_n(ctypes.c_void_p(fl.data_ptr()), W, self.host_epoch, 1, 60_000_000):
+                    raise TimeoutError("megakernel all-reduce flag never arrived")
+                acc = torch.zeros(v1 - v0, dtype=torch.float32)
+                for r in range(W):
+                    acc += heap.peer_view(part, (me + r) % W).view(-1)[v0:v1].float()
+                if a[2] >= 0:
+                    acc += P[a[2]].view(-1)[v0:v1].float()
+                P[a[3]].view(-1)[v0:v1] = acc.to(P[a[3]].dtype)
+
+
+from .dense import MegaDenseModel  # noqa: E402,F401
