@@ -48,14 +48,14 @@ static int encode_tmap(CUtensorMap* out, const void* base, int rank, const cuuin
   return 0;
 }
 
-template <int kMode, int BN, int kCtaGroup, bool kFP8 = false>
+template <int kMode, int BN, int kCtaGroup, bool kFP8 = false, int kAccStages = 2>
 static int launch_cfg(const Params& p, int grid, cudaStream_t stream) {
   // deepest pipeline that fits in 227 KB next to the 32 KB epilogue staging
   constexpr int kStageBytes = SmemLayout<BN, 1, kCtaGroup, 0, kFP8>::kStageBytes;
   constexpr int kMaxStages = (232448 - 1024 - 2 * kCBlockBytes - 384) / kStageBytes;
   constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
   using L = SmemLayout<BN, kStages, kCtaGroup, 0, kFP8>;
-  auto kern = gemm_kernel<kMode, BN, kStages, kCtaGroup, kFP8>;
+  auto kern = gemm_kernel<kMode, BN, kStages, kCtaGroup, kFP8, kAccStages>;
   static bool attr_set = false;
   if (!attr_set) {
     TD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -81,7 +81,11 @@ template <int kMode>
 static int dispatch_fp8(const Params& p, int bn, int cg, int grid, cudaStream_t s) {
   if (bn == 128 && cg == 2) return launch_cfg<kMode, 128, 2, true>(p, grid, s);
   if (bn == 128 && cg == 1) return launch_cfg<kMode, 128, 1, true>(p, grid, s);
-  drv::set_error("MXFP8 path supports bn = 128 (cta_group 1 or 2)");
+  // 256-wide tiles halve the L2->SM operand traffic per FLOP (the bf16 kernel is already L2-bound at 64 B/clk/SM);
+  // TMEM then holds ONE 256-column accumulator + the scale-factor ring, so the epilogue is not overlapped
+  if (bn == 256 && cg == 2) return launch_cfg<kMode, 256, 2, true, 1>(p, grid, s);
+  if (bn == 256 && cg == 1) return launch_cfg<kMode, 256, 1, true, 1>(p, grid, s);
+  drv::set_error("MXFP8 path supports bn = 128 / 256 (cta_group 1 or 2)");
   return -1;
 }
 

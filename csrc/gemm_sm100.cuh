@@ -217,13 +217,13 @@ TD_DEVICE void ag_comm_cta(const Params& p, uint32_t ph, int comm_idx) {
 // -------------------------------------------------------------------------------------------------
 // the kernel
 // -------------------------------------------------------------------------------------------------
-template <int kMode, int BN, int kStages, int kCtaGroup, bool kFP8 = false>
+template <int kMode, int BN, int kStages, int kCtaGroup, bool kFP8 = false, int kAccStages = 2>
 __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant__ Params p) {
   using L = SmemLayout<BN, kStages, kCtaGroup, 0, kFP8>;
   constexpr int kBKElems = kFP8 ? 128 : BK;              // K elements per 128-byte smem row
   constexpr int kSFCols = 4 + 4 * ((BN + 127) / 128);    // TMEM columns of scale factors per pipeline stage (A + B)
-  constexpr int kSFBase = 2 * BN;                        // scale factors live after the two accumulator stages
-  static_assert(!kFP8 || (2 * BN + kStages * kSFCols <= 512), "TMEM: accumulators + scale-factor ring exceed 512 columns");
+  constexpr int kSFBase = kAccStages * BN;               // scale factors live after the accumulator stage(s)
+  static_assert(!kFP8 || (kAccStages * BN + kStages * kSFCols <= 512), "TMEM: accumulators + scale-factor ring exceed 512 columns");
   constexpr int TM = BM * kCtaGroup;                     // rows of C per cluster tile
   constexpr int kTmemCols = kFP8 ? 512 : tmem_cols_for(BN);
   constexpr int kNumCBlocks = (BN + kCBlockCols - 1) / kCBlockCols;
@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
           if constexpr (kCtaGroup == 1) ptx::mma_commit(tmem_full + acc);
           else ptx::mma_commit_2sm(tmem_full + acc, 0b11);
           prof_record(p.prof, static_cast<int>(blockIdx.x) * 8 + 1, 4, false);
-          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+          if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
         }
       }
       __syncwarp();
@@ -545,7 +545,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
           }
         }
         if (lane == 0) prof_record(p.prof, static_cast<int>(blockIdx.x) * 8 + warp, 5, false);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
       }
       if (p.use_tma_store && et == 0) ptx::bulk_wait<0>();
       __syncwarp();

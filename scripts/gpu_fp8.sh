@@ -9,13 +9,13 @@ from triton_dist.ops.gemm import GemmConfig
 for (M, N, K) in [(4096, 12288, 6144), (8192, 8192, 8192)]:
     a = quantize_mxfp8(torch.randn(M, K, device="cuda", dtype=torch.bfloat16)); b = quantize_mxfp8(torch.randn(N, K, device="cuda", dtype=torch.bfloat16))
     out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-    for cg in (1, 2):
-        cfg = GemmConfig(bn=128, cta_group=cg, group_m=8, use_tma_store=True)
+    for cg, bn in ((2, 128), (1, 256), (2, 256)):
+        cfg = GemmConfig(bn=bn, cta_group=cg, group_m=8, use_tma_store=True)
         for _ in range(3): gemm_mxfp8(a, b, out=out, config=cfg)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(10): gemm_mxfp8(a, b, out=out, config=cfg)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
-        print(json.dumps(dict(M=M, N=N, K=K, cg=cg, ms=ms, tflops=2 * M * N * K / ms / 1e9)))
+        print(json.dumps(dict(M=M, N=N, K=K, cg=cg, bn=bn, ms=ms, tflops=2 * M * N * K / ms / 1e9)))
 PY

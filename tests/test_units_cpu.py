@@ -1,0 +1,180 @@
+"""CPU-only unit tests: build/import, symmetric heap allocator, lazy allocator, autotuner cache, routing sort,
+GDN chunked forward, MXFP8 quantisation round trip, single-process model backends, megakernel task graph."""
+import math
+import os
+
+import pytest
+import torch
+
+os.environ.setdefault("TD_FORCE_HOST_BACKEND", "1")
+
+
+@pytest.fixture(scope="module")
+def dist_env():
+    import triton_dist.utils as U
+    os.environ.setdefault("MASTER_PORT", "29677")
+    U.initialize_distributed(seed=0)
+    yield U
+    U.finalize_distributed()
+
+
+def test_native_libs_build_and_load():
+    from triton_dist import _C
+    assert _C.host_lib() is not None
+    assert _C.cuda_lib() is not None          # loads without a GPU (driver entry points resolved lazily)
+    assert any("libtd_host" in p for p in _C.loaded_libraries())
+
+
+def test_symmetric_heap_alloc_free(dist_env):
+    U = dist_env
+    heap = U.get_heap()
+    a = U.nvshmem_create_tensor((1000,), torch.float32)
+    b = U.nvshmem_create_tensor((3, 5), torch.bfloat16)
+    assert heap.contains(a) and heap.contains(b) and a.abs().sum() == 0
+    off_a = heap.offset_of(a)
+    U.nvshmem_free_tensor_sync(a)
+    c = U.nvshmem_create_tensor((10,), torch.int32)
+    assert heap.offset_of(c) == off_a                    # first fit reuses the hole
+    views = U.nvshmem_create_tensors((4,), torch.int32, U.rank(), 1)
+    assert len(views) == 1 and views[0].shape == (4,)
+    with pytest.raises(ValueError):
+        heap.offset_of(torch.zeros(4))
+
+
+def test_primitives_host(dist_env):
+    from triton_dist import language as dl
+    U = dist_env
+    sig = U.nvshmem_create_tensor((8,), torch.int32)
+    dl.notify(sig[0:1], U.rank(), signal=5, sig_op="set")
+    dl.notify(sig[1:2], U.rank(), signal=2, sig_op="add")
+    dl.notify(sig[1:2], U.rank(), signal=3, sig_op="add")
+    assert sig[0] == 5 and sig[1] == 5
+    assert dl.wait(sig[0:2], 2, wait_value=5) == 5
+    os.environ["TD_HOST_TIMEOUT_US"] = "20000"
+    with pytest.raises(TimeoutError):                    # hang detection instead of spinning forever
+        dl.wait(sig[2:3], 1, wait_value=1)
+    os.environ.pop("TD_HOST_TIMEOUT_US")
+    U.barrier_all_on_stream()
+
+
+def test_lazy_allocator(dist_env):
+    from triton_dist.utils import LazyAllocator
+    la = LazyAllocator()
+    a = la.declare("a", (100, 7), torch.bfloat16)
+    b = la.declare("b", (3,), torch.int64)
+    assert la.total_bytes() >= 100 * 7 * 2 + 24 and set(la.breakdown()) == {"a", "b"}
+    with pytest.raises(RuntimeError):
+        a.get()
+    la.materialize()
+    assert a.get().shape == (100, 7) and b.get().dtype == torch.int64
+    la.free()
+
+
+def test_autotune_cache(tmp_path, monkeypatch):
+    import triton_dist.tune as T
+    monkeypatch.setattr(T, "CACHE_DIR", tmp_path)
+    calls = []
+
+    @T.autotune([{"k": 1}, {"k": 3}, {"k": 2}], key_fn=lambda x, **kw: str(tuple(x.shape)), warmup=1, rep=2)
+    def f(x, config=None):
+        calls.append(config["k"])
+        import time
+        time.sleep(0.002 * config["k"])
+        return x * config["k"]
+
+    out = f(torch.ones(4))
+    assert out[0] == 1 and f.best_config(torch.ones(4)) == {"k": 1}
+    n = len(calls)
+    f(torch.ones(4))
+    assert len(calls) == n + 1                           # cached: no re-tuning
+    assert f(torch.ones(4), autotune=False)[0] == 1
+
+
+def test_moe_align_sort_and_grouped_gemm_host():
+    from triton_dist.ops import moe as M
+    torch.manual_seed(0)
+    T, topk, E, H, N = 37, 2, 5, 16, 24
+    ids = torch.stack([torch.randperm(E)[:topk] for _ in range(T)]).to(torch.int32)
+    r = M.moe_align_sort(ids, E, 8)
+    flat = r.sorted_ids[r.sorted_ids != r.pad_id]
+    assert sorted(flat.tolist()) == list(range(T * topk))
+    offs = r.expert_offsets.tolist()
+    for e in range(E):
+        seg = r.sorted_ids[offs[e]:offs[e + 1]]
+        real = seg[seg != r.pad_id]
+        assert torch.all(ids.view(-1)[real.long()] == e) and (offs[e + 1] - offs[e]) % 8 == 0
+    x = torch.randn(T, H)
+    w = torch.randn(E, N, H)
+    c = M.moe_forward_local(x, w, ids)
+    ref = torch.stack([x[t] @ w[int(ids[t, j])].t() for t in range(T) for j in range(topk)])
+    torch.testing.assert_close(c, ref, atol=1e-4, rtol=1e-4)
+    wts = torch.rand(T, topk)
+    red = M.reduce_topk(c, wts, topk)
+    torch.testing.assert_close(red, (ref.view(T, topk, N) * wts[..., None]).sum(1), atol=1e-4, rtol=1e-4)
+
+
+def test_gdn_chunk_matches_recurrence():
+    from triton_dist.ops.gdn import chunk_gated_delta_rule_fwd, gated_delta_rule_recurrent
+    torch.manual_seed(0)
+    B, T, H, Dk, Dv = 2, 70, 2, 16, 8
+    q, k, v = torch.randn(B, T, H, Dk), torch.nn.functional.normalize(torch.randn(B, T, H, Dk), dim=-1), torch.randn(B, T, H, Dv)
+    g, beta = -torch.rand(B, T, H) * 0.3, torch.rand(B, T, H)
+    o1, s1 = gated_delta_rule_recurrent(q, k, v, g, beta)
+    o2, s2 = chunk_gated_delta_rule_fwd(q, k, v, g, beta, chunk_size=16)
+    torch.testing.assert_close(o1, o2, atol=1e-4, rtol=1e-4)
+    torch.testing.assert_close(s1, s2, atol=1e-4, rtol=1e-4)
+
+
+def test_mxfp8_roundtrip_and_tiled_scale_layout():
+    from triton_dist.ops.fp8 import dequantize_mxfp8, gemm_mxfp8, quantize_mxfp8
+    torch.manual_seed(0)
+    x = torch.randn(130, 256) * 5
+    t = quantize_mxfp8(x)
+    assert t.sf.shape == (2, 2, 512)
+    d = dequantize_mxfp8(t)
+    assert ((d - x).abs() / x.abs().clamp(min=1e-3)).median() < 0.05
+    # scale byte of (row 33, k-block 1, chunk 2): chunk (0,1), byte (33 % 32) * 16 + (33 // 32) * 4 + 2
+    e = math.ceil(math.log2(x[33, 128 + 64:128 + 96].abs().max().item() / 448.0))
+    assert int(t.sf[0, 1, 1 * 16 + 1 * 4 + 2]) == e + 127
+    y = gemm_mxfp8(t, quantize_mxfp8(torch.randn(64, 256)))
+    assert y.shape == (130, 64)
+
+
+def test_model_backends_agree_single_process(dist_env):
+    from triton_dist.models import Engine, ModelConfig
+    for name in ("tiny-dense", "tiny-moe"):
+        cfg = ModelConfig(model_name=name, max_length=64, dtype=torch.float32, rank=0, world_size=1)
+        eng = Engine(cfg, temperature=0.0)
+        ids = torch.randint(0, 1000, (2, 5))
+        ref = eng.serve(ids, 4, backend="torch")
+        for be in ("triton_dist", "triton_dist_AR"):
+            assert torch.equal(eng.serve(ids, 4, backend=be), ref), (name, be)
+
+
+def test_megakernel_graph_single_process(dist_env):
+    from triton_dist.mega_kernel import MegaDenseModel
+    from triton_dist.models import AutoLLM, KV_Cache, ModelConfig
+    cfg = ModelConfig(model_name="tiny-dense", max_length=64, dtype=torch.float32, rank=0, world_size=1)
+    m = AutoLLM.from_pretrained(cfg)
+    B = 2
+    kv = KV_Cache(m.num_layers, B, 64, m.num_key_value_heads, m.head_dim, torch.float32, 1, "cpu")
+    kv.rand_fill_kv_cache(7)
+    kv2 = KV_Cache(m.num_layers, B, 64, m.num_key_value_heads, m.head_dim, torch.float32, 1, "cpu")
+    kv2.k_cache.copy_(kv.k_cache); kv2.v_cache.copy_(kv.v_cache); kv2.kv_offset.copy_(kv.kv_offset)
+    mega = MegaDenseModel(m, B, kv2, schedule="zig_zag")
+    ids = torch.randint(0, 1000, (B, 1))
+    ref = m.inference(ids, kv.kv_offset.to(torch.int64)[:, None], kv)
+    torch.testing.assert_close(mega.mega_forward(ids), ref, atol=1e-4, rtol=1e-4)
+    act = mega.builder.get_sm_activity()
+    assert act["tasks"] == sum(v for k, v in act.items() if k not in ("tasks", "counters", "ctas"))
+
+
+def test_bench_reference_arm_reports_unavailable():
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and "unavailable" in d
