@@ -216,3 +216,80 @@ TD_API int td_qk_norm_rope_kv(const void* qkv, void* q_out, void* k_cache, void*
   TD_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Skinny GEMM (decode): out[b, n] = sum_k x[b, k] * W[n, k]  for b < B <= 8.
+// At M <= 8 a 128-row tcgen05 tile wastes 94% of the tensor core and the op is purely weight-streaming, so this is
+// a CUDA-core GEMV: one warp per 4 rows of W (4 independent 16-byte loads per lane in flight), x staged in shared
+// memory, fp32 accumulation, warp-shuffle reduction.  Same math as the megakernel's LINEAR task (csrc/megakernel.cu).
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+template <bool kBF16>
+__global__ void __launch_bounds__(256) gemv_kernel(const uint4* __restrict__ x, const uint4* __restrict__ W, void* __restrict__ out,
+                                                   int B, int N, int K, int ldx /*elements*/, int ldo) {
+  extern __shared__ __align__(16) uint8_t gsm[];
+  uint4* xs = reinterpret_cast<uint4*>(gsm);
+  const int kvec = K / 8;
+  for (int i = threadIdx.x; i < B * kvec; i += blockDim.x) xs[i] = x[(i / kvec) * (ldx / 8) + (i % kvec)];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int R = 4;
+  const int rows_per_cta = (blockDim.x / 32) * R;
+  for (int n0 = blockIdx.x * rows_per_cta + warp * R; n0 < N; n0 += gridDim.x * rows_per_cta) {
+    float acc[R][8];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int b = 0; b < 8; ++b) acc[r][b] = 0.f;
+    for (int kv = lane; kv < kvec; kv += 32) {
+      uint4 wv[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) wv[r] = (n0 + r < N) ? ptx::ld_nc_v4(W + static_cast<size_t>(n0 + r) * kvec + kv) : make_uint4(0, 0, 0, 0);
+      float wf[R][8];
+#pragma unroll
+      for (int r = 0; r < R; ++r) unpack8<kBF16>(wv[r], wf[r]);
+#pragma unroll
+      for (int b = 0; b < 8; ++b)
+        if (b < B) {
+          float xf[8];
+          unpack8<kBF16>(xs[b * kvec + kv], xf);
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[r][b] += wf[r][e] * xf[e];
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int b = 0; b < 8; ++b)
+        if (b < B) {
+          const float v = warp_sum(acc[r][b]);
+          if (lane == 0 && n0 + r < N) {
+            if constexpr (kBF16) reinterpret_cast<__nv_bfloat16*>(out)[static_cast<size_t>(b) * ldo + n0 + r] = __float2bfloat16(v);
+            else reinterpret_cast<__half*>(out)[static_cast<size_t>(b) * ldo + n0 + r] = __float2half(v);
+          }
+        }
+  }
+}
+}  // namespace
+
+TD_API int td_gemv(const void* x, const void* W, void* out, int B, int N, int K, int ldx, int ldo, int is_bf16, void* stream) {
+  if (B < 1 || B > 8 || K % 8 || ldx % 8) { td::drv::set_error("gemv: 1 <= B <= 8, K % 8 == 0"); return -1; }
+  const size_t smem = static_cast<size_t>(B) * K * 2;
+  if (smem > 200 * 1024) { td::drv::set_error("gemv: B * K too large for shared memory"); return -1; }
+  static size_t smem_set = 0;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (smem > 48 * 1024 && smem > smem_set) {
+    TD_CUDA_CHECK(cudaFuncSetAttribute(gemv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    TD_CUDA_CHECK(cudaFuncSetAttribute(gemv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    smem_set = 200 * 1024;
+  }
+  const int rows_per_cta = 8 * 4;
+  int grid = (N + rows_per_cta - 1) / rows_per_cta;
+  if (grid > 148 * 4) grid = 148 * 4;
+  if (is_bf16) gemv_kernel<true><<<grid, 256, smem, s>>>((const uint4*)x, (const uint4*)W, out, B, N, K, ldx, ldo);
+  else gemv_kernel<false><<<grid, 256, smem, s>>>((const uint4*)x, (const uint4*)W, out, B, N, K, ldx, ldo);
+  TD_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

@@ -120,3 +120,12 @@ def test_megakernel_single_gpu():
         torch.cuda.synchronize()
         torch.testing.assert_close(out, ref, atol=6e-2, rtol=6e-2)
         kv.inc_offset(1); kv2.inc_offset(1)
+
+
+@pytest.mark.parametrize("M", [1, 3, 8])
+def test_gemv_decode_path(M):
+    from triton_dist.ops.gemm import gemm
+    a = torch.randn(M, 4096, device="cuda", dtype=torch.bfloat16)
+    b = torch.randn(1000, 4096, device="cuda", dtype=torch.bfloat16)
+    c = gemm(a, b)
+    torch.testing.assert_close(c.float(), a.float() @ b.float().t(), atol=0.5, rtol=2e-2)

@@ -66,6 +66,20 @@ def fill_common(args: _C.GemmArgs, a_rows: int, A_ptr: int, lda: int, B: torch.T
     args.world = 1
 
 
+_C.register("td_gemv", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p])
+
+
+def gemv(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Skinny GEMM for decode (M <= 8): weight-streaming CUDA-core kernel (csrc/elementwise.cu ``gemv_kernel``)."""
+    M, K = a.shape
+    N = b.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=a.dtype, device=a.device)
+    _C.check(_C.cuda_lib().td_gemv(a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, a.stride(0), out.stride(0),
+                                   int(a.dtype == torch.bfloat16), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "td_gemv")
+    return out
+
+
 def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None,
          config: Optional[GemmConfig] = None, out_parity=None) -> torch.Tensor:
     """``out[M,N] = a[M,K] @ b[N,K].T`` with fp32 accumulation in TMEM.  ``b`` is an ``nn.Linear`` weight.
@@ -82,6 +96,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None,
         raise ValueError("shape/dtype mismatch")
     if out is None:
         out = torch.empty((M, N), dtype=a.dtype, device=a.device)
+    if (M <= 8 and config is None and out_parity is None and b.is_contiguous() and out.stride(1) == 1 and M * K * 2 <= 200 * 1024
+            and a.stride(0) % 8 == 0):
+        return gemv(a, b, out)           # decode: tensor cores cannot help at M <= 8, stream the weights instead
     cfg = config or default_config(M, N, K)
     args = _C.GemmArgs()
     args.mode = 0
