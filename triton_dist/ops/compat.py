@@ -1,0 +1,159 @@
+"""Remaining entry points of the reference's op namespace, composed from the kernels in this package.
+
+Each is the same contract as the reference function it names; where the reference fuses two steps in one Triton kernel
+and we currently run two of our kernels back to back on one stream, the docstring says so.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from .. import utils as U
+from . import comm
+from . import moe as M
+from .all_to_all import (AllToAllContext, all_to_all_single_2d, create_all_to_all_single_2d_context)
+from .elementwise import silu_mul
+from .gemm import gemm
+
+
+def _lin(x, w):
+    return gemm(x, w) if x.is_cuda else torch.nn.functional.linear(x, w)
+
+
+# ---- reduce_scatter.py ---------------------------------------------------------------------------------------
+def create_reduce_scater_2d_ctx(max_M: int, N: int, rank: int, world_size: int, local_world_size: int, dtype: torch.dtype, **_):
+    return comm.create_allreduce_ctx(max_M * N * torch.empty(0, dtype=dtype).element_size(), rank, world_size, local_world_size)
+
+
+def reduce_scatter_2d_op(input: torch.Tensor, ctx, output: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(reduce_scatter.py:822) scatter + local reduce -> here one pull-reduce kernel (NVLS ld_reduce when available)."""
+    return comm.reduce_scatter(input, ctx, output)
+
+
+def ring_reduce(slabs: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(reduce_scatter.py:780) out = sum over the leading (source) dimension, fp32 accumulation."""
+    out = torch.empty(slabs.shape[1:], dtype=slabs.dtype, device=slabs.device) if out is None else out
+    return comm.reduce_tensor(out, slabs.contiguous())
+
+
+# ---- swiglu.py ------------------------------------------------------------------------------------------------
+def swiglu_backward(grad_out: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """d/dx of silu(x[..., :I]) * x[..., I:]  (swiglu.py backward kernels)."""
+    I = x.shape[-1] // 2
+    g, u = x[..., :I].float(), x[..., I:].float()
+    sg = torch.sigmoid(g)
+    dg = grad_out.float() * u * (sg + g * sg * (1 - sg))
+    du = grad_out.float() * g * sg
+    return torch.cat([dg, du], dim=-1).to(x.dtype)
+
+
+# ---- group_gemm.py --------------------------------------------------------------------------------------------
+def moe_grouped_gemm_2weights(x_sorted, w_gate, w_up, routing, split: str = "N"):
+    """(group_gemm.py:318/:402) two weights sharing the A operand: run as one grouped GEMM on the stacked weight."""
+    w = torch.cat([w_gate, w_up], dim=1)
+    return M.moe_grouped_gemm(x_sorted, w, routing)
+
+
+def transposed_moe_grouped_gemm(x_sorted: torch.Tensor, dy_sorted: torch.Tensor, routing, num_experts: int) -> torch.Tensor:
+    """(group_gemm.py:503-727) weight gradient per expert: dW[e] = dY_e^T @ X_e over that expert's (padded) rows.
+    The operands are row(token)-major, i.e. MN-major for this product; each expert's slab is transposed once and fed to
+    the K-major tcgen05 GEMM (pad rows are zero, so they do not contribute)."""
+    offs = routing.expert_offsets.tolist()
+    N, K = dy_sorted.shape[1], x_sorted.shape[1]
+    dW = torch.zeros((num_experts, N, K), dtype=x_sorted.dtype, device=x_sorted.device)
+    for e in range(num_experts):
+        s, t = offs[e], offs[e + 1]
+        if t > s:
+            a = dy_sorted[s:t].t().contiguous()      # [N, rows]
+            b = x_sorted[s:t].t().contiguous()       # [K, rows]
+            dW[e] = _lin(a, b) if (t - s) % 8 == 0 else (a.float() @ b.float().t()).to(dW.dtype)
+    return dW
+
+
+def calc_gather_scatter_index_triton(topk_ids: torch.Tensor, num_experts: int, block_m: int = 128):
+    """(moe_utils.py:308) -> (gather_index = sorted flat ids, expert tile ids, padded offsets)."""
+    r = M.moe_align_sort(topk_ids, num_experts, block_m)
+    return r.sorted_ids, r.tile_expert, r.expert_offsets
+
+
+histogram_by_expert_triton = M.histogram_by_expert
+reduce_topk_tma = reduce_topk_non_tma = M.reduce_topk
+
+
+# ---- all_to_all_single_gemm.py / Ulysses GEMM fusions ----------------------------------------------------------
+def create_all_to_all_single_gemm_context(max_rows_per_peer: int, K: int, dtype: torch.dtype) -> AllToAllContext:
+    return create_all_to_all_single_2d_context(max_rows_per_peer, K, dtype)
+
+
+def all_to_all_single_gemm(ctx: AllToAllContext, x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """(all_to_all_single_gemm.py:74-188) AllToAll (rows) then ``@ w.T``; here: push all-to-all kernel + tcgen05 GEMM on
+    the same stream (the GEMM starts when the whole exchange has landed)."""
+    return _lin(all_to_all_single_2d(ctx, x), w)
+
+
+def gemm_only(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    return _lin(x, w)
+
+
+class SpUlysessQKVGemmAll2AllKernel:
+    """(sp_ulysess_qkv_gemm_all2all.py:545-963) QKV projection of the local sequence shard, then head<->sequence
+    all-to-all: ``[S/W, H] -> q,k,v [S, heads/W, D]``."""
+
+    def __init__(self, max_local_seq: int, num_q_heads: int, num_kv_heads: int, head_dim: int, dtype, rank: int, world_size: int):
+        from ..parallel.sp import UlyssesSPAllToAllLayer
+        self.Hq, self.Hkv, self.D, self.W = num_q_heads, num_kv_heads, head_dim, world_size
+        self.a2a_q = UlyssesSPAllToAllLayer(max_local_seq, num_q_heads, head_dim, dtype, rank, world_size)
+        self.a2a_kv = UlyssesSPAllToAllLayer(max_local_seq, num_kv_heads, head_dim, dtype, rank, world_size)
+
+    def forward(self, x: torch.Tensor, wqkv: torch.Tensor):
+        qkv = _lin(x, wqkv)
+        S = x.shape[0]
+        q, k, v = qkv.split([self.Hq * self.D, self.Hkv * self.D, self.Hkv * self.D], dim=-1)
+        return (self.a2a_q.pre_attn_a2a(q.reshape(S, self.Hq, self.D).contiguous()),
+                self.a2a_kv.pre_attn_a2a(k.reshape(S, self.Hkv, self.D).contiguous()),
+                self.a2a_kv.pre_attn_a2a(v.reshape(S, self.Hkv, self.D).contiguous()))
+
+    pre_attn_a2a = qkv_pack_a2a = forward
+
+    def finalize(self):
+        self.a2a_q.finalize(); self.a2a_kv.finalize()
+
+
+class SpUlysessOAll2AllGemmKernel:
+    """(sp_ulysess_o_all2all_gemm.py) attention output ``[S, heads/W, D]`` -> all-to-all -> ``[S/W, heads * D] @ wo.T``."""
+
+    def __init__(self, max_local_seq: int, num_q_heads: int, head_dim: int, dtype, rank: int, world_size: int):
+        from ..parallel.sp import UlyssesSPAllToAllLayer
+        self.a2a = UlyssesSPAllToAllLayer(max_local_seq, num_q_heads, head_dim, dtype, rank, world_size)
+
+    def forward(self, attn_out: torch.Tensor, wo: torch.Tensor) -> torch.Tensor:
+        o = self.a2a.post_attn_a2a(attn_out)
+        return _lin(o.reshape(o.shape[0], -1).contiguous(), wo)
+
+    post_attn_a2a = forward
+
+    def finalize(self):
+        self.a2a.finalize()
+
+
+UlyssesSpInferPreAttnContext = SpUlysessQKVGemmAll2AllKernel
+
+
+def ulysses_sp_infer_gemm_a2a_op(ctx: SpUlysessQKVGemmAll2AllKernel, x, wqkv):
+    return ctx.forward(x, wqkv)
+
+
+# ---- ep_a2a.py (normal mode) ----------------------------------------------------------------------------------
+def ep_dispatch_token_inplace(layer, x, topk_idx):
+    """(ep_a2a.py:881) throughput-mode dispatch = the same NVLink push protocol with bf16 payloads."""
+    return layer.dispatch(x, None, topk_idx)
+
+
+def ep_combine_token_inplace(layer, expert_out, topk_idx, topk_weights, meta):
+    return layer.combine(expert_out, topk_idx, topk_weights, meta)
+
+
+def get_ag_splits_and_recv_offset_for_dispatch(topk_idx: torch.Tensor, num_experts: int):
+    """(ep_a2a.py:765) per-expert token counts on this rank (the receive offsets are produced inside dispatch)."""
+    return M.histogram_by_expert(topk_idx, num_experts)
