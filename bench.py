@@ -238,6 +238,29 @@ def main():
             "nccl_cublas_ms_per_step": round(ms_nccl, 4), "speedup_vs_nccl_cublas": round(ms_nccl / ms_step, 3),
             "published_reference_speedup_vs_nccl": PUBLISHED_RS_SPEEDUP,
         })
+        # BASELINE config #3: the same GEMM-RS with block-scaled fp8 operands (MXFP8: e4m3 + UE8M0 scale per 32 K-elements)
+        try:
+            from triton_dist.ops.fp8 import quantize_mxfp8
+            from triton_dist.ops.gemm import GemmConfig
+            from triton_dist.ops.gemm_rs import gemm_rs_mxfp8
+            qa, qb = quantize_mxfp8(sets[0]["rs_a"]), quantize_mxfp8(sets[0]["rs_b"])
+            best = None
+            Mr = RS["M"] // W
+            for bn in (128, 256):
+                cg = 2 if Mr % 256 == 0 else 1
+                cfg = GemmConfig(bn=bn, cta_group=cg, group_m=max(1, Mr // (128 * cg)) if W > 1 else 8, use_tma_store=(W == 1))
+                try:
+                    t = timed(lambda i: gemm_rs_mxfp8(qa, qb, rs_ctx, out=rs_out, gemm_config=cfg), steps2, 3)
+                except Exception as e:      # noqa: BLE001
+                    continue
+                if best is None or t < best[0]:
+                    best = (t, bn, cg)
+            if best:
+                result["gemm_rs_mxfp8"] = {"ms": round(best[0], 4), "tflops_total": round(flops_rs / best[0] / 1e9, 1), "bn": best[1],
+                                           "cta_group": best[2], "note": "operands pre-quantised (weights offline, activations by the producer)"}
+            del qa, qb
+        except Exception as e:      # noqa: BLE001
+            result["gemm_rs_mxfp8"] = {"error": str(e)[:200]}
         if W > 1:
             result["vs_baseline"] = round((ms_nccl / ms_step) / PUBLISHED_RS_SPEEDUP, 3)
             result["vs_baseline_note"] = ("BASELINE.md publishes only speedups over PyTorch+NCCL (closest point: GEMM-RS m4096 n12288 k49152 "

@@ -14,10 +14,11 @@
 //     allocator, warps4-7 = epilogue (tcgen05.ld -> 16-bit -> swizzled smem -> TMA store or coalesced st.global).
 //   * optional CTA pairs (cta_group::2, UMMA 256 x BN x 16) with the B tile split across the pair.
 //   * double-buffered TMEM accumulators: the epilogue of tile i overlaps the mainloop of tile i+1.
-//   * kAG: "comm CTAs" of the same grid pull the peers' A shards over NVLink with TMA bulk copies
-//     (peer HBM -> smem ring -> local symmetric workspace) and bump per-(source, 128-row chunk) arrival
-//     counters; the TMA producer warp of a GEMM CTA acquires the counters of the rows it is about to load.
-//     The reference signals once per source rank from the host copy engine (allgather.py:100-124).
+//   * kAG: "comm CTAs" of the same grid PUSH this rank's A shard into every peer's symmetric workspace over
+//     NVLink (coalesced 16-byte stores, one byte-slice per comm CTA, nearest consumer first) and publish one
+//     release flag per (source, slice) on the destination; the TMA producer warp of a GEMM CTA acquires the
+//     flags of the rows it is about to load.  The reference copies with the host copy engine and signals once
+//     per source rank (allgather.py:100-124).
 //   * kRS: the reduce-scatter is a ring fused into the epilogue: the tile for owner o is computed by rank
 //     o-1 first, pushed (coalesced 16-byte stores over NVLink) into rank o-2's staging buffer, which adds
 //     its own TMEM accumulator and forwards, ... until rank o adds the last partial and writes the output.
@@ -42,10 +43,6 @@ constexpr int kCBlockCols = 64;                       // epilogue staging block:
 constexpr int kCBlockBytes = BM * kCBlockCols * 2;
 constexpr int kAGRowsPerChunk = 128;                  // AG arrival-flag granularity (rows of a source shard)
 constexpr int kAGMaxSlices = 64;                      // max comm CTAs (= arrival flags per source rank)
-constexpr int kCommPieceBytes = 16 * 1024;            // one TMA bulk copy
-constexpr int kCommRingSlots = 12;                    // 192 KB smem ring in a comm CTA
-constexpr int kCommLag = 8;                           // pushed pieces allowed to be incomplete before the oldest is awaited
-constexpr int kCommLoadAhead = 3;                     // local loads issued ahead of the store stream
 
 enum Mode : int { kPlain = 0, kAG = 1, kRS = 2 };
 
@@ -122,8 +119,7 @@ struct SmemLayout {
   static constexpr int kNumBars = 2 * kStages + 4;
   static constexpr int kExtraOff = ((kBarOff + kNumBars * 8 + 16 + 127) / 128) * 128;   // optional comm ring (AG mode)
   static constexpr int kGemmBytes = kExtraOff + kExtra;
-  static constexpr int kCommBytes = kCommRingSlots * kCommPieceBytes + 256;   // comm CTA: kCommStreams x 2 x 16 KB rings + mbarriers
-  static constexpr int kTotal = (kGemmBytes > kCommBytes ? kGemmBytes : kCommBytes) + 1024;  // + alignment slack
+  static constexpr int kTotal = kGemmBytes + 1024;  // + alignment slack (comm CTAs use no shared memory)
   static_assert(kStageBytes % 1024 == 0, "stage must keep 1024 B alignment for SWIZZLE_128B");
   static_assert(kTotal <= 232448, "exceeds 227 KB of shared memory");
 };
