@@ -78,9 +78,8 @@ def packed_tile_experts(counts: torch.Tensor, cap: int, block_m: int = 128) -> t
 def grouped_ffn_packed(x_packed: torch.Tensor, counts: torch.Tensor, w_gate_up: torch.Tensor, w_down: torch.Tensor) -> torch.Tensor:
     """SwiGLU FFN over the packed rows: x_packed [epr, cap, H] -> [epr, cap, H]; rows >= count are don't-care."""
     epr, cap, H = x_packed.shape
-    if cap % 128 == 0 and x_packed.is_cuda or not x_packed.is_cuda:
-        te = packed_tile_experts(counts, cap, 128) if cap % 128 == 0 else None
-    if te is None or (x_packed.is_cuda and cap % 128):
+    te = packed_tile_experts(counts, cap, 128) if cap % 128 == 0 else None
+    if te is None:
         out = torch.zeros_like(x_packed)
         for le in range(epr):
             n = int(counts[le])
