@@ -109,6 +109,27 @@ for n in ([2048, 65536, 1 << 20, 16 << 20, 64 << 20] if not quick else [65536, 1
         if n > (1 << 20) and m == comm.AllReduceMethod.OneShot: continue
         t = timed(lambda: comm.all_reduce(x, m, arctx, output=o), 20, 5)
         emit(dict(op="all_reduce", bytes=n, W=W, method=m.name, us=t * 1e3, nccl_us=t_nccl * 1e3, busbw_gbs=2 * (W - 1) / W * n / t / 1e6))
+# small-message latency without Python launch overhead: 20 calls captured in one CUDA graph
+def graph_us(fn, n=20):
+    s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(3): fn()
+    torch.cuda.current_stream().wait_stream(s); torch.cuda.synchronize(); dist.barrier(group=grp)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(n): fn()
+    torch.cuda.synchronize(); dist.barrier(group=grp)
+    return timed(g.replay, 10, 3) * 1e3 / n
+for n in (2048, 8192, 65536, 1 << 20):
+    x = torch.randn(n // 2, device=dev, dtype=bf); o = torch.empty_like(x)
+    try:
+        t_nccl = graph_us(lambda: dist.all_reduce(x, group=grp))
+    except Exception as e:
+        t_nccl = float("nan")
+    for m in (comm.AllReduceMethod.OneShot, comm.AllReduceMethod.OneShot_Multimem, comm.AllReduceMethod.TwoShot_Multimem):
+        if "Multimem" in m.name and not U.is_nvshmem_multimem_supported(): continue
+        t = graph_us(lambda: comm.all_reduce(x, m, arctx, output=o))
+        emit(dict(op="all_reduce_graph", bytes=n, W=W, method=m.name, us=t, nccl_us=t_nccl))
 if me == 0:
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(rows, open(f"gpurun_out/sweep_dist_n{W}.json", "w"), indent=1)
