@@ -87,6 +87,8 @@ class ClockSampler:
 def main():
     args = parse()
     if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return 0
         print(json.dumps({"impl": "reference", "unavailable":
                           "reference setup.py downloads LLVM/Triton/NVSHMEM deps at build time (urllib URLError: no network); "
                           "pip install --no-index of /root/reference/python fails in metadata preparation (see DESIGN.md)"}))
