@@ -27,7 +27,7 @@ struct TdGemmArgs {
   long long rank, world; unsigned long long symm_base, symm_stride, mc_base;
   void* phase;
   // AG
-  long long ag_rows_per_rank, ag_copy_local, ag_skip_wait;
+  long long ag_rows_per_rank, ag_copy_local, ag_skip_wait;   // ag_skip_wait: 1 = GEMM-only twin, 2 = transfer done by the copy engine (1 flag per source)
   const void* ag_a_local; void* ag_ws; long long ag_ws_buf_bytes; void* ag_flags; void* ag_ready;
   // RS
   long long rs_rows_per_rank; void* rs_stage; long long rs_stage_buf_bytes; void* rs_flags; void* rs_out; long long rs_ldo;
@@ -157,7 +157,7 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
   p.symm.rank = (int)a->rank; p.symm.world = (int)a->world;
   p.symm.base = a->symm_base; p.symm.stride = a->symm_stride; p.symm.mc_base = a->mc_base;
   p.phase = reinterpret_cast<uint32_t*>(a->phase);
-  p.ag_rows_per_rank = (int)a->ag_rows_per_rank; p.ag_copy_local = (int)a->ag_copy_local; p.ag_skip_wait = (int)a->ag_skip_wait;
+  p.ag_rows_per_rank = (int)a->ag_rows_per_rank; p.ag_copy_local = (int)a->ag_copy_local; p.ag_skip_wait = (a->ag_skip_wait == 1) ? 1 : 0;
   p.ag_a_local = a->ag_a_local; p.ag_ws = reinterpret_cast<char*>(a->ag_ws); p.ag_ws_buf_bytes = a->ag_ws_buf_bytes;
   p.ag_flags = reinterpret_cast<uint32_t*>(a->ag_flags); p.ag_ready = reinterpret_cast<uint32_t*>(a->ag_ready);
   p.rs_rows_per_rank = (int)a->rs_rows_per_rank; p.rs_stage = reinterpret_cast<char*>(a->rs_stage);
@@ -176,10 +176,12 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
   if (gemm_ctas < cg) { drv::set_error("no CTAs left for the GEMM (n_comm_ctas too large)"); return -1; }
   if (gemm_ctas / cg > tiles) gemm_ctas = tiles * cg;
   if (a->tile_expert && a->group_m > 1) p.group_m = 1;   // grouped: keep experts' tiles together (n fastest)
-  if (a->mode == kAG && a->world > 1 && !a->ag_skip_wait) {
+  if (a->mode == kAG && a->world > 1 && a->ag_skip_wait == 0) {
     if (p.n_comm_ctas < cg) p.n_comm_ctas = 16;
     if (p.n_comm_ctas > kAGMaxSlices) p.n_comm_ctas = kAGMaxSlices;
   }
+  if (a->mode == kAG && a->ag_skip_wait == 2) p.n_comm_ctas = 0;      // copy-engine transport: every SM runs GEMM tiles
+  p.ag_nslices = (a->ag_skip_wait == 2) ? 1 : p.n_comm_ctas;
   grid = gemm_ctas + p.n_comm_ctas;
 
   if (a->mode == kRS) {

@@ -83,7 +83,7 @@ struct Params {
   int ag_rows_per_rank;      // rows of A owned by each rank
   int ag_copy_local;         // 1: comm CTAs copy a_local -> workspace; 0: caller already wrote the workspace
   int ag_skip_wait;          // GEMM-only twin: never wait (measures exposed communication)
-  int pad1;
+  int ag_nslices;            // arrival flags per source rank (= comm CTAs, or 1 when the copy engine does the transfer)
   const void* ag_a_local;    // my shard [rows_per_rank, K]
   char* ag_ws;               // my workspace: 2 buffers of [world * rows_per_rank, K] (symmetric)
   long long ag_ws_buf_bytes; // bytes of one buffer
@@ -156,7 +156,7 @@ TD_DEVICE void ag_wait_rows(const Params& p, uint32_t ph, int row0, int row1) {
   const int Ms = p.ag_rows_per_rank;
   const size_t row_bytes = static_cast<size_t>(p.K) * 2;
   const size_t shard_bytes = static_cast<size_t>(Ms) * row_bytes;
-  const size_t slice = ag_slice_bytes(shard_bytes, p.n_comm_ctas);
+  const size_t slice = ag_slice_bytes(shard_bytes, p.ag_nslices);
   const uint32_t* flags = p.ag_flags + (ph & 1u) * p.symm.world * kAGMaxSlices;
   int r = row0;
   while (r < row1) {
@@ -188,7 +188,7 @@ TD_DEVICE void ag_comm_cta(const Params& p, uint32_t ph, int comm_idx) {
   const int W = p.symm.world, me = p.symm.rank, Ms = p.ag_rows_per_rank;
   const size_t row_bytes = static_cast<size_t>(p.K) * 2;
   const size_t shard_bytes = static_cast<size_t>(Ms) * row_bytes;
-  const size_t slice = ag_slice_bytes(shard_bytes, p.n_comm_ctas);
+  const size_t slice = ag_slice_bytes(shard_bytes, p.ag_nslices);
   const size_t b0 = min(shard_bytes, slice * comm_idx), b1 = min(shard_bytes, b0 + slice);
   char* ws = p.ag_ws + (ph & 1u) * p.ag_ws_buf_bytes;
   const size_t shard_off = static_cast<size_t>(me) * Ms * row_bytes;

@@ -66,6 +66,15 @@ for (M, N, K) in AG_SHAPES:
                               exposed_us=(t - t_twin) * 1e3, tflops=flops / t / 1e9, speedup=t_nccl / t, max_err=err))
                 except Exception as e:
                     emit(dict(op="ag_gemm", M=M, N=N, K=K, cg=cg, bn=bn, n_comm=nc, error=str(e)[:200]))
+            try:
+                cfg = GemmConfig(bn=bn, cta_group=cg, group_m=max(1, (M // W) // (128 * cg)), use_tma_store=True, n_comm_ctas=0)
+                c = ag_gemm(A, B.t(), ctx, gemm_config=cfg, out=out, transport="copy_engine")
+                err = (c.float() - ref).abs().max().item()
+                t = timed(lambda: ag_gemm(A, B.t(), ctx, gemm_config=cfg, out=out, transport="copy_engine"))
+                emit(dict(op="ag_gemm", M=M, N=N, K=K, W=W, impl="ours(copy_engine)", cg=cg, bn=bn, n_comm=0, ms=t, gemm_only_ms=t_twin,
+                          exposed_us=(t - t_twin) * 1e3, tflops=flops / t / 1e9, speedup=t_nccl / t, max_err=err))
+            except Exception as e:
+                emit(dict(op="ag_gemm", M=M, N=N, K=K, cg=cg, bn=bn, impl="ours(copy_engine)", error=str(e)[:200]))
     U.barrier_all_host(); ctx.finalize()
 
 for (M, N, K) in RS_SHAPES:

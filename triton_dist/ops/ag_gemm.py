@@ -41,7 +41,7 @@ class AllGatherGEMMTensorParallelContext:
     phase: torch.Tensor = None         # local int32 [4]
     n_comm_ctas: int = 16
     host_phase: int = 0                # emulation backend / bookkeeping mirror
-    _twin: "AllGatherGEMMTensorParallelContext" = None
+    _ce_stream: object = None
 
     @property
     def symm_workspace(self):
@@ -116,9 +116,15 @@ def default_ag_config(M: int, N: int, K: int, world: int) -> GemmConfig:
 
 def ag_gemm(A: torch.Tensor, B: torch.Tensor, ctx: AllGatherGEMMTensorParallelContext,
             gemm_config: Optional[GemmConfig] = None, straggler_option=None, debug: bool = False,
-            out: Optional[torch.Tensor] = None, skip_wait: bool = False, profiler=None, **_unused) -> torch.Tensor:
+            out: Optional[torch.Tensor] = None, skip_wait: bool = False, profiler=None, transport: str = "sm",
+            **_unused) -> torch.Tensor:
     """A: ``[M/W, K]`` local shard, B: ``[K, N/W]`` -> ``[M, N/W]``.  ``skip_wait`` runs the GEMM-only twin
-    (flags ignored) used to measure exposed communication, like the reference's ``fake_barrier`` path."""
+    (flags ignored) used to measure exposed communication, like the reference's ``fake_barrier`` path.
+
+    ``transport="sm"`` (default): comm CTAs inside the GEMM kernel push the shard.  ``transport="copy_engine"``: the
+    shard is pushed by the DMA engines on a side stream (one ``cudaMemcpyAsync`` + one release-flag kernel per peer, as
+    the reference's copy-engine producer, allgather.py:100-124) while all SMs run GEMM tiles that wait on the same
+    per-source flags; not CUDA-graph replayable (flag values are written from the host-tracked phase)."""
     W = ctx.num_ranks
     Ms, K = A.shape
     Bnk = _as_nk(B)
@@ -155,12 +161,33 @@ def ag_gemm(A: torch.Tensor, B: torch.Tensor, ctx: AllGatherGEMMTensorParallelCo
     args.ag_flags, args.ag_ready = ctx.flags.data_ptr(), ctx.ready.data_ptr()
     if skip_wait:
         args.n_comm_ctas = 0
+    if transport == "copy_engine" and not skip_wait:
+        _ce_push(ctx, A, ph, Ms, K)
+        args.ag_skip_wait, args.ag_copy_local, args.n_comm_ctas = 2, 1, 0
     if profiler is not None:
         profiler.attach(args)
     _C.check(_C.cuda_lib().td_gemm_launch(C.byref(args), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
              "td_gemm_launch(ag)")
     ctx.host_phase = ph
+    if transport == "copy_engine" and not skip_wait:
+        torch.cuda.current_stream().wait_stream(ctx._ce_stream)     # A may be reused only after the DMA reads finished
     return out
+
+
+def _ce_push(ctx, A, ph, Ms, K):
+    """Copy-engine transport: push my shard into every rank's workspace[ph & 1] and raise flag[src=me][0] = ph there."""
+    from .. import language as dl
+    heap = U.get_heap()
+    if getattr(ctx, "_ce_stream", None) is None:
+        ctx._ce_stream = torch.cuda.Stream(priority=-1)
+    W, me, par = ctx.num_ranks, ctx.rank, ph & 1
+    ctx._ce_stream.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(ctx._ce_stream):
+        for dist_ in range(W):
+            d = (me - dist_ + W) % W
+            dst = heap.peer_view(ctx.workspace, d)[par, me * Ms:(me + 1) * Ms, :K]
+            dst.copy_(A, non_blocking=True)
+            dl.notify(ctx.flags[par, me, 0:1], d, signal=ph, sig_op="set")
 
 
 def gemm_only(A_full: torch.Tensor, B: torch.Tensor, out: Optional[torch.Tensor] = None,
