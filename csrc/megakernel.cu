@@ -36,7 +36,9 @@ struct MKParams {
   const int* queue_off;        // [grid + 1] range of each CTA's queue
   void* const* ptrs;           // pointer table referenced by the tasks
   uint32_t* sb;                // scoreboard counters (monotone)
-  uint32_t* epoch;             // [0] completed steps, [1] exit counter
+  uint32_t* epoch;             // [0] completed steps, [1] exit counter, [2] dynamic-scheduler cursor
+  int dynamic;                 // 1: one global queue, CTAs fetch the next task with atomicAdd (runtime scheduler)
+  int num_tasks;
   SymmCtx symm;
   int B;
 };
@@ -324,8 +326,19 @@ __global__ void __launch_bounds__(kMKThreads, 1) mega_kernel(const MKParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ float red[32];
   const uint32_t epoch = p.epoch[0] + 1;
-  const int q0 = p.queue_off[blockIdx.x], q1 = p.queue_off[blockIdx.x + 1];
-  for (int qi = q0; qi < q1; ++qi) {
+  __shared__ int s_next;
+  int qi = p.dynamic ? 0 : p.queue_off[blockIdx.x];
+  const int q1 = p.dynamic ? p.num_tasks : p.queue_off[blockIdx.x + 1];
+  while (true) {
+    if (p.dynamic) {
+      // runtime scheduler (reference core/scheduler.py: global queue + atomic_add): tasks are stored in topological
+      // order, so whoever holds task k only ever waits for tasks < k, which are done or held by a running CTA
+      if (threadIdx.x == 0) s_next = static_cast<int>(atomicAdd(p.epoch + 2, 1u));
+      __syncthreads();
+      qi = s_next;
+      __syncthreads();
+    }
+    if (qi >= q1) break;
     const Task& t = p.tasks[qi];
     if (t.dep_idx >= 0) {
       if (threadIdx.x == 0) {
@@ -348,11 +361,12 @@ __global__ void __launch_bounds__(kMKThreads, 1) mega_kernel(const MKParams p) {
       __threadfence();
       ptx::red_release_gpu_add(p.sb + t.sig_idx, 1u);
     }
+    if (!p.dynamic) ++qi;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    if (atomicAdd(p.epoch + 1, 1u) == gridDim.x - 1) { p.epoch[1] = 0; __threadfence(); p.epoch[0] = epoch; }
+    if (atomicAdd(p.epoch + 1, 1u) == gridDim.x - 1) { p.epoch[1] = 0; p.epoch[2] = 0; __threadfence(); p.epoch[0] = epoch; }
   }
 }
 
@@ -363,7 +377,7 @@ struct TdSymmArgs { long long rank, world; unsigned long long base, stride, mc_b
 struct TdMegaArgs {
   TdSymmArgs symm;
   const void* tasks; const void* queue_off; const void* ptrs; void* sb; void* epoch;
-  long long B, grid, smem_bytes;
+  long long B, grid, smem_bytes, dynamic, num_tasks;
 };
 
 TD_API int td_mega_task_size() { return (int)sizeof(Task); }
@@ -374,7 +388,7 @@ TD_API int td_mega_launch(const TdMegaArgs* a, void* stream) {
   p.tasks = (const Task*)a->tasks; p.queue_off = (const int*)a->queue_off; p.ptrs = (void* const*)a->ptrs;
   p.sb = (uint32_t*)a->sb; p.epoch = (uint32_t*)a->epoch;
   p.symm.rank = (int)a->symm.rank; p.symm.world = (int)a->symm.world; p.symm.base = a->symm.base; p.symm.stride = a->symm.stride; p.symm.mc_base = a->symm.mc_base;
-  p.B = (int)a->B;
+  p.B = (int)a->B; p.dynamic = (int)a->dynamic; p.num_tasks = (int)a->num_tasks;
   static long long smem_set = 0;
   if (a->smem_bytes > smem_set) {
     TD_CUDA_CHECK(cudaFuncSetAttribute(mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a->smem_bytes));

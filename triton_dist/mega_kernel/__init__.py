@@ -26,7 +26,8 @@ TASK_NAMES = {1: "rms_norm", 2: "linear", 3: "qk_norm_rope_update_kvcache", 4: "
 
 class _MegaArgs(C.Structure):
     _fields_ = [("symm", SymmArgs), ("tasks", C.c_void_p), ("queue_off", C.c_void_p), ("ptrs", C.c_void_p), ("sb", C.c_void_p),
-                ("epoch", C.c_void_p), ("B", C.c_longlong), ("grid", C.c_longlong), ("smem_bytes", C.c_longlong)]
+                ("epoch", C.c_void_p), ("B", C.c_longlong), ("grid", C.c_longlong), ("smem_bytes", C.c_longlong),
+                ("dynamic", C.c_longlong), ("num_tasks", C.c_longlong)]
 
 
 _C.register("td_mega_launch", C.c_int, [C.POINTER(_MegaArgs), C.c_void_p])
@@ -147,7 +148,10 @@ class ModelBuilder:
 
     # ---- scheduling + compile ----
     def schedule(self) -> List[List[Task]]:
-        """Static per-CTA queues.  round_robin: task i -> CTA i % n;  zig_zag: alternate direction every sweep."""
+        """Static per-CTA queues.  round_robin: task i -> CTA i % n;  zig_zag: alternate direction every sweep;
+        dynamic: one global queue in program order, CTAs pull tasks with an atomic counter at run time."""
+        if self.schedule_policy == "dynamic":
+            return [list(self.tasks)] + [[] for _ in range(self.num_sms - 1)]
         n = self.num_sms
         queues: List[List[Task]] = [[] for _ in range(n)]
         for i, t in enumerate(self.tasks):
@@ -185,6 +189,7 @@ class ModelBuilder:
         a.tasks, a.queue_off, a.ptrs = self.task_tensor.data_ptr(), self.queue_off.data_ptr(), self.ptr_tensor.data_ptr()
         a.sb, a.epoch = self.sb.data_ptr(), self.epoch.data_ptr()
         a.B, a.grid, a.smem_bytes = self.B, self.num_sms, self.max_smem
+        a.dynamic, a.num_tasks = int(self.schedule_policy == "dynamic"), len(self.tasks)
         _C.check(_C.cuda_lib().td_mega_launch(C.byref(a), C.c_void_p((stream or torch.cuda.current_stream()).cuda_stream)), "td_mega_launch")
 
     # emulation: interpret the task list in program order with torch ops on the same buffers

@@ -390,3 +390,21 @@ def barrier_async(pg=None):
 from .lazy import LazyAllocator, LazyTensor, NVSHMEMLazyAllocator  # noqa: E402,F401
 from .topology import (get_device_info, get_intranode_max_speed_gbps, get_nvlink_max_speed_gbps,  # noqa: E402,F401
                        has_fullmesh_nvlink, get_numa_node)
+
+
+def generate_data(configs, device=None):
+    """Yield fresh random tensors for ``[(shape, dtype, scale), ...]`` (reference: utils.py:_make_tensor/generate_data):
+    tests draw new inputs every iteration so stale-buffer bugs cannot hide behind identical data."""
+    device = device or _STATE["device"]
+    while True:
+        yield [rand_tensor(shape, dtype, device, scale) for (shape, dtype, scale) in configs]
+
+
+def triton_dist_key() -> str:
+    """Hash of the native sources (cache-key ingredient of the autotuner; reference: utils.py triton_dist_key)."""
+    import hashlib
+    from pathlib import Path
+    h = hashlib.sha1()
+    for p in sorted((Path(__file__).resolve().parents[2] / "csrc").rglob("*.cu*")):
+        h.update(p.read_bytes())
+    return h.hexdigest()[:16]
