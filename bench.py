@@ -125,9 +125,13 @@ def main():
     ag_ctx = create_ag_gemm_context(AG["M"], AG["N"] // W, AG["K"], bf)
     rs_ctx = create_gemm_rs_context(RS["M"], RS["N"], output_dtype=bf)
 
+    from triton_dist.ops.ag_gemm import default_ag_config
+    from triton_dist.ops.gemm import GemmConfig
+    ag_choice = {"transport": "sm", "cfg": None}
+
     def step_ours(i):
         s = sets[i % nset]
-        ag_gemm(s["ag_a"], s["ag_b"].t(), ag_ctx, out=ag_out)
+        ag_gemm(s["ag_a"], s["ag_b"].t(), ag_ctx, out=ag_out, gemm_config=ag_choice["cfg"], transport=ag_choice["transport"])
         gemm_rs(s["rs_a"], s["rs_b"].t(), rs_ctx, out=rs_out)
 
     ag_full = torch.empty(AG["M"], AG["K"], device=dev, dtype=bf)
@@ -187,6 +191,23 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=grp)
         return t[0].item(), t[1].item()
 
+    # ---- untimed autotune of the all-gather transport (the reference autotunes ag_gemm too: allgather_gemm.py:565-619):
+    # in-kernel SM push with 16 / 32 comm CTAs vs copy-engine push; every rank adopts the max-over-ranks winner ----
+    if W > 1:
+        base = default_ag_config(AG["M"], AG["N"] // W, AG["K"], W)
+        cands = [("sm", GemmConfig(base.bn, base.cta_group, base.group_m, True, 0, nc)) for nc in (16, 32)]
+        cands.append(("copy_engine", GemmConfig(base.bn, base.cta_group, base.group_m, True, 0, 0)))
+        best = None
+        for tr, cfg in cands:
+            ag_choice.update(transport=tr, cfg=cfg)
+            try:
+                t = timed(lambda i: ag_gemm(sets[i % nset]["ag_a"], sets[i % nset]["ag_b"].t(), ag_ctx, out=ag_out, gemm_config=cfg, transport=tr), 8, 3)
+            except Exception:      # noqa: BLE001
+                continue
+            if best is None or t < best[0]:
+                best = (t, tr, cfg)
+        ag_choice.update(transport=best[1], cfg=best[2])
+
     # ---- headline ----
     sampler = ClockSampler()
     if me == 0:
@@ -204,14 +225,16 @@ def main():
         "dtype": "bf16", "data": "synthetic (random-init operands of the named shapes)",
         "config": {"model": "ag_gemm M4096 N4096 K4096 + gemm_rs M4096 N12288 K49152", "global_batch": 4096, "seq_len": 1,
                    "parallelism": f"tp{W}", "l2": f"inputs rotate over {nset} sets ({(ag_bytes + rs_bytes) * nset >> 20} MiB/rank > 2x L2)"},
-        "gpu_launches": 2 * args.steps, "impl": "ours", "native_libs": [os.path.basename(p) for p in _C.loaded_libraries()],
+        "gpu_launches": (2 + (W if ag_choice["transport"] == "copy_engine" and W > 1 else 0)) * args.steps, "impl": "ours",
+        "ag_transport": {"transport": ag_choice["transport"], "n_comm_ctas": ag_choice["cfg"].n_comm_ctas if ag_choice["cfg"] else 0}, "native_libs": [os.path.basename(p) for p in _C.loaded_libraries()],
         "clocks": clocks,
     }
 
     if not args.quick:
         steps2 = max(5, args.steps // 2)
         # per-op split + GEMM-only twins + NCCL/cuBLAS baseline
-        s_ag = lambda i: ag_gemm(sets[i % nset]["ag_a"], sets[i % nset]["ag_b"].t(), ag_ctx, out=ag_out)
+        s_ag = lambda i: ag_gemm(sets[i % nset]["ag_a"], sets[i % nset]["ag_b"].t(), ag_ctx, out=ag_out, gemm_config=ag_choice["cfg"],
+                                 transport=ag_choice["transport"])
         s_rs = lambda i: gemm_rs(sets[i % nset]["rs_a"], sets[i % nset]["rs_b"].t(), rs_ctx, out=rs_out)
         t_ag, t_rs = timed_parts(s_ag, s_rs, steps2, 3)
         tw_ag, tw_rs = timed_parts(lambda i: gemm(ag_full, sets[i % nset]["ag_b"], out=ag_out),
@@ -291,7 +314,7 @@ def main():
                     if i + 1 < n:
                         nxt = prefetch(i + 1)          # overlaps this step's compute (double buffered)
                     s = sets[i % nset]
-                    ag_gemm(dev_in[i % 2]["ag_a"], s["ag_b"].t(), ag_ctx, out=ag_out)
+                    ag_gemm(dev_in[i % 2]["ag_a"], s["ag_b"].t(), ag_ctx, out=ag_out, gemm_config=ag_choice["cfg"], transport=ag_choice["transport"])
                     gemm_rs(dev_in[i % 2]["rs_a"], s["rs_b"].t(), rs_ctx, out=rs_out)
                     checks.copy_(rs_out[0, :1].float() + ag_out[0, :1].float(), non_blocking=True)
                     copy_stream.wait_stream(torch.cuda.current_stream())   # next prefetch may not clobber live inputs

@@ -20,4 +20,17 @@ from ...ops.ep_a2a import combine_kernel_v2, create_ep_ll_a2a_ctx, dispatch_kern
 from ...ops.elementwise import swiglu_forward  # noqa: F401
 from ...ops.gdn import chunk_gated_delta_rule_fwd  # noqa: F401
 from ...parallel.sp import (create_sp_ag_attention_context_intra_node, fused_sp_ag_attn_intra_node)  # noqa: F401
+from ...ops.moe import histogram_by_expert as bincount  # noqa: F401
+from ...ops.compat import (SpUlysessOAll2AllGemmKernel, SpUlysessQKVGemmAll2AllKernel, UlyssesSpInferPreAttnContext,  # noqa: F401
+                           all_to_all_single_gemm, all_to_all_vdev_2d_offset, calc_gather_scatter_index_triton,
+                           create_all_to_all_single_gemm_context, create_reduce_scater_2d_ctx,
+                           create_ulysses_sp_pre_attn_comm_context, ep_combine_token_inplace, ep_dispatch_token_inplace,
+                           fused_sp_ag_attn_inter_node, get_ag_splits_and_recv_offset_for_dispatch, histogram_by_expert_triton,
+                           mega_kernel_dispatch_token_moe_grouped_gemm, mega_kernel_moe_grouped_gemm_combine_token,
+                           moe_grouped_gemm_2weights, pre_attn_qkv_pack_a2a_op, qkv_bsnd_to_bnsd, reduce_scatter_2d_op,
+                           reduce_topk_non_tma, reduce_topk_tma, ring_reduce, swiglu_backward, transposed_moe_grouped_gemm,
+                           ulysses_sp_infer_gemm_a2a_op)
+from ...ops.perf_model import (estimate_all_gather_time_ms, estimate_gemm_sol_time_ms, estimate_reduce_scatter_time_ms,  # noqa: F401
+                               get_dram_gbps, get_nic_gbps_per_gpu, get_tensorcore_tflops)
+from ...ops.p2p import p2p_get, p2p_put, p2p_set_signal, p2p_wait_signal  # noqa: F401
 from . import allreduce  # noqa: F401

@@ -70,3 +70,13 @@ def wait(barrier_ptrs: torch.Tensor, num_barriers: int = 1, scope: str = "sys", 
 def consume_token(value, token):
     """Identity; keeps the data dependence explicit in protocol code (DistributedOpToLLVM.cpp:231-241)."""
     return value
+
+
+import contextlib
+
+
+@contextlib.contextmanager
+def simt_exec_region():
+    """Device-side concept of the reference DSL (a region executed per thread instead of per block).  The CUDA kernels
+    of this framework are written in SIMT form already, so the host mirror is a no-op context."""
+    yield

@@ -2,6 +2,7 @@
 from .config import ARCHS, ArchConfig, ModelConfig  # noqa: F401
 from .kv_cache import KV_Cache  # noqa: F401
 from .dense import DenseLLM  # noqa: F401
+from .qwen_moe import Qwen3MoE  # noqa: F401
 from .utils import logger, sample_token, seed_everything  # noqa: F401
 
 

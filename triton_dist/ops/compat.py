@@ -157,3 +157,61 @@ def ep_combine_token_inplace(layer, expert_out, topk_idx, topk_weights, meta):
 def get_ag_splits_and_recv_offset_for_dispatch(topk_idx: torch.Tensor, num_experts: int):
     """(ep_a2a.py:765) per-expert token counts on this rank (the receive offsets are produced inside dispatch)."""
     return M.histogram_by_expert(topk_idx, num_experts)
+
+
+# ---- ulysses_sp_dispatch.py -----------------------------------------------------------------------------------
+def create_ulysses_sp_pre_attn_comm_context(max_local_seq: int, num_q_heads: int, num_kv_heads: int, head_dim: int, dtype,
+                                            rank: Optional[int] = None, world_size: Optional[int] = None):
+    """(ulysses_sp_dispatch.py:546) one context holding the q and kv all-to-all workspaces."""
+    heap = U.get_heap()
+    r = heap.rank if rank is None else rank
+    w = heap.world if world_size is None else world_size
+    return SpUlysessQKVGemmAll2AllKernel(max_local_seq, num_q_heads, num_kv_heads, head_dim, dtype, r, w)
+
+
+def pre_attn_qkv_pack_a2a_op(ctx: SpUlysessQKVGemmAll2AllKernel, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor):
+    """(ulysses_sp_dispatch.py:606) seq-sharded ``[S/W, H, D]`` q/k/v -> head-sharded ``[S, H/W, D]``."""
+    return ctx.a2a_q.pre_attn_a2a(q), ctx.a2a_kv.pre_attn_a2a(k), ctx.a2a_kv.pre_attn_a2a(v)
+
+
+def qkv_bsnd_to_bnsd(x: torch.Tensor) -> torch.Tensor:
+    """(ulysses_sp_dispatch.py:411) ``[B, S, N, D] -> [B, N, S, D]`` contiguous."""
+    out = torch.empty((x.shape[0], x.shape[2], x.shape[1], x.shape[3]), dtype=x.dtype, device=x.device)
+    out.copy_(x.transpose(1, 2))
+    return out
+
+
+# ---- all_to_all_vdev_2d_offset.py -------------------------------------------------------------------------------
+def all_to_all_vdev_2d_offset(ctx: AllToAllContext, send: torch.Tensor, in_splits: torch.Tensor, in_offsets: torch.Tensor,
+                              experts_per_rank: int):
+    """(all_to_all_vdev_2d_offset.py) variable all-to-all where the rows for (dst rank d, local expert e) start at
+    ``in_offsets[d * epr + e]`` (the rows are not packed).  The send buffer is compacted with one gather, then the
+    device-split all-to-all kernel runs; returns ``(recv, recv_splits[W, epr], recv_offsets)``."""
+    from .all_to_all import all_to_all_vdev_2d
+    n = in_splits.numel()
+    cum = torch.cumsum(in_splits.to(torch.int64), 0)
+    total = int(cum[-1].item()) if n else 0
+    seg = torch.repeat_interleave(torch.arange(n, device=send.device), in_splits.to(torch.int64), output_size=total)
+    within = torch.arange(total, device=send.device) - (cum - in_splits.to(torch.int64))[seg]
+    rows = in_offsets.to(torch.int64)[seg] + within
+    return all_to_all_vdev_2d(ctx, send.index_select(0, rows).contiguous(), in_splits, experts_per_rank)
+
+
+# ---- sp_ag_attention_inter_node.py --------------------------------------------------------------------------------
+def fused_sp_ag_attn_inter_node(ctx, q_shard, k_shard, v_shard, **kw):
+    """Multi-node variant of the context-parallel prefill.  This framework targets one NVSwitch domain (<= 72 GPUs on
+    NVL72 are one "node" for the symmetric heap), so it is the intra-node path (sp_ag_attention_inter_node.py:116-190)."""
+    from ..parallel.sp import fused_sp_ag_attn_intra_node
+    return fused_sp_ag_attn_intra_node(ctx, q_shard, k_shard, v_shard, **kw)
+
+
+# ---- ep_all2all_fused.py (Mega-EP entry points) -------------------------------------------------------------------
+def mega_kernel_dispatch_token_moe_grouped_gemm(ep_moe, x: torch.Tensor, topk_idx: torch.Tensor, topk_w: torch.Tensor):
+    """(ep_all2all_fused.py:839) dispatch + first grouped GEMM (+SwiGLU): returns the packed activations and the handle
+    combine needs.  ``ep_moe`` is a :class:`triton_dist.parallel.ep.EP_MoE`."""
+    return ep_moe.dispatch_group_gemm(x, topk_idx, topk_w)
+
+
+def mega_kernel_moe_grouped_gemm_combine_token(ep_moe, act: torch.Tensor, handle):
+    """(ep_all2all_fused.py:1020) second grouped GEMM + combine (weighted top-k reduce on the source rank)."""
+    return ep_moe.group_gemm_combine(act, handle)

@@ -161,10 +161,30 @@ class EP_MoE:
         shp = x.shape
         x2 = x.reshape(-1, shp[-1]).contiguous()
         ids, w = self._route(x2)
+        act, handle = self.dispatch_group_gemm(x2, ids, w)
+        return self.group_gemm_combine(act, handle).view(shp)
+
+    # the two halves the reference exposes as Mega-EP entry points (ep_all2all_fused.py:839, :1020)
+    def dispatch_group_gemm(self, x2: torch.Tensor, ids: torch.Tensor, w: torch.Tensor):
+        """dispatch -> grouped GEMM (gate|up) -> SwiGLU on the packed ``[epr, cap, *]`` layout."""
         rx, rs, cnt, meta = self.a2a.dispatch(x2, None, ids)
         xin = EP.dequant_fp8(rx, rs, self.dtype) if rs is not None else rx
-        y = grouped_ffn_packed(xin, cnt, self.w_gate_up, self.w_down)
-        return self.a2a.combine(y, ids, w, meta).view(shp)
+        epr, cap, H = xin.shape
+        if cap % 128:
+            return xin, (ids, w, meta, cnt, None)
+        r = M.SortedRouting(None, packed_tile_experts(cnt, cap, 128), None, None, epr * cap, 128, -1)
+        act = silu_mul(M.moe_grouped_gemm(xin.view(epr * cap, H), self.w_gate_up, r))
+        return act, (ids, w, meta, cnt, r)
+
+    def group_gemm_combine(self, act: torch.Tensor, handle) -> torch.Tensor:
+        """grouped GEMM (down) -> combine (weighted top-k reduce at the token's source rank)."""
+        ids, w, meta, cnt, r = handle
+        if r is None:
+            y = grouped_ffn_packed(act, cnt, self.w_gate_up, self.w_down)
+        else:
+            epr = cnt.numel()
+            y = M.moe_grouped_gemm(act, self.w_down, r).view(epr, -1, self.hidden)
+        return self.a2a.combine(y, ids, w, meta)
 
 
 # ------------------------------------------------------------------------------------------------------------
