@@ -1,0 +1,377 @@
+// Flash-attention forward for sm_100a: QK^T and PV on tcgen05 tensor cores, accumulators (S double-buffered, O) in
+// TMEM, Q/K/V staged by TMA, online softmax by one warpgroup reading S straight out of TMEM (one query row per
+// thread, no shuffles), P handed back to the tensor core through swizzled shared memory.
+//
+// Used by: prefill attention of the TP layers, context-parallel prefill over the gathered KV
+// (reference: kernels/nvidia/sp_ag_attention_intra_node.py:257-427 -- a Triton flash kernel with BM=128, BN=64,
+// varlen + GQA + causal + zig-zag), Ulysses attention.
+//
+// CTA = one 128-query tile of one (batch, q-head); 6 warps:
+//   warp 0      TMA producer: Q once, then K/V tiles of 128 keys through a 2-stage ring
+//   warp 1      TMEM allocation + MMA issuer (one elected thread): S[j&1] = Q K_j^T, O += P_j V_j
+//   warps 2-5   softmax: S -> registers (tcgen05.ld), mask, running max with lazy rescale, exp2, P (bf16) -> smem,
+//               O rescale in TMEM when the max moved, final O / l -> global (+ LSE)
+// QK^T of tile j+1 is issued before PV of tile j, so the tensor core works on S_{j+1} while the softmax warps
+// process S_j (the two S buffers ping-pong).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "runtime/driver.h"
+#include "td/ptx.cuh"
+
+namespace td {
+namespace fa {
+
+constexpr int BMQ = 128;          // queries per CTA
+constexpr int BNK = 128;          // keys per pipeline step
+constexpr int HD = 128;           // head dim
+constexpr int kThreads = 192;
+constexpr int kKVStages = 2;
+constexpr int kTileBytes = 128 * 128 * 2;     // one [128, 128] 16-bit tile = two 16 KB swizzle slabs
+constexpr int kSlab = 128 * 128;              // bytes of one [128 rows, 64 elements] slab
+
+struct Params {
+  CUtensorMap tmap_q, tmap_k, tmap_v;
+  void* o;                 // [B, Sq, Hq, D]
+  float* lse;              // [B, Hq, Sq] natural-log LSE (optional)
+  const int* q_tile_pos;   // [B, ceil(Sq/128)] position of the first query of each tile in the KV sequence (optional)
+  long long o_stride_b, o_stride_s, o_stride_h;
+  int B, Sq, Sk, Hq, Hkv;
+  int causal, is_bf16;
+  float scale_log2;        // sm_scale * log2(e)
+};
+
+struct Smem {
+  static constexpr int kQ = 0;
+  static constexpr int kK = kQ + kTileBytes;
+  static constexpr int kV = kK + kKVStages * kTileBytes;
+  static constexpr int kP = kV + kKVStages * kTileBytes;
+  static constexpr int kBar = kP + kTileBytes;
+  static constexpr int kTotal = kBar + 256 + 1024;
+};
+
+enum Bar { Q_FULL = 0, K_FULL = 1, V_FULL = 3, KV_EMPTY = 5, S_FULL = 7, S_FREE = 9, P_READY = 11, PV_DONE = 12, NBAR = 13 };
+
+__global__ void __launch_bounds__(kThreads, 1) flash_fwd_kernel(const __grid_constant__ Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::kBar);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + NBAR);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q_tile = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
+  const int kv_head = head / (p.Hq / p.Hkv);
+  const int n_q_tiles = gridDim.x;
+  const int q_row0 = q_tile * BMQ;
+  const int q_pos0 = p.q_tile_pos ? p.q_tile_pos[batch * n_q_tiles + q_tile] : q_row0 + (p.Sk - p.Sq);
+  const int rows_here = min(BMQ, p.Sq - q_row0);
+
+  int n_tiles = (p.Sk + BNK - 1) / BNK;
+  if (p.causal) n_tiles = min(n_tiles, (q_pos0 + rows_here - 1) / BNK + 1);
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&p.tmap_q);
+    ptx::prefetch_tensormap(&p.tmap_k);
+    ptx::prefetch_tensormap(&p.tmap_v);
+    ptx::mbar_init(&bars[Q_FULL], 1);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&bars[K_FULL + s], 1);
+      ptx::mbar_init(&bars[V_FULL + s], 1);
+      ptx::mbar_init(&bars[KV_EMPTY + s], 1);
+      ptx::mbar_init(&bars[S_FULL + s], 1);
+      ptx::mbar_init(&bars[S_FREE + s], 128);
+    }
+    ptx::mbar_init(&bars[P_READY], 128);
+    ptx::mbar_init(&bars[PV_DONE], 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc<1>(tmem_ptr_smem, 512);
+    ptx::tmem_relinquish<1>();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_o = tmem_base + 256;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(&bars[Q_FULL], kTileBytes);
+      ptx::tma_load_4d(&p.tmap_q, &bars[Q_FULL], smem + Smem::kQ, 0, q_row0, head, batch);
+      ptx::tma_load_4d(&p.tmap_q, &bars[Q_FULL], smem + Smem::kQ + kSlab, 64, q_row0, head, batch);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j & 1;
+        if (j >= kKVStages) ptx::mbar_wait(&bars[KV_EMPTY + st], ((j >> 1) - 1) & 1);
+        uint8_t* ks = smem + Smem::kK + st * kTileBytes;
+        uint8_t* vs = smem + Smem::kV + st * kTileBytes;
+        ptx::mbar_arrive_expect_tx(&bars[K_FULL + st], kTileBytes);
+        ptx::tma_load_4d(&p.tmap_k, &bars[K_FULL + st], ks, 0, j * BNK, kv_head, batch, ptx::kEvictLast);
+        ptx::tma_load_4d(&p.tmap_k, &bars[K_FULL + st], ks + kSlab, 64, j * BNK, kv_head, batch, ptx::kEvictLast);
+        ptx::mbar_arrive_expect_tx(&bars[V_FULL + st], kTileBytes);
+        ptx::tma_load_4d(&p.tmap_v, &bars[V_FULL + st], vs, 0, j * BNK, kv_head, batch, ptx::kEvictLast);
+        ptx::tma_load_4d(&p.tmap_v, &bars[V_FULL + st], vs + kSlab, 64, j * BNK, kv_head, batch, ptx::kEvictLast);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t fmt = p.is_bf16 ? 1u : 0u;
+      const uint32_t idesc_qk = ptx::make_idesc(fmt, fmt, BMQ, BNK);
+      const uint32_t idesc_pv = ptx::make_idesc(fmt, fmt, BMQ, HD, 0, 1);       // V is the MN-major B operand
+      const uint32_t q_addr = ptx::smem_u32(smem + Smem::kQ);
+      const uint32_t p_addr = ptx::smem_u32(smem + Smem::kP);
+      auto issue_qk = [&](int j) {
+        const int st = j & 1, b = j & 1;
+        ptx::mbar_wait(&bars[K_FULL + st], (j >> 1) & 1);
+        if (j >= 2) ptx::mbar_wait(&bars[S_FREE + b], ((j >> 1) - 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t k_addr = ptx::smem_u32(smem + Smem::kK + st * kTileBytes);
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * kSlab + (kk & 3) * 32;
+          ptx::mma_f16<1>(tmem_base + b * BNK, ptx::make_smem_desc_k128(q_addr + off), ptx::make_smem_desc_k128(k_addr + off),
+                          idesc_qk, kk > 0 ? 1u : 0u);
+        }
+        ptx::mma_commit(&bars[S_FULL + b]);
+      };
+      ptx::mbar_wait(&bars[Q_FULL], 0);
+      if (n_tiles > 0) issue_qk(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j & 1;
+        if (j + 1 < n_tiles) issue_qk(j + 1);
+        ptx::mbar_wait(&bars[V_FULL + st], (j >> 1) & 1);
+        ptx::mbar_wait(&bars[P_READY], j & 1);
+        ptx::tc_fence_after();
+        const uint32_t v_addr = ptx::smem_u32(smem + Smem::kV + st * kTileBytes);
+#pragma unroll
+        for (int kk = 0; kk < BNK / 16; ++kk) {
+          const uint64_t a = ptx::make_smem_desc_k128(p_addr + (kk >> 2) * kSlab + (kk & 3) * 32);
+          const uint64_t bdesc = ptx::make_smem_desc_mn128(v_addr + kk * 16 * 128, kSlab);
+          ptx::mma_f16<1>(tmem_o, a, bdesc, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+        }
+        ptx::mma_commit(&bars[KV_EMPTY + st]);
+        ptx::mma_commit(&bars[PV_DONE]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax / correction / epilogue
+    const int quad = warp & 3;                       // TMEM lane quadrant this warp may touch
+    const int row = quad * 32 + lane;                // query row inside the tile
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const int q_pos = q_pos0 + row;
+    const uint32_t p_row = ptx::smem_u32(smem + Smem::kP) + row * 128;
+    float m_ref = -INFINITY, l = 0.f;
+
+    for (int j = 0; j < n_tiles; ++j) {
+      const int b = j & 1;
+      ptx::mbar_wait(&bars[S_FULL + b], (j >> 1) & 1);
+      ptx::tc_fence_after();
+      uint32_t s[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) ptx::tmem_ld_32x32b_x32(tmem_base + lane_off + b * BNK + c * 32, s[c]);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&bars[S_FREE + b]);
+
+      const int key0 = j * BNK;
+      const bool need_mask = (p.causal && key0 + BNK - 1 > q_pos0) || (key0 + BNK > p.Sk);
+      float mx = -INFINITY;
+      if (need_mask) {
+        const int limit = p.causal ? min(p.Sk - 1, q_pos) : p.Sk - 1;       // last visible key
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float v = __uint_as_float(s[c][i]);
+            v = (key0 + c * 32 + i <= limit) ? v : -INFINITY;
+            s[c][i] = __float_as_uint(v);
+            mx = fmaxf(mx, v);
+          }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s[c][i]));
+      }
+      mx *= p.scale_log2;
+      // lazy rescale: keep the old reference max unless the new one is more than 2^8 larger (p stays <= 256)
+      const bool bump = mx > m_ref + 8.f;
+      float alpha = 1.f;
+      if (bump) {
+        alpha = (m_ref == -INFINITY) ? 0.f : ptx::ex2_approx(m_ref - mx);
+        m_ref = mx;
+        l *= alpha;
+      }
+      const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float e = ptx::ex2_approx(fmaf(__uint_as_float(s[c][i]), p.scale_log2, neg_m));
+          sum += e;
+          s[c][i] = __float_as_uint(e);
+        }
+      l += sum;
+
+      // P buffer and O are free once PV of the previous tile has completed
+      if (j > 0) {
+        ptx::mbar_wait(&bars[PV_DONE], (j - 1) & 1);
+        ptx::tc_fence_after();
+      }
+      // P (bf16 / fp16) -> K-major SWIZZLE_128B: 16-byte chunk c16 of row r lands at chunk (c16 ^ (r & 7))
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 v;
+          if (p.is_bf16) {
+            v.x = ptx::pack_bf16x2(__uint_as_float(s[c][g * 8 + 0]), __uint_as_float(s[c][g * 8 + 1]));
+            v.y = ptx::pack_bf16x2(__uint_as_float(s[c][g * 8 + 2]), __uint_as_float(s[c][g * 8 + 3]));
+            v.z = ptx::pack_bf16x2(__uint_as_float(s[c][g * 8 + 4]), __uint_as_float(s[c][g * 8 + 5]));
+            v.w = ptx::pack_bf16x2(__uint_as_float(s[c][g * 8 + 6]), __uint_as_float(s[c][g * 8 + 7]));
+          } else {
+            v.x = ptx::pack_f16x2(__uint_as_float(s[c][g * 8 + 0]), __uint_as_float(s[c][g * 8 + 1]));
+            v.y = ptx::pack_f16x2(__uint_as_float(s[c][g * 8 + 2]), __uint_as_float(s[c][g * 8 + 3]));
+            v.z = ptx::pack_f16x2(__uint_as_float(s[c][g * 8 + 4]), __uint_as_float(s[c][g * 8 + 5]));
+            v.w = ptx::pack_f16x2(__uint_as_float(s[c][g * 8 + 6]), __uint_as_float(s[c][g * 8 + 7]));
+          }
+          const int col = c * 32 + g * 8;                 // first key of this 16-byte chunk
+          const int slab = col >> 6, c16 = (col & 63) >> 3;
+          ptx::st_shared_v4(p_row + slab * kSlab + ((c16 ^ (row & 7)) << 4), v);
+        }
+      // O *= alpha for the rows whose reference max moved (warp-uniform branch: tcgen05.ld/st are warp collectives)
+      if (j > 0 && __any_sync(0xFFFFFFFFu, bump)) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t o[32];
+          ptx::tmem_ld_32x32b_x32(tmem_o + lane_off + c * 32, o);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          ptx::tmem_st_32x32b_x32(tmem_o + lane_off + c * 32, o);
+        }
+        ptx::tmem_st_wait();
+      }
+      ptx::fence_proxy_async_smem();        // generic-proxy P stores -> visible to the tensor core (async proxy)
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&bars[P_READY]);
+    }
+
+    // epilogue: O / l -> global, LSE
+    if (n_tiles > 0) {
+      ptx::mbar_wait(&bars[PV_DONE], (n_tiles - 1) & 1);
+      ptx::tc_fence_after();
+    }
+    const float inv_l = l > 0.f ? 1.f / l : 0.f;
+    const bool live = row < rows_here;
+    char* o_row = reinterpret_cast<char*>(p.o) +
+                  2 * (static_cast<long long>(batch) * p.o_stride_b + static_cast<long long>(q_row0 + row) * p.o_stride_s +
+                       static_cast<long long>(head) * p.o_stride_h);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t o[32];
+      if (n_tiles > 0) {
+        ptx::tmem_ld_32x32b_x32(tmem_o + lane_off + c * 32, o);
+        ptx::tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = 0u;
+      }
+      if (live) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 v;
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(o[g * 8 + i]) * inv_l;
+          if (p.is_bf16) {
+            v.x = ptx::pack_bf16x2(f[0], f[1]); v.y = ptx::pack_bf16x2(f[2], f[3]);
+            v.z = ptx::pack_bf16x2(f[4], f[5]); v.w = ptx::pack_bf16x2(f[6], f[7]);
+          } else {
+            v.x = ptx::pack_f16x2(f[0], f[1]); v.y = ptx::pack_f16x2(f[2], f[3]);
+            v.z = ptx::pack_f16x2(f[4], f[5]); v.w = ptx::pack_f16x2(f[6], f[7]);
+          }
+          ptx::st_v4(o_row + (c * 32 + g * 8) * 2, v);
+        }
+      }
+    }
+    if (p.lse && live) {
+      const float lse = (l > 0.f) ? (m_ref + log2f(l)) * 0.6931471805599453f : -INFINITY;
+      p.lse[(static_cast<long long>(batch) * p.Hq + head) * p.Sq + q_row0 + row] = lse;
+    }
+    ptx::tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+}  // namespace fa
+}  // namespace td
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+struct TdFlashArgs {
+  const void* q; const void* k; const void* v; void* o; float* lse; const int* q_tile_pos;
+  long long B, Sq, Sk, Hq, Hkv, D;
+  long long q_stride_b, q_stride_s, q_stride_h;       // element strides; the head dim is contiguous
+  long long k_stride_b, k_stride_s, k_stride_h;
+  long long v_stride_b, v_stride_s, v_stride_h;
+  long long o_stride_b, o_stride_s, o_stride_h;
+  double sm_scale;
+  long long causal, is_bf16;
+};
+
+static int fa_tmap(CUtensorMap* out, const void* base, long long S, long long H, long long B, long long sb, long long ss,
+                   long long sh, int is_bf16) {
+  auto enc = td::drv::cuTensorMapEncodeTiled_fn();
+  if (!enc) { td::drv::set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return -1; }
+  const cuuint64_t dims[4] = {128, (cuuint64_t)S, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)ss * 2, (cuuint64_t)sh * 2, (cuuint64_t)sb * 2};
+  const cuuint32_t box[4] = {64, 128, 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base),
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { td::drv::set_error("flash_attn: cuTensorMapEncodeTiled failed: %s", td::drv::err_str(r)); return -1; }
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int td_flash_attn_fwd(const TdFlashArgs* a, void* stream_) {
+  using namespace td::fa;
+  if (a->D != HD) { td::drv::set_error("flash_attn: head_dim must be 128"); return -1; }
+  if (a->Hq % a->Hkv != 0) { td::drv::set_error("flash_attn: Hq must be a multiple of Hkv"); return -1; }
+  const long long st[] = {a->q_stride_b, a->q_stride_s, a->q_stride_h, a->k_stride_b, a->k_stride_s, a->k_stride_h,
+                          a->v_stride_b, a->v_stride_s, a->v_stride_h, a->o_stride_s, a->o_stride_h, a->o_stride_b};
+  for (long long s : st)
+    if (s % 8 != 0) { td::drv::set_error("flash_attn: strides must be multiples of 8 elements (16 bytes)"); return -1; }
+  Params p{};
+  if (fa_tmap(&p.tmap_q, a->q, a->Sq, a->Hq, a->B, a->q_stride_b, a->q_stride_s, a->q_stride_h, (int)a->is_bf16)) return -1;
+  if (fa_tmap(&p.tmap_k, a->k, a->Sk, a->Hkv, a->B, a->k_stride_b, a->k_stride_s, a->k_stride_h, (int)a->is_bf16)) return -1;
+  if (fa_tmap(&p.tmap_v, a->v, a->Sk, a->Hkv, a->B, a->v_stride_b, a->v_stride_s, a->v_stride_h, (int)a->is_bf16)) return -1;
+  p.o = a->o; p.lse = a->lse; p.q_tile_pos = a->q_tile_pos;
+  p.o_stride_b = a->o_stride_b; p.o_stride_s = a->o_stride_s; p.o_stride_h = a->o_stride_h;
+  p.B = (int)a->B; p.Sq = (int)a->Sq; p.Sk = (int)a->Sk; p.Hq = (int)a->Hq; p.Hkv = (int)a->Hkv;
+  p.causal = (int)a->causal; p.is_bf16 = (int)a->is_bf16;
+  p.scale_log2 = static_cast<float>(a->sm_scale * 1.4426950408889634);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(flash_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::kTotal);
+    if (e != cudaSuccess) { td::drv::set_error("flash_attn: smem attribute: %s", cudaGetErrorString(e)); return -1; }
+    attr_set = true;
+  }
+  dim3 grid((unsigned)((a->Sq + BMQ - 1) / BMQ), (unsigned)a->Hq, (unsigned)a->B);
+  flash_fwd_kernel<<<grid, kThreads, Smem::kTotal, reinterpret_cast<cudaStream_t>(stream_)>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { td::drv::set_error("flash_attn launch: %s", cudaGetErrorString(e)); return -1; }
+  return 0;
+}

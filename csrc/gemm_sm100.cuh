@@ -81,7 +81,7 @@ struct Params {
   uint32_t* phase;
   // ---- AG ----
   int ag_rows_per_rank;      // rows of A owned by each rank
-  int ag_copy_local;         // 1: comm CTAs copy a_local -> workspace; 0: caller already wrote the workspace
+  int ag_copy_local;         // 1: comm CTAs copy a_local -> workspace; 0: caller already wrote the workspace; 2: all-to-all (block d of a_local -> rank d)
   int ag_skip_wait;          // GEMM-only twin: never wait (measures exposed communication)
   int ag_nslices;            // arrival flags per source rank (= comm CTAs, or 1 when the copy engine does the transfer)
   const void* ag_a_local;    // my shard [rows_per_rank, K]
@@ -198,7 +198,9 @@ TD_DEVICE void ag_comm_cta(const Params& p, uint32_t ph, int comm_idx) {
   for (int dist = p.ag_copy_local ? 0 : 1; dist < W; ++dist) {
     const int d = (me - dist + W) % W;
     if (threadIdx.x == 0) prof_record(p.prof, pslot, 1, true);
-    if (b1 > b0) copy16_strided(symm_at(p.symm, ws, d) + shard_off + b0, src, b1 - b0, threadIdx.x, kThreads);
+    // ag_copy_local == 2: all-to-all flavour -- a_local is [world, rows_per_rank, K] and block d goes to rank d
+    const size_t a2a_off = (p.ag_copy_local == 2) ? static_cast<size_t>(d) * shard_bytes : 0;
+    if (b1 > b0) copy16_strided(symm_at(p.symm, ws, d) + shard_off + b0, src + a2a_off, b1 - b0, threadIdx.x, kThreads);
     __syncthreads();
     if (threadIdx.x == 0) {
       prof_record(p.prof, pslot, 1, false);

@@ -128,6 +128,14 @@ TD_DEVICE void tma_load_3d(const void* tmap, uint64_t* bar, void* smem, int c0, 
       "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(hint)
       : "memory");
 }
+TD_DEVICE void tma_load_4d(const void* tmap, uint64_t* bar, void* smem, int c0, int c1, int c2, int c3,
+                           uint64_t hint = kEvictNormal) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(hint)
+      : "memory");
+}
 // 2-CTA variants: both CTAs of a pair issue their own load; the transaction bytes land on the
 // LEADER CTA's mbarrier (peer bit cleared), which is the barrier the MMA issuer waits on.
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
@@ -314,6 +322,20 @@ TD_DEVICE void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
       : "memory");
 }
 TD_DEVICE void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// registers -> TMEM, same 32x32b shape (thread i <-> lane base+i, 32 consecutive columns)
+TD_DEVICE void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+TD_DEVICE void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+TD_DEVICE float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // ----------------------------------------------------------------------------------------------
 // UMMA descriptors
@@ -330,6 +352,18 @@ TD_DEVICE uint64_t make_smem_desc_k128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                            // SWIZZLE_128B   [61,64)
   return d;
 }
+// MN-major operand with the 128-byte swizzle: a [k rows, 64 elements (128 B)] TMA box per 64-wide slice of the
+// M/N extent.  Canonical form ((8,n),(8,k)) : ((1,LBO),(8,SBO)) in 16-byte units: 8-row (k) groups are 1024 B apart
+// (SBO), consecutive 64-element M/N slices are `lbo_bytes` apart.
+TD_DEVICE uint64_t make_smem_desc_mn128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 // Non-swizzled descriptor used for scale-factor tcgen05.cp (rows of 16 B, 8-row groups 128 B apart)
 TD_DEVICE uint64_t make_smem_desc_noswizzle(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -342,12 +376,13 @@ TD_DEVICE uint64_t make_smem_desc_noswizzle(uint32_t smem_addr, uint32_t lbo_byt
 
 // Instruction descriptor, kind::f16 / kind::f8f6f4 (dense, fp32 accumulate, both operands K-major).
 //   a_fmt/b_fmt: kind::f16 -> 0 = fp16, 1 = bf16 ; kind::f8f6f4 -> 0 = e4m3, 1 = e5m2
-__host__ __device__ constexpr uint32_t make_idesc(uint32_t a_fmt, uint32_t b_fmt, uint32_t M, uint32_t N) {
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t a_fmt, uint32_t b_fmt, uint32_t M, uint32_t N,
+                                                  uint32_t a_mn_major = 0, uint32_t b_mn_major = 0) {
   return (1u << 4)              // c_format = F32   [4,6)
          | (a_fmt << 7)         // a_format         [7,10)
          | (b_fmt << 10)        // b_format         [10,13)
-         | (0u << 15)           // a_major = K
-         | (0u << 16)           // b_major = K
+         | (a_mn_major << 15)   // a_major: 0 = K, 1 = MN
+         | (b_mn_major << 16)   // b_major: 0 = K, 1 = MN
          | ((N >> 3) << 17)     // n_dim            [17,23)
          | ((M >> 4) << 24);    // m_dim            [24,29)
 }

@@ -136,6 +136,21 @@ def case_ag_gemm():
             dist.all_gather_into_tensor(full, A.view(-1), group=U.get_triton_dist_world())
             ref = full.view(M, K).float() @ Wt.float().t()
             _assert_close(C, ref, 0.5 if big else 1e-3, 2e-2 if big else 1e-4, f"ag_gemm {M}x{N}x{K} it{it}")
+        # AllToAll + GEMM in the same kernel (all_to_all_single_gemm.py:74-188): block d of x goes to rank d
+        from triton_dist.ops.compat import all_to_all_single_gemm
+        for it in range(3):
+            X = (torch.randn(M, K, device=dev) * 0.5).to(dtype)
+            Wt = (torch.randn(N, K, device=dev) * 0.5).to(dtype)
+            C = all_to_all_single_gemm(ctx, X, Wt)
+            recv = torch.empty_like(X)
+            if dev.type == "cuda":
+                dist.all_to_all_single(recv, X, group=U.get_triton_dist_world())
+            else:
+                allx = torch.empty(W * M * K, dtype=dtype)
+                dist.all_gather_into_tensor(allx, X.view(-1), group=U.get_triton_dist_world())
+                Ms = M // W
+                recv = torch.cat([allx.view(W, M, K)[s, me * Ms:(me + 1) * Ms] for s in range(W)])
+            _assert_close(C, recv.float() @ Wt.float().t(), 0.5 if big else 1e-3, 2e-2 if big else 1e-4, f"a2a_gemm {M}x{N}x{K} it{it}")
         U.barrier_all_host()
         ctx.finalize()
 

@@ -117,22 +117,29 @@ def default_ag_config(M: int, N: int, K: int, world: int) -> GemmConfig:
 def ag_gemm(A: torch.Tensor, B: torch.Tensor, ctx: AllGatherGEMMTensorParallelContext,
             gemm_config: Optional[GemmConfig] = None, straggler_option=None, debug: bool = False,
             out: Optional[torch.Tensor] = None, skip_wait: bool = False, profiler=None, transport: str = "sm",
-            **_unused) -> torch.Tensor:
+            all_to_all: bool = False, **_unused) -> torch.Tensor:
     """A: ``[M/W, K]`` local shard, B: ``[K, N/W]`` -> ``[M, N/W]``.  ``skip_wait`` runs the GEMM-only twin
     (flags ignored) used to measure exposed communication, like the reference's ``fake_barrier`` path.
 
     ``transport="sm"`` (default): comm CTAs inside the GEMM kernel push the shard.  ``transport="copy_engine"``: the
     shard is pushed by the DMA engines on a side stream (one ``cudaMemcpyAsync`` + one release-flag kernel per peer, as
     the reference's copy-engine producer, allgather.py:100-124) while all SMs run GEMM tiles that wait on the same
-    per-source flags; not CUDA-graph replayable (flag values are written from the host-tracked phase)."""
+    per-source flags; not CUDA-graph replayable (flag values are written from the host-tracked phase).
+
+    ``all_to_all=True``: A is ``[W * Ms, K]`` and row block d goes to rank d (instead of the same shard to everyone);
+    the result is ``concat_s(block from rank s) @ B`` -- the AllToAll + GEMM of the Ulysses o-projection
+    (reference all_to_all_single_gemm.py:74-188) in the same single kernel."""
     W = ctx.num_ranks
     Ms, K = A.shape
+    if all_to_all:
+        assert Ms % W == 0
+        Ms //= W
     Bnk = _as_nk(B)
     N = Bnk.shape[0]
     M = Ms * W
     assert K == ctx.K and Bnk.shape[1] == K and M <= ctx.max_M and A.dtype == ctx.dtype == Bnk.dtype
     if not A.is_cuda:
-        return _ag_gemm_host(A, Bnk, ctx, out)
+        return _ag_gemm_host(A, Bnk, ctx, out, all_to_all)
     if out is None:
         out = torch.empty((M, N), dtype=A.dtype, device=A.device)
     cfg = gemm_config or default_ag_config(M, N, K, W)
@@ -144,7 +151,8 @@ def ag_gemm(A: torch.Tensor, B: torch.Tensor, ctx: AllGatherGEMMTensorParallelCo
     heap = U.get_heap()
     A = A.contiguous()
     ph = ctx.host_phase + 1
-    zero_copy = heap.contains(A) and A.data_ptr() == ctx.workspace[ph & 1][ctx.rank * Ms:].data_ptr()
+    zero_copy = (not all_to_all) and heap.contains(A) and A.data_ptr() == ctx.workspace[ph & 1][ctx.rank * Ms:].data_ptr()
+    assert not (all_to_all and transport == "copy_engine"), "all_to_all flavour uses the in-kernel push"
     args = _C.GemmArgs()
     args.mode = 1
     ws_buf_bytes = ctx.max_M * K * A.element_size()
@@ -156,7 +164,7 @@ def ag_gemm(A: torch.Tensor, B: torch.Tensor, ctx: AllGatherGEMMTensorParallelCo
     r, w, base, stride, mc = U.symm_ctx_fields()
     args.rank, args.world, args.symm_base, args.symm_stride, args.mc_base = r, w, base, stride, mc
     args.phase = ctx.phase.data_ptr()
-    args.ag_rows_per_rank, args.ag_copy_local, args.ag_skip_wait = Ms, 0 if zero_copy else 1, int(skip_wait)
+    args.ag_rows_per_rank, args.ag_copy_local, args.ag_skip_wait = Ms, 2 if all_to_all else (0 if zero_copy else 1), int(skip_wait)
     args.ag_a_local, args.ag_ws, args.ag_ws_buf_bytes = A.data_ptr(), ctx.workspace.data_ptr(), ws_buf_bytes
     args.ag_flags, args.ag_ready = ctx.flags.data_ptr(), ctx.ready.data_ptr()
     if skip_wait:
@@ -208,7 +216,7 @@ gemm_non_persistent = gemm_persistent
 # ------------------------------------------------------------------------------------------------------------
 # emulation (no GPU): same protocol on the shared-memory heap
 # ------------------------------------------------------------------------------------------------------------
-def _ag_gemm_host(A, Bnk, ctx, out):
+def _ag_gemm_host(A, Bnk, ctx, out, all_to_all=False):
     """Same push protocol as the device kernel: my shard goes into EVERY rank's workspace (nearest consumer first),
     each arrival is published with a release flag carrying the phase number; the GEMM consumes sources in arrival
     order after acquiring their flags.  Workspaces are double buffered by call parity, nothing is reset."""
@@ -217,6 +225,8 @@ def _ag_gemm_host(A, Bnk, ctx, out):
     lib = _C.host_lib()
     W, me = ctx.num_ranks, ctx.rank
     Ms, K = A.shape
+    if all_to_all:
+        Ms //= W
     ctx.host_phase += 1
     ph = ctx.host_phase
     par = ph & 1
@@ -226,7 +236,7 @@ def _ag_gemm_host(A, Bnk, ctx, out):
     for dist_ in range(W):
         d = (me - dist_ + W) % W
         dst_ws = heap.peer_view(ctx.workspace, d)[par]
-        dst_ws[me * Ms:(me + 1) * Ms].copy_(A)
+        dst_ws[me * Ms:(me + 1) * Ms].copy_(A[d * Ms:(d + 1) * Ms] if all_to_all else A)
         lib.tdh_notify32(ctypes.c_void_p(heap.peer_ptr(flag_off(me), d)), ph, 1)
     # 2. consume in arrival order
     N = Bnk.shape[0]

@@ -82,14 +82,19 @@ reduce_topk_tma = reduce_topk_non_tma = M.reduce_topk
 
 
 # ---- all_to_all_single_gemm.py / Ulysses GEMM fusions ----------------------------------------------------------
-def create_all_to_all_single_gemm_context(max_rows_per_peer: int, K: int, dtype: torch.dtype) -> AllToAllContext:
-    return create_all_to_all_single_2d_context(max_rows_per_peer, K, dtype)
+def create_all_to_all_single_gemm_context(max_rows_per_peer: int, K: int, dtype: torch.dtype, N: int = 0):
+    """Workspace + per-source arrival flags of the fused AllToAll+GEMM (the all-gather GEMM context: same protocol)."""
+    from .ag_gemm import create_ag_gemm_context
+    heap = U.get_heap()
+    return create_ag_gemm_context(max_rows_per_peer * heap.world, N, K, dtype, heap.rank, heap.world)
 
 
-def all_to_all_single_gemm(ctx: AllToAllContext, x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
-    """(all_to_all_single_gemm.py:74-188) AllToAll (rows) then ``@ w.T``; here: push all-to-all kernel + tcgen05 GEMM on
-    the same stream (the GEMM starts when the whole exchange has landed)."""
-    return _lin(all_to_all_single_2d(ctx, x), w)
+def all_to_all_single_gemm(ctx, x: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(all_to_all_single_gemm.py:74-188) ``x``: [W * rows, K], row block d goes to rank d; returns
+    ``concat_s(block received from s) @ w.T``.  ONE kernel: comm CTAs push block d into rank d's workspace and raise
+    per-(source, slice) flags, the tcgen05 GEMM tiles of the same launch wait on the flags of the source they read."""
+    from .ag_gemm import ag_gemm
+    return ag_gemm(x, w.t(), ctx, out=out, all_to_all=True)
 
 
 def gemm_only(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
