@@ -7,7 +7,7 @@ using namespace td::gemm;
 
 // Every field is 8 bytes wide so the ctypes mirror (triton_dist/_C.py: GemmArgs) cannot get padding wrong.
 struct TdGemmArgs {
-  long long mode;            // 0 plain, 1 AG, 2 RS
+  long long mode;            // 0 plain, 1 AG, 2 RS, 3 AR (rs_* fields: staging / flags / out; rs_rows_per_rank = flag capacity)
   long long is_bf16;         // 1 bf16, 0 fp16, 2 = MXFP8 inputs (e4m3 + UE8M0 scales per 32 K-elements), bf16 output
   long long bn;              // 32 / 64 / 128 / 256
   long long cta_group;       // 1 or 2
@@ -123,7 +123,7 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
     cuuint32_t box[2] = {(cuuint32_t)bk_elems, (cuuint32_t)(bn / cg)};
     if (encode_tmap(&p.tmap_b, a->B, 2, dims, strides, box, bf16)) return -1;
   }
-  p.use_tma_store = (a->use_tma_store && bn >= 64 && a->mode != kRS && a->ldc % 8 == 0) ? 1 : 0;
+  p.use_tma_store = (a->use_tma_store && bn >= 64 && a->mode != kRS && a->mode != kAR && a->ldc % 8 == 0) ? 1 : 0;
   if (p.use_tma_store) {  // C: {N, rows, nbuf}
     cuuint64_t dims[3] = {(cuuint64_t)a->N, (cuuint64_t)a->c_rows, (cuuint64_t)(a->c_nbuf > 0 ? a->c_nbuf : 1)};
     cuuint64_t strides[2] = {(cuuint64_t)a->ldc * 2, (cuuint64_t)(a->c_nbuf > 1 ? a->c_buf_stride_bytes : a->c_rows * a->ldc * 2)};
@@ -163,6 +163,7 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
   p.rs_rows_per_rank = (int)a->rs_rows_per_rank; p.rs_stage = reinterpret_cast<char*>(a->rs_stage);
   p.rs_stage_buf_bytes = a->rs_stage_buf_bytes; p.rs_flags = reinterpret_cast<uint32_t*>(a->rs_flags);
   p.rs_out = a->rs_out; p.rs_ldo = a->rs_ldo;
+  p.rs_flag_tiles = (int)a->rs_rows_per_rank;
 
   int dev = 0, sms = 0;
   TD_CUDA_CHECK(cudaGetDevice(&dev));
@@ -184,6 +185,13 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
   p.ag_nslices = (a->ag_skip_wait == 2) ? 1 : p.n_comm_ctas;
   grid = gemm_ctas + p.n_comm_ctas;
 
+  if (a->mode == kAR) {
+    if (fp8) { drv::set_error("gemm_ar: MXFP8 inputs are not wired to the fused all-reduce yet"); return -1; }
+    if (p.n_comm_ctas < cg) { drv::set_error("gemm_ar needs comm CTAs"); return -1; }
+    if (p.num_m * cg * p.num_n > p.rs_flag_tiles) { drv::set_error("gemm_ar: flag array too small for this shape"); return -1; }
+    if (p.N % 8 != 0 || a->rs_ldo % 8 != 0) { drv::set_error("gemm_ar: N and the output row stride must be multiples of 8"); return -1; }
+    if (p.symm.world * cg > 256) { drv::set_error("gemm_ar: world too large"); return -1; }
+  }
   if (a->mode == kRS) {
     if (p.rs_rows_per_rank % TM != 0) { drv::set_error("gemm_rs ring path needs (M / world) %% (128 * cta_group) == 0"); return -1; }
     if (p.N % 8 != 0) { drv::set_error("N must be a multiple of 8"); return -1; }
@@ -201,6 +209,7 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
     case kPlain: return dispatch<kPlain>(p, bn, cg, grid, stream);
     case kAG: return dispatch<kAG>(p, bn, cg, grid, stream);
     case kRS: return dispatch<kRS>(p, bn, cg, grid, stream);
+    case kAR: return dispatch<kAR>(p, bn, cg, grid, stream);
     default: drv::set_error("bad mode"); return -1;
   }
 }

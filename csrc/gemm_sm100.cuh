@@ -8,6 +8,10 @@
 //                                                 python/little_kernel/benchmark/gemm_sm100/gemm_level9.py)
 //   kAG    : AllGather(A) fused with GEMM   (ref: kernels/nvidia/allgather_gemm.py:200-306 + allgather.py:100-124)
 //   kRS    : GEMM fused with ReduceScatter  (ref: kernels/nvidia/gemm_reduce_scatter.py:218-332 + reduce_scatter.py)
+//   kAR    : GEMM fused with AllReduce      (ref: kernels/nvidia/gemm_allreduce.py:565-604 kernel_fused_gemm_allreduce):
+//            the epilogue stores the partial tile into this rank's symmetric staging buffer and raises flag[tile][me]
+//            on every rank; comm CTAs of the same grid wait for all W flags of a tile, multimem.ld_reduce it through
+//            the NVSwitch (or sum the peers' copies over P2P) and write the reduced tile to the local output
 //
 // B200-first design (not a translation of the reference):
 //   * warp-specialised CTA: warp0 = TMA producer, warp1 = single-thread tcgen05.mma issuer, warp2 = TMEM
@@ -44,7 +48,7 @@ constexpr int kCBlockBytes = BM * kCBlockCols * 2;
 constexpr int kAGRowsPerChunk = 128;                  // AG arrival-flag granularity (rows of a source shard)
 constexpr int kAGMaxSlices = 64;                      // max comm CTAs (= arrival flags per source rank)
 
-enum Mode : int { kPlain = 0, kAG = 1, kRS = 2 };
+enum Mode : int { kPlain = 0, kAG = 1, kRS = 2, kAR = 3 };
 
 struct Params {
   CUtensorMap tmap_a;   // dims {K, rows_a, nbuf}, box {64, 128, 1}, SWIZZLE_128B
@@ -95,6 +99,8 @@ struct Params {
   char* rs_stage;            // symmetric: 2 buffers of [M, N] 16-bit running partial sums, written by rank+1
   long long rs_stage_buf_bytes;
   uint32_t* rs_flags;        // symmetric: [2][num_m * num_n], written by rank+1 with the phase number
+                             // (kAR: [2][rs_flag_tiles][world], flag[tile][r] = phase once rank r staged that 128-row block)
+  int rs_flag_tiles;         // kAR: flag capacity per parity, in (128-row block, n tile) units
   void* rs_out;              // [rows_per_rank, N] final output (local)
   long long rs_ldo;
 };
@@ -213,6 +219,55 @@ TD_DEVICE void ag_comm_cta(const Params& p, uint32_t ph, int comm_idx) {
 }
 
 // -------------------------------------------------------------------------------------------------
+// AR consumer side (comm CTA c): tiles c, c + n_comm, ... in the order the GEMM produces them.  A tile is
+// complete when all W ranks have published flag[par][tile][rank] = phase; the reduction is one
+// multimem.ld_reduce per 16 bytes (the switch adds the W staging copies) or W peer loads without NVLS.
+// -------------------------------------------------------------------------------------------------
+template <int kCtaGroup, int BN>
+TD_DEVICE void ar_comm_cta(const Params& p, uint32_t ph, int comm_idx) {
+  constexpr int TM = BM * kCtaGroup;
+  const int W = p.symm.world;
+  const int total_tiles = p.num_m * p.num_n;
+  char* stage = p.rs_stage + (ph & 1u) * p.rs_stage_buf_bytes;
+  const uint32_t* flags = p.rs_flags + static_cast<size_t>(ph & 1u) * p.rs_flag_tiles * W;
+  constexpr int kChunksPerRow = BN / 8;
+  for (int t = comm_idx; t < total_tiles; t += p.n_comm_ctas) {
+    int m_tile, n_tile;
+    tile_coords(p, t, m_tile, n_tile);
+    if (static_cast<int>(threadIdx.x) < W * kCtaGroup) {      // one waiter per (row half, source rank)
+      const int half = static_cast<int>(threadIdx.x) / W, src = static_cast<int>(threadIdx.x) % W;
+      wait_ge<true>(flags + static_cast<size_t>((m_tile * kCtaGroup + half) * p.num_n + n_tile) * W + src, ph);
+    }
+    __syncthreads();
+    const int row0 = m_tile * TM, col0 = n_tile * BN;
+    for (int i = threadIdx.x; i < TM * kChunksPerRow; i += kThreads) {
+      const int r = row0 + i / kChunksPerRow, c = col0 + (i % kChunksPerRow) * 8;
+      if (r >= p.M || c >= p.N) continue;
+      char* src = stage + (static_cast<size_t>(r) * p.N + c) * 2;
+      uint4 v;
+      if (p.symm.mc_base) {
+        v = p.in_is_bf16 ? ptx::multimem_ld_reduce_bf16x8(symm_mc(p.symm, src)) : ptx::multimem_ld_reduce_f16x8(symm_mc(p.symm, src));
+      } else {
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int s = 0; s < W; ++s) {
+          const uint4 x = ptx::ld_relaxed_sys_v4(symm_at(p.symm, src, (p.symm.rank + s) % W));
+          const uint32_t w4[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (p.in_is_bf16) { acc[2 * e] += ptx::bf16_lo(w4[e]); acc[2 * e + 1] += ptx::bf16_hi(w4[e]); }
+            else { const __half2 hh = *reinterpret_cast<const __half2*>(&w4[e]); acc[2 * e] += __low2float(hh); acc[2 * e + 1] += __high2float(hh); }
+          }
+        }
+        if (p.in_is_bf16) { v.x = ptx::pack_bf16x2(acc[0], acc[1]); v.y = ptx::pack_bf16x2(acc[2], acc[3]); v.z = ptx::pack_bf16x2(acc[4], acc[5]); v.w = ptx::pack_bf16x2(acc[6], acc[7]); }
+        else { v.x = ptx::pack_f16x2(acc[0], acc[1]); v.y = ptx::pack_f16x2(acc[2], acc[3]); v.z = ptx::pack_f16x2(acc[4], acc[5]); v.w = ptx::pack_f16x2(acc[6], acc[7]); }
+      }
+      ptx::st_v4(reinterpret_cast<char*>(p.rs_out) + (static_cast<size_t>(r) * p.rs_ldo + c) * 2, v);
+    }
+    __syncthreads();
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
 // the kernel
 // -------------------------------------------------------------------------------------------------
 template <int kMode, int BN, int kStages, int kCtaGroup, bool kFP8 = false, int kAccStages = 2>
@@ -244,6 +299,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     // dedicated comm CTA (fills the SMs the GEMM has no tiles for): deep ring, one driving thread
     if constexpr (kMode == kAG) {
       ag_comm_cta(p, ph, static_cast<int>(blockIdx.x) - n_gemm_ctas);
+    }
+    if constexpr (kMode == kAR) {
+      ar_comm_cta<kCtaGroup, BN>(p, ph, static_cast<int>(blockIdx.x) - n_gemm_ctas);
     }
   } else {
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
@@ -429,6 +487,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
           }
         }
 
+        if constexpr (kMode == kAR) {     // partial tile -> my symmetric staging buffer (same coordinates as C)
+          dst_base = p.rs_stage + (ph & 1u) * p.rs_stage_buf_bytes; dst_ld = p.N; dst_row_off = 0;
+        }
+
         ptx::mbar_wait(tmem_full + acc, acc_phase);
         ptx::tc_fence_after();
         if (lane == 0) prof_record(p.prof, static_cast<int>(blockIdx.x) * 8 + warp, 5, true);
@@ -541,6 +603,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             }
             __syncwarp();
           }
+        }
+        if constexpr (kMode == kAR) {
+          // each CTA of a pair stages its own 128 rows and publishes its own flag word (index carries the CTA rank);
+          // the consumer waits for every (row half, source rank) word of the tile
+          ptx::named_bar_sync(2, kEpiThreads);
+          if (et == 0) {
+            const int W = p.symm.world, me = p.symm.rank;
+            uint32_t* f = p.rs_flags + static_cast<size_t>(ph & 1u) * p.rs_flag_tiles * W +
+                          static_cast<size_t>((m_tile * kCtaGroup + static_cast<int>(cta_rank)) * p.num_n + n_tile) * W + me;
+            ptx::fence_acq_rel_sys();
+            for (int d = 0; d < W; ++d) ptx::st_relaxed_sys(symm_at(p.symm, f, (me + d) % W), ph);
+          }
+          __syncwarp();
         }
         if (lane == 0) prof_record(p.prof, static_cast<int>(blockIdx.x) * 8 + warp, 5, false);
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }

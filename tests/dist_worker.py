@@ -182,6 +182,35 @@ def case_gemm_rs():
         ctx.finalize()
 
 
+def case_gemm_ar():
+    """GEMM + AllReduce: two-kernel path and the single fused kernel (gemm_allreduce.py:565-604,669-731)."""
+    from triton_dist.ops.gemm_ar import (create_gemm_ar_context, create_ll_gemm_ar_context, gemm_allreduce_op,
+                                         low_latency_gemm_allreduce_op)
+    from triton_dist.ops.gemm import GemmConfig
+    dev = U.current_device()
+    W, me = U.world_size(), U.rank()
+    big = dev.type == "cuda"
+    dtype = torch.bfloat16 if big else torch.float32
+    shapes = [(128, 4096, 512), (16, 1024, 1024), (256, 2048, 256), (200, 520, 264), (512, 1024, 512)] if big else [(8, 16, 24)]
+    for (M, N, K) in shapes:
+        ctx = create_ll_gemm_ar_context(None, me, W, W, max_M=M, N=N, dtype=dtype)
+        cfgs = [None]
+        if big:
+            cfgs += [GemmConfig(128, 2, 8, False, 0, 16), GemmConfig(256, 1, 8, False, 0, 8)]
+        for it in range(6):
+            A = (torch.randn(M, K, device=dev) * 0.5).to(dtype)
+            Wt = (torch.randn(N, K, device=dev) * 0.5).to(dtype)
+            ref = A.float() @ Wt.float().t()
+            dist.all_reduce(ref, group=U.get_triton_dist_world())
+            straggler = (it % W, 2_000_000) if (big and it in (1, 4)) else None
+            out = low_latency_gemm_allreduce_op(ctx, A, Wt, gemm_config=cfgs[it % len(cfgs)], straggler_option=straggler)
+            _assert_close(out, ref, 1.0 if big else 1e-3, 3e-2 if big else 1e-4, f"ll_gemm_ar {M}x{N}x{K} it{it}")
+            out2 = gemm_allreduce_op(ctx, A, Wt)
+            _assert_close(out2, ref, 1.0 if big else 1e-3, 3e-2 if big else 1e-4, f"gemm_ar {M}x{N}x{K} it{it}")
+        U.barrier_all_host()
+        ctx.finalize()
+
+
 def case_moe():
     """ag_group_gemm + run_moe_reduce_rs vs the masked-matmul golden (reference: test_ag_moe.py, test_moe_reduce_rs.py)."""
     from triton_dist.ops import moe as M

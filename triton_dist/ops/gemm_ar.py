@@ -3,10 +3,17 @@
 Reference: ``create_gemm_ar_context`` / ``gemm_allreduce_op`` / ``low_latency_gemm_allreduce_op``
 (/root/reference/python/triton_dist/kernels/nvidia/gemm_allreduce.py:103-127,669-731) and ``GemmARLayer``.
 
-Current realisation: the tcgen05 GEMM's TMA-store epilogue writes the partial product *directly into the
-symmetric staging buffer* of the all-reduce context (zero copy), then the NVLS all-reduce kernel
-(multimem.ld_reduce / multimem.st, csrc/comm_kernels.cu) runs on the same stream with its staging copy skipped.
-Two launches, no host sync, graph-capturable; the message never makes an extra HBM round trip.
+Two realisations:
+
+* ``low_latency_gemm_allreduce_op`` -- ONE kernel (mode kAR of csrc/gemm_sm100.cuh, the counterpart of the reference's
+  ``kernel_fused_gemm_allreduce`` :565-604): GEMM CTAs stage each partial tile in the symmetric buffer and raise a
+  per-(tile, rank) flag on every rank; comm CTAs of the same grid wait for all W flags of a tile and reduce it with
+  ``multimem.ld_reduce`` through the NVSwitch (P2P loads without NVLS) straight into the local output.  Tiles are
+  reduced while later tiles are still being computed; double-buffered by the device-resident call counter, so it is
+  CUDA-graph replayable and never resets flags.
+* ``gemm_allreduce_op`` -- for large M (bandwidth bound): the tcgen05 GEMM's TMA-store epilogue writes the partial
+  product directly into the staging buffer of the all-reduce context (zero copy), then the two-shot NVLS all-reduce
+  kernel runs on the same stream with its staging copy skipped (two launches, no host sync, graph-capturable).
 """
 from __future__ import annotations
 
@@ -15,10 +22,13 @@ from typing import Optional
 
 import torch
 
+import ctypes as C
+
+from .. import _C
 from .. import utils as U
 from . import comm
 from .ag_gemm import _as_nk
-from .gemm import GemmConfig, default_config, gemm
+from .gemm import GemmConfig, default_config, fill_common, gemm
 
 
 @dataclass
@@ -30,11 +40,22 @@ class GemmARContext:
     world_size: int
     ar_ctx: comm.AllReduceContext = None
     calls: int = 0
+    # fused single-kernel path
+    stage: torch.Tensor = None       # symmetric [2, max_M, N]
+    flags: torch.Tensor = None       # symmetric int32 [2, flag_tiles, W]
+    phase: torch.Tensor = None       # local int32 [4] device-resident call counter
+    flag_tiles: int = 0
+    num_comm_sms: int = 16
 
     def finalize(self):
         if self.ar_ctx is not None:
             self.ar_ctx.finalize()
             self.ar_ctx = None
+        heap = U.get_heap()
+        for t in (self.stage, self.flags):
+            if t is not None:
+                heap.free_tensor(t)
+        self.stage = self.flags = None
 
 
 def create_gemm_ar_context(ar_stream=None, rank: Optional[int] = None, world_size: Optional[int] = None,
@@ -49,7 +70,61 @@ def create_gemm_ar_context(ar_stream=None, rank: Optional[int] = None, world_siz
     return ctx
 
 
-create_ll_gemm_ar_context = create_gemm_ar_context
+def create_ll_gemm_ar_context(ar_stream=None, rank: Optional[int] = None, world_size: Optional[int] = None,
+                              local_world_size: Optional[int] = None, max_M: int = 0, N: int = 0,
+                              dtype: torch.dtype = torch.bfloat16, NUM_COMM_SMS: int = 16, **_unused) -> GemmARContext:
+    """Context of the single-kernel GEMM+AllReduce (reference :127, double-buffered ``num_phases=2``)."""
+    ctx = create_gemm_ar_context(ar_stream, rank, world_size, local_world_size, max_M, N, dtype)
+    heap = U.get_heap()
+    ctx.stage = heap.tensor((2, max_M, N), dtype)
+    ctx.flag_tiles = max(((max_M + 127) // 128) * ((N + 31) // 32), 8)
+    ctx.flags = heap.tensor((2, ctx.flag_tiles, ctx.world_size), torch.int32)
+    ctx.phase = torch.zeros(4, dtype=torch.int32, device=heap.device)
+    ctx.num_comm_sms = NUM_COMM_SMS
+    U.barrier_all_host()
+    return ctx
+
+
+def default_ar_config(M: int, N: int, K: int, n_comm: int = 16) -> GemmConfig:
+    """Small-M decode shapes: narrow tiles so that enough CTAs work on the K-reduction; the comm CTAs take the SMs the
+    GEMM has no tile for."""
+    if M > 128 and N >= 256:
+        return GemmConfig(bn=128, cta_group=2, group_m=8, use_tma_store=False, n_comm_ctas=n_comm)
+    bn = 32 if N < 64 else 64 if N <= 8192 else 128
+    return GemmConfig(bn=bn, cta_group=1, group_m=8, use_tma_store=False, n_comm_ctas=n_comm)
+
+
+def low_latency_gemm_allreduce_op(ctx: GemmARContext, a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None,
+                                  gemm_config: Optional[GemmConfig] = None, straggler_option=None, **_unused) -> torch.Tensor:
+    """Single fused kernel; falls back to :func:`gemm_allreduce_op` when the context has no fused buffers."""
+    w = b if (b.shape[1] == a.shape[1] and b.stride(1) == 1) else _as_nk(b)
+    M, K = a.shape
+    N = w.shape[0]
+    if (not a.is_cuda) or ctx.world_size == 1 or ctx.stage is None:
+        return gemm_allreduce_op(ctx, a, w, out, gemm_config, straggler_option=straggler_option)
+    assert M <= ctx.max_M and N == ctx.N
+    if out is None:
+        out = torch.empty((M, N), dtype=a.dtype, device=a.device)
+    if straggler_option and straggler_option[0] == ctx.rank:
+        torch.cuda._sleep(int(straggler_option[1]))
+    cfg = gemm_config or default_ar_config(M, N, K, ctx.num_comm_sms)
+    if cfg.n_comm_ctas <= 0:
+        cfg = GemmConfig(cfg.bn, cfg.cta_group, cfg.group_m, False, cfg.num_sms, ctx.num_comm_sms)
+    a = a.contiguous()
+    args = _C.GemmArgs()
+    args.mode = 3
+    fill_common(args, M, a.data_ptr(), a.stride(0), w, out.data_ptr(), M, out.stride(0), M, N, K,
+                GemmConfig(cfg.bn, cfg.cta_group, cfg.group_m, False, cfg.num_sms, cfg.n_comm_ctas), a.dtype == torch.bfloat16)
+    r, wd, base, stride, mc = U.symm_ctx_fields()
+    args.rank, args.world, args.symm_base, args.symm_stride, args.mc_base = r, wd, base, stride, mc
+    args.phase = ctx.phase.data_ptr()
+    args.rs_rows_per_rank = ctx.flag_tiles
+    args.rs_stage, args.rs_stage_buf_bytes = ctx.stage.data_ptr(), ctx.max_M * N * a.element_size()
+    args.rs_flags, args.rs_out, args.rs_ldo = ctx.flags.data_ptr(), out.data_ptr(), out.stride(0)
+    _C.check(_C.cuda_lib().td_gemm_launch(C.byref(args), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+             "td_gemm_launch(ar)")
+    ctx.calls += 1
+    return out
 
 
 def gemm_allreduce_op(ctx: GemmARContext, a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None,
@@ -79,8 +154,6 @@ def gemm_allreduce_op(ctx: GemmARContext, a: torch.Tensor, b: torch.Tensor, out:
     comm.all_reduce(stage0, method, ctx.ar_ctx, output=out, straggler_option=straggler_option)
     return out
 
-
-low_latency_gemm_allreduce_op = gemm_allreduce_op
 
 
 def gemm_op(ctx, a, b, out=None):

@@ -6,7 +6,7 @@ import torch
 
 from .. import utils as U
 from ..ops import comm
-from ..ops.gemm_ar import create_gemm_ar_context, gemm_allreduce_op
+from ..ops.gemm_ar import create_gemm_ar_context, create_ll_gemm_ar_context, gemm_allreduce_op, low_latency_gemm_allreduce_op
 
 
 class GemmARLayer:
@@ -14,10 +14,12 @@ class GemmARLayer:
                  local_world_size: int, persistent: bool = True, use_ll_kernel: bool = False, copy_to_local: bool = True,
                  NUM_COMM_SMS: int = 16):
         heap = U.get_heap()
-        self.ctx = create_gemm_ar_context(None, heap.rank, heap.world, local_world_size, max_M, N, output_dtype)
+        self.use_ll_kernel = use_ll_kernel
+        make = create_ll_gemm_ar_context if use_ll_kernel else create_gemm_ar_context
+        self.ctx = make(None, heap.rank, heap.world, local_world_size, max_M, N, output_dtype, NUM_COMM_SMS=NUM_COMM_SMS)
 
     def forward(self, x: torch.Tensor, weight: torch.Tensor, bias=None, scale_a=None, scale_b=None) -> torch.Tensor:
-        out = gemm_allreduce_op(self.ctx, x, weight)
+        out = (low_latency_gemm_allreduce_op if self.use_ll_kernel else gemm_allreduce_op)(self.ctx, x, weight)
         return out if bias is None else out + bias
 
     __call__ = forward

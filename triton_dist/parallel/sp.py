@@ -96,6 +96,8 @@ def fused_sp_ag_attn_intra_node(ctx: SPAllGatherAttentionContextIntraNode, q_sha
         k_all, v_all = k_shard[None], v_shard[None]
     S = S_local * W
     dev = q_shard.device
+    if q_shard.is_cuda and D == 128 and U.get_bool_env("TD_TCGEN05_PREFILL", False):
+        return _sp_attn_tcgen05(q_shard, k_all, v_all, W, r, is_causal, enable_zig_zag and W > 1, sm_scale)
     if enable_zig_zag and W > 1:
         pos = torch.stack([zigzag_positions(S, W, s, dev) for s in range(W)])      # [W, S_local]
     else:
@@ -109,6 +111,29 @@ def fused_sp_ag_attn_intra_node(ctx: SPAllGatherAttentionContextIntraNode, q_sha
     o = torch.nn.functional.scaled_dot_product_attention(q_shard.transpose(0, 1)[None], kk.transpose(0, 1)[None], vv.transpose(0, 1)[None],
                                                          attn_mask=mask[None, None] if mask is not None else None, scale=sm_scale)
     return o[0].transpose(0, 1).contiguous()
+
+
+def _sp_attn_tcgen05(q_shard, k_all, v_all, W, r, is_causal, zigzag, sm_scale):
+    """Attention of the local q block over the gathered KV with the tcgen05 flash kernel.  With zig-zag sharding rank s
+    holds chunks s and 2W-1-s of 2W; the gathered KV is put back into natural order (a view permutation + one copy) so
+    the causal mask is ``key <= q_pos`` with consecutive positions inside every 128-query tile."""
+    from ..ops.flash_attn import flash_attn_fwd
+    _, S_local, Hkv, D = k_all.shape
+    S = S_local * W
+    if zigzag:
+        c = S_local // 2
+        assert c % 128 == 0, "zig-zag chunks must be multiples of the 128-query tile"
+        order = torch.empty(2 * W, dtype=torch.long)
+        for s in range(W):
+            order[s], order[2 * W - 1 - s] = 2 * s, 2 * s + 1          # natural chunk -> index in the gathered layout
+        k_nat = k_all.reshape(2 * W, c, Hkv, D)[order.to(k_all.device)].reshape(1, S, Hkv, D)
+        v_nat = v_all.reshape(2 * W, c, Hkv, D)[order.to(v_all.device)].reshape(1, S, Hkv, D)
+        starts = torch.cat([torch.arange(r * c, (r + 1) * c, 128), torch.arange((2 * W - 1 - r) * c, (2 * W - r) * c, 128)])
+    else:
+        k_nat, v_nat = k_all.reshape(1, S, Hkv, D), v_all.reshape(1, S, Hkv, D)
+        starts = torch.arange(r * S_local, (r + 1) * S_local, 128)
+    tile_pos = starts.to(torch.int32).to(q_shard.device).view(1, -1).contiguous()
+    return flash_attn_fwd(q_shard[None], k_nat, v_nat, causal=is_causal, sm_scale=sm_scale, q_tile_pos=tile_pos)[0]
 
 
 # ------------------------------------------------------------------------------------------------------------

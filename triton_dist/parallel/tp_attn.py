@@ -18,9 +18,11 @@ from ..ops import comm
 from ..ops.ag_gemm import ag_gemm, create_ag_gemm_context
 from ..ops.elementwise import qk_norm_rope_kv
 from ..ops.flash_decode import gqa_fwd_batch_decode
-from ..ops.gemm_ar import create_gemm_ar_context, gemm_allreduce_op
+from ..ops.gemm_ar import create_gemm_ar_context, create_ll_gemm_ar_context, gemm_allreduce_op, low_latency_gemm_allreduce_op
 from ..ops.gemm_rs import create_gemm_rs_context, gemm_rs
 from .tp_mlp import _linear, shard_local
+
+_TCGEN05_PREFILL_DEFAULT = False     # flipped once the kernel is validated on hardware (tests/test_flash_attn_gpu.py)
 
 try:  # library attention for prefill
     from flash_attn import flash_attn_with_kvcache as _fa_kvcache
@@ -32,6 +34,16 @@ def prefill_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Ten
                       sm_scale: float) -> torch.Tensor:
     """q: [B, S, Hq, D]; caches [B, max_len, Hkv, D] already contain the new tokens; causal."""
     B, S, Hq, D = q.shape
+    if q.is_cuda and D == 128 and U.get_bool_env("TD_TCGEN05_PREFILL", _TCGEN05_PREFILL_DEFAULT):
+        # our tcgen05 flash-attention kernel (csrc/flash_attn_sm100.cu); one launch when all sequences share a length
+        from ..ops.flash_attn import flash_attn_fwd
+        lens = kv_lens.tolist()
+        if all(x == lens[0] for x in lens):
+            return flash_attn_fwd(q, k_cache, v_cache, causal=True, sm_scale=sm_scale, sk=lens[0])
+        out = torch.empty_like(q)
+        for b, L in enumerate(lens):
+            flash_attn_fwd(q[b:b + 1], k_cache[b:b + 1], v_cache[b:b + 1], causal=True, sm_scale=sm_scale, sk=L, out=out[b:b + 1])
+        return out
     if q.is_cuda and _fa_kvcache is not None:
         return _fa_kvcache(q, k_cache, v_cache, cache_seqlens=kv_lens.to(torch.int32), softmax_scale=sm_scale, causal=True)
     outs = []
@@ -94,7 +106,7 @@ class TP_Attn:
                                                 self.world_size, self.world_size)
 
     def _init_gemm_ar_ctx(self, max_M: int, dtype=torch.bfloat16):
-        self.gemm_ar_ctx = create_gemm_ar_context(None, self.rank, self.world_size, self.world_size, max_M, self.hidden, dtype)
+        self.gemm_ar_ctx = (create_ll_gemm_ar_context if (max_M <= 256 and U.get_bool_env('TD_GEMM_AR_FUSED', False)) else create_gemm_ar_context)(None, self.rank, self.world_size, self.world_size, max_M, self.hidden, dtype)
 
     def finalize(self):
         for c in (self.ag_ctx, self.rs_ctx, self.ar_ctx, self.gemm_ar_ctx):
@@ -154,7 +166,7 @@ class TP_Attn:
         bsz, q_len, H = x.shape
         qkv = _linear(x.reshape(-1, H), self.wqkv)
         o = self._attn_core(qkv, position_ids, kv_cache, layer_idx, bsz, q_len)
-        out = gemm_allreduce_op(self.gemm_ar_ctx, o, self.wo)
+        out = low_latency_gemm_allreduce_op(self.gemm_ar_ctx, o, self.wo)
         return out.view(bsz, q_len, H)
 
     def fwd(self, *a, **k):

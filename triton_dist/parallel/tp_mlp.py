@@ -17,7 +17,7 @@ from ..ops import comm
 from ..ops.ag_gemm import ag_gemm, create_ag_gemm_context
 from ..ops.elementwise import silu_mul
 from ..ops.gemm import gemm
-from ..ops.gemm_ar import create_gemm_ar_context, gemm_allreduce_op
+from ..ops.gemm_ar import create_gemm_ar_context, create_ll_gemm_ar_context, gemm_allreduce_op, low_latency_gemm_allreduce_op
 from ..ops.gemm_rs import create_gemm_rs_context, gemm_rs
 
 
@@ -74,7 +74,7 @@ class TP_MLP:
                                                 self.world_size, self.world_size)
 
     def _init_gemm_ar_ctx(self, max_M: int, dtype=torch.bfloat16):
-        self.gemm_ar_ctx = create_gemm_ar_context(None, self.rank, self.world_size, self.world_size, max_M,
+        self.gemm_ar_ctx = (create_ll_gemm_ar_context if (max_M <= 256 and U.get_bool_env('TD_GEMM_AR_FUSED', False)) else create_gemm_ar_context)(None, self.rank, self.world_size, self.world_size, max_M,
                                                   self.down_proj.shape[0], dtype)
 
     def finalize(self):
@@ -119,7 +119,7 @@ class TP_MLP:
         shp = x.shape
         x2 = x.reshape(-1, shp[-1])
         h = silu_mul(_linear(x2, self.gate_up_proj))
-        out = gemm_allreduce_op(self.gemm_ar_ctx, h, self.down_proj)
+        out = low_latency_gemm_allreduce_op(self.gemm_ar_ctx, h, self.down_proj)
         return out.view(shp)
 
     def fwd(self, x):
