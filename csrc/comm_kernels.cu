@@ -436,7 +436,29 @@ __global__ void wait_kernel(const uint32_t* addr, int n, uint32_t value, int geq
   if (geq) td::wait<true, true>(addr, n, value);
   else td::wait<false, true>(addr, n, value);
 }
+__global__ void wait_phase_copy_kernel(const uint32_t* flags, int n, const uint32_t* phase, const char* src, size_t buf_bytes,
+                                       char* dst, size_t nbytes) {
+  // graph-replayable consumer of a parity-double-buffered receive area: the expected flag value and the buffer half
+  // both come from the device-resident call counter the producer kernel just advanced
+  const uint32_t ph = phase[0];
+  if (threadIdx.x < 32) td::wait<true, true>(flags + (ph & 1u) * n, n, ph);
+  __syncthreads();
+  if (dst != nullptr)
+    td::copy16_strided(dst, src + (ph & 1u) * buf_bytes, nbytes, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
 }  // namespace
+
+TD_API int td_wait_phase_copy(const void* flags, int n, const void* phase, const void* src, size_t buf_bytes, void* dst,
+                              size_t nbytes, void* stream) {
+  if (n < 1 || n > 32) { td::drv::set_error("td_wait_phase_copy: 1 <= n <= 32"); return -1; }
+  if (nbytes % 16 != 0) { td::drv::set_error("td_wait_phase_copy: nbytes must be a multiple of 16"); return -1; }
+  const int grid = dst ? static_cast<int>(std::min<size_t>(128, (nbytes / 16 + 255) / 256 + 1)) : 1;
+  wait_phase_copy_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint32_t*>(flags), n, reinterpret_cast<const uint32_t*>(phase), reinterpret_cast<const char*>(src),
+      buf_bytes, reinterpret_cast<char*>(dst), nbytes);
+  TD_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
 
 TD_API int td_signal(void* addr, unsigned int value, int op, void* stream) {
   signal_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<uint32_t*>(addr), value, op);

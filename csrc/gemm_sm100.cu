@@ -164,6 +164,10 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
   p.rs_stage_buf_bytes = a->rs_stage_buf_bytes; p.rs_flags = reinterpret_cast<uint32_t*>(a->rs_flags);
   p.rs_out = a->rs_out; p.rs_ldo = a->rs_ldo;
   p.rs_flag_tiles = (int)a->rs_rows_per_rank;
+  if (a->mode == kAR && a->ag_rows_per_rank > 0) {   // scatter flavour borrows the (unused) ag_* fields
+    p.a2a_cols_per_rank = (int)a->ag_copy_local; p.a2a_rows_per_src = (int)a->ag_rows_per_rank;
+    p.a2a_count = reinterpret_cast<uint32_t*>(a->ag_ready);
+  }
 
   int dev = 0, sms = 0;
   TD_CUDA_CHECK(cudaGetDevice(&dev));
@@ -187,8 +191,17 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
 
   if (a->mode == kAR) {
     if (fp8) { drv::set_error("gemm_ar: MXFP8 inputs are not wired to the fused all-reduce yet"); return -1; }
+    if (p.a2a_cols_per_rank > 0) {
+      if (p.a2a_cols_per_rank % bn != 0 || p.a2a_cols_per_rank * p.symm.world != p.N) {
+        drv::set_error("gemm_a2a: N must be world * cols_per_rank and cols_per_rank a multiple of the tile width"); return -1;
+      }
+      if (p.M > p.a2a_rows_per_src) { drv::set_error("gemm_a2a: M exceeds the receive slot"); return -1; }
+      p.n_comm_ctas = 0;
+      grid = gemm_ctas;
+    } else {
     if (p.n_comm_ctas < cg) { drv::set_error("gemm_ar needs comm CTAs"); return -1; }
     if (p.num_m * cg * p.num_n > p.rs_flag_tiles) { drv::set_error("gemm_ar: flag array too small for this shape"); return -1; }
+    }
     if (p.N % 8 != 0 || a->rs_ldo % 8 != 0) { drv::set_error("gemm_ar: N and the output row stride must be multiples of 8"); return -1; }
     if (p.symm.world * cg > 256) { drv::set_error("gemm_ar: world too large"); return -1; }
   }

@@ -101,6 +101,10 @@ struct Params {
   uint32_t* rs_flags;        // symmetric: [2][num_m * num_n], written by rank+1 with the phase number
                              // (kAR: [2][rs_flag_tiles][world], flag[tile][r] = phase once rank r staged that 128-row block)
   int rs_flag_tiles;         // kAR: flag capacity per parity, in (128-row block, n tile) units
+  int a2a_cols_per_rank;     // kAR scatter flavour (> 0): output columns [d*c, (d+1)*c) go to rank d, rows land at
+                             // me * a2a_rows_per_src (GEMM + all-to-all: Ulysses QKV projection); no comm CTAs
+  int a2a_rows_per_src;
+  uint32_t* a2a_count;       // local [world] tile counters (last tile for a destination publishes the flag)
   void* rs_out;              // [rows_per_rank, N] final output (local)
   long long rs_ldo;
 };
@@ -487,8 +491,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
           }
         }
 
-        if constexpr (kMode == kAR) {     // partial tile -> my symmetric staging buffer (same coordinates as C)
-          dst_base = p.rs_stage + (ph & 1u) * p.rs_stage_buf_bytes; dst_ld = p.N; dst_row_off = 0;
+        int a2a_dst = 0;
+        if constexpr (kMode == kAR) {
+          if (p.a2a_cols_per_rank > 0) {   // scatter flavour: the tile's column block belongs to rank a2a_dst
+            a2a_dst = col_base / p.a2a_cols_per_rank;
+            dst_base = symm_at(p.symm, p.rs_stage + (ph & 1u) * p.rs_stage_buf_bytes, a2a_dst) -
+                       static_cast<size_t>(a2a_dst) * p.a2a_cols_per_rank * 2;
+            dst_ld = p.a2a_cols_per_rank; dst_row_off = -p.symm.rank * p.a2a_rows_per_src;
+          } else {                         // partial tile -> my symmetric staging buffer (same coordinates as C)
+            dst_base = p.rs_stage + (ph & 1u) * p.rs_stage_buf_bytes; dst_ld = p.N; dst_row_off = 0;
+          }
         }
 
         ptx::mbar_wait(tmem_full + acc, acc_phase);
@@ -608,7 +620,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
           // each CTA of a pair stages its own 128 rows and publishes its own flag word (index carries the CTA rank);
           // the consumer waits for every (row half, source rank) word of the tile
           ptx::named_bar_sync(2, kEpiThreads);
-          if (et == 0) {
+          if (et == 0 && p.a2a_cols_per_rank > 0) {
+            // count finished 128-row blocks per destination; the last one tells that rank "all of my rows have landed"
+            const int W = p.symm.world, me = p.symm.rank;
+            const uint32_t per_dst = static_cast<uint32_t>(p.num_m * kCtaGroup * (p.a2a_cols_per_rank / BN));
+            ptx::fence_acq_rel_sys();
+            if (ptx::atom_add_acq_rel_gpu(p.a2a_count + a2a_dst, 1u) == per_dst - 1u) {
+              p.a2a_count[a2a_dst] = 0;
+              ptx::fence_acq_rel_sys();
+              ptx::st_release_sys(symm_at(p.symm, p.rs_flags + (ph & 1u) * W + me, a2a_dst), ph);
+            }
+          } else if (et == 0) {
             const int W = p.symm.world, me = p.symm.rank;
             uint32_t* f = p.rs_flags + static_cast<size_t>(ph & 1u) * p.rs_flag_tiles * W +
                           static_cast<size_t>((m_tile * kCtaGroup + static_cast<int>(cta_rank)) * p.num_n + n_tile) * W + me;

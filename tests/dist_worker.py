@@ -211,6 +211,32 @@ def case_gemm_ar():
         ctx.finalize()
 
 
+def case_gemm_a2a():
+    """GEMM with the all-to-all of its output columns fused into the epilogue (ulysses_sp_infer_gemm_a2a.py:143-289)."""
+    from triton_dist.ops.gemm_a2a import create_gemm_a2a_context, gemm_all_to_all
+    dev = U.current_device()
+    W, me = U.world_size(), U.rank()
+    big = dev.type == "cuda"
+    dtype = torch.bfloat16 if big else torch.float32
+    shapes = [(256, 256, 512), (100, 128, 264), (512, 384, 1024), (32, 64, 128)] if big else [(6, 8, 16)]
+    for (M, c, K) in shapes:
+        ctx = create_gemm_a2a_context(M, c, dtype)
+        for it in range(5):
+            X = (torch.randn(M, K, device=dev) * 0.5).to(dtype)
+            Wt = (torch.randn(W * c, K, device=dev) * 0.5).to(dtype)
+            if it in (1, 3) and big and me == it % W:
+                torch.cuda._sleep(2_000_000)
+            out = gemm_all_to_all(ctx, X, Wt)
+            # golden: every rank's full product, gathered; my columns of each
+            y = (X.float() @ Wt.float().t())
+            ally = torch.empty(W * M * W * c, dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(ally, y.reshape(-1).contiguous(), group=U.get_triton_dist_world())
+            ref = ally.view(W, M, W * c)[:, :, me * c:(me + 1) * c].reshape(W * M, c)
+            _assert_close(out, ref, 0.5 if big else 1e-3, 2e-2 if big else 1e-4, f"gemm_a2a {M}x{c}x{K} it{it}")
+        U.barrier_all_host()
+        ctx.finalize()
+
+
 def case_moe():
     """ag_group_gemm + run_moe_reduce_rs vs the masked-matmul golden (reference: test_ag_moe.py, test_moe_reduce_rs.py)."""
     from triton_dist.ops import moe as M

@@ -33,4 +33,6 @@ from ...ops.compat import (SpUlysessOAll2AllGemmKernel, SpUlysessQKVGemmAll2AllK
 from ...ops.perf_model import (estimate_all_gather_time_ms, estimate_gemm_sol_time_ms, estimate_reduce_scatter_time_ms,  # noqa: F401
                                get_dram_gbps, get_nic_gbps_per_gpu, get_tensorcore_tflops)
 from ...ops.p2p import p2p_get, p2p_put, p2p_set_signal, p2p_wait_signal  # noqa: F401
+from ...ops.gemm_a2a import GemmA2AContext, create_gemm_a2a_context, gemm_all_to_all  # noqa: F401
+from ...ops.flash_attn import flash_attn_fwd, flash_attn_varlen  # noqa: F401
 from . import allreduce  # noqa: F401

@@ -145,7 +145,13 @@ class SpUlysessOAll2AllGemmKernel:
 UlyssesSpInferPreAttnContext = SpUlysessQKVGemmAll2AllKernel
 
 
-def ulysses_sp_infer_gemm_a2a_op(ctx: SpUlysessQKVGemmAll2AllKernel, x, wqkv):
+def ulysses_sp_infer_gemm_a2a_op(ctx, x, wqkv):
+    """(ulysses_sp_infer_gemm_a2a.py:455) ``ctx``: a :class:`SpUlysessQKVGemmAll2AllKernel` (GEMM then all-to-all) or a
+    :class:`triton_dist.ops.gemm_a2a.GemmA2AContext` (all-to-all fused into the GEMM epilogue; ``wqkv`` rows grouped by
+    destination rank)."""
+    from .gemm_a2a import GemmA2AContext, gemm_all_to_all
+    if isinstance(ctx, GemmA2AContext):
+        return gemm_all_to_all(ctx, x, wqkv)
     return ctx.forward(x, wqkv)
 
 
