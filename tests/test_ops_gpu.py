@@ -129,3 +129,24 @@ def test_gemv_decode_path(M):
     b = torch.randn(1000, 4096, device="cuda", dtype=torch.bfloat16)
     c = gemm(a, b)
     torch.testing.assert_close(c.float(), a.float() @ b.float().t(), atol=0.5, rtol=2e-2)
+
+
+@pytest.mark.parametrize("T", [1, 7, 300])
+def test_gdn_recurrent_kernel(T):
+    """Fused recurrent gated-delta-rule kernel and the chunked forward vs the sequential fp32 reference."""
+    from triton_dist.ops.gdn import chunk_gated_delta_rule_fwd, fused_recurrent_gated_delta_rule, gated_delta_rule_recurrent
+    torch.manual_seed(T)
+    B, H, Dk, Dv = 2, 3, 128, 128
+    q = torch.randn(B, T, H, Dk, device="cuda", dtype=torch.bfloat16)
+    k = torch.nn.functional.normalize(torch.randn(B, T, H, Dk, device="cuda"), dim=-1).to(torch.bfloat16)
+    v = torch.randn(B, T, H, Dv, device="cuda", dtype=torch.bfloat16)
+    g = -torch.rand(B, T, H, device="cuda") * 0.2
+    beta = torch.rand(B, T, H, device="cuda")
+    s0 = torch.randn(B, H, Dk, Dv, device="cuda") * 0.1
+    ref_o, ref_s = gated_delta_rule_recurrent(q.float(), k.float(), v.float(), g, beta, None, s0)
+    o, s = fused_recurrent_gated_delta_rule(q, k, v, g, beta, None, s0)
+    torch.testing.assert_close(o.float(), ref_o, atol=3e-2, rtol=3e-2)
+    torch.testing.assert_close(s, ref_s, atol=2e-2, rtol=2e-2)
+    o2, s2 = chunk_gated_delta_rule_fwd(q, k, v, g, beta, None, s0)
+    torch.testing.assert_close(o2.float(), ref_o, atol=3e-2, rtol=3e-2)
+    torch.testing.assert_close(s2, ref_s, atol=2e-2, rtol=2e-2)

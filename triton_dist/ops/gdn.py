@@ -30,12 +30,38 @@ def gated_delta_rule_recurrent(q, k, v, g, beta, scale: Optional[float] = None, 
     return o.to(q.dtype), S
 
 
+def fused_recurrent_gated_delta_rule(q, k, v, g, beta, scale: Optional[float] = None, initial_state=None):
+    """Token-sequential CUDA kernel (csrc/gdn_kernels.cu): the [Dk, Dv] state lives in registers for the whole call --
+    the decode-step / short-prompt companion of the chunked forward.  Returns (o, final_state fp32 [B,H,Dk,Dv])."""
+    if not q.is_cuda:
+        return gated_delta_rule_recurrent(q, k, v, g, beta, scale, initial_state)
+    import ctypes as C
+    from .. import _C
+    B, T, H, Dk = q.shape
+    Dv = v.shape[-1]
+    scale = scale if scale is not None else Dk ** -0.5
+    state = (torch.zeros(B, H, Dk, Dv, dtype=torch.float32, device=q.device) if initial_state is None
+             else initial_state.float().clone().contiguous())
+    o = torch.empty(B, T, H, Dv, dtype=q.dtype, device=q.device)
+    dt = {torch.float16: 0, torch.bfloat16: 1, torch.float32: 2}[q.dtype]
+    fn = _C.cuda_lib().td_gdn_recurrent
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p] * 7 + [C.c_int] * 5 + [C.c_float, C.c_int, C.c_void_p]
+    _C.check(fn(q.contiguous().data_ptr(), k.contiguous().data_ptr(), v.contiguous().data_ptr(), g.float().contiguous().data_ptr(),
+                beta.float().contiguous().data_ptr(), state.data_ptr(), o.data_ptr(), B, T, H, Dk, Dv, float(scale), dt,
+                C.c_void_p(torch.cuda.current_stream().cuda_stream)), "td_gdn_recurrent")
+    return o, state
+
+
 def chunk_gated_delta_rule_fwd(q, k, v, g, beta, scale: Optional[float] = None, initial_state=None, output_final_state: bool = True,
                                chunk_size: int = 64) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """Chunk-parallel forward (WY representation): within a chunk the delta-rule updates are resolved with one
     unit-lower-triangular solve, chunks are chained through the [Dk, Dv] state."""
     B, T, H, Dk = q.shape
     Dv = v.shape[-1]
+    if q.is_cuda and T <= 16 and Dk in (64, 128, 256):          # decode steps: state-in-registers kernel
+        o, S = fused_recurrent_gated_delta_rule(q, k, v, g, beta, scale, initial_state)
+        return o, (S if output_final_state else None)
     scale = scale if scale is not None else Dk ** -0.5
     C = chunk_size
     pad = (C - T % C) % C
