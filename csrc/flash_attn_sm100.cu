@@ -25,12 +25,11 @@ namespace td {
 namespace fa {
 
 constexpr int BMQ = 128;          // queries per CTA
-constexpr int BNK = 128;          // keys per pipeline step
 constexpr int HD = 128;           // head dim
 constexpr int kThreads = 192;
 constexpr int kKVStages = 2;
-constexpr int kTileBytes = 128 * 128 * 2;     // one [128, 128] 16-bit tile = two 16 KB swizzle slabs
-constexpr int kSlab = 128 * 128;              // bytes of one [128 rows, 64 elements] slab
+constexpr int kQBytes = BMQ * HD * 2;         // Q tile: two [128 rows, 64 elements] 16 KB swizzle slabs
+constexpr int kSlab = 128 * 128;              // bytes of one [128 rows, 64 elements] slab (Q, P)
 
 struct Params {
   CUtensorMap tmap_q, tmap_k, tmap_v;
@@ -43,20 +42,30 @@ struct Params {
   float scale_log2;        // sm_scale * log2(e)
 };
 
+// BNK = keys per pipeline step.  128: one CTA per SM (197 KB smem, 384 TMEM columns).  64: TWO CTAs per SM (115 KB, 256
+// columns each) -- the softmax of one CTA runs under the MMAs of the other, which is what the kernel is bound by.
+template <int BNK>
 struct Smem {
+  static constexpr int kKVSlab = BNK * 128;            // [BNK keys, 64 elements]
+  static constexpr int kKVTile = 2 * kKVSlab;          // [BNK keys, 128 elements]
+  static constexpr int kPBytes = BMQ * BNK * 2;        // BNK / 64 slabs of [128 rows, 64 keys]
   static constexpr int kQ = 0;
-  static constexpr int kK = kQ + kTileBytes;
-  static constexpr int kV = kK + kKVStages * kTileBytes;
-  static constexpr int kP = kV + kKVStages * kTileBytes;
-  static constexpr int kBar = kP + kTileBytes;
-  static constexpr int kTotal = kBar + 256 + 1024;
+  static constexpr int kK = kQ + kQBytes;
+  static constexpr int kV = kK + kKVStages * kKVTile;
+  static constexpr int kP = kV + kKVStages * kKVTile;
+  static constexpr int kBar = kP + kPBytes;
+  static constexpr int kTotal = kBar + 256;            // dynamic smem starts 1024-byte aligned (checked at run time)
+  static constexpr int kTmemCols = (2 * BNK + HD) <= 256 ? 256 : 512;
 };
 
 enum Bar { Q_FULL = 0, K_FULL = 1, V_FULL = 3, KV_EMPTY = 5, S_FULL = 7, S_FREE = 9, P_READY = 11, PV_DONE = 12, NBAR = 13 };
 
-__global__ void __launch_bounds__(kThreads, 1) flash_fwd_kernel(const __grid_constant__ Params p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+template <int BNK>
+__global__ void __launch_bounds__(kThreads, BNK == 64 ? 2 : 1) flash_fwd_kernel(const __grid_constant__ Params p) {
+  using Smem = fa::Smem<BNK>;
+  constexpr int kKVTile = Smem::kKVTile, kKVSlab = Smem::kKVSlab;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();      // SWIZZLE_128B atoms need 1024-byte alignment
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::kBar);
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + NBAR);
 
@@ -88,32 +97,32 @@ __global__ void __launch_bounds__(kThreads, 1) flash_fwd_kernel(const __grid_con
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc<1>(tmem_ptr_smem, 512);
+    ptx::tmem_alloc<1>(tmem_ptr_smem, Smem::kTmemCols);
     ptx::tmem_relinquish<1>();
   }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const uint32_t tmem_o = tmem_base + 256;
+  const uint32_t tmem_o = tmem_base + 2 * BNK;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      ptx::mbar_arrive_expect_tx(&bars[Q_FULL], kTileBytes);
+      ptx::mbar_arrive_expect_tx(&bars[Q_FULL], kQBytes);
       ptx::tma_load_4d(&p.tmap_q, &bars[Q_FULL], smem + Smem::kQ, 0, q_row0, head, batch);
       ptx::tma_load_4d(&p.tmap_q, &bars[Q_FULL], smem + Smem::kQ + kSlab, 64, q_row0, head, batch);
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j & 1;
         if (j >= kKVStages) ptx::mbar_wait(&bars[KV_EMPTY + st], ((j >> 1) - 1) & 1);
-        uint8_t* ks = smem + Smem::kK + st * kTileBytes;
-        uint8_t* vs = smem + Smem::kV + st * kTileBytes;
-        ptx::mbar_arrive_expect_tx(&bars[K_FULL + st], kTileBytes);
+        uint8_t* ks = smem + Smem::kK + st * kKVTile;
+        uint8_t* vs = smem + Smem::kV + st * kKVTile;
+        ptx::mbar_arrive_expect_tx(&bars[K_FULL + st], kKVTile);
         ptx::tma_load_4d(&p.tmap_k, &bars[K_FULL + st], ks, 0, j * BNK, kv_head, batch, ptx::kEvictLast);
-        ptx::tma_load_4d(&p.tmap_k, &bars[K_FULL + st], ks + kSlab, 64, j * BNK, kv_head, batch, ptx::kEvictLast);
-        ptx::mbar_arrive_expect_tx(&bars[V_FULL + st], kTileBytes);
+        ptx::tma_load_4d(&p.tmap_k, &bars[K_FULL + st], ks + kKVSlab, 64, j * BNK, kv_head, batch, ptx::kEvictLast);
+        ptx::mbar_arrive_expect_tx(&bars[V_FULL + st], kKVTile);
         ptx::tma_load_4d(&p.tmap_v, &bars[V_FULL + st], vs, 0, j * BNK, kv_head, batch, ptx::kEvictLast);
-        ptx::tma_load_4d(&p.tmap_v, &bars[V_FULL + st], vs + kSlab, 64, j * BNK, kv_head, batch, ptx::kEvictLast);
+        ptx::tma_load_4d(&p.tmap_v, &bars[V_FULL + st], vs + kKVSlab, 64, j * BNK, kv_head, batch, ptx::kEvictLast);
       }
     }
   } else if (warp == 1) {
@@ -129,11 +138,11 @@ __global__ void __launch_bounds__(kThreads, 1) flash_fwd_kernel(const __grid_con
         ptx::mbar_wait(&bars[K_FULL + st], (j >> 1) & 1);
         if (j >= 2) ptx::mbar_wait(&bars[S_FREE + b], ((j >> 1) - 1) & 1);
         ptx::tc_fence_after();
-        const uint32_t k_addr = ptx::smem_u32(smem + Smem::kK + st * kTileBytes);
+        const uint32_t k_addr = ptx::smem_u32(smem + Smem::kK + st * kKVTile);
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * kSlab + (kk & 3) * 32;
-          ptx::mma_f16<1>(tmem_base + b * BNK, ptx::make_smem_desc_k128(q_addr + off), ptx::make_smem_desc_k128(k_addr + off),
+          const uint32_t qoff = (kk >> 2) * kSlab + (kk & 3) * 32, koff = (kk >> 2) * kKVSlab + (kk & 3) * 32;
+          ptx::mma_f16<1>(tmem_base + b * BNK, ptx::make_smem_desc_k128(q_addr + qoff), ptx::make_smem_desc_k128(k_addr + koff),
                           idesc_qk, kk > 0 ? 1u : 0u);
         }
         ptx::mma_commit(&bars[S_FULL + b]);
@@ -146,11 +155,11 @@ __global__ void __launch_bounds__(kThreads, 1) flash_fwd_kernel(const __grid_con
         ptx::mbar_wait(&bars[V_FULL + st], (j >> 1) & 1);
         ptx::mbar_wait(&bars[P_READY], j & 1);
         ptx::tc_fence_after();
-        const uint32_t v_addr = ptx::smem_u32(smem + Smem::kV + st * kTileBytes);
+        const uint32_t v_addr = ptx::smem_u32(smem + Smem::kV + st * kKVTile);
 #pragma unroll
         for (int kk = 0; kk < BNK / 16; ++kk) {
           const uint64_t a = ptx::make_smem_desc_k128(p_addr + (kk >> 2) * kSlab + (kk & 3) * 32);
-          const uint64_t bdesc = ptx::make_smem_desc_mn128(v_addr + kk * 16 * 128, kSlab);
+          const uint64_t bdesc = ptx::make_smem_desc_mn128(v_addr + kk * 16 * 128, kKVSlab);
           ptx::mma_f16<1>(tmem_o, a, bdesc, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
         }
         ptx::mma_commit(&bars[KV_EMPTY + st]);
@@ -170,9 +179,10 @@ __global__ void __launch_bounds__(kThreads, 1) flash_fwd_kernel(const __grid_con
       const int b = j & 1;
       ptx::mbar_wait(&bars[S_FULL + b], (j >> 1) & 1);
       ptx::tc_fence_after();
-      uint32_t s[4][32];
+      constexpr int NC = BNK / 32;
+      uint32_t s[NC][32];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) ptx::tmem_ld_32x32b_x32(tmem_base + lane_off + b * BNK + c * 32, s[c]);
+      for (int c = 0; c < NC; ++c) ptx::tmem_ld_32x32b_x32(tmem_base + lane_off + b * BNK + c * 32, s[c]);
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(&bars[S_FREE + b]);
@@ -183,7 +193,7 @@ __global__ void __launch_bounds__(kThreads, 1) flash_fwd_kernel(const __grid_con
       if (need_mask) {
         const int limit = p.causal ? min(p.Sk - 1, q_pos) : p.Sk - 1;       // last visible key
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < NC; ++c)
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             float v = __uint_as_float(s[c][i]);
@@ -193,7 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) flash_fwd_kernel(const __grid_con
           }
       } else {
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < NC; ++c)
 #pragma unroll
           for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s[c][i]));
       }
@@ -209,7 +219,7 @@ __global__ void __launch_bounds__(kThreads, 1) flash_fwd_kernel(const __grid_con
       const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
       float sum = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+      for (int c = 0; c < NC; ++c)
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const float e = ptx::ex2_approx(fmaf(__uint_as_float(s[c][i]), p.scale_log2, neg_m));
@@ -225,7 +235,7 @@ __global__ void __launch_bounds__(kThreads, 1) flash_fwd_kernel(const __grid_con
       }
       // P (bf16 / fp16) -> K-major SWIZZLE_128B: 16-byte chunk c16 of row r lands at chunk (c16 ^ (r & 7))
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+      for (int c = 0; c < NC; ++c)
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 v;
@@ -310,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, 1) flash_fwd_kernel(const __grid_con
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<1>(tmem_base, 512);
+    ptx::tmem_dealloc<1>(tmem_base, Smem::kTmemCols);
   }
 }
 
@@ -329,15 +339,31 @@ struct TdFlashArgs {
   long long o_stride_b, o_stride_s, o_stride_h;
   double sm_scale;
   long long causal, is_bf16;
+  long long block_n;          // keys per step: 64 (two CTAs per SM, default) or 128
 };
 
+template <int BNK>
+static int fa_launch(const td::fa::Params& p, dim3 grid, cudaStream_t s) {
+  using namespace td::fa;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(flash_fwd_kernel<BNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BNK>::kTotal);
+    if (e != cudaSuccess) { td::drv::set_error("flash_attn: smem attribute: %s", cudaGetErrorString(e)); return -1; }
+    attr_set = true;
+  }
+  flash_fwd_kernel<BNK><<<grid, kThreads, Smem<BNK>::kTotal, s>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { td::drv::set_error("flash_attn launch: %s", cudaGetErrorString(e)); return -1; }
+  return 0;
+}
+
 static int fa_tmap(CUtensorMap* out, const void* base, long long S, long long H, long long B, long long sb, long long ss,
-                   long long sh, int is_bf16) {
+                   long long sh, int is_bf16, int box_rows) {
   auto enc = td::drv::cuTensorMapEncodeTiled_fn();
   if (!enc) { td::drv::set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return -1; }
   const cuuint64_t dims[4] = {128, (cuuint64_t)S, (cuuint64_t)H, (cuuint64_t)B};
   const cuuint64_t strides[3] = {(cuuint64_t)ss * 2, (cuuint64_t)sh * 2, (cuuint64_t)sb * 2};
-  const cuuint32_t box[4] = {64, 128, 1, 1};
+  const cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(out, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base),
                    dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -355,23 +381,16 @@ extern "C" __attribute__((visibility("default"))) int td_flash_attn_fwd(const Td
   for (long long s : st)
     if (s % 8 != 0) { td::drv::set_error("flash_attn: strides must be multiples of 8 elements (16 bytes)"); return -1; }
   Params p{};
-  if (fa_tmap(&p.tmap_q, a->q, a->Sq, a->Hq, a->B, a->q_stride_b, a->q_stride_s, a->q_stride_h, (int)a->is_bf16)) return -1;
-  if (fa_tmap(&p.tmap_k, a->k, a->Sk, a->Hkv, a->B, a->k_stride_b, a->k_stride_s, a->k_stride_h, (int)a->is_bf16)) return -1;
-  if (fa_tmap(&p.tmap_v, a->v, a->Sk, a->Hkv, a->B, a->v_stride_b, a->v_stride_s, a->v_stride_h, (int)a->is_bf16)) return -1;
+  const int bnk = a->block_n == 128 ? 128 : 64;
+  if (fa_tmap(&p.tmap_q, a->q, a->Sq, a->Hq, a->B, a->q_stride_b, a->q_stride_s, a->q_stride_h, (int)a->is_bf16, BMQ)) return -1;
+  if (fa_tmap(&p.tmap_k, a->k, a->Sk, a->Hkv, a->B, a->k_stride_b, a->k_stride_s, a->k_stride_h, (int)a->is_bf16, bnk)) return -1;
+  if (fa_tmap(&p.tmap_v, a->v, a->Sk, a->Hkv, a->B, a->v_stride_b, a->v_stride_s, a->v_stride_h, (int)a->is_bf16, bnk)) return -1;
   p.o = a->o; p.lse = a->lse; p.q_tile_pos = a->q_tile_pos;
   p.o_stride_b = a->o_stride_b; p.o_stride_s = a->o_stride_s; p.o_stride_h = a->o_stride_h;
   p.B = (int)a->B; p.Sq = (int)a->Sq; p.Sk = (int)a->Sk; p.Hq = (int)a->Hq; p.Hkv = (int)a->Hkv;
   p.causal = (int)a->causal; p.is_bf16 = (int)a->is_bf16;
   p.scale_log2 = static_cast<float>(a->sm_scale * 1.4426950408889634);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(flash_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::kTotal);
-    if (e != cudaSuccess) { td::drv::set_error("flash_attn: smem attribute: %s", cudaGetErrorString(e)); return -1; }
-    attr_set = true;
-  }
   dim3 grid((unsigned)((a->Sq + BMQ - 1) / BMQ), (unsigned)a->Hq, (unsigned)a->B);
-  flash_fwd_kernel<<<grid, kThreads, Smem::kTotal, reinterpret_cast<cudaStream_t>(stream_)>>>(p);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) { td::drv::set_error("flash_attn launch: %s", cudaGetErrorString(e)); return -1; }
-  return 0;
+  cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream_);
+  return bnk == 128 ? fa_launch<128>(p, grid, st_) : fa_launch<64>(p, grid, st_);
 }

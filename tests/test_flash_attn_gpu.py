@@ -6,6 +6,11 @@ pytestmark = pytest.mark.gpu
 
 
 def _check(B, Sq, Sk, Hq, Hkv, causal, dtype, cache_len=None, tile_pos=False):
+    for bn in (64, 128):
+        _check_bn(B, Sq, Sk, Hq, Hkv, causal, dtype, cache_len, tile_pos, bn)
+
+
+def _check_bn(B, Sq, Sk, Hq, Hkv, causal, dtype, cache_len, tile_pos, bn):
     from triton_dist.ops.flash_attn import flash_attn_fwd, flash_attn_reference
     torch.manual_seed(Sq * 7 + Sk)
     L = cache_len or Sk
@@ -18,7 +23,7 @@ def _check(B, Sq, Sk, Hq, Hkv, causal, dtype, cache_len=None, tile_pos=False):
         starts = torch.randint(0, max(1, (Sk - 128) // 64), (B, nt), device="cuda", dtype=torch.int32) * 64
         q_tile_pos = starts.contiguous()
         q_pos = (starts.long()[:, :, None] + torch.arange(128, device="cuda")[None, None]).reshape(B, -1)[:, :Sq]
-    out, lse = flash_attn_fwd(q, k, v, causal=causal, q_tile_pos=q_tile_pos, sk=Sk, return_lse=True)
+    out, lse = flash_attn_fwd(q, k, v, causal=causal, q_tile_pos=q_tile_pos, sk=Sk, return_lse=True, block_n=bn)
     ref, ref_lse = flash_attn_reference(q, k, v, causal, None, q_pos, Sk)
     torch.testing.assert_close(out.float(), ref, atol=2e-2, rtol=2e-2)
     torch.testing.assert_close(lse, ref_lse, atol=2e-2, rtol=1e-2)
@@ -55,18 +60,21 @@ def test_flash_perf():
     q = torch.randn(B, S, H, 128, device="cuda", dtype=torch.bfloat16)
     k = torch.randn(B, S, 8, 128, device="cuda", dtype=torch.bfloat16)
     v = torch.randn(B, S, 8, 128, device="cuda", dtype=torch.bfloat16)
-    for _ in range(3):
-        flash_attn_fwd(q, k, v)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(10):
-        flash_attn_fwd(q, k, v)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 10
-    tf = 4 * B * H * S * S * 128 / 2 / ms / 1e9
-    print(f"\nflash_attn causal 8Kx8K 32h: {ms:.3f} ms  {tf:.0f} TFLOP/s")
+    tf = 0.0
+    for bn in (64, 128):
+        for _ in range(3):
+            flash_attn_fwd(q, k, v, block_n=bn)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10):
+            flash_attn_fwd(q, k, v, block_n=bn)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        t = 4 * B * H * S * S * 128 / 2 / ms / 1e9
+        tf = max(tf, t)
+        print(f"\nflash_attn causal 8Kx8K 32h block_n={bn}: {ms:.3f} ms  {t:.0f} TFLOP/s")
     try:
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         qq, kk, vv = q.transpose(1, 2), k.transpose(1, 2).repeat_interleave(4, 1), v.transpose(1, 2).repeat_interleave(4, 1)

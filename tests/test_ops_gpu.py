@@ -85,6 +85,7 @@ def test_engine_single_gpu_backends_agree():
     import triton_dist.utils as U
     from triton_dist.models import Engine, ModelConfig
     U.initialize_distributed(seed=0)
+    assert U.current_device().type == "cuda", "GPU tests must run on the CUDA backend"
     cfg = ModelConfig(model_name="tiny-dense", max_length=64, dtype=torch.bfloat16, rank=0, world_size=1)
     eng = Engine(cfg, temperature=0.0)
     ids = torch.randint(0, 1000, (4, 6), device="cuda")
@@ -105,6 +106,7 @@ def test_megakernel_single_gpu():
     from triton_dist.mega_kernel import MegaDenseModel
     from triton_dist.models import AutoLLM, KV_Cache, ModelConfig
     U.initialize_distributed(seed=0)
+    assert U.current_device().type == "cuda", "GPU tests must run on the CUDA backend"
     cfg = ModelConfig(model_name="tiny-dense", max_length=64, dtype=torch.bfloat16, rank=0, world_size=1)
     m = AutoLLM.from_pretrained(cfg)
     B = 4

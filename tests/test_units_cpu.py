@@ -6,16 +6,19 @@ import os
 import pytest
 import torch
 
-os.environ.setdefault("TD_FORCE_HOST_BACKEND", "1")
 
 
 @pytest.fixture(scope="module")
 def dist_env():
+    # the emulation backend is forced only for the lifetime of this module's tests: setting it at import time would leak
+    # into `pytest -m gpu` runs (pytest imports every test module during collection) and silently put GPU tests on the CPU
     import triton_dist.utils as U
     os.environ.setdefault("MASTER_PORT", "29677")
+    os.environ["TD_FORCE_HOST_BACKEND"] = "1"
     U.initialize_distributed(seed=0)
     yield U
     U.finalize_distributed()
+    os.environ.pop("TD_FORCE_HOST_BACKEND", None)
 
 
 def test_native_libs_build_and_load():
