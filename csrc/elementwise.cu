@@ -241,23 +241,35 @@ __global__ void __launch_bounds__(256) gemv_kernel(const uint4* __restrict__ x, 
     for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int b = 0; b < 8; ++b) acc[r][b] = 0.f;
-    for (int kv = lane; kv < kvec; kv += 32) {
-      uint4 wv[R];
+    constexpr int U = 2;      // k-steps in flight per lane: R * U independent 16-byte loads
+    for (int kv0 = lane; kv0 < kvec; kv0 += 32 * U) {
+      uint4 wv[U][R];
 #pragma unroll
-      for (int r = 0; r < R; ++r) wv[r] = (n0 + r < N) ? ptx::ld_nc_v4(W + static_cast<size_t>(n0 + r) * kvec + kv) : make_uint4(0, 0, 0, 0);
-      float wf[R][8];
+      for (int u = 0; u < U; ++u)
 #pragma unroll
-      for (int r = 0; r < R; ++r) unpack8<kBF16>(wv[r], wf[r]);
-#pragma unroll
-      for (int b = 0; b < 8; ++b)
-        if (b < B) {
-          float xf[8];
-          unpack8<kBF16>(xs[b * kvec + kv], xf);
-#pragma unroll
-          for (int r = 0; r < R; ++r)
-#pragma unroll
-            for (int e = 0; e < 8; ++e) acc[r][b] += wf[r][e] * xf[e];
+        for (int r = 0; r < R; ++r) {
+          const int kv = kv0 + u * 32;
+          wv[u][r] = (n0 + r < N && kv < kvec) ? ptx::ld_nc_v4(W + static_cast<size_t>(n0 + r) * kvec + kv) : make_uint4(0, 0, 0, 0);
         }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int kv = kv0 + u * 32;
+        if (kv < kvec) {
+          float wf[R][8];
+#pragma unroll
+          for (int r = 0; r < R; ++r) unpack8<kBF16>(wv[u][r], wf[r]);
+#pragma unroll
+          for (int b = 0; b < 8; ++b)
+            if (b < B) {
+              float xf[8];
+              unpack8<kBF16>(xs[b * kvec + kv], xf);
+#pragma unroll
+              for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[r][b] += wf[r][e] * xf[e];
+            }
+        }
+      }
     }
 #pragma unroll
     for (int r = 0; r < R; ++r)

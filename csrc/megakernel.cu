@@ -129,30 +129,41 @@ TD_DEVICE void task_linear(const MKParams& p, const Task& t, uint8_t* smem) {
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int R = 4;      // W rows in flight per warp
+  constexpr int R = 4;      // W rows per warp
+  constexpr int U = 2;      // k-steps in flight: R * U independent 16-byte loads per lane (8 KB per warp, 64 KB per SM)
   for (int j0 = warp * R; j0 < n_cnt; j0 += (kMKThreads / 32) * R) {
     float acc[R][kMaxB];
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int b = 0; b < kMaxB; ++b) acc[r][b] = 0.f;
-    for (int kv = lane; kv < kvec; kv += 32) {
-      uint4 wv[R];
+    for (int kv0 = lane; kv0 < kvec; kv0 += 32 * U) {
+      uint4 wv[U][R];
 #pragma unroll
-      for (int r = 0; r < R; ++r)
-        wv[r] = (j0 + r < n_cnt) ? ptx::ld_nc_v4(W + static_cast<size_t>(n0 + j0 + r) * kvec + kv) : make_uint4(0, 0, 0, 0);
-      float wf[R][8];
+      for (int u = 0; u < U; ++u)
 #pragma unroll
-      for (int r = 0; r < R; ++r) unpack8(wv[r], wf[r]);
+        for (int r = 0; r < R; ++r) {
+          const int kv = kv0 + u * 32;
+          wv[u][r] = (j0 + r < n_cnt && kv < kvec) ? ptx::ld_nc_v4(W + static_cast<size_t>(n0 + j0 + r) * kvec + kv) : make_uint4(0, 0, 0, 0);
+        }
 #pragma unroll
-      for (int b = 0; b < kMaxB; ++b) {
-        if (b < B) {
-          float xf[8];
-          unpack8(xs[b * kvec + kv], xf);
+      for (int u = 0; u < U; ++u) {
+        const int kv = kv0 + u * 32;
+        if (kv < kvec) {
+          float wf[R][8];
 #pragma unroll
-          for (int r = 0; r < R; ++r)
+          for (int r = 0; r < R; ++r) unpack8(wv[u][r], wf[r]);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) acc[r][b] += wf[r][e] * xf[e];
+          for (int b = 0; b < kMaxB; ++b) {
+            if (b < B) {
+              float xf[8];
+              unpack8(xs[b * kvec + kv], xf);
+#pragma unroll
+              for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[r][b] += wf[r][e] * xf[e];
+            }
+          }
         }
       }
     }
@@ -322,6 +333,13 @@ TD_DEVICE void task_allreduce(const MKParams& p, const Task& t, uint32_t epoch) 
   }
 }
 
+TD_DEVICE void prefetch_linear_weights(const MKParams& p, const Task& t) {
+  if (t.type != T_LINEAR) return;
+  const char* W = reinterpret_cast<const char*>(p.ptrs[t.a[1]]) + static_cast<size_t>(t.a[5]) * t.a[3] * 2;
+  size_t bytes = static_cast<size_t>(t.a[6]) * t.a[3] * 2;
+  for (size_t off = 0; off < bytes; off += 65536) ptx::prefetch_l2_bulk(W + off, static_cast<uint32_t>(min(bytes - off, size_t(65536))));
+}
+
 __global__ void __launch_bounds__(kMKThreads, 1) mega_kernel(const MKParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ float red[32];
@@ -340,6 +358,13 @@ __global__ void __launch_bounds__(kMKThreads, 1) mega_kernel(const MKParams p) {
     }
     if (qi >= q1) break;
     const Task& t = p.tasks[qi];
+    // weight prefetch (reference model_builder "prefetch" tasks): the W tile of a LINEAR task is one contiguous region;
+    // pull it (and the tile of this CTA's next task) DRAM -> L2 before sitting on the dependency, so the stream of weight
+    // bytes does not stop at phase boundaries
+    if (threadIdx.x == 0) {
+      prefetch_linear_weights(p, t);
+      if (!p.dynamic && qi + 1 < q1) prefetch_linear_weights(p, p.tasks[qi + 1]);
+    }
     if (t.dep_idx >= 0) {
       if (threadIdx.x == 0) {
         const uint32_t target = epoch * static_cast<uint32_t>(t.dep_count);

@@ -177,6 +177,10 @@ TD_DEVICE void tma_reduce_add_2d(const void* tmap, const void* smem, int c0, int
                "r"(smem_u32(smem)), "r"(c0), "r"(c1)
                : "memory");
 }
+// DRAM -> L2 prefetch of a contiguous region (16-byte aligned, size a multiple of 16): fire and forget
+TD_DEVICE void prefetch_l2_bulk(const void* gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gmem)), "r"(bytes) : "memory");
+}
 TD_DEVICE void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 TD_DEVICE void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
