@@ -195,8 +195,9 @@ def main():
     # in-kernel SM push with 16 / 32 comm CTAs vs copy-engine push; every rank adopts the max-over-ranks winner ----
     if W > 1:
         base = default_ag_config(AG["M"], AG["N"] // W, AG["K"], W)
-        cands = [("sm", GemmConfig(base.bn, base.cta_group, base.group_m, True, 0, nc)) for nc in (16, 32)]
-        cands.append(("copy_engine", GemmConfig(base.bn, base.cta_group, base.group_m, True, 0, 0)))
+        bns = sorted({base.bn, 128, 256})
+        cands = [("sm", GemmConfig(bn, base.cta_group, base.group_m, True, 0, nc)) for nc in (16, 32, 48) for bn in bns]
+        cands += [("copy_engine", GemmConfig(bn, base.cta_group, base.group_m, True, 0, 0)) for bn in bns]
         best = None
         for tr, cfg in cands:
             ag_choice.update(transport=tr, cfg=cfg)
@@ -226,7 +227,8 @@ def main():
         "config": {"model": "ag_gemm M4096 N4096 K4096 + gemm_rs M4096 N12288 K49152", "global_batch": 4096, "seq_len": 1,
                    "parallelism": f"tp{W}", "l2": f"inputs rotate over {nset} sets ({(ag_bytes + rs_bytes) * nset >> 20} MiB/rank > 2x L2)"},
         "gpu_launches": (2 + (W if ag_choice["transport"] == "copy_engine" and W > 1 else 0)) * args.steps, "impl": "ours",
-        "ag_transport": {"transport": ag_choice["transport"], "n_comm_ctas": ag_choice["cfg"].n_comm_ctas if ag_choice["cfg"] else 0}, "native_libs": [os.path.basename(p) for p in _C.loaded_libraries()],
+        "ag_transport": {"transport": ag_choice["transport"], "n_comm_ctas": ag_choice["cfg"].n_comm_ctas if ag_choice["cfg"] else 0,
+                         "bn": ag_choice["cfg"].bn if ag_choice["cfg"] else 0}, "native_libs": [os.path.basename(p) for p in _C.loaded_libraries()],
         "clocks": clocks,
     }
 

@@ -107,7 +107,9 @@ def default_ag_config(M: int, N: int, K: int, world: int) -> GemmConfig:
     rows = M // max(world, 1)
     nc = 16 if world > 1 else 0
     if rows % 256 == 0 and N >= 256:
-        return GemmConfig(bn=256, cta_group=2, group_m=max(1, rows // 256), use_tma_store=True, n_comm_ctas=nc)
+        # few tiles (TP8 column shards): 128-wide tiles fill the SMs and halve the tail after the last shard arrives
+        bn = 128 if (world > 1 and (M // 256) * ((N + 255) // 256) < 60 and N % 128 == 0) else 256
+        return GemmConfig(bn=bn, cta_group=2, group_m=max(1, rows // 256), use_tma_store=True, n_comm_ctas=nc)
     gm = max(1, rows // 128) if rows % 128 == 0 else 1
     if N >= 256:
         return GemmConfig(bn=256, cta_group=1, group_m=gm, use_tma_store=True, n_comm_ctas=nc)
