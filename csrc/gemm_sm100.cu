@@ -31,6 +31,8 @@ struct TdGemmArgs {
   const void* ag_a_local; void* ag_ws; long long ag_ws_buf_bytes; void* ag_flags; void* ag_ready;
   // RS
   long long rs_rows_per_rank; void* rs_stage; long long rs_stage_buf_bytes; void* rs_flags; void* rs_out; long long rs_ldo;
+  // gather / scatter (MoE grouped GEMM without the gather_rows / scatter_rows passes)
+  const void* a_gather; long long a_gather_div; long long a_gather_pad; long long a_src_rows; const void* c_scatter;
 };
 
 static int encode_tmap(CUtensorMap* out, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
@@ -123,7 +125,18 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
     cuuint32_t box[2] = {(cuuint32_t)bk_elems, (cuuint32_t)(bn / cg)};
     if (encode_tmap(&p.tmap_b, a->B, 2, dims, strides, box, bf16)) return -1;
   }
-  p.use_tma_store = (a->use_tma_store && bn >= 64 && a->mode != kRS && a->mode != kAR && a->ldc % 8 == 0) ? 1 : 0;
+  if (a->a_gather) {   // gathered A: {K, source rows}, box {64 elements, 1 row}; one gather4 moves 4 rows x 128 B
+    if (cg != 1 || fp8) { drv::set_error("gathered A needs cta_group 1 and 16-bit inputs"); return -1; }
+    cuuint64_t dims[2] = {(cuuint64_t)a->K, (cuuint64_t)a->a_src_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)a->lda * esz};
+    cuuint32_t box[2] = {(cuuint32_t)bk_elems, 1};
+    if (encode_tmap(&p.tmap_ag, a->A, 2, dims, strides, box, bf16)) return -1;
+    p.a_gather = reinterpret_cast<const int*>(a->a_gather);
+    p.a_gather_div = (int)(a->a_gather_div > 0 ? a->a_gather_div : 1); p.a_gather_pad = (int)a->a_gather_pad;
+  }
+  p.c_scatter = reinterpret_cast<const int*>(a->c_scatter);
+  if (!a->a_gather) p.a_gather_pad = (int)a->a_gather_pad;
+  p.use_tma_store = (a->use_tma_store && !a->c_scatter && bn >= 64 && a->mode != kRS && a->mode != kAR && a->ldc % 8 == 0) ? 1 : 0;
   if (p.use_tma_store) {  // C: {N, rows, nbuf}
     cuuint64_t dims[3] = {(cuuint64_t)a->N, (cuuint64_t)a->c_rows, (cuuint64_t)(a->c_nbuf > 0 ? a->c_nbuf : 1)};
     cuuint64_t strides[2] = {(cuuint64_t)a->ldc * 2, (cuuint64_t)(a->c_nbuf > 1 ? a->c_buf_stride_bytes : a->c_rows * a->ldc * 2)};

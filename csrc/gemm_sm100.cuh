@@ -104,6 +104,12 @@ struct Params {
   int a2a_cols_per_rank;     // kAR scatter flavour (> 0): output columns [d*c, (d+1)*c) go to rank d, rows land at
                              // me * a2a_rows_per_src (GEMM + all-to-all: Ulysses QKV projection); no comm CTAs
   int a2a_rows_per_src;
+  // gather / scatter (MoE): A rows of a tile are fetched by TMA tile::gather4 from arbitrary rows of the source matrix
+  // (a_gather[row] = id, source row = id / a_gather_div, id == a_gather_pad -> zero row); C rows are written to
+  // c_scatter[row] (generic-store epilogue; < 0 or == pad -> skipped)
+  const int* a_gather; int a_gather_div; int a_gather_pad;
+  const int* c_scatter;
+  CUtensorMap tmap_ag;       // {K, rows} with box {64, 1}
   uint32_t* a2a_count;       // local [world] tile counters (last tile for a destination publishes the flag)
   void* rs_out;              // [rows_per_rank, N] final output (local)
   long long rs_ldo;
@@ -343,7 +349,38 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     const int worker = static_cast<int>(blockIdx.x) / kCtaGroup;
     const int total_tiles = p.num_m * p.num_n;
 
-    if (warp == 0) {
+    if (warp == 0 && p.a_gather != nullptr) {
+      // ================================ TMA producer, gathered A (whole warp) ================================
+      // lane l owns rows 4l..4l+3 of the 128-row tile: one tile::gather4 per k-block per lane, B by lane 0
+      if constexpr (kCtaGroup == 1 && !kFP8) {
+        int stage = 0; uint32_t phase = 0;
+        for (int t = worker; t < total_tiles; t += n_workers) {
+          int m_tile, n_tile;
+          tile_coords(p, t, m_tile, n_tile);
+          int expert = 0;
+          if (p.tile_expert) { expert = p.tile_expert[m_tile]; if (expert < 0) continue; }
+          const int row0 = m_tile * TM;
+          const int brow0 = expert * p.expert_rows + n_tile * BN;
+          int4 id = make_int4(-1, -1, -1, -1);
+          if (row0 + 4 * lane < p.M) id = *reinterpret_cast<const int4*>(p.a_gather + row0 + 4 * lane);
+          const int dv = p.a_gather_div, pad = p.a_gather_pad;
+          const int r0 = (id.x == pad || id.x < 0) ? -1 : id.x / dv, r1 = (id.y == pad || id.y < 0) ? -1 : id.y / dv;
+          const int r2 = (id.z == pad || id.z < 0) ? -1 : id.z / dv, r3 = (id.w == pad || id.w < 0) ? -1 : id.w / dv;
+          for (int kb = 0; kb < p.num_k; ++kb) {
+            if (lane == 0) {
+              ptx::mbar_wait(empty_bar + stage, phase ^ 1u);
+              ptx::mbar_arrive_expect_tx(full_bar + stage, L::kTxBytes);
+            }
+            __syncwarp();
+            uint8_t* sa = smem + stage * L::kStageBytes;
+            ptx::tma_gather4_2d(&p.tmap_ag, full_bar + stage, sa + lane * 512, kb * kBKElems, r0, r1, r2, r3);
+            if (lane == 0) ptx::tma_load_2d(&p.tmap_b, full_bar + stage, sa + L::kABytes, kb * kBKElems, brow0, ptx::kEvictLast);
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+      __syncwarp();
+    } else if (warp == 0) {
       // ================================ TMA producer ================================
       if (lane == 0) {
         int stage = 0; uint32_t phase = 0;
@@ -597,8 +634,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
               const int grow = row_base + r;
               const int gcol = gcol0 + chunk * 8;
               if (chunk < kChunks && grow < p.M && gcol < p.N) {
+                int drow = grow - dst_row_off;
+                if (p.c_scatter) { drow = p.c_scatter[grow]; if (drow < 0 || drow == p.a_gather_pad) continue; }
                 const uint4 o = ptx::ld_shared_v4(cbuf_u32 + r * 128 + ((chunk ^ (r & 7)) << 4));
-                ptx::st_v4(dst_base + (static_cast<size_t>(grow - dst_row_off) * dst_ld + gcol) * 2, o);
+                ptx::st_v4(dst_base + (static_cast<size_t>(drow) * dst_ld + gcol) * 2, o);
               }
             }
           }

@@ -136,6 +136,16 @@ TD_DEVICE void tma_load_4d(const void* tmap, uint64_t* bar, void* smem, int c0, 
       "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(hint)
       : "memory");
 }
+// tile::gather4: four arbitrary rows (r0..r3) of a 2-D tensor, `box[0]` elements starting at column c0, land as four
+// consecutive 128-byte rows of the swizzled smem tile (the tensor map's box is {cols, 1}); OOB rows are zero-filled.
+TD_DEVICE void tma_gather4_2d(const void* tmap, uint64_t* bar, void* smem, int c0, int r0, int r1, int r2, int r3,
+                              uint64_t hint = kEvictNormal) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes.cta_group::1.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "l"(hint)
+      : "memory");
+}
 // 2-CTA variants: both CTAs of a pair issue their own load; the transaction bytes land on the
 // LEADER CTA's mbarrier (peer bit cleared), which is the barrier the MMA issuer waits on.
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;

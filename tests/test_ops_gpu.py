@@ -152,3 +152,21 @@ def test_gdn_recurrent_kernel(T):
     o2, s2 = chunk_gated_delta_rule_fwd(q, k, v, g, beta, None, s0)
     torch.testing.assert_close(o2.float(), ref_o, atol=3e-2, rtol=3e-2)
     torch.testing.assert_close(s2, ref_s, atol=2e-2, rtol=2e-2)
+
+
+@pytest.mark.parametrize("T,E,topk,K,N", [(300, 8, 2, 512, 768), (1024, 32, 4, 1024, 256), (64, 16, 8, 256, 512)])
+def test_moe_tma_gather(T, E, topk, K, N):
+    """Grouped GEMM with TMA tile::gather4 A rows + scattered epilogue vs the gather_rows -> GEMM -> scatter_rows pipeline
+    and vs an fp32 reference."""
+    from triton_dist.ops import moe as M
+    torch.manual_seed(T + E)
+    x = (torch.randn(T, K, device="cuda") * 0.5).to(torch.bfloat16)
+    w = (torch.randn(E, N, K, device="cuda") * 0.1).to(torch.bfloat16)
+    ids = torch.stack([torch.randperm(E, device="cuda")[:topk] for _ in range(T)]).to(torch.int32)
+    r = M.moe_align_sort(ids, E, 128)
+    fused = M.moe_grouped_gemm_fused(x, w, r, topk, T * topk)
+    staged = M.scatter_rows(M.moe_grouped_gemm(M.gather_rows(x, r, div=topk), w, r), r, T * topk)
+    ref = torch.einsum("tk,tjnk->tjn", x.float(), w.float()[ids.long()]).reshape(T * topk, N)
+    torch.testing.assert_close(staged.float(), ref, atol=5e-2, rtol=3e-2)
+    torch.testing.assert_close(fused.float(), ref, atol=5e-2, rtol=3e-2)
+    assert torch.equal(fused, staged)

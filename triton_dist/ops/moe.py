@@ -155,6 +155,36 @@ bincount = histogram_by_expert
 # ------------------------------------------------------------------------------------------------------------
 # grouped GEMM
 # ------------------------------------------------------------------------------------------------------------
+def moe_grouped_gemm_fused(src: torch.Tensor, w: torch.Tensor, routing: SortedRouting, div: int, n_out_rows: int,
+                           out: Optional[torch.Tensor] = None, config: Optional[GemmConfig] = None) -> torch.Tensor:
+    """``out[id] = src[id // div] @ w[expert(id)].T`` for every routed pair id = token * topk + k, in ONE kernel: the A rows
+    of each tile are fetched with TMA ``tile::gather4`` straight from ``src`` (no gather_rows pass) and the epilogue writes
+    each row to its final place (no scatter_rows pass).  The sm_100a counterpart of the reference's gather/scatter
+    grouped GEMM (allgather_group_gemm.py:536-609, which cannot use TMA for the gathered operand)."""
+    K = src.shape[1]
+    E, N, Kw = w.shape
+    assert Kw == K and src.is_cuda and src.stride(1) == 1
+    out = torch.empty((n_out_rows, N), dtype=src.dtype, device=src.device) if out is None else out
+    cfg = config or GemmConfig(bn=256 if N >= 256 else 128, cta_group=1, group_m=1, use_tma_store=False)
+    assert cfg.cta_group == 1 and routing.block_m == 128
+    args = _C.GemmArgs()
+    args.mode = 0
+    fill_common(args, src.shape[0], src.data_ptr(), src.stride(0), w.reshape(E * N, K), out.data_ptr(), n_out_rows, out.stride(0),
+                routing.capacity, N, K, GemmConfig(cfg.bn, 1, 1, False, cfg.num_sms, 0), src.dtype == torch.bfloat16)
+    args.tile_expert, args.num_experts = routing.tile_expert.data_ptr(), E
+    args.a_gather, args.a_gather_div, args.a_gather_pad = routing.sorted_ids.data_ptr(), div, routing.pad_id
+    args.a_src_rows, args.c_scatter = src.shape[0], routing.sorted_ids.data_ptr()
+    _C.check(_C.cuda_lib().td_gemm_launch(C.byref(args), _s()), "td_gemm_launch(grouped, gather4)")
+    return out
+
+
+def _use_tma_gather(x: torch.Tensor) -> bool:
+    return x.is_cuda and U.get_bool_env("TD_MOE_TMA_GATHER", _TMA_GATHER_DEFAULT)
+
+
+_TMA_GATHER_DEFAULT = False     # flipped once validated on hardware (tests/test_ops_gpu.py::test_moe_tma_gather)
+
+
 def moe_grouped_gemm(x_sorted: torch.Tensor, w: torch.Tensor, routing: SortedRouting, out: Optional[torch.Tensor] = None,
                      config: Optional[GemmConfig] = None) -> torch.Tensor:
     """``y_sorted[i] = x_sorted[i] @ w[expert_of_row(i)].T``;  x_sorted: [capacity, K] (expert-sorted, padded),
@@ -188,6 +218,8 @@ def moe_forward_local(x: torch.Tensor, w: torch.Tensor, topk_ids: torch.Tensor, 
     E = w.shape[0] if num_experts is None else num_experts
     topk = topk_ids.shape[1]
     r = moe_align_sort(topk_ids, E, 128)
+    if _use_tma_gather(x):
+        return moe_grouped_gemm_fused(x.contiguous(), w, r, topk, topk_ids.numel())
     xs = gather_rows(x, r, div=topk)
     ys = moe_grouped_gemm(xs, w, r)
     return scatter_rows(ys, r, topk_ids.numel())
@@ -246,6 +278,8 @@ def ag_group_gemm(a: torch.Tensor, b: torch.Tensor, ctx: MoEAllGatherGroupGEMMCo
         a_full = a
     # 2. route: expert-major, and within an expert by arrival stage of the source rank
     r = moe_align_sort(full_topk_ids, ctx.num_experts, 128, tokens_per_rank=tpr, rank=ctx.rank, world=W)
+    if _use_tma_gather(a_full):
+        return moe_grouped_gemm_fused(a_full, b, r, ctx.topk, T * ctx.topk, out=out)
     xs = gather_rows(a_full, r, div=ctx.topk)
     ys = moe_grouped_gemm(xs, b, r)
     return scatter_rows(ys, r, T * ctx.topk, out=out)
@@ -294,9 +328,12 @@ def _moe_down_partial(x, w, chosen_experts, expert_weight, ctx):
     if w.stride(2) != 1:
         w = w.contiguous()
     r = moe_align_sort(chosen_experts, ctx.num_experts, 128)
-    xs = gather_rows(x, r, div=1)                  # rows of x are already (token, k) pairs
-    ys = moe_grouped_gemm(xs, w, r)
-    y = scatter_rows(ys, r, chosen_experts.numel())
+    if _use_tma_gather(x):
+        y = moe_grouped_gemm_fused(x.contiguous(), w, r, 1, chosen_experts.numel())
+    else:
+        xs = gather_rows(x, r, div=1)                  # rows of x are already (token, k) pairs
+        ys = moe_grouped_gemm(xs, w, r)
+        y = scatter_rows(ys, r, chosen_experts.numel())
     return reduce_topk(y, expert_weight, ctx.topk)
 
 
