@@ -365,7 +365,35 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
           if (row0 + 4 * lane < p.M) id = *reinterpret_cast<const int4*>(p.a_gather + row0 + 4 * lane);
           const int dv = p.a_gather_div, pad = p.a_gather_pad;
           const int r0 = (id.x == pad || id.x < 0) ? -1 : id.x / dv, r1 = (id.y == pad || id.y < 0) ? -1 : id.y / dv;
-          const int r2 = (id.z == pad || id.z < 0) ? -1 : id.z / dv, r3 = (id.w == pad || id.w < 0) ? -1 : id.w / dv;
+          int r2 = (id.z == pad || id.z < 0) ? -1 : id.z / dv, r3 = (id.w == pad || id.w < 0) ? -1 : id.w / dv;
+          int r0m = r0, r1m = r1;
+          if constexpr (kMode == kAG) {
+            // fused AllGather + grouped GEMM: the rows live in the all-gather workspace; each lane waits for the byte
+            // slices (source rank, comm CTA) that carry ITS four rows, then the rows are gathered by TMA
+            const int rr[4] = {r0, r1, r2, r3};
+            const int Ms = p.ag_rows_per_rank;
+            const size_t row_bytes = static_cast<size_t>(p.K) * 2;
+            const size_t slice = ag_slice_bytes(static_cast<size_t>(Ms) * row_bytes, p.ag_nslices);
+            const uint32_t* flags = p.ag_flags + (ph & 1u) * p.symm.world * kAGMaxSlices;
+            if (!p.ag_skip_wait) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                if (rr[q] < 0) continue;
+                const int s = rr[q] / Ms;
+                if (s == p.symm.rank && !p.ag_copy_local) continue;
+                const size_t b0 = static_cast<size_t>(rr[q] - s * Ms) * row_bytes;
+                for (int c = static_cast<int>(b0 / slice); c <= static_cast<int>((b0 + row_bytes - 1) / slice); ++c)
+                  wait_ge<true>(flags + s * kAGMaxSlices + c, ph);
+              }
+              ptx::fence_proxy_async();
+            }
+            const int par_rows = static_cast<int>((ph & 1u) * (p.ag_ws_buf_bytes / row_bytes));   // parity half of the workspace
+            if (r0m >= 0) r0m += par_rows;
+            if (r1m >= 0) r1m += par_rows;
+            if (r2 >= 0) r2 += par_rows;
+            if (r3 >= 0) r3 += par_rows;
+          }
+          __syncwarp();
           for (int kb = 0; kb < p.num_k; ++kb) {
             if (lane == 0) {
               ptx::mbar_wait(empty_bar + stage, phase ^ 1u);
@@ -373,7 +401,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             }
             __syncwarp();
             uint8_t* sa = smem + stage * L::kStageBytes;
-            ptx::tma_gather4_2d(&p.tmap_ag, full_bar + stage, sa + lane * 512, kb * kBKElems, r0, r1, r2, r3);
+            ptx::tma_gather4_2d(&p.tmap_ag, full_bar + stage, sa + lane * 512, kb * kBKElems, r0m, r1m, r2, r3);
             if (lane == 0) ptx::tma_load_2d(&p.tmap_b, full_bar + stage, sa + L::kABytes, kb * kBKElems, brow0, ptx::kEvictLast);
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }

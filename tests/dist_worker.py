@@ -269,6 +269,21 @@ def case_moe():
     ag.finalize(); rs.finalize()
 
 
+def case_moe_fused():
+    """AllGather + grouped GEMM in one kernel (TMA tile::gather4 producer waiting on arrival flags) and the gather4 /
+    scatter grouped GEMM of the down projection; GPU only (the emulation backend runs the staged path in case_moe)."""
+    dev = U.current_device()
+    if dev.type != "cuda":
+        return
+    os.environ["TD_MOE_AG_FUSED"] = "1"
+    os.environ["TD_MOE_TMA_GATHER"] = "1"
+    try:
+        case_moe()
+    finally:
+        os.environ.pop("TD_MOE_AG_FUSED", None)
+        os.environ.pop("TD_MOE_TMA_GATHER", None)
+
+
 def case_tp_e2e():
     """TP inference demo: every backend must reproduce the torch (NCCL) backend's greedy tokens (test_tp_e2e.py --check)."""
     from triton_dist.models import Engine, ModelConfig

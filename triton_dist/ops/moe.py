@@ -239,11 +239,15 @@ class MoEAllGatherGroupGEMMContext:
     rank: int
     world_size: int
     ag_ctx: comm.FastAllGatherContext = None
+    fused_ctx: object = None        # AllGatherGEMMTensorParallelContext of the single-kernel path (workspace + flags)
 
     def finalize(self):
         if self.ag_ctx is not None:
             self.ag_ctx.finalize()
             self.ag_ctx = None
+        if self.fused_ctx is not None:
+            self.fused_ctx.finalize()
+            self.fused_ctx = None
 
 
 def create_ag_group_gemm_context(max_ntokens: int, N_per_rank: int, K: int, num_experts: int, topk: int, dtype: torch.dtype,
@@ -255,7 +259,43 @@ def create_ag_group_gemm_context(max_ntokens: int, N_per_rank: int, K: int, num_
     ctx = MoEAllGatherGroupGEMMContext(max_ntokens, N_per_rank, K, num_experts, topk, dtype, rank, world_size)
     shard_bytes = (max_ntokens // world_size) * K * torch.empty(0, dtype=dtype).element_size()
     ctx.ag_ctx = comm.create_fast_allgather_context(max(shard_bytes, 1024), rank, world_size, grid_max=64)
+    if heap.device.type == "cuda" and world_size > 1 and U.get_bool_env("TD_MOE_AG_FUSED", False):
+        from .ag_gemm import create_ag_gemm_context
+        ctx.fused_ctx = create_ag_gemm_context(max_ntokens, N_per_rank, K, dtype, rank, world_size)
     return ctx
+
+
+def _ag_group_gemm_fused(a: torch.Tensor, b: torch.Tensor, ctx: MoEAllGatherGroupGEMMContext, r: SortedRouting, T: int,
+                         out: Optional[torch.Tensor], n_comm: int = 16) -> torch.Tensor:
+    """AllGather(tokens) + grouped GEMM in ONE kernel: comm CTAs push this rank's tokens into every peer's workspace
+    (the ag_gemm protocol), the GEMM producer warp waits -- per lane, for the four rows it fetches -- on the arrival flags
+    of the slices that carry them and gathers the rows by TMA ``tile::gather4``; the epilogue scatters to (token, k) order.
+    Tiles are ordered by expert and, inside an expert, by the arrival stage of the source rank (moe_align_sort)."""
+    g = ctx.fused_ctx
+    W, me = ctx.world_size, ctx.rank
+    Ms, K = a.shape
+    E, N, _ = b.shape
+    out = torch.empty((T * ctx.topk, N), dtype=a.dtype, device=a.device) if out is None else out
+    a = a.contiguous()
+    args = _C.GemmArgs()
+    args.mode = 1
+    cfg = GemmConfig(bn=256 if N >= 256 else 128, cta_group=1, group_m=1, use_tma_store=False, n_comm_ctas=n_comm)
+    ws_buf_bytes = g.max_M * K * a.element_size()
+    fill_common(args, 2 * g.max_M, g.workspace.data_ptr(), K, b.reshape(E * N, K), out.data_ptr(), T * ctx.topk, out.stride(0),
+                r.capacity, N, K, cfg, a.dtype == torch.bfloat16)
+    args.a_nbuf, args.a_buf_stride_bytes = 2, ws_buf_bytes
+    args.tile_expert, args.num_experts = r.tile_expert.data_ptr(), E
+    args.a_gather, args.a_gather_div, args.a_gather_pad = r.sorted_ids.data_ptr(), ctx.topk, r.pad_id
+    args.a_src_rows, args.c_scatter = 2 * g.max_M, r.sorted_ids.data_ptr()
+    rk, w, base, stride, mc = U.symm_ctx_fields()
+    args.rank, args.world, args.symm_base, args.symm_stride, args.mc_base = rk, w, base, stride, mc
+    args.phase = g.phase.data_ptr()
+    args.ag_rows_per_rank, args.ag_copy_local, args.ag_skip_wait = Ms, 1, 0
+    args.ag_a_local, args.ag_ws, args.ag_ws_buf_bytes = a.data_ptr(), g.workspace.data_ptr(), ws_buf_bytes
+    args.ag_flags, args.ag_ready = g.flags.data_ptr(), g.ready.data_ptr()
+    _C.check(_C.cuda_lib().td_gemm_launch(C.byref(args), _s()), "td_gemm_launch(ag + grouped, gather4)")
+    g.host_phase += 1
+    return out
 
 
 def ag_group_gemm(a: torch.Tensor, b: torch.Tensor, ctx: MoEAllGatherGroupGEMMContext, full_topk_ids: torch.Tensor,
@@ -271,6 +311,9 @@ def ag_group_gemm(a: torch.Tensor, b: torch.Tensor, ctx: MoEAllGatherGroupGEMMCo
     T = full_topk_ids.shape[0]
     tpr = a.shape[0]
     assert tpr * W == T
+    if W > 1 and ctx.fused_ctx is not None and a.is_cuda and T <= ctx.fused_ctx.max_M:
+        r = moe_align_sort(full_topk_ids, ctx.num_experts, 128, tokens_per_rank=tpr, rank=ctx.rank, world=W)
+        return _ag_group_gemm_fused(a, b, ctx, r, T, out)
     # 1. all-gather the tokens (push over NVLink; consumers sorted by arrival stage below)
     if W > 1:
         a_full = comm.fast_allgather(a.contiguous(), ctx.ag_ctx, mode="push").view(T, a.shape[1])
