@@ -58,10 +58,16 @@ struct Smem {
   static constexpr int kTmemCols = (2 * BNK + HD) <= 256 ? 256 : 512;
 };
 
-enum Bar { Q_FULL = 0, K_FULL = 1, V_FULL = 3, KV_EMPTY = 5, S_FULL = 7, S_FREE = 9, P_READY = 11, PV_DONE = 12, NBAR = 13 };
+enum Bar { Q_FULL = 0, K_FULL = 1, V_FULL = 3, KV_EMPTY = 5, S_FULL = 7, S_FREE = 9, P_READY = 11, PV_DONE = 12, Q_TMEM = 13, NBAR = 14 };
 
-template <int BNK>
-__global__ void __launch_bounds__(kThreads, BNK == 64 ? 2 : 1) flash_fwd_kernel(const __grid_constant__ Params p) {
+// kTS ("tensor-core operands from TMEM"): Q is copied to TMEM once and P is written over its S buffer as packed 16-bit
+// pairs, so both MMAs take their A operand from TMEM and only K / V are read from shared memory.  With M = N = 128 a
+// tcgen05.mma whose two operands come from smem needs 8 KB per 64 clk = the full 128 B/clk of the SM's shared memory, and
+// the TMA writes and P stores compete for the same port: the smem-operand version is shared-memory bound (224 KB per
+// 128x128 tile), the TMEM-operand version moves 128 KB per tile.
+template <int BNK, bool kTS = false>
+__global__ void __launch_bounds__(kThreads, (BNK == 64 && !kTS) ? 2 : 1) flash_fwd_kernel(const __grid_constant__ Params p) {
+  static_assert(!kTS || BNK == 128, "TMEM-operand variant: S0 | S1 | O | Q = 448 columns");
   using Smem = fa::Smem<BNK>;
   constexpr int kKVTile = Smem::kKVTile, kKVSlab = Smem::kKVSlab;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -94,10 +100,11 @@ __global__ void __launch_bounds__(kThreads, BNK == 64 ? 2 : 1) flash_fwd_kernel(
     }
     ptx::mbar_init(&bars[P_READY], 128);
     ptx::mbar_init(&bars[PV_DONE], 1);
+    ptx::mbar_init(&bars[Q_TMEM], 128);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc<1>(tmem_ptr_smem, Smem::kTmemCols);
+    ptx::tmem_alloc<1>(tmem_ptr_smem, kTS ? 512 : Smem::kTmemCols);
     ptx::tmem_relinquish<1>();
   }
   ptx::tc_fence_before();
@@ -105,6 +112,7 @@ __global__ void __launch_bounds__(kThreads, BNK == 64 ? 2 : 1) flash_fwd_kernel(
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const uint32_t tmem_o = tmem_base + 2 * BNK;
+  const uint32_t tmem_q = tmem_base + 2 * BNK + HD;          // kTS only: Q as 64 columns of packed 16-bit pairs
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -142,12 +150,16 @@ __global__ void __launch_bounds__(kThreads, BNK == 64 ? 2 : 1) flash_fwd_kernel(
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk) {
           const uint32_t qoff = (kk >> 2) * kSlab + (kk & 3) * 32, koff = (kk >> 2) * kKVSlab + (kk & 3) * 32;
-          ptx::mma_f16<1>(tmem_base + b * BNK, ptx::make_smem_desc_k128(q_addr + qoff), ptx::make_smem_desc_k128(k_addr + koff),
-                          idesc_qk, kk > 0 ? 1u : 0u);
+          if constexpr (kTS)
+            ptx::mma_f16_ts(tmem_base + b * BNK, tmem_q + kk * 8, ptx::make_smem_desc_k128(k_addr + koff), idesc_qk, kk > 0 ? 1u : 0u);
+          else
+            ptx::mma_f16<1>(tmem_base + b * BNK, ptx::make_smem_desc_k128(q_addr + qoff), ptx::make_smem_desc_k128(k_addr + koff),
+                            idesc_qk, kk > 0 ? 1u : 0u);
         }
         ptx::mma_commit(&bars[S_FULL + b]);
       };
-      ptx::mbar_wait(&bars[Q_FULL], 0);
+      if constexpr (kTS) { ptx::mbar_wait(&bars[Q_TMEM], 0); ptx::tc_fence_after(); }
+      else ptx::mbar_wait(&bars[Q_FULL], 0);
       if (n_tiles > 0) issue_qk(0);
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j & 1;
@@ -160,7 +172,8 @@ __global__ void __launch_bounds__(kThreads, BNK == 64 ? 2 : 1) flash_fwd_kernel(
         for (int kk = 0; kk < BNK / 16; ++kk) {
           const uint64_t a = ptx::make_smem_desc_k128(p_addr + (kk >> 2) * kSlab + (kk & 3) * 32);
           const uint64_t bdesc = ptx::make_smem_desc_mn128(v_addr + kk * 16 * 128, kKVSlab);
-          ptx::mma_f16<1>(tmem_o, a, bdesc, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+          if constexpr (kTS) ptx::mma_f16_ts(tmem_o, tmem_base + (j & 1) * BNK + kk * 8, bdesc, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+          else ptx::mma_f16<1>(tmem_o, a, bdesc, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
         }
         ptx::mma_commit(&bars[KV_EMPTY + st]);
         ptx::mma_commit(&bars[PV_DONE]);
@@ -174,6 +187,25 @@ __global__ void __launch_bounds__(kThreads, BNK == 64 ? 2 : 1) flash_fwd_kernel(
     const int q_pos = q_pos0 + row;
     const uint32_t p_row = ptx::smem_u32(smem + Smem::kP) + row * 128;
     float m_ref = -INFINITY, l = 0.f;
+
+    if constexpr (kTS) {
+      // Q: swizzled smem (TMA) -> registers -> TMEM, one row per thread; column c holds elements (2c, 2c+1)
+      ptx::mbar_wait(&bars[Q_FULL], 0);
+      const uint32_t q_row = ptx::smem_u32(smem + Smem::kQ) + row * 128;
+#pragma unroll
+      for (int slab = 0; slab < 2; ++slab) {
+        uint32_t qv[32];
+#pragma unroll
+        for (int c16 = 0; c16 < 8; ++c16) {
+          const uint4 v = ptx::ld_shared_v4(q_row + slab * kSlab + ((c16 ^ (row & 7)) << 4));
+          qv[c16 * 4 + 0] = v.x; qv[c16 * 4 + 1] = v.y; qv[c16 * 4 + 2] = v.z; qv[c16 * 4 + 3] = v.w;
+        }
+        ptx::tmem_st_32x32b_x32(tmem_q + lane_off + slab * 32, qv);
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&bars[Q_TMEM]);
+    }
 
     for (int j = 0; j < n_tiles; ++j) {
       const int b = j & 1;
@@ -228,32 +260,55 @@ __global__ void __launch_bounds__(kThreads, BNK == 64 ? 2 : 1) flash_fwd_kernel(
         }
       l += sum;
 
-      // P buffer and O are free once PV of the previous tile has completed
-      if (j > 0) {
-        ptx::mbar_wait(&bars[PV_DONE], (j - 1) & 1);
-        ptx::tc_fence_after();
-      }
-      // P (bf16 / fp16) -> K-major SWIZZLE_128B: 16-byte chunk c16 of row r lands at chunk (c16 ^ (r & 7))
+      if constexpr (kTS) {
+        // P (packed 16-bit pairs) overwrites the first BNK/2 columns of this tile's S buffer: same thread, same row.  The
+        // previous reader of that buffer (PV of tile j-2) retired before QK of tile j was issued (tcgen05 ops of one
+        // thread execute in order), so no wait is needed here.
 #pragma unroll
-      for (int c = 0; c < NC; ++c)
+        for (int c = 0; c < NC; c += 2) {
+          uint32_t pk[32];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 v;
-          if (p.is_bf16) {
-            v.x = ptx::pack_bf16x2(__uint_as_float(s[c][g * 8 + 0]), __uint_as_float(s[c][g * 8 + 1]));
-            v.y = ptx::pack_bf16x2(__uint_as_float(s[c][g * 8 + 2]), __uint_as_float(s[c][g * 8 + 3]));
-            v.z = ptx::pack_bf16x2(__uint_as_float(s[c][g * 8 + 4]), __uint_as_float(s[c][g * 8 + 5]));
-            v.w = ptx::pack_bf16x2(__uint_as_float(s[c][g * 8 + 6]), __uint_as_float(s[c][g * 8 + 7]));
-          } else {
-            v.x = ptx::pack_f16x2(__uint_as_float(s[c][g * 8 + 0]), __uint_as_float(s[c][g * 8 + 1]));
-            v.y = ptx::pack_f16x2(__uint_as_float(s[c][g * 8 + 2]), __uint_as_float(s[c][g * 8 + 3]));
-            v.z = ptx::pack_f16x2(__uint_as_float(s[c][g * 8 + 4]), __uint_as_float(s[c][g * 8 + 5]));
-            v.w = ptx::pack_f16x2(__uint_as_float(s[c][g * 8 + 6]), __uint_as_float(s[c][g * 8 + 7]));
+          for (int i = 0; i < 16; ++i) {
+            pk[i] = p.is_bf16 ? ptx::pack_bf16x2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1]))
+                              : ptx::pack_f16x2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1]));
+            pk[16 + i] = p.is_bf16 ? ptx::pack_bf16x2(__uint_as_float(s[c + 1][2 * i]), __uint_as_float(s[c + 1][2 * i + 1]))
+                                   : ptx::pack_f16x2(__uint_as_float(s[c + 1][2 * i]), __uint_as_float(s[c + 1][2 * i + 1]));
           }
-          const int col = c * 32 + g * 8;                 // first key of this 16-byte chunk
-          const int slab = col >> 6, c16 = (col & 63) >> 3;
-          ptx::st_shared_v4(p_row + slab * kSlab + ((c16 ^ (row & 7)) << 4), v);
+          ptx::tmem_st_32x32b_x32(tmem_base + lane_off + b * BNK + c * 16, pk);
         }
+        // O may only be touched after PV of the previous tile has completed -- needed only when some row rescales
+        if (j > 0 && __any_sync(0xFFFFFFFFu, bump)) {
+          ptx::mbar_wait(&bars[PV_DONE], (j - 1) & 1);
+          ptx::tc_fence_after();
+        }
+      } else {
+      // P buffer and O are free once PV of the previous tile has completed
+        if (j > 0) {
+          ptx::mbar_wait(&bars[PV_DONE], (j - 1) & 1);
+          ptx::tc_fence_after();
+        }
+        // P (bf16 / fp16) -> K-major SWIZZLE_128B: 16-byte chunk c16 of row r lands at chunk (c16 ^ (r & 7))
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 v;
+            if (p.is_bf16) {
+              v.x = ptx::pack_bf16x2(__uint_as_float(s[c][g * 8 + 0]), __uint_as_float(s[c][g * 8 + 1]));
+              v.y = ptx::pack_bf16x2(__uint_as_float(s[c][g * 8 + 2]), __uint_as_float(s[c][g * 8 + 3]));
+              v.z = ptx::pack_bf16x2(__uint_as_float(s[c][g * 8 + 4]), __uint_as_float(s[c][g * 8 + 5]));
+              v.w = ptx::pack_bf16x2(__uint_as_float(s[c][g * 8 + 6]), __uint_as_float(s[c][g * 8 + 7]));
+            } else {
+              v.x = ptx::pack_f16x2(__uint_as_float(s[c][g * 8 + 0]), __uint_as_float(s[c][g * 8 + 1]));
+              v.y = ptx::pack_f16x2(__uint_as_float(s[c][g * 8 + 2]), __uint_as_float(s[c][g * 8 + 3]));
+              v.z = ptx::pack_f16x2(__uint_as_float(s[c][g * 8 + 4]), __uint_as_float(s[c][g * 8 + 5]));
+              v.w = ptx::pack_f16x2(__uint_as_float(s[c][g * 8 + 6]), __uint_as_float(s[c][g * 8 + 7]));
+            }
+            const int col = c * 32 + g * 8;                 // first key of this 16-byte chunk
+            const int slab = col >> 6, c16 = (col & 63) >> 3;
+            ptx::st_shared_v4(p_row + slab * kSlab + ((c16 ^ (row & 7)) << 4), v);
+          }
+      }
       // O *= alpha for the rows whose reference max moved (warp-uniform branch: tcgen05.ld/st are warp collectives)
       if (j > 0 && __any_sync(0xFFFFFFFFu, bump)) {
 #pragma unroll
@@ -267,7 +322,8 @@ __global__ void __launch_bounds__(kThreads, BNK == 64 ? 2 : 1) flash_fwd_kernel(
         }
         ptx::tmem_st_wait();
       }
-      ptx::fence_proxy_async_smem();        // generic-proxy P stores -> visible to the tensor core (async proxy)
+      if constexpr (kTS) ptx::tmem_st_wait();
+      else ptx::fence_proxy_async_smem();   // generic-proxy P stores -> visible to the tensor core (async proxy)
       ptx::tc_fence_before();
       ptx::mbar_arrive(&bars[P_READY]);
     }
@@ -320,7 +376,7 @@ __global__ void __launch_bounds__(kThreads, BNK == 64 ? 2 : 1) flash_fwd_kernel(
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<1>(tmem_base, Smem::kTmemCols);
+    ptx::tmem_dealloc<1>(tmem_base, kTS ? 512 : Smem::kTmemCols);
   }
 }
 
@@ -339,19 +395,19 @@ struct TdFlashArgs {
   long long o_stride_b, o_stride_s, o_stride_h;
   double sm_scale;
   long long causal, is_bf16;
-  long long block_n;          // keys per step: 64 (two CTAs per SM, default) or 128
+  long long block_n;          // keys per step: 64 (two CTAs per SM, default) or 128; 129 = 128 with Q and P in TMEM
 };
 
-template <int BNK>
+template <int BNK, bool kTS = false>
 static int fa_launch(const td::fa::Params& p, dim3 grid, cudaStream_t s) {
   using namespace td::fa;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(flash_fwd_kernel<BNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BNK>::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(flash_fwd_kernel<BNK, kTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BNK>::kTotal);
     if (e != cudaSuccess) { td::drv::set_error("flash_attn: smem attribute: %s", cudaGetErrorString(e)); return -1; }
     attr_set = true;
   }
-  flash_fwd_kernel<BNK><<<grid, kThreads, Smem<BNK>::kTotal, s>>>(p);
+  flash_fwd_kernel<BNK, kTS><<<grid, kThreads, Smem<BNK>::kTotal, s>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { td::drv::set_error("flash_attn launch: %s", cudaGetErrorString(e)); return -1; }
   return 0;
@@ -381,7 +437,7 @@ extern "C" __attribute__((visibility("default"))) int td_flash_attn_fwd(const Td
   for (long long s : st)
     if (s % 8 != 0) { td::drv::set_error("flash_attn: strides must be multiples of 8 elements (16 bytes)"); return -1; }
   Params p{};
-  const int bnk = a->block_n == 128 ? 128 : 64;
+  const int bnk = (a->block_n == 128 || a->block_n == 129) ? 128 : 64;
   if (fa_tmap(&p.tmap_q, a->q, a->Sq, a->Hq, a->B, a->q_stride_b, a->q_stride_s, a->q_stride_h, (int)a->is_bf16, BMQ)) return -1;
   if (fa_tmap(&p.tmap_k, a->k, a->Sk, a->Hkv, a->B, a->k_stride_b, a->k_stride_s, a->k_stride_h, (int)a->is_bf16, bnk)) return -1;
   if (fa_tmap(&p.tmap_v, a->v, a->Sk, a->Hkv, a->B, a->v_stride_b, a->v_stride_s, a->v_stride_h, (int)a->is_bf16, bnk)) return -1;
@@ -392,5 +448,6 @@ extern "C" __attribute__((visibility("default"))) int td_flash_attn_fwd(const Td
   p.scale_log2 = static_cast<float>(a->sm_scale * 1.4426950408889634);
   dim3 grid((unsigned)((a->Sq + BMQ - 1) / BMQ), (unsigned)a->Hq, (unsigned)a->B);
   cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream_);
+  if (a->block_n == 129) return fa_launch<128, true>(p, grid, st_);
   return bnk == 128 ? fa_launch<128>(p, grid, st_) : fa_launch<64>(p, grid, st_);
 }

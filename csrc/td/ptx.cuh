@@ -257,6 +257,14 @@ TD_DEVICE void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// A operand sourced from TMEM (lane = row, each 32-bit column holds two consecutive K elements), B from smem
+TD_DEVICE void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // fp8 (e4m3/e5m2) inputs, fp32 accumulate, no block scaling
 template <int kCtaGroup>
 TD_DEVICE void mma_f8f6f4(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
