@@ -2,8 +2,8 @@
 
 API mirrors /root/reference/python/triton_dist/layers/nvidia/tp_attn.py:70-321.  Projections run on the fused
 ops (ag_gemm / gemm_rs / gemm_ar); q/k-norm + RoPE + KV append is one CUDA kernel (csrc/elementwise.cu); decode
-attention is our split-KV flash-decode (csrc/attention.cu); prefill attention is a library call
-(flash_attn_with_kvcache, as in the reference :242) with a torch SDPA fallback.
+attention is our split-KV flash-decode (csrc/attention.cu); prefill attention is our tcgen05 flash-attention kernel
+(csrc/flash_attn_sm100.cu; the reference calls flash_attn_with_kvcache :242, kept as the fallback for head_dim != 128).
 """
 from __future__ import annotations
 
@@ -22,7 +22,7 @@ from ..ops.gemm_ar import create_gemm_ar_context, create_ll_gemm_ar_context, gem
 from ..ops.gemm_rs import create_gemm_rs_context, gemm_rs
 from .tp_mlp import _linear, shard_local
 
-_TCGEN05_PREFILL_DEFAULT = False     # flipped once the kernel is validated on hardware (tests/test_flash_attn_gpu.py)
+_TCGEN05_PREFILL_DEFAULT = True      # validated on B200 (tests/test_flash_attn_gpu.py: 13/13)
 
 try:  # library attention for prefill
     from flash_attn import flash_attn_with_kvcache as _fa_kvcache
