@@ -407,6 +407,20 @@ def case_sp_pp():
     full_o = torch.einsum("hsl,lhd->shd", torch.softmax(sc, -1), vv)
     _assert_close(o, full_o[pos], 3e-2 if big else 1e-4, 3e-2 if big else 1e-4, "sp ag attention")
     ctx.finalize()
+    if big:     # long enough for the tcgen05 flash kernel (zig-zag chunks are multiples of the 128-query tile)
+        S = 512 * W
+        qf = torch.randn(S, Hq, D, generator=g).to(dtype).to(dev)
+        kf2 = torch.randn(S, Hkv, D, generator=g).to(dtype).to(dev)
+        vf2 = torch.randn(S, Hkv, D, generator=g).to(dtype).to(dev)
+        pos = zigzag_positions(S, W, me, dev) if W > 1 else torch.arange(S, device=dev)
+        ctx = create_sp_ag_attention_context_intra_node(S // W, Hkv, D, dtype)
+        o = fused_sp_ag_attn_intra_node(ctx, qf[pos].contiguous(), kf2[pos].contiguous(), vf2[pos].contiguous(), is_causal=True)
+        kk, vv = kf2.float().repeat_interleave(Hq // Hkv, 1), vf2.float().repeat_interleave(Hq // Hkv, 1)
+        sc = torch.einsum("shd,lhd->hsl", qf.float(), kk) / math.sqrt(D)
+        sc = sc.masked_fill(~(torch.arange(S, device=dev)[None, :] <= torch.arange(S, device=dev)[:, None])[None], float("-inf"))
+        full_o = torch.einsum("hsl,lhd->shd", torch.softmax(sc, -1), vv)
+        _assert_close(o, full_o[pos], 3e-2, 3e-2, "sp ag attention (tcgen05 flash, zig-zag)")
+        ctx.finalize()
     # ---- PP send/recv ring ----
     for backend in (("triton_dist", "torch") if big else ("triton_dist",)):
         pp = PPCommLayer(1024, dtype, me, W, backend=backend, group=grp)

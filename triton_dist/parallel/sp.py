@@ -96,7 +96,9 @@ def fused_sp_ag_attn_intra_node(ctx: SPAllGatherAttentionContextIntraNode, q_sha
         k_all, v_all = k_shard[None], v_shard[None]
     S = S_local * W
     dev = q_shard.device
-    if q_shard.is_cuda and D == 128 and U.get_bool_env("TD_TCGEN05_PREFILL", True):
+    zz = enable_zig_zag and W > 1
+    if (q_shard.is_cuda and D == 128 and q_shard.dtype in (torch.bfloat16, torch.float16) and U.get_bool_env("TD_TCGEN05_PREFILL", True)
+            and (not zz or (S_local // 2) % 128 == 0)):
         return _sp_attn_tcgen05(q_shard, k_all, v_all, W, r, is_causal, enable_zig_zag and W > 1, sm_scale)
     if enable_zig_zag and W > 1:
         pos = torch.stack([zigzag_positions(S, W, s, dev) for s in range(W)])      # [W, S_local]
