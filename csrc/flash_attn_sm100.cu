@@ -380,6 +380,280 @@ __global__ void __launch_bounds__(kThreads, (BNK == 64 && !kTS) ? 2 : 1) flash_f
   }
 }
 
+
+// =================================================================================================================
+// v2: 128-key tiles, Q and P as TMEM A operands, 3-stage K/V ring, TWO softmax warpgroups that split the columns of
+// every S tile (two resident warps per scheduler hide the tcgen05.ld / MUFU / reduction latencies one warp per
+// scheduler cannot), 4-way ILP in the row reductions, CTAs ordered longest-first for causal masks and adjacent CTAs =
+// the q-heads of one GQA group (their K/V tiles hit in L2).
+// =================================================================================================================
+constexpr int kThreadsV2 = 320;
+constexpr int kStagesV2 = 3;
+constexpr int kKVTileV2 = 128 * 128 * 2;
+struct SmemV2 {
+  static constexpr int kQ = 0;                          // reused for the max / sum exchange once Q sits in TMEM
+  static constexpr int kK = kQ + kQBytes;
+  static constexpr int kV = kK + kStagesV2 * kKVTileV2;
+  static constexpr int kBar = kV + kStagesV2 * kKVTileV2;
+  static constexpr int kTotal = kBar + 256;
+};
+enum BarV2 { V2_Q_FULL = 0, V2_K_FULL = 1, V2_V_FULL = 4, V2_KV_EMPTY = 7, V2_S_FULL = 10, V2_P_READY = 12, V2_PV_DONE = 13, V2_Q_TMEM = 14, V2_NBAR = 15 };
+
+__global__ void __launch_bounds__(kThreadsV2, 1) flash_fwd_kernel_v2(const __grid_constant__ Params p, int n_q_tiles) {
+  constexpr int BNK = 128;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SmemV2::kBar);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + V2_NBAR);
+  float* xmax = reinterpret_cast<float*>(smem + SmemV2::kQ);               // [2 parity][2 halves][128]
+  float* xsum = xmax + 2 * 2 * 128;                                        // [2 halves][128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per_tile = p.Hq * p.B;
+  const int tile_rank = static_cast<int>(blockIdx.x) / per_tile, hb = static_cast<int>(blockIdx.x) % per_tile;
+  const int q_tile = p.causal ? n_q_tiles - 1 - tile_rank : tile_rank;     // causal: most keys first
+  const int head = hb % p.Hq, batch = hb / p.Hq;
+  const int kv_head = head / (p.Hq / p.Hkv);
+  const int q_row0 = q_tile * BMQ;
+  const int q_pos0 = p.q_tile_pos ? p.q_tile_pos[batch * n_q_tiles + q_tile] : q_row0 + (p.Sk - p.Sq);
+  const int rows_here = min(BMQ, p.Sq - q_row0);
+  int n_tiles = (p.Sk + BNK - 1) / BNK;
+  if (p.causal) n_tiles = min(n_tiles, (q_pos0 + rows_here - 1) / BNK + 1);
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&p.tmap_q);
+    ptx::prefetch_tensormap(&p.tmap_k);
+    ptx::prefetch_tensormap(&p.tmap_v);
+    ptx::mbar_init(&bars[V2_Q_FULL], 1);
+    for (int s = 0; s < kStagesV2; ++s) {
+      ptx::mbar_init(&bars[V2_K_FULL + s], 1);
+      ptx::mbar_init(&bars[V2_V_FULL + s], 1);
+      ptx::mbar_init(&bars[V2_KV_EMPTY + s], 1);
+    }
+    ptx::mbar_init(&bars[V2_S_FULL], 1);
+    ptx::mbar_init(&bars[V2_S_FULL + 1], 1);
+    ptx::mbar_init(&bars[V2_P_READY], 256);
+    ptx::mbar_init(&bars[V2_PV_DONE], 1);
+    ptx::mbar_init(&bars[V2_Q_TMEM], 256);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc<1>(tmem_ptr_smem, 512);
+    ptx::tmem_relinquish<1>();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_o = tmem_base + 2 * BNK;
+  const uint32_t tmem_q = tmem_base + 2 * BNK + HD;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(&bars[V2_Q_FULL], kQBytes);
+      ptx::tma_load_4d(&p.tmap_q, &bars[V2_Q_FULL], smem + SmemV2::kQ, 0, q_row0, head, batch);
+      ptx::tma_load_4d(&p.tmap_q, &bars[V2_Q_FULL], smem + SmemV2::kQ + kSlab, 64, q_row0, head, batch);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j % kStagesV2, use = j / kStagesV2;
+        if (use > 0) ptx::mbar_wait(&bars[V2_KV_EMPTY + st], (use - 1) & 1);
+        uint8_t* ks = smem + SmemV2::kK + st * kKVTileV2;
+        uint8_t* vs = smem + SmemV2::kV + st * kKVTileV2;
+        ptx::mbar_arrive_expect_tx(&bars[V2_K_FULL + st], kKVTileV2);
+        ptx::tma_load_4d(&p.tmap_k, &bars[V2_K_FULL + st], ks, 0, j * BNK, kv_head, batch, ptx::kEvictLast);
+        ptx::tma_load_4d(&p.tmap_k, &bars[V2_K_FULL + st], ks + kSlab, 64, j * BNK, kv_head, batch, ptx::kEvictLast);
+        ptx::mbar_arrive_expect_tx(&bars[V2_V_FULL + st], kKVTileV2);
+        ptx::tma_load_4d(&p.tmap_v, &bars[V2_V_FULL + st], vs, 0, j * BNK, kv_head, batch, ptx::kEvictLast);
+        ptx::tma_load_4d(&p.tmap_v, &bars[V2_V_FULL + st], vs + kSlab, 64, j * BNK, kv_head, batch, ptx::kEvictLast);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t fmt = p.is_bf16 ? 1u : 0u;
+      const uint32_t idesc_qk = ptx::make_idesc(fmt, fmt, BMQ, BNK);
+      const uint32_t idesc_pv = ptx::make_idesc(fmt, fmt, BMQ, HD, 0, 1);
+      // tcgen05 operations of one thread execute in issue order: QK(j+2) (which overwrites S[j&1], holding P_j) is issued
+      // after PV(j), and PV(j) is issued only after every softmax thread has read S_j and written P_j -> no S_FREE barrier
+      auto issue_qk = [&](int j) {
+        const int st = j % kStagesV2;
+        ptx::mbar_wait(&bars[V2_K_FULL + st], (j / kStagesV2) & 1);
+        ptx::tc_fence_after();
+        const uint32_t k_addr = ptx::smem_u32(smem + SmemV2::kK + st * kKVTileV2);
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk)
+          ptx::mma_f16_ts(tmem_base + (j & 1) * BNK, tmem_q + kk * 8,
+                          ptx::make_smem_desc_k128(k_addr + (kk >> 2) * kSlab + (kk & 3) * 32), idesc_qk, kk > 0 ? 1u : 0u);
+        ptx::mma_commit(&bars[V2_S_FULL + (j & 1)]);
+      };
+      ptx::mbar_wait(&bars[V2_Q_TMEM], 0);
+      ptx::tc_fence_after();
+      if (n_tiles > 0) issue_qk(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j % kStagesV2;
+        if (j + 1 < n_tiles) issue_qk(j + 1);
+        ptx::mbar_wait(&bars[V2_V_FULL + st], (j / kStagesV2) & 1);
+        ptx::mbar_wait(&bars[V2_P_READY], j & 1);
+        ptx::tc_fence_after();
+        const uint32_t v_addr = ptx::smem_u32(smem + SmemV2::kV + st * kKVTileV2);
+#pragma unroll
+        for (int kk = 0; kk < BNK / 16; ++kk)
+          ptx::mma_f16_ts(tmem_o, tmem_base + (j & 1) * BNK + kk * 8, ptx::make_smem_desc_mn128(v_addr + kk * 16 * 128, kSlab), idesc_pv,
+                          (j > 0 || kk > 0) ? 1u : 0u);
+        ptx::mma_commit(&bars[V2_KV_EMPTY + st]);
+        ptx::mma_commit(&bars[V2_PV_DONE]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax: 2 warpgroups x 64 columns
+    const int half = (warp - 2) >> 2;                // which 64 columns of S / O this thread owns
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const int q_pos = q_pos0 + row;
+    float m_ref = -INFINITY, l = 0.f;
+
+    // Q slab `half` (64 elements = 32 packed columns): swizzled smem -> registers -> TMEM
+    ptx::mbar_wait(&bars[V2_Q_FULL], 0);
+    {
+      const uint32_t q_row = ptx::smem_u32(smem + SmemV2::kQ) + half * kSlab + row * 128;
+      uint32_t qv[32];
+#pragma unroll
+      for (int c16 = 0; c16 < 8; ++c16) {
+        const uint4 v = ptx::ld_shared_v4(q_row + ((c16 ^ (row & 7)) << 4));
+        qv[c16 * 4 + 0] = v.x; qv[c16 * 4 + 1] = v.y; qv[c16 * 4 + 2] = v.z; qv[c16 * 4 + 3] = v.w;
+      }
+      ptx::tmem_st_32x32b_x32(tmem_q + lane_off + half * 32, qv);
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&bars[V2_Q_TMEM]);
+    }
+    ptx::named_bar_sync(3, 256);                     // every row of Q has been read: its smem becomes the exchange area
+
+    for (int j = 0; j < n_tiles; ++j) {
+      const int b = j & 1;
+      ptx::mbar_wait(&bars[V2_S_FULL + b], (j >> 1) & 1);
+      ptx::tc_fence_after();
+      uint32_t s[2][32];
+      ptx::tmem_ld_32x32b_x32(tmem_base + lane_off + b * BNK + half * 64, s[0]);
+      ptx::tmem_ld_32x32b_x32(tmem_base + lane_off + b * BNK + half * 64 + 32, s[1]);
+      ptx::tmem_ld_wait();
+
+      const int key0 = j * BNK + half * 64;
+      const bool need_mask = (p.causal && j * BNK + BNK - 1 > q_pos0) || (j * BNK + BNK > p.Sk);
+      if (need_mask) {
+        const int limit = p.causal ? min(p.Sk - 1, q_pos) : p.Sk - 1;
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (key0 + c * 32 + i > limit) s[c][i] = 0xFF800000u;      // -inf
+      }
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(s[c][i]));
+      const float mx_local = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      xmax[(b * 2 + half) * 128 + row] = mx_local;
+      ptx::tc_fence_before();                          // my S reads are complete before the partner half may overwrite
+      ptx::named_bar_sync(3, 256);                     // columns 32..63 of this buffer with its packed P
+      ptx::tc_fence_after();
+      float mx = fmaxf(mx_local, xmax[(b * 2 + (half ^ 1)) * 128 + row]) * p.scale_log2;
+
+      const bool bump = mx > m_ref + 8.f;
+      float alpha = 1.f;
+      if (bump) {
+        alpha = (m_ref == -INFINITY) ? 0.f : ptx::ex2_approx(m_ref - mx);
+        m_ref = mx;
+        l *= alpha;
+      }
+      const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t pk[32];
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float e0 = ptx::ex2_approx(fmaf(__uint_as_float(s[c][i]), p.scale_log2, neg_m));
+          const float e1 = ptx::ex2_approx(fmaf(__uint_as_float(s[c][i + 1]), p.scale_log2, neg_m));
+          sum4[(i >> 1) & 3] += e0 + e1;
+          pk[c * 16 + (i >> 1)] = p.is_bf16 ? ptx::pack_bf16x2(e0, e1) : ptx::pack_f16x2(e0, e1);
+        }
+      l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+      // P (64 keys of this half = 32 packed columns) over the S buffer
+      ptx::tmem_st_32x32b_x32(tmem_base + lane_off + b * BNK + half * 32, pk);
+      if (j > 0 && __any_sync(0xFFFFFFFFu, bump)) {
+        ptx::mbar_wait(&bars[V2_PV_DONE], (j - 1) & 1);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t o[32];
+          ptx::tmem_ld_32x32b_x32(tmem_o + lane_off + half * 64 + c * 32, o);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          ptx::tmem_st_32x32b_x32(tmem_o + lane_off + half * 64 + c * 32, o);
+        }
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&bars[V2_P_READY]);
+    }
+
+    // epilogue: total row sum across the two halves, O / l -> global (each half its 64 columns), LSE
+    xsum[half * 128 + row] = l;
+    ptx::named_bar_sync(3, 256);
+    l += xsum[(half ^ 1) * 128 + row];
+    if (n_tiles > 0) {
+      ptx::mbar_wait(&bars[V2_PV_DONE], (n_tiles - 1) & 1);
+      ptx::tc_fence_after();
+    }
+    const float inv_l = l > 0.f ? 1.f / l : 0.f;
+    const bool live = row < rows_here;
+    char* o_row = reinterpret_cast<char*>(p.o) +
+                  2 * (static_cast<long long>(batch) * p.o_stride_b + static_cast<long long>(q_row0 + row) * p.o_stride_s +
+                       static_cast<long long>(head) * p.o_stride_h + half * 64);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      if (n_tiles > 0) {
+        ptx::tmem_ld_32x32b_x32(tmem_o + lane_off + half * 64 + c * 32, o);
+        ptx::tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = 0u;
+      }
+      if (live) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 v;
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(o[g * 8 + i]) * inv_l;
+          if (p.is_bf16) {
+            v.x = ptx::pack_bf16x2(f[0], f[1]); v.y = ptx::pack_bf16x2(f[2], f[3]);
+            v.z = ptx::pack_bf16x2(f[4], f[5]); v.w = ptx::pack_bf16x2(f[6], f[7]);
+          } else {
+            v.x = ptx::pack_f16x2(f[0], f[1]); v.y = ptx::pack_f16x2(f[2], f[3]);
+            v.z = ptx::pack_f16x2(f[4], f[5]); v.w = ptx::pack_f16x2(f[6], f[7]);
+          }
+          ptx::st_v4(o_row + (c * 32 + g * 8) * 2, v);
+        }
+      }
+    }
+    if (p.lse && live && half == 0) {
+      const float lse = (l > 0.f) ? (m_ref + log2f(l)) * 0.6931471805599453f : -INFINITY;
+      p.lse[(static_cast<long long>(batch) * p.Hq + head) * p.Sq + q_row0 + row] = lse;
+    }
+    ptx::tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
 }  // namespace fa
 }  // namespace td
 
@@ -437,7 +711,7 @@ extern "C" __attribute__((visibility("default"))) int td_flash_attn_fwd(const Td
   for (long long s : st)
     if (s % 8 != 0) { td::drv::set_error("flash_attn: strides must be multiples of 8 elements (16 bytes)"); return -1; }
   Params p{};
-  const int bnk = (a->block_n == 128 || a->block_n == 129) ? 128 : 64;
+  const int bnk = (a->block_n >= 128) ? 128 : 64;
   if (fa_tmap(&p.tmap_q, a->q, a->Sq, a->Hq, a->B, a->q_stride_b, a->q_stride_s, a->q_stride_h, (int)a->is_bf16, BMQ)) return -1;
   if (fa_tmap(&p.tmap_k, a->k, a->Sk, a->Hkv, a->B, a->k_stride_b, a->k_stride_s, a->k_stride_h, (int)a->is_bf16, bnk)) return -1;
   if (fa_tmap(&p.tmap_v, a->v, a->Sk, a->Hkv, a->B, a->v_stride_b, a->v_stride_s, a->v_stride_h, (int)a->is_bf16, bnk)) return -1;
@@ -448,6 +722,19 @@ extern "C" __attribute__((visibility("default"))) int td_flash_attn_fwd(const Td
   p.scale_log2 = static_cast<float>(a->sm_scale * 1.4426950408889634);
   dim3 grid((unsigned)((a->Sq + BMQ - 1) / BMQ), (unsigned)a->Hq, (unsigned)a->B);
   cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream_);
+  if (a->block_n == 130) {     // v2 kernel
+    static bool v2_attr = false;
+    if (!v2_attr) {
+      cudaError_t e = cudaFuncSetAttribute(flash_fwd_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemV2::kTotal);
+      if (e != cudaSuccess) { td::drv::set_error("flash_attn v2: smem attribute: %s", cudaGetErrorString(e)); return -1; }
+      v2_attr = true;
+    }
+    const int nq = (int)((a->Sq + BMQ - 1) / BMQ);
+    flash_fwd_kernel_v2<<<dim3((unsigned)(nq * a->Hq * a->B)), kThreadsV2, SmemV2::kTotal, st_>>>(p, nq);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { td::drv::set_error("flash_attn v2 launch: %s", cudaGetErrorString(e)); return -1; }
+    return 0;
+  }
   if (a->block_n == 129) return fa_launch<128, true>(p, grid, st_);
   return bnk == 128 ? fa_launch<128>(p, grid, st_) : fa_launch<64>(p, grid, st_);
 }

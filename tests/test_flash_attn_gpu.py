@@ -6,7 +6,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _check(B, Sq, Sk, Hq, Hkv, causal, dtype, cache_len=None, tile_pos=False):
-    for bn in (64, 128, 129):          # 129 = 128-key tiles with Q / P operands in TMEM
+    for bn in (64, 128, 129, 130):     # 129 = 128-key tiles with Q / P operands in TMEM, 130 = v2 kernel
         _check_bn(B, Sq, Sk, Hq, Hkv, causal, dtype, cache_len, tile_pos, bn)
 
 
@@ -23,7 +23,7 @@ def _check_bn(B, Sq, Sk, Hq, Hkv, causal, dtype, cache_len, tile_pos, bn):
         starts = torch.randint(0, max(1, (Sk - 128) // 64), (B, nt), device="cuda", dtype=torch.int32) * 64
         q_tile_pos = starts.contiguous()
         q_pos = (starts.long()[:, :, None] + torch.arange(128, device="cuda")[None, None]).reshape(B, -1)[:, :Sq]
-    out, lse = flash_attn_fwd(q, k, v, causal=causal, q_tile_pos=q_tile_pos, sk=Sk, return_lse=True, block_n=min(bn, 128), tmem_operands=(bn == 129))
+    out, lse = flash_attn_fwd(q, k, v, causal=causal, q_tile_pos=q_tile_pos, sk=Sk, return_lse=True, block_n=min(bn, 128), tmem_operands=(bn == 129), v2=(bn == 130))
     ref, ref_lse = flash_attn_reference(q, k, v, causal, None, q_pos, Sk)
     torch.testing.assert_close(out.float(), ref, atol=2e-2, rtol=2e-2)
     torch.testing.assert_close(lse, ref_lse, atol=2e-2, rtol=1e-2)
@@ -61,14 +61,14 @@ def test_flash_perf():
     k = torch.randn(B, S, 8, 128, device="cuda", dtype=torch.bfloat16)
     v = torch.randn(B, S, 8, 128, device="cuda", dtype=torch.bfloat16)
     tf = 0.0
-    for bn in (64, 128, 129):
+    for bn in (64, 128, 129, 130):
         for _ in range(3):
-            flash_attn_fwd(q, k, v, block_n=min(bn, 128), tmem_operands=(bn == 129))
+            flash_attn_fwd(q, k, v, block_n=min(bn, 128), tmem_operands=(bn == 129), v2=(bn == 130))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
         for _ in range(10):
-            flash_attn_fwd(q, k, v, block_n=min(bn, 128), tmem_operands=(bn == 129))
+            flash_attn_fwd(q, k, v, block_n=min(bn, 128), tmem_operands=(bn == 129), v2=(bn == 130))
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
