@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(kThreads, (BNK == 64 && !kTS) ? 2 : 1) flash_f
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + NBAR);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q_tile = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
+  const int q_tile = p.causal ? static_cast<int>(gridDim.x - 1 - blockIdx.x) : static_cast<int>(blockIdx.x);   // causal: longest tiles first
+  const int head = blockIdx.y, batch = blockIdx.z;
   const int kv_head = head / (p.Hq / p.Hkv);
   const int n_q_tiles = gridDim.x;
   const int q_row0 = q_tile * BMQ;
