@@ -106,6 +106,61 @@ TD_DEVICE void task_rmsnorm(const MKParams& p, const Task& t, float* red) {
 }
 
 // ---- LINEAR (GEMV tile): out[b, n0 + j] = sum_k act(x)[b, k] * W[n0 + j, k].  a: x, w, out, K, ldo, n0, n_cnt, act, ldx ----
+// One CTA per SM means 8 warps have to keep the SM's share of HBM bandwidth busy (~45 KB in flight): every lane keeps
+// R * U independent 16-byte weight loads in flight; the batch dimension is a template parameter so the decode case
+// (B = 1) can afford U = 4 without spilling.
+template <int MB, int U>
+TD_DEVICE void linear_rows(const uint4* __restrict__ W, const uint4* __restrict__ xs, __nv_bfloat16* __restrict__ out, int B, int kvec,
+                           int ldo, int n0, int n_cnt) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int R = 4;
+  for (int j0 = warp * R; j0 < n_cnt; j0 += (kMKThreads / 32) * R) {
+    float acc[R][MB];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int b = 0; b < MB; ++b) acc[r][b] = 0.f;
+    for (int kv0 = lane; kv0 < kvec; kv0 += 32 * U) {
+      uint4 wv[U][R];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int kv = kv0 + u * 32;
+          wv[u][r] = (j0 + r < n_cnt && kv < kvec) ? ptx::ld_nc_v4(W + static_cast<size_t>(n0 + j0 + r) * kvec + kv) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int kv = kv0 + u * 32;
+        if (kv < kvec) {
+#pragma unroll
+          for (int b = 0; b < MB; ++b) {
+            if (b < B) {
+              float xf[8];
+              unpack8(xs[b * kvec + kv], xf);
+#pragma unroll
+              for (int r = 0; r < R; ++r) {
+                float wf[8];
+                unpack8(wv[u][r], wf);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[r][b] += wf[e] * xf[e];
+              }
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int b = 0; b < MB; ++b)
+        if (b < B) {
+          const float v = warp_sum(acc[r][b]);
+          if (lane == 0 && j0 + r < n_cnt) out[static_cast<size_t>(b) * ldo + n0 + j0 + r] = __float2bfloat16(v);
+        }
+  }
+}
+
 TD_DEVICE void task_linear(const MKParams& p, const Task& t, uint8_t* smem) {
   const uint4* x = (const uint4*)p.ptrs[t.a[0]];
   const uint4* W = (const uint4*)p.ptrs[t.a[1]];
@@ -113,7 +168,6 @@ TD_DEVICE void task_linear(const MKParams& p, const Task& t, uint8_t* smem) {
   const int K = t.a[3], ldo = t.a[4], n0 = t.a[5], n_cnt = t.a[6], act = t.a[7], ldx = t.a[8];
   const int kvec = K / 8;
   const int B = p.B;
-  // stage act(x) [B, K] in shared memory as fp32?  bf16 is enough: 16 B vectors
   uint4* xs = reinterpret_cast<uint4*>(smem);
   for (int i = threadIdx.x; i < B * kvec; i += kMKThreads) {
     const int b = i / kvec, kv = i % kvec;
@@ -128,54 +182,9 @@ TD_DEVICE void task_linear(const MKParams& p, const Task& t, uint8_t* smem) {
     }
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int R = 4;      // W rows per warp
-  constexpr int U = 2;      // k-steps in flight: R * U independent 16-byte loads per lane (8 KB per warp, 64 KB per SM)
-  for (int j0 = warp * R; j0 < n_cnt; j0 += (kMKThreads / 32) * R) {
-    float acc[R][kMaxB];
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-      for (int b = 0; b < kMaxB; ++b) acc[r][b] = 0.f;
-    for (int kv0 = lane; kv0 < kvec; kv0 += 32 * U) {
-      uint4 wv[U][R];
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const int kv = kv0 + u * 32;
-          wv[u][r] = (j0 + r < n_cnt && kv < kvec) ? ptx::ld_nc_v4(W + static_cast<size_t>(n0 + j0 + r) * kvec + kv) : make_uint4(0, 0, 0, 0);
-        }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int kv = kv0 + u * 32;
-        if (kv < kvec) {
-          float wf[R][8];
-#pragma unroll
-          for (int r = 0; r < R; ++r) unpack8(wv[u][r], wf[r]);
-#pragma unroll
-          for (int b = 0; b < kMaxB; ++b) {
-            if (b < B) {
-              float xf[8];
-              unpack8(xs[b * kvec + kv], xf);
-#pragma unroll
-              for (int r = 0; r < R; ++r)
-#pragma unroll
-                for (int e = 0; e < 8; ++e) acc[r][b] += wf[r][e] * xf[e];
-            }
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-      for (int b = 0; b < kMaxB; ++b)
-        if (b < B) {
-          const float v = warp_sum(acc[r][b]);
-          if (lane == 0 && j0 + r < n_cnt) out[static_cast<size_t>(b) * ldo + n0 + j0 + r] = __float2bfloat16(v);
-        }
-  }
+  if (B == 1) linear_rows<1, 4>(W, xs, out, B, kvec, ldo, n0, n_cnt);
+  else if (B <= 4) linear_rows<4, 2>(W, xs, out, B, kvec, ldo, n0, n_cnt);
+  else linear_rows<kMaxB, 2>(W, xs, out, B, kvec, ldo, n0, n_cnt);
 }
 
 // ---- QKROPE: q/k RMSNorm + RoPE + KV append.  a: qkv, q_out, kcache, vcache, qn(-1), kn(-1), pos, Hq, Hkv, max_len, eps, theta ----
