@@ -80,6 +80,32 @@ try:
         U.barrier_all_host(); gctx.finalize()
 except Exception as e:
     emit(dict(op="gemm_ar", error=str(e)[:300]))
+# intra-kernel profiles of the two headline kernels (one call each; Perfetto traces + summaries for offline analysis)
+try:
+    from triton_dist.tools.profiler import ProfilerBuffer, export_to_perfetto_trace, summarize
+    os.makedirs("gpurun_out", exist_ok=True)
+    M, N, K = 4096, 12288, 49152
+    rctx = create_gemm_rs_context(M, N, output_dtype=bf)
+    A = (torch.randn(M, K // W, device=dev) * 0.1).to(bf); Bw = (torch.randn(N, K // W, device=dev) * 0.1).to(bf)
+    for _ in range(3): gemm_rs(A, Bw.t(), rctx)
+    pb = ProfilerBuffer(); torch.cuda.synchronize(); dist.barrier(group=grp)
+    gemm_rs(A, Bw.t(), rctx, profiler=pb); torch.cuda.synchronize()
+    if me == 0:
+        emit(dict(op="profile_gemm_rs", summary=summarize(pb)))
+        export_to_perfetto_trace(pb, f"gpurun_out/gemm_rs_trace_n{W}.json.gz", rank=me)
+    U.barrier_all_host(); rctx.finalize(); del A, Bw
+    M, N, K = 4096, 4096, 4096
+    actx = create_ag_gemm_context(M, N // W, K, bf)
+    A = torch.randn(M // W, K, device=dev, dtype=bf); Bw = torch.randn(N // W, K, device=dev, dtype=bf)
+    for _ in range(3): ag_gemm(A, Bw.t(), actx)
+    pb = ProfilerBuffer(); torch.cuda.synchronize(); dist.barrier(group=grp)
+    ag_gemm(A, Bw.t(), actx, profiler=pb); torch.cuda.synchronize()
+    if me == 0:
+        emit(dict(op="profile_ag_gemm", summary=summarize(pb)))
+        export_to_perfetto_trace(pb, f"gpurun_out/ag_gemm_trace_n{W}.json.gz", rank=me)
+    U.barrier_all_host(); actx.finalize()
+except Exception as e:
+    emit(dict(op="profile", error=str(e)[:300]))
 if me == 0:
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(rows, open(f"gpurun_out/extras_dist_n{W}.json", "w"), indent=1)

@@ -77,7 +77,8 @@ def default_rs_config(M: int, N: int, K: int, world: int) -> GemmConfig:
 
 def gemm_rs(A: torch.Tensor, B: torch.Tensor, ctx: GEMMReduceScatterTensorParallelContext,
             gemm_config: Optional[GemmConfig] = None, persistent: bool = True, fuse_scatter: bool = True,
-            reduce_st: bool = False, out: Optional[torch.Tensor] = None, straggler_option=None, **_unused) -> torch.Tensor:
+            reduce_st: bool = False, out: Optional[torch.Tensor] = None, straggler_option=None, profiler=None,
+            **_unused) -> torch.Tensor:
     """A: ``[M, K/W]``, B: ``[K/W, N]`` (``.t()`` view of a ``[N, K/W]`` weight) -> ``[M/W, N]``."""
     W = ctx.world_size
     M, K = A.shape
@@ -114,6 +115,8 @@ def gemm_rs(A: torch.Tensor, B: torch.Tensor, ctx: GEMMReduceScatterTensorParall
     args.rs_rows_per_rank = Mr
     args.rs_stage, args.rs_stage_buf_bytes = ctx.stage.data_ptr(), ctx.max_M * N * A.element_size()
     args.rs_flags, args.rs_out, args.rs_ldo = ctx.flags.data_ptr(), out.data_ptr(), out.stride(0)
+    if profiler is not None:
+        profiler.attach(args)
     _C.check(_C.cuda_lib().td_gemm_launch(C.byref(args), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
              "td_gemm_launch(rs)")
     ctx.host_phase += 1
