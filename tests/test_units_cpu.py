@@ -181,3 +181,37 @@ def test_bench_reference_arm_reports_unavailable():
     assert r.returncode == 0
     d = json.loads(r.stdout.strip().splitlines()[-1])
     assert d["impl"] == "reference" and "unavailable" in d
+
+
+def test_flash_attn_reference_paths():
+    """CPU path of flash_attn_fwd (the golden the GPU kernel is tested against): causal offsets, per-tile positions, LSE."""
+    from triton_dist.ops.flash_attn import flash_attn_fwd, flash_attn_reference, flash_attn_varlen
+    torch.manual_seed(0)
+    q, k, v = torch.randn(2, 130, 4, 128), torch.randn(2, 300, 2, 128), torch.randn(2, 300, 2, 128)
+    o, lse = flash_attn_fwd(q, k, v, causal=True, return_lse=True)
+    # brute force for one (batch, head, row): query i sits at position 300 - 130 + i
+    b, h, i = 1, 3, 17
+    pos = 300 - 130 + i
+    s = (q[b, i, h] @ k[b, :pos + 1, h // 2].t()) / math.sqrt(128)
+    ref = torch.softmax(s, -1) @ v[b, :pos + 1, h // 2]
+    torch.testing.assert_close(o[b, i, h], ref, atol=1e-4, rtol=1e-4)
+    torch.testing.assert_close(lse[b, h, i], torch.logsumexp(s, -1), atol=1e-4, rtol=1e-4)
+    # explicit tile positions reproduce the default layout
+    tp = torch.tensor([[170, 298], [170, 298]], dtype=torch.int32)
+    o2 = flash_attn_fwd(q, k, v, causal=True, q_tile_pos=tp)
+    torch.testing.assert_close(o2, o)
+    # varlen = per-sequence calls
+    cu = torch.tensor([0, 50, 130])
+    ov = flash_attn_varlen(q[0], k[0, :130], v[0, :130], cu, cu)
+    o_first, _ = flash_attn_reference(q[0:1, :50], k[0:1, :50], v[0:1, :50], True)
+    torch.testing.assert_close(ov[:50], o_first[0], atol=1e-5, rtol=1e-5)
+
+
+def test_gdn_recurrent_cpu_fallback():
+    from triton_dist.ops.gdn import fused_recurrent_gated_delta_rule, gated_delta_rule_recurrent
+    torch.manual_seed(1)
+    q, k, v = torch.randn(1, 5, 2, 16), torch.randn(1, 5, 2, 16), torch.randn(1, 5, 2, 8)
+    g, beta = -torch.rand(1, 5, 2) * 0.1, torch.rand(1, 5, 2)
+    o, s = fused_recurrent_gated_delta_rule(q, k, v, g, beta)
+    o2, s2 = gated_delta_rule_recurrent(q, k, v, g, beta)
+    torch.testing.assert_close(o, o2); torch.testing.assert_close(s, s2)

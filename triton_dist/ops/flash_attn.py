@@ -72,6 +72,9 @@ def flash_attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bo
             q_pos = (q_tile_pos.long()[:, :, None] + torch.arange(Q_TILE)[None, None, :]).reshape(B, -1)[:, :Sq]
         o, lse = flash_attn_reference(q, k, v, causal, sm_scale, q_pos, Sk)
         o = o.to(q.dtype)
+        if out is not None:
+            out.copy_(o)
+            o = out
         return (o, lse) if return_lse else o
     assert D == 128 and q.dtype in (torch.bfloat16, torch.float16) and k.dtype == q.dtype == v.dtype
     assert q.stride(3) == 1 and k.stride(3) == 1 and v.stride(3) == 1
