@@ -269,19 +269,20 @@ def case_moe():
     ag.finalize(); rs.finalize()
 
 
-def case_moe_fused():
-    """AllGather + grouped GEMM in one kernel (TMA tile::gather4 producer waiting on arrival flags) and the gather4 /
-    scatter grouped GEMM of the down projection; GPU only (the emulation backend runs the staged path in case_moe)."""
-    dev = U.current_device()
-    if dev.type != "cuda":
-        return
-    os.environ["TD_MOE_AG_FUSED"] = "1"
-    os.environ["TD_MOE_TMA_GATHER"] = "1"
+def case_moe_staged():
+    """The multi-kernel MoE path (all-gather kernel -> gather_rows -> grouped GEMM -> scatter_rows); ``case_moe`` runs the
+    default single-kernel path on GPUs (AllGather + grouped GEMM with a TMA tile::gather4 producer waiting on arrival flags)."""
+    os.environ["TD_MOE_AG_FUSED"] = "0"
+    os.environ["TD_MOE_TMA_GATHER"] = "0"
     try:
         case_moe()
     finally:
         os.environ.pop("TD_MOE_AG_FUSED", None)
         os.environ.pop("TD_MOE_TMA_GATHER", None)
+
+
+def case_moe_fused():
+    case_moe()
 
 
 def case_tp_e2e():

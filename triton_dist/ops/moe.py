@@ -182,7 +182,7 @@ def _use_tma_gather(x: torch.Tensor) -> bool:
     return x.is_cuda and U.get_bool_env("TD_MOE_TMA_GATHER", _TMA_GATHER_DEFAULT)
 
 
-_TMA_GATHER_DEFAULT = False     # flipped once validated on hardware (tests/test_ops_gpu.py::test_moe_tma_gather)
+_TMA_GATHER_DEFAULT = True      # validated on B200: bit-identical to the staged path (tests/test_ops_gpu.py::test_moe_tma_gather)
 
 
 def moe_grouped_gemm(x_sorted: torch.Tensor, w: torch.Tensor, routing: SortedRouting, out: Optional[torch.Tensor] = None,
@@ -259,7 +259,7 @@ def create_ag_group_gemm_context(max_ntokens: int, N_per_rank: int, K: int, num_
     ctx = MoEAllGatherGroupGEMMContext(max_ntokens, N_per_rank, K, num_experts, topk, dtype, rank, world_size)
     shard_bytes = (max_ntokens // world_size) * K * torch.empty(0, dtype=dtype).element_size()
     ctx.ag_ctx = comm.create_fast_allgather_context(max(shard_bytes, 1024), rank, world_size, grid_max=64)
-    if heap.device.type == "cuda" and world_size > 1 and U.get_bool_env("TD_MOE_AG_FUSED", False):
+    if heap.device.type == "cuda" and world_size > 1 and U.get_bool_env("TD_MOE_AG_FUSED", True):
         from .ag_gemm import create_ag_gemm_context
         ctx.fused_ctx = create_ag_gemm_context(max_ntokens, N_per_rank, K, dtype, rank, world_size)
     return ctx

@@ -106,7 +106,7 @@ class TP_Attn:
                                                 self.world_size, self.world_size)
 
     def _init_gemm_ar_ctx(self, max_M: int, dtype=torch.bfloat16):
-        self.gemm_ar_ctx = (create_ll_gemm_ar_context if (max_M <= 256 and U.get_bool_env('TD_GEMM_AR_FUSED', False)) else create_gemm_ar_context)(None, self.rank, self.world_size, self.world_size, max_M, self.hidden, dtype)
+        self.gemm_ar_ctx = (create_ll_gemm_ar_context if (max_M <= 256 and U.get_bool_env('TD_GEMM_AR_FUSED', True)) else create_gemm_ar_context)(None, self.rank, self.world_size, self.world_size, max_M, self.hidden, dtype)
 
     def finalize(self):
         for c in (self.ag_ctx, self.rs_ctx, self.ar_ctx, self.gemm_ar_ctx):
