@@ -33,6 +33,7 @@ struct TdGemmArgs {
   long long rs_rows_per_rank; void* rs_stage; long long rs_stage_buf_bytes; void* rs_flags; void* rs_out; long long rs_ldo;
   // gather / scatter (MoE grouped GEMM without the gather_rows / scatter_rows passes)
   const void* a_gather; long long a_gather_div; long long a_gather_pad; long long a_src_rows; const void* c_scatter;
+  long long expert_stride_rows;   // grouped mode: rows between consecutive experts in B (0 = N); lets a launch use an N-slice of every expert
 };
 
 static int encode_tmap(CUtensorMap* out, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
@@ -120,7 +121,8 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
     if (encode_tmap(&p.tmap_a, a->A, 3, dims, strides, box, bf16)) return -1;
   }
   {  // B: {K, N}
-    cuuint64_t dims[2] = {(cuuint64_t)a->K, (cuuint64_t)(a->N * (a->tile_expert ? a->num_experts : 1))};
+    const long long estride = a->expert_stride_rows > 0 ? a->expert_stride_rows : a->N;
+    cuuint64_t dims[2] = {(cuuint64_t)a->K, (cuuint64_t)(a->tile_expert ? (a->num_experts - 1) * estride + a->N : a->N)};
     cuuint64_t strides[1] = {(cuuint64_t)a->ldb * esz};
     cuuint32_t box[2] = {(cuuint32_t)bk_elems, (cuuint32_t)(bn / cg)};
     if (encode_tmap(&p.tmap_b, a->B, 2, dims, strides, box, bf16)) return -1;
@@ -146,7 +148,7 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
   p.c_phase = (a->c_nbuf > 1) ? reinterpret_cast<const uint32_t*>(a->c_phase) : nullptr;
   p.c_buf_stride_bytes = a->c_buf_stride_bytes;
   p.tile_expert = reinterpret_cast<const int*>(a->tile_expert);
-  p.expert_rows = (int)a->N;
+  p.expert_rows = (int)(a->expert_stride_rows > 0 ? a->expert_stride_rows : a->N);
   p.prof.buf = reinterpret_cast<unsigned long long*>(a->prof_buf); p.prof.cap = (int)a->prof_cap; p.prof.num_slots = (int)a->prof_slots;
   const int TM = BM * cg;
   p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K;

@@ -54,6 +54,7 @@ class GemmArgs(C.Structure):
         ("rs_rows_per_rank", c_ll), ("rs_stage", c_void_p), ("rs_stage_buf_bytes", c_ll), ("rs_flags", c_void_p),
         ("rs_out", c_void_p), ("rs_ldo", c_ll),
         ("a_gather", c_void_p), ("a_gather_div", c_ll), ("a_gather_pad", c_ll), ("a_src_rows", c_ll), ("c_scatter", c_void_p),
+        ("expert_stride_rows", c_ll),
     ]]
 
 

@@ -156,21 +156,26 @@ bincount = histogram_by_expert
 # grouped GEMM
 # ------------------------------------------------------------------------------------------------------------
 def moe_grouped_gemm_fused(src: torch.Tensor, w: torch.Tensor, routing: SortedRouting, div: int, n_out_rows: int,
-                           out: Optional[torch.Tensor] = None, config: Optional[GemmConfig] = None) -> torch.Tensor:
+                           out: Optional[torch.Tensor] = None, config: Optional[GemmConfig] = None,
+                           n_slice: Optional[Tuple[int, int]] = None) -> torch.Tensor:
     """``out[id] = src[id // div] @ w[expert(id)].T`` for every routed pair id = token * topk + k, in ONE kernel: the A rows
     of each tile are fetched with TMA ``tile::gather4`` straight from ``src`` (no gather_rows pass) and the epilogue writes
     each row to its final place (no scatter_rows pass).  The sm_100a counterpart of the reference's gather/scatter
     grouped GEMM (allgather_group_gemm.py:536-609, which cannot use TMA for the gathered operand)."""
     K = src.shape[1]
-    E, N, Kw = w.shape
-    assert Kw == K and src.is_cuda and src.stride(1) == 1
+    E, N_full, Kw = w.shape
+    assert Kw == K and src.is_cuda and src.stride(1) == 1 and w.is_contiguous()
+    n0, N = n_slice if n_slice is not None else (0, N_full)          # columns [n0, n0 + N) of every expert's weight
     out = torch.empty((n_out_rows, N), dtype=src.dtype, device=src.device) if out is None else out
     cfg = config or GemmConfig(bn=256 if N >= 256 else 128, cta_group=1, group_m=1, use_tma_store=False)
     assert cfg.cta_group == 1 and routing.block_m == 128
     args = _C.GemmArgs()
     args.mode = 0
-    fill_common(args, src.shape[0], src.data_ptr(), src.stride(0), w.reshape(E * N, K), out.data_ptr(), n_out_rows, out.stride(0),
+    w2 = w.reshape(E * N_full, K)
+    fill_common(args, src.shape[0], src.data_ptr(), src.stride(0), w2, out.data_ptr(), n_out_rows, out.stride(0),
                 routing.capacity, N, K, GemmConfig(cfg.bn, 1, 1, False, cfg.num_sms, 0), src.dtype == torch.bfloat16)
+    args.B = w2.data_ptr() + n0 * K * w.element_size()
+    args.expert_stride_rows = N_full
     args.tile_expert, args.num_experts = routing.tile_expert.data_ptr(), E
     args.a_gather, args.a_gather_div, args.a_gather_pad = routing.sorted_ids.data_ptr(), div, routing.pad_id
     args.a_src_rows, args.c_scatter = src.shape[0], routing.sorted_ids.data_ptr()
@@ -384,11 +389,46 @@ def run_moe_reduce_rs(x: torch.Tensor, w: torch.Tensor, chosen_experts: torch.Te
                       ctx: MoEReduceRSContext, n_chunks: int = 2, **_unused) -> torch.Tensor:
     """x: ``[T*topk, K/W]``, w: ``[E, K/W, N]`` (or K-major ``[E, N, K/W]``), chosen_experts/expert_weight: ``[T, topk]``
     -> ``[T/W, N]`` = reduce_scatter_ranks( sum_j weight[t,j] * (x[t*topk+j] @ w[e_tj]) )."""
-    part = _moe_down_partial(x, w, chosen_experts, expert_weight, ctx)
     W = ctx.world_size
+    wk = w.transpose(1, 2) if (w.shape[1] == x.shape[1] and w.shape[2] != x.shape[1]) else w      # -> [E, N, K/W]
+    N = wk.shape[1]
+    T = chosen_experts.shape[0]
+    if (W > 1 and x.is_cuda and n_chunks > 1 and _use_tma_gather(x) and wk.is_contiguous() and N % (n_chunks * 128) == 0
+            and ((T // W) * (N // n_chunks) * x.element_size()) % 16 == 0):
+        return _moe_reduce_rs_chunked(x, wk, chosen_experts, expert_weight, ctx, n_chunks)
+    part = _moe_down_partial(x, w, chosen_experts, expert_weight, ctx)
     if W == 1:
         return part
     return comm.reduce_scatter(part.contiguous(), ctx.ar_ctx)
+
+
+def _moe_reduce_rs_chunked(x, wk, chosen_experts, expert_weight, ctx, n_chunks):
+    """The reference's overlap (moe_reduce_rs.py:168-246,549-619): N is split into chunks; while the grouped GEMM of chunk c+1
+    runs on the compute stream, chunk c goes through top-k reduce -> reduce-scatter (NVLS pull-reduce) on a side stream."""
+    W, topk = ctx.world_size, ctx.topk
+    T = chosen_experts.shape[0]
+    N = wk.shape[1]
+    Nc = N // n_chunks
+    r = moe_align_sort(chosen_experts, ctx.num_experts, 128)
+    xc = x.contiguous()
+    out = torch.empty((T // W, N), dtype=x.dtype, device=x.device)
+    main = torch.cuda.current_stream()
+    if getattr(ctx, "_rs_stream", None) is None:
+        ctx._rs_stream = torch.cuda.Stream(priority=-1)
+    side = ctx._rs_stream
+    side.wait_stream(main)
+    for c in range(n_chunks):
+        y = moe_grouped_gemm_fused(xc, wk, r, 1, T * topk, n_slice=(c * Nc, Nc))
+        part = reduce_topk(y, expert_weight, topk)                     # [T, Nc]
+        ev = torch.cuda.Event()
+        ev.record(main)
+        part.record_stream(side)
+        with torch.cuda.stream(side):
+            side.wait_event(ev)
+            o = comm.reduce_scatter(part, ctx.ar_ctx)
+            out[:, c * Nc:(c + 1) * Nc].copy_(o)
+    main.wait_stream(side)
+    return out
 
 
 def run_moe_reduce_ar(x, w, chosen_experts, expert_weight, ctx: MoEReduceRSContext, **_unused) -> torch.Tensor:
