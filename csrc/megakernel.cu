@@ -24,7 +24,7 @@ namespace {
 constexpr int kMKThreads = 256;
 constexpr int kMaxB = 8;
 
-enum TaskType : int { T_RMSNORM = 1, T_LINEAR = 2, T_QKROPE = 3, T_ATTN = 4, T_ALLREDUCE = 5, T_COPY = 6 };
+enum TaskType : int { T_RMSNORM = 1, T_LINEAR = 2, T_QKROPE = 3, T_ATTN = 4, T_ALLREDUCE = 5, T_COPY = 6, T_ATTN_COMBINE = 7 };
 
 struct Task {            // 16 x int32
   int type, dep_idx, dep_count, sig_idx;
@@ -169,6 +169,41 @@ TD_DEVICE void task_linear(const MKParams& p, const Task& t, uint8_t* smem) {
   const int kvec = K / 8;
   const int B = p.B;
   uint4* xs = reinterpret_cast<uint4*>(smem);
+  if (act == 2) {
+    // RMSNorm fused into the operand staging (a[9] = norm weight, a[10] = eps): every CTA normalises the (tiny) activation
+    // row itself, which removes a single-CTA task and a grid-wide dependency per norm
+    const uint4* nw = (const uint4*)p.ptrs[t.a[9]];
+    const float eps = __int_as_float(t.a[10]);
+    float* red = reinterpret_cast<float*>(smem + static_cast<size_t>(B) * kvec * 16);       // [kMaxB][8 warps]
+    float ssq[kMaxB];
+#pragma unroll
+    for (int b = 0; b < kMaxB; ++b) {
+      ssq[b] = 0.f;
+      if (b < B)
+        for (int kv = threadIdx.x; kv < kvec; kv += kMKThreads) {
+          float f[8];
+          unpack8(x[b * (ldx / 8) + kv], f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) ssq[b] += f[e] * f[e];
+        }
+      ssq[b] = warp_sum(ssq[b]);
+      if ((threadIdx.x & 31) == 0 && b < B) red[b * 8 + (threadIdx.x >> 5)] = ssq[b];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < B * kvec; i += kMKThreads) {
+      const int b = i / kvec, kv = i % kvec;
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < kMKThreads / 32; ++w) tot += red[b * 8 + w];
+      const float rs = rsqrtf(tot / static_cast<float>(K) + eps);
+      float f[8], g[8];
+      unpack8(x[b * (ldx / 8) + kv], f);
+      unpack8(nw[kv], g);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = f[e] * rs * g[e];
+      xs[i] = pack8(f);
+    }
+  } else
   for (int i = threadIdx.x; i < B * kvec; i += kMKThreads) {
     const int b = i / kvec, kv = i % kvec;
     if (act == 0) xs[i] = x[b * (ldx / 8) + kv];
@@ -244,8 +279,11 @@ TD_DEVICE void task_attn(const MKParams& p, const Task& t, uint8_t* smem) {
   uint2* out = (uint2*)p.ptrs[t.a[4]];
   const int b = t.a[5], kvh = t.a[6], Hq = t.a[7], Hkv = t.a[8], max_len = t.a[9];
   const float scale = __int_as_float(t.a[10]);
+  const int split = t.a[11] & 0xFFFF, n_splits = max(1, t.a[11] >> 16);   // split-KV: this task owns keys [j0, j1)
   const int G = Hq / Hkv;                       // <= 8
   const int len = pos[b] + 1;
+  const int per = (len + n_splits - 1) / n_splits;
+  const int j0 = split * per, j1 = min(len, j0 + per);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int NW = kMKThreads / 32;
   float qf[8][4], m[8], l[8], o[8][4];
@@ -256,7 +294,7 @@ TD_DEVICE void task_attn(const MKParams& p, const Task& t, uint8_t* smem) {
       qf[g][0] = ptx::bf16_lo(r.x) * scale; qf[g][1] = ptx::bf16_hi(r.x) * scale; qf[g][2] = ptx::bf16_lo(r.y) * scale; qf[g][3] = ptx::bf16_hi(r.y) * scale;
     }
   }
-  for (int j = warp; j < len; j += NW) {
+  for (int j = j0 + warp; j < j1; j += NW) {
     const size_t row = ((static_cast<size_t>(b) * max_len + j) * Hkv + kvh) * 32 + lane;
     const uint2 kr = kc[row], vr = vc[row];
     const float kf[4] = {ptx::bf16_lo(kr.x), ptx::bf16_hi(kr.x), ptx::bf16_lo(kr.y), ptx::bf16_hi(kr.y)};
@@ -292,8 +330,37 @@ TD_DEVICE void task_attn(const MKParams& p, const Task& t, uint8_t* smem) {
       const float c = (sm_m[w * 8 + g] == -INFINITY) ? 0.f : __expf(sm_m[w * 8 + g] - mm);
       ll += sm_l[w * 8 + g] * c; o0 += sm_o[(w * 8 + g) * 128 + 2 * d2] * c; o1 += sm_o[(w * 8 + g) * 128 + 2 * d2 + 1] * c;
     }
+    if (n_splits > 1) {
+      // partial (m, l, o) of this split: part[(((b * Hkv + kvh) * n_splits + split) * 8 + g) * 130 + {0: m, 1: l, 2..129: o}]
+      float* part = reinterpret_cast<float*>(out) + ((static_cast<size_t>(b * Hkv + kvh) * n_splits + split) * 8 + g) * 130;
+      if (d2 == 0) { part[0] = mm; part[1] = ll; }
+      part[2 + 2 * d2] = o0; part[3 + 2 * d2] = o1;
+    } else {
+      const float inv = ll > 0.f ? 1.f / ll : 0.f;
+      reinterpret_cast<uint32_t*>(out)[(static_cast<size_t>(b) * Hq + kvh * G + g) * 64 + d2] = ptx::pack_bf16x2(o0 * inv, o1 * inv);
+    }
+  }
+}
+
+// ---- ATTN_COMBINE: LSE-merge of the split-KV partials of (b, kv head).  a: part, out, b, kvh, Hq, Hkv, n_splits ----
+TD_DEVICE void task_attn_combine(const MKParams& p, const Task& t) {
+  const float* part = (const float*)p.ptrs[t.a[0]];
+  uint32_t* out = (uint32_t*)p.ptrs[t.a[1]];
+  const int b = t.a[2], kvh = t.a[3], Hq = t.a[4], Hkv = t.a[5], n_splits = t.a[6];
+  const int G = Hq / Hkv;
+  for (int idx = threadIdx.x; idx < G * 64; idx += kMKThreads) {
+    const int g = idx / 64, d2 = idx % 64;
+    const float* base = part + (static_cast<size_t>(b * Hkv + kvh) * n_splits * 8 + g) * 130;
+    float mm = -INFINITY;
+    for (int s = 0; s < n_splits; ++s) mm = fmaxf(mm, base[static_cast<size_t>(s) * 8 * 130]);
+    float ll = 0.f, o0 = 0.f, o1 = 0.f;
+    for (int s = 0; s < n_splits; ++s) {
+      const float* ps = base + static_cast<size_t>(s) * 8 * 130;
+      const float c = (ps[0] == -INFINITY) ? 0.f : __expf(ps[0] - mm);
+      ll += ps[1] * c; o0 += ps[2 + 2 * d2] * c; o1 += ps[3 + 2 * d2] * c;
+    }
     const float inv = ll > 0.f ? 1.f / ll : 0.f;
-    reinterpret_cast<uint32_t*>(out)[(static_cast<size_t>(b) * Hq + kvh * G + g) * 64 + d2] = ptx::pack_bf16x2(o0 * inv, o1 * inv);
+    out[(static_cast<size_t>(b) * Hq + kvh * G + g) * 64 + d2] = ptx::pack_bf16x2(o0 * inv, o1 * inv);
   }
 }
 
@@ -387,6 +454,7 @@ __global__ void __launch_bounds__(kMKThreads, 1) mega_kernel(const MKParams p) {
       case T_LINEAR: task_linear(p, t, smem); break;
       case T_QKROPE: task_qkrope(p, t); break;
       case T_ATTN: task_attn(p, t, smem); break;
+      case T_ATTN_COMBINE: task_attn_combine(p, t); break;
       case T_ALLREDUCE: task_allreduce(p, t, epoch); break;
       default: break;
     }

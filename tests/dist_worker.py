@@ -496,7 +496,7 @@ def case_mega():
     kv.k_cache.copy_((torch.randn(kv.k_cache.shape, generator=g) * 0.5).to(dtype)); kv.v_cache.copy_((torch.randn(kv.v_cache.shape, generator=g) * 0.5).to(dtype))
     kv.kv_offset.fill_(9)
     kv2.k_cache.copy_(kv.k_cache); kv2.v_cache.copy_(kv.v_cache); kv2.kv_offset.copy_(kv.kv_offset)
-    mega = MegaDenseModel(m, B, kv2)
+    mega = MegaDenseModel(m, B, kv2, attn_splits=3)
     for step in range(3):
         ids = torch.randint(0, 1000, (B, 1), generator=torch.Generator().manual_seed(40 + step)).to(dev)
         pos = kv.kv_offset.to(torch.int64)[:, None]

@@ -114,7 +114,7 @@ def test_megakernel_single_gpu():
     kv, kv2 = mk(), mk()
     kv.rand_fill_kv_cache(17)
     kv2.k_cache.copy_(kv.k_cache); kv2.v_cache.copy_(kv.v_cache); kv2.kv_offset.copy_(kv.kv_offset)
-    mega = MegaDenseModel(m, B, kv2)
+    mega = MegaDenseModel(m, B, kv2, attn_splits=3)
     for step in range(3):
         ids = torch.randint(0, 1000, (B, 1), device="cuda")
         ref = m.inference(ids, kv.kv_offset.to(torch.int64)[:, None], kv)

@@ -20,7 +20,7 @@ from .. import _C
 from .. import utils as U
 from ..ops.comm import SymmArgs, symm_args
 
-T_RMSNORM, T_LINEAR, T_QKROPE, T_ATTN, T_ALLREDUCE = 1, 2, 3, 4, 5
+T_RMSNORM, T_LINEAR, T_QKROPE, T_ATTN, T_ALLREDUCE, T_ATTN_COMBINE = 1, 2, 3, 4, 5, 7
 TASK_NAMES = {1: "rms_norm", 2: "linear", 3: "qk_norm_rope_update_kvcache", 4: "flash_decode", 5: "allreduce"}
 
 
@@ -98,15 +98,20 @@ class ModelBuilder:
                                                      self.ptr(residual_out), x.shape[-1], _fbits(eps)]))
         return sig, 1
 
-    def make_linear(self, x, weight, out, dep, act_silu_mul: bool = False, tile_n: Optional[int] = None):
-        """out[B, N] = act(x) @ weight[N, K]^T (GEMV tiles).  ``act_silu_mul``: x is [B, 2K] = (gate | up)."""
+    def make_linear(self, x, weight, out, dep, act_silu_mul: bool = False, tile_n: Optional[int] = None, norm_weight=None,
+                    eps: float = 1e-6):
+        """out[B, N] = act(x) @ weight[N, K]^T (GEMV tiles).  ``act_silu_mul``: x is [B, 2K] = (gate | up).
+        ``norm_weight``: RMSNorm(x) * norm_weight is applied while the operand is staged (no separate norm task)."""
         N, K = weight.shape
         tn = tile_n or max(8, ((N + self.num_sms - 1) // self.num_sms + 7) // 8 * 8)
         sig = self.counter()
         n_tiles = 0
+        d = dep or (-1, 0)
+        act = 2 if norm_weight is not None else int(act_silu_mul)
+        assert not (norm_weight is not None and act_silu_mul)
         for n0 in range(0, N, tn):
-            self._add(Task(T_LINEAR, dep[0], dep[1], sig, [self.ptr(x), self.ptr(weight), self.ptr(out), K, out.shape[-1], n0,
-                                                           min(tn, N - n0), int(act_silu_mul), x.shape[-1]]))
+            self._add(Task(T_LINEAR, d[0], d[1], sig, [self.ptr(x), self.ptr(weight), self.ptr(out), K, out.shape[-1], n0,
+                                                       min(tn, N - n0), act, x.shape[-1], self.ptr(norm_weight), _fbits(eps)]))
             n_tiles += 1
         self.max_smem = max(self.max_smem, self.B * K * 2 + 256)
         return sig, n_tiles
@@ -120,15 +125,34 @@ class ModelBuilder:
                                                        k_cache.shape[1], _fbits(eps), _fbits(theta)]))
         return sig, 1
 
-    def make_flash_decode(self, q, k_cache, v_cache, positions, out, Hq, Hkv, sm_scale, dep):
+    def make_flash_decode(self, q, k_cache, v_cache, positions, out, Hq, Hkv, sm_scale, dep, n_splits: int = 1, scratch=None):
+        """GQA decode.  ``n_splits`` > 1: split-KV -- every (batch, kv head) becomes n_splits tasks that write (m, l, o) partials
+        to ``scratch`` (fp32 [B, Hkv, n_splits, 8, 130]) plus one combine task, so a handful of heads still fills the SMs."""
         sig = self.counter()
         n = 0
+        if n_splits <= 1:
+            for b in range(self.B):
+                for kvh in range(Hkv):
+                    self._add(Task(T_ATTN, dep[0], dep[1], sig, [self.ptr(q), self.ptr(k_cache), self.ptr(v_cache), self.ptr(positions),
+                                                                 self.ptr(out), b, kvh, Hq, Hkv, k_cache.shape[1], _fbits(sm_scale), 0]))
+                    n += 1
+            return sig, n
+        assert scratch is not None and scratch.dtype == torch.float32 and scratch.numel() >= self.B * Hkv * n_splits * 8 * 130
         for b in range(self.B):
             for kvh in range(Hkv):
-                self._add(Task(T_ATTN, dep[0], dep[1], sig, [self.ptr(q), self.ptr(k_cache), self.ptr(v_cache), self.ptr(positions),
-                                                             self.ptr(out), b, kvh, Hq, Hkv, k_cache.shape[1], _fbits(sm_scale)]))
-                n += 1
-        return sig, n
+                for s in range(n_splits):
+                    self._add(Task(T_ATTN, dep[0], dep[1], sig, [self.ptr(q), self.ptr(k_cache), self.ptr(v_cache), self.ptr(positions),
+                                                                 self.ptr(scratch), b, kvh, Hq, Hkv, k_cache.shape[1], _fbits(sm_scale),
+                                                                 s | (n_splits << 16)]))
+                    n += 1
+        sig2 = self.counter()
+        m = 0
+        for b in range(self.B):
+            for kvh in range(Hkv):
+                self._add(Task(T_ATTN_COMBINE, sig, n, sig2, [self.ptr(scratch), self.ptr(out), b, kvh, Hq, Hkv, n_splits]))
+                m += 1
+        self.metrics["flash_decode_combine"] = self.metrics.get("flash_decode_combine", 0) + m
+        return sig2, m
 
     make_flash_attn = make_flash_decode
 
@@ -215,8 +239,12 @@ class ModelBuilder:
             elif t.type == T_LINEAR:
                 K, n0, nc, act = a[3], a[5], a[6], a[7]
                 x = P[a[0]].view(B, -1).float()
-                if act:
+                if act == 1:
                     x = torch.nn.functional.silu(x[:, :K]) * x[:, K:2 * K]
+                elif act == 2:
+                    eps = struct.unpack("f", struct.pack("i", a[10]))[0]
+                    x = x[:, :K]
+                    x = (x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps) * P[a[9]].float()).to(P[a[0]].dtype).float()
                 else:
                     x = x[:, :K]
                 P[a[2]].view(B, -1)[:, n0:n0 + nc] = (x @ P[a[1]][n0:n0 + nc].float().t()).to(P[a[2]].dtype)
@@ -241,9 +269,32 @@ class ModelBuilder:
                 scale = struct.unpack("f", struct.pack("i", a[10]))[0]
                 L = int(P[a[3]].view(-1)[b]) + 1
                 q = P[a[0]].view(B, Hq, -1)[b, kvh * G:(kvh + 1) * G].float()
-                k, v = P[a[1]][b, :L, kvh].float(), P[a[2]][b, :L, kvh].float()
-                pr = torch.softmax(q @ k.t() * scale, -1)
-                P[a[4]].view(B, Hq, -1)[b, kvh * G:(kvh + 1) * G] = (pr @ v).to(P[a[4]].dtype)
+                split, ns = (a[11] & 0xFFFF, max(1, a[11] >> 16)) if len(a) > 11 else (0, 1)
+                per = (L + ns - 1) // ns
+                j0, j1 = split * per, min(L, split * per + per)
+                k, v = P[a[1]][b, j0:j1, kvh].float(), P[a[2]][b, j0:j1, kvh].float()
+                if ns == 1:
+                    pr = torch.softmax(q @ k.t() * scale, -1)
+                    P[a[4]].view(B, Hq, -1)[b, kvh * G:(kvh + 1) * G] = (pr @ v).to(P[a[4]].dtype)
+                else:
+                    part = P[a[4]].view(-1, 130)
+                    sc = q @ k.t() * scale if j1 > j0 else torch.empty(G, 0)
+                    mm = sc.max(-1).values if j1 > j0 else torch.full((G,), float("-inf"))
+                    e = torch.exp(sc - mm[:, None]) if j1 > j0 else sc
+                    base = ((b * Hkv + kvh) * ns + split) * 8
+                    part[base:base + G, 0] = mm
+                    part[base:base + G, 1] = e.sum(-1) if j1 > j0 else 0.0
+                    part[base:base + G, 2:] = (e @ v) if j1 > j0 else 0.0
+            elif t.type == T_ATTN_COMBINE:
+                b, kvh, Hq, Hkv, ns = a[2], a[3], a[4], a[5], a[6]
+                G = Hq // Hkv
+                part = P[a[0]].view(-1, 130)
+                rows = torch.stack([part[((b * Hkv + kvh) * ns + s_) * 8:((b * Hkv + kvh) * ns + s_) * 8 + G] for s_ in range(ns)])   # [ns, G, 130]
+                mm = rows[:, :, 0].max(0).values
+                c = torch.where(torch.isinf(rows[:, :, 0]), torch.zeros_like(rows[:, :, 0]), torch.exp(rows[:, :, 0] - mm[None]))
+                ll = (rows[:, :, 1] * c).sum(0)
+                o = (rows[:, :, 2:] * c[:, :, None]).sum(0) / ll[:, None]
+                P[a[1]].view(B, Hq, -1)[b, kvh * G:(kvh + 1) * G] = o.to(P[a[1]].dtype)
             elif t.type == T_ALLREDUCE:
                 part, flags = P[a[0]], P[a[1]]
                 v0, v1, sl = a[4] * 8, a[5] * 8, a[8]

@@ -1,7 +1,7 @@
 """Dense-LLM decode step on the megakernel (reference: mega_triton_kernel/models/dense.py:108-201, ``mega_forwrad``).
 
-Builds, for every layer:  rms_norm -> qkv_proj -> qk_norm_rope_update_kvcache -> flash_decode -> o_proj -> allreduce(+residual)
--> rms_norm -> fc1 -> (silu*mul fused into) fc2 -> allreduce(+residual).  Embedding, final norm and lm_head stay
+Builds, for every layer:  (rms_norm fused into) qkv_proj -> qk_norm_rope_update_kvcache -> split-KV flash_decode -> combine -> o_proj
+-> allreduce(+residual) -> (rms_norm fused into) fc1 -> (silu*mul fused into) fc2 -> allreduce(+residual).  Embedding, final norm and lm_head stay
 outside the persistent kernel (as in the reference, which copies the embedded tokens into the hidden-state buffer and
 runs the builder)."""
 from __future__ import annotations
@@ -16,7 +16,8 @@ from ..parallel.tp_mlp import _linear
 
 
 class MegaDenseModel:
-    def __init__(self, model: DenseLLM, batch: int, kv_cache: KV_Cache, num_sms=None, schedule: str = "round_robin"):
+    def __init__(self, model: DenseLLM, batch: int, kv_cache: KV_Cache, num_sms=None, schedule: str = "round_robin",
+                 fuse_norm: bool = True, attn_splits: int = 0):
         from . import ModelBuilder
         self.model, self.B, self.kv = model, batch, kv_cache
         a = model.arch
@@ -38,21 +39,33 @@ class MegaDenseModel:
         self.n_slices = 4
         self.flags = heap.tensor((2 * L, self.n_slices, max(W, 4)), torch.int32)
         self.positions = torch.zeros(B, dtype=torch.int32, device=dev)
+        # split-KV: enough attention tasks to cover the SMs (B * Hkv heads alone leave most of them idle)
+        if attn_splits <= 0:
+            attn_splits = max(1, min(16, mb.num_sms // max(1, B * Hkv), kv_cache.max_length // 64))
+        self.attn_splits = attn_splits
+        self.attn_scratch = torch.zeros((B * Hkv * attn_splits * 8 * 130,), dtype=torch.float32, device=dev) if attn_splits > 1 else None
         U.barrier_all_host()
         dep = None
         for li, layer in enumerate(model.layers):
             mb.cur_layer = li
             k_cache, v_cache = kv_cache.layer(li)
             at, ml = layer.attn, layer.mlp
-            d = mb.make_rms_norm(self.h, layer.input_norm_w, self.xn, layer.eps, dep=dep)
-            d = mb.make_qkv_proj(self.xn, at.wqkv, self.qkv, d)
+            if fuse_norm:
+                d = mb.make_qkv_proj(self.h, at.wqkv, self.qkv, dep, norm_weight=layer.input_norm_w, eps=layer.eps)
+            else:
+                d = mb.make_rms_norm(self.h, layer.input_norm_w, self.xn, layer.eps, dep=dep)
+                d = mb.make_qkv_proj(self.xn, at.wqkv, self.qkv, d)
             d = mb.make_qk_norm_rope_update_kvcache(self.qkv, self.q_rot, k_cache, v_cache, at.q_norm_w, at.k_norm_w, self.positions,
                                                     Hq, Hkv, at.eps, at.rope_theta, d)
-            d = mb.make_flash_decode(self.q_rot, k_cache, v_cache, self.positions, self.attn_out, Hq, Hkv, at.sm_scale, d)
+            d = mb.make_flash_decode(self.q_rot, k_cache, v_cache, self.positions, self.attn_out, Hq, Hkv, at.sm_scale, d,
+                                     n_splits=attn_splits, scratch=self.attn_scratch)
             d = mb.make_o_proj(self.attn_out, at.wo, self.parts[2 * li], d)
             d = mb.make_allreduce(self.parts[2 * li], self.flags[2 * li], self.h, self.h, d, self.n_slices)
-            d = mb.make_rms_norm(self.h, layer.post_norm_w, self.xn, layer.eps, dep=d)
-            d = mb.make_fc1(self.xn, ml.gate_up_proj, self.gu, d)
+            if fuse_norm:
+                d = mb.make_fc1(self.h, ml.gate_up_proj, self.gu, d, norm_weight=layer.post_norm_w, eps=layer.eps)
+            else:
+                d = mb.make_rms_norm(self.h, layer.post_norm_w, self.xn, layer.eps, dep=d)
+                d = mb.make_fc1(self.xn, ml.gate_up_proj, self.gu, d)
             d = mb.make_fc2(self.gu, ml.down_proj, self.parts[2 * li + 1], d, act_silu_mul=True)
             dep = mb.make_allreduce(self.parts[2 * li + 1], self.flags[2 * li + 1], self.h, self.h, d, self.n_slices)
         self.builder = mb.compile()
