@@ -21,7 +21,7 @@ from .. import utils as U
 from ..ops.comm import SymmArgs, symm_args
 
 T_RMSNORM, T_LINEAR, T_QKROPE, T_ATTN, T_ALLREDUCE, T_ATTN_COMBINE = 1, 2, 3, 4, 5, 7
-TASK_NAMES = {1: "rms_norm", 2: "linear", 3: "qk_norm_rope_update_kvcache", 4: "flash_decode", 5: "allreduce"}
+TASK_NAMES = {1: "rms_norm", 2: "linear", 3: "qk_norm_rope_update_kvcache", 4: "flash_decode", 5: "allreduce", 7: "flash_decode_combine"}
 
 
 class _MegaArgs(C.Structure):
@@ -151,7 +151,6 @@ class ModelBuilder:
             for kvh in range(Hkv):
                 self._add(Task(T_ATTN_COMBINE, sig, n, sig2, [self.ptr(scratch), self.ptr(out), b, kvh, Hq, Hkv, n_splits]))
                 m += 1
-        self.metrics["flash_decode_combine"] = self.metrics.get("flash_decode_combine", 0) + m
         return sig2, m
 
     make_flash_attn = make_flash_decode
