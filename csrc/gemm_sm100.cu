@@ -202,6 +202,16 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
   }
   if (a->mode == kAG && a->ag_skip_wait == 2) p.n_comm_ctas = 0;      // copy-engine transport: every SM runs GEMM tiles
   p.ag_nslices = (a->ag_skip_wait == 2) ? 1 : p.n_comm_ctas;
+  if (a->mode == kAG && !fp8 && !a->a_gather && a->ag_skip_wait != 2 && a->ag_copy_local != 0 && a->ag_a_local &&
+      a->ag_rows_per_rank % BM == 0) {
+    // tiles of the local rows are loaded straight from the caller's shard: {K, local rows}, same 64 x 128 box
+    const long long lrows = a->ag_copy_local == 2 ? a->ag_rows_per_rank * a->world : a->ag_rows_per_rank;
+    cuuint64_t dims[2] = {(cuuint64_t)a->K, (cuuint64_t)lrows};
+    cuuint64_t strides[1] = {(cuuint64_t)a->K * esz};
+    cuuint32_t box[2] = {(cuuint32_t)bk_elems, BM};
+    if (encode_tmap(&p.tmap_al, a->ag_a_local, 2, dims, strides, box, bf16)) return -1;
+    p.ag_local_direct = 1;
+  }
   grid = gemm_ctas + p.n_comm_ctas;
 
   if (a->mode == kAR) {

@@ -87,6 +87,8 @@ struct Params {
   int ag_rows_per_rank;      // rows of A owned by each rank
   int ag_copy_local;         // 1: comm CTAs copy a_local -> workspace; 0: caller already wrote the workspace; 2: all-to-all (block d of a_local -> rank d)
   int ag_skip_wait;          // GEMM-only twin: never wait (measures exposed communication)
+  int ag_local_direct;       // 1: tiles of my own rows read a_local through tmap_al (no local copy, no flag wait)
+  CUtensorMap tmap_al;       // {K, rows of a_local}
   int ag_nslices;            // arrival flags per source rank (= comm CTAs, or 1 when the copy engine does the transfer)
   const void* ag_a_local;    // my shard [rows_per_rank, K]
   char* ag_ws;               // my workspace: 2 buffers of [world * rows_per_rank, K] (symmetric)
@@ -178,7 +180,7 @@ TD_DEVICE void ag_wait_rows(const Params& p, uint32_t ph, int row0, int row1) {
   while (r < row1) {
     const int s = r / Ms;
     const int r_end = min(row1, (s + 1) * Ms);
-    if (s != p.symm.rank || p.ag_copy_local) {
+    if (s != p.symm.rank || (p.ag_copy_local && !p.ag_local_direct)) {
       const size_t b0 = static_cast<size_t>(r - s * Ms) * row_bytes, b1 = static_cast<size_t>(r_end - s * Ms) * row_bytes;
       for (int c = static_cast<int>(b0 / slice); c <= static_cast<int>((b1 - 1) / slice); ++c)
         wait_ge<true>(flags + s * kAGMaxSlices + c, ph);
@@ -211,12 +213,12 @@ TD_DEVICE void ag_comm_cta(const Params& p, uint32_t ph, int comm_idx) {
   const char* src = (p.ag_copy_local ? reinterpret_cast<const char*>(p.ag_a_local) : ws + shard_off) + b0;
   uint32_t* my_flag = p.ag_flags + (ph & 1u) * W * kAGMaxSlices + me * kAGMaxSlices + comm_idx;
   const int pslot = static_cast<int>(blockIdx.x) * 8;
-  for (int dist = p.ag_copy_local ? 0 : 1; dist < W; ++dist) {
+  for (int dist = (p.ag_copy_local && !p.ag_local_direct) ? 0 : 1; dist < W; ++dist) {
     const int d = (me - dist + W) % W;
     if (threadIdx.x == 0) prof_record(p.prof, pslot, 1, true);
     // ag_copy_local == 2: all-to-all flavour -- a_local is [world, rows_per_rank, K] and block d goes to rank d
     const size_t a2a_off = (p.ag_copy_local == 2) ? static_cast<size_t>(d) * shard_bytes : 0;
-    if (b1 > b0) copy16_strided(symm_at(p.symm, ws, d) + shard_off + b0, src + a2a_off, b1 - b0, threadIdx.x, kThreads);
+    if (b1 > b0) copy16_strided_deep(symm_at(p.symm, ws, d) + shard_off + b0, src + a2a_off, b1 - b0, threadIdx.x, kThreads);
     __syncthreads();
     if (threadIdx.x == 0) {
       prof_record(p.prof, pslot, 1, false);
@@ -425,6 +427,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             prof_record(p.prof, static_cast<int>(blockIdx.x) * 8, 3, false);
           }
           const int abuf = (kMode == kAG) ? static_cast<int>(ph & 1u) : 0;
+          // my own rows come straight from the caller's tensor (no local copy into the workspace)
+          bool a_local = false; int lrow0 = 0;
+          if constexpr (kMode == kAG) {
+            if (p.ag_local_direct && row0 >= p.symm.rank * p.ag_rows_per_rank && row0 < (p.symm.rank + 1) * p.ag_rows_per_rank) {
+              a_local = true;
+              lrow0 = (p.ag_copy_local == 2) ? row0 : row0 - p.symm.rank * p.ag_rows_per_rank;
+            }
+          }
           for (int kb = 0; kb < p.num_k; ++kb) {
             ptx::mbar_wait(empty_bar + stage, phase ^ 1u);
             uint8_t* sa = smem + stage * L::kStageBytes;
@@ -433,7 +443,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             uint8_t* ssfb = ssfa + L::kSFABytes;
             if constexpr (kCtaGroup == 1) {
               ptx::mbar_arrive_expect_tx(full_bar + stage, L::kTxBytes);
-              ptx::tma_load_3d(&p.tmap_a, full_bar + stage, sa, kb * kBKElems, row0, abuf);
+              if (a_local) ptx::tma_load_2d(&p.tmap_al, full_bar + stage, sa, kb * kBKElems, lrow0);
+              else ptx::tma_load_3d(&p.tmap_a, full_bar + stage, sa, kb * kBKElems, row0, abuf);
               ptx::tma_load_2d(&p.tmap_b, full_bar + stage, sb, kb * kBKElems, brow0, ptx::kEvictLast);
               if constexpr (kFP8) {
                 ptx::tma_load_2d(&p.tmap_sfa, full_bar + stage, ssfa, 0, (row0 / 128) * p.num_k + kb);
@@ -445,7 +456,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
               // both CTAs land their bytes on the LEADER's barrier; the leader expects both halves
               if (is_leader) ptx::mbar_arrive_expect_tx(full_bar + stage, 2 * L::kTxBytes);
               else ptx::mbar_arrive_cluster(full_bar + stage, 0);
-              ptx::tma_load_3d_2sm(&p.tmap_a, full_bar + stage, sa, kb * kBKElems, row0, abuf);
+              if (a_local) ptx::tma_load_2d_2sm(&p.tmap_al, full_bar + stage, sa, kb * kBKElems, lrow0);
+              else ptx::tma_load_3d_2sm(&p.tmap_a, full_bar + stage, sa, kb * kBKElems, row0, abuf);
               ptx::tma_load_2d_2sm(&p.tmap_b, full_bar + stage, sb, kb * kBKElems, brow0, ptx::kEvictLast);
               if constexpr (kFP8) {
                 ptx::tma_load_2d_2sm(&p.tmap_sfa, full_bar + stage, ssfa, 0, (row0 / 128) * p.num_k + kb);

@@ -105,7 +105,7 @@ def default_ag_config(M: int, N: int, K: int, world: int) -> GemmConfig:
     """Tiles of one source rank form one L2 band (``group_m`` = m-tiles per source), so the arrival order of the
     shards is respected while B tiles are re-read once per source rather than once per m-tile."""
     rows = M // max(world, 1)
-    nc = 16 if world > 1 else 0
+    nc = (32 if world >= 4 else 16) if world > 1 else 0      # comm CTAs: the push is latency/port bound, 32 SMs fill NVLink at TP>=4
     if rows % 256 == 0 and N >= 256:
         # few tiles (TP8 column shards): 128-wide tiles fill the SMs and halve the tail after the last shard arrives
         bn = 128 if (world > 1 and (M // 256) * ((N + 255) // 256) < 60 and N % 128 == 0) else 256
