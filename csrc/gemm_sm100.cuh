@@ -252,14 +252,31 @@ TD_DEVICE void ar_comm_cta(const Params& p, uint32_t ph, int comm_idx) {
     }
     __syncthreads();
     const int row0 = m_tile * TM, col0 = n_tile * BN;
-    for (int i = threadIdx.x; i < TM * kChunksPerRow; i += kThreads) {
-      const int r = row0 + i / kChunksPerRow, c = col0 + (i % kChunksPerRow) * 8;
-      if (r >= p.M || c >= p.N) continue;
-      char* src = stage + (static_cast<size_t>(r) * p.N + c) * 2;
-      uint4 v;
-      if (p.symm.mc_base) {
-        v = p.in_is_bf16 ? ptx::multimem_ld_reduce_bf16x8(symm_mc(p.symm, src)) : ptx::multimem_ld_reduce_f16x8(symm_mc(p.symm, src));
-      } else {
+    if (p.symm.mc_base) {
+      // NVLS: 4 independent multimem.ld_reduce per thread in flight (the switch round trip is ~2 us)
+      constexpr int U = 4;
+      for (int i0 = threadIdx.x; i0 < TM * kChunksPerRow; i0 += U * kThreads) {
+        uint4 v[U]; char* dst[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = i0 + u * kThreads;
+          const int r = row0 + i / kChunksPerRow, c = col0 + (i % kChunksPerRow) * 8;
+          dst[u] = nullptr;
+          if (i < TM * kChunksPerRow && r < p.M && c < p.N) {
+            char* src = stage + (static_cast<size_t>(r) * p.N + c) * 2;
+            v[u] = p.in_is_bf16 ? ptx::multimem_ld_reduce_bf16x8(symm_mc(p.symm, src)) : ptx::multimem_ld_reduce_f16x8(symm_mc(p.symm, src));
+            dst[u] = reinterpret_cast<char*>(p.rs_out) + (static_cast<size_t>(r) * p.rs_ldo + c) * 2;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (dst[u]) ptx::st_v4(dst[u], v[u]);
+      }
+    } else {
+      for (int i = threadIdx.x; i < TM * kChunksPerRow; i += kThreads) {
+        const int r = row0 + i / kChunksPerRow, c = col0 + (i % kChunksPerRow) * 8;
+        if (r >= p.M || c >= p.N) continue;
+        char* src = stage + (static_cast<size_t>(r) * p.N + c) * 2;
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int s = 0; s < W; ++s) {
           const uint4 x = ptx::ld_relaxed_sys_v4(symm_at(p.symm, src, (p.symm.rank + s) % W));
@@ -270,10 +287,11 @@ TD_DEVICE void ar_comm_cta(const Params& p, uint32_t ph, int comm_idx) {
             else { const __half2 hh = *reinterpret_cast<const __half2*>(&w4[e]); acc[2 * e] += __low2float(hh); acc[2 * e + 1] += __high2float(hh); }
           }
         }
+        uint4 v;
         if (p.in_is_bf16) { v.x = ptx::pack_bf16x2(acc[0], acc[1]); v.y = ptx::pack_bf16x2(acc[2], acc[3]); v.z = ptx::pack_bf16x2(acc[4], acc[5]); v.w = ptx::pack_bf16x2(acc[6], acc[7]); }
         else { v.x = ptx::pack_f16x2(acc[0], acc[1]); v.y = ptx::pack_f16x2(acc[2], acc[3]); v.z = ptx::pack_f16x2(acc[4], acc[5]); v.w = ptx::pack_f16x2(acc[6], acc[7]); }
+        ptx::st_v4(reinterpret_cast<char*>(p.rs_out) + (static_cast<size_t>(r) * p.rs_ldo + c) * 2, v);
       }
-      ptx::st_v4(reinterpret_cast<char*>(p.rs_out) + (static_cast<size_t>(r) * p.rs_ldo + c) * 2, v);
     }
     __syncthreads();
   }

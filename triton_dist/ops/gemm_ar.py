@@ -85,13 +85,16 @@ def create_ll_gemm_ar_context(ar_stream=None, rank: Optional[int] = None, world_
     return ctx
 
 
-def default_ar_config(M: int, N: int, K: int, n_comm: int = 16) -> GemmConfig:
+def default_ar_config(M: int, N: int, K: int, n_comm: int = 16, num_sms: int = 148) -> GemmConfig:
     """Small-M decode shapes: narrow tiles so that enough CTAs work on the K-reduction; the comm CTAs take the SMs the
-    GEMM has no tile for."""
+    GEMM has no tile for (a comm CTA reduces its tiles one after the other and each NVLS round trip is ~2 us, so every idle
+    SM is worth using: 8xB200, M=128 N=5120: 16 comm CTAs 75 us)."""
     if M > 128 and N >= 256:
-        return GemmConfig(bn=128, cta_group=2, group_m=8, use_tma_store=False, n_comm_ctas=n_comm)
+        tiles = ((M + 255) // 256) * ((N + 127) // 128) * 2
+        return GemmConfig(bn=128, cta_group=2, group_m=8, use_tma_store=False, n_comm_ctas=max(n_comm, min(64, (num_sms - tiles) // 2 * 2)))
     bn = 32 if N < 64 else 64 if N <= 8192 else 128
-    return GemmConfig(bn=bn, cta_group=1, group_m=8, use_tma_store=False, n_comm_ctas=n_comm)
+    tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
+    return GemmConfig(bn=bn, cta_group=1, group_m=8, use_tma_store=False, n_comm_ctas=max(n_comm, min(64, num_sms - tiles)))
 
 
 def low_latency_gemm_allreduce_op(ctx: GemmARContext, a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None,
