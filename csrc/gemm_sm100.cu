@@ -202,6 +202,13 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
   }
   if (a->mode == kAG && a->ag_skip_wait == 2) p.n_comm_ctas = 0;      // copy-engine transport: every SM runs GEMM tiles
   p.ag_nslices = (a->ag_skip_wait == 2) ? 1 : p.n_comm_ctas;
+  if (a->mode == kAG && a->ag_skip_wait == 0 && p.n_comm_ctas > 0 && a->world <= 4) {
+    // few destinations: publish each CTA's share in 4 (TP2) / 2 (TP4) interleaved sub-slices (finer arrival flags)
+    int nsub = a->world == 2 ? 4 : 2;
+    const size_t shard = (size_t)a->ag_rows_per_rank * a->K * esz;
+    while (nsub > 1 && (p.n_comm_ctas * nsub > kAGMaxSlices || shard / (p.n_comm_ctas * nsub) < (64u << 10))) nsub >>= 1;
+    p.ag_nslices = p.n_comm_ctas * nsub;
+  }
   if (a->mode == kAG && !fp8 && !a->a_gather && a->ag_skip_wait != 2 && a->ag_copy_local != 0 && a->ag_a_local &&
       a->ag_rows_per_rank % BM == 0) {
     // tiles of the local rows are loaded straight from the caller's shard: {K, local rows}, same 64 x 128 box

@@ -207,25 +207,32 @@ TD_DEVICE void ag_comm_cta(const Params& p, uint32_t ph, int comm_idx) {
   const size_t row_bytes = static_cast<size_t>(p.K) * 2;
   const size_t shard_bytes = static_cast<size_t>(Ms) * row_bytes;
   const size_t slice = ag_slice_bytes(shard_bytes, p.ag_nslices);
-  const size_t b0 = min(shard_bytes, slice * comm_idx), b1 = min(shard_bytes, b0 + slice);
   char* ws = p.ag_ws + (ph & 1u) * p.ag_ws_buf_bytes;
   const size_t shard_off = static_cast<size_t>(me) * Ms * row_bytes;
-  const char* src = (p.ag_copy_local ? reinterpret_cast<const char*>(p.ag_a_local) : ws + shard_off) + b0;
-  uint32_t* my_flag = p.ag_flags + (ph & 1u) * W * kAGMaxSlices + me * kAGMaxSlices + comm_idx;
+  const char* src0 = p.ag_copy_local ? reinterpret_cast<const char*>(p.ag_a_local) : ws + shard_off;
+  uint32_t* flag_base = p.ag_flags + (ph & 1u) * W * kAGMaxSlices + me * kAGMaxSlices;
   const int pslot = static_cast<int>(blockIdx.x) * 8;
+  // ag_nslices = n_comm * nsub: with few destinations (TP2 / TP4) a CTA cuts its share into nsub sub-slices that are
+  // interleaved over the shard (sub-slice j of all CTAs = the j-th 1/nsub of the rows), each published separately, so
+  // the consumer's first remote tiles become ready after 1/nsub of the transfer instead of at its end
+  const int nsub = max(1, p.ag_nslices / max(1, p.n_comm_ctas));
   for (int dist = (p.ag_copy_local && !p.ag_local_direct) ? 0 : 1; dist < W; ++dist) {
     const int d = (me - dist + W) % W;
-    if (threadIdx.x == 0) prof_record(p.prof, pslot, 1, true);
     // ag_copy_local == 2: all-to-all flavour -- a_local is [world, rows_per_rank, K] and block d goes to rank d
     const size_t a2a_off = (p.ag_copy_local == 2) ? static_cast<size_t>(d) * shard_bytes : 0;
-    if (b1 > b0) copy16_strided_deep(symm_at(p.symm, ws, d) + shard_off + b0, src + a2a_off, b1 - b0, threadIdx.x, kThreads);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      prof_record(p.prof, pslot, 1, false);
-      prof_record(p.prof, pslot, 6, true);
-      ptx::fence_acq_rel_sys();
-      ptx::st_relaxed_sys(symm_at(p.symm, my_flag, d), ph);
-      prof_record(p.prof, pslot, 6, false);
+    for (int j = 0; j < nsub; ++j) {
+      const int sidx = j * p.n_comm_ctas + comm_idx;
+      const size_t b0 = min(shard_bytes, slice * sidx), b1 = min(shard_bytes, b0 + slice);
+      if (threadIdx.x == 0) prof_record(p.prof, pslot, 1, true);
+      if (b1 > b0) copy16_strided_deep(symm_at(p.symm, ws, d) + shard_off + b0, src0 + a2a_off + b0, b1 - b0, threadIdx.x, kThreads);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        prof_record(p.prof, pslot, 1, false);
+        prof_record(p.prof, pslot, 6, true);
+        ptx::fence_acq_rel_sys();
+        ptx::st_relaxed_sys(symm_at(p.symm, flag_base + sidx, d), ph);
+        prof_record(p.prof, pslot, 6, false);
+      }
     }
   }
 }
