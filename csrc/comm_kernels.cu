@@ -295,9 +295,16 @@ __global__ void __launch_bounds__(kCommThreads, 1) allgather_kernel(const AGPara
 // ---------------------------------------------------------------------------------------------------------
 // memory ops (reference: kernels/nvidia/memory_ops.py copy_tensor / fill_tensor / reduce_tensor)
 // ---------------------------------------------------------------------------------------------------------
-__global__ void copy_kernel(uint4* dst, const uint4* src, long long nvec) {
-  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvec; v += (long long)gridDim.x * blockDim.x)
-    dst[v] = src[v];
+__global__ void copy_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, long long nvec) {
+  // 4 independent 16-byte loads per thread before the stores (a grid of a few CTAs per SM then saturates HBM)
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  for (; v + 3 * stride < nvec; v += 4 * stride) {
+    const uint4 a = ptx::ld_nc_v4(src + v), b = ptx::ld_nc_v4(src + v + stride), c = ptx::ld_nc_v4(src + v + 2 * stride),
+                d = ptx::ld_nc_v4(src + v + 3 * stride);
+    dst[v] = a; dst[v + stride] = b; dst[v + 2 * stride] = c; dst[v + 3 * stride] = d;
+  }
+  for (; v < nvec; v += stride) dst[v] = src[v];
 }
 __global__ void fill_kernel(uint32_t* dst, uint32_t value, long long n) {
   for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < n; v += (long long)gridDim.x * blockDim.x)
@@ -400,6 +407,7 @@ TD_API int td_allgather(const TdAGArgs* a, void* stream) {
 
 TD_API int td_copy(void* dst, const void* src, long long nbytes, int grid, void* stream) {
   if (nbytes % 16) { td::drv::set_error("td_copy: nbytes must be a multiple of 16"); return -1; }
+  if (grid <= 0) grid = static_cast<int>(std::min<long long>(148 * 8, (nbytes / 16 + 1023) / 1024 + 1));   // auto: up to 8 CTAs per SM
   copy_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<uint4*>(dst),
                                                                          reinterpret_cast<const uint4*>(src), nbytes / 16);
   TD_CUDA_CHECK(cudaGetLastError());

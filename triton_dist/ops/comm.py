@@ -374,7 +374,8 @@ def _allgather_host(shard, ctx: FastAllGatherContext, output):
 # ------------------------------------------------------------------------------------------------------------
 # memory ops (memory_ops.py)
 # ------------------------------------------------------------------------------------------------------------
-def copy_tensor(dst: torch.Tensor, src: torch.Tensor, num_sms: int = 32, stream=None):
+def copy_tensor(dst: torch.Tensor, src: torch.Tensor, num_sms: int = 0, stream=None):
+    """Vectorised device copy (memory_ops.py copy_tensor).  ``num_sms`` > 0 bounds the grid (copy next to a GEMM); 0 = whole GPU."""
     nbytes = src.numel() * src.element_size()
     if not src.is_cuda or nbytes % 16 or not (dst.is_contiguous() and src.is_contiguous()):
         dst.copy_(src)
