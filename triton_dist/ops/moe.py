@@ -71,9 +71,10 @@ def moe_align_sort(topk_ids: torch.Tensor, num_experts: int, block_m: int = 128,
     pad_id = n
     if not ids.is_cuda:
         stage = ((torch.arange(n) // topk) // tokens_per_rank - rank) % world if tokens_per_rank > 0 else torch.zeros(n, dtype=torch.long)
-        key = ids.long() * (world + 1) * (n + 1) + stage * (n + 1) + torch.arange(n)
+        valid = (ids >= 0) & (ids < num_experts)                         # unrouted slots (id < 0) are dropped, like the CUDA kernel
+        key = torch.where(valid, ids.long(), torch.full_like(ids.long(), num_experts)) * (world + 1) * (n + 1) + stage * (n + 1) + torch.arange(n)
         order = torch.argsort(key)
-        counts = torch.bincount(ids.long(), minlength=num_experts)
+        counts = torch.bincount(ids.long()[valid], minlength=num_experts)
         padded = (counts + block_m - 1) // block_m * block_m
         offs = torch.zeros(num_experts + 1, dtype=torch.int64)
         offs[1:] = torch.cumsum(padded, 0)
