@@ -156,12 +156,19 @@ def ulysses_sp_infer_gemm_a2a_op(ctx, x, wqkv):
 
 
 # ---- ep_a2a.py (normal mode) ----------------------------------------------------------------------------------
-def ep_dispatch_token_inplace(layer, x, topk_idx):
-    """(ep_a2a.py:881) throughput-mode dispatch = the same NVLink push protocol with bf16 payloads."""
+def ep_dispatch_token_inplace(layer, x, topk_idx, topk_weights=None):
+    """(ep_a2a.py:881) throughput-mode dispatch.  ``layer``: :class:`triton_dist.parallel.ep.EPNormalAll2AllLayer` (token saving,
+    index-list receive side) or the low-latency layer (same NVLink push protocol with bf16 payloads)."""
+    from ..parallel.ep import EPNormalAll2AllLayer
+    if isinstance(layer, EPNormalAll2AllLayer):
+        return layer.dispatch(x, topk_idx, topk_weights)
     return layer.dispatch(x, None, topk_idx)
 
 
 def ep_combine_token_inplace(layer, expert_out, topk_idx, topk_weights, meta):
+    from ..parallel.ep import EPNormalAll2AllLayer
+    if isinstance(layer, EPNormalAll2AllLayer):
+        return layer.combine(expert_out, meta, topk_idx)
     return layer.combine(expert_out, topk_idx, topk_weights, meta)
 
 

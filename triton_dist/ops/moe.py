@@ -158,15 +158,23 @@ bincount = histogram_by_expert
 # ------------------------------------------------------------------------------------------------------------
 def moe_grouped_gemm_fused(src: torch.Tensor, w: torch.Tensor, routing: SortedRouting, div: int, n_out_rows: int,
                            out: Optional[torch.Tensor] = None, config: Optional[GemmConfig] = None,
-                           n_slice: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+                           n_slice: Optional[Tuple[int, int]] = None, gather_idx: Optional[torch.Tensor] = None,
+                           gather: bool = True, scatter: bool = True) -> torch.Tensor:
     """``out[id] = src[id // div] @ w[expert(id)].T`` for every routed pair id = token * topk + k, in ONE kernel: the A rows
     of each tile are fetched with TMA ``tile::gather4`` straight from ``src`` (no gather_rows pass) and the epilogue writes
     each row to its final place (no scatter_rows pass).  The sm_100a counterpart of the reference's gather/scatter
-    grouped GEMM (allgather_group_gemm.py:536-609, which cannot use TMA for the gathered operand)."""
+    grouped GEMM (allgather_group_gemm.py:536-609, which cannot use TMA for the gathered operand).
+
+    ``gather_idx`` (int32 [capacity], -1 = zero row) replaces ``sorted_ids // div`` as the source row of every sorted position
+    (rows that are addressed through a second level of indirection, e.g. EP receive buffers); ``gather=False``: ``src`` already is
+    the sorted, padded layout; ``scatter=False``: the output stays in the sorted layout ``[capacity, N]``."""
     K = src.shape[1]
     E, N_full, Kw = w.shape
     assert Kw == K and src.is_cuda and src.stride(1) == 1 and w.is_contiguous()
     n0, N = n_slice if n_slice is not None else (0, N_full)          # columns [n0, n0 + N) of every expert's weight
+    assert not (gather_idx is not None and scatter), "an explicit gather index and the scatter epilogue use different pad ids"
+    if not scatter:
+        n_out_rows = routing.capacity
     out = torch.empty((n_out_rows, N), dtype=src.dtype, device=src.device) if out is None else out
     cfg = config or GemmConfig(bn=256 if N >= 256 else 128, cta_group=1, group_m=1, use_tma_store=False)
     assert cfg.cta_group == 1 and routing.block_m == 128
@@ -178,8 +186,18 @@ def moe_grouped_gemm_fused(src: torch.Tensor, w: torch.Tensor, routing: SortedRo
     args.B = w2.data_ptr() + n0 * K * w.element_size()
     args.expert_stride_rows = N_full
     args.tile_expert, args.num_experts = routing.tile_expert.data_ptr(), E
-    args.a_gather, args.a_gather_div, args.a_gather_pad = routing.sorted_ids.data_ptr(), div, routing.pad_id
-    args.a_src_rows, args.c_scatter = src.shape[0], routing.sorted_ids.data_ptr()
+    if gather:
+        if gather_idx is not None:
+            assert gather_idx.dtype == torch.int32 and gather_idx.numel() == routing.capacity and gather_idx.is_contiguous()
+            args.a_gather, args.a_gather_div, args.a_gather_pad = gather_idx.data_ptr(), 1, -1
+        else:
+            args.a_gather, args.a_gather_div, args.a_gather_pad = routing.sorted_ids.data_ptr(), div, routing.pad_id
+        args.a_src_rows = src.shape[0]
+    else:
+        assert src.shape[0] == routing.capacity
+        args.a_gather_pad = routing.pad_id
+    if scatter:
+        args.c_scatter = routing.sorted_ids.data_ptr()
     _C.check(_C.cuda_lib().td_gemm_launch(C.byref(args), _s()), "td_gemm_launch(grouped, gather4)")
     return out
 

@@ -51,6 +51,32 @@ class EPLowLatencyAllToAllLayer:
         self.ctx.finalize()
 
 
+class EPNormalAll2AllLayer:
+    """Throughput-mode EP layer (token saving; reference layers/nvidia/ep_a2a_layer.py: preprocess / dispatch /
+    dispatch_postprocess / combine) on ops/ep_normal.py.  ``dispatch`` returns the handle the expert FFN consumes through
+    index lists (no receive-side copy); ``combine`` pre-reduces per token on the expert rank."""
+
+    def __init__(self, ep_config: "EPConfig"):
+        from ..ops import ep_normal as EN
+        self.cfg, self.EN = ep_config, EN
+        self.ctx = EN.create_ep_normal_ctx(ep_config.max_tokens, ep_config.hidden, ep_config.topk, ep_config.num_experts, ep_config.dtype)
+
+    def preprocess(self, topk_indices: torch.Tensor):
+        return M.histogram_by_expert(topk_indices, self.cfg.num_experts)
+
+    def dispatch(self, x: torch.Tensor, topk_indices: torch.Tensor, topk_weights: torch.Tensor):
+        return self.EN.ep_dispatch_normal(self.ctx, x, topk_indices, topk_weights)
+
+    def expert_ffn(self, handle, w_gate_up: torch.Tensor, w_down: torch.Tensor) -> torch.Tensor:
+        return self.EN.ep_expert_ffn_normal(self.ctx, handle, w_gate_up, w_down)
+
+    def combine(self, y_pairs: torch.Tensor, handle, topk_indices: torch.Tensor) -> torch.Tensor:
+        return self.EN.ep_combine_normal(self.ctx, y_pairs, handle, topk_indices)
+
+    def finalize(self):
+        self.ctx.finalize()
+
+
 class EPAll2AllLayer(EPLowLatencyAllToAllLayer):
     """Throughput ("normal") mode: same protocol, bf16 payload, capacity sized for prefill-scale token counts."""
 
