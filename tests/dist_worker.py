@@ -528,6 +528,14 @@ def case_ep_moe():
         _assert_close(x.grad, xr.grad, 1e-3, 1e-3, "ep autograd dx")
     U.barrier_all_host()
     moe.finalize()
+    if not big or U.get_bool_env("TD_EP_NORMAL_GPU", False):
+        # the same layer on the throughput-mode (token saving) exchange
+        moe._init_ctx(T, mode="normal")
+        for it in range(2):
+            x = (torch.randn(T, H, generator=torch.Generator().manual_seed(70 + it * W + me)) * 0.5).to(dtype).to(dev)
+            _assert_close(moe.dist_triton_fwd(x), moe.torch_fwd(x), 5e-2 if big else 1e-3, 5e-2 if big else 1e-3, f"ep_moe normal it{it}")
+        U.barrier_all_host()
+        moe.finalize()
 
 
 def case_mega():

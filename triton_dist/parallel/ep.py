@@ -133,8 +133,15 @@ class EP_MoE:
         self.num_experts, self.topk, self.norm_topk_prob = router.shape[0], topk, norm_topk_prob
         self.hidden, self.dtype = router.shape[1], w_gate_up.dtype
 
-    def _init_ctx(self, max_tokens: int, online_quant_fp8: bool = False):
+    def _init_ctx(self, max_tokens: int, online_quant_fp8: bool = False, mode: str = "low_latency"):
+        """``mode``: "low_latency" (per-(token, k) messages, optional fp8, packed per-expert receive layout) or "normal"
+        (throughput mode: token saving, index-list receive side, local pre-reduce on combine)."""
         max_m = (max_tokens + 127) // 128 * 128          # packed layout stays tile aligned
+        self.mode = mode
+        if mode == "normal":
+            self.a2a = EPNormalAll2AllLayer(EPConfig(max_m, self.hidden, self.topk, self.num_experts, self.rank, self.world_size,
+                                                     False, self.dtype))
+            return
         self.a2a = EPLowLatencyAllToAllLayer(max_m, self.hidden, self.topk, self.num_experts, online_quant_fp8, self.rank,
                                              self.world_size, self.dtype)
 
@@ -187,6 +194,10 @@ class EP_MoE:
         shp = x.shape
         x2 = x.reshape(-1, shp[-1]).contiguous()
         ids, w = self._route(x2)
+        if getattr(self, "mode", "low_latency") == "normal":
+            h = self.a2a.dispatch(x2, ids, w.float())
+            y = self.a2a.expert_ffn(h, self.w_gate_up, self.w_down)
+            return self.a2a.combine(y, h, ids).view(shp)
         act, handle = self.dispatch_group_gemm(x2, ids, w)
         return self.group_gemm_combine(act, handle).view(shp)
 
