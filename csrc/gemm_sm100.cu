@@ -27,7 +27,7 @@ struct TdGemmArgs {
   long long rank, world; unsigned long long symm_base, symm_stride, mc_base;
   void* phase;
   // AG
-  long long ag_rows_per_rank, ag_copy_local, ag_skip_wait;   // ag_skip_wait: 1 = GEMM-only twin, 2 = transfer done by the copy engine (1 flag per source)
+  long long ag_rows_per_rank, ag_copy_local, ag_skip_wait;   // ag_skip_wait: 1 = GEMM-only twin, 2 = transfer done by the copy engine (1 flag per source), 3 = NVLS multicast push
   const void* ag_a_local; void* ag_ws; long long ag_ws_buf_bytes; void* ag_flags; void* ag_ready;
   // RS
   long long rs_rows_per_rank; void* rs_stage; long long rs_stage_buf_bytes; void* rs_flags; void* rs_out; long long rs_ldo;
@@ -202,6 +202,22 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
   }
   if (a->mode == kAG && a->ag_skip_wait == 2) p.n_comm_ctas = 0;      // copy-engine transport: every SM runs GEMM tiles
   p.ag_nslices = (a->ag_skip_wait == 2) ? 1 : p.n_comm_ctas;
+  if (a->mode == kAG && a->ag_skip_wait == 3) {
+    // NVLS multicast transport: every rank writes its shard once to the multicast alias; sub-slice j = the rows of the j-th
+    // m tile of the shard, consumed in (j, source) order
+    if (!a->mc_base) { drv::set_error("ag_gemm: multicast transport needs an NVLS multicast mapping"); return -1; }
+    if (a->ag_copy_local == 2) { drv::set_error("ag_gemm: the all-to-all flavour cannot use the multicast transport"); return -1; }
+    if (p.n_comm_ctas < cg) { drv::set_error("ag_gemm: the multicast transport needs n_comm_ctas >= cta_group"); return -1; }
+    const int tps = (int)(a->ag_rows_per_rank / TM);
+    int nsub = (a->ag_rows_per_rank % TM == 0 && tps >= 1) ? tps : 1;
+    while (nsub > 1 && p.n_comm_ctas * nsub > kAGMaxSlices) nsub >>= 1;
+    p.ag_multicast = 1;
+    p.ag_nslices = p.n_comm_ctas * nsub;
+    if (a->ag_rows_per_rank % TM == 0 && nsub == tps && tps > 1 && !a->tile_expert) {
+      p.ag_interleave = tps; p.group_m = (int)a->world; p.m_rot = 0;
+    }
+    grid = gemm_ctas + p.n_comm_ctas;
+  }
   if (a->mode == kAG && a->ag_skip_wait == 0 && p.n_comm_ctas > 0 && a->world <= 4) {
     // few destinations: publish each CTA's share in 4 (TP2) / 2 (TP4) interleaved sub-slices (finer arrival flags)
     int nsub = a->world == 2 ? 4 : 2;

@@ -87,6 +87,9 @@ struct Params {
   int ag_rows_per_rank;      // rows of A owned by each rank
   int ag_copy_local;         // 1: comm CTAs copy a_local -> workspace; 0: caller already wrote the workspace; 2: all-to-all (block d of a_local -> rank d)
   int ag_skip_wait;          // GEMM-only twin: never wait (measures exposed communication)
+  int ag_multicast;          // 1: comm CTAs write my shard ONCE to the NVLS multicast alias of the workspace (the switch fans it
+                             //    out to every rank) and publish the flags on all ranks -- one stage instead of world-1
+  int ag_interleave;         // > 0 (= m tiles per source): tile order visits the j-th tile of every source before the (j+1)-th
   int ag_local_direct;       // 1: tiles of my own rows read a_local through tmap_al (no local copy, no flag wait)
   CUtensorMap tmap_al;       // {K, rows of a_local}
   int ag_nslices;            // arrival flags per source rank (= comm CTAs, or 1 when the copy engine does the transfer)
@@ -160,6 +163,14 @@ TD_DEVICE void tile_coords(const Params& p, int t, int& m_tile, int& n_tile) {
   const int band_m = min(p.num_m - first_m, p.group_m);
   const int r = t - band * per_band;
   n_tile = r / band_m;
+  if (p.ag_interleave > 0) {
+    // multicast all-gather: all shards arrive concurrently, sub-slice by sub-slice -> consume the j-th tile of every source
+    // (own source first) before the (j+1)-th.  Logical index L = j * world + source offset.
+    const int L = first_m + r % band_m;
+    const int j = L / p.symm.world, s = (p.symm.rank + L % p.symm.world) % p.symm.world;
+    m_tile = s * p.ag_interleave + j;
+    return;
+  }
   m_tile = first_m + r % band_m + p.m_rot;
   if (m_tile >= p.num_m) m_tile -= p.num_m;
 }
@@ -216,6 +227,38 @@ TD_DEVICE void ag_comm_cta(const Params& p, uint32_t ph, int comm_idx) {
   // interleaved over the shard (sub-slice j of all CTAs = the j-th 1/nsub of the rows), each published separately, so
   // the consumer's first remote tiles become ready after 1/nsub of the transfer instead of at its end
   const int nsub = max(1, p.ag_nslices / max(1, p.n_comm_ctas));
+  if (p.ag_multicast) {
+    // NVLS transport: one multimem.st per 16 bytes reaches every rank's workspace (including mine); egress is the shard
+    // itself, not (world - 1) copies of it, so a handful of CTAs is enough and there is a single fence per sub-slice
+    char* ws_mc = symm_mc(p.symm, ws) + shard_off;
+    for (int j = 0; j < nsub; ++j) {
+      const int sidx = j * p.n_comm_ctas + comm_idx;
+      const size_t b0 = min(shard_bytes, slice * sidx), b1 = min(shard_bytes, b0 + slice);
+      if (threadIdx.x == 0) prof_record(p.prof, pslot, 1, true);
+      const size_t n = (b1 - b0) >> 4;
+      const uint4* sv = reinterpret_cast<const uint4*>(src0 + b0);
+      uint4* dv = reinterpret_cast<uint4*>(ws_mc + b0);
+      constexpr int U = 8;
+      size_t i = threadIdx.x;
+      for (; i + (U - 1) * static_cast<size_t>(kThreads) < n; i += U * static_cast<size_t>(kThreads)) {
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = ptx::ld_nc_v4(sv + i + u * static_cast<size_t>(kThreads));
+#pragma unroll
+        for (int u = 0; u < U; ++u) ptx::multimem_st_v4(dv + i + u * static_cast<size_t>(kThreads), v[u]);
+      }
+      for (; i < n; i += kThreads) ptx::multimem_st_v4(dv + i, ptx::ld_nc_v4(sv + i));
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        prof_record(p.prof, pslot, 1, false);
+        prof_record(p.prof, pslot, 6, true);
+        ptx::fence_acq_rel_sys();
+        for (int d = 0; d < W; ++d) ptx::st_relaxed_sys(symm_at(p.symm, flag_base + sidx, (me + d) % W), ph);
+        prof_record(p.prof, pslot, 6, false);
+      }
+    }
+    return;
+  }
   for (int dist = (p.ag_copy_local && !p.ag_local_direct) ? 0 : 1; dist < W; ++dist) {
     const int d = (me - dist + W) % W;
     // ag_copy_local == 2: all-to-all flavour -- a_local is [world, rows_per_rank, K] and block d goes to rank d

@@ -127,6 +127,7 @@ def ag_gemm(A: torch.Tensor, B: torch.Tensor, ctx: AllGatherGEMMTensorParallelCo
     shard is pushed by the DMA engines on a side stream (one ``cudaMemcpyAsync`` + one release-flag kernel per peer, as
     the reference's copy-engine producer, allgather.py:100-124) while all SMs run GEMM tiles that wait on the same
     per-source flags; not CUDA-graph replayable (flag values are written from the host-tracked phase).
+    ``transport="multicast"`` (opt-in): comm CTAs write the shard once to the NVLS multicast alias, the switch fans it out.
 
     ``all_to_all=True``: A is ``[W * Ms, K]`` and row block d goes to rank d (instead of the same shard to everyone);
     the result is ``concat_s(block from rank s) @ B`` -- the AllToAll + GEMM of the Ulysses o-projection
@@ -171,6 +172,12 @@ def ag_gemm(A: torch.Tensor, B: torch.Tensor, ctx: AllGatherGEMMTensorParallelCo
     args.ag_flags, args.ag_ready = ctx.flags.data_ptr(), ctx.ready.data_ptr()
     if skip_wait:
         args.n_comm_ctas = 0
+    if transport == "multicast" and not skip_wait:
+        # NVLS: comm CTAs write the shard once to the multicast alias of the workspace (csrc/gemm_sm100.cuh, ag_multicast).
+        # Written after this round's GPU budget was spent -- hardware validation pending, hence opt-in only.
+        assert not all_to_all and U.is_nvshmem_multimem_supported()
+        args.ag_skip_wait, args.ag_copy_local = 3, 1
+        args.n_comm_ctas = max(2, cfg.n_comm_ctas if cfg.n_comm_ctas and cfg.n_comm_ctas <= 16 else 8)
     if transport == "copy_engine" and not skip_wait:
         _ce_push(ctx, A, ph, Ms, K)
         args.ag_skip_wait, args.ag_copy_local, args.n_comm_ctas = 2, 1, 0
