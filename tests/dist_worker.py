@@ -514,18 +514,21 @@ def case_ep_moe():
     if not big:
         x = torch.randn(T, H, generator=torch.Generator().manual_seed(99 + me)).to(dtype).to(dev).requires_grad_(True)
         ids, w = moe._route(x.detach())
+        w = w.detach().clone().requires_grad_(True)
         y = TritonDistFusedEpMoeFunction.apply_moe(x, ids, w, moe.a2a, moe.w_gate_up, moe.w_down)
-        y.sum().backward()
+        (y * torch.linspace(0.5, 1.5, H)).sum().backward()
         xr = x.detach().clone().requires_grad_(True)
+        wr = w.detach().clone().requires_grad_(True)
         acc = torch.zeros(T, H)
         for k in range(topk):
             for t in range(T):
                 e = int(ids[t, k])
                 h = gall[e].float() @ xr[t].float()
                 h = torch.nn.functional.silu(h[:I]) * h[I:]
-                acc[t] = acc[t] + w[t, k] * (dall[e].float() @ h)
-        acc.sum().backward()
+                acc[t] = acc[t] + wr[t, k] * (dall[e].float() @ h)
+        (acc * torch.linspace(0.5, 1.5, H)).sum().backward()
         _assert_close(x.grad, xr.grad, 1e-3, 1e-3, "ep autograd dx")
+        _assert_close(w.grad, wr.grad, 1e-3, 1e-3, "ep autograd d(routing weights)")
     U.barrier_all_host()
     moe.finalize()
     if not big or U.get_bool_env("TD_EP_NORMAL_GPU", False):

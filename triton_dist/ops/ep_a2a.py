@@ -162,6 +162,17 @@ def ep_ll_combine(ctx: EPLowLatencyContext, expert_out: torch.Tensor, topk_idx: 
     return out
 
 
+def last_combined_rows(ctx: EPLowLatencyContext, T: int) -> torch.Tensor:
+    """The un-weighted expert outputs ``[T * topk, H]`` that the most recent :func:`ep_ll_combine` received on this rank (row
+    ``t * topk + k``).  The weighting happens on the token's owner, so these rows are exactly what the gradient w.r.t. the routing
+    weights needs (d w[t, k] = <row(t, k), d out[t]>).  The buffer half comes from the device-resident call counter (no host sync)."""
+    n = T * ctx.topk
+    if not ctx.comb.is_cuda:
+        return ctx.comb[ctx.host_calls_c & 1, :n].clone()
+    half = (ctx.phase_c[0:1] & 1).long()
+    return torch.index_select(ctx.comb, 0, half)[0, :n].clone()
+
+
 # reference spellings
 def dispatch_kernel_v2(ctx, x, topk_idx, **kw):
     return ep_ll_dispatch(ctx, x, topk_idx, **kw)

@@ -249,12 +249,14 @@ class _Combine(torch.autograd.Function):
         meta = EP.DispatchMetaInfo(src_info, recv_range)
         out = layer.combine(y.detach().contiguous(), ids, w.detach(), meta)
         ctx.layer, ctx.meta = layer, meta
-        ctx.save_for_backward(y, ids, w)
+        # un-weighted rows as they arrived on this rank: needed for the gradient of the routing weights
+        rows = EP.last_combined_rows(layer.ctx, ids.shape[0]) if w.requires_grad else None
+        ctx.save_for_backward(y, ids, w, rows)
         return out
 
     @staticmethod
     def backward(ctx, g_out):
-        y, ids, w = ctx.saved_tensors
+        y, ids, w, rows = ctx.saved_tensors
         layer = ctx.layer
         # d y_row(t,k) = w[t,k] * g_out[t]: deliver g_out rows with the forward routing, scale on the expert side with
         # the (all-gathered) routing weights
@@ -274,11 +276,12 @@ class _Combine(torch.autograd.Function):
                 if c:
                     scale[le, s:s + c] = w_all[src].reshape(-1)[meta2.recv_token_source_indices[le, s:s + c].long()]
         g_y = (g_rows.float() * scale[..., None]).to(y.dtype)
-        # d w[t,k] = <y_row(t,k), g_out[t]>: bring the forward expert outputs back un-weighted
-        ones = torch.ones(ids.shape, dtype=torch.float32, device=w.device)
-        # (row order of the second dispatch can differ from the forward one; wgrad of the router weights is computed
-        #  from a dedicated exchange of per-pair dot products instead of re-using g_y's layout)
+        # d w[t, k] = <y_row(t, k), g_out[t]>: the un-weighted rows were delivered to this rank by the forward combine
         g_w = None
+        if rows is not None:
+            T, topk = ids.shape
+            g_w = (rows.float().view(T, topk, -1) * g_out.float()[:, None, :]).sum(-1)
+            g_w = torch.where(ids >= 0, g_w, torch.zeros_like(g_w)).to(w.dtype)
         return g_y, None, g_w, None, None, None
 
 
