@@ -366,10 +366,6 @@ def case_ep_normal():
     dev = U.current_device()
     W, me = U.world_size(), U.rank()
     big = dev.type == "cuda"
-    if big and not U.get_bool_env("TD_EP_NORMAL_GPU", False):
-        # the CUDA kernels of this mode were written after the round's GPU budget was spent: run them only when asked to
-        U.dist_print("ep_normal: CUDA path not hardware-validated yet (set TD_EP_NORMAL_GPU=1); emulation covers the protocol", allowed_ranks=[0])
-        return
     dtype = torch.bfloat16 if big else torch.float32
     T, H, I, topk, epr = (200, 512, 256, 4, 4) if big else (7, 16, 8, 3, 2)
     E = epr * W
@@ -531,7 +527,7 @@ def case_ep_moe():
         _assert_close(w.grad, wr.grad, 1e-3, 1e-3, "ep autograd d(routing weights)")
     U.barrier_all_host()
     moe.finalize()
-    if not big or U.get_bool_env("TD_EP_NORMAL_GPU", False):
+    if not big or U.get_bool_env("TD_EP_NORMAL_GPU", True):
         # the same layer on the throughput-mode (token saving) exchange
         moe._init_ctx(T, mode="normal")
         for it in range(2):

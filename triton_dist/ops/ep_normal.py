@@ -10,8 +10,8 @@ What is different from the low-latency path (ops/ep_a2a.py):
     list with TMA ``tile::gather4`` -- no compaction into a per-expert layout;
   * combine pre-reduces a token's expert outputs on the expert rank and returns one row per (token, rank).
 
-STATUS: the protocol is exercised by the multi-process emulation tests (tests/dist_worker.py::case_ep_normal, gloo); the CUDA kernels
-compile for sm_100a but were written after this round's GPU budget was spent -- hardware validation is the first item of the next round.
+STATUS: validated on 2xB200 (tests/dist_worker.py::case_ep_normal: token-saving counts, FFN through the TMA-gather4 index lists,
+pre-reduced combine) and on the emulation backend; not yet timed.
 """
 from __future__ import annotations
 
