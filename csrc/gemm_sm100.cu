@@ -95,10 +95,10 @@ static int dispatch_fp8(const Params& p, int bn, int cg, int grid, cudaStream_t 
 template <int kMode>
 static int dispatch(const Params& p, int bn, int cg, int grid, cudaStream_t s) {
 #define TD_CASE(BN_, CG_) if (bn == BN_ && cg == CG_) return launch_cfg<kMode, BN_, CG_>(p, grid, s);
-  TD_CASE(256, 2) TD_CASE(256, 1) TD_CASE(128, 2) TD_CASE(128, 1)
+  TD_CASE(256, 2) TD_CASE(256, 1) TD_CASE(192, 2) TD_CASE(192, 1) TD_CASE(128, 2) TD_CASE(128, 1)
   TD_CASE(64, 2) TD_CASE(64, 1) TD_CASE(32, 2) TD_CASE(32, 1)
 #undef TD_CASE
-  drv::set_error("unsupported tile config (bn must be 32/64/128/256, cta_group 1/2)");
+  drv::set_error("unsupported tile config (bn must be 32/64/128/192/256, cta_group 1/2)");
   return -1;
 }
 
