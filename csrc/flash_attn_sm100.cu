@@ -655,6 +655,267 @@ __global__ void __launch_bounds__(kThreadsV2, 1) flash_fwd_kernel_v2(const __gri
   }
 }
 
+
+// =================================================================================================================
+// v3 (opt-in, written after the round's GPU budget was spent): TWO 128-query tiles per CTA, one softmax warpgroup per tile.
+// The two tiles are independent instruction streams over the same K/V tiles: while warpgroup 0 is in the latency chain of
+// its tile (tcgen05.ld -> max -> ex2 -> tcgen05.st -> barrier), the tensor core works on the other tile's MMAs and
+// warpgroup 1 keeps the MUFU pipe busy.  TMEM: S0 | S1 | O0 | O1 = 512 columns, P_i overwrites S_i (TMEM A operand of PV_i);
+// Q stays in shared memory.  MMA issue order per K/V tile j:  PV0(j) QK0(j+1) PV1(j) QK1(j+1).
+// =================================================================================================================
+constexpr int kThreadsV3 = 320;
+struct SmemV3 {
+  static constexpr int kQ = 0;                               // 2 x [128, 128]
+  static constexpr int kK = kQ + 2 * kQBytes;
+  static constexpr int kV = kK + 2 * kKVTileV2;              // 2 stages
+  static constexpr int kBar = kV + 2 * kKVTileV2;
+  static constexpr int kTotal = kBar + 256;
+};
+enum BarV3 { V3_Q_FULL = 0, V3_K_FULL = 1, V3_V_FULL = 3, V3_KV_EMPTY = 5, V3_S_FULL = 7, V3_P_READY = 9, V3_PV_DONE = 11, V3_NBAR = 13 };
+
+__global__ void __launch_bounds__(kThreadsV3, 1) flash_fwd_kernel_v3(const __grid_constant__ Params p, int n_q_tiles) {
+  constexpr int BNK = 128;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SmemV3::kBar);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + V3_NBAR);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_pairs = (n_q_tiles + 1) / 2;                                  // CTAs per (head, batch): two q tiles each
+  const int per_tile = p.Hq * p.B;
+  const int pair_rank = static_cast<int>(blockIdx.x) / per_tile, hb = static_cast<int>(blockIdx.x) % per_tile;
+  const int qp = p.causal ? n_pairs - 1 - pair_rank : pair_rank;            // causal: most keys first
+  const int head = hb % p.Hq, batch = hb / p.Hq;
+  const int kv_head = head / (p.Hq / p.Hkv);
+  int q_row0[2], q_pos0[2], rows_here[2], nt[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int qt = 2 * qp + i;
+    q_row0[i] = qt * BMQ;
+    rows_here[i] = max(0, min(BMQ, p.Sq - q_row0[i]));
+    q_pos0[i] = (p.q_tile_pos && qt < n_q_tiles) ? p.q_tile_pos[batch * n_q_tiles + qt] : q_row0[i] + (p.Sk - p.Sq);
+    nt[i] = (p.Sk + BNK - 1) / BNK;
+    if (p.causal) nt[i] = min(nt[i], (q_pos0[i] + max(rows_here[i], 1) - 1) / BNK + 1);
+    if (rows_here[i] == 0) nt[i] = 0;
+  }
+  const int n_tiles = max(nt[0], nt[1]);          // both tiles walk the same K/V tiles; a tile past its causal range is fully masked
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&p.tmap_q);
+    ptx::prefetch_tensormap(&p.tmap_k);
+    ptx::prefetch_tensormap(&p.tmap_v);
+    ptx::mbar_init(&bars[V3_Q_FULL], 1);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&bars[V3_K_FULL + s], 1);
+      ptx::mbar_init(&bars[V3_V_FULL + s], 1);
+      ptx::mbar_init(&bars[V3_KV_EMPTY + s], 1);
+      ptx::mbar_init(&bars[V3_S_FULL + s], 1);
+      ptx::mbar_init(&bars[V3_P_READY + s], 128);
+      ptx::mbar_init(&bars[V3_PV_DONE + s], 1);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc<1>(tmem_ptr_smem, 512);
+    ptx::tmem_relinquish<1>();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(&bars[V3_Q_FULL], 2 * kQBytes);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        ptx::tma_load_4d(&p.tmap_q, &bars[V3_Q_FULL], smem + SmemV3::kQ + i * kQBytes, 0, q_row0[i], head, batch);
+        ptx::tma_load_4d(&p.tmap_q, &bars[V3_Q_FULL], smem + SmemV3::kQ + i * kQBytes + kSlab, 64, q_row0[i], head, batch);
+      }
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j & 1;
+        if (j >= 2) ptx::mbar_wait(&bars[V3_KV_EMPTY + st], ((j >> 1) - 1) & 1);
+        uint8_t* ks = smem + SmemV3::kK + st * kKVTileV2;
+        uint8_t* vs = smem + SmemV3::kV + st * kKVTileV2;
+        ptx::mbar_arrive_expect_tx(&bars[V3_K_FULL + st], kKVTileV2);
+        ptx::tma_load_4d(&p.tmap_k, &bars[V3_K_FULL + st], ks, 0, j * BNK, kv_head, batch, ptx::kEvictLast);
+        ptx::tma_load_4d(&p.tmap_k, &bars[V3_K_FULL + st], ks + kSlab, 64, j * BNK, kv_head, batch, ptx::kEvictLast);
+        ptx::mbar_arrive_expect_tx(&bars[V3_V_FULL + st], kKVTileV2);
+        ptx::tma_load_4d(&p.tmap_v, &bars[V3_V_FULL + st], vs, 0, j * BNK, kv_head, batch, ptx::kEvictLast);
+        ptx::tma_load_4d(&p.tmap_v, &bars[V3_V_FULL + st], vs + kSlab, 64, j * BNK, kv_head, batch, ptx::kEvictLast);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t fmt = p.is_bf16 ? 1u : 0u;
+      const uint32_t idesc_qk = ptx::make_idesc(fmt, fmt, BMQ, BNK);
+      const uint32_t idesc_pv = ptx::make_idesc(fmt, fmt, BMQ, HD, 0, 1);
+      // S_i = Q_i K_j^T into TMEM columns [i * 128, +128); in-order issue protects S_i / P_i (see v2)
+      auto issue_qk = [&](int i, int j) {
+        const int st = j & 1;
+        ptx::mbar_wait(&bars[V3_K_FULL + st], (j >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t q_addr = ptx::smem_u32(smem + SmemV3::kQ + i * kQBytes);
+        const uint32_t k_addr = ptx::smem_u32(smem + SmemV3::kK + st * kKVTileV2);
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * kSlab + (kk & 3) * 32;
+          ptx::mma_f16<1>(tmem_base + i * BNK, ptx::make_smem_desc_k128(q_addr + off), ptx::make_smem_desc_k128(k_addr + off), idesc_qk,
+                          kk > 0 ? 1u : 0u);
+        }
+        ptx::mma_commit(&bars[V3_S_FULL + i]);
+      };
+      auto issue_pv = [&](int i, int j) {
+        const int st = j & 1;
+        ptx::mbar_wait(&bars[V3_V_FULL + st], (j >> 1) & 1);
+        ptx::mbar_wait(&bars[V3_P_READY + i], j & 1);
+        ptx::tc_fence_after();
+        const uint32_t v_addr = ptx::smem_u32(smem + SmemV3::kV + st * kKVTileV2);
+#pragma unroll
+        for (int kk = 0; kk < BNK / 16; ++kk)
+          ptx::mma_f16_ts(tmem_base + 2 * BNK + i * HD, tmem_base + i * BNK + kk * 8, ptx::make_smem_desc_mn128(v_addr + kk * 16 * 128, kSlab),
+                          idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+        ptx::mma_commit(&bars[V3_PV_DONE + i]);
+      };
+      ptx::mbar_wait(&bars[V3_Q_FULL], 0);
+      if (n_tiles > 0) { issue_qk(0, 0); issue_qk(1, 0); }
+      for (int j = 0; j < n_tiles; ++j) {
+        issue_pv(0, j);
+        if (j + 1 < n_tiles) issue_qk(0, j + 1);
+        issue_pv(1, j);
+        ptx::mma_commit(&bars[V3_KV_EMPTY + (j & 1)]);          // K_j / V_j are no longer read once PV1(j) retires
+        if (j + 1 < n_tiles) issue_qk(1, j + 1);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax: warpgroup i owns query tile i
+    const int i = (warp - 2) >> 2;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t tmem_s = tmem_base + i * BNK, tmem_o = tmem_base + 2 * BNK + i * HD;
+    const int q_pos = q_pos0[i] + row;
+    const bool tile_live = rows_here[i] > 0;
+    float m_ref = -INFINITY, l = 0.f;
+
+    for (int j = 0; j < n_tiles; ++j) {
+      ptx::mbar_wait(&bars[V3_S_FULL + i], j & 1);
+      ptx::tc_fence_after();
+      uint32_t s[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) ptx::tmem_ld_32x32b_x32(tmem_s + lane_off + c * 32, s[c]);
+      ptx::tmem_ld_wait();
+
+      const int key0 = j * BNK;
+      const bool need_mask = !tile_live || (p.causal && key0 + BNK - 1 > q_pos0[i]) || (key0 + BNK > p.Sk);
+      if (need_mask) {
+        const int limit = !tile_live ? -1 : (p.causal ? min(p.Sk - 1, q_pos) : p.Sk - 1);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (key0 + c * 32 + e > limit) s[c][e] = 0xFF800000u;
+      }
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int e = 0; e < 32; ++e) mx4[e & 3] = fmaxf(mx4[e & 3], __uint_as_float(s[c][e]));
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * p.scale_log2;
+      const bool bump = mx > m_ref + 8.f;
+      float alpha = 1.f;
+      if (bump) {
+        alpha = (m_ref == -INFINITY) ? 0.f : ptx::ex2_approx(m_ref - mx);
+        m_ref = mx;
+        l *= alpha;
+      }
+      const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 4; c += 2) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const float a0 = ptx::ex2_approx(fmaf(__uint_as_float(s[c][e]), p.scale_log2, neg_m));
+          const float a1 = ptx::ex2_approx(fmaf(__uint_as_float(s[c][e + 1]), p.scale_log2, neg_m));
+          const float b0 = ptx::ex2_approx(fmaf(__uint_as_float(s[c + 1][e]), p.scale_log2, neg_m));
+          const float b1 = ptx::ex2_approx(fmaf(__uint_as_float(s[c + 1][e + 1]), p.scale_log2, neg_m));
+          sum4[(e >> 1) & 3] += (a0 + a1) + (b0 + b1);
+          pk[e >> 1] = p.is_bf16 ? ptx::pack_bf16x2(a0, a1) : ptx::pack_f16x2(a0, a1);
+          pk[16 + (e >> 1)] = p.is_bf16 ? ptx::pack_bf16x2(b0, b1) : ptx::pack_f16x2(b0, b1);
+        }
+        ptx::tmem_st_32x32b_x32(tmem_s + lane_off + c * 16, pk);        // packed pairs of keys [c*32, c*32+64)
+      }
+      l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+      if (j > 0 && __any_sync(0xFFFFFFFFu, bump)) {
+        ptx::mbar_wait(&bars[V3_PV_DONE + i], (j - 1) & 1);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t o[32];
+          ptx::tmem_ld_32x32b_x32(tmem_o + lane_off + c * 32, o);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+          ptx::tmem_st_32x32b_x32(tmem_o + lane_off + c * 32, o);
+        }
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&bars[V3_P_READY + i]);
+    }
+
+    if (n_tiles > 0) {
+      ptx::mbar_wait(&bars[V3_PV_DONE + i], (n_tiles - 1) & 1);
+      ptx::tc_fence_after();
+    }
+    const float inv_l = l > 0.f ? 1.f / l : 0.f;
+    const bool live = row < rows_here[i];
+    char* o_row = reinterpret_cast<char*>(p.o) +
+                  2 * (static_cast<long long>(batch) * p.o_stride_b + static_cast<long long>(q_row0[i] + row) * p.o_stride_s +
+                       static_cast<long long>(head) * p.o_stride_h);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t o[32];
+      if (n_tiles > 0) {
+        ptx::tmem_ld_32x32b_x32(tmem_o + lane_off + c * 32, o);
+        ptx::tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) o[e] = 0u;
+      }
+      if (live) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 v;
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(o[g * 8 + e]) * inv_l;
+          if (p.is_bf16) {
+            v.x = ptx::pack_bf16x2(f[0], f[1]); v.y = ptx::pack_bf16x2(f[2], f[3]);
+            v.z = ptx::pack_bf16x2(f[4], f[5]); v.w = ptx::pack_bf16x2(f[6], f[7]);
+          } else {
+            v.x = ptx::pack_f16x2(f[0], f[1]); v.y = ptx::pack_f16x2(f[2], f[3]);
+            v.z = ptx::pack_f16x2(f[4], f[5]); v.w = ptx::pack_f16x2(f[6], f[7]);
+          }
+          ptx::st_v4(o_row + (c * 32 + g * 8) * 2, v);
+        }
+      }
+    }
+    if (p.lse && live) {
+      const float lse = (l > 0.f) ? (m_ref + log2f(l)) * 0.6931471805599453f : -INFINITY;
+      p.lse[(static_cast<long long>(batch) * p.Hq + head) * p.Sq + q_row0[i] + row] = lse;
+    }
+    ptx::tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
 }  // namespace fa
 }  // namespace td
 
@@ -723,6 +984,19 @@ extern "C" __attribute__((visibility("default"))) int td_flash_attn_fwd(const Td
   p.scale_log2 = static_cast<float>(a->sm_scale * 1.4426950408889634);
   dim3 grid((unsigned)((a->Sq + BMQ - 1) / BMQ), (unsigned)a->Hq, (unsigned)a->B);
   cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream_);
+  if (a->block_n == 131) {     // v3 kernel (opt-in): two q tiles per CTA
+    static bool v3_attr = false;
+    if (!v3_attr) {
+      cudaError_t e = cudaFuncSetAttribute(flash_fwd_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemV3::kTotal);
+      if (e != cudaSuccess) { td::drv::set_error("flash_attn v3: smem attribute: %s", cudaGetErrorString(e)); return -1; }
+      v3_attr = true;
+    }
+    const int nq = (int)((a->Sq + BMQ - 1) / BMQ);
+    flash_fwd_kernel_v3<<<dim3((unsigned)(((nq + 1) / 2) * a->Hq * a->B)), kThreadsV3, SmemV3::kTotal, st_>>>(p, nq);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { td::drv::set_error("flash_attn v3 launch: %s", cudaGetErrorString(e)); return -1; }
+    return 0;
+  }
   if (a->block_n == 130) {     // v2 kernel
     static bool v2_attr = false;
     if (!v2_attr) {

@@ -54,7 +54,7 @@ def flash_attn_reference(q, k, v, causal=True, sm_scale=None, q_pos: Optional[to
 
 def flash_attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = True, sm_scale: Optional[float] = None,
                    q_tile_pos: Optional[torch.Tensor] = None, sk: Optional[int] = None, return_lse: bool = False,
-                   out: Optional[torch.Tensor] = None, block_n: int = 64, tmem_operands: bool = False, v2: Optional[bool] = None):
+                   out: Optional[torch.Tensor] = None, block_n: int = 64, tmem_operands: bool = False, v2: Optional[bool] = None, v3: bool = False):
     """q: [B, Sq, Hq, 128]; k, v: [B, Sk, Hkv, 128] (any batch/seq/head strides, head dim contiguous).
 
     ``q_tile_pos``: int32 [B, ceil(Sq / 128)] -- KV position of the first query of every 128-query tile (queries inside
@@ -62,7 +62,8 @@ def flash_attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bo
     keys that exist (a KV cache longer than the sequence).  ``block_n``: keys per pipeline step -- 64 runs two CTAs per
     SM (softmax of one under the MMAs of the other), 128 one CTA per SM with twice the tile.  ``tmem_operands``: 128-key
     tiles with Q and P held in TMEM (both MMAs read only K / V from shared memory).  ``v2``: TMEM operands + two softmax
-    warpgroups splitting the columns + 3-stage K/V ring + longest-first CTA order."""
+    warpgroups splitting the columns + 3-stage K/V ring + longest-first CTA order (default).  ``v3`` (opt-in, not yet validated on
+    hardware): two query tiles per CTA with one softmax warpgroup each."""
     B, Sq, Hq, D = q.shape
     Sk = k.shape[1] if sk is None else int(sk)
     sm_scale = sm_scale or 1.0 / math.sqrt(D)
@@ -93,9 +94,9 @@ def flash_attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bo
     a.v_stride_b, a.v_stride_s, a.v_stride_h = v.stride(0), v.stride(1), v.stride(2)
     a.o_stride_b, a.o_stride_s, a.o_stride_h = out.stride(0), out.stride(1), out.stride(2)
     a.sm_scale, a.causal, a.is_bf16 = float(sm_scale), int(causal), int(q.dtype == torch.bfloat16)
-    if v2 is None:            # default: the v2 kernel unless a v1 variant was asked for explicitly
-        v2 = (block_n == 64 and not tmem_operands)
-    a.block_n = 130 if v2 else 129 if tmem_operands else (128 if block_n == 128 else 64)
+    if v2 is None:            # default: the v2 kernel unless another variant was asked for explicitly
+        v2 = (block_n == 64 and not tmem_operands and not v3)
+    a.block_n = 131 if v3 else 130 if v2 else 129 if tmem_operands else (128 if block_n == 128 else 64)
     _C.check(_C.cuda_lib().td_flash_attn_fwd(C.byref(a), c_void_p(torch.cuda.current_stream().cuda_stream)), "td_flash_attn_fwd")
     return (out, lse) if return_lse else out
 
