@@ -13,3 +13,12 @@ def test_cpu_world2(case):
 
 def test_cpu_world3_ring():
     run_dist(["gemm_rs", "ag_gemm"], nproc=3, env_extra=CPU_ENV)
+
+
+def test_cpu_world3_fused_and_ep():
+    """Non-power-of-two world: GEMM+AR, GEMM+all-to-all, both EP modes (the tiny model of the mega case needs heads % world == 0)."""
+    run_dist(["gemm_ar", "gemm_a2a", "ep_ll", "ep_normal"], nproc=3, env_extra=CPU_ENV)
+
+
+def test_cpu_world4_collectives():
+    run_dist(["allreduce", "allgather", "moe", "sp_pp"], nproc=4, env_extra=CPU_ENV)
