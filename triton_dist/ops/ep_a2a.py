@@ -234,7 +234,7 @@ def _dispatch_host(ctx, x, topk_idx):
             for i in range(cnt):
                 m = ctx.staging[par, le, src, i]
                 src_info[le, start + i] = int(m[:4].view(torch.int32)[0])
-                recv_x[le, start + i] = m[16:16 + H * xb.element_size() * 0 + xb.shape[1]].view(ctx.dtype)
+                recv_x[le, start + i] = m[16:16 + xb.shape[1]].view(ctx.dtype)
     return recv_x, None, recv_count, DispatchMetaInfo(src_info, recv_range)
 
 
