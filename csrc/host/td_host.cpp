@@ -11,6 +11,7 @@
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fcntl.h>
 #include <string>
@@ -92,13 +93,31 @@ TDH_API int tdh_heap_destroy(void* hp) {
   return 0;
 }
 
+// ---- chaos mode: TD_HOST_CHAOS_US=N makes every notify / first wait poll sleep a random 0..N microseconds, i.e. ranks
+// drift apart by arbitrary amounts between protocol steps.  Parity double-buffering, phase counters and slot reuse must
+// survive any such schedule (tests/test_dist_cpu.py::test_cpu_chaos); the reference only has hand-placed stragglers.
+static long long chaos_us() {
+  static long long v = -1;
+  if (v < 0) { const char* e = getenv("TD_HOST_CHAOS_US"); v = e ? atoll(e) : 0; }
+  return v;
+}
+static void chaos() {
+  const long long n = chaos_us();
+  if (n <= 0) return;
+  static thread_local unsigned long long st = 0x9E3779B97F4A7C15ull ^ static_cast<unsigned long long>(getpid()) * 0xD1B54A32D192ED03ull;
+  st ^= st << 13; st ^= st >> 7; st ^= st << 17;                       // xorshift64
+  std::this_thread::sleep_for(std::chrono::microseconds(static_cast<long long>(st % static_cast<unsigned long long>(n + 1))));
+}
+
 // ---- signal primitives (same semantics as td::notify / td::wait on the device) ----------------------
 // op: 1 = SET, 2 = ADD  (DistributedAttrDefs.td:36-44)
 TDH_API void tdh_notify32(void* addr, unsigned int value, int op) {
+  chaos();
   if (op == 2) a32(addr)->fetch_add(value, std::memory_order_release);
   else a32(addr)->store(value, std::memory_order_release);
 }
 TDH_API void tdh_notify64(void* addr, unsigned long long value, int op) {
+  chaos();
   if (op == 2) a64(addr)->fetch_add(value, std::memory_order_release);
   else a64(addr)->store(value, std::memory_order_release);
 }
@@ -111,6 +130,7 @@ TDH_API unsigned int tdh_atomic_cas32(void* addr, unsigned int cmp, unsigned int
 }
 // cmp: 0 = EQ, 1 = GE (signed distance, wrap-safe).  Returns 0 on success, 1 on timeout (hang detection).
 TDH_API int tdh_wait32(void* addr, unsigned int value, int cmp, long long timeout_us) {
+  chaos();
   const auto t0 = std::chrono::steady_clock::now();
   unsigned spins = 0;
   while (true) {

@@ -22,3 +22,10 @@ def test_cpu_world3_fused_and_ep():
 
 def test_cpu_world4_collectives():
     run_dist(["allreduce", "allgather", "moe", "sp_pp"], nproc=4, env_extra=CPU_ENV)
+
+
+def test_cpu_chaos():
+    """Random 0..3 ms delays in front of every notify / wait: ranks drift apart arbitrarily between protocol steps, so parity
+    double-buffering, phase counters and slot reuse of every multi-call case are exercised under skew."""
+    env = dict(CPU_ENV, TD_HOST_CHAOS_US="3000")
+    run_dist(["ag_gemm", "gemm_rs", "gemm_ar", "gemm_a2a", "allreduce", "ep_ll", "ep_normal"], nproc=3, env_extra=env)
