@@ -10,6 +10,8 @@ for a in "$@"; do
     *) ARGS+=("$a");;
   esac
 done
+REPO_ROOT="$(cd "$(dirname "${BASH_SOURCE[0]}")/.." && pwd)"
+export PYTHONPATH="$REPO_ROOT${PYTHONPATH:+:$PYTHONPATH}"      # run from a checkout without installing the package
 export TD_SYMM_HEAP_SIZE=${TD_SYMM_HEAP_SIZE:-${NVSHMEM_SYMMETRIC_SIZE:-4g}}
 export CUDA_DEVICE_MAX_CONNECTIONS=${CUDA_DEVICE_MAX_CONNECTIONS:-1}
 export NCCL_DEBUG=${NCCL_DEBUG:-ERROR}
