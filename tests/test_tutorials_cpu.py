@@ -1,0 +1,20 @@
+"""The tutorials run end to end on the emulation backend (torchrun, gloo, 2 ranks) -- they are the first thing a user tries."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from _launch import ROOT, free_port
+
+
+@pytest.mark.parametrize("script,expect", [("01_notify_wait.py", "rounds OK"), ("03_ag_gemm_gemm_rs.py", "ag_gemm -> gemm_rs OK"),
+                                           ("06_sequence_parallel_attention.py", "gemm + all-to-all")])
+def test_tutorial(script, expect):
+    env = dict(os.environ, TD_FORCE_HOST_BACKEND="1", CUDA_VISIBLE_DEVICES="", TD_SYMM_HEAP_SIZE="256m", OMP_NUM_THREADS="2",
+               PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(free_port()), os.path.join(ROOT, "tutorials", script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert expect in r.stdout + r.stderr
