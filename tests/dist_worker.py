@@ -404,6 +404,28 @@ def case_ep_normal():
         _assert_close(out, ref, 0.15 if big else 1e-4, 5e-2 if big else 1e-4, f"ep_normal it{it}")
     U.barrier_all_host()
     ctx.finalize()
+    if not big:
+        # the Mega-EP style op object (lazy sizing -> materialize -> dispatch+GEMM half -> GEMM+combine half)
+        from triton_dist.parallel.ep import EPConfig, EpAll2AllFusedOp
+        op = EpAll2AllFusedOp(EPConfig(T, H, topk, E, me, W, False, dtype))
+        assert op.get_nvshmem_size() > 0 and op.layer is None
+        op.materialize()
+        g = torch.Generator().manual_seed(555 + me)
+        x = (torch.randn(T, H, generator=g) * 0.5).to(dtype)
+        idx = torch.stack([torch.randperm(E, generator=g)[:topk] for _ in range(T)]).to(torch.int32)
+        wts = torch.softmax(torch.randn(T, topk, generator=g), -1)
+        assert int(op.preprocess(idx).sum()) == T * topk
+        act, handle = op.mega_dispatch_group_gemm(x, idx, wts, my_gu)
+        out = op.mega_group_gemm_combine(act, handle, my_dn)
+        ref = torch.zeros(T, H)
+        for t in range(T):
+            for k in range(topk):
+                e = int(idx[t, k])
+                hh = x[t].float() @ w_gu[e].float().t()
+                ref[t] += float(wts[t, k]) * ((torch.nn.functional.silu(hh[:I]) * hh[I:]).to(dtype).float() @ w_dn[e].float().t())
+        _assert_close(out, ref, 1e-4, 1e-4, "EpAll2AllFusedOp")
+        U.barrier_all_host()
+        op.finalize()
 
 
 def case_sp_pp():

@@ -47,6 +47,35 @@ class EPLowLatencyAllToAllLayer:
     def combine(self, expert_out: torch.Tensor, topk_indices: torch.Tensor, topk_weights: torch.Tensor, meta):
         return EP.ep_ll_combine(self.ctx, expert_out, topk_indices, topk_weights, meta)
 
+    # ---- tracing (reference: dump_dispatch_trace / dump_combine_trace, ep_ll_a2a_layer.py) ------------------
+    def _dump_trace(self, name: str, fn, path: str, iters: int = 5):
+        """Device-timed spans of ``iters`` calls written as a Chrome / Perfetto trace (one track per rank)."""
+        import json
+        spans = []
+        if torch.cuda.is_available() and self.ctx.staging.is_cuda:
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+            origin = torch.cuda.Event(enable_timing=True)
+            origin.record()
+            for a, b in evs:
+                a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            spans = [(origin.elapsed_time(a) * 1e3, a.elapsed_time(b) * 1e3) for a, b in evs]
+        else:
+            import time
+            t0 = time.perf_counter()
+            for _ in range(iters):
+                s0 = time.perf_counter(); fn(); spans.append(((s0 - t0) * 1e6, (time.perf_counter() - s0) * 1e6))
+        ev = [{"name": name, "ph": "X", "ts": ts, "dur": dur, "pid": f"rank{self.ctx.rank}", "tid": name} for ts, dur in spans]
+        with open(path, "w") as f:
+            json.dump({"traceEvents": ev}, f)
+        return spans
+
+    def dump_dispatch_trace(self, send_tokens: torch.Tensor, topk_indices: torch.Tensor, path: str = "ep_dispatch_trace.json", iters: int = 5):
+        return self._dump_trace("ep_ll_dispatch", lambda: self.dispatch(send_tokens, None, topk_indices), path, iters)
+
+    def dump_combine_trace(self, expert_out, topk_indices, topk_weights, meta, path: str = "ep_combine_trace.json", iters: int = 5):
+        return self._dump_trace("ep_ll_combine", lambda: self.combine(expert_out, topk_indices, topk_weights, meta), path, iters)
+
     def finalize(self):
         self.ctx.finalize()
 
@@ -301,4 +330,71 @@ class TritonDistFusedEpMoeFunction(torch.autograd.Function):
         return _Combine.apply(y.to(rx.dtype), ids, w, src_info, recv_range, layer)
 
 
-EpAll2AllFusedOp = EP_MoE
+class EpAll2AllFusedOp:
+    """The reference's Mega-EP op (layers/nvidia/ep_a2a_fused_layer.py:71-763): lazily sized symmetric buffers, then
+    ``mega_dispatch_group_gemm`` (dispatch + gate/up grouped GEMM + SwiGLU) and ``mega_group_gemm_combine`` (down grouped GEMM +
+    combine).  Here the two halves run on the throughput-mode exchange: received rows are consumed in place through TMA gather4 index
+    lists (no receive-side copy between dispatch and the GEMM), the down GEMM's epilogue scatters to pair order, and combine
+    pre-reduces per token on the expert rank."""
+
+    def __init__(self, ep_config: EPConfig):
+        self.cfg = ep_config
+        self.layer: Optional[EPNormalAll2AllLayer] = None
+
+    # lazy allocation (the reference sizes the NVSHMEM heap from these numbers before materialising)
+    def get_nvshmem_size(self) -> int:
+        c = self.cfg
+        esz = torch.empty(0, dtype=c.dtype).element_size()
+        W = c.world_size
+        per_parity = W * c.max_tokens * c.hidden * esz * 2 + W * c.max_tokens * c.topk * 16 + W * c.max_tokens * 16 + W * 16 + W * 4
+        return 2 * per_parity
+
+    get_nvshmem_size_gb = lambda self: self.get_nvshmem_size() / 2 ** 30
+
+    def materialize(self):
+        if self.layer is None:
+            self.layer = EPNormalAll2AllLayer(self.cfg)
+        return self
+
+    def preprocess(self, topk_indices: torch.Tensor):
+        return M.histogram_by_expert(topk_indices, self.cfg.num_experts)
+
+    def mega_dispatch_group_gemm(self, x: torch.Tensor, topk_indices: torch.Tensor, topk_weights: torch.Tensor, w_gate_up: torch.Tensor):
+        """-> (activations in the sorted expert layout, handle)."""
+        from ..ops import ep_normal as EN
+        self.materialize()
+        h = self.layer.dispatch(x, topk_indices, topk_weights)
+        epr = self.layer.ctx.experts_per_rank
+        r = M.moe_align_sort(h.pair_expert.view(-1, 1), epr, 128)
+        n_pairs = h.pair_expert.numel()
+        if h.rx_flat.is_cuda:
+            valid = r.sorted_ids != r.pad_id
+            g = torch.where(valid, h.pair_row[r.sorted_ids.clamp(max=n_pairs - 1).long()], torch.full_like(r.sorted_ids, -1))
+            hid = M.moe_grouped_gemm_fused(h.rx_flat, w_gate_up, r, 1, r.capacity, gather_idx=g, scatter=False)
+        else:
+            ids = r.sorted_ids.long()
+            valid = ids != r.pad_id
+            xs = torch.zeros((r.capacity, h.rx_flat.shape[1]), dtype=h.rx_flat.dtype)
+            xs[valid] = h.rx_flat[h.pair_row[ids[valid]].long()]
+            hid = M.moe_grouped_gemm(xs, w_gate_up, r)
+        return silu_mul(hid), (h, r, topk_indices)
+
+    mega_preprocess_group_gemm = mega_dispatch_group_gemm
+
+    def mega_group_gemm_combine(self, act: torch.Tensor, handle, w_down: torch.Tensor) -> torch.Tensor:
+        h, r, topk_indices = handle
+        n_pairs = h.pair_expert.numel()
+        if act.is_cuda:
+            y = M.moe_grouped_gemm_fused(act, w_down, r, 1, n_pairs, gather=False)
+        else:
+            ys = M.moe_grouped_gemm(act, w_down, r)
+            ids = r.sorted_ids.long()
+            valid = ids != r.pad_id
+            y = torch.zeros((n_pairs, ys.shape[1]), dtype=ys.dtype)
+            y[ids[valid]] = ys[valid]
+        return self.layer.combine(y, h, topk_indices)
+
+    def finalize(self):
+        if self.layer is not None:
+            self.layer.finalize()
+            self.layer = None
