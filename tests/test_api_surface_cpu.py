@@ -24,3 +24,29 @@ def test_api_surface(mod):
     m = importlib.import_module(mod)
     missing = [n for n in CHECK[mod].split() if not hasattr(m, n)]
     assert not missing, f"{mod} lacks {missing}"
+
+
+LAYER_METHODS = {
+    "TP_MLP": "_init_parameters _init_ctx torch_fwd dist_triton_fwd dist_triton_AR_fwd dist_triton_gemm_ar_fwd torch_ag_gemm dist_triton_ag_gemm torch_gemm_rs dist_triton_gemm_rs",
+    "TP_Attn": "_init_parameters _init_ctx torch_fwd dist_triton_fwd dist_triton_AR_fwd dist_triton_gemm_ar_fwd",
+    "TP_MoE": "torch_fwd dist_triton_fwd",
+    "EP_MoE": "torch_fwd dist_triton_fwd",
+    "EPAll2AllLayer": "preprocess dispatch combine dispatch_postprocess",
+    "EPLowLatencyAllToAllLayer": "dispatch combine dump_dispatch_trace dump_combine_trace",
+    "EpAll2AllFusedOp": "preprocess mega_preprocess_group_gemm mega_dispatch_group_gemm mega_group_gemm_combine get_nvshmem_size materialize",
+    "GemmARLayer": "forward",
+    "AllGatherLayer": "forward_pull forward_push_2d forward_push_3d forward_push_2d_ll forward_push_numa_2d forward_push_2d_ll_multimem",
+    "SpGQAFlashDecodeAttention": "forward",
+    "UlyssesSPAllToAllLayer": "pre_attn_qkv_pack_a2a",
+    "CommOp": "read write set_signal wait_signal",
+    "PPCommLayer": "send recv",
+}
+
+
+@pytest.mark.parametrize("cls", sorted(LAYER_METHODS))
+def test_layer_methods(cls):
+    """Method names of the reference's layer classes."""
+    import triton_dist.layers.nvidia as L
+    c = getattr(L, cls)
+    missing = [n for n in LAYER_METHODS[cls].split() if not hasattr(c, n)]
+    assert not missing, f"{cls} lacks {missing}"
