@@ -24,7 +24,7 @@ namespace {
 constexpr int kMKThreads = 256;
 constexpr int kMaxB = 8;
 
-enum TaskType : int { T_RMSNORM = 1, T_LINEAR = 2, T_QKROPE = 3, T_ATTN = 4, T_ALLREDUCE = 5, T_COPY = 6, T_ATTN_COMBINE = 7 };
+enum TaskType : int { T_RMSNORM = 1, T_LINEAR = 2, T_QKROPE = 3, T_ATTN = 4, T_ALLREDUCE = 5, T_COPY = 6, T_ATTN_COMBINE = 7, T_SILU_MUL = 8, T_ADD = 9, T_PREFETCH = 10 };
 
 struct Task {            // 16 x int32
   int type, dep_idx, dep_count, sig_idx;
@@ -342,6 +342,43 @@ TD_DEVICE void task_attn(const MKParams& p, const Task& t, uint8_t* smem) {
   }
 }
 
+// ---- stand-alone element-wise tasks of the reference's builder (the dense model fuses them into neighbouring tasks) ----
+// SILU_MUL: out[b, i] = silu(x[b, i]) * x[b, I + i].  a: x, out, I, v0, v1 (16-byte vector range of the [B, I] output)
+TD_DEVICE void task_silu_mul(const MKParams& p, const Task& t) {
+  const uint4* x = (const uint4*)p.ptrs[t.a[0]];
+  uint4* out = (uint4*)p.ptrs[t.a[1]];
+  const int ivec = t.a[2] / 8;
+  for (int v = t.a[3] + threadIdx.x; v < t.a[4]; v += kMKThreads) {
+    const int b = v / ivec, i = v % ivec;
+    float g[8], u[8];
+    unpack8(x[static_cast<size_t>(b) * 2 * ivec + i], g);
+    unpack8(x[static_cast<size_t>(b) * 2 * ivec + ivec + i], u);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) g[e] = g[e] / (1.f + __expf(-g[e])) * u[e];
+    out[v] = pack8(g);
+  }
+}
+// ADD: out = lhs + rhs over 16-byte vectors [v0, v1).  a: lhs, rhs, out, v0, v1
+TD_DEVICE void task_add(const MKParams& p, const Task& t) {
+  const uint4* a = (const uint4*)p.ptrs[t.a[0]];
+  const uint4* b = (const uint4*)p.ptrs[t.a[1]];
+  uint4* out = (uint4*)p.ptrs[t.a[2]];
+  for (int v = t.a[3] + threadIdx.x; v < t.a[4]; v += kMKThreads) {
+    float x[8], y[8];
+    unpack8(a[v], x); unpack8(b[v], y);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] += y[e];
+    out[v] = pack8(x);
+  }
+}
+// PREFETCH: pull bytes [off, off + n) of a weight into L2 ahead of the tasks that stream it.  a: w, off_kb, n_kb
+TD_DEVICE void task_prefetch(const MKParams& p, const Task& t) {
+  const char* w = reinterpret_cast<const char*>(p.ptrs[t.a[0]]) + static_cast<size_t>(t.a[1]) * 1024;
+  const size_t bytes = static_cast<size_t>(t.a[2]) * 1024;
+  for (size_t off = static_cast<size_t>(threadIdx.x) * 16384; off < bytes; off += static_cast<size_t>(kMKThreads) * 16384)
+    ptx::prefetch_l2_bulk(w + off, static_cast<uint32_t>(min(bytes - off, size_t(16384))));
+}
+
 // ---- ATTN_COMBINE: LSE-merge of the split-KV partials of (b, kv head).  a: part, out, b, kvh, Hq, Hkv, n_splits ----
 TD_DEVICE void task_attn_combine(const MKParams& p, const Task& t) {
   const float* part = (const float*)p.ptrs[t.a[0]];
@@ -455,6 +492,9 @@ __global__ void __launch_bounds__(kMKThreads, 1) mega_kernel(const MKParams p) {
       case T_QKROPE: task_qkrope(p, t); break;
       case T_ATTN: task_attn(p, t, smem); break;
       case T_ATTN_COMBINE: task_attn_combine(p, t); break;
+      case T_SILU_MUL: task_silu_mul(p, t); break;
+      case T_ADD: task_add(p, t); break;
+      case T_PREFETCH: task_prefetch(p, t); break;
       case T_ALLREDUCE: task_allreduce(p, t, epoch); break;
       default: break;
     }

@@ -215,3 +215,20 @@ def test_gdn_recurrent_cpu_fallback():
     o, s = fused_recurrent_gated_delta_rule(q, k, v, g, beta)
     o2, s2 = gated_delta_rule_recurrent(q, k, v, g, beta)
     torch.testing.assert_close(o, o2); torch.testing.assert_close(s, s2)
+
+
+def test_megakernel_elementwise_tasks(dist_env):
+    """make_silu_mul_up / make_add / make_prefetch of the builder (task graph interpreted by the emulation path)."""
+    from triton_dist.mega_kernel import ModelBuilder
+    B, inter = 3, 64
+    mb = ModelBuilder(B, num_sms=4)
+    x = torch.randn(B, 2 * inter)
+    act, r, out = torch.zeros(B, inter), torch.randn(B, inter), torch.zeros(B, inter)
+    w = torch.randn(256, 64)
+    d = mb.make_prefetch(w)
+    d = mb.make_silu_mul_up(x, act, dep=d)
+    mb.make_add(act, r, out, dep=d)
+    mb.compile().run()
+    ref = torch.nn.functional.silu(x[:, :inter]) * x[:, inter:]
+    torch.testing.assert_close(act, ref)
+    torch.testing.assert_close(out, ref + r)

@@ -20,8 +20,8 @@ from .. import _C
 from .. import utils as U
 from ..ops.comm import SymmArgs, symm_args
 
-T_RMSNORM, T_LINEAR, T_QKROPE, T_ATTN, T_ALLREDUCE, T_ATTN_COMBINE = 1, 2, 3, 4, 5, 7
-TASK_NAMES = {1: "rms_norm", 2: "linear", 3: "qk_norm_rope_update_kvcache", 4: "flash_decode", 5: "allreduce", 7: "flash_decode_combine"}
+T_RMSNORM, T_LINEAR, T_QKROPE, T_ATTN, T_ALLREDUCE, T_ATTN_COMBINE, T_SILU_MUL, T_ADD, T_PREFETCH = 1, 2, 3, 4, 5, 7, 8, 9, 10
+TASK_NAMES = {1: "rms_norm", 2: "linear", 3: "qk_norm_rope_update_kvcache", 4: "flash_decode", 5: "allreduce", 7: "flash_decode_combine", 8: "silu_mul_up", 9: "add", 10: "prefetch"}
 
 
 class _MegaArgs(C.Structure):
@@ -166,6 +166,36 @@ class ModelBuilder:
                                                               self.ptr(residual_out), s * per, min(nvec, (s + 1) * per), 0, n_slices, s]))
         return sig, n_slices
 
+    # stand-alone element-wise / prefetch tasks of the reference's builder (model_builder.py:336,451,494); the dense model uses the
+    # fused forms (SwiGLU inside fc2's operand staging, residual add inside the all-reduce, weight prefetch inside the dispatcher)
+    def _elementwise(self, ttype, ptrs, nvec, dep, extra=()):
+        sig = self.counter()
+        d = dep or (-1, 0)
+        n_tasks = max(1, min(self.num_sms, (nvec + 2047) // 2048))
+        per = (nvec + n_tasks - 1) // n_tasks
+        for i in range(n_tasks):
+            self._add(Task(ttype, d[0], d[1], sig, list(ptrs) + list(extra) + [i * per, min(nvec, (i + 1) * per)]))
+        return sig, n_tasks
+
+    def make_silu_mul_up(self, fc1_out, act_out, dep=None):
+        """act_out[B, I] = silu(fc1_out[:, :I]) * fc1_out[:, I:]."""
+        inter = fc1_out.shape[-1] // 2
+        return self._elementwise(T_SILU_MUL, [self.ptr(fc1_out), self.ptr(act_out)], self.B * inter // 8, dep, extra=[inter])
+
+    def make_add(self, lhs, rhs, output, dep=None):
+        return self._elementwise(T_ADD, [self.ptr(lhs), self.ptr(rhs), self.ptr(output)], output.numel() // 8, dep)
+
+    def make_prefetch(self, weight, dep=None):
+        """DRAM -> L2 prefetch of a whole weight, spread over the CTAs (one 16 KB bulk prefetch per thread per step)."""
+        sig = self.counter()
+        d = dep or (-1, 0)
+        kb = (weight.numel() * weight.element_size()) // 1024
+        n_tasks = max(1, min(self.num_sms, (kb + 4095) // 4096))
+        per = (kb + n_tasks - 1) // n_tasks
+        for i in range(n_tasks):
+            self._add(Task(T_PREFETCH, d[0], d[1], sig, [self.ptr(weight), i * per, max(0, min(kb, (i + 1) * per) - i * per)]))
+        return sig, n_tasks
+
     def make_barrier_all_intra_node(self, *a, **k):
         return None   # not needed: the all-reduce tasks carry their own epoch flags
 
@@ -294,6 +324,16 @@ class ModelBuilder:
                 ll = (rows[:, :, 1] * c).sum(0)
                 o = (rows[:, :, 2:] * c[:, :, None]).sum(0) / ll[:, None]
                 P[a[1]].view(B, Hq, -1)[b, kvh * G:(kvh + 1) * G] = o.to(P[a[1]].dtype)
+            elif t.type == T_SILU_MUL:
+                inter = a[2]
+                x = P[a[0]].view(B, -1).float()
+                y = (torch.nn.functional.silu(x[:, :inter]) * x[:, inter:2 * inter]).to(P[a[1]].dtype)
+                P[a[1]].view(-1)[a[3] * 8:a[4] * 8] = y.reshape(-1)[a[3] * 8:a[4] * 8]
+            elif t.type == T_ADD:
+                v0, v1 = a[3] * 8, a[4] * 8
+                P[a[2]].view(-1)[v0:v1] = (P[a[0]].view(-1)[v0:v1].float() + P[a[1]].view(-1)[v0:v1].float()).to(P[a[2]].dtype)
+            elif t.type == T_PREFETCH:
+                pass
             elif t.type == T_ALLREDUCE:
                 part, flags = P[a[0]], P[a[1]]
                 v0, v1, sl = a[4] * 8, a[5] * 8, a[8]
