@@ -408,3 +408,45 @@ def triton_dist_key() -> str:
     for p in sorted((Path(__file__).resolve().parents[2] / "csrc").rglob("*.cu*")):
         h.update(p.read_bytes())
     return h.hexdigest()[:16]
+
+
+# ------------------------------------------------------------------------------------------------------------
+# reference spellings of the stream-ordered flag / copy helpers and the device search helpers
+# (kernels/nvidia/common_ops.py:264-414)
+# ------------------------------------------------------------------------------------------------------------
+def _set_signal_cuda(signal, value: int, stream=None):
+    """cuStreamWriteValue32 on ``stream`` (``signal``: 1-element int32 tensor or raw pointer)."""
+    return set_signal(signal, value, stream)
+
+
+def _wait_eq_cuda(signal, value: int, stream=None):
+    """cuStreamWaitValue32(EQ) on ``stream``."""
+    return wait_eq(signal, value, stream)
+
+
+def _memcpy_async_cuda(dst: torch.Tensor, src: torch.Tensor, stream=None):
+    """cudaMemcpyAsync on ``stream`` (peer views of the symmetric heap are ordinary device pointers: the copy engine moves them)."""
+    if stream is None or not dst.is_cuda:
+        dst.copy_(src, non_blocking=True)
+        return dst
+    with torch.cuda.stream(stream):
+        dst.copy_(src, non_blocking=True)
+    return dst
+
+
+def bisect_left(sorted_values: torch.Tensor, x) -> torch.Tensor:
+    """First index i with sorted_values[i] >= x (the reference's device search helper; here ``torch.searchsorted``)."""
+    xv = torch.as_tensor(x, device=sorted_values.device, dtype=sorted_values.dtype)
+    return torch.searchsorted(sorted_values, xv, right=False)
+
+
+def bisect_right(sorted_values: torch.Tensor, x) -> torch.Tensor:
+    xv = torch.as_tensor(x, device=sorted_values.device, dtype=sorted_values.dtype)
+    return torch.searchsorted(sorted_values, xv, right=True)
+
+
+def get_device_property(device=None):
+    """``torch.cuda.get_device_properties`` of the current device (SM count, name, memory); None without a GPU."""
+    if not torch.cuda.is_available():
+        return None
+    return torch.cuda.get_device_properties(device if device is not None else torch.cuda.current_device())
