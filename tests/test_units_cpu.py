@@ -232,3 +232,24 @@ def test_megakernel_elementwise_tasks(dist_env):
     ref = torch.nn.functional.silu(x[:, :inter]) * x[:, inter:]
     torch.testing.assert_close(act, ref)
     torch.testing.assert_close(out, ref + r)
+
+
+def test_jit_compile_user_kernel():
+    """A user kernel written against the device header compiles for sm_100a (no GPU needed) and exports its launcher."""
+    from triton_dist.jit import SymmCtx, compile_cuda
+    lib = compile_cuda(r"""
+        #include "td/primitives.cuh"
+        using namespace td;
+        __global__ void ring(SymmCtx c, uint32_t* flag, float* data, uint32_t round) {
+          const int nxt = (c.rank + 1) % c.world;
+          symm_at(c, data, nxt)[threadIdx.x] = c.rank * 100.f + round;
+          __syncthreads();
+          if (threadIdx.x == 0) notify(c, flag, nxt, round);
+          if (threadIdx.x < 32) wait<true, true>(flag, 1, round);
+        }
+        extern "C" void launch_ring(SymmCtx c, void* flag, void* data, unsigned round, void* stream) {
+          ring<<<1, 64, 0, (cudaStream_t)stream>>>(c, (uint32_t*)flag, (float*)data, round);
+        }""", name="ring_test")
+    assert hasattr(lib, "launch_ring")
+    import ctypes
+    assert ctypes.sizeof(SymmCtx) == 32

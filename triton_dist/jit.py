@@ -1,0 +1,65 @@
+"""Compile-and-load for user CUDA kernels written against the device header (``csrc/td/primitives.cuh`` / ``ptx.cuh``).
+
+The reference lets users write distributed kernels in its Triton dialect (``triton_dist.jit``, python/triton_dist/jit.py:274-313) or in
+the little_kernel DSL whose runtime shells out to nvcc and loads the result through the driver API
+(python/little_kernel/runtime/compiler.py, cuda_runtime.py).  Here a kernel is CUDA C++: ``compile_cuda(source)`` runs
+``nvcc -gencode arch=compute_100a,code=sm_100a`` with the header tree on the include path, caches the shared object by content hash and
+returns a ``ctypes.CDLL``.  The source provides its own ``extern "C"`` launcher(s); ``symm_args()`` gives the struct the device
+primitives need (rank, world, heap base / stride, multicast base).
+
+    lib = compile_cuda(r'''
+        #include "td/primitives.cuh"
+        using namespace td;
+        __global__ void ring(SymmCtx c, uint32_t* flag, float* data, uint32_t round) {
+          const int nxt = (c.rank + 1) % c.world;
+          symm_at(c, data, nxt)[threadIdx.x] = c.rank * 100.f + round;           // data, then ...
+          __syncthreads();
+          if (threadIdx.x == 0) notify(c, flag, nxt, round);                      // ... the flag (release, system scope)
+          if (threadIdx.x < 32) wait<true, true>(flag, 1, round);                 // my predecessor's flag (acquire)
+        }
+        extern "C" void launch_ring(SymmCtx c, void* flag, void* data, unsigned round, void* stream) {
+          ring<<<1, 64, 0, (cudaStream_t)stream>>>(c, (uint32_t*)flag, (float*)data, round);
+        }''')
+"""
+from __future__ import annotations
+
+import ctypes as C
+import hashlib
+import os
+import subprocess
+from pathlib import Path
+from typing import Sequence
+
+from . import _build
+
+_CACHE = Path(os.environ.get("TD_JIT_CACHE", str(_build.ROOT / "build" / "jit")))
+
+
+class SymmCtx(C.Structure):
+    """Mirror of ``td::SymmCtx`` (csrc/td/primitives.cuh) for by-value kernel arguments."""
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("base", C.c_ulonglong), ("stride", C.c_ulonglong), ("mc_base", C.c_ulonglong)]
+
+
+def symm_ctx() -> SymmCtx:
+    """The symmetric-heap description of this process (after ``initialize_distributed``)."""
+    from . import utils as U
+    r, w, base, stride, mc = U.symm_ctx_fields()
+    return SymmCtx(int(r), int(w), int(base), int(stride), int(mc))
+
+
+def compile_cuda(source: str, extra_flags: Sequence[str] = (), name: str = "kernel") -> C.CDLL:
+    """nvcc -> shared object -> ``ctypes.CDLL``.  Works without a GPU (cross-compiles sm_100a); launching needs one."""
+    flags = list(_build.GENCODE) + ["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-cudart", "shared",
+                                    "-I", str(_build.CSRC)] + list(extra_flags)
+    key = hashlib.sha256((source + "\0" + " ".join(flags)).encode()).hexdigest()[:16]
+    _CACHE.mkdir(parents=True, exist_ok=True)
+    so = _CACHE / f"{name}_{key}.so"
+    if not so.exists():
+        src = _CACHE / f"{name}_{key}.cu"
+        src.write_text(source)
+        tmp = _CACHE / f"{name}_{key}.{os.getpid()}.tmp.so"
+        r = subprocess.run([_build._nvcc(), "-shared", *flags, "-o", str(tmp), str(src)], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed:\n{r.stderr[-4000:]}")
+        os.replace(tmp, so)
+    return C.CDLL(str(so))
