@@ -85,6 +85,14 @@ def create_ll_gemm_ar_context(ar_stream=None, rank: Optional[int] = None, world_
     return ctx
 
 
+def create_gemm_ar_context_auto(rank: int, world_size: int, max_M: int, N: int, dtype: torch.dtype = torch.bfloat16) -> GemmARContext:
+    """What the TP layers use: the single-kernel (low-latency) context for decode-sized batches (max_M <= 256, as the
+    reference's GemmARLayer picks its LL kernel, tp_mlp.py:197-199), the two-kernel NVLS context otherwise.
+    ``TD_GEMM_AR_FUSED=0`` forces the two-kernel path."""
+    make = create_ll_gemm_ar_context if (max_M <= 256 and U.get_bool_env("TD_GEMM_AR_FUSED", True)) else create_gemm_ar_context
+    return make(None, rank, world_size, world_size, max_M, N, dtype)
+
+
 def default_ar_config(M: int, N: int, K: int, n_comm: int = 16, num_sms: int = 148) -> GemmConfig:
     """Small-M decode shapes: narrow tiles so that enough CTAs work on the K-reduction; the comm CTAs take the SMs the
     GEMM has no tile for (a comm CTA reduces its tiles one after the other and each NVLS round trip is ~2 us, so every idle

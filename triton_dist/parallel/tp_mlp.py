@@ -17,7 +17,7 @@ from ..ops import comm
 from ..ops.ag_gemm import ag_gemm, create_ag_gemm_context
 from ..ops.elementwise import silu_mul
 from ..ops.gemm import gemm
-from ..ops.gemm_ar import create_gemm_ar_context, create_ll_gemm_ar_context, gemm_allreduce_op, low_latency_gemm_allreduce_op
+from ..ops.gemm_ar import create_gemm_ar_context_auto, low_latency_gemm_allreduce_op
 from ..ops.gemm_rs import create_gemm_rs_context, gemm_rs
 
 
@@ -74,8 +74,7 @@ class TP_MLP:
                                                 self.world_size, self.world_size)
 
     def _init_gemm_ar_ctx(self, max_M: int, dtype=torch.bfloat16):
-        self.gemm_ar_ctx = (create_ll_gemm_ar_context if (max_M <= 256 and U.get_bool_env('TD_GEMM_AR_FUSED', True)) else create_gemm_ar_context)(None, self.rank, self.world_size, self.world_size, max_M,
-                                                  self.down_proj.shape[0], dtype)
+        self.gemm_ar_ctx = create_gemm_ar_context_auto(self.rank, self.world_size, max_M, self.down_proj.shape[0], dtype)
 
     def finalize(self):
         for c in (self.ag_ctx, self.rs_ctx, self.ar_ctx, self.gemm_ar_ctx):
