@@ -198,6 +198,9 @@ def main():
         bns = sorted({base.bn, 128, 256})
         cands = [("sm", GemmConfig(bn, base.cta_group, base.group_m, True, 0, nc)) for nc in (16, 32, 48) for bn in bns]
         cands += [("copy_engine", GemmConfig(bn, base.cta_group, base.group_m, True, 0, 0)) for bn in bns]
+        if os.environ.get("TD_AG_MULTICAST", "0") == "1" and U.is_nvshmem_multimem_supported():
+            # opt-in: NVLS multicast push (validated for numerics at TP2, not yet timed at TP8 -- see docs/status.md)
+            cands += [("multicast", GemmConfig(bn, base.cta_group, base.group_m, True, 0, nc)) for nc in (8, 16) for bn in bns]
         best = None
         for tr, cfg in cands:
             ag_choice.update(transport=tr, cfg=cfg)

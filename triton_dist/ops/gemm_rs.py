@@ -66,6 +66,9 @@ def default_rs_config(M: int, N: int, K: int, world: int) -> GemmConfig:
     per owner block instead of once per m-tile (measured: group_m=1 made the 4096x12288x6144 GEMM DRAM bound)."""
     mr = M // max(world, 1)
     if mr % 256 == 0 and N >= 256:
+        if U.get_bool_env("TD_RS_BN192", False) and N % 192 == 0:
+            # opt-in (not yet timed on hardware): 192-wide tiles trade 10.4 waves of 256x256 for 13.8 shorter ones on 74 CTA pairs
+            return GemmConfig(bn=192, cta_group=2, group_m=max(1, mr // 256), use_tma_store=False)
         return GemmConfig(bn=256, cta_group=2, group_m=max(1, mr // 256), use_tma_store=False)
     gm = max(1, mr // 128)
     if mr % 128 == 0 and N >= 256:
