@@ -196,7 +196,9 @@ def main():
     if W > 1:
         base = default_ag_config(AG["M"], AG["N"] // W, AG["K"], W)
         bns = sorted({base.bn, 128, 256})
-        cands = [("sm", GemmConfig(bn, base.cta_group, base.group_m, True, 0, nc)) for nc in (16, 32, 48) for bn in bns]
+        # comm-CTA counts: 16/32/48 fill the NVLink port to different degrees; 20/24 leave 64/62 CTA pairs, i.e. the 64 tiles of the
+        # TP8 column shard (128-wide tiles) still fit in one wave
+        cands = [("sm", GemmConfig(bn, base.cta_group, base.group_m, True, 0, nc)) for nc in (16, 20, 24, 32, 48) for bn in bns]
         cands += [("copy_engine", GemmConfig(bn, base.cta_group, base.group_m, True, 0, 0)) for bn in bns]
         if os.environ.get("TD_AG_MULTICAST", "0") == "1" and U.is_nvshmem_multimem_supported():
             # opt-in: NVLS multicast push (validated for numerics at TP2, not yet timed at TP8 -- see docs/status.md)
