@@ -253,3 +253,58 @@ def test_jit_compile_user_kernel():
     assert hasattr(lib, "launch_ring")
     import ctypes
     assert ctypes.sizeof(SymmCtx) == 32
+
+
+def test_symmetric_heap_fuzz(dist_env):
+    """Random allocate / free sequences: live tensors never overlap, stay 256-byte aligned inside the segment, and freeing
+    everything returns the heap to one hole (the next big allocation lands at the first offset again)."""
+    import random
+    U = dist_env
+    heap = U.get_heap()
+    rng = random.Random(1234)
+    probe = U.nvshmem_create_tensor((8,), torch.uint8)
+    first = heap.offset_of(probe)
+    U.nvshmem_free_tensor_sync(probe)
+    live = []
+    for step in range(300):
+        if live and (rng.random() < 0.45 or len(live) > 40):
+            t = live.pop(rng.randrange(len(live)))
+            U.nvshmem_free_tensor_sync(t)
+        else:
+            n = rng.choice([1, 7, 64, 1000, 4096, 100_000])
+            t = U.nvshmem_create_tensor((n,), rng.choice([torch.uint8, torch.bfloat16, torch.float32, torch.int64]))
+            t.fill_(step % 100)
+            live.append(t)
+        spans = sorted((heap.offset_of(t), heap.offset_of(t) + t.numel() * t.element_size()) for t in live)
+        for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+            assert a1 <= b0, "live symmetric tensors overlap"
+        assert all(s[0] % 256 == 0 for s in spans)
+    for t in live:
+        U.nvshmem_free_tensor_sync(t)
+    again = U.nvshmem_create_tensor((1 << 20,), torch.uint8)
+    assert heap.offset_of(again) == first
+    U.nvshmem_free_tensor_sync(again)
+
+
+def test_moe_align_sort_properties():
+    """Routing invariants for random inputs (emulation path = the specification of the CUDA kernel): every routed pair appears exactly
+    once, inside its expert's tile range; unrouted pairs never appear; expert segments are tile aligned."""
+    from triton_dist.ops import moe as M
+    g = torch.Generator().manual_seed(5)
+    for trial in range(20):
+        T = int(torch.randint(1, 200, (1,), generator=g))
+        E = int(torch.randint(1, 12, (1,), generator=g))
+        topk = int(torch.randint(1, min(E, 4) + 1, (1,), generator=g))
+        bm = [16, 64, 128][trial % 3]
+        ids = torch.stack([torch.randperm(E, generator=g)[:topk] for _ in range(T)]).to(torch.int32)
+        ids[torch.rand(T, topk, generator=g) < 0.1] = -1
+        r = M.moe_align_sort(ids, E, bm)
+        flat = ids.reshape(-1)
+        s = r.sorted_ids
+        valid = s[s != r.pad_id].long()
+        assert sorted(valid.tolist()) == sorted(torch.nonzero(flat >= 0).flatten().tolist())
+        assert r.capacity % bm == 0 and all(int(o) % bm == 0 for o in r.expert_offsets)
+        for pos in torch.nonzero(s != r.pad_id).flatten().tolist():
+            e = int(flat[int(s[pos])])
+            assert int(r.expert_offsets[e]) <= pos < int(r.expert_offsets[e + 1])
+            assert int(r.tile_expert[pos // bm]) == e
