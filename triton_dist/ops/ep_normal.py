@@ -143,30 +143,44 @@ def ep_dispatch_normal(ctx: EPNormalContext, x: torch.Tensor, topk_idx: torch.Te
     return EPNormalHandle(par, ctx.rx[par].view(W * ctx.T_max, H), pair_expert, pair_row, rcnt, T)
 
 
-def ep_expert_ffn_normal(ctx: EPNormalContext, h: EPNormalHandle, w_gate_up: torch.Tensor, w_down: torch.Tensor) -> torch.Tensor:
-    """SwiGLU FFN of the local experts over the received pairs; returns ``y_pairs`` [W * P_max, H] in received-pair order.
-    w_gate_up: [epr, 2I, H], w_down: [epr, H, I].  On GPUs the gate/up GEMM gathers its rows from ``rx`` by TMA and the down GEMM
-    scatters its rows to pair order from the epilogue (dispatch + grouped GEMM / grouped GEMM + combine of the reference's Mega-EP)."""
+def ep_ffn_up_normal(ctx: EPNormalContext, h: EPNormalHandle, w_gate_up: torch.Tensor):
+    """Gate/up grouped GEMM + SwiGLU over the received pairs.  Returns ``(act [capacity, I] in the expert-sorted layout, routing)``.
+    On GPUs the GEMM gathers its rows straight out of ``rx`` with TMA tile::gather4 (index list = received row of every sorted pair)."""
     from .elementwise import silu_mul
-    epr = ctx.experts_per_rank
-    r = M.moe_align_sort(h.pair_expert.view(-1, 1), epr, 128)
+    r = M.moe_align_sort(h.pair_expert.view(-1, 1), ctx.experts_per_rank, 128)
     n_pairs = h.pair_expert.numel()
     if h.rx_flat.is_cuda:
         valid = r.sorted_ids != r.pad_id
         g = torch.where(valid, h.pair_row[r.sorted_ids.clamp(max=n_pairs - 1).long()], torch.full_like(r.sorted_ids, -1))
         hid = M.moe_grouped_gemm_fused(h.rx_flat, w_gate_up, r, 1, r.capacity, gather_idx=g, scatter=False)
-        act = silu_mul(hid)
-        return M.moe_grouped_gemm_fused(act, w_down, r, 1, n_pairs, gather_idx=None, gather=False)
+    else:
+        ids = r.sorted_ids.long()
+        valid = ids != r.pad_id
+        xs = torch.zeros((r.capacity, h.rx_flat.shape[1]), dtype=h.rx_flat.dtype)
+        xs[valid] = h.rx_flat[h.pair_row[ids[valid]].long()]
+        hid = M.moe_grouped_gemm(xs, w_gate_up, r)
+    return silu_mul(hid), r
+
+
+def ep_ffn_down_normal(ctx: EPNormalContext, h: EPNormalHandle, act: torch.Tensor, r, w_down: torch.Tensor) -> torch.Tensor:
+    """Down grouped GEMM; rows leave the epilogue in received-pair order ``[W * P_max, H]`` (what combine consumes)."""
+    n_pairs = h.pair_expert.numel()
+    if act.is_cuda:
+        return M.moe_grouped_gemm_fused(act, w_down, r, 1, n_pairs, gather=False)
+    ys = M.moe_grouped_gemm(act, w_down, r)
     ids = r.sorted_ids.long()
     valid = ids != r.pad_id
-    xs = torch.zeros((r.capacity, h.rx_flat.shape[1]), dtype=h.rx_flat.dtype)
-    xs[valid] = h.rx_flat[h.pair_row[ids[valid]].long()]
-    hid = M.moe_grouped_gemm(xs, w_gate_up, r)
-    act = silu_mul(hid)
-    ys = M.moe_grouped_gemm(act, w_down, r)
     y = torch.zeros((n_pairs, ys.shape[1]), dtype=ys.dtype)
     y[ids[valid]] = ys[valid]
     return y
+
+
+def ep_expert_ffn_normal(ctx: EPNormalContext, h: EPNormalHandle, w_gate_up: torch.Tensor, w_down: torch.Tensor) -> torch.Tensor:
+    """SwiGLU FFN of the local experts over the received pairs; returns ``y_pairs`` [W * P_max, H] in received-pair order.
+    w_gate_up: [epr, 2I, H], w_down: [epr, H, I].  The two halves are the dispatch + grouped GEMM / grouped GEMM + combine stages of the
+    reference's Mega-EP op (:func:`ep_ffn_up_normal`, :func:`ep_ffn_down_normal`)."""
+    act, r = ep_ffn_up_normal(ctx, h, w_gate_up)
+    return ep_ffn_down_normal(ctx, h, act, r, w_down)
 
 
 def ep_combine_normal(ctx: EPNormalContext, y_pairs: torch.Tensor, h: EPNormalHandle, topk_idx: torch.Tensor) -> torch.Tensor:

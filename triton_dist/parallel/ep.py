@@ -364,34 +364,15 @@ class EpAll2AllFusedOp:
         from ..ops import ep_normal as EN
         self.materialize()
         h = self.layer.dispatch(x, topk_indices, topk_weights)
-        epr = self.layer.ctx.experts_per_rank
-        r = M.moe_align_sort(h.pair_expert.view(-1, 1), epr, 128)
-        n_pairs = h.pair_expert.numel()
-        if h.rx_flat.is_cuda:
-            valid = r.sorted_ids != r.pad_id
-            g = torch.where(valid, h.pair_row[r.sorted_ids.clamp(max=n_pairs - 1).long()], torch.full_like(r.sorted_ids, -1))
-            hid = M.moe_grouped_gemm_fused(h.rx_flat, w_gate_up, r, 1, r.capacity, gather_idx=g, scatter=False)
-        else:
-            ids = r.sorted_ids.long()
-            valid = ids != r.pad_id
-            xs = torch.zeros((r.capacity, h.rx_flat.shape[1]), dtype=h.rx_flat.dtype)
-            xs[valid] = h.rx_flat[h.pair_row[ids[valid]].long()]
-            hid = M.moe_grouped_gemm(xs, w_gate_up, r)
-        return silu_mul(hid), (h, r, topk_indices)
+        act, r = EN.ep_ffn_up_normal(self.layer.ctx, h, w_gate_up)
+        return act, (h, r, topk_indices)
 
     mega_preprocess_group_gemm = mega_dispatch_group_gemm
 
     def mega_group_gemm_combine(self, act: torch.Tensor, handle, w_down: torch.Tensor) -> torch.Tensor:
+        from ..ops import ep_normal as EN
         h, r, topk_indices = handle
-        n_pairs = h.pair_expert.numel()
-        if act.is_cuda:
-            y = M.moe_grouped_gemm_fused(act, w_down, r, 1, n_pairs, gather=False)
-        else:
-            ys = M.moe_grouped_gemm(act, w_down, r)
-            ids = r.sorted_ids.long()
-            valid = ids != r.pad_id
-            y = torch.zeros((n_pairs, ys.shape[1]), dtype=ys.dtype)
-            y[ids[valid]] = ys[valid]
+        y = EN.ep_ffn_down_normal(self.layer.ctx, h, act, r, w_down)
         return self.layer.combine(y, h, topk_indices)
 
     def finalize(self):
