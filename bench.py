@@ -128,6 +128,7 @@ def main():
     from triton_dist.ops.ag_gemm import default_ag_config
     from triton_dist.ops.gemm import GemmConfig
     ag_choice = {"transport": "sm", "cfg": None}
+    ag_autotune_log = []
 
     def step_ours(i):
         s = sets[i % nset]
@@ -210,6 +211,8 @@ def main():
                 t = timed(lambda i: ag_gemm(sets[i % nset]["ag_a"], sets[i % nset]["ag_b"].t(), ag_ctx, out=ag_out, gemm_config=cfg, transport=tr), 8, 3)
             except Exception:      # noqa: BLE001
                 continue
+            # isolated (back-to-back ag_gemm only) device time of every candidate, max over ranks: reported for analysis
+            ag_autotune_log.append({"transport": tr, "n_comm_ctas": cfg.n_comm_ctas, "bn": cfg.bn, "us": round(t * 1e3, 1)})
             if best is None or t < best[0]:
                 best = (t, tr, cfg)
         ag_choice.update(transport=best[1], cfg=best[2])
@@ -233,7 +236,7 @@ def main():
                    "parallelism": f"tp{W}", "l2": f"inputs rotate over {nset} sets ({(ag_bytes + rs_bytes) * nset >> 20} MiB/rank > 2x L2)"},
         "gpu_launches": (2 + (W if ag_choice["transport"] == "copy_engine" and W > 1 else 0)) * args.steps, "impl": "ours",
         "ag_transport": {"transport": ag_choice["transport"], "n_comm_ctas": ag_choice["cfg"].n_comm_ctas if ag_choice["cfg"] else 0,
-                         "bn": ag_choice["cfg"].bn if ag_choice["cfg"] else 0}, "native_libs": [os.path.basename(p) for p in _C.loaded_libraries()],
+                         "bn": ag_choice["cfg"].bn if ag_choice["cfg"] else 0, "isolated_us_per_candidate": ag_autotune_log}, "native_libs": [os.path.basename(p) for p in _C.loaded_libraries()],
         "clocks": clocks,
     }
 
