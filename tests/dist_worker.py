@@ -115,6 +115,47 @@ def case_allreduce():
     ctx.finalize()
 
 
+def case_allreduce_ll():
+    """Flag-in-data low-latency all-reduce (opt-in; GPU only): numerics over many back-to-back calls (buffer halves and phases are
+    reused), with a straggler, plus its CUDA-graph latency next to the NVLS one-shot kernel."""
+    from triton_dist.ops import comm
+    dev = U.current_device()
+    if dev.type != "cuda":
+        return
+    W = U.world_size()
+    ctx = comm.create_allreduce_ctx(1 << 20, U.rank(), W, W)
+    gen = torch.Generator().manual_seed(77)
+    for it in range(40):
+        n = int(torch.randint(1, 2048, (1,), generator=gen).item()) * 8
+        for dtype in (torch.bfloat16, torch.float16, torch.float32):
+            x = (torch.randn(n, device=dev) * 0.5).to(dtype)
+            ref = x.clone()
+            dist.all_reduce(ref, group=U.get_triton_dist_world())
+            if it in (3, 17) and U.rank() == it % W:
+                torch.cuda._sleep(2_000_000)
+            out = comm.all_reduce(x, comm.AllReduceMethod.OneShot_LL, ctx)
+            tol = 2e-2 if dtype != torch.float32 else 1e-4
+            _assert_close(out, ref, tol * 4, tol, f"allreduce LL {dtype} n={n} it{it}")
+    x = torch.randn(4096, device=dev).to(torch.bfloat16)
+    o = torch.empty_like(x)
+    for name, m in (("OneShot_LL", comm.AllReduceMethod.OneShot_LL), ("OneShot_Multimem", comm.AllReduceMethod.OneShot_Multimem)):
+        for _ in range(3):
+            comm.all_reduce(x, m, ctx, output=o)
+        torch.cuda.synchronize(); dist.barrier(group=U.get_triton_dist_world())
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(20):
+                comm.all_reduce(x, m, ctx, output=o)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g.replay(); torch.cuda.synchronize(); dist.barrier(group=U.get_triton_dist_world())
+        e0.record()
+        for _ in range(10):
+            g.replay()
+        e1.record(); torch.cuda.synchronize()
+        U.dist_print(f"all_reduce 8 KB {name}: {e0.elapsed_time(e1) / 200 * 1e3:.2f} us per call (CUDA graph)", allowed_ranks=[0])
+    ctx.finalize()
+
+
 def case_ag_gemm():
     from triton_dist.ops.ag_gemm import ag_gemm, create_ag_gemm_context
     dev = U.current_device()

@@ -50,3 +50,13 @@ def test_flash_v3_perf():
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
         print(f"\nflash {name}: {ms:.3f} ms  {4 * 32 * 8192 * 8192 * 128 / 2 / ms / 1e9:.0f} TFLOP/s")
+
+
+def test_allreduce_ll_two_gpus():
+    """Flag-in-data all-reduce (csrc/allreduce_ll.cu) on 2 GPUs."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from _launch import run_dist
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    print(run_dist(["allreduce_ll"], nproc=2, timeout=200)[-600:])

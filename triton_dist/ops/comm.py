@@ -80,6 +80,7 @@ class AllReduceMethod(enum.Enum):
     TwoShot_Multimem = 6
     TwoShot_Multimem_ST = 7
     AllReduce_Max = 8
+    OneShot_LL = 9          # flag-in-data low-latency protocol for tiny messages (csrc/allreduce_ll.cu); opt-in, see docs/status.md
 
 
 class OverlappingAllReduceMethod(enum.Enum):
@@ -137,10 +138,11 @@ class AllReduceContext:
     host_calls: int = 0             # emulation backend
 
     def finalize(self):
-        for t in (self.stage, self.stage2, self.slots):
+        for t in (self.stage, self.stage2, self.slots, getattr(self, "ll_buf", None)):
             if t is not None:
                 U.get_heap().free_tensor(t)
         self.stage = self.stage2 = self.slots = None
+        self.ll_buf = None
 
     def symm_input(self, nbytes: int, dtype: torch.dtype) -> torch.Tensor:
         """Zero-copy entry: the staging buffer the NEXT call will reduce; a producer may write straight into it
@@ -194,6 +196,10 @@ def all_reduce(x: torch.Tensor, method=AllReduceMethod.Unknown, ctx: AllReduceCo
         method = AllReduceMethod.OneShot if method == AllReduceMethod.OneShot_Multimem else AllReduceMethod.TwoShot
     if straggler_option and straggler_option[0] == ctx.rank:
         torch.cuda._sleep(int(straggler_option[1]))
+    if method == AllReduceMethod.OneShot_LL:
+        if nbytes <= _LL_MAX_BYTES:
+            return _all_reduce_ll(x, ctx, output, stream)
+        method = get_auto_allreduce_method(nbytes)
     lib = _C.cuda_lib()
     xb = x.view(torch.uint8).view(-1)
     ob = output.view(torch.uint8).view(-1)
@@ -212,6 +218,37 @@ def all_reduce(x: torch.Tensor, method=AllReduceMethod.Unknown, ctx: AllReduceCo
         a.slots, a.phase = ctx.slots.data_ptr(), ctx.phase.data_ptr()
         _C.check(lib.td_allreduce(C.byref(a), _stream(stream)), "td_allreduce")
         off += n
+    return output
+
+
+_LL_MAX_BYTES = 64 << 10
+
+
+class _ARLLArgs(C.Structure):
+    _fields_ = [("rank", c_ll), ("world", c_ll), ("base", C.c_ulonglong), ("stride", C.c_ulonglong), ("mc_base", C.c_ulonglong),
+                ("inp", c_void_p), ("out", c_void_p), ("buf", c_void_p), ("max_words", c_ll), ("nbytes", c_ll), ("phase", c_void_p),
+                ("dtype", c_ll), ("grid", c_ll)]
+
+
+_C.register("td_allreduce_ll", C.c_int, [C.POINTER(_ARLLArgs), c_void_p])
+
+
+def _all_reduce_ll(x: torch.Tensor, ctx: AllReduceContext, output: torch.Tensor, stream=None) -> torch.Tensor:
+    """Flag-in-data all-reduce (<= 64 KB): one kernel, no fence, no barrier.  Its buffer is created on first use (a collective
+    allocation: every rank reaches the first LL call together) and is never touched by the other methods."""
+    W = ctx.world_size
+    max_words = _LL_MAX_BYTES // 4
+    if getattr(ctx, "ll_buf", None) is None:
+        ctx.ll_buf = U.get_heap().tensor((2, W, max_words, 2), torch.int32)
+        ctx.ll_phase = torch.zeros(4, dtype=torch.int32, device=x.device)
+        U.barrier_all_host()
+    a = _ARLLArgs()
+    r, w, base, stride, mc = U.symm_ctx_fields()
+    a.rank, a.world, a.base, a.stride, a.mc_base = r, w, base, stride, mc
+    a.inp, a.out, a.buf = x.data_ptr(), output.data_ptr(), ctx.ll_buf.data_ptr()
+    a.max_words, a.nbytes, a.phase = max_words, x.numel() * x.element_size(), ctx.ll_phase.data_ptr()
+    a.dtype, a.grid = _DT[x.dtype], 0
+    _C.check(_C.cuda_lib().td_allreduce_ll(C.byref(a), _stream(stream)), "td_allreduce_ll")
     return output
 
 
