@@ -167,7 +167,9 @@ __global__ void __launch_bounds__(128) qk_norm_rope_kv_kernel(
     const int kvh = is_v ? h - Hq - Hkv : h - Hq;
     uint2* cache = is_v ? v_cache : k_cache;
     const size_t b = batch_idx ? batch_idx[t] : 0;
-    cache[((b * max_len + pos) * Hkv + kvh) * 32 + lane] = o;
+    // never write past the cache row: a position beyond max_len would land in the next batch row / past the allocation
+    // (Engine.serve and KV_Cache.inc_offset reject such requests on the host; this is the device-side guard)
+    if (pos >= 0 && pos < max_len) cache[((b * max_len + pos) * Hkv + kvh) * 32 + lane] = o;
   }
 }
 

@@ -34,6 +34,11 @@ struct TdGemmArgs {
   // gather / scatter (MoE grouped GEMM without the gather_rows / scatter_rows passes)
   const void* a_gather; long long a_gather_div; long long a_gather_pad; long long a_src_rows; const void* c_scatter;
   long long expert_stride_rows;   // grouped mode: rows between consecutive experts in B (0 = N); lets a launch use an N-slice of every expert
+  // split-K tail (0 / null = off): fp32 scratch + flags (zero-initialised, re-armed by the kernel)
+  void* sk_ws; long long sk_ws_bytes; void* sk_flags; long long sk_flag_count; long long sk_max_parts;
+  long long rs_skip_wait;         // RS GEMM-only twin
+  long long rs_fp32;              // RS ring partial sums in fp32 (staging buffers are [M, N] fp32)
+  long long ag_kslices;           // multicast AG: requested number of K slices (0 = default)
 };
 
 static int encode_tmap(CUtensorMap* out, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
@@ -191,10 +196,6 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
   grid -= grid % cg;
   if (p.n_comm_ctas % cg) p.n_comm_ctas += cg - p.n_comm_ctas % cg;
   const int tiles = p.num_m * p.num_n;
-  // never launch more GEMM clusters than tiles (idle CTAs would only spin up TMEM)
-  int gemm_ctas = grid - p.n_comm_ctas;
-  if (gemm_ctas < cg) { drv::set_error("no CTAs left for the GEMM (n_comm_ctas too large)"); return -1; }
-  if (gemm_ctas / cg > tiles) gemm_ctas = tiles * cg;
   if (a->tile_expert && a->group_m > 1) p.group_m = 1;   // grouped: keep experts' tiles together (n fastest)
   if (a->mode == kAG && a->world > 1 && a->ag_skip_wait == 0) {
     if (p.n_comm_ctas < cg) p.n_comm_ctas = 16;
@@ -203,20 +204,21 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
   if (a->mode == kAG && a->ag_skip_wait == 2) p.n_comm_ctas = 0;      // copy-engine transport: every SM runs GEMM tiles
   p.ag_nslices = (a->ag_skip_wait == 2) ? 1 : p.n_comm_ctas;
   if (a->mode == kAG && a->ag_skip_wait == 3) {
-    // NVLS multicast transport: every rank writes its shard once to the multicast alias; sub-slice j = the rows of the j-th
-    // m tile of the shard, consumed in (j, source) order
+    // NVLS multicast transport: every rank writes its shard once to the multicast alias, K slice by K slice
     if (!a->mc_base) { drv::set_error("ag_gemm: multicast transport needs an NVLS multicast mapping"); return -1; }
     if (a->ag_copy_local == 2) { drv::set_error("ag_gemm: the all-to-all flavour cannot use the multicast transport"); return -1; }
-    if (p.n_comm_ctas < cg) { drv::set_error("ag_gemm: the multicast transport needs n_comm_ctas >= cta_group"); return -1; }
-    const int tps = (int)(a->ag_rows_per_rank / TM);
-    int nsub = (a->ag_rows_per_rank % TM == 0 && tps >= 1) ? tps : 1;
-    while (nsub > 1 && p.n_comm_ctas * nsub > kAGMaxSlices) nsub >>= 1;
+    if (a->a_gather || fp8) { drv::set_error("ag_gemm: the multicast transport takes dense 16-bit A"); return -1; }
+    if (a->ag_rows_per_rank % BM != 0) { drv::set_error("ag_gemm: multicast transport needs (M / world) %% 128 == 0"); return -1; }
+    if (p.n_comm_ctas < cg) p.n_comm_ctas = 16;
+    int ks = (int)(a->ag_kslices > 0 ? a->ag_kslices : 8);
+    if (ks > p.num_k) ks = p.num_k;
+    while (ks > 1 && p.n_comm_ctas * ks > kAGMaxSlices) --ks;
+    if (p.n_comm_ctas * ks > kAGMaxSlices) { drv::set_error("ag_gemm: too many comm CTAs for the flag array"); return -1; }
     p.ag_multicast = 1;
-    p.ag_nslices = p.n_comm_ctas * nsub;
-    if (a->ag_rows_per_rank % TM == 0 && nsub == tps && tps > 1 && !a->tile_expert) {
-      p.ag_interleave = tps; p.group_m = (int)a->world; p.m_rot = 0;
-    }
-    grid = gemm_ctas + p.n_comm_ctas;
+    p.ag_kb_per_slice = (p.num_k + ks - 1) / ks;
+    p.ag_kslices = (p.num_k + p.ag_kb_per_slice - 1) / p.ag_kb_per_slice;
+    p.ag_rows_per_cta = (int)((a->ag_rows_per_rank + p.n_comm_ctas - 1) / p.n_comm_ctas);
+    p.ag_nslices = p.n_comm_ctas * p.ag_kslices;
   }
   if (a->mode == kAG && a->ag_skip_wait == 0 && p.n_comm_ctas > 0 && a->world <= 4) {
     // few destinations: publish each CTA's share in 4 (TP2) / 2 (TP4) interleaved sub-slices (finer arrival flags)
@@ -235,6 +237,31 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
     if (encode_tmap(&p.tmap_al, a->ag_a_local, 2, dims, strides, box, bf16)) return -1;
     p.ag_local_direct = 1;
   }
+  p.rs_skip_wait = (int)a->rs_skip_wait; p.rs_fp32 = (int)a->rs_fp32;
+  if (p.n_comm_ctas % cg) p.n_comm_ctas += cg - p.n_comm_ctas % cg;
+  if (a->mode == kAR && p.a2a_cols_per_rank > 0) p.n_comm_ctas = 0;     // GEMM + all-to-all: the epilogue scatters, no comm CTAs
+  int gemm_ctas = grid - p.n_comm_ctas;      // comm CTAs must be co-resident with the GEMM CTAs: the grid never exceeds the SMs
+  if (gemm_ctas < cg) { drv::set_error("no CTAs left for the GEMM (n_comm_ctas too large)"); return -1; }
+
+  // ---- split-K tail: cut the tiles of the last partial wave into K ranges so that idle clusters share them ----
+  p.sk_full = tiles; p.sk_rem = 0; p.sk_parts = 1; p.total_units = tiles;
+  if (a->sk_ws && a->sk_flags && a->mode != kAR && !a->tile_expert && !a->a_gather && !a->c_scatter) {
+    const int workers = gemm_ctas / cg;
+    const int full = (tiles / workers) * workers, rem = tiles - full;
+    if (rem > 0) {
+      int parts = workers / rem;
+      if (parts > (int)a->sk_max_parts) parts = (int)a->sk_max_parts;
+      while (parts > 1 && p.num_k / parts < 16) --parts;
+      const long long need = (long long)rem * (parts - 1) * cg * BM * bn * 4;
+      if (parts > 1 && need <= a->sk_ws_bytes && (long long)rem * (parts - 1) * cg <= a->sk_flag_count) {
+        p.sk_full = full; p.sk_rem = rem; p.sk_parts = parts; p.total_units = full + rem * parts;
+        p.sk_ws = reinterpret_cast<float*>(a->sk_ws); p.sk_flags = reinterpret_cast<uint32_t*>(a->sk_flags);
+      }
+    }
+  }
+
+  // never launch more GEMM clusters than work units (idle CTAs would only spin up TMEM)
+  if (gemm_ctas / cg > p.total_units) gemm_ctas = p.total_units * cg;
   grid = gemm_ctas + p.n_comm_ctas;
 
   if (a->mode == kAR) {
@@ -244,8 +271,6 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
         drv::set_error("gemm_a2a: N must be world * cols_per_rank and cols_per_rank a multiple of the tile width"); return -1;
       }
       if (p.M > p.a2a_rows_per_src) { drv::set_error("gemm_a2a: M exceeds the receive slot"); return -1; }
-      p.n_comm_ctas = 0;
-      grid = gemm_ctas;
     } else {
     if (p.n_comm_ctas < cg) { drv::set_error("gemm_ar needs comm CTAs"); return -1; }
     if (p.num_m * cg * p.num_n > p.rs_flag_tiles) { drv::set_error("gemm_ar: flag array too small for this shape"); return -1; }

@@ -46,7 +46,7 @@ constexpr int kEpiThreads = 128;
 constexpr int kCBlockCols = 64;                       // epilogue staging block: 128 rows x 64 cols (16-bit) = 16 KB
 constexpr int kCBlockBytes = BM * kCBlockCols * 2;
 constexpr int kAGRowsPerChunk = 128;                  // AG arrival-flag granularity (rows of a source shard)
-constexpr int kAGMaxSlices = 64;                      // max comm CTAs (= arrival flags per source rank)
+constexpr int kAGMaxSlices = 256;                     // arrival flags per source rank (comm CTAs x sub-slices / K slices)
 
 enum Mode : int { kPlain = 0, kAG = 1, kRS = 2, kAR = 3 };
 
@@ -88,8 +88,10 @@ struct Params {
   int ag_copy_local;         // 1: comm CTAs copy a_local -> workspace; 0: caller already wrote the workspace; 2: all-to-all (block d of a_local -> rank d)
   int ag_skip_wait;          // GEMM-only twin: never wait (measures exposed communication)
   int ag_multicast;          // 1: comm CTAs write my shard ONCE to the NVLS multicast alias of the workspace (the switch fans it
-                             //    out to every rank) and publish the flags on all ranks -- one stage instead of world-1
-  int ag_interleave;         // > 0 (= m tiles per source): tile order visits the j-th tile of every source before the (j+1)-th
+                             //    out to every rank), K slice by K slice, and publish flag[me][slice * n_comm + cta] on all ranks
+  int ag_kslices;            // multicast: number of K slices (every tile starts after 1/ag_kslices of the transfer and follows it)
+  int ag_kb_per_slice;       // k-blocks (128 bytes of a row) per K slice
+  int ag_rows_per_cta;       // shard rows pushed by one comm CTA
   int ag_local_direct;       // 1: tiles of my own rows read a_local through tmap_al (no local copy, no flag wait)
   CUtensorMap tmap_al;       // {K, rows of a_local}
   int ag_nslices;            // arrival flags per source rank (= comm CTAs, or 1 when the copy engine does the transfer)
@@ -100,6 +102,8 @@ struct Params {
   uint32_t* ag_ready;        // [world]: ag_ready[s] >= p  <=>  rank s has its phase-p shard in ITS workspace (symmetric)
   // ---- RS (ring) ----
   int rs_rows_per_rank;      // M / world, multiple of BM * cta_group
+  int rs_skip_wait;          // GEMM-only twin: never wait for the partial of rank+1 (adds whatever the staging holds)
+  int rs_fp32;               // 1: running partial sums travel in fp32 (one rounding at the owner instead of W-1 roundings)
   int pad2;
   char* rs_stage;            // symmetric: 2 buffers of [M, N] 16-bit running partial sums, written by rank+1
   long long rs_stage_buf_bytes;
@@ -118,7 +122,25 @@ struct Params {
   uint32_t* a2a_count;       // local [world] tile counters (last tile for a destination publishes the flag)
   void* rs_out;              // [rows_per_rank, N] final output (local)
   long long rs_ldo;
+  // ---- split-K tail: the last partial wave of tiles is cut into sk_parts K ranges that run on otherwise idle clusters;
+  // parts > 0 park their fp32 accumulator in sk_ws, part 0 adds them in its epilogue (wave quantisation: 768 tiles on
+  // 74 CTA pairs = 10.4 waves -> 10.5 instead of 11)
+  int sk_full, sk_rem, sk_parts, total_units;
+  float* sk_ws;              // [sk_rem][sk_parts - 1][cta_group][BM * BN] fp32
+  uint32_t* sk_flags;        // [sk_rem][sk_parts - 1][cta_group], 0 between launches
 };
+
+// one schedulable unit of work: a tile and a K range of it
+struct Unit { int tile, kb0, kb1, part, slot; };
+TD_DEVICE Unit get_unit(const Params& p, int u) {
+  Unit x;
+  if (u < p.sk_full || p.sk_parts <= 1) { x.tile = u; x.kb0 = 0; x.kb1 = p.num_k; x.part = 0; x.slot = -1; return x; }
+  const int i = u - p.sk_full;
+  x.slot = i % p.sk_rem; x.part = i / p.sk_rem; x.tile = p.sk_full + x.slot;
+  x.kb0 = static_cast<int>(static_cast<long long>(x.part) * p.num_k / p.sk_parts);
+  x.kb1 = static_cast<int>(static_cast<long long>(x.part + 1) * p.num_k / p.sk_parts);
+  return x;
+}
 
 // -------------------------------------------------------------------------------------------------
 // shared-memory carve-up (GEMM CTAs)
@@ -163,14 +185,6 @@ TD_DEVICE void tile_coords(const Params& p, int t, int& m_tile, int& n_tile) {
   const int band_m = min(p.num_m - first_m, p.group_m);
   const int r = t - band * per_band;
   n_tile = r / band_m;
-  if (p.ag_interleave > 0) {
-    // multicast all-gather: all shards arrive concurrently, sub-slice by sub-slice -> consume the j-th tile of every source
-    // (own source first) before the (j+1)-th.  Logical index L = j * world + source offset.
-    const int L = first_m + r % band_m;
-    const int j = L / p.symm.world, s = (p.symm.rank + L % p.symm.world) % p.symm.world;
-    m_tile = s * p.ag_interleave + j;
-    return;
-  }
   m_tile = first_m + r % band_m + p.m_rot;
   if (m_tile >= p.num_m) m_tile -= p.num_m;
 }
@@ -202,6 +216,16 @@ TD_DEVICE void ag_wait_rows(const Params& p, uint32_t ph, int row0, int row1) {
   ptx::fence_proxy_async();
 }
 
+// K-sliced (multicast) transport: rows [r_local, r_local + BM) of source s, K slice j.  Comm CTA c of the source pushes rows
+// [c * rows_per_cta, (c + 1) * rows_per_cta) of every slice and publishes flag[s][j * n_comm + c].
+TD_DEVICE void ag_wait_kslice(const Params& p, uint32_t ph, int s, int r_local, int j) {
+  const uint32_t* flags = p.ag_flags + (ph & 1u) * p.symm.world * kAGMaxSlices + s * kAGMaxSlices + j * p.n_comm_ctas;
+  const int c0 = r_local / p.ag_rows_per_cta;
+  const int c1 = (min(r_local + BM, p.ag_rows_per_rank) - 1) / p.ag_rows_per_cta;
+  for (int c = c0; c <= c1; ++c) wait_ge<true>(flags + c, ph);
+  ptx::fence_proxy_async();
+}
+
 // -------------------------------------------------------------------------------------------------
 // AG producer side (comm CTA c): PUSH byte slice c of my shard into every rank's workspace, nearest consumer
 // first (rank-1 starts with my rows right after its own; at any moment every rank pushes to a different peer,
@@ -229,31 +253,36 @@ TD_DEVICE void ag_comm_cta(const Params& p, uint32_t ph, int comm_idx) {
   const int nsub = max(1, p.ag_nslices / max(1, p.n_comm_ctas));
   if (p.ag_multicast) {
     // NVLS transport: one multimem.st per 16 bytes reaches every rank's workspace (including mine); egress is the shard
-    // itself, not (world - 1) copies of it, so a handful of CTAs is enough and there is a single fence per sub-slice
+    // itself, not (world - 1) copies of it, so a handful of CTAs is enough.  The shard travels K slice by K slice
+    // (all rows of columns [j * seg, (j + 1) * seg)), so on the consumer EVERY tile starts after 1 / ag_kslices of the
+    // transfer and its mainloop follows the arrival: the tail after the last byte is one K slice of MMAs + the epilogue.
     char* ws_mc = symm_mc(p.symm, ws) + shard_off;
-    for (int j = 0; j < nsub; ++j) {
-      const int sidx = j * p.n_comm_ctas + comm_idx;
-      const size_t b0 = min(shard_bytes, slice * sidx), b1 = min(shard_bytes, b0 + slice);
+    const int r0 = comm_idx * p.ag_rows_per_cta, r1 = min(Ms, r0 + p.ag_rows_per_cta);
+    const size_t seg_bytes = static_cast<size_t>(p.ag_kb_per_slice) * 128;
+    for (int j = 0; j < p.ag_kslices; ++j) {
+      const size_t col0 = j * seg_bytes;
+      const int seg16 = static_cast<int>((min(row_bytes, col0 + seg_bytes) - col0) >> 4);
+      const int n = max(0, r1 - r0) * seg16;
       if (threadIdx.x == 0) prof_record(p.prof, pslot, 1, true);
-      const size_t n = (b1 - b0) >> 4;
-      const uint4* sv = reinterpret_cast<const uint4*>(src0 + b0);
-      uint4* dv = reinterpret_cast<uint4*>(ws_mc + b0);
       constexpr int U = 8;
-      size_t i = threadIdx.x;
-      for (; i + (U - 1) * static_cast<size_t>(kThreads) < n; i += U * static_cast<size_t>(kThreads)) {
-        uint4 v[U];
+      for (int i0 = threadIdx.x; i0 < n; i0 += U * kThreads) {
+        uint4 v[U]; size_t off[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) v[u] = ptx::ld_nc_v4(sv + i + u * static_cast<size_t>(kThreads));
+        for (int u = 0; u < U; ++u) {
+          const int i = i0 + u * kThreads;
+          off[u] = static_cast<size_t>(r0 + i / seg16) * row_bytes + col0 + static_cast<size_t>(i % seg16) * 16;
+          if (i < n) v[u] = ptx::ld_nc_v4(src0 + off[u]);
+        }
 #pragma unroll
-        for (int u = 0; u < U; ++u) ptx::multimem_st_v4(dv + i + u * static_cast<size_t>(kThreads), v[u]);
+        for (int u = 0; u < U; ++u)
+          if (i0 + u * kThreads < n) ptx::multimem_st_v4(ws_mc + off[u], v[u]);
       }
-      for (; i < n; i += kThreads) ptx::multimem_st_v4(dv + i, ptx::ld_nc_v4(sv + i));
       __syncthreads();
       if (threadIdx.x == 0) {
         prof_record(p.prof, pslot, 1, false);
         prof_record(p.prof, pslot, 6, true);
         ptx::fence_acq_rel_sys();
-        for (int d = 0; d < W; ++d) ptx::st_relaxed_sys(symm_at(p.symm, flag_base + sidx, (me + d) % W), ph);
+        for (int d = 0; d < W; ++d) ptx::st_relaxed_sys(symm_at(p.symm, flag_base + j * p.n_comm_ctas + comm_idx, (me + d) % W), ph);
         prof_record(p.prof, pslot, 6, false);
       }
     }
@@ -424,9 +453,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
       // lane l owns rows 4l..4l+3 of the 128-row tile: one tile::gather4 per k-block per lane, B by lane 0
       if constexpr (kCtaGroup == 1 && !kFP8) {
         int stage = 0; uint32_t phase = 0;
-        for (int t = worker; t < total_tiles; t += n_workers) {
+        for (int u = worker; u < p.total_units; u += n_workers) {
+          const Unit un = get_unit(p, u);
           int m_tile, n_tile;
-          tile_coords(p, t, m_tile, n_tile);
+          tile_coords(p, un.tile, m_tile, n_tile);
           int expert = 0;
           if (p.tile_expert) { expert = p.tile_expert[m_tile]; if (expert < 0) continue; }
           const int row0 = m_tile * TM;
@@ -464,7 +494,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             if (r3 >= 0) r3 += par_rows;
           }
           __syncwarp();
-          for (int kb = 0; kb < p.num_k; ++kb) {
+          for (int kb = un.kb0; kb < un.kb1; ++kb) {
             if (lane == 0) {
               ptx::mbar_wait(empty_bar + stage, phase ^ 1u);
               ptx::mbar_arrive_expect_tx(full_bar + stage, L::kTxBytes);
@@ -482,16 +512,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
       // ================================ TMA producer ================================
       if (lane == 0) {
         int stage = 0; uint32_t phase = 0;
-        for (int t = worker; t < total_tiles; t += n_workers) {
+        for (int u = worker; u < p.total_units; u += n_workers) {
+          const Unit un = get_unit(p, u);
           int m_tile, n_tile;
-          tile_coords(p, t, m_tile, n_tile);
+          tile_coords(p, un.tile, m_tile, n_tile);
           int expert = 0;
           if (p.tile_expert) { expert = p.tile_expert[m_tile]; if (expert < 0) continue; }
           const int row0 = m_tile * TM + static_cast<int>(cta_rank) * BM;       // my 128 rows of A
           const int brow0 = expert * p.expert_rows + n_tile * BN + static_cast<int>(cta_rank) * (BN / kCtaGroup);
           if constexpr (kMode == kAG) {
             prof_record(p.prof, static_cast<int>(blockIdx.x) * 8, 3, true);
-            if (!p.ag_skip_wait && row0 < p.M) ag_wait_rows(p, ph, row0, min(p.M, row0 + BM));
+            if (!p.ag_skip_wait && !p.ag_kslices && row0 < p.M) ag_wait_rows(p, ph, row0, min(p.M, row0 + BM));
             prof_record(p.prof, static_cast<int>(blockIdx.x) * 8, 3, false);
           }
           const int abuf = (kMode == kAG) ? static_cast<int>(ph & 1u) : 0;
@@ -503,7 +534,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
               lrow0 = (p.ag_copy_local == 2) ? row0 : row0 - p.symm.rank * p.ag_rows_per_rank;
             }
           }
-          for (int kb = 0; kb < p.num_k; ++kb) {
+          // K-sliced all-gather: before the first k-block of every K slice, acquire that slice of my 128 rows
+          const bool ks_wait = (kMode == kAG) && p.ag_kslices > 0 && !p.ag_skip_wait && !a_local && row0 < p.M;
+          const int ks_src = ks_wait ? row0 / p.ag_rows_per_rank : 0;
+          for (int kb = un.kb0; kb < un.kb1; ++kb) {
+            if constexpr (kMode == kAG) {
+              if (ks_wait && (kb == un.kb0 || kb % p.ag_kb_per_slice == 0))
+                ag_wait_kslice(p, ph, ks_src, row0 - ks_src * p.ag_rows_per_rank, kb / p.ag_kb_per_slice);
+            }
             ptx::mbar_wait(empty_bar + stage, phase ^ 1u);
             uint8_t* sa = smem + stage * L::kStageBytes;
             uint8_t* sb = sa + L::kABytes;
@@ -546,17 +584,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         (void)idesc;
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int t = worker; t < total_tiles; t += n_workers) {
+        for (int u = worker; u < p.total_units; u += n_workers) {
+          const Unit un = get_unit(p, u);
           if (p.tile_expert) {
             int m_tile, n_tile;
-            tile_coords(p, t, m_tile, n_tile);
+            tile_coords(p, un.tile, m_tile, n_tile);
             if (p.tile_expert[m_tile] < 0) continue;
           }
           ptx::mbar_wait(tmem_empty + acc, acc_phase ^ 1u);        // epilogue has drained this accumulator
           ptx::tc_fence_after();
           prof_record(p.prof, static_cast<int>(blockIdx.x) * 8 + 1, 4, true);
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-          for (int kb = 0; kb < p.num_k; ++kb) {
+          for (int kb = un.kb0; kb < un.kb1; ++kb) {
             ptx::mbar_wait(full_bar + stage, phase);
             ptx::tc_fence_after();
             const uint32_t sa = ptx::smem_u32(smem + stage * L::kStageBytes);
@@ -566,7 +605,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
 #pragma unroll
               for (int k = 0; k < BK / UMMA_K; ++k) {
                 // advance 32 B (= 16 bf16) along K inside the 128-byte swizzle atom: +2 in the 16-byte address field
-                ptx::mma_f16<kCtaGroup>(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                ptx::mma_f16<kCtaGroup>(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb > un.kb0 || k != 0) ? 1u : 0u);
               }
             } else {
               // MXFP8: stage the UE8M0 scale factors of this k-block into TMEM (smem -> TMEM, 32 lanes x 16 B, replicated
@@ -583,7 +622,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const uint32_t idm = ptx::make_idesc_mx(0u, 0u, TM, BN, static_cast<uint32_t>(k), static_cast<uint32_t>(k));
-                ptx::mma_mxf8<kCtaGroup>(d_tmem, adesc + 2u * k, bdesc + 2u * k, idm, (kb | k) != 0 ? 1u : 0u, sf_tmem, sf_tmem + 4);
+                ptx::mma_mxf8<kCtaGroup>(d_tmem, adesc + 2u * k, bdesc + 2u * k, idm, (kb > un.kb0 || k != 0) ? 1u : 0u, sf_tmem, sf_tmem + 4);
               }
             }
             if constexpr (kCtaGroup == 1) ptx::mma_commit(empty_bar + stage);
@@ -605,12 +644,44 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
       uint8_t* smem_c = smem + L::kCOff;
       int acc = 0; uint32_t acc_phase = 0;
       uint32_t blk_iter = 0;                         // staging buffer = blk_iter & 1
-      for (int t = worker; t < total_tiles; t += n_workers) {
+      for (int u = worker; u < p.total_units; u += n_workers) {
+        const Unit un = get_unit(p, u);
         int m_tile, n_tile;
-        tile_coords(p, t, m_tile, n_tile);
+        tile_coords(p, un.tile, m_tile, n_tile);
         if (p.tile_expert && p.tile_expert[m_tile] < 0) continue;
         const int row_base = m_tile * TM + static_cast<int>(cta_rank) * BM;   // global row of tile row 0
         const int col_base = n_tile * BN;
+
+        if (un.part > 0) {
+          // ---- split-K helper unit: park the fp32 accumulator of my K range in the workspace, raise the flag ----
+          // layout per (32-column chunk, warp quadrant): [8 x 16-byte piece][32 lanes] -> every st.v4 / ld.v4 of a warp is
+          // 512 contiguous bytes, and the reader (same row <-> thread mapping) adds piece by piece
+          const size_t pidx = static_cast<size_t>(un.slot * (p.sk_parts - 1) + un.part - 1) * kCtaGroup + cta_rank;
+          float* wsb = p.sk_ws + pidx * (BM * BN);
+          ptx::mbar_wait(tmem_full + acc, acc_phase);
+          ptx::tc_fence_after();
+#pragma unroll 1
+          for (int ch = 0; ch < BN / 32; ++ch) {
+            uint32_t v[32];
+            ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * BN + ch * 32), v);
+            ptx::tmem_ld_wait();
+            float* dst = wsb + (ch * 4 + ew) * 1024 + lane * 4;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) ptx::st_v4(dst + q * 128, make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+          }
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (kCtaGroup == 1) ptx::mbar_arrive(tmem_empty + acc);
+            else ptx::mbar_arrive_cluster(tmem_empty + acc, 0);
+          }
+          ptx::named_bar_sync(2, kEpiThreads);
+          if (et == 0) { __threadfence(); ptx::st_release_gpu(p.sk_flags + pidx, 1u); }
+          __syncwarp();
+          if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
+          continue;
+        }
+        const int sk_n = (un.slot >= 0) ? p.sk_parts - 1 : 0;     // partial accumulators to add (split-K part 0)
 
         // ---- RS ring bookkeeping for this tile ----
         int rs_step = 0; bool rs_final = false;
@@ -618,6 +689,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         char* dst_base = reinterpret_cast<char*>(p.C) + cbuf * p.c_buf_stride_bytes;
         long long dst_ld = p.ldc;
         int dst_row_off = 0;                         // subtract from the global row for the destination
+        bool f32_in = false, f32_out = false;        // fp32 ring staging (rs_fp32)
         if constexpr (kMode == kRS) {
           const int W = p.symm.world, me = p.symm.rank;
           const int owner = (m_tile * TM) / p.rs_rows_per_rank;
@@ -626,7 +698,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
           char* stage_buf = p.rs_stage + (ph & 1u) * p.rs_stage_buf_bytes;
           if (rs_step > 0) {
             rs_in = stage_buf;
-            if (et == 0) wait_ge<true>(p.rs_flags + (ph & 1u) * total_tiles + m_tile * p.num_n + n_tile, ph);
+            if (et == 0 && !p.rs_skip_wait) wait_ge<true>(p.rs_flags + (ph & 1u) * total_tiles + m_tile * p.num_n + n_tile, ph);
             __syncwarp();
           }
           if (rs_final) {
@@ -634,6 +706,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
           } else {
             dst_base = symm_at(p.symm, stage_buf, (me - 1 + W) % W); dst_ld = p.N; dst_row_off = 0;
           }
+          f32_in = p.rs_fp32 && rs_step > 0;
+          f32_out = p.rs_fp32 && !rs_final;
         }
 
         int a2a_dst = 0;
@@ -651,18 +725,24 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         ptx::mbar_wait(tmem_full + acc, acc_phase);
         ptx::tc_fence_after();
         if (lane == 0) prof_record(p.prof, static_cast<int>(blockIdx.x) * 8 + warp, 5, true);
-        if constexpr (kMode == kRS) { if (rs_step > 0) ptx::named_bar_sync(2, kEpiThreads); }  // flag acquired by et==0
+        if (sk_n > 0) {     // the helper units of this tile run concurrently on other clusters: wait for their partials
+          if (et < sk_n) {
+            const uint32_t* f = p.sk_flags + static_cast<size_t>(un.slot * (p.sk_parts - 1) + et) * kCtaGroup + cta_rank;
+            while (ptx::ld_acquire_gpu(f) == 0u) {}
+          }
+          ptx::named_bar_sync(2, kEpiThreads);
+        } else if constexpr (kMode == kRS) { if (rs_step > 0) ptx::named_bar_sync(2, kEpiThreads); }  // flag acquired by et==0
 
 #pragma unroll 1
-        for (int cb = 0; cb < kNumCBlocks; ++cb, ++blk_iter) {
+        for (int cb = 0; cb < kNumCBlocks; ++cb) {
           uint8_t* cstage = smem_c + (blk_iter & 1u) * kCBlockBytes;
-          const uint32_t cbuf_u32 = ptx::smem_u32(cstage);
+          uint32_t cbuf_u32 = ptx::smem_u32(cstage);
           if (p.use_tma_store) {       // the TMA store that last used this buffer must have finished reading it
             if (et == 0) ptx::bulk_wait_read<1>();
             __syncwarp();
             ptx::named_bar_sync(1, kEpiThreads);
           }
-          // ---- TMEM -> registers -> 16-bit -> swizzled smem ----
+          // ---- TMEM -> registers -> 16-bit (or fp32 ring partial) -> swizzled smem ----
 #pragma unroll
           for (int h = 0; h < kColsPerBlock / 32; ++h) {
             uint32_t v[32];
@@ -673,11 +753,34 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             float f[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+            if (sk_n > 0) {
+              const int ch = cb * (kColsPerBlock / 32) + h;
+              for (int pp = 0; pp < sk_n; ++pp) {
+                const size_t pidx = static_cast<size_t>(un.slot * (p.sk_parts - 1) + pp) * kCtaGroup + cta_rank;
+                const float* src = p.sk_ws + pidx * (BM * BN) + (ch * 4 + ew) * 1024 + lane * 4;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const uint4 x = ptx::ld_relaxed_sys_v4(src + q * 128);
+                  f[4 * q] += __uint_as_float(x.x); f[4 * q + 1] += __uint_as_float(x.y);
+                  f[4 * q + 2] += __uint_as_float(x.z); f[4 * q + 3] += __uint_as_float(x.w);
+                }
+              }
+            }
             if constexpr (kMode == kRS) {
               if (rs_step > 0) {   // add the running partial pushed by rank+1 (same global coordinates)
                 const int grow = row_base + my_row;
                 const int gcol = col_base + cb * kCBlockCols + h * 32;
-                if (grow < p.M) {
+                if (grow < p.M && f32_in) {
+                  const char* src = rs_in + (static_cast<size_t>(grow) * p.N + gcol) * 4;
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) {
+                    if (gcol + q * 4 < p.N) {
+                      const uint4 x = ptx::ld_relaxed_sys_v4(src + q * 16);
+                      f[4 * q] += __uint_as_float(x.x); f[4 * q + 1] += __uint_as_float(x.y);
+                      f[4 * q + 2] += __uint_as_float(x.z); f[4 * q + 3] += __uint_as_float(x.w);
+                    }
+                  }
+                } else if (grow < p.M) {
                   const char* src = rs_in + (static_cast<size_t>(grow) * p.N + gcol) * 2;
 #pragma unroll
                   for (int q = 0; q < 4; ++q) {
@@ -700,6 +803,33 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                 }
               }
             }
+            if (kMode == kRS && f32_out) {
+              // fp32 ring partial: these 32 columns are one 128-byte row of their own staging block (own smem buffer)
+              if (h > 0) { ++blk_iter; cbuf_u32 = ptx::smem_u32(smem_c + (blk_iter & 1u) * kCBlockBytes); }
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                ptx::st_shared_v4(cbuf_u32 + my_row * 128 + ((q ^ (my_row & 7)) << 4),
+                                  make_uint4(__float_as_uint(f[4 * q]), __float_as_uint(f[4 * q + 1]), __float_as_uint(f[4 * q + 2]), __float_as_uint(f[4 * q + 3])));
+              if (cb == kNumCBlocks - 1 && h == kColsPerBlock / 32 - 1) {
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                  if constexpr (kCtaGroup == 1) ptx::mbar_arrive(tmem_empty + acc);
+                  else ptx::mbar_arrive_cluster(tmem_empty + acc, 0);
+                }
+              }
+              ptx::named_bar_sync(1, kEpiThreads);
+              const int gcol = col_base + cb * kCBlockCols + h * 32 + (et & 7) * 4;
+#pragma unroll
+              for (int r = et >> 3; r < BM; r += kEpiThreads / 8) {
+                const int grow = row_base + r;
+                if (grow < p.M && gcol < p.N) {
+                  const uint4 o = ptx::ld_shared_v4(cbuf_u32 + r * 128 + (((et & 7) ^ (r & 7)) << 4));
+                  ptx::st_v4(dst_base + (static_cast<size_t>(grow - dst_row_off) * dst_ld + gcol) * 4, o);
+                }
+              }
+              continue;
+            }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               uint4 o;
@@ -714,6 +844,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
               ptx::st_shared_v4(cbuf_u32 + my_row * 128 + ((chunk ^ (my_row & 7)) << 4), o);
             }
           }
+          ++blk_iter;
+          if (kMode == kRS && f32_out) continue;     // fp32 partial already stored block by block
           if (cb == kNumCBlocks - 1) {
             // accumulator fully read: hand the TMEM stage back to the MMA issuer (on the leader CTA)
             ptx::tc_fence_before();
@@ -749,6 +881,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
               }
             }
           }
+        }
+        if (sk_n > 0) {      // partials consumed: re-arm the flags for the next launch
+          ptx::named_bar_sync(2, kEpiThreads);
+          if (et < sk_n) p.sk_flags[static_cast<size_t>(un.slot * (p.sk_parts - 1) + et) * kCtaGroup + cta_rank] = 0u;
         }
         if constexpr (kMode == kRS) {
           if (!rs_final) {

@@ -1,0 +1,19 @@
+#!/bin/bash
+# One GPU session (edited per session; results land in gpurun_out/).  Usage: gpurun -- bash scripts/gpu_run.sh <stage>
+set -x
+mkdir -p gpurun_out
+export TD_NO_AUTOBUILD=1
+stage=${1:-a}
+if [ "$stage" = "a" ]; then
+  timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"
+  timeout 600 python -m pytest tests/test_gemm_gpu.py -x -q > gpurun_out/test_gemm.log 2>&1; echo "gemm tests rc=$?"; tail -5 gpurun_out/test_gemm.log
+  timeout 300 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_ref_n1.json 2> gpurun_out/bench_ref_n1.err; echo "ref rc=$?"; tail -c 1500 gpurun_out/bench_ref_n1.json
+  timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"; tail -c 3000 gpurun_out/bench_n1.json
+  TD_SPLITK=0 timeout 300 python bench.py --gpus 1 --steps 20 --warmup 5 --quick > gpurun_out/bench_n1_nosplit.json 2> gpurun_out/bench_n1_nosplit.err; tail -c 600 gpurun_out/bench_n1_nosplit.json
+  timeout 900 python -m pytest tests -m gpu -x -q --deselect tests/test_gemm_gpu.py > gpurun_out/test_gpu.log 2>&1; echo "gpu tests rc=$?"; tail -8 gpurun_out/test_gpu.log
+fi
+if [ "$stage" = "b" ]; then
+  N=${2:-2}
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tests/dist_worker.py ag_gemm gemm_rs > gpurun_out/dist_ag_rs_n$N.log 2>&1; echo "dist rc=$?"; tail -15 gpurun_out/dist_ag_rs_n$N.log
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "bench rc=$?"; tail -c 4000 gpurun_out/bench_n$N.json; tail -5 gpurun_out/bench_n$N.err
+fi

@@ -161,22 +161,27 @@ def case_ag_gemm():
     dev = U.current_device()
     W, me = U.world_size(), U.rank()
     big = dev.type == "cuda"
-    shapes = [(512 * W, 512, 1024), (256 * W, 256, 512), (384 * W, 768, 256), (100 * W, 264, 520)] if big else \
-             [(16 * W, 24, 32), (5 * W, 8, 16)]
+    shapes = [(512 * W, 512, 1024), (256 * W, 256, 512), (384 * W, 768, 256), (100 * W, 264, 520), (512 * W, 512, 4096),
+              (128 * W, 1280, 2112)] if big else [(16 * W, 24, 32), (5 * W, 8, 16)]
     dtype = torch.bfloat16 if big else torch.float32
+    transports = ["sm"] + (["multicast"] if (big and U.is_nvshmem_multimem_supported()) else []) if big else ["auto"]
     for (M, N, K) in shapes:
         ctx = create_ag_gemm_context(M, N, K, dtype)
         if big:
             ctx.workspace.view(torch.int16).fill_(0x7FC0)      # poison (bf16 NaN pattern)
-        for it in range(5):
-            A = (torch.randn(M // W, K, device=dev) * 0.5).to(dtype)
-            Wt = (torch.randn(N, K, device=dev) * 0.5).to(dtype)
-            straggler = (it % W, 3_000_000) if (big and it in (1, 3)) else None
-            C = ag_gemm(A, Wt.t(), ctx, straggler_option=straggler)
-            full = torch.empty(M * K, device=dev, dtype=dtype)
-            dist.all_gather_into_tensor(full, A.view(-1), group=U.get_triton_dist_world())
-            ref = full.view(M, K).float() @ Wt.float().t()
-            _assert_close(C, ref, 0.5 if big else 1e-3, 2e-2 if big else 1e-4, f"ag_gemm {M}x{N}x{K} it{it}")
+        for tr in transports:
+            if tr == "multicast" and (M // W) % 128 != 0:
+                continue
+            for it in range(5):
+                A = (torch.randn(M // W, K, device=dev) * 0.5).to(dtype)
+                Wt = (torch.randn(N, K, device=dev) * 0.5).to(dtype)
+                straggler = (it % W, 3_000_000) if (big and it in (1, 3)) else None
+                ks = (0, 4, 16, 3, 8)[it] if tr == "multicast" else 0
+                C = ag_gemm(A, Wt.t(), ctx, straggler_option=straggler, transport=tr, kslices=ks)
+                full = torch.empty(M * K, device=dev, dtype=dtype)
+                dist.all_gather_into_tensor(full, A.view(-1), group=U.get_triton_dist_world())
+                ref = full.view(M, K).float() @ Wt.float().t()
+                _assert_close(C, ref, 0.5 if big else 1e-3, 2e-2 if big else 1e-4, f"ag_gemm[{tr}] {M}x{N}x{K} it{it}")
         # AllToAll + GEMM in the same kernel (all_to_all_single_gemm.py:74-188): block d of x goes to rank d
         from triton_dist.ops.compat import all_to_all_single_gemm
         for it in range(3):
@@ -201,11 +206,12 @@ def case_gemm_rs():
     dev = U.current_device()
     W, me = U.world_size(), U.rank()
     big = dev.type == "cuda"
-    shapes = [(256 * W, 512, 512), (128 * W, 256, 1024), (512 * W, 1024, 256), (128 * W, 264, 136), (40 * W, 256, 128)] if big else \
-             [(8 * W, 16, 24), (3 * W, 8, 8)]
+    shapes = [(256 * W, 512, 512), (128 * W, 256, 1024), (512 * W, 1024, 256), (128 * W, 264, 136), (40 * W, 256, 128),
+              (256 * W, 5120, 2048), (256 * W, 2560, 4096)] if big else [(8 * W, 16, 24), (3 * W, 8, 8)]
     dtype = torch.bfloat16 if big else torch.float32
-    for (M, N, K) in shapes:
-        ctx = create_gemm_rs_context(M, N, output_dtype=dtype)
+    for si, (M, N, K) in enumerate(shapes):
+        # every other shape runs the fp32 ring (partial sums travel in fp32: one rounding at the owner)
+        ctx = create_gemm_rs_context(M, N, output_dtype=dtype, fp32_ring=bool(big and si % 2 == 1))
         for it in range(5):
             A = (torch.randn(M, K, device=dev) * 0.5).to(dtype)
             Wt = (torch.randn(N, K, device=dev) * 0.5).to(dtype)
@@ -218,7 +224,8 @@ def case_gemm_rs():
             else:   # gloo has no reduce_scatter_tensor
                 dist.all_reduce(full, group=U.get_triton_dist_world())
                 ref = full[me * (M // W):(me + 1) * (M // W)]
-            _assert_close(C, ref, 1.0 if big else 1e-3, 3e-2 if big else 1e-4, f"gemm_rs {M}x{N}x{K} it{it}")
+            _assert_close(C, ref, (0.25 if ctx.fp32_ring else 1.0) if big else 1e-3, 3e-2 if big else 1e-4,
+                          f"gemm_rs {M}x{N}x{K} it{it} fp32_ring={ctx.fp32_ring}")
         U.barrier_all_host()
         ctx.finalize()
 

@@ -16,3 +16,17 @@ def test_gpu_world2(case):
     if _ngpu() < 2:
         pytest.skip("needs >= 2 GPUs")
     run_dist([case], nproc=2, timeout=300)
+
+
+@pytest.mark.parametrize("case", ["ag_gemm", "gemm_rs", "gemm_ar", "moe", "ep_ll", "ep_normal", "mega", "tp_e2e"])
+def test_gpu_world4(case):
+    if _ngpu() < 4:
+        pytest.skip("needs >= 4 GPUs")
+    run_dist([case], nproc=4, timeout=420)
+
+
+@pytest.mark.parametrize("case", ["ag_gemm", "gemm_rs", "gemm_ar", "moe", "ep_ll", "ep_normal", "mega", "tp_e2e"])
+def test_gpu_world8(case):
+    if _ngpu() < 8:
+        pytest.skip("needs >= 8 GPUs")
+    run_dist([case], nproc=8, timeout=600)

@@ -173,6 +173,8 @@ def test_megakernel_graph_single_process(dist_env):
 
 
 def test_bench_reference_arm_reports_unavailable():
+    """No GPU here: the reference arm (the reference's own little_kernel sm_100a GEMM at N=1) must say so and exit 0; it also
+    stays `unavailable` for N > 1 (the multi-GPU reference ops need the Triton/NVSHMEM stack that cannot be built offline)."""
     import json
     import subprocess
     import sys
@@ -181,6 +183,9 @@ def test_bench_reference_arm_reports_unavailable():
     assert r.returncode == 0
     d = json.loads(r.stdout.strip().splitlines()[-1])
     assert d["impl"] == "reference" and "unavailable" in d
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "8"], capture_output=True, text=True,
+                       timeout=120)
+    assert r.returncode == 0 and "unavailable" in json.loads(r.stdout.strip().splitlines()[-1])
 
 
 def test_flash_attn_reference_paths():

@@ -55,6 +55,8 @@ class GemmArgs(C.Structure):
         ("rs_out", c_void_p), ("rs_ldo", c_ll),
         ("a_gather", c_void_p), ("a_gather_div", c_ll), ("a_gather_pad", c_ll), ("a_src_rows", c_ll), ("c_scatter", c_void_p),
         ("expert_stride_rows", c_ll),
+        ("sk_ws", c_void_p), ("sk_ws_bytes", c_ll), ("sk_flags", c_void_p), ("sk_flag_count", c_ll), ("sk_max_parts", c_ll),
+        ("rs_skip_wait", c_ll), ("rs_fp32", c_ll), ("ag_kslices", c_ll),
     ]]
 
 
@@ -139,7 +141,17 @@ def host_lib():
     return _host
 
 
+_native_calls = 0
+
+
+def native_calls() -> int:
+    """Number of successful native launcher calls so far (every kernel launch goes through :func:`check`)."""
+    return _native_calls
+
+
 def check(rc: int, what: str = "native call"):
+    global _native_calls
+    _native_calls += 1
     if rc != 0:
         msg = cuda_lib().td_last_error().decode(errors="replace") if _cuda is not None else ""
         raise NativeError(f"{what} failed: {msg}")

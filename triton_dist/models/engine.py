@@ -78,6 +78,9 @@ class Engine:
               ar_method=comm.AllReduceMethod.Unknown) -> torch.Tensor:
         """input_ids: [bsz, prompt_len] (identical on all ranks) -> generated tokens [bsz, gen_len]."""
         bsz, prompt_len = input_ids.shape
+        max_len = getattr(self.model, "max_length", None) or getattr(getattr(self.model, "cfg", None), "max_length", None)
+        if max_len is not None and prompt_len + gen_len > max_len:
+            raise ValueError(f"serve(): prompt_len + gen_len = {prompt_len + gen_len} exceeds the KV cache (max_length = {max_len})")
         W, r = self.world_size, self.rank
         input_ids = input_ids.to(self.device)
         self._init_kv_cache(bsz)

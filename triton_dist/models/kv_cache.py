@@ -19,6 +19,7 @@ class KV_Cache:
         self.kv_offset = torch.zeros(batch_size, dtype=torch.int32, device=device)
         self._bidx = {}
         self._lens = torch.zeros(batch_size, dtype=torch.int32, device=device)
+        self._host_len = 0      # host mirror of the longest sequence (eager calls only; Engine.serve bounds graph replays)
 
     def layer(self, idx: int):
         return self.k_cache[idx], self.v_cache[idx]
@@ -38,12 +39,17 @@ class KV_Cache:
         return self.kv_offset
 
     def inc_offset(self, n: int = 1):
+        if self._host_len + n > self.max_length:
+            raise ValueError(f"KV cache overflow: {self._host_len} + {n} tokens > max_length {self.max_length}")
+        self._host_len += n
         self.kv_offset += n
 
     def clear(self):
+        self._host_len = 0
         self.kv_offset.zero_()
 
     def rand_fill_kv_cache(self, offset: int):
         self.k_cache.normal_(0, 0.5)
         self.v_cache.normal_(0, 0.5)
+        self._host_len = int(offset)
         self.kv_offset.fill_(offset)

@@ -4,11 +4,19 @@ Reference: ``create_ag_gemm_context`` / ``ag_gemm`` (/root/reference/python/trit
 allgather_gemm.py:511-619) -- there the all-gather is W-1 host-issued ``cudaMemcpyAsync`` + one
 ``cuStreamWriteValue`` flag per source rank (allgather.py:100-124) around a Triton persistent GEMM.
 
-Here (csrc/gemm_sm100.cuh, mode kAG) the gather runs INSIDE the GEMM kernel: ``n_comm_ctas`` CTAs PUSH this rank's
-shard into every peer's workspace over NVLink with TMA bulk copies (posted writes; a pull design measured only
-~7 GB/s per SM on 8xB200) and publish per-(source, 128-row chunk, sub-piece) flags on the destination; the tcgen05
-GEMM CTAs start on the local rows (tile order rotated by rank) and consume remote rows as they land.  No host
-barrier: workspaces are double buffered by call parity and flags carry monotone phase numbers kept on the device.
+Here (csrc/gemm_sm100.cuh, mode kAG) the gather runs INSIDE the GEMM kernel.  Two in-kernel transports:
+
+* ``multicast`` (NVLS, default when the heap has a multicast mapping): ``n_comm_ctas`` CTAs write this rank's shard ONCE
+  to the multicast alias of the workspace with ``multimem.st`` -- the NVSwitch fans it out to every rank, so egress is
+  1x the shard instead of (W-1)x -- K slice by K slice, publishing one flag per (source, K slice, comm CTA).  The TMA
+  producer of a GEMM CTA acquires the flag of a K slice right before its first k-block, so EVERY tile starts after
+  1/8 of the transfer and its mainloop follows the arrival; the tail after the last byte is one K slice + epilogue.
+* ``sm`` (P2P): comm CTAs push the shard into every peer's workspace with coalesced 16-byte stores (posted writes; a
+  pull design measured only ~7 GB/s per SM on 8xB200) and publish per-(source, byte slice) flags; the GEMM CTAs start
+  on the local rows (tile order rotated by rank) and consume remote rows as they land.
+
+No host barrier: workspaces are double buffered by call parity and flags carry monotone phase numbers kept on the
+device.  ``copy_engine`` is the reference's host-driven transport, kept for comparison.
 """
 from __future__ import annotations
 
@@ -36,7 +44,7 @@ class AllGatherGEMMTensorParallelContext:
     num_ranks: int
     num_local_ranks: int
     workspace: torch.Tensor = None     # symmetric [2, max_M, K]
-    flags: torch.Tensor = None         # symmetric int32 [2, W, 64]
+    flags: torch.Tensor = None         # symmetric int32 [2, W, 256]
     ready: torch.Tensor = None         # symmetric int32 [W]
     phase: torch.Tensor = None         # local int32 [4]
     n_comm_ctas: int = 16
@@ -49,7 +57,10 @@ class AllGatherGEMMTensorParallelContext:
 
     def local_input_buffer(self, rows: int) -> torch.Tensor:
         """Zero-copy entry: where the NEXT call expects my shard ([rows, K] inside the workspace).  A producer
-        (e.g. the previous layer's epilogue) may write there directly and pass it as ``A``."""
+        (e.g. the previous layer's epilogue) may write there directly and pass it as ``A``.  Host-counter based: not usable
+        inside a CUDA-graph capture (the device-side parity alternates on replay)."""
+        if self.workspace.is_cuda and torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("local_input_buffer() cannot be used while capturing a CUDA graph")
         ph = self._phase_value() + 1
         buf = self.workspace[ph & 1]
         return buf[self.rank * rows:(self.rank + 1) * rows]
@@ -67,8 +78,12 @@ class AllGatherGEMMTensorParallelContext:
 
 def create_ag_gemm_context(max_M: int, N: int, K: int, dtype: torch.dtype, rank: Optional[int] = None,
                            num_ranks: Optional[int] = None, num_local_ranks: Optional[int] = None,
-                           n_comm_ctas: int = 16, **_unused) -> AllGatherGEMMTensorParallelContext:
-    """``max_M`` = largest gathered M (rows of all ranks together); ``N`` = this rank's N shard."""
+                           n_comm_ctas: int = 16, BLOCK_M: Optional[int] = None, BLOCK_N: Optional[int] = None,
+                           BLOCK_K: Optional[int] = None, stages: Optional[int] = None, ag_intranode_stream=None,
+                           ag_internode_stream=None, for_correctness: bool = False) -> AllGatherGEMMTensorParallelContext:
+    """``max_M`` = largest gathered M (rows of all ranks together); ``N`` = this rank's N shard.  The reference's Triton
+    tile hints (``BLOCK_*``, ``stages``) and side streams are accepted for signature parity and have no effect here: tiles
+    come from ``gemm_config`` and the gather runs inside the kernel (no streams)."""
     heap = U.get_heap()
     rank = heap.rank if rank is None else rank
     num_ranks = heap.world if num_ranks is None else num_ranks
@@ -78,7 +93,7 @@ def create_ag_gemm_context(max_M: int, N: int, K: int, dtype: torch.dtype, rank:
     ctx.ready = heap.tensor((max(num_ranks, 4),), torch.int32)
     max_ms = (max_M + num_ranks - 1) // num_ranks
     chunks = (max_ms + _CHUNK_ROWS - 1) // _CHUNK_ROWS
-    ctx.flags = heap.tensor((2, num_ranks, 64), torch.int32)      # [parity][src][slice], written remotely by the sources
+    ctx.flags = heap.tensor((2, num_ranks, 256), torch.int32)      # [parity][src][slice], written remotely by the sources
     ctx.phase = torch.zeros(4, dtype=torch.int32, device=heap.device)
     U.barrier_all_host()
     return ctx
@@ -118,16 +133,18 @@ def default_ag_config(M: int, N: int, K: int, world: int) -> GemmConfig:
 
 def ag_gemm(A: torch.Tensor, B: torch.Tensor, ctx: AllGatherGEMMTensorParallelContext,
             gemm_config: Optional[GemmConfig] = None, straggler_option=None, debug: bool = False,
-            out: Optional[torch.Tensor] = None, skip_wait: bool = False, profiler=None, transport: str = "sm",
-            all_to_all: bool = False, **_unused) -> torch.Tensor:
+            out: Optional[torch.Tensor] = None, skip_wait: bool = False, profiler=None, transport: str = "auto",
+            all_to_all: bool = False, kslices: int = 0) -> torch.Tensor:
     """A: ``[M/W, K]`` local shard, B: ``[K, N/W]`` -> ``[M, N/W]``.  ``skip_wait`` runs the GEMM-only twin
     (flags ignored) used to measure exposed communication, like the reference's ``fake_barrier`` path.
 
-    ``transport="sm"`` (default): comm CTAs inside the GEMM kernel push the shard.  ``transport="copy_engine"``: the
+    ``transport="auto"`` (default): ``multicast`` when the heap has an NVLS mapping and ``M/W % 128 == 0``, else ``sm``
+    (override with env ``TD_AG_TRANSPORT``).  ``transport="sm"``: comm CTAs push the shard to every peer (P2P stores).
+    ``transport="copy_engine"``: the
     shard is pushed by the DMA engines on a side stream (one ``cudaMemcpyAsync`` + one release-flag kernel per peer, as
     the reference's copy-engine producer, allgather.py:100-124) while all SMs run GEMM tiles that wait on the same
     per-source flags; not CUDA-graph replayable (flag values are written from the host-tracked phase).
-    ``transport="multicast"`` (opt-in): comm CTAs write the shard once to the NVLS multicast alias, the switch fans it out.
+    ``transport="multicast"``: comm CTAs write the shard once to the NVLS multicast alias in ``kslices`` K slices (default 8).
 
     ``all_to_all=True``: A is ``[W * Ms, K]`` and row block d goes to rank d (instead of the same shard to everyone);
     the result is ``concat_s(block from rank s) @ B`` -- the AllToAll + GEMM of the Ulysses o-projection
@@ -153,8 +170,13 @@ def ag_gemm(A: torch.Tensor, B: torch.Tensor, ctx: AllGatherGEMMTensorParallelCo
         torch.cuda._sleep(int(straggler_option[1]))
     heap = U.get_heap()
     A = A.contiguous()
+    if transport == "auto":
+        transport = resolve_transport(Ms, all_to_all)
     ph = ctx.host_phase + 1
-    zero_copy = (not all_to_all) and heap.contains(A) and A.data_ptr() == ctx.workspace[ph & 1][ctx.rank * Ms:].data_ptr()
+    # zero-copy (A already sits in my slot of the workspace half this call uses) is decided from the HOST mirror of the call
+    # counter; inside a CUDA-graph capture the kernel's device-side parity alternates on replay, so it is never assumed there
+    zero_copy = ((not all_to_all) and (not torch.cuda.is_current_stream_capturing()) and heap.contains(A)
+                 and A.data_ptr() == ctx.workspace[ph & 1][ctx.rank * Ms:].data_ptr())
     assert not (all_to_all and transport == "copy_engine"), "all_to_all flavour uses the in-kernel push"
     args = _C.GemmArgs()
     args.mode = 1
@@ -173,11 +195,11 @@ def ag_gemm(A: torch.Tensor, B: torch.Tensor, ctx: AllGatherGEMMTensorParallelCo
     if skip_wait:
         args.n_comm_ctas = 0
     if transport == "multicast" and not skip_wait:
-        # NVLS: comm CTAs write the shard once to the multicast alias of the workspace (csrc/gemm_sm100.cuh, ag_multicast).
-        # Written after this round's GPU budget was spent -- hardware validation pending, hence opt-in only.
-        assert not all_to_all and U.is_nvshmem_multimem_supported()
-        args.ag_skip_wait, args.ag_copy_local = 3, 1
-        args.n_comm_ctas = max(2, cfg.n_comm_ctas if cfg.n_comm_ctas and cfg.n_comm_ctas <= 16 else 8)
+        # NVLS: comm CTAs write the shard once to the multicast alias of the workspace (csrc/gemm_sm100.cuh, ag_multicast)
+        assert not all_to_all and U.is_nvshmem_multimem_supported() and Ms % 128 == 0
+        args.ag_skip_wait = 3
+        args.n_comm_ctas = max(2, min(cfg.n_comm_ctas or 16, 32))
+        args.ag_kslices = kslices
     if transport == "copy_engine" and not skip_wait:
         _ce_push(ctx, A, ph, Ms, K)
         args.ag_skip_wait, args.ag_copy_local, args.n_comm_ctas = 2, 1, 0
@@ -189,6 +211,17 @@ def ag_gemm(A: torch.Tensor, B: torch.Tensor, ctx: AllGatherGEMMTensorParallelCo
     if transport == "copy_engine" and not skip_wait:
         torch.cuda.current_stream().wait_stream(ctx._ce_stream)     # A may be reused only after the DMA reads finished
     return out
+
+
+def resolve_transport(rows_per_rank: int, all_to_all: bool = False) -> str:
+    """The transport ``transport="auto"`` picks (env ``TD_AG_TRANSPORT`` overrides)."""
+    import os
+    forced = os.environ.get("TD_AG_TRANSPORT", "")
+    if forced:
+        return forced
+    if (not all_to_all) and rows_per_rank % 128 == 0 and U.is_nvshmem_multimem_supported():
+        return "multicast"
+    return "sm"
 
 
 def _ce_push(ctx, A, ph, Ms, K):

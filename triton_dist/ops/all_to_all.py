@@ -81,7 +81,8 @@ def fast_all_to_all(ctx: AllToAllContext, send_tensor: torch.Tensor, send_split_
                     send_scale: Optional[torch.Tensor] = None, num_sms: int = 32):
     """send_tensor: [rows, hidden] sorted by destination expert; send_split_cumsum: int32 [E + 1] (device);
     Returns (recv_splits [W, experts_per_rank] int32, recv_tensor [W, max_m, hidden], recv_scale | None) -- views of the
-    symmetric receive buffer of this call's parity (valid until the call after next)."""
+    symmetric receive buffer of this call's parity (valid until the call after next).  While a CUDA graph is being captured
+    the results are device-selected COPIES of the half the kernel wrote (replay safe)."""
     W, g = ctx.world_size, ctx.experts_per_rank
     assert send_tensor.is_contiguous() and send_split_cumsum.numel() == W * g + 1
     cum = send_split_cumsum.to(torch.int32).contiguous()
@@ -103,6 +104,15 @@ def fast_all_to_all(ctx: AllToAllContext, send_tensor: torch.Tensor, send_split_
     a.recv_meta, a.flags, a.phase = ctx.recv_meta.data_ptr(), ctx.flags.data_ptr(), ctx.phase.data_ptr()
     _C.check(_C.cuda_lib().td_all_to_all(C.byref(a), c_void_p(torch.cuda.current_stream().cuda_stream)), "td_all_to_all")
     ctx.host_calls = ph
+    if torch.cuda.is_current_stream_capturing():
+        # The kernel picks the receive half from its DEVICE-resident call counter, so a replayed graph alternates halves while
+        # a view chosen from the host counter would stay frozen at the capture-time parity.  Under capture the half is
+        # therefore selected on the device too: phase[0] (already advanced by the kernel, stream-ordered) & 1.
+        sel = (ctx.phase[0:1] & 1).to(torch.int64)
+        meta = ctx.recv_meta.index_select(0, sel)[0]
+        buf = ctx.recv_buf.index_select(0, sel)[0]
+        sc = ctx.recv_scale.index_select(0, sel)[0] if send_scale is not None else None
+        return meta[:, :g], buf, sc
     meta = ctx.recv_meta[par]
     return meta[:, :g], ctx.recv_buf[par], (ctx.recv_scale[par] if send_scale is not None else None)
 

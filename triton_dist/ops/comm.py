@@ -138,6 +138,13 @@ class AllReduceContext:
     host_calls: int = 0             # emulation backend
 
     def finalize(self):
+        """Collective: every rank must call it.  Frees symmetric memory only after every rank has drained its stream and
+        arrived (a peer may still be writing flags into these slots otherwise, and a recycled offset would see them)."""
+        if self.stage is None:
+            return
+        if self.stage.is_cuda:
+            torch.cuda.synchronize()
+        U.barrier_all_host()
         for t in (self.stage, self.stage2, self.slots, getattr(self, "ll_buf", None)):
             if t is not None:
                 U.get_heap().free_tensor(t)
@@ -145,12 +152,31 @@ class AllReduceContext:
         self.ll_buf = None
 
     def symm_input(self, nbytes: int, dtype: torch.dtype) -> torch.Tensor:
-        """Zero-copy entry: the staging buffer the NEXT call will reduce; a producer may write straight into it
-        and pass it as ``x`` (the kernel then skips its staging copy)."""
-        calls = self.host_calls if not self.stage.is_cuda else int(self.phase[0].item())
-        par = (calls + 1) & 1
+        """Zero-copy entry: the staging half the NEXT collective on this context will reduce; a producer may write straight
+        into it and pass it as ``x`` (the kernel then skips its staging copy).  The half is chosen from the host mirror of
+        the call counter (no device sync); it is only valid until the next collective on this context, and not inside a
+        CUDA-graph capture (a replay alternates halves) -- :func:`all_reduce` rejects a stale or offset view."""
+        if self.stage.is_cuda and torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("symm_input() cannot be used while capturing a CUDA graph: write the device-selected half via "
+                               "gemm(out_parity=(ctx.phase, ctx.workspace_nbytes)) and pass the stage base instead")
+        par = (self.host_calls + 1) & 1
         es = torch.empty(0, dtype=dtype).element_size()
         return self.stage[par * self.workspace_nbytes: par * self.workspace_nbytes + nbytes].view(dtype)[: nbytes // es]
+
+    def zero_copy_ok(self, ptr: int, device_parity: bool) -> bool:
+        """Is ``ptr`` a legal zero-copy input?  Only (a) the stage base when the producer wrote the DEVICE-selected half
+        (``gemm(out_parity=...)`` contract) or (b) exactly the half the next call reduces.  Any other pointer into the
+        staging area (stale half, offset view) would be silently replaced by the other half's content: raise."""
+        base = self.stage.data_ptr()
+        if not (base <= ptr < base + 2 * self.workspace_nbytes):
+            return False
+        if device_parity and ptr == base:
+            return True
+        par = (self.host_calls + 1) & 1
+        if ptr == base + par * self.workspace_nbytes and not (self.stage.is_cuda and torch.cuda.is_current_stream_capturing()):
+            return True
+        raise ValueError("all_reduce/reduce_scatter: input lies inside the context's staging area but is not the half the next "
+                         "call reduces (stale symm_input() view, or a view at an offset); pass a fresh symm_input() or a plain tensor")
 
 
 def create_allreduce_ctx(workspace_nbytes: int, rank: int, world_size: int, local_world_size: int,
@@ -176,8 +202,9 @@ def _ar_grid(nbytes: int, max_sm: int, grid_max: int) -> int:
 
 def all_reduce(x: torch.Tensor, method=AllReduceMethod.Unknown, ctx: AllReduceContext = None,
                output: Optional[torch.Tensor] = None, max_sm: int = -1, straggler_option=None,
-               stream=None) -> torch.Tensor:
-    """SUM all-reduce of ``x`` over the symmetric team.  Messages larger than the workspace are chunked."""
+               stream=None, device_parity_input: bool = False) -> torch.Tensor:
+    """SUM all-reduce of ``x`` over the symmetric team.  Messages larger than the workspace are chunked.
+    ``device_parity_input``: ``x`` is the stage base and the producer already wrote the device-selected half."""
     assert ctx is not None, "create_allreduce_ctx() first"
     assert x.is_contiguous()
     if output is None:
@@ -212,11 +239,12 @@ def all_reduce(x: torch.Tensor, method=AllReduceMethod.Unknown, ctx: AllReduceCo
         a.method, a.dtype = _KERNEL_METHOD[method], _DT[x.dtype]
         a.grid = _ar_grid(n, max_sm, ctx.grid_max)
         src = xb[off:off + n]
-        a.in_symm = 1 if (heap.contains(src) and ctx.stage.data_ptr() <= src.data_ptr() < ctx.stage.data_ptr() + 2 * ctx.workspace_nbytes) else 0
+        a.in_symm = 1 if ctx.zero_copy_ok(src.data_ptr(), device_parity_input) else 0
         a.inp, a.out = src.data_ptr(), ob[off:off + n].data_ptr()
         a.stage, a.stage2, a.stage_bytes, a.nbytes = ctx.stage.data_ptr(), ctx.stage2.data_ptr(), ctx.workspace_nbytes, n
         a.slots, a.phase = ctx.slots.data_ptr(), ctx.phase.data_ptr()
         _C.check(lib.td_allreduce(C.byref(a), _stream(stream)), "td_allreduce")
+        ctx.host_calls += 1          # host mirror of the device call counter (every collective launch advances it by one)
         off += n
     return output
 
@@ -253,7 +281,7 @@ def _all_reduce_ll(x: torch.Tensor, ctx: AllReduceContext, output: torch.Tensor,
 
 
 def reduce_scatter(x: torch.Tensor, ctx: AllReduceContext, output: Optional[torch.Tensor] = None, max_sm: int = -1,
-                   stream=None) -> torch.Tensor:
+                   stream=None, device_parity_input: bool = False) -> torch.Tensor:
     """SUM reduce-scatter along dim 0: every rank contributes ``x`` ([W * n, ...]) and receives its ``n`` rows.
     Staging (zero-copy if ``x`` is ``ctx.symm_input``) -> per-CTA flag barrier -> each rank pulls and reduces only
     its own slice (NVLS ``multimem.ld_reduce`` when available, P2P loads otherwise)."""
@@ -273,7 +301,7 @@ def reduce_scatter(x: torch.Tensor, ctx: AllReduceContext, output: Optional[torc
         raise ValueError("reduce_scatter: per-rank slice must be a multiple of 16 bytes")
     heap = U.get_heap()
     xb = x.view(torch.uint8).view(-1)
-    in_stage = heap.contains(xb) and ctx.stage.data_ptr() <= xb.data_ptr() < ctx.stage.data_ptr() + 2 * ctx.workspace_nbytes
+    in_stage = ctx.zero_copy_ok(xb.data_ptr(), device_parity_input)
     def mk(method, grid, inp):
         a = _ARArgs()
         a.symm = symm_args()
@@ -297,6 +325,7 @@ def reduce_scatter(x: torch.Tensor, ctx: AllReduceContext, output: Optional[torc
     a.stage, a.stage2, a.stage_bytes, a.nbytes = ctx.stage.data_ptr(), ctx.stage2.data_ptr(), ctx.workspace_nbytes, nbytes
     a.slots, a.phase = ctx.slots.data_ptr(), ctx.phase.data_ptr()
     _C.check(_C.cuda_lib().td_allreduce(C.byref(a), _stream(stream)), "td_allreduce(reduce_scatter)")
+    ctx.host_calls += 1
     return output
 
 

@@ -66,6 +66,29 @@ def fill_common(args: _C.GemmArgs, a_rows: int, A_ptr: int, lda: int, B: torch.T
     args.world = 1
 
 
+_SK_SCRATCH = {}
+_SK_WS_BYTES = 20 << 20      # >= workers * 128 * cta_group * BN * 4 for every tile shape (74 pairs x 256 x 256 fp32 = 19.4 MB)
+_SK_FLAGS = 1024
+
+
+def attach_splitk(args: _C.GemmArgs, device: torch.device, max_parts: int = 4) -> None:
+    """Give the launch the split-K tail scratch (csrc/gemm_sm100.cuh ``sk_*``): the tiles of the last partial wave are cut
+    into K ranges that run on the otherwise idle CTA pairs (768 tiles on 74 pairs: 10.5 waves instead of 11).  One scratch
+    per (device, stream) -- two GEMMs on different streams never share partial sums.  ``TD_SPLITK=0`` turns it off."""
+    import os
+    if os.environ.get("TD_SPLITK", "1") == "0":
+        return
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    sc = _SK_SCRATCH.get(key)
+    if sc is None:
+        if torch.cuda.is_current_stream_capturing():
+            return                      # never allocate inside a capture; the unsplit schedule is always valid
+        sc = (torch.empty(_SK_WS_BYTES, dtype=torch.uint8, device=device), torch.zeros(_SK_FLAGS, dtype=torch.int32, device=device))
+        _SK_SCRATCH[key] = sc
+    args.sk_ws, args.sk_ws_bytes = sc[0].data_ptr(), _SK_WS_BYTES
+    args.sk_flags, args.sk_flag_count, args.sk_max_parts = sc[1].data_ptr(), _SK_FLAGS, max_parts
+
+
 _C.register("td_gemv", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p])
 
 
@@ -81,11 +104,12 @@ def gemv(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -
 
 
 def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None,
-         config: Optional[GemmConfig] = None, out_parity=None) -> torch.Tensor:
+         config: Optional[GemmConfig] = None, out_parity=None, split_k: bool = True) -> torch.Tensor:
     """``out[M,N] = a[M,K] @ b[N,K].T`` with fp32 accumulation in TMEM.  ``b`` is an ``nn.Linear`` weight.
 
     ``out_parity=(phase_tensor, stride_bytes)``: ``out`` is half 0 of a parity-double-buffered staging area; the
-    kernel writes half ``(phase_tensor[0] + 1) & 1`` chosen ON THE DEVICE (CUDA-graph replay safe)."""
+    kernel writes half ``(phase_tensor[0] + 1) & 1`` chosen ON THE DEVICE (CUDA-graph replay safe).
+    ``split_k``: allow the split-K tail schedule (see :func:`attach_splitk`)."""
     if not a.is_cuda:
         raise RuntimeError("triton_dist.ops.gemm needs CUDA tensors (sm_100a kernel); the CPU path is emulation-only")
     _check_operand(a, "a")
@@ -106,6 +130,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None,
                 a.dtype == torch.bfloat16)
     if out_parity is not None:
         args.c_phase, args.c_nbuf, args.c_buf_stride_bytes = out_parity[0].data_ptr(), 2, int(out_parity[1])
+    if split_k:
+        attach_splitk(args, a.device)
     lib = _C.cuda_lib()
     _C.check(lib.td_gemm_launch(C.byref(args), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "td_gemm_launch")
     return out

@@ -60,7 +60,8 @@ class GemmARContext:
 
 def create_gemm_ar_context(ar_stream=None, rank: Optional[int] = None, world_size: Optional[int] = None,
                            local_world_size: Optional[int] = None, max_M: int = 0, N: int = 0,
-                           dtype: torch.dtype = torch.bfloat16, **_unused) -> GemmARContext:
+                           dtype: torch.dtype = torch.bfloat16, **ref_hints) -> GemmARContext:
+    U.accept_ref_hints("create_gemm_ar_context", ref_hints, ('MIN_BLOCK_SIZE_M', 'MIN_BLOCK_SIZE_N', 'NUM_COMM_SMS', 'TILE_MAP_LEVEL'))
     heap = U.get_heap()
     rank = heap.rank if rank is None else rank
     world_size = heap.world if world_size is None else world_size
@@ -72,8 +73,9 @@ def create_gemm_ar_context(ar_stream=None, rank: Optional[int] = None, world_siz
 
 def create_ll_gemm_ar_context(ar_stream=None, rank: Optional[int] = None, world_size: Optional[int] = None,
                               local_world_size: Optional[int] = None, max_M: int = 0, N: int = 0,
-                              dtype: torch.dtype = torch.bfloat16, NUM_COMM_SMS: int = 16, **_unused) -> GemmARContext:
+                              dtype: torch.dtype = torch.bfloat16, NUM_COMM_SMS: int = 16, **ref_hints) -> GemmARContext:
     """Context of the single-kernel GEMM+AllReduce (reference :127, double-buffered ``num_phases=2``)."""
+    U.accept_ref_hints("create_ll_gemm_ar_context", ref_hints, ('MIN_BLOCK_SIZE_M', 'MIN_BLOCK_SIZE_N', 'num_phases'))
     ctx = create_gemm_ar_context(ar_stream, rank, world_size, local_world_size, max_M, N, dtype)
     heap = U.get_heap()
     ctx.stage = heap.tensor((2, max_M, N), dtype)
@@ -106,8 +108,9 @@ def default_ar_config(M: int, N: int, K: int, n_comm: int = 16, num_sms: int = 1
 
 
 def low_latency_gemm_allreduce_op(ctx: GemmARContext, a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None,
-                                  gemm_config: Optional[GemmConfig] = None, straggler_option=None, **_unused) -> torch.Tensor:
+                                  gemm_config: Optional[GemmConfig] = None, straggler_option=None, **ref_hints) -> torch.Tensor:
     """Single fused kernel; falls back to :func:`gemm_allreduce_op` when the context has no fused buffers."""
+    U.accept_ref_hints("low_latency_gemm_allreduce_op", ref_hints, ('copy_to_local', 'USE_MULTIMEM_ST', 'TILE_MAP_LEVEL', 'A_scale', 'B_scale'))
     w = b if (b.shape[1] == a.shape[1] and b.stride(1) == 1) else _as_nk(b)
     M, K = a.shape
     N = w.shape[0]
@@ -145,8 +148,9 @@ def low_latency_gemm_allreduce_op(ctx: GemmARContext, a: torch.Tensor, b: torch.
 
 
 def gemm_allreduce_op(ctx: GemmARContext, a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None,
-                      gemm_config: Optional[GemmConfig] = None, method=None, straggler_option=None, **_unused) -> torch.Tensor:
+                      gemm_config: Optional[GemmConfig] = None, method=None, straggler_option=None, **ref_hints) -> torch.Tensor:
     """``a``: [M, K/W]; ``b``: weight [N, K/W] (K-major) or its ``.t()`` view -> all-reduced [M, N]."""
+    U.accept_ref_hints("gemm_allreduce_op", ref_hints, ('copy_to_local', 'USE_MULTIMEM_ST', 'As', 'Bs', 'pg'))
     w = b if (b.shape[1] == a.shape[1] and b.stride(1) == 1) else _as_nk(b)
     M, K = a.shape
     N = w.shape[0]
@@ -168,7 +172,7 @@ def gemm_allreduce_op(ctx: GemmARContext, a: torch.Tensor, b: torch.Tensor, out:
     gemm(a, w, out=stage0, config=gemm_config or default_config(M, N, K), out_parity=(ctx.ar_ctx.phase, ws))
     if method is None:
         method = comm.get_auto_allreduce_method(nbytes)
-    comm.all_reduce(stage0, method, ctx.ar_ctx, output=out, straggler_option=straggler_option)
+    comm.all_reduce(stage0, method, ctx.ar_ctx, output=out, straggler_option=straggler_option, device_parity_input=True)
     return out
 
 

@@ -20,7 +20,7 @@ import torch
 
 from .. import _C
 from .. import utils as U
-from .gemm import GemmConfig, fill_common, gemm
+from .gemm import GemmConfig, attach_splitk, fill_common, gemm
 from .ag_gemm import _as_nk
 
 
@@ -32,15 +32,18 @@ class GEMMReduceScatterTensorParallelContext:
     world_size: int
     local_world_size: int
     output_dtype: torch.dtype
-    stage: torch.Tensor = None      # symmetric [2, max_M, N]
+    stage: torch.Tensor = None      # symmetric [2, max_M, N] (16-bit, or fp32 when fp32_ring)
+    fp32_ring: bool = False         # running partial sums travel in fp32: one rounding at the owner instead of W-1
     flags: torch.Tensor = None      # symmetric int32 [2, max_tiles]
     phase: torch.Tensor = None      # local int32 [4]
-    scratch: torch.Tensor = None    # symmetric [max_M, N] (fallback path only, lazily allocated)
+    scratch: object = None          # AllReduceContext of the ragged-M path (GEMM -> NVLS reduce-scatter), lazily allocated
     host_phase: int = 0
 
     def finalize(self):
         heap = U.get_heap()
-        for t in (self.stage, self.flags, self.scratch):
+        if self.scratch is not None:
+            self.scratch.finalize()
+        for t in (self.stage, self.flags):
             if t is not None:
                 heap.free_tensor(t)
         self.stage = self.flags = self.scratch = None
@@ -48,12 +51,18 @@ class GEMMReduceScatterTensorParallelContext:
 
 def create_gemm_rs_context(max_M: int, N: int, rank: Optional[int] = None, world_size: Optional[int] = None,
                            local_world_size: Optional[int] = None, output_dtype: torch.dtype = torch.bfloat16,
-                           rs_stream=None, reduce_st: bool = False, **_unused) -> GEMMReduceScatterTensorParallelContext:
+                           rs_stream=None, reduce_st: bool = False, fp32_ring: Optional[bool] = None,
+                           **ref_hints) -> GEMMReduceScatterTensorParallelContext:
+    """``fp32_ring`` (default: env ``TD_RS_FP32``, off): stage the ring's running partial sums in fp32.  The bf16 ring
+    rounds the partial at every hop (W-1 roundings); fp32 staging rounds once at the owner like an fp32 reduce, at twice the
+    NVLink bytes (hidden behind the mainloop for K/W >= 2048, see profiles/gemm_rs_numerics.md)."""
+    U.accept_ref_hints("create_gemm_rs_context", ref_hints, ())
     heap = U.get_heap()
     rank = heap.rank if rank is None else rank
     world_size = heap.world if world_size is None else world_size
     ctx = GEMMReduceScatterTensorParallelContext(max_M, N, rank, world_size, local_world_size or world_size, output_dtype)
-    ctx.stage = heap.tensor((2, max_M, N), output_dtype)
+    ctx.fp32_ring = U.get_bool_env("TD_RS_FP32", False) if fp32_ring is None else bool(fp32_ring)
+    ctx.stage = heap.tensor((2, max_M, N), torch.float32 if ctx.fp32_ring else output_dtype)
     max_tiles = max(((max_M + 127) // 128) * ((N + 31) // 32), world_size, 8)
     ctx.flags = heap.tensor((2, max_tiles), torch.int32)
     ctx.phase = torch.zeros(4, dtype=torch.int32, device=heap.device)
@@ -81,8 +90,11 @@ def default_rs_config(M: int, N: int, K: int, world: int) -> GemmConfig:
 def gemm_rs(A: torch.Tensor, B: torch.Tensor, ctx: GEMMReduceScatterTensorParallelContext,
             gemm_config: Optional[GemmConfig] = None, persistent: bool = True, fuse_scatter: bool = True,
             reduce_st: bool = False, out: Optional[torch.Tensor] = None, straggler_option=None, profiler=None,
-            **_unused) -> torch.Tensor:
-    """A: ``[M, K/W]``, B: ``[K/W, N]`` (``.t()`` view of a ``[N, K/W]`` weight) -> ``[M/W, N]``."""
+            skip_wait: bool = False, **ref_hints) -> torch.Tensor:
+    """A: ``[M, K/W]``, B: ``[K/W, N]`` (``.t()`` view of a ``[N, K/W]`` weight) -> ``[M/W, N]``.
+    ``skip_wait`` runs the GEMM-only twin: same tiles, same epilogue and pushes, but nobody waits for the partial of the
+    previous rank (numerically meaningless; measures the exposed communication as fused - twin)."""
+    U.accept_ref_hints("gemm_rs", ref_hints, ())
     W = ctx.world_size
     M, K = A.shape
     Bnk = _as_nk(B)
@@ -116,8 +128,10 @@ def gemm_rs(A: torch.Tensor, B: torch.Tensor, ctx: GEMMReduceScatterTensorParall
     args.rank, args.world, args.symm_base, args.symm_stride, args.mc_base = r, w, base, stride, mc
     args.phase = ctx.phase.data_ptr()
     args.rs_rows_per_rank = Mr
-    args.rs_stage, args.rs_stage_buf_bytes = ctx.stage.data_ptr(), ctx.max_M * N * A.element_size()
+    args.rs_stage, args.rs_stage_buf_bytes = ctx.stage.data_ptr(), ctx.max_M * N * ctx.stage.element_size()
     args.rs_flags, args.rs_out, args.rs_ldo = ctx.flags.data_ptr(), out.data_ptr(), out.stride(0)
+    args.rs_fp32, args.rs_skip_wait = int(ctx.fp32_ring), int(skip_wait)
+    attach_splitk(args, A.device)
     if profiler is not None:
         profiler.attach(args)
     _C.check(_C.cuda_lib().td_gemm_launch(C.byref(args), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
@@ -127,24 +141,21 @@ def gemm_rs(A: torch.Tensor, B: torch.Tensor, ctx: GEMMReduceScatterTensorParall
 
 
 def _gemm_rs_fallback(A, Bnk, ctx, out):
-    """Shapes the ring cannot tile (M/W not a multiple of 128): local GEMM into a symmetric buffer, barrier,
-    then every rank pulls and sums its rows from all peers (P2P loads)."""
-    heap = U.get_heap()
-    W, me = ctx.world_size, ctx.rank
+    """Shapes the ring cannot tile (M/W not a multiple of 128 -- every small-batch decode step): two kernels, no host
+    barrier, no eager math.  The tcgen05 GEMM writes its partial product straight into the reduce-scatter staging half
+    that the DEVICE-resident call counter selects (CUDA-graph replay safe), then the NVLS pull-reduce kernel
+    (``multimem.ld_reduce`` through the switch; P2P loads without NVLS) gives every rank its rows."""
+    from . import comm
     M, N = A.shape[0], Bnk.shape[0]
-    Mr = M // W
     if ctx.scratch is None:
-        ctx.scratch = heap.tensor((ctx.max_M, ctx.N), ctx.output_dtype)
-        U.barrier_all_host()
-    U.barrier_all_on_stream()                      # peers finished reading the previous call's scratch
-    gemm(A, Bnk, out=ctx.scratch[:M])
-    U.barrier_all_on_stream()
-    acc = torch.zeros((Mr, N), dtype=torch.float32, device=A.device)
-    for j in range(W):
-        p = (me + j) % W
-        acc += heap.peer_view(ctx.scratch, p)[me * Mr:(me + 1) * Mr].float()
-    out.copy_(acc.to(out.dtype))
-    return out
+        # collective lazy allocation: every rank reaches its first ragged call together
+        ctx.scratch = comm.create_allreduce_ctx(ctx.max_M * ctx.N * torch.empty(0, dtype=ctx.output_dtype).element_size(),
+                                                ctx.rank, ctx.world_size, ctx.local_world_size)
+    ar = ctx.scratch
+    nbytes = M * N * A.element_size()
+    stage0 = ar.stage[:nbytes].view(A.dtype).view(M, N)
+    gemm(A, Bnk, out=stage0, out_parity=(ar.phase, ar.workspace_nbytes))
+    return comm.reduce_scatter(stage0, ar, output=out, device_parity_input=True)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -216,8 +227,10 @@ def gemm_rs_mxfp8(a, b, ctx: GEMMReduceScatterTensorParallelContext, out: Option
     args.rank, args.world, args.symm_base, args.symm_stride, args.mc_base = r, w, base, stride, mc
     args.phase = ctx.phase.data_ptr()
     args.rs_rows_per_rank = Mr
-    args.rs_stage, args.rs_stage_buf_bytes = ctx.stage.data_ptr(), ctx.max_M * N * 2
+    args.rs_stage, args.rs_stage_buf_bytes = ctx.stage.data_ptr(), ctx.max_M * N * ctx.stage.element_size()
     args.rs_flags, args.rs_out, args.rs_ldo = ctx.flags.data_ptr(), out.data_ptr(), out.stride(0)
+    args.rs_fp32 = int(ctx.fp32_ring)
+    attach_splitk(args, a.q.device)
     _C.check(_C.cuda_lib().td_gemm_launch(C.byref(args), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "td_gemm_launch(rs, mxfp8)")
     ctx.host_phase += 1
     return out

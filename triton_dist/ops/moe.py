@@ -276,7 +276,8 @@ class MoEAllGatherGroupGEMMContext:
 
 def create_ag_group_gemm_context(max_ntokens: int, N_per_rank: int, K: int, num_experts: int, topk: int, dtype: torch.dtype,
                                  rank: Optional[int] = None, world_size: Optional[int] = None, local_world_size=None,
-                                 **_unused) -> MoEAllGatherGroupGEMMContext:
+                                 **ref_hints) -> MoEAllGatherGroupGEMMContext:
+    U.accept_ref_hints("create_ag_group_gemm_context", ref_hints, ('BLOCK_M', 'BLOCK_N', 'BLOCK_K', 'GROUP_SIZE_M', 'stages', 'num_warps', 'ag_stream', 'group_gemm_stream', 'for_correctness'))
     heap = U.get_heap()
     rank = heap.rank if rank is None else rank
     world_size = heap.world if world_size is None else world_size
@@ -374,7 +375,8 @@ class MoEReduceRSContext:
 
 def create_moe_rs_context(rank: Optional[int], world_size: Optional[int], local_world_size, max_token_num: int,
                           hidden_dim: int, num_experts: int, topk: int, dtype: torch.dtype, n_chunks_max: int = 8,
-                          **_unused) -> MoEReduceRSContext:
+                          **ref_hints) -> MoEReduceRSContext:
+    U.accept_ref_hints("create_moe_rs_context", ref_hints, ('rs_stream', 'reduction_stream'))
     heap = U.get_heap()
     rank = heap.rank if rank is None else rank
     world_size = heap.world if world_size is None else world_size
@@ -405,9 +407,10 @@ def _moe_down_partial(x, w, chosen_experts, expert_weight, ctx):
 
 
 def run_moe_reduce_rs(x: torch.Tensor, w: torch.Tensor, chosen_experts: torch.Tensor, expert_weight: torch.Tensor,
-                      ctx: MoEReduceRSContext, n_chunks: int = 2, **_unused) -> torch.Tensor:
+                      ctx: MoEReduceRSContext, n_chunks: int = 2, **ref_hints) -> torch.Tensor:
     """x: ``[T*topk, K/W]``, w: ``[E, K/W, N]`` (or K-major ``[E, N, K/W]``), chosen_experts/expert_weight: ``[T, topk]``
     -> ``[T/W, N]`` = reduce_scatter_ranks( sum_j weight[t,j] * (x[t*topk+j] @ w[e_tj]) )."""
+    U.accept_ref_hints("run_moe_reduce_rs", ref_hints, ('persistent', 'config'))
     W = ctx.world_size
     wk = w.transpose(1, 2) if (w.shape[1] == x.shape[1] and w.shape[2] != x.shape[1]) else w      # -> [E, N, K/W]
     N = wk.shape[1]
@@ -450,7 +453,8 @@ def _moe_reduce_rs_chunked(x, wk, chosen_experts, expert_weight, ctx, n_chunks):
     return out
 
 
-def run_moe_reduce_ar(x, w, chosen_experts, expert_weight, ctx: MoEReduceRSContext, **_unused) -> torch.Tensor:
+def run_moe_reduce_ar(x, w, chosen_experts, expert_weight, ctx: MoEReduceRSContext, **ref_hints) -> torch.Tensor:
+    U.accept_ref_hints("run_moe_reduce_ar", ref_hints, ('n_chunks', 'persistent', 'config'))
     part = _moe_down_partial(x, w, chosen_experts, expert_weight, ctx)
     if ctx.world_size == 1:
         return part

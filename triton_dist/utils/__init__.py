@@ -36,6 +36,19 @@ _STATE = {
 # ------------------------------------------------------------------------------------------------------------
 # env helpers (utils.py:890-911)
 # ------------------------------------------------------------------------------------------------------------
+def accept_ref_hints(fn: str, kwargs: dict, allowed: tuple = ()) -> None:
+    """Entry points keep the reference's signatures; arguments that only steer the reference's Triton kernels or its host
+    streams (tile hints, side streams) are accepted by NAME and documented as having no effect here.  Anything else raises
+    -- an argument is never silently dropped."""
+    bad = [k for k in kwargs if k not in allowed]
+    if bad:
+        raise TypeError(f"{fn}() got unexpected keyword argument(s) {bad}; reference-only hints accepted (no effect on "
+                        f"the sm_100a kernels): {list(allowed)}")
+    for k in ("A_scale", "B_scale", "As", "Bs", "scale_a", "scale_b"):
+        if kwargs.get(k) is not None:
+            raise NotImplementedError(f"{fn}(): {k} was given but this entry point does not apply scales")
+
+
 def get_bool_env(name: str, default: bool = False) -> bool:
     v = os.environ.get(name)
     if v is None:
@@ -208,9 +221,12 @@ def nvshmem_create_tensors(shape, dtype: torch.dtype, rank: int, local_world_siz
 
 
 def nvshmem_free_tensor_sync(t: torch.Tensor):
+    """Collective free (like the reference's ``nvshmem_free``): drain my stream, wait until every rank has done the same,
+    then release the offset -- a peer may still be writing flags / data into the tensor until it reaches the barrier."""
     heap = get_heap()
     if heap.is_cuda:
         torch.cuda.synchronize()
+    barrier_all_host()
     heap.free_tensor(t)
 
 
