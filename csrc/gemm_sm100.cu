@@ -39,6 +39,8 @@ struct TdGemmArgs {
   long long rs_skip_wait;         // RS GEMM-only twin
   long long rs_fp32;              // RS ring partial sums in fp32 (staging buffers are [M, N] fp32)
   long long ag_kslices;           // multicast AG: requested number of K slices (0 = default)
+  // mode 4 (MoE reduce-RS / reduce-AR): rs_stage = partial [2][T][N], rs_flags = [2][num_n][W][n_comm], rs_out = output
+  const void* row_scale; void* mrs_counter; const void* mrs_total_padded; long long mrs_T, mrs_topk, mrs_allreduce;
 };
 
 static int encode_tmap(CUtensorMap* out, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
@@ -238,6 +240,16 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
     p.ag_local_direct = 1;
   }
   p.rs_skip_wait = (int)a->rs_skip_wait; p.rs_fp32 = (int)a->rs_fp32;
+  p.row_scale = reinterpret_cast<const float*>(a->row_scale);
+  if (a->mode == kMoeRS) {
+    if (cg != 1 || fp8 || !a->a_gather || !a->c_scatter || !a->tile_expert) { drv::set_error("moe_reduce_rs: needs the gather4 grouped GEMM (cta_group 1, 16-bit)"); return -1; }
+    if (p.n_comm_ctas < 1 || !a->mrs_counter || !a->mrs_total_padded || !a->rs_stage || !a->rs_flags || !a->rs_out) { drv::set_error("moe_reduce_rs: missing buffers / comm CTAs"); return -1; }
+    if (p.N % 8 != 0 || a->rs_ldo % 8 != 0 || a->ldc % 8 != 0) { drv::set_error("moe_reduce_rs: N and row strides must be multiples of 8"); return -1; }
+    if (!a->mrs_allreduce && a->mrs_T % a->world != 0) { drv::set_error("moe_reduce_rs: tokens must divide by the world size"); return -1; }
+    p.mrs_counter = reinterpret_cast<uint32_t*>(a->mrs_counter); p.mrs_total_padded = reinterpret_cast<const int*>(a->mrs_total_padded);
+    p.mrs_T = (int)a->mrs_T; p.mrs_topk = (int)a->mrs_topk; p.mrs_allreduce = (int)a->mrs_allreduce;
+    p.group_m = p.num_m;      // n-tile major order: a chunk of output columns completes as early as possible
+  }
   if (p.n_comm_ctas % cg) p.n_comm_ctas += cg - p.n_comm_ctas % cg;
   if (a->mode == kAR && p.a2a_cols_per_rank > 0) p.n_comm_ctas = 0;     // GEMM + all-to-all: the epilogue scatters, no comm CTAs
   int gemm_ctas = grid - p.n_comm_ctas;      // comm CTAs must be co-resident with the GEMM CTAs: the grid never exceeds the SMs
@@ -296,6 +308,10 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
     case kAG: return dispatch<kAG>(p, bn, cg, grid, stream);
     case kRS: return dispatch<kRS>(p, bn, cg, grid, stream);
     case kAR: return dispatch<kAR>(p, bn, cg, grid, stream);
+    case kMoeRS:
+      if (bn == 256) return launch_cfg<kMoeRS, 256, 1>(p, grid, stream);
+      if (bn == 128) return launch_cfg<kMoeRS, 128, 1>(p, grid, stream);
+      drv::set_error("moe_reduce_rs: bn must be 128 or 256"); return -1;
     default: drv::set_error("bad mode"); return -1;
   }
 }

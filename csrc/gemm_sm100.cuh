@@ -12,6 +12,12 @@
 //            the epilogue stores the partial tile into this rank's symmetric staging buffer and raises flag[tile][me]
 //            on every rank; comm CTAs of the same grid wait for all W flags of a tile, multimem.ld_reduce it through
 //            the NVSwitch (or sum the peers' copies over P2P) and write the reduced tile to the local output
+//   kMoeRS : grouped (MoE) GEMM + weighted top-k reduce + ReduceScatter / AllReduce in ONE kernel
+//            (ref: kernels/nvidia/moe_reduce_rs.py:168-246 producer with per-chunk flags, :549-619 consumer;
+//             moe_reduce_ar.py:563): tiles run n-tile major; the epilogue scales every row by its routing weight and
+//            scatters it to (token, k) order; comm CTAs of the same grid wait for "all m tiles of n tile c done", sum the
+//            top-k rows of each token into this rank's symmetric partial, flag the peers, and one chunk later every owner
+//            pulls the cross-rank sum of ITS rows with multimem.ld_reduce (NVSwitch adds the W partials in fp32)
 //
 // B200-first design (not a translation of the reference):
 //   * warp-specialised CTA: warp0 = TMA producer, warp1 = single-thread tcgen05.mma issuer, warp2 = TMEM
@@ -48,7 +54,7 @@ constexpr int kCBlockBytes = BM * kCBlockCols * 2;
 constexpr int kAGRowsPerChunk = 128;                  // AG arrival-flag granularity (rows of a source shard)
 constexpr int kAGMaxSlices = 256;                     // arrival flags per source rank (comm CTAs x sub-slices / K slices)
 
-enum Mode : int { kPlain = 0, kAG = 1, kRS = 2, kAR = 3 };
+enum Mode : int { kPlain = 0, kAG = 1, kRS = 2, kAR = 3, kMoeRS = 4 };
 
 struct Params {
   CUtensorMap tmap_a;   // dims {K, rows_a, nbuf}, box {64, 128, 1}, SWIZZLE_128B
@@ -122,6 +128,12 @@ struct Params {
   uint32_t* a2a_count;       // local [world] tile counters (last tile for a destination publishes the flag)
   void* rs_out;              // [rows_per_rank, N] final output (local)
   long long rs_ldo;
+  // ---- MoE reduce-RS / reduce-AR (kMoeRS) ----
+  const float* row_scale;    // optional: the C row scattered to id is multiplied by row_scale[id] (routing weight) in the epilogue
+  uint32_t* mrs_counter;     // local [2][num_n]: finished m tiles per n tile; this call's parity counts, the other is zeroed
+  const int* mrs_total_padded;   // device: padded row count of the routing (valid m tiles = *p / 128)
+  int mrs_T, mrs_topk, mrs_allreduce, pad4;
+  // (partial: rs_stage [2][T][N] 16-bit symmetric; flags: rs_flags [2][num_n][W][n_comm]; output: rs_out / rs_ldo)
   // ---- split-K tail: the last partial wave of tiles is cut into sk_parts K ranges that run on otherwise idle clusters;
   // parts > 0 park their fp32 accumulator in sk_ws, part 0 adds them in its epilogue (wave quantisation: 768 tiles on
   // 74 CTA pairs = 10.4 waves -> 10.5 instead of 11)
@@ -264,18 +276,21 @@ TD_DEVICE void ag_comm_cta(const Params& p, uint32_t ph, int comm_idx) {
       const int seg16 = static_cast<int>((min(row_bytes, col0 + seg_bytes) - col0) >> 4);
       const int n = max(0, r1 - r0) * seg16;
       if (threadIdx.x == 0) prof_record(p.prof, pslot, 1, true);
-      constexpr int U = 8;
+      // 16 independent 16-byte loads per thread before the first store (the copy loop is bound by the latency of its reads)
+      constexpr int U = 16;
+      auto off_of = [&](int i) { return static_cast<size_t>(r0 + i / seg16) * row_bytes + col0 + static_cast<size_t>(i % seg16) * 16; };
       for (int i0 = threadIdx.x; i0 < n; i0 += U * kThreads) {
-        uint4 v[U]; size_t off[U];
+        uint4 v[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int i = i0 + u * kThreads;
-          off[u] = static_cast<size_t>(r0 + i / seg16) * row_bytes + col0 + static_cast<size_t>(i % seg16) * 16;
-          if (i < n) v[u] = ptx::ld_nc_v4(src0 + off[u]);
+          if (i < n) v[u] = ptx::ld_nc_v4(src0 + off_of(i));
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u)
-          if (i0 + u * kThreads < n) ptx::multimem_st_v4(ws_mc + off[u], v[u]);
+        for (int u = 0; u < U; ++u) {
+          const int i = i0 + u * kThreads;
+          if (i < n) ptx::multimem_st_v4(ws_mc + off_of(i), v[u]);
+        }
       }
       __syncthreads();
       if (threadIdx.x == 0) {
@@ -377,6 +392,99 @@ TD_DEVICE void ar_comm_cta(const Params& p, uint32_t ph, int comm_idx) {
 }
 
 // -------------------------------------------------------------------------------------------------
+// MoE reduce-RS comm CTA ci: per n tile c (= chunk of BN output columns)
+//   (1) wait until every valid m tile of chunk c has been scattered to y (= p.C, [T * topk, N], rows already weighted)
+//   (2) sum the top-k rows of my token slice into my symmetric partial part[t][chunk]
+//   (3) release-flag every rank: flag[par][c][me][ci] = phase
+//   (4) one chunk later: wait for the W ranks' flags of the slices that cover the rows I pull and reduce them through the
+//       NVSwitch (multimem.ld_reduce, fp32 accumulation) -- or W peer loads without NVLS -- into the output
+// Reduce-scatter: rank r pulls tokens [r * T / W, (r + 1) * T / W); all-reduce: every rank pulls every token.
+// -------------------------------------------------------------------------------------------------
+template <int BN>
+TD_DEVICE void moe_rs_comm_cta(const Params& p, uint32_t ph, int ci) {
+  const int W = p.symm.world, me = p.symm.rank, nc = p.n_comm_ctas, T = p.mrs_T, topk = p.mrs_topk, N = p.N;
+  const uint32_t par = ph & 1u;
+  uint32_t* counter = p.mrs_counter + par * p.num_n;
+  if (ci == 0)
+    for (int i = threadIdx.x; i < p.num_n; i += kThreads) p.mrs_counter[(par ^ 1u) * p.num_n + i] = 0u;   // the NEXT call's counters
+  char* part = p.rs_stage + par * p.rs_stage_buf_bytes;
+  const char* y = reinterpret_cast<const char*>(p.C);
+  const uint32_t* flags = p.rs_flags + static_cast<size_t>(par) * p.num_n * W * nc;
+  const uint32_t valid_tiles = static_cast<uint32_t>(*p.mrs_total_padded / BM);
+  const int tok_per_cta = (T + nc - 1) / nc;
+  const int t0 = min(T, ci * tok_per_cta), t1 = min(T, t0 + tok_per_cta);
+  int r0, r1, out_row0;
+  if (p.mrs_allreduce) { r0 = t0; r1 = t1; out_row0 = 0; }
+  else {
+    const int Tr = T / W, rows_per = (Tr + nc - 1) / nc;
+    r0 = me * Tr + min(Tr, ci * rows_per); r1 = me * Tr + min(Tr, (ci + 1) * rows_per); out_row0 = me * Tr;
+  }
+  constexpr int kCPR = BN / 8;                         // 16-byte chunks per row of one n tile
+  for (int c = 0; c <= p.num_n; ++c) {
+    if (c < p.num_n) {
+      if (threadIdx.x == 0) { while (ptx::ld_acquire_gpu(counter + c) < valid_tiles) {} }
+      __syncthreads();
+      const int col0 = c * BN;
+      for (int i = threadIdx.x; i < (t1 - t0) * kCPR; i += kThreads) {
+        const int t = t0 + i / kCPR, col = col0 + (i % kCPR) * 8;
+        if (col >= N) continue;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int k = 0; k < topk; ++k) {
+          const uint4 x = ptx::ld_relaxed_sys_v4(y + (static_cast<size_t>(t * topk + k) * p.ldc + col) * 2);
+          const uint32_t w4[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (p.in_is_bf16) { acc[2 * e] += ptx::bf16_lo(w4[e]); acc[2 * e + 1] += ptx::bf16_hi(w4[e]); }
+            else { const __half2 hh = *reinterpret_cast<const __half2*>(&w4[e]); acc[2 * e] += __low2float(hh); acc[2 * e + 1] += __high2float(hh); }
+          }
+        }
+        uint4 v;
+        if (p.in_is_bf16) { v.x = ptx::pack_bf16x2(acc[0], acc[1]); v.y = ptx::pack_bf16x2(acc[2], acc[3]); v.z = ptx::pack_bf16x2(acc[4], acc[5]); v.w = ptx::pack_bf16x2(acc[6], acc[7]); }
+        else { v.x = ptx::pack_f16x2(acc[0], acc[1]); v.y = ptx::pack_f16x2(acc[2], acc[3]); v.z = ptx::pack_f16x2(acc[4], acc[5]); v.w = ptx::pack_f16x2(acc[6], acc[7]); }
+        ptx::st_v4(part + (static_cast<size_t>(t) * N + col) * 2, v);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        ptx::fence_acq_rel_sys();
+        uint32_t* f = p.rs_flags + ((static_cast<size_t>(par) * p.num_n + c) * W + me) * nc + ci;
+        for (int d = 0; d < W; ++d) ptx::st_relaxed_sys(symm_at(p.symm, f, (me + d) % W), ph);
+      }
+    }
+    if (c >= 1 && r1 > r0) {
+      const int cc = c - 1, col0 = cc * BN;
+      const int j0 = r0 / tok_per_cta, j1 = (r1 - 1) / tok_per_cta;
+      for (int i = threadIdx.x; i < W * (j1 - j0 + 1); i += kThreads)
+        wait_ge<true>(flags + (static_cast<size_t>(cc) * W + i % W) * nc + j0 + i / W, ph);
+      __syncthreads();
+      for (int i = threadIdx.x; i < (r1 - r0) * kCPR; i += kThreads) {
+        const int t = r0 + i / kCPR, col = col0 + (i % kCPR) * 8;
+        if (col >= N) continue;
+        char* src = part + (static_cast<size_t>(t) * N + col) * 2;
+        uint4 v;
+        if (p.symm.mc_base) {
+          v = p.in_is_bf16 ? ptx::multimem_ld_reduce_bf16x8(symm_mc(p.symm, src)) : ptx::multimem_ld_reduce_f16x8(symm_mc(p.symm, src));
+        } else {
+          float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          for (int s = 0; s < W; ++s) {
+            const uint4 x = ptx::ld_relaxed_sys_v4(symm_at(p.symm, src, (me + s) % W));
+            const uint32_t w4[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (p.in_is_bf16) { acc[2 * e] += ptx::bf16_lo(w4[e]); acc[2 * e + 1] += ptx::bf16_hi(w4[e]); }
+              else { const __half2 hh = *reinterpret_cast<const __half2*>(&w4[e]); acc[2 * e] += __low2float(hh); acc[2 * e + 1] += __high2float(hh); }
+            }
+          }
+          if (p.in_is_bf16) { v.x = ptx::pack_bf16x2(acc[0], acc[1]); v.y = ptx::pack_bf16x2(acc[2], acc[3]); v.z = ptx::pack_bf16x2(acc[4], acc[5]); v.w = ptx::pack_bf16x2(acc[6], acc[7]); }
+          else { v.x = ptx::pack_f16x2(acc[0], acc[1]); v.y = ptx::pack_f16x2(acc[2], acc[3]); v.z = ptx::pack_f16x2(acc[4], acc[5]); v.w = ptx::pack_f16x2(acc[6], acc[7]); }
+        }
+        ptx::st_v4(reinterpret_cast<char*>(p.rs_out) + (static_cast<size_t>(t - out_row0) * p.rs_ldo + col) * 2, v);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
 // the kernel
 // -------------------------------------------------------------------------------------------------
 template <int kMode, int BN, int kStages, int kCtaGroup, bool kFP8 = false, int kAccStages = 2>
@@ -411,6 +519,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     }
     if constexpr (kMode == kAR) {
       ar_comm_cta<kCtaGroup, BN>(p, ph, static_cast<int>(blockIdx.x) - n_gemm_ctas);
+    }
+    if constexpr (kMode == kMoeRS) {
+      moe_rs_comm_cta<BN>(p, ph, static_cast<int>(blockIdx.x) - n_gemm_ctas);
     }
   } else {
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
@@ -682,6 +793,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
           continue;
         }
         const int sk_n = (un.slot >= 0) ? p.sk_parts - 1 : 0;     // partial accumulators to add (split-K part 0)
+        float row_scale = 1.f;
+        if (p.row_scale != nullptr && p.c_scatter != nullptr) {   // routing weight of the (token, k) pair this row is scattered to
+          const int grow = row_base + my_row;
+          const int id = grow < p.M ? p.c_scatter[grow] : -1;
+          row_scale = (id >= 0 && id != p.a_gather_pad) ? p.row_scale[id] : 0.f;
+        }
 
         // ---- RS ring bookkeeping for this tile ----
         int rs_step = 0; bool rs_final = false;
@@ -753,6 +870,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             float f[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+            if (p.row_scale != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] *= row_scale;
+            }
             if (sk_n > 0) {
               const int ch = cb * (kColsPerBlock / 32) + h;
               for (int pp = 0; pp < sk_n; ++pp) {
@@ -898,6 +1019,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             }
             __syncwarp();
           }
+        }
+        if constexpr (kMode == kMoeRS) {
+          // this tile's rows are in y: count it for its n tile (the comm CTAs wait for all valid m tiles of a chunk)
+          ptx::named_bar_sync(2, kEpiThreads);
+          if (et == 0) { __threadfence(); ptx::red_release_gpu_add(p.mrs_counter + (ph & 1u) * p.num_n + n_tile, 1u); }
+          __syncwarp();
         }
         if constexpr (kMode == kAR) {
           // each CTA of a pair stages its own 128 rows and publishes its own flag word (index carries the CTA rank);

@@ -14,6 +14,14 @@ if [ "$stage" = "a" ]; then
 fi
 if [ "$stage" = "b" ]; then
   N=${2:-2}
-  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tests/dist_worker.py ag_gemm gemm_rs > gpurun_out/dist_ag_rs_n$N.log 2>&1; echo "dist rc=$?"; tail -15 gpurun_out/dist_ag_rs_n$N.log
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tests/dist_worker.py ag_gemm gemm_rs moe_rs moe > gpurun_out/dist_ag_rs_n$N.log 2>&1; echo "dist rc=$?"; tail -15 gpurun_out/dist_ag_rs_n$N.log
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "bench rc=$?"; tail -c 4000 gpurun_out/bench_n$N.json; tail -5 gpurun_out/bench_n$N.err
+fi
+if [ "$stage" = "c" ]; then
+  N=${2:-8}
+  TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+  timeout 400 $TR --master-port 29521 tests/dist_worker.py ag_gemm gemm_rs moe_rs > gpurun_out/dist_n$N.log 2>&1; echo "dist rc=$?"; tail -6 gpurun_out/dist_n$N.log
+  timeout 500 $TR --master-port 29522 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "bench rc=$?"; tail -c 2500 gpurun_out/bench_n$N.json; tail -3 gpurun_out/bench_n$N.err
+  timeout 300 $TR --master-port 29523 triton_dist/benchmark/bench_moe_reduce_rs.py --json gpurun_out/moe_reduce_rs_n$N.json > gpurun_out/moe_rs_n$N.log 2>&1; echo "moe rc=$?"; tail -3 gpurun_out/moe_rs_n$N.log
+  timeout 200 $TR --master-port 29524 scripts/gpu_prof_ag.py transport=multicast bn=128 cta_group=1 n_comm=16 kslices=8 > gpurun_out/prof_ag_mc_n$N.log 2>&1; echo "prof rc=$?"; tail -8 gpurun_out/prof_ag_mc_n$N.log
 fi

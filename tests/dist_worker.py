@@ -317,6 +317,39 @@ def case_moe():
     ag.finalize(); rs.finalize()
 
 
+def case_moe_rs():
+    """Single-kernel grouped GEMM + weighted top-k reduce + ReduceScatter / AllReduce (mode kMoeRS) vs the masked-matmul golden;
+    several shapes (256- and 128-wide n tiles, ragged last n tile), >= 4 calls per context (parity double buffering), a straggler."""
+    from triton_dist.ops import moe as M
+    dev = U.current_device()
+    W, me = U.world_size(), U.rank()
+    big = dev.type == "cuda"
+    dtype = torch.bfloat16 if big else torch.float32
+    grp = U.get_triton_dist_world()
+    shapes = [(256 * W, 512, 1024, 8, 2), (128 * W, 384, 512, 4, 2), (64 * W, 1032, 256, 8, 4)] if big else [(8 * W, 16, 32, 4, 2)]
+    for (T, H, I, E, topk) in shapes:
+        rs = M.create_moe_rs_context(me, W, W, T * topk, H, E, topk, dtype)
+        for it in range(5):
+            g = torch.Generator(device="cpu").manual_seed(7 + it)          # same routing on all ranks
+            ids = torch.rand(T, E, generator=g).topk(topk, dim=1).indices.to(torch.int32).to(dev)
+            wts = torch.softmax(torch.randn(T, topk, generator=g), -1).to(dev)
+            h = (torch.randn(T * topk, I // W, device=dev) * 0.5).to(dtype)
+            w_dn = (torch.randn(E, H, I // W, device=dev) * 0.2).to(dtype)
+            if big and it == 2:
+                torch.cuda._sleep(3_000_000 * (1 + me))
+            gold_full = M.moe_reduce_rs_torch(h, w_dn.transpose(1, 2), ids, wts, grp, 1, 0).float()      # my partial [T, H] (fp32)
+            dist.all_reduce(gold_full, group=grp)
+            if it % 2 == 0:
+                out = M.run_moe_reduce_rs(h, w_dn, ids, wts, rs)
+                _assert_close(out, gold_full[me * (T // W):(me + 1) * (T // W)], 0.5 if big else 1e-3, 3e-2 if big else 1e-4,
+                              f"moe_reduce_rs T{T} H{H} it{it}")
+            else:
+                out = M.run_moe_reduce_ar(h, w_dn, ids, wts, rs)
+                _assert_close(out, gold_full, 0.5 if big else 1e-3, 3e-2 if big else 1e-4, f"moe_reduce_ar T{T} H{H} it{it}")
+        U.barrier_all_host()
+        rs.finalize()
+
+
 def case_moe_staged():
     """The multi-kernel MoE path (all-gather kernel -> gather_rows -> grouped GEMM -> scatter_rows); ``case_moe`` runs the
     default single-kernel path on GPUs (AllGather + grouped GEMM with a TMA tile::gather4 producer waiting on arrival flags)."""

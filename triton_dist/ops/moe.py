@@ -366,11 +366,26 @@ class MoEReduceRSContext:
     topk: int
     dtype: torch.dtype
     ar_ctx: comm.AllReduceContext = None
+    # single-kernel path (csrc/gemm_sm100.cuh, mode kMoeRS)
+    part: torch.Tensor = None        # symmetric [2, T, N]: my top-k-reduced partial, pulled by the owners through the NVSwitch
+    flags: torch.Tensor = None       # symmetric int32 [2, max_n_tiles, W, n_comm]
+    counter: torch.Tensor = None     # local int32 [2, max_n_tiles]: finished m tiles per n tile
+    phase: torch.Tensor = None       # local int32 [4]
+    y: torch.Tensor = None           # local [T * topk, N]: weighted expert outputs in (token, k) order
+    n_comm: int = 16
 
     def finalize(self):
         if self.ar_ctx is not None:
             self.ar_ctx.finalize()
             self.ar_ctx = None
+        heap = U.get_heap()
+        for t in (self.part, self.flags):
+            if t is not None:
+                heap.free_tensor(t)
+        self.part = self.flags = None
+
+
+_MRS_MAX_NTILES = 64
 
 
 def create_moe_rs_context(rank: Optional[int], world_size: Optional[int], local_world_size, max_token_num: int,
@@ -384,6 +399,12 @@ def create_moe_rs_context(rank: Optional[int], world_size: Optional[int], local_
     T = max_token_num // topk
     ctx.ar_ctx = comm.create_allreduce_ctx(max(T * hidden_dim * torch.empty(0, dtype=dtype).element_size(), 1024), rank,
                                            world_size, world_size)
+    if heap.device.type == "cuda" and world_size > 1 and U.get_bool_env("TD_MOE_RS_FUSED", True):
+        ctx.part = heap.tensor((2, T, hidden_dim), dtype)
+        ctx.flags = heap.tensor((2, _MRS_MAX_NTILES, world_size, 32), torch.int32)
+        ctx.counter = torch.zeros((2, _MRS_MAX_NTILES), dtype=torch.int32, device=heap.device)
+        ctx.phase = torch.zeros(4, dtype=torch.int32, device=heap.device)
+        U.barrier_all_host()
     return ctx
 
 
@@ -406,6 +427,55 @@ def _moe_down_partial(x, w, chosen_experts, expert_weight, ctx):
     return reduce_topk(y, expert_weight, ctx.topk)
 
 
+def _moe_reduce_fused(x, wk, chosen_experts, expert_weight, ctx: MoEReduceRSContext, allreduce: bool,
+                      out: Optional[torch.Tensor] = None, n_comm: Optional[int] = None, bn: Optional[int] = None) -> torch.Tensor:
+    """Grouped GEMM + weighted top-k reduce + ReduceScatter (or AllReduce) in ONE kernel (csrc/gemm_sm100.cuh, kMoeRS):
+    TMA-gather4 grouped GEMM tiles in n-tile-major order; the epilogue multiplies each row by its routing weight and scatters
+    it to (token, k) order; comm CTAs of the same grid, per n tile: wait for all m tiles -> sum the top-k rows into my symmetric
+    partial -> flag the peers -> (one chunk later) every owner pulls the cross-rank sum of its rows with multimem.ld_reduce.
+    No reduce_topk kernel, no side stream, no final copy.  Reference: moe_reduce_rs.py:168-246 + 549-619 (two kernels and a
+    stream pair), moe_reduce_ar.py:563."""
+    W, topk = ctx.world_size, ctx.topk
+    T = chosen_experts.shape[0]
+    E, N, K = wk.shape
+    assert x.shape == (T * topk, K) and T * topk <= ctx.max_token_num and N == ctx.hidden_dim
+    bn = bn or (256 if N % 256 == 0 else 128)
+    num_n = (N + bn - 1) // bn
+    assert num_n <= _MRS_MAX_NTILES, "moe_reduce_rs: too many n tiles for the flag array"
+    n_comm = min(32, n_comm or ctx.n_comm)
+    r = moe_align_sort(chosen_experts, ctx.num_experts, 128)
+    if ctx.y is None or ctx.y.shape[0] < T * topk:
+        ctx.y = torch.empty((ctx.max_token_num, N), dtype=x.dtype, device=x.device)
+    rows_out = T if allreduce else T // W
+    out = torch.empty((rows_out, N), dtype=x.dtype, device=x.device) if out is None else out
+    scale = expert_weight.reshape(-1).to(torch.float32).contiguous()
+    xc = x.contiguous()
+    args = _C.GemmArgs()
+    args.mode = 4
+    fill_common(args, xc.shape[0], xc.data_ptr(), xc.stride(0), wk.reshape(E * N, K), ctx.y.data_ptr(), T * topk, ctx.y.stride(0),
+                r.capacity, N, K, GemmConfig(bn, 1, 1, False, 0, n_comm), x.dtype == torch.bfloat16)
+    args.tile_expert, args.num_experts = r.tile_expert.data_ptr(), E
+    args.a_gather, args.a_gather_div, args.a_gather_pad = r.sorted_ids.data_ptr(), 1, r.pad_id
+    args.a_src_rows, args.c_scatter = xc.shape[0], r.sorted_ids.data_ptr()
+    rk, w_, base, stride, mc = U.symm_ctx_fields()
+    args.rank, args.world, args.symm_base, args.symm_stride, args.mc_base = rk, w_, base, stride, mc
+    args.phase = ctx.phase.data_ptr()
+    args.rs_stage, args.rs_stage_buf_bytes = ctx.part.data_ptr(), ctx.part[0].numel() * ctx.part.element_size()
+    args.rs_flags, args.rs_out, args.rs_ldo = ctx.flags.data_ptr(), out.data_ptr(), out.stride(0)
+    args.row_scale, args.mrs_counter, args.mrs_total_padded = scale.data_ptr(), ctx.counter.data_ptr(), r.total_padded.data_ptr()
+    args.mrs_T, args.mrs_topk, args.mrs_allreduce = T, topk, int(allreduce)
+    _C.check(_C.cuda_lib().td_gemm_launch(C.byref(args), _s()), "td_gemm_launch(moe_reduce_rs)")
+    return out
+
+
+def _fused_ok(x, wk, ctx, T, allreduce):
+    W = ctx.world_size
+    return (W > 1 and x.is_cuda and ctx.part is not None and _use_tma_gather(x) and wk.is_contiguous() and wk.shape[1] % 8 == 0
+            and wk.shape[1] == ctx.hidden_dim and ctx.part.shape[1] >= T and ctx.part.shape[2] == wk.shape[1] and (allreduce or T % W == 0)
+            and (wk.shape[1] + 127) // 128 <= _MRS_MAX_NTILES and x.dtype in (torch.bfloat16, torch.float16)
+            and U.get_bool_env("TD_MOE_RS_FUSED", True))
+
+
 def run_moe_reduce_rs(x: torch.Tensor, w: torch.Tensor, chosen_experts: torch.Tensor, expert_weight: torch.Tensor,
                       ctx: MoEReduceRSContext, n_chunks: int = 2, **ref_hints) -> torch.Tensor:
     """x: ``[T*topk, K/W]``, w: ``[E, K/W, N]`` (or K-major ``[E, N, K/W]``), chosen_experts/expert_weight: ``[T, topk]``
@@ -415,6 +485,8 @@ def run_moe_reduce_rs(x: torch.Tensor, w: torch.Tensor, chosen_experts: torch.Te
     wk = w.transpose(1, 2) if (w.shape[1] == x.shape[1] and w.shape[2] != x.shape[1]) else w      # -> [E, N, K/W]
     N = wk.shape[1]
     T = chosen_experts.shape[0]
+    if _fused_ok(x, wk, ctx, T, False):
+        return _moe_reduce_fused(x, wk, chosen_experts, expert_weight, ctx, False)
     if (W > 1 and x.is_cuda and n_chunks > 1 and _use_tma_gather(x) and wk.is_contiguous() and N % (n_chunks * 128) == 0
             and ((T // W) * (N // n_chunks) * x.element_size()) % 16 == 0):
         return _moe_reduce_rs_chunked(x, wk, chosen_experts, expert_weight, ctx, n_chunks)
@@ -455,6 +527,9 @@ def _moe_reduce_rs_chunked(x, wk, chosen_experts, expert_weight, ctx, n_chunks):
 
 def run_moe_reduce_ar(x, w, chosen_experts, expert_weight, ctx: MoEReduceRSContext, **ref_hints) -> torch.Tensor:
     U.accept_ref_hints("run_moe_reduce_ar", ref_hints, ('n_chunks', 'persistent', 'config'))
+    wk = w.transpose(1, 2) if (w.shape[1] == x.shape[1] and w.shape[2] != x.shape[1]) else w      # -> [E, N, K/W]
+    if _fused_ok(x, wk, ctx, chosen_experts.shape[0], True):
+        return _moe_reduce_fused(x, wk, chosen_experts, expert_weight, ctx, True)
     part = _moe_down_partial(x, w, chosen_experts, expert_weight, ctx)
     if ctx.world_size == 1:
         return part
