@@ -343,12 +343,12 @@ def main():
     ag_ctx = create_ag_gemm_context(AG["M"], AG["N"] // W, AG["K"], bf)
     rs_ctx = create_gemm_rs_context(RS["M"], RS["N"], output_dtype=bf)
 
-    ag_choice = {"transport": "auto", "cfg": None, "kslices": 0}
+    ag_choice = {"transport": "auto", "cfg": None, "kslices": 0, "groups": 0}
     ag_autotune_log = []
 
     def run_ag(a, b_nk, out, skip_wait=False):
         return ag_gemm(a, b_nk.t(), ag_ctx, out=out, gemm_config=ag_choice["cfg"], transport=ag_choice["transport"],
-                       kslices=ag_choice["kslices"], skip_wait=skip_wait)
+                       kslices=ag_choice["kslices"], comm_groups=ag_choice["groups"], skip_wait=skip_wait)
 
     def step_ours(i):
         s = sets[i % nset]
@@ -467,29 +467,30 @@ def main():
         Ms = AG["M"] // W
         cands = []
         if U.is_nvshmem_multimem_supported() and Ms % 128 == 0:
-            for cg in ((1, 2) if Ms % 256 == 0 else (1,)):
+            for cg in ((2, 1) if Ms % 256 == 0 else (1,)):
                 gm = max(1, Ms // (128 * cg))
-                for bn in (128, 256):
-                    for nc, ks in ((16, 8), (8, 8), (16, 4), (24, 8), (16, 16)):
-                        cands.append(("multicast", GemmConfig(bn, cg, gm, True, 0, nc), ks))
+                for bn in (256, 128):
+                    # (comm CTAs, K slices, CTA groups): groups x slices-in-flight; every tile must stay resident (one wave)
+                    for nc, ks, gr in ((24, 8, 3), (32, 8, 4), (16, 8, 2), (32, 16, 4), (48, 16, 6), (16, 4, 1), (16, 4, 2)):
+                        cands.append(("multicast", GemmConfig(bn, cg, gm, True, 0, nc), ks, gr))
         for nc in (16, 32):
             for bn in sorted({base.bn, 128}):
-                cands.append(("sm", GemmConfig(bn, base.cta_group, base.group_m, True, 0, nc), 0))
-        cands.append(("copy_engine", GemmConfig(base.bn, base.cta_group, base.group_m, True, 0, 0), 0))
+                cands.append(("sm", GemmConfig(bn, base.cta_group, base.group_m, True, 0, nc), 0, 0))
+        cands.append(("copy_engine", GemmConfig(base.bn, base.cta_group, base.group_m, True, 0, 0), 0, 0))
         best = None
-        for tr, cfg, ks in cands:
-            ag_choice.update(transport=tr, cfg=cfg, kslices=ks)
+        for tr, cfg, ks, gr in cands:
+            ag_choice.update(transport=tr, cfg=cfg, kslices=ks, groups=gr)
             try:
                 t = timed(lambda i: run_ag(sets[i % nset]["ag_a"], sets[i % nset]["ag_b"], ag_out), 8, 3)
             except Exception as e:      # noqa: BLE001
                 ag_autotune_log.append({"transport": tr, "n_comm_ctas": cfg.n_comm_ctas, "bn": cfg.bn, "cta_group": cfg.cta_group,
-                                        "kslices": ks, "error": str(e)[:80]})
+                                        "kslices": ks, "groups": gr, "error": str(e)[:80]})
                 continue
             ag_autotune_log.append({"transport": tr, "n_comm_ctas": cfg.n_comm_ctas, "bn": cfg.bn, "cta_group": cfg.cta_group,
-                                    "kslices": ks, "us": round(t * 1e3, 1)})
+                                    "kslices": ks, "groups": gr, "us": round(t * 1e3, 1)})
             if best is None or t < best[0]:
-                best = (t, tr, cfg, ks)
-        ag_choice.update(transport=best[1], cfg=best[2], kslices=best[3])
+                best = (t, tr, cfg, ks, gr)
+        ag_choice.update(transport=best[1], cfg=best[2], kslices=best[3], groups=best[4])
 
     ok, errs = check_outputs()
     if not ok:
@@ -521,7 +522,7 @@ def main():
                                                                  "nccl_cublas_rs": errs[3]}},
         "ag_transport": {"transport": ag_choice["transport"], "n_comm_ctas": ag_choice["cfg"].n_comm_ctas if ag_choice["cfg"] else 0,
                          "bn": ag_choice["cfg"].bn if ag_choice["cfg"] else 0, "cta_group": ag_choice["cfg"].cta_group if ag_choice["cfg"] else 0,
-                         "kslices": ag_choice["kslices"], "isolated_us_per_candidate": ag_autotune_log},
+                         "kslices": ag_choice["kslices"], "comm_groups": ag_choice["groups"], "isolated_us_per_candidate": ag_autotune_log},
         "native_libs": [os.path.basename(p) for p in _C.loaded_libraries()],
         "clocks": clocks,
     }

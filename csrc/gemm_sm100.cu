@@ -38,9 +38,9 @@ struct TdGemmArgs {
   void* sk_ws; long long sk_ws_bytes; void* sk_flags; long long sk_flag_count; long long sk_max_parts;
   long long rs_skip_wait;         // RS GEMM-only twin
   long long rs_fp32;              // RS ring partial sums in fp32 (staging buffers are [M, N] fp32)
-  long long ag_kslices;           // multicast AG: requested number of K slices (0 = default)
+  long long ag_kslices;           // multicast AG: requested number of K slices (0 = default) + 256 * comm-CTA groups (0 = default)
   // mode 4 (MoE reduce-RS / reduce-AR): rs_stage = partial [2][T][N], rs_flags = [2][num_n][W][n_comm], rs_out = output
-  const void* row_scale; void* mrs_counter; const void* mrs_total_padded; long long mrs_T, mrs_topk, mrs_allreduce;
+  const void* row_scale; void* mrs_counter; const void* mrs_total_padded; long long mrs_T, mrs_topk, mrs_allreduce, mrs_chunk_n;
 };
 
 static int encode_tmap(CUtensorMap* out, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
@@ -211,16 +211,21 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
     if (a->ag_copy_local == 2) { drv::set_error("ag_gemm: the all-to-all flavour cannot use the multicast transport"); return -1; }
     if (a->a_gather || fp8) { drv::set_error("ag_gemm: the multicast transport takes dense 16-bit A"); return -1; }
     if (a->ag_rows_per_rank % BM != 0) { drv::set_error("ag_gemm: multicast transport needs (M / world) %% 128 == 0"); return -1; }
-    if (p.n_comm_ctas < cg) p.n_comm_ctas = 16;
-    int ks = (int)(a->ag_kslices > 0 ? a->ag_kslices : 8);
+    if (p.n_comm_ctas < cg) p.n_comm_ctas = 24;
+    int ks = (int)((a->ag_kslices & 255) > 0 ? (a->ag_kslices & 255) : 8);
+    int groups = (int)((a->ag_kslices >> 8) > 0 ? (a->ag_kslices >> 8) : 3);
     if (ks > p.num_k) ks = p.num_k;
-    while (ks > 1 && p.n_comm_ctas * ks > kAGMaxSlices) --ks;
-    if (p.n_comm_ctas * ks > kAGMaxSlices) { drv::set_error("ag_gemm: too many comm CTAs for the flag array"); return -1; }
+    if (groups > ks) groups = ks;
+    while (groups > 1 && (p.n_comm_ctas % groups != 0 || p.n_comm_ctas / groups < 1)) --groups;
+    const int n_c = p.n_comm_ctas / groups;
+    while (ks > 1 && n_c * ks > kAGMaxSlices) --ks;
+    if (n_c * ks > kAGMaxSlices) { drv::set_error("ag_gemm: too many comm CTAs for the flag array"); return -1; }
     p.ag_multicast = 1;
+    p.ag_ctas_per_group = n_c;
     p.ag_kb_per_slice = (p.num_k + ks - 1) / ks;
     p.ag_kslices = (p.num_k + p.ag_kb_per_slice - 1) / p.ag_kb_per_slice;
-    p.ag_rows_per_cta = (int)((a->ag_rows_per_rank + p.n_comm_ctas - 1) / p.n_comm_ctas);
-    p.ag_nslices = p.n_comm_ctas * p.ag_kslices;
+    p.ag_rows_per_cta = (int)((a->ag_rows_per_rank + n_c - 1) / n_c);
+    p.ag_nslices = n_c * p.ag_kslices;
   }
   if (a->mode == kAG && a->ag_skip_wait == 0 && p.n_comm_ctas > 0 && a->world <= 4) {
     // few destinations: publish each CTA's share in 4 (TP2) / 2 (TP4) interleaved sub-slices (finer arrival flags)
@@ -242,13 +247,25 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
   p.rs_skip_wait = (int)a->rs_skip_wait; p.rs_fp32 = (int)a->rs_fp32;
   p.row_scale = reinterpret_cast<const float*>(a->row_scale);
   if (a->mode == kMoeRS) {
-    if (cg != 1 || fp8 || !a->a_gather || !a->c_scatter || !a->tile_expert) { drv::set_error("moe_reduce_rs: needs the gather4 grouped GEMM (cta_group 1, 16-bit)"); return -1; }
+    if (fp8 || !a->c_scatter || !a->tile_expert) { drv::set_error("moe_reduce_rs: needs a 16-bit grouped GEMM with the scatter epilogue"); return -1; }
     if (p.n_comm_ctas < 1 || !a->mrs_counter || !a->mrs_total_padded || !a->rs_stage || !a->rs_flags || !a->rs_out) { drv::set_error("moe_reduce_rs: missing buffers / comm CTAs"); return -1; }
     if (p.N % 8 != 0 || a->rs_ldo % 8 != 0 || a->ldc % 8 != 0) { drv::set_error("moe_reduce_rs: N and row strides must be multiples of 8"); return -1; }
     if (!a->mrs_allreduce && a->mrs_T % a->world != 0) { drv::set_error("moe_reduce_rs: tokens must divide by the world size"); return -1; }
     p.mrs_counter = reinterpret_cast<uint32_t*>(a->mrs_counter); p.mrs_total_padded = reinterpret_cast<const int*>(a->mrs_total_padded);
     p.mrs_T = (int)a->mrs_T; p.mrs_topk = (int)a->mrs_topk; p.mrs_allreduce = (int)a->mrs_allreduce;
-    p.group_m = p.num_m;      // n-tile major order: a chunk of output columns completes as early as possible
+    {  // chunk schedule: mrs_chunk_n > 0 = uniform chunks of that many n tiles; 0 = shrinking chunks (~35 % of what is left), so
+       // the operand A is re-read only a handful of times while the exposed reduce + pull tail is a single n tile
+      int rem = p.num_n, nchunks = 0, start = 0;
+      while (rem > 0) {
+        int sz = a->mrs_chunk_n > 0 ? (int)a->mrs_chunk_n : (int)(rem * 0.35 + 0.5);
+        if (sz < 1) sz = 1;
+        if (sz > rem || nchunks == 15) sz = rem;
+        p.mrs_chunk_start[nchunks++] = start;
+        start += sz; rem -= sz;
+      }
+      p.mrs_chunk_start[nchunks] = start;
+      p.mrs_n_chunks = nchunks;
+    }
   }
   if (p.n_comm_ctas % cg) p.n_comm_ctas += cg - p.n_comm_ctas % cg;
   if (a->mode == kAR && p.a2a_cols_per_rank > 0) p.n_comm_ctas = 0;     // GEMM + all-to-all: the epilogue scatters, no comm CTAs
@@ -309,8 +326,10 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
     case kRS: return dispatch<kRS>(p, bn, cg, grid, stream);
     case kAR: return dispatch<kAR>(p, bn, cg, grid, stream);
     case kMoeRS:
-      if (bn == 256) return launch_cfg<kMoeRS, 256, 1>(p, grid, stream);
-      if (bn == 128) return launch_cfg<kMoeRS, 128, 1>(p, grid, stream);
+      if (bn == 256 && cg == 2) return launch_cfg<kMoeRS, 256, 2>(p, grid, stream);
+      if (bn == 256 && cg == 1) return launch_cfg<kMoeRS, 256, 1>(p, grid, stream);
+      if (bn == 128 && cg == 2) return launch_cfg<kMoeRS, 128, 2>(p, grid, stream);
+      if (bn == 128 && cg == 1) return launch_cfg<kMoeRS, 128, 1>(p, grid, stream);
       drv::set_error("moe_reduce_rs: bn must be 128 or 256"); return -1;
     default: drv::set_error("bad mode"); return -1;
   }

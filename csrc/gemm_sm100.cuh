@@ -98,6 +98,8 @@ struct Params {
   int ag_kslices;            // multicast: number of K slices (every tile starts after 1/ag_kslices of the transfer and follows it)
   int ag_kb_per_slice;       // k-blocks (128 bytes of a row) per K slice
   int ag_rows_per_cta;       // shard rows pushed by one comm CTA
+  int ag_ctas_per_group;     // multicast: comm CTAs form n_comm / this groups; group g pushes K slices g, g + G, ... (a release
+                             // fence after NVLink stores costs ~7 us of pure latency: G groups keep G slices in flight)
   int ag_local_direct;       // 1: tiles of my own rows read a_local through tmap_al (no local copy, no flag wait)
   CUtensorMap tmap_al;       // {K, rows of a_local}
   int ag_nslices;            // arrival flags per source rank (= comm CTAs, or 1 when the copy engine does the transfer)
@@ -130,9 +132,12 @@ struct Params {
   long long rs_ldo;
   // ---- MoE reduce-RS / reduce-AR (kMoeRS) ----
   const float* row_scale;    // optional: the C row scattered to id is multiplied by row_scale[id] (routing weight) in the epilogue
-  uint32_t* mrs_counter;     // local [2][num_n]: finished m tiles per n tile; this call's parity counts, the other is zeroed
+  uint32_t* mrs_counter;     // local [2][chunks + 1]: finished CTA tiles per chunk (+ CTAs done zeroing); this call's parity counts,
+                             // the other parity is zeroed for the next call
   const int* mrs_total_padded;   // device: padded row count of the routing (valid m tiles = *p / 128)
-  int mrs_T, mrs_topk, mrs_allreduce, pad4;
+  int mrs_T, mrs_topk, mrs_allreduce;
+  int mrs_n_chunks;          // column chunks: tiles run chunk-major, then m, then n inside the chunk (A is re-read once per chunk)
+  int mrs_chunk_start[17];   // first n tile of every chunk (+ end); chunks shrink towards the end so the exposed tail is one n tile
   // (partial: rs_stage [2][T][N] 16-bit symmetric; flags: rs_flags [2][num_n][W][n_comm]; output: rs_out / rs_ldo)
   // ---- split-K tail: the last partial wave of tiles is cut into sk_parts K ranges that run on otherwise idle clusters;
   // parts > 0 park their fp32 accumulator in sk_ws, part 0 adds them in its epilogue (wave quantisation: 768 tiles on
@@ -191,6 +196,17 @@ __host__ __device__ inline size_t ag_slice_bytes(size_t shard_bytes, int n_comm)
 
 // tile index -> (m tile, n tile); band-swizzled (m fastest inside a band of group_m tiles), then rotated
 TD_DEVICE void tile_coords(const Params& p, int t, int& m_tile, int& n_tile) {
+  if (p.mrs_n_chunks > 0) {     // MoE reduce-RS: chunk of n tiles (outer), m tile, n tile inside the chunk (inner)
+    int c = 0, r = t;
+    while (c + 1 < p.mrs_n_chunks && r >= p.num_m * (p.mrs_chunk_start[c + 1] - p.mrs_chunk_start[c])) {
+      r -= p.num_m * (p.mrs_chunk_start[c + 1] - p.mrs_chunk_start[c]);
+      ++c;
+    }
+    const int cn = p.mrs_chunk_start[c + 1] - p.mrs_chunk_start[c];
+    m_tile = r / cn;
+    n_tile = p.mrs_chunk_start[c] + r % cn;
+    return;
+  }
   const int per_band = p.group_m * p.num_n;
   const int band = t / per_band;
   const int first_m = band * p.group_m;
@@ -231,7 +247,7 @@ TD_DEVICE void ag_wait_rows(const Params& p, uint32_t ph, int row0, int row1) {
 // K-sliced (multicast) transport: rows [r_local, r_local + BM) of source s, K slice j.  Comm CTA c of the source pushes rows
 // [c * rows_per_cta, (c + 1) * rows_per_cta) of every slice and publishes flag[s][j * n_comm + c].
 TD_DEVICE void ag_wait_kslice(const Params& p, uint32_t ph, int s, int r_local, int j) {
-  const uint32_t* flags = p.ag_flags + (ph & 1u) * p.symm.world * kAGMaxSlices + s * kAGMaxSlices + j * p.n_comm_ctas;
+  const uint32_t* flags = p.ag_flags + (ph & 1u) * p.symm.world * kAGMaxSlices + s * kAGMaxSlices + j * p.ag_ctas_per_group;
   const int c0 = r_local / p.ag_rows_per_cta;
   const int c1 = (min(r_local + BM, p.ag_rows_per_rank) - 1) / p.ag_rows_per_cta;
   for (int c = c0; c <= c1; ++c) wait_ge<true>(flags + c, ph);
@@ -269,9 +285,11 @@ TD_DEVICE void ag_comm_cta(const Params& p, uint32_t ph, int comm_idx) {
     // (all rows of columns [j * seg, (j + 1) * seg)), so on the consumer EVERY tile starts after 1 / ag_kslices of the
     // transfer and its mainloop follows the arrival: the tail after the last byte is one K slice of MMAs + the epilogue.
     char* ws_mc = symm_mc(p.symm, ws) + shard_off;
-    const int r0 = comm_idx * p.ag_rows_per_cta, r1 = min(Ms, r0 + p.ag_rows_per_cta);
+    const int n_c = p.ag_ctas_per_group, n_groups = p.n_comm_ctas / n_c;
+    const int grp = comm_idx / n_c, cta = comm_idx % n_c;
+    const int r0 = cta * p.ag_rows_per_cta, r1 = min(Ms, r0 + p.ag_rows_per_cta);
     const size_t seg_bytes = static_cast<size_t>(p.ag_kb_per_slice) * 128;
-    for (int j = 0; j < p.ag_kslices; ++j) {
+    for (int j = grp; j < p.ag_kslices; j += n_groups) {
       const size_t col0 = j * seg_bytes;
       const int seg16 = static_cast<int>((min(row_bytes, col0 + seg_bytes) - col0) >> 4);
       const int n = max(0, r1 - r0) * seg16;
@@ -297,7 +315,7 @@ TD_DEVICE void ag_comm_cta(const Params& p, uint32_t ph, int comm_idx) {
         prof_record(p.prof, pslot, 1, false);
         prof_record(p.prof, pslot, 6, true);
         ptx::fence_acq_rel_sys();
-        for (int d = 0; d < W; ++d) ptx::st_relaxed_sys(symm_at(p.symm, flag_base + j * p.n_comm_ctas + comm_idx, (me + d) % W), ph);
+        for (int d = 0; d < W; ++d) ptx::st_relaxed_sys(symm_at(p.symm, flag_base + j * n_c + cta, (me + d) % W), ph);
         prof_record(p.prof, pslot, 6, false);
       }
     }
@@ -400,87 +418,101 @@ TD_DEVICE void ar_comm_cta(const Params& p, uint32_t ph, int comm_idx) {
 //       NVSwitch (multimem.ld_reduce, fp32 accumulation) -- or W peer loads without NVLS -- into the output
 // Reduce-scatter: rank r pulls tokens [r * T / W, (r + 1) * T / W); all-reduce: every rank pulls every token.
 // -------------------------------------------------------------------------------------------------
+TD_DEVICE void acc_16bit(float (&acc)[8], const uint4& x, bool bf16) {
+  const uint32_t w4[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    if (bf16) { acc[2 * e] += ptx::bf16_lo(w4[e]); acc[2 * e + 1] += ptx::bf16_hi(w4[e]); }
+    else { const __half2 hh = *reinterpret_cast<const __half2*>(&w4[e]); acc[2 * e] += __low2float(hh); acc[2 * e + 1] += __high2float(hh); }
+  }
+}
+TD_DEVICE uint4 pack_16bit(const float (&acc)[8], bool bf16) {
+  uint4 v;
+  if (bf16) { v.x = ptx::pack_bf16x2(acc[0], acc[1]); v.y = ptx::pack_bf16x2(acc[2], acc[3]); v.z = ptx::pack_bf16x2(acc[4], acc[5]); v.w = ptx::pack_bf16x2(acc[6], acc[7]); }
+  else { v.x = ptx::pack_f16x2(acc[0], acc[1]); v.y = ptx::pack_f16x2(acc[2], acc[3]); v.z = ptx::pack_f16x2(acc[4], acc[5]); v.w = ptx::pack_f16x2(acc[6], acc[7]); }
+  return v;
+}
+
+// MoE reduce-RS, every CTA at kernel start: zero my slice of this call's partial buffer (the epilogues ADD into it), then count
+// myself in.  part[par] was last read by the peers' pulls of call i-2, which all ended before any peer flagged call i-1 -- and I
+// only finished call i-1 after seeing those flags -- so it is free.  Epilogues wait for all CTAs before their first reduction.
+TD_DEVICE void moe_rs_zero_part(const Params& p, uint32_t ph) {
+  const uint32_t par = ph & 1u;
+  uint4* part = reinterpret_cast<uint4*>(p.rs_stage + par * p.rs_stage_buf_bytes);
+  const size_t n16 = static_cast<size_t>(p.mrs_T) * p.N * 2 / 16;
+  const size_t per = (n16 + gridDim.x - 1) / gridDim.x;
+  const size_t i0 = min(n16, per * blockIdx.x), i1 = min(n16, i0 + per);
+  for (size_t i = i0 + threadIdx.x; i < i1; i += kThreads) part[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  if (threadIdx.x == 0) { __threadfence(); ptx::red_release_gpu_add(p.mrs_counter + par * (p.mrs_n_chunks + 1) + p.mrs_n_chunks, 1u); }
+}
+
+// MoE reduce-RS comm CTA ci: for every column chunk (in the order the GEMM finishes them) wait for the W ranks' "chunk done"
+// flags and reduce the rows I pull through the NVSwitch (multimem.ld_reduce, fp32 accumulation; W peer loads without NVLS).
+// Reduce-scatter: rank r pulls tokens [r * T / W, (r + 1) * T / W); all-reduce: every rank pulls every token.
 template <int BN>
 TD_DEVICE void moe_rs_comm_cta(const Params& p, uint32_t ph, int ci) {
-  const int W = p.symm.world, me = p.symm.rank, nc = p.n_comm_ctas, T = p.mrs_T, topk = p.mrs_topk, N = p.N;
+  const int W = p.symm.world, me = p.symm.rank, nc = p.n_comm_ctas, T = p.mrs_T, N = p.N;
+  const int n_chunks = p.mrs_n_chunks;
   const uint32_t par = ph & 1u;
-  uint32_t* counter = p.mrs_counter + par * p.num_n;
+  const bool bf16 = p.in_is_bf16 != 0;
   if (ci == 0)
-    for (int i = threadIdx.x; i < p.num_n; i += kThreads) p.mrs_counter[(par ^ 1u) * p.num_n + i] = 0u;   // the NEXT call's counters
+    for (int i = threadIdx.x; i <= n_chunks; i += kThreads) p.mrs_counter[(par ^ 1u) * (n_chunks + 1) + i] = 0u;   // the NEXT call's counters
   char* part = p.rs_stage + par * p.rs_stage_buf_bytes;
-  const char* y = reinterpret_cast<const char*>(p.C);
-  const uint32_t* flags = p.rs_flags + static_cast<size_t>(par) * p.num_n * W * nc;
-  const uint32_t valid_tiles = static_cast<uint32_t>(*p.mrs_total_padded / BM);
-  const int tok_per_cta = (T + nc - 1) / nc;
-  const int t0 = min(T, ci * tok_per_cta), t1 = min(T, t0 + tok_per_cta);
+  const uint32_t* flags = p.rs_flags + static_cast<size_t>(par) * n_chunks * W;
   int r0, r1, out_row0;
-  if (p.mrs_allreduce) { r0 = t0; r1 = t1; out_row0 = 0; }
+  if (p.mrs_allreduce) { const int per = (T + nc - 1) / nc; r0 = min(T, ci * per); r1 = min(T, r0 + per); out_row0 = 0; }
   else {
     const int Tr = T / W, rows_per = (Tr + nc - 1) / nc;
     r0 = me * Tr + min(Tr, ci * rows_per); r1 = me * Tr + min(Tr, (ci + 1) * rows_per); out_row0 = me * Tr;
   }
-  constexpr int kCPR = BN / 8;                         // 16-byte chunks per row of one n tile
-  for (int c = 0; c <= p.num_n; ++c) {
-    if (c < p.num_n) {
-      if (threadIdx.x == 0) { while (ptx::ld_acquire_gpu(counter + c) < valid_tiles) {} }
-      __syncthreads();
-      const int col0 = c * BN;
-      for (int i = threadIdx.x; i < (t1 - t0) * kCPR; i += kThreads) {
-        const int t = t0 + i / kCPR, col = col0 + (i % kCPR) * 8;
-        if (col >= N) continue;
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int k = 0; k < topk; ++k) {
-          const uint4 x = ptx::ld_relaxed_sys_v4(y + (static_cast<size_t>(t * topk + k) * p.ldc + col) * 2);
-          const uint32_t w4[4] = {x.x, x.y, x.z, x.w};
+  constexpr int U = 8;          // multimem.ld_reduce round trips (~3 us through the switch) in flight per thread
+  for (int c = 0; c < n_chunks; ++c) {
+    if (static_cast<int>(threadIdx.x) < W) wait_ge<true>(flags + static_cast<size_t>(c) * W + threadIdx.x, ph);
+    __syncthreads();
+    const int col0 = p.mrs_chunk_start[c] * BN, col1 = min(N, p.mrs_chunk_start[c + 1] * BN);
+    const int cpr = (col1 - col0) / 8;                   // 16-byte pieces per row of this chunk
+    const int items = (r1 - r0) * cpr;
+    for (int i0 = threadIdx.x; i0 < items; i0 += U * kThreads) {
+      uint4 v[U];
+      if (p.symm.mc_base) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (p.in_is_bf16) { acc[2 * e] += ptx::bf16_lo(w4[e]); acc[2 * e + 1] += ptx::bf16_hi(w4[e]); }
-            else { const __half2 hh = *reinterpret_cast<const __half2*>(&w4[e]); acc[2 * e] += __low2float(hh); acc[2 * e + 1] += __high2float(hh); }
+        for (int u = 0; u < U; ++u) {
+          const int i = i0 + u * kThreads;
+          if (i < items) {
+            char* src = part + (static_cast<size_t>(r0 + i / cpr) * N + col0 + (i % cpr) * 8) * 2;
+            v[u] = bf16 ? ptx::multimem_ld_reduce_bf16x8(symm_mc(p.symm, src)) : ptx::multimem_ld_reduce_f16x8(symm_mc(p.symm, src));
           }
         }
-        uint4 v;
-        if (p.in_is_bf16) { v.x = ptx::pack_bf16x2(acc[0], acc[1]); v.y = ptx::pack_bf16x2(acc[2], acc[3]); v.z = ptx::pack_bf16x2(acc[4], acc[5]); v.w = ptx::pack_bf16x2(acc[6], acc[7]); }
-        else { v.x = ptx::pack_f16x2(acc[0], acc[1]); v.y = ptx::pack_f16x2(acc[2], acc[3]); v.z = ptx::pack_f16x2(acc[4], acc[5]); v.w = ptx::pack_f16x2(acc[6], acc[7]); }
-        ptx::st_v4(part + (static_cast<size_t>(t) * N + col) * 2, v);
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        ptx::fence_acq_rel_sys();
-        uint32_t* f = p.rs_flags + ((static_cast<size_t>(par) * p.num_n + c) * W + me) * nc + ci;
-        for (int d = 0; d < W; ++d) ptx::st_relaxed_sys(symm_at(p.symm, f, (me + d) % W), ph);
-      }
-    }
-    if (c >= 1 && r1 > r0) {
-      const int cc = c - 1, col0 = cc * BN;
-      const int j0 = r0 / tok_per_cta, j1 = (r1 - 1) / tok_per_cta;
-      for (int i = threadIdx.x; i < W * (j1 - j0 + 1); i += kThreads)
-        wait_ge<true>(flags + (static_cast<size_t>(cc) * W + i % W) * nc + j0 + i / W, ph);
-      __syncthreads();
-      for (int i = threadIdx.x; i < (r1 - r0) * kCPR; i += kThreads) {
-        const int t = r0 + i / kCPR, col = col0 + (i % kCPR) * 8;
-        if (col >= N) continue;
-        char* src = part + (static_cast<size_t>(t) * N + col) * 2;
-        uint4 v;
-        if (p.symm.mc_base) {
-          v = p.in_is_bf16 ? ptx::multimem_ld_reduce_bf16x8(symm_mc(p.symm, src)) : ptx::multimem_ld_reduce_f16x8(symm_mc(p.symm, src));
-        } else {
-          float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          for (int s = 0; s < W; ++s) {
-            const uint4 x = ptx::ld_relaxed_sys_v4(symm_at(p.symm, src, (me + s) % W));
-            const uint32_t w4[4] = {x.x, x.y, x.z, x.w};
+      } else {
+        float acc[U][8];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (p.in_is_bf16) { acc[2 * e] += ptx::bf16_lo(w4[e]); acc[2 * e + 1] += ptx::bf16_hi(w4[e]); }
-              else { const __half2 hh = *reinterpret_cast<const __half2*>(&w4[e]); acc[2 * e] += __low2float(hh); acc[2 * e + 1] += __high2float(hh); }
-            }
-          }
-          if (p.in_is_bf16) { v.x = ptx::pack_bf16x2(acc[0], acc[1]); v.y = ptx::pack_bf16x2(acc[2], acc[3]); v.z = ptx::pack_bf16x2(acc[4], acc[5]); v.w = ptx::pack_bf16x2(acc[6], acc[7]); }
-          else { v.x = ptx::pack_f16x2(acc[0], acc[1]); v.y = ptx::pack_f16x2(acc[2], acc[3]); v.z = ptx::pack_f16x2(acc[4], acc[5]); v.w = ptx::pack_f16x2(acc[6], acc[7]); }
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[u][e] = 0.f;
         }
-        ptx::st_v4(reinterpret_cast<char*>(p.rs_out) + (static_cast<size_t>(t - out_row0) * p.rs_ldo + col) * 2, v);
+        for (int s = 0; s < W; ++s) {
+          uint4 x[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * kThreads;
+            if (i < items) x[u] = ptx::ld_relaxed_sys_v4(symm_at(p.symm, part + (static_cast<size_t>(r0 + i / cpr) * N + col0 + (i % cpr) * 8) * 2, (me + s) % W));
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (i0 + u * kThreads < items) acc_16bit(acc[u], x[u], bf16);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = pack_16bit(acc[u], bf16);
       }
-      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * kThreads;
+        if (i < items)
+          ptx::st_v4(reinterpret_cast<char*>(p.rs_out) + (static_cast<size_t>(r0 + i / cpr - out_row0) * p.rs_ldo + col0 + (i % cpr) * 8) * 2, v[u]);
+      }
     }
+    __syncthreads();
   }
 }
 
@@ -512,6 +544,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
   const int n_gemm_ctas = static_cast<int>(gridDim.x) - p.n_comm_ctas;
   const bool is_comm = static_cast<int>(blockIdx.x) >= n_gemm_ctas;
 
+  if constexpr (kMode == kMoeRS) moe_rs_zero_part(p, ph);
   if (is_comm) {
     // dedicated comm CTA (fills the SMs the GEMM has no tiles for): deep ring, one driving thread
     if constexpr (kMode == kAG) {
@@ -755,6 +788,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
       uint8_t* smem_c = smem + L::kCOff;
       int acc = 0; uint32_t acc_phase = 0;
       uint32_t blk_iter = 0;                         // staging buffer = blk_iter & 1
+      bool mrs_zero_seen = false;
+      (void)mrs_zero_seen;
       for (int u = worker; u < p.total_units; u += n_workers) {
         const Unit un = get_unit(p, u);
         int m_tile, n_tile;
@@ -839,6 +874,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
           }
         }
 
+        if constexpr (kMode == kMoeRS) {
+          // rows are ADDED to their token's row of my symmetric partial (top-k reduce at L2); first make sure it has been zeroed
+          dst_base = p.rs_stage + (ph & 1u) * p.rs_stage_buf_bytes; dst_ld = p.N; dst_row_off = 0;
+          if (!mrs_zero_seen) {
+            if (et == 0) {
+              const uint32_t* zc = p.mrs_counter + (ph & 1u) * (p.mrs_n_chunks + 1) + p.mrs_n_chunks;
+              while (ptx::ld_acquire_gpu(zc) < gridDim.x) {}
+            }
+            ptx::named_bar_sync(2, kEpiThreads);
+            mrs_zero_seen = true;
+          }
+        }
         ptx::mbar_wait(tmem_full + acc, acc_phase);
         ptx::tc_fence_after();
         if (lane == 0) prof_record(p.prof, static_cast<int>(blockIdx.x) * 8 + warp, 5, true);
@@ -998,7 +1045,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                 int drow = grow - dst_row_off;
                 if (p.c_scatter) { drow = p.c_scatter[grow]; if (drow < 0 || drow == p.a_gather_pad) continue; }
                 const uint4 o = ptx::ld_shared_v4(cbuf_u32 + r * 128 + ((chunk ^ (r & 7)) << 4));
-                ptx::st_v4(dst_base + (static_cast<size_t>(drow) * dst_ld + gcol) * 2, o);
+                if constexpr (kMode == kMoeRS) {
+                  char* d = dst_base + (static_cast<size_t>(drow / p.mrs_topk) * dst_ld + gcol) * 2;     // pair id -> token row
+                  if (p.in_is_bf16) ptx::red_add_bf16x8(d, o); else ptx::red_add_f16x8(d, o);
+                } else {
+                  ptx::st_v4(dst_base + (static_cast<size_t>(drow) * dst_ld + gcol) * 2, o);
+                }
               }
             }
           }
@@ -1021,9 +1073,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
           }
         }
         if constexpr (kMode == kMoeRS) {
-          // this tile's rows are in y: count it for its n tile (the comm CTAs wait for all valid m tiles of a chunk)
+          // this CTA tile has been added to the partial: count it for its column chunk; whoever completes the chunk tells every
+          // rank (release at system scope, cumulative over all CTAs' reductions through the gpu-scope counter)
           ptx::named_bar_sync(2, kEpiThreads);
-          if (et == 0) { __threadfence(); ptx::red_release_gpu_add(p.mrs_counter + (ph & 1u) * p.num_n + n_tile, 1u); }
+          if (et == 0) {
+            int c = 0;
+            while (c + 1 < p.mrs_n_chunks && n_tile >= p.mrs_chunk_start[c + 1]) ++c;
+            const uint32_t expected = static_cast<uint32_t>(*p.mrs_total_padded / BM) * (p.mrs_chunk_start[c + 1] - p.mrs_chunk_start[c]);
+            __threadfence();
+            if (ptx::atom_add_acq_rel_gpu(p.mrs_counter + (ph & 1u) * (p.mrs_n_chunks + 1) + c, 1u) == expected - 1u) {
+              const int W = p.symm.world, me = p.symm.rank;
+              uint32_t* f = p.rs_flags + (static_cast<size_t>(ph & 1u) * p.mrs_n_chunks + c) * W + me;
+              ptx::fence_acq_rel_sys();
+              for (int d = 0; d < W; ++d) ptx::st_relaxed_sys(symm_at(p.symm, f, (me + d) % W), ph);
+            }
+          }
           __syncwarp();
         }
         if constexpr (kMode == kAR) {

@@ -542,6 +542,14 @@ TD_DEVICE void multimem_red_add_u32(uint32_t* mc, uint32_t v) {
   asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(mc), "r"(v) : "memory");
 }
 
+// 16-byte vector reductions at L2 (REDG.E.ADD.BF16x8 / F16x8): 8 packed 16-bit adds per instruction, no return value
+TD_DEVICE void red_add_bf16x8(void* p, const uint4& v) {
+  asm volatile("red.relaxed.gpu.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+TD_DEVICE void red_add_f16x8(void* p, const uint4& v) {
+  asm volatile("red.relaxed.gpu.global.add.noftz.v4.f16x2 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // numeric packing
 // ----------------------------------------------------------------------------------------------

@@ -326,7 +326,7 @@ def case_moe_rs():
     big = dev.type == "cuda"
     dtype = torch.bfloat16 if big else torch.float32
     grp = U.get_triton_dist_world()
-    shapes = [(256 * W, 512, 1024, 8, 2), (128 * W, 384, 512, 4, 2), (64 * W, 1032, 256, 8, 4)] if big else [(8 * W, 16, 32, 4, 2)]
+    shapes = [(256 * W, 512, 1024, 8, 2), (128 * W, 384, 512, 4, 2), (64 * W, 1032, 256, 8, 4), (1024 * W, 1280, 512, 8, 2)] if big else [(8 * W, 16, 32, 4, 2)]
     for (T, H, I, E, topk) in shapes:
         rs = M.create_moe_rs_context(me, W, W, T * topk, H, E, topk, dtype)
         for it in range(5):

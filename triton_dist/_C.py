@@ -58,7 +58,7 @@ class GemmArgs(C.Structure):
         ("sk_ws", c_void_p), ("sk_ws_bytes", c_ll), ("sk_flags", c_void_p), ("sk_flag_count", c_ll), ("sk_max_parts", c_ll),
         ("rs_skip_wait", c_ll), ("rs_fp32", c_ll), ("ag_kslices", c_ll),
         ("row_scale", c_void_p), ("mrs_counter", c_void_p), ("mrs_total_padded", c_void_p), ("mrs_T", c_ll), ("mrs_topk", c_ll),
-        ("mrs_allreduce", c_ll),
+        ("mrs_allreduce", c_ll), ("mrs_chunk_n", c_ll),
     ]]
 
 

@@ -91,9 +91,16 @@ def main():
 
     res = {"config": f"Mixtral-8x7B down-proj + topk reduce + RS: T={T} top{topk}/{E} N={H} K={args.inter}/{W}", "world": W}
     flops = 2.0 * T * topk * H * K
+    sweep = {}
+    for ncomm in (8, 16, 24, 32):          # comm CTAs of the fused kernel (the rest of the SMs run GEMM tiles)
+        ctx.n_comm = ncomm
+        sweep[ncomm] = round(timed(fused), 4)
+    ctx.n_comm = min(sweep, key=sweep.get)
     for name, fn in (("fused", fused), ("staged", staged), ("nccl", nccl)):
         ms = timed(fn)
         res[name] = {"ms": round(ms, 4), "tflops_per_gpu": round(flops / ms / 1e9, 1), "max_abs_err": round(errs[name], 4)}
+    res["fused"]["n_comm_ctas"] = ctx.n_comm
+    res["fused"]["ms_by_n_comm_ctas"] = sweep
     res["fused_vs_staged"] = round(res["staged"]["ms"] / res["fused"]["ms"], 3)
     res["fused_vs_nccl"] = round(res["nccl"]["ms"] / res["fused"]["ms"], 3)
     # roofline: grouped GEMM at the measured bf16 peak vs the bytes every rank must ship ((W-1)/W of its [T, N] partial)

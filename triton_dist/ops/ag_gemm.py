@@ -134,7 +134,7 @@ def default_ag_config(M: int, N: int, K: int, world: int) -> GemmConfig:
 def ag_gemm(A: torch.Tensor, B: torch.Tensor, ctx: AllGatherGEMMTensorParallelContext,
             gemm_config: Optional[GemmConfig] = None, straggler_option=None, debug: bool = False,
             out: Optional[torch.Tensor] = None, skip_wait: bool = False, profiler=None, transport: str = "auto",
-            all_to_all: bool = False, kslices: int = 0) -> torch.Tensor:
+            all_to_all: bool = False, kslices: int = 0, comm_groups: int = 0) -> torch.Tensor:
     """A: ``[M/W, K]`` local shard, B: ``[K, N/W]`` -> ``[M, N/W]``.  ``skip_wait`` runs the GEMM-only twin
     (flags ignored) used to measure exposed communication, like the reference's ``fake_barrier`` path.
 
@@ -144,7 +144,9 @@ def ag_gemm(A: torch.Tensor, B: torch.Tensor, ctx: AllGatherGEMMTensorParallelCo
     shard is pushed by the DMA engines on a side stream (one ``cudaMemcpyAsync`` + one release-flag kernel per peer, as
     the reference's copy-engine producer, allgather.py:100-124) while all SMs run GEMM tiles that wait on the same
     per-source flags; not CUDA-graph replayable (flag values are written from the host-tracked phase).
-    ``transport="multicast"``: comm CTAs write the shard once to the NVLS multicast alias in ``kslices`` K slices (default 8).
+    ``transport="multicast"``: comm CTAs write the shard once to the NVLS multicast alias in ``kslices`` K slices (default 8);
+    the ``n_comm_ctas`` CTAs form ``comm_groups`` groups (default 3) that push alternate slices, so that many release fences
+    (~7 us of latency each after NVLink stores, measured) are in flight at once.
 
     ``all_to_all=True``: A is ``[W * Ms, K]`` and row block d goes to rank d (instead of the same shard to everyone);
     the result is ``concat_s(block from rank s) @ B`` -- the AllToAll + GEMM of the Ulysses o-projection
@@ -198,8 +200,8 @@ def ag_gemm(A: torch.Tensor, B: torch.Tensor, ctx: AllGatherGEMMTensorParallelCo
         # NVLS: comm CTAs write the shard once to the multicast alias of the workspace (csrc/gemm_sm100.cuh, ag_multicast)
         assert not all_to_all and U.is_nvshmem_multimem_supported() and Ms % 128 == 0
         args.ag_skip_wait = 3
-        args.n_comm_ctas = max(2, min(cfg.n_comm_ctas or 16, 32))
-        args.ag_kslices = kslices
+        args.n_comm_ctas = max(2, min(cfg.n_comm_ctas or 24, 64))
+        args.ag_kslices = (kslices & 255) | (comm_groups << 8)
     if transport == "copy_engine" and not skip_wait:
         _ce_push(ctx, A, ph, Ms, K)
         args.ag_skip_wait, args.ag_copy_local, args.n_comm_ctas = 2, 1, 0

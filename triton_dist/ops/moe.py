@@ -28,7 +28,7 @@ from .gemm import GemmConfig, fill_common
 
 c_void_p, c_int, c_ll = C.c_void_p, C.c_int, C.c_longlong
 _C.register("td_moe_align_sort", c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                                         c_int, c_int, c_int, c_int, c_void_p])
+                                         c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p])
 _C.register("td_gather_rows", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_void_p])
 _C.register("td_scatter_rows", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p])
 _C.register("td_topk_reduce", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p])
@@ -91,9 +91,11 @@ def moe_align_sort(topk_ids: torch.Tensor, num_experts: int, block_m: int = 128,
     tile_expert = torch.empty(cap // block_m, dtype=torch.int32, device=dev)
     offs = torch.empty(num_experts + 1, dtype=torch.int32, device=dev)
     total = torch.empty(1, dtype=torch.int32, device=dev)
+    buckets = num_experts * (world if tokens_per_rank > 0 else 1)
+    ws = torch.empty(buckets * ((n + 1023) // 1024 + 1) + buckets, dtype=torch.int32, device=dev)     # histogram / scan scratch
     _C.check(_C.cuda_lib().td_moe_align_sort(ids.data_ptr(), n, num_experts, block_m, cap, pad_id, sorted_ids.data_ptr(),
                                              tile_expert.data_ptr(), offs.data_ptr(), total.data_ptr(), topk, tokens_per_rank,
-                                             rank, world, _s()), "td_moe_align_sort")
+                                             rank, world, ws.data_ptr(), ws.numel() * 4, _s()), "td_moe_align_sort")
     return SortedRouting(sorted_ids, tile_expert, offs, total, cap, block_m, pad_id)
 
 
@@ -176,13 +178,15 @@ def moe_grouped_gemm_fused(src: torch.Tensor, w: torch.Tensor, routing: SortedRo
     if not scatter:
         n_out_rows = routing.capacity
     out = torch.empty((n_out_rows, N), dtype=src.dtype, device=src.device) if out is None else out
-    cfg = config or GemmConfig(bn=256 if N >= 256 else 128, cta_group=1, group_m=1, use_tma_store=False)
-    assert cfg.cta_group == 1 and routing.block_m == 128
+    cg = routing.block_m // 128
+    cfg = config or GemmConfig(bn=256 if N >= 256 else 128, cta_group=cg, group_m=1, use_tma_store=False)
+    assert routing.block_m in (128, 256) and cfg.cta_group == cg, "routing block_m must equal the GEMM tile height (128 * cta_group)"
+    assert cg == 1 or not gather, "the TMA gather4 producer runs with cta_group 1; CTA pairs take pre-sorted rows (gather=False)"
     args = _C.GemmArgs()
     args.mode = 0
     w2 = w.reshape(E * N_full, K)
     fill_common(args, src.shape[0], src.data_ptr(), src.stride(0), w2, out.data_ptr(), n_out_rows, out.stride(0),
-                routing.capacity, N, K, GemmConfig(cfg.bn, 1, 1, False, cfg.num_sms, 0), src.dtype == torch.bfloat16)
+                routing.capacity, N, K, GemmConfig(cfg.bn, cg, 1, False, cfg.num_sms, 0), src.dtype == torch.bfloat16)
     args.B = w2.data_ptr() + n0 * K * w.element_size()
     args.expert_stride_rows = N_full
     args.tile_expert, args.num_experts = routing.tile_expert.data_ptr(), E
@@ -200,6 +204,20 @@ def moe_grouped_gemm_fused(src: torch.Tensor, w: torch.Tensor, routing: SortedRo
         args.c_scatter = routing.sorted_ids.data_ptr()
     _C.check(_C.cuda_lib().td_gemm_launch(C.byref(args), _s()), "td_gemm_launch(grouped, gather4)")
     return out
+
+
+_PAIRS_FOR_CTA_PAIRS = 4096     # from this many routed pairs on, the grouped GEMM is compute bound: pre-sort rows, use 2-CTA tiles
+
+
+def moe_grouped_gemm_presorted(src: torch.Tensor, w: torch.Tensor, topk_ids: torch.Tensor, num_experts: int, div: int,
+                               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Large routed batches: one memory-bound ``gather_rows`` pass puts the rows in expert order (padded to 256), then the
+    full-rate 2-CTA 256x256 tcgen05 tiles run on plain tiled TMA and the epilogue scatters straight to (token, k) order.
+    Measured on B200 (Mixtral down projection, 16 K pairs): the tile::gather4 producer issues 32 TMA instructions per
+    k-block and runs at ~0.45 PFLOP/s, this path at the plain-GEMM rate; gather4 stays the choice for small (decode) batches."""
+    r = moe_align_sort(topk_ids, num_experts, 256)
+    xs = gather_rows(src, r, div=div)
+    return moe_grouped_gemm_fused(xs, w, r, div, topk_ids.numel(), out=out, gather=False, scatter=True)
 
 
 def _use_tma_gather(x: torch.Tensor) -> bool:
@@ -241,6 +259,8 @@ def moe_forward_local(x: torch.Tensor, w: torch.Tensor, topk_ids: torch.Tensor, 
     """``c[t * topk + j] = x[t] @ w[ids[t, j]].T`` for local tokens (no communication)."""
     E = w.shape[0] if num_experts is None else num_experts
     topk = topk_ids.shape[1]
+    if x.is_cuda and topk_ids.numel() >= _PAIRS_FOR_CTA_PAIRS and _use_tma_gather(x):
+        return moe_grouped_gemm_presorted(x.contiguous(), w, topk_ids, E, topk)
     r = moe_align_sort(topk_ids, E, 128)
     if _use_tma_gather(x):
         return moe_grouped_gemm_fused(x.contiguous(), w, r, topk, topk_ids.numel())
@@ -367,11 +387,11 @@ class MoEReduceRSContext:
     dtype: torch.dtype
     ar_ctx: comm.AllReduceContext = None
     # single-kernel path (csrc/gemm_sm100.cuh, mode kMoeRS)
-    part: torch.Tensor = None        # symmetric [2, T, N]: my top-k-reduced partial, pulled by the owners through the NVSwitch
-    flags: torch.Tensor = None       # symmetric int32 [2, max_n_tiles, W, n_comm]
-    counter: torch.Tensor = None     # local int32 [2, max_n_tiles]: finished m tiles per n tile
+    part: torch.Tensor = None        # symmetric [2, T, N]: my top-k-reduced partial (built by L2 reductions in the epilogue),
+                                     # pulled by the owners through the NVSwitch
+    flags: torch.Tensor = None       # symmetric int32 [2, chunks, W]: 'rank s finished column chunk c' (phase numbers)
+    counter: torch.Tensor = None     # local int32 [2, chunks + 1]: finished CTA tiles per chunk (+ CTAs done zeroing)
     phase: torch.Tensor = None       # local int32 [4]
-    y: torch.Tensor = None           # local [T * topk, N]: weighted expert outputs in (token, k) order
     n_comm: int = 16
 
     def finalize(self):
@@ -417,10 +437,14 @@ def _moe_down_partial(x, w, chosen_experts, expert_weight, ctx):
         w = w.transpose(1, 2)                      # [E, K/W, N] -> [E, N, K/W]
     if w.stride(2) != 1:
         w = w.contiguous()
-    r = moe_align_sort(chosen_experts, ctx.num_experts, 128)
-    if _use_tma_gather(x):
+    r = None
+    if x.is_cuda and chosen_experts.numel() >= _PAIRS_FOR_CTA_PAIRS and _use_tma_gather(x):
+        y = moe_grouped_gemm_presorted(x.contiguous(), w, chosen_experts, ctx.num_experts, 1)
+    elif _use_tma_gather(x):
+        r = moe_align_sort(chosen_experts, ctx.num_experts, 128)
         y = moe_grouped_gemm_fused(x.contiguous(), w, r, 1, chosen_experts.numel())
     else:
+        r = moe_align_sort(chosen_experts, ctx.num_experts, 128)
         xs = gather_rows(x, r, div=1)                  # rows of x are already (token, k) pairs
         ys = moe_grouped_gemm(xs, w, r)
         y = scatter_rows(ys, r, chosen_experts.numel())
@@ -428,13 +452,16 @@ def _moe_down_partial(x, w, chosen_experts, expert_weight, ctx):
 
 
 def _moe_reduce_fused(x, wk, chosen_experts, expert_weight, ctx: MoEReduceRSContext, allreduce: bool,
-                      out: Optional[torch.Tensor] = None, n_comm: Optional[int] = None, bn: Optional[int] = None) -> torch.Tensor:
+                      out: Optional[torch.Tensor] = None, n_comm: Optional[int] = None, bn: Optional[int] = None,
+                      chunk_n: int = 0) -> torch.Tensor:
     """Grouped GEMM + weighted top-k reduce + ReduceScatter (or AllReduce) in ONE kernel (csrc/gemm_sm100.cuh, kMoeRS):
-    TMA-gather4 grouped GEMM tiles in n-tile-major order; the epilogue multiplies each row by its routing weight and scatters
-    it to (token, k) order; comm CTAs of the same grid, per n tile: wait for all m tiles -> sum the top-k rows into my symmetric
-    partial -> flag the peers -> (one chunk later) every owner pulls the cross-rank sum of its rows with multimem.ld_reduce.
-    No reduce_topk kernel, no side stream, no final copy.  Reference: moe_reduce_rs.py:168-246 + 549-619 (two kernels and a
-    stream pair), moe_reduce_ar.py:563."""
+    grouped tcgen05 tiles run column-chunk major (chunks shrink towards the end); the epilogue multiplies each row by its
+    routing weight and ADDS it to its token's row of this rank's symmetric partial with 16-byte L2 reductions
+    (``red.add.v4.bf16x2``) -- the top-k reduce needs no pass and no (token, k) buffer; the CTA that finishes a chunk
+    release-flags all ranks; comm CTAs of the same grid pull the cross-rank sum of the rows this rank owns through the NVSwitch
+    (``multimem.ld_reduce``, fp32 accumulation).  No reduce_topk kernel, no side stream, no final copy.  The partial is 16-bit:
+    with top-k > 2 the L2 adds round more than once per element (use the staged path when that matters).
+    Reference: moe_reduce_rs.py:168-246 + 549-619 (two kernels and a stream pair), moe_reduce_ar.py:563."""
     W, topk = ctx.world_size, ctx.topk
     T = chosen_experts.shape[0]
     E, N, K = wk.shape
@@ -443,20 +470,23 @@ def _moe_reduce_fused(x, wk, chosen_experts, expert_weight, ctx: MoEReduceRSCont
     num_n = (N + bn - 1) // bn
     assert num_n <= _MRS_MAX_NTILES, "moe_reduce_rs: too many n tiles for the flag array"
     n_comm = min(32, n_comm or ctx.n_comm)
-    r = moe_align_sort(chosen_experts, ctx.num_experts, 128)
-    if ctx.y is None or ctx.y.shape[0] < T * topk:
-        ctx.y = torch.empty((ctx.max_token_num, N), dtype=x.dtype, device=x.device)
+    big = T * topk >= _PAIRS_FOR_CTA_PAIRS          # compute bound: pre-sorted rows + CTA pairs; else the gather4 producer
+    r = moe_align_sort(chosen_experts, ctx.num_experts, 256 if big else 128)
+    assert T > 0
     rows_out = T if allreduce else T // W
     out = torch.empty((rows_out, N), dtype=x.dtype, device=x.device) if out is None else out
     scale = expert_weight.reshape(-1).to(torch.float32).contiguous()
-    xc = x.contiguous()
+    xc = gather_rows(x.contiguous(), r, div=1) if big else x.contiguous()
     args = _C.GemmArgs()
     args.mode = 4
-    fill_common(args, xc.shape[0], xc.data_ptr(), xc.stride(0), wk.reshape(E * N, K), ctx.y.data_ptr(), T * topk, ctx.y.stride(0),
-                r.capacity, N, K, GemmConfig(bn, 1, 1, False, 0, n_comm), x.dtype == torch.bfloat16)
+    fill_common(args, xc.shape[0], xc.data_ptr(), xc.stride(0), wk.reshape(E * N, K), ctx.part.data_ptr(), T, N,
+                r.capacity, N, K, GemmConfig(bn, 2 if big else 1, 1, False, 0, n_comm), x.dtype == torch.bfloat16)
     args.tile_expert, args.num_experts = r.tile_expert.data_ptr(), E
-    args.a_gather, args.a_gather_div, args.a_gather_pad = r.sorted_ids.data_ptr(), 1, r.pad_id
-    args.a_src_rows, args.c_scatter = xc.shape[0], r.sorted_ids.data_ptr()
+    if not big:
+        args.a_gather, args.a_gather_div = r.sorted_ids.data_ptr(), 1
+        args.a_src_rows = xc.shape[0]
+    args.a_gather_pad, args.c_scatter = r.pad_id, r.sorted_ids.data_ptr()
+    args.mrs_chunk_n = chunk_n
     rk, w_, base, stride, mc = U.symm_ctx_fields()
     args.rank, args.world, args.symm_base, args.symm_stride, args.mc_base = rk, w_, base, stride, mc
     args.phase = ctx.phase.data_ptr()
@@ -503,8 +533,9 @@ def _moe_reduce_rs_chunked(x, wk, chosen_experts, expert_weight, ctx, n_chunks):
     T = chosen_experts.shape[0]
     N = wk.shape[1]
     Nc = N // n_chunks
-    r = moe_align_sort(chosen_experts, ctx.num_experts, 128)
-    xc = x.contiguous()
+    big = T * topk >= _PAIRS_FOR_CTA_PAIRS
+    r = moe_align_sort(chosen_experts, ctx.num_experts, 256 if big else 128)
+    xc = gather_rows(x.contiguous(), r, div=1) if big else x.contiguous()
     out = torch.empty((T // W, N), dtype=x.dtype, device=x.device)
     main = torch.cuda.current_stream()
     if getattr(ctx, "_rs_stream", None) is None:
@@ -512,7 +543,7 @@ def _moe_reduce_rs_chunked(x, wk, chosen_experts, expert_weight, ctx, n_chunks):
     side = ctx._rs_stream
     side.wait_stream(main)
     for c in range(n_chunks):
-        y = moe_grouped_gemm_fused(xc, wk, r, 1, T * topk, n_slice=(c * Nc, Nc))
+        y = moe_grouped_gemm_fused(xc, wk, r, 1, T * topk, n_slice=(c * Nc, Nc), gather=not big)
         part = reduce_topk(y, expert_weight, topk)                     # [T, Nc]
         ev = torch.cuda.Event()
         ev.record(main)
