@@ -343,12 +343,12 @@ def main():
     ag_ctx = create_ag_gemm_context(AG["M"], AG["N"] // W, AG["K"], bf)
     rs_ctx = create_gemm_rs_context(RS["M"], RS["N"], output_dtype=bf)
 
-    ag_choice = {"transport": "auto", "cfg": None, "kslices": 0, "groups": 0}
+    ag_choice = {"transport": "auto", "cfg": None, "kslices": 0, "groups": 0, "tail": 0}
     ag_autotune_log = []
 
     def run_ag(a, b_nk, out, skip_wait=False):
         return ag_gemm(a, b_nk.t(), ag_ctx, out=out, gemm_config=ag_choice["cfg"], transport=ag_choice["transport"],
-                       kslices=ag_choice["kslices"], comm_groups=ag_choice["groups"], skip_wait=skip_wait)
+                       kslices=ag_choice["kslices"], comm_groups=ag_choice["groups"], tail_pct=ag_choice["tail"], skip_wait=skip_wait)
 
     def step_ours(i):
         s = sets[i % nset]
@@ -466,31 +466,32 @@ def main():
         base = default_ag_config(AG["M"], AG["N"] // W, AG["K"], W)
         Ms = AG["M"] // W
         cands = []
-        if U.is_nvshmem_multimem_supported() and Ms % 128 == 0:
-            for cg in ((2, 1) if Ms % 256 == 0 else (1,)):
+        if Ms % 128 == 0:
+            # K-sliced transports: (comm CTAs, K slices, CTA groups, % of K in the last round of slices)
+            for cg, bn in (((2, 256), (2, 128)) if Ms % 256 == 0 else ((1, 256), (1, 128))):
                 gm = max(1, Ms // (128 * cg))
-                for bn in (256, 128):
-                    # (comm CTAs, K slices, CTA groups): groups x slices-in-flight; every tile must stay resident (one wave)
-                    for nc, ks, gr in ((24, 8, 3), (32, 8, 4), (16, 8, 2), (32, 16, 4), (48, 16, 6), (16, 4, 1), (16, 4, 2)):
-                        cands.append(("multicast", GemmConfig(bn, cg, gm, True, 0, nc), ks, gr))
-        for nc in (16, 32):
-            for bn in sorted({base.bn, 128}):
-                cands.append(("sm", GemmConfig(bn, base.cta_group, base.group_m, True, 0, nc), 0, 0))
-        cands.append(("copy_engine", GemmConfig(base.bn, base.cta_group, base.group_m, True, 0, 0), 0, 0))
+                for nc, ks, gr, tail in ((32, 2, 1, 0), (32, 4, 2, 0), (32, 4, 2, 12), (32, 6, 2, 10), (48, 6, 2, 10), (32, 3, 1, 10), (48, 4, 2, 0)):
+                    cands.append(("sm_k", GemmConfig(bn, cg, gm, True, 0, nc), ks, gr, tail))
+            if U.is_nvshmem_multimem_supported():
+                cg = 2 if Ms % 256 == 0 else 1
+                for nc, ks, gr in ((24, 8, 3), (16, 4, 2)):
+                    cands.append(("multicast", GemmConfig(128, cg, max(1, Ms // (128 * cg)), True, 0, nc), ks, gr, 0))
+        cands.append(("sm", GemmConfig(128 if Ms % 256 == 0 else base.bn, base.cta_group, base.group_m, True, 0, 32), 0, 0, 0))
+        cands.append(("sm", GemmConfig(base.bn, base.cta_group, base.group_m, True, 0, 16), 0, 0, 0))
         best = None
-        for tr, cfg, ks, gr in cands:
-            ag_choice.update(transport=tr, cfg=cfg, kslices=ks, groups=gr)
+        for tr, cfg, ks, gr, tail in cands:
+            ag_choice.update(transport=tr, cfg=cfg, kslices=ks, groups=gr, tail=tail)
             try:
                 t = timed(lambda i: run_ag(sets[i % nset]["ag_a"], sets[i % nset]["ag_b"], ag_out), 8, 3)
             except Exception as e:      # noqa: BLE001
                 ag_autotune_log.append({"transport": tr, "n_comm_ctas": cfg.n_comm_ctas, "bn": cfg.bn, "cta_group": cfg.cta_group,
-                                        "kslices": ks, "groups": gr, "error": str(e)[:80]})
+                                        "kslices": ks, "groups": gr, "tail_pct": tail, "error": str(e)[:80]})
                 continue
             ag_autotune_log.append({"transport": tr, "n_comm_ctas": cfg.n_comm_ctas, "bn": cfg.bn, "cta_group": cfg.cta_group,
-                                    "kslices": ks, "groups": gr, "us": round(t * 1e3, 1)})
+                                    "kslices": ks, "groups": gr, "tail_pct": tail, "us": round(t * 1e3, 1)})
             if best is None or t < best[0]:
-                best = (t, tr, cfg, ks, gr)
-        ag_choice.update(transport=best[1], cfg=best[2], kslices=best[3], groups=best[4])
+                best = (t, tr, cfg, ks, gr, tail)
+        ag_choice.update(transport=best[1], cfg=best[2], kslices=best[3], groups=best[4], tail=best[5])
 
     ok, errs = check_outputs()
     if not ok:
@@ -522,7 +523,7 @@ def main():
                                                                  "nccl_cublas_rs": errs[3]}},
         "ag_transport": {"transport": ag_choice["transport"], "n_comm_ctas": ag_choice["cfg"].n_comm_ctas if ag_choice["cfg"] else 0,
                          "bn": ag_choice["cfg"].bn if ag_choice["cfg"] else 0, "cta_group": ag_choice["cfg"].cta_group if ag_choice["cfg"] else 0,
-                         "kslices": ag_choice["kslices"], "comm_groups": ag_choice["groups"], "isolated_us_per_candidate": ag_autotune_log},
+                         "kslices": ag_choice["kslices"], "comm_groups": ag_choice["groups"], "tail_pct": ag_choice["tail"], "isolated_us_per_candidate": ag_autotune_log},
         "native_libs": [os.path.basename(p) for p in _C.loaded_libraries()],
         "clocks": clocks,
     }

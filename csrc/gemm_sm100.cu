@@ -38,7 +38,7 @@ struct TdGemmArgs {
   void* sk_ws; long long sk_ws_bytes; void* sk_flags; long long sk_flag_count; long long sk_max_parts;
   long long rs_skip_wait;         // RS GEMM-only twin
   long long rs_fp32;              // RS ring partial sums in fp32 (staging buffers are [M, N] fp32)
-  long long ag_kslices;           // multicast AG: requested number of K slices (0 = default) + 256 * comm-CTA groups (0 = default)
+  long long ag_kslices;           // K-sliced AG: K slices (bits 0-7, 0 = default) | comm-CTA groups << 8 | percent of K in the last round << 16
   // mode 4 (MoE reduce-RS / reduce-AR): rs_stage = partial [2][T][N], rs_flags = [2][num_n][W][n_comm], rs_out = output
   const void* row_scale; void* mrs_counter; const void* mrs_total_padded; long long mrs_T, mrs_topk, mrs_allreduce, mrs_chunk_n;
 };
@@ -205,25 +205,48 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
   }
   if (a->mode == kAG && a->ag_skip_wait == 2) p.n_comm_ctas = 0;      // copy-engine transport: every SM runs GEMM tiles
   p.ag_nslices = (a->ag_skip_wait == 2) ? 1 : p.n_comm_ctas;
-  if (a->mode == kAG && a->ag_skip_wait == 3) {
-    // NVLS multicast transport: every rank writes its shard once to the multicast alias, K slice by K slice
-    if (!a->mc_base) { drv::set_error("ag_gemm: multicast transport needs an NVLS multicast mapping"); return -1; }
-    if (a->ag_copy_local == 2) { drv::set_error("ag_gemm: the all-to-all flavour cannot use the multicast transport"); return -1; }
-    if (a->a_gather || fp8) { drv::set_error("ag_gemm: the multicast transport takes dense 16-bit A"); return -1; }
-    if (a->ag_rows_per_rank % BM != 0) { drv::set_error("ag_gemm: multicast transport needs (M / world) %% 128 == 0"); return -1; }
-    if (p.n_comm_ctas < cg) p.n_comm_ctas = 24;
-    int ks = (int)((a->ag_kslices & 255) > 0 ? (a->ag_kslices & 255) : 8);
-    int groups = (int)((a->ag_kslices >> 8) > 0 ? (a->ag_kslices >> 8) : 3);
+  if (a->mode == kAG && (a->ag_skip_wait == 3 || a->ag_skip_wait == 4)) {
+    // K-sliced transports: 3 = NVLS multicast (every rank writes its shard once to the multicast alias), 4 = unicast P2P stores
+    // to every peer; both publish one flag per (source, K slice, comm CTA) after ONE release fence per slice
+    const bool mcast = a->ag_skip_wait == 3;
+    if (mcast && !a->mc_base) { drv::set_error("ag_gemm: multicast transport needs an NVLS multicast mapping"); return -1; }
+    if (a->ag_copy_local == 2) { drv::set_error("ag_gemm: the all-to-all flavour cannot use the K-sliced transports"); return -1; }
+    if (a->a_gather || fp8) { drv::set_error("ag_gemm: the K-sliced transports take dense 16-bit A"); return -1; }
+    if (a->ag_rows_per_rank % BM != 0) { drv::set_error("ag_gemm: K-sliced transports need (M / world) %% 128 == 0"); return -1; }
+    if (!mcast && !a->ag_a_local) { drv::set_error("ag_gemm: the P2P K-sliced transport reads the caller's shard (ag_a_local)"); return -1; }
+    if (p.n_comm_ctas < cg) p.n_comm_ctas = mcast ? 24 : 32;
+    int ks = (int)((a->ag_kslices & 255) > 0 ? (a->ag_kslices & 255) : (mcast ? 8 : 2));
+    int groups = (int)((a->ag_kslices >> 8) > 0 ? (a->ag_kslices >> 8) : (mcast ? 3 : 1));
     if (ks > p.num_k) ks = p.num_k;
     if (groups > ks) groups = ks;
     while (groups > 1 && (p.n_comm_ctas % groups != 0 || p.n_comm_ctas / groups < 1)) --groups;
     const int n_c = p.n_comm_ctas / groups;
     while (ks > 1 && n_c * ks > kAGMaxSlices) --ks;
     if (n_c * ks > kAGMaxSlices) { drv::set_error("ag_gemm: too many comm CTAs for the flag array"); return -1; }
-    p.ag_multicast = 1;
+    p.ag_multicast = mcast ? 1 : 0;
     p.ag_ctas_per_group = n_c;
-    p.ag_kb_per_slice = (p.num_k + ks - 1) / ks;
-    p.ag_kslices = (p.num_k + p.ag_kb_per_slice - 1) / p.ag_kb_per_slice;
+    if (ks > 16) ks = 16;
+    {  // slice schedule: the comm CTAs work in rounds of `groups` slices that land together; the LAST round carries ~tail_pct
+       // of K (what the MMAs still have to do after the last byte), the earlier rounds share the rest evenly
+      const int tail_pct = (int)(((a->ag_kslices >> 16) & 255) > 0 ? ((a->ag_kslices >> 16) & 255) : 0);
+      const int rounds = (ks + groups - 1) / groups;
+      int kb = 0;
+      for (int j = 0; j < ks; ++j) {
+        p.ag_slice_kb[j] = kb;
+        const int round = j / groups, in_round = (round == rounds - 1) ? ks - round * groups : groups;
+        double frac;
+        if (tail_pct > 0 && rounds > 1) frac = (round == rounds - 1) ? tail_pct / 100.0 / in_round : (1.0 - tail_pct / 100.0) / ((rounds - 1) * groups);
+        else frac = 1.0 / ks;
+        int n = (int)(frac * p.num_k + 0.5);
+        if (n < 1) n = 1;
+        const int left = ks - 1 - j;                      // keep at least one k-block for every later slice
+        if (kb + n > p.num_k - left) n = p.num_k - left - kb;
+        if (j == ks - 1) n = p.num_k - kb;
+        kb += n;
+      }
+      p.ag_slice_kb[ks] = p.num_k;
+      p.ag_kslices = ks;
+    }
     p.ag_rows_per_cta = (int)((a->ag_rows_per_rank + n_c - 1) / n_c);
     p.ag_nslices = n_c * p.ag_kslices;
   }

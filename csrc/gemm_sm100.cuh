@@ -96,7 +96,8 @@ struct Params {
   int ag_multicast;          // 1: comm CTAs write my shard ONCE to the NVLS multicast alias of the workspace (the switch fans it
                              //    out to every rank), K slice by K slice, and publish flag[me][slice * n_comm + cta] on all ranks
   int ag_kslices;            // multicast: number of K slices (every tile starts after 1/ag_kslices of the transfer and follows it)
-  int ag_kb_per_slice;       // k-blocks (128 bytes of a row) per K slice
+  int ag_slice_kb[18];       // first k-block (128 bytes of a row) of every K slice (+ end): the last slices are short, so the work left
+                             // after the last byte has landed is a few k-blocks
   int ag_rows_per_cta;       // shard rows pushed by one comm CTA
   int ag_ctas_per_group;     // multicast: comm CTAs form n_comm / this groups; group g pushes K slices g, g + G, ... (a release
                              // fence after NVLink stores costs ~7 us of pure latency: G groups keep G slices in flight)
@@ -279,19 +280,22 @@ TD_DEVICE void ag_comm_cta(const Params& p, uint32_t ph, int comm_idx) {
   // interleaved over the shard (sub-slice j of all CTAs = the j-th 1/nsub of the rows), each published separately, so
   // the consumer's first remote tiles become ready after 1/nsub of the transfer instead of at its end
   const int nsub = max(1, p.ag_nslices / max(1, p.n_comm_ctas));
-  if (p.ag_multicast) {
-    // NVLS transport: one multimem.st per 16 bytes reaches every rank's workspace (including mine); egress is the shard
+  if (p.ag_kslices > 0) {
+    // K-sliced transports.  ag_multicast = 1 (NVLS): one multimem.st per 16 bytes reaches every rank's workspace; egress is the shard
     // itself, not (world - 1) copies of it, so a handful of CTAs is enough.  The shard travels K slice by K slice
     // (all rows of columns [j * seg, (j + 1) * seg)), so on the consumer EVERY tile starts after 1 / ag_kslices of the
     // transfer and its mainloop follows the arrival: the tail after the last byte is one K slice of MMAs + the epilogue.
-    char* ws_mc = symm_mc(p.symm, ws) + shard_off;
+    // ag_multicast = 0 (P2P): the same slices are stored to every peer's workspace with unicast 16-byte stores -- the rows are
+    // READ once and written W-1 times, and there is ONE release fence per (CTA, slice) for all destinations (a fence after
+    // NVLink stores costs ~7 us of latency: the per-destination fences of the row-sliced path cost 7 x that).  Measured on
+    // 8xB200: multimem.st tops out near 380 GB/s of ingress per GPU, unicast stores reach the link rate.
+    char* ws_mc = p.ag_multicast ? symm_mc(p.symm, ws) + shard_off : nullptr;
     const int n_c = p.ag_ctas_per_group, n_groups = p.n_comm_ctas / n_c;
     const int grp = comm_idx / n_c, cta = comm_idx % n_c;
     const int r0 = cta * p.ag_rows_per_cta, r1 = min(Ms, r0 + p.ag_rows_per_cta);
-    const size_t seg_bytes = static_cast<size_t>(p.ag_kb_per_slice) * 128;
     for (int j = grp; j < p.ag_kslices; j += n_groups) {
-      const size_t col0 = j * seg_bytes;
-      const int seg16 = static_cast<int>((min(row_bytes, col0 + seg_bytes) - col0) >> 4);
+      const size_t col0 = static_cast<size_t>(p.ag_slice_kb[j]) * 128;
+      const int seg16 = static_cast<int>((min(row_bytes, static_cast<size_t>(p.ag_slice_kb[j + 1]) * 128) - col0) >> 4);
       const int n = max(0, r1 - r0) * seg16;
       if (threadIdx.x == 0) prof_record(p.prof, pslot, 1, true);
       // 16 independent 16-byte loads per thread before the first store (the copy loop is bound by the latency of its reads)
@@ -304,10 +308,21 @@ TD_DEVICE void ag_comm_cta(const Params& p, uint32_t ph, int comm_idx) {
           const int i = i0 + u * kThreads;
           if (i < n) v[u] = ptx::ld_nc_v4(src0 + off_of(i));
         }
+        if (p.ag_multicast) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int i = i0 + u * kThreads;
-          if (i < n) ptx::multimem_st_v4(ws_mc + off_of(i), v[u]);
+          for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * kThreads;
+            if (i < n) ptx::multimem_st_v4(ws_mc + off_of(i), v[u]);
+          }
+        } else {
+          for (int q = 1; q < W; ++q) {          // every rank starts with a different peer: all links busy at any instant
+            char* dst = symm_at(p.symm, ws, (me + q) % W) + shard_off;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const int i = i0 + u * kThreads;
+              if (i < n) ptx::st_na_v4(dst + off_of(i), v[u]);
+            }
+          }
         }
       }
       __syncthreads();
@@ -315,7 +330,7 @@ TD_DEVICE void ag_comm_cta(const Params& p, uint32_t ph, int comm_idx) {
         prof_record(p.prof, pslot, 1, false);
         prof_record(p.prof, pslot, 6, true);
         ptx::fence_acq_rel_sys();
-        for (int d = 0; d < W; ++d) ptx::st_relaxed_sys(symm_at(p.symm, flag_base + j * n_c + cta, (me + d) % W), ph);
+        for (int d = (p.ag_multicast || !p.ag_local_direct) ? 0 : 1; d < W; ++d) ptx::st_relaxed_sys(symm_at(p.symm, flag_base + j * n_c + cta, (me + d) % W), ph);
         prof_record(p.prof, pslot, 6, false);
       }
     }
@@ -681,10 +696,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
           // K-sliced all-gather: before the first k-block of every K slice, acquire that slice of my 128 rows
           const bool ks_wait = (kMode == kAG) && p.ag_kslices > 0 && !p.ag_skip_wait && !a_local && row0 < p.M;
           const int ks_src = ks_wait ? row0 / p.ag_rows_per_rank : 0;
+          int ks_j = 0, ks_next = un.kb0;                 // current K slice and the k-block at which the next acquire is due
           for (int kb = un.kb0; kb < un.kb1; ++kb) {
             if constexpr (kMode == kAG) {
-              if (ks_wait && (kb == un.kb0 || kb % p.ag_kb_per_slice == 0))
-                ag_wait_kslice(p, ph, ks_src, row0 - ks_src * p.ag_rows_per_rank, kb / p.ag_kb_per_slice);
+              if (ks_wait && kb == ks_next) {
+                while (ks_j + 1 < p.ag_kslices && kb >= p.ag_slice_kb[ks_j + 1]) ++ks_j;
+                ag_wait_kslice(p, ph, ks_src, row0 - ks_src * p.ag_rows_per_rank, ks_j);
+                ks_next = p.ag_slice_kb[ks_j + 1];
+              }
             }
             ptx::mbar_wait(empty_bar + stage, phase ^ 1u);
             uint8_t* sa = smem + stage * L::kStageBytes;

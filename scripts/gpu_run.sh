@@ -21,16 +21,29 @@ fi
 if [ "$stage" = "c" ]; then
   N=${2:-8}
   TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-  timeout 400 $TR --master-port 29521 tests/dist_worker.py ag_gemm gemm_rs moe_rs > gpurun_out/dist_n$N.log 2>&1; echo "dist rc=$?"; tail -6 gpurun_out/dist_n$N.log
+  timeout 600 $TR --master-port 29521 tests/dist_worker.py ag_gemm gemm_rs moe_rs gemm_ar moe ep_ll ep_normal mega tp_e2e allreduce > gpurun_out/dist_n$N.log 2>&1; echo "dist rc=$?"; tail -12 gpurun_out/dist_n$N.log
   timeout 500 $TR --master-port 29522 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "bench rc=$?"; tail -c 2500 gpurun_out/bench_n$N.json; tail -3 gpurun_out/bench_n$N.err
   timeout 300 $TR --master-port 29523 triton_dist/benchmark/bench_moe_reduce_rs.py --json gpurun_out/moe_reduce_rs_n$N.json > gpurun_out/moe_rs_n$N.log 2>&1; echo "moe rc=$?"; tail -3 gpurun_out/moe_rs_n$N.log
-  timeout 200 $TR --master-port 29524 scripts/gpu_prof_ag.py transport=multicast bn=128 cta_group=1 n_comm=16 kslices=8 > gpurun_out/prof_ag_mc_n$N.log 2>&1; echo "prof rc=$?"; tail -8 gpurun_out/prof_ag_mc_n$N.log
+  timeout 200 $TR --master-port 29524 scripts/gpu_prof_ag.py transport=sm_k bn=256 cta_group=2 n_comm=32 kslices=2 groups=1 > gpurun_out/prof_ag_mc_n$N.log 2>&1; echo "prof rc=$?"; tail -8 gpurun_out/prof_ag_mc_n$N.log
+  timeout 200 $TR --master-port 29526 scripts/gpu_prof_ag.py transport=sm_k bn=256 cta_group=2 n_comm=48 kslices=4 groups=2 > gpurun_out/prof_ag_mc2_n$N.log 2>&1; echo "prof2 rc=$?"; tail -8 gpurun_out/prof_ag_mc2_n$N.log
 fi
 if [ "$stage" = "d" ]; then
   N=${2:-2}
   TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-  timeout 300 python -m pytest tests/test_ops_gpu.py -x -q -k "moe or sort or align" > gpurun_out/test_moe_ops.log 2>&1; echo "moe ops rc=$?"; tail -3 gpurun_out/test_moe_ops.log
-  timeout 400 $TR --master-port 29531 tests/dist_worker.py moe moe_rs ep_normal ep_moe > gpurun_out/dist_d_n$N.log 2>&1; echo "dist rc=$?"; tail -5 gpurun_out/dist_d_n$N.log
+  timeout 400 $TR --master-port 29531 tests/dist_worker.py ag_gemm moe tp_e2e > gpurun_out/dist_d_n$N.log 2>&1; echo "dist rc=$?"; tail -5 gpurun_out/dist_d_n$N.log
   timeout 300 $TR --master-port 29533 triton_dist/benchmark/bench_moe_reduce_rs.py --json gpurun_out/moe_reduce_rs_n$N.json > gpurun_out/moe_rs_n$N.log 2>&1; echo "moe rc=$?"; tail -3 gpurun_out/moe_rs_n$N.log
-  timeout 200 $TR --master-port 29534 scripts/gpu_prof_ag.py transport=multicast bn=256 cta_group=2 n_comm=24 kslices=8 groups=3 > gpurun_out/prof_ag_mc_n$N.log 2>&1; echo "prof rc=$?"; tail -8 gpurun_out/prof_ag_mc_n$N.log
+  timeout 200 $TR --master-port 29534 scripts/gpu_prof_ag.py transport=sm_k bn=256 cta_group=2 n_comm=32 kslices=2 groups=1 > gpurun_out/prof_ag_mc_n$N.log 2>&1; echo "prof rc=$?"; tail -8 gpurun_out/prof_ag_mc_n$N.log
+fi
+if [ "$stage" = "e" ]; then
+  N=${2:-2}
+  TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+  timeout 500 $TR --master-port 29542 bench.py --gpus $N --steps 20 --warmup 5 --quick > gpurun_out/bench_quick_n$N.json 2> gpurun_out/bench_quick_n$N.err; echo "bench rc=$?"; tail -c 3000 gpurun_out/bench_quick_n$N.json; tail -3 gpurun_out/bench_quick_n$N.err
+  for cfg in "transport=sm_k bn=256 cta_group=2 n_comm=32 kslices=2 groups=1" "transport=sm_k bn=256 cta_group=2 n_comm=32 kslices=4 groups=2" "transport=sm bn=256 cta_group=2 n_comm=32"; do
+    timeout 200 $TR --master-port 29544 scripts/gpu_prof_ag.py $cfg > gpurun_out/prof_e.log 2>&1; echo "prof [$cfg] rc=$?"; tail -6 gpurun_out/prof_e.log
+  done
+fi
+if [ "$stage" = "f" ]; then
+  N=${2:-2}
+  TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+  timeout 400 $TR --master-port 29551 tests/dist_worker.py ag_gemm gemm_rs ep_normal > gpurun_out/dist_f_n$N.log 2>&1; echo "dist rc=$?"; tail -4 gpurun_out/dist_f_n$N.log
 fi

@@ -164,20 +164,20 @@ def case_ag_gemm():
     shapes = [(512 * W, 512, 1024), (256 * W, 256, 512), (384 * W, 768, 256), (100 * W, 264, 520), (512 * W, 512, 4096),
               (128 * W, 1280, 2112)] if big else [(16 * W, 24, 32), (5 * W, 8, 16)]
     dtype = torch.bfloat16 if big else torch.float32
-    transports = ["sm"] + (["multicast"] if (big and U.is_nvshmem_multimem_supported()) else []) if big else ["auto"]
+    transports = (["sm", "sm_k"] + (["multicast"] if U.is_nvshmem_multimem_supported() else [])) if big else ["auto"]
     for (M, N, K) in shapes:
         ctx = create_ag_gemm_context(M, N, K, dtype)
         if big:
             ctx.workspace.view(torch.int16).fill_(0x7FC0)      # poison (bf16 NaN pattern)
         for tr in transports:
-            if tr == "multicast" and (M // W) % 128 != 0:
+            if tr in ("multicast", "sm_k") and (M // W) % 128 != 0:
                 continue
             for it in range(5):
                 A = (torch.randn(M // W, K, device=dev) * 0.5).to(dtype)
                 Wt = (torch.randn(N, K, device=dev) * 0.5).to(dtype)
                 straggler = (it % W, 3_000_000) if (big and it in (1, 3)) else None
-                ks = (0, 4, 16, 3, 8)[it] if tr == "multicast" else 0
-                C = ag_gemm(A, Wt.t(), ctx, straggler_option=straggler, transport=tr, kslices=ks)
+                ks = (0, 4, 16, 3, 8)[it] if tr in ("multicast", "sm_k") else 0
+                C = ag_gemm(A, Wt.t(), ctx, straggler_option=straggler, transport=tr, kslices=ks, comm_groups=(0, 2, 4, 1, 3)[it], tail_pct=(0, 10, 25, 0, 12)[it])
                 full = torch.empty(M * K, device=dev, dtype=dtype)
                 dist.all_gather_into_tensor(full, A.view(-1), group=U.get_triton_dist_world())
                 ref = full.view(M, K).float() @ Wt.float().t()
@@ -482,7 +482,7 @@ def case_ep_normal():
                 hh = x[t].float() @ w_gu[e].float().t()
                 act = torch.nn.functional.silu(hh[:I]) * hh[I:]
                 ref[t] += float(wts[t, k]) * (act.to(dtype).float() @ w_dn[e].float().t())
-        _assert_close(out, ref, 0.15 if big else 1e-4, 5e-2 if big else 1e-4, f"ep_normal it{it}")
+        _assert_close(out, ref, 0.3 if big else 1e-4, 5e-2 if big else 1e-4, f"ep_normal it{it}")
     U.barrier_all_host()
     ctx.finalize()
     if not big:

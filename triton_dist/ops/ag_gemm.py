@@ -6,7 +6,10 @@ allgather_gemm.py:511-619) -- there the all-gather is W-1 host-issued ``cudaMemc
 
 Here (csrc/gemm_sm100.cuh, mode kAG) the gather runs INSIDE the GEMM kernel.  Two in-kernel transports:
 
-* ``multicast`` (NVLS, default when the heap has a multicast mapping): ``n_comm_ctas`` CTAs write this rank's shard ONCE
+* ``sm_k`` (default): the K-sliced protocol of ``multicast`` below with unicast P2P stores to every peer (rows read once,
+  one release fence per slice for all destinations) -- measured fastest on 8xB200, where ``multimem.st`` tops out near
+  380 GB/s of ingress per GPU.
+* ``multicast`` (NVLS): ``n_comm_ctas`` CTAs write this rank's shard ONCE
   to the multicast alias of the workspace with ``multimem.st`` -- the NVSwitch fans it out to every rank, so egress is
   1x the shard instead of (W-1)x -- K slice by K slice, publishing one flag per (source, K slice, comm CTA).  The TMA
   producer of a GEMM CTA acquires the flag of a K slice right before its first k-block, so EVERY tile starts after
@@ -134,12 +137,16 @@ def default_ag_config(M: int, N: int, K: int, world: int) -> GemmConfig:
 def ag_gemm(A: torch.Tensor, B: torch.Tensor, ctx: AllGatherGEMMTensorParallelContext,
             gemm_config: Optional[GemmConfig] = None, straggler_option=None, debug: bool = False,
             out: Optional[torch.Tensor] = None, skip_wait: bool = False, profiler=None, transport: str = "auto",
-            all_to_all: bool = False, kslices: int = 0, comm_groups: int = 0) -> torch.Tensor:
+            all_to_all: bool = False, kslices: int = 0, comm_groups: int = 0, tail_pct: int = 0) -> torch.Tensor:
     """A: ``[M/W, K]`` local shard, B: ``[K, N/W]`` -> ``[M, N/W]``.  ``skip_wait`` runs the GEMM-only twin
     (flags ignored) used to measure exposed communication, like the reference's ``fake_barrier`` path.
 
-    ``transport="auto"`` (default): ``multicast`` when the heap has an NVLS mapping and ``M/W % 128 == 0``, else ``sm``
-    (override with env ``TD_AG_TRANSPORT``).  ``transport="sm"``: comm CTAs push the shard to every peer (P2P stores).
+    ``transport="auto"`` (default): ``sm_k`` when ``M/W % 128 == 0``, else ``sm`` (override with env ``TD_AG_TRANSPORT``).
+    ``transport="sm_k"``: comm CTAs push the shard K slice by K slice to every peer with unicast stores -- rows are read once,
+    one release fence per (CTA, slice) covers all destinations, and every tile follows the arrival of its K slices
+    (``kslices``, default 2; ``comm_groups`` groups of CTAs push alternate slices; ``tail_pct`` > 0 makes the LAST round of
+    slices carry only that percentage of K, so the MMAs left after the last byte has landed are a few k-blocks).
+    ``transport="sm"``: row-sliced P2P push, one fence per (CTA, destination) -- kept for ragged shards and the all-to-all flavour.
     ``transport="copy_engine"``: the
     shard is pushed by the DMA engines on a side stream (one ``cudaMemcpyAsync`` + one release-flag kernel per peer, as
     the reference's copy-engine producer, allgather.py:100-124) while all SMs run GEMM tiles that wait on the same
@@ -201,7 +208,13 @@ def ag_gemm(A: torch.Tensor, B: torch.Tensor, ctx: AllGatherGEMMTensorParallelCo
         assert not all_to_all and U.is_nvshmem_multimem_supported() and Ms % 128 == 0
         args.ag_skip_wait = 3
         args.n_comm_ctas = max(2, min(cfg.n_comm_ctas or 24, 64))
-        args.ag_kslices = (kslices & 255) | (comm_groups << 8)
+        args.ag_kslices = (kslices & 255) | (comm_groups << 8) | ((tail_pct & 255) << 16)
+    if transport == "sm_k" and not skip_wait:
+        # P2P K-sliced push: rows read once, stored to every peer, ONE release fence per (comm CTA, K slice) for all destinations
+        assert not all_to_all and Ms % 128 == 0
+        args.ag_skip_wait = 4
+        args.n_comm_ctas = max(2, min(cfg.n_comm_ctas or 32, 64))
+        args.ag_kslices = (kslices & 255) | (comm_groups << 8) | ((tail_pct & 255) << 16)
     if transport == "copy_engine" and not skip_wait:
         _ce_push(ctx, A, ph, Ms, K)
         args.ag_skip_wait, args.ag_copy_local, args.n_comm_ctas = 2, 1, 0
@@ -221,8 +234,8 @@ def resolve_transport(rows_per_rank: int, all_to_all: bool = False) -> str:
     forced = os.environ.get("TD_AG_TRANSPORT", "")
     if forced:
         return forced
-    if (not all_to_all) and rows_per_rank % 128 == 0 and U.is_nvshmem_multimem_supported():
-        return "multicast"
+    if (not all_to_all) and rows_per_rank % 128 == 0:
+        return "sm_k"
     return "sm"
 
 
