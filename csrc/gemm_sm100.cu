@@ -41,6 +41,10 @@ struct TdGemmArgs {
   long long ag_kslices;           // K-sliced AG: K slices (bits 0-7, 0 = default) | comm-CTA groups << 8 | percent of K in the last round << 16
   // mode 4 (MoE reduce-RS / reduce-AR): rs_stage = partial [2][T][N], rs_flags = [2][num_n][W][n_comm], rs_out = output
   const void* row_scale; void* mrs_counter; const void* mrs_total_padded; long long mrs_T, mrs_topk, mrs_allreduce, mrs_chunk_n;
+  // mode 5 (Mega-EP dispatch + grouped GEMM): A = ag_ws (symmetric rx [2][rows_cap][K]), flags = ag_flags [2][epr][W][cpd];
+  // mode 6 (Mega-EP grouped GEMM + combine): rs_stage = comb [2][pairs][N] symmetric, rs_flags = done [2][W], c_route = return addresses
+  const void* epd_send_off; const void* epd_send_ids; const void* epd_dest_off; const void* epd_x;
+  long long epd_topk, epd_epr, epd_cpd, epd_rows_cap; void* epd_meta; const void* c_route;
 };
 
 static int encode_tmap(CUtensorMap* out, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
@@ -290,6 +294,22 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
       p.mrs_n_chunks = nchunks;
     }
   }
+  if (a->mode == kEPD) {
+    if (fp8 || !a->tile_expert || a->a_gather) { drv::set_error("mega_ep dispatch: 16-bit grouped GEMM on the delivered rows"); return -1; }
+    if (!a->epd_send_off || !a->epd_send_ids || !a->epd_dest_off || !a->epd_x || !a->epd_meta || !a->ag_ws || !a->ag_flags || a->epd_cpd < 1) {
+      drv::set_error("mega_ep dispatch: missing buffers"); return -1;
+    }
+    p.epd_send_off = (const int*)a->epd_send_off; p.epd_send_ids = (const int*)a->epd_send_ids; p.epd_dest_off = (const int*)a->epd_dest_off;
+    p.epd_x = (const char*)a->epd_x; p.epd_topk = (int)a->epd_topk; p.epd_epr = (int)a->epd_epr; p.epd_cpd = (int)a->epd_cpd;
+    p.epd_rows_cap = (int)a->epd_rows_cap; p.epd_meta = (uint32_t*)a->epd_meta; p.epd_flags = (uint32_t*)a->ag_flags;
+    p.n_comm_ctas = (int)(a->world * a->epd_cpd);
+    if (a->K % 8) { drv::set_error("mega_ep dispatch: hidden size must be a multiple of 8"); return -1; }
+  }
+  if (a->mode == kEPC) {
+    if (fp8 || !a->tile_expert || !a->c_route || !a->rs_stage || !a->rs_flags) { drv::set_error("mega_ep combine: missing buffers"); return -1; }
+    p.c_route = (const uint32_t*)a->c_route; p.n_comm_ctas = 0; p.use_tma_store = 0;
+    if (p.N % 8) { drv::set_error("mega_ep combine: N must be a multiple of 8"); return -1; }
+  }
   if (p.n_comm_ctas % cg) p.n_comm_ctas += cg - p.n_comm_ctas % cg;
   if (a->mode == kAR && p.a2a_cols_per_rank > 0) p.n_comm_ctas = 0;     // GEMM + all-to-all: the epilogue scatters, no comm CTAs
   int gemm_ctas = grid - p.n_comm_ctas;      // comm CTAs must be co-resident with the GEMM CTAs: the grid never exceeds the SMs
@@ -348,6 +368,18 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
     case kAG: return dispatch<kAG>(p, bn, cg, grid, stream);
     case kRS: return dispatch<kRS>(p, bn, cg, grid, stream);
     case kAR: return dispatch<kAR>(p, bn, cg, grid, stream);
+    case kEPD:
+      if (bn == 256 && cg == 2) return launch_cfg<kEPD, 256, 2>(p, grid, stream);
+      if (bn == 256 && cg == 1) return launch_cfg<kEPD, 256, 1>(p, grid, stream);
+      if (bn == 128 && cg == 2) return launch_cfg<kEPD, 128, 2>(p, grid, stream);
+      if (bn == 128 && cg == 1) return launch_cfg<kEPD, 128, 1>(p, grid, stream);
+      drv::set_error("mega_ep: bn must be 128 or 256"); return -1;
+    case kEPC:
+      if (bn == 256 && cg == 2) return launch_cfg<kEPC, 256, 2>(p, grid, stream);
+      if (bn == 256 && cg == 1) return launch_cfg<kEPC, 256, 1>(p, grid, stream);
+      if (bn == 128 && cg == 2) return launch_cfg<kEPC, 128, 2>(p, grid, stream);
+      if (bn == 128 && cg == 1) return launch_cfg<kEPC, 128, 1>(p, grid, stream);
+      drv::set_error("mega_ep: bn must be 128 or 256"); return -1;
     case kMoeRS:
       if (bn == 256 && cg == 2) return launch_cfg<kMoeRS, 256, 2>(p, grid, stream);
       if (bn == 256 && cg == 1) return launch_cfg<kMoeRS, 256, 1>(p, grid, stream);

@@ -18,6 +18,14 @@
 //            scatters it to (token, k) order; comm CTAs of the same grid wait for "all m tiles of n tile c done", sum the
 //            top-k rows of each token into this rank's symmetric partial, flag the peers, and one chunk later every owner
 //            pulls the cross-rank sum of ITS rows with multimem.ld_reduce (NVSwitch adds the W partials in fp32)
+//   kEPD   : Mega-EP half 1 -- expert-parallel DISPATCH fused with the grouped (gate/up) GEMM (ref: kernels/nvidia/
+//            ep_all2all_fused.py:73-835 tile kernels + :839 mega_dispatch_group_gemm): comm CTAs of the same grid store every routed
+//            token row straight into its final, expert-sorted and tile-aligned position of the destination rank's A matrix
+//            (positions come from the all-gathered per-expert counts, so there is no receive-side index list, sort or copy) and
+//            release one flag per (local expert, source, comm CTA); the tcgen05 tiles of an expert start when its flags are up.
+//   kEPC   : Mega-EP half 2 -- grouped (down) GEMM fused with the COMBINE transfer (ref :1020 mega_group_gemm_combine): the epilogue
+//            stores every output row straight to its (token, k) slot on the rank that owns the token (return address =
+//            source << 24 | pair id, delivered by the dispatch); the last CTA release-flags all ranks.
 //
 // B200-first design (not a translation of the reference):
 //   * warp-specialised CTA: warp0 = TMA producer, warp1 = single-thread tcgen05.mma issuer, warp2 = TMEM
@@ -54,7 +62,7 @@ constexpr int kCBlockBytes = BM * kCBlockCols * 2;
 constexpr int kAGRowsPerChunk = 128;                  // AG arrival-flag granularity (rows of a source shard)
 constexpr int kAGMaxSlices = 256;                     // arrival flags per source rank (comm CTAs x sub-slices / K slices)
 
-enum Mode : int { kPlain = 0, kAG = 1, kRS = 2, kAR = 3, kMoeRS = 4 };
+enum Mode : int { kPlain = 0, kAG = 1, kRS = 2, kAR = 3, kMoeRS = 4, kEPD = 5, kEPC = 6 };
 
 struct Params {
   CUtensorMap tmap_a;   // dims {K, rows_a, nbuf}, box {64, 128, 1}, SWIZZLE_128B
@@ -140,6 +148,15 @@ struct Params {
   int mrs_n_chunks;          // column chunks: tiles run chunk-major, then m, then n inside the chunk (A is re-read once per chunk)
   int mrs_chunk_start[17];   // first n tile of every chunk (+ end); chunks shrink towards the end so the exposed tail is one n tile
   // (partial: rs_stage [2][T][N] 16-bit symmetric; flags: rs_flags [2][num_n][W][n_comm]; output: rs_out / rs_ldo)
+  // ---- Mega-EP (kEPD / kEPC) ----
+  const int* epd_send_off;   // [E + 1]: my (token, k) pairs sorted by GLOBAL expert
+  const int* epd_send_ids;   // pair ids (token * topk + k) in that order
+  const int* epd_dest_off;   // [E]: first row of MY rows of that expert inside the destination's sorted A
+  const char* epd_x;         // my tokens [T, K] 16-bit
+  int epd_topk, epd_epr, epd_cpd, epd_rows_cap;   // cpd = comm CTAs per destination rank (n_comm = world * cpd)
+  uint32_t* epd_meta;        // symmetric [2][rows_cap]: return address (source << 24 | pair id) of every delivered row
+  uint32_t* epd_flags;       // symmetric [2][epr][world][cpd]: phase once that CTA's rows of the expert have landed
+  const uint32_t* c_route;   // kEPC epilogue: C row i goes to rank (v >> 24), row (v & 0xffffff) of rs_stage; 0xffffffff = skip
   // ---- split-K tail: the last partial wave of tiles is cut into sk_parts K ranges that run on otherwise idle clusters;
   // parts > 0 park their fp32 accumulator in sk_ws, part 0 adds them in its epilogue (wave quantisation: 768 tiles on
   // 74 CTA pairs = 10.4 waves -> 10.5 instead of 11)
@@ -532,6 +549,55 @@ TD_DEVICE void moe_rs_comm_cta(const Params& p, uint32_t ph, int ci) {
 }
 
 // -------------------------------------------------------------------------------------------------
+// Mega-EP dispatch comm CTA: CTA ci serves destination d = (me + ci / cpd) % W (every rank starts with itself, then a different
+// peer each) and, expert by expert (local expert e of d = global expert d * epr + e), stores its share of my rows routed to
+// that expert -- one warp per row, 16 B vectors, 4 loads in flight per lane -- into rows [dest_off[g], ...) of d's A matrix
+// plus the 4-byte return address; then ONE release fence and the flag of (e, me, my sub-index) on d.  Experts are sent in
+// the order the destination's GEMM consumes them.
+// -------------------------------------------------------------------------------------------------
+TD_DEVICE void epd_comm_cta(const Params& p, uint32_t ph, int ci) {
+  const int W = p.symm.world, me = p.symm.rank, cpd = p.epd_cpd;
+  const int d = (me + ci / cpd) % W, sub = ci % cpd;
+  const uint32_t par = ph & 1u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = kThreads / 32;
+  const size_t row_bytes = static_cast<size_t>(p.K) * 2;
+  const int vecs = static_cast<int>(row_bytes >> 4);
+  char* rx = symm_at(p.symm, p.ag_ws + par * p.ag_ws_buf_bytes, d);
+  uint32_t* meta = symm_at(p.symm, p.epd_meta + static_cast<size_t>(par) * p.epd_rows_cap, d);
+  for (int e = 0; e < p.epd_epr; ++e) {
+    const int g = d * p.epd_epr + e;
+    const int base = p.epd_send_off[g], n = p.epd_send_off[g + 1] - base, drow0 = p.epd_dest_off[g];
+    for (int i = sub * wpc + warp; i < n; i += cpd * wpc) {
+      const int drow = drow0 + i;
+      if (drow >= p.epd_rows_cap) continue;                       // over capacity: dropped (the host sized the buffers)
+      const int pair = p.epd_send_ids[base + i];
+      const uint4* src = reinterpret_cast<const uint4*>(p.epd_x + static_cast<size_t>(pair / p.epd_topk) * row_bytes);
+      uint4* dst = reinterpret_cast<uint4*>(rx + static_cast<size_t>(drow) * row_bytes);
+      int v = lane;
+      for (; v + 96 < vecs; v += 128) {
+        const uint4 a0 = ptx::ld_nc_v4(src + v), a1 = ptx::ld_nc_v4(src + v + 32), a2 = ptx::ld_nc_v4(src + v + 64), a3 = ptx::ld_nc_v4(src + v + 96);
+        ptx::st_na_v4(dst + v, a0); ptx::st_na_v4(dst + v + 32, a1); ptx::st_na_v4(dst + v + 64, a2); ptx::st_na_v4(dst + v + 96, a3);
+      }
+      for (; v < vecs; v += 32) ptx::st_na_v4(dst + v, ptx::ld_nc_v4(src + v));
+      if (lane == 0) meta[drow] = (static_cast<uint32_t>(me) << 24) | static_cast<uint32_t>(pair);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      ptx::fence_acq_rel_sys();
+      uint32_t* f = p.epd_flags + ((static_cast<size_t>(par) * p.epd_epr + e) * W + me) * cpd + sub;
+      ptx::st_relaxed_sys(symm_at(p.symm, f, d), ph);
+    }
+  }
+}
+// consumer: all rows of local expert e (from every source, every comm CTA) have landed in my A matrix
+TD_DEVICE void epd_wait_expert(const Params& p, uint32_t ph, int e) {
+  const int n = p.symm.world * p.epd_cpd;
+  const uint32_t* f = p.epd_flags + (static_cast<size_t>(ph & 1u) * p.epd_epr + e) * n;
+  for (int i = 0; i < n; ++i) wait_ge<true>(f + i, ph);
+  ptx::fence_proxy_async();
+}
+
+// -------------------------------------------------------------------------------------------------
 // the kernel
 // -------------------------------------------------------------------------------------------------
 template <int kMode, int BN, int kStages, int kCtaGroup, bool kFP8 = false, int kAccStages = 2>
@@ -570,6 +636,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     }
     if constexpr (kMode == kMoeRS) {
       moe_rs_comm_cta<BN>(p, ph, static_cast<int>(blockIdx.x) - n_gemm_ctas);
+    }
+    if constexpr (kMode == kEPD) {
+      epd_comm_cta(p, ph, static_cast<int>(blockIdx.x) - n_gemm_ctas);
     }
   } else {
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
@@ -671,6 +740,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
       // ================================ TMA producer ================================
       if (lane == 0) {
         int stage = 0; uint32_t phase = 0;
+        int epd_seen = -1;
+        (void)epd_seen;
         for (int u = worker; u < p.total_units; u += n_workers) {
           const Unit un = get_unit(p, u);
           int m_tile, n_tile;
@@ -684,7 +755,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             if (!p.ag_skip_wait && !p.ag_kslices && row0 < p.M) ag_wait_rows(p, ph, row0, min(p.M, row0 + BM));
             prof_record(p.prof, static_cast<int>(blockIdx.x) * 8, 3, false);
           }
-          const int abuf = (kMode == kAG) ? static_cast<int>(ph & 1u) : 0;
+          const int abuf = (kMode == kAG || kMode == kEPD) ? static_cast<int>(ph & 1u) : 0;
+          if constexpr (kMode == kEPD) {
+            if (!p.ag_skip_wait && expert != epd_seen) { epd_wait_expert(p, ph, expert); epd_seen = expert; }
+          }
           // my own rows come straight from the caller's tensor (no local copy into the workspace)
           bool a_local = false; int lrow0 = 0;
           if constexpr (kMode == kAG) {
@@ -1064,7 +1138,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                 int drow = grow - dst_row_off;
                 if (p.c_scatter) { drow = p.c_scatter[grow]; if (drow < 0 || drow == p.a_gather_pad) continue; }
                 const uint4 o = ptx::ld_shared_v4(cbuf_u32 + r * 128 + ((chunk ^ (r & 7)) << 4));
-                if constexpr (kMode == kMoeRS) {
+                if constexpr (kMode == kEPC) {
+                  const uint32_t v = p.c_route[grow];               // return address delivered by the dispatch
+                  if (v == 0xffffffffu) continue;
+                  char* rb = symm_at(p.symm, p.rs_stage + (ph & 1u) * p.rs_stage_buf_bytes, static_cast<int>(v >> 24));
+                  ptx::st_v4(rb + (static_cast<size_t>(v & 0xffffffu) * p.N + gcol) * 2, o);
+                } else if constexpr (kMode == kMoeRS) {
                   char* d = dst_base + (static_cast<size_t>(drow / p.mrs_topk) * dst_ld + gcol) * 2;     // pair id -> token row
                   if (p.in_is_bf16) ptx::red_add_bf16x8(d, o); else ptx::red_add_f16x8(d, o);
                 } else {
@@ -1137,6 +1216,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
       }
       if (p.use_tma_store && et == 0) ptx::bulk_wait<0>();
       __syncwarp();
+      if constexpr (kMode == kEPC) {
+        // my rows have been stored to their owners: make them visible system wide before this CTA counts itself out
+        ptx::named_bar_sync(2, kEpiThreads);
+        if (et == 0) ptx::fence_acq_rel_sys();
+      }
     }
 
     // ---- teardown ----
@@ -1154,6 +1238,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         p.phase[1] = 0;
         __threadfence();
         p.phase[0] = ph;
+        if constexpr (kMode == kEPC) {     // every CTA fenced its stores (sys scope) before counting out: tell all owners
+          ptx::fence_acq_rel_sys();
+          for (int d = 0; d < p.symm.world; ++d)
+            ptx::st_release_sys(symm_at(p.symm, p.rs_flags + (ph & 1u) * p.symm.world + p.symm.rank, d), ph);
+        }
       }
     }
   }

@@ -45,5 +45,5 @@ fi
 if [ "$stage" = "f" ]; then
   N=${2:-2}
   TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-  timeout 400 $TR --master-port 29551 tests/dist_worker.py ag_gemm gemm_rs ep_normal > gpurun_out/dist_f_n$N.log 2>&1; echo "dist rc=$?"; tail -4 gpurun_out/dist_f_n$N.log
+  timeout 90 $TR --master-port 29551 tests/dist_worker.py ep_mega > gpurun_out/dist_f_n$N.log 2>&1; echo "dist rc=$?"; grep -v "^\[W\|^W0\|OMP_NUM\|^\*\*" gpurun_out/dist_f_n$N.log | tail -25
 fi

@@ -350,6 +350,38 @@ def case_moe_rs():
         rs.finalize()
 
 
+def case_ep_mega():
+    """Mega-EP (dispatch || grouped GEMM, grouped GEMM || combine: csrc/gemm_sm100.cuh kEPD / kEPC) vs the fp32 golden computed
+    with all experts' weights; unbalanced routing (some experts empty), several calls per context (parity), a straggler."""
+    from triton_dist.ops import ep_mega as EM
+    dev = U.current_device()
+    if dev.type != "cuda":
+        return
+    W, me = U.world_size(), U.rank()
+    bf = torch.bfloat16
+    for (T, H, I, epr, topk) in [(512, 512, 256, 4, 2), (300, 1024, 512, 2, 4), (1024, 256, 128, 8, 3)]:
+        E = epr * W
+        ctx = EM.create_ep_mega_context(T, H, topk, E, bf, capacity_factor=3.0)
+        g = torch.Generator(device="cpu").manual_seed(11)
+        w_gu_all = (torch.randn(E, 2 * I, H, generator=g) * 0.05).to(bf).to(dev)
+        w_dn_all = (torch.randn(E, H, I, generator=g) * 0.05).to(bf).to(dev)
+        w_gu, w_dn = w_gu_all[me * epr:(me + 1) * epr].contiguous(), w_dn_all[me * epr:(me + 1) * epr].contiguous()
+        for it in range(4):
+            x = (torch.randn(T, H, device=dev) * 0.5).to(bf)
+            logits = torch.randn(T, E, device=dev)
+            if it >= 2:
+                logits[:, E // 2:] -= 4.0          # unbalanced: the upper half of the experts is (almost) never chosen
+            ids = logits.topk(topk, dim=1).indices.to(torch.int32)
+            wts = torch.softmax(torch.randn(T, topk, device=dev), -1)
+            if it == 1:
+                torch.cuda._sleep(2_000_000 * (1 + me))
+            out = EM.mega_ep_moe(ctx, x, ids, wts, w_gu, w_dn)
+            ref = EM.mega_ep_moe_reference(x, ids, wts, w_gu_all, w_dn_all)
+            _assert_close(out, ref, 0.05, 5e-2, f"ep_mega T{T} H{H} it{it}")
+        U.barrier_all_host()
+        ctx.finalize()
+
+
 def case_moe_staged():
     """The multi-kernel MoE path (all-gather kernel -> gather_rows -> grouped GEMM -> scatter_rows); ``case_moe`` runs the
     default single-kernel path on GPUs (AllGather + grouped GEMM with a TMA tile::gather4 producer waiting on arrival flags)."""
@@ -489,7 +521,7 @@ def case_ep_normal():
         # the Mega-EP style op object (lazy sizing -> materialize -> dispatch+GEMM half -> GEMM+combine half)
         from triton_dist.parallel.ep import EPConfig, EpAll2AllFusedOp
         op = EpAll2AllFusedOp(EPConfig(T, H, topk, E, me, W, False, dtype))
-        assert op.get_nvshmem_size() > 0 and op.layer is None
+        assert op.get_nvshmem_size() > 0 and op.ctx is None
         op.materialize()
         g = torch.Generator().manual_seed(555 + me)
         x = (torch.randn(T, H, generator=g) * 0.5).to(dtype)

@@ -59,6 +59,8 @@ class GemmArgs(C.Structure):
         ("rs_skip_wait", c_ll), ("rs_fp32", c_ll), ("ag_kslices", c_ll),
         ("row_scale", c_void_p), ("mrs_counter", c_void_p), ("mrs_total_padded", c_void_p), ("mrs_T", c_ll), ("mrs_topk", c_ll),
         ("mrs_allreduce", c_ll), ("mrs_chunk_n", c_ll),
+        ("epd_send_off", c_void_p), ("epd_send_ids", c_void_p), ("epd_dest_off", c_void_p), ("epd_x", c_void_p),
+        ("epd_topk", c_ll), ("epd_epr", c_ll), ("epd_cpd", c_ll), ("epd_rows_cap", c_ll), ("epd_meta", c_void_p), ("c_route", c_void_p),
     ]]
 
 

@@ -332,50 +332,81 @@ class TritonDistFusedEpMoeFunction(torch.autograd.Function):
 
 class EpAll2AllFusedOp:
     """The reference's Mega-EP op (layers/nvidia/ep_a2a_fused_layer.py:71-763): lazily sized symmetric buffers, then
-    ``mega_dispatch_group_gemm`` (dispatch + gate/up grouped GEMM + SwiGLU) and ``mega_group_gemm_combine`` (down grouped GEMM +
-    combine).  Here the two halves run on the throughput-mode exchange: received rows are consumed in place through TMA gather4 index
-    lists (no receive-side copy between dispatch and the GEMM), the down GEMM's epilogue scatters to pair order, and combine
-    pre-reduces per token on the expert rank."""
+    ``mega_dispatch_group_gemm`` (dispatch fused with the gate/up grouped GEMM) and ``mega_group_gemm_combine`` (down grouped GEMM
+    fused with the combine transfer).  Each half is ONE kernel here (ops/ep_mega.py, csrc/gemm_sm100.cuh modes kEPD / kEPC): comm
+    CTAs store every routed row straight into its final expert-sorted position on the destination while the tcgen05 tiles of
+    already-complete experts run; the down projection's epilogue delivers every output row to its (token, k) slot on the owner."""
 
-    def __init__(self, ep_config: EPConfig):
+    def __init__(self, ep_config: EPConfig, capacity_factor: float = 2.0):
         self.cfg = ep_config
-        self.layer: Optional[EPNormalAll2AllLayer] = None
+        self.capacity_factor = capacity_factor
+        self.ctx = None
 
     # lazy allocation (the reference sizes the NVSHMEM heap from these numbers before materialising)
     def get_nvshmem_size(self) -> int:
         c = self.cfg
         esz = torch.empty(0, dtype=c.dtype).element_size()
-        W = c.world_size
-        per_parity = W * c.max_tokens * c.hidden * esz * 2 + W * c.max_tokens * c.topk * 16 + W * c.max_tokens * 16 + W * 16 + W * 4
-        return 2 * per_parity
+        rows = int(c.max_tokens * c.topk * self.capacity_factor) + (c.num_experts // c.world_size) * 255
+        return 2 * (rows * c.hidden * esz + rows * 4) + 2 * c.max_tokens * c.topk * c.hidden * esz + 4096
 
     get_nvshmem_size_gb = lambda self: self.get_nvshmem_size() / 2 ** 30
 
     def materialize(self):
-        if self.layer is None:
-            self.layer = EPNormalAll2AllLayer(self.cfg)
+        if U.get_heap().device.type != "cuda":
+            self._host_layer()
+            return self
+        if self.ctx is None:
+            from ..ops import ep_mega as EM
+            c = self.cfg
+            self.ctx = EM.create_ep_mega_context(c.max_tokens, c.hidden, c.topk, c.num_experts, c.dtype, self.capacity_factor)
         return self
 
     def preprocess(self, topk_indices: torch.Tensor):
         return M.histogram_by_expert(topk_indices, self.cfg.num_experts)
 
     def mega_dispatch_group_gemm(self, x: torch.Tensor, topk_indices: torch.Tensor, topk_weights: torch.Tensor, w_gate_up: torch.Tensor):
-        """-> (activations in the sorted expert layout, handle)."""
-        from ..ops import ep_normal as EN
+        """-> (SwiGLU activations in my expert-sorted layout ``[rows_cap, I]``, handle)."""
+        from ..ops import ep_mega as EM
+        from ..ops.elementwise import silu_mul
         self.materialize()
-        h = self.layer.dispatch(x, topk_indices, topk_weights)
-        act, r = EN.ep_ffn_up_normal(self.layer.ctx, h, w_gate_up)
-        return act, (h, r, topk_indices)
+        if not x.is_cuda:
+            return self._host_dispatch(x, topk_indices, topk_weights, w_gate_up)
+        h, handle = EM.mega_dispatch_group_gemm(self.ctx, x, topk_indices, w_gate_up)
+        return silu_mul(h), (handle, topk_weights)
 
     mega_preprocess_group_gemm = mega_dispatch_group_gemm
 
     def mega_group_gemm_combine(self, act: torch.Tensor, handle, w_down: torch.Tensor) -> torch.Tensor:
+        from ..ops import ep_mega as EM
+        if not act.is_cuda:
+            return self._host_combine(act, handle, w_down)
+        hd, topk_weights = handle
+        return EM.mega_group_gemm_combine(self.ctx, act, hd, w_down, topk_weights)
+
+    # emulation backend: the throughput-mode exchange executes the same dispatch / combine protocol on the shared-memory heap
+    def _host_layer(self):
+        if getattr(self, "_layer", None) is None:
+            self._layer = EPNormalAll2AllLayer(self.cfg)
+        return self._layer
+
+    def _host_dispatch(self, x, topk_indices, topk_weights, w_gate_up):
+        from ..ops import ep_normal as EN
+        layer = self._host_layer()
+        h = layer.dispatch(x, topk_indices, topk_weights)
+        act, r = EN.ep_ffn_up_normal(layer.ctx, h, w_gate_up)
+        return act, (h, r, topk_indices)
+
+    def _host_combine(self, act, handle, w_down):
         from ..ops import ep_normal as EN
         h, r, topk_indices = handle
-        y = EN.ep_ffn_down_normal(self.layer.ctx, h, act, r, w_down)
-        return self.layer.combine(y, h, topk_indices)
+        layer = self._host_layer()
+        y = EN.ep_ffn_down_normal(layer.ctx, h, act, r, w_down)
+        return layer.combine(y, h, topk_indices)
 
     def finalize(self):
-        if self.layer is not None:
-            self.layer.finalize()
-            self.layer = None
+        if self.ctx is not None:
+            self.ctx.finalize()
+            self.ctx = None
+        if getattr(self, "_layer", None) is not None:
+            self._layer.finalize()
+            self._layer = None
