@@ -6,6 +6,8 @@
 // straight streaming design: one CTA per (batch, kv head, split), 4 warps striding over the split's positions,
 // lanes splitting head_dim=128 (8 B per lane per row -> fully coalesced 256 B rows), online softmax in fp32,
 // then an in-CTA merge of the 4 warps and a tiny combine kernel that merges splits (and ranks).
+#include <cstdlib>
+
 #include "td/ptx.cuh"
 #include "runtime/driver.h"
 
@@ -129,6 +131,146 @@ __global__ void __launch_bounds__(kWarps * 32) decode_splitkv_kernel(const Decod
   }
 }
 
+// ---- v2: bandwidth-oriented streaming kernel -------------------------------------------------------------------------------
+// ncu of the kernel above (B=8, 8 K context, 8 kv heads): 0.86 TB/s -- two 8-byte loads per lane per array in flight are ~8 KB
+// per SM, Little's law needs ~45 KB.  Here 8 lanes cover one 256-byte row with 16-byte loads, a warp covers 4 rows per load
+// instruction and keeps kU = 4 K loads + 4 V loads in flight per lane (8 KB per warp, 64 KB per 8-warp CTA).  Every 8-lane group
+// runs its own online softmax over the rows it sees (32 independent states per CTA), merged through shared memory at the end.
+constexpr int kWarps2 = 8;
+constexpr int kU = 4;
+
+template <bool kBF16>
+TD_DEVICE void unpack8(const uint4& r, float (&f)[8]) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    if constexpr (kBF16) { f[2 * e] = ptx::bf16_lo(w[e]); f[2 * e + 1] = ptx::bf16_hi(w[e]); }
+    else { const __half2 h = *reinterpret_cast<const __half2*>(&w[e]); f[2 * e] = __low2float(h); f[2 * e + 1] = __high2float(h); }
+  }
+}
+
+template <bool kBF16, int G>
+__global__ void __launch_bounds__(kWarps2 * 32, (G <= 4) ? 2 : 1) decode_splitkv_kernel_v2(const DecodeParams p) {
+  const int b = blockIdx.x, kvh = blockIdx.y, sp = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane >> 3, l8 = lane & 7;          // row inside the warp's group of 4, 16-byte piece of the row
+  const int len = p.kv_lens[b];
+  const int per = (len + p.S - 1) / p.S;
+  const int j0 = sp * per, j1 = min(len, j0 + per);
+  const uint4* kc = reinterpret_cast<const uint4*>(p.k_cache);
+  const uint4* vc = reinterpret_cast<const uint4*>(p.v_cache);
+
+  float q[G][8];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    unpack8<kBF16>(reinterpret_cast<const uint4*>(p.q)[(static_cast<size_t>(b) * p.Hq + kvh * G + g) * 16 + l8], q[g]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) q[g][e] *= p.sm_scale;
+  }
+  float m[G], l[G], o[G][8];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    m[g] = -INFINITY; l[g] = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[g][e] = 0.f;
+  }
+  auto row_off = [&](int j) -> size_t {
+    size_t row;
+    if (p.block_table) {
+      const int page = p.block_table[static_cast<size_t>(b) * p.max_pages + j / p.page_size];
+      row = static_cast<size_t>(page) * p.page_size + (j % p.page_size);
+    } else {
+      row = static_cast<size_t>(b) * p.max_len + j;
+    }
+    return (row * p.Hkv + kvh) * 16 + l8;
+  };
+  constexpr int kRowsPerIter = kWarps2 * 4 * kU;      // 128 positions per CTA iteration
+  for (int jb = j0; jb < j1; jb += kRowsPerIter) {
+    uint4 kr[kU], vr[kU];
+    int jj[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      jj[u] = jb + (u * kWarps2 + warp) * 4 + sub;
+      if (jj[u] < j1) { const size_t off = row_off(jj[u]); kr[u] = ptx::ld_nc_v4(kc + off); vr[u] = ptx::ld_nc_v4(vc + off); }
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const bool ok = jj[u] < j1;
+      float kf[8], vf[8];
+      if (ok) { unpack8<kBF16>(kr[u], kf); unpack8<kBF16>(vr[u], vf); }
+      else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { kf[e] = 0.f; vf[e] = 0.f; }
+      }
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        float s = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s += q[g][e] * kf[e];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (p.soft_cap > 0.f) s = p.soft_cap * tanhf(s / p.soft_cap);
+        if (!ok) s = -INFINITY;
+        const float mn = fmaxf(m[g], s);
+        if (mn > -INFINITY) {
+          const float corr = __expf(m[g] - mn), pj = __expf(s - mn);
+          l[g] = l[g] * corr + pj;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[g][e] = o[g][e] * corr + pj * vf[e];
+          m[g] = mn;
+        }
+      }
+    }
+  }
+  // merge: first the 4 row groups of a warp with shuffles (lanes l8, l8 + 8, l8 + 16, l8 + 24 hold the same columns) ...
+#pragma unroll
+  for (int off = 8; off <= 16; off <<= 1) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const float mo = __shfl_xor_sync(0xffffffffu, m[g], off), lo = __shfl_xor_sync(0xffffffffu, l[g], off);
+      const float mn = fmaxf(m[g], mo);
+      const float ca = (m[g] == -INFINITY) ? 0.f : __expf(m[g] - mn), cb = (mo == -INFINITY) ? 0.f : __expf(mo - mn);
+      l[g] = l[g] * ca + lo * cb;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float oo = __shfl_xor_sync(0xffffffffu, o[g][e], off);
+        o[g][e] = o[g][e] * ca + oo * cb;
+      }
+      m[g] = mn;
+    }
+  }
+  // ... then the 8 warps through shared memory
+  constexpr int kStates = kWarps2;
+  __shared__ float sm_m[kStates][G], sm_l[kStates][G];
+  __shared__ float sm_o[kStates][G][kD];
+  const int st = warp;
+  if (sub == 0) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      if (l8 == 0) { sm_m[st][g] = m[g]; sm_l[st][g] = l[g]; }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sm_o[st][g][l8 * 8 + e] = o[g][e];
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < G * kD; idx += kWarps2 * 32) {
+    const int g = idx / kD, d = idx % kD;
+    float mm = -INFINITY;
+#pragma unroll 4
+    for (int w = 0; w < kStates; ++w) mm = fmaxf(mm, sm_m[w][g]);
+    float ll = 0.f, oo = 0.f;
+#pragma unroll 4
+    for (int w = 0; w < kStates; ++w) {
+      const float c = (sm_m[w][g] == -INFINITY) ? 0.f : __expf(sm_m[w][g] - mm);
+      ll += sm_l[w][g] * c; oo += sm_o[w][g][d] * c;
+    }
+    const size_t hq = static_cast<size_t>(b) * p.Hq + kvh * G + g;
+    p.o_part[(hq * p.S + sp) * kD + d] = ll > 0.f ? oo / ll : 0.f;
+    if (d == 0) p.lse_part[hq * p.S + sp] = ll > 0.f ? mm + __logf(ll) : -INFINITY;
+  }
+}
+
 // out[b, h, :] = sum_s w_s * o_part[b, h, s, :],  w_s = exp(lse_s - lse_total); one warp per (b, h)
 // n_parts = S (intra-rank) or W * S / W ... any flat list of partials for that head.
 template <bool kBF16>
@@ -180,6 +322,18 @@ __global__ void decode_combine_f32_kernel(float* o_out, float* lse_out, const fl
 template <bool kBF16>
 int launch_split(const DecodeParams& p, int G, cudaStream_t s) {
   dim3 grid(p.B, p.Hkv, p.S);
+  static const bool use_v1 = [] { const char* e = getenv("TD_DECODE_V1"); return e && e[0] == '1'; }();
+  if (!use_v1) {
+    switch (G) {
+      case 1: decode_splitkv_kernel_v2<kBF16, 1><<<grid, kWarps2 * 32, 0, s>>>(p); break;
+      case 2: decode_splitkv_kernel_v2<kBF16, 2><<<grid, kWarps2 * 32, 0, s>>>(p); break;
+      case 4: decode_splitkv_kernel_v2<kBF16, 4><<<grid, kWarps2 * 32, 0, s>>>(p); break;
+      case 8: decode_splitkv_kernel_v2<kBF16, 8><<<grid, kWarps2 * 32, 0, s>>>(p); break;
+      default: td::drv::set_error("flash_decode: q heads per kv head must be 1, 2, 4 or 8"); return -1;
+    }
+    TD_CUDA_CHECK(cudaGetLastError());
+    return 0;
+  }
   switch (G) {
     case 1: decode_splitkv_kernel<kBF16, 1><<<grid, kWarps * 32, 0, s>>>(p); break;
     case 2: decode_splitkv_kernel<kBF16, 2><<<grid, kWarps * 32, 0, s>>>(p); break;

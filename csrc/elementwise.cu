@@ -6,6 +6,8 @@
 // (/root/reference/python/triton_dist/layers/nvidia/tp_attn.py:61-68,165-176, tp_mlp.py:159); the megakernel has
 // Triton versions (mega_triton_kernel/kernels/{norm,activation,rope}.py); swiglu.py:374 has fwd/bwd.
 // Here they are small CUDA kernels so that the whole decode step is our code and graph-capturable.
+#include <algorithm>
+
 #include "td/ptx.cuh"
 #include "runtime/driver.h"
 
@@ -105,6 +107,29 @@ __global__ void silu_mul_kernel(uint4* __restrict__ out, const uint4* __restrict
   }
 }
 
+// dx[m, :I] = dy * u * sig(g) * (1 + g * (1 - sig(g))),  dx[m, I:] = dy * g * sig(g)     (backward of silu(g) * u)
+template <bool kBF16>
+__global__ void silu_mul_bwd_kernel(uint4* __restrict__ dx, const uint4* __restrict__ dy, const uint4* __restrict__ x, long long M, int I) {
+  const int nvec = I / 8;
+  const long long total = M * nvec;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long m = t / nvec;
+    const int i = static_cast<int>(t - m * nvec);
+    float g[8], u[8], d[8], dg[8], du[8];
+    unpack8<kBF16>(x[m * 2 * nvec + i], g);
+    unpack8<kBF16>(x[m * 2 * nvec + nvec + i], u);
+    unpack8<kBF16>(dy[t], d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float sg = 1.f / (1.f + __expf(-g[e]));
+      dg[e] = d[e] * u[e] * sg * (1.f + g[e] * (1.f - sg));
+      du[e] = d[e] * g[e] * sg;
+    }
+    dx[m * 2 * nvec + i] = pack8<kBF16>(dg);
+    dx[m * 2 * nvec + nvec + i] = pack8<kBF16>(du);
+  }
+}
+
 // One warp per (token, head).  qkv: [T, (Hq + 2 Hkv) * 128]; q heads are normalised + rotated and written to
 // q_out [T, Hq, 128]; k heads normalised + rotated and appended to k_cache; v heads appended to v_cache.
 // cache layout [B, max_len, Hkv, 128]; token t goes to (batch_idx[t], positions[t]).  head_dim fixed at 128.
@@ -184,6 +209,18 @@ TD_API int td_rmsnorm(void* out, const void* x, const void* w, const void* resid
     rmsnorm_kernel<true><<<(unsigned)rows, 256, 0, s>>>((uint4*)out, (const uint4*)x, (const uint4*)w, (const uint4*)residual, (uint4*)residual_out, H, eps);
   else
     rmsnorm_kernel<false><<<(unsigned)rows, 256, 0, s>>>((uint4*)out, (const uint4*)x, (const uint4*)w, (const uint4*)residual, (uint4*)residual_out, H, eps);
+  TD_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+TD_API int td_silu_mul_bwd(void* dx, const void* dy, const void* x, long long M, int I, int is_bf16, void* stream) {
+  if (I % 8) { td::drv::set_error("silu_mul_bwd: I must be a multiple of 8"); return -1; }
+  if (M == 0) return 0;
+  const long long total = M * (I / 8);
+  const int grid = (int)std::min<long long>(148 * 8, (total + 255) / 256);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (is_bf16) silu_mul_bwd_kernel<true><<<grid, 256, 0, s>>>((uint4*)dx, (const uint4*)dy, (const uint4*)x, M, I);
+  else silu_mul_bwd_kernel<false><<<grid, 256, 0, s>>>((uint4*)dx, (const uint4*)dy, (const uint4*)x, M, I);
   TD_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -45,6 +45,7 @@ struct TdGemmArgs {
   // mode 6 (Mega-EP grouped GEMM + combine): rs_stage = comb [2][pairs][N] symmetric, rs_flags = done [2][W], c_route = return addresses
   const void* epd_send_off; const void* epd_send_ids; const void* epd_dest_off; const void* epd_x;
   long long epd_topk, epd_epr, epd_cpd, epd_rows_cap; void* epd_meta; const void* c_route;
+  const void* segk_off; long long segk_n;      // segmented-K batch (mode 0): C is [segk_n][M][N] (c_nbuf / c_buf_stride_bytes)
 };
 
 static int encode_tmap(CUtensorMap* out, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
@@ -156,7 +157,7 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
     cuuint32_t box[3] = {kCBlockCols, BM, 1};
     if (encode_tmap(&p.tmap_c, a->C, 3, dims, strides, box, fp8 ? 1 : bf16)) return -1;
   }
-  p.c_phase = (a->c_nbuf > 1) ? reinterpret_cast<const uint32_t*>(a->c_phase) : nullptr;
+  p.c_phase = (a->c_nbuf > 1 && !a->segk_off) ? reinterpret_cast<const uint32_t*>(a->c_phase) : nullptr;
   p.c_buf_stride_bytes = a->c_buf_stride_bytes;
   p.tile_expert = reinterpret_cast<const int*>(a->tile_expert);
   p.expert_rows = (int)(a->expert_stride_rows > 0 ? a->expert_stride_rows : a->N);
@@ -332,6 +333,12 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
     }
   }
 
+  if (a->segk_off) {
+    if (a->mode != kPlain || a->tile_expert || a->a_gather || fp8 || a->segk_n < 1) { drv::set_error("segmented-K batch: plain 16-bit GEMM only"); return -1; }
+    p.segk_off = (const int*)a->segk_off; p.segk_n = (int)a->segk_n; p.segk_tiles = tiles;
+    p.sk_full = tiles; p.sk_rem = 0; p.sk_parts = 1; p.sk_ws = nullptr;
+    p.total_units = tiles * p.segk_n;
+  }
   // never launch more GEMM clusters than work units (idle CTAs would only spin up TMEM)
   if (gemm_ctas / cg > p.total_units) gemm_ctas = p.total_units * cg;
   grid = gemm_ctas + p.n_comm_ctas;

@@ -157,6 +157,10 @@ struct Params {
   uint32_t* epd_meta;        // symmetric [2][rows_cap]: return address (source << 24 | pair id) of every delivered row
   uint32_t* epd_flags;       // symmetric [2][epr][world][cpd]: phase once that CTA's rows of the expert have landed
   const uint32_t* c_route;   // kEPC epilogue: C row i goes to rank (v >> 24), row (v & 0xffffff) of rs_stage; 0xffffffff = skip
+  // ---- segmented-K batch (weight gradients of a grouped GEMM): batch e multiplies the k-blocks [segk_off[e], segk_off[e+1]) of
+  // the SAME A / B matrices (reduction dimension = tokens, one segment per expert) into its own output C[e]
+  const int* segk_off;       // device int32 [segk_n + 1] in k-blocks; null = off
+  int segk_n, segk_tiles;    // batches, tiles per batch (num_m * num_n)
   // ---- split-K tail: the last partial wave of tiles is cut into sk_parts K ranges that run on otherwise idle clusters;
   // parts > 0 park their fp32 accumulator in sk_ws, part 0 adds them in its epilogue (wave quantisation: 768 tiles on
   // 74 CTA pairs = 10.4 waves -> 10.5 instead of 11)
@@ -166,9 +170,15 @@ struct Params {
 };
 
 // one schedulable unit of work: a tile and a K range of it
-struct Unit { int tile, kb0, kb1, part, slot; };
+struct Unit { int tile, kb0, kb1, part, slot, batch; };
 TD_DEVICE Unit get_unit(const Params& p, int u) {
   Unit x;
+  x.batch = 0;
+  if (p.segk_off != nullptr) {
+    x.batch = u / p.segk_tiles; x.tile = u - x.batch * p.segk_tiles;
+    x.kb0 = p.segk_off[x.batch]; x.kb1 = p.segk_off[x.batch + 1]; x.part = 0; x.slot = -1;
+    return x;
+  }
   if (u < p.sk_full || p.sk_parts <= 1) { x.tile = u; x.kb0 = 0; x.kb1 = p.num_k; x.part = 0; x.slot = -1; return x; }
   const int i = u - p.sk_full;
   x.slot = i % p.sk_rem; x.part = i / p.sk_rem; x.tile = p.sk_full + x.slot;
@@ -744,6 +754,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         (void)epd_seen;
         for (int u = worker; u < p.total_units; u += n_workers) {
           const Unit un = get_unit(p, u);
+          if (un.kb1 <= un.kb0) continue;                    // empty K segment (the output was zero-filled by the caller)
           int m_tile, n_tile;
           tile_coords(p, un.tile, m_tile, n_tile);
           int expert = 0;
@@ -823,6 +834,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         int acc = 0; uint32_t acc_phase = 0;
         for (int u = worker; u < p.total_units; u += n_workers) {
           const Unit un = get_unit(p, u);
+          if (un.kb1 <= un.kb0) continue;
           if (p.tile_expert) {
             int m_tile, n_tile;
             tile_coords(p, un.tile, m_tile, n_tile);
@@ -885,10 +897,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
       (void)mrs_zero_seen;
       for (int u = worker; u < p.total_units; u += n_workers) {
         const Unit un = get_unit(p, u);
+        if (un.kb1 <= un.kb0) continue;
         int m_tile, n_tile;
         tile_coords(p, un.tile, m_tile, n_tile);
         if (p.tile_expert && p.tile_expert[m_tile] < 0) continue;
         const int row_base = m_tile * TM + static_cast<int>(cta_rank) * BM;   // global row of tile row 0
+        const int cbuf_u = p.segk_off ? un.batch : cbuf;                      // output buffer of this unit
         const int col_base = n_tile * BN;
 
         if (un.part > 0) {
@@ -931,7 +945,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         // ---- RS ring bookkeeping for this tile ----
         int rs_step = 0; bool rs_final = false;
         const char* rs_in = nullptr;                 // running partial received from rank+1 (local memory)
-        char* dst_base = reinterpret_cast<char*>(p.C) + cbuf * p.c_buf_stride_bytes;
+        char* dst_base = reinterpret_cast<char*>(p.C) + cbuf_u * p.c_buf_stride_bytes;
         long long dst_ld = p.ldc;
         int dst_row_off = 0;                         // subtract from the global row for the destination
         bool f32_in = false, f32_out = false;        // fp32 ring staging (rs_fp32)
@@ -1122,7 +1136,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
           const int gcol0 = col_base + cb * kCBlockCols;
           if (p.use_tma_store) {
             if (et == 0 && gcol0 < p.N && row_base < p.M) {
-              ptx::tma_store_3d(&p.tmap_c, cstage, gcol0, row_base, cbuf);
+              ptx::tma_store_3d(&p.tmap_c, cstage, gcol0, row_base, cbuf_u);
               ptx::bulk_commit();
             }
             __syncwarp();

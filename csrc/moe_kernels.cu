@@ -133,6 +133,33 @@ __global__ void scatter_rows_kernel(uint4* __restrict__ dst, const uint4* __rest
   }
 }
 
+// dst[c, i] = ids[i] >= 0 ? src[ids[i], c] : 0   (16-bit elements): the token-major ("MN-major") operands of a weight-gradient
+// product, re-laid out reduction-major so the K-major tcgen05 GEMM can consume them; pad positions become zero columns.
+// 64 x 64 tile per CTA through shared memory: 16-byte global loads along src rows, 16-byte global stores along dst rows.
+__global__ void __launch_bounds__(256) transpose_gather_kernel(uint16_t* __restrict__ dst, const uint16_t* __restrict__ src,
+                                                              const int* __restrict__ ids, int n_out, int cols, long long ld_src) {
+  __shared__ uint16_t tile[64][64 + 8];          // [c][i], row pitch 144 B keeps the 16-byte reads aligned
+  const int i0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  for (int q = threadIdx.x; q < 64 * 8; q += 256) {
+    const int r = q >> 3, ch = q & 7;            // row of the tile (position i0 + r), 8-column chunk
+    const int i = i0 + r, c = c0 + ch * 8;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (i < n_out && c < cols) {
+      const int id = ids ? ids[i] : i;
+      if (id >= 0) v = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(id) * ld_src + c);
+    }
+    const uint16_t* e = reinterpret_cast<const uint16_t*>(&v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tile[ch * 8 + k][r] = e[k];
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < 64 * 8; q += 256) {
+    const int cr = q >> 3, ch = q & 7;           // dst row c0 + cr, 8 consecutive positions
+    const int c = c0 + cr, i = i0 + ch * 8;
+    if (c < cols && i < n_out) *reinterpret_cast<uint4*>(dst + static_cast<size_t>(c) * n_out + i) = *reinterpret_cast<const uint4*>(&tile[cr][ch * 8]);
+  }
+}
+
 template <bool kBF16>
 __global__ void topk_reduce_kernel(uint4* __restrict__ out, const uint4* __restrict__ y, const float* __restrict__ w, int T,
                                    int topk, int vec_per_row) {
@@ -211,6 +238,16 @@ TD_API int td_scatter_rows(void* dst, const void* src, const void* ids, const vo
   const int grid = (int)min((long long)148 * 8, (total + 255) / 256);
   scatter_rows_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>((uint4*)dst, (const uint4*)src, (const int*)ids,
                                                                                  (const int*)n_rows_ptr, n_rows_max, vpr, pad_id);
+  TD_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+TD_API int td_transpose_gather(void* dst, const void* src, const void* ids, int n_out, int cols, long long ld_src, void* stream) {
+  if (n_out % 8 || cols % 8 || ld_src % 8) { td::drv::set_error("transpose_gather: sizes must be multiples of 8 elements"); return -1; }
+  if (n_out == 0 || cols == 0) return 0;
+  dim3 grid((n_out + 63) / 64, (cols + 63) / 64);
+  transpose_gather_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>((uint16_t*)dst, (const uint16_t*)src, (const int*)ids,
+                                                                                   n_out, cols, ld_src);
   TD_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -170,3 +170,53 @@ def test_moe_tma_gather(T, E, topk, K, N):
     torch.testing.assert_close(staged.float(), ref, atol=5e-2, rtol=3e-2)
     torch.testing.assert_close(fused.float(), ref, atol=5e-2, rtol=3e-2)
     assert torch.equal(fused, staged)
+
+
+@pytest.mark.parametrize("splits", [[300, 0, 1000, 64, 37], [256, 256, 256, 256], [1, 2047]])
+@pytest.mark.parametrize("nk", [(512, 768), (256, 1032)])
+def test_transposed_moe_grouped_gemm(splits, nk):
+    """Weight gradient of a grouped GEMM: one transpose-gather pass per operand + ONE segmented-K batch launch vs fp32 per-expert
+    products (ragged segments, an empty expert, segments that are not multiples of the 64-token k-block)."""
+    from triton_dist.ops.moe import transposed_moe_grouped_gemm
+    torch.manual_seed(3)
+    N, K = nk
+    Mtot = sum(splits)
+    dy = (torch.randn(Mtot, N, device="cuda") * 0.5).to(torch.bfloat16)
+    x = (torch.randn(Mtot, K, device="cuda") * 0.5).to(torch.bfloat16)
+    sp = torch.tensor(splits, device="cuda", dtype=torch.int32)
+    for _ in range(2):
+        dw = transposed_moe_grouped_gemm(dy, x, sp)
+    torch.cuda.synchronize()
+    s = 0
+    for g, n in enumerate(splits):
+        ref = dy[s:s + n].float().t() @ x[s:s + n].float()
+        torch.testing.assert_close(dw[g].float(), ref, atol=0.02 * (max(n, 1) ** 0.5) + 0.05, rtol=2e-2)
+        s += n
+
+
+def test_swiglu_backward_kernel():
+    from triton_dist.ops.elementwise import silu_mul_backward
+    torch.manual_seed(4)
+    x = torch.randn(300, 2 * 264, device="cuda", dtype=torch.bfloat16)
+    gy = torch.randn(300, 264, device="cuda", dtype=torch.bfloat16)
+    xf = x.float().requires_grad_(True)
+    (torch.nn.functional.silu(xf[:, :264]) * xf[:, 264:]).backward(gy.float())
+    torch.testing.assert_close(silu_mul_backward(gy, x).float(), xf.grad, atol=3e-2, rtol=3e-2)
+
+
+@pytest.mark.parametrize("G", [1, 4, 8])
+@pytest.mark.parametrize("lens", [[1, 77, 500, 4096], [8192, 3]])
+def test_flash_decode_v2_lengths(G, lens):
+    """The bandwidth-oriented split-KV kernel (8 lanes per row, 4 + 4 loads in flight per lane) vs the fp32 reference: ragged
+    lengths incl. shorter than one CTA iteration, every supported GQA group size."""
+    from triton_dist.ops.flash_decode import _decode_reference, gqa_fwd_batch_decode
+    torch.manual_seed(5)
+    B, Hkv, L = len(lens), 2, max(lens)
+    kc = torch.randn(B, L, Hkv, 128, device="cuda", dtype=torch.bfloat16)
+    vc = torch.randn(B, L, Hkv, 128, device="cuda", dtype=torch.bfloat16)
+    q = torch.randn(B, Hkv * G, 128, device="cuda", dtype=torch.bfloat16)
+    kv = torch.tensor(lens, device="cuda", dtype=torch.int32)
+    out = gqa_fwd_batch_decode(q, kc, vc, kv)
+    ref = _decode_reference(q, kc, vc, kv, 128 ** -0.5)
+    ref = ref[0] if isinstance(ref, tuple) else ref
+    torch.testing.assert_close(out.float(), ref.float(), atol=2e-2, rtol=2e-2)

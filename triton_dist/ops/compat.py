@@ -38,14 +38,7 @@ def ring_reduce(slabs: torch.Tensor, out: Optional[torch.Tensor] = None) -> torc
 
 
 # ---- swiglu.py ------------------------------------------------------------------------------------------------
-def swiglu_backward(grad_out: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
-    """d/dx of silu(x[..., :I]) * x[..., I:]  (swiglu.py backward kernels)."""
-    I = x.shape[-1] // 2
-    g, u = x[..., :I].float(), x[..., I:].float()
-    sg = torch.sigmoid(g)
-    dg = grad_out.float() * u * (sg + g * sg * (1 - sg))
-    du = grad_out.float() * g * sg
-    return torch.cat([dg, du], dim=-1).to(x.dtype)
+from .elementwise import silu_mul_backward as swiglu_backward  # noqa: E402,F401  (one kernel: csrc/elementwise.cu silu_mul_bwd_kernel)
 
 
 # ---- group_gemm.py --------------------------------------------------------------------------------------------
@@ -55,20 +48,7 @@ def moe_grouped_gemm_2weights(x_sorted, w_gate, w_up, routing, split: str = "N")
     return M.moe_grouped_gemm(x_sorted, w, routing)
 
 
-def transposed_moe_grouped_gemm(x_sorted: torch.Tensor, dy_sorted: torch.Tensor, routing, num_experts: int) -> torch.Tensor:
-    """(group_gemm.py:503-727) weight gradient per expert: dW[e] = dY_e^T @ X_e over that expert's (padded) rows.
-    The operands are row(token)-major, i.e. MN-major for this product; each expert's slab is transposed once and fed to
-    the K-major tcgen05 GEMM (pad rows are zero, so they do not contribute)."""
-    offs = routing.expert_offsets.tolist()
-    N, K = dy_sorted.shape[1], x_sorted.shape[1]
-    dW = torch.zeros((num_experts, N, K), dtype=x_sorted.dtype, device=x_sorted.device)
-    for e in range(num_experts):
-        s, t = offs[e], offs[e + 1]
-        if t > s:
-            a = dy_sorted[s:t].t().contiguous()      # [N, rows]
-            b = x_sorted[s:t].t().contiguous()       # [K, rows]
-            dW[e] = _lin(a, b) if (t - s) % 8 == 0 else (a.float() @ b.float().t()).to(dW.dtype)
-    return dW
+transposed_moe_grouped_gemm = M.transposed_moe_grouped_gemm      # one launch, segmented-K batch mode (ops/moe.py)
 
 
 def calc_gather_scatter_index_triton(topk_ids: torch.Tensor, num_experts: int, block_m: int = 128):

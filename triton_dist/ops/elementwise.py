@@ -14,6 +14,7 @@ from .. import _C
 c_void_p, c_ll, c_int, c_float = C.c_void_p, C.c_longlong, C.c_int, C.c_float
 _C.register("td_rmsnorm", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_float, c_int, c_void_p])
 _C.register("td_silu_mul", c_int, [c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p])
+_C.register("td_silu_mul_bwd", c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p])
 _C.register("td_qk_norm_rope_kv", c_int, [c_void_p] * 8 + [c_int, c_int, c_int, c_ll, c_float, c_float, c_int, c_void_p])
 
 
@@ -54,6 +55,24 @@ def silu_mul(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tenso
 
 
 swiglu_forward = silu_mul
+
+
+def silu_mul_backward(grad_out: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """d/dx of ``silu(x[..., :I]) * x[..., I:]`` in one kernel (reference swiglu.py backward kernels)."""
+    I = x.shape[-1] // 2
+    if not x.is_cuda or x.dtype not in (torch.bfloat16, torch.float16) or I % 8:
+        g, u = x[..., :I].float(), x[..., I:].float()
+        sg = torch.sigmoid(g)
+        return torch.cat([grad_out.float() * u * (sg + g * sg * (1 - sg)), grad_out.float() * g * sg], dim=-1).to(x.dtype)
+    x = x.contiguous()
+    gy = grad_out.to(x.dtype).contiguous()
+    M = x.numel() // (2 * I)
+    dx = torch.empty_like(x)
+    _C.check(_C.cuda_lib().td_silu_mul_bwd(dx.data_ptr(), gy.data_ptr(), x.data_ptr(), M, I, int(x.dtype == torch.bfloat16), _s()), "td_silu_mul_bwd")
+    return dx
+
+
+swiglu_backward = silu_mul_backward
 
 
 def rope_reference(x: torch.Tensor, positions: torch.Tensor, theta: float) -> torch.Tensor:

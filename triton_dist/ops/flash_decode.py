@@ -36,7 +36,7 @@ def default_num_splits(B: int, Hkv: int, max_len: int, sms: int = 148) -> int:
     return int(max(1, min(want, (max_len + 255) // 256, 64)))
 
 
-def _decode_reference(q, k_cache, v_cache, kv_lens, sm_scale, block_table=None, page_size=0):
+def _decode_reference(q, k_cache, v_cache, kv_lens, sm_scale, block_table=None, page_size=0, soft_cap: float = 0.0):
     B, Hq, D = q.shape
     outs, lses = [], []
     for b in range(B):
@@ -52,6 +52,8 @@ def _decode_reference(q, k_cache, v_cache, kv_lens, sm_scale, block_table=None, 
         kk = k.float().repeat_interleave(G, dim=1)          # [L, Hq, D]
         vv = v.float().repeat_interleave(G, dim=1)
         s = torch.einsum("hd,lhd->hl", q[b].float(), kk) * sm_scale
+        if soft_cap and soft_cap > 0:
+            s = soft_cap * torch.tanh(s / soft_cap)
         lse = torch.logsumexp(s, dim=-1)
         p = torch.softmax(s, dim=-1)
         outs.append(torch.einsum("hl,lhd->hd", p, vv))
@@ -67,7 +69,7 @@ def gqa_fwd_batch_decode_partial(q: torch.Tensor, k_cache: torch.Tensor, v_cache
     sm_scale = sm_scale if sm_scale is not None else 1.0 / math.sqrt(D)
     if not q.is_cuda or D != 128:
         page = k_cache.shape[1] if block_table is not None else 0
-        return _decode_reference(q, k_cache, v_cache, kv_lens, sm_scale, block_table, page)
+        return _decode_reference(q, k_cache, v_cache, kv_lens, sm_scale, block_table, page, soft_cap)
     Hkv = k_cache.shape[-2]
     if block_table is not None:
         page_size, max_pages, max_len = k_cache.shape[1], block_table.shape[1], 0

@@ -33,6 +33,7 @@ _C.register("td_gather_rows", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_
 _C.register("td_scatter_rows", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p])
 _C.register("td_topk_reduce", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p])
 _C.register("td_bincount", c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p])
+_C.register("td_transpose_gather", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll, c_void_p])
 
 
 def _s():
@@ -218,6 +219,73 @@ def moe_grouped_gemm_presorted(src: torch.Tensor, w: torch.Tensor, topk_ids: tor
     r = moe_align_sort(topk_ids, num_experts, 256)
     xs = gather_rows(src, r, div=div)
     return moe_grouped_gemm_fused(xs, w, r, div, topk_ids.numel(), out=out, gather=False, scatter=True)
+
+
+def transpose_gather(src: torch.Tensor, ids: Optional[torch.Tensor], n_out: int) -> torch.Tensor:
+    """``out[c, i] = src[ids[i], c]`` (zero column where ``ids[i] < 0``; identity if ``ids`` is None): token-major matrix ->
+    reduction-major operand of a weight-gradient GEMM, one memory-bound pass."""
+    rows, cols = src.shape
+    out = torch.empty((cols, n_out), dtype=src.dtype, device=src.device)
+    if not src.is_cuda or cols % 8 or n_out % 8 or src.stride(0) % 8 or src.stride(1) != 1:
+        idx = torch.arange(n_out, device=src.device) if ids is None else ids.long()
+        ok = (idx >= 0) & (idx < rows)
+        g = torch.zeros((n_out, cols), dtype=src.dtype, device=src.device)
+        g[ok] = src[idx[ok]]
+        out.copy_(g.t())
+        return out
+    _C.check(_C.cuda_lib().td_transpose_gather(out.data_ptr(), src.data_ptr(), ids.data_ptr() if ids is not None else None, n_out, cols,
+                                               src.stride(0), _s()), "td_transpose_gather")
+    return out
+
+
+def transposed_moe_grouped_gemm(grad_output: torch.Tensor, original_input: torch.Tensor, split_size: torch.Tensor,
+                                split_size_cum_per_expert: Optional[torch.Tensor] = None, grad_weight: Optional[torch.Tensor] = None,
+                                **ref_hints) -> torch.Tensor:
+    """Weight gradient of a grouped GEMM (reference kernels/nvidia/group_gemm.py:503-727, :988):
+    ``grad_weight[g] = grad_output[rows of g].T @ original_input[rows of g]`` for expert-contiguous rows with ``split_size[g]`` rows
+    each.  Both operands are token-major, i.e. MN-major for this product: one ``transpose_gather`` pass per operand lays them out
+    reduction-major with every expert's segment padded to 64 tokens (zero columns), then ONE launch of the tcgen05 GEMM in its
+    segmented-K batch mode computes all experts (batch g reduces over the k-blocks of its own segment; csrc/gemm_sm100.cuh
+    ``segk_off``).  No per-expert Python loop, no host sync."""
+    U.accept_ref_hints("transposed_moe_grouped_gemm", ref_hints, ("BLOCK_SIZE_M", "BLOCK_SIZE_N", "BLOCK_SIZE_K", "GROUP_SIZE_M", "num_warps",
+                                                                  "num_stages", "persistent", "sm_margin"))
+    M_, N = grad_output.shape
+    M2, K = original_input.shape
+    G = split_size.numel()
+    assert M_ == M2 and grad_output.dtype == original_input.dtype
+    dev = grad_output.device
+    split = split_size.to(torch.int64)
+    cum = torch.cumsum(split, 0) - split if split_size_cum_per_expert is None else (split_size_cum_per_expert.to(torch.int64) - split)
+    if grad_weight is None:
+        grad_weight = torch.zeros((G, N, K), dtype=grad_output.dtype, device=dev)
+    else:
+        assert grad_weight.shape == (G, N, K) and grad_weight.is_contiguous()
+        grad_weight.zero_()                       # batches with an empty segment are skipped by the kernel
+    if not grad_output.is_cuda or N % 8 or K % 8:
+        for g in range(G):
+            s, n = int(cum[g]), int(split[g])
+            if n:
+                grad_weight[g] = (grad_output[s:s + n].float().t() @ original_input[s:s + n].float()).to(grad_weight.dtype)
+        return grad_weight
+    pad = (split + 63) // 64 * 64
+    pend = torch.cumsum(pad, 0)
+    pstart = pend - pad
+    Mp = (M_ + 63 * G + 63) // 64 * 64             # static upper bound of the padded length (no host sync)
+    pos = torch.arange(Mp, device=dev)
+    e = torch.searchsorted(pend, pos, right=True).clamp(max=G - 1)
+    j = pos - pstart[e]
+    ids = torch.where((pos < pend[-1]) & (j < split[e]), cum[e] + j, torch.full_like(pos, -1)).to(torch.int32)
+    a_t = transpose_gather(grad_output, ids, Mp)   # [N, Mp]
+    b_t = transpose_gather(original_input, ids, Mp)  # [K, Mp]
+    seg = torch.cat([pstart, pend[-1:]]).div(64, rounding_mode="floor").to(torch.int32).contiguous()
+    cfg = GemmConfig(bn=256 if K % 256 == 0 else 128, cta_group=2 if N % 256 == 0 else 1, group_m=8, use_tma_store=True)
+    args = _C.GemmArgs()
+    args.mode = 0
+    fill_common(args, N, a_t.data_ptr(), Mp, b_t, grad_weight.data_ptr(), N, K, N, K, Mp, cfg, grad_output.dtype == torch.bfloat16)
+    args.c_nbuf, args.c_buf_stride_bytes = G, N * K * grad_weight.element_size()
+    args.segk_off, args.segk_n = seg.data_ptr(), G
+    _C.check(_C.cuda_lib().td_gemm_launch(C.byref(args), _s()), "td_gemm_launch(wgrad, segmented K)")
+    return grad_weight
 
 
 def _use_tma_gather(x: torch.Tensor) -> bool:
