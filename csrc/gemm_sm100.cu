@@ -46,6 +46,7 @@ struct TdGemmArgs {
   const void* epd_send_off; const void* epd_send_ids; const void* epd_dest_off; const void* epd_x;
   long long epd_topk, epd_epr, epd_cpd, epd_rows_cap; void* epd_meta; const void* c_route;
   const void* segk_off; long long segk_n;      // segmented-K batch (mode 0): C is [segk_n][M][N] (c_nbuf / c_buf_stride_bytes)
+  const void* scale_a; const void* scale_b;    // fp32 per-row [M] / per-column [N] scales applied in the epilogue (8-bit kinds)
 };
 
 static int encode_tmap(CUtensorMap* out, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
@@ -117,13 +118,14 @@ static int dispatch(const Params& p, int bn, int cg, int grid, cudaStream_t s) {
 TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int cg = static_cast<int>(a->cta_group), bn = static_cast<int>(a->bn);
-  const bool fp8 = a->is_bf16 == 2;
-  const int bf16 = fp8 ? 2 : (a->is_bf16 != 0 ? 1 : 0);      // tensor-map dtype code of A / B
-  const int esz = fp8 ? 1 : 2;
-  if (a->K % (fp8 ? 128 : 8) != 0 || (a->lda * esz) % 16 != 0 || (a->ldb * esz) % 16 != 0) {
+  const bool fp8 = a->is_bf16 == 2;                            // MXFP8 (block scaled)
+  const bool q8 = a->is_bf16 == 3 || a->is_bf16 == 4;          // 3 = int8 x int8 (kind::i8), 4 = e4m3 per-tensor / per-channel scaled
+  const int bf16 = (fp8 || q8) ? 2 : (a->is_bf16 != 0 ? 1 : 0);      // tensor-map dtype code of A / B
+  const int esz = (fp8 || q8) ? 1 : 2;
+  if (a->K % ((fp8 || q8) ? 128 : 8) != 0 || (a->lda * esz) % 16 != 0 || (a->ldb * esz) % 16 != 0) {
     drv::set_error("K must be a multiple of 8 (16-bit) / 128 (MXFP8) and rows 16-byte aligned"); return -1;
   }
-  const int bk_elems = fp8 ? 128 : BK;
+  const int bk_elems = (fp8 || q8) ? 128 : BK;
   Params p;
   memset(&p, 0, sizeof(p));
   {  // A: {K, rows, nbuf}
@@ -155,7 +157,7 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
     cuuint64_t dims[3] = {(cuuint64_t)a->N, (cuuint64_t)a->c_rows, (cuuint64_t)(a->c_nbuf > 0 ? a->c_nbuf : 1)};
     cuuint64_t strides[2] = {(cuuint64_t)a->ldc * 2, (cuuint64_t)(a->c_nbuf > 1 ? a->c_buf_stride_bytes : a->c_rows * a->ldc * 2)};
     cuuint32_t box[3] = {kCBlockCols, BM, 1};
-    if (encode_tmap(&p.tmap_c, a->C, 3, dims, strides, box, fp8 ? 1 : bf16)) return -1;
+    if (encode_tmap(&p.tmap_c, a->C, 3, dims, strides, box, (fp8 || q8) ? 1 : bf16)) return -1;
   }
   p.c_phase = (a->c_nbuf > 1 && !a->segk_off) ? reinterpret_cast<const uint32_t*>(a->c_phase) : nullptr;
   p.c_buf_stride_bytes = a->c_buf_stride_bytes;
@@ -179,6 +181,12 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
   if (p.group_m > p.num_m) p.group_m = p.num_m;
   p.m_rot = (int)(((a->m_rot % p.num_m) + p.num_m) % p.num_m);
   p.in_is_bf16 = (a->is_bf16 != 0) ? 1 : 0;      // 16-bit outputs / partial sums are bf16 unless fp16 inputs
+  p.in_kind = a->is_bf16 == 3 ? 1 : a->is_bf16 == 4 ? 2 : 0;
+  p.bk_elems = bk_elems;
+  p.scale_a = reinterpret_cast<const float*>(a->scale_a); p.scale_b = reinterpret_cast<const float*>(a->scale_b);
+  if (q8 && (a->mode == kAG || a->mode == kMoeRS || a->mode == kEPD || a->mode == kEPC || a->a_gather)) {
+    drv::set_error("8-bit (int8 / e4m3 per-tensor) inputs: plain, gemm_rs and gemm_ar modes only"); return -1;
+  }
   p.n_comm_ctas = (int)a->n_comm_ctas;
   p.C = a->C; p.ldc = a->ldc;
   p.symm.rank = (int)a->rank; p.symm.world = (int)a->world;

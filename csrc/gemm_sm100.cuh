@@ -75,6 +75,11 @@ struct Params {
   int group_m;               // L2 swizzle band height (in m tiles)
   int m_rot;                 // rotate the m-tile order by this many tiles (rank-dependent arrival order)
   int in_is_bf16;            // 1 = bf16, 0 = fp16 (inputs and 16-bit outputs)
+  int in_kind;               // 0 = 16-bit inputs (kind::f16); 1 = int8 x int8 -> int32 (kind::i8); 2 = e4m3 x e4m3 -> fp32 (kind::f8f6f4),
+                             // both with 128 K-elements per 128-byte smem row and per-row / per-column dequantisation scales
+  int bk_elems;              // K elements per smem row (64 for 16-bit, 128 for the 8-bit kinds)
+  const float* scale_a;      // optional fp32 [M] per-row scale of C (8-bit kinds: activation scales)
+  const float* scale_b;      // optional fp32 [N] per-column scale of C (8-bit kinds: weight scales)
   int use_tma_store;
   int n_comm_ctas;           // CTAs [gridDim.x - n_comm_ctas, gridDim.x) run the collective
   int pad0;
@@ -613,7 +618,7 @@ TD_DEVICE void epd_wait_expert(const Params& p, uint32_t ph, int e) {
 template <int kMode, int BN, int kStages, int kCtaGroup, bool kFP8 = false, int kAccStages = 2>
 __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant__ Params p) {
   using L = SmemLayout<BN, kStages, kCtaGroup, 0, kFP8>;
-  constexpr int kBKElems = kFP8 ? 128 : BK;              // K elements per 128-byte smem row
+  const int kBKElems = kFP8 ? 128 : p.bk_elems;         // K elements per 128-byte smem row (128 for every 8-bit kind)
   constexpr int kSFCols = 4 + 4 * ((BN + 127) / 128);    // TMEM columns of scale factors per pipeline stage (A + B)
   constexpr int kSFBase = kAccStages * BN;               // scale factors live after the accumulator stage(s)
   static_assert(!kFP8 || (kAccStages * BN + kStages * kSFCols <= 512), "TMEM: accumulators + scale-factor ring exceed 512 columns");
@@ -828,7 +833,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     } else if (warp == 1) {
       // ================================ MMA issuer (leader CTA, one thread) ================================
       if (is_leader && lane == 0) {
-        const uint32_t idesc = ptx::make_idesc(p.in_is_bf16 ? 1u : 0u, p.in_is_bf16 ? 1u : 0u, TM, BN);
+        const uint32_t idesc = p.in_kind == 1 ? ptx::make_idesc_i8(TM, BN)
+                               : p.in_kind == 2 ? ptx::make_idesc(0u, 0u, TM, BN)
+                                                : ptx::make_idesc(p.in_is_bf16 ? 1u : 0u, p.in_is_bf16 ? 1u : 0u, TM, BN);
         (void)idesc;
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
@@ -854,7 +861,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
 #pragma unroll
               for (int k = 0; k < BK / UMMA_K; ++k) {
                 // advance 32 B (= 16 bf16) along K inside the 128-byte swizzle atom: +2 in the 16-byte address field
-                ptx::mma_f16<kCtaGroup>(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb > un.kb0 || k != 0) ? 1u : 0u);
+                const uint32_t accf = (kb > un.kb0 || k != 0) ? 1u : 0u;
+                if (p.in_kind == 0) ptx::mma_f16<kCtaGroup>(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, accf);
+                else if (p.in_kind == 1) ptx::mma_i8<kCtaGroup>(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, accf);
+                else ptx::mma_f8f6f4<kCtaGroup>(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, accf);
               }
             } else {
               // MXFP8: stage the UE8M0 scale factors of this k-block into TMEM (smem -> TMEM, 32 lanes x 16 B, replicated
@@ -1022,8 +1032,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             ptx::tmem_ld_32x32b_x32(taddr, v);
             ptx::tmem_ld_wait();
             float f[32];
+            if (p.in_kind == 1) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+              for (int i = 0; i < 32; ++i) f[i] = static_cast<float>(static_cast<int>(v[i]));      // int32 accumulators
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+            }
+            if (p.scale_a != nullptr || p.scale_b != nullptr) {       // dequantise: C = acc * scale_a[row] * scale_b[col]
+              const int grow = row_base + my_row, gcol = col_base + cb * kCBlockCols + h * 32;
+              const float sa = (p.scale_a != nullptr && grow < p.M) ? p.scale_a[grow] : 1.f;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] *= sa * ((p.scale_b != nullptr && gcol + i < p.N) ? p.scale_b[gcol + i] : 1.f);
+            }
             if (p.row_scale != nullptr) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] *= row_scale;

@@ -281,6 +281,22 @@ TD_DEVICE void mma_f8f6f4(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint3
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// int8 x int8 -> int32 accumulate (sm_100a has kind::i8; the accumulator columns hold int32)
+template <int kCtaGroup>
+TD_DEVICE void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (kCtaGroup == 1)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // MX block-scaled fp8: UE8M0 scale factors staged in TMEM (one per 32 K-elements)
 template <int kCtaGroup>
 TD_DEVICE void mma_mxf8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
@@ -407,6 +423,10 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t a_fmt, uint32_t b_fmt
          | (b_mn_major << 16)   // b_major: 0 = K, 1 = MN
          | ((N >> 3) << 17)     // n_dim            [17,23)
          | ((M >> 4) << 24);    // m_dim            [24,29)
+}
+// kind::i8: signed 8-bit operands (a/b format 1 = INT8), int32 accumulator (c_format 2 = S32), both K-major
+__host__ __device__ constexpr uint32_t make_idesc_i8(uint32_t M, uint32_t N) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 // Block-scaled variant (kind::mxf8f6f4.block_scale): scale_format=1 (UE8M0) at bit 23, sf ids at [4,6) / [29,31)
 __host__ __device__ constexpr uint32_t make_idesc_mx(uint32_t a_fmt, uint32_t b_fmt, uint32_t M, uint32_t N,

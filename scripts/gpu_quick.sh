@@ -3,7 +3,7 @@
 set -x
 export TD_NO_AUTOBUILD=1 PYTHONPATH=$PWD:$PYTHONPATH
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_ops_gpu.py -x -q > gpurun_out/test_ops.log 2>&1; echo "ops rc=$?"; tail -5 gpurun_out/test_ops.log
+timeout 600 python -m pytest tests/test_ops_gpu.py tests/test_gemm_gpu.py -q > gpurun_out/test_ops.log 2>&1; echo "ops rc=$?"; tail -15 gpurun_out/test_ops.log
 timeout 120 python - <<'PY' > gpurun_out/quick_timing.log 2>&1
 import torch, json, time
 import triton_dist.utils as U

@@ -259,6 +259,42 @@ def case_gemm_ar():
         ctx.finalize()
 
 
+def case_gemm_q8():
+    """Quantised fused ops: int8 x scale GEMM + AllReduce (reference gemm_allreduce.py:383-447) and int8 / per-tensor fp8 gemm_rs
+    (test_gemm_rs.py:130-145) vs fp32 math on the dequantised operands + NCCL."""
+    from triton_dist.ops.gemm_ar import create_gemm_ar_context, gemm_allreduce_op
+    from triton_dist.ops.gemm_rs import create_gemm_rs_context, gemm_rs
+    dev = U.current_device()
+    if dev.type != "cuda":
+        return
+    W, me = U.world_size(), U.rank()
+    grp = U.get_triton_dist_world()
+    for (M, N, K) in [(128 * W, 512, 256), (256 * W, 1280, 384)]:
+        actx = create_gemm_ar_context(None, me, W, W, M, N, torch.bfloat16)
+        rctx = create_gemm_rs_context(M, N, output_dtype=torch.bfloat16)
+        for it, kind in enumerate(["int8", "fp8", "int8"]):
+            if kind == "int8":
+                a = torch.randint(-127, 128, (M, K), device=dev, dtype=torch.int8)
+                b = torch.randint(-127, 128, (N, K), device=dev, dtype=torch.int8)
+            else:
+                a = (torch.randn(M, K, device=dev) * 0.5).to(torch.float8_e4m3fn)
+                b = (torch.randn(N, K, device=dev) * 0.5).to(torch.float8_e4m3fn)
+            sa = torch.rand(M, device=dev) * 0.02 + 0.001
+            sb = torch.rand(N, device=dev) * 0.02 + 0.001
+            full = (a.float() @ b.float().t()) * sa[:, None] * sb[None, :]
+            ref_ar = full.clone()
+            dist.all_reduce(ref_ar, group=grp)
+            out = gemm_allreduce_op(actx, a, b, As=sa, Bs=sb)
+            tol = 2e-2 * ref_ar.abs().max().item() + 1e-2
+            _assert_close(out, ref_ar, tol, 3e-2, f"gemm_ar {kind} {M}x{N}x{K} it{it}")
+            ref_rs = torch.empty(M // W, N, device=dev, dtype=torch.float32)
+            dist.reduce_scatter_tensor(ref_rs, full, group=grp)
+            out2 = gemm_rs(a, b.t(), rctx, scale_a=sa, scale_b=sb)
+            _assert_close(out2, ref_rs, tol, 3e-2, f"gemm_rs {kind} {M}x{N}x{K} it{it}")
+        U.barrier_all_host()
+        actx.finalize(); rctx.finalize()
+
+
 def case_gemm_a2a():
     """GEMM with the all-to-all of its output columns fused into the epilogue (ulysses_sp_infer_gemm_a2a.py:143-289)."""
     from triton_dist.ops.gemm_a2a import create_gemm_a2a_context, gemm_all_to_all
@@ -378,6 +414,36 @@ def case_ep_mega():
             out = EM.mega_ep_moe(ctx, x, ids, wts, w_gu, w_dn)
             ref = EM.mega_ep_moe_reference(x, ids, wts, w_gu_all, w_dn_all)
             _assert_close(out, ref, 0.05, 5e-2, f"ep_mega T{T} H{H} it{it}")
+        # training path: forward + backward through the same kernels vs torch autograd on the dense formulation
+        from triton_dist.function.nvidia import mega_ep_moe_autograd
+        for it in range(2):
+            x = (torch.randn(T, H, device=dev) * 0.5).to(bf).requires_grad_(True)
+            ids = torch.randn(T, E, device=dev).topk(topk, dim=1).indices.to(torch.int32)
+            wts = torch.softmax(torch.randn(T, topk, device=dev), -1).requires_grad_(True)
+            wg, wd = w_gu.clone().requires_grad_(True), w_dn.clone().requires_grad_(True)
+            g_out = (torch.randn(T, H, device=dev) * 0.1).to(bf)
+            out = mega_ep_moe_autograd(ctx, x, ids, wts, wg, wd)
+            out.backward(g_out)
+            # dense golden (fp32 math, bf16 rounding where the kernels round), gradients of ALL experts summed over ranks
+            xr = x.detach().float().requires_grad_(True)
+            wr = wts.detach().float().requires_grad_(True)
+            ga, da = w_gu_all.float().requires_grad_(True), w_dn_all.float().requires_grad_(True)
+            o = torch.zeros(T, H, device=dev)
+            for k in range(topk):
+                e = ids[:, k].long()
+                hh = torch.einsum("th,tih->ti", xr, ga[e])
+                a = torch.nn.functional.silu(hh[:, :I]) * hh[:, I:]
+                o = o + wr[:, k:k + 1] * torch.einsum("ti,thi->th", a, da[e])
+            o.backward(g_out.float())
+            dist.all_reduce(ga.grad, group=U.get_triton_dist_world()); dist.all_reduce(da.grad, group=U.get_triton_dist_world())
+            _assert_close(out.detach(), o.detach(), 0.05, 5e-2, f"ep_mega autograd fwd it{it}")
+            _assert_close(x.grad, xr.grad, 0.05, 6e-2, f"ep_mega dX it{it}")
+            _assert_close(wts.grad, wr.grad, 0.08, 6e-2, f"ep_mega d(routing w) it{it}")
+            sl = slice(me * epr, (me + 1) * epr)
+            scale_g = max(1.0, ga.grad[sl].abs().max().item())
+            _assert_close(wg.grad / scale_g, ga.grad[sl] / scale_g, 0.03, 6e-2, f"ep_mega dW_gate_up it{it}")
+            scale_d = max(1.0, da.grad[sl].abs().max().item())
+            _assert_close(wd.grad / scale_d, da.grad[sl] / scale_d, 0.03, 6e-2, f"ep_mega dW_down it{it}")
         U.barrier_all_host()
         ctx.finalize()
 
@@ -603,6 +669,12 @@ def case_sp_pp():
         sc = sc.masked_fill(~(torch.arange(S, device=dev)[None, :] <= torch.arange(S, device=dev)[:, None])[None], float("-inf"))
         full_o = torch.einsum("hsl,lhd->shd", torch.softmax(sc, -1), vv)
         _assert_close(o, full_o[pos], 3e-2, 3e-2, "sp ag attention (tcgen05 flash, zig-zag)")
+        # the same attention with the KV all-gather overlapped with the local-chunk flash call + LSE merge of the partials
+        from triton_dist.parallel.sp import fused_sp_ag_attn_overlapped
+        for zz in (True, False):
+            pp = pos if zz else torch.arange(me * (S // W), (me + 1) * (S // W), device=dev)
+            o2 = fused_sp_ag_attn_overlapped(ctx, qf[pp].contiguous(), kf2[pp].contiguous(), vf2[pp].contiguous(), is_causal=True, enable_zig_zag=zz)
+            _assert_close(o2, full_o[pp], 3e-2, 3e-2, f"sp ag attention overlapped (zig-zag={zz})")
         ctx.finalize()
     # ---- PP send/recv ring ----
     for backend in (("triton_dist", "torch") if big else ("triton_dist",)):

@@ -63,3 +63,27 @@ def test_gemm_splitk_tail(cfg, shape, tma_store):
         torch.testing.assert_close(c0.float(), ref, **tol)
         # same fp32 sums up to the association order of the K split: differences are bf16 rounding flips only
         assert (c1.float() - c0.float()).abs().max().item() <= 0.02 * ref.abs().max().item() + 1e-2
+
+
+@pytest.mark.parametrize("kind", ["int8", "fp8"])
+@pytest.mark.parametrize("shape", [(512, 768, 1024), (300, 264, 512), (4096, 4096, 4096)])
+def test_gemm_scaled_8bit(kind, shape):
+    """int8 x int8 (tcgen05 kind::i8, exact int32 accumulation) and e4m3 x e4m3 (kind::f8f6f4) with per-row / per-channel
+    dequantisation scales applied in the epilogue, vs the fp32 product of the dequantised operands."""
+    from triton_dist.ops.gemm import gemm_scaled
+    torch.manual_seed(6)
+    M, N, K = shape
+    if kind == "int8":
+        a = torch.randint(-127, 128, (M, K), device="cuda", dtype=torch.int8)
+        b = torch.randint(-127, 128, (N, K), device="cuda", dtype=torch.int8)
+    else:
+        a = (torch.randn(M, K, device="cuda") * 0.5).to(torch.float8_e4m3fn)
+        b = (torch.randn(N, K, device="cuda") * 0.5).to(torch.float8_e4m3fn)
+    sa = torch.rand(M, device="cuda") * 0.02 + 0.001
+    sb = torch.rand(N, device="cuda") * 0.02 + 0.001
+    ref = (a.float() @ b.float().t()) * sa[:, None] * sb[None, :]
+    out = gemm_scaled(a, b, sa, sb)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out.float(), ref, atol=2e-2 * ref.abs().max().item() + 1e-3, rtol=2e-2)
+    out2 = gemm_scaled(a, b, 0.01, None)                      # per-tensor scale, no weight scale
+    torch.testing.assert_close(out2.float(), (a.float() @ b.float().t()) * 0.01, atol=2e-2 * (ref.abs().max().item() / 0.01 * 0.01 * 100) + 1e-2, rtol=2e-2)

@@ -99,6 +99,8 @@ class EPMegaHandle:
     n_rows: torch.Tensor          # int32 [1] rows in use (device)
     parity: int
     T: int
+    tot_me: torch.Tensor = None   # int32 [epr]: rows of every local expert
+    eoff_me: torch.Tensor = None  # int32 [epr]: first row of every local expert's (256-aligned) segment
 
 
 def _preprocess(ctx: EPMegaContext, topk_ids: torch.Tensor):
@@ -130,7 +132,7 @@ def _preprocess(ctx: EPMegaContext, topk_ids: torch.Tensor):
     re = tile_expert.repeat_interleave(_TILE)
     re_c = re.clamp(min=0).long()
     valid = (re >= 0) & ((rows - eoff[me][re_c]) < tot.view(W, epr)[me][re_c])
-    return srt, send_off, dest_off, tile_expert, valid, ends[-1:].contiguous()
+    return srt, send_off, dest_off, tile_expert, valid, ends[-1:].contiguous(), tot.view(W, epr)[me].contiguous(), eoff[me].contiguous()
 
 
 def mega_dispatch_group_gemm(ctx: EPMegaContext, x: torch.Tensor, topk_ids: torch.Tensor, w_gate_up: torch.Tensor,
@@ -142,7 +144,7 @@ def mega_dispatch_group_gemm(ctx: EPMegaContext, x: torch.Tensor, topk_ids: torc
     assert H == ctx.hidden and T <= ctx.max_tokens and topk_ids.shape == (T, ctx.topk) and x.dtype == ctx.dtype
     E_l, N, K = w_gate_up.shape
     assert E_l == epr and K == H and w_gate_up.is_contiguous()
-    srt, send_off, dest_off, tile_expert, valid, n_rows = _preprocess(ctx, topk_ids)
+    srt, send_off, dest_off, tile_expert, valid, n_rows, tot_me, eoff_me = _preprocess(ctx, topk_ids)
     ctx.calls += 1
     par = ctx.calls & 1
     h = torch.empty((ctx.rows_cap, N), dtype=x.dtype, device=x.device)
@@ -164,7 +166,7 @@ def mega_dispatch_group_gemm(ctx: EPMegaContext, x: torch.Tensor, topk_ids: torc
     _C.check(_C.cuda_lib().td_gemm_launch(C.byref(args), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "td_gemm_launch(mega_ep dispatch)")
     # return addresses of my rows (what the senders wrote), padding rows masked out
     route = torch.where(valid, ctx.meta[par], torch.full_like(ctx.meta[par], -1)).contiguous()
-    return h, EPMegaHandle(tile_expert, route, n_rows, par, T)
+    return h, EPMegaHandle(tile_expert, route, n_rows, par, T, tot_me, eoff_me)
 
 
 def mega_group_gemm_combine(ctx: EPMegaContext, act: torch.Tensor, handle: EPMegaHandle, w_down: torch.Tensor,

@@ -135,3 +135,60 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None,
     lib = _C.cuda_lib()
     _C.check(lib.td_gemm_launch(C.byref(args), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "td_gemm_launch")
     return out
+
+
+_Q8_CODE = {torch.int8: 3}
+if hasattr(torch, "float8_e4m3fn"):
+    _Q8_CODE[torch.float8_e4m3fn] = 4
+
+
+def _scale_vec(s, n: int, device) -> Optional[torch.Tensor]:
+    """None | python float | 0-d / 1-element tensor (per-tensor) | [n] tensor (per-row / per-channel) -> fp32 [n] or None."""
+    if s is None:
+        return None
+    if not isinstance(s, torch.Tensor):
+        s = torch.tensor(float(s), device=device)
+    s = s.to(device=device, dtype=torch.float32).reshape(-1)
+    if s.numel() == 1:
+        s = s.expand(n)
+    assert s.numel() == n, f"scale has {s.numel()} entries, expected 1 or {n}"
+    return s.contiguous()
+
+
+def gemm_scaled(a: torch.Tensor, b: torch.Tensor, scale_a=None, scale_b=None, out: Optional[torch.Tensor] = None,
+                config: Optional[GemmConfig] = None, out_parity=None, out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """8-bit GEMM with dequantisation in the epilogue: ``out[M, N] = (a[M, K] @ b[N, K].T) * scale_a[:, None] * scale_b[None, :]``.
+    ``a`` / ``b``: int8 (tcgen05 ``kind::i8``, exact int32 accumulation) or float8_e4m3fn (``kind::f8f6f4``, fp32 accumulation);
+    ``scale_a``: per-tensor or per-row [M]; ``scale_b``: per-tensor or per-output-channel [N].  The reference's int8 GEMM+AllReduce
+    (kernels/nvidia/gemm_allreduce.py:383-447) and the per-tensor fp8 / int8 gemm_rs dtypes (test_gemm_rs.py:130-145) map here."""
+    if not a.is_cuda:
+        acc = a.to(torch.float32) @ b.to(torch.float32).t()
+        sa, sb = _scale_vec(scale_a, a.shape[0], a.device), _scale_vec(scale_b, b.shape[0], a.device)
+        if sa is not None:
+            acc = acc * sa[:, None]
+        if sb is not None:
+            acc = acc * sb[None, :]
+        res = acc.to(out_dtype)
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
+    assert a.dtype == b.dtype and a.dtype in _Q8_CODE, f"gemm_scaled takes int8 or float8_e4m3fn operands, got {a.dtype}"
+    M, K = a.shape
+    N, Kb = b.shape
+    assert K == Kb and K % 128 == 0 and a.stride(1) == 1 and b.stride(1) == 1 and a.stride(0) % 16 == 0 and b.stride(0) % 16 == 0
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    assert out.dtype == torch.bfloat16
+    sa, sb = _scale_vec(scale_a, M, a.device), _scale_vec(scale_b, N, a.device)
+    cfg = config or default_config(M, N, K)
+    args = _C.GemmArgs()
+    args.mode = 0
+    fill_common(args, M, a.data_ptr(), a.stride(0), b, out.data_ptr(), M, out.stride(0), M, N, K, cfg, True)
+    args.is_bf16 = _Q8_CODE[a.dtype]
+    args.scale_a = sa.data_ptr() if sa is not None else None
+    args.scale_b = sb.data_ptr() if sb is not None else None
+    if out_parity is not None:
+        args.c_phase, args.c_nbuf, args.c_buf_stride_bytes = out_parity[0].data_ptr(), 2, int(out_parity[1])
+    _C.check(_C.cuda_lib().td_gemm_launch(C.byref(args), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "td_gemm_launch(8-bit)")
+    return out

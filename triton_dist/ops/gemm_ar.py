@@ -108,9 +108,15 @@ def default_ar_config(M: int, N: int, K: int, n_comm: int = 16, num_sms: int = 1
 
 
 def low_latency_gemm_allreduce_op(ctx: GemmARContext, a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None,
-                                  gemm_config: Optional[GemmConfig] = None, straggler_option=None, **ref_hints) -> torch.Tensor:
-    """Single fused kernel; falls back to :func:`gemm_allreduce_op` when the context has no fused buffers."""
-    U.accept_ref_hints("low_latency_gemm_allreduce_op", ref_hints, ('copy_to_local', 'USE_MULTIMEM_ST', 'TILE_MAP_LEVEL', 'A_scale', 'B_scale'))
+                                  gemm_config: Optional[GemmConfig] = None, straggler_option=None, A_scale=None, B_scale=None,
+                                  **ref_hints) -> torch.Tensor:
+    """Single fused kernel; falls back to :func:`gemm_allreduce_op` when the context has no fused buffers.  Quantised operands
+    (int8 / float8_e4m3fn with ``A_scale`` / ``B_scale``) take the two-kernel path (scaled tcgen05 GEMM -> NVLS all-reduce)."""
+    U.accept_ref_hints("low_latency_gemm_allreduce_op", ref_hints, ('copy_to_local', 'USE_MULTIMEM_ST', 'TILE_MAP_LEVEL'))
+    if a.dtype not in (torch.bfloat16, torch.float16, torch.float32):
+        return gemm_allreduce_op(ctx, a, b, out=out, gemm_config=None, straggler_option=straggler_option, As=A_scale, Bs=B_scale)
+    if A_scale is not None or B_scale is not None:
+        raise NotImplementedError("low_latency_gemm_allreduce_op: scales apply to int8 / float8_e4m3fn operands")
     w = b if (b.shape[1] == a.shape[1] and b.stride(1) == 1) else _as_nk(b)
     M, K = a.shape
     N = w.shape[0]
@@ -148,13 +154,35 @@ def low_latency_gemm_allreduce_op(ctx: GemmARContext, a: torch.Tensor, b: torch.
 
 
 def gemm_allreduce_op(ctx: GemmARContext, a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None,
-                      gemm_config: Optional[GemmConfig] = None, method=None, straggler_option=None, **ref_hints) -> torch.Tensor:
-    """``a``: [M, K/W]; ``b``: weight [N, K/W] (K-major) or its ``.t()`` view -> all-reduced [M, N]."""
-    U.accept_ref_hints("gemm_allreduce_op", ref_hints, ('copy_to_local', 'USE_MULTIMEM_ST', 'As', 'Bs', 'pg'))
+                      gemm_config: Optional[GemmConfig] = None, method=None, straggler_option=None, As=None, Bs=None,
+                      **ref_hints) -> torch.Tensor:
+    """``a``: [M, K/W]; ``b``: weight [N, K/W] (K-major) or its ``.t()`` view -> all-reduced [M, N].
+    int8 (or float8_e4m3fn) ``a`` / ``b`` with ``As`` (per-row or per-tensor activation scales) and ``Bs`` (per-output-channel
+    or per-tensor weight scales): the reference's quantised GEMM+AllReduce (gemm_allreduce.py:383-447) -- tcgen05 ``kind::i8``
+    with the dequantisation in the epilogue, partial sums all-reduced in bf16."""
+    U.accept_ref_hints("gemm_allreduce_op", ref_hints, ('copy_to_local', 'USE_MULTIMEM_ST', 'pg'))
     w = b if (b.shape[1] == a.shape[1] and b.stride(1) == 1) else _as_nk(b)
     M, K = a.shape
     N = w.shape[0]
     assert M <= ctx.max_M and N == ctx.N
+    quant = a.dtype not in (torch.bfloat16, torch.float16, torch.float32)
+    if quant:
+        from .gemm import gemm_scaled
+        odt = ctx.dtype if ctx.dtype in (torch.bfloat16,) else torch.bfloat16
+        if out is None:
+            out = torch.empty((M, N), dtype=odt, device=a.device)
+        if not a.is_cuda or ctx.world_size == 1:
+            part = gemm_scaled(a, w, As, Bs, out_dtype=odt)
+            return part if ctx.world_size == 1 else comm.all_reduce(part, comm.AllReduceMethod.OneShot, ctx.ar_ctx, output=out)
+        nbytes = M * N * 2
+        ctx.calls += 1
+        stage0 = ctx.ar_ctx.stage[:nbytes].view(odt).view(M, N)
+        gemm_scaled(a, w, As, Bs, out=stage0, config=gemm_config or default_config(M, N, K), out_parity=(ctx.ar_ctx.phase, ctx.ar_ctx.workspace_nbytes))
+        comm.all_reduce(stage0, method or comm.get_auto_allreduce_method(nbytes), ctx.ar_ctx, output=out, straggler_option=straggler_option,
+                        device_parity_input=True)
+        return out
+    if As is not None or Bs is not None:
+        raise NotImplementedError("gemm_allreduce_op: As / Bs scales apply to int8 / float8_e4m3fn operands")
     if out is None:
         out = torch.empty((M, N), dtype=a.dtype, device=a.device)
     if not a.is_cuda:

@@ -90,10 +90,13 @@ def default_rs_config(M: int, N: int, K: int, world: int) -> GemmConfig:
 def gemm_rs(A: torch.Tensor, B: torch.Tensor, ctx: GEMMReduceScatterTensorParallelContext,
             gemm_config: Optional[GemmConfig] = None, persistent: bool = True, fuse_scatter: bool = True,
             reduce_st: bool = False, out: Optional[torch.Tensor] = None, straggler_option=None, profiler=None,
-            skip_wait: bool = False, **ref_hints) -> torch.Tensor:
+            skip_wait: bool = False, scale_a=None, scale_b=None, **ref_hints) -> torch.Tensor:
     """A: ``[M, K/W]``, B: ``[K/W, N]`` (``.t()`` view of a ``[N, K/W]`` weight) -> ``[M/W, N]``.
     ``skip_wait`` runs the GEMM-only twin: same tiles, same epilogue and pushes, but nobody waits for the partial of the
-    previous rank (numerically meaningless; measures the exposed communication as fused - twin)."""
+    previous rank (numerically meaningless; measures the exposed communication as fused - twin).
+    int8 / float8_e4m3fn ``A`` and ``B`` (the reference's per-tensor fp8 / int8 gemm_rs dtypes, test_gemm_rs.py:130-145) run on
+    tcgen05 ``kind::i8`` / ``kind::f8f6f4`` with ``scale_a`` / ``scale_b`` applied in the epilogue BEFORE the ring (the running
+    partial sums travel dequantised, in bf16 or fp32)."""
     U.accept_ref_hints("gemm_rs", ref_hints, ())
     W = ctx.world_size
     M, K = A.shape
@@ -101,12 +104,21 @@ def gemm_rs(A: torch.Tensor, B: torch.Tensor, ctx: GEMMReduceScatterTensorParall
     N = Bnk.shape[0]
     assert M % W == 0 and M <= ctx.max_M and N == ctx.N and Bnk.shape[1] == K
     Mr = M // W
+    quant = A.dtype not in (torch.bfloat16, torch.float16, torch.float32)
+    if quant:
+        from .gemm import _Q8_CODE, _scale_vec, gemm_scaled
     if not A.is_cuda:
+        if quant:
+            part_in = (A.float() * (1.0 if scale_a is None else _scale_vec(scale_a, M, A.device)[:, None])).to(ctx.output_dtype)
+            Bq = (Bnk.float() * (1.0 if scale_b is None else _scale_vec(scale_b, N, A.device)[:, None])).to(ctx.output_dtype)
+            return _gemm_rs_host(part_in, Bq, ctx, out)
         return _gemm_rs_host(A, Bnk, ctx, out)
     if out is None:
-        out = torch.empty((Mr, N), dtype=A.dtype, device=A.device)
+        out = torch.empty((Mr, N), dtype=ctx.output_dtype if quant else A.dtype, device=A.device)
     cfg = gemm_config or default_rs_config(M, N, K, W)
     if W == 1:
+        if quant:
+            return gemm_scaled(A, Bnk, scale_a, scale_b, out=out)
         return gemm(A, Bnk, out=out, config=GemmConfig(cfg.bn, cfg.cta_group, 8, True, cfg.num_sms, 0))
     if straggler_option and straggler_option[0] == ctx.rank:
         torch.cuda._sleep(int(straggler_option[1]))
@@ -115,13 +127,20 @@ def gemm_rs(A: torch.Tensor, B: torch.Tensor, ctx: GEMMReduceScatterTensorParall
         if Mr % 128 == 0:
             cfg = GemmConfig(cfg.bn, 1, 1, False, cfg.num_sms, 0)
             tm = 128
+        elif quant:
+            raise ValueError("quantised gemm_rs needs (M / world) % 128 == 0")
         else:
             return _gemm_rs_fallback(A, Bnk, ctx, out)
     A = A.contiguous()
     args = _C.GemmArgs()
     args.mode = 2
     fill_common(args, M, A.data_ptr(), A.stride(0), Bnk, out.data_ptr(), Mr, out.stride(0), M, N, K,
-                GemmConfig(cfg.bn, cfg.cta_group, cfg.group_m, False, cfg.num_sms, 0), A.dtype == torch.bfloat16)
+                GemmConfig(cfg.bn, cfg.cta_group, cfg.group_m, False, cfg.num_sms, 0), quant or A.dtype == torch.bfloat16)
+    if quant:
+        assert A.dtype == Bnk.dtype and A.dtype in _Q8_CODE and K % 128 == 0 and out.dtype == torch.bfloat16
+        args.is_bf16 = _Q8_CODE[A.dtype]
+        sa, sb = _scale_vec(scale_a, M, A.device), _scale_vec(scale_b, N, A.device)
+        args.scale_a, args.scale_b = (sa.data_ptr() if sa is not None else None), (sb.data_ptr() if sb is not None else None)
     # first the tiles owned by rank+1 (the chain for owner o starts at rank o-1 and ends at o)
     args.m_rot = (((ctx.rank + 1) % W) * Mr) // tm
     r, w, base, stride, mc = U.symm_ctx_fields()

@@ -19,7 +19,14 @@ class GemmARLayer:
         self.ctx = make(None, heap.rank, heap.world, local_world_size, max_M, N, output_dtype, NUM_COMM_SMS=NUM_COMM_SMS)
 
     def forward(self, x: torch.Tensor, weight: torch.Tensor, bias=None, scale_a=None, scale_b=None) -> torch.Tensor:
-        out = (low_latency_gemm_allreduce_op if self.use_ll_kernel else gemm_allreduce_op)(self.ctx, x, weight)
+        """16-bit ``x`` / ``weight``: fused GEMM + AllReduce.  int8 / float8_e4m3fn operands: ``scale_a`` (per-tensor or per-row) and
+        ``scale_b`` (per-tensor or per-output-channel) are applied in the GEMM epilogue (reference gemm_allreduce_layer.py:143)."""
+        if x.dtype in (torch.bfloat16, torch.float16, torch.float32):
+            if scale_a is not None or scale_b is not None:
+                raise ValueError("GemmARLayer: scale_a / scale_b are dequantisation scales of int8 / float8_e4m3fn operands")
+            out = (low_latency_gemm_allreduce_op if self.use_ll_kernel else gemm_allreduce_op)(self.ctx, x, weight)
+        else:
+            out = gemm_allreduce_op(self.ctx, x, weight, As=scale_a, Bs=scale_b)
         return out if bias is None else out + bias
 
     __call__ = forward

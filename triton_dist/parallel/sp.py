@@ -115,6 +115,81 @@ def fused_sp_ag_attn_intra_node(ctx: SPAllGatherAttentionContextIntraNode, q_sha
     return o[0].transpose(0, 1).contiguous()
 
 
+def merge_attention_partials(o1: torch.Tensor, lse1: torch.Tensor, o2: torch.Tensor, lse2: torch.Tensor):
+    """Combine two attention results over DISJOINT key sets: ``o = (e^{l1} o1 + e^{l2} o2) / (e^{l1} + e^{l2})``.
+    o: [S, H, D] (normalised), lse: [H, S] (-inf where a query saw no key of that set)."""
+    m = torch.maximum(lse1, lse2)
+    m = torch.where(torch.isfinite(m), m, torch.zeros_like(m))
+    w1, w2 = torch.exp(lse1 - m), torch.exp(lse2 - m)
+    den = (w1 + w2).clamp_min(1e-30)
+    a1, a2 = (w1 / den).transpose(0, 1)[..., None], (w2 / den).transpose(0, 1)[..., None]
+    return (o1.float() * a1 + o2.float() * a2).to(o1.dtype), m + torch.log(den)
+
+
+def fused_sp_ag_attn_overlapped(ctx: SPAllGatherAttentionContextIntraNode, q_shard: torch.Tensor, k_shard: torch.Tensor,
+                                v_shard: torch.Tensor, is_causal: bool = True, enable_zig_zag: bool = True,
+                                sm_scale: Optional[float] = None) -> torch.Tensor:
+    """Context-parallel attention with the KV all-gather OVERLAPPED with compute (the reference gathers per-batch KV on a side
+    stream while attention runs, sp_ag_attention_intra_node.py:106-183, and its inter-node variant starts on arrived chunks,
+    sp_ag_attention_inter_node.py:116-190).  Here: the K / V shards are pushed to every peer on a side stream while the tcgen05
+    flash kernel already attends to the LOCAL keys (1/W of the work, ready immediately); the remote keys follow in two
+    non-causal calls -- under zig-zag sharding every remote chunk is either fully visible or fully invisible to a query
+    half, so ``sk`` bounds replace masks -- and the partial results are merged through their log-sum-exps."""
+    from ..ops.flash_attn import flash_attn_fwd
+    W, r = ctx.world_size, ctx.rank
+    S_local, Hq, D = q_shard.shape
+    Hkv = k_shard.shape[1]
+    sm_scale = sm_scale or 1.0 / math.sqrt(D)
+    zz = enable_zig_zag and W > 1 and is_causal
+    ok = (q_shard.is_cuda and W > 1 and is_causal and D == 128 and q_shard.dtype in (torch.bfloat16, torch.float16)
+          and ((S_local // 2) % 128 == 0 if zz else S_local % 128 == 0))
+    if not ok:
+        return fused_sp_ag_attn_intra_node(ctx, q_shard, k_shard, v_shard, is_causal, enable_zig_zag, sm_scale)
+    main = torch.cuda.current_stream()
+    if getattr(ctx, "_ag_stream", None) is None:
+        ctx._ag_stream = torch.cuda.Stream(priority=-1)
+    side = ctx._ag_stream
+    side.wait_stream(main)
+    kc, vc = k_shard.contiguous(), v_shard.contiguous()
+    with torch.cuda.stream(side):
+        k_all = comm.fast_allgather(kc, ctx.ag_k, mode="push").view(W, S_local, Hkv, D)
+        v_all = comm.fast_allgather(vc, ctx.ag_v, mode="push").view(W, S_local, Hkv, D)
+        ev = torch.cuda.Event()
+        ev.record(side)
+    k_all.record_stream(main); v_all.record_stream(main)
+    dev = q_shard.device
+    n_tiles = S_local // 128
+    # ---- local keys (no waiting): zig-zag halves A = chunk r, B = chunk 2W-1-r laid out back to back as positions [0, 2c) ----
+    tile_pos = (torch.arange(n_tiles, device=dev, dtype=torch.int32) * 128).view(1, -1).contiguous()
+    o_loc, lse_loc = flash_attn_fwd(q_shard[None], kc[None], vc[None], causal=True, sm_scale=sm_scale, q_tile_pos=tile_pos, return_lse=True)
+    o, lse = o_loc[0], lse_loc[0]
+    main.wait_event(ev)
+    if zz:
+        c = S_local // 2
+        # natural order of the remote chunks: chunk i of 2W lives in rank (i < W ? i : 2W-1-i), first / second half
+        kc2, vc2 = k_all.reshape(W, 2, c, Hkv, D), v_all.reshape(W, 2, c, Hkv, D)
+        nat = [(i, 0) if i < W else (2 * W - 1 - i, 1) for i in range(2 * W)]
+        rem = [i for i in range(2 * W) if i not in (r, 2 * W - 1 - r)]
+        idx_r = torch.tensor([nat[i][0] for i in rem], device=dev)
+        idx_h = torch.tensor([nat[i][1] for i in rem], device=dev)
+        k_rem = kc2[idx_r, idx_h].reshape(1, len(rem) * c, Hkv, D)
+        v_rem = vc2[idx_r, idx_h].reshape(1, len(rem) * c, Hkv, D)
+        vis_a, vis_b = r, 2 * W - 2 - r               # remote chunks below my half A / below my half B (chunk r itself is local)
+        parts = ((slice(0, c), vis_a), (slice(c, 2 * c), vis_b))
+    else:
+        k_rem, v_rem = k_all[:r].reshape(1, r * S_local, Hkv, D), v_all[:r].reshape(1, r * S_local, Hkv, D)
+        parts = ((slice(0, S_local), r * S_local // max(S_local, 1)),)
+        c = S_local
+    out = torch.empty_like(q_shard)
+    for sl, n_vis in parts:
+        if n_vis <= 0:
+            out[sl] = o[sl]
+            continue
+        o_r, lse_r = flash_attn_fwd(q_shard[None, sl], k_rem, v_rem, causal=False, sm_scale=sm_scale, sk=n_vis * c, return_lse=True)
+        out[sl], _ = merge_attention_partials(o[sl], lse[:, sl], o_r[0], lse_r[0])
+    return out
+
+
 def _sp_attn_tcgen05(q_shard, k_all, v_all, W, r, is_causal, zigzag, sm_scale):
     """Attention of the local q block over the gathered KV with the tcgen05 flash kernel.  With zig-zag sharding rank s
     holds chunks s and 2W-1-s of 2W; the gathered KV is put back into natural order (a view permutation + one copy) so
