@@ -133,9 +133,10 @@ __global__ void __launch_bounds__(kWarps * 32) decode_splitkv_kernel(const Decod
 
 // ---- v2: bandwidth-oriented streaming kernel -------------------------------------------------------------------------------
 // ncu of the kernel above (B=8, 8 K context, 8 kv heads): 0.86 TB/s -- two 8-byte loads per lane per array in flight are ~8 KB
-// per SM, Little's law needs ~45 KB.  Here 8 lanes cover one 256-byte row with 16-byte loads, a warp covers 4 rows per load
-// instruction and keeps kU = 4 K loads + 4 V loads in flight per lane (8 KB per warp, 64 KB per 8-warp CTA).  Every 8-lane group
-// runs its own online softmax over the rows it sees (32 independent states per CTA), merged through shared memory at the end.
+// per SM, Little's law needs ~45 KB.  Here 16 lanes cover one 256-byte row with 16-byte loads, a warp covers 2 rows per load
+// instruction and keeps kU = 4 K loads + 4 V loads in flight per lane (4 KB per warp, 32 KB per 8-warp CTA, two CTAs per SM).
+// Every 16-lane group runs its own online softmax over the rows it sees (16 independent states per CTA), merged by one shuffle
+// round inside the warp and through shared memory across warps.
 constexpr int kWarps2 = 8;
 constexpr int kU = 4;
 
@@ -153,7 +154,7 @@ template <bool kBF16, int G>
 __global__ void __launch_bounds__(kWarps2 * 32, (G <= 4) ? 2 : 1) decode_splitkv_kernel_v2(const DecodeParams p) {
   const int b = blockIdx.x, kvh = blockIdx.y, sp = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int sub = lane >> 3, l8 = lane & 7;          // row inside the warp's group of 4, 16-byte piece of the row
+  const int sub = lane >> 4, l8 = lane & 15;         // row inside the warp's pair, 16-byte piece (8 elements) of the 128-wide row
   const int len = p.kv_lens[b];
   const int per = (len + p.S - 1) / p.S;
   const int j0 = sp * per, j1 = min(len, j0 + per);
@@ -184,13 +185,13 @@ __global__ void __launch_bounds__(kWarps2 * 32, (G <= 4) ? 2 : 1) decode_splitkv
     }
     return (row * p.Hkv + kvh) * 16 + l8;
   };
-  constexpr int kRowsPerIter = kWarps2 * 4 * kU;      // 128 positions per CTA iteration
+  constexpr int kRowsPerIter = kWarps2 * 2 * kU;      // 64 positions per CTA iteration
   for (int jb = j0; jb < j1; jb += kRowsPerIter) {
     uint4 kr[kU], vr[kU];
     int jj[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
-      jj[u] = jb + (u * kWarps2 + warp) * 4 + sub;
+      jj[u] = jb + (u * kWarps2 + warp) * 2 + sub;
       if (jj[u] < j1) { const size_t off = row_off(jj[u]); kr[u] = ptx::ld_nc_v4(kc + off); vr[u] = ptx::ld_nc_v4(vc + off); }
     }
 #pragma unroll
@@ -210,6 +211,7 @@ __global__ void __launch_bounds__(kWarps2 * 32, (G <= 4) ? 2 : 1) decode_splitkv
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
         s += __shfl_xor_sync(0xffffffffu, s, 4);
+        s += __shfl_xor_sync(0xffffffffu, s, 8);
         if (p.soft_cap > 0.f) s = p.soft_cap * tanhf(s / p.soft_cap);
         if (!ok) s = -INFINITY;
         const float mn = fmaxf(m[g], s);
@@ -223,9 +225,9 @@ __global__ void __launch_bounds__(kWarps2 * 32, (G <= 4) ? 2 : 1) decode_splitkv
       }
     }
   }
-  // merge: first the 4 row groups of a warp with shuffles (lanes l8, l8 + 8, l8 + 16, l8 + 24 hold the same columns) ...
+  // merge: first the 2 row groups of a warp with one shuffle round (lanes l and l + 16 hold the same columns) ...
 #pragma unroll
-  for (int off = 8; off <= 16; off <<= 1) {
+  for (int off = 16; off <= 16; off <<= 1) {
 #pragma unroll
     for (int g = 0; g < G; ++g) {
       const float mo = __shfl_xor_sync(0xffffffffu, m[g], off), lo = __shfl_xor_sync(0xffffffffu, l[g], off);

@@ -47,3 +47,11 @@ if [ "$stage" = "f" ]; then
   TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
   timeout 90 $TR --master-port 29551 tests/dist_worker.py ep_mega > gpurun_out/dist_f_n$N.log 2>&1; echo "dist rc=$?"; grep -v "^\[W\|^W0\|OMP_NUM\|^\*\*" gpurun_out/dist_f_n$N.log | tail -25
 fi
+if [ "$stage" = "g" ]; then
+  N=${2:-2}
+  TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+  timeout 300 python -m pytest tests/test_ops_gpu.py -q -k "decode or engine or mega" > gpurun_out/test_decode.log 2>&1; echo "decode rc=$?"; tail -4 gpurun_out/test_decode.log
+  for c in ep_mega gemm_q8 sp_pp; do
+    timeout 150 $TR --master-port 29561 tests/dist_worker.py $c > gpurun_out/dist_g_$c.log 2>&1; echo "dist $c rc=$?"; grep -v "^\[W\|^W0\|OMP_NUM\|^\*\*" gpurun_out/dist_g_$c.log | grep "CASE\|Error\|error" | head -8
+  done
+fi
