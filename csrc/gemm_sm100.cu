@@ -405,4 +405,22 @@ TD_API int td_gemm_launch(const TdGemmArgs* a, void* stream_) {
   }
 }
 
+// A 2-D tensor map for user (JIT) kernels: row-major [rows, cols] of 1/2/4-byte elements, box {box_inner, box_outer}
+TD_API int td_make_tma_2d(void* out_map, const void* base, long long rows, long long cols, long long ld, int elem_bytes, int box_inner,
+                          int box_outer, int swizzle) {
+  auto enc = drv::cuTensorMapEncodeTiled_fn();
+  if (!enc) { drv::set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return -1; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * elem_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+  const CUtensorMapSwizzle sw = swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = enc(reinterpret_cast<CUtensorMap*>(out_map), dt, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { drv::set_error("cuTensorMapEncodeTiled failed: %s", drv::err_str(r)); return -1; }
+  return 0;
+}
+
 TD_API const char* td_last_error() { return td::drv::g_last_error; }

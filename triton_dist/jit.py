@@ -63,3 +63,58 @@ def compile_cuda(source: str, extra_flags: Sequence[str] = (), name: str = "kern
             raise RuntimeError(f"nvcc failed:\n{r.stderr[-4000:]}")
         os.replace(tmp, so)
     return C.CDLL(str(so))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# launch helpers (reference: little_kernel/runtime/{kernel,tma_descriptor}.py -- argument marshalling, cluster dims, TMA maps)
+# ------------------------------------------------------------------------------------------------------------
+def _marshal(arg):
+    """torch tensors -> device pointers, ints / floats / bools -> C scalars, SymmCtx / ctypes values pass through."""
+    import torch
+    if isinstance(arg, torch.Tensor):
+        return C.c_void_p(arg.data_ptr())
+    if isinstance(arg, bool):
+        return C.c_int(int(arg))
+    if isinstance(arg, int):
+        return C.c_longlong(arg) if abs(arg) >= 2 ** 31 else C.c_int(arg)
+    if isinstance(arg, float):
+        return C.c_float(arg)
+    if arg is None:
+        return C.c_void_p(None)
+    return arg
+
+
+class JitKernel:
+    """A launcher exported by a ``compile_cuda`` module, callable with tensors / scalars.  The C launcher's last parameter must be
+    the ``void* stream``; ``kernel(*args, stream=None)`` appends the current CUDA stream."""
+
+    def __init__(self, lib: C.CDLL, name: str):
+        self.fn = getattr(lib, name)
+        self.fn.restype = None
+        self.name = name
+
+    def __call__(self, *args, stream=None):
+        import torch
+        s = (stream or torch.cuda.current_stream()).cuda_stream if torch.cuda.is_available() else 0
+        self.fn(*[_marshal(a) for a in args], C.c_void_p(s))
+
+
+def kernel(source: str, launcher: str, extra_flags: Sequence[str] = ()) -> JitKernel:
+    """``compile_cuda`` + argument marshalling: returns a callable for the ``extern "C"`` launcher ``launcher``."""
+    return JitKernel(compile_cuda(source, extra_flags, name=launcher), launcher)
+
+
+def make_tma_2d(t, box_inner: int, box_outer: int, swizzle: int = 128):
+    """A ``CUtensorMap`` (128-byte opaque ctypes buffer) over a 2-D row-major tensor -- what little_kernel's
+    ``create_tma_2d_descriptor`` returns; pass it by value (``__grid_constant__ const CUtensorMap``) to a JIT kernel."""
+    from . import _C
+    lib = _C.cuda_lib()
+    if not hasattr(lib, "td_make_tma_2d"):
+        raise RuntimeError("td_make_tma_2d is not exported by libtd_b200.so")
+    buf = (C.c_ubyte * 128)()
+    fn = lib.td_make_tma_2d
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int]
+    rows, cols = t.shape
+    _C.check(fn(buf, t.data_ptr(), rows, cols, t.stride(0), t.element_size(), box_inner, box_outer, swizzle), "td_make_tma_2d")
+    return buf

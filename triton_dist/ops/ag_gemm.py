@@ -307,3 +307,39 @@ def _ag_gemm_host(A, Bnk, ctx, out, all_to_all=False):
             raise TimeoutError(f"ag_gemm: shard of rank {s} never arrived (phase {ph})")
         out[s * Ms:(s + 1) * Ms] = (ws[s * Ms:(s + 1) * Ms].float() @ bt).to(A.dtype)
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# autotuned entry point (reference: ag_gemm is wrapped by triton_dist.tune.autotune, allgather_gemm.py:565-619)
+# ------------------------------------------------------------------------------------------------------------
+from ..tune import autotune  # noqa: E402
+
+AG_GEMM_TUNE_SPACE = (
+    [dict(transport="sm_k", bn=bn, cta_group=cg, n_comm=nc, kslices=ks, groups=gr, tail=tail)
+     for (bn, cg) in ((256, 2), (128, 2), (256, 1)) for (nc, ks, gr, tail) in ((32, 2, 1, 0), (32, 4, 2, 12), (48, 6, 2, 10), (32, 1, 1, 0))]
+    + [dict(transport="multicast", bn=128, cta_group=2, n_comm=24, kslices=8, groups=3, tail=0),
+       dict(transport="sm", bn=256, cta_group=2, n_comm=16, kslices=0, groups=0, tail=0),
+       dict(transport="sm", bn=128, cta_group=2, n_comm=32, kslices=0, groups=0, tail=0)])
+
+
+def _ag_prune(cfg, A, B, ctx, **_):
+    Ms = A.shape[0]
+    if cfg["transport"] in ("sm_k", "multicast") and Ms % 128:
+        return False
+    if cfg["transport"] == "multicast" and not U.is_nvshmem_multimem_supported():
+        return False
+    return cfg["cta_group"] == 1 or Ms % 256 == 0
+
+
+@autotune(AG_GEMM_TUNE_SPACE, key_fn=lambda A, B, ctx, **kw: f"{tuple(A.shape)}x{tuple(B.shape)}@tp{ctx.num_ranks}", prune_fn=_ag_prune,
+          warmup=3, rep=8)
+def ag_gemm_tuned(A: torch.Tensor, B: torch.Tensor, ctx: AllGatherGEMMTensorParallelContext, out: Optional[torch.Tensor] = None,
+                  config: Optional[dict] = None) -> torch.Tensor:
+    """``ag_gemm`` with transport / tile / comm-CTA configuration chosen by the function-level autotuner: every candidate is
+    timed with CUDA events, the MAX over ranks decides (pass ``autotune_pg=group``), the winner is cached on disk per
+    (shape, world size, GPU).  ``ag_gemm_tuned(A, B, ctx, autotune=False)`` uses the first (default) configuration."""
+    c = config or AG_GEMM_TUNE_SPACE[0]
+    Ms = A.shape[0]
+    cfg = GemmConfig(c["bn"], c["cta_group"], max(1, Ms // (128 * c["cta_group"])), True, 0, c["n_comm"])
+    return ag_gemm(A, B, ctx, gemm_config=cfg, out=out, transport=c["transport"] if A.is_cuda else "auto", kslices=c["kslices"],
+                   comm_groups=c["groups"], tail_pct=c["tail"])
