@@ -45,6 +45,8 @@
 //   * all flags carry monotonically increasing phase numbers kept in device memory: no flag reset, no
 //     host barrier between calls, and a captured CUDA graph replays correctly.
 #pragma once
+#include <type_traits>
+
 #include "td/primitives.cuh"
 #include "td/profiler.cuh"
 
@@ -851,43 +853,50 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
           ptx::tc_fence_after();
           prof_record(p.prof, static_cast<int>(blockIdx.x) * 8 + 1, 4, true);
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+          // the k loop is instantiated once per operand kind (16-bit / int8 / e4m3): no per-MMA branch in the issuing thread
+          auto k_loop = [&](auto kind_c) {
+            constexpr int kKind = decltype(kind_c)::value;
           for (int kb = un.kb0; kb < un.kb1; ++kb) {
-            ptx::mbar_wait(full_bar + stage, phase);
-            ptx::tc_fence_after();
-            const uint32_t sa = ptx::smem_u32(smem + stage * L::kStageBytes);
-            const uint64_t adesc = ptx::make_smem_desc_k128(sa);
-            const uint64_t bdesc = ptx::make_smem_desc_k128(sa + L::kABytes);
-            if constexpr (!kFP8) {
+              ptx::mbar_wait(full_bar + stage, phase);
+              ptx::tc_fence_after();
+              const uint32_t sa = ptx::smem_u32(smem + stage * L::kStageBytes);
+              const uint64_t adesc = ptx::make_smem_desc_k128(sa);
+              const uint64_t bdesc = ptx::make_smem_desc_k128(sa + L::kABytes);
+              if constexpr (!kFP8) {
 #pragma unroll
-              for (int k = 0; k < BK / UMMA_K; ++k) {
-                // advance 32 B (= 16 bf16) along K inside the 128-byte swizzle atom: +2 in the 16-byte address field
-                const uint32_t accf = (kb > un.kb0 || k != 0) ? 1u : 0u;
-                if (p.in_kind == 0) ptx::mma_f16<kCtaGroup>(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, accf);
-                else if (p.in_kind == 1) ptx::mma_i8<kCtaGroup>(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, accf);
-                else ptx::mma_f8f6f4<kCtaGroup>(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, accf);
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                  // advance 32 B (= 16 bf16) along K inside the 128-byte swizzle atom: +2 in the 16-byte address field
+                  const uint32_t accf = (kb > un.kb0 || k != 0) ? 1u : 0u;
+                  if constexpr (kKind == 0) ptx::mma_f16<kCtaGroup>(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, accf);
+                  else if constexpr (kKind == 1) ptx::mma_i8<kCtaGroup>(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, accf);
+                  else ptx::mma_f8f6f4<kCtaGroup>(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, accf);
+                }
+              } else {
+                // MXFP8: stage the UE8M0 scale factors of this k-block into TMEM (smem -> TMEM, 32 lanes x 16 B, replicated
+                // to the four lane quadrants), then 4 block-scaled MMAs of K = 32; sf_id selects the byte of each 32-bit
+                // scale word that belongs to the K-chunk.  tcgen05.cp and tcgen05.mma execute in issue order, so the
+                // TMEM slot of this smem stage is free again by the time it is reused kStages k-blocks later.
+                const uint32_t sf_tmem = tmem_base + static_cast<uint32_t>(kSFBase + stage * kSFCols);
+                const uint32_t ssfa = sa + L::kABytes + L::kBBytes;
+                ptx::tmem_cp_32x128b_warpx4<kCtaGroup>(sf_tmem, ptx::make_smem_desc_noswizzle(ssfa, 0, 128));
+#pragma unroll
+                for (int g = 0; g < (BN + 127) / 128; ++g)
+                  ptx::tmem_cp_32x128b_warpx4<kCtaGroup>(sf_tmem + 4 + 4 * g,
+                                                          ptx::make_smem_desc_noswizzle(ssfa + L::kSFABytes + g * kSFChunk, 0, 128));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint32_t idm = ptx::make_idesc_mx(0u, 0u, TM, BN, static_cast<uint32_t>(k), static_cast<uint32_t>(k));
+                  ptx::mma_mxf8<kCtaGroup>(d_tmem, adesc + 2u * k, bdesc + 2u * k, idm, (kb > un.kb0 || k != 0) ? 1u : 0u, sf_tmem, sf_tmem + 4);
+                }
               }
-            } else {
-              // MXFP8: stage the UE8M0 scale factors of this k-block into TMEM (smem -> TMEM, 32 lanes x 16 B, replicated
-              // to the four lane quadrants), then 4 block-scaled MMAs of K = 32; sf_id selects the byte of each 32-bit
-              // scale word that belongs to the K-chunk.  tcgen05.cp and tcgen05.mma execute in issue order, so the
-              // TMEM slot of this smem stage is free again by the time it is reused kStages k-blocks later.
-              const uint32_t sf_tmem = tmem_base + static_cast<uint32_t>(kSFBase + stage * kSFCols);
-              const uint32_t ssfa = sa + L::kABytes + L::kBBytes;
-              ptx::tmem_cp_32x128b_warpx4<kCtaGroup>(sf_tmem, ptx::make_smem_desc_noswizzle(ssfa, 0, 128));
-#pragma unroll
-              for (int g = 0; g < (BN + 127) / 128; ++g)
-                ptx::tmem_cp_32x128b_warpx4<kCtaGroup>(sf_tmem + 4 + 4 * g,
-                                                        ptx::make_smem_desc_noswizzle(ssfa + L::kSFABytes + g * kSFChunk, 0, 128));
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint32_t idm = ptx::make_idesc_mx(0u, 0u, TM, BN, static_cast<uint32_t>(k), static_cast<uint32_t>(k));
-                ptx::mma_mxf8<kCtaGroup>(d_tmem, adesc + 2u * k, bdesc + 2u * k, idm, (kb > un.kb0 || k != 0) ? 1u : 0u, sf_tmem, sf_tmem + 4);
-              }
+              if constexpr (kCtaGroup == 1) ptx::mma_commit(empty_bar + stage);
+              else ptx::mma_commit_2sm(empty_bar + stage, 0b11);
+              if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
-            if constexpr (kCtaGroup == 1) ptx::mma_commit(empty_bar + stage);
-            else ptx::mma_commit_2sm(empty_bar + stage, 0b11);
-            if (++stage == kStages) { stage = 0; phase ^= 1u; }
-          }
+          };
+          if (kFP8 || p.in_kind == 0) k_loop(std::integral_constant<int, 0>{});
+          else if (p.in_kind == 1) k_loop(std::integral_constant<int, 1>{});
+          else k_loop(std::integral_constant<int, 2>{});
           if constexpr (kCtaGroup == 1) ptx::mma_commit(tmem_full + acc);
           else ptx::mma_commit_2sm(tmem_full + acc, 0b11);
           prof_record(p.prof, static_cast<int>(blockIdx.x) * 8 + 1, 4, false);

@@ -55,3 +55,14 @@ if [ "$stage" = "g" ]; then
     timeout 150 $TR --master-port 29561 tests/dist_worker.py $c > gpurun_out/dist_g_$c.log 2>&1; echo "dist $c rc=$?"; grep -v "^\[W\|^W0\|OMP_NUM\|^\*\*" gpurun_out/dist_g_$c.log | grep "CASE\|Error\|error" | head -8
   done
 fi
+if [ "$stage" = "h" ]; then
+  N=${2:-8}
+  TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+  timeout 420 $TR --master-port 29571 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "bench rc=$?"; tail -c 1500 gpurun_out/bench_n$N.json; tail -3 gpurun_out/bench_n$N.err
+  for c in "ag_gemm gemm_rs moe_rs gemm_ar gemm_q8" "moe ep_ll ep_normal ep_mega" "mega tp_e2e sp_pp allreduce"; do
+    timeout 240 $TR --master-port 29572 tests/dist_worker.py $c > gpurun_out/dist_h_tmp.log 2>&1; echo "dist [$c] rc=$?"; cat gpurun_out/dist_h_tmp.log >> gpurun_out/dist_all_n$N.log; grep "CASE\|Error" gpurun_out/dist_h_tmp.log | head -12
+  done
+  timeout 200 $TR --master-port 29573 triton_dist/benchmark/bench_moe_reduce_rs.py --json gpurun_out/moe_reduce_rs_n$N.json > gpurun_out/moe_rs_n$N.log 2>&1; echo "moe rc=$?"; tail -2 gpurun_out/moe_rs_n$N.log | cut -c1-900
+  timeout 240 $TR --master-port 29574 triton_dist/benchmark/bench_ep_mega.py --json gpurun_out/ep_mega_n$N.json > gpurun_out/ep_mega_n$N.log 2>&1; echo "ep_mega rc=$?"; tail -2 gpurun_out/ep_mega_n$N.log | cut -c1-900
+  timeout 240 $TR --master-port 29575 scripts/bench_qwen3.py > gpurun_out/qwen3_n$N.log 2>&1; echo "qwen3 rc=$?"; tail -4 gpurun_out/qwen3_n$N.log | cut -c1-900
+fi
