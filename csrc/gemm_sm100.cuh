@@ -856,7 +856,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
           // the k loop is instantiated once per operand kind (16-bit / int8 / e4m3): no per-MMA branch in the issuing thread
           auto k_loop = [&](auto kind_c) {
             constexpr int kKind = decltype(kind_c)::value;
-          for (int kb = un.kb0; kb < un.kb1; ++kb) {
+            for (int kb = un.kb0; kb < un.kb1; ++kb) {
               ptx::mbar_wait(full_bar + stage, phase);
               ptx::tc_fence_after();
               const uint32_t sa = ptx::smem_u32(smem + stage * L::kStageBytes);

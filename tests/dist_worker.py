@@ -391,11 +391,11 @@ def case_ep_mega():
     with all experts' weights; unbalanced routing (some experts empty), several calls per context (parity), a straggler."""
     from triton_dist.ops import ep_mega as EM
     dev = U.current_device()
-    if dev.type != "cuda":
-        return
     W, me = U.world_size(), U.rank()
-    bf = torch.bfloat16
-    for (T, H, I, epr, topk) in [(512, 512, 256, 4, 2), (300, 1024, 512, 2, 4), (1024, 256, 128, 8, 3)]:
+    big = dev.type == "cuda"
+    bf = torch.bfloat16 if big else torch.float32
+    shapes = [(512, 512, 256, 4, 2), (300, 1024, 512, 2, 4), (1024, 256, 128, 8, 3)] if big else [(24, 16, 8, 2, 2), (10, 8, 8, 3, 3)]
+    for (T, H, I, epr, topk) in shapes:
         E = epr * W
         ctx = EM.create_ep_mega_context(T, H, topk, E, bf, capacity_factor=3.0)
         g = torch.Generator(device="cpu").manual_seed(11)
@@ -409,11 +409,15 @@ def case_ep_mega():
                 logits[:, E // 2:] -= 4.0          # unbalanced: the upper half of the experts is (almost) never chosen
             ids = logits.topk(topk, dim=1).indices.to(torch.int32)
             wts = torch.softmax(torch.randn(T, topk, device=dev), -1)
-            if it == 1:
+            if it == 1 and big:
                 torch.cuda._sleep(2_000_000 * (1 + me))
             out = EM.mega_ep_moe(ctx, x, ids, wts, w_gu, w_dn)
             ref = EM.mega_ep_moe_reference(x, ids, wts, w_gu_all, w_dn_all)
-            _assert_close(out, ref, 0.05, 5e-2, f"ep_mega T{T} H{H} it{it}")
+            _assert_close(out, ref, 0.05 if big else 1e-4, 5e-2 if big else 1e-4, f"ep_mega T{T} H{H} it{it}")
+        if not big:
+            U.barrier_all_host()
+            ctx.finalize()
+            continue
         # training path: forward + backward through the same kernels vs torch autograd on the dense formulation
         from triton_dist.function.nvidia import mega_ep_moe_autograd
         for it in range(2):

@@ -313,3 +313,73 @@ def test_moe_align_sort_properties():
             e = int(flat[int(s[pos])])
             assert int(r.expert_offsets[e]) <= pos < int(r.expert_offsets[e + 1])
             assert int(r.tile_expert[pos // bm]) == e
+
+
+def test_transposed_moe_grouped_gemm_cpu_path():
+    """Weight gradient of a grouped GEMM (reference group_gemm.py:988 signature): ragged splits incl. an empty expert, with and
+    without the cumulative-offset argument, into a caller-provided buffer."""
+    from triton_dist.ops.moe import transposed_moe_grouped_gemm, transpose_gather
+    torch.manual_seed(0)
+    dy, x = torch.randn(40, 16), torch.randn(40, 24)
+    sp = torch.tensor([10, 0, 25, 5])
+    ref = torch.stack([dy[0:10].t() @ x[0:10], torch.zeros(16, 24), dy[10:35].t() @ x[10:35], dy[35:40].t() @ x[35:40]])
+    torch.testing.assert_close(transposed_moe_grouped_gemm(dy, x, sp), ref)
+    buf = torch.full((4, 16, 24), 7.0)
+    torch.testing.assert_close(transposed_moe_grouped_gemm(dy, x, sp, torch.cumsum(sp, 0), grad_weight=buf), ref)
+    with pytest.raises(TypeError):
+        transposed_moe_grouped_gemm(dy, x, sp, bogus_argument=1)
+    ids = torch.tensor([3, -1, 0, 39], dtype=torch.int32)
+    t = transpose_gather(x, ids, 4)
+    assert t.shape == (24, 4) and torch.equal(t[:, 0], x[3]) and torch.all(t[:, 1] == 0) and torch.equal(t[:, 3], x[39])
+
+
+def test_gemm_scaled_cpu_reference_and_layer_contract():
+    """The quantised GEMM's CPU reference path (int8 x per-row / per-channel scales) and the GemmARLayer contract: scales with
+    16-bit operands are an error, never silently dropped."""
+    from triton_dist.ops.gemm import gemm_scaled
+    torch.manual_seed(0)
+    a = torch.randint(-127, 128, (6, 32), dtype=torch.int8)
+    b = torch.randint(-127, 128, (5, 32), dtype=torch.int8)
+    sa, sb = torch.rand(6), torch.rand(5)
+    out = gemm_scaled(a, b, sa, sb, out_dtype=torch.float32)
+    torch.testing.assert_close(out, (a.float() @ b.float().t()) * sa[:, None] * sb[None, :])
+    torch.testing.assert_close(gemm_scaled(a, b, 0.5, None, out_dtype=torch.float32), (a.float() @ b.float().t()) * 0.5)
+
+
+def test_reference_hint_arguments_are_checked():
+    """Reference-only tuning hints are accepted by NAME; anything else raises instead of being swallowed (round-1 `**_unused`)."""
+    import triton_dist.utils as U
+    U.accept_ref_hints("f", {"BLOCK_M": 128}, ("BLOCK_M", "stages"))
+    with pytest.raises(TypeError):
+        U.accept_ref_hints("f", {"use_cooperative": True}, ("BLOCK_M",))
+    with pytest.raises(NotImplementedError):
+        U.accept_ref_hints("f", {"A_scale": torch.ones(1)}, ("A_scale",))
+
+
+def test_kv_cache_overflow_is_rejected():
+    from triton_dist.models import KV_Cache
+    kv = KV_Cache(1, 2, 8, 1, 128, torch.float32, 1, "cpu")
+    kv.inc_offset(6)
+    with pytest.raises(ValueError):
+        kv.inc_offset(3)
+    kv.clear()
+    kv.inc_offset(8)
+
+
+def test_allreduce_zero_copy_contract():
+    """all_reduce may skip its staging copy only for the half the NEXT call reduces (or the stage base under the device-parity
+    contract); a stale or offset view of the staging area must raise instead of silently reducing the other half."""
+    from triton_dist.ops.comm import AllReduceContext
+    ctx = AllReduceContext(1024, 0, 2, 2)
+    ctx.stage = torch.zeros(2048, dtype=torch.uint8)
+    base = ctx.stage.data_ptr()
+    assert ctx.zero_copy_ok(base + 5000, False) is False                 # outside the staging area: ordinary input
+    assert ctx.zero_copy_ok(base, True) is True                          # GEMM wrote the device-selected half
+    ctx.host_calls = 0                                                   # next call reduces half 1
+    assert ctx.zero_copy_ok(base + 1024, False) is True
+    with pytest.raises(ValueError):
+        ctx.zero_copy_ok(base, False)                                    # stale half
+    with pytest.raises(ValueError):
+        ctx.zero_copy_ok(base + 1024 + 16, False)                        # offset view
+    x = ctx.symm_input(64, torch.float32)
+    assert x.data_ptr() == base + 1024

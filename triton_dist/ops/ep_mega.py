@@ -147,6 +147,8 @@ def mega_dispatch_group_gemm(ctx: EPMegaContext, x: torch.Tensor, topk_ids: torc
     srt, send_off, dest_off, tile_expert, valid, n_rows, tot_me, eoff_me = _preprocess(ctx, topk_ids)
     ctx.calls += 1
     par = ctx.calls & 1
+    if not x.is_cuda:
+        return _dispatch_gemm_host(ctx, x, topk_ids, w_gate_up, srt, send_off, dest_off, tile_expert, valid, n_rows, tot_me, eoff_me, par)
     h = torch.empty((ctx.rows_cap, N), dtype=x.dtype, device=x.device)
     cfg = config or GemmConfig(bn=256 if N % 256 == 0 else 128, cta_group=2, group_m=1, use_tma_store=True)
     xc = x.contiguous()
@@ -176,6 +178,8 @@ def mega_group_gemm_combine(ctx: EPMegaContext, act: torch.Tensor, handle: EPMeg
     W, epr = ctx.world_size, ctx.experts_per_rank
     E_l, N, K = w_down.shape
     assert E_l == epr and N == ctx.hidden and act.shape == (ctx.rows_cap, K) and w_down.is_contiguous()
+    if not act.is_cuda:
+        return _gemm_combine_host(ctx, act, handle, w_down, topk_weights)
     cfg = config or GemmConfig(bn=256 if N % 256 == 0 else 128, cta_group=2, group_m=1, use_tma_store=False)
     actc = act.contiguous()
     args = _C.GemmArgs()
@@ -193,6 +197,74 @@ def mega_group_gemm_combine(ctx: EPMegaContext, act: torch.Tensor, handle: EPMeg
     par = handle.parity
     for s in range(W):
         U.wait_eq(ctx.done[par * W + s:par * W + s + 1], ctx.calls, geq=True)
+    T = handle.T
+    return M.reduce_topk(ctx.comb[par][:T * ctx.topk], topk_weights.to(torch.float32), ctx.topk)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# emulation (no GPU): the SAME protocol on the shared-memory heap -- direct placement from the all-gathered counts, one
+# release flag per (local expert, source), return addresses, rows scattered to their owners, per-rank done flags
+# ------------------------------------------------------------------------------------------------------------
+def _dispatch_gemm_host(ctx, x, topk_ids, w_gate_up, srt, send_off, dest_off, tile_expert, valid, n_rows, tot_me, eoff_me, par):
+    import ctypes
+    heap, lib = U.get_heap(), _C.host_lib()
+    W, me, epr, topk = ctx.world_size, ctx.rank, ctx.experts_per_rank, ctx.topk
+    ph = ctx.calls
+    timeout = U.get_int_env("TD_HOST_TIMEOUT_US", 60_000_000)
+    so, ids_sorted, doff = send_off.tolist(), srt.sorted_ids, dest_off.tolist()
+    for e in range(epr):                                     # experts in the order the destination consumes them
+        for q in range(W):
+            d = (me + q) % W
+            g = d * epr + e
+            n = so[g + 1] - so[g]
+            if n:
+                pairs = ids_sorted[so[g]:so[g + 1]].long()
+                rows = torch.arange(doff[g], doff[g] + n)
+                keep = rows < ctx.rows_cap
+                heap.peer_view(ctx.rx, d)[par][rows[keep]] = x[pairs[keep] // topk]
+                heap.peer_view(ctx.meta, d)[par][rows[keep]] = ((me << 24) | pairs[keep]).to(torch.int32)
+            flag = ctx.flags[par, e, me, 0:1]
+            lib.tdh_notify32(ctypes.c_void_p(heap.peer_ptr(flag.data_ptr(), d)), ph, 1)
+    N = w_gate_up.shape[1]
+    h = torch.zeros((ctx.rows_cap, N), dtype=x.dtype)
+    te = tile_expert.tolist()
+    seen = set()
+    for t, e in enumerate(te):
+        if e < 0:
+            continue
+        if e not in seen:                                    # the tile's expert: all sources have delivered
+            for s_ in range(W):
+                if lib.tdh_wait32(ctypes.c_void_p(ctx.flags[par, e, s_, 0:1].data_ptr()), ph, 1, timeout):
+                    raise TimeoutError(f"mega_ep: rows of expert {e} from rank {s_} never arrived (call {ph})")
+            seen.add(e)
+        r0 = t * _TILE
+        h[r0:r0 + _TILE] = (ctx.rx[par][r0:r0 + _TILE].float() @ w_gate_up[e].float().t()).to(x.dtype)
+    route = torch.where(valid, ctx.meta[par], torch.full_like(ctx.meta[par], -1)).contiguous()
+    return h, EPMegaHandle(tile_expert, route, n_rows, par, x.shape[0], tot_me, eoff_me)
+
+
+def _gemm_combine_host(ctx, act, handle, w_down, topk_weights):
+    import ctypes
+    heap, lib = U.get_heap(), _C.host_lib()
+    W, me = ctx.world_size, ctx.rank
+    ph, par = ctx.calls, handle.parity
+    timeout = U.get_int_env("TD_HOST_TIMEOUT_US", 60_000_000)
+    route = handle.route
+    for t, e in enumerate(handle.tile_expert.tolist()):
+        if e < 0:
+            continue
+        r0 = t * _TILE
+        y = (act[r0:r0 + _TILE].float() @ w_down[e].float().t()).to(act.dtype)
+        rt = route[r0:r0 + _TILE]
+        for s_ in range(W):                                  # the epilogue's remote scatter: row -> (owner, pair slot)
+            m = (rt >= 0) & ((rt >> 24) == s_)
+            if m.any():
+                heap.peer_view(ctx.comb, s_)[par][(rt[m] & 0xFFFFFF).long()] = y[m]
+    for d in range(W):
+        lib.tdh_notify32(ctypes.c_void_p(heap.peer_ptr(ctx.done[par * W + me:par * W + me + 1].data_ptr(), d)), ph, 1)
+    for s_ in range(W):
+        if lib.tdh_wait32(ctypes.c_void_p(ctx.done[par * W + s_:par * W + s_ + 1].data_ptr()), ph, 1, timeout):
+            raise TimeoutError(f"mega_ep: rank {s_} never finished its combine stores (call {ph})")
     T = handle.T
     return M.reduce_topk(ctx.comb[par][:T * ctx.topk], topk_weights.to(torch.float32), ctx.topk)
 
