@@ -1,5 +1,9 @@
 #!/bin/bash
-# One GPU session (edited per session; results land in gpurun_out/).  Usage: gpurun -- bash scripts/gpu_run.sh <stage>
+# GPU validation stages (results land in gpurun_out/; the summaries that matter are copied to profiles/).
+#   gpurun            -- bash scripts/gpu_run.sh a        1 GPU : smoke, GEMM tests, bench (ours + reference arm), all GPU tests
+#   gpurun --gpus N   -- bash scripts/gpu_run.sh b|d|e|f|g N    : distributed cases / op benchmarks / traces at N = 2
+#   gpurun --gpus 8   -- bash scripts/gpu_run.sh c|h 8          : full bench, all distributed cases, MoE / Mega-EP / Qwen3 benchmarks
+# every multi-rank command runs under its own `timeout` (a hang must never reach gpurun's limit)
 set -x
 mkdir -p gpurun_out
 export TD_NO_AUTOBUILD=1

@@ -634,6 +634,18 @@ def case_sp_pp():
     z = uly.post_attn_a2a(y)
     assert torch.equal(z.cpu(), x.cpu())
     uly.finalize()
+    # q, k, v in ONE packed all-to-all
+    from triton_dist.parallel.sp import UlyssesQKVPackAllToAll
+    Hkv_u = W
+    pk = UlyssesQKVPackAllToAll(S_l, H, Hkv_u, D, dtype, me, W)
+    kfull = torch.randn(S_l * W, Hkv_u, D, generator=g).to(dtype).to(dev)
+    vfull = torch.randn(S_l * W, Hkv_u, D, generator=g).to(dtype).to(dev)
+    sl = slice(me * S_l, (me + 1) * S_l)
+    for _ in range(3):
+        q2, k2, v2 = pk(full[sl].contiguous(), kfull[sl].contiguous(), vfull[sl].contiguous())
+        assert torch.equal(q2.cpu(), full[:, me * (H // W):(me + 1) * (H // W)].cpu())
+        assert torch.equal(k2.cpu(), kfull[:, me:me + 1].cpu()) and torch.equal(v2.cpu(), vfull[:, me:me + 1].cpu())
+    pk.finalize()
     # ---- SP flash decode ----
     B, Hq, Hkv, L_l = 2, 4, 1, 40
     q = torch.randn(B, Hq, D, generator=g).to(dtype).to(dev)

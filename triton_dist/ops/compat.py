@@ -88,21 +88,23 @@ class SpUlysessQKVGemmAll2AllKernel:
     def __init__(self, max_local_seq: int, num_q_heads: int, num_kv_heads: int, head_dim: int, dtype, rank: int, world_size: int):
         from ..parallel.sp import UlyssesSPAllToAllLayer
         self.Hq, self.Hkv, self.D, self.W = num_q_heads, num_kv_heads, head_dim, world_size
+        from ..parallel.sp import UlyssesQKVPackAllToAll
         self.a2a_q = UlyssesSPAllToAllLayer(max_local_seq, num_q_heads, head_dim, dtype, rank, world_size)
         self.a2a_kv = UlyssesSPAllToAllLayer(max_local_seq, num_kv_heads, head_dim, dtype, rank, world_size)
+        self.pack = UlyssesQKVPackAllToAll(max_local_seq, num_q_heads, num_kv_heads, head_dim, dtype, rank, world_size)
 
     def forward(self, x: torch.Tensor, wqkv: torch.Tensor):
+        """QKV GEMM on the tcgen05 kernel, then q, k, v in ONE packed all-to-all (the fully fused alternative -- the all-to-all in
+        the GEMM epilogue -- is :func:`triton_dist.ops.gemm_a2a.gemm_all_to_all`, see ``ulysses_sp_infer_gemm_a2a_op``)."""
         qkv = _lin(x, wqkv)
         S = x.shape[0]
         q, k, v = qkv.split([self.Hq * self.D, self.Hkv * self.D, self.Hkv * self.D], dim=-1)
-        return (self.a2a_q.pre_attn_a2a(q.reshape(S, self.Hq, self.D).contiguous()),
-                self.a2a_kv.pre_attn_a2a(k.reshape(S, self.Hkv, self.D).contiguous()),
-                self.a2a_kv.pre_attn_a2a(v.reshape(S, self.Hkv, self.D).contiguous()))
+        return self.pack(q.reshape(S, self.Hq, self.D), k.reshape(S, self.Hkv, self.D), v.reshape(S, self.Hkv, self.D))
 
     pre_attn_a2a = qkv_pack_a2a = forward
 
     def finalize(self):
-        self.a2a_q.finalize(); self.a2a_kv.finalize()
+        self.a2a_q.finalize(); self.a2a_kv.finalize(); self.pack.finalize()
 
 
 class SpUlysessOAll2AllGemmKernel:
@@ -168,8 +170,8 @@ def create_ulysses_sp_pre_attn_comm_context(max_local_seq: int, num_q_heads: int
 
 
 def pre_attn_qkv_pack_a2a_op(ctx: SpUlysessQKVGemmAll2AllKernel, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor):
-    """(ulysses_sp_dispatch.py:606) seq-sharded ``[S/W, H, D]`` q/k/v -> head-sharded ``[S, H/W, D]``."""
-    return ctx.a2a_q.pre_attn_a2a(q), ctx.a2a_kv.pre_attn_a2a(k), ctx.a2a_kv.pre_attn_a2a(v)
+    """(ulysses_sp_dispatch.py:606) seq-sharded ``[S/W, H, D]`` q/k/v -> head-sharded ``[S, H/W, D]``: ONE packed all-to-all."""
+    return ctx.pack(q, k, v)
 
 
 def qkv_bsnd_to_bnsd(x: torch.Tensor) -> torch.Tensor:
@@ -204,12 +206,17 @@ def fused_sp_ag_attn_inter_node(ctx, q_shard, k_shard, v_shard, **kw):
 
 
 # ---- ep_all2all_fused.py (Mega-EP entry points) -------------------------------------------------------------------
-def mega_kernel_dispatch_token_moe_grouped_gemm(ep_moe, x: torch.Tensor, topk_idx: torch.Tensor, topk_w: torch.Tensor):
-    """(ep_all2all_fused.py:839) dispatch + first grouped GEMM (+SwiGLU): returns the packed activations and the handle
-    combine needs.  ``ep_moe`` is a :class:`triton_dist.parallel.ep.EP_MoE`."""
-    return ep_moe.dispatch_group_gemm(x, topk_idx, topk_w)
+def mega_kernel_dispatch_token_moe_grouped_gemm(op, x: torch.Tensor, topk_idx: torch.Tensor, topk_w: torch.Tensor, w_gate_up=None):
+    """(ep_all2all_fused.py:839) dispatch fused with the first grouped GEMM (+ SwiGLU): returns the activations in the expert-sorted
+    layout and the handle the second half needs.  ``op``: a :class:`triton_dist.parallel.ep.EpAll2AllFusedOp` (ONE kernel,
+    csrc/gemm_sm100.cuh mode kEPD; pass ``w_gate_up``) or an :class:`~triton_dist.parallel.ep.EP_MoE` layer (its own weights)."""
+    if hasattr(op, "mega_dispatch_group_gemm"):
+        return op.mega_dispatch_group_gemm(x, topk_idx, topk_w, w_gate_up)
+    return op.dispatch_group_gemm(x, topk_idx, topk_w)
 
 
-def mega_kernel_moe_grouped_gemm_combine_token(ep_moe, act: torch.Tensor, handle):
-    """(ep_all2all_fused.py:1020) second grouped GEMM + combine (weighted top-k reduce on the source rank)."""
-    return ep_moe.group_gemm_combine(act, handle)
+def mega_kernel_moe_grouped_gemm_combine_token(op, act: torch.Tensor, handle, w_down=None):
+    """(ep_all2all_fused.py:1020) second grouped GEMM fused with the combine transfer (mode kEPC) + weighted top-k reduce on the owner."""
+    if hasattr(op, "mega_group_gemm_combine"):
+        return op.mega_group_gemm_combine(act, handle, w_down)
+    return op.group_gemm_combine(act, handle)

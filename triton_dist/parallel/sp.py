@@ -244,3 +244,36 @@ class UlyssesSPAllToAllLayer:
 
     def finalize(self):
         self.ctx.finalize()
+
+
+class UlyssesQKVPackAllToAll:
+    """q, k and v in ONE all-to-all (reference ulysses_sp_dispatch.py:39-277 packs the three tensors per destination inside its
+    kernel): the heads every destination owns -- Hq/W query heads and Hkv/W key and value heads -- are packed into one
+    ``[(Hq + 2 Hkv) / W * D]``-wide row per local token (one copy pass), a single launch of the all-to-all kernel moves them
+    (one fence + one flag round instead of three), and the results are views of the receive buffer."""
+
+    def __init__(self, max_local_seq: int, num_q_heads: int, num_kv_heads: int, head_dim: int, dtype: torch.dtype, rank: int, world_size: int):
+        assert num_q_heads % world_size == 0 and num_kv_heads % world_size == 0
+        self.rank, self.world_size = rank, world_size
+        self.Hq, self.Hkv, self.D = num_q_heads, num_kv_heads, head_dim
+        self.cols = (num_q_heads + 2 * num_kv_heads) // world_size * head_dim
+        self.ctx = create_all_to_all_single_2d_context(max_local_seq, self.cols, dtype)
+
+    def forward(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor):
+        """q ``[S/W, Hq, D]``, k / v ``[S/W, Hkv, D]`` -> q ``[S, Hq/W, D]``, k / v ``[S, Hkv/W, D]``."""
+        W, D = self.world_size, self.D
+        S_l = q.shape[0]
+        hq, hkv = self.Hq // W, self.Hkv // W
+        send = torch.empty((W, S_l, self.cols), dtype=q.dtype, device=q.device)
+        send[:, :, :hq * D] = q.view(S_l, W, hq * D).transpose(0, 1)
+        send[:, :, hq * D:(hq + hkv) * D] = k.view(S_l, W, hkv * D).transpose(0, 1)
+        send[:, :, (hq + hkv) * D:] = v.view(S_l, W, hkv * D).transpose(0, 1)
+        recv = all_to_all_single_2d(self.ctx, send.view(W * S_l, self.cols))
+        r = recv.view(W * S_l, self.cols)
+        return (r[:, :hq * D].reshape(W * S_l, hq, D), r[:, hq * D:(hq + hkv) * D].reshape(W * S_l, hkv, D),
+                r[:, (hq + hkv) * D:].reshape(W * S_l, hkv, D))
+
+    __call__ = forward
+
+    def finalize(self):
+        self.ctx.finalize()
