@@ -265,9 +265,9 @@ class UlyssesQKVPackAllToAll:
         S_l = q.shape[0]
         hq, hkv = self.Hq // W, self.Hkv // W
         send = torch.empty((W, S_l, self.cols), dtype=q.dtype, device=q.device)
-        send[:, :, :hq * D] = q.view(S_l, W, hq * D).transpose(0, 1)
-        send[:, :, hq * D:(hq + hkv) * D] = k.view(S_l, W, hkv * D).transpose(0, 1)
-        send[:, :, (hq + hkv) * D:] = v.view(S_l, W, hkv * D).transpose(0, 1)
+        send[:, :, :hq * D] = q.reshape(S_l, W, hq * D).transpose(0, 1)
+        send[:, :, hq * D:(hq + hkv) * D] = k.reshape(S_l, W, hkv * D).transpose(0, 1)
+        send[:, :, (hq + hkv) * D:] = v.reshape(S_l, W, hkv * D).transpose(0, 1)
         recv = all_to_all_single_2d(self.ctx, send.view(W * S_l, self.cols))
         r = recv.view(W * S_l, self.cols)
         return (r[:, :hq * D].reshape(W * S_l, hq, D), r[:, hq * D:(hq + hkv) * D].reshape(W * S_l, hkv, D),
