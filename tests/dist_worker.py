@@ -259,6 +259,48 @@ def case_gemm_ar():
         ctx.finalize()
 
 
+def case_a2a():
+    """Device-split all-to-all family (low_latency_all_to_all.py / all_to_all_vdev_2d_offset.py): packed splits and the offset
+    variant (rows of every (rank, expert) segment start at arbitrary offsets of the send buffer) vs a gathered golden."""
+    from triton_dist.ops.all_to_all import all_to_all_vdev_2d, create_all_to_all_context
+    from triton_dist.ops.compat import all_to_all_vdev_2d_offset
+    dev = U.current_device()
+    W, me = U.world_size(), U.rank()
+    big = dev.type == "cuda"
+    dtype = torch.bfloat16 if big else torch.float32
+    g_, Hd, max_m = 2, 64, 48
+    ctx = create_all_to_all_context(max_m, Hd, experts_per_rank=g_, dtype=dtype)
+    grp = U.get_triton_dist_world()
+    for it in range(4):
+        gen = torch.Generator().manual_seed(31 + it)                      # every rank draws ALL ranks' splits (same seed)
+        all_sp = torch.randint(0, 7, (W, W * g_), generator=gen)
+        sp = all_sp[me].to(torch.int32).to(dev)
+        n = int(all_sp[me].sum())
+        x = (torch.randn(n, Hd, generator=torch.Generator().manual_seed(100 * it + me)) * 0.5).to(dtype).to(dev)
+        out, out_sp = all_to_all_vdev_2d(ctx, x, sp)
+        # golden: rank s's rows for me are its segments [me*g_, (me+1)*g_)
+        exp = []
+        for s_ in range(W):
+            xs = (torch.randn(int(all_sp[s_].sum()), Hd, generator=torch.Generator().manual_seed(100 * it + s_)) * 0.5).to(dtype)
+            c = torch.cumsum(all_sp[s_], 0)
+            lo, hi = int(c[me * g_] - all_sp[s_][me * g_]), int(c[(me + 1) * g_ - 1])
+            exp.append(xs[lo:hi])
+        exp = torch.cat(exp)
+        assert torch.equal(out.cpu().float(), exp.float()), f"a2a it{it}"
+        assert torch.equal(out_sp.cpu(), all_sp[:, me * g_:(me + 1) * g_].to(torch.int32))
+        # offset variant: the same segments scattered over a larger buffer with gaps
+        gap = 3
+        offs = (torch.cumsum(all_sp[me] + gap, 0) - all_sp[me] - gap + 1).to(torch.int32)
+        big_buf = torch.zeros(n + gap * W * g_ + 4, Hd, dtype=dtype, device=dev)
+        c = torch.cumsum(all_sp[me], 0) - all_sp[me]
+        for j in range(W * g_):
+            big_buf[int(offs[j]):int(offs[j]) + int(all_sp[me][j])] = x[int(c[j]):int(c[j]) + int(all_sp[me][j])]
+        out2, _ = all_to_all_vdev_2d_offset(ctx, big_buf, sp, offs.to(dev), g_)
+        assert torch.equal(out2.cpu().float(), exp.float()), f"a2a offset it{it}"
+    U.barrier_all_host()
+    ctx.finalize()
+
+
 def case_gemm_q8():
     """Quantised fused ops: int8 x scale GEMM + AllReduce (reference gemm_allreduce.py:383-447) and int8 / per-tensor fp8 gemm_rs
     (test_gemm_rs.py:130-145) vs fp32 math on the dequantised operands + NCCL."""

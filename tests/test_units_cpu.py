@@ -383,3 +383,33 @@ def test_allreduce_zero_copy_contract():
         ctx.zero_copy_ok(base + 1024 + 16, False)                        # offset view
     x = ctx.symm_input(64, torch.float32)
     assert x.data_ptr() == base + 1024
+
+
+def test_checkpoint_loading_matches_hf_logits(tmp_path):
+    """Weight loading: a HF-format Qwen3 checkpoint written to disk is loaded through ``AutoLLM.from_pretrained``
+    (``random_init=False``, local directory: config.json -> ArchConfig, safetensors -> sharded TP weights) and the prefill logits
+    match the HF model's own forward."""
+    transformers = pytest.importorskip("transformers")
+    import triton_dist.utils as U
+    from triton_dist.models import AutoLLM, KV_Cache, ModelConfig
+    try:
+        cfg_hf = transformers.Qwen3Config(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4,
+                                          num_key_value_heads=2, head_dim=128, vocab_size=320, max_position_embeddings=128,
+                                          tie_word_embeddings=False, rope_theta=1e6)
+        torch.manual_seed(0)
+        hf = transformers.Qwen3ForCausalLM(cfg_hf).to(torch.float32).eval()
+    except Exception as e:      # noqa: BLE001
+        pytest.skip(f"transformers cannot build a Qwen3 model here: {e}")
+    hf.save_pretrained(str(tmp_path))
+    U.initialize_distributed(seed=0)
+    mc = ModelConfig(model_name=str(tmp_path), max_length=32, dtype=torch.float32, rank=0, world_size=1, random_init=False)
+    m = AutoLLM.from_pretrained(mc)
+    assert m.num_layers == 2 and m.head_dim == 128
+    ids = torch.randint(0, 320, (2, 7))
+    kv = KV_Cache(m.num_layers, 2, 32, m.num_key_value_heads, m.head_dim, torch.float32, 1, "cpu")
+    pos = torch.arange(7)[None, :].expand(2, -1).contiguous()
+    logits = m.inference(ids, pos, kv)
+    with torch.no_grad():
+        ref = hf(ids).logits[:, -1]
+    got = logits if logits.dim() == 2 else logits[:, -1]
+    torch.testing.assert_close(got.float(), ref.float(), atol=2e-3, rtol=2e-3)

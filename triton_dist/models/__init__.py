@@ -17,7 +17,11 @@ class AutoLLM:
     def from_pretrained(model_config: ModelConfig, group=None):
         cls = AutoLLM.model_mapping().get(model_config.model_name)
         if cls is None:
-            raise KeyError(f"unsupported model {model_config.model_name}")
+            import os
+            if os.path.isfile(os.path.join(model_config.model_name, "config.json")):     # local HF checkpoint directory
+                cls = Qwen3MoE if model_config.arch().num_experts else DenseLLM
+            else:
+                raise KeyError(f"unsupported model {model_config.model_name}")
         return cls(model_config, group)
 
 

@@ -46,6 +46,23 @@ ARCHS = {
 }
 
 
+def arch_from_hf_config(path: str) -> ArchConfig:
+    """ArchConfig of a local HF checkpoint directory (``config.json``), the way the reference reads ``AutoConfig``
+    (models/dense.py:126-135)."""
+    import json
+    import os
+    c = json.load(open(os.path.join(path, "config.json")))
+    heads = c["num_attention_heads"]
+    return ArchConfig(
+        hidden_size=c["hidden_size"], intermediate_size=c.get("intermediate_size", 0), num_hidden_layers=c["num_hidden_layers"],
+        num_attention_heads=heads, num_key_value_heads=c.get("num_key_value_heads", heads),
+        head_dim=c.get("head_dim") or c["hidden_size"] // heads, vocab_size=c["vocab_size"],
+        rms_norm_eps=c.get("rms_norm_eps", 1e-6), rope_theta=c.get("rope_theta", 1e6),
+        qk_norm="qwen3" in c.get("model_type", "").lower(), tie_word_embeddings=c.get("tie_word_embeddings", False),
+        num_experts=c.get("num_experts", 0) or 0, num_experts_per_tok=c.get("num_experts_per_tok", 0) or 0,
+        moe_intermediate_size=c.get("moe_intermediate_size", 0) or 0, norm_topk_prob=c.get("norm_topk_prob", True))
+
+
 @dataclass
 class ModelConfig:
     model_name: str = "Qwen/Qwen3-32B"
@@ -59,9 +76,13 @@ class ModelConfig:
     num_layers_override: Optional[int] = None
 
     def arch(self) -> ArchConfig:
-        if self.model_name not in ARCHS:
-            raise KeyError(f"unknown architecture '{self.model_name}'; known: {sorted(ARCHS)}")
-        a = ARCHS[self.model_name]
+        import os
+        if self.model_name not in ARCHS and os.path.isfile(os.path.join(self.model_name, "config.json")):
+            a = arch_from_hf_config(self.model_name)          # a local HF checkpoint directory (weights are loaded from it)
+        elif self.model_name not in ARCHS:
+            raise KeyError(f"unknown architecture '{self.model_name}'; known: {sorted(ARCHS)} (or a local HF checkpoint directory)")
+        else:
+            a = ARCHS[self.model_name]
         if self.num_layers_override:
             import dataclasses
             a = dataclasses.replace(a, num_hidden_layers=self.num_layers_override)

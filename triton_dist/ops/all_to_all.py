@@ -179,5 +179,3 @@ def all_to_all_vdev_2d(ctx: AllToAllContext, x: torch.Tensor, in_splits: torch.T
     return all_to_all_post_process(ctx, splits, recv), splits.clone()
 
 
-all_to_all_vdev_2d_offset = all_to_all_vdev_2d
-all_to_all_v_offset_op = all_to_all_vdev_2d

@@ -185,16 +185,17 @@ def qkv_bsnd_to_bnsd(x: torch.Tensor) -> torch.Tensor:
 def all_to_all_vdev_2d_offset(ctx: AllToAllContext, send: torch.Tensor, in_splits: torch.Tensor, in_offsets: torch.Tensor,
                               experts_per_rank: int):
     """(all_to_all_vdev_2d_offset.py) variable all-to-all where the rows for (dst rank d, local expert e) start at
-    ``in_offsets[d * epr + e]`` (the rows are not packed).  The send buffer is compacted with one gather, then the
-    device-split all-to-all kernel runs; returns ``(recv, recv_splits[W, epr], recv_offsets)``."""
+    ``in_offsets[d * epr + e]`` (the rows are not packed).  The send buffer is compacted with ONE device-side gather whose index
+    is built without reading the splits on the host (positions beyond the total are dummies the kernel never sends), then the
+    device-split all-to-all kernel runs; returns ``(recv, recv_splits[W, epr])``."""
     from .all_to_all import all_to_all_vdev_2d
-    n = in_splits.numel()
-    cum = torch.cumsum(in_splits.to(torch.int64), 0)
-    total = int(cum[-1].item()) if n else 0
-    seg = torch.repeat_interleave(torch.arange(n, device=send.device), in_splits.to(torch.int64), output_size=total)
-    within = torch.arange(total, device=send.device) - (cum - in_splits.to(torch.int64))[seg]
-    rows = in_offsets.to(torch.int64)[seg] + within
-    return all_to_all_vdev_2d(ctx, send.index_select(0, rows).contiguous(), in_splits, experts_per_rank)
+    sp = in_splits.to(torch.int64)
+    cum = torch.cumsum(sp, 0)
+    R = send.shape[0]                                   # static upper bound of the packed length: no .item()
+    pos = torch.arange(R, device=send.device)
+    seg = torch.searchsorted(cum, pos, right=True).clamp(max=sp.numel() - 1)
+    rows = torch.where(pos < cum[-1], in_offsets.to(torch.int64)[seg] + pos - (cum - sp)[seg], torch.zeros_like(pos))
+    return all_to_all_vdev_2d(ctx, send.index_select(0, rows.clamp(0, R - 1)).contiguous(), in_splits)
 
 
 # ---- sp_ag_attention_inter_node.py --------------------------------------------------------------------------------
