@@ -83,6 +83,20 @@ def case_allgather():
         assert torch.equal(bufs[me].cpu().view(-1), ref.cpu())
         assert torch.all(flags[me][:W].cpu() == it)
         U.barrier_all_on_stream()
+    # ring producers (1-D: W-1 hops; 2-D: ring inside a group + across groups), same buffers, later signal values
+    from triton_dist.ops.allgather import AllGatherMethod, cp_engine_producer_all_gather
+    sig = 4
+    for method in (AllGatherMethod.Ring1D_IntraNode, AllGatherMethod.Ring2D_IntraNode):
+        for it in range(3):
+            local = torch.randn(64, 32, device=dev)
+            cp_engine_producer_all_gather(me, W, local, bufs, flags, signal_value=sig, method=method)
+            if dev.type == "cuda":
+                torch.cuda.synchronize()
+            ref = torch.empty(64 * W * 32, device=dev)
+            dist.all_gather_into_tensor(ref, local.view(-1), group=U.get_triton_dist_world())
+            assert torch.equal(bufs[me].cpu().view(-1), ref.cpu()), (method, it)
+            U.barrier_all_host()                               # nobody overwrites a buffer a peer is still checking
+            sig += 1
     ctx.finalize()
 
 
