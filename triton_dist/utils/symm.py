@@ -207,14 +207,15 @@ class SymmetricHeap:
             # ship rank 0's fd to everyone: reuse the all-to-all exchanger (every rank contributes a dummy fd)
             dummy = fd if self.rank == 0 else os.open(os.devnull, os.O_RDONLY)
             fds = _exchange_fds(dummy, self.rank, self.world, self.group)
-            if self.rank != 0:
-                _C.check(lib.td_heap_mc_import(h, fds[0]), "td_heap_mc_import")
+            # never raise between collectives: a local failure becomes a status every rank sees in the next all-gather,
+            # so all ranks take the same (fallback) path instead of pairing mismatched collectives
+            imp_rc = lib.td_heap_mc_import(h, fds[0]) if self.rank != 0 else 0
             for f in fds:
                 try:
                     os.close(f)
                 except OSError:
                     pass
-            rc = lib.td_heap_mc_add_device(h)
+            rc = lib.td_heap_mc_add_device(h) if imp_rc == 0 else 1
             rcs = [None] * self.world
             dist.all_gather_object(rcs, rc, group=self.group)
             if any(rcs):
