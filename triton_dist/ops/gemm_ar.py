@@ -107,6 +107,9 @@ def default_ar_config(M: int, N: int, K: int, n_comm: int = 16, num_sms: int = 1
     return GemmConfig(bn=bn, cta_group=1, group_m=8, use_tma_store=False, n_comm_ctas=max(n_comm, min(64, num_sms - tiles)))
 
 
+_FUSED_MAX_M = 32      # rows up to which the one-kernel GEMM + AllReduce is the auto choice (see low_latency_gemm_allreduce_op)
+
+
 def low_latency_gemm_allreduce_op(ctx: GemmARContext, a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None,
                                   gemm_config: Optional[GemmConfig] = None, straggler_option=None, A_scale=None, B_scale=None,
                                   **ref_hints) -> torch.Tensor:
@@ -129,6 +132,11 @@ def low_latency_gemm_allreduce_op(ctx: GemmARContext, a: torch.Tensor, b: torch.
         part = gemm(a, w)
         return comm.all_reduce(part, None, ctx.ar_ctx, output=out, straggler_option=straggler_option)
     assert M <= ctx.max_M and N == ctx.N
+    if gemm_config is None and M > _FUSED_MAX_M and not U.get_bool_env("TD_GEMM_AR_FORCE_FUSED", False):
+        # measured on 8xB200 (profiles/extras_8xB200.json): the single kernel wins at M = 16 (30.0 vs 31.8 us) but loses at M = 128
+        # (75 vs 44 us: few comm CTAs reduce many tiles, ~2 us NVLS round trip each) -> above the crossover take the two-kernel path
+        # (tcgen05 GEMM into the device-selected staging half, then the two-shot NVLS all-reduce) unless a config is given explicitly
+        return gemm_allreduce_op(ctx, a, w, out, None, straggler_option=straggler_option)
     if out is None:
         out = torch.empty((M, N), dtype=a.dtype, device=a.device)
     if straggler_option and straggler_option[0] == ctx.rank:
