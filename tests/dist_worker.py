@@ -816,6 +816,42 @@ def case_ep_moe():
         moe.finalize()
 
 
+def case_lk():
+    """Kernels written in the Python DSL (triton_dist.lk) on the symmetric heap: ring shift + push all-gather.  GPU backend: the
+    generated CUDA is launched; emulation backend: the same Python source runs in the CPU interpreter (threads emulated), with
+    symm_at / notify / wait on the shared-memory heap."""
+    from triton_dist import lk
+    from triton_dist.lk.kernels import simt as K
+    W, me = U.world_size(), U.rank()
+    n = 200
+    dst = U.nvshmem_create_tensor((n,), torch.float32)
+    out = U.nvshmem_create_tensor((W * n,), torch.float32)
+    flags = U.nvshmem_create_tensor((16 + W,), torch.int32)
+    flags.zero_()
+    U.barrier_all_on_stream()
+    ctx = lk.symm_ctx()
+    gpu = dst.is_cuda
+
+    def run(kernel, grid, *args):
+        if gpu:
+            kernel[grid](*args)
+        else:
+            kernel.interpret(grid, *args)
+
+    for phase in range(1, 4):
+        src = torch.arange(n, dtype=torch.float32, device=dst.device) + 1000.0 * me + phase
+        run(K.ring_shift, 1, ctx, src, dst, flags[0:1], n, phase)
+        prev = (me - 1 + W) % W
+        _assert_close(dst, torch.arange(n, dtype=torch.float32) + 1000.0 * prev + phase, 0, 0, f"lk ring_shift phase {phase}")
+        shard = torch.full((n,), float(me * 10 + phase), dtype=torch.float32, device=dst.device)
+        run(K.allgather_push, W, ctx, shard, out, flags[16:], n, phase)
+        want = torch.cat([torch.full((n,), float(r * 10 + phase)) for r in range(W)])
+        _assert_close(out, want, 0, 0, f"lk allgather_push phase {phase}")
+        U.barrier_all_on_stream()        # nobody overwrites dst / out of a rank that is still checking them
+    for t in (flags, out, dst):
+        U.nvshmem_free_tensor_sync(t)
+
+
 def case_mega():
     """Megakernel decode step (task graph + scoreboard + in-kernel all-reduce) vs the layer-by-layer TP model."""
     from triton_dist.models import AutoLLM, KV_Cache, ModelConfig

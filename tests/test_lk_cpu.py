@@ -1,0 +1,195 @@
+"""The Python kernel DSL (triton_dist.lk) without a GPU: generated C++ text, nvcc cross-compilation for sm_100a (incl. the tcgen05 GEMM
+ladder: the SASS must contain the Blackwell tensor-core / TMA instructions), and the CPU interpreter against PyTorch.
+Reference test strategy: python/little_kernel/tests/unit/* (pure-python codegen tests that run without a GPU)."""
+import shutil
+import subprocess
+
+import pytest
+import torch
+
+from triton_dist import lk
+from triton_dist.lk import CompileError, ll
+from triton_dist.lk.kernels import simt as K
+
+N_CONST = 4
+
+
+def _body(kernel) -> str:
+    src = kernel.cuda_source()
+    return src[src.index('extern "C" __global__'):src.index('extern "C" int lk_launch')]
+
+
+def test_codegen_types_and_scoping():
+    @lk.kernel(block=64)
+    def k(x: ll.ptr[ll.bf16], y: ll.ptr[ll.f32], n: ll.i32, s: ll.u32):
+        i = ll.blockIdx.x * 64 + ll.threadIdx.x
+        if i < n:
+            v = x[i] * 2            # bf16 * literal -> computed in fp32
+        else:
+            v = 0.0                 # same variable in both arms: ONE declaration at function scope (Python scoping)
+        w = s >> 1                  # unsigned stays unsigned, the literal adopts the type
+        q = i // 3 + i % 3          # integer floor-div / mod
+        r = i / 4                   # true division of ints -> float
+        y[i] = v + w + q + r
+    body = _body(k)
+    assert "__launch_bounds__(64)" in body and "__nv_bfloat16* x" in body
+    assert body.count("float v;") == 1 and "uint32_t w;" in body and "int q;" in body and "float r;" in body
+    assert "((float)(x[i])) * 2.0f" in body
+    assert "(s >> 1u)" in body and "(i / 3)" in body and "(i % 3)" in body and "((float)(i) / (float)(4))" in body
+
+
+def test_codegen_constants_static_loops_and_pruning():
+    FLAG = False
+
+    @lk.kernel
+    def k(y: ll.ptr[ll.i32]):
+        acc: ll.i32 = 0
+        for j in ll.static_range(N_CONST):          # unrolled by the code generator, j is a constant in the body
+            acc += j * 10
+        if FLAG:                                    # closure constant: the branch is pruned
+            acc = -1
+        if N_CONST > 2 and ll.threadIdx.x == 0:     # constant part of the condition folds away
+            y[0] = acc + (N_CONST << 2)
+    body = _body(k)
+    assert "for (" not in body and "acc = (acc + 30);" in body and "-1" not in body
+    assert "if ((((int)threadIdx.x) == 0))" in body and "(acc + 16)" in body
+
+
+def test_codegen_device_function_specialisation():
+    def scale(v, f: ll.constexpr):
+        return v * f
+
+    @lk.kernel
+    def k(a: ll.ptr[ll.f32], b: ll.ptr[ll.i32]):
+        a[0] = scale(a[1], 2.0)
+        a[2] = scale(a[3], 2.0)          # same types + same constant: one specialisation
+        b[0] = scale(b[1], 3)            # int operand, other constant: a second one
+    src = k.cuda_source()
+    assert src.count("__device__ __forceinline__ float lk_scale__0(float v)") == 1
+    assert src.count("__device__ __forceinline__ int lk_scale__1(int v)") == 1
+    assert src.count("lk_scale__0(") == 3 and "(v * 3)" in src and "(v * 2.0f)" in src
+
+
+def test_codegen_shared_memory_layout_and_intrinsics():
+    @lk.kernel(block=128, cluster=(2, 1, 1))
+    def k(t: ll.TmaDescriptor, out: ll.ptr[ll.u32]):
+        ll.align_memory(1024)
+        tile = ll.dyn_shared([2, 128 * 64], ll.bf16, align=1024)
+        bar = ll.dyn_shared([2], ll.u64)
+        st = ll.shared([4, 8], ll.f32)
+        st[1, 2] = 1.0
+        if ll.warp_id() == 0 and ll.elect_one():
+            ll.mbar_init(bar + 1, 1)
+            ll.fence_barrier_init()
+            ll.mbar_arrive_expect_tx(bar + 1, 128 * 64 * 2)
+            ll.tma_load_2d(t, bar + 1, tile[1], 0, 0)
+        ll.cluster_sync()
+        ll.mbar_wait(bar + 1, 0)
+        out[0] = ll.smem_addr(tile[1]) + ll.cluster_rank()
+    body = _body(k)
+    assert "const __grid_constant__ CUtensorMap t" in body
+    assert "reinterpret_cast<__nv_bfloat16*>(lk_dyn + 0)" in body and "reinterpret_cast<uint64_t*>(lk_dyn + 32768)" in body
+    assert "__shared__ __align__(16) float st[32];" in body and "st[10] = 1.0f;" in body
+    assert "td::ptx::tma_load_2d(&t, (bar + (1)), (tile + 8192), 0, 0)" in body
+    assert k.dyn_smem_bytes == 32768 + 16 + 1024          # carve + alignment slack
+    assert "lk_dyn_raw + ((1024u - (td::ptx::smem_u32(lk_dyn_raw) & 1023u)) & 1023u)" in body
+
+
+def test_compile_errors_are_located():
+    @lk.kernel
+    def undefined(y: ll.ptr[ll.f32]):
+        y[0] = nope        # noqa: F821
+
+    @lk.kernel
+    def bad_break(y: ll.ptr[ll.f32]):
+        for j in ll.static_range(4):
+            if y[j] > 0:
+                break
+
+    @lk.kernel
+    def runtime_constexpr(y: ll.ptr[ll.i32]):
+        n: ll.constexpr = y[0]
+
+    @lk.kernel
+    def no_annotation(y):
+        pass
+
+    for kern, frag in ((undefined, "'nope' is not defined"), (bad_break, "statically unrolled"), (runtime_constexpr, "constexpr"),
+                       (no_annotation, "type annotation")):
+        with pytest.raises(CompileError) as e:
+            kern.cuda_source()
+        assert frag in str(e.value) and kern.name in str(e.value)
+
+
+def test_inline_asm_and_casts():
+    @lk.kernel
+    def k(p: ll.ptr[ll.u32], q: ll.ptr[ll.f32]):
+        v: ll.u32 = 0
+        ll.asm("mov.u32 %0, %%smid;", outputs=[v], memory=False)
+        ll.asm("red.release.sys.global.add.u32 [%0], %1;", inputs=[p, v])
+        q[0] = ll.uint_as_float(ll.u32(ll.i64(v) << 3))
+        b = ll.ptr_cast(q, ll.u8)
+        b[1] = 7
+    body = _body(k)
+    assert 'asm volatile("mov.u32 %0, %%smid;" : "=r"(v) : )' in body
+    assert '"l"(p), "r"(v) : "memory")' in body
+    assert "reinterpret_cast<uint8_t*>(q)" in body and "((uint32_t)((((int64_t)(v)) << 3ll)))" in body
+
+
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.skipif(shutil.which("nvcc") is None and not __import__("os").path.exists("/usr/local/cuda/bin/nvcc"), reason="needs nvcc")
+def test_nvcc_compiles_examples_and_gemm_ladder_emits_tcgen05():
+    for kern in (K.saxpy, K.block_sum, K.softmax_rows, K.histogram, K.ring_shift, K.allgather_push):
+        kern.compile()
+    from triton_dist import jit
+    from triton_dist.lk.kernels.gemm_sm100 import get_gemm
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    for cg, needles in ((1, ("UTCHMMA", "UTMALDG.2D", "LDTM.x32", "UTCBAR")),
+                        (2, ("UTCHMMA.2CTA", "UTMALDG.2D.2CTA", "UTCBAR.2CTA.MULTICAST", "UTCATOMSWS.2CTA"))):
+        g = get_gemm(256, 4, cg)
+        g.compile()
+        so = g._lib._name
+        sass = subprocess.run([cuobjdump, "-sass", so], capture_output=True, text=True).stdout
+        assert "sm_100a" in sass
+        for n in needles:
+            assert n in sass, (cg, n)
+    assert jit._CACHE.exists()
+
+
+# ------------------------------------------------------------------------------------------------------------
+def test_interpreter_matches_torch():
+    torch.manual_seed(0)
+    x, y = torch.randn(1000), torch.randn(1000)
+    ref = 2.5 * x + y
+    K.saxpy.interpret((1000 + 127) // 128, x, y, 2.5, 1000)
+    torch.testing.assert_close(y, ref)
+
+    xb = torch.randn(3000).bfloat16()
+    out = torch.zeros(1)
+    K.block_sum.interpret(4, xb, out, 3000)                 # shuffles + shared memory + atomics, 4 blocks x 128 threads
+    torch.testing.assert_close(out[0], xb.float().sum(), atol=1e-2, rtol=1e-4)
+
+    m = torch.randn(5, 300)
+    sm = torch.empty_like(m)
+    K.softmax_rows.interpret(5, m, sm, 300)
+    torch.testing.assert_close(sm, m.softmax(-1), atol=1e-6, rtol=1e-5)
+
+    ids = torch.randint(0, 60, (2000,), dtype=torch.int32)
+    cnt = torch.zeros(60, dtype=torch.int32)
+    K.histogram.interpret(3, ids, cnt, 2000, 60)            # dynamic shared memory
+    assert torch.equal(cnt, torch.bincount(ids.long(), minlength=60).int())
+
+
+def test_interpreter_integer_wraparound_and_errors():
+    assert ll.u32(-1) == 0xFFFFFFFF and ll.i32(0x80000000) == -(1 << 31) and ll.u8(257) == 1 and ll.bf16(1.001) == 1.0
+
+    @lk.kernel(block=32)
+    def boom(y: ll.ptr[ll.f32]):
+        if ll.threadIdx.x == 3:
+            ll.trap()
+        ll.syncthreads()
+
+    with pytest.raises(RuntimeError, match="trap"):
+        boom.interpret(1, torch.zeros(1))                    # one thread fails: the block's barrier is aborted, no hang
+    with pytest.raises(NotImplementedError):
+        ll.tma_load_2d(None, None, None, 0, 0)               # no CPU meaning

@@ -1,0 +1,70 @@
+"""DSL kernels (triton_dist.lk) on a B200.  Sorted last on purpose: the SIMT kernels are plain CUDA, the tcgen05 GEMM ladder runs in a
+subprocess (a faulting kernel must not poison the CUDA context of the rest of the suite) and was written after the round's GPU budget
+was spent -- it is checked against fp32 but marked ``xfail(strict=False)`` until it has been seen passing on hardware."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_lk_simt_kernels():
+    from triton_dist.lk.kernels import simt as K
+    torch.manual_seed(0)
+    n = 100_003
+    x, y = torch.randn(n, device="cuda"), torch.randn(n, device="cuda")
+    ref = 1.5 * x + y
+    K.saxpy[(n + 127) // 128](x, y, 1.5, n)
+    torch.testing.assert_close(y, ref)
+
+    xb = torch.randn(1 << 20, device="cuda").bfloat16()
+    out = torch.zeros(1, device="cuda")
+    K.block_sum[148](xb, out, xb.numel())
+    torch.testing.assert_close(out[0], xb.float().sum(), atol=0.5, rtol=1e-3)
+
+    m = torch.randn(64, 5000, device="cuda")
+    sm = torch.empty_like(m)
+    K.softmax_rows[64](m, sm, 5000)
+    torch.testing.assert_close(sm, m.softmax(-1), atol=1e-6, rtol=1e-4)
+
+    ids = torch.randint(0, 256, (1 << 18,), device="cuda", dtype=torch.int32)
+    cnt = torch.zeros(256, device="cuda", dtype=torch.int32)
+    K.histogram[64](ids, cnt, ids.numel(), 256)
+    assert torch.equal(cnt, torch.bincount(ids.long(), minlength=256).int())
+    attrs = K.softmax_rows.attributes()
+    assert attrs["local_bytes"] == 0 and attrs["regs"] > 0
+
+
+_GEMM_SNIPPET = r"""
+import sys, torch
+sys.path.insert(0, {root!r})
+from triton_dist.lk.kernels.gemm_sm100 import run_gemm
+torch.manual_seed(0)
+for (M, N, K) in ((256, 256, 128), (512, 768, 512), (1000, 392, 320), (4096, 4096, 4096)):
+    a = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    b = (torch.randn(N, K, device="cuda") * 0.5).bfloat16()
+    ref = a.float() @ b.float().t()
+    c = run_gemm(a, b, cta_group={cg})
+    torch.cuda.synchronize()
+    torch.testing.assert_close(c.float(), ref, atol=0.5, rtol=2e-2)
+print("LK_GEMM_OK")
+"""
+
+
+@pytest.mark.xfail(strict=False, reason="DSL tcgen05 GEMM ladder: compiled and SASS-checked, not yet run on hardware")
+@pytest.mark.parametrize("cg", [1, 2])
+def test_lk_gemm_ladder(cg):
+    r = subprocess.run([sys.executable, "-c", _GEMM_SNIPPET.format(root=ROOT, cg=cg)], capture_output=True, text=True, timeout=240, cwd=ROOT)
+    assert r.returncode == 0 and "LK_GEMM_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_lk_symmetric_heap_kernels_two_gpus():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from _launch import run_dist
+    run_dist(["lk"], nproc=2, timeout=240)

@@ -1,0 +1,220 @@
+"""CPU interpreter for DSL kernels: the Python function itself is the semantics.
+
+Every CUDA thread of a block is a Python thread (``__syncthreads`` is a ``threading.Barrier``, a warp shuffle is an exchange buffer
+per warp), the blocks of a small grid run concurrently (larger grids block by block), pointers are views over flat CPU tensors, shared arrays are per-block numpy arrays.  The
+distributed primitives (``symm_at`` / ``notify`` / ``wait``) map onto the emulation backend of this framework
+(``triton_dist.language`` over the shared-memory heap), so a multi-rank DSL kernel can be executed by N CPU processes -- the same way
+``tests/test_dist_cpu.py`` runs every fused-op protocol.  TMA / tcgen05 intrinsics have no CPU meaning and raise.
+
+The reference has no counterpart (its DSL kernels only run on a GPU, python/little_kernel/tests/conftest.py:50-63 gates them); this is
+what lets the DSL be tested in the CPU-only tier.
+"""
+from __future__ import annotations
+
+import threading
+from typing import Any, Dict, List, Tuple
+
+import numpy as np
+
+from . import types as T
+
+_tls = threading.local()
+_atomic_lock = threading.Lock()
+
+
+class BlockState:
+    def __init__(self, nthreads: int):
+        self.nthreads = nthreads
+        self.barrier = threading.Barrier(nthreads)
+        self.shared: Dict[Any, np.ndarray] = {}
+        self.lock = threading.Lock()
+        nwarps = (nthreads + 31) // 32
+        self.warp_size = [min(32, nthreads - w * 32) for w in range(nwarps)]
+        self.warp_barrier = [threading.Barrier(n) for n in self.warp_size]
+        self.warp_xchg: List[List[Any]] = [[None] * 32 for _ in range(nwarps)]
+        self.error = None
+
+
+class ThreadCtx:
+    def __init__(self, tid, bid, bdim, gdim, block: BlockState, dyn_smem: np.ndarray):
+        self.tid, self.bid, self.bdim, self.gdim, self.block = tid, bid, bdim, gdim, block
+        self.linear = tid[0] + bdim[0] * (tid[1] + bdim[1] * tid[2])
+        self.dyn_smem = dyn_smem
+        self.dyn_off = 0
+
+
+def cur() -> ThreadCtx:
+    c = getattr(_tls, "ctx", None)
+    if c is None:
+        raise RuntimeError("DSL intrinsic called outside a kernel (use kernel.interpret(...) on CPU or launch it on a GPU)")
+    return c
+
+
+def active() -> bool:
+    return getattr(_tls, "ctx", None) is not None
+
+
+# ------------------------------------------------------------------------------------------------------------
+class Ptr:
+    """A typed pointer into a flat CPU tensor (or numpy array): ``p[i]``, ``p[i] = v``, ``p + n``."""
+
+    def __init__(self, base, off: int = 0, elem: T.Type = None, owner=None):
+        self.base, self.off, self.elem, self.owner = base, int(off), elem, owner if owner is not None else base
+
+    def __getitem__(self, i):
+        v = self.base[self.off + int(i)]
+        return v.item() if hasattr(v, "item") else v
+
+    def __setitem__(self, i, v):
+        self.base[self.off + int(i)] = v
+
+    def __add__(self, n):
+        return Ptr(self.base, self.off + int(n), self.elem, self.owner)
+
+    __radd__ = __add__
+
+    def __sub__(self, n):
+        if isinstance(n, Ptr):
+            return self.off - n.off
+        return Ptr(self.base, self.off - int(n), self.elem, self.owner)
+
+    def tensor(self):
+        """The underlying torch tensor from this element on (for the host mirror of the distributed primitives)."""
+        return self.base[self.off:]
+
+
+class SharedArray:
+    def __init__(self, arr: np.ndarray, shape):
+        self.arr, self.shape = arr, tuple(shape)
+
+    def _flat(self, idx):
+        if not isinstance(idx, tuple):
+            return int(idx)
+        f = 0
+        for i, s in zip(idx, self.shape):
+            f = f * s + int(i)
+        return f
+
+    def __getitem__(self, idx):
+        v = self.arr[self._flat(idx)]
+        return v.item() if hasattr(v, "item") else v
+
+    def __setitem__(self, idx, v):
+        self.arr[self._flat(idx)] = v
+
+    def __add__(self, n):
+        return Ptr(self.arr, int(n))
+
+
+_NP = {"bool": np.bool_, "i8": np.int8, "u8": np.uint8, "i16": np.int16, "u16": np.uint16, "i32": np.int32, "u32": np.uint32,
+       "i64": np.int64, "u64": np.uint64, "f16": np.float16, "bf16": np.float32, "f32": np.float32, "f64": np.float64, "e4m3": np.float32}
+
+
+def np_dtype(t: T.Type):
+    return _NP.get(getattr(t, "name", ""), np.uint8)
+
+
+def shared_array(key, shape, dtype, per_block=True) -> SharedArray:
+    c = cur()
+    shape = T.shape_tuple(shape)
+    n = int(np.prod(shape))
+    if not per_block:
+        return SharedArray(np.zeros(n, dtype=np_dtype(dtype)), shape)
+    with c.block.lock:
+        arr = c.block.shared.get(key)
+        if arr is None:
+            arr = c.block.shared[key] = np.zeros(n, dtype=np_dtype(dtype))
+    return SharedArray(arr, shape)
+
+
+def syncthreads():
+    cur().block.barrier.wait()
+
+
+def warp_exchange(value, src_lane_of):
+    """All lanes of the calling warp publish ``value``; lane l gets the value of lane ``src_lane_of(l)`` (its own when out of range)."""
+    c = cur()
+    w, lane = c.linear // 32, c.linear % 32
+    blk = c.block
+    blk.warp_xchg[w][lane] = value
+    blk.warp_barrier[w].wait()
+    src = src_lane_of(lane)
+    out = blk.warp_xchg[w][src] if 0 <= src < blk.warp_size[w] else value
+    blk.warp_barrier[w].wait()
+    return out
+
+
+def warp_collect(value) -> list:
+    c = cur()
+    w, lane = c.linear // 32, c.linear % 32
+    blk = c.block
+    blk.warp_xchg[w][lane] = value
+    blk.warp_barrier[w].wait()
+    out = list(blk.warp_xchg[w][:blk.warp_size[w]])
+    blk.warp_barrier[w].wait()
+    return out
+
+
+def atomic_rmw(p: Ptr, i, fn):
+    with _atomic_lock:
+        old = p[i]
+        p[i] = fn(old)
+    return old
+
+
+# ------------------------------------------------------------------------------------------------------------
+def _wrap_arg(a, ty):
+    import torch
+    if isinstance(a, torch.Tensor):
+        if a.is_cuda:
+            raise ValueError("interpret() runs on CPU tensors")
+        return Ptr(a.view(-1) if a.is_contiguous() else a.reshape(-1), 0, getattr(ty, "elem", None), owner=a)
+    if isinstance(ty, T.Scalar):
+        return ty.wrap(a)
+    return a
+
+
+MAX_CONCURRENT_THREADS = 2048
+
+
+def run(fn, param_types, grid, block, args, dyn_smem_bytes: int = 0):
+    """Blocks of a small grid (<= MAX_CONCURRENT_THREADS emulated threads in total) run concurrently, so kernels whose blocks depend on
+    each other (or on other ranks, block by block) make progress as on a GPU; larger grids run one block after the other."""
+    grid = tuple(grid) + (1,) * (3 - len(tuple(grid))) if not isinstance(grid, int) else (grid, 1, 1)
+    block = tuple(block) + (1,) * (3 - len(tuple(block))) if not isinstance(block, int) else (block, 1, 1)
+    nthreads = block[0] * block[1] * block[2]
+    wrapped = [_wrap_arg(a, t) for a, t in zip(args, param_types)]
+    bids = [(bx, by, bz) for bz in range(grid[2]) for by in range(grid[1]) for bx in range(grid[0])]
+    tids: List[Tuple[int, int, int]] = [(x, y, z) for z in range(block[2]) for y in range(block[1]) for x in range(block[0])]
+    errors: List[BaseException] = []
+
+    def body(tid, bid, blk, dyn):
+        _tls.ctx = ThreadCtx(tid, bid, block, grid, blk, dyn)
+        try:
+            fn(*wrapped)
+        except threading.BrokenBarrierError:
+            pass
+        except BaseException as e:      # noqa: BLE001
+            errors.append(e)
+            blk.barrier.abort()
+            for b in blk.warp_barrier:
+                b.abort()
+        finally:
+            _tls.ctx = None
+
+    per_wave = max(1, MAX_CONCURRENT_THREADS // nthreads) if len(bids) * nthreads <= MAX_CONCURRENT_THREADS else 1
+    for w0 in range(0, len(bids), per_wave):
+        ths = []
+        for bid in bids[w0:w0 + per_wave]:
+            blk = BlockState(nthreads)
+            dyn = np.zeros(max(dyn_smem_bytes, 1), dtype=np.uint8)
+            if nthreads == 1 and per_wave == 1:
+                body(tids[0], bid, blk, dyn)
+                continue
+            ths += [threading.Thread(target=body, args=(t, bid, blk, dyn), daemon=True) for t in tids]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        if errors:
+            raise errors[0]
