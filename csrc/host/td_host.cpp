@@ -172,3 +172,32 @@ TDH_API int tdh_barrier_all(void* hp, unsigned long long slots_off, unsigned int
 }
 
 TDH_API void tdh_memcpy(void* dst, const void* src, unsigned long long n) { memcpy(dst, src, n); }
+
+// ------------------------------------------------------------------------------------------------
+// DLPack capsule payloads built and destroyed in C: the deleter of a tensor that aliases heap memory can run at any time (another
+// thread, the garbage collector, interpreter shutdown) -- it must not be a Python callback.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct DlDevice { int32_t device_type; int32_t device_id; };
+struct DlDataType { uint8_t code; uint8_t bits; uint16_t lanes; };
+struct DlTensor { void* data; DlDevice device; int32_t ndim; DlDataType dtype; int64_t* shape; int64_t* strides; uint64_t byte_offset; };
+struct DlManagedTensor { DlTensor dl_tensor; void* manager_ctx; void (*deleter)(DlManagedTensor*); };
+struct DlOwned { DlManagedTensor mt; int64_t shape[8]; };
+void dl_delete(DlManagedTensor* m) { delete reinterpret_cast<DlOwned*>(m); }
+}  // namespace
+
+TDH_API void* tdh_dl_make(void* data, int ndim, const int64_t* shape, int code, int bits, int device_type, int device_id) {
+  if (ndim < 0 || ndim > 8) return nullptr;
+  DlOwned* o = new DlOwned();
+  for (int i = 0; i < ndim; ++i) o->shape[i] = shape[i];
+  o->mt.dl_tensor.data = data;
+  o->mt.dl_tensor.device = {device_type, device_id};
+  o->mt.dl_tensor.ndim = ndim;
+  o->mt.dl_tensor.dtype = {static_cast<uint8_t>(code), static_cast<uint8_t>(bits), 1};
+  o->mt.dl_tensor.shape = o->shape;
+  o->mt.dl_tensor.strides = nullptr;
+  o->mt.dl_tensor.byte_offset = 0;
+  o->mt.manager_ctx = nullptr;
+  o->mt.deleter = dl_delete;
+  return &o->mt;
+}

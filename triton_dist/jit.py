@@ -47,11 +47,26 @@ def symm_ctx() -> SymmCtx:
     return SymmCtx(int(r), int(w), int(base), int(stride), int(mc))
 
 
+_HDR_DIGEST = None
+
+
+def _headers_digest() -> str:
+    global _HDR_DIGEST
+    if _HDR_DIGEST is None:
+        h = hashlib.sha256()
+        for f in sorted((_build.CSRC / "td").glob("*.cuh")):
+            h.update(f.read_bytes())
+        _HDR_DIGEST = h.hexdigest()[:16]
+    return _HDR_DIGEST
+
+
 def compile_cuda(source: str, extra_flags: Sequence[str] = (), name: str = "kernel") -> C.CDLL:
     """nvcc -> shared object -> ``ctypes.CDLL``.  Works without a GPU (cross-compiles sm_100a); launching needs one."""
     flags = list(_build.GENCODE) + ["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-cudart", "shared",
                                     "-I", str(_build.CSRC)] + list(extra_flags)
-    key = hashlib.sha256((source + "\0" + " ".join(flags)).encode()).hexdigest()[:16]
+    # the key must not depend on where the checkout lives (the cache travels with the tree to the GPU box), but it must change when
+    # the device headers do
+    key = hashlib.sha256((source + "\0" + " ".join(flags).replace(str(_build.CSRC), "$CSRC") + "\0" + _headers_digest()).encode()).hexdigest()[:16]
     _CACHE.mkdir(parents=True, exist_ok=True)
     so = _CACHE / f"{name}_{key}.so"
     if not so.exists():
