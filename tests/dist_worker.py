@@ -852,6 +852,123 @@ def case_lk():
         U.nvshmem_free_tensor_sync(t)
 
 
+SHMEM_TEST_SRC = r"""
+#include "td/shmem.cuh"
+using namespace td;
+// every function family of the NVSHMEM-style header once: fcollect over the world team, broadcast inside the even team,
+// put-with-signal around the ring (64-bit signals, CMP_GE wait), thread / warp scoped puts, team translation, barrier_all
+__global__ void shmem_selftest(SymmCtx c, uint32_t* slots, uint32_t* epoch, float* fc_dst, float* bc_dst, float* ring_dst,
+                               uint64_t* sig, int* misc, const float* src, int n, uint64_t phase) {
+  shmem::Sync s{slots, epoch};
+  const shmem::Team world = shmem::team_world(c);
+  const shmem::Team even{0, 2, (c.world + 1) / 2};
+  shmem::fcollect_block(c, world, s, fc_dst, src, (size_t)n);
+  shmem::broadcast_block(c, even, s, bc_dst, src, (size_t)n, /*root=*/(int)(phase % even.size));
+  const int nxt = (shmem::my_pe(c) + 1) % shmem::n_pes(c);
+  shmem::putmem_signal_block(c, ring_dst, src, (size_t)n * sizeof(float), sig, phase, shmem::SIGNAL_SET, nxt);
+  if (threadIdx.x == 0) {
+    shmem::signal_wait_until(sig, shmem::CMP_GE, phase);
+    misc[0] = shmem::team_translate_pe(world, c.rank, even);            // my index in the even team or -1
+    misc[1] = shmem::team_my_pe(c, even);
+    shmem::int_p(c, misc + 2, c.rank * 10 + (int)phase, nxt);           // thread-scope put of one int
+  }
+  if (threadIdx.x < 32) shmem::putmem_warp(c, ring_dst + n, src, 3 * sizeof(float) + 2, nxt);   // unaligned size: byte tail
+  shmem::quiet();
+  shmem::barrier_all_block(c, s);
+}
+extern "C" void launch_shmem_selftest(SymmCtx c, void* slots, void* epoch, void* fc, void* bc, void* ring, void* sig, void* misc,
+                                      void* src, int n, unsigned long long phase, void* stream) {
+  shmem_selftest<<<1, 128, 0, (cudaStream_t)stream>>>(c, (uint32_t*)slots, (uint32_t*)epoch, (float*)fc, (float*)bc, (float*)ring,
+                                                      (uint64_t*)sig, (int*)misc, (const float*)src, n, phase);
+}
+"""
+
+
+def case_shmem():
+    """NVSHMEM-style API: the Python (host-initiated / stream-ordered) mirror on both backends, the device header csrc/td/shmem.cuh
+    through a JIT kernel on the GPU backend (reference: test_nvshmem_api.py, test_team_split.py, test_ring_put.py)."""
+    from triton_dist.language import shmem as S
+    W, me = U.world_size(), U.rank()
+    dev = U.current_device()
+    n = 96
+    world = S.team_world()
+    even = S.team_split_strided(world, 0, 2, (W + 1) // 2)
+    odd = S.team_split_strided(world, 1, 2, W // 2) if W >= 2 else None
+    assert S.team_my_pe(world) == me and S.team_n_pes(even) == (W + 1) // 2
+    assert S.team_my_pe(even) == (me // 2 if me % 2 == 0 else -1)
+    if odd is not None:
+        assert S.team_translate_pe(world, 1, odd) == 0 and S.team_translate_pe(world, 0, odd) == -1
+        assert S.team_translate_pe(odd, 0, world) == 1
+    sync = S.Sync()
+    fc = U.nvshmem_create_tensor((W * n,), torch.float32)
+    bc = U.nvshmem_create_tensor((n,), torch.float32)
+    ring = U.nvshmem_create_tensor((2 * n,), torch.float32)
+    sig = U.nvshmem_create_tensor((4,), torch.int32)
+    for t in (fc, bc, ring, sig):
+        t.zero_()
+    U.barrier_all_on_stream()
+    for phase in range(1, 4):
+        src = torch.arange(n, dtype=torch.float32, device=dev) + 100.0 * me + phase
+        S.fcollect(world, sync, fc, src)
+        want = torch.cat([torch.arange(n, dtype=torch.float32) + 100.0 * r + phase for r in range(W)])
+        _assert_close(fc, want, 0, 0, f"shmem fcollect phase {phase}")
+        root = phase % even.size
+        S.broadcast(even, sync, bc, src, root)
+        if S.team_my_pe(even) >= 0:
+            _assert_close(bc, torch.arange(n, dtype=torch.float32) + 100.0 * even.pe(root) + phase, 0, 0, f"shmem broadcast phase {phase}")
+        nxt, prev = (me + 1) % W, (me - 1 + W) % W
+        S.putmem_signal(ring, src, sig[0:1], phase, S.SIGNAL_SET, nxt)
+        S.signal_wait_until(sig[0:1], S.CMP_GE, phase)
+        _assert_close(ring[:n], torch.arange(n, dtype=torch.float32) + 100.0 * prev + phase, 0, 0, f"shmem ring phase {phase}")
+        S.signal_op(sig[1:2], 1, S.SIGNAL_ADD, 0)                 # everyone adds 1 on PE 0
+        S.barrier_all(sync)
+        if me == 0:
+            if sig.is_cuda:
+                torch.cuda.synchronize()
+            assert int(sig[1].item()) == W * phase, (sig, phase)
+            if not sig.is_cuda:
+                assert S.signal_wait_until(sig[1:2], S.CMP_GT, W * phase - 1) == W * phase
+        got = torch.empty(n, dtype=torch.float32, device=dev)
+        S.getmem(got, ring, nxt)                                  # what I wrote into my successor
+        _assert_close(got, src, 0, 0, f"shmem getmem phase {phase}")
+        S.barrier_all(sync)
+    if fc.is_cuda:
+        # ---- the device header, one kernel ----
+        from triton_dist import jit
+        lib = jit.compile_cuda(SHMEM_TEST_SRC, name="shmem_selftest")
+        k = jit.JitKernel(lib, "launch_shmem_selftest")
+        slots = U.nvshmem_create_tensor((2 * W,), torch.int32)
+        sig64 = U.nvshmem_create_tensor((2,), torch.int64)
+        misc = U.nvshmem_create_tensor((4,), torch.int32)
+        epoch = torch.zeros(1, dtype=torch.int32, device=dev)
+        for t in (slots, sig64, misc, fc, bc, ring):
+            t.zero_()
+        U.barrier_all_on_stream()
+        ctx = jit.symm_ctx()
+        for phase in range(1, 4):
+            src = torch.arange(n, dtype=torch.float32, device=dev) * 0.5 + 7.0 * me + phase
+            k(ctx, slots, epoch, fc, bc, ring, sig64, misc, src, n, phase)
+            torch.cuda.synchronize()
+            want = torch.cat([torch.arange(n, dtype=torch.float32) * 0.5 + 7.0 * r + phase for r in range(W)])
+            _assert_close(fc, want, 0, 0, f"shmem.cuh fcollect phase {phase}")
+            root = phase % even.size
+            if me % 2 == 0:
+                _assert_close(bc, torch.arange(n, dtype=torch.float32) * 0.5 + 7.0 * even.pe(root) + phase, 0, 0, f"shmem.cuh broadcast {phase}")
+            prev = (me - 1 + W) % W
+            pv = torch.arange(n, dtype=torch.float32) * 0.5 + 7.0 * prev + phase
+            _assert_close(ring[:n], pv, 0, 0, f"shmem.cuh putmem_signal phase {phase}")
+            _assert_close(ring[n:n + 3], pv[:3], 0, 0, f"shmem.cuh putmem_warp phase {phase}")
+            m = misc.cpu().tolist()
+            assert m[0] == (me // 2 if me % 2 == 0 else -1) and m[1] == m[0] and m[2] == prev * 10 + phase, (me, m)
+            assert int(epoch.item()) == 3 * phase and int(sig64[0].item()) == phase
+            U.barrier_all_on_stream()
+        for t in (misc, sig64, slots):
+            U.nvshmem_free_tensor_sync(t)
+    sync.finalize()
+    for t in (sig, ring, bc, fc):
+        U.nvshmem_free_tensor_sync(t)
+
+
 def case_mega():
     """Megakernel decode step (task graph + scoreboard + in-kernel all-reduce) vs the layer-by-layer TP model."""
     from triton_dist.models import AutoLLM, KV_Cache, ModelConfig

@@ -424,3 +424,24 @@ def test_calibrated_perf_models_match_measurements():
     assert 0.39 < rs < 0.53, rs                    # measured 0.456-0.461 ms
     tr = P.pick_ag_transport(4096, 512, 4096, 8)
     assert tr[0] in ("sm_k", "multicast") and tr[-1] <= ag + 1e-9
+
+
+def test_shmem_device_header_compiles_for_sm100a():
+    """The NVSHMEM-style device header (csrc/td/shmem.cuh): the self-test kernel of the `shmem` distributed case cross-compiles, and
+    the Python mirror's team arithmetic agrees with NVSHMEM's strided-split semantics."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from dist_worker import SHMEM_TEST_SRC
+    from triton_dist import jit
+    from triton_dist.language.shmem import Team, team_split_strided, team_translate_pe
+    lib = jit.compile_cuda(SHMEM_TEST_SRC, name="shmem_selftest")
+    assert hasattr(lib, "launch_shmem_selftest")
+    world = Team(0, 1, 8)
+    even = team_split_strided(world, 0, 2, 4)
+    quads = team_split_strided(even, 1, 2, 2)            # members 2 and 6 of the world
+    assert even.pes == [0, 2, 4, 6] and quads.pes == [2, 6]
+    assert team_translate_pe(quads, 1, world) == 6 and team_translate_pe(world, 6, even) == 3 and team_translate_pe(world, 3, even) == -1
+    import pytest
+    with pytest.raises(ValueError):
+        team_split_strided(world, 4, 2, 3)

@@ -67,3 +67,12 @@ def test_lk_symmetric_heap_kernels_two_gpus():
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from _launch import run_dist
     run_dist(["lk"], nproc=2, timeout=240)
+
+
+def test_shmem_header_two_gpus():
+    """csrc/td/shmem.cuh (NVSHMEM-style device API) through a JIT kernel + the stream-ordered Python mirror."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from _launch import run_dist
+    run_dist(["shmem"], nproc=2, timeout=240)
