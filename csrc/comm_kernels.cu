@@ -292,6 +292,56 @@ __global__ void __launch_bounds__(kCommThreads, 1) allgather_kernel(const AGPara
   }
 }
 
+// NVLS variants of the push modes (reference: low_latency_allgather.py:570-700 _recv_ll_and_multimem_st_* /
+// _forward_push_2d_ll_multimem_kernel): one multimem.st per element instead of `world` unicast stores -- the NVSwitch
+// replicates the packet, so a rank's NVLink egress is 1x its shard instead of (world - 1)x.
+//   kLL = false : 16-byte multimem stores into slot[rank] of every rank, then the cross-GPU barrier
+//   kLL = true  : 8-byte atoms {4 B data, 4 B flag = call id} with multimem.st.b64; receivers spin on the flags, no barrier
+template <bool kLL>
+__global__ void __launch_bounds__(kCommThreads, 1) allgather_mc_kernel(const AGParams p) {
+  const SymmCtx& c = p.symm;
+  const int W = c.world;
+  const uint32_t ph = p.phase[0] + 1;
+  const uint32_t par = ph & 1u;
+  uint32_t* my_slots = p.slots + blockIdx.x * 2 * W;
+  const long long per = (p.nvec + gridDim.x - 1) / gridDim.x;
+  const long long v0 = min(p.nvec, per * blockIdx.x), v1 = min(p.nvec, v0 + per);
+  if constexpr (kLL) {
+    uint2* buf = reinterpret_cast<uint2*>(p.buf + par * p.buf_bytes);
+    uint2* mc = symm_mc(c, buf + c.rank * p.nvec);
+    const uint32_t* in32 = reinterpret_cast<const uint32_t*>(p.in);
+    uint32_t* out32 = reinterpret_cast<uint32_t*>(p.out);
+    for (long long v = v0 + threadIdx.x; v < v1; v += kCommThreads) {
+      const unsigned long long atom = static_cast<unsigned long long>(in32[v]) | (static_cast<unsigned long long>(ph) << 32);
+      asm volatile("multimem.st.relaxed.sys.global.b64 [%0], %1;" ::"l"(mc + v), "l"(atom) : "memory");
+    }
+    for (int s = 0; s < W; ++s) {
+      for (long long v = v0 + threadIdx.x; v < v1; v += kCommThreads) {
+        const uint2* src = buf + s * p.nvec + v;
+        uint32_t d, f;
+        do {
+          asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(d), "=r"(f) : "l"(src) : "memory");
+        } while (f != ph);
+        out32[s * p.nvec + v] = d;
+      }
+    }
+  } else {
+    uint4* buf = reinterpret_cast<uint4*>(p.buf + par * p.buf_bytes);
+    uint4* mc = symm_mc(c, buf + c.rank * p.nvec);
+    for (long long v = v0 + threadIdx.x; v < v1; v += kCommThreads) ptx::multimem_st_v4(mc + v, p.in[v]);
+    barrier_all_block(c, my_slots, ph);       // __syncthreads + fence.acq_rel.sys + release flags: the multicast stores are visible
+    if (reinterpret_cast<uint4*>(p.out) != buf)
+      for (int s = 0; s < W; ++s)
+        for (long long v = v0 + threadIdx.x; v < v1; v += kCommThreads)
+          p.out[s * p.nvec + v] = ptx::ld_relaxed_sys_v4(buf + s * p.nvec + v);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(p.phase + 1, 1u) == gridDim.x - 1) { p.phase[1] = 0; __threadfence(); p.phase[0] = ph; }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // memory ops (reference: kernels/nvidia/memory_ops.py copy_tensor / fill_tensor / reduce_tensor)
 // ---------------------------------------------------------------------------------------------------------
@@ -391,7 +441,15 @@ TD_API int td_allgather(const TdAGArgs* a, void* stream) {
   p.slots = reinterpret_cast<uint32_t*>(a->slots); p.phase = reinterpret_cast<uint32_t*>(a->phase);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int grid = (int)a->grid;
-  if (a->mode == 2) {
+  if (a->mode == 3 || a->mode == 4) {
+    // NVLS variants: 3 = multimem push + barrier, 4 = multimem LL atoms
+    if (!p.symm.mc_base) { td::drv::set_error("allgather: the multimem modes need the NVLS multicast mapping of the heap"); return -1; }
+    const long long unit = a->mode == 3 ? 16 : 4;
+    if (a->shard_bytes % unit) { td::drv::set_error("allgather (multimem): shard size is not a multiple of the access size"); return -1; }
+    p.nvec = a->shard_bytes / unit;
+    if (a->mode == 3) allgather_mc_kernel<false><<<grid, kCommThreads, 0, s>>>(p);
+    else allgather_mc_kernel<true><<<grid, kCommThreads, 0, s>>>(p);
+  } else if (a->mode == 2) {
     if (a->shard_bytes % 4) { td::drv::set_error("allgather LL: shard must be a multiple of 4 bytes"); return -1; }
     p.nvec = a->shard_bytes / 4;
     allgather_kernel<2><<<grid, kCommThreads, 0, s>>>(p);

@@ -100,6 +100,38 @@ def case_allgather():
     ctx.finalize()
 
 
+def case_allgather_mc():
+    """NVLS variants of the fast all-gather (multimem push + barrier, multimem LL atoms), interleaved with the unicast modes on the
+    same context so parity buffers / phase counters are shared (reference: low_latency_allgather.py:623-700).  Without the multicast
+    mapping (emulation backend, or a driver without NVLS) the names resolve to their unicast twins."""
+    from triton_dist.ops import comm
+    W = U.world_size()
+    dev = U.current_device()
+    ctx = comm.create_fast_allgather_context(1 << 20)
+    for it in range(4):
+        for mode in ("push_multimem", "push_2d_ll_multimem", "push", "ll_multimem", "push_2d_multimem"):
+            for n in (16, 1000, 4100, 65536):
+                x = torch.randn(n, device=dev).to(torch.bfloat16 if n % 8 == 0 else torch.float32)
+                out = comm.fast_allgather(x, ctx, mode=mode)
+                ref = torch.empty(W * x.numel(), dtype=x.dtype, device=dev)
+                dist.all_gather_into_tensor(ref, x, group=U.get_triton_dist_world())
+                assert torch.equal(out.cpu().view(-1), ref.cpu()), (mode, n, it)
+    ctx.finalize()
+    from triton_dist.layers.nvidia import AllGatherLayer
+    layer = AllGatherLayer(1 << 18)
+    for name in ("forward_pull", "forward_push_2d", "forward_push_3d", "forward_push_2d_ll", "forward_push_numa_2d", "forward_push_numa_2d_ll",
+                 "forward_push_multimem", "forward_push_2d_ll_multimem", "forward"):
+        if dev.type != "cuda" and name == "forward_pull":
+            continue
+        for n in (64, 30000):
+            x = torch.randn(n, device=dev)
+            out = getattr(layer, name)(x)
+            ref = torch.empty(W * n, device=dev)
+            dist.all_gather_into_tensor(ref, x, group=U.get_triton_dist_world())
+            assert torch.equal(out.cpu().view(-1), ref.cpu()), (name, n)
+    layer.finalize()
+
+
 def case_allreduce():
     from triton_dist.ops import comm
     dev = U.current_device()

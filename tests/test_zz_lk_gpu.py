@@ -76,3 +76,12 @@ def test_shmem_header_two_gpus():
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from _launch import run_dist
     run_dist(["shmem"], nproc=2, timeout=240)
+
+
+def test_allgather_multimem_two_gpus():
+    """NVLS all-gather kernels (multimem push, multimem LL) written after the GPU budget of the round was spent."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from _launch import run_dist
+    run_dist(["allgather_mc"], nproc=2, timeout=240)

@@ -388,8 +388,11 @@ def create_fast_allgather_context(max_shard_bytes: int, rank: Optional[int] = No
     return ctx
 
 
+# kernel modes: 0 pull, 1 push, 2 push-LL (flag-in-data), 3 multimem push (NVLS), 4 multimem LL (NVLS).  The reference's staged
+# variants (push_3d, push_numa_2d*: low_latency_allgather.py:74-530) stage through one GPU per NUMA node / node because PCIe or
+# inter-node links are the bottleneck there; inside one NVSwitch domain every peer is one hop away, so they map onto the direct modes.
 _AG_MODES = {"pull": 0, "push": 1, "push_2d": 1, "push_3d": 1, "push_numa_2d": 1, "push_2d_ll": 2, "ll": 2,
-             "push_2d_ll_multimem": 2, "push_numa_2d_ll": 2}
+             "push_multimem": 3, "push_2d_multimem": 3, "push_2d_ll_multimem": 4, "ll_multimem": 4, "push_numa_2d_ll": 2}
 
 
 def fast_allgather(shard: torch.Tensor, ctx: FastAllGatherContext, mode: str = "push", output: Optional[torch.Tensor] = None,
@@ -406,8 +409,10 @@ def fast_allgather(shard: torch.Tensor, ctx: FastAllGatherContext, mode: str = "
     if not shard.is_cuda:
         return _allgather_host(shard, ctx, output)
     m = _AG_MODES[mode]
-    if m != 2 and nbytes % 16:
-        m = 2
+    if m in (3, 4) and not (U.is_nvshmem_multimem_supported() and W > 1):
+        m = 1 if m == 3 else 2          # no NVLS mapping (or a single rank): the unicast twin of the same protocol
+    if m in (0, 1, 3) and nbytes % 16:
+        m = 4 if m == 3 else 2
     a = _AGArgs()
     a.symm = symm_args()
     a.mode = m

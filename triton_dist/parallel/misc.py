@@ -36,8 +36,15 @@ class GemmARLayer:
 
 
 class AllGatherLayer:
+    """Low-latency all-gather layer (reference: layers/nvidia/low_latency_allgather_layer.py:33-140).  Five kernels behind the
+    reference's method names: pull, push, push-LL (flag-in-data), and the two NVLS forms (multimem push, multimem LL).  The staged
+    variants of the reference (push_3d, push_numa_2d*) relay through one GPU per NUMA node / node because PCIe or inter-node links
+    are their bottleneck; inside one NVSwitch domain every peer is one hop away, so those names run the direct kernel of the same
+    protocol family (LL stays LL).  ``stages`` is accepted for source compatibility: buffers are double-buffered by call parity."""
+
     def __init__(self, max_shard_bytes: int, stages: int = 2):
         self.ctx = comm.create_fast_allgather_context(max_shard_bytes)
+        self.stages = stages
 
     def _fwd(self, x, mode):
         return comm.fast_allgather(x, self.ctx, mode=mode)
@@ -48,7 +55,18 @@ class AllGatherLayer:
     def forward_push_2d_ll(self, x): return self._fwd(x, "push_2d_ll")
     def forward_push_numa_2d(self, x): return self._fwd(x, "push")
     def forward_push_numa_2d_ll(self, x): return self._fwd(x, "push_2d_ll")
-    def forward_push_2d_ll_multimem(self, x): return self._fwd(x, "push_2d_ll")
+    def forward_push_multimem(self, x): return self._fwd(x, "push_multimem")
+    def forward_push_2d_ll_multimem(self, x): return self._fwd(x, "push_2d_ll_multimem")
+
+    def forward(self, x, mode: str = "auto"):
+        """auto: LL for tiny shards (no barrier round-trip), NVLS push for the rest when the multicast mapping exists."""
+        if mode == "auto":
+            nbytes = x.numel() * x.element_size()
+            mc = U.is_nvshmem_multimem_supported()
+            mode = ("push_2d_ll_multimem" if mc else "push_2d_ll") if nbytes <= (8 << 10) else ("push_multimem" if mc else "push")
+        return self._fwd(x, mode)
+
+    __call__ = forward
 
     def finalize(self):
         self.ctx.finalize()
