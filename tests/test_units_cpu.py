@@ -426,6 +426,41 @@ def test_calibrated_perf_models_match_measurements():
     assert tr[0] in ("sm_k", "multicast") and tr[-1] <= ag + 1e-9
 
 
+def test_gemm_and_collective_models_match_measured_tables():
+    """Tile-wave GEMM model vs profiles/README.md section 1 (cta_group 1 sweep) + the round-2 default (cta_group 2), all-reduce fits vs
+    section 3, EP dispatch / combine vs section 9: within 15 %; the pickers choose what the measurements chose."""
+    import torch
+    from triton_dist.ops import perf_model as P
+    gemm_us = [((4096, 4096, 4096, 1, 256), 105.5), ((4096, 4096, 4096, 1, 128), 150.0), ((8192, 8192, 8192, 1, 256), 780.0),
+               ((8192, 8192, 8192, 1, 128), 1350.0), ((4096, 12288, 6144, 1, 256), 458.0), ((4096, 12288, 6144, 1, 128), 769.0),
+               ((8192, 1536, 4096, 1, 256), 87.1), ((8192, 1536, 4096, 1, 128), 138.0), ((4096, 4096, 4096, 2, 256), 88.7),
+               ((4096, 12288, 6144, 2, 256), 397.0)]
+    for (M, N, K, cg, bn), us in gemm_us:
+        est = P.estimate_gemm_ms(M, N, K, cg, bn) * 1e3
+        assert 0.85 <= est / us <= 1.15, (M, N, K, cg, bn, est, us)
+    assert P.pick_gemm_config(4096, 4096, 4096)[:2] == (2, 256)
+    assert P.estimate_gemm_ms(4096, 4096, 4096) >= P.estimate_gemm_sol_time_ms(4096, 4096, 4096) * 0.95      # never (much) below the SOL
+    ar_us = [(65536, "OneShot", 34.3), (65536, "TwoShot", 26.8), (65536, "OneShot_Multimem", 22.4), (65536, "TwoShot_Multimem", 23.1),
+             (1 << 24, "TwoShot", 103.3), (1 << 24, "OneShot_Multimem", 226.7), (1 << 24, "TwoShot_Multimem", 85.0)]
+    for n, m, us in ar_us:
+        assert abs(P.estimate_allreduce_us(n, 8, m) - us) / us < 0.05, (n, m)
+    assert P.pick_allreduce_method(65536)[0] == "OneShot_Multimem" and P.pick_allreduce_method(1 << 24)[0] == "TwoShot_Multimem"
+    assert P.pick_allreduce_method(1 << 24, 8, multimem_ok=False)[0] == "TwoShot"
+    assert P.estimate_allreduce_us(1 << 24, 2, "TwoShot") < P.estimate_allreduce_us(1 << 24, 8, "TwoShot")      # less traffic per rank
+    assert abs(P.estimate_ep_dispatch_us(128, 7168, 8, 8, 1) - 52.6) / 52.6 < 0.1
+    assert abs(P.estimate_ep_dispatch_us(128, 7168, 8, 8, 2) - 71.9) / 71.9 < 0.1
+    assert abs(P.estimate_ep_combine_us(128, 7168, 8) - 57.6) / 57.6 < 0.15
+    # LL skips the barrier: cheaper for tiny shards, more expensive (2x bytes) for big ones
+    assert P.estimate_fast_allgather_us(2048, 8, "push_2d_ll") < P.estimate_fast_allgather_us(2048, 8, "push")
+    assert P.estimate_fast_allgather_us(1 << 20, 8, "push_2d_ll") > P.estimate_fast_allgather_us(1 << 20, 8, "push")
+    # the reference's signatures (comm_perf_model.py:94-131, gemm_perf_model.py:49-235)
+    assert P.estimate_all_gather_time_ms(1 << 30, 8, 8, 770.0, 50.0) == P.estimate_all_gather_time_ms(1 << 30, 8)
+    assert P.get_max_tensorcore_tflops(torch.bfloat16, 1965, "NVIDIA B200") == 2250.0
+    assert P.get_tensorcore_tflops_by_device_name(torch.float8_e4m3fn, "NVIDIA B200") == 4500.0
+    assert P.get_dram_gbps_by_device_name("NVIDIA H800") == 3350.0 and P.get_device_multi_processor_count("B200") == 148
+    assert P.get_tflops_approx("B200", 74, 4, torch.bfloat16) == 1125.0
+
+
 def test_shmem_device_header_compiles_for_sm100a():
     """The NVSHMEM-style device header (csrc/td/shmem.cuh): the self-test kernel of the `shmem` distributed case cross-compiles, and
     the Python mirror's team arithmetic agrees with NVSHMEM's strided-split semantics."""

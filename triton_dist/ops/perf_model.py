@@ -46,12 +46,22 @@ def get_nic_gbps_per_gpu() -> float:
     return 0.0       # single NVSwitch domain
 
 
-def estimate_all_gather_time_ms(nbytes_total: int, world: int, gbps: float = NVLINK_MEASURED_GBS) -> float:
-    return nbytes_total * (world - 1) / world / (gbps * 1e9) * 1e3
+def _intranode_gbps(world, *legacy) -> float:
+    """The reference passes (local_world_size, intranode_bw_in_gbps, internode_bw_in_gbps) (comm_perf_model.py:94-131); here the second
+    positional argument may be the bandwidth directly.  Everything is one NVSwitch domain, so only the intra-node number matters."""
+    if len(legacy) >= 2:
+        return float(legacy[1])
+    if len(legacy) == 1:
+        return float(legacy[0])
+    return NVLINK_MEASURED_GBS
 
 
-def estimate_reduce_scatter_time_ms(nbytes_total: int, world: int, gbps: float = NVLINK_MEASURED_GBS) -> float:
-    return nbytes_total * (world - 1) / world / (gbps * 1e9) * 1e3
+def estimate_all_gather_time_ms(nbytes_total: int, world: int, *legacy) -> float:
+    return nbytes_total * (world - 1) / world / (_intranode_gbps(world, *legacy) * 1e9) * 1e3
+
+
+def estimate_reduce_scatter_time_ms(nbytes_total: int, world: int, *legacy) -> float:
+    return nbytes_total * (world - 1) / world / (_intranode_gbps(world, *legacy) * 1e9) * 1e3
 
 
 def fused_roofline_ms(flops_per_rank: float, nvlink_bytes_per_rank: float, dtype=torch.bfloat16) -> float:
@@ -127,3 +137,162 @@ def pick_ag_transport(M: int, N_local: int, K: int, world: int, multicast_ok: bo
             if best is None or t < best[-1]:
                 best = (tr, ks, gr, nc, t)
     return best
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Device table / tensor-core peak helpers in the reference's spelling (gemm_perf_model.py:49-235)
+# ------------------------------------------------------------------------------------------------------------
+_DEVICE_TABLE = {
+    # name fragment: (dense bf16 TFLOP/s, dense fp8 TFLOP/s, HBM GB/s, SMs, boost MHz)
+    "B200": (2250.0, 4500.0, 7700.0, 148, 1965),
+    "B300": (2250.0, 4500.0, 7700.0, 148, 1965),
+    "GB200": (2500.0, 5000.0, 8000.0, 148, 1965),
+    "H100": (989.0, 1979.0, 3350.0, 132, 1830),
+    "H800": (989.0, 1979.0, 3350.0, 132, 1830),
+    "H200": (989.0, 1979.0, 4800.0, 132, 1830),
+}
+
+
+def _device_entry(device_name=None):
+    if device_name is None:
+        device_name = measured_peaks().get("gpu_name") or (torch.cuda.get_device_name() if torch.cuda.is_available() else "B200")
+    for k in sorted(_DEVICE_TABLE, key=len, reverse=True):
+        if k in str(device_name):
+            return _DEVICE_TABLE[k]
+    return _DEVICE_TABLE["B200"]
+
+
+def is_fp8_dtype(dtype: torch.dtype) -> bool:
+    return dtype in (torch.float8_e4m3fn, torch.float8_e5m2, torch.float8_e4m3fnuz, torch.float8_e5m2fnuz)
+
+
+def get_tensorcore_tflops_by_device_name(dtype: torch.dtype, device_name=None) -> float:
+    bf, f8, *_ = _device_entry(device_name)
+    if is_fp8_dtype(dtype) or dtype == torch.int8:
+        return f8
+    if dtype == torch.float32:
+        return bf / 2            # tf32
+    return bf
+
+
+def get_max_tensorcore_tflops(dtype: torch.dtype, clock_rate_mhz=None, device=None) -> float:
+    """Nominal dense peak scaled to a clock (the reference derives it from SM count x per-SM rate x clock)."""
+    entry = _device_entry(device)
+    peak = get_tensorcore_tflops_by_device_name(dtype, device)
+    return peak if not clock_rate_mhz else peak * float(clock_rate_mhz) / entry[4]
+
+
+def get_full_tflops_approx(dtype: torch.dtype, device=None) -> float:
+    return get_max_tensorcore_tflops(dtype, None, device)
+
+
+def get_tflops_approx(device, num_ctas: int, num_warps: int, dtype: torch.dtype) -> float:
+    """Share of the tensor-core peak a grid of ``num_ctas`` CTAs can reach (one tcgen05 issuer per CTA feeds one SM)."""
+    sms = _device_entry(device)[3]
+    return get_full_tflops_approx(dtype, device) * min(num_ctas, sms) / sms
+
+
+def get_dram_gbps_by_device_name(device_name=None) -> float:
+    return _device_entry(device_name)[2]
+
+
+def get_device_multi_processor_count(device=None) -> int:
+    return _device_entry(device)[3]
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Tile-level GEMM model of csrc/gemm_sm100.cuh (waves of tiles on CTAs / CTA pairs)
+# ------------------------------------------------------------------------------------------------------------
+# sustained mainloop rate of ONE CTA in TFLOP/s by (cta_group, BN): fitted to profiles/README.md section 1 (cta_group 1) and the round-2
+# plain-GEMM numbers (cta_group 2).  128-wide tiles re-read B twice as often per FLOP and are shared-memory bound.
+_CTA_RATE = {(2, 256): TILE_RATE_TFLOPS_PER_PAIR / 2, (2, 192): TILE_RATE_TFLOPS_PER_PAIR / 2 * 0.97, (2, 128): 8.6,
+             (1, 256): 10.0, (1, 192): 9.6, (1, 128): 6.3}
+GEMM_PROLOGUE_US = 5.0                    # launch, tensormap prefetch, barrier init, TMEM alloc, first TMA round trip
+
+
+def estimate_gemm_ms(M: int, N: int, K: int, cta_group: int = 2, bn: int = 256, sms: int = 148, split_k_tail: bool = True,
+                     dtype: torch.dtype = torch.bfloat16) -> float:
+    """What the persistent tcgen05 GEMM of this repo takes: ceil-waves of (128 * cta_group) x bn tiles over the CTAs (pairs), the last
+    partial wave shortened by the split-K tail schedule; never below the HBM time of the operands."""
+    tm = 128 * cta_group
+    tiles = -(-M // tm) * -(-N // bn)
+    workers = max(1, sms // cta_group)
+    rate = _CTA_RATE.get((cta_group, bn), _CTA_RATE[(cta_group, 256)] * bn / 256) * cta_group
+    if is_fp8_dtype(dtype):
+        rate *= 1.6                       # measured MXFP8 / bf16 ratio of the same kernel (2.5 vs 1.55 PFLOP/s)
+    tile_us = 2.0 * tm * bn * K / (rate * 1e12) * 1e6
+    full, rem = divmod(tiles, workers)
+    last = 0.0
+    if rem:
+        parts = min(4, workers // rem) if split_k_tail else 1
+        last = 1.0 / max(parts, 1) + (0.08 if parts > 1 else 0.0)      # reduction of the partial accumulators
+    es = torch.empty(0, dtype=dtype).element_size()
+    t_mem = (M * K + N * K) * es / (get_dram_gbps() * 1e9) * 1e6
+    return (max((full + last) * tile_us, t_mem) + GEMM_PROLOGUE_US) * 1e-3
+
+
+def pick_gemm_config(M: int, N: int, K: int, sms: int = 148):
+    """Model-cheapest (cta_group, bn) -- what ``tools/tune/tune_gemm.py`` finds by measurement."""
+    best = None
+    for cg, bn in ((2, 256), (2, 128), (1, 256), (1, 128)):
+        t = estimate_gemm_ms(M, N, K, cg, bn, sms)
+        if best is None or t < best[-1]:
+            best = (cg, bn, t)
+    return best
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Collective models: t = alpha + beta * bytes, fitted at 8 x B200 (profiles/README.md section 3), scaled with the world size by the
+# traffic each algorithm moves per rank
+# ------------------------------------------------------------------------------------------------------------
+# method: (alpha_us at W = 8, beta in us per byte at W = 8, traffic factor as a function of W used to rescale beta)
+_AR_FIT = {
+    "OneShot": (33.4, 1.40e-5, lambda w: (w - 1)),                  # every rank reads (W-1) full buffers over P2P
+    "TwoShot": (26.5, 4.578e-6, lambda w: 2.0 * (w - 1) / w),       # reduce-scatter + all-gather over P2P
+    "OneShot_Multimem": (21.6, 1.2225e-5, lambda w: float(w)),      # every rank ld_reduces the whole buffer: the switch reads W copies per rank
+    "TwoShot_Multimem": (22.9, 3.704e-6, lambda w: 1.0),            # ld_reduce of 1/W + multimem.st broadcast: ~W-independent per rank
+}
+
+
+def estimate_allreduce_us(nbytes: int, world: int = 8, method: str = "TwoShot_Multimem") -> float:
+    a, b, f = _AR_FIT[method]
+    if world <= 1:
+        return 5.0
+    return a * (0.8 + 0.2 * world / 8.0) + b * f(world) / f(8) * nbytes
+
+
+def pick_allreduce_method(nbytes: int, world: int = 8, multimem_ok: bool = True):
+    names = [n for n in _AR_FIT if multimem_ok or "Multimem" not in n]
+    best = min(names, key=lambda n: estimate_allreduce_us(nbytes, world, n))
+    return best, estimate_allreduce_us(nbytes, world, best)
+
+
+BARRIER_US = 9.0                          # cross-GPU flag barrier inside a kernel (release fence + one NVLink round trip)
+COMM_KERNEL_LAUNCH_US = 6.0
+
+
+def estimate_fast_allgather_us(shard_bytes: int, world: int = 8, mode: str = "push") -> float:
+    """Small / medium message all-gather kernels (ops/comm.py fast_allgather): LL modes skip the barrier but move 2x the bytes."""
+    if world <= 1:
+        return COMM_KERNEL_LAUNCH_US
+    ll = "ll" in mode
+    mc = "multimem" in mode
+    wire = shard_bytes * (2 if ll else 1)
+    if mc:
+        t = wire * world / (NVLS_MULTICAST_INGRESS_GBS * 1e9) * 1e6          # ingress of W shards; egress is 1x
+    else:
+        t = wire * (world - 1) / (NVLINK_ALLGATHER_PATTERN_GBS * 1e9) * 1e6
+    return COMM_KERNEL_LAUNCH_US + t + (2.5 if ll else BARRIER_US)
+
+
+def estimate_ep_dispatch_us(tokens_per_rank: int, hidden: int, topk: int, world: int = 8, bytes_per_elem: int = 1) -> float:
+    """EP low-latency dispatch (csrc/ep_kernels.cu): every (token, k) row crosses NVLink once; fitted to 52.6 us (fp8) / 71.9 us (bf16)
+    at 128 tokens x top-8 x 7168 on 8 ranks."""
+    payload = tokens_per_rank * topk * hidden * bytes_per_elem * (world - 1) / max(world, 1)
+    return 38.0 + payload / (NVLINK_ALLGATHER_PATTERN_GBS * 1e9) * 1e6 * (8.0 / 7.0)
+
+
+def estimate_ep_combine_us(tokens_per_rank: int, hidden: int, topk: int, world: int = 8) -> float:
+    """Combine returns bf16 rows and reduces top-k on the owner: 57.6 us (fp8 run: 110.2 - 52.6) / 70.5 us (bf16 run) measured."""
+    payload = tokens_per_rank * topk * hidden * 2 * (world - 1) / max(world, 1)
+    return 36.0 + payload / (NVLINK_ALLGATHER_PATTERN_GBS * 1e9) * 1e6 * (8.0 / 7.0)
