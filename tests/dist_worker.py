@@ -409,6 +409,39 @@ def case_gemm_a2a():
         ctx.finalize()
 
 
+def case_gemm_a2a_q8():
+    """Quantised GEMM + all-to-all (Ulysses inference flavour): int8 x int8 with per-row input scales and per-channel weight scales,
+    dequantised in the epilogue, bf16 on the wire (reference: ulysses_sp_infer_gemm_a2a.py:143-260).  GPU: two-kernel default and the
+    fused one-kernel variant; emulation: the same flag protocol as the 16-bit op."""
+    from triton_dist.ops.compat import ulysses_sp_infer_gemm_a2a_op
+    from triton_dist.ops.gemm_a2a import create_gemm_a2a_context, gemm_all_to_all
+    W, me = U.world_size(), U.rank()
+    dev = U.current_device()
+    M, K, c = 128, 256, 64
+    ctx = create_gemm_a2a_context(M, c, torch.bfloat16)
+    g = torch.Generator().manual_seed(5)
+    w8 = torch.randint(-8, 8, (W * c, K), generator=g, dtype=torch.int8).to(dev)            # same weight on every rank
+    sb = (torch.rand(W * c, generator=g) * 0.05 + 0.01).to(dev)
+    variants = (None, True) if dev.type == "cuda" else (None,)
+    for it in range(3):
+        for fused in variants:
+            gx = torch.Generator().manual_seed(100 * it + me)
+            x8 = torch.randint(-8, 8, (M, K), generator=gx, dtype=torch.int8).to(dev)
+            sa = (torch.rand(M, generator=gx) * 0.1 + 0.02).to(dev)
+            if fused is None:
+                out = ulysses_sp_infer_gemm_a2a_op(ctx, x8, w8, input_scale=sa, weight_scale=sb)
+            else:
+                out = gemm_all_to_all(ctx, x8, w8, scale_a=sa, scale_b=sb, fused=True)
+            # reference: every rank's dequantised product, my column block of each
+            mine = ((x8.float() @ w8.float().t()) * sa[:, None] * sb[None, :]).to(torch.bfloat16)
+            full = [torch.empty_like(mine) for _ in range(W)]
+            dist.all_gather(full, mine, group=U.get_triton_dist_world())
+            ref = torch.cat([f[:, me * c:(me + 1) * c] for f in full], 0)
+            _assert_close(out, ref, 2e-2, 2e-2, f"gemm_a2a_q8 it {it} fused {fused}")
+    U.barrier_all_host()
+    ctx.finalize()
+
+
 def case_moe():
     """ag_group_gemm + run_moe_reduce_rs vs the masked-matmul golden (reference: test_ag_moe.py, test_moe_reduce_rs.py)."""
     from triton_dist.ops import moe as M

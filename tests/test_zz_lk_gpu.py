@@ -85,3 +85,12 @@ def test_allgather_multimem_two_gpus():
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from _launch import run_dist
     run_dist(["allgather_mc"], nproc=2, timeout=240)
+
+
+def test_gemm_a2a_quantised_two_gpus():
+    """int8 GEMM + all-to-all: the two-kernel path (validated halves) and the fused one-kernel variant (new combination)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from _launch import run_dist
+    run_dist(["gemm_a2a_q8"], nproc=2, timeout=240)

@@ -127,13 +127,16 @@ class SpUlysessOAll2AllGemmKernel:
 UlyssesSpInferPreAttnContext = SpUlysessQKVGemmAll2AllKernel
 
 
-def ulysses_sp_infer_gemm_a2a_op(ctx, x, wqkv):
+def ulysses_sp_infer_gemm_a2a_op(ctx, x, wqkv, input_scale=None, weight_scale=None):
     """(ulysses_sp_infer_gemm_a2a.py:455) ``ctx``: a :class:`SpUlysessQKVGemmAll2AllKernel` (GEMM then all-to-all) or a
     :class:`triton_dist.ops.gemm_a2a.GemmA2AContext` (all-to-all fused into the GEMM epilogue; ``wqkv`` rows grouped by
-    destination rank)."""
+    destination rank).  int8 / float8_e4m3fn ``x`` and ``wqkv`` with ``input_scale`` (per row) / ``weight_scale`` (per output
+    channel) run the quantised flavour (dequantisation in the tcgen05 epilogue, bf16 on the wire)."""
     from .gemm_a2a import GemmA2AContext, gemm_all_to_all
     if isinstance(ctx, GemmA2AContext):
-        return gemm_all_to_all(ctx, x, wqkv)
+        return gemm_all_to_all(ctx, x, wqkv, scale_a=input_scale, scale_b=weight_scale)
+    if input_scale is not None or weight_scale is not None:
+        raise NotImplementedError("quantised operands need a GemmA2AContext (create_gemm_a2a_context)")
     return ctx.forward(x, wqkv)
 
 
