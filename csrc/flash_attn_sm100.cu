@@ -40,6 +40,8 @@ struct Params {
   int B, Sq, Sk, Hq, Hkv;
   int causal, is_bf16;
   float scale_log2;        // sm_scale * log2(e)
+  const int* cu_q;         // varlen (v2 kernel): int32 [B + 1] cumulative query lengths; Sq / Sk then hold the packed totals
+  const int* cu_k;         // varlen: int32 [B + 1] cumulative key lengths
 };
 
 // BNK = keys per pipeline step.  128: one CTA per SM (197 KB smem, 384 TMEM columns).  64: TWO CTAs per SM (115 KB, 256
@@ -400,6 +402,11 @@ struct SmemV2 {
 };
 enum BarV2 { V2_Q_FULL = 0, V2_K_FULL = 1, V2_V_FULL = 4, V2_KV_EMPTY = 7, V2_S_FULL = 10, V2_P_READY = 12, V2_PV_DONE = 13, V2_Q_TMEM = 14, V2_NBAR = 15 };
 
+// kVarlen: packed variable-length batch -- sequence `batch` owns rows [cu_q[b], cu_q[b+1]) of Q / O and [cu_k[b], cu_k[b+1]) of K / V
+// (tensor maps over the packed [T, H, D] tensors, batch coordinate 0); CTAs of query tiles a sequence does not have exit at once.
+// Rows of a tile past the end of its sequence belong to the next sequence: they are loaded, never stored (`live`), and keys past
+// the end are masked exactly like the tail of a padded batch.
+template <bool kVarlen>
 __global__ void __launch_bounds__(kThreadsV2, 1) flash_fwd_kernel_v2(const __grid_constant__ Params p, int n_q_tiles) {
   constexpr int BNK = 128;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -416,9 +423,16 @@ __global__ void __launch_bounds__(kThreadsV2, 1) flash_fwd_kernel_v2(const __gri
   const int head = hb % p.Hq, batch = hb / p.Hq;
   const int kv_head = head / (p.Hq / p.Hkv);
   const int q_row0 = q_tile * BMQ;
-  const int q_pos0 = p.q_tile_pos ? p.q_tile_pos[batch * n_q_tiles + q_tile] : q_row0 + (p.Sk - p.Sq);
-  const int rows_here = min(BMQ, p.Sq - q_row0);
-  int n_tiles = (p.Sk + BNK - 1) / BNK;
+  int Sq = p.Sq, Sk = p.Sk, q_base = 0, k_base = 0, tb = batch;          // tb: batch coordinate of the tensor maps / output
+  if constexpr (kVarlen) {
+    q_base = p.cu_q[batch]; Sq = p.cu_q[batch + 1] - q_base;
+    k_base = p.cu_k[batch]; Sk = p.cu_k[batch + 1] - k_base;
+    tb = 0;
+    if (q_row0 >= Sq || Sk <= 0) return;       // uniform for the CTA, before any barrier / TMEM state exists
+  }
+  const int q_pos0 = p.q_tile_pos ? p.q_tile_pos[batch * n_q_tiles + q_tile] : q_row0 + (Sk - Sq);
+  const int rows_here = min(BMQ, Sq - q_row0);
+  int n_tiles = (Sk + BNK - 1) / BNK;
   if (p.causal) n_tiles = min(n_tiles, (q_pos0 + rows_here - 1) / BNK + 1);
 
   if (warp == 0 && lane == 0) {
@@ -452,19 +466,19 @@ __global__ void __launch_bounds__(kThreadsV2, 1) flash_fwd_kernel_v2(const __gri
   if (warp == 0) {
     if (lane == 0) {
       ptx::mbar_arrive_expect_tx(&bars[V2_Q_FULL], kQBytes);
-      ptx::tma_load_4d(&p.tmap_q, &bars[V2_Q_FULL], smem + SmemV2::kQ, 0, q_row0, head, batch);
-      ptx::tma_load_4d(&p.tmap_q, &bars[V2_Q_FULL], smem + SmemV2::kQ + kSlab, 64, q_row0, head, batch);
+      ptx::tma_load_4d(&p.tmap_q, &bars[V2_Q_FULL], smem + SmemV2::kQ, 0, q_base + q_row0, head, tb);
+      ptx::tma_load_4d(&p.tmap_q, &bars[V2_Q_FULL], smem + SmemV2::kQ + kSlab, 64, q_base + q_row0, head, tb);
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j % kStagesV2, use = j / kStagesV2;
         if (use > 0) ptx::mbar_wait(&bars[V2_KV_EMPTY + st], (use - 1) & 1);
         uint8_t* ks = smem + SmemV2::kK + st * kKVTileV2;
         uint8_t* vs = smem + SmemV2::kV + st * kKVTileV2;
         ptx::mbar_arrive_expect_tx(&bars[V2_K_FULL + st], kKVTileV2);
-        ptx::tma_load_4d(&p.tmap_k, &bars[V2_K_FULL + st], ks, 0, j * BNK, kv_head, batch, ptx::kEvictLast);
-        ptx::tma_load_4d(&p.tmap_k, &bars[V2_K_FULL + st], ks + kSlab, 64, j * BNK, kv_head, batch, ptx::kEvictLast);
+        ptx::tma_load_4d(&p.tmap_k, &bars[V2_K_FULL + st], ks, 0, k_base + j * BNK, kv_head, tb, ptx::kEvictLast);
+        ptx::tma_load_4d(&p.tmap_k, &bars[V2_K_FULL + st], ks + kSlab, 64, k_base + j * BNK, kv_head, tb, ptx::kEvictLast);
         ptx::mbar_arrive_expect_tx(&bars[V2_V_FULL + st], kKVTileV2);
-        ptx::tma_load_4d(&p.tmap_v, &bars[V2_V_FULL + st], vs, 0, j * BNK, kv_head, batch, ptx::kEvictLast);
-        ptx::tma_load_4d(&p.tmap_v, &bars[V2_V_FULL + st], vs + kSlab, 64, j * BNK, kv_head, batch, ptx::kEvictLast);
+        ptx::tma_load_4d(&p.tmap_v, &bars[V2_V_FULL + st], vs, 0, k_base + j * BNK, kv_head, tb, ptx::kEvictLast);
+        ptx::tma_load_4d(&p.tmap_v, &bars[V2_V_FULL + st], vs + kSlab, 64, k_base + j * BNK, kv_head, tb, ptx::kEvictLast);
       }
     }
   } else if (warp == 1) {
@@ -539,9 +553,9 @@ __global__ void __launch_bounds__(kThreadsV2, 1) flash_fwd_kernel_v2(const __gri
       ptx::tmem_ld_wait();
 
       const int key0 = j * BNK + half * 64;
-      const bool need_mask = (p.causal && j * BNK + BNK - 1 > q_pos0) || (j * BNK + BNK > p.Sk);
+      const bool need_mask = (p.causal && j * BNK + BNK - 1 > q_pos0) || (j * BNK + BNK > Sk);
       if (need_mask) {
-        const int limit = p.causal ? min(p.Sk - 1, q_pos) : p.Sk - 1;
+        const int limit = p.causal ? min(Sk - 1, q_pos) : Sk - 1;
 #pragma unroll
         for (int c = 0; c < 2; ++c)
 #pragma unroll
@@ -611,7 +625,7 @@ __global__ void __launch_bounds__(kThreadsV2, 1) flash_fwd_kernel_v2(const __gri
     const float inv_l = l > 0.f ? 1.f / l : 0.f;
     const bool live = row < rows_here;
     char* o_row = reinterpret_cast<char*>(p.o) +
-                  2 * (static_cast<long long>(batch) * p.o_stride_b + static_cast<long long>(q_row0 + row) * p.o_stride_s +
+                  2 * (static_cast<long long>(tb) * p.o_stride_b + static_cast<long long>(q_base + q_row0 + row) * p.o_stride_s +
                        static_cast<long long>(head) * p.o_stride_h + half * 64);
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
@@ -643,7 +657,7 @@ __global__ void __launch_bounds__(kThreadsV2, 1) flash_fwd_kernel_v2(const __gri
     }
     if (p.lse && live && half == 0) {
       const float lse = (l > 0.f) ? (m_ref + log2f(l)) * 0.6931471805599453f : -INFINITY;
-      p.lse[(static_cast<long long>(batch) * p.Hq + head) * p.Sq + q_row0 + row] = lse;
+      p.lse[(static_cast<long long>(tb) * p.Hq + head) * p.Sq + q_base + q_row0 + row] = lse;     // varlen: [Hq, total_q]
     }
     ptx::tc_fence_before();
   }
@@ -932,6 +946,8 @@ struct TdFlashArgs {
   double sm_scale;
   long long causal, is_bf16;
   long long block_n;          // keys per step: 64 (two CTAs per SM, default) or 128; 129 = 128 with Q and P in TMEM
+  const int* cu_q; const int* cu_k;   // varlen (block_n 130 only): cumulative lengths, B = number of sequences, Sq / Sk = packed totals
+  long long max_sq;                   // varlen: longest query sequence (grid bound)
 };
 
 template <int BNK, bool kTS = false>
@@ -974,9 +990,15 @@ extern "C" __attribute__((visibility("default"))) int td_flash_attn_fwd(const Td
     if (s % 8 != 0) { td::drv::set_error("flash_attn: strides must be multiples of 8 elements (16 bytes)"); return -1; }
   Params p{};
   const int bnk = (a->block_n >= 128) ? 128 : 64;
-  if (fa_tmap(&p.tmap_q, a->q, a->Sq, a->Hq, a->B, a->q_stride_b, a->q_stride_s, a->q_stride_h, (int)a->is_bf16, BMQ)) return -1;
-  if (fa_tmap(&p.tmap_k, a->k, a->Sk, a->Hkv, a->B, a->k_stride_b, a->k_stride_s, a->k_stride_h, (int)a->is_bf16, bnk)) return -1;
-  if (fa_tmap(&p.tmap_v, a->v, a->Sk, a->Hkv, a->B, a->v_stride_b, a->v_stride_s, a->v_stride_h, (int)a->is_bf16, bnk)) return -1;
+  const bool varlen = a->cu_q != nullptr;
+  if (varlen && (a->block_n != 130 || a->cu_k == nullptr || a->q_tile_pos != nullptr || a->max_sq <= 0)) {
+    td::drv::set_error("flash_attn varlen: v2 kernel only, needs cu_seqlens_k and max_seqlen_q, no q_tile_pos"); return -1;
+  }
+  const long long tmB = varlen ? 1 : a->B;           // packed tensors: one "batch" of Sq / Sk total rows
+  if (fa_tmap(&p.tmap_q, a->q, a->Sq, a->Hq, tmB, a->q_stride_b, a->q_stride_s, a->q_stride_h, (int)a->is_bf16, BMQ)) return -1;
+  if (fa_tmap(&p.tmap_k, a->k, a->Sk, a->Hkv, tmB, a->k_stride_b, a->k_stride_s, a->k_stride_h, (int)a->is_bf16, bnk)) return -1;
+  if (fa_tmap(&p.tmap_v, a->v, a->Sk, a->Hkv, tmB, a->v_stride_b, a->v_stride_s, a->v_stride_h, (int)a->is_bf16, bnk)) return -1;
+  p.cu_q = a->cu_q; p.cu_k = a->cu_k;
   p.o = a->o; p.lse = a->lse; p.q_tile_pos = a->q_tile_pos;
   p.o_stride_b = a->o_stride_b; p.o_stride_s = a->o_stride_s; p.o_stride_h = a->o_stride_h;
   p.B = (int)a->B; p.Sq = (int)a->Sq; p.Sk = (int)a->Sk; p.Hq = (int)a->Hq; p.Hkv = (int)a->Hkv;
@@ -1000,12 +1022,14 @@ extern "C" __attribute__((visibility("default"))) int td_flash_attn_fwd(const Td
   if (a->block_n == 130) {     // v2 kernel
     static bool v2_attr = false;
     if (!v2_attr) {
-      cudaError_t e = cudaFuncSetAttribute(flash_fwd_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemV2::kTotal);
+      cudaError_t e = cudaFuncSetAttribute(flash_fwd_kernel_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemV2::kTotal);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_fwd_kernel_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemV2::kTotal);
       if (e != cudaSuccess) { td::drv::set_error("flash_attn v2: smem attribute: %s", cudaGetErrorString(e)); return -1; }
       v2_attr = true;
     }
-    const int nq = (int)((a->Sq + BMQ - 1) / BMQ);
-    flash_fwd_kernel_v2<<<dim3((unsigned)(nq * a->Hq * a->B)), kThreadsV2, SmemV2::kTotal, st_>>>(p, nq);
+    const int nq = (int)(((varlen ? a->max_sq : a->Sq) + BMQ - 1) / BMQ);
+    if (varlen) flash_fwd_kernel_v2<true><<<dim3((unsigned)(nq * a->Hq * a->B)), kThreadsV2, SmemV2::kTotal, st_>>>(p, nq);
+    else flash_fwd_kernel_v2<false><<<dim3((unsigned)(nq * a->Hq * a->B)), kThreadsV2, SmemV2::kTotal, st_>>>(p, nq);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { td::drv::set_error("flash_attn v2 launch: %s", cudaGetErrorString(e)); return -1; }
     return 0;

@@ -829,6 +829,44 @@ def case_sp_pp():
         pp.finalize()
 
 
+def case_sp_varlen():
+    """Context-parallel attention over a packed variable-length batch: every rank holds len_b / W tokens of each sequence (zig-zag
+    inside each sequence), ONE gather of the packed KV, attention per sequence (reference: sp_ag_attention_intra_node.py:279-360)."""
+    import math
+    from triton_dist.parallel.sp import create_sp_ag_attention_context_intra_node, fused_sp_ag_attn_varlen, zigzag_positions
+    dev = U.current_device()
+    W, me = U.world_size(), U.rank()
+    big = dev.type == "cuda"
+    dtype = torch.bfloat16 if big else torch.float32
+    Hq, Hkv, D = 4, 2, 128
+    unit = 256 * W if big else 4 * W            # sequence lengths: multiples of 2W (zig-zag) -- and of the 128-query tile on a GPU
+    lens = [unit, 3 * unit, 2 * unit]
+    g = torch.Generator().manual_seed(11)
+    qs = [torch.randn(L, Hq, D, generator=g).to(dtype).to(dev) for L in lens]
+    ks = [torch.randn(L, Hkv, D, generator=g).to(dtype).to(dev) for L in lens]
+    vs = [torch.randn(L, Hkv, D, generator=g).to(dtype).to(dev) for L in lens]
+    for zz in (True, False):
+        def mine(L):
+            return zigzag_positions(L, W, me, dev) if (zz and W > 1) else torch.arange(me * (L // W), (me + 1) * (L // W), device=dev)
+        pos = [mine(L) for L in lens]
+        q_sh = torch.cat([q[p] for q, p in zip(qs, pos)]).contiguous()
+        k_sh = torch.cat([k[p] for k, p in zip(ks, pos)]).contiguous()
+        v_sh = torch.cat([v[p] for v, p in zip(vs, pos)]).contiguous()
+        cu = torch.tensor([0] + list(torch.tensor([L // W for L in lens]).cumsum(0)), dtype=torch.int32, device=dev)
+        ctx = create_sp_ag_attention_context_intra_node(q_sh.shape[0], Hkv, D, dtype)
+        for it in range(2):
+            o = fused_sp_ag_attn_varlen(ctx, q_sh, k_sh, v_sh, cu, is_causal=True, enable_zig_zag=zz)
+            ofs = 0
+            for q, k, v, p, L in zip(qs, ks, vs, pos, lens):
+                kk, vv = k.float().repeat_interleave(Hq // Hkv, 1), v.float().repeat_interleave(Hq // Hkv, 1)
+                sc = torch.einsum("shd,lhd->hsl", q.float(), kk) / math.sqrt(D)
+                sc = sc.masked_fill(~(torch.arange(L, device=dev)[None, :] <= torch.arange(L, device=dev)[:, None])[None], float("-inf"))
+                full_o = torch.einsum("hsl,lhd->shd", torch.softmax(sc, -1), vv)
+                _assert_close(o[ofs:ofs + L // W], full_o[p], 3e-2 if big else 1e-4, 3e-2 if big else 1e-4, f"sp varlen zz={zz} L={L}")
+                ofs += L // W
+        ctx.finalize()
+
+
 def case_ep_moe():
     """EP_MoE layer (route -> dispatch -> grouped FFN -> combine) vs the gathered golden; autograd through dispatch/combine."""
     from triton_dist.parallel.ep import EP_MoE, TritonDistFusedEpMoeFunction

@@ -480,3 +480,22 @@ def test_shmem_device_header_compiles_for_sm100a():
     import pytest
     with pytest.raises(ValueError):
         team_split_strided(world, 4, 2, 3)
+
+
+def test_flash_attn_varlen_reference_path():
+    """Packed variable-length attention (CPU path): per-sequence bottom-right causal masks, LSE in [Hq, Tq] layout."""
+    import torch
+    from triton_dist.ops.flash_attn import flash_attn_reference, flash_attn_varlen
+    torch.manual_seed(0)
+    lens_q, lens_k = [5, 130, 0, 64], [9, 130, 4, 200]
+    cq = torch.tensor([0] + list(torch.tensor(lens_q).cumsum(0)), dtype=torch.int32)
+    ck = torch.tensor([0] + list(torch.tensor(lens_k).cumsum(0)), dtype=torch.int32)
+    q, k, v = torch.randn(sum(lens_q), 4, 128), torch.randn(sum(lens_k), 2, 128), torch.randn(sum(lens_k), 2, 128)
+    out, lse = flash_attn_varlen(q, k, v, cq, ck, True, return_lse=True)
+    assert out.shape == q.shape and lse.shape == (4, sum(lens_q))
+    for i in range(len(lens_q)):
+        a, b, c, d = int(cq[i]), int(cq[i + 1]), int(ck[i]), int(ck[i + 1])
+        if b > a:
+            ref, ref_lse = flash_attn_reference(q[None, a:b], k[None, c:d], v[None, c:d], True)
+            torch.testing.assert_close(out[a:b], ref[0])
+            torch.testing.assert_close(lse[:, a:b], ref_lse[0])

@@ -24,7 +24,8 @@ class _FlashArgs(C.Structure):
                 ("k_stride_b", c_ll), ("k_stride_s", c_ll), ("k_stride_h", c_ll),
                 ("v_stride_b", c_ll), ("v_stride_s", c_ll), ("v_stride_h", c_ll),
                 ("o_stride_b", c_ll), ("o_stride_s", c_ll), ("o_stride_h", c_ll),
-                ("sm_scale", c_double), ("causal", c_ll), ("is_bf16", c_ll), ("block_n", c_ll)]
+                ("sm_scale", c_double), ("causal", c_ll), ("is_bf16", c_ll), ("block_n", c_ll),
+                ("cu_q", c_void_p), ("cu_k", c_void_p), ("max_sq", c_ll)]
 
 
 _C.register("td_flash_attn_fwd", c_int, [C.POINTER(_FlashArgs), c_void_p])
@@ -102,13 +103,47 @@ def flash_attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bo
 
 
 def flash_attn_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_seqlens_q: torch.Tensor, cu_seqlens_k: torch.Tensor,
-                      causal: bool = True, sm_scale: Optional[float] = None) -> torch.Tensor:
-    """Packed variable-length batch: q [Tq, Hq, D], k/v [Tk, Hkv, D]; one launch per sequence (the host reads the
-    cumulative lengths once)."""
+                      causal: bool = True, sm_scale: Optional[float] = None, max_seqlen_q: Optional[int] = None,
+                      return_lse: bool = False, one_launch: Optional[bool] = None):
+    """Packed variable-length batch (``flash_attn_varlen_func`` semantics): q [Tq, Hq, D], k / v [Tk, Hkv, D], ``cu_seqlens_*`` int32
+    [B + 1].  Causal masks are bottom-right aligned per sequence (query i of a sequence sees its keys up to ``Sk - Sq + i``).
+
+    ``one_launch=True`` (or ``TD_FLASH_VARLEN_KERNEL=1``): ONE launch of the varlen instantiation of the v2 kernel -- the cumulative
+    lengths stay on the device (no host sync; ``max_seqlen_q`` bounds the grid, default: Tq), CTAs of tiles a sequence does not have
+    exit immediately.  Default: one launch per sequence (the host reads the cumulative lengths once); the one-launch kernel compiles
+    but has not run on hardware yet.  With ``return_lse`` the LSE comes back as [Hq, Tq]."""
+    import os
+    Tq, Hq, D = q.shape
+    if one_launch is None:
+        one_launch = os.environ.get("TD_FLASH_VARLEN_KERNEL", "0") == "1"
+    B = cu_seqlens_q.numel() - 1
+    if q.is_cuda and one_launch:
+        assert D == 128 and q.dtype in (torch.bfloat16, torch.float16) and k.dtype == q.dtype == v.dtype
+        assert q.stride(2) == 1 and k.stride(2) == 1 and v.stride(2) == 1
+        assert cu_seqlens_q.dtype == torch.int32 and cu_seqlens_k.dtype == torch.int32 and cu_seqlens_q.is_cuda and cu_seqlens_k.is_cuda
+        out = torch.empty((Tq, Hq, D), dtype=q.dtype, device=q.device)
+        lse = torch.empty((Hq, Tq), dtype=torch.float32, device=q.device) if return_lse else None
+        a = _FlashArgs()
+        a.q, a.k, a.v, a.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+        a.lse = lse.data_ptr() if lse is not None else None
+        a.B, a.Sq, a.Sk, a.Hq, a.Hkv, a.D = B, Tq, k.shape[0], Hq, k.shape[1], D
+        a.q_stride_b, a.q_stride_s, a.q_stride_h = Tq * q.stride(0), q.stride(0), q.stride(1)
+        a.k_stride_b, a.k_stride_s, a.k_stride_h = k.shape[0] * k.stride(0), k.stride(0), k.stride(1)
+        a.v_stride_b, a.v_stride_s, a.v_stride_h = v.shape[0] * v.stride(0), v.stride(0), v.stride(1)
+        a.o_stride_b, a.o_stride_s, a.o_stride_h = Tq * out.stride(0), out.stride(0), out.stride(1)
+        a.sm_scale, a.causal, a.is_bf16 = float(sm_scale or 1.0 / math.sqrt(D)), int(causal), int(q.dtype == torch.bfloat16)
+        a.block_n = 130
+        a.cu_q, a.cu_k = cu_seqlens_q.data_ptr(), cu_seqlens_k.data_ptr()
+        a.max_sq = int(max_seqlen_q) if max_seqlen_q else Tq
+        _C.check(_C.cuda_lib().td_flash_attn_fwd(C.byref(a), c_void_p(torch.cuda.current_stream().cuda_stream)), "td_flash_attn_fwd(varlen)")
+        return (out, lse) if return_lse else out
     out = torch.empty_like(q)
+    lse = torch.full((Hq, Tq), float("-inf"), dtype=torch.float32, device=q.device) if return_lse else None
     cq, ck = cu_seqlens_q.tolist(), cu_seqlens_k.tolist()
     for i in range(len(cq) - 1):
-        if cq[i + 1] > cq[i]:
-            flash_attn_fwd(q[None, cq[i]:cq[i + 1]], k[None, ck[i]:ck[i + 1]], v[None, ck[i]:ck[i + 1]], causal, sm_scale,
-                           out=out[None, cq[i]:cq[i + 1]])
-    return out
+        if cq[i + 1] > cq[i] and ck[i + 1] > ck[i]:
+            r = flash_attn_fwd(q[None, cq[i]:cq[i + 1]], k[None, ck[i]:ck[i + 1]], v[None, ck[i]:ck[i + 1]], causal, sm_scale,
+                               out=out[None, cq[i]:cq[i + 1]], return_lse=return_lse)
+            if return_lse:
+                lse[:, cq[i]:cq[i + 1]] = r[1][0]
+    return (out, lse) if return_lse else out

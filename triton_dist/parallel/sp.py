@@ -94,6 +94,13 @@ def fused_sp_ag_attn_intra_node(ctx: SPAllGatherAttentionContextIntraNode, q_sha
         v_all = comm.fast_allgather(v_shard.contiguous(), ctx.ag_v, mode="push").view(W, S_local, Hkv, D)
     else:
         k_all, v_all = k_shard[None], v_shard[None]
+    return _sp_attend(q_shard, k_all, v_all, W, r, is_causal, enable_zig_zag, sm_scale)
+
+
+def _sp_attend(q_shard, k_all, v_all, W, r, is_causal, enable_zig_zag, sm_scale):
+    """Attention of this rank's queries [S/W, Hq, D] over the gathered KV [W, S/W, Hkv, D] of ONE sequence."""
+    S_local, Hq, D = q_shard.shape
+    Hkv = k_all.shape[2]
     S = S_local * W
     dev = q_shard.device
     zz = enable_zig_zag and W > 1
@@ -113,6 +120,32 @@ def fused_sp_ag_attn_intra_node(ctx: SPAllGatherAttentionContextIntraNode, q_sha
     o = torch.nn.functional.scaled_dot_product_attention(q_shard.transpose(0, 1)[None], kk.transpose(0, 1)[None], vv.transpose(0, 1)[None],
                                                          attn_mask=mask[None, None] if mask is not None else None, scale=sm_scale)
     return o[0].transpose(0, 1).contiguous()
+
+
+def fused_sp_ag_attn_varlen(ctx: SPAllGatherAttentionContextIntraNode, q_shard: torch.Tensor, k_shard: torch.Tensor, v_shard: torch.Tensor,
+                            cu_seqlens_q: torch.Tensor, is_causal: bool = True, enable_zig_zag: bool = True,
+                            sm_scale: Optional[float] = None) -> torch.Tensor:
+    """Packed variable-length batch under context parallelism (reference: sp_ag_attention_intra_node.py:106-183 + :279-360 -- q shard
+    lengths in ``cu_seqlens_q``, per-batch KV gathers).  Every rank holds ``len_b / W`` tokens of every sequence b, packed back to back:
+    q/k/v_shard [sum_b len_b / W, H, D], ``cu_seqlens_q`` int32 [B + 1] = cumulative SHARD lengths (identical on all ranks).  The whole
+    packed K and V shards are gathered ONCE (two all-gather kernels for the batch instead of two per sequence); attention then runs per
+    sequence over its slice of the gathered KV.  Returns [sum_b len_b / W, Hq, D]."""
+    W, r = ctx.world_size, ctx.rank
+    T_local, Hq, D = q_shard.shape
+    Hkv = k_shard.shape[1]
+    sm_scale = sm_scale or 1.0 / math.sqrt(D)
+    if W > 1:
+        k_all = comm.fast_allgather(k_shard.contiguous(), ctx.ag_k, mode="push").view(W, T_local, Hkv, D)
+        v_all = comm.fast_allgather(v_shard.contiguous(), ctx.ag_v, mode="push").view(W, T_local, Hkv, D)
+    else:
+        k_all, v_all = k_shard[None], v_shard[None]
+    cu = cu_seqlens_q.tolist()          # one host read per call (the reference reads every boundary with .item())
+    out = torch.empty_like(q_shard)
+    for b in range(len(cu) - 1):
+        a, e = cu[b], cu[b + 1]
+        if e > a:
+            out[a:e] = _sp_attend(q_shard[a:e], k_all[:, a:e], v_all[:, a:e], W, r, is_causal, enable_zig_zag, sm_scale)
+    return out
 
 
 def merge_attention_partials(o1: torch.Tensor, lse1: torch.Tensor, o2: torch.Tensor, lse2: torch.Tensor):
