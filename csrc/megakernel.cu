@@ -10,6 +10,11 @@
 // Design points:
 //   * decode with B <= 8 tokens is HBM-bound: linears are weight-streaming GEMVs on CUDA cores (tensor cores cannot
 //     help at M <= 8), 16-byte loads, 4 rows of W in flight per warp;
+//   * 9 <= B <= 64 tokens: the same LINEAR tasks run on the tensor cores (mma.sync m16n8k16, fp32 accumulate): still
+//     weight-streaming -- every lane keeps 8 independent 16-byte weight loads in flight and feeds them to the MMAs straight
+//     from registers (the K order inside a 32-wide chunk is permuted identically for both operands, so a lane's 16 bytes
+//     ARE its B fragments), the activations are staged once per K chunk in fragment order (conflict-free 16-byte LDS).
+//     tcgen05 needs 128-row tiles and a TMEM round trip per task; at <= 64 rows per tile the warp-level MMA is the fit;
 //   * scoreboard counters are never reset: task k waits for  sb[dep] >= epoch * dep_count  where `epoch` is a
 //     device-resident step counter (CUDA-graph replayable, no memset);
 //   * the tensor-parallel all-reduce is a task too: one-shot over NVLink (multimem.ld_reduce when the heap has a
@@ -161,7 +166,172 @@ TD_DEVICE void linear_rows(const uint4* __restrict__ W, const uint4* __restrict_
   }
 }
 
+// ---- LINEAR on tensor cores (9 <= B <= 64) ------------------------------------------------------------------------------
+constexpr int kMmaMaxB = 64;
+constexpr int kMmaStageBytes = 128 * 1024;       // activation fragments of one K chunk: Bpad x KC x 2 bytes
+
+TD_DEVICE void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// 8 activated elements x[b, kv*8 .. kv*8+7] (act 0: plain, 1: silu(gate) * up, 2: RMSNorm with the row's rs and the norm weight)
+TD_DEVICE uint4 linear_act8(const uint4* x, int b, int kv, int act, int ldx8, int kvec, const float* rs, const uint4* nw) {
+  if (act == 0) return x[b * ldx8 + kv];
+  float f[8], g[8];
+  unpack8(x[b * ldx8 + kv], f);
+  if (act == 1) {
+    unpack8(x[b * ldx8 + kvec + kv], g);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = f[e] / (1.f + __expf(-f[e])) * g[e];
+  } else {
+    unpack8(nw[kv], g);
+    const float r = rs[b];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = f[e] * r * g[e];
+  }
+  return pack8(f);
+}
+
+// mt = 16-row tiles of the (padded) batch (1..4).  The task's n_cnt columns are 8-column GROUPS.  With >= 8 groups warp w owns groups
+// {pass * 8 NGW + w + 8 i}; with fewer, 8 / G warps share one group and split the K chunks between them (partial sums meet in shared
+// memory) so that every warp streams weights whatever the tile width.  NGW groups x U chunks = 8 independent 16-byte weight loads per
+// lane.  Lane (g = lane / 4, tig = lane % 4).
+// Fragment layout of the staged activations: frag[((m * C32 + c) * 32 + lane) * 2 + hi] (uint4) = row m*16 + g + 8*hi,
+// elements k = c*32 + tig*8 .. +7 -- exactly the 8 k's of the lane's weight vector, so for the two MMAs of a 32-wide chunk
+// (s = 0, 1):  A regs = {X[2s], Y[2s], X[2s+1], Y[2s+1]},  B regs = {Wv[2s], Wv[2s+1]}.
+template <int NGW>
+TD_DEVICE void linear_mma(const MKParams& p, const Task& t, uint8_t* smem) {
+  constexpr int MTMAX = kMmaMaxB / 16, U = 8 / NGW, NW = kMKThreads / 32;
+  const uint4* x = (const uint4*)p.ptrs[t.a[0]];
+  const uint4* W = (const uint4*)p.ptrs[t.a[1]];
+  __nv_bfloat16* out = (__nv_bfloat16*)p.ptrs[t.a[2]];
+  const int K = t.a[3], ldo = t.a[4], n0 = t.a[5], n_cnt = t.a[6], act = t.a[7], ldx8 = t.a[8] / 8;
+  const uint4* nw = act == 2 ? (const uint4*)p.ptrs[t.a[9]] : nullptr;
+  const int kvec = K / 8, B = p.B, mt = (B + 15) / 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
+  uint4* frag = reinterpret_cast<uint4*>(smem);
+  float* rs = reinterpret_cast<float*>(smem + kMmaStageBytes);          // [64] per-row rsqrt(mean square) for act 2
+  if (act == 2) {
+    const float eps = __int_as_float(t.a[10]);
+    for (int b = warp; b < B; b += NW) {
+      float ss = 0.f;
+      for (int kv = lane; kv < kvec; kv += 32) {
+        float f[8];
+        unpack8(x[b * ldx8 + kv], f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ss += f[e] * f[e];
+      }
+      ss = warp_sum(ss);
+      if (lane == 0) rs[b] = rsqrtf(ss / static_cast<float>(K) + eps);
+    }
+  }
+  const int KC = min(K, (kMmaStageBytes / (mt * 16 * 2)) / 32 * 32);  // elements of K staged at a time (multiple of 32)
+  const int groups = n_cnt / 8;
+  int G = 1;
+  while (G < groups && G < NW) G <<= 1;
+  const int kparts = NW / G;                       // warps that share one group and split the K chunks (1 when groups >= 8)
+  const int gi = warp % G, kp = warp / G;
+  for (int pass0 = 0; pass0 < groups; pass0 += G * NGW) {
+    float acc[NGW][MTMAX][4];
+#pragma unroll
+    for (int i = 0; i < NGW; ++i)
+#pragma unroll
+      for (int m = 0; m < MTMAX; ++m)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[i][m][e] = 0.f;
+    for (int kc0 = 0; kc0 < K; kc0 += KC) {
+      const int kc = min(KC, K - kc0), C32 = kc / 32;
+      __syncthreads();                                                  // previous chunk fully consumed (and rs written)
+      for (int i = threadIdx.x; i < mt * 16 * (kc / 8); i += kMKThreads) {
+        const int b = i / (kc / 8), kg = i % (kc / 8);
+        const uint4 v = b < B ? linear_act8(x, b, kc0 / 8 + kg, act, ldx8, kvec, rs, nw) : make_uint4(0, 0, 0, 0);
+        const int m = b >> 4, r = b & 15;
+        frag[(((m * C32 + (kg >> 2)) * 32 + (r & 7) * 4 + (kg & 3)) << 1) + (r >> 3)] = v;
+      }
+      __syncthreads();
+      for (int c0 = kp * U; c0 < C32; c0 += U * kparts) {
+        uint4 wv[U][NGW];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int i = 0; i < NGW; ++i) {
+            const int ng = pass0 + gi + i * G;
+            const bool ok = (c0 + u < C32) && (ng < groups);
+            wv[u][i] = ok ? ptx::ld_nc_v4(W + static_cast<size_t>(n0 + ng * 8 + g) * kvec + (kc0 / 8) + (c0 + u) * 4 + tig)
+                          : make_uint4(0, 0, 0, 0);
+          }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (c0 + u < C32) {
+#pragma unroll
+            for (int m = 0; m < MTMAX; ++m) {
+              if (m < mt) {
+                const uint4* fp = frag + (((m * C32 + c0 + u) * 32 + lane) << 1);
+                const uint4 X = fp[0], Y = fp[1];
+#pragma unroll
+                for (int i = 0; i < NGW; ++i) {
+                  mma_bf16_16816(acc[i][m], X.x, Y.x, X.y, Y.y, wv[u][i].x, wv[u][i].y);
+                  mma_bf16_16816(acc[i][m], X.z, Y.z, X.w, Y.w, wv[u][i].z, wv[u][i].w);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    if (kparts > 1) {
+      // K was split between the warps of a group: partial sums of warps kp > 0 go through shared memory to warp kp == 0
+      __syncthreads();                                                  // every warp is done with the staged fragments
+      float* part = reinterpret_cast<float*>(smem);                     // [NW][NGW][MTMAX][4][32]
+      if (kp > 0) {
+#pragma unroll
+        for (int i = 0; i < NGW; ++i)
+#pragma unroll
+          for (int m = 0; m < MTMAX; ++m)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) part[(((warp * NGW + i) * MTMAX + m) * 4 + e) * 32 + lane] = acc[i][m][e];
+      }
+      __syncthreads();
+      if (kp == 0) {
+        for (int q = 1; q < kparts; ++q) {
+          const int w2 = q * G + gi;
+#pragma unroll
+          for (int i = 0; i < NGW; ++i)
+#pragma unroll
+            for (int m = 0; m < MTMAX; ++m)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) acc[i][m][e] += part[(((w2 * NGW + i) * MTMAX + m) * 4 + e) * 32 + lane];
+        }
+      }
+    }
+    // D fragment: c0, c1 = row g, columns tig*2 + {0, 1}; c2, c3 = row g + 8
+    if (kp == 0) {
+#pragma unroll
+      for (int i = 0; i < NGW; ++i) {
+        const int ng = pass0 + gi + i * G;
+        if (ng < groups) {
+          const int col = n0 + ng * 8 + tig * 2;
+#pragma unroll
+          for (int m = 0; m < MTMAX; ++m) {
+            const int r0 = m * 16 + g, r1 = r0 + 8;
+            if (r0 < B) *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(r0) * ldo + col) = ptx::pack_bf16x2(acc[i][m][0], acc[i][m][1]);
+            if (r1 < B) *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(r1) * ldo + col) = ptx::pack_bf16x2(acc[i][m][2], acc[i][m][3]);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();        // the next task may restage smem
+}
+
 TD_DEVICE void task_linear(const MKParams& p, const Task& t, uint8_t* smem) {
+  if (p.B > kMaxB) {
+    if (t.a[6] > 8 * (kMKThreads / 32)) linear_mma<2>(p, t, smem);      // more than 8 column groups: two per warp
+    else linear_mma<1>(p, t, smem);
+    return;
+  }
   const uint4* x = (const uint4*)p.ptrs[t.a[0]];
   const uint4* W = (const uint4*)p.ptrs[t.a[1]];
   __nv_bfloat16* out = (__nv_bfloat16*)p.ptrs[t.a[2]];
@@ -525,7 +695,8 @@ struct TdMegaArgs {
 TD_API int td_mega_task_size() { return (int)sizeof(Task); }
 
 TD_API int td_mega_launch(const TdMegaArgs* a, void* stream) {
-  if (a->B < 1 || a->B > kMaxB) { td::drv::set_error("megakernel: batch must be 1..8"); return -1; }
+  if (a->B < 1 || a->B > kMmaMaxB) { td::drv::set_error("megakernel: batch must be 1..64 (1..8: GEMV tasks, 9..64: tensor-core tasks)"); return -1; }
+  if (a->B > kMaxB && a->smem_bytes < kMmaStageBytes + 256) { td::drv::set_error("megakernel: tensor-core linears need 128 KB + 256 B of dynamic shared memory"); return -1; }
   MKParams p;
   p.tasks = (const Task*)a->tasks; p.queue_off = (const int*)a->queue_off; p.ptrs = (void* const*)a->ptrs;
   p.sb = (uint32_t*)a->sb; p.epoch = (uint32_t*)a->epoch;

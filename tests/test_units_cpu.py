@@ -172,6 +172,29 @@ def test_megakernel_graph_single_process(dist_env):
     assert act["tasks"] == sum(v for k, v in act.items() if k not in ("tasks", "counters", "ctas"))
 
 
+def test_megakernel_batches_above_8_use_tensor_core_tiles(dist_env):
+    """Decode batches of 9..64 tokens: the LINEAR tasks get tensor-core tile shapes (8-column groups, a power-of-two number of groups
+    per tile, 128 KB fragment staging) and the task list still reproduces the per-op model (host interpretation of the same tasks)."""
+    from triton_dist.mega_kernel import T_LINEAR, MegaDenseModel
+    from triton_dist.models import AutoLLM, KV_Cache, ModelConfig
+    cfg = ModelConfig(model_name="tiny-dense", max_length=64, dtype=torch.float32, rank=0, world_size=1)
+    m = AutoLLM.from_pretrained(cfg)
+    B = 24
+    kv = KV_Cache(m.num_layers, B, 64, m.num_key_value_heads, m.head_dim, torch.float32, 1, "cpu")
+    kv.rand_fill_kv_cache(5)
+    kv2 = KV_Cache(m.num_layers, B, 64, m.num_key_value_heads, m.head_dim, torch.float32, 1, "cpu")
+    kv2.k_cache.copy_(kv.k_cache); kv2.v_cache.copy_(kv.v_cache); kv2.kv_offset.copy_(kv.kv_offset)
+    mega = MegaDenseModel(m, B, kv2)
+    lin = [t for t in mega.builder.tasks if t.type == T_LINEAR]
+    assert lin and all(t.args[3] % 32 == 0 and t.args[6] % 8 == 0 and t.args[6] <= 128 for t in lin)
+    assert mega.builder.max_smem >= 128 * 1024 + 256
+    ids = torch.randint(0, 1000, (B, 1))
+    ref = m.inference(ids, kv.kv_offset.to(torch.int64)[:, None], kv)
+    torch.testing.assert_close(mega.mega_forward(ids), ref, atol=1e-4, rtol=1e-4)
+    with pytest.raises(AssertionError):
+        MegaDenseModel(m, 65, kv2)
+
+
 def test_bench_reference_arm_reports_unavailable():
     """No GPU here: the reference arm (the reference's own little_kernel sm_100a GEMM at N=1) must say so and exit 0; it also
     stays `unavailable` for N > 1 (the multi-GPU reference ops need the Triton/NVSHMEM stack that cannot be built offline)."""

@@ -127,3 +127,36 @@ def test_flash_varlen_one_launch(causal):
         torch.testing.assert_close(lse[:, a:b], ref_lse[0], atol=2e-2, rtol=1e-2)
     torch.testing.assert_close(out.float(), loop.float(), atol=2e-2, rtol=2e-2)
     torch.testing.assert_close(lse, lse2, atol=2e-2, rtol=1e-2)
+
+
+_MEGA_SNIPPET = r"""
+import sys, torch
+sys.path.insert(0, {root!r})
+import triton_dist.utils as U
+from triton_dist.mega_kernel import MegaDenseModel
+from triton_dist.models import AutoLLM, KV_Cache, ModelConfig
+U.initialize_distributed(seed=0)
+cfg = ModelConfig(model_name="tiny-dense", max_length=64, dtype=torch.bfloat16, rank=0, world_size=1)
+m = AutoLLM.from_pretrained(cfg)
+B = {B}
+mk = lambda: KV_Cache(m.num_layers, B, 64, m.num_key_value_heads, m.head_dim, torch.bfloat16, 1, "cuda")
+kv, kv2 = mk(), mk()
+kv.rand_fill_kv_cache(17)
+kv2.k_cache.copy_(kv.k_cache); kv2.v_cache.copy_(kv.v_cache); kv2.kv_offset.copy_(kv.kv_offset)
+mega = MegaDenseModel(m, B, kv2, attn_splits=2)
+for step in range(3):
+    ids = torch.randint(0, 1000, (B, 1), device="cuda")
+    ref = m.inference(ids, kv.kv_offset.to(torch.int64)[:, None], kv)
+    out = mega.mega_forward(ids)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out, ref, atol=6e-2, rtol=6e-2)
+    kv.inc_offset(1); kv2.inc_offset(1)
+print("MEGA_TC_OK")
+"""
+
+
+@pytest.mark.xfail(strict=False, reason="tensor-core LINEAR tasks of the megakernel (mma.sync path for 9..64 tokens): compiled, not yet run on hardware")
+@pytest.mark.parametrize("B", [16, 40])
+def test_megakernel_tensor_core_linears(B):
+    r = subprocess.run([sys.executable, "-c", _MEGA_SNIPPET.format(root=ROOT, B=B)], capture_output=True, text=True, timeout=240, cwd=ROOT)
+    assert r.returncode == 0 and "MEGA_TC_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]

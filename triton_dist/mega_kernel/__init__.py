@@ -56,7 +56,7 @@ class ModelBuilder:
     """Records ops of one decode step, tiles them into tasks, schedules them, launches the persistent kernel."""
 
     def __init__(self, batch: int, num_sms: Optional[int] = None, schedule: str = "round_robin"):
-        assert 1 <= batch <= 8
+        assert 1 <= batch <= 64, "megakernel decode batch: 1..8 (GEMV tasks) or 9..64 (tensor-core tasks)"
         self.B = batch
         self.device = U.current_device()
         self.is_cuda = self.device.type == "cuda"
@@ -104,6 +104,15 @@ class ModelBuilder:
         ``norm_weight``: RMSNorm(x) * norm_weight is applied while the operand is staged (no separate norm task)."""
         N, K = weight.shape
         tn = tile_n or max(8, ((N + self.num_sms - 1) // self.num_sms + 7) // 8 * 8)
+        if self.B > 8:
+            # tensor-core tasks (csrc/megakernel.cu linear_mma): 8-column groups; a power-of-two number of groups per tile lets the
+            # warps of a CTA share a group along K when there are fewer than 8 of them
+            assert K % 32 == 0 and N % 8 == 0, "tensor-core linear tasks need K % 32 == 0 and N % 8 == 0"
+            if tile_n is None:
+                tn = 8
+                while tn < 128 and (N + tn - 1) // tn > self.num_sms:
+                    tn *= 2
+            assert tn % 8 == 0 and tn <= 128
         sig = self.counter()
         n_tiles = 0
         d = dep or (-1, 0)
@@ -113,7 +122,7 @@ class ModelBuilder:
             self._add(Task(T_LINEAR, d[0], d[1], sig, [self.ptr(x), self.ptr(weight), self.ptr(out), K, out.shape[-1], n0,
                                                        min(tn, N - n0), act, x.shape[-1], self.ptr(norm_weight), _fbits(eps)]))
             n_tiles += 1
-        self.max_smem = max(self.max_smem, self.B * K * 2 + 256)
+        self.max_smem = max(self.max_smem, (128 * 1024 + 512) if self.B > 8 else (self.B * K * 2 + 256))
         return sig, n_tiles
 
     make_qkv_proj = make_o_proj = make_fc1 = make_fc2 = make_linear
