@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(kEPThreads, 1) ep_combine_kernel(const EPCombi
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int k = 0; k < p.topk; ++k) {
       const int e = p.topk_idx[t * p.topk + k];
-      if (e < 0 || e >= p.E) continue;            // same validity predicate as dispatch: a pair that was never sent has no row to add
+      if (e < 0 || e >= p.epr * W) continue;      // same validity predicate as dispatch: a pair that was never sent has no row to add
       const float w = p.topk_w[t * p.topk + k];
       const uint4 x = ptx::ld_relaxed_sys_v4(comb_local + (static_cast<size_t>(t) * p.topk + k) * p.H * 2 + v * 16);
       const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
