@@ -160,3 +160,22 @@ print("MEGA_TC_OK")
 def test_megakernel_tensor_core_linears(B):
     r = subprocess.run([sys.executable, "-c", _MEGA_SNIPPET.format(root=ROOT, B=B)], capture_output=True, text=True, timeout=240, cwd=ROOT)
     assert r.returncode == 0 and "MEGA_TC_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+@pytest.mark.xfail(strict=False, reason="DSL GDN chunk kernels: exact in the CPU interpreter, not yet run on hardware")
+@pytest.mark.parametrize("T", [64, 300])
+def test_gdn_chunk_dsl_kernels(T):
+    from triton_dist.lk.kernels.gdn_chunk import chunk_gated_delta_rule_lk
+    from triton_dist.ops.gdn import gated_delta_rule_recurrent
+    torch.manual_seed(T)
+    B, H, DK, DV = 2, 4, 128, 128
+    q = (torch.randn(B, T, H, DK, device="cuda") * 0.5).bfloat16()
+    k = torch.nn.functional.normalize(torch.randn(B, T, H, DK, device="cuda"), dim=-1).bfloat16()
+    v = (torch.randn(B, T, H, DV, device="cuda") * 0.5).bfloat16()
+    g, beta = -torch.rand(B, T, H, device="cuda") * 0.3, torch.rand(B, T, H, device="cuda")
+    s0 = torch.randn(B, H, DK, DV, device="cuda") * 0.1
+    o, S = chunk_gated_delta_rule_lk(q, k, v, g, beta, initial_state=s0)
+    torch.cuda.synchronize()
+    ro, rS = gated_delta_rule_recurrent(q, k, v, g, beta, initial_state=s0)
+    torch.testing.assert_close(o.float(), ro.float(), atol=3e-2, rtol=3e-2)
+    torch.testing.assert_close(S, rS, atol=3e-2, rtol=3e-2)

@@ -130,7 +130,9 @@ class FnCompiler:
         names = [p.arg for p in a.args]
         defaults = [None] * (len(names) - len(a.defaults)) + list(a.defaults)
         for idx, (p, d) in enumerate(zip(a.args, defaults)):
-            ann = self._eval_annotation(p.annotation)
+            ann = getattr(self.pyfn, "__annotations__", {}).get(p.arg)
+            if ann is None or isinstance(ann, str):       # strings: ``from __future__ import annotations`` -- evaluate the AST node
+                ann = self._eval_annotation(p.annotation)
             v = arg_vals[idx] if arg_vals is not None and idx < len(arg_vals) else None
             if v is None and d is not None and not self.is_kernel:
                 v = self.expr(d)

@@ -62,6 +62,14 @@ def chunk_gated_delta_rule_fwd(q, k, v, g, beta, scale: Optional[float] = None, 
     if q.is_cuda and T <= 16 and Dk in (64, 128, 256):          # decode steps: state-in-registers kernel
         o, S = fused_recurrent_gated_delta_rule(q, k, v, g, beta, scale, initial_state)
         return o, (S if output_final_state else None)
+    import os
+    if (q.is_cuda and os.environ.get("TD_GDN_CHUNK_KERNEL", "0") == "1" and Dv <= Dk + 1 and (Dv % 32 == 0 or Dv <= 32)
+            and q.dtype in (torch.bfloat16, torch.float16, torch.float32)):
+        # prefill on our own kernels: the two DSL kernels of lk/kernels/gdn_chunk.py (chunk preparation in parallel, then the
+        # state scan); opt-in until they have run on hardware -- the CPU interpreter reproduces the recurrence to 1e-7
+        from ..lk.kernels.gdn_chunk import chunk_gated_delta_rule_lk
+        o, S = chunk_gated_delta_rule_lk(q, k, v, g, beta, scale, initial_state, chunk_size)
+        return o, (S if output_final_state else None)
     scale = scale if scale is not None else Dk ** -0.5
     C = chunk_size
     pad = (C - T % C) % C
