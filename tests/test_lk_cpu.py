@@ -153,6 +153,15 @@ def test_nvcc_compiles_examples_and_gemm_ladder_emits_tcgen05():
         assert "sm_100a" in sass
         for n in needles:
             assert n in sass, (cg, n)
+    from triton_dist.lk.kernels.gemm_sm100 import make_gemm_persistent
+    pk = make_gemm_persistent(256, 6, 2)                       # the persistent rung: two TMEM accumulators, ring across tiles
+    pk.compile()
+    sass = subprocess.run([cuobjdump, "-sass", pk._lib._name], capture_output=True, text=True).stdout
+    for n in ("UTCHMMA.2CTA", "UTMALDG.2D.2CTA", "UTCBAR.2CTA.MULTICAST", "LDTM.x32"):
+        assert n in sass, n
+    assert pk.dyn_smem_bytes < 227 * 1024
+    with pytest.raises(AssertionError):
+        make_gemm_persistent(256, 6, 1)                        # 48 KB per stage x 6 does not fit one SM
     assert jit._CACHE.exists()
 
 

@@ -202,3 +202,31 @@ print("GDN_OK")
 @pytest.mark.parametrize("T", [64, 300])
 def test_gdn_chunk_dsl_kernels(T):
     _isolated(_GDN_SNIPPET.format(T=T), "GDN_OK")
+
+
+_PGEMM_SNIPPET = r"""
+import torch
+from triton_dist.lk.kernels.gemm_sm100 import run_gemm_persistent
+torch.manual_seed(0)
+for (M, N, K) in ((256, 256, 128), (512, 768, 512), (1000, 392, 320), (4096, 4096, 4096), (8192, 2048, 1024)):
+    a = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    b = (torch.randn(N, K, device="cuda") * 0.5).bfloat16()
+    ref = a.float() @ b.float().t()
+    c = run_gemm_persistent(a, b)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(c.float(), ref, atol=0.5, rtol=2e-2)
+a = torch.randn(4096, 4096, device="cuda", dtype=torch.bfloat16); b = torch.randn(4096, 4096, device="cuda", dtype=torch.bfloat16)
+c = run_gemm_persistent(a, b)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(20):
+    run_gemm_persistent(a, b, out=c)
+e1.record(); torch.cuda.synchronize()
+print("lk persistent gemm 4096^3: %.1f us" % (e0.elapsed_time(e1) / 20 * 1e3))
+print("PGEMM_OK")
+"""
+
+
+@pytest.mark.xfail(strict=False, reason="persistent rung of the DSL GEMM ladder: compiled and SASS-checked, not yet run on hardware")
+def test_lk_gemm_persistent():
+    _isolated(_PGEMM_SNIPPET, "PGEMM_OK")

@@ -8,6 +8,10 @@ kernel of this framework (csrc/gemm_sm100.cuh) so that both share the hardware-v
   ``tcgen05.mma`` issuer, warps 2..5 = epilogue (``tcgen05.ld`` -> bf16 -> 16-byte global stores).
 * ``gemm_2cta``: a 2-CTA cluster per 256 x BN tile (``cta_group::2``): each CTA loads its 128 rows of A and half of B, all bytes land on
   the leader's mbarrier, the leader issues M = 256 MMAs, ``tcgen05.commit`` multicasts to both CTAs, each CTA drains its own TMEM half.
+* ``gemm_persistent`` (``make_gemm_persistent``): the ladder's endpoint -- one cluster per SM pair walks the tiles (group-M swizzled
+  order), the smem ring runs across tile boundaries, TWO TMEM accumulators let the epilogue of tile i overlap the mainloop of tile
+  i + 1 (``tmem_full`` / ``tmem_empty`` mbarriers, one arrival per epilogue warp of the pair).  Same protocol as the hand-written
+  kernel; it compiles and its first hardware run is pending (the first two rungs pass on a B200).
 
 ``run_gemm(a, b, variant=)`` builds the tensor maps and launches; ``python -m triton_dist.lk.kernels.gemm_sm100`` on a B200 checks both
 against fp32 and prints their throughput next to the hand-written kernel.
@@ -144,6 +148,184 @@ def make_gemm(BN: int = 256, STAGES: int = 4, cta_group: int = 1):
     return gemm
 
 
+def make_gemm_persistent(BN: int = 256, STAGES: int = 6, cta_group: int = 2, GROUP_M: int = 8):
+    """Persistent warp-specialised kernel: 256 threads = TMA warp, MMA warp, TMEM warp, (idle), 4 epilogue warps."""
+    assert BN in (128, 256) and cta_group in (1, 2)
+    B_ROWS = BN // cta_group
+    A_BYTES, B_BYTES = BM * BK * 2, B_ROWS * BK * 2
+    TX_BYTES = A_BYTES + B_BYTES
+    TMEM_COLS = 2 * BN                                          # two accumulators
+    IDESC = ll.make_idesc(1, 1, BM * cta_group, BN)
+    TILE_M = BM * cta_group
+    P_THREADS = 256
+    assert STAGES * TX_BYTES + 4096 <= 227 * 1024, "smem ring too large: lower STAGES (cta_group 1 with BN = 256 fits 4 stages)"
+
+    @lk.kernel(block=P_THREADS, cluster=(cta_group, 1, 1))
+    def gemm(tA: ll.TmaDescriptor, tB: ll.TmaDescriptor, C: ll.ptr[ll.bf16], M: ll.i32, N: ll.i32, K: ll.i32, num_m: ll.i32, num_n: ll.i32):
+        ll.align_memory(1024)
+        sA = ll.dyn_shared([STAGES, BM * BK], ll.bf16, align=1024)
+        sB = ll.dyn_shared([STAGES, B_ROWS * BK], ll.bf16, align=1024)
+        full = ll.dyn_shared([STAGES], ll.u64)
+        empty = ll.dyn_shared([STAGES], ll.u64)
+        tfull = ll.dyn_shared([2], ll.u64)                      # accumulator complete (one tcgen05.commit)
+        tempty = ll.dyn_shared([2], ll.u64)                     # accumulator drained (one arrival per epilogue warp of the pair)
+        tmem_slot = ll.dyn_shared([4], ll.u32)
+
+        warp = ll.warp_id()
+        lane = ll.lane_id()
+        cta = ll.cluster_rank() if cta_group == 2 else 0
+        n_workers = ll.gridDim.x // cta_group
+        worker = ll.blockIdx.x // cta_group
+        total = num_m * num_n
+        nkb = (K + BK - 1) // BK
+        per_band = GROUP_M * num_n
+
+        if warp == 0 and lane == 0:
+            ll.prefetch_tensormap(tA)
+            ll.prefetch_tensormap(tB)
+        if warp == 1 and lane == 0:
+            for s in ll.static_range(STAGES):
+                ll.mbar_init(full + s, cta_group)
+                ll.mbar_init(empty + s, 1)
+            for i in ll.static_range(2):
+                ll.mbar_init(tfull + i, 1)
+                ll.mbar_init(tempty + i, 4 * cta_group)
+            ll.fence_barrier_init()
+        if warp == 2:
+            ll.tmem_alloc(tmem_slot, TMEM_COLS, cta_group=cta_group)
+            ll.tmem_relinquish(cta_group=cta_group)
+        ll.tc_fence_before()
+        if cta_group == 2:
+            ll.cluster_sync()
+        else:
+            ll.syncthreads()
+        ll.tc_fence_after()
+        tmem = tmem_slot[0]
+
+        if warp == 0:
+            # ---------------- TMA producer: the ring keeps running across tile boundaries ----------------
+            if ll.elect_one():
+                stage = 0
+                phase = 0
+                u = worker
+                while u < total:
+                    band = u // per_band
+                    first_m = band * GROUP_M
+                    band_m = min(num_m - first_m, GROUP_M)
+                    r = u - band * per_band
+                    m0 = (first_m + r % band_m) * TILE_M + cta * BM
+                    n0 = (r // band_m) * BN + cta * B_ROWS
+                    for kb in range(nkb):
+                        ll.mbar_wait(empty + stage, phase ^ 1)
+                        if cta_group == 1:
+                            ll.mbar_arrive_expect_tx(full + stage, TX_BYTES)
+                            ll.tma_load_2d(tA, full + stage, sA[stage], kb * BK, m0)
+                            ll.tma_load_2d(tB, full + stage, sB[stage], kb * BK, n0)
+                        else:
+                            if cta == 0:
+                                ll.mbar_arrive_expect_tx(full + stage, 2 * TX_BYTES)
+                            else:
+                                ll.mbar_arrive_cluster(full + stage, 0)
+                            ll.tma_load_2d_2sm(tA, full + stage, sA[stage], kb * BK, m0)
+                            ll.tma_load_2d_2sm(tB, full + stage, sB[stage], kb * BK, n0)
+                        stage += 1
+                        if stage == STAGES:
+                            stage = 0
+                            phase ^= 1
+                    u += n_workers
+            ll.syncwarp()
+        elif warp == 1:
+            # ---------------- MMA issuer: alternates between the two TMEM accumulators ----------------
+            if cta == 0 and ll.elect_one():
+                stage2 = 0
+                phase2 = 0
+                acc = 0
+                acc_phase = 0
+                u2 = worker
+                while u2 < total:
+                    ll.mbar_wait(tempty + acc, acc_phase ^ 1)   # the epilogue has drained this accumulator
+                    ll.tc_fence_after()
+                    d_tmem = tmem + ll.u32(acc * BN)
+                    for kb in range(nkb):
+                        ll.mbar_wait(full + stage2, phase2)
+                        ll.tc_fence_after()
+                        adesc = ll.make_smem_desc_k128(ll.smem_addr(sA[stage2]))
+                        bdesc = ll.make_smem_desc_k128(ll.smem_addr(sB[stage2]))
+                        for k in ll.static_range(BK // UMMA_K):
+                            accumulate = ll.u32(1) if k > 0 else ll.u32(kb > 0)
+                            ll.mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, accumulate, cta_group=cta_group)
+                        if cta_group == 1:
+                            ll.mma_commit(empty + stage2)
+                        else:
+                            ll.mma_commit_2sm(empty + stage2, 3)
+                        stage2 += 1
+                        if stage2 == STAGES:
+                            stage2 = 0
+                            phase2 ^= 1
+                    if cta_group == 1:
+                        ll.mma_commit(tfull + acc)
+                    else:
+                        ll.mma_commit_2sm(tfull + acc, 3)
+                    acc += 1
+                    if acc == 2:
+                        acc = 0
+                        acc_phase ^= 1
+                    u2 += n_workers
+            ll.syncwarp()
+        elif warp >= 4:
+            # ---------------- epilogue warps: drain accumulator `acc3` while the MMA warp fills the other one ----------------
+            quad = warp - 4                                     # == warp % 4: the TMEM lanes this warp may read
+            acc3 = 0
+            acc_phase3 = 0
+            regs = ll.local([32], ll.u32)
+            u3 = worker
+            while u3 < total:
+                band3 = u3 // per_band
+                first3 = band3 * GROUP_M
+                bm3 = min(num_m - first3, GROUP_M)
+                r3 = u3 - band3 * per_band
+                row = (first3 + r3 % bm3) * TILE_M + cta * BM + quad * 32 + lane
+                c0 = (r3 // bm3) * BN
+                ll.mbar_wait(tfull + acc3, acc_phase3)
+                ll.tc_fence_after()
+                for c in ll.static_range(BN // 32):
+                    ll.tmem_ld_32x32b_x32(tmem + ll.u32((quad * 32) << 16) + ll.u32(acc3 * BN + c * 32), regs)
+                    ll.tmem_ld_wait()
+                    if row < M:
+                        dst = C + (ll.i64(row) * N + c0 + c * 32)
+                        for j in ll.static_range(4):
+                            if c0 + c * 32 + j * 8 < N:
+                                v = ll.make_uint4(
+                                    ll.pack_bf16x2(ll.uint_as_float(regs[8 * j + 0]), ll.uint_as_float(regs[8 * j + 1])),
+                                    ll.pack_bf16x2(ll.uint_as_float(regs[8 * j + 2]), ll.uint_as_float(regs[8 * j + 3])),
+                                    ll.pack_bf16x2(ll.uint_as_float(regs[8 * j + 4]), ll.uint_as_float(regs[8 * j + 5])),
+                                    ll.pack_bf16x2(ll.uint_as_float(regs[8 * j + 6]), ll.uint_as_float(regs[8 * j + 7])))
+                                ll.st_v4(dst + j * 8, v)
+                ll.tc_fence_before()
+                ll.syncwarp()
+                if lane == 0:
+                    if cta_group == 1:
+                        ll.mbar_arrive(tempty + acc3)
+                    else:
+                        ll.mbar_arrive_cluster(tempty + acc3, 0)  # both CTAs' warps arrive on the LEADER's barrier
+                acc3 += 1
+                if acc3 == 2:
+                    acc3 = 0
+                    acc_phase3 ^= 1
+                u3 += n_workers
+        ll.tc_fence_before()
+        if cta_group == 2:
+            ll.cluster_sync()
+        else:
+            ll.syncthreads()
+        if warp == 2:
+            ll.tmem_dealloc(tmem, TMEM_COLS, cta_group=cta_group)
+
+    gemm.name = f"lk_gemm_persistent_bn{BN}_s{STAGES}_cg{cta_group}"
+    gemm.tile = (TILE_M, BN, BK, B_ROWS)
+    return gemm
+
+
 _CACHE = {}
 
 
@@ -152,6 +334,26 @@ def get_gemm(BN=256, STAGES=4, cta_group=1):
     if key not in _CACHE:
         _CACHE[key] = make_gemm(*key)
     return _CACHE[key]
+
+
+def run_gemm_persistent(a, b, out=None, BN: int = 256, STAGES: int = 6, cta_group: int = 2, num_sms: int = 148):
+    """The persistent rung: grid = one cluster per SM (pair); same operand contract as :func:`run_gemm`."""
+    import torch
+    M, K = a.shape
+    N = b.shape[0]
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and b.shape[1] == K and K % BK == 0 and N % 8 == 0
+    key = ("persistent", BN, STAGES, cta_group)
+    if key not in _CACHE:
+        _CACHE[key] = make_gemm_persistent(BN, STAGES, cta_group)
+    k = _CACHE[key]
+    tile_m, _, _, b_rows = k.tile
+    out = torch.empty(M, N, device=a.device, dtype=torch.bfloat16) if out is None else out
+    tA = lk.tma_2d(a, BK, BM)
+    tB = lk.tma_2d(b, BK, b_rows)
+    num_m, num_n = (M + tile_m - 1) // tile_m, (N + BN - 1) // BN
+    workers = max(1, min(num_sms // cta_group, num_m * num_n))
+    k[workers * cta_group](tA, tB, out, M, N, K, num_m, num_n)
+    return out
 
 
 def run_gemm(a, b, out=None, BN: int = 256, STAGES: int = 4, cta_group: int = 1):
