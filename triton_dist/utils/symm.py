@@ -27,6 +27,34 @@ from .. import _C
 # ----------------------------------------------------------------------------------------------------------------
 
 
+class _DLDevice(C.Structure):
+    _fields_ = [("device_type", C.c_int), ("device_id", C.c_int)]
+
+
+class _DLDataType(C.Structure):
+    _fields_ = [("code", C.c_uint8), ("bits", C.c_uint8), ("lanes", C.c_uint16)]
+
+
+class _DLTensor(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("device", _DLDevice), ("ndim", C.c_int), ("dtype", _DLDataType),
+                ("shape", C.POINTER(C.c_int64)), ("strides", C.POINTER(C.c_int64)), ("byte_offset", C.c_uint64)]
+
+
+class _DLManagedTensor(C.Structure):
+    pass
+
+
+_DELETER = C.CFUNCTYPE(None, C.POINTER(_DLManagedTensor))
+_DLManagedTensor._fields_ = [("dl_tensor", _DLTensor), ("manager_ctx", C.c_void_p), ("deleter", _DELETER)]
+
+_KEEPALIVE = {}
+
+
+@_DELETER
+def _dl_deleter(mt_ptr):
+    _KEEPALIVE.pop(C.addressof(mt_ptr.contents), None)
+
+
 _DL_CODES = {
     torch.float32: (2, 32), torch.float16: (2, 16), torch.float64: (2, 64), torch.bfloat16: (4, 16),
     torch.int8: (0, 8), torch.int16: (0, 16), torch.int32: (0, 32), torch.int64: (0, 64),
@@ -38,11 +66,41 @@ _PyCapsule_New.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
 _dl_make = None
 
 
+def _tensor_from_ptr_ctypes(ptr: int, shape: Sequence[int], dtype: torch.dtype, device: torch.device) -> torch.Tensor:
+    """The original construction (ctypes-built DLManagedTensor, Python deleter): the path every hardware run of this repository
+    has exercised; kept for CUDA tensors."""
+    view_as = None
+    if dtype not in _DL_CODES:   # fp8 & friends: carry as uint8, reinterpret afterwards
+        view_as, dtype = dtype, torch.uint8
+        assert torch.empty(0, dtype=view_as).element_size() == 1
+    shape = [int(s) for s in shape]
+    code, bits = _DL_CODES[dtype]
+    ndim = len(shape)
+    shape_arr = (C.c_int64 * max(ndim, 1))(*shape)
+    mt = _DLManagedTensor()
+    mt.dl_tensor.data = C.c_void_p(ptr)
+    mt.dl_tensor.device = _DLDevice(2 if device.type == "cuda" else 1, device.index or 0)
+    mt.dl_tensor.ndim = ndim
+    mt.dl_tensor.dtype = _DLDataType(code, bits, 1)
+    mt.dl_tensor.shape = C.cast(shape_arr, C.POINTER(C.c_int64))
+    mt.dl_tensor.strides = None
+    mt.dl_tensor.byte_offset = 0
+    mt.manager_ctx = None
+    mt.deleter = _dl_deleter
+    _KEEPALIVE[C.addressof(mt)] = (mt, shape_arr)
+    cap = _PyCapsule_New(C.addressof(mt), b"dltensor", None)
+    t = torch.from_dlpack(cap)
+    return t.view(view_as) if view_as is not None else t
+
+
 def tensor_from_ptr(ptr: int, shape: Sequence[int], dtype: torch.dtype, device: torch.device) -> torch.Tensor:
-    """Alias ``ptr`` as a contiguous tensor of ``shape``/``dtype`` living on ``device`` (no ownership).  The DLPack payload and its
-    deleter live in libtd_host.so (``tdh_dl_make``): a tensor may die on any thread, inside the garbage collector or during interpreter
-    shutdown, where a Python-level deleter is not safe to call."""
+    """Alias ``ptr`` as a contiguous tensor of ``shape``/``dtype`` living on ``device`` (no ownership).  Host (emulation backend)
+    tensors: the DLPack payload and its deleter live in libtd_host.so (``tdh_dl_make``) -- such a tensor may die on any thread (the DSL
+    interpreter runs kernels on Python threads), inside the garbage collector or during interpreter shutdown, where a Python-level
+    deleter is not safe to call.  CUDA tensors keep the ctypes construction that all hardware runs have used."""
     global _dl_make
+    if device.type == "cuda":
+        return _tensor_from_ptr_ctypes(ptr, shape, dtype, device)
     if _dl_make is None:
         lib = _C.host_lib()
         lib.tdh_dl_make.restype = C.c_void_p
