@@ -224,3 +224,66 @@ def test_gdn_chunk_kernels_in_the_interpreter_match_the_recurrence():
     prep, scan = get_kernels(64, 128, 128, 32, ll.bf16)
     prep.compile(); scan.compile()
     assert 90_000 < prep.dyn_smem_bytes < 110_000 and scan.dyn_smem_bytes < 30_000
+
+
+def _clamp(v, lo, hi):
+    return min(max(v, lo), hi)
+
+
+def _lerp(a, b, t: ll.constexpr):
+    return a + (b - a) * t
+
+
+def test_statement_coverage_codegen_and_interpreter_agree_with_python():
+    """while / continue / break, tuple swap, negative and unrolled ranges, conditional expressions, 64-bit pointer offsets, bit
+    operators, struct fields: the generated C++ compiles with nvcc and the interpreter gives the values plain Python arithmetic gives."""
+    @lk.kernel(block=64)
+    def k1(x: ll.ptr[ll.f32], y: ll.ptr[ll.i32], z: ll.ptr[ll.u8], n: ll.i32, big: ll.i64, flag: ll.bool_):
+        tid = ll.threadIdx.x
+        i = tid
+        acc: ll.f32 = 0.0
+        cnt = 0
+        while i < n:
+            if x[i] < 0.0:
+                i += 64
+                continue
+            acc += x[i]
+            cnt += 1
+            if cnt > 1000:
+                break
+            i += 64
+        a, b = cnt, tid
+        a, b = b, a
+        y[tid] = a * N_CONST + b
+        for j in range(10, 0, -2):
+            acc -= 0.5
+        for j in ll.unroll(range(4)):
+            acc += _lerp(1.0, 3.0, 0.5)
+        z[tid] = ll.u8(_clamp(cnt, 0, 255)) if flag else ll.u8(0)
+        x[tid] = acc if not (tid == 0 or tid == 63) else -acc
+        p = x + big
+        if p != x and tid == 0:
+            y[64] = ll.i32(big >> 3) & 0xFF
+        y[65 + tid] = (tid << 2) ^ (tid % 3) | (1 if tid > 5 else 0)
+        v4 = ll.make_uint4(1, 2, 3, 4)
+        v4.x = ll.u32(tid)
+        y[200 + tid] = ll.i32(v4.x + v4.w)
+
+    body = _body(k1)
+    for frag in ("while ((i < n)) {", "continue;", "break;", "for (j = 10; j > 0; j += -2) {", "#pragma unroll", "acc = (acc + 2.0f);",
+                 "lk_t3 = b;", "(flag ? ((uint8_t)(lk__clamp__0(cnt, 0, 255))) : ((uint8_t)0))", "p = (x + (big));", "(big >> 3ll)",
+                 "v4.x = ((uint32_t)(tid));", "int64_t big, bool flag"):
+        assert frag in body, frag
+    k1.compile()
+    x = torch.randn(256)
+    xr = x.clone()
+    y = torch.zeros(512, dtype=torch.int32)
+    z = torch.zeros(64, dtype=torch.uint8)
+    k1.interpret(1, x, y, z, 256, 16, True)
+    cnt = torch.stack([(xr[t::64] >= 0).sum() for t in range(64)])
+    t = torch.arange(64)
+    assert torch.equal(y[:64], (t * N_CONST + cnt).int()) and torch.equal(z, cnt.clamp(0, 255).to(torch.uint8))
+    assert int(y[64]) == 2 and torch.equal(y[65:129], ((t << 2) ^ (t % 3) | (t > 5).long()).int()) and torch.equal(y[200:264], (t + 4).int())
+    acc = torch.stack([xr[tt::64][xr[tt::64] >= 0].sum() for tt in range(64)]) - 2.5 + 8.0
+    acc[0], acc[63] = -acc[0], -acc[63]
+    torch.testing.assert_close(x[:64], acc, atol=1e-5, rtol=1e-5)

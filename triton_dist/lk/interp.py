@@ -82,6 +82,23 @@ class Ptr:
         """The underlying torch tensor from this element on (for the host mirror of the distributed primitives)."""
         return self.base[self.off:]
 
+    def _addr(self):
+        b = self.base
+        a = b.data_ptr() if hasattr(b, "data_ptr") else b.__array_interface__["data"][0]
+        es = b.element_size() if hasattr(b, "element_size") else b.itemsize
+        return a + self.off * es
+
+    def __eq__(self, o):
+        return isinstance(o, Ptr) and self._addr() == o._addr()
+
+    def __ne__(self, o):
+        return not self.__eq__(o)
+
+    def __lt__(self, o):
+        return self._addr() < o._addr()
+
+    __hash__ = None
+
 
 class SharedArray:
     def __init__(self, arr: np.ndarray, shape):

@@ -339,7 +339,8 @@ st_v4 = _i("st_v4", None, "td::ptx::st_v4({0}, {1})", 2)
 st_na_v4 = _i("st_na_v4", None, "td::ptx::st_na_v4({0}, {1})", 2)
 ld_shared_v4 = _i("ld_shared_v4", uint4, "td::ptx::ld_shared_v4({0})", 1)
 st_shared_v4 = _i("st_shared_v4", None, "td::ptx::st_shared_v4({0}, {1})", 2)
-make_uint4 = _i("make_uint4", uint4, "make_uint4({0}, {1}, {2}, {3})", 4)
+make_uint4 = _i("make_uint4", uint4, "make_uint4({0}, {1}, {2}, {3})", 4,
+                interp=lambda x, y, z, w: __import__("types").SimpleNamespace(x=u32(x), y=u32(y), z=u32(z), w=u32(w)))
 ldg = _i("ldg", _elem, "__ldg({0})", 1, interp=_ld)
 prefetch_l2 = _i("prefetch_l2", None, "td::ptx::prefetch_l2_bulk({0}, {1})", 2)
 # NVLS multicast
