@@ -287,3 +287,47 @@ def test_statement_coverage_codegen_and_interpreter_agree_with_python():
     acc = torch.stack([xr[tt::64][xr[tt::64] >= 0].sum() for tt in range(64)]) - 2.5 + 8.0
     acc[0], acc[63] = -acc[0], -acc[63]
     torch.testing.assert_close(x[:64], acc, atol=1e-5, rtol=1e-5)
+
+
+def test_gemm_ladder_runs_in_the_cpu_pipeline_model():
+    """The tcgen05 GEMM ladder executed by the interpreter's functional model of the Blackwell pipeline (mbarrier phases and tx counts,
+    TMA, tensor memory, cta_group::1 / ::2 MMAs and multicast commits): every rung -- including the persistent one with two accumulators
+    and a ring that runs across tiles -- reproduces A @ B^T on ragged shapes, i.e. no wrong phase, stage or tile index, no deadlock."""
+    from triton_dist.lk.kernels.gemm_sm100 import run_gemm, run_gemm_persistent
+    torch.manual_seed(0)
+
+    def check(fn, M, N, K, **kw):
+        a, b = (torch.randn(M, K) * 0.5).bfloat16(), (torch.randn(N, K) * 0.5).bfloat16()
+        c = fn(a, b, **kw)
+        torch.testing.assert_close(c.float(), a.float() @ b.float().t(), atol=0.15, rtol=2e-2)
+
+    check(run_gemm, 200, 264, 320, cta_group=1, BN=128, STAGES=2)       # ragged M / N, 5 k-blocks through a 2-stage ring
+    check(run_gemm, 300, 392, 192, cta_group=2, STAGES=2)               # 2-CTA pairs, 2 x 2 tiles
+    check(run_gemm_persistent, 600, 520, 192, num_sms=2)                # ONE cluster walks 3 x 3 tiles: ring + accumulators wrap
+
+
+def test_pipeline_model_reports_protocol_errors(monkeypatch):
+    """A barrier that can never complete is reported as a deadlock with the barrier's state; a warp reading TMEM lanes it does not own
+    and an MMA issued by the wrong CTA are rejected."""
+    from triton_dist.lk import pipeline as P
+    monkeypatch.setattr(P, "TIMEOUT_S", 0.5)
+
+    @lk.kernel(block=32)
+    def stuck(y: ll.ptr[ll.f32]):
+        bar = ll.dyn_shared([1], ll.u64)
+        if ll.threadIdx.x == 0:
+            ll.mbar_init(bar, 2)            # two arrivals expected ...
+            ll.mbar_arrive(bar)             # ... one ever comes
+        ll.syncthreads()
+        ll.mbar_wait(bar, 0)
+
+    with pytest.raises(P.Deadlock, match="pending arrivals 1"):
+        stuck.interpret(1, torch.zeros(1))
+
+    @lk.kernel(block=64)
+    def wrong_lanes(y: ll.ptr[ll.f32]):
+        regs = ll.local([32], ll.u32)
+        ll.tmem_ld_32x32b_x32(ll.u32(0), regs)      # warp 1 must read lanes 32..63
+
+    with pytest.raises(RuntimeError, match="may only read TMEM lanes 32"):
+        wrong_lanes.interpret(1, torch.zeros(1))

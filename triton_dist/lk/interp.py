@@ -33,6 +33,13 @@ class BlockState:
         self.warp_barrier = [threading.Barrier(n) for n in self.warp_size]
         self.warp_xchg: List[List[Any]] = [[None] * 32 for _ in range(nwarps)]
         self.error = None
+        # Blackwell async-pipeline model (see ``pipeline.py``): mbarriers keyed by (shared-array key, index), a 128-lane x 512-column
+        # tensor memory, and the CTAs of this block's cluster
+        self.mbarriers: Dict[Any, Any] = {}
+        self.tmem = np.zeros((128, 512), dtype=np.float32)
+        self.cluster: List["BlockState"] = [self]
+        self.cta_rank = 0
+        self.cluster_barrier = self.barrier
 
 
 class ThreadCtx:
@@ -68,8 +75,12 @@ class Ptr:
     def __setitem__(self, i, v):
         self.base[self.off + int(i)] = v
 
+    skey = None                                      # set for pointers into shared arrays (mbarrier identity)
+
     def __add__(self, n):
-        return Ptr(self.base, self.off + int(n), self.elem, self.owner)
+        p = Ptr(self.base, self.off + int(n), self.elem, self.owner)
+        p.skey = self.skey
+        return p
 
     __radd__ = __add__
 
@@ -101,26 +112,44 @@ class Ptr:
 
 
 class SharedArray:
-    def __init__(self, arr: np.ndarray, shape):
-        self.arr, self.shape = arr, tuple(shape)
+    """A (view of a) per-block shared array.  ``key`` names the allocation -- identical in every CTA of a launch, which is how the
+    cluster model finds "the same address in the peer CTA" -- and ``base`` is the element offset of this view inside it."""
+
+    def __init__(self, arr: np.ndarray, shape, key=None, base: int = 0):
+        self.arr, self.shape, self.key, self.base = arr, tuple(shape), key, int(base)
 
     def _flat(self, idx):
         if not isinstance(idx, tuple):
-            return int(idx)
+            idx = (idx,)
         f = 0
-        for i, s in zip(idx, self.shape):
-            f = f * s + int(i)
+        for k, i in enumerate(idx):
+            stride = 1
+            for d in self.shape[k + 1:]:
+                stride *= d
+            f += int(i) * stride
         return f
 
     def __getitem__(self, idx):
-        v = self.arr[self._flat(idx)]
+        n = len(idx) if isinstance(idx, tuple) else 1
+        if n < len(self.shape):                      # fewer indices than dimensions: a row view (``sA[stage]``)
+            return SharedArray(self.arr, self.shape[n:], self.key, self.base + self._flat(idx))
+        v = self.arr[self.base + self._flat(idx)]
         return v.item() if hasattr(v, "item") else v
 
     def __setitem__(self, idx, v):
-        self.arr[self._flat(idx)] = v
+        self.arr[self.base + self._flat(idx)] = v
 
     def __add__(self, n):
-        return Ptr(self.arr, int(n))
+        p = Ptr(self.arr, self.base + int(n))
+        p.skey = self.key
+        return p
+
+    @property
+    def numel(self):
+        n = 1
+        for d in self.shape:
+            n *= d
+        return n
 
 
 _NP = {"bool": np.bool_, "i8": np.int8, "u8": np.uint8, "i16": np.int16, "u16": np.uint16, "i32": np.int32, "u32": np.uint32,
@@ -141,7 +170,7 @@ def shared_array(key, shape, dtype, per_block=True) -> SharedArray:
         arr = c.block.shared.get(key)
         if arr is None:
             arr = c.block.shared[key] = np.zeros(n, dtype=np_dtype(dtype))
-    return SharedArray(arr, shape)
+    return SharedArray(arr, shape, key)
 
 
 def syncthreads():
@@ -194,7 +223,7 @@ def _wrap_arg(a, ty):
 MAX_CONCURRENT_THREADS = 2048
 
 
-def run(fn, param_types, grid, block, args, dyn_smem_bytes: int = 0):
+def run(fn, param_types, grid, block, args, dyn_smem_bytes: int = 0, cluster=(1, 1, 1)):
     """Blocks of a small grid (<= MAX_CONCURRENT_THREADS emulated threads in total) run concurrently, so kernels whose blocks depend on
     each other (or on other ranks, block by block) make progress as on a GPU; larger grids run one block after the other."""
     grid = tuple(grid) + (1,) * (3 - len(tuple(grid))) if not isinstance(grid, int) else (grid, 1, 1)
@@ -213,17 +242,32 @@ def run(fn, param_types, grid, block, args, dyn_smem_bytes: int = 0):
             pass
         except BaseException as e:      # noqa: BLE001
             errors.append(e)
-            blk.barrier.abort()
-            for b in blk.warp_barrier:
-                b.abort()
+            for member in blk.cluster:
+                member.barrier.abort()
+                member.cluster_barrier.abort()
+                for b in member.warp_barrier:
+                    b.abort()
+                for mb in list(member.mbarriers.values()):
+                    mb.abort()
         finally:
             _tls.ctx = None
 
+    csize = int(cluster[0]) * int(cluster[1]) * int(cluster[2]) if not isinstance(cluster, int) else int(cluster)
+    if csize > 1 and (cluster[1] != 1 or cluster[2] != 1 or grid[0] % csize):
+        raise ValueError("the interpreter models clusters along x only (grid.x must be a multiple of the cluster size)")
     per_wave = max(1, MAX_CONCURRENT_THREADS // nthreads) if len(bids) * nthreads <= MAX_CONCURRENT_THREADS else 1
+    per_wave = max(csize, per_wave // csize * csize)              # the CTAs of a cluster always run together
     for w0 in range(0, len(bids), per_wave):
         ths = []
-        for bid in bids[w0:w0 + per_wave]:
-            blk = BlockState(nthreads)
+        wave = bids[w0:w0 + per_wave]
+        blocks = [BlockState(nthreads) for _ in wave]
+        if csize > 1:
+            for c0 in range(0, len(blocks), csize):
+                members = blocks[c0:c0 + csize]
+                cb = threading.Barrier(nthreads * len(members))
+                for r, b in enumerate(members):
+                    b.cluster, b.cta_rank, b.cluster_barrier = members, r, cb
+        for bid, blk in zip(wave, blocks):
             dyn = np.zeros(max(dyn_smem_bytes, 1), dtype=np.uint8)
             if nthreads == 1 and per_wave == 1:
                 body(tids[0], bid, blk, dyn)

@@ -352,7 +352,10 @@ def run_gemm_persistent(a, b, out=None, BN: int = 256, STAGES: int = 6, cta_grou
     tB = lk.tma_2d(b, BK, b_rows)
     num_m, num_n = (M + tile_m - 1) // tile_m, (N + BN - 1) // BN
     workers = max(1, min(num_sms // cta_group, num_m * num_n))
-    k[workers * cta_group](tA, tB, out, M, N, K, num_m, num_n)
+    if a.is_cuda:
+        k[workers * cta_group](tA, tB, out, M, N, K, num_m, num_n)
+    else:
+        k.interpret(workers * cta_group, tA, tB, out, M, N, K, num_m, num_n)
     return out
 
 
@@ -368,7 +371,10 @@ def run_gemm(a, b, out=None, BN: int = 256, STAGES: int = 4, cta_group: int = 1)
     tA = lk.tma_2d(a, BK, BM)                   # box: 64 elements (128 B, SWIZZLE_128B) x 128 rows
     tB = lk.tma_2d(b, BK, b_rows)
     grid = ((N + BN - 1) // BN * cta_group, (M + tile_m - 1) // tile_m)
-    k[grid](tA, tB, out, M, N, K)
+    if a.is_cuda:
+        k[grid](tA, tB, out, M, N, K)
+    else:                       # CPU tensors: the interpreter's functional pipeline model (a few tiles at most)
+        k.interpret(grid, tA, tB, out, M, N, K)
     return out
 
 

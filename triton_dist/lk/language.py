@@ -518,3 +518,29 @@ def unroll(r, factor: Optional[int] = None):
 def static_range(*a):
     """``for i in ll.static_range(n)``: unrolled by the code generator; ``i`` is a compile-time constant in the body."""
     return range(*a)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU meaning of the asynchronous-pipeline intrinsics: the functional model of ``pipeline.py`` (mbarrier phases and transaction
+# counts, TMA tile loads, tensor memory, cta_group::1 / ::2 MMAs and commits) -- the GEMM ladder runs in the interpreter
+# ------------------------------------------------------------------------------------------------------------
+def _install_pipeline_model():
+    from . import pipeline as P
+    noop = lambda *a, **k: None      # noqa: E731
+    table = {
+        "mbar_init": P.mbar_init, "mbar_arrive": P.mbar_arrive, "mbar_arrive_cluster": P.mbar_arrive_cluster,
+        "mbar_arrive_expect_tx": P.mbar_arrive_expect_tx, "mbar_expect_tx": P.mbar_expect_tx, "mbar_wait": P.mbar_wait,
+        "mbar_try_wait": P.mbar_try_wait, "fence_barrier_init": noop, "fence_proxy_async": noop, "fence_proxy_async_smem": noop,
+        "prefetch_tensormap": noop, "tma_load_2d": P.tma_load_2d, "tma_load_2d_2sm": P.tma_load_2d_2sm,
+        "tmem_alloc": P.tmem_alloc, "tmem_relinquish": noop, "tmem_dealloc": noop, "tc_fence_before": noop, "tc_fence_after": noop,
+        "mma_f16": P.mma_f16, "mma_commit": P.mma_commit, "mma_commit_2sm": P.mma_commit_2sm,
+        "tmem_ld_32x32b_x32": P.tmem_ld_32x32b_x32, "tmem_ld_32x32b_x16": lambda t, r: P.tmem_ld_32x32b_x32(t, r, 16), "tmem_ld_wait": noop,
+        "make_smem_desc_k128": P.make_smem_desc_k128, "smem_addr": P.smem_addr, "pack_bf16x2": P.pack_bf16x2, "st_v4": P.st_v4,
+        "bf16_lo": lambda w: P._bf16_val(w), "bf16_hi": lambda w: P._bf16_val(int(w) >> 16),
+        "cluster_sync": P.cluster_sync, "cluster_rank": lambda: I.cur().block.cta_rank, "cluster_size": lambda: len(I.cur().block.cluster),
+    }
+    for name, fn in table.items():
+        INTRINSICS[name]._interp = fn
+
+
+_install_pipeline_model()
