@@ -1072,6 +1072,27 @@ def case_shmem():
         U.nvshmem_free_tensor_sync(t)
 
 
+def case_lk_ag_gemm():
+    """AllGather + GEMM as ONE kernel written in the Python DSL (comm CTAs push shards + release-add flags, tcgen05 tiles acquire the
+    flags of the rows they need).  GPU: the generated CUDA; emulation: the interpreter with the functional pipeline model, across ranks."""
+    from triton_dist.lk.kernels.ag_gemm import LkAgGemmContext, run_ag_gemm
+    W, me = U.world_size(), U.rank()
+    dev = U.current_device()
+    gpu = dev.type == "cuda"
+    Ms, K, N = (256, 512, 768) if gpu else (128, 128, 256)
+    ctx = LkAgGemmContext(Ms, K, BN=256, STAGES=2 if not gpu else 4, N_COMM=2 if not gpu else 4)
+    g = torch.Generator().manual_seed(21)
+    b = (torch.randn(N, K, generator=g) * 0.5).to(torch.bfloat16).to(dev)
+    for it in range(3 if gpu else 2):
+        ga = torch.Generator().manual_seed(1000 * it + me)
+        a = (torch.randn(Ms, K, generator=ga) * 0.5).to(torch.bfloat16).to(dev)
+        out = run_ag_gemm(ctx, a, b)
+        full = torch.empty(W * Ms, K, dtype=torch.bfloat16, device=dev)
+        dist.all_gather_into_tensor(full, a, group=U.get_triton_dist_world())
+        _assert_close(out, full.float() @ b.float().t(), 0.25, 2e-2, f"lk ag_gemm call {it}")
+    ctx.finalize()
+
+
 def case_mega():
     """Megakernel decode step (task graph + scoreboard + in-kernel all-reduce) vs the layer-by-layer TP model."""
     from triton_dist.models import AutoLLM, KV_Cache, ModelConfig

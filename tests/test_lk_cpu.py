@@ -114,8 +114,14 @@ def test_compile_errors_are_located():
     def no_annotation(y):
         pass
 
+    @lk.kernel
+    def two_types(y: ll.ptr[ll.u32]):
+        for v in range(4):
+            y[v] = 0
+        v = ll.make_uint4(1, 2, 3, 4)          # noqa: F841  (a local has ONE type per function)
+
     for kern, frag in ((undefined, "'nope' is not defined"), (bad_break, "statically unrolled"), (runtime_constexpr, "constexpr"),
-                       (no_annotation, "type annotation")):
+                       (no_annotation, "type annotation"), (two_types, "use another name")):
         with pytest.raises(CompileError) as e:
             kern.cuda_source()
         assert frag in str(e.value) and kern.name in str(e.value)
@@ -153,6 +159,11 @@ def test_nvcc_compiles_examples_and_gemm_ladder_emits_tcgen05():
         assert "sm_100a" in sass
         for n in needles:
             assert n in sass, (cg, n)
+    from triton_dist.lk.kernels.ag_gemm import make_ag_gemm
+    ag = make_ag_gemm(256, 4, 4)                               # comm CTAs + tcgen05 tiles in one kernel
+    ag.compile()
+    sass = subprocess.run([cuobjdump, "-sass", ag._lib._name], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass and "UTMALDG.2D" in sass and "td::notify" in ag.cuda_source() and "td::wait_ge<true>" in ag.cuda_source()
     from triton_dist.lk.kernels.gemm_sm100 import make_gemm_persistent
     pk = make_gemm_persistent(256, 6, 2)                       # the persistent rung: two TMEM accumulators, ring across tiles
     pk.compile()

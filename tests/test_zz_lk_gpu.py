@@ -230,3 +230,13 @@ print("PGEMM_OK")
 @pytest.mark.xfail(strict=False, reason="persistent rung of the DSL GEMM ladder: compiled and SASS-checked, not yet run on hardware")
 def test_lk_gemm_persistent():
     _isolated(_PGEMM_SNIPPET, "PGEMM_OK")
+
+
+def test_lk_ag_gemm_two_gpus():
+    """AllGather + GEMM written in the DSL (comm CTAs + tcgen05 tiles in one kernel); verified across processes in the CPU pipeline
+    model, queued for its first hardware run."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from _launch import run_dist
+    run_dist(["lk_ag_gemm"], nproc=2, timeout=240)

@@ -631,6 +631,11 @@ class FnCompiler:
         ty = self.vars[name]
         if isinstance(ty, T.Array):
             raise self.err(f"array '{name}' cannot be reassigned", node)
+        if v.ty is not None and (isinstance(ty, T.Struct) != isinstance(v.ty, T.Struct)
+                                 or (isinstance(ty, T.Struct) and ty is not v.ty)
+                                 or (isinstance(ty, T.Pointer) != isinstance(v.ty, (T.Pointer, T.Array)) and not v.is_const)):
+            raise self.err(f"'{name}' is a {ty.cname} (the type of its first assignment in this function) and cannot hold a "
+                           f"{v.ty.cname}: locals have one type per function -- use another name", node)
         code = self.cast(v, ty).code if isinstance(ty, (T.Scalar, T.Pointer)) else self.rvalue(v)
         self.emit(f"{self.cident(name)} = {code};")
 

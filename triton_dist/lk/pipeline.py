@@ -299,3 +299,10 @@ def st_v4(dst, v):
         vals += [_bf16_val(w), _bf16_val(int(w) >> 16)]
     for i, x in enumerate(vals):
         dst[i] = x
+
+
+def ld_v4(src):
+    """16-byte load of 8 bf16 (``src`` points into a bf16 / fp16 tensor) -> the four packed 32-bit words."""
+    import types
+    f = [src[i] for i in range(8)]
+    return types.SimpleNamespace(x=pack_bf16x2(f[0], f[1]), y=pack_bf16x2(f[2], f[3]), z=pack_bf16x2(f[4], f[5]), w=pack_bf16x2(f[6], f[7]))
