@@ -212,7 +212,7 @@ def test_interpreter_integer_wraparound_and_errors():
     with pytest.raises(RuntimeError, match="trap"):
         boom.interpret(1, torch.zeros(1))                    # one thread fails: the block's barrier is aborted, no hang
     with pytest.raises(NotImplementedError):
-        ll.tma_load_2d(None, None, None, 0, 0)               # no CPU meaning
+        ll.multimem_st_v4(None, None)                        # NVLS has no CPU meaning
 
 
 def test_gdn_chunk_kernels_in_the_interpreter_match_the_recurrence():
