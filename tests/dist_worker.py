@@ -1093,6 +1093,27 @@ def case_lk_ag_gemm():
     ctx.finalize()
 
 
+def case_lk_gemm_rs():
+    """GEMM + ReduceScatter as ONE DSL kernel: tcgen05 tiles reduce straight into the owner's buffer (16-byte bf16x2 reductions over
+    symm_at addresses), per-tile release-add of the owner's counter, collector CTAs acquire it.  GPU: generated CUDA; emulation: the
+    interpreter across ranks (pipeline model + CAS-emulated reductions)."""
+    from triton_dist.lk.kernels.gemm_rs import LkGemmRsContext, run_gemm_rs
+    W, me = U.world_size(), U.rank()
+    dev = U.current_device()
+    gpu = dev.type == "cuda"
+    Ms, K, N = (256, 512, 768) if gpu else (128, 128, 256)
+    ctx = LkGemmRsContext(Ms, N, BN=256, STAGES=2 if not gpu else 4, N_COLLECT=2 if not gpu else 4)
+    for it in range(3 if gpu else 2):
+        g = torch.Generator().manual_seed(500 * it + me)
+        a = (torch.randn(W * Ms, K, generator=g) * 0.25).to(torch.bfloat16).to(dev)
+        b = (torch.randn(N, K, generator=g) * 0.25).to(torch.bfloat16).to(dev)
+        out = run_gemm_rs(ctx, a, b)
+        part = a.float() @ b.float().t()                      # my K shard's contribution to all rows
+        dist.all_reduce(part, group=U.get_triton_dist_world())
+        _assert_close(out, part[me * Ms:(me + 1) * Ms], 0.3, 3e-2, f"lk gemm_rs call {it}")
+    ctx.finalize()
+
+
 def case_mega():
     """Megakernel decode step (task graph + scoreboard + in-kernel all-reduce) vs the layer-by-layer TP model."""
     from triton_dist.models import AutoLLM, KV_Cache, ModelConfig

@@ -164,6 +164,11 @@ def test_nvcc_compiles_examples_and_gemm_ladder_emits_tcgen05():
     ag.compile()
     sass = subprocess.run([cuobjdump, "-sass", ag._lib._name], capture_output=True, text=True).stdout
     assert "UTCHMMA" in sass and "UTMALDG.2D" in sass and "td::notify" in ag.cuda_source() and "td::wait_ge<true>" in ag.cuda_source()
+    from triton_dist.lk.kernels.gemm_rs import make_gemm_rs
+    rs = make_gemm_rs(256, 4, 4)                               # tcgen05 tiles + bf16x2 reductions into the owner + collector CTAs
+    rs.compile()
+    sass = subprocess.run([cuobjdump, "-sass", rs._lib._name], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass and "REDG.E.ADD.BF16" in sass and "REDG.E.ADD.STRONG.SYS" in sass        # tile reductions + counter release-add
     from triton_dist.lk.kernels.gemm_sm100 import make_gemm_persistent
     pk = make_gemm_persistent(256, 6, 2)                       # the persistent rung: two TMEM accumulators, ring across tiles
     pk.compile()

@@ -240,3 +240,12 @@ def test_lk_ag_gemm_two_gpus():
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from _launch import run_dist
     run_dist(["lk_ag_gemm"], nproc=2, timeout=240)
+
+
+def test_lk_gemm_rs_two_gpus():
+    """GEMM + ReduceScatter written in the DSL (tile epilogues reduce into the owner over NVLink, collector CTAs acquire the counter)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from _launch import run_dist
+    run_dist(["lk_gemm_rs"], nproc=2, timeout=240)

@@ -536,7 +536,7 @@ def _install_pipeline_model():
         "mma_f16": P.mma_f16, "mma_commit": P.mma_commit, "mma_commit_2sm": P.mma_commit_2sm,
         "tmem_ld_32x32b_x32": P.tmem_ld_32x32b_x32, "tmem_ld_32x32b_x16": lambda t, r: P.tmem_ld_32x32b_x32(t, r, 16), "tmem_ld_wait": noop,
         "make_smem_desc_k128": P.make_smem_desc_k128, "smem_addr": P.smem_addr, "pack_bf16x2": P.pack_bf16x2, "st_v4": P.st_v4,
-        "ld_v4": P.ld_v4, "ld_nc_v4": P.ld_v4, "st_na_v4": P.st_v4,
+        "ld_v4": P.ld_v4, "ld_nc_v4": P.ld_v4, "st_na_v4": P.st_v4, "red_add_bf16x8": P.red_add_bf16x8,
         "bf16_lo": lambda w: P._bf16_val(w), "bf16_hi": lambda w: P._bf16_val(int(w) >> 16),
         "cluster_sync": P.cluster_sync, "cluster_rank": lambda: I.cur().block.cta_rank, "cluster_size": lambda: len(I.cur().block.cluster),
     }

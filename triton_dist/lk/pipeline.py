@@ -306,3 +306,23 @@ def ld_v4(src):
     import types
     f = [src[i] for i in range(8)]
     return types.SimpleNamespace(x=pack_bf16x2(f[0], f[1]), y=pack_bf16x2(f[2], f[3]), z=pack_bf16x2(f[4], f[5]), w=pack_bf16x2(f[6], f[7]))
+
+
+def red_add_bf16x8(dst, v):
+    """``red.global.add.noftz.v4.bf16x2``: eight bf16 additions, each 32-bit word updated atomically (CAS loop on the word through the
+    host library, so concurrent adders in OTHER PROCESSES -- ranks of the emulation backend -- are handled like on the GPU)."""
+    import ctypes
+    from .. import _C
+    lib = _C.host_lib()
+    base = dst.base
+    es = base.element_size()
+    assert es == 2 and dst.off % 2 == 0, "red_add_bf16x8 needs a 4-byte aligned pointer into a 16-bit tensor"
+    addr = base.data_ptr() + dst.off * es
+    for i, w in enumerate((v.x, v.y, v.z, v.w)):
+        a = ctypes.c_void_p(addr + 4 * i)
+        while True:
+            old = int(lib.tdh_ld_acquire32(a))
+            lo = _bf16_bits(_bf16_val(old) + _bf16_val(w))
+            hi = _bf16_bits(_bf16_val(old >> 16) + _bf16_val(int(w) >> 16))
+            if int(lib.tdh_atomic_cas32(a, old, lo | (hi << 16))) == old:
+                break
