@@ -109,6 +109,23 @@ if gpu:
     err = (c.float() - a.float() @ b.float().t()).abs().max().item()
     U.dist_print(f"lk tcgen05 gemm: max err {err:.3f}", allowed_ranks=[0])
     assert err < 0.5
+# ---- 4. compute + communication in one Python function --------------------------------------------------------------------------
+# lk/kernels/ag_gemm.py (comm CTAs push shards + release-add flags, tcgen05 tiles acquire them) and lk/kernels/gemm_rs.py (tile
+# epilogues reduce into the owner over NVLink, collector CTAs acquire the arrival counter) are the two halves of a tensor-parallel MLP
+# as single DSL kernels.  On GPUs this runs them; on the emulation backend the interpreter's pipeline model does (slow: tiny shapes).
+if gpu or W == 2:
+    from triton_dist.lk.kernels.ag_gemm import LkAgGemmContext, run_ag_gemm  # noqa: E402
+    Ms, K2, N2 = (256, 512, 768) if gpu else (128, 64, 128)
+    agc = LkAgGemmContext(Ms, K2, BN=128, STAGES=2, N_COMM=2)
+    a_sh = (torch.randn(Ms, K2, device=dev) * 0.5).bfloat16()
+    b_w = (torch.randn(N2, K2, generator=torch.Generator().manual_seed(5)) * 0.5).bfloat16().to(dev)
+    y = run_ag_gemm(agc, a_sh, b_w)
+    full_a = torch.empty(W * Ms, K2, dtype=torch.bfloat16, device=dev)
+    torch.distributed.all_gather_into_tensor(full_a, a_sh, group=U.get_triton_dist_world())
+    err2 = (y.float() - full_a.float() @ b_w.float().t()).abs().max().item()
+    U.dist_print(f"lk ag_gemm (one DSL kernel, {agc.kernel.n_comm} comm CTAs): max err {err2:.3f}", allowed_ranks=[0])
+    assert err2 < 0.3
+    agc.finalize()
 U.barrier_all_host()
 U.nvshmem_free_tensor_sync(flag)
 U.nvshmem_free_tensor_sync(inbox)
