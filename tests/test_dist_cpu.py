@@ -29,3 +29,10 @@ def test_cpu_chaos():
     double-buffering, phase counters and slot reuse of every multi-call case are exercised under skew."""
     env = dict(CPU_ENV, TD_HOST_CHAOS_US="3000")
     run_dist(["ag_gemm", "gemm_rs", "gemm_ar", "gemm_a2a", "allreduce", "ep_ll", "ep_normal", "ep_mega"], nproc=3, env_extra=env)
+
+
+def test_cpu_chaos_dsl_and_shmem():
+    """The DSL's fused kernels (comm CTAs + tcgen05 tiles in the pipeline model), the NVSHMEM-style mirror and the NVLS all-gather
+    names under random skew at a non-power-of-two world."""
+    env = dict(CPU_ENV, TD_HOST_CHAOS_US="3000", TD_HOST_TIMEOUT_US="120000000")
+    run_dist(["lk_ag_gemm", "lk_gemm_rs", "shmem", "allgather_mc", "lk"], nproc=3, env_extra=env, timeout=900)
