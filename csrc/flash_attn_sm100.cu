@@ -42,6 +42,7 @@ struct Params {
   float scale_log2;        // sm_scale * log2(e)
   const int* cu_q;         // varlen (v2 kernel): int32 [B + 1] cumulative query lengths; Sq / Sk then hold the packed totals
   const int* cu_k;         // varlen: int32 [B + 1] cumulative key lengths
+  const int* seqused_k;    // varlen, optional: int32 [B] keys actually used of each sequence's slot (padded KV caches)
 };
 
 // BNK = keys per pipeline step.  128: one CTA per SM (197 KB smem, 384 TMEM columns).  64: TWO CTAs per SM (115 KB, 256
@@ -426,7 +427,7 @@ __global__ void __launch_bounds__(kThreadsV2, 1) flash_fwd_kernel_v2(const __gri
   int Sq = p.Sq, Sk = p.Sk, q_base = 0, k_base = 0, tb = batch;          // tb: batch coordinate of the tensor maps / output
   if constexpr (kVarlen) {
     q_base = p.cu_q[batch]; Sq = p.cu_q[batch + 1] - q_base;
-    k_base = p.cu_k[batch]; Sk = p.cu_k[batch + 1] - k_base;
+    k_base = p.cu_k[batch]; Sk = p.seqused_k ? p.seqused_k[batch] : p.cu_k[batch + 1] - k_base;
     tb = 0;
     if (q_row0 >= Sq || Sk <= 0) return;       // uniform for the CTA, before any barrier / TMEM state exists
   }
@@ -948,6 +949,7 @@ struct TdFlashArgs {
   long long block_n;          // keys per step: 64 (two CTAs per SM, default) or 128; 129 = 128 with Q and P in TMEM
   const int* cu_q; const int* cu_k;   // varlen (block_n 130 only): cumulative lengths, B = number of sequences, Sq / Sk = packed totals
   long long max_sq;                   // varlen: longest query sequence (grid bound)
+  const int* seqused_k;               // varlen, optional: keys used per sequence (the slot [cu_k[b], cu_k[b+1]) may be longer)
 };
 
 template <int BNK, bool kTS = false>
@@ -998,7 +1000,7 @@ extern "C" __attribute__((visibility("default"))) int td_flash_attn_fwd(const Td
   if (fa_tmap(&p.tmap_q, a->q, a->Sq, a->Hq, tmB, a->q_stride_b, a->q_stride_s, a->q_stride_h, (int)a->is_bf16, BMQ)) return -1;
   if (fa_tmap(&p.tmap_k, a->k, a->Sk, a->Hkv, tmB, a->k_stride_b, a->k_stride_s, a->k_stride_h, (int)a->is_bf16, bnk)) return -1;
   if (fa_tmap(&p.tmap_v, a->v, a->Sk, a->Hkv, tmB, a->v_stride_b, a->v_stride_s, a->v_stride_h, (int)a->is_bf16, bnk)) return -1;
-  p.cu_q = a->cu_q; p.cu_k = a->cu_k;
+  p.cu_q = a->cu_q; p.cu_k = a->cu_k; p.seqused_k = a->seqused_k;
   p.o = a->o; p.lse = a->lse; p.q_tile_pos = a->q_tile_pos;
   p.o_stride_b = a->o_stride_b; p.o_stride_s = a->o_stride_s; p.o_stride_h = a->o_stride_h;
   p.B = (int)a->B; p.Sq = (int)a->Sq; p.Sk = (int)a->Sk; p.Hq = (int)a->Hq; p.Hkv = (int)a->Hkv;

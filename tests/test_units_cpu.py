@@ -522,3 +522,12 @@ def test_flash_attn_varlen_reference_path():
             ref, ref_lse = flash_attn_reference(q[None, a:b], k[None, c:d], v[None, c:d], True)
             torch.testing.assert_close(out[a:b], ref[0])
             torch.testing.assert_close(lse[:, a:b], ref_lse[0])
+    # a padded KV cache viewed as a packed tensor: slot b holds max_len rows of which seqused_k[b] exist
+    B, S, max_len = 3, 5, 20
+    q2, k2, v2 = torch.randn(B * S, 4, 128), torch.randn(B * max_len, 2, 128), torch.randn(B * max_len, 2, 128)
+    ar, used = torch.arange(B + 1, dtype=torch.int32), torch.tensor([7, 20, 12], dtype=torch.int32)
+    o2 = flash_attn_varlen(q2, k2, v2, ar * S, ar * max_len, True, seqused_k=used)
+    for b in range(B):
+        n = int(used[b])
+        ref, _ = flash_attn_reference(q2[None, b * S:(b + 1) * S], k2[None, b * max_len:b * max_len + n], v2[None, b * max_len:b * max_len + n], True)
+        torch.testing.assert_close(o2[b * S:(b + 1) * S], ref[0])

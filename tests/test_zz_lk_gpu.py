@@ -133,6 +133,19 @@ for i in range(len(lens_q)):
     torch.testing.assert_close(lse[:, a:b], ref_lse[0], atol=2e-2, rtol=1e-2)
 torch.testing.assert_close(out.float(), loop.float(), atol=2e-2, rtol=2e-2)
 torch.testing.assert_close(lse, lse2, atol=2e-2, rtol=1e-2)
+# padded KV cache as a packed tensor (what the opt-in one-launch prefill of TP_Attn uses)
+B, S, max_len = 3, 130, 512
+q2 = torch.randn(B * S, 8, 128, device="cuda", dtype=torch.bfloat16)
+k2 = torch.randn(B * max_len, 2, 128, device="cuda", dtype=torch.bfloat16)
+v2 = torch.randn(B * max_len, 2, 128, device="cuda", dtype=torch.bfloat16)
+ar = torch.arange(B + 1, device="cuda", dtype=torch.int32)
+used = torch.tensor([130, 512, 300], device="cuda", dtype=torch.int32)
+o2 = flash_attn_varlen(q2, k2, v2, ar * S, ar * max_len, causal, max_seqlen_q=S, one_launch=True, seqused_k=used)
+torch.cuda.synchronize()
+for b in range(B):
+    n = int(used[b])
+    ref, _ = flash_attn_reference(q2[None, b * S:(b + 1) * S], k2[None, b * max_len:b * max_len + n], v2[None, b * max_len:b * max_len + n], causal)
+    torch.testing.assert_close(o2[b * S:(b + 1) * S].float(), ref[0], atol=2e-2, rtol=2e-2)
 print("VARLEN_OK")
 """
 

@@ -25,7 +25,7 @@ class _FlashArgs(C.Structure):
                 ("v_stride_b", c_ll), ("v_stride_s", c_ll), ("v_stride_h", c_ll),
                 ("o_stride_b", c_ll), ("o_stride_s", c_ll), ("o_stride_h", c_ll),
                 ("sm_scale", c_double), ("causal", c_ll), ("is_bf16", c_ll), ("block_n", c_ll),
-                ("cu_q", c_void_p), ("cu_k", c_void_p), ("max_sq", c_ll)]
+                ("cu_q", c_void_p), ("cu_k", c_void_p), ("max_sq", c_ll), ("seqused_k", c_void_p)]
 
 
 _C.register("td_flash_attn_fwd", c_int, [C.POINTER(_FlashArgs), c_void_p])
@@ -104,14 +104,15 @@ def flash_attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bo
 
 def flash_attn_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_seqlens_q: torch.Tensor, cu_seqlens_k: torch.Tensor,
                       causal: bool = True, sm_scale: Optional[float] = None, max_seqlen_q: Optional[int] = None,
-                      return_lse: bool = False, one_launch: Optional[bool] = None):
+                      return_lse: bool = False, one_launch: Optional[bool] = None, seqused_k: Optional[torch.Tensor] = None):
     """Packed variable-length batch (``flash_attn_varlen_func`` semantics): q [Tq, Hq, D], k / v [Tk, Hkv, D], ``cu_seqlens_*`` int32
     [B + 1].  Causal masks are bottom-right aligned per sequence (query i of a sequence sees its keys up to ``Sk - Sq + i``).
 
     ``one_launch=True`` (or ``TD_FLASH_VARLEN_KERNEL=1``): ONE launch of the varlen instantiation of the v2 kernel -- the cumulative
     lengths stay on the device (no host sync; ``max_seqlen_q`` bounds the grid, default: Tq), CTAs of tiles a sequence does not have
     exit immediately.  Default: one launch per sequence (the host reads the cumulative lengths once); the one-launch kernel compiles
-    but has not run on hardware yet.  With ``return_lse`` the LSE comes back as [Hq, Tq]."""
+    but has not run on hardware yet.  With ``return_lse`` the LSE comes back as [Hq, Tq].  ``seqused_k`` (int32 [B]): only the first
+    ``seqused_k[b]`` keys of slot ``[cu_seqlens_k[b], cu_seqlens_k[b+1])`` exist -- a padded KV cache viewed as a packed tensor."""
     import os
     Tq, Hq, D = q.shape
     if one_launch is None:
@@ -135,14 +136,21 @@ def flash_attn_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_seql
         a.block_n = 130
         a.cu_q, a.cu_k = cu_seqlens_q.data_ptr(), cu_seqlens_k.data_ptr()
         a.max_sq = int(max_seqlen_q) if max_seqlen_q else Tq
+        if seqused_k is not None:
+            assert seqused_k.dtype == torch.int32 and seqused_k.is_cuda and seqused_k.numel() == B
+            a.seqused_k = seqused_k.data_ptr()
         _C.check(_C.cuda_lib().td_flash_attn_fwd(C.byref(a), c_void_p(torch.cuda.current_stream().cuda_stream)), "td_flash_attn_fwd(varlen)")
         return (out, lse) if return_lse else out
     out = torch.empty_like(q)
     lse = torch.full((Hq, Tq), float("-inf"), dtype=torch.float32, device=q.device) if return_lse else None
     cq, ck = cu_seqlens_q.tolist(), cu_seqlens_k.tolist()
+    if seqused_k is not None:
+        ck_end = [ck[i] + int(n) for i, n in enumerate(seqused_k.tolist())]
+    else:
+        ck_end = ck[1:]
     for i in range(len(cq) - 1):
-        if cq[i + 1] > cq[i] and ck[i + 1] > ck[i]:
-            r = flash_attn_fwd(q[None, cq[i]:cq[i + 1]], k[None, ck[i]:ck[i + 1]], v[None, ck[i]:ck[i + 1]], causal, sm_scale,
+        if cq[i + 1] > cq[i] and ck_end[i] > ck[i]:
+            r = flash_attn_fwd(q[None, cq[i]:cq[i + 1]], k[None, ck[i]:ck_end[i]], v[None, ck[i]:ck_end[i]], causal, sm_scale,
                                out=out[None, cq[i]:cq[i + 1]], return_lse=return_lse)
             if return_lse:
                 lse[:, cq[i]:cq[i + 1]] = r[1][0]

@@ -37,6 +37,15 @@ def prefill_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Ten
     if q.is_cuda and D == 128 and U.get_bool_env("TD_TCGEN05_PREFILL", _TCGEN05_PREFILL_DEFAULT):
         # our tcgen05 flash-attention kernel (csrc/flash_attn_sm100.cu); one launch when all sequences share a length
         from ..ops.flash_attn import flash_attn_fwd
+        if U.get_bool_env("TD_FLASH_VARLEN_KERNEL", False) and q.is_contiguous() and k_cache.is_contiguous() and v_cache.is_contiguous():
+            # ONE launch for unequal lengths and no host read of kv_lens: the batch as a packed tensor (every query sequence has S rows,
+            # every KV slot max_len rows of which kv_lens[b] are used); opt-in until the varlen instantiation has run on hardware
+            from ..ops.flash_attn import flash_attn_varlen
+            max_len = k_cache.shape[1]
+            ar = torch.arange(B + 1, device=q.device, dtype=torch.int32)
+            o = flash_attn_varlen(q.view(B * S, Hq, D), k_cache.view(B * max_len, -1, D), v_cache.view(B * max_len, -1, D), ar * S, ar * max_len,
+                                  causal=True, sm_scale=sm_scale, max_seqlen_q=S, one_launch=True, seqused_k=kv_lens.to(torch.int32))
+            return o.view(B, S, Hq, D)
         lens = kv_lens.tolist()
         if all(x == lens[0] for x in lens):
             return flash_attn_fwd(q, k_cache, v_cache, causal=True, sm_scale=sm_scale, sk=lens[0])
