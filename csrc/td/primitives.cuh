@@ -63,9 +63,9 @@ template <bool kGreaterEqual = false, bool kSysScope = true>
 TD_DEVICE uint32_t wait(const uint32_t* flags, int n, uint32_t value) {
   const uint32_t lane = ptx::lane_id();
   if (static_cast<int>(lane) < n) {
-    uint32_t v;
+    uint32_t v; TD_SPIN_GUARD(guard)
     do {
-      v = kSysScope ? ptx::ld_acquire_sys(flags + lane) : ptx::ld_acquire_gpu(flags + lane);
+      v = kSysScope ? ptx::ld_acquire_sys(flags + lane) : ptx::ld_acquire_gpu(flags + lane); TD_SPIN_POLL(guard, "td::wait", flags + lane, v, value)
     } while (kGreaterEqual ? (static_cast<int32_t>(v - value) < 0) : (v != value));
   }
   __syncwarp();
@@ -75,9 +75,9 @@ TD_DEVICE uint32_t wait(const uint32_t* flags, int n, uint32_t value) {
 // one that subsequently issues the async-proxy loads, followed by a proxy fence).
 template <bool kSysScope = true>
 TD_DEVICE void wait_ge(const uint32_t* flag, uint32_t value) {
-  uint32_t v;
+  uint32_t v; TD_SPIN_GUARD(guard)
   do {
-    v = kSysScope ? ptx::ld_acquire_sys(flag) : ptx::ld_acquire_gpu(flag);
+    v = kSysScope ? ptx::ld_acquire_sys(flag) : ptx::ld_acquire_gpu(flag); TD_SPIN_POLL(guard, "td::wait_ge", flag, v, value)
   } while (static_cast<int32_t>(v - value) < 0);
 }
 // consume_token: identity in hand-written CUDA -- kept so device code reads like the reference's kernels.
@@ -97,7 +97,7 @@ TD_DEVICE void barrier_all_block(const SymmCtx& c, uint32_t* slots, uint32_t epo
     ptx::fence_acq_rel_sys();
     ptx::st_release_sys(symm_at(c, arr + c.rank, t), epoch);   // write my arrival into peer t's slot[me]
     uint32_t v;
-    do { v = ptx::ld_acquire_sys(arr + t); } while (static_cast<int32_t>(v - epoch) < 0);  // peer t arrived at me
+    TD_SPIN_GUARD(guard) do { v = ptx::ld_acquire_sys(arr + t); TD_SPIN_POLL(guard, "td::barrier_all_block (peer = thread)", arr + t, v, epoch) } while (static_cast<int32_t>(v - epoch) < 0);  // peer t arrived at me
   }
   __syncthreads();
 }
@@ -109,7 +109,7 @@ TD_DEVICE void grid_barrier(uint32_t* counter, uint32_t target) {
   __syncthreads();
   if (threadIdx.x == 0) {
     ptx::red_release_gpu_add(counter, 1u);
-    while (static_cast<int32_t>(ptx::ld_acquire_gpu(counter) - target) < 0) {
+    TD_SPIN_GUARD(guard) while (static_cast<int32_t>(ptx::ld_acquire_gpu(counter) - target) < 0) { TD_SPIN_POLL(guard, "td::grid_barrier", counter, 0ull, target)
     }
   }
   __syncthreads();

@@ -12,7 +12,7 @@
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
-
+#include "spin_guard.cuh"
 #define TD_DEVICE __device__ __forceinline__
 
 namespace td {
@@ -96,8 +96,8 @@ TD_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-TD_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
+TD_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) { TD_SPIN_GUARD(guard)
+  while (!mbar_try_wait(bar, parity)) { TD_SPIN_POLL(guard, "mbarrier wait (expected = parity)", bar, 0ull, parity)
   }
 }
 

@@ -151,7 +151,11 @@ TD_DEVICE bool cmp_holds(int cmp, uint64_t v, uint64_t ref) {
 // spins (acquire, system scope) until `*sig cmp value` holds; returns the value that satisfied the condition
 TD_DEVICE uint64_t signal_wait_until(const uint64_t* sig, int cmp, uint64_t value) {
   uint64_t v;
-  do { v = ptx::ld_acquire_sys(sig); } while (!cmp_holds(cmp, v, value));
+  TD_SPIN_GUARD(guard)
+  do {
+    v = ptx::ld_acquire_sys(sig);
+    TD_SPIN_POLL(guard, "shmem::signal_wait_until", sig, v, value)
+  } while (!cmp_holds(cmp, v, value));
   return v;
 }
 
@@ -205,7 +209,11 @@ TD_DEVICE void team_sync_impl(const SymmCtx& c, const Team& t, const Sync& s) {
     for (int i = tid; i < t.size; i += nthr) ptx::st_release_sys(symm_at(c, arr + c.rank, team_pe(t, i)), epoch);
     for (int i = tid; i < t.size; i += nthr) {
       uint32_t v;
-      do { v = ptx::ld_acquire_sys(arr + team_pe(t, i)); } while (static_cast<int32_t>(v - epoch) < 0);
+      TD_SPIN_GUARD(guard)
+      do {
+        v = ptx::ld_acquire_sys(arr + team_pe(t, i));
+        TD_SPIN_POLL(guard, "shmem team barrier (slot of a member)", arr + team_pe(t, i), v, epoch)
+      } while (static_cast<int32_t>(v - epoch) < 0);
     }
   }
   if (kGroup == 2) __syncthreads();

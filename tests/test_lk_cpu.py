@@ -347,3 +347,29 @@ def test_pipeline_model_reports_protocol_errors(monkeypatch):
 
     with pytest.raises(RuntimeError, match="may only read TMEM lanes 32"):
         wrong_lanes.interpret(1, torch.zeros(1))
+
+
+def test_debug_wait_variant_guards_spin_loops(monkeypatch):
+    """TD_DEBUG_WAITS=<ms>: kernels compiled against the device headers get timer-guarded waits that print a diagnostic and trap
+    (hang detection); without it the hooks vanish."""
+    from triton_dist import _build
+    src = r"""
+#include "td/primitives.cuh"
+using namespace td;
+__global__ void waits(SymmCtx c, uint32_t* flags, uint32_t* slots) {
+  wait<true, true>(flags, 4, 7u);
+  if (threadIdx.x == 0) wait_ge<true>(flags + 8, 3u);
+  barrier_all_block(c, slots, 5u);
+}
+extern "C" void launch_waits(SymmCtx c, void* f, void* s, void* stream) { waits<<<1, 64, 0, (cudaStream_t)stream>>>(c, (uint32_t*)f, (uint32_t*)s); }
+"""
+    from triton_dist import jit
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    monkeypatch.delenv("TD_DEBUG_WAITS", raising=False)
+    assert _build.debug_wait_timeout_ns() is None
+    plain = subprocess.run([cuobjdump, "-sass", jit.compile_cuda(src, name="waits")._name], capture_output=True, text=True).stdout
+    monkeypatch.setenv("TD_DEBUG_WAITS", "2500")
+    assert _build.debug_wait_timeout_ns() == 2_500_000_000
+    guarded = subprocess.run([cuobjdump, "-sass", jit.compile_cuda(src, name="waits")._name], capture_output=True, text=True).stdout
+    assert "GLOBALTIMER" not in plain and "BPT.TRAP" not in plain
+    assert "GLOBALTIMER" in guarded and "BPT.TRAP" in guarded

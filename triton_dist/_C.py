@@ -27,6 +27,11 @@ class NativeError(RuntimeError):
 
 def _ensure_built(which: str) -> Path:
     name = {"cuda": "libtd_b200.so", "host": "libtd_host.so"}[which]
+    if which == "cuda":
+        from . import _build as _b
+        tmo = _b.debug_wait_timeout_ns()
+        if tmo is not None:           # hang-detection variant (TD_DEBUG_WAITS=<ms>): built on first use, the default library is untouched
+            name = f"libtd_b200_dbg{tmo // 1000000}.so"
     path = _LIBDIR / name
     if os.environ.get("TD_NO_AUTOBUILD") == "1" and path.exists():
         return path
@@ -166,7 +171,7 @@ def loaded_libraries():
     """Which native libraries this process has actually loaded (used by tests and bench.py)."""
     out = []
     if _cuda is not None:
-        out.append(str(_LIBDIR / "libtd_b200.so"))
+        out.append(getattr(_cuda, "_name", str(_LIBDIR / "libtd_b200.so")))
     if _host is not None:
         out.append(str(_LIBDIR / "libtd_host.so"))
     return out

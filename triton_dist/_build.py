@@ -102,23 +102,38 @@ def _compile_objects(sources, compiler_cmd, tag, verbose):
     return objs, bool(jobs)
 
 
+def debug_wait_timeout_ns():
+    """``TD_DEBUG_WAITS=<milliseconds>`` selects the hang-detection variant of the device code: every spin loop of the primitives
+    (td::wait / wait_ge / barrier_all_block / grid_barrier / mbarrier waits / shmem waits) traps with a diagnostic after that long."""
+    v = os.environ.get("TD_DEBUG_WAITS", "")
+    if not v or v == "0":
+        return None
+    try:
+        ms = float(v)
+    except ValueError:
+        ms = 5000.0
+    return int(max(ms, 1.0) * 1e6)
+
+
 def build_cuda(verbose: bool = False, force: bool = False) -> Path:
-    """Compile every ``csrc/*.cu`` + ``csrc/runtime/*.cu`` into ``libtd_b200.so`` (sm_100a only)."""
+    """Compile every ``csrc/*.cu`` + ``csrc/runtime/*.cu`` into ``libtd_b200.so`` (sm_100a only).  With ``TD_DEBUG_WAITS`` set the
+    hang-detection variant ``libtd_b200_dbg<ms>.so`` is built (and loaded by ``_C.cuda_lib``) instead; the default library is untouched."""
     with _BuildLock():
         return _build_cuda_locked(verbose, force)
 
 
 def _build_cuda_locked(verbose: bool, force: bool) -> Path:
     LIBDIR.mkdir(parents=True, exist_ok=True)
-    out = LIBDIR / "libtd_b200.so"
+    tmo = debug_wait_timeout_ns()
+    out = LIBDIR / ("libtd_b200.so" if tmo is None else f"libtd_b200_dbg{tmo // 1000000}.so")
     cu = sorted(CSRC.glob("*.cu")) + sorted((CSRC / "runtime").glob("*.cu"))
     inc = ["-I", str(CSRC)]
-    cmd = [_nvcc()] + GENCODE + NVCC_FLAGS + inc
+    cmd = [_nvcc()] + GENCODE + NVCC_FLAGS + inc + ([] if tmo is None else [f"-DTD_WAIT_TIMEOUT_NS={tmo}ull"])
     if verbose or os.environ.get("TD_VERBOSE_BUILD") == "1":
         cmd = cmd + ["-Xptxas", "-v"]
     if force:
         shutil.rmtree(OBJDIR, ignore_errors=True)
-    objs, rebuilt = _compile_objects(cu, cmd, "cu", verbose)
+    objs, rebuilt = _compile_objects(cu, cmd, "cu" if tmo is None else "cudbg", verbose)
     if rebuilt or not out.exists():
         link = [_nvcc(), "-shared", "-cudart", "shared", "-o", str(out)] + [str(o) for o in objs] + [
             "-Xlinker", "-rpath", "-Xlinker", "/usr/local/cuda/lib64", "-ldl", "-lpthread"]

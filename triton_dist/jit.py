@@ -64,6 +64,9 @@ def compile_cuda(source: str, extra_flags: Sequence[str] = (), name: str = "kern
     """nvcc -> shared object -> ``ctypes.CDLL``.  Works without a GPU (cross-compiles sm_100a); launching needs one."""
     flags = list(_build.GENCODE) + ["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-cudart", "shared",
                                     "-I", str(_build.CSRC)] + list(extra_flags)
+    tmo = _build.debug_wait_timeout_ns()
+    if tmo is not None:               # TD_DEBUG_WAITS: user / DSL kernels get the guarded waits too
+        flags.append(f"-DTD_WAIT_TIMEOUT_NS={tmo}ull")
     # the key must not depend on where the checkout lives (the cache travels with the tree to the GPU box), but it must change when
     # the device headers do
     key = hashlib.sha256((source + "\0" + " ".join(flags).replace(str(_build.CSRC), "$CSRC") + "\0" + _headers_digest()).encode()).hexdigest()[:16]
