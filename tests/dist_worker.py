@@ -1114,6 +1114,57 @@ def case_lk_gemm_rs():
     ctx.finalize()
 
 
+def case_ep_fn_api():
+    """The process-wide EP op API of the autograd functions (reference: function/nvidia/common.py): init_triton_dist_ep_op ->
+    init_triton_dist_ep_ctx -> fused_ep_moe (forward vs the golden; forward + backward on the CUDA backend) -> deinit; split_mbs gives
+    two ops / streams."""
+    from triton_dist.function import nvidia as F
+    from triton_dist.ops import ep_mega as EM
+    dev = U.current_device()
+    W, me = U.world_size(), U.rank()
+    big = dev.type == "cuda"
+    bf = torch.bfloat16 if big else torch.float32
+    T, H, I, epr, topk = (256, 256, 128, 2, 2) if big else (12, 16, 8, 2, 2)
+    E = epr * W
+    grp = U.get_triton_dist_world()
+    assert not F.triton_dist_ep_op_initialized("mega")
+    op = F.init_triton_dist_ep_op(grp, T, H, topk, me, E, W, dtype=bf, num_sm=16, capacity=3.0, ep_implementation="mega")
+    assert F.triton_dist_ep_op_initialized("mega") and F.get_triton_dist_ep_op(0) is op and F.get_ep_capacity("mega") == 3.0
+    ectx = F.init_triton_dist_ep_ctx(grp, topk, E, "mega")
+    assert ectx.ep_op is op and ectx.num_experts_per_rank == epr and ectx.max_num_tiles >= epr
+    cfg = F.get_moe_optim_config(use_mega=True, is_forward=True)
+    assert isinstance(cfg, F.MoEOptimConfig) and cfg.num_dispatch_sms > 0
+    g = torch.Generator(device="cpu").manual_seed(3)
+    w_gu_all = (torch.randn(E, 2 * I, H, generator=g) * 0.05).to(bf).to(dev)
+    w_dn_all = (torch.randn(E, H, I, generator=g) * 0.05).to(bf).to(dev)
+    w_gu, w_dn = w_gu_all[me * epr:(me + 1) * epr].contiguous(), w_dn_all[me * epr:(me + 1) * epr].contiguous()
+    for it in range(2):
+        x = (torch.randn(T, H, device=dev) * 0.5).to(bf)
+        ids = torch.randn(T, E, device=dev).topk(topk, dim=1).indices.to(torch.int32)
+        wts = torch.softmax(torch.randn(T, topk, device=dev), -1)
+        if big:
+            xg, wg = x.clone().requires_grad_(True), w_gu.clone().requires_grad_(True)
+            out = F.fused_ep_moe(xg, ids, wts, wg, w_dn, ectx)
+            out.float().sum().backward()
+            assert xg.grad is not None and wg.grad is not None and torch.isfinite(xg.grad.float()).all()
+        else:
+            out = EM.mega_ep_moe(ectx.ep_op, x, ids, wts, w_gu, w_dn)          # the emulation backend mirrors the forward protocol
+        ref = EM.mega_ep_moe_reference(x, ids, wts, w_gu_all, w_dn_all)
+        _assert_close(out.detach(), ref, 0.05 if big else 1e-4, 5e-2 if big else 1e-4, f"fused_ep_moe it{it}")
+    U.barrier_all_host()
+    F.deinit_triton_dist_ep_op("mega")
+    assert not F.triton_dist_ep_op_initialized("mega")
+    F.init_triton_dist_ep_op(grp, T, H, topk, me, E, W, dtype=bf, capacity=3.0, ep_implementation="split_mbs")
+    assert F.triton_dist_ep_op_initialized("split_mbs") and F.get_triton_dist_ep_op(1) is not F.get_triton_dist_ep_op(2)
+    c1, c2 = F.init_triton_dist_ep_ctx(grp, topk, E, "split_mbs", 0), F.init_triton_dist_ep_ctx(grp, topk, E, "split_mbs", 1)
+    assert c1.ep_op is F.get_triton_dist_ep_op(1) and c2.ep_op is F.get_triton_dist_ep_op(2)
+    U.barrier_all_host()
+    F.deinit_triton_dist_ep_op("split_mbs")
+    F.set_triton_dist_moe_profile_enabled(True, "/tmp/td_prof")
+    assert F.get_triton_dist_moe_profile_enabled()["enabled"] and F.get_triton_dist_profile_output_dir() == "/tmp/td_prof"
+    F.set_triton_dist_moe_profile_enabled(False)
+
+
 def case_mega():
     """Megakernel decode step (task graph + scoreboard + in-kernel all-reduce) vs the layer-by-layer TP model."""
     from triton_dist.models import AutoLLM, KV_Cache, ModelConfig

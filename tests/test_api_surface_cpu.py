@@ -9,6 +9,7 @@ CHECK = {
  "triton_dist.kernels.nvidia": "ag_gemm create_ag_gemm_context gemm_persistent gemm_non_persistent gemm_rs create_gemm_rs_context create_gemm_ar_context create_ll_gemm_ar_context gemm_allreduce_op low_latency_gemm_allreduce_op ag_group_gemm create_ag_group_gemm_context create_moe_rs_context run_moe_reduce_rs fast_allgather create_fast_allgather_context fast_all_to_all create_all_to_all_context all_to_all_post_process create_ep_ll_a2a_ctx dispatch_kernel_v2 combine_kernel_v2 fused_sp_ag_attn_intra_node fused_sp_ag_attn_inter_node create_sp_ag_attention_context_intra_node gqa_fwd_batch_decode gqa_fwd_batch_decode_persistent gqa_fwd_batch_decode_intra_rank all_to_all_single_2d create_all_to_all_single_2d_context all_to_all_single_gemm create_all_to_all_single_gemm_context create_ulysses_sp_pre_attn_comm_context chunk_gated_delta_rule_fwd get_auto_all_gather_method AllGatherMethod cp_engine_producer_all_gather_intra_node cp_engine_producer_all_gather_inter_node moe_grouped_gemm moe_grouped_gemm_2weights transposed_moe_grouped_gemm run_moe_reduce_ar create_moe_ar_context ep_dispatch_token_inplace ep_combine_token_inplace bincount all_to_all_vdev_2d all_to_all_vdev_2d_offset pre_attn_qkv_pack_a2a_op qkv_bsnd_to_bnsd ulysses_sp_infer_gemm_a2a_op copy_tensor fill_tensor reduce_tensor swiglu_forward swiglu_backward matmul reduce_scatter_2d_op create_reduce_scater_2d_ctx ring_reduce calc_gather_scatter_index_triton histogram_by_expert_triton reduce_topk_tma get_tensorcore_tflops estimate_gemm_sol_time_ms estimate_reduce_scatter_time_ms estimate_all_gather_time_ms SpUlysessQKVGemmAll2AllKernel SpUlysessOAll2AllGemmKernel mega_kernel_dispatch_token_moe_grouped_gemm mega_kernel_moe_grouped_gemm_combine_token",
  "triton_dist.kernels.nvidia.allreduce": "create_allreduce_ctx all_reduce get_auto_allreduce_method",
  "triton_dist.kernels.allreduce": "AllReduceMethod OverlappingAllReduceMethod to_allreduce_method get_allreduce_methods",
+ "triton_dist.function.nvidia": "TritonDistFusedEpMoeFunction MegaEpMoeFunction mega_ep_moe_autograd fused_ep_moe init_triton_dist_ep_op deinit_triton_dist_ep_op init_triton_dist_ep_ctx triton_dist_ep_op_initialized get_ep_capacity get_triton_dist_ep_stream get_triton_dist_ep_op TritonDistEpContext MoEOptimConfig get_moe_optim_config set_triton_dist_moe_profile_enabled get_triton_dist_moe_profile_enabled get_triton_dist_profile_output_dir custom_fwd custom_bwd",
  "triton_dist.layers.nvidia": "TP_MLP TP_Attn TP_MoE EP_MoE EPAll2AllLayer EPLowLatencyAllToAllLayer EpAll2AllFusedOp GemmARLayer AllGatherLayer SpGQAFlashDecodeAttention UlyssesSPAllToAllLayer CommOp PPCommLayer",
  "triton_dist.models": "ModelConfig AutoLLM AutoTokenizer DenseLLM Qwen3MoE KV_Cache Engine",
  "triton_dist.tune": "autotune",
