@@ -51,3 +51,29 @@ def test_layer_methods(cls):
     c = getattr(L, cls)
     missing = [n for n in LAYER_METHODS[cls].split() if not hasattr(c, n)]
     assert not missing, f"{cls} lacks {missing}"
+
+
+def test_reference_module_paths_resolve():
+    """Code written against the reference imports per-op modules (``triton_dist.kernels.nvidia.allgather_gemm`` ...): one meta-path
+    finder (triton_dist/_module_map.py) maps every such path onto this package's modules; modules that exist on disk are untouched."""
+    import importlib
+    import triton_dist
+    from triton_dist import _module_map
+    from triton_dist.kernels.nvidia.allgather_gemm import ag_gemm, create_ag_gemm_context  # noqa: F401
+    from triton_dist.kernels.nvidia.gemm_reduce_scatter import create_gemm_rs_context, gemm_rs  # noqa: F401
+    from triton_dist.kernels.nvidia.low_latency_all_to_all_v2 import combine_kernel_v2, create_ep_ll_a2a_ctx, dispatch_kernel_v2  # noqa: F401
+    from triton_dist.kernels.nvidia.moe_reduce_rs import create_moe_rs_context, run_moe_reduce_rs  # noqa: F401
+    from triton_dist.language.extra import libshmem_device
+    from triton_dist.layers.nvidia.ep_a2a_fused_layer import EpAll2AllFusedOp  # noqa: F401
+    from triton_dist.layers.nvidia.tp_mlp import TP_MLP
+    from triton_dist.mega_triton_kernel.models.dense import MegaDenseModel  # noqa: F401
+    assert ag_gemm.__module__ == "triton_dist.ops.ag_gemm" and TP_MLP.__module__ == "triton_dist.parallel.tp_mlp"
+    assert callable(libshmem_device.putmem_signal) and callable(libshmem_device.fcollect)
+    import triton_dist.kernels.nvidia.allreduce as ar
+    assert ar.__file__.endswith("allreduce.py")                       # a real module is not shadowed
+    for name in _module_map.MODULE_MAP:                               # every mapped path imports and lists names
+        m = importlib.import_module(name)
+        assert dir(m), name
+    with pytest.raises(ImportError):
+        from triton_dist.kernels.nvidia.allgather_gemm import does_not_exist  # noqa: F401
+    assert triton_dist.__version__

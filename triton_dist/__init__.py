@@ -7,3 +7,6 @@ is a hand-written CUDA kernel (tcgen05 / TMEM / TMA, P2P + NVLS over NVLink 5) l
 __version__ = "0.1.0"
 
 from . import utils  # noqa: F401
+from . import _module_map as _mm
+
+_mm.install()       # reference module paths (triton_dist.kernels.nvidia.allgather_gemm, ...) resolve to this package's modules
