@@ -88,6 +88,11 @@ MODULE_MAP = {
     "triton_dist.language.extra.cuda": ["triton_dist.language.shmem", "triton_dist.language"],
     "triton_dist.language.extra.cuda.language_extra": ["triton_dist.language", "triton_dist.language.shmem"],
     "triton_dist.language.extra.cuda.libnvshmem_device": ["triton_dist.language.shmem"],
+    # tools / misc
+    "triton_dist.nv_utils": ["triton_dist.utils", "triton_dist._build"],
+    "triton_dist.tools.profiler.context": ["triton_dist.tools.profiler"],
+    "triton_dist.tools.profiler.language": ["triton_dist.tools.profiler"],
+    "triton_dist.tools.profiler.viewer": ["triton_dist.tools.profiler"],
     # megakernel
     "triton_dist.mega_triton_kernel": ["triton_dist.mega_kernel"],
     "triton_dist.mega_triton_kernel.core": ["triton_dist.mega_kernel"],
@@ -98,6 +103,14 @@ MODULE_MAP = {
     "triton_dist.mega_triton_kernel.models": ["triton_dist.mega_kernel.dense", "triton_dist.mega_kernel"],
     "triton_dist.mega_triton_kernel.models.dense": ["triton_dist.mega_kernel.dense"],
     "triton_dist.mega_triton_kernel.models.model_builder": ["triton_dist.mega_kernel"],
+    "triton_dist.mega_triton_kernel.models.utils": ["triton_dist.mega_kernel"],
+    "triton_dist.mega_triton_kernel.kernels.task_context": ["triton_dist.mega_kernel"],
+    "triton_dist.mega_triton_kernel.kernels": ["triton_dist.mega_kernel"],
+    "triton_dist.mega_triton_kernel.tasks.allreduce": ["triton_dist.mega_kernel"],
+    "triton_dist.mega_triton_kernel.tasks.flash_decode": ["triton_dist.mega_kernel"],
+    "triton_dist.mega_triton_kernel.tasks.norm": ["triton_dist.mega_kernel"],
+    "triton_dist.mega_triton_kernel.tasks.linear": ["triton_dist.mega_kernel"],
+    "triton_dist.mega_triton_kernel.tasks": ["triton_dist.mega_kernel"],
 }
 _FAMILY = {_K: "triton_dist.kernels.nvidia", _L: "triton_dist.layers.nvidia"}
 
