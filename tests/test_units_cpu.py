@@ -531,3 +531,38 @@ def test_flash_attn_varlen_reference_path():
         n = int(used[b])
         ref, _ = flash_attn_reference(q2[None, b * S:(b + 1) * S], k2[None, b * max_len:b * max_len + n], v2[None, b * max_len:b * max_len + n], True)
         torch.testing.assert_close(o2[b * S:(b + 1) * S], ref[0])
+
+
+def test_paged_kv_cache_feeds_flash_decode():
+    """Pages scattered by a random block table: appending through the table and decoding through it equals the dense cache."""
+    import math
+    import torch
+    from triton_dist.models import PagedKVCache
+    from triton_dist.ops.flash_decode import _decode_reference, gqa_fwd_batch_decode_partial
+    torch.manual_seed(0)
+    B, Hq, Hkv, D, L = 3, 4, 2, 128, 2
+    cache = PagedKVCache(PAGE_SIZE=4, num_layers=L, batch_size=B, max_length=40, num_kv_heads=Hkv, head_dim=D, dtype=torch.float32, device="cpu")
+    dense_k = torch.zeros(L, B, 40, Hkv, D)
+    dense_v = torch.zeros(L, B, 40, Hkv, D)
+    for S in (7, 1, 1, 5):                                  # a prefill and a few decode steps
+        for layer in range(L):
+            k_new, v_new = torch.randn(B, S, Hkv, D), torch.randn(B, S, Hkv, D)
+            cache.append(layer, k_new, v_new)
+            p0 = int(cache.kv_lens[0])
+            dense_k[layer, :, p0:p0 + S], dense_v[layer, :, p0:p0 + S] = k_new, v_new
+        cache.inc_offset(S)
+    assert int(cache.kv_lens[0]) == 14
+    q = torch.randn(B, Hq, D)
+    for layer in range(L):
+        kc, vc, bt, lens = cache.get_layer_kv_cache(layer)
+        o, lse = gqa_fwd_batch_decode_partial(q, kc, vc, lens, block_table=bt)
+        ro, rl = _decode_reference(q, dense_k[layer], dense_v[layer], lens, 1.0 / math.sqrt(D))
+        torch.testing.assert_close(o, ro)
+        torch.testing.assert_close(lse, rl)
+        gk, gv = cache.gather_dense(layer)
+        torch.testing.assert_close(gk[:, :14], dense_k[layer][:, :14])
+    import pytest
+    with pytest.raises(ValueError):
+        cache.inc_offset(100)
+    from triton_dist.mega_triton_kernel.models.paged_kv_cache import PagedKVCache as P2          # the reference's module path
+    assert P2 is PagedKVCache

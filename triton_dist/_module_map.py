@@ -102,6 +102,7 @@ MODULE_MAP = {
     "triton_dist.mega_triton_kernel.core.graph": ["triton_dist.mega_kernel"],
     "triton_dist.mega_triton_kernel.models": ["triton_dist.mega_kernel.dense", "triton_dist.mega_kernel"],
     "triton_dist.mega_triton_kernel.models.dense": ["triton_dist.mega_kernel.dense"],
+    "triton_dist.mega_triton_kernel.models.paged_kv_cache": ["triton_dist.models.paged_kv_cache"],
     "triton_dist.mega_triton_kernel.models.model_builder": ["triton_dist.mega_kernel"],
     "triton_dist.mega_triton_kernel.models.utils": ["triton_dist.mega_kernel"],
     "triton_dist.mega_triton_kernel.kernels.task_context": ["triton_dist.mega_kernel"],

@@ -49,3 +49,4 @@ class _ByteTokenizer:
 
 
 from .engine import Engine  # noqa: E402,F401
+from .paged_kv_cache import PagedKVCache  # noqa: E402,F401
