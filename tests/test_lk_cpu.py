@@ -373,3 +373,19 @@ extern "C" void launch_waits(SymmCtx c, void* f, void* s, void* stream) { waits<
     guarded = subprocess.run([cuobjdump, "-sass", jit.compile_cuda(src, name="waits")._name], capture_output=True, text=True).stdout
     assert "GLOBALTIMER" not in plain and "BPT.TRAP" not in plain
     assert "GLOBALTIMER" in guarded and "BPT.TRAP" in guarded
+
+
+def test_aot_export_of_dsl_kernels(tmp_path):
+    """tools/compile_aot: a DSL kernel becomes <name>.cu + <name>.so + a C header whose prototype a plain C compiler accepts."""
+    from triton_dist.tools import compile_aot
+    compile_aot.main(["triton_dist.lk.kernels.simt:block_sum", "triton_dist.lk.kernels.gemm_sm100:get_gemm(256, 4, 2)", "--out", str(tmp_path)])
+    for name in ("block_sum", "lk_gemm_bn256_s4_cg2"):
+        assert (tmp_path / f"{name}.so").stat().st_size > 10_000 and (tmp_path / f"{name}.cu").exists()
+    hdr = (tmp_path / "block_sum.h").read_text()
+    assert "int lk_launch_block_sum(void* x /* __nv_bfloat16* */, float* out, int n, unsigned gx" in hdr
+    assert "const void* tA /* CUtensorMap on the host */" in (tmp_path / "lk_gemm_bn256_s4_cg2.h").read_text()
+    (tmp_path / "use.c").write_text('#include "block_sum.h"\nint f(void* x, float* o, int n, void* s) { return lk_launch_block_sum(x, o, n, 4, 1, 1, 128, 1, 1, 1, 1, 1, 0, s); }\n')
+    r = subprocess.run(["gcc", "-c", str(tmp_path / "use.c"), "-I", str(tmp_path), "-o", str(tmp_path / "use.o")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    import ctypes
+    assert hasattr(ctypes.CDLL(str(tmp_path / "block_sum.so")), "lk_launch_block_sum")

@@ -90,6 +90,8 @@ MODULE_MAP = {
     "triton_dist.language.extra.cuda.libnvshmem_device": ["triton_dist.language.shmem"],
     # tools / misc
     "triton_dist.nv_utils": ["triton_dist.utils", "triton_dist._build"],
+    "triton_dist.tools.compile": ["triton_dist.tools.compile_aot"],
+    "triton_dist.tools.compile.compile": ["triton_dist.tools.compile_aot"],
     "triton_dist.tools.profiler.context": ["triton_dist.tools.profiler"],
     "triton_dist.tools.profiler.language": ["triton_dist.tools.profiler"],
     "triton_dist.tools.profiler.viewer": ["triton_dist.tools.profiler"],
