@@ -23,7 +23,7 @@ import numpy as np
 
 from . import interp as I
 
-TIMEOUT_S = float(os.environ.get("TD_LK_INTERP_TIMEOUT_S", "30"))
+TIMEOUT_S = float(os.environ.get("TD_LK_INTERP_TIMEOUT_S", "120"))
 K_TILE = 64                         # elements per staged tile row (128 bytes of bf16: one SWIZZLE_128B atom)
 
 
