@@ -389,3 +389,26 @@ def test_aot_export_of_dsl_kernels(tmp_path):
     assert r.returncode == 0, r.stderr
     import ctypes
     assert hasattr(ctypes.CDLL(str(tmp_path / "block_sum.so")), "lk_launch_block_sum")
+
+
+PRIMES = (2, 3, 5, 7, 11, 13, 17, 19)
+WEIGHTS = [0.5, 0.25, 0.125, 0.0625]
+
+
+def test_python_sequences_become_lookup_tables():
+    """A module-level list / tuple of numbers indexed with a run-time value is emitted once as a constant table (compile-time indices
+    still fold); the interpreter indexes the Python object."""
+    @lk.kernel(block=32)
+    def k(y: ll.ptr[ll.f32], z: ll.ptr[ll.i32]):
+        t = ll.threadIdx.x
+        z[t] = PRIMES[t % 8] + PRIMES[3]
+        y[t] = WEIGHTS[t & 3] * 2.0 + WEIGHTS[t % 4]
+    body = _body(k)
+    assert body.count("const int lk_tbl0[8] = {2, 3, 5, 7, 11, 13, 17, 19};") == 1 and "const float lk_tbl1[4] = {0.5f, 0.25f, 0.125f, 0.0625f};" in body
+    assert "(lk_tbl0[(t % 8)] + 7)" in body and body.count("lk_tbl1[") == 3            # one declaration, two uses
+    k.compile()
+    y, z = torch.zeros(32), torch.zeros(32, dtype=torch.int32)
+    k.interpret(1, y, z)
+    t = torch.arange(32)
+    assert torch.equal(z, (torch.tensor(PRIMES)[t % 8] + 7).int())
+    torch.testing.assert_close(y, torch.tensor(WEIGHTS)[t % 4] * 3.0)

@@ -226,6 +226,26 @@ class FnCompiler:
         else:
             self.decls.append(f"{arr.elem.cname} {c}[{arr.numel}];")
 
+    def _table_type(self, values) -> T.Scalar:
+        if any(isinstance(x, float) for x in values):
+            return T.f32
+        ty = T.i32
+        for x in values:
+            t = T.type_of_const(int(x))
+            ty = t if t.bits > ty.bits or (t.bits == ty.bits and t.kind == "u") else ty
+        return ty
+
+    def const_table(self, values) -> str:
+        key = ("tbl", tuple(values))
+        name = self.tables.get(key) if hasattr(self, "tables") else None
+        if name is None:
+            if not hasattr(self, "tables"):
+                self.tables = {}
+            ty = self._table_type(values)
+            name = self.tables[key] = f"lk_tbl{len(self.tables)}"
+            self.decls.append(f"const {ty.cname} {name}[{len(values)}] = {{{', '.join(ty.literal(ty.wrap(x)) for x in values)}}};")
+        return name
+
     def align_dyn_shared(self, a: int):
         self.dyn_off = (self.dyn_off + a - 1) // a * a
         self.dyn_align = max(self.dyn_align, a)
@@ -457,8 +477,11 @@ class FnCompiler:
             o = b.const if b.is_const else b.obj
             i = self.expr(node.slice)
             key = i.const if i.is_const else i.obj
-            if key is None and i.ty is not None:
-                raise self.err("indexing a compile-time sequence needs a compile-time index", node)
+            if not i.is_const and i.ty is not None:
+                # a Python list / tuple of numbers indexed at run time: materialised once as a constant lookup table
+                if isinstance(o, (list, tuple)) and o and all(isinstance(x, (bool, int, float)) for x in o):
+                    return Val(f"{self.const_table(o)}[{i.code}]", self._table_type(o))
+                raise self.err("indexing a compile-time sequence at run time needs a flat list / tuple of numbers", node)
             try:
                 return self.wrap(o[key], node)
             except Exception as e:      # noqa: BLE001
