@@ -566,3 +566,18 @@ def test_paged_kv_cache_feeds_flash_decode():
         cache.inc_offset(100)
     from triton_dist.mega_triton_kernel.models.paged_kv_cache import PagedKVCache as P2          # the reference's module path
     assert P2 is PagedKVCache
+
+
+def test_engine_profile_option_writes_a_trace(dist_env, tmp_path):
+    """Engine.enable_profile (reference: models/engine.py profiler over the first decode steps): a chrome trace per rank."""
+    import os
+    import torch
+    from triton_dist.models import Engine, ModelConfig
+    cfg = ModelConfig(model_name="tiny-dense", max_length=64, dtype=torch.float32, rank=0, world_size=1)
+    eng = Engine(cfg, temperature=0.0)
+    ids = torch.randint(0, 1000, (2, 5))
+    ref = eng.serve(ids, 5, backend="torch", use_cuda_graph=False)
+    eng.enable_profile, eng.profile_steps, eng.profile_dir = True, 2, str(tmp_path)
+    out = eng.serve(ids, 5, backend="torch", use_cuda_graph=False)
+    assert torch.equal(out, ref)                                        # profiling does not change the tokens
+    assert os.path.getsize(eng.last_trace) > 1000 and eng.last_trace.endswith("decode_torch_rank0.json")

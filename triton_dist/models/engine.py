@@ -111,7 +111,32 @@ class Engine:
         t0 = time.time()
         if self.device.type == "cuda":
             torch.cuda.synchronize()
+        # optional torch profiler over the first ``profile_steps`` decode steps (reference: engine.py:149-182, `enable_profile`, 64 steps):
+        # one chrome trace per rank under ``profile_dir``
+        profiler, prof_left = None, 0
+        if getattr(self, "enable_profile", False):
+            import os
+            acts = [torch.profiler.ProfilerActivity.CPU] + ([torch.profiler.ProfilerActivity.CUDA] if self.device.type == "cuda" else [])
+            profiler = torch.profiler.profile(activities=acts, record_shapes=False)
+            prof_left = int(getattr(self, "profile_steps", 64))
+            self._profile_dir = getattr(self, "profile_dir", "prof")
+            os.makedirs(self._profile_dir, exist_ok=True)
+            profiler.__enter__()
+
+        def _stop_profile():
+            nonlocal profiler
+            if profiler is not None:
+                if self.device.type == "cuda":
+                    torch.cuda.synchronize()
+                profiler.__exit__(None, None, None)
+                self.last_trace = f"{self._profile_dir}/decode_{backend}_rank{r}.json"
+                profiler.export_chrome_trace(self.last_trace)
+                profiler = None
+
         for _ in range(gen_len - 1):
+            if profiler is not None and prof_left == 0:
+                _stop_profile()
+            prof_left -= 1
             load_inputs(next_tok)
             if use_graph:
                 self.graph.replay()
@@ -127,6 +152,7 @@ class Engine:
                 dist.broadcast(next_tok, src=dist.get_global_rank(self.group, 0), group=self.group)
             self.kv_cache.inc_offset(1)
             out.append(next_tok)
+        _stop_profile()
         if self.device.type == "cuda":
             torch.cuda.synchronize()
         self.last_decode_ms = (time.time() - t0) * 1e3 / max(1, gen_len - 1)
