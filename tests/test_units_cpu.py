@@ -581,3 +581,36 @@ def test_engine_profile_option_writes_a_trace(dist_env, tmp_path):
     out = eng.serve(ids, 5, backend="torch", use_cuda_graph=False)
     assert torch.equal(out, ref)                                        # profiling does not change the tokens
     assert os.path.getsize(eng.last_trace) > 1000 and eng.last_trace.endswith("decode_torch_rank0.json")
+
+
+def test_reference_utils_helpers(dist_env):
+    """The generic helpers of the reference's utils.py (platform predicates, CUDA_CHECK, decorators, dtype sizes, lazy tensor specs)."""
+    import torch
+    import triton_dist.utils as U
+    assert U.is_cuda() and not U.is_hip() and not U.is_maca() and U.get_shmem_backend() == "td_symm_heap"
+    assert U.is_shmem_initialized() and len(U.get_shmem_hash()) == 16 and U.get_shmem_version()
+    U.init_nvshmem_by_torch_process_group(None)
+    U.CUDA_CHECK(0); U.CUDA_CHECK((0, "payload"))
+    with pytest.raises(RuntimeError):
+        U.CUDA_CHECK(700)
+    assert U.get_dtype_size(torch.bfloat16) == 2 and U.get_dtype_size(torch.int64) == 8 and U.is_fp8_dtype(torch.float8_e4m3fn)
+    assert U.get_device_max_shared_memory_size(0) >= 227 * 1024 and U.support_launch_cooperative_grid()
+
+    @U.requires(lambda: True)
+    def ok():
+        return 1
+
+    @U.requires(U.is_hip)
+    def needs_hip():
+        return 2
+
+    assert ok() == 1
+    with pytest.raises(AssertionError):
+        needs_hip()
+    alloc = U.LazyAllocator(symmetric=True)
+    lt = alloc.create_tensor((4, 8), torch.float32, name="buf")
+    assert isinstance(lt.spec, U.LazyTensorSpec) and lt.spec.nbytes == 128 and U.get_underlying_tensor(lt) is None and not lt.is_materialized
+    alloc.materialize()
+    assert U.get_underlying_tensor(lt).shape == (4, 8)
+    U.nvshmem_free_lazy_tensor(lt)
+    assert U.get_underlying_tensor(lt) is None

@@ -466,3 +466,11 @@ def get_device_property(device=None):
     if not torch.cuda.is_available():
         return None
     return torch.cuda.get_device_properties(device if device is not None else torch.cuda.current_device())
+
+from .extras import (CUDA_CHECK, TorchStreamWrapper, cuda_occupancy_max_activate_blocks_per_multiprocessor, get_cpu_info_linux,  # noqa: E402,F401
+                     get_device_max_shared_memory_size, get_dtype_size, get_group_numa_world_size, get_numa_node_count_in_group,
+                     get_nvshmem_hash, get_nvshmem_version, get_shmem_backend, get_shmem_hash, get_shmem_version, get_smi_device_index,
+                     init_nvshmem_by_torch_process_group, is_cuda, is_fp8_dtype, is_hip, is_maca, is_mori_shmem, is_rocshmem,
+                     is_shmem_initialized, requires, requires_p2p_native_atomic, support_launch_cooperative_grid,
+                     torch_stream_max_priority, triton_packed_version, warn_if_cuda_launch_blocking)
+from .lazy import LazyTensorSpec, get_underlying_tensor, nvshmem_free_lazy_tensor  # noqa: E402,F401

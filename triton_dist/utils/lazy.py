@@ -5,9 +5,30 @@ Tensors are *declared* first (shape/dtype/name); ``total_bytes()``/``breakdown()
 without touching memory; ``materialize()`` performs the collective allocations in declaration order."""
 from __future__ import annotations
 
+from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
 import torch
+
+
+@dataclass
+class LazyTensorSpec:
+    """What a lazy tensor will be once materialised (reference: utils.py:1064-1090)."""
+    name: str
+    shape: List[int]
+    dtype: torch.dtype
+    fill_value: Optional[float] = None
+
+    @property
+    def numel(self) -> int:
+        n = 1
+        for s in self.shape:
+            n *= int(s)
+        return n
+
+    @property
+    def nbytes(self) -> int:
+        return self.numel * torch.empty(0, dtype=self.dtype).element_size()
 
 
 class LazyTensor:
@@ -29,6 +50,15 @@ class LazyTensor:
     def get(self) -> torch.Tensor:
         if self._tensor is None:
             raise RuntimeError(f"LazyTensor '{self.name}' used before LazyAllocator.materialize()")
+        return self._tensor
+
+    @property
+    def spec(self) -> LazyTensorSpec:
+        return LazyTensorSpec(self.name, list(self.shape), self.dtype, getattr(self, "fill_value", None))
+
+    is_materialized = materialized
+
+    def get_underlying_tensor(self) -> Optional[torch.Tensor]:
         return self._tensor
 
     def __repr__(self):
@@ -82,3 +112,19 @@ class LazyAllocator:
 class NVSHMEMLazyAllocator(LazyAllocator):
     def __init__(self):
         super().__init__(symmetric=True)
+
+
+def get_underlying_tensor(t):
+    """A LazyTensor's tensor (None before materialisation); plain tensors pass through."""
+    return t.get_underlying_tensor() if isinstance(t, LazyTensor) else t
+
+
+def nvshmem_free_lazy_tensor(t):
+    """Collective free of one materialised lazy tensor."""
+    from . import nvshmem_free_tensor_sync
+    if isinstance(t, LazyTensor):
+        if t._tensor is not None:
+            nvshmem_free_tensor_sync(t._tensor)
+            t._tensor = None
+    elif t is not None:
+        nvshmem_free_tensor_sync(t)
