@@ -614,3 +614,53 @@ def test_reference_utils_helpers(dist_env):
     assert U.get_underlying_tensor(lt).shape == (4, 8)
     U.nvshmem_free_lazy_tensor(lt)
     assert U.get_underlying_tensor(lt) is None
+
+
+def test_reference_tooling_names(tmp_path):
+    """profiler_utils / tune / autotuner / test.utils helpers a user of the reference expects, with behaviour (not just names)."""
+    import json
+    import torch
+    from triton_dist import autotuner, profiler_utils as PU, tune
+    from triton_dist.test.utils import bitwise_equal
+    # traces: per-rank processing keeps lanes apart, the parallel dumper writes one valid gzip stream
+    tr = {"traceEvents": [{"ph": "X", "pid": 7, "tid": 1, "name": "k", "ts": 0, "dur": 5},
+                          {"ph": "M", "pid": 7, "name": "process_name", "args": {"name": "python"}}], "displayTimeUnit": "ms"}
+    p1 = PU.process_trace_json(tr, rank=3)
+    assert p1["traceEvents"][0]["pid"] == 7 + 3_000_000 and p1["traceEvents"][1]["args"]["name"].startswith("rank 3")
+    big = {"traceEvents": [dict(tr["traceEvents"][0], ts=i) for i in range(1234)], "displayTimeUnit": "ms"}
+    PU.ParallelJsonDumper(workers=3, chunk_events=100).dump(big, str(tmp_path / "t.json.gz"))
+    back = PU.load_json(str(tmp_path / "t.json.gz"))
+    assert len(back["traceEvents"]) == 1234 and back["traceEvents"][1233]["ts"] == 1233
+    with PU.get_torch_prof_ctx(False) as prof:
+        assert prof is None
+    with PU.AutoExportProfiler("unit", str(tmp_path), merge=False) as prof:
+        torch.ones(8).sum()
+    out, ms, peak = PU.benchmark_latency_memory(lambda: torch.ones(16).sum(), 3, 1)
+    assert float(out) == 16.0 and ms >= 0 and peak >= 0
+    # tune records
+    from triton_dist.ops import GemmConfig
+    rec = {"cfg": GemmConfig(256, 2, 8, True), "dtype": torch.bfloat16, "t": torch.zeros(2, 3)}
+    tune.store_autotune_data(tmp_path / "a" / "rec.json", rec)
+    got = tune.load_autotune_data(tmp_path / "a" / "rec.json")
+    assert got["cfg"]["bn"] == 256 and got["dtype"] == "torch.bfloat16" and got["t"]["__tensor__"] == [2, 3]
+    assert tune.to_hashable({"b": [1, 2], "a": torch.zeros(4)}) == (("a", ("tensor", (4,), "torch.float32")), ("b", (1, 2)))
+    assert "bn=256" in tune.pretty_triton_config_repr(GemmConfig(256, 2, 8, True)) and tune.get_hardware_info()["device"]
+    assert tune.get_triton_dist_version() and "torch" in tune.get_deps() and set(tune.get_git_info()) == {"commit", "dirty"}
+    h = tune.log_to_file(str(tmp_path / "tune.log"))
+    tune.log.info("hello")
+    h.flush()
+    assert "hello" in open(tmp_path / "tune.log").read()
+    tune.log.removeHandler(h)
+    # contextual autotuner, class form
+    calls = []
+
+    def step():
+        calls.append(autotuner.override_for("op", "default"))
+        return calls[-1]
+
+    t = autotuner.ContextualAutoTuner(step, {"op": ["a", "b"]}, warmup=1, rep=1)
+    assert t() in ("a", "b") and t.best["op"] in ("a", "b") and len(t.results) == 2
+    x = torch.tensor([0.0, float("nan")])
+    assert bitwise_equal(x, x.clone()) and not bitwise_equal(torch.tensor([0.0]), torch.tensor([-0.0]))
+    from triton_dist.models.utils import MyLogger
+    MyLogger().log("ok", "info")

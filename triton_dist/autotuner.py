@@ -51,3 +51,30 @@ def contextual_autotune(spaces: Dict[str, List[Any]], is_dist: bool = False, pg=
         wrapped.best = best
         return wrapped
     return deco
+
+
+class ContextualAutoTuner:
+    """Class form of :func:`contextual_autotune` (reference: autotuner.py ``ContextualAutoTuner``): wraps a function, tunes on the first
+    call, exposes the winning assignment and the whole timing table."""
+
+    def __init__(self, fn: Callable, spaces: Dict[str, List[Any]], is_dist: bool = False, pg=None, warmup: int = 3, rep: int = 5):
+        self.fn, self.spaces, self.is_dist, self.pg, self.warmup, self.rep = fn, spaces, is_dist, pg, warmup, rep
+        self.best: Dict[str, Any] = {}
+        self.results: List[Any] = []
+
+    def tune(self, *args, **kwargs):
+        names = list(self.spaces)
+        self.results = []
+        for combo in itertools.product(*[self.spaces[n] for n in names]):
+            assign = dict(zip(names, combo))
+            with _install(assign):
+                ms = _time_call(lambda: self.fn(*args, **kwargs), self.warmup, self.rep, self.pg if self.is_dist else None)
+            self.results.append((ms, assign))
+        self.best = dict(min(self.results, key=lambda r: r[0])[1])
+        return self.best
+
+    def __call__(self, *args, **kwargs):
+        if not self.best:
+            self.tune(*args, **kwargs)
+        with _install(self.best):
+            return self.fn(*args, **kwargs)

@@ -46,3 +46,31 @@ def sample_token(logits: torch.Tensor, temperature: float = 0.6, top_p: float = 
     sorted_p = sorted_p / sorted_p.sum(dim=-1, keepdim=True)
     nxt = torch.multinomial(sorted_p, 1)
     return idx.gather(-1, nxt)
+
+
+class MyLogger:
+    """Level-keyed wrapper over the package logger (reference: models/utils.py:45-70); ``TRITON_DIST_DEBUG=1`` enables debug output."""
+
+    def __init__(self):
+        import os
+        self.logger = logger
+        if os.getenv("TRITON_DIST_DEBUG", "").lower() in ("true", "1", "t"):
+            self.logger.setLevel(logging.DEBUG)
+
+    def log(self, msg, level: str = "info"):
+        getattr(self.logger, {"warn": "warning"}.get(level, level), self.logger.info)(msg)
+
+
+def init_model_cpu(model_name: str, dtype: torch.dtype):
+    """A Hugging Face causal LM on the CPU: from a LOCAL checkpoint directory (there is no network here), or -- with ``RANDOM_PARAMS=1``
+    or when only a config is available -- randomly initialised from the config.  The reference downloads by name
+    (models/utils.py:108-127); ``DenseLLM.init_parameters`` consumes the result the same way."""
+    import os
+    from transformers import AutoConfig, AutoModelForCausalLM
+    with torch.no_grad():
+        if os.environ.get("RANDOM_PARAMS", "0").lower() in ("1", "true", "yes") or not any(
+                os.path.exists(os.path.join(model_name, f)) for f in ("model.safetensors", "pytorch_model.bin", "model.safetensors.index.json")):
+            config = AutoConfig.from_pretrained(model_name)
+            model = AutoModelForCausalLM.from_config(config, torch_dtype=dtype)
+            return model
+        return AutoModelForCausalLM.from_pretrained(model_name, torch_dtype=dtype)

@@ -32,3 +32,10 @@ def assert_bitwise_equal(x: torch.Tensor, y: torch.Tensor):
     if xb.shape != yb.shape or not torch.equal(xb, yb):
         n = int((xb != yb).sum()) if xb.shape == yb.shape else -1
         raise AssertionError(f"tensors differ bitwise ({n} bytes)")
+
+
+def bitwise_equal(x: torch.Tensor, y: torch.Tensor) -> bool:
+    """True when the two tensors have identical bytes (NaN == NaN, -0.0 != +0.0)."""
+    if x.shape != y.shape or x.dtype != y.dtype:
+        return False
+    return bool(torch.equal(x.contiguous().view(torch.uint8), y.contiguous().view(torch.uint8)))

@@ -148,3 +148,118 @@ def autotune(config_space: Iterable[Dict[str, Any]], key_fn: Optional[Callable] 
     def deco(fn):
         return AutoTuner(fn, list(config_space), key_fn, prune_fn, warmup, rep, config_kw)
     return deco
+
+
+# ------------------------------------------------------------------------------------------------------------
+# record keeping helpers of the reference's tune.py (hashable keys, JSON encoding of configs, hardware / version info, log control)
+# ------------------------------------------------------------------------------------------------------------
+def to_hashable(obj):
+    """Nested lists / dicts / tensors-shapes -> a hashable, order-independent key."""
+    if isinstance(obj, torch.Tensor):
+        return ("tensor", tuple(obj.shape), str(obj.dtype))
+    if isinstance(obj, dict):
+        return tuple(sorted((k, to_hashable(v)) for k, v in obj.items()))
+    if isinstance(obj, (list, tuple, set)):
+        return tuple(to_hashable(v) for v in obj)
+    if hasattr(obj, "__dataclass_fields__"):
+        return (type(obj).__name__,) + tuple((f, to_hashable(getattr(obj, f))) for f in obj.__dataclass_fields__)
+    return obj
+
+
+class TuneRecordEncoder(json.JSONEncoder):
+    """Serialises what tuning records contain: dataclass configs, dtypes, devices, tensors (as shape / dtype), paths."""
+
+    def default(self, o):
+        if hasattr(o, "__dataclass_fields__"):
+            return {"__dataclass__": type(o).__name__, **{f: getattr(o, f) for f in o.__dataclass_fields__}}
+        if isinstance(o, (torch.dtype, torch.device, Path)):
+            return str(o)
+        if isinstance(o, torch.Tensor):
+            return {"__tensor__": list(o.shape), "dtype": str(o.dtype)}
+        return super().default(o)
+
+
+def from_json(text: str):
+    return json.loads(text)
+
+
+def store_autotune_data(path, data: Dict[str, Any]):
+    path = Path(path)
+    path.parent.mkdir(parents=True, exist_ok=True)
+    path.write_text(json.dumps(data, indent=1, cls=TuneRecordEncoder))
+
+
+def load_autotune_data(path) -> Dict[str, Any]:
+    try:
+        return json.loads(Path(path).read_text())
+    except (OSError, ValueError):
+        return {}
+
+
+def pretty_triton_config_repr(cfg) -> str:
+    """One-line description of a configuration (dataclass, dict, or anything with a repr)."""
+    if hasattr(cfg, "__dataclass_fields__"):
+        return type(cfg).__name__ + "(" + ", ".join(f"{f}={getattr(cfg, f)}" for f in cfg.__dataclass_fields__) + ")"
+    if isinstance(cfg, dict):
+        return ", ".join(f"{k}={v}" for k, v in cfg.items())
+    return repr(cfg)
+
+
+def get_hardware_info() -> Dict[str, Any]:
+    if not torch.cuda.is_available():
+        return {"device": "cpu"}
+    p = torch.cuda.get_device_properties(0)
+    return {"device": p.name, "sms": p.multi_processor_count, "memory_gb": round(p.total_memory / 2 ** 30, 1), "cuda": torch.version.cuda,
+            "capability": f"{p.major}.{p.minor}", "num_gpus": torch.cuda.device_count()}
+
+
+hw_hash = _hw_hash
+
+
+def get_triton_dist_version() -> str:
+    from . import __version__
+    return __version__
+
+
+def get_git_info() -> Dict[str, str]:
+    import subprocess
+    root = Path(__file__).resolve().parent.parent
+    try:
+        rev = subprocess.run(["git", "-C", str(root), "rev-parse", "--short", "HEAD"], capture_output=True, text=True, timeout=5).stdout.strip()
+        dirty = bool(subprocess.run(["git", "-C", str(root), "status", "--porcelain"], capture_output=True, text=True, timeout=5).stdout.strip())
+    except Exception:      # noqa: BLE001
+        rev, dirty = "", False
+    return {"commit": rev, "dirty": str(dirty)}
+
+
+def get_deps() -> Dict[str, str]:
+    return {"torch": torch.__version__, "cuda": str(torch.version.cuda), "triton_dist": get_triton_dist_version()}
+
+
+def get_cuda_extra_args() -> Dict[str, Any]:
+    """What a cache entry must also depend on for CUDA kernels (the reference hashes Triton launch extras): the native library digest."""
+    from . import _build
+    lib = _build.LIBDIR / "libtd_b200.so"
+    return {"lib_mtime": int(lib.stat().st_mtime) if lib.exists() else 0}
+
+
+def log_to_file(path: str, level: int = logging.INFO):
+    h = logging.FileHandler(path)
+    h.setLevel(level)
+    h.setFormatter(logging.Formatter("%(asctime)s %(name)s %(levelname)s %(message)s"))
+    log.addHandler(h)
+    log.setLevel(min(log.level or level, level))
+    return h
+
+
+def set_stream_handler_log_level(level: int):
+    found = False
+    for h in log.handlers:
+        if isinstance(h, logging.StreamHandler) and not isinstance(h, logging.FileHandler):
+            h.setLevel(level)
+            found = True
+    if not found:
+        h = logging.StreamHandler()
+        h.setLevel(level)
+        log.addHandler(h)
+    log.setLevel(min(log.level or level, level))
