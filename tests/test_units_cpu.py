@@ -664,3 +664,39 @@ def test_reference_tooling_names(tmp_path):
     assert bitwise_equal(x, x.clone()) and not bitwise_equal(torch.tensor([0.0]), torch.tensor([-0.0]))
     from triton_dist.models.utils import MyLogger
     MyLogger().log("ok", "info")
+
+
+def test_reference_per_module_names_behave(dist_env):
+    """User-facing names of the reference's per-op modules that are thin spellings here: every all-gather method name, the moe_utils
+    torch goldens, layer helpers, context-class names."""
+    import torch
+    from triton_dist.kernels.nvidia import low_latency_allgather as LL
+    from triton_dist.kernels.nvidia import moe_utils as MU
+    from triton_dist.kernels.nvidia.all_to_all_single_2d import AllToAllSingle2DContext
+    from triton_dist.kernels.nvidia.gemm_reduce_scatter import gemm_rs_op  # noqa: F401
+    from triton_dist.layers.nvidia.ep_a2a_layer import DispatchCombineContext, EPAllToAllLayoutDesc
+    from triton_dist.layers.nvidia.ep_moe import prepare_moe_metadata_using_kernel
+    from triton_dist.layers.nvidia.tp_attn import layer_norm
+    from triton_dist.layers.nvidia.tp_moe import shard_local
+    from triton_dist.ops.all_to_all import AllToAllContext
+    assert AllToAllSingle2DContext is AllToAllContext and DispatchCombineContext is EPAllToAllLayoutDesc
+    ctx = LL.create_fast_allgather_context(1 << 12)
+    x = torch.randn(100)
+    for name in ("fast_allgather_pull", "fast_allgather_push_2d", "fast_allgather_push_3d", "fast_allgather_push_2d_ll",
+                 "fast_allgather_push_2d_ll_multimem", "fast_allgather_push_numa_2d", "fast_allgather_push_numa_2d_ll"):
+        torch.testing.assert_close(getattr(LL, name)(ctx, x).view(-1), x)                 # world 1: the gather is the shard itself
+    with pytest.raises(NotImplementedError):
+        LL.fast_allgather_push_numa_2d_ll_multinode(ctx, x)
+    ctx.finalize()
+    ids = torch.tensor([[2, 0], [1, 2], [0, 0]], dtype=torch.int32)
+    assert MU.histogram_by_expert_torch(ids, 4).tolist() == [3, 1, 2, 0]
+    sc = MU.calc_scatter_index_torch(ids, 4)
+    ga = MU.calc_gather_index_torch(ids, 4)
+    flat = ids.reshape(-1)
+    assert torch.equal(flat[ga.long()], torch.sort(flat, stable=True).values) and torch.equal(ga[sc.reshape(-1).long()], torch.arange(6, dtype=torch.int32))
+    h = torch.randn(3, 2, 16)
+    w = torch.rand(16) + 0.5
+    torch.testing.assert_close(layer_norm(h, w, 1e-6), h * torch.rsqrt(h.pow(2).mean(-1, keepdim=True) + 1e-6) * w, atol=1e-5, rtol=1e-5)
+    assert torch.equal(shard_local(torch.arange(12).view(3, 4), 2, 1, 1), torch.tensor([[2, 3], [6, 7], [10, 11]]))
+    sorted_ids, tile_expert, offs = prepare_moe_metadata_using_kernel(ids, 4, block_m=4)
+    assert offs.numel() == 5 and sorted_ids.numel() % 4 == 0 and tile_expert.numel() == sorted_ids.numel() // 4

@@ -155,6 +155,8 @@ class _Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
         for prefix, family in _FAMILY.items():
             if spec.name.startswith(prefix):
                 targets.append(family)
+                if prefix == _K and _O + "compat" not in targets:
+                    targets.append(_O + "compat")          # reference spellings that are thin wrappers / aliases (incl. lazily resolved ones)
         return _Facade(spec.name, targets)
 
     def exec_module(self, module):

@@ -224,3 +224,111 @@ def mega_kernel_moe_grouped_gemm_combine_token(op, act: torch.Tensor, handle, w_
     if hasattr(op, "mega_group_gemm_combine"):
         return op.mega_group_gemm_combine(act, handle, w_down)
     return op.group_gemm_combine(act, handle)
+
+
+# ---- low_latency_allgather.py: one entry point per method name (reference :819-960) -------------------------------
+def _fast_ag(mode):
+    def f(ctx, symm_buffer: torch.Tensor, output: Optional[torch.Tensor] = None):
+        from . import comm
+        return comm.fast_allgather(symm_buffer, ctx, mode=mode, output=output)
+    f.__name__ = f"fast_allgather_{mode}"
+    f.__doc__ = f"``fast_allgather(shard, ctx, mode={mode!r})`` (kernel table: ops/comm.py ``_AG_MODES``)."
+    return f
+
+
+fast_allgather_pull = _fast_ag("pull")
+fast_allgather_push_2d = _fast_ag("push_2d")
+fast_allgather_push_3d = _fast_ag("push_3d")
+fast_allgather_push_2d_ll = _fast_ag("push_2d_ll")
+fast_allgather_push_2d_ll_multimem = _fast_ag("push_2d_ll_multimem")
+fast_allgather_push_numa_2d = _fast_ag("push_numa_2d")
+fast_allgather_push_numa_2d_ll = _fast_ag("push_numa_2d_ll")
+fast_allgather_push_multimem = _fast_ag("push_multimem")
+
+
+def fast_allgather_push_numa_2d_ll_multinode(*_a, **_k):
+    raise NotImplementedError("multi-node all-gather is out of scope (single NVSwitch domain); use fast_allgather_push_numa_2d_ll")
+
+
+# ---- allgather.py copy-engine producers by name -------------------------------------------------------------------
+def cp_engine_producer_all_gather_full_mesh_push(rank, num_ranks, local_tensor, remote_tensor_buffers, barrier_buffers, stream=None, **kw):
+    from .allgather import cp_engine_producer_all_gather_intra_node
+    return cp_engine_producer_all_gather_intra_node(rank, num_ranks, local_tensor, remote_tensor_buffers, barrier_buffers, **kw)
+
+
+def cp_engine_producer_all_gather_full_mesh_pull(rank, num_ranks, local_tensor, remote_tensor_buffers, barrier_buffers, stream=None,
+                                                 signal_value: int = 1, **_):
+    """Pull flavour: publish my shard in my own buffer, raise my flag on every peer, then copy every peer's shard once its flag
+    arrived (the push producer of ops/allgather.py writes into the peers instead)."""
+    from .. import language as dl
+    M = local_tensor.shape[0]
+    remote_tensor_buffers[rank][rank * M:(rank + 1) * M].copy_(local_tensor)
+    for q in range(1, num_ranks):
+        dl.notify(barrier_buffers[rank][rank:rank + 1], (rank + q) % num_ranks, signal=signal_value, sig_op="set")
+    barrier_buffers[rank][rank:rank + 1].fill_(signal_value)
+    for q in range(1, num_ranks):
+        src = (rank + q) % num_ranks
+        dl.wait(barrier_buffers[rank][src:src + 1], 1, wait_value=signal_value)
+        remote_tensor_buffers[rank][src * M:(src + 1) * M].copy_(remote_tensor_buffers[src][src * M:(src + 1) * M])
+
+
+def cp_engine_producer_all_gather_ring_push_numa_2d(rank, num_ranks, local_tensor, remote_tensor_buffers, barrier_buffers, **kw):
+    """The NUMA-staged ring exists for PCIe / multi-socket topologies; inside one NVSwitch domain it is the 2-D ring."""
+    from .allgather import cp_engine_producer_all_gather_ring_push_2d
+    return cp_engine_producer_all_gather_ring_push_2d(rank, num_ranks, local_tensor, remote_tensor_buffers, barrier_buffers, **kw)
+
+
+# ---- context classes under the reference's names ------------------------------------------------------------------
+def _ctx_aliases():
+    from . import all_to_all as _a2a, comm as _comm, ep_a2a as _ep, gemm_a2a as _ga, gemm_ar as _gar
+    from ..parallel import sp as _sp
+    return dict(AllToAllSingle2DContext=_a2a.AllToAllContext, AllToAllSingleGemmContext=_ga.GemmA2AContext,
+                MoEAllGatherGroupGEMMTensorParallelContext=M.MoEAllGatherGroupGEMMContext, MoEReduceARContext=M.MoEReduceRSContext,
+                ReduceScatter2DContext=_comm.AllReduceContext, LLGemmARContext=_gar.GemmARContext, EPContext=_ep.EPLowLatencyContext,
+                LowlatencyDispatchContext=_ep.EPLowLatencyContext, LowlatencyCombineContext=_ep.EPLowLatencyContext,
+                SPAllGatherAttentionContextInterNode=_sp.SPAllGatherAttentionContextIntraNode,
+                UlyssesSPPreAttnCommContext=SpUlysessQKVGemmAll2AllKernel)
+
+
+def __getattr__(name):                      # resolved lazily: the context classes live in modules that import this one
+    table = _ctx_aliases()
+    if name in table:
+        return table[name]
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
+
+
+def create_sp_ag_attention_context_inter_node(*a, **k):
+    from ..parallel.sp import create_sp_ag_attention_context_intra_node
+    return create_sp_ag_attention_context_intra_node(*a, **k)
+
+
+def gemm_rs_op(A, B, ctx, *a, **k):
+    """(gemm_reduce_scatter.py ``gemm_rs_op``) the functional spelling of :func:`triton_dist.ops.gemm_rs.gemm_rs`."""
+    from .gemm_rs import gemm_rs
+    return gemm_rs(A, B, ctx, *a, **k)
+
+
+# ---- moe_utils.py torch goldens -----------------------------------------------------------------------------------
+def histogram_by_expert_torch(topk_ids: torch.Tensor, num_experts: int) -> torch.Tensor:
+    return torch.bincount(topk_ids.reshape(-1).long().clamp_min(0), minlength=num_experts)[:num_experts].to(torch.int32)
+
+
+def calc_scatter_index_torch(topk_ids: torch.Tensor, num_experts: int) -> torch.Tensor:
+    """scatter_index[t, k] = row of pair (t, k) in the expert-sorted order (stable)."""
+    flat = topk_ids.reshape(-1).long()
+    order = torch.sort(flat, stable=True).indices
+    scatter = torch.empty_like(order)
+    scatter[order] = torch.arange(flat.numel(), device=flat.device)
+    return scatter.view_as(topk_ids).to(torch.int32)
+
+
+def calc_gather_index_from_scatter_index(scatter_index: torch.Tensor) -> torch.Tensor:
+    flat = scatter_index.reshape(-1).long()
+    gather = torch.empty_like(flat)
+    gather[flat] = torch.arange(flat.numel(), device=flat.device)
+    return gather.to(torch.int32)
+
+
+def calc_gather_index_torch(topk_ids: torch.Tensor, num_experts: int) -> torch.Tensor:
+    """gather_index[i] = flat (token * topk + k) index of the i-th row of the expert-sorted order."""
+    return calc_gather_index_from_scatter_index(calc_scatter_index_torch(topk_ids, num_experts))

@@ -11,6 +11,8 @@ computes wgrad per expert.
 """
 from __future__ import annotations
 
+import dataclasses
+
 from dataclasses import dataclass
 from typing import Optional
 
@@ -410,3 +412,24 @@ class EpAll2AllFusedOp:
         if getattr(self, "_layer", None) is not None:
             self._layer.finalize()
             self._layer = None
+
+
+@dataclasses.dataclass
+class EPAllToAllLayoutDesc:
+    """What a dispatch produced, for the combine that follows (reference: layers/nvidia/ep_a2a_layer.py ``EPAllToAllLayoutDesc``):
+    per-expert receive counts of this rank, the routing of the local tokens, and the kernel's own handle."""
+    num_dispatch_token_cur_rank: Optional[torch.Tensor] = None      # int32 [experts_per_rank]: rows received per local expert
+    topk_indices: Optional[torch.Tensor] = None                     # [T, topk] routing of MY tokens
+    topk_weights: Optional[torch.Tensor] = None
+    handle: object = None                                           # DispatchMetaInfo (low latency) / EPNormalHandle (throughput mode)
+
+
+DispatchCombineContext = EPAllToAllLayoutDesc
+
+
+def prepare_moe_metadata_using_kernel(topk_ids: torch.Tensor, num_experts: int, block_m: int = 128):
+    """Routing metadata for a grouped GEMM in one sort kernel (reference: layers/nvidia/ep_moe.py): (sorted pair ids, tile -> expert map,
+    padded per-expert row offsets [E + 1])."""
+    from ..ops import moe as _M
+    r = _M.moe_align_sort(topk_ids, num_experts, block_m)
+    return r.sorted_ids, r.tile_expert, r.expert_offsets

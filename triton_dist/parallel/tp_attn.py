@@ -180,3 +180,11 @@ class TP_Attn:
 
     def fwd(self, *a, **k):
         raise NotImplementedError("use torch_fwd / dist_triton_fwd / dist_triton_AR_fwd / dist_triton_gemm_ar_fwd")
+
+
+def layer_norm(x: torch.Tensor, w: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    """RMSNorm over the last dimension with weight ``w`` (the helper the reference's tp_attn.py exposes under this name for its
+    q / k norms): the CUDA rmsnorm kernel on a GPU, fp32 math otherwise."""
+    from ..ops.elementwise import rmsnorm
+    shp = x.shape
+    return rmsnorm(x.reshape(-1, shp[-1]), w, eps).reshape(shp)

@@ -119,3 +119,10 @@ class TP_MoE:
         return out.view(shp)
 
     dist_triton_gemm_ar_fwd = dist_triton_AR_fwd
+
+
+def shard_local(t: torch.Tensor, world_size: int, dim: int, local_rank: int) -> torch.Tensor:
+    """This rank's slice of ``t`` along ``dim`` (reference: layers/nvidia/tp_moe.py ``shard_local``)."""
+    assert t.shape[dim] % world_size == 0
+    n = t.shape[dim] // world_size
+    return t.narrow(dim, local_rank * n, n).contiguous()
