@@ -319,7 +319,7 @@ def test_gemm_ladder_runs_in_the_cpu_pipeline_model():
 
     check(run_gemm, 200, 264, 320, cta_group=1, BN=128, STAGES=2)       # ragged M / N, 5 k-blocks through a 2-stage ring
     check(run_gemm, 300, 392, 192, cta_group=2, STAGES=2)               # 2-CTA pairs, 2 x 2 tiles
-    check(run_gemm_persistent, 520, 300, 192, num_sms=2)                # ONE cluster walks 3 x 2 tiles: ring + accumulators wrap
+    check(run_gemm_persistent, 520, 328, 192, num_sms=2)                # ONE cluster walks 3 x 2 tiles: ring + accumulators wrap
 
 
 def test_pipeline_model_reports_protocol_errors(monkeypatch):
