@@ -412,3 +412,21 @@ def test_python_sequences_become_lookup_tables():
     t = torch.arange(32)
     assert torch.equal(z, (torch.tensor(PRIMES)[t % 8] + 7).int())
     torch.testing.assert_close(y, torch.tensor(WEIGHTS)[t % 4] * 3.0)
+
+
+def test_warp_mma_linear_matches_matmul_in_the_interpreter():
+    """The megakernel's tensor-core LINEAR algorithm as a DSL kernel (mma.sync m16n8k16 with the interpreter's model of the PTX
+    fragment layout): fragment-ordered staging, the shared K permutation of weights and activations, K split across warps with a
+    shared-memory reduction, several column passes, ragged batches -- against x @ W^T."""
+    from triton_dist.lk.kernels.linear_mma import make_linear_mma, run_linear_mma
+    torch.manual_seed(0)
+    for (B, K, N, tn, KC) in ((24, 96, 32, 16, 64),          # 2 groups -> 4 warps share one group along K; chunks of 64 + 32
+                              (40, 64, 64, 64, 64),           # 8 groups: one per warp
+                              (17, 128, 128, 128, 128)):      # 16 groups: two passes
+        x, W = (torch.randn(B, K) * 0.5).bfloat16(), (torch.randn(N, K) * 0.5).bfloat16()
+        o = run_linear_mma(x, W, tile_n=tn, KC=KC, interpret=True)
+        torch.testing.assert_close(o.float(), x.float() @ W.float().t(), atol=6e-2, rtol=2e-2)
+    k = make_linear_mma(256)
+    k.compile()
+    sass = subprocess.run([shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump", "-sass", k._lib._name], capture_output=True, text=True).stdout
+    assert sass.count("HMMA") >= 8

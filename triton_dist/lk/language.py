@@ -410,6 +410,11 @@ make_smem_desc_k128 = _i("make_smem_desc_k128", u64, "td::ptx::make_smem_desc_k1
 make_smem_desc_mn128 = _i("make_smem_desc_mn128", u64, "td::ptx::make_smem_desc_mn128({0}, {1})", 2)
 
 
+mma_m16n8k16_bf16 = _i("mma_m16n8k16_bf16", None, "td::mma_sync::m16n8k16_bf16({0} + ({1}), {2}, {3}, {4}, {5}, {6}, {7})", 8,
+                       doc="warp-level mma.sync m16n8k16 bf16 -> fp32: (acc f32 array, offset, a0, a1, a2, a3, b0, b1) with packed bf16x2 registers; "
+                           "accumulates the lane's 4 results into acc[offset .. offset + 3]")
+
+
 def make_idesc(a_fmt: int, b_fmt: int, M: int, N: int, a_mn_major: int = 0, b_mn_major: int = 0) -> int:
     """kind::f16 / f8f6f4 instruction descriptor (fp32 accumulate) -- plain Python, folded at compile time (mirrors
     ``td::ptx::make_idesc``, csrc/td/ptx.cuh)."""
@@ -536,7 +541,7 @@ def _install_pipeline_model():
         "mma_f16": P.mma_f16, "mma_commit": P.mma_commit, "mma_commit_2sm": P.mma_commit_2sm,
         "tmem_ld_32x32b_x32": P.tmem_ld_32x32b_x32, "tmem_ld_32x32b_x16": lambda t, r: P.tmem_ld_32x32b_x32(t, r, 16), "tmem_ld_wait": noop,
         "make_smem_desc_k128": P.make_smem_desc_k128, "smem_addr": P.smem_addr, "pack_bf16x2": P.pack_bf16x2, "st_v4": P.st_v4,
-        "ld_v4": P.ld_v4, "ld_nc_v4": P.ld_v4, "st_na_v4": P.st_v4, "red_add_bf16x8": P.red_add_bf16x8,
+        "mma_m16n8k16_bf16": P.mma_m16n8k16_bf16, "ld_v4": P.ld_v4, "ld_nc_v4": P.ld_v4, "st_na_v4": P.st_v4, "red_add_bf16x8": P.red_add_bf16x8,
         "bf16_lo": lambda w: P._bf16_val(w), "bf16_hi": lambda w: P._bf16_val(int(w) >> 16),
         "cluster_sync": P.cluster_sync, "cluster_rank": lambda: I.cur().block.cta_rank, "cluster_size": lambda: len(I.cur().block.cluster),
     }

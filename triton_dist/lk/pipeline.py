@@ -326,3 +326,27 @@ def red_add_bf16x8(dst, v):
             hi = _bf16_bits(_bf16_val(old >> 16) + _bf16_val(int(w) >> 16))
             if int(lib.tdh_atomic_cas32(a, old, lo | (hi << 16))) == old:
                 break
+
+
+def mma_m16n8k16_bf16(acc, off, a0, a1, a2, a3, b0, b1):
+    """Warp-collective ``mma.sync.m16n8k16`` (bf16 x bf16 -> fp32) following the PTX fragment layout: every lane contributes its A / B
+    registers (packed bf16 pairs); lane 4g + tig receives D(g, 2tig..2tig+1) and D(g + 8, ...) accumulated into ``acc[off .. off+3]``."""
+    regs = I.warp_collect((int(a0), int(a1), int(a2), int(a3), int(b0), int(b1)))
+    if len(regs) != 32:
+        raise RuntimeError("mma.sync needs a full warp")
+    A = np.zeros((16, 16), np.float32)
+    B = np.zeros((16, 8), np.float32)
+    for lane, (r0, r1, r2, r3, q0, q1) in enumerate(regs):
+        g, tig = lane >> 2, lane & 3
+        for w, (row, col) in ((r0, (g, 2 * tig)), (r1, (g + 8, 2 * tig)), (r2, (g, 2 * tig + 8)), (r3, (g + 8, 2 * tig + 8))):
+            A[row, col], A[row, col + 1] = _bf16_val(w), _bf16_val(w >> 16)
+        for w, k in ((q0, 2 * tig), (q1, 2 * tig + 8)):
+            B[k, g], B[k + 1, g] = _bf16_val(w), _bf16_val(w >> 16)
+    D = A @ B
+    lane = I.cur().linear % 32
+    g, tig = lane >> 2, lane & 3
+    off = int(off)
+    acc[off + 0] = acc[off + 0] + float(D[g, 2 * tig])
+    acc[off + 1] = acc[off + 1] + float(D[g, 2 * tig + 1])
+    acc[off + 2] = acc[off + 2] + float(D[g + 8, 2 * tig])
+    acc[off + 3] = acc[off + 3] + float(D[g + 8, 2 * tig + 1])
