@@ -29,7 +29,8 @@ namespace {
 constexpr int kMKThreads = 256;
 constexpr int kMaxB = 8;
 
-enum TaskType : int { T_RMSNORM = 1, T_LINEAR = 2, T_QKROPE = 3, T_ATTN = 4, T_ALLREDUCE = 5, T_COPY = 6, T_ATTN_COMBINE = 7, T_SILU_MUL = 8, T_ADD = 9, T_PREFETCH = 10 };
+enum TaskType : int { T_RMSNORM = 1, T_LINEAR = 2, T_QKROPE = 3, T_ATTN = 4, T_ALLREDUCE = 5, T_COPY = 6, T_ATTN_COMBINE = 7, T_SILU_MUL = 8, T_ADD = 9, T_PREFETCH = 10,
+                      T_QKROPE_PAGED = 11, T_ATTN_PAGED = 12 };   // paged KV cache: a[9] = page_size | max_pages << 16, block table = ptrs[index of vcache + 1]
 
 struct Task {            // 16 x int32
   int type, dep_idx, dep_count, sig_idx;
@@ -393,6 +394,7 @@ TD_DEVICE void task_linear(const MKParams& p, const Task& t, uint8_t* smem) {
 }
 
 // ---- QKROPE: q/k RMSNorm + RoPE + KV append.  a: qkv, q_out, kcache, vcache, qn(-1), kn(-1), pos, Hq, Hkv, max_len, eps, theta ----
+template <bool kPaged>
 TD_DEVICE void task_qkrope(const MKParams& p, const Task& t) {
   const uint2* qkv = (const uint2*)p.ptrs[t.a[0]];
   uint2* q_out = (uint2*)p.ptrs[t.a[1]];
@@ -435,12 +437,19 @@ TD_DEVICE void task_qkrope(const MKParams& p, const Task& t) {
     if (h < Hq) q_out[(static_cast<size_t>(b) * Hq + h) * 32 + lane] = o;
     else {
       const int kvh = is_v ? h - Hq - Hkv : h - Hq;
-      (is_v ? vc : kc)[((static_cast<size_t>(b) * max_len + ps) * Hkv + kvh) * 32 + lane] = o;
+      size_t tok = static_cast<size_t>(b) * max_len + ps;
+      if constexpr (kPaged) {          // max_len packs (page_size, max_pages); pages of a sequence are listed in its block-table row
+        const int page_size = max_len & 0xFFFF, max_pages = max_len >> 16;
+        const int* bt = (const int*)p.ptrs[t.a[3] + 1];
+        tok = static_cast<size_t>(bt[b * max_pages + ps / page_size]) * page_size + ps % page_size;
+      }
+      (is_v ? vc : kc)[(tok * Hkv + kvh) * 32 + lane] = o;
     }
   }
 }
 
 // ---- ATTN: GQA decode for (b, kv head) over the whole context.  a: q, kcache, vcache, pos, out, b, kvh, Hq, Hkv, max_len, scale ----
+template <bool kPaged>
 TD_DEVICE void task_attn(const MKParams& p, const Task& t, uint8_t* smem) {
   const uint2* q = (const uint2*)p.ptrs[t.a[0]];
   const uint2* kc = (const uint2*)p.ptrs[t.a[1]];
@@ -465,7 +474,13 @@ TD_DEVICE void task_attn(const MKParams& p, const Task& t, uint8_t* smem) {
     }
   }
   for (int j = j0 + warp; j < j1; j += NW) {
-    const size_t row = ((static_cast<size_t>(b) * max_len + j) * Hkv + kvh) * 32 + lane;
+    size_t tok = static_cast<size_t>(b) * max_len + j;
+    if constexpr (kPaged) {
+      const int page_size = max_len & 0xFFFF, max_pages = max_len >> 16;
+      const int* bt = (const int*)p.ptrs[t.a[2] + 1];
+      tok = static_cast<size_t>(bt[b * max_pages + j / page_size]) * page_size + j % page_size;
+    }
+    const size_t row = (tok * Hkv + kvh) * 32 + lane;
     const uint2 kr = kc[row], vr = vc[row];
     const float kf[4] = {ptx::bf16_lo(kr.x), ptx::bf16_hi(kr.x), ptx::bf16_lo(kr.y), ptx::bf16_hi(kr.y)};
     const float vf[4] = {ptx::bf16_lo(vr.x), ptx::bf16_hi(vr.x), ptx::bf16_lo(vr.y), ptx::bf16_hi(vr.y)};
@@ -659,8 +674,10 @@ __global__ void __launch_bounds__(kMKThreads, 1) mega_kernel(const MKParams p) {
     switch (t.type) {
       case T_RMSNORM: task_rmsnorm(p, t, red); break;
       case T_LINEAR: task_linear(p, t, smem); break;
-      case T_QKROPE: task_qkrope(p, t); break;
-      case T_ATTN: task_attn(p, t, smem); break;
+      case T_QKROPE: task_qkrope<false>(p, t); break;
+      case T_ATTN: task_attn<false>(p, t, smem); break;
+      case T_QKROPE_PAGED: task_qkrope<true>(p, t); break;
+      case T_ATTN_PAGED: task_attn<true>(p, t, smem); break;
       case T_ATTN_COMBINE: task_attn_combine(p, t); break;
       case T_SILU_MUL: task_silu_mul(p, t); break;
       case T_ADD: task_add(p, t); break;

@@ -700,3 +700,32 @@ def test_reference_per_module_names_behave(dist_env):
     assert torch.equal(shard_local(torch.arange(12).view(3, 4), 2, 1, 1), torch.tensor([[2, 3], [6, 7], [10, 11]]))
     sorted_ids, tile_expert, offs = prepare_moe_metadata_using_kernel(ids, 4, block_m=4)
     assert offs.numel() == 5 and sorted_ids.numel() % 4 == 0 and tile_expert.numel() == sorted_ids.numel() // 4
+
+
+def test_megakernel_with_a_paged_kv_cache(dist_env):
+    """The megakernel's KV tasks through a block table (T_QKROPE_PAGED / T_ATTN_PAGED): same logits as the dense-cache model, pages
+    scattered by a random table, two decode steps (the second reads the token the first one stored through the table)."""
+    from triton_dist.mega_kernel import T_ATTN_PAGED, T_QKROPE_PAGED, MegaDenseModel
+    from triton_dist.models import AutoLLM, KV_Cache, ModelConfig, PagedKVCache
+    cfg = ModelConfig(model_name="tiny-dense", max_length=64, dtype=torch.float32, rank=0, world_size=1)
+    m = AutoLLM.from_pretrained(cfg)
+    B, ctx_len = 3, 9
+    dense = KV_Cache(m.num_layers, B, 64, m.num_key_value_heads, m.head_dim, torch.float32, 1, "cpu")
+    dense.rand_fill_kv_cache(ctx_len)
+    paged = PagedKVCache(PAGE_SIZE=4, num_layers=m.num_layers, batch_size=B, max_length=64, num_kv_heads=m.num_key_value_heads,
+                         head_dim=m.head_dim, dtype=torch.float32, device="cpu", seed=3)
+    for li in range(m.num_layers):
+        k, v = dense.layer(li)
+        paged.append(li, k[:, :ctx_len], v[:, :ctx_len])
+    paged.inc_offset(ctx_len)
+    mega = MegaDenseModel(m, B, paged, attn_splits=2)
+    kinds = {t.type for t in mega.builder.tasks}
+    assert T_QKROPE_PAGED in kinds and T_ATTN_PAGED in kinds
+    for step in range(2):
+        ids = torch.randint(0, 1000, (B, 1))
+        ref = m.inference(ids, dense.kv_offset.to(torch.int64)[:, None], dense)
+        torch.testing.assert_close(mega.mega_forward(ids), ref, atol=1e-4, rtol=1e-4)
+        dense.inc_offset(1)
+        paged.inc_offset(1)
+    gk, _ = paged.gather_dense(0)
+    torch.testing.assert_close(gk[:, :ctx_len + 2], dense.layer(0)[0][:, :ctx_len + 2])       # the stored tokens landed in the right pages

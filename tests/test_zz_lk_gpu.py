@@ -190,6 +190,42 @@ def test_megakernel_tensor_core_linears(B):
     assert r.returncode == 0 and "MEGA_TC_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
+_MEGA_PAGED_SNIPPET = r"""
+import sys, torch
+sys.path.insert(0, {root!r})
+import triton_dist.utils as U
+from triton_dist.mega_kernel import MegaDenseModel
+from triton_dist.models import AutoLLM, KV_Cache, ModelConfig, PagedKVCache
+U.initialize_distributed(seed=0)
+cfg = ModelConfig(model_name="tiny-dense", max_length=64, dtype=torch.bfloat16, rank=0, world_size=1)
+m = AutoLLM.from_pretrained(cfg)
+B, ctx_len = 4, 17
+kv = KV_Cache(m.num_layers, B, 64, m.num_key_value_heads, m.head_dim, torch.bfloat16, 1, "cuda")
+kv.rand_fill_kv_cache(ctx_len)
+paged = PagedKVCache(PAGE_SIZE=8, num_layers=m.num_layers, batch_size=B, max_length=64, num_kv_heads=m.num_key_value_heads,
+                     head_dim=m.head_dim, dtype=torch.bfloat16, device="cuda", seed=5)
+for li in range(m.num_layers):
+    k, v = kv.layer(li)
+    paged.append(li, k[:, :ctx_len], v[:, :ctx_len])
+paged.inc_offset(ctx_len)
+mega = MegaDenseModel(m, B, paged, attn_splits=2)
+for step in range(3):
+    ids = torch.randint(0, 1000, (B, 1), device="cuda")
+    ref = m.inference(ids, kv.kv_offset.to(torch.int64)[:, None], kv)
+    out = mega.mega_forward(ids)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out, ref, atol=6e-2, rtol=6e-2)
+    kv.inc_offset(1); paged.inc_offset(1)
+print("MEGA_PAGED_OK")
+"""
+
+
+@pytest.mark.xfail(strict=False, reason="paged-KV task types of the megakernel: exact in the host interpretation, compiled, not yet run on hardware")
+def test_megakernel_paged_kv_cache():
+    r = subprocess.run([sys.executable, "-c", _MEGA_PAGED_SNIPPET.format(root=ROOT)], capture_output=True, text=True, timeout=150, cwd=ROOT)
+    assert r.returncode == 0 and "MEGA_PAGED_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
 _GDN_SNIPPET = r"""
 import torch
 from triton_dist.lk.kernels.gdn_chunk import chunk_gated_delta_rule_lk

@@ -21,7 +21,8 @@ from .. import utils as U
 from ..ops.comm import SymmArgs, symm_args
 
 T_RMSNORM, T_LINEAR, T_QKROPE, T_ATTN, T_ALLREDUCE, T_ATTN_COMBINE, T_SILU_MUL, T_ADD, T_PREFETCH = 1, 2, 3, 4, 5, 7, 8, 9, 10
-TASK_NAMES = {1: "rms_norm", 2: "linear", 3: "qk_norm_rope_update_kvcache", 4: "flash_decode", 5: "allreduce", 7: "flash_decode_combine", 8: "silu_mul_up", 9: "add", 10: "prefetch"}
+T_QKROPE_PAGED, T_ATTN_PAGED = 11, 12      # paged KV cache (block table; reference: mega_triton_kernel/models/paged_kv_cache.py)
+TASK_NAMES = {1: "rms_norm", 2: "linear", 3: "qk_norm_rope_update_kvcache", 4: "flash_decode", 5: "allreduce", 7: "flash_decode_combine", 8: "silu_mul_up", 9: "add", 10: "prefetch", 11: "qk_norm_rope_update_paged_kvcache", 12: "flash_decode_paged"}
 
 
 class _MegaArgs(C.Structure):
@@ -81,6 +82,13 @@ class ModelBuilder:
             self.ptrs.append(t)
         return self._ptr_idx[key]
 
+    def ptr_pair(self, t: torch.Tensor, follower: torch.Tensor) -> int:
+        """Two ADJACENT pointer-table entries (t, follower): the paged tasks find the block table at ``index of the value cache + 1``
+        without spending another task argument."""
+        idx = len(self.ptrs)
+        self.ptrs += [t, follower]
+        return idx
+
     def counter(self) -> int:
         self.n_counters += 1
         return self.n_counters - 1
@@ -127,16 +135,35 @@ class ModelBuilder:
 
     make_qkv_proj = make_o_proj = make_fc1 = make_fc2 = make_linear
 
-    def make_qk_norm_rope_update_kvcache(self, qkv, q_out, k_cache, v_cache, q_norm_w, k_norm_w, positions, Hq, Hkv, eps, theta, dep):
+    @staticmethod
+    def _paged_arg(k_cache, block_table):
+        """(page_size | max_pages << 16) for caches shaped [pages, page_size, Hkv, D] with a [B, max_pages] int32 block table."""
+        page_size, max_pages = k_cache.shape[1], block_table.shape[1]
+        assert block_table.dtype == torch.int32 and block_table.is_contiguous() and page_size < (1 << 16) and max_pages < (1 << 15)
+        return page_size | (max_pages << 16)
+
+    def make_qk_norm_rope_update_kvcache(self, qkv, q_out, k_cache, v_cache, q_norm_w, k_norm_w, positions, Hq, Hkv, eps, theta, dep,
+                                         block_table=None):
+        """``block_table`` (int32 [B, max_pages]): ``k_cache`` / ``v_cache`` are page pools [pages, page_size, Hkv, D] and the new token of
+        sequence b is stored in page ``block_table[b, pos // page_size]`` (reference: the megakernel's paged KV cache)."""
         sig = self.counter()
-        self._add(Task(T_QKROPE, dep[0], dep[1], sig, [self.ptr(qkv), self.ptr(q_out), self.ptr(k_cache), self.ptr(v_cache),
-                                                       self.ptr(q_norm_w), self.ptr(k_norm_w), self.ptr(positions), Hq, Hkv,
-                                                       k_cache.shape[1], _fbits(eps), _fbits(theta)]))
+        if block_table is None:
+            self._add(Task(T_QKROPE, dep[0], dep[1], sig, [self.ptr(qkv), self.ptr(q_out), self.ptr(k_cache), self.ptr(v_cache),
+                                                           self.ptr(q_norm_w), self.ptr(k_norm_w), self.ptr(positions), Hq, Hkv,
+                                                           k_cache.shape[1], _fbits(eps), _fbits(theta)]))
+        else:
+            self._add(Task(T_QKROPE_PAGED, dep[0], dep[1], sig, [self.ptr(qkv), self.ptr(q_out), self.ptr(k_cache), self.ptr_pair(v_cache, block_table),
+                                                                 self.ptr(q_norm_w), self.ptr(k_norm_w), self.ptr(positions), Hq, Hkv,
+                                                                 self._paged_arg(k_cache, block_table), _fbits(eps), _fbits(theta)]))
         return sig, 1
 
-    def make_flash_decode(self, q, k_cache, v_cache, positions, out, Hq, Hkv, sm_scale, dep, n_splits: int = 1, scratch=None):
+    def make_flash_decode(self, q, k_cache, v_cache, positions, out, Hq, Hkv, sm_scale, dep, n_splits: int = 1, scratch=None,
+                          block_table=None):
         """GQA decode.  ``n_splits`` > 1: split-KV -- every (batch, kv head) becomes n_splits tasks that write (m, l, o) partials
-        to ``scratch`` (fp32 [B, Hkv, n_splits, 8, 130]) plus one combine task, so a handful of heads still fills the SMs."""
+        to ``scratch`` (fp32 [B, Hkv, n_splits, 8, 130]) plus one combine task, so a handful of heads still fills the SMs.
+        ``block_table``: paged KV cache (see ``make_qk_norm_rope_update_kvcache``)."""
+        if block_table is not None:
+            return self._make_flash_decode_paged(q, k_cache, v_cache, positions, out, Hq, Hkv, sm_scale, dep, n_splits, scratch, block_table)
         sig = self.counter()
         n = 0
         if n_splits <= 1:
@@ -153,6 +180,34 @@ class ModelBuilder:
                     self._add(Task(T_ATTN, dep[0], dep[1], sig, [self.ptr(q), self.ptr(k_cache), self.ptr(v_cache), self.ptr(positions),
                                                                  self.ptr(scratch), b, kvh, Hq, Hkv, k_cache.shape[1], _fbits(sm_scale),
                                                                  s | (n_splits << 16)]))
+                    n += 1
+        sig2 = self.counter()
+        m = 0
+        for b in range(self.B):
+            for kvh in range(Hkv):
+                self._add(Task(T_ATTN_COMBINE, sig, n, sig2, [self.ptr(scratch), self.ptr(out), b, kvh, Hq, Hkv, n_splits]))
+                m += 1
+        return sig2, m
+
+    def _make_flash_decode_paged(self, q, k_cache, v_cache, positions, out, Hq, Hkv, sm_scale, dep, n_splits, scratch, block_table):
+        packed = self._paged_arg(k_cache, block_table)
+        vidx = self.ptr_pair(v_cache, block_table)
+        sig = self.counter()
+        n = 0
+        if n_splits <= 1:
+            for b in range(self.B):
+                for kvh in range(Hkv):
+                    self._add(Task(T_ATTN_PAGED, dep[0], dep[1], sig, [self.ptr(q), self.ptr(k_cache), vidx, self.ptr(positions),
+                                                                       self.ptr(out), b, kvh, Hq, Hkv, packed, _fbits(sm_scale), 0]))
+                    n += 1
+            return sig, n
+        assert scratch is not None and scratch.dtype == torch.float32 and scratch.numel() >= self.B * Hkv * n_splits * 8 * 130
+        for b in range(self.B):
+            for kvh in range(Hkv):
+                for s in range(n_splits):
+                    self._add(Task(T_ATTN_PAGED, dep[0], dep[1], sig, [self.ptr(q), self.ptr(k_cache), vidx, self.ptr(positions),
+                                                                       self.ptr(scratch), b, kvh, Hq, Hkv, packed, _fbits(sm_scale),
+                                                                       s | (n_splits << 16)]))
                     n += 1
         sig2 = self.counter()
         m = 0
@@ -286,7 +341,7 @@ class ModelBuilder:
                 else:
                     x = x[:, :K]
                 P[a[2]].view(B, -1)[:, n0:n0 + nc] = (x @ P[a[1]][n0:n0 + nc].float().t()).to(P[a[2]].dtype)
-            elif t.type == T_QKROPE:
+            elif t.type in (T_QKROPE, T_QKROPE_PAGED):
                 Hq, Hkv = a[7], a[8]
                 eps = struct.unpack("f", struct.pack("i", a[10]))[0]
                 theta = struct.unpack("f", struct.pack("i", a[11]))[0]
@@ -299,9 +354,15 @@ class ModelBuilder:
                 q, k = rope_reference(q, pos, theta), rope_reference(k, pos, theta)
                 P[a[1]].view(B, Hq, -1).copy_(q)
                 for b in range(B):
-                    P[a[2]][b, int(pos[b])] = k[b]
-                    P[a[3]][b, int(pos[b])] = v[b]
-            elif t.type == T_ATTN:
+                    if t.type == T_QKROPE_PAGED:
+                        ps_, bt = a[9] & 0xFFFF, P[a[3] + 1]
+                        page, slot = int(bt[b, int(pos[b]) // ps_]), int(pos[b]) % ps_
+                        P[a[2]][page, slot] = k[b]
+                        P[a[3]][page, slot] = v[b]
+                    else:
+                        P[a[2]][b, int(pos[b])] = k[b]
+                        P[a[3]][b, int(pos[b])] = v[b]
+            elif t.type in (T_ATTN, T_ATTN_PAGED):
                 b, kvh, Hq, Hkv = a[5], a[6], a[7], a[8]
                 G = Hq // Hkv
                 scale = struct.unpack("f", struct.pack("i", a[10]))[0]
@@ -310,7 +371,13 @@ class ModelBuilder:
                 split, ns = (a[11] & 0xFFFF, max(1, a[11] >> 16)) if len(a) > 11 else (0, 1)
                 per = (L + ns - 1) // ns
                 j0, j1 = split * per, min(L, split * per + per)
-                k, v = P[a[1]][b, j0:j1, kvh].float(), P[a[2]][b, j0:j1, kvh].float()
+                if t.type == T_ATTN_PAGED:
+                    ps_, bt = a[9] & 0xFFFF, P[a[2] + 1]
+                    jj = torch.arange(j0, j1)
+                    pages, slots = bt[b, jj // ps_].long(), jj % ps_
+                    k, v = P[a[1]][pages, slots, kvh].float(), P[a[2]][pages, slots, kvh].float()
+                else:
+                    k, v = P[a[1]][b, j0:j1, kvh].float(), P[a[2]][b, j0:j1, kvh].float()
                 if ns == 1:
                     pr = torch.softmax(q @ k.t() * scale, -1)
                     P[a[4]].view(B, Hq, -1)[b, kvh * G:(kvh + 1) * G] = (pr @ v).to(P[a[4]].dtype)

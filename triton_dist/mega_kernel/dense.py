@@ -46,9 +46,14 @@ class MegaDenseModel:
         self.attn_scratch = torch.zeros((B * Hkv * attn_splits * 8 * 130,), dtype=torch.float32, device=dev) if attn_splits > 1 else None
         U.barrier_all_host()
         dep = None
+        from ..models.paged_kv_cache import PagedKVCache
+        self.paged = isinstance(kv_cache, PagedKVCache)
         for li, layer in enumerate(model.layers):
             mb.cur_layer = li
-            k_cache, v_cache = kv_cache.layer(li)
+            if self.paged:          # one page pool for all layers, a block table per layer
+                k_cache, v_cache, bt = kv_cache.key_cache, kv_cache.value_cache, kv_cache.block_tables[li].contiguous()
+            else:
+                (k_cache, v_cache), bt = kv_cache.layer(li), None
             at, ml = layer.attn, layer.mlp
             if fuse_norm:
                 d = mb.make_qkv_proj(self.h, at.wqkv, self.qkv, dep, norm_weight=layer.input_norm_w, eps=layer.eps)
@@ -56,9 +61,9 @@ class MegaDenseModel:
                 d = mb.make_rms_norm(self.h, layer.input_norm_w, self.xn, layer.eps, dep=dep)
                 d = mb.make_qkv_proj(self.xn, at.wqkv, self.qkv, d)
             d = mb.make_qk_norm_rope_update_kvcache(self.qkv, self.q_rot, k_cache, v_cache, at.q_norm_w, at.k_norm_w, self.positions,
-                                                    Hq, Hkv, at.eps, at.rope_theta, d)
+                                                    Hq, Hkv, at.eps, at.rope_theta, d, block_table=bt)
             d = mb.make_flash_decode(self.q_rot, k_cache, v_cache, self.positions, self.attn_out, Hq, Hkv, at.sm_scale, d,
-                                     n_splits=attn_splits, scratch=self.attn_scratch)
+                                     n_splits=attn_splits, scratch=self.attn_scratch, block_table=bt)
             d = mb.make_o_proj(self.attn_out, at.wo, self.parts[2 * li], d)
             d = mb.make_allreduce(self.parts[2 * li], self.flags[2 * li], self.h, self.h, d, self.n_slices)
             if fuse_norm:
@@ -75,7 +80,7 @@ class MegaDenseModel:
         """input_ids: [B, 1] -> fp32 logits [B, V].  Positions come from the KV cache's device-side offsets."""
         m = self.model
         self.h.copy_(torch.nn.functional.embedding(input_ids.view(-1), m.embed_tokens))
-        self.positions.copy_(self.kv.kv_offset[: self.B])
+        self.positions.copy_((self.kv.kv_lens if self.paged else self.kv.kv_offset)[: self.B])
         self.builder.run()
         hn = rmsnorm(self.h, m.norm_w, m.arch.rms_norm_eps)
         return _linear(hn, m.lm_head).float()
