@@ -30,7 +30,7 @@ constexpr int kMKThreads = 256;
 constexpr int kMaxB = 8;
 
 enum TaskType : int { T_RMSNORM = 1, T_LINEAR = 2, T_QKROPE = 3, T_ATTN = 4, T_ALLREDUCE = 5, T_COPY = 6, T_ATTN_COMBINE = 7, T_SILU_MUL = 8, T_ADD = 9, T_PREFETCH = 10,
-                      T_QKROPE_PAGED = 11, T_ATTN_PAGED = 12 };   // paged KV cache: a[9] = page_size | max_pages << 16, block table = ptrs[index of vcache + 1]
+                      T_QKROPE_PAGED = 11, T_ATTN_PAGED = 12, T_FLASH_ATTN = 13, T_QKROPE_SPLIT = 14 };   // paged KV cache: a[9] = page_size | max_pages << 16, block table = ptrs[index of vcache + 1]
 
 struct Task {            // 16 x int32
   int type, dep_idx, dep_count, sig_idx;
@@ -172,6 +172,12 @@ constexpr int kMmaMaxB = 64;
 constexpr int kMmaStageBytes = 128 * 1024;       // activation fragments of one K chunk: Bpad x KC x 2 bytes
 
 TD_DEVICE void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+TD_DEVICE void mma_bf16_16816p(float* d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {   // d: 4 accumulators
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
@@ -394,7 +400,9 @@ TD_DEVICE void task_linear(const MKParams& p, const Task& t, uint8_t* smem) {
 }
 
 // ---- QKROPE: q/k RMSNorm + RoPE + KV append.  a: qkv, q_out, kcache, vcache, qn(-1), kn(-1), pos, Hq, Hkv, max_len, eps, theta ----
-template <bool kPaged>
+// kMode 0: dense cache [B, max_len, Hkv, D];  1: paged (see T_QKROPE_PAGED);  2: prefill split -- rows are B x S tokens, a[9] = S, the
+// position of token (b, s) is pos[b] + s (pos = tokens already in the cache) and k / v go to dense [B * S, Hkv, D] outputs.
+template <int kMode>
 TD_DEVICE void task_qkrope(const MKParams& p, const Task& t) {
   const uint2* qkv = (const uint2*)p.ptrs[t.a[0]];
   uint2* q_out = (uint2*)p.ptrs[t.a[1]];
@@ -411,7 +419,7 @@ TD_DEVICE void task_qkrope(const MKParams& p, const Task& t) {
     const int b = wi / heads, h = wi % heads;
     const uint2 raw = qkv[(static_cast<size_t>(b) * heads + h) * 32 + lane];
     float f[4] = {ptx::bf16_lo(raw.x), ptx::bf16_hi(raw.x), ptx::bf16_lo(raw.y), ptx::bf16_hi(raw.y)};
-    const int ps = pos[b];
+    const int ps = (kMode == 2) ? pos[b / max_len] + b % max_len : pos[b];
     const bool is_v = h >= Hq + Hkv;
     if (!is_v) {
       const uint2* nw = (h < Hq) ? qn : kn;
@@ -438,7 +446,8 @@ TD_DEVICE void task_qkrope(const MKParams& p, const Task& t) {
     else {
       const int kvh = is_v ? h - Hq - Hkv : h - Hq;
       size_t tok = static_cast<size_t>(b) * max_len + ps;
-      if constexpr (kPaged) {          // max_len packs (page_size, max_pages); pages of a sequence are listed in its block-table row
+      if constexpr (kMode == 2) tok = b;
+      if constexpr (kMode == 1) {      // max_len packs (page_size, max_pages); pages of a sequence are listed in its block-table row
         const int page_size = max_len & 0xFFFF, max_pages = max_len >> 16;
         const int* bt = (const int*)p.ptrs[t.a[3] + 1];
         tok = static_cast<size_t>(bt[b * max_pages + ps / page_size]) * page_size + ps % page_size;
@@ -524,6 +533,130 @@ TD_DEVICE void task_attn(const MKParams& p, const Task& t, uint8_t* smem) {
       const float inv = ll > 0.f ? 1.f / ll : 0.f;
       reinterpret_cast<uint32_t*>(out)[(static_cast<size_t>(b) * Hq + kvh * G + g) * 64 + d2] = ptx::pack_bf16x2(o0 * inv, o1 * inv);
     }
+  }
+}
+
+// ---- FLASH_ATTN: prefill attention for 128 query rows of one (batch, q head) on warp-level tensor cores (FA2 dataflow on mma.sync).
+// a: q, k, v, out, b, h, q block | causal << 30, S, Hq | Hkv << 16, q token stride / 128 | kv token stride / 128 << 16, scale, soft cap.
+// Same statements as the DSL kernel triton_dist/lk/kernels/flash_mma.py (which the CPU interpreter runs against the fp32 reference):
+// a lane's 16-byte loads of its two query rows are its A fragments (the order of d inside a 32-wide chunk is permuted identically for
+// q and k); K row-major in shared memory, V transposed as packed key pairs; scores stay in registers between the two MMAs.
+TD_DEVICE void task_flash_attn(const MKParams& p, const Task& t, uint8_t* smem) {
+  constexpr int D = 128, BKV = 64, KS = 80, VS = 36, BQ = kMKThreads / 32 * 16;
+  const __nv_bfloat16* q = (const __nv_bfloat16*)p.ptrs[t.a[0]];
+  const __nv_bfloat16* k = (const __nv_bfloat16*)p.ptrs[t.a[1]];
+  const __nv_bfloat16* v = (const __nv_bfloat16*)p.ptrs[t.a[2]];
+  uint32_t* ow = (uint32_t*)p.ptrs[t.a[3]];
+  const int b = t.a[4], h = t.a[5], qb = t.a[6] & 0xFFFFFF, S = t.a[7], Hq = t.a[8] & 0xFFFF, Hkv = t.a[8] >> 16;
+  const bool causal = (t.a[6] >> 30) & 1;
+  const int q_ts = (t.a[9] & 0xFFFF) * D, kv_ts = (t.a[9] >> 16) * D, o_ts = Hq * D;
+  const float scale = __int_as_float(t.a[10]), softcap = __int_as_float(t.a[11]);
+  uint32_t* Ksm = reinterpret_cast<uint32_t*>(smem);
+  uint32_t* Vt = Ksm + BKV * KS;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
+  const int kvh = h / (Hq / Hkv);
+  const int q0 = qb * BQ, r0 = q0 + warp * 16 + g;
+  uint32_t qf[32];
+#pragma unroll
+  for (int hi = 0; hi < 2; ++hi) {
+    const int row = r0 + 8 * hi;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint4 qv = make_uint4(0, 0, 0, 0);
+      if (row < S) qv = *reinterpret_cast<const uint4*>(q + ((static_cast<size_t>(b) * S + row) * q_ts + h * D + c * 32 + tig * 8));
+      qf[(2 * c) * 4 + hi] = qv.x; qf[(2 * c) * 4 + 2 + hi] = qv.y; qf[(2 * c + 1) * 4 + hi] = qv.z; qf[(2 * c + 1) * 4 + 2 + hi] = qv.w;
+    }
+  }
+  float o[64], s[32];
+#pragma unroll
+  for (int e = 0; e < 64; ++e) o[e] = 0.f;
+  float m0 = -1.0e30f, m1 = -1.0e30f, l0 = 0.f, l1 = 0.f;
+  const int kv_end = causal ? min(S, q0 + BQ) : S;
+  const __nv_bfloat16* kbase = k + (static_cast<size_t>(b) * S * kv_ts + kvh * D);
+  const __nv_bfloat16* vbase = v + (static_cast<size_t>(b) * S * kv_ts + kvh * D);
+  for (int kv0 = 0; kv0 < kv_end; kv0 += BKV) {
+    __syncthreads();
+    for (int i = tid; i < BKV * 16; i += kMKThreads) {
+      const int key = i >> 4, ch = i & 15;
+      uint4 kq = make_uint4(0, 0, 0, 0);
+      if (kv0 + key < S) kq = *reinterpret_cast<const uint4*>(kbase + (static_cast<size_t>(kv0 + key) * kv_ts + ch * 8));
+      *reinterpret_cast<uint4*>(Ksm + key * KS + ch * 4) = kq;
+    }
+    for (int i = tid; i < 32 * 16; i += kMKThreads) {
+      const int pj = i & 31, ch = i >> 5;
+      uint4 va = make_uint4(0, 0, 0, 0), vb = make_uint4(0, 0, 0, 0);
+      if (kv0 + 2 * pj < S) va = *reinterpret_cast<const uint4*>(vbase + (static_cast<size_t>(kv0 + 2 * pj) * kv_ts + ch * 8));
+      if (kv0 + 2 * pj + 1 < S) vb = *reinterpret_cast<const uint4*>(vbase + (static_cast<size_t>(kv0 + 2 * pj + 1) * kv_ts + ch * 8));
+      uint32_t* dst = Vt + (ch * 8) * VS + pj;
+      dst[0 * VS] = (va.x & 0xFFFFu) | (vb.x << 16); dst[1 * VS] = (va.x >> 16) | (vb.x & 0xFFFF0000u);
+      dst[2 * VS] = (va.y & 0xFFFFu) | (vb.y << 16); dst[3 * VS] = (va.y >> 16) | (vb.y & 0xFFFF0000u);
+      dst[4 * VS] = (va.z & 0xFFFFu) | (vb.z << 16); dst[5 * VS] = (va.z >> 16) | (vb.z & 0xFFFF0000u);
+      dst[6 * VS] = (va.w & 0xFFFFu) | (vb.w << 16); dst[7 * VS] = (va.w >> 16) | (vb.w & 0xFFFF0000u);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 32; ++e) s[e] = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint4 kw = *reinterpret_cast<const uint4*>(Ksm + (nt * 8 + g) * KS + c * 16 + tig * 4);
+        mma_bf16_16816p(s + nt * 4, qf[(2 * c) * 4 + 0], qf[(2 * c) * 4 + 1], qf[(2 * c) * 4 + 2], qf[(2 * c) * 4 + 3], kw.x, kw.y);
+        mma_bf16_16816p(s + nt * 4, qf[(2 * c + 1) * 4 + 0], qf[(2 * c + 1) * 4 + 1], qf[(2 * c + 1) * 4 + 2], qf[(2 * c + 1) * 4 + 3], kw.z, kw.w);
+      }
+    }
+    float mx0 = -1.0e30f, mx1 = -1.0e30f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float x = s[nt * 4 + j] * scale;
+        if (softcap > 0.f) x = softcap * tanhf(x / softcap);
+        x *= 1.4426950408889634f;
+        const int kj = kv0 + nt * 8 + tig * 2 + (j & 1), qi = r0 + 8 * (j >> 1);
+        if (kj >= S || (causal && kj > qi)) x = -1.0e30f;
+        s[nt * 4 + j] = x;
+        if (j < 2) mx0 = fmaxf(mx0, x); else mx1 = fmaxf(mx1, x);
+      }
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    const float corr0 = exp2f(m0 - mn0), corr1 = exp2f(m1 - mn1);
+    m0 = mn0; m1 = mn1;
+    float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float pv = 0.f;                                     // masked scores contribute exactly 0 (also when a whole row is masked)
+        if (s[nt * 4 + j] > -1.0e29f) pv = exp2f(s[nt * 4 + j] - (j < 2 ? mn0 : mn1));
+        s[nt * 4 + j] = pv;
+        if (j < 2) rs0 += pv; else rs1 += pv;
+      }
+    }
+    l0 = l0 * corr0 + rs0; l1 = l1 * corr1 + rs1;         // per-lane partial row sums; reduced over the quad once, at the end
+#pragma unroll
+    for (int dt = 0; dt < 16; ++dt) { o[dt * 4 + 0] *= corr0; o[dt * 4 + 1] *= corr0; o[dt * 4 + 2] *= corr1; o[dt * 4 + 3] *= corr1; }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const uint32_t pa0 = ptx::pack_bf16x2(s[(2 * kk) * 4 + 0], s[(2 * kk) * 4 + 1]), pa1 = ptx::pack_bf16x2(s[(2 * kk) * 4 + 2], s[(2 * kk) * 4 + 3]);
+      const uint32_t pa2 = ptx::pack_bf16x2(s[(2 * kk + 1) * 4 + 0], s[(2 * kk + 1) * 4 + 1]), pa3 = ptx::pack_bf16x2(s[(2 * kk + 1) * 4 + 2], s[(2 * kk + 1) * 4 + 3]);
+#pragma unroll
+      for (int dt = 0; dt < 16; ++dt) {
+        const uint32_t* vw = Vt + (dt * 8 + g) * VS + kk * 8 + tig;
+        mma_bf16_16816p(o + dt * 4, pa0, pa1, pa2, pa3, vw[0], vw[4]);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float inv0 = l0 > 0.f ? 1.f / l0 : 0.f, inv1 = l1 > 0.f ? 1.f / l1 : 0.f;
+#pragma unroll
+  for (int dt = 0; dt < 16; ++dt) {
+    const int col = h * D + dt * 8 + tig * 2;
+    if (r0 < S) ow[((static_cast<size_t>(b) * S + r0) * o_ts + col) >> 1] = ptx::pack_bf16x2(o[dt * 4 + 0] * inv0, o[dt * 4 + 1] * inv0);
+    if (r0 + 8 < S) ow[((static_cast<size_t>(b) * S + r0 + 8) * o_ts + col) >> 1] = ptx::pack_bf16x2(o[dt * 4 + 2] * inv1, o[dt * 4 + 3] * inv1);
   }
 }
 
@@ -638,6 +771,9 @@ TD_DEVICE void prefetch_linear_weights(const MKParams& p, const Task& t) {
   for (size_t off = 0; off < bytes; off += 65536) ptx::prefetch_l2_bulk(W + off, static_cast<uint32_t>(min(bytes - off, size_t(65536))));
 }
 
+// kPrefill = true adds the FLASH_ATTN (prefill attention) task to the interpreter; the decode-only instantiation is register-for-register
+// the kernel without it (the prefill task's 96 accumulators would otherwise raise the whole switch to the 255-register cap).
+template <bool kPrefill>
 __global__ void __launch_bounds__(kMKThreads, 1) mega_kernel(const MKParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ float red[32];
@@ -674,10 +810,12 @@ __global__ void __launch_bounds__(kMKThreads, 1) mega_kernel(const MKParams p) {
     switch (t.type) {
       case T_RMSNORM: task_rmsnorm(p, t, red); break;
       case T_LINEAR: task_linear(p, t, smem); break;
-      case T_QKROPE: task_qkrope<false>(p, t); break;
+      case T_QKROPE: task_qkrope<0>(p, t); break;
       case T_ATTN: task_attn<false>(p, t, smem); break;
-      case T_QKROPE_PAGED: task_qkrope<true>(p, t); break;
+      case T_QKROPE_PAGED: task_qkrope<1>(p, t); break;
+      case T_QKROPE_SPLIT: if constexpr (kPrefill) task_qkrope<2>(p, t); break;
       case T_ATTN_PAGED: task_attn<true>(p, t, smem); break;
+      case T_FLASH_ATTN: if constexpr (kPrefill) task_flash_attn(p, t, smem); break;
       case T_ATTN_COMBINE: task_attn_combine(p, t); break;
       case T_SILU_MUL: task_silu_mul(p, t); break;
       case T_ADD: task_add(p, t); break;
@@ -718,13 +856,15 @@ TD_API int td_mega_launch(const TdMegaArgs* a, void* stream) {
   p.tasks = (const Task*)a->tasks; p.queue_off = (const int*)a->queue_off; p.ptrs = (void* const*)a->ptrs;
   p.sb = (uint32_t*)a->sb; p.epoch = (uint32_t*)a->epoch;
   p.symm.rank = (int)a->symm.rank; p.symm.world = (int)a->symm.world; p.symm.base = a->symm.base; p.symm.stride = a->symm.stride; p.symm.mc_base = a->symm.mc_base;
-  p.B = (int)a->B; p.dynamic = (int)a->dynamic; p.num_tasks = (int)a->num_tasks;
-  static long long smem_set = 0;
-  if (a->smem_bytes > smem_set) {
-    TD_CUDA_CHECK(cudaFuncSetAttribute(mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a->smem_bytes));
-    smem_set = a->smem_bytes;
+  p.B = (int)a->B; p.dynamic = (int)(a->dynamic & 1); p.num_tasks = (int)a->num_tasks;
+  const bool prefill = (a->dynamic & 2) != 0;        // bit 1 of `dynamic`: the task list contains FLASH_ATTN tasks
+  static long long smem_set[2] = {0, 0};
+  if (a->smem_bytes > smem_set[prefill]) {
+    TD_CUDA_CHECK(cudaFuncSetAttribute(prefill ? mega_kernel<true> : mega_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a->smem_bytes));
+    smem_set[prefill] = a->smem_bytes;
   }
-  mega_kernel<<<(int)a->grid, kMKThreads, (size_t)a->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  if (prefill) mega_kernel<true><<<(int)a->grid, kMKThreads, (size_t)a->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  else mega_kernel<false><<<(int)a->grid, kMKThreads, (size_t)a->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   TD_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

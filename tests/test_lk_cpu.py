@@ -430,3 +430,38 @@ def test_warp_mma_linear_matches_matmul_in_the_interpreter():
     k.compile()
     sass = subprocess.run([shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump", "-sass", k._lib._name], capture_output=True, text=True).stdout
     assert sass.count("HMMA") >= 8
+
+
+def _attn_ref(q, k, v, causal, scale, softcap):
+    B, S, Hq, _ = q.shape
+    G = Hq // k.shape[2]
+    qf, kf, vf = q.float().permute(0, 2, 1, 3), k.float().permute(0, 2, 1, 3).repeat_interleave(G, 1), v.float().permute(0, 2, 1, 3).repeat_interleave(G, 1)
+    s = qf @ kf.transpose(-1, -2) * scale
+    if softcap > 0:
+        s = softcap * torch.tanh(s / softcap)
+    if causal:
+        s = s.masked_fill(torch.triu(torch.ones(S, S, dtype=torch.bool), 1), float("-inf"))
+    return (torch.softmax(s, -1) @ vf).permute(0, 2, 1, 3)
+
+
+def test_flash_attention_on_mma_sync_in_the_interpreter():
+    """The megakernel's FLASH_ATTN (prefill) algorithm as a DSL kernel: A fragments straight from 16-byte query loads with the shared
+    d permutation, K row-major / V transposed-as-key-pairs in shared memory, scores kept in registers between the two MMAs, online
+    softmax over quads -- against the fp32 reference.  Covers GQA, a packed qkv tensor (strided views), two KV tiles with a ragged tail,
+    causal and full masks, the soft cap, and the reinterpreting ``ll.ptr_cast`` the epilogue stores through."""
+    from triton_dist.lk.kernels.flash_mma import make_flash_mma, run_flash_mma
+    torch.manual_seed(0)
+    B, S, Hq, Hkv = 1, 66, 2, 1
+    qkv = torch.randn(B, S, Hq + 2 * Hkv, 128).bfloat16()
+    q, k, v = qkv[:, :, :Hq], qkv[:, :, Hq:Hq + Hkv], qkv[:, :, Hq + Hkv:]
+    o = run_flash_mma(q, k, v, causal=True, threads=32, interpret=True)
+    torch.testing.assert_close(o.float(), _attn_ref(q, k, v, True, 128 ** -0.5, 0.0), atol=2e-2, rtol=2e-2)
+    B, S, Hq, Hkv = 2, 20, 1, 1
+    q, k, v = (torch.randn(B, S, Hq, 128) * 2).bfloat16(), torch.randn(B, S, Hkv, 128).bfloat16(), torch.randn(B, S, Hkv, 128).bfloat16()
+    o = run_flash_mma(q, k, v, causal=False, softcap=5.0, sm_scale=0.2, threads=32, interpret=True)
+    torch.testing.assert_close(o.float(), _attn_ref(q, k, v, False, 0.2, 5.0), atol=2e-2, rtol=2e-2)
+    kern = make_flash_mma(256)
+    kern.compile()
+    sass = subprocess.run([shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump", "-sass", kern._lib._name], capture_output=True, text=True).stdout
+    assert sass.count("HMMA") >= 128 and "STL" not in sass          # 64 + 64 MMAs per KV tile, no spills
+

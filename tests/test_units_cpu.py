@@ -729,3 +729,39 @@ def test_megakernel_with_a_paged_kv_cache(dist_env):
         paged.inc_offset(1)
     gk, _ = paged.gather_dense(0)
     torch.testing.assert_close(gk[:, :ctx_len + 2], dense.layer(0)[0][:, :ctx_len + 2])       # the stored tokens landed in the right pages
+
+
+def test_megakernel_prefill_tasks(dist_env):
+    """Builder ops of the reference's prefill path (make_qkv_pack_qk_norm_rope_split_v -> make_flash_attn, make_qkv_pack_flash_attn) in
+    the host interpretation: positions offset by kv_lens, v split out untouched, causal and soft-capped full attention over GQA heads."""
+    from triton_dist.mega_kernel import T_FLASH_ATTN, ModelBuilder
+    from triton_dist.ops.elementwise import rope_reference
+    torch.manual_seed(0)
+    B, S, Hq, Hkv = 2, 12, 4, 2
+    mb = ModelBuilder(B * S)
+    qkv = torch.randn(B, S, Hq + 2 * Hkv, 128).bfloat16()
+    kv_lens = torch.tensor([3, 0], dtype=torch.int32)
+    qw, kw = torch.rand(128).bfloat16() + 0.5, torch.rand(128).bfloat16() + 0.5
+    q_o, k_o, v_o = torch.zeros(B, S, Hq, 128).bfloat16(), torch.zeros(B, S, Hkv, 128).bfloat16(), torch.zeros(B, S, Hkv, 128).bfloat16()
+    out, out2 = torch.zeros(B, S, Hq, 128).bfloat16(), torch.zeros(B, S, Hq, 128).bfloat16()
+    d = mb.make_qkv_pack_qk_norm_rope_split_v(qkv, kv_lens, qw, kw, q_o, k_o, v_o, 1e-6, 1e6)
+    mb.make_flash_attn(q_o, k_o, v_o, out, dep=d)
+    mb.make_qkv_pack_flash_attn(qkv, out2, is_causal=False, soft_cap=3.0)
+    mb.compile().run()
+    assert mb.get_sm_activity()["flash_attn"] == 2 * B * Hq and mb.has_prefill and sum(t.type == T_FLASH_ATTN for t in mb.tasks) == 16
+
+    def ref(q, k, v, causal, cap):
+        G = Hq // Hkv
+        s = q.float().permute(0, 2, 1, 3) @ k.float().permute(0, 2, 1, 3).repeat_interleave(G, 1).transpose(-1, -2) * 128 ** -0.5
+        s = cap * torch.tanh(s / cap) if cap > 0 else s
+        if causal:
+            s = s.masked_fill(torch.triu(torch.ones(S, S, dtype=torch.bool), 1), float("-inf"))
+        return (torch.softmax(s, -1) @ v.float().permute(0, 2, 1, 3).repeat_interleave(G, 1)).permute(0, 2, 1, 3)
+
+    torch.testing.assert_close(out2.float(), ref(qkv[:, :, :Hq], qkv[:, :, Hq:Hq + Hkv], qkv[:, :, Hq + Hkv:], False, 3.0), atol=2e-2, rtol=2e-2)
+    torch.testing.assert_close(out.float(), ref(q_o, k_o, v_o, True, 0.0), atol=2e-2, rtol=2e-2)
+    assert torch.equal(v_o, qkv[:, :, Hq + Hkv:])
+    pos = (kv_lens[:, None] + torch.arange(S)[None]).reshape(-1)
+    nrm = lambda z, w: ((z.float() * torch.rsqrt(z.float().pow(2).mean(-1, keepdim=True) + 1e-6)) * w.float()).to(z.dtype)
+    torch.testing.assert_close(k_o.view(B * S, Hkv, 128), rope_reference(nrm(qkv[:, :, Hq:Hq + Hkv].reshape(B * S, Hkv, 128), kw), pos, 1e6))
+

@@ -89,6 +89,21 @@ class Ptr:
             return self.off - n.off
         return Ptr(self.base, self.off - int(n), self.elem, self.owner)
 
+    def reinterpret(self, elem: T.Type):
+        """``reinterpret_cast<elem*>(p)``: the same bytes viewed as another element type (torch bases; byte offset must be aligned)."""
+        import torch
+        b = self.base
+        if not isinstance(b, torch.Tensor) or getattr(elem, "torch_name", None) is None:
+            return self
+        new_dt = getattr(torch, elem.torch_name)
+        if new_dt == b.dtype:
+            return self
+        raw = b[self.off:].view(torch.uint8)
+        es = torch.empty(0, dtype=new_dt).element_size()
+        p = Ptr(raw[: raw.numel() // es * es].view(new_dt), 0, elem, self.owner)
+        p.skey = self.skey
+        return p
+
     def tensor(self):
         """The underlying torch tensor from this element on (for the host mirror of the distributed primitives)."""
         return self.base[self.off:]
@@ -214,7 +229,13 @@ def _wrap_arg(a, ty):
     if isinstance(a, torch.Tensor):
         if a.is_cuda:
             raise ValueError("interpret() runs on CPU tensors")
-        return Ptr(a.view(-1) if a.is_contiguous() else a.reshape(-1), 0, getattr(ty, "elem", None), owner=a)
+        if a.is_contiguous():
+            flat = a.view(-1)
+        else:       # a strided view (say, the k heads of a packed qkv tensor): point at its first element inside the WHOLE storage, as the
+            # device pointer would -- the kernel brings its own strides, and its stores must land in the caller's tensor
+            n = a.untyped_storage().nbytes() // a.element_size() - a.storage_offset()
+            flat = torch.as_strided(a, (n,), (1,))
+        return Ptr(flat, 0, getattr(ty, "elem", None), owner=a)
     if isinstance(ty, T.Scalar):
         return ty.wrap(a)
     return a

@@ -256,7 +256,7 @@ def _emit_ptr_cast(cg, args, kwargs, node):
 
 
 def _interp_ptr_cast(p, ty):
-    return p
+    return p.reinterpret(ty) if hasattr(p, "reinterpret") else p
 
 
 val_cast = Intrinsic("val_cast", None, emit=_emit_val_cast, interp=lambda v, ty: ty.wrap(v))

@@ -22,7 +22,9 @@ from ..ops.comm import SymmArgs, symm_args
 
 T_RMSNORM, T_LINEAR, T_QKROPE, T_ATTN, T_ALLREDUCE, T_ATTN_COMBINE, T_SILU_MUL, T_ADD, T_PREFETCH = 1, 2, 3, 4, 5, 7, 8, 9, 10
 T_QKROPE_PAGED, T_ATTN_PAGED = 11, 12      # paged KV cache (block table; reference: mega_triton_kernel/models/paged_kv_cache.py)
-TASK_NAMES = {1: "rms_norm", 2: "linear", 3: "qk_norm_rope_update_kvcache", 4: "flash_decode", 5: "allreduce", 7: "flash_decode_combine", 8: "silu_mul_up", 9: "add", 10: "prefetch", 11: "qk_norm_rope_update_paged_kvcache", 12: "flash_decode_paged"}
+T_FLASH_ATTN, T_QKROPE_SPLIT = 13, 14      # prefill: tensor-core attention over [B, S, H, 128] and the qk-norm + rope that feeds it
+FLASH_BQ = 128                              # query rows per FLASH_ATTN task (8 warps x 16)
+TASK_NAMES = {1: "rms_norm", 2: "linear", 3: "qk_norm_rope_update_kvcache", 4: "flash_decode", 5: "allreduce", 7: "flash_decode_combine", 8: "silu_mul_up", 9: "add", 10: "prefetch", 11: "qk_norm_rope_update_paged_kvcache", 12: "flash_decode_paged", 13: "flash_attn", 14: "qkv_pack_qk_norm_rope_split_v"}
 
 
 class _MegaArgs(C.Structure):
@@ -76,7 +78,7 @@ class ModelBuilder:
     def ptr(self, t: Optional[torch.Tensor]) -> int:
         if t is None:
             return -1
-        key = t.data_ptr()
+        key = (t.data_ptr(), tuple(t.shape), tuple(t.stride()))   # views that start at the same address are distinct entries (host interpretation)
         if key not in self._ptr_idx:
             self._ptr_idx[key] = len(self.ptrs)
             self.ptrs.append(t)
@@ -217,7 +219,53 @@ class ModelBuilder:
                 m += 1
         return sig2, m
 
-    make_flash_attn = make_flash_decode
+    # ---- prefill (reference: model_builder.py make_flash_attn / make_qkv_pack_flash_attn / make_qkv_pack_qk_norm_rope_split_v) ----
+    def make_flash_attn(self, q, k, v, output, sm_scale=None, soft_cap: float = 0.0, is_causal: bool = True, dep=None):
+        """output[B, S, Hq, 128] = attention(q[B, S, Hq, 128], k / v[B, S, Hkv, 128]); one task per (batch, q head, 128 query rows) on
+        the warp-level tensor cores.  q / k / v may be views into one packed qkv tensor (token stride a multiple of 128 elements)."""
+        Bq, S, Hq, d = q.shape
+        Hkv = k.shape[2]
+        assert d == 128 and tuple(k.shape) == tuple(v.shape) == (Bq, S, Hkv, d) and Hq % Hkv == 0 and tuple(output.shape) == (Bq, S, Hq, d)
+        assert output.is_contiguous() and k.stride(1) == v.stride(1)
+        for t in (q, k, v, output):
+            assert t.dtype == torch.bfloat16 or not self.is_cuda, "the FLASH_ATTN task is a bf16 kernel"
+            assert t.stride(3) == 1 and t.stride(2) == d and t.stride(1) % d == 0 and t.stride(0) == S * t.stride(1)
+        q_h, kv_h = q.stride(1) // d, k.stride(1) // d
+        assert q_h < (1 << 16) and kv_h < (1 << 15) and Hq < (1 << 16) and Hkv < (1 << 15)
+        scale = float(sm_scale) if sm_scale is not None else d ** -0.5
+        self.max_smem = max(self.max_smem, (64 * 80 + 128 * 36) * 4)
+        self.has_prefill = True
+        sig = self.counter()
+        dd = dep or (-1, 0)
+        n = 0
+        for b in range(Bq):
+            for h in range(Hq):
+                for qb in range((S + FLASH_BQ - 1) // FLASH_BQ):
+                    self._add(Task(T_FLASH_ATTN, dd[0], dd[1], sig, [self.ptr(q), self.ptr(k), self.ptr(v), self.ptr(output), b, h,
+                                                                     qb | (int(bool(is_causal)) << 30), S, Hq | (Hkv << 16), q_h | (kv_h << 16),
+                                                                     _fbits(scale), _fbits(float(soft_cap))]))
+                    n += 1
+        return sig, n
+
+    def make_qkv_pack_flash_attn(self, qkv, output, sm_scale=None, soft_cap: float = 0.0, is_causal: bool = True, dep=None):
+        """qkv: [B, S, Hq + 2 Hkv, 128] packed, output: [B, S, Hq, 128]."""
+        Hq = output.shape[2]
+        Hkv = (qkv.shape[2] - Hq) // 2
+        return self.make_flash_attn(qkv[:, :, :Hq], qkv[:, :, Hq:Hq + Hkv], qkv[:, :, Hq + Hkv:], output, sm_scale, soft_cap, is_causal, dep)
+
+    def make_qkv_pack_qk_norm_rope_split_v(self, qkv, kv_lens, q_norm_w, k_norm_w, q_out, k_out, v_out, eps: float, theta: float, dep=None):
+        """Prefill form of the qk-norm + rope task: qkv [B, S, Hq + 2 Hkv, 128] -> q_out [B, S, Hq, 128], k_out / v_out [B, S, Hkv, 128];
+        token (b, s) is rotated at position ``kv_lens[b] + s``.  The builder's batch is the token count B * S."""
+        Bq, S, heads, d = qkv.shape
+        Hq, Hkv = q_out.shape[2], k_out.shape[2]
+        assert d == 128 and heads == Hq + 2 * Hkv and Bq * S == self.B, "create the builder with batch = B * S tokens"
+        assert qkv.is_contiguous() and q_out.is_contiguous() and k_out.is_contiguous() and v_out.is_contiguous() and kv_lens.dtype == torch.int32
+        self.has_prefill = True
+        sig = self.counter()
+        dd = dep or (-1, 0)
+        self._add(Task(T_QKROPE_SPLIT, dd[0], dd[1], sig, [self.ptr(qkv), self.ptr(q_out), self.ptr(k_out), self.ptr(v_out), self.ptr(q_norm_w),
+                                                           self.ptr(k_norm_w), self.ptr(kv_lens), Hq, Hkv, S, _fbits(eps), _fbits(theta)]))
+        return sig, 1
 
     def make_allreduce(self, part_symm, flags_symm, residual, residual_out, dep, n_slices: int = 4):
         """residual_out = residual + sum over ranks of part (one-shot over NVLink; fused residual add)."""
@@ -306,7 +354,8 @@ class ModelBuilder:
         a.tasks, a.queue_off, a.ptrs = self.task_tensor.data_ptr(), self.queue_off.data_ptr(), self.ptr_tensor.data_ptr()
         a.sb, a.epoch = self.sb.data_ptr(), self.epoch.data_ptr()
         a.B, a.grid, a.smem_bytes = self.B, self.num_sms, self.max_smem
-        a.dynamic, a.num_tasks = int(self.schedule_policy == "dynamic"), len(self.tasks)
+        # bit 1 selects the kernel instantiation that also interprets the prefill task types (the decode-only one keeps its registers)
+        a.dynamic, a.num_tasks = int(self.schedule_policy == "dynamic") | (2 if getattr(self, "has_prefill", False) else 0), len(self.tasks)
         _C.check(_C.cuda_lib().td_mega_launch(C.byref(a), C.c_void_p((stream or torch.cuda.current_stream()).cuda_stream)), "td_mega_launch")
 
     # emulation: interpret the task list in program order with torch ops on the same buffers
@@ -390,6 +439,34 @@ class ModelBuilder:
                     part[base:base + G, 0] = mm
                     part[base:base + G, 1] = e.sum(-1) if j1 > j0 else 0.0
                     part[base:base + G, 2:] = (e @ v) if j1 > j0 else 0.0
+            elif t.type == T_QKROPE_SPLIT:
+                Hq, Hkv, S = a[7], a[8], a[9]
+                eps = struct.unpack("f", struct.pack("i", a[10]))[0]
+                theta = struct.unpack("f", struct.pack("i", a[11]))[0]
+                qkv = P[a[0]].view(B, Hq + 2 * Hkv, -1)
+                q, k, v = qkv[:, :Hq], qkv[:, Hq:Hq + Hkv], qkv[:, Hq + Hkv:]
+                nrm = lambda z, w: ((z.float() * torch.rsqrt(z.float().pow(2).mean(-1, keepdim=True) + eps)) * w.float()).to(z.dtype)
+                if a[4] >= 0:
+                    q, k = nrm(q, P[a[4]]), nrm(k, P[a[5]])
+                pos = (P[a[6]].view(-1)[:B // S, None] + torch.arange(S, dtype=torch.int32)[None]).reshape(-1)
+                P[a[1]].view(B, Hq, -1).copy_(rope_reference(q, pos, theta))
+                P[a[2]].view(B, Hkv, -1).copy_(rope_reference(k, pos, theta))
+                P[a[3]].view(B, Hkv, -1).copy_(v)
+            elif t.type == T_FLASH_ATTN:
+                if a[5] or (a[6] & 0xFFFFFF):
+                    continue                                  # the (head 0, q block 0) task of a batch entry does the whole entry on the host
+                b, S, Hq, Hkv = a[4], a[7], a[8] & 0xFFFF, a[8] >> 16
+                causal = bool((a[6] >> 30) & 1)
+                scale = struct.unpack("f", struct.pack("i", a[10]))[0]
+                cap = struct.unpack("f", struct.pack("i", a[11]))[0]
+                q, k, v, out = (P[a[i]][b].float() for i in range(4))                    # [S, H, 128]
+                G = Hq // Hkv
+                sc = torch.einsum("shd,thd->hst", q, k.repeat_interleave(G, 1)) * scale
+                if cap > 0:
+                    sc = cap * torch.tanh(sc / cap)
+                if causal:
+                    sc = sc.masked_fill(torch.triu(torch.ones(S, S, dtype=torch.bool), 1), float("-inf"))
+                P[a[3]][b] = torch.einsum("hst,thd->shd", torch.softmax(sc, -1), v.repeat_interleave(G, 1)).to(P[a[3]].dtype)
             elif t.type == T_ATTN_COMBINE:
                 b, kvh, Hq, Hkv, ns = a[2], a[3], a[4], a[5], a[6]
                 G = Hq // Hkv
