@@ -1195,6 +1195,39 @@ def case_mega():
     mega.finalize()
 
 
+def case_mega_server():
+    """The megakernel text-generation service across ranks: rank 0 serves a socket from a thread and broadcasts every request, the other
+    ranks follow; per-op prefill, token-by-token prefill and the paged KV cache must generate the same tokens (greedy and seeded)."""
+    import threading
+    from triton_dist.mega_kernel.server import Client, MegaServer
+    dev = U.current_device()
+    me = U.rank()
+    dtype = torch.bfloat16 if dev.type == "cuda" else torch.float32
+    seen = []
+    for kw in (dict(prefill="per_op"), dict(prefill="stepwise"), dict(page_size=4)):
+        srv = MegaServer("tiny-dense", max_length=64, dtype=dtype, port=0, max_prompt=32, **kw)
+        if me == 0:
+            ready = threading.Event()
+            th = threading.Thread(target=srv.serve_forever, kwargs=dict(ready=ready), daemon=True)
+            th.start()
+            assert ready.wait(60)
+            with Client(port=srv.port) as c:
+                r = c.ask("hi there", max_new_tokens=5, temperature=0.0)
+                r2 = c.request({"prompt_ids": [1, 2, 3], "max_new_tokens": 4, "seed": 7})
+                assert r["status"] == r2["status"] == "success" and r["prompt_tokens"] == 8 and len(r["token_ids"]) == 5, (r, r2)
+                assert c.request({"cmd": "stats"})["requests"] == 2 and c.request({"nothing": 1})["status"] == "error"
+                assert c.request({"cmd": "shutdown"})["status"] == "success"
+            th.join(60)
+            assert not th.is_alive()
+            seen.append((r["token_ids"], r2["token_ids"]))
+        else:
+            srv.serve_forever()
+        U.barrier_all_host()
+        srv.finalize()
+    if me == 0 and dev.type != "cuda":          # fp32 emulation: the three prefill routes agree token for token
+        assert seen[0] == seen[1] == seen[2], seen
+
+
 CASES = {k[5:]: v for k, v in list(globals().items()) if k.startswith("case_")}
 
 if __name__ == "__main__":

@@ -765,3 +765,31 @@ def test_megakernel_prefill_tasks(dist_env):
     nrm = lambda z, w: ((z.float() * torch.rsqrt(z.float().pow(2).mean(-1, keepdim=True) + 1e-6)) * w.float()).to(z.dtype)
     torch.testing.assert_close(k_o.view(B * S, Hkv, 128), rope_reference(nrm(qkv[:, :, Hq:Hq + Hkv].reshape(B * S, Hkv, 128), kw), pos, 1e6))
 
+
+def test_mega_server_single_rank(dist_env):
+    """Socket server + client on one rank: JSON-lines protocol, stats, error replies, seeded sampling is reproducible, shutdown."""
+    import json
+    import threading
+    from triton_dist.mega_kernel.server import Client, MegaServer
+    srv = MegaServer("tiny-dense", max_length=48, dtype=torch.float32, port=0, max_prompt=16)
+    ready = threading.Event()
+    th = threading.Thread(target=srv.serve_forever, kwargs=dict(ready=ready), daemon=True)
+    th.start()
+    assert ready.wait(60)
+    try:
+        with Client(port=srv.port) as c:
+            a = c.request({"prompt_ids": [5, 6, 7], "max_new_tokens": 6, "seed": 11})
+            b = c.request({"prompt_ids": [5, 6, 7], "max_new_tokens": 6, "seed": 11})
+            assert a["status"] == "success" and a["token_ids"] == b["token_ids"] and a["generated_tokens"] == 6 and a["processing_time"] > 0
+            assert c.request({"prompt_ids": list(range(17))})["status"] == "error"           # longer than max_prompt
+            assert c.request({"prompt_ids": list(range(1, 17)), "max_new_tokens": 1000})["generated_tokens"] == 48 - 16   # clipped to the cache
+            st = c.request({"cmd": "stats"})
+            assert st["requests"] == 3 and st["generated_tokens"] == 6 + 6 + 32
+            c.f.write(b"not json\n"); c.f.flush()
+            assert json.loads(c.f.readline())["status"] == "error"
+            assert c.request({"cmd": "shutdown"})["status"] == "success"
+    finally:
+        th.join(60)
+        srv.finalize()
+    assert not th.is_alive()
+
