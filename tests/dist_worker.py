@@ -1195,6 +1195,32 @@ def case_mega():
     mega.finalize()
 
 
+def case_ep_metadata():
+    """Routing metadata ops of the throughput-mode EP path (reference ep_a2a_intra_node.py:423): all-gathered per-expert histograms ->
+    receive offsets / token counts, and the per-token rows relative to the destination rank's buffer."""
+    from triton_dist.ops import ep_metadata as EM
+    dev = U.current_device()
+    W, me = U.world_size(), U.rank()
+    epr, T, topk = 2, 11 + U.rank(), 2
+    E = W * epr
+    g = torch.Generator().manual_seed(5 + me)
+    idx = torch.stack([torch.randperm(E, generator=g)[:topk] for _ in range(T)]).to(torch.int32).to(dev)
+    offs, n_recv, n_in, full = EM.get_ag_splits_and_recv_offset_for_dispatch_intra_node(idx, E)
+    hists = [torch.zeros(E + 1, dtype=torch.int32, device=dev) for _ in range(W)]
+    torch.distributed.all_gather(hists, EM.expert_histogram(idx, E))
+    want = torch.stack(hists)
+    assert torch.equal(full.cpu(), want.cpu()), (full, want)
+    for r in range(W):
+        run = 0
+        for e in range(epr):
+            for s_ in range(W):
+                assert int(offs[r, e, s_]) == run
+                run += int(want[s_, r * epr + e])
+        assert int(n_recv[r]) == run
+    assert int(n_in[me]) == T * topk
+    U.barrier_all_host()
+
+
 def case_mega_server():
     """The megakernel text-generation service across ranks: rank 0 serves a socket from a thread and broadcasts every request, the other
     ranks follow; per-op prefill, token-by-token prefill and the paged KV cache must generate the same tokens (greedy and seeded)."""

@@ -77,3 +77,69 @@ def test_reference_module_paths_resolve():
     with pytest.raises(ImportError):
         from triton_dist.kernels.nvidia.allgather_gemm import does_not_exist  # noqa: F401
     assert triton_dist.__version__
+
+
+# SURVEY.md section 2.4 / 2.5 names every reference source file with its public entry points: each of them must resolve under the
+# reference's own module path (triton_dist/_module_map.py maps those paths onto this package's subsystems)
+K='triton_dist.kernels.nvidia.'
+L='triton_dist.layers.nvidia.'
+PER_FILE = {
+ K+'allgather': 'AllGatherMethod get_auto_all_gather_method cp_engine_producer_all_gather_intra_node cp_engine_producer_all_gather_inter_node',
+ K+'allgather_gemm': 'create_ag_gemm_context ag_gemm gemm_persistent gemm_non_persistent',
+ K+'ag_gemm_threadblock_swizzle': 'threadblock_swizzle_allgather_gemm_kernel',
+ K+'reduce_scatter': 'ReduceScatter2DContext create_reduce_scater_2d_ctx reduce_scatter_2d_op ring_reduce',
+ K+'gemm_reduce_scatter': 'create_gemm_rs_context gemm_rs',
+ K+'gemm_rs_threadblock_swizzle': 'threadblock_swizzle_gemm_reduce_scatter_kernel',
+ 'triton_dist.kernels.allreduce': 'AllReduceMethod OverlappingAllReduceMethod to_allreduce_method get_auto_all_reduce_method',
+ K+'allreduce': 'create_allreduce_ctx all_reduce get_auto_allreduce_method',
+ K+'gemm_allreduce': 'create_gemm_ar_context create_ll_gemm_ar_context gemm_allreduce_op low_latency_gemm_allreduce_op gemm_op allreduce_op',
+ K+'group_gemm': 'moe_grouped_gemm moe_grouped_gemm_2weights transposed_moe_grouped_gemm',
+ K+'moe_utils': 'calc_gather_scatter_index_triton calc_gather_scatter_index_v2_triton histogram_by_expert_triton reduce_topk_tma reduce_topk_non_tma',
+ K+'allgather_group_gemm': 'create_ag_group_gemm_context ag_group_gemm',
+ K+'moe_reduce_rs': 'create_moe_rs_context run_moe_reduce_rs run_moe_reduce_rs_triton_non_overlap',
+ K+'moe_reduce_ar': 'create_moe_ar_context run_moe_reduce_ar',
+ K+'low_latency_all_to_all': 'create_all_to_all_context fast_all_to_all all_to_all_post_process',
+ K+'low_latency_all_to_all_v2': 'create_ep_ll_a2a_ctx LowlatencyDispatchContext LowlatencyCombineContext',
+ K+'ep_a2a': 'ep_dispatch_token_inplace ep_combine_token_inplace get_ag_splits_and_recv_offset_for_dispatch bincount get_dispatch_send_reqs',
+ K+'ep_a2a_intra_node': 'get_ag_splits_and_recv_offset_for_dispatch_intra_node',
+ K+'ep_all2all_fused': 'mega_kernel_dispatch_token_moe_grouped_gemm mega_kernel_moe_grouped_gemm_combine_token get_ag_splits_and_recv_offset_for_dispatch',
+ K+'all_to_all_vdev_2d_offset': 'create_context all_to_all_vdev_2d all_to_all_vdev_2d_offset all_to_all_v_offset_op all_to_all_v_offset_op_v2',
+ K+'all_to_all_single_2d': 'create_all_to_all_single_2d_context all_to_all_single_2d',
+ K+'all_to_all_single_gemm': 'create_all_to_all_single_gemm_context all_to_all_single_gemm gemm_only',
+ K+'sp_ag_attention_intra_node': 'create_sp_ag_attention_context_intra_node fused_sp_ag_attn_intra_node',
+ K+'sp_ag_attention_inter_node': 'create_sp_ag_attention_context_inter_node fused_sp_ag_attn_inter_node',
+ K+'flash_decode': 'gqa_fwd_batch_decode gqa_fwd_batch_decode_persistent gqa_fwd_batch_decode_intra_rank gqa_fwd_batch_decode_aot gqa_fwd_batch_decode_persistent_aot gqa_fwd_batch_decode_intra_rank_aot',
+ K+'low_latency_allgather': 'create_fast_allgather_context fast_allgather',
+ K+'ulysses_sp_dispatch': 'create_ulysses_sp_pre_attn_comm_context pre_attn_qkv_pack_a2a_op qkv_bsnd_to_bnsd',
+ K+'sp_ulysess_qkv_gemm_all2all': 'SpUlysessQKVGemmAll2AllKernel',
+ K+'sp_ulysess_o_all2all_gemm': 'SpUlysessOAll2AllGemmKernel',
+ K+'ulysses_sp_infer_gemm_a2a': 'UlyssesSpInferPreAttnContext ulysses_sp_infer_gemm_a2a_op pre_attn_a2a_comm_only',
+ K+'p2p': 'p2p_set_signal p2p_wait_signal p2p_copy_kernel p2p_put_kernel p2p_copy_remote_to_local_kernel',
+ K+'memory_ops': 'copy_tensor fill_tensor reduce_tensor',
+ K+'swiglu': 'swiglu_forward swiglu_backward',
+ K+'gdn': 'chunk_gated_delta_rule_fwd',
+ K+'gemm': 'get_config_space matmul matmul_tma matmul_persistent matmul_tma_persistent matmul_descriptor_persistent',
+ K+'gemm_perf_model': 'get_tensorcore_tflops get_dram_gbps estimate_gemm_sol_time_ms',
+ K+'comm_perf_model': 'estimate_reduce_scatter_time_ms estimate_all_gather_time_ms get_nic_gbps_per_gpu',
+ L+'tp_mlp': 'TP_MLP', L+'tp_attn': 'TP_Attn', L+'tp_moe': 'TP_MoE', L+'ep_moe': 'EP_MoE',
+ L+'ep_a2a_layer': 'EPConfig DispatchCombineContext EPAll2AllLayer',
+ L+'ep_ll_a2a_layer': 'EPLowLatencyAllToAllLayer',
+ L+'ep_a2a_fused_layer': 'EpAll2AllFusedOp',
+ L+'gemm_allreduce_layer': 'GemmARLayer',
+ L+'low_latency_allgather_layer': 'AllGatherLayer',
+ L+'sp_flash_decode_layer': 'SpGQAFlashDecodeAttention',
+ L+'ulysses_sp_a2a_layer': 'UlyssesSPAllToAllLayer',
+ L+'p2p': 'CommOp', L+'pp_block': 'PPCommLayer PyTorchP2P',
+ 'triton_dist.function.nvidia.ep_moe_fused': 'TritonDistFusedEpMoeFunction',
+ 'triton_dist.function.nvidia.common': 'init_triton_dist_ep_op MoEOptimConfig',
+ 'triton_dist.mega_triton_kernel': 'ModelBuilder',
+ 'triton_dist.mega_triton_kernel.models': 'DenseModel',
+}
+
+
+@pytest.mark.parametrize("mod", sorted(PER_FILE))
+def test_reference_file_entry_points(mod):
+    m = importlib.import_module(mod)
+    missing = [n for n in PER_FILE[mod].split() if not hasattr(m, n)]
+    assert not missing, f"{mod} lacks {missing}"
+

@@ -793,3 +793,76 @@ def test_mega_server_single_rank(dist_env):
         srv.finalize()
     assert not th.is_alive()
 
+
+def test_tile_orders_for_arriving_and_leaving_rows():
+    """AG + GEMM / GEMM + RS tile orders: permutations; on one node the in-kernel rotations (AG starts at the local shard, RS at rank + 1
+    and ends with the own rows); on several nodes the own node first (AG) / last (RS), straddling tiles with the later / earlier node."""
+    import numpy as np
+    from triton_dist.ops import tile_swizzle as TS
+    for (M, W, nn, bm) in ((4096, 8, 1, 128), (4096, 8, 2, 128), (1536, 4, 2, 256), (2048 * 3, 6, 3, 128), (1152, 8, 4, 128)):
+        n_tiles = -(-M // bm)
+        for r in range(W):
+            ag, rs = TS.allgather_gemm_tile_order(M, r, W, nn, bm), TS.gemm_reduce_scatter_tile_order(M, r, W, nn, bm)
+            assert sorted(ag.tolist()) == sorted(rs.tolist()) == list(range(n_tiles))
+            assert TS.threadblock_swizzle_allgather_gemm_kernel(0, M, r, W, nn, bm) == ag[0]
+            assert TS.threadblock_swizzle_gemm_reduce_scatter_kernel(n_tiles - 1, M, r, W, nn, bm) == rs[-1]
+            lw, m_rank, m_node = W // nn, M // W, M // nn
+            node = r // lw
+            # AG: the first tile contains rows of the local shard (or starts right at / after it when the shard is smaller than a tile)
+            assert ag[0] * bm < (r + 1) * m_rank and (ag[0] + 1) * bm > r * m_rank or ag[0] * bm >= r * m_rank
+            # tiles entirely inside the own node come before any tile entirely inside another node (AG) / after all of them (RS)
+            inside = lambda t, n: t * bm >= n * m_node and min(M, (t + 1) * bm) <= (n + 1) * m_node
+            own_pos_ag = [i for i, t in enumerate(ag) if inside(t, node)]
+            other_pos_ag = [i for i, t in enumerate(ag) if any(inside(t, n) for n in range(nn) if n != node)]
+            own_pos_rs = [i for i, t in enumerate(rs) if inside(t, node)]
+            other_pos_rs = [i for i, t in enumerate(rs) if any(inside(t, n) for n in range(nn) if n != node)]
+            if own_pos_ag and other_pos_ag:
+                assert max(own_pos_ag) < min(other_pos_ag) and min(own_pos_rs) > max(other_pos_rs)
+            if nn == 1 and m_rank % bm == 0:
+                tpr = m_rank // bm
+                assert ag.tolist() == [(i + r * tpr) % n_tiles for i in range(n_tiles)]
+                assert rs.tolist() == [(i + ((r + 1) % W) * tpr) % n_tiles for i in range(n_tiles)]
+    # a tile straddling nodes 0 | 1 (M_node = 576, bm = 128 -> tile 4 holds rows 512..639): AG visits it with the later node, RS with the earlier
+    M, W, nn, bm = 1152, 8, 2, 128
+    ag0, rs0 = TS.allgather_gemm_tile_order(M, 0, W, nn, bm).tolist(), TS.gemm_reduce_scatter_tile_order(M, 0, W, nn, bm).tolist()
+    assert ag0.index(4) >= 4 and set(ag0[:4]) == {0, 1, 2, 3}            # rank 0 (node 0): own-node tiles 0..3 first, the straddler with node 1
+    assert rs0.index(4) < 5 and set(rs0[5:]) == {0, 1, 2, 3}              # RS from node 0 visits node 1 first; the straddler goes with it (earlier)
+    assert TS.tile_order_table(np.asarray(ag0, dtype=np.int32)).dtype == torch.int32
+
+
+def test_ep_routing_metadata():
+    """get_dispatch_send_reqs / recv_offsets_from_splits against brute force."""
+    from triton_dist.ops import ep_metadata as EM
+    g = torch.Generator().manual_seed(0)
+    W, epr, lw, T, topk = 4, 3, 2, 37, 3
+    E = W * epr
+    idx = torch.stack([torch.randperm(E, generator=g)[:topk] for _ in range(T)]).to(torch.int32)
+    idx[5, 1] = -1                                                                   # a dropped slot
+    reqs, counts = EM.get_dispatch_send_reqs(idx, epr, lw, nnodes=W // lw)
+    for n in range(W // lw):
+        want = [t for t in range(T) if any(0 <= int(e) and int(e) // (epr * lw) == n for e in idx[t])]
+        assert reqs[n, :len(want)].tolist() == want and int(counts[n]) == len(want) and (reqs[n, len(want):] == -1).all()
+    hist = EM.expert_histogram(idx, E)
+    assert int(hist[-1]) == 1 and int(hist.sum()) == T * topk
+    full = torch.randint(0, 9, (W, E + 1), generator=g, dtype=torch.int32)
+    offs, n_recv, n_in = EM.recv_offsets_from_splits(full, epr)
+    for r in range(W):
+        run = 0
+        for e in range(epr):
+            for s in range(W):
+                assert int(offs[r, e, s]) == run
+                run += int(full[s, r * epr + e])
+        assert int(n_recv[r]) == run and int(n_in[r]) == int(full[r, :E].sum())
+
+
+def test_gemm_config_space_and_matmul_names():
+    import importlib
+    G = importlib.import_module("triton_dist.ops.gemm")       # ``triton_dist.ops.gemm`` the attribute is the function
+    space = G.get_config_space()
+    assert len({c.key() for c in space}) == len(space) and {c.bn for c in space} == {32, 64, 128, 192, 256} and {c.cta_group for c in space} == {1, 2}
+    assert len(G.get_config_space(persistent=False)) < len(space)
+    b = torch.randn(8, 16)
+    assert G._as_weight(b).shape == (16, 8) and G._as_weight(b).is_contiguous()
+    assert G._as_weight(torch.randn(16, 8).t()).data_ptr() != 0                     # a [K, N] view of an [N, K] weight is used in place
+    assert G.matmul_tma_persistent is G.matmul_tma and G.matmul_persistent is G.matmul
+

@@ -81,3 +81,12 @@ class MegaEpMoeFunction(torch.autograd.Function):
 
 def mega_ep_moe_autograd(mctx: EM.EPMegaContext, x, topk_ids, topk_w, w_gate_up, w_down):
     return MegaEpMoeFunction.apply(x, topk_ids, topk_w, w_gate_up, w_down, mctx)
+
+
+def __getattr__(name):
+    # the reference's class name for the EP-MoE autograd function; the layer-level implementation lives with the EP layers
+    if name == "TritonDistFusedEpMoeFunction":
+        from ...parallel.ep import TritonDistFusedEpMoeFunction
+        return TritonDistFusedEpMoeFunction
+    raise AttributeError(name)
+

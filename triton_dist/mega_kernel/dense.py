@@ -91,3 +91,7 @@ class MegaDenseModel:
         heap = U.get_heap()
         heap.free_tensor(self.parts)
         heap.free_tensor(self.flags)
+
+
+DenseModel = MegaDenseModel     # the reference's class name (mega_triton_kernel/models/dense.py)
+

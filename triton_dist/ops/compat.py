@@ -332,3 +332,56 @@ def calc_gather_index_from_scatter_index(scatter_index: torch.Tensor) -> torch.T
 def calc_gather_index_torch(topk_ids: torch.Tensor, num_experts: int) -> torch.Tensor:
     """gather_index[i] = flat (token * topk + k) index of the i-th row of the expert-sorted order."""
     return calc_gather_index_from_scatter_index(calc_scatter_index_torch(topk_ids, num_experts))
+
+
+# ---- names of the reference that map onto one implementation here ---------------------------------------------------------------
+from .ep_metadata import (get_ag_splits_and_recv_offset_for_dispatch_intra_node, get_dispatch_send_reqs,  # noqa: E402,F401
+                          recv_offsets_from_splits)
+from .tile_swizzle import (threadblock_swizzle_allgather_gemm, threadblock_swizzle_allgather_gemm_kernel,  # noqa: E402,F401
+                           threadblock_swizzle_gemm_reduce_scatter, threadblock_swizzle_gemm_reduce_scatter_kernel)
+
+calc_gather_scatter_index_v2_triton = calc_gather_scatter_index_triton      # (moe_utils.py:341) one implementation: the align/sort kernel
+
+
+def run_moe_reduce_rs_triton_non_overlap(x, w, chosen_experts, expert_weight, ctx=None, group=None, **_hints):
+    """(moe_reduce_rs.py:825) the NON-overlapped baseline the fused op is compared against: grouped GEMM, weighted top-k reduce, then
+    one NCCL ``reduce_scatter_tensor`` -- three steps back to back, no chunking, no symmetric buffers."""
+    W, me = U.world_size(), U.rank()
+    return M.moe_reduce_rs_torch(x, w, chosen_experts, expert_weight, group or U.get_triton_dist_world(), W, me)
+
+
+def create_context(max_num_token: int, token_len_elem: int, num_expert_per_rank: int = 1, dtype: torch.dtype = torch.bfloat16, **_hints):
+    """(all_to_all_vdev_2d_offset.py:528) context of the variable-size 2-D all-to-all: rows of ``token_len_elem`` elements, at most
+    ``max_num_token`` rows per peer."""
+    from .all_to_all import create_all_to_all_context
+    W = U.world_size()
+    return create_all_to_all_context(max_num_token, token_len_elem, U.rank(), num_expert_per_rank * W, W, num_expert_per_rank, dtype)
+
+
+def all_to_all_v_offset_op(ctx, rank_in_row: bool = True, input: torch.Tensor = None, output: torch.Tensor = None,
+                           in_splits: torch.Tensor = None, in_offset: torch.Tensor = None, has_input_offset: bool = False, **_hints):
+    """(all_to_all_vdev_2d_offset.py:637) the common entry of ``all_to_all_vdev_2d`` (packed rows) and ``..._offset`` (rows of every
+    (destination, expert) group start at ``in_offset``).  Returns ``(received rows, recv_splits)``; ``output`` is filled when given."""
+    from .all_to_all import all_to_all_vdev_2d
+    epr = ctx.experts_per_rank if hasattr(ctx, "experts_per_rank") else max(1, in_splits.numel() // U.world_size())
+    if has_input_offset or in_offset is not None:
+        recv, splits = all_to_all_vdev_2d_offset(ctx, input, in_splits.reshape(-1), in_offset.reshape(-1), epr)
+    else:
+        recv, splits = all_to_all_vdev_2d(ctx, input, in_splits.reshape(-1))
+    if output is not None:
+        output[: recv.shape[0]].copy_(recv)
+    return recv, splits
+
+
+all_to_all_v_offset_op_v2 = all_to_all_v_offset_op
+
+# flash_decode.py *_aot: every kernel of this framework is compiled ahead of time by nvcc, the AOT entry points are the same functions
+
+
+def pre_attn_a2a_comm_only(ctx, qkv_local: torch.Tensor):
+    """(ulysses_sp_infer_gemm_a2a.py:394) the all-to-all half of the inference Ulysses op without the GEMM: ``qkv_local``
+    [S / W, (Hq + 2 Hkv) * D] seq-sharded projections -> head-sharded (q, k, v) [S, H / W, D]."""
+    S_loc = qkv_local.shape[0]
+    q, k, v = qkv_local.view(S_loc, -1, ctx.D).split([ctx.Hq, ctx.Hkv, ctx.Hkv], dim=1)
+    return ctx.pack(q.contiguous(), k.contiguous(), v.contiguous())
+

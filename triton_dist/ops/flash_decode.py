@@ -120,3 +120,8 @@ def gqa_fwd_batch_decode(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.
 
 gqa_fwd_batch_decode_persistent = gqa_fwd_batch_decode
 gqa_fwd_batch_decode_intra_rank = gqa_fwd_batch_decode_partial
+# the reference's *_aot entry points call kernels compiled ahead of time (flash_decode.py:763-1132); every kernel here is nvcc-built AOT
+gqa_fwd_batch_decode_aot = gqa_fwd_batch_decode
+gqa_fwd_batch_decode_persistent_aot = gqa_fwd_batch_decode_persistent
+gqa_fwd_batch_decode_intra_rank_aot = gqa_fwd_batch_decode_intra_rank
+

@@ -192,3 +192,44 @@ def gemm_scaled(a: torch.Tensor, b: torch.Tensor, scale_a=None, scale_b=None, ou
         args.c_phase, args.c_nbuf, args.c_buf_stride_bytes = out_parity[0].data_ptr(), 2, int(out_parity[1])
     _C.check(_C.cuda_lib().td_gemm_launch(C.byref(args), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "td_gemm_launch(8-bit)")
     return out
+
+
+# ---- the reference's local-GEMM entry points (kernels/nvidia/gemm.py:382-907) ------------------------------------------------------
+def get_config_space(persistent: bool = True, device_id: int = 0):
+    """Every tile configuration the sm_100a kernel accepts -- the search space of the tuning tools (tools/tune/tune_gemm.py).
+    ``persistent=False`` keeps only the configurations that use all SMs with the default grid (the kernel itself is always a
+    persistent, warp-specialised tcgen05 kernel; there is no one-tile-per-CTA variant to fall back to)."""
+    space = []
+    for cta_group in (2, 1):
+        for bn in (256, 192, 128, 64, 32):
+            for group_m in ((8,) if not persistent else (1, 4, 8, 16)):
+                for tma_store in (True, False):
+                    space.append(GemmConfig(bn=bn, cta_group=cta_group, group_m=group_m, use_tma_store=tma_store))
+    return space
+
+
+def _as_weight(b: torch.Tensor) -> torch.Tensor:
+    """The reference's ``matmul(a, b)`` takes ``b`` as [K, N]; the kernel wants the ``nn.Linear`` layout [N, K] (K-major)."""
+    bt = b.t()
+    return bt if bt.is_contiguous() else bt.contiguous()
+
+
+def _cfg(a, b, config, tma_store: bool):
+    base = config if isinstance(config, GemmConfig) else default_config(a.shape[0], b.shape[1], a.shape[1])
+    return GemmConfig(base.bn, base.cta_group, base.group_m, tma_store, base.num_sms, base.n_comm_ctas)
+
+
+def matmul(a: torch.Tensor, b: torch.Tensor, config: Optional[GemmConfig] = None) -> torch.Tensor:
+    """``a[M, K] @ b[K, N]`` with the direct-store epilogue (TMEM -> registers -> 16-byte global stores)."""
+    return gemm(a, _as_weight(b), config=_cfg(a, b, config, False))
+
+
+def matmul_tma(a: torch.Tensor, b: torch.Tensor, config: Optional[GemmConfig] = None, warp_specialize: bool = True) -> torch.Tensor:
+    """``a[M, K] @ b[K, N]`` with the TMA-store epilogue (TMEM -> swizzled shared memory -> ``cp.async.bulk.tensor`` store).
+    The kernel is always warp-specialised (TMA / MMA / epilogue warps); ``warp_specialize`` is accepted for call compatibility."""
+    return gemm(a, _as_weight(b), config=_cfg(a, b, config, True))
+
+
+matmul_persistent = matmul                                   # the kernel is persistent in both epilogue flavours
+matmul_tma_persistent = matmul_descriptor_persistent = matmul_tma
+
