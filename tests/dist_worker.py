@@ -1072,6 +1072,52 @@ def case_shmem():
         U.nvshmem_free_tensor_sync(t)
 
 
+def case_lk_shmem():
+    """The OpenSHMEM-style device API from a DSL kernel (triton_dist.lk.shmem -> csrc/td/shmem.cuh): the same self-test as the CUDA one in
+    case_shmem, written in Python.  GPU backend: generated CUDA; emulation: the interpreter runs transfers, signals and the arrival-flag
+    barriers on the shared-memory heap across processes."""
+    from triton_dist import lk
+    from triton_dist.lk.kernels import simt as K
+    W, me = U.world_size(), U.rank()
+    dev = U.current_device()
+    n = 48
+    fc = U.nvshmem_create_tensor((W * n,), torch.float32)
+    bc = U.nvshmem_create_tensor((n,), torch.float32)
+    ring = U.nvshmem_create_tensor((2 * n,), torch.float32)
+    slots = U.nvshmem_create_tensor((2 * W,), torch.int32)
+    sig64 = U.nvshmem_create_tensor((2,), torch.int64)
+    misc = U.nvshmem_create_tensor((4,), torch.int32)
+    epoch = torch.zeros(1, dtype=torch.int32, device=dev)
+    for t in (slots, sig64, misc, fc, bc, ring):
+        t.zero_()
+    U.barrier_all_on_stream()
+    ctx = lk.symm_ctx()
+    n_even = (W + 1) // 2
+    for phase in range(1, 4):
+        src = torch.arange(n, dtype=torch.float32, device=dev) * 0.5 + 7.0 * me + phase
+        args = (ctx, slots, epoch, fc, bc, ring, sig64, misc, src, n, phase)
+        if dev.type == "cuda":
+            K.shmem_selftest[1](*args)
+            torch.cuda.synchronize()
+        else:
+            K.shmem_selftest.interpret(1, *args)
+        want = torch.cat([torch.arange(n, dtype=torch.float32) * 0.5 + 7.0 * r + phase for r in range(W)])
+        _assert_close(fc, want, 0, 0, f"lk.shmem fcollect phase {phase}")
+        root_pe = 2 * (phase % n_even)
+        if me % 2 == 0:
+            _assert_close(bc, torch.arange(n, dtype=torch.float32) * 0.5 + 7.0 * root_pe + phase, 0, 0, f"lk.shmem broadcast {phase}")
+        prev = (me - 1 + W) % W
+        pv = torch.arange(n, dtype=torch.float32) * 0.5 + 7.0 * prev + phase
+        _assert_close(ring[:n], pv, 0, 0, f"lk.shmem putmem_signal phase {phase}")
+        _assert_close(ring[n:n + 3], pv[:3], 0, 0, f"lk.shmem putmem_warp phase {phase}")
+        m = misc.cpu().tolist()
+        assert m[0] == (me // 2 if me % 2 == 0 else -1) and m[1] == m[0] and m[2] == prev * 10 + phase, (me, m)
+        assert int(epoch.item()) == 3 * phase and int(sig64[0].item()) == phase, (epoch, sig64)
+        U.barrier_all_on_stream()
+    for t in (misc, sig64, slots, ring, bc, fc):
+        U.nvshmem_free_tensor_sync(t)
+
+
 def case_lk_ag_gemm():
     """AllGather + GEMM as ONE kernel written in the Python DSL (comm CTAs push shards + release-add flags, tcgen05 tiles acquire the
     flags of the rows they need).  GPU: the generated CUDA; emulation: the interpreter with the functional pipeline model, across ranks."""

@@ -143,3 +143,38 @@ def test_reference_file_entry_points(mod):
     missing = [n for n in PER_FILE[mod].split() if not hasattr(m, n)]
     assert not missing, f"{mod} lacks {missing}"
 
+
+# SURVEY.md sections 2.2 / 2.3 / 2.7 / 2.9: device language, NVSHMEM-style device API, runtime helpers, megakernel sub-modules, tools
+LANGUAGE_AND_RUNTIME = {
+ 'triton_dist.language': 'wait consume_token notify symm_at rank num_ranks simt_exec_region vector make_vector zeros_vector extern_call',
+ 'triton_dist.language.extra.cuda.language_extra': '__syncthreads __fence tma_sync multimem_st_b32 multimem_st_b64 multimem_st_v2 multimem_st_v4 multimem_ld_reduce_v4 tid ntid laneid red_release arrive_inc ld ld_vector st_vector ld_acquire st atomic_add atomic_add_per_warp wait_eq __shfl_sync_i32 __shfl_up_sync_i32 __shfl_down_sync_i32 __ballot_sync atomic_cas globaltimer smid membar fence pack_b32_v2 pack unpack',
+ 'triton_dist.language.extra.cuda.libnvshmem_device': 'NVSHMEM_CMP_EQ NVSHMEM_CMP_GE NVSHMEM_SIGNAL_SET NVSHMEM_SIGNAL_ADD my_pe n_pes team_my_pe team_n_pes int_p remote_ptr remote_mc_ptr barrier barrier_block barrier_warp barrier_all barrier_all_block barrier_all_warp sync_all sync_all_block sync_all_warp team_sync_block team_sync_warp quiet fence getmem getmem_nbi getmem_warp getmem_block getmem_nbi_block putmem putmem_nbi putmem_warp putmem_block putmem_nbi_block putmem_signal putmem_signal_nbi putmem_signal_block putmem_signal_nbi_block putmem_signal_warp signal_op signal_wait_until broadcast broadcast_warp broadcast_block broadcastmem_block fcollect fcollect_block team_translate_pe',
+ 'triton_dist.language.extra.libshmem_device': 'my_pe n_pes putmem_block getmem_block signal_op signal_wait_until barrier_all',
+ 'triton_dist.kernels.nvidia.common_ops': 'unsafe_barrier_on_this_grid cooperative_barrier_on_this_grid barrier_all_intra_node_atomic_cas_block barrier_all_intra_node_non_atomic barrier_all_intra_node_non_atomic_block _wait_eq_cuda _set_signal_cuda _memcpy_async_cuda bisect_left bisect_right bisect_left_aligned bisect_right_aligned BarrierAllContext barrier_all_on_stream',
+ 'triton_dist.utils': 'wait_until_max_gpu_clock_or_warning triton_dist_key barrier_async generate_data _make_tensor init_seed has_fullmesh_nvlink get_nvlink_max_speed_gbps get_intranode_max_speed_gbps LazyTensor LazyAllocator NVSHMEMLazyAllocator nvshmem_create_tensors',
+ 'triton_dist.nv_utils': 'has_fullmesh_nvlink get_nvlink_max_speed_gbps get_intranode_max_speed_gbps',
+ 'triton_dist.jit': 'jit',
+ 'triton_dist.tools.compile_aot': 'aot_compile_spaces',
+ 'triton_dist.tune': 'autotune',
+ 'triton_dist.autotuner': 'contextual_autotune ContextualAutoTuner',
+ 'triton_dist.tools.profiler': 'Profiler ProfilerBuffer alloc_profiler_buffer reset_profiler_buffer export_to_perfetto_trace',
+ 'triton_dist.tools.profiler.language': 'Profiler',
+ 'triton_dist.tools.profiler.viewer': 'export_to_perfetto_trace',
+ 'triton_dist.tools.tune.tune_gemm': 'main',
+ 'triton_dist.tools.tune.find_topk': 'main',
+ 'triton_dist.benchmark.bench_allgather_gemm': '', 'triton_dist.benchmark.bench_tp_mlp': '', 'triton_dist.benchmark.bench_tp_attn': '', 'triton_dist.benchmark.bench_pp': '',
+ 'triton_dist.models.engine': 'Engine', 'triton_dist.models.utils': 'logger seed_everything sample_token init_model_cpu',
+ 'triton_dist.models.kv_cache': 'KV_Cache', 'triton_dist.models.config': 'ModelConfig', 'triton_dist.models.dense': 'DenseLLM DenseLLMLayer', 'triton_dist.models.qwen_moe': 'Qwen3MoE',
+ 'triton_dist.mega_triton_kernel.core.scheduler': '', 'triton_dist.mega_triton_kernel.core.code_generator': '', 'triton_dist.mega_triton_kernel.core.registry': '', 'triton_dist.mega_triton_kernel.core.config': '',
+ 'triton_dist.mega_triton_kernel.tasks.flash_attn': '', 'triton_dist.mega_triton_kernel.tasks.prefetch': '', 'triton_dist.mega_triton_kernel.tasks.barrier':'', 'triton_dist.mega_triton_kernel.tasks.elementwise':'', 'triton_dist.mega_triton_kernel.tasks.activation':'',
+ 'triton_dist.mega_triton_kernel.kernels.flash_attn': '', 'triton_dist.mega_triton_kernel.kernels.linear': '',
+ 'triton_dist.mega_triton_kernel.test.models.model_server': '', 'triton_dist.mega_triton_kernel.test.models.chat': '',
+}
+
+
+@pytest.mark.parametrize("mod", sorted(LANGUAGE_AND_RUNTIME))
+def test_language_runtime_and_tool_names(mod):
+    m = importlib.import_module(mod)
+    missing = [n for n in LANGUAGE_AND_RUNTIME[mod].split() if not hasattr(m, n)]
+    assert not missing, f"{mod} lacks {missing}"
+

@@ -1,6 +1,7 @@
 """The Python kernel DSL (triton_dist.lk) without a GPU: generated C++ text, nvcc cross-compilation for sm_100a (incl. the tcgen05 GEMM
 ladder: the SASS must contain the Blackwell tensor-core / TMA instructions), and the CPU interpreter against PyTorch.
 Reference test strategy: python/little_kernel/tests/unit/* (pure-python codegen tests that run without a GPU)."""
+import os
 import shutil
 import subprocess
 
@@ -464,4 +465,70 @@ def test_flash_attention_on_mma_sync_in_the_interpreter():
     kern.compile()
     sass = subprocess.run([shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump", "-sass", kern._lib._name], capture_output=True, text=True).stdout
     assert sass.count("HMMA") >= 128 and "STL" not in sass          # 64 + 64 MMAs per KV tile, no spills
+
+
+def test_language_extra_and_stdlib_in_dsl_kernels(tmp_path):
+    """The reference's helper vocabulary as DSL intrinsics (scoped ld / st / atomics / red / fences lower to ONE PTX instruction each),
+    the device-side binary searches, the grid barrier and extern_call: generated CUDA compiles for sm_100a, the interpreter gives the
+    same answers; the AOT registry exports a registered kernel."""
+    from triton_dist.lk import language_extra as le, stdlib
+
+    @lk.kernel(block=64)
+    def le_selftest(cnt: ll.ptr[ll.u32], flag: ll.ptr[ll.u32], out: ll.ptr[ll.u32], big: ll.ptr[ll.u64], fl: ll.ptr[ll.f32],
+                    sorted_vals: ll.ptr[ll.i32], n_sorted: ll.i32, bar: ll.ptr[ll.u32]):
+        t = le.tid(0)
+        n = le.ntid(0)
+        old = le.atomic_add(cnt, 1, scope="gpu", semantic="relaxed")
+        out[ll.blockIdx.x * 80 + t] = old
+        le.red_release(cnt + 1, 2, scope="sys")
+        le.__syncthreads()
+        if t == 0 and ll.blockIdx.x == 0:
+            le.st(flag, 7, scope="sys", semantic="release")
+            le.fence("acq_rel", "sys")
+            le.membar("gpu")
+            big[0] = le.pack_b32_v2(3, 4)
+            out[n] = le.atomic_cas(cnt + 2, 0, 99, scope="sys", semantic="acq_rel")
+            out[n + 3] = le.unpack_hi(big[0])
+            le.atomic_add(fl, 1.5)
+        if t == 1 and ll.blockIdx.x == 0:
+            le.wait_eq(flag, 7)
+            out[n + 1] = le.ld(flag, scope="sys", semantic="acquire") + le.ld_acquire(flag, "gpu")
+        v = le.__shfl_down_sync_i32(0xFFFFFFFF, t, 1)
+        b = le.__ballot_sync(0xFFFFFFFF, t % 2 == 0)
+        w = le.atomic_add_per_warp(cnt + 3, 1)
+        if t == 5 and ll.blockIdx.x == 0:
+            out[n + 2] = ll.u32(v) + (b & 0xF) + w * 0 + le.laneid()
+            out[n + 4] = stdlib.bisect_left(sorted_vals, n_sorted, 7) * 100 + stdlib.bisect_right(sorted_vals, n_sorted, 7)
+            out[n + 5] = ll.u32(stdlib.extern_call("td::ptx::bf16_hi", ll.f32, ll.u32(0x40400000)))       # bf16 3.0 in the high half
+        stdlib.grid_barrier(bar, ll.gridDim.x)
+        if t == 0:
+            out[ll.blockIdx.x * 80 + 79] = le.ld(cnt, scope="gpu", semantic="acquire")        # every block sees every block's adds
+
+    src = le_selftest.cuda_source()
+    for needle in ("atom.relaxed.gpu.global.add.u32", "red.release.sys.global.add.u32", "st.release.sys.global.b32", "fence.acq_rel.sys",
+                   "membar.gl", "atom.acq_rel.sys.global.cas.b32", "ld.acquire.sys.global.b32", "atom.relaxed.gpu.global.add.f32",
+                   "td::grid_barrier", "td::ptx::bf16_hi("):
+        assert needle in src, needle
+    le_selftest.compile()
+    cnt, flag, out = torch.zeros(8, dtype=torch.int32), torch.zeros(1, dtype=torch.int32), torch.zeros(160, dtype=torch.int32)
+    big, fl, bar = torch.zeros(1, dtype=torch.int64), torch.zeros(1), torch.zeros(1, dtype=torch.int32)
+    vals = torch.tensor([1, 3, 7, 7, 7, 9, 12], dtype=torch.int32)
+    stdlib.EXTERN_INTERP["td::ptx::bf16_hi"] = lambda w: torch.tensor([int(w) >> 16], dtype=torch.int16).view(torch.bfloat16).float().item()
+    le_selftest.interpret(2, cnt, flag, out, big, fl, vals, vals.numel(), bar)
+    assert cnt[:4].tolist() == [128, 256, 99, 4] and flag.item() == 7 and fl.item() == 1.5 and big.item() == (4 << 32) | 3
+    assert sorted(out[:64].tolist() + out[80:144].tolist()) == list(range(128))
+    assert out[64:70].tolist() == [0, 14, 16, 4, 2 * 100 + 5, 3] and out[79].item() == 128 and out[159].item() == 128
+
+    from triton_dist.tools import compile_aot as A
+
+    @A.aot_compile_spaces({"saxpy_aot": {}})
+    @lk.kernel(block=128)
+    def saxpy_for_aot(x: ll.ptr[ll.f32], y: ll.ptr[ll.f32], a: ll.f32, n: ll.i32):
+        i = ll.blockIdx.x * 128 + ll.threadIdx.x
+        if i < n:
+            y[i] = a * x[i] + y[i]
+
+    infos = A.export_registered(tmp_path, names=["saxpy_aot"])
+    assert len(infos) == 1 and os.path.exists(infos[0]["so"]) and "lk_launch_saxpy_for_aot" in open(infos[0]["header"]).read()
+    A.AOT_REGISTRY.pop("saxpy_aot")
 

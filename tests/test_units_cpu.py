@@ -866,3 +866,15 @@ def test_gemm_config_space_and_matmul_names():
     assert G._as_weight(torch.randn(16, 8).t()).data_ptr() != 0                     # a [K, N] view of an [N, K] weight is used in place
     assert G.matmul_tma_persistent is G.matmul_tma and G.matmul_persistent is G.matmul
 
+
+def test_host_vector_and_extern_call():
+    import ctypes
+    from triton_dist import language as dl
+    a, b = dl.make_vector([1.0, 2.0, 3.0], torch.float32), dl.zeros_vector(3) + 2.0
+    assert ((a + b) * a - 1.0).data.tolist() == [2.0, 7.0, 14.0] and len(a) == 3
+    assert a.to(torch.int32).dtype == torch.int32 and a.recast(torch.int32)[0].item() == 0x3F800000
+    assert dl.extern_call(ctypes.CDLL(None), "abs", (-5,), restype=ctypes.c_int, argtypes=[ctypes.c_int]) == 5
+    from triton_dist.utils import _make_tensor
+    t = _make_tensor((4, 4), torch.float32, (0.0, 3.0), device="cpu")
+    assert torch.equal(t, torch.full((4, 4), 3.0))
+

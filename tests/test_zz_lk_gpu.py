@@ -353,3 +353,12 @@ def test_mega_server_two_gpus():
     from _launch import run_dist
     run_dist(["mega_server"], nproc=2, timeout=240)
 
+
+@pytest.mark.xfail(strict=False, reason="OpenSHMEM-style device API from a DSL kernel: passes in the interpreter across processes, compiled, not yet run on hardware")
+def test_lk_shmem_two_gpus():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from _launch import run_dist
+    run_dist(["lk_shmem"], nproc=2, timeout=240)
+

@@ -23,8 +23,8 @@ _P = "triton_dist.parallel."
 
 MODULE_MAP = {
     # kernels
-    "triton_dist.kernels.common_ops": ["triton_dist.utils", _O + "comm"],
-    _K + "common_ops": ["triton_dist.utils", _O + "comm"],
+    "triton_dist.kernels.common_ops": ["triton_dist.utils", _O + "comm", "triton_dist.lk.stdlib", _O + "compat"],
+    _K + "common_ops": ["triton_dist.utils", _O + "comm", "triton_dist.lk.stdlib", _O + "compat"],
     _K + "allgather_gemm": [_O + "ag_gemm"],
     _K + "ag_gemm_threadblock_swizzle": [_O + "ag_gemm"],
     _K + "allgather": [_O + "allgather"],
@@ -82,12 +82,12 @@ MODULE_MAP = {
     "triton_dist.language.distributed_ops": ["triton_dist.language"],
     "triton_dist.language.simt_ops": ["triton_dist.language"],
     "triton_dist.language.extra": ["triton_dist.language.shmem", "triton_dist.language"],
-    "triton_dist.language.extra.libshmem_device": ["triton_dist.language.shmem"],
-    "triton_dist.language.extra.language_extra": ["triton_dist.language", "triton_dist.language.shmem"],
+    "triton_dist.language.extra.libshmem_device": ["triton_dist.lk.shmem", "triton_dist.language.shmem"],
+    "triton_dist.language.extra.language_extra": ["triton_dist.lk.language_extra", "triton_dist.language", "triton_dist.language.shmem"],
     "triton_dist.language.extra.utils": ["triton_dist.language"],
     "triton_dist.language.extra.cuda": ["triton_dist.language.shmem", "triton_dist.language"],
-    "triton_dist.language.extra.cuda.language_extra": ["triton_dist.language", "triton_dist.language.shmem"],
-    "triton_dist.language.extra.cuda.libnvshmem_device": ["triton_dist.language.shmem"],
+    "triton_dist.language.extra.cuda.language_extra": ["triton_dist.lk.language_extra", "triton_dist.language", "triton_dist.language.shmem"],
+    "triton_dist.language.extra.cuda.libnvshmem_device": ["triton_dist.lk.shmem", "triton_dist.language.shmem"],
     # tools / misc
     "triton_dist.nv_utils": ["triton_dist.utils", "triton_dist._build"],
     "triton_dist.tools.compile": ["triton_dist.tools.compile_aot"],
@@ -114,6 +114,31 @@ MODULE_MAP = {
     "triton_dist.mega_triton_kernel.tasks.norm": ["triton_dist.mega_kernel"],
     "triton_dist.mega_triton_kernel.tasks.linear": ["triton_dist.mega_kernel"],
     "triton_dist.mega_triton_kernel.tasks": ["triton_dist.mega_kernel"],
+    "triton_dist.mega_triton_kernel.core.code_generator": ["triton_dist.mega_kernel"],
+    "triton_dist.mega_triton_kernel.core.registry": ["triton_dist.mega_kernel"],
+    "triton_dist.mega_triton_kernel.core.config": ["triton_dist.mega_kernel"],
+    "triton_dist.mega_triton_kernel.core.utils": ["triton_dist.mega_kernel"],
+    "triton_dist.mega_triton_kernel.tasks.flash_attn": ["triton_dist.mega_kernel"],
+    "triton_dist.mega_triton_kernel.tasks.prefetch": ["triton_dist.mega_kernel"],
+    "triton_dist.mega_triton_kernel.tasks.barrier": ["triton_dist.mega_kernel"],
+    "triton_dist.mega_triton_kernel.tasks.elementwise": ["triton_dist.mega_kernel"],
+    "triton_dist.mega_triton_kernel.tasks.activation": ["triton_dist.mega_kernel"],
+    "triton_dist.mega_triton_kernel.tasks.utils": ["triton_dist.mega_kernel"],
+    "triton_dist.mega_triton_kernel.kernels.flash_attn": ["triton_dist.lk.kernels.flash_mma", "triton_dist.mega_kernel"],
+    "triton_dist.mega_triton_kernel.kernels.flash_decode": ["triton_dist.mega_kernel"],
+    "triton_dist.mega_triton_kernel.kernels.linear": ["triton_dist.lk.kernels.linear_mma", "triton_dist.mega_kernel"],
+    "triton_dist.mega_triton_kernel.kernels.norm": ["triton_dist.mega_kernel"],
+    "triton_dist.mega_triton_kernel.kernels.allreduce": ["triton_dist.mega_kernel"],
+    "triton_dist.mega_triton_kernel.kernels.activation": ["triton_dist.mega_kernel"],
+    "triton_dist.mega_triton_kernel.kernels.elementwise": ["triton_dist.mega_kernel"],
+    "triton_dist.mega_triton_kernel.kernels.prefetch": ["triton_dist.mega_kernel"],
+    "triton_dist.mega_triton_kernel.kernels.barrier": ["triton_dist.mega_kernel"],
+    "triton_dist.mega_triton_kernel.kernels.mlp_fc1": ["triton_dist.mega_kernel"],
+    "triton_dist.mega_triton_kernel.kernels.utils": ["triton_dist.mega_kernel"],
+    "triton_dist.mega_triton_kernel.test": ["triton_dist.mega_kernel.server"],
+    "triton_dist.mega_triton_kernel.test.models": ["triton_dist.mega_kernel.server"],
+    "triton_dist.mega_triton_kernel.test.models.model_server": ["triton_dist.mega_kernel.server"],
+    "triton_dist.mega_triton_kernel.test.models.chat": ["triton_dist.mega_kernel.server"],
 }
 _FAMILY = {_K: "triton_dist.kernels.nvidia", _L: "triton_dist.layers.nvidia"}
 

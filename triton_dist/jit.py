@@ -136,3 +136,12 @@ def make_tma_2d(t, box_inner: int, box_outer: int, swizzle: int = 128):
     rows, cols = t.shape
     _C.check(fn(buf, t.data_ptr(), rows, cols, t.stride(0), t.element_size(), box_inner, box_outer, swizzle), "td_make_tma_2d")
     return buf
+
+
+def jit(fn=None, **kernel_options):
+    """``@triton_dist.jit.jit`` -- the decorator role of the reference's ``triton_dist.jit`` (jit.py:274-313: ``triton.jit`` plus the
+    NVSHMEM device library).  Kernels are authored in the Python DSL here: this is :func:`triton_dist.lk.kernel` (typed AST -> CUDA C++
+    over csrc/td/*.cuh -> nvcc), and the symmetric-heap device API comes with the generated source's headers instead of a bitcode link."""
+    from . import lk
+    return lk.kernel(fn, **kernel_options) if fn is not None else lk.kernel(**kernel_options)
+

@@ -80,3 +80,68 @@ def simt_exec_region():
     """Device-side concept of the reference DSL (a region executed per thread instead of per block).  The CUDA kernels
     of this framework are written in SIMT form already, so the host mirror is a no-op context."""
     yield
+
+
+# ---- per-thread vectors of the SIMT region (reference: language/simt_ops.py:35-286) --------------------------------------------------
+class vector:
+    """A short fixed-length vector held by one thread: element-wise ``+ - *``, ``to`` (convert), ``recast`` (reinterpret the bits).
+    In device code of this framework that is a register array (``ll.local`` in the DSL, a C array in CUDA); this host mirror backs the
+    emulation tests and documentation examples."""
+
+    def __init__(self, data):
+        self.data = data if isinstance(data, torch.Tensor) else torch.as_tensor(data)
+
+    def _bin(self, other, op):
+        o = other.data if isinstance(other, vector) else other
+        return vector(op(self.data, o))
+
+    def __add__(self, o):
+        return self._bin(o, torch.add)
+
+    def __sub__(self, o):
+        return self._bin(o, torch.sub)
+
+    def __mul__(self, o):
+        return self._bin(o, torch.mul)
+
+    __radd__, __rmul__ = __add__, __mul__
+
+    def __getitem__(self, i):
+        return self.data[i]
+
+    def __setitem__(self, i, v):
+        self.data[i] = v
+
+    def __len__(self):
+        return self.data.numel()
+
+    def to(self, dtype):
+        return vector(self.data.to(dtype))
+
+    def recast(self, dtype):
+        return vector(self.data.contiguous().view(dtype))
+
+    @property
+    def dtype(self):
+        return self.data.dtype
+
+
+def make_vector(values, dtype=None) -> vector:
+    return vector(torch.as_tensor(list(values), dtype=dtype))
+
+
+def zeros_vector(n: int, dtype=torch.float32) -> vector:
+    return vector(torch.zeros(n, dtype=dtype))
+
+
+def extern_call(lib, symbol: str, args=(), restype=None, argtypes=None):
+    """Call ``symbol`` of a shared library (path or loaded ``ctypes.CDLL``) -- the host counterpart of the reference's device-side
+    ``extern_call`` (language/core.py:85-116); inside DSL kernels use ``triton_dist.lk.stdlib.extern_call``."""
+    import ctypes
+    handle = ctypes.CDLL(lib) if isinstance(lib, str) else lib
+    fn = getattr(handle, symbol)
+    fn.restype = restype
+    if argtypes is not None:
+        fn.argtypes = list(argtypes)
+    return fn(*args)
+

@@ -3,7 +3,7 @@ PyTorch; tests/test_zz_lk_gpu.py checks the compiled code).  They double as the 
 from __future__ import annotations
 
 from triton_dist import lk
-from triton_dist.lk import ll
+from triton_dist.lk import ll, shmem
 
 BLOCK = 128
 NWARPS = BLOCK // 32
@@ -137,3 +137,29 @@ def allgather_push(ctx: ll.SymmCtx, shard: ll.ptr[ll.f32], out: ll.ptr[ll.f32], 
     if tid < 32:
         ll.wait(flags, world, phase)
     ll.syncthreads()
+
+
+@lk.kernel(block=128)
+def shmem_selftest(ctx: ll.SymmCtx, slots: ll.ptr[ll.u32], epoch: ll.ptr[ll.u32], fc_dst: ll.ptr[ll.f32], bc_dst: ll.ptr[ll.f32],
+                   ring_dst: ll.ptr[ll.f32], sig: ll.ptr[ll.u64], misc: ll.ptr[ll.i32], src: ll.ptr[ll.f32], n: ll.i32, phase: ll.u64):
+    """Every family of the OpenSHMEM-style device API (``triton_dist.lk.shmem``) once: fcollect over the world team, broadcast inside
+    the even team, put-with-signal around the ring (64-bit signal, CMP_GE wait), a thread-scope ``int_p``, a warp-scope put with an
+    unaligned byte count, team translation, quiet, barrier_all -- the DSL twin of the CUDA self-test in tests/dist_worker.py."""
+    s = shmem.make_sync(slots, epoch)
+    world = shmem.team_world(ctx)
+    W = shmem.n_pes(ctx)
+    even = shmem.team_split_strided(0, 2, (W + 1) // 2)
+    shmem.fcollect_block(ctx, world, s, fc_dst, src, n)
+    shmem.broadcast_block(ctx, even, s, bc_dst, src, n, ll.i32(phase % ll.u64((W + 1) // 2)))
+    nxt = (shmem.my_pe(ctx) + 1) % W
+    shmem.putmem_signal_block(ctx, ring_dst, src, n * 4, sig, phase, shmem.SIGNAL_SET, nxt)
+    if ll.threadIdx.x == 0:
+        shmem.signal_wait_until(sig, shmem.CMP_GE, phase)
+        misc[0] = shmem.team_translate_pe(world, shmem.my_pe(ctx), even)       # my index in the even team or -1
+        misc[1] = shmem.team_my_pe(ctx, even)
+        shmem.int_p(ctx, misc + 2, shmem.my_pe(ctx) * 10 + ll.i32(phase), nxt)
+    if ll.threadIdx.x < 32:
+        shmem.putmem_warp(ctx, ring_dst + n, src, 3 * 4 + 2, nxt)              # unaligned size: byte tail
+    shmem.quiet()
+    shmem.barrier_all_block(ctx, s)
+

@@ -385,3 +385,15 @@ def pre_attn_a2a_comm_only(ctx, qkv_local: torch.Tensor):
     q, k, v = qkv_local.view(S_loc, -1, ctx.D).split([ctx.Hq, ctx.Hkv, ctx.Hkv], dim=1)
     return ctx.pack(q.contiguous(), k.contiguous(), v.contiguous())
 
+
+# ---- common_ops.py device barriers: one symmetric-heap barrier here (csrc/td/primitives.cuh ``barrier_all_block``: flag flip on a
+# monotone epoch, the non-atomic protocol of the reference :172-224; the CAS variant :154-168 exists there for hardware without native
+# P2P atomics ordering -- NVLink 5 needs neither) --------------------------------------------------------------------------------------
+def __getattr__(name, _prev=globals().get("__getattr__")):
+    if name in ("barrier_all_intra_node_atomic_cas_block", "barrier_all_intra_node_non_atomic", "barrier_all_intra_node_non_atomic_block"):
+        from ..lk import ll
+        return ll.barrier_all_block
+    if _prev is not None:
+        return _prev(name)
+    raise AttributeError(name)
+

@@ -416,6 +416,13 @@ def generate_data(configs, device=None):
         yield [rand_tensor(shape, dtype, device, scale) for (shape, dtype, scale) in configs]
 
 
+def _make_tensor(shape, dtype, init_args, device=None):
+    """One random tensor ``scale * randn + bias`` (reference: utils.py ``_make_tensor``; ``init_args`` = ``(scale, bias)`` or ``scale``)."""
+    scale, bias = init_args if isinstance(init_args, (tuple, list)) else (init_args, 0.0)
+    t = rand_tensor(shape, dtype, device or _STATE["device"], scale)
+    return t + bias if bias else t
+
+
 def triton_dist_key() -> str:
     """Hash of the native sources (cache-key ingredient of the autotuner; reference: utils.py triton_dist_key)."""
     import hashlib
