@@ -1118,6 +1118,63 @@ def case_lk_shmem():
         U.nvshmem_free_tensor_sync(t)
 
 
+def case_lk_ep():
+    """Expert-parallel dispatch / combine as two DSL kernels (warp per (token, k), local slot counters, count + flag publication after a
+    grid barrier; pull-combine with fp32 accumulation): dispatch -> every expert scales its rows by (expert id + 1) -> combine, against
+    the dense formula.  Three calls reuse the phase-numbered flags; one call overflows the per-source capacity on purpose."""
+    from triton_dist.lk.kernels.ep_a2a import LkEpAllToAll
+    W, me = U.world_size(), U.rank()
+    dev = U.current_device()
+    gpu = dev.type == "cuda"
+    T, H, topk, epr = (96, 256, 4, 2) if gpu else (10, 32, 2, 2)
+    E = W * epr
+    ep = LkEpAllToAll(T, H, topk, E)
+    for it in range(3):
+        g = torch.Generator().manual_seed(100 * it + me)
+        x = (torch.randn(T, H, generator=g) * 0.5).to(torch.bfloat16).to(dev)
+        ids = torch.stack([torch.randperm(E, generator=g)[:topk] for _ in range(T)]).to(torch.int32)
+        ids[it % T, 0] = -1                                        # one dropped slot
+        w = torch.rand(T, topk, generator=g).to(dev)
+        recv_x, meta, cnt = ep.dispatch(x, ids.to(dev))
+        if gpu:
+            torch.cuda.synchronize()
+        cnt_h = cnt.cpu().tolist()
+        # what every source sends me: pairs whose expert lives here
+        all_ids = [torch.zeros(T, topk, dtype=torch.int32, device=dev) for _ in range(W)]
+        torch.distributed.all_gather(all_ids, ids.to(dev))
+        for src in range(W):
+            want = int(((all_ids[src].cpu() >= me * epr) & (all_ids[src].cpu() < (me + 1) * epr)).sum())
+            assert cnt_h[src] == want, (it, me, src, cnt_h, want)
+        # the experts: row r of source s belongs to local expert meta[s, r, 1] -> scale by (global expert id + 1)
+        ep.y_buf.zero_()
+        for src in range(W):
+            n = cnt_h[src]
+            if n:
+                scale = (meta[src, :n, 1] + me * epr + 1).to(torch.float32)[:, None]
+                ep.y_buf[src, :n] = (recv_x[src, :n].float() * scale).to(torch.bfloat16)
+        out = ep.combine(w)
+        valid = (ids >= 0).to(dev)
+        coef = (w * (ids.to(dev).clamp(min=0) + 1).float() * valid).sum(-1, keepdim=True)
+        # bf16 rounding of every expert output, then an fp32 sum: compare against the same two-step formula
+        ref = sum(((x.float() * (ids[:, k].to(dev).clamp(min=0) + 1).float()[:, None]).to(torch.bfloat16).float() * (w[:, k] * valid[:, k])[:, None])
+                  for k in range(topk))
+        _assert_close(out, ref.cpu(), 2e-2, 2e-2, f"lk ep combine iteration {it}")
+        assert coef.shape == (T, 1)
+    ep.finalize()
+    # capacity overflow: with room for one row per (source, destination) the extra pairs are dropped, not written out of bounds
+    ep2 = LkEpAllToAll(4, 32 if not gpu else 256, 1, E, cap=1)
+    x = torch.ones(4, ep2.H, dtype=torch.bfloat16, device=dev)
+    ids = torch.zeros(4, 1, dtype=torch.int32, device=dev)         # everyone routes all 4 tokens to expert 0 (rank 0)
+    _, _, cnt = ep2.dispatch(x, ids)
+    if gpu:
+        torch.cuda.synchronize()
+    if me == 0:
+        assert cnt.cpu().tolist() == [1] * W, cnt
+    assert sorted(ep2.send_slot[:4].cpu().tolist()) == [-1, -1, -1, 0]
+    U.barrier_all_on_stream()
+    ep2.finalize()
+
+
 def case_lk_ag_gemm():
     """AllGather + GEMM as ONE kernel written in the Python DSL (comm CTAs push shards + release-add flags, tcgen05 tiles acquire the
     flags of the rows they need).  GPU: the generated CUDA; emulation: the interpreter with the functional pipeline model, across ranks."""

@@ -362,3 +362,12 @@ def test_lk_shmem_two_gpus():
     from _launch import run_dist
     run_dist(["lk_shmem"], nproc=2, timeout=240)
 
+
+@pytest.mark.xfail(strict=False, reason="EP dispatch / combine written in the DSL: passes in the interpreter across processes (world 2 / 3), compiled, not yet run on hardware")
+def test_lk_ep_two_gpus():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from _launch import run_dist
+    run_dist(["lk_ep"], nproc=2, timeout=240)
+
