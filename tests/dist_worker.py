@@ -1114,6 +1114,34 @@ def case_lk_shmem():
         assert m[0] == (me // 2 if me % 2 == 0 else -1) and m[1] == m[0] and m[2] == prev * 10 + phase, (me, m)
         assert int(epoch.item()) == 3 * phase and int(sig64[0].item()) == phase, (epoch, sig64)
         U.barrier_all_on_stream()
+    # ---- the remaining scopes / spellings ----
+    n2 = 16
+    buf = U.nvshmem_create_tensor((6 * n2 + 2 * W * n2,), torch.int32)
+    got = torch.zeros(4 * n2, dtype=torch.int32, device=dev)
+    for t in (buf, sig64, misc, slots):
+        t.zero_()
+    epoch.zero_()
+    U.barrier_all_on_stream()
+    for phase in range(1, 3):
+        src2 = (torch.arange(n2, dtype=torch.int32) + 1000 * me + 10 * phase).to(dev)
+        args = (ctx, slots, epoch, buf, got, sig64, misc, src2, n2, phase)
+        if dev.type == "cuda":
+            K.shmem_selftest_scopes[1](*args)
+            torch.cuda.synchronize()
+        else:
+            K.shmem_selftest_scopes.interpret(1, *args)
+        row = lambda r: torch.arange(n2, dtype=torch.int32) + 1000 * r + 10 * phase
+        prv, pprv, nxt = (me - 1 + W) % W, (me - 2 + 2 * W) % W, (me + 1) % W
+        for reg in range(3):
+            assert torch.equal(buf[reg * n2:(reg + 1) * n2].cpu(), row(prv)), ("put", reg, phase)
+            assert torch.equal(got[reg * n2:(reg + 1) * n2].cpu(), row(pprv)), ("get", reg, phase)
+        assert torch.equal(got[3 * n2:4 * n2].cpu(), row(me)), "remote_ptr loads what I stored on my successor"
+        assert torch.equal(buf[3 * n2:4 * n2].cpu(), row(phase % W)), "broadcastmem_block"
+        assert torch.equal(buf[6 * n2:6 * n2 + W * n2].cpu(), torch.cat([row(r) for r in range(W)])), "fcollect_warp"
+        m = misc.cpu().tolist()
+        assert m[:3] == [W - 1, W, me] and int(sig64[1].item()) == phase and (me != 0 or int(sig64[0].item()) == W * phase), (m, sig64)
+        U.barrier_all_on_stream()
+    U.nvshmem_free_tensor_sync(buf)
     for t in (misc, sig64, slots, ring, bc, fc):
         U.nvshmem_free_tensor_sync(t)
 

@@ -163,3 +163,62 @@ def shmem_selftest(ctx: ll.SymmCtx, slots: ll.ptr[ll.u32], epoch: ll.ptr[ll.u32]
     shmem.quiet()
     shmem.barrier_all_block(ctx, s)
 
+
+@lk.kernel(block=64)
+def shmem_selftest_scopes(ctx: ll.SymmCtx, slots: ll.ptr[ll.u32], epoch: ll.ptr[ll.u32], buf: ll.ptr[ll.i32], got: ll.ptr[ll.i32],
+                          sig: ll.ptr[ll.u64], misc: ll.ptr[ll.i32], src: ll.ptr[ll.i32], n: ll.i32, phase: ll.u64):
+    """The remaining spellings of ``triton_dist.lk.shmem``: thread- and warp-scope puts / gets, byte-count broadcast and warp-scope
+    fcollect, team syncs in every scope, ``remote_ptr``, ``team_pe`` / ``team_n_pes``, signal ADD and the other comparisons.
+    ``buf``: symmetric int32 [6 * n + 2 * W * n]; ``got``: local int32 [4 * n]."""
+    s = shmem.make_sync(slots, epoch)
+    world = shmem.team_world(ctx)
+    W = shmem.n_pes(ctx)
+    me = shmem.my_pe(ctx)
+    nxt = (me + 1) % W
+    prv = (me + W - 1) % W
+    tid = ll.threadIdx.x
+    # region 0: thread-scope put to the successor; region 1: warp-scope nbi put; region 2: block-scope rma put
+    if tid == 0:
+        shmem.putmem(ctx, buf, src, n * 4, nxt)
+    if tid < 32:
+        shmem.putmem_nbi_warp(ctx, buf + n, src, n * 4, nxt)
+    shmem.putmem_rma_block(ctx, buf + 2 * n, src, n * 4, nxt)
+    shmem.fence()
+    shmem.sync_all_block(ctx, s)                                        # everybody's three regions are filled
+    # gets in the three scopes read the PREDECESSOR's copies of what its predecessor wrote
+    if tid == 0:
+        shmem.getmem(ctx, got, buf, n * 4, prv)
+    if tid < 32:
+        shmem.getmem_nbi_warp(ctx, got + n, buf + n, n * 4, prv)
+    shmem.getmem_block(ctx, got + 2 * n, buf + 2 * n, n * 4, prv)
+    rp = shmem.remote_ptr(ctx, buf, nxt)                                # plain loads through the peer mapping
+    if tid < n:
+        got[3 * n + tid] = rp[tid]
+    # collectives in byte-count / warp spellings
+    shmem.broadcastmem_block(ctx, world, s, buf + 3 * n, src, n * 4, ll.i32(phase % ll.u64(W)))
+    if tid < 32:
+        shmem.fcollect_warp(ctx, world, s, buf + 6 * n, src, n)
+        shmem.team_sync_warp(ctx, world, s)
+        shmem.barrier_warp(ctx, world, s)
+        shmem.sync_all_warp(ctx, s)
+        shmem.barrier_all_warp(ctx, s)
+    if tid == 0:
+        shmem.team_sync(ctx, world, s)
+        shmem.barrier(ctx, world, s)
+        shmem.sync_all(ctx, s)
+        shmem.barrier_all(ctx, s)
+        shmem.signal_op(ctx, sig, 1, shmem.SIGNAL_ADD, 0)              # everyone adds 1 on PE 0
+        shmem.signal_op(ctx, sig + 1, phase, shmem.SIGNAL_SET, nxt)
+        shmem.signal_wait_until(sig + 1, shmem.CMP_EQ, phase)
+        shmem.signal_wait_until(sig + 1, shmem.CMP_NE, phase + 1)
+        shmem.signal_wait_until(sig + 1, shmem.CMP_GT, phase - 1)
+        shmem.signal_wait_until(sig + 1, shmem.CMP_LE, phase)
+        shmem.signal_wait_until(sig + 1, shmem.CMP_LT, phase + 1)
+        if me == 0:
+            shmem.signal_wait_until(sig, shmem.CMP_GE, phase * ll.u64(W))
+        misc[0] = shmem.team_pe(world, W - 1)
+        misc[1] = shmem.team_n_pes(world)
+        misc[2] = shmem.team_translate_pe(world, me, world)
+    shmem.team_sync_block(ctx, world, s)
+    shmem.barrier_block(ctx, world, s)
+
