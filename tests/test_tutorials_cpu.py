@@ -10,7 +10,8 @@ from _launch import ROOT, free_port
 
 @pytest.mark.parametrize("script,expect", [("01_notify_wait.py", "rounds OK"), ("03_ag_gemm_gemm_rs.py", "ag_gemm -> gemm_rs OK"),
                                            ("06_sequence_parallel_attention.py", "gemm + all-to-all"), ("09_mega_ep_and_fused_moe.py", "fused MoE tutorial OK"),
-                                           ("10_kernel_dsl.py", "kernel DSL tutorial OK")])
+                                           ("10_kernel_dsl.py", "kernel DSL tutorial OK"),
+                                           ("11_distributed_kernels_in_python.py", "distributed DSL kernels tutorial OK")])
 def test_tutorial(script, expect):
     env = dict(os.environ, TD_FORCE_HOST_BACKEND="1", CUDA_VISIBLE_DEVICES="", TD_SYMM_HEAP_SIZE="256m", OMP_NUM_THREADS="2",
                PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))

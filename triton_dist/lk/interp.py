@@ -217,6 +217,21 @@ def warp_collect(value) -> list:
 
 
 def atomic_rmw(p: Ptr, i, fn):
+    """``old = p[i]; p[i] = fn(old); return old`` atomically.  32-bit integers in torch tensors go through a hardware CAS loop
+    (libtd_host): the word may live on the emulation backend's shared-memory heap, where the other parties are other PROCESSES and a
+    Python lock would protect nothing.  Everything else (floats, 64-bit, numpy shared arrays) is only ever contended by the threads
+    of this interpreter and takes the lock."""
+    base = p.base
+    if hasattr(base, "data_ptr") and base.element_size() == 4 and not base.dtype.is_floating_point:
+        from .. import _C
+        lib = _C.host_lib()
+        addr = base.data_ptr() + (p.off + int(i)) * 4
+        signed = base.dtype.is_signed
+        while True:
+            raw = int(lib.tdh_ld_acquire32(addr))
+            old = raw - (1 << 32) if signed and raw >> 31 else raw
+            if int(lib.tdh_atomic_cas32(addr, raw, int(fn(old)) & 0xFFFFFFFF)) == raw:
+                return old
     with _atomic_lock:
         old = p[i]
         p[i] = fn(old)
