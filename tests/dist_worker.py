@@ -1352,6 +1352,42 @@ def case_ep_metadata():
     U.barrier_all_host()
 
 
+def case_mega_paged():
+    """Megakernel decode step through a paged KV cache (block-table task types) with TP-sharded heads, vs the layer-by-layer model on a
+    dense cache holding the same tokens."""
+    from triton_dist.models import AutoLLM, KV_Cache, ModelConfig
+    from triton_dist.mega_kernel import MegaDenseModel
+    dev = U.current_device()
+    W, me = U.world_size(), U.rank()
+    big = dev.type == "cuda"
+    dtype = torch.bfloat16 if big else torch.float32
+    cfg = ModelConfig(model_name="tiny-dense", max_length=64, dtype=dtype, rank=me, world_size=W)
+    m = AutoLLM.from_pretrained(cfg, U.get_triton_dist_world())
+    m.set_fwd("torch")
+    B = 2
+    kv = KV_Cache(m.num_layers, B, 64, m.num_key_value_heads, m.head_dim, dtype, W, dev)
+    g = torch.Generator(device="cpu").manual_seed(3 + me)
+    kv.k_cache.copy_((torch.randn(kv.k_cache.shape, generator=g) * 0.5).to(dtype)); kv.v_cache.copy_((torch.randn(kv.v_cache.shape, generator=g) * 0.5).to(dtype))
+    kv.kv_offset.fill_(9)
+    from triton_dist.models import PagedKVCache
+    L = int(kv.kv_offset[0])
+    paged = PagedKVCache(PAGE_SIZE=8, num_layers=m.num_layers, batch_size=B, max_length=64, num_kv_heads=kv.kv_heads, head_dim=m.head_dim,
+                         dtype=dtype, device=dev, seed=11 + me)
+    for li in range(m.num_layers):
+        k, v = kv.layer(li)
+        paged.append(li, k[:, :L], v[:, :L])
+    paged.inc_offset(L)
+    mega_p = MegaDenseModel(m, B, paged, attn_splits=2)
+    for step in range(2):
+        ids = torch.randint(0, 1000, (B, 1), generator=torch.Generator().manual_seed(70 + step)).to(dev)
+        ref = m.inference(ids, kv.kv_offset.to(torch.int64)[:, None], kv)
+        out = mega_p.mega_forward(ids)
+        _assert_close(out, ref, 6e-2 if big else 1e-4, 6e-2 if big else 1e-4, f"megakernel paged logits step {step}")
+        kv.inc_offset(1); paged.inc_offset(1)
+    U.barrier_all_host()
+    mega_p.finalize()
+
+
 def case_mega_server():
     """The megakernel text-generation service across ranks: rank 0 serves a socket from a thread and broadcasts every request, the other
     ranks follow; per-op prefill, token-by-token prefill and the paged KV cache must generate the same tokens (greedy and seeded)."""
