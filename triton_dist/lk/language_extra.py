@@ -52,7 +52,20 @@ def _elem(cg, v, node):
 
 
 def _reg(e: Scalar):
-    return ("l" if e.bits == 64 else ("f" if e.is_float else "r")), ("b" if not e.is_float else "b") + str(e.bits)
+    """(asm constraint letter, typeless PTX suffix) of a 32- / 64-bit scalar."""
+    if e.is_float:
+        return ("d" if e.bits == 64 else "f"), "b" + str(e.bits)
+    return ("l" if e.bits == 64 else "r"), "b" + str(e.bits)
+
+
+def _helper(cg, name: str, src: str) -> str:
+    """Define a ``__device__`` helper once per generated translation unit (calls stay plain expressions: no GNU statement expressions,
+    which nvcc's front end does not accept as operands of another asm statement)."""
+    key = ("language_extra", name)
+    if key not in cg.module.device_keys:
+        cg.module.device_keys[key] = (name, T.void)
+        cg.module.device_src.append(src)
+    return name
 
 
 def _emit_ld(cg, args, kwargs, node):
@@ -65,8 +78,10 @@ def _emit_ld(cg, args, kwargs, node):
         if sem not in ("relaxed", "acquire"):
             raise CompileError("language_extra.ld: semantic is relaxed or acquire", node, cg)
         q = f"ld.{sem}.{scope}.global"
-    p = cg.rvalue(args[0])
-    return Val(f'({{ {e.cname} v_; asm volatile("{q}.{suffix} %0, [%1];" : "={c}"(v_) : "l"({p}) : "memory"); v_; }})', e)
+    fn = _helper(cg, f"le_ld_{sem}_{scope}_{e.name}",
+                 f'__device__ __forceinline__ {e.cname} le_ld_{sem}_{scope}_{e.name}(const {e.cname}* p) {{ {e.cname} v; '
+                 f'asm volatile("{q}.{suffix} %0, [%1];" : "={c}"(v) : "l"(p) : "memory"); return v; }}')
+    return Val(f"{fn}({cg.rvalue(args[0])})", e)
 
 
 def _emit_st(cg, args, kwargs, node):
@@ -75,37 +90,49 @@ def _emit_st(cg, args, kwargs, node):
     c, suffix = _reg(e)
     if sem not in ("relaxed", "release"):
         raise CompileError("language_extra.st: semantic is relaxed or release", node, cg)
-    p, v = cg.rvalue(args[0]), cg.rvalue(args[1])
-    return Val(f'asm volatile("st.{sem}.{scope}.global.{suffix} [%0], %1;" ::"l"({p}), "{c}"(({e.cname})({v})) : "memory")', T.void)
+    fn = _helper(cg, f"le_st_{sem}_{scope}_{e.name}",
+                 f'__device__ __forceinline__ void le_st_{sem}_{scope}_{e.name}({e.cname}* p, {e.cname} v) {{ '
+                 f'asm volatile("st.{sem}.{scope}.global.{suffix} [%0], %1;" ::"l"(p), "{c}"(v) : "memory"); }}')
+    return Val(f"{fn}({cg.rvalue(args[0])}, ({e.cname})({cg.rvalue(args[1])}))", T.void)
+
+
+def _arith_type(e: Scalar) -> str:
+    # 64-bit signed adds are issued as .u64 (two's complement: the same bits; PTX has no atom.add.s64)
+    return ("f" if e.is_float else ("s" if e.kind == "i" and e.bits == 32 else "u")) + str(e.bits)
 
 
 def _emit_atomic(op):
     def emit(cg, args, kwargs, node):
         n_pos = 3 if op == "cas" else 2
         scope, sem = _scope_sem(cg, args, kwargs, node, n_pos, "gpu", "relaxed")
+        if sem not in ("relaxed", "acquire", "release", "acq_rel"):
+            raise CompileError(f"language_extra.atomic_{op}: semantic is relaxed / acquire / release / acq_rel", node, cg)
         e = _elem(cg, args[0], node)
         c, _ = _reg(e)
-        ty = ("f" if e.is_float else ("s" if e.kind == "i" and op != "cas" else ("u" if op != "cas" else "b"))) + str(e.bits)
-        if op == "cas":
-            ty = "b" + str(e.bits)
         p = cg.rvalue(args[0])
         if op == "cas":
-            a, b = cg.rvalue(args[1]), cg.rvalue(args[2])
-            asm = f'"atom.{sem}.{scope}.global.cas.{ty} %0, [%1], %2, %3;" : "={c}"(v_) : "l"({p}), "{c}"(({e.cname})({a})), "{c}"(({e.cname})({b}))'
-        else:
-            a = cg.rvalue(args[1])
-            asm = f'"atom.{sem}.{scope}.global.{op}.{ty} %0, [%1], %2;" : "={c}"(v_) : "l"({p}), "{c}"(({e.cname})({a}))'
-        return Val(f"({{ {e.cname} v_; asm volatile({asm} : \"memory\"); v_; }})", e)
+            fn = _helper(cg, f"le_cas_{sem}_{scope}_{e.name}",
+                         f'__device__ __forceinline__ {e.cname} le_cas_{sem}_{scope}_{e.name}({e.cname}* p, {e.cname} cmp, {e.cname} val) {{ {e.cname} v; '
+                         f'asm volatile("atom.{sem}.{scope}.global.cas.b{e.bits} %0, [%1], %2, %3;" : "={c}"(v) : "l"(p), "{c}"(cmp), "{c}"(val) : "memory"); '
+                         f'return v; }}')
+            return Val(f"{fn}({p}, ({e.cname})({cg.rvalue(args[1])}), ({e.cname})({cg.rvalue(args[2])}))", e)
+        fn = _helper(cg, f"le_atom_{op}_{sem}_{scope}_{e.name}",
+                     f'__device__ __forceinline__ {e.cname} le_atom_{op}_{sem}_{scope}_{e.name}({e.cname}* p, {e.cname} a) {{ {e.cname} v; '
+                     f'asm volatile("atom.{sem}.{scope}.global.{op}.{_arith_type(e)} %0, [%1], %2;" : "={c}"(v) : "l"(p), "{c}"(a) : "memory"); return v; }}')
+        return Val(f"{fn}({p}, ({e.cname})({cg.rvalue(args[1])}))", e)
     return emit
 
 
 def _emit_red(cg, args, kwargs, node):
     scope, sem = _scope_sem(cg, args, kwargs, node, 2, "gpu", "release")
+    if sem not in ("relaxed", "release"):
+        raise CompileError("language_extra.red_release: semantic is relaxed or release", node, cg)
     e = _elem(cg, args[0], node)
     c, _ = _reg(e)
-    ty = ("f" if e.is_float else ("s" if e.kind == "i" else "u")) + str(e.bits)
-    p, v = cg.rvalue(args[0]), cg.rvalue(args[1])
-    return Val(f'asm volatile("red.{sem}.{scope}.global.add.{ty} [%0], %1;" ::"l"({p}), "{c}"(({e.cname})({v})) : "memory")', T.void)
+    fn = _helper(cg, f"le_red_{sem}_{scope}_{e.name}",
+                 f'__device__ __forceinline__ void le_red_{sem}_{scope}_{e.name}({e.cname}* p, {e.cname} a) {{ '
+                 f'asm volatile("red.{sem}.{scope}.global.add.{_arith_type(e)} [%0], %1;" ::"l"(p), "{c}"(a) : "memory"); }}')
+    return Val(f"{fn}({cg.rvalue(args[0])}, ({e.cname})({cg.rvalue(args[1])}))", T.void)
 
 
 def _emit_fence(cg, args, kwargs, node):
@@ -177,7 +204,13 @@ def _interp_wait_eq(p, value, scope="sys", semantic="acquire"):
     ll._interp_wait(p, 1, value, False)
 
 
-wait_eq = _i("le_wait_eq", None, "({{ while (td::ptx::ld_acquire_sys({0}) != (uint32_t)({1})) {{}} }})", 2, interp=_interp_wait_eq,
+def _emit_wait_eq(cg, args, kwargs, node):
+    fn = _helper(cg, "le_wait_eq_u32", "__device__ __forceinline__ void le_wait_eq_u32(const uint32_t* p, uint32_t v) "
+                                       "{ while (td::ptx::ld_acquire_sys(p) != v) {} }")
+    return Val(f"{fn}({cg.rvalue(args[0])}, (uint32_t)({cg.rvalue(args[1])}))", T.void)
+
+
+wait_eq = Intrinsic("le_wait_eq", None, emit=_emit_wait_eq, interp=_interp_wait_eq,
              doc="wait_eq(ptr, value): the calling thread spins (acquire, system scope) until *ptr == value")
 
 
