@@ -610,6 +610,32 @@ def case_tp_e2e():
         U.barrier_all_host()
 
 
+def case_engine_mega():
+    """``Engine.serve(backend="mega")``: prefill per-op, then every decode step is one persistent-kernel launch on the engine's own model and
+    KV cache; greedy tokens must match the torch backend.  MoE models are rejected."""
+    from triton_dist.models import Engine, ModelConfig
+    dev = U.current_device()
+    W, me = U.world_size(), U.rank()
+    big = dev.type == "cuda"
+    cfg = ModelConfig(model_name="tiny-dense", max_length=64, dtype=torch.bfloat16 if big else torch.float32, rank=me, world_size=W)
+    eng = Engine(cfg, temperature=0.0)
+    ids = torch.randint(0, 1000, (3, 5), generator=torch.Generator().manual_seed(9))
+    ref = eng.serve(ids, 6, backend="torch", use_cuda_graph=False)
+    for graph in ((False, True) if big else (False,)):
+        out = eng.serve(ids, 6, backend="mega", use_cuda_graph=graph)
+        agree = (out == ref).float().mean().item()
+        assert agree >= (0.7 if big else 1.0), (graph, agree, out.tolist(), ref.tolist())
+    eng.finalize()
+    moe = Engine(ModelConfig(model_name="tiny-moe", max_length=64, dtype=cfg.dtype, rank=me, world_size=W), temperature=0.0)
+    try:
+        moe.serve(ids, 2, backend="mega", use_cuda_graph=False)
+        raise AssertionError("the mega backend must reject MoE models")
+    except ValueError:
+        pass
+    U.barrier_all_host()
+    moe.finalize()
+
+
 def case_ep_ll():
     """EP low-latency dispatch + combine vs a gathered golden (reference: test_ep_ll_a2a.py)."""
     from triton_dist.ops import ep_a2a as EP

@@ -380,3 +380,12 @@ def test_mega_paged_two_gpus():
     from _launch import run_dist
     run_dist(["mega_paged"], nproc=2, timeout=240)
 
+
+@pytest.mark.xfail(strict=False, reason="Engine.serve(backend='mega'): composition of validated parts, matches the torch backend on the emulation backend, not yet run on hardware")
+def test_engine_mega_backend_two_gpus():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from _launch import run_dist
+    run_dist(["engine_mega"], nproc=2, timeout=300)
+

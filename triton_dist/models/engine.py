@@ -41,8 +41,20 @@ class Engine:
                                  self.world_size, self.device)
 
     def set_backend(self, backend: str, bsz: int, ar_method=comm.AllReduceMethod.Unknown):
-        """torch | triton_dist | triton_dist_AR | triton_dist_gemm_ar"""
+        """torch | triton_dist | triton_dist_AR | triton_dist_gemm_ar | mega (the whole decode step as one persistent kernel:
+        ``triton_dist.mega_kernel.MegaDenseModel`` on this engine's model and KV cache; dense models, batch <= 64)"""
         self.backend = backend
+        if backend == "mega":
+            from ..mega_kernel import MegaDenseModel
+            from .dense import DenseLLM
+            if not isinstance(self.model, DenseLLM) or type(self.model).__name__ != "DenseLLM":
+                raise ValueError("backend='mega' needs a dense model (the megakernel task graph has no MoE tasks)")
+            self.model.set_fwd("torch")
+            if getattr(self, "mega", None) is not None:
+                self.mega.finalize()
+            self.mega = MegaDenseModel(self.model, bsz, self.kv_cache)
+            U.barrier_all_host()
+            return
         self.model.set_fwd(backend)
         if backend == "triton_dist":
             assert bsz % self.world_size == 0, "triton_dist (AG+RS) mode shards the batch over ranks"
@@ -54,6 +66,8 @@ class Engine:
         U.barrier_all_host()
 
     def _decode_step(self, ids: torch.Tensor, pos: torch.Tensor) -> torch.Tensor:
+        if self.backend == "mega":
+            return self.mega.mega_forward(ids)          # positions: the KV cache's device-side offsets
         return self.model.inference(ids, pos, self.kv_cache)
 
     def _init_cuda_graph(self, static_ids: torch.Tensor, static_pos: torch.Tensor):
@@ -162,4 +176,7 @@ class Engine:
 
     def finalize(self):
         self.graph = None
+        if getattr(self, "mega", None) is not None:
+            self.mega.finalize()
+            self.mega = None
         self.model.finalize()
