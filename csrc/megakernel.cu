@@ -333,11 +333,14 @@ TD_DEVICE void linear_mma(const MKParams& p, const Task& t, uint8_t* smem) {
   __syncthreads();        // the next task may restage smem
 }
 
+template <bool kTensorCore>
 TD_DEVICE void task_linear(const MKParams& p, const Task& t, uint8_t* smem) {
-  if (p.B > kMaxB) {
-    if (t.a[6] > 8 * (kMKThreads / 32)) linear_mma<2>(p, t, smem);      // more than 8 column groups: two per warp
-    else linear_mma<1>(p, t, smem);
-    return;
+  if constexpr (kTensorCore) {
+    if (p.B > kMaxB) {
+      if (t.a[6] > 8 * (kMKThreads / 32)) linear_mma<2>(p, t, smem);      // more than 8 column groups: two per warp
+      else linear_mma<1>(p, t, smem);
+      return;
+    }
   }
   const uint4* x = (const uint4*)p.ptrs[t.a[0]];
   const uint4* W = (const uint4*)p.ptrs[t.a[1]];
@@ -771,9 +774,10 @@ TD_DEVICE void prefetch_linear_weights(const MKParams& p, const Task& t) {
   for (size_t off = 0; off < bytes; off += 65536) ptx::prefetch_l2_bulk(W + off, static_cast<uint32_t>(min(bytes - off, size_t(65536))));
 }
 
-// kPrefill = true adds the FLASH_ATTN (prefill attention) task to the interpreter; the decode-only instantiation is register-for-register
-// the kernel without it (the prefill task's 96 accumulators would otherwise raise the whole switch to the 255-register cap).
-template <bool kPrefill>
+// Instantiations of the interpreter (kVariant bit 0: prefill task types FLASH_ATTN / QKROPE_SPLIT; bit 1: tensor-core LINEAR body for
+// 9..64 tokens; bit 2: paged-KV task types).  Variant 0 -- decode with 1..8 tokens -- contains exactly the task bodies that have run on hardware; the prefill
+// task's 96 accumulators and the mma.sync LINEAR body would otherwise shape the register allocation of the whole switch.
+template <int kVariant>
 __global__ void __launch_bounds__(kMKThreads, 1) mega_kernel(const MKParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ float red[32];
@@ -809,13 +813,13 @@ __global__ void __launch_bounds__(kMKThreads, 1) mega_kernel(const MKParams p) {
     }
     switch (t.type) {
       case T_RMSNORM: task_rmsnorm(p, t, red); break;
-      case T_LINEAR: task_linear(p, t, smem); break;
+      case T_LINEAR: task_linear<(kVariant & 2) != 0>(p, t, smem); break;
       case T_QKROPE: task_qkrope<0>(p, t); break;
       case T_ATTN: task_attn<false>(p, t, smem); break;
-      case T_QKROPE_PAGED: task_qkrope<1>(p, t); break;
-      case T_QKROPE_SPLIT: if constexpr (kPrefill) task_qkrope<2>(p, t); break;
-      case T_ATTN_PAGED: task_attn<true>(p, t, smem); break;
-      case T_FLASH_ATTN: if constexpr (kPrefill) task_flash_attn(p, t, smem); break;
+      case T_QKROPE_PAGED: if constexpr ((kVariant & 4) != 0) task_qkrope<1>(p, t); break;
+      case T_QKROPE_SPLIT: if constexpr ((kVariant & 1) != 0) task_qkrope<2>(p, t); break;
+      case T_ATTN_PAGED: if constexpr ((kVariant & 4) != 0) task_attn<true>(p, t, smem); break;
+      case T_FLASH_ATTN: if constexpr ((kVariant & 1) != 0) task_flash_attn(p, t, smem); break;
       case T_ATTN_COMBINE: task_attn_combine(p, t); break;
       case T_SILU_MUL: task_silu_mul(p, t); break;
       case T_ADD: task_add(p, t); break;
@@ -857,14 +861,17 @@ TD_API int td_mega_launch(const TdMegaArgs* a, void* stream) {
   p.sb = (uint32_t*)a->sb; p.epoch = (uint32_t*)a->epoch;
   p.symm.rank = (int)a->symm.rank; p.symm.world = (int)a->symm.world; p.symm.base = a->symm.base; p.symm.stride = a->symm.stride; p.symm.mc_base = a->symm.mc_base;
   p.B = (int)a->B; p.dynamic = (int)(a->dynamic & 1); p.num_tasks = (int)a->num_tasks;
-  const bool prefill = (a->dynamic & 2) != 0;        // bit 1 of `dynamic`: the task list contains FLASH_ATTN tasks
-  static long long smem_set[2] = {0, 0};
-  if (a->smem_bytes > smem_set[prefill]) {
-    TD_CUDA_CHECK(cudaFuncSetAttribute(prefill ? mega_kernel<true> : mega_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a->smem_bytes));
-    smem_set[prefill] = a->smem_bytes;
+  // bit 1 of `dynamic`: the task list contains prefill task types; batches above 8 tokens need the tensor-core LINEAR body
+  const int variant = ((a->dynamic & 2) ? 1 : 0) | (a->B > kMaxB ? 2 : 0) | ((a->dynamic & 4) ? 4 : 0);      // bit 2 of `dynamic`: paged-KV tasks
+  using KernelFn = void (*)(const MKParams);
+  static const KernelFn kernels[8] = {mega_kernel<0>, mega_kernel<1>, mega_kernel<2>, mega_kernel<3>,
+                                      mega_kernel<4>, mega_kernel<5>, mega_kernel<6>, mega_kernel<7>};
+  static long long smem_set[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (a->smem_bytes > smem_set[variant]) {
+    TD_CUDA_CHECK(cudaFuncSetAttribute(kernels[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a->smem_bytes));
+    smem_set[variant] = a->smem_bytes;
   }
-  if (prefill) mega_kernel<true><<<(int)a->grid, kMKThreads, (size_t)a->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(p);
-  else mega_kernel<false><<<(int)a->grid, kMKThreads, (size_t)a->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  kernels[variant]<<<(int)a->grid, kMKThreads, (size_t)a->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   TD_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

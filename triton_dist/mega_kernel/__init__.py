@@ -354,8 +354,11 @@ class ModelBuilder:
         a.tasks, a.queue_off, a.ptrs = self.task_tensor.data_ptr(), self.queue_off.data_ptr(), self.ptr_tensor.data_ptr()
         a.sb, a.epoch = self.sb.data_ptr(), self.epoch.data_ptr()
         a.B, a.grid, a.smem_bytes = self.B, self.num_sms, self.max_smem
-        # bit 1 selects the kernel instantiation that also interprets the prefill task types (the decode-only one keeps its registers)
-        a.dynamic, a.num_tasks = int(self.schedule_policy == "dynamic") | (2 if getattr(self, "has_prefill", False) else 0), len(self.tasks)
+        # bits 1 / 2 select the kernel instantiation that also interprets the prefill / paged-KV task types (the plain decode
+        # instantiation contains only the task bodies that have run on hardware)
+        has_paged = any(t.type in (T_QKROPE_PAGED, T_ATTN_PAGED) for t in self.tasks)
+        a.dynamic = int(self.schedule_policy == "dynamic") | (2 if getattr(self, "has_prefill", False) else 0) | (4 if has_paged else 0)
+        a.num_tasks = len(self.tasks)
         _C.check(_C.cuda_lib().td_mega_launch(C.byref(a), C.c_void_p((stream or torch.cuda.current_stream()).cuda_stream)), "td_mega_launch")
 
     # emulation: interpret the task list in program order with torch ops on the same buffers
