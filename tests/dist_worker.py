@@ -83,20 +83,6 @@ def case_allgather():
         assert torch.equal(bufs[me].cpu().view(-1), ref.cpu())
         assert torch.all(flags[me][:W].cpu() == it)
         U.barrier_all_on_stream()
-    # ring producers (1-D: W-1 hops; 2-D: ring inside a group + across groups), same buffers, later signal values
-    from triton_dist.ops.allgather import AllGatherMethod, cp_engine_producer_all_gather
-    sig = 4
-    for method in (AllGatherMethod.Ring1D_IntraNode, AllGatherMethod.Ring2D_IntraNode):
-        for it in range(3):
-            local = torch.randn(64, 32, device=dev)
-            cp_engine_producer_all_gather(me, W, local, bufs, flags, signal_value=sig, method=method)
-            if dev.type == "cuda":
-                torch.cuda.synchronize()
-            ref = torch.empty(64 * W * 32, device=dev)
-            dist.all_gather_into_tensor(ref, local.view(-1), group=U.get_triton_dist_world())
-            assert torch.equal(bufs[me].cpu().view(-1), ref.cpu()), (method, it)
-            U.barrier_all_host()                               # nobody overwrites a buffer a peer is still checking
-            sig += 1
     ctx.finalize()
 
 
@@ -781,18 +767,6 @@ def case_sp_pp():
     z = uly.post_attn_a2a(y)
     assert torch.equal(z.cpu(), x.cpu())
     uly.finalize()
-    # q, k, v in ONE packed all-to-all
-    from triton_dist.parallel.sp import UlyssesQKVPackAllToAll
-    Hkv_u = W
-    pk = UlyssesQKVPackAllToAll(S_l, H, Hkv_u, D, dtype, me, W)
-    kfull = torch.randn(S_l * W, Hkv_u, D, generator=g).to(dtype).to(dev)
-    vfull = torch.randn(S_l * W, Hkv_u, D, generator=g).to(dtype).to(dev)
-    sl = slice(me * S_l, (me + 1) * S_l)
-    for _ in range(3):
-        q2, k2, v2 = pk(full[sl].contiguous(), kfull[sl].contiguous(), vfull[sl].contiguous())
-        assert torch.equal(q2.cpu(), full[:, me * (H // W):(me + 1) * (H // W)].cpu())
-        assert torch.equal(k2.cpu(), kfull[:, me:me + 1].cpu()) and torch.equal(v2.cpu(), vfull[:, me:me + 1].cpu())
-    pk.finalize()
     # ---- SP flash decode ----
     B, Hq, Hkv, L_l = 2, 4, 1, 40
     q = torch.randn(B, Hq, D, generator=g).to(dtype).to(dev)
@@ -1376,6 +1350,51 @@ def case_ep_metadata():
         assert int(n_recv[r]) == run
     assert int(n_in[me]) == T * topk
     U.barrier_all_host()
+
+
+def case_allgather_ring():
+    """Ring copy-engine all-gather producers (1-D: W-1 hops; 2-D: ring inside a group + across groups) on the reference's buffer / flag
+    contract (allgather.py:127-200)."""
+    from triton_dist.ops.allgather import create_allgather_buffers
+    W, me = U.world_size(), U.rank()
+    dev = U.current_device()
+    bufs, flags = create_allgather_buffers(64 * W, 32, torch.float32)
+    U.barrier_all_on_stream()
+    from triton_dist.ops.allgather import AllGatherMethod, cp_engine_producer_all_gather
+    sig = 4
+    for method in (AllGatherMethod.Ring1D_IntraNode, AllGatherMethod.Ring2D_IntraNode):
+        for it in range(3):
+            local = torch.randn(64, 32, device=dev)
+            cp_engine_producer_all_gather(me, W, local, bufs, flags, signal_value=sig, method=method)
+            if dev.type == "cuda":
+                torch.cuda.synchronize()
+            ref = torch.empty(64 * W * 32, device=dev)
+            dist.all_gather_into_tensor(ref, local.view(-1), group=U.get_triton_dist_world())
+            assert torch.equal(bufs[me].cpu().view(-1), ref.cpu()), (method, it)
+            U.barrier_all_host()                               # nobody overwrites a buffer a peer is still checking
+            sig += 1
+
+
+def case_ulysses_pack():
+    """Ulysses q, k, v in ONE packed all-to-all (``UlyssesQKVPackAllToAll``): seq-sharded [S/W, H, D] -> head-sharded [S, H/W, D]."""
+    W, me = U.world_size(), U.rank()
+    dev = U.current_device()
+    big = dev.type == "cuda"
+    dtype = torch.bfloat16 if big else torch.float32
+    g = torch.Generator().manual_seed(5)
+    S_l, H, D = 8, 2 * W, 128
+    full = torch.randn(S_l * W, H, D, generator=g).to(dtype).to(dev)
+    from triton_dist.parallel.sp import UlyssesQKVPackAllToAll
+    Hkv_u = W
+    pk = UlyssesQKVPackAllToAll(S_l, H, Hkv_u, D, dtype, me, W)
+    kfull = torch.randn(S_l * W, Hkv_u, D, generator=g).to(dtype).to(dev)
+    vfull = torch.randn(S_l * W, Hkv_u, D, generator=g).to(dtype).to(dev)
+    sl = slice(me * S_l, (me + 1) * S_l)
+    for _ in range(3):
+        q2, k2, v2 = pk(full[sl].contiguous(), kfull[sl].contiguous(), vfull[sl].contiguous())
+        assert torch.equal(q2.cpu(), full[:, me * (H // W):(me + 1) * (H // W)].cpu())
+        assert torch.equal(k2.cpu(), kfull[:, me:me + 1].cpu()) and torch.equal(v2.cpu(), vfull[:, me:me + 1].cpu())
+    pk.finalize()
 
 
 def case_mega_paged():

@@ -11,7 +11,7 @@ def _ngpu():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-@pytest.mark.parametrize("case", ["primitives", "allgather", "allreduce", "a2a", "ag_gemm", "gemm_rs", "gemm_ar", "gemm_q8", "gemm_a2a", "moe", "moe_rs", "moe_staged", "tp_e2e", "ep_ll", "ep_normal", "ep_mega", "sp_pp", "ep_moe", "mega"])
+@pytest.mark.parametrize("case", ["primitives", "allgather", "allreduce", "ag_gemm", "gemm_rs", "gemm_ar", "gemm_q8", "gemm_a2a", "moe", "moe_rs", "moe_staged", "tp_e2e", "ep_ll", "ep_normal", "ep_mega", "sp_pp", "ep_moe", "mega"])
 def test_gpu_world2(case):
     if _ngpu() < 2:
         pytest.skip("needs >= 2 GPUs")

@@ -389,3 +389,13 @@ def test_engine_mega_backend_two_gpus():
     from _launch import run_dist
     run_dist(["engine_mega"], nproc=2, timeout=300)
 
+
+@pytest.mark.xfail(strict=False, reason="host-level compositions written after the last full hardware session (emulation-tested): variable all-to-all cases, ring copy-engine all-gather producers, packed Ulysses all-to-all")
+@pytest.mark.parametrize("case", ["a2a", "allgather_ring", "ulysses_pack"])
+def test_late_host_level_cases_two_gpus(case):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from _launch import run_dist
+    run_dist([case], nproc=2, timeout=240)
+
