@@ -452,12 +452,12 @@ def test_flash_attention_on_mma_sync_in_the_interpreter():
     causal and full masks, the soft cap, and the reinterpreting ``ll.ptr_cast`` the epilogue stores through."""
     from triton_dist.lk.kernels.flash_mma import make_flash_mma, run_flash_mma
     torch.manual_seed(0)
-    B, S, Hq, Hkv = 1, 66, 2, 1
+    B, S, Hq, Hkv = 1, 66, 1, 1
     qkv = torch.randn(B, S, Hq + 2 * Hkv, 128).bfloat16()
     q, k, v = qkv[:, :, :Hq], qkv[:, :, Hq:Hq + Hkv], qkv[:, :, Hq + Hkv:]
     o = run_flash_mma(q, k, v, causal=True, threads=32, interpret=True)
     torch.testing.assert_close(o.float(), _attn_ref(q, k, v, True, 128 ** -0.5, 0.0), atol=2e-2, rtol=2e-2)
-    B, S, Hq, Hkv = 2, 20, 1, 1
+    B, S, Hq, Hkv = 1, 20, 2, 1                     # GQA: two query heads share one KV head
     q, k, v = (torch.randn(B, S, Hq, 128) * 2).bfloat16(), torch.randn(B, S, Hkv, 128).bfloat16(), torch.randn(B, S, Hkv, 128).bfloat16()
     o = run_flash_mma(q, k, v, causal=False, softcap=5.0, sm_scale=0.2, threads=32, interpret=True)
     torch.testing.assert_close(o.float(), _attn_ref(q, k, v, False, 0.2, 5.0), atol=2e-2, rtol=2e-2)
