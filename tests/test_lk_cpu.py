@@ -532,3 +532,19 @@ def test_language_extra_and_stdlib_in_dsl_kernels(tmp_path):
     assert len(infos) == 1 and os.path.exists(infos[0]["so"]) and "lk_launch_saxpy_for_aot" in open(infos[0]["header"]).read()
     A.AOT_REGISTRY.pop("saxpy_aot")
 
+
+def test_dsl_microbenchmarks_compile_and_check_out_in_the_interpreter():
+    """The micro-benchmark suite written in the DSL (triton_dist/lk/bench: FMA / SFU / mma.sync throughput, FMA and pointer-chase
+    latencies, sync latency, global copy / read, shared-memory bank conflicts, shuffles, integer IPC, occupancy probe): every kernel
+    cross-compiles for sm_100a and, at toy sizes in the interpreter, produces the closed-form output its runner checks."""
+    from triton_dist.lk.bench import BENCHES, KERNELS, run_all
+    assert len(KERNELS) == 13 and set(BENCHES) == set(KERNELS)
+    for k in KERNELS.values():
+        k.compile()
+    res = run_all(interpret=True)
+    assert set(res) == set(BENCHES) and all(r["ok"] for r in res.values()), {n: r["ok"] for n, r in res.items()}
+    sass = subprocess.run([shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump", "-sass", KERNELS["mma_sync_throughput"]._lib._name],
+                          capture_output=True, text=True).stdout
+    assert sass.count("HMMA") >= 4 and "MUFU.EX2" in subprocess.run(
+        [shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump", "-sass", KERNELS["sfu_throughput"]._lib._name], capture_output=True, text=True).stdout
+

@@ -292,9 +292,25 @@ def _bf16_val(bits: int) -> float:
     return struct.unpack("f", struct.pack("I", (int(bits) & 0xFFFF) << 16))[0]
 
 
+def _torch_bytes(p):
+    """(uint8 view of the tensor behind ``p``, byte offset) for pointers into torch tensors of any element type; None otherwise."""
+    base = getattr(p, "base", None)
+    if base is None or not hasattr(base, "data_ptr"):
+        return None
+    import torch
+    return base.view(torch.uint8), p.off * base.element_size()
+
+
 def st_v4(dst, v):
-    """16-byte store of 8 bf16 (``dst`` points into a bf16 tensor)."""
-    vals = []
+    """16-byte store of the four packed 32-bit words of ``v`` -- byte exact, whatever the element type of the tensor ``dst`` points into."""
+    tb = _torch_bytes(dst)
+    if tb is not None:
+        import torch
+        raw, off = tb
+        words = torch.tensor([int(v.x) & 0xFFFFFFFF, int(v.y) & 0xFFFFFFFF, int(v.z) & 0xFFFFFFFF, int(v.w) & 0xFFFFFFFF], dtype=torch.int64)
+        raw[off:off + 16] = words.to(torch.int32).view(torch.uint8)
+        return
+    vals = []                                            # numpy-backed (shared) arrays of 16-bit floats
     for w in (v.x, v.y, v.z, v.w):
         vals += [_bf16_val(w), _bf16_val(int(w) >> 16)]
     for i, x in enumerate(vals):
@@ -302,8 +318,14 @@ def st_v4(dst, v):
 
 
 def ld_v4(src):
-    """16-byte load of 8 bf16 (``src`` points into a bf16 / fp16 tensor) -> the four packed 32-bit words."""
+    """16-byte load -> the four packed 32-bit words (byte exact for pointers into torch tensors of any element type)."""
     import types
+    tb = _torch_bytes(src)
+    if tb is not None:
+        import torch
+        raw, off = tb
+        w = raw[off:off + 16].clone().view(torch.int32).tolist()
+        return types.SimpleNamespace(x=w[0] & 0xFFFFFFFF, y=w[1] & 0xFFFFFFFF, z=w[2] & 0xFFFFFFFF, w=w[3] & 0xFFFFFFFF)
     f = [src[i] for i in range(8)]
     return types.SimpleNamespace(x=pack_bf16x2(f[0], f[1]), y=pack_bf16x2(f[2], f[3]), z=pack_bf16x2(f[4], f[5]), w=pack_bf16x2(f[6], f[7]))
 
