@@ -399,3 +399,12 @@ def test_late_host_level_cases_two_gpus(case):
     from _launch import run_dist
     run_dist([case], nproc=2, timeout=240)
 
+
+@pytest.mark.xfail(strict=False, reason="DSL micro-benchmark suite: kernels verified in the interpreter, first hardware run pending")
+def test_lk_microbenchmarks():
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    r = subprocess.run([sys.executable, "-m", "triton_dist.lk.bench", "--json", os.path.join(out, "lk_microbench.json")], capture_output=True, text=True,
+                       timeout=240, cwd=ROOT, env=dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", "")))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
