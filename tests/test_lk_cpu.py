@@ -321,6 +321,11 @@ def test_gemm_ladder_runs_in_the_cpu_pipeline_model():
     check(run_gemm, 200, 264, 320, cta_group=1, BN=128, STAGES=2)       # ragged M / N, 5 k-blocks through a 2-stage ring
     check(run_gemm, 300, 392, 192, cta_group=2, STAGES=2)               # 2-CTA pairs, 2 x 2 tiles
     check(run_gemm_persistent, 520, 328, 192, num_sms=2)                # ONE cluster walks 3 x 2 tiles: ring + accumulators wrap
+    # the ladder as a table: a single-stage level, a 1-CTA persistent level and the endpoint, on one ragged problem
+    from triton_dist.lk.kernels.gemm_sm100 import LEVELS, test_all_levels
+    assert sorted(LEVELS) == list(range(1, 10))
+    res = test_all_levels(200, 264, 192, device="cpu", levels=(1, 6, 9), num_sms=2)
+    assert set(res) == {1, 6, 9} and all(err < 0.15 for err, _ in res.values()), res
 
 
 def test_pipeline_model_reports_protocol_errors(monkeypatch):

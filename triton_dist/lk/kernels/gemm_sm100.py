@@ -321,7 +321,7 @@ def make_gemm_persistent(BN: int = 256, STAGES: int = 6, cta_group: int = 2, GRO
         if warp == 2:
             ll.tmem_dealloc(tmem, TMEM_COLS, cta_group=cta_group)
 
-    gemm.name = f"lk_gemm_persistent_bn{BN}_s{STAGES}_cg{cta_group}"
+    gemm.name = f"lk_gemm_persistent_bn{BN}_s{STAGES}_cg{cta_group}" + ("" if GROUP_M == 8 else f"_gm{GROUP_M}")
     gemm.tile = (TILE_M, BN, BK, B_ROWS)
     return gemm
 
@@ -336,15 +336,15 @@ def get_gemm(BN=256, STAGES=4, cta_group=1):
     return _CACHE[key]
 
 
-def run_gemm_persistent(a, b, out=None, BN: int = 256, STAGES: int = 6, cta_group: int = 2, num_sms: int = 148):
+def run_gemm_persistent(a, b, out=None, BN: int = 256, STAGES: int = 6, cta_group: int = 2, num_sms: int = 148, GROUP_M: int = 8):
     """The persistent rung: grid = one cluster per SM (pair); same operand contract as :func:`run_gemm`."""
     import torch
     M, K = a.shape
     N = b.shape[0]
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and b.shape[1] == K and K % BK == 0 and N % 8 == 0
-    key = ("persistent", BN, STAGES, cta_group)
+    key = ("persistent", BN, STAGES, cta_group, GROUP_M)
     if key not in _CACHE:
-        _CACHE[key] = make_gemm_persistent(BN, STAGES, cta_group)
+        _CACHE[key] = make_gemm_persistent(BN, STAGES, cta_group, GROUP_M)
     k = _CACHE[key]
     tile_m, _, _, b_rows = k.tile
     out = torch.empty(M, N, device=a.device, dtype=torch.bfloat16) if out is None else out
@@ -376,6 +376,54 @@ def run_gemm(a, b, out=None, BN: int = 256, STAGES: int = 4, cta_group: int = 1)
     else:                       # CPU tensors: the interpreter's functional pipeline model (a few tiles at most)
         k.interpret(grid, tA, tB, out, M, N, K)
     return out
+
+
+# The ladder as a table (reference: gemm_level1..9.py + test_all_levels.py): each level adds ONE idea to the previous one; all of them are
+# configurations of the two factories above, so every level shares the hardware-validated PTX wrappers and runs in the CPU pipeline model.
+LEVELS = {
+    1: ("1 CTA per 128 x 128 tile, single-stage: TMA -> tcgen05.mma -> tcgen05.ld, nothing overlaps", dict(fn="tile", BN=128, STAGES=1, cta_group=1)),
+    2: ("2-stage smem ring: the next TMA load overlaps the current MMAs", dict(fn="tile", BN=128, STAGES=2, cta_group=1)),
+    3: ("4-stage ring: loads run a full pipeline depth ahead", dict(fn="tile", BN=128, STAGES=4, cta_group=1)),
+    4: ("256-wide tiles: half the A traffic per FLOP, the whole 512-column TMEM budget of one accumulator", dict(fn="tile", BN=256, STAGES=4, cta_group=1)),
+    5: ("cta_group::2: a CTA pair shares one 256 x 256 tile, B is split across the pair, commits are multicast", dict(fn="tile", BN=256, STAGES=4, cta_group=2)),
+    6: ("persistent 1-CTA workers: the smem ring runs across tile boundaries", dict(fn="persistent", BN=128, STAGES=4, cta_group=1, GROUP_M=1)),
+    7: ("persistent + two TMEM accumulators: the epilogue of tile i overlaps the mainloop of tile i + 1", dict(fn="persistent", BN=256, STAGES=4, cta_group=1, GROUP_M=1)),
+    8: ("persistent CTA pairs, 6-stage ring, row-major tile order", dict(fn="persistent", BN=256, STAGES=6, cta_group=2, GROUP_M=1)),
+    9: ("level 8 with the group-M swizzled tile order (L2 reuse of B across neighbouring M tiles): the hand-written kernel's schedule",
+        dict(fn="persistent", BN=256, STAGES=6, cta_group=2, GROUP_M=8)),
+}
+
+
+def run_level(level: int, a, b, out=None, num_sms: int = 148):
+    """Run one level of the ladder (same operand contract as :func:`run_gemm`)."""
+    _, cfg = LEVELS[level]
+    if cfg["fn"] == "tile":
+        return run_gemm(a, b, out, cfg["BN"], cfg["STAGES"], cfg["cta_group"])
+    return run_gemm_persistent(a, b, out, cfg["BN"], cfg["STAGES"], cfg["cta_group"], num_sms=num_sms, GROUP_M=cfg["GROUP_M"])
+
+
+def test_all_levels(M: int = 4096, N: int = 4096, K: int = 4096, device: str = "cuda", levels=None, num_sms: int = 148):
+    """Check every level against fp32 and (on a GPU) time it -- the reference's ``test_all_levels.py``.  Returns ``{level: (max error, ms)}``."""
+    import torch
+    torch.manual_seed(0)
+    a = (torch.randn(M, K, device=device) * 0.5).bfloat16()
+    b = (torch.randn(N, K, device=device) * 0.5).bfloat16()
+    ref = a.float() @ b.float().t()
+    res = {}
+    for lv in (levels or sorted(LEVELS)):
+        c = run_level(lv, a, b, num_sms=num_sms)
+        ms = 0.0
+        if a.is_cuda:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            torch.cuda.synchronize()
+            ev[0].record()
+            for _ in range(10):
+                run_level(lv, a, b, out=c, num_sms=num_sms)
+            ev[1].record()
+            torch.cuda.synchronize()
+            ms = ev[0].elapsed_time(ev[1]) / 10
+        res[lv] = ((c.float() - ref).abs().max().item(), ms)
+    return res
 
 
 if __name__ == "__main__":
