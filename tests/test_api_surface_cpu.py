@@ -152,7 +152,7 @@ LANGUAGE_AND_RUNTIME = {
  'triton_dist.language.extra.libshmem_device': 'my_pe n_pes putmem_block getmem_block signal_op signal_wait_until barrier_all',
  'triton_dist.kernels.nvidia.common_ops': 'unsafe_barrier_on_this_grid cooperative_barrier_on_this_grid barrier_all_intra_node_atomic_cas_block barrier_all_intra_node_non_atomic barrier_all_intra_node_non_atomic_block _wait_eq_cuda _set_signal_cuda _memcpy_async_cuda bisect_left bisect_right bisect_left_aligned bisect_right_aligned BarrierAllContext barrier_all_on_stream',
  'triton_dist.utils': 'wait_until_max_gpu_clock_or_warning triton_dist_key barrier_async generate_data _make_tensor init_seed has_fullmesh_nvlink get_nvlink_max_speed_gbps get_intranode_max_speed_gbps LazyTensor LazyAllocator NVSHMEMLazyAllocator nvshmem_create_tensors',
- 'triton_dist.nv_utils': 'has_fullmesh_nvlink get_nvlink_max_speed_gbps get_intranode_max_speed_gbps',
+ 'triton_dist.nv_utils': 'has_fullmesh_nvlink get_nvlink_max_speed_gbps get_intranode_max_speed_gbps ensure_nvml_initialized with_pynvml nvsmi get_max_gpu_clock_rate_in_khz get_current_gpu_clock_rate_in_khz get_nvlink_adjacency_matrix has_fullmesh_nvlink_pynvml calculate_pcie_bandwidth_gbps get_pcie_link_max_speed_gbps get_numa_node get_device_name gpu_uuid_string get_physical_gpu_uuid get_physical_device_count is_gpu_max_performance_mode get_nvlink get_nvcc',
  'triton_dist.jit': 'jit',
  'triton_dist.tools.compile_aot': 'aot_compile_spaces',
  'triton_dist.tune': 'autotune',

@@ -878,3 +878,17 @@ def test_host_vector_and_extern_call():
     t = _make_tensor((4, 4), torch.float32, (0.0, 3.0), device="cpu")
     assert torch.equal(t, torch.full((4, 4), 3.0))
 
+
+def test_nvml_helpers_degrade_without_a_gpu():
+    import importlib
+    nv = importlib.import_module("triton_dist.nv_utils")
+    raw, eff = nv.calculate_pcie_bandwidth_gbps(5, 16)
+    assert raw == 512.0 and abs(eff - 63.0) < 0.1 and nv.calculate_pcie_bandwidth_gbps(2, 8) == (40.0, 4.0)
+    assert nv.gpu_uuid_string(bytes(range(16))) == "GPU-00010203-0405-0607-0809-0a0b0c0d0e0f"
+    assert nv.get_nvcc().endswith("nvcc") and isinstance(nv.get_physical_device_count(), int)
+    assert nv.is_gpu_max_performance_mode(0) in (True, False) and nv.get_pcie_link_max_speed_gbps(0) > 0
+    m = nv.get_nvlink_adjacency_matrix()
+    assert isinstance(m, list) and nv.has_fullmesh_nvlink_pynvml() in (True, False)
+    from triton_dist.utils import _is_cuda_launch_blocking, _torch_has_fp8
+    assert _is_cuda_launch_blocking() in (True, False) and _torch_has_fp8()
+

@@ -89,7 +89,7 @@ MODULE_MAP = {
     "triton_dist.language.extra.cuda.language_extra": ["triton_dist.lk.language_extra", "triton_dist.language", "triton_dist.language.shmem"],
     "triton_dist.language.extra.cuda.libnvshmem_device": ["triton_dist.lk.shmem", "triton_dist.language.shmem"],
     # tools / misc
-    "triton_dist.nv_utils": ["triton_dist.utils", "triton_dist._build"],
+    "triton_dist.nv_utils": ["triton_dist.utils.topology", "triton_dist.utils", "triton_dist._build"],
     "triton_dist.tools.compile": ["triton_dist.tools.compile_aot"],
     "triton_dist.tools.compile.compile": ["triton_dist.tools.compile_aot"],
     "triton_dist.tools.profiler.context": ["triton_dist.tools.profiler"],

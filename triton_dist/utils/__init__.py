@@ -481,3 +481,12 @@ from .extras import (CUDA_CHECK, TorchStreamWrapper, cuda_occupancy_max_activate
                      is_shmem_initialized, requires, requires_p2p_native_atomic, support_launch_cooperative_grid,
                      torch_stream_max_priority, triton_packed_version, warn_if_cuda_launch_blocking)
 from .lazy import LazyTensorSpec, get_underlying_tensor, nvshmem_free_lazy_tensor  # noqa: E402,F401
+
+
+def _is_cuda_launch_blocking() -> bool:
+    return os.environ.get("CUDA_LAUNCH_BLOCKING", "0") == "1"
+
+
+def _torch_has_fp8() -> bool:
+    return hasattr(torch, "float8_e4m3fn") and hasattr(torch, "float8_e5m2")
+
