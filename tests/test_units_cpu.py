@@ -892,3 +892,45 @@ def test_nvml_helpers_degrade_without_a_gpu():
     from triton_dist.utils import _is_cuda_launch_blocking, _torch_has_fp8
     assert _is_cuda_launch_blocking() in (True, False) and _torch_has_fp8()
 
+
+def test_double_tree_topology_schedulers_and_bookkeeping_helpers():
+    from triton_dist.mega_kernel import SchedulingStrategy, enque_tasks, round_robin_scheduler, zig_zag_scheduler
+    from triton_dist.ops import comm, perf_model as PM
+    from triton_dist.ops.gdn import prepare_chunk_indices, prepare_chunk_offsets, prepare_lens
+    from triton_dist.tools.profiler import ProfilerBuffer, decode_tag, parse_to_tracks
+    for N in (2, 4, 8, 32):
+        trees = [{}, {}]
+        for r in range(N):
+            t = comm.get_tree_parent_and_children(N, r)
+            trees[0][r], trees[1][r] = t[:3], t[3:]
+        for T, root in zip(trees, (0, N - 1)):
+            seen, stack = set(), [root]
+            while stack:
+                x = stack.pop()
+                assert x not in seen
+                seen.add(x)
+                for c in T[x][1:]:
+                    if c >= 0:
+                        assert T[c][0] == x
+                        stack.append(c)
+            assert seen == set(range(N)) and T[root][0] == -1
+        interior = [{r for r in T if T[r][1] >= 0 or T[r][2] >= 0} for T in trees]
+        assert not (interior[0] & interior[1])                    # complementary: nobody forwards in both trees
+    assert comm.get_max_chunk_nbytes(1 << 20, 8, "oneshot") == 1 << 20
+    assert round_robin_scheduler(list(range(7)), 3) == [[0, 3, 6], [1, 4], [2, 5]]
+    assert zig_zag_scheduler(list(range(7)), 3) == [[0, 5, 6], [1, 4], [2, 3]]
+    assert enque_tasks(list(range(4)), 3, SchedulingStrategy.RUNTIME) == [[0, 1, 2, 3], [], []]
+    assert abs(PM.get_tensorcore_tflops_by_calc(torch.bfloat16, clock_rate_mhz=1860.0) - 2255.0) < 5 and "fp8" in PM.get_tensorcore_dtype_support()
+    assert PM.get_tensorcore_tflops_by_calc(torch.float8_e4m3fn, clock_rate_mhz=1860.0) == 2 * PM.get_tensorcore_tflops_by_calc(torch.bfloat16, clock_rate_mhz=1860.0)
+    assert 60 < PM.get_simd_tflops(torch.float32) < 80
+    cu = torch.tensor([0, 5, 5, 70, 134], dtype=torch.int32)
+    assert prepare_lens(cu).tolist() == [5, 0, 65, 64]
+    assert prepare_chunk_indices(cu, 64).tolist() == [[0, 0], [2, 0], [2, 1], [3, 0]] and prepare_chunk_offsets(cu, 64).tolist() == [0, 1, 1, 3, 4]
+    pb = ProfilerBuffer(max_num_profile_slots=16, cap=8, device="cpu")
+    ev = lambda tag, start, ns: (tag << 56) | (int(start) << 55) | ns
+    pb.buf[9, 0] = 3
+    pb.buf[9, 1], pb.buf[9, 2], pb.buf[9, 3] = ev(4, True, 1000), ev(4, False, 3500), ev(5, True, 4000)
+    assert decode_tag(ev(4, True, 1000)) == dict(tag=4, start=True, ns=1000)
+    tr = parse_to_tracks(pb)
+    assert list(tr) == ["cta1.w1"] and tr["cta1.w1"][0]["dur_us"] == 2.5 and tr["cta1.w1"][1]["dur_us"] is None
+

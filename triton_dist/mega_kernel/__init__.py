@@ -9,10 +9,11 @@ On the emulation backend ``run()`` interprets the same task list with PyTorch op
 from __future__ import annotations
 
 import ctypes as C
+import enum
 import math
 import struct
 from dataclasses import dataclass, field
-from typing import Dict, List, Optional
+from typing import Dict, List, Optional, Sequence
 
 import torch
 
@@ -53,6 +54,55 @@ class Task:
     def pack(self) -> List[int]:
         a = list(self.args) + [0] * (12 - len(self.args))
         return [self.type, self.dep_idx, self.dep_count, self.sig_idx] + a
+
+
+class SchedulingStrategy(enum.Enum):
+    """Reference: mega_triton_kernel/core/scheduler.py ``SchedulingStrategy``."""
+    ROUND_ROBIN = "round_robin"
+    ZIG_ZAG = "zig_zag"
+    RUNTIME = "dynamic"
+
+
+def round_robin_scheduler(tasks: Sequence, num_queues: int) -> List[list]:
+    """Task i -> queue i % n: consecutive tiles of one op land on different SMs."""
+    queues: List[list] = [[] for _ in range(num_queues)]
+    for i, t in enumerate(tasks):
+        queues[i % num_queues].append(t)
+    return queues
+
+
+def zig_zag_scheduler(tasks: Sequence, num_queues: int) -> List[list]:
+    """Alternate the direction of every sweep (0..n-1, n-1..0, ...): the SM that got the last tile of a sweep -- typically the one that
+    finishes last -- gets the first tile of the next, which evens out per-SM load when tile counts are not multiples of n."""
+    queues: List[list] = [[] for _ in range(num_queues)]
+    for i, t in enumerate(tasks):
+        sweep, pos = divmod(i, num_queues)
+        queues[pos if sweep % 2 == 0 else num_queues - 1 - pos].append(t)
+    return queues
+
+
+def enque_tasks(tasks: Sequence, num_queues: int, strategy="round_robin") -> List[list]:
+    """Tasks (in program = topological order) -> per-CTA work queues.  ``dynamic``: queue 0 holds everything, the kernel's CTAs pop from
+    it with an atomic counter."""
+    name = strategy.value if isinstance(strategy, SchedulingStrategy) else str(strategy)
+    if name == "dynamic":
+        return [list(tasks)] + [[] for _ in range(num_queues - 1)]
+    if name == "zig_zag":
+        return zig_zag_scheduler(tasks, num_queues)
+    if name == "round_robin":
+        return round_robin_scheduler(tasks, num_queues)
+    raise ValueError(f"unknown scheduling strategy {strategy!r}")
+
+
+def work_queue_list_to_device_tensor(queues: Sequence[Sequence["Task"]], device=None):
+    """(task tensor int32 [num_tasks, 16] in queue order, queue offsets int32 [num_queues + 1]) -- what the kernel indexes."""
+    flat, off = [], [0]
+    for q in queues:
+        for t in q:
+            flat.extend(t.pack())
+        off.append(off[-1] + len(q))
+    return (torch.tensor(flat, dtype=torch.int32, device=device).view(-1, 16) if flat else torch.zeros((0, 16), dtype=torch.int32, device=device),
+            torch.tensor(off, dtype=torch.int32, device=device))
 
 
 class ModelBuilder:
@@ -313,28 +363,14 @@ class ModelBuilder:
 
     # ---- scheduling + compile ----
     def schedule(self) -> List[List[Task]]:
-        """Static per-CTA queues.  round_robin: task i -> CTA i % n;  zig_zag: alternate direction every sweep;
-        dynamic: one global queue in program order, CTAs pull tasks with an atomic counter at run time."""
-        if self.schedule_policy == "dynamic":
-            return [list(self.tasks)] + [[] for _ in range(self.num_sms - 1)]
-        n = self.num_sms
-        queues: List[List[Task]] = [[] for _ in range(n)]
-        for i, t in enumerate(self.tasks):
-            sweep, pos = divmod(i, n)
-            cta = pos if (self.schedule_policy == "round_robin" or sweep % 2 == 0) else n - 1 - pos
-            queues[cta].append(t)
-        return queues
+        """Static per-CTA queues (``round_robin_scheduler`` / ``zig_zag_scheduler``) or one global queue in program order that CTAs
+        pull from with an atomic counter at run time (``"dynamic"``)."""
+        return enque_tasks(self.tasks, self.num_sms, self.schedule_policy)
 
     def compile(self):
         queues = self.schedule()
-        flat, off = [], [0]
-        for q in queues:
-            for t in q:
-                flat.extend(t.pack())
-            off.append(off[-1] + len(q))
         self.order = [t for q in queues for t in q]
-        self.task_tensor = torch.tensor(flat, dtype=torch.int32, device=self.device).view(-1, 16)
-        self.queue_off = torch.tensor(off, dtype=torch.int32, device=self.device)
+        self.task_tensor, self.queue_off = work_queue_list_to_device_tensor(queues, self.device)
         self.ptr_tensor = torch.tensor([t.data_ptr() for t in self.ptrs], dtype=torch.int64, device=self.device)
         self.sb = torch.zeros(max(self.n_counters, 1), dtype=torch.int32, device=self.device)
         self.epoch = torch.zeros(4, dtype=torch.int32, device=self.device)

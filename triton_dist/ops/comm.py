@@ -124,6 +124,44 @@ def get_auto_allreduce_method(nbytes: int) -> AllReduceMethod:
 get_auto_all_reduce_method = get_auto_allreduce_method
 
 
+def workspace_bytes_per_in_byte(world_size: int, method) -> int:
+    """Staging bytes per input byte.  The reference's push kernels need ``world`` (one-shot: every peer's copy lands in my workspace) or
+    2 (two-shot) (allreduce.py:52-60); the kernels here PULL -- every rank stages its own input once and peers read it over NVLink or
+    through the multicast mapping -- so the answer is 1 for every method (the parity double-buffer is part of the context, not of the
+    per-call budget)."""
+    to_allreduce_method(method) if not isinstance(method, AllReduceMethod) else method
+    return 1
+
+
+def get_max_chunk_nbytes(workspace_nbytes: int, world_size: int, method) -> int:
+    """Largest message one launch handles; ``all_reduce`` splits longer inputs into chunks of this size."""
+    return workspace_nbytes // workspace_bytes_per_in_byte(world_size, method)
+
+
+def get_tree_parent_and_children(N: int, rank: int):
+    """Two complementary binary trees over ``N`` (power of two) ranks, the topology of a double-tree all-reduce (reference:
+    allreduce.py ``get_tree_parent_and_children``; NCCL's double binary tree): every rank is an interior node in at most one of them,
+    so both trees together use every link in both directions.
+
+    Tree A is the in-order perfect binary tree over labels 1..N-1 (the children of a node with lowest set bit b are ``x -/+ b/2``)
+    hung under rank 0; tree B is tree A with every label decreased by one (mod N), i.e. hung under rank N-1.
+    Returns ``(parent_a, left_a, right_a, parent_b, left_b, right_b)``, -1 where there is none."""
+    assert N >= 2 and N & (N - 1) == 0 and 0 <= rank < N
+
+    def in_tree_a(x):
+        if x == 0:                                   # super-root: one child, the root of the perfect tree
+            return -1, N // 2, -1
+        b = x & -x
+        k = (x // b - 1) // 2
+        parent = 0 if b == N // 2 else (x + b if k % 2 == 0 else x - b)
+        return (parent, x - b // 2, x + b // 2) if b > 1 else (parent, -1, -1)
+
+    pa, la, ra = in_tree_a(rank)
+    pb, lb, rb = in_tree_a((rank + 1) % N)
+    back = lambda x: -1 if x < 0 else (x - 1) % N
+    return pa, la, ra, back(pb), back(lb), back(rb)
+
+
 @dataclass
 class AllReduceContext:
     workspace_nbytes: int

@@ -107,3 +107,26 @@ def chunk_gated_delta_rule_fwd(q, k, v, g, beta, scale: Optional[float] = None, 
         S = S * gcum[:, :, c, -1].exp()[..., None, None] + (kc[:, :, c] * decay_end).transpose(-1, -2) @ delta
     o = out.permute(0, 2, 3, 1, 4).reshape(B, Tp, H, Dv)[:, :T].to(v.dtype)
     return o, (S if output_final_state else None)
+
+
+# ---- variable-length bookkeeping of the chunked forward (reference: kernels/nvidia/gdn.py prepare_lens / prepare_chunk_indices / prepare_chunk_offsets) --
+def prepare_lens(cu_seqlens: torch.Tensor) -> torch.Tensor:
+    """Sequence lengths from cumulative lengths [B + 1]."""
+    return cu_seqlens[1:] - cu_seqlens[:-1]
+
+
+def prepare_chunk_indices(cu_seqlens: torch.Tensor, chunk_size: int) -> torch.Tensor:
+    """[total_chunks, 2] rows ``(sequence, chunk inside the sequence)``: the work list of a kernel that takes one chunk per CTA over a
+    packed batch.  Device-side (repeat_interleave + arange), no host read of the lengths besides the output size."""
+    n = (prepare_lens(cu_seqlens) + chunk_size - 1) // chunk_size                       # chunks per sequence
+    seq = torch.repeat_interleave(torch.arange(n.numel(), device=cu_seqlens.device), n)
+    first = torch.cumsum(n, 0) - n
+    within = torch.arange(seq.numel(), device=cu_seqlens.device) - first[seq]
+    return torch.stack([seq, within], 1).to(cu_seqlens.dtype)
+
+
+def prepare_chunk_offsets(cu_seqlens: torch.Tensor, chunk_size: int) -> torch.Tensor:
+    """[B + 1] cumulative chunk counts: chunks of sequence b are ``offsets[b] .. offsets[b + 1]`` of the packed chunk list."""
+    n = (prepare_lens(cu_seqlens) + chunk_size - 1) // chunk_size
+    return torch.cat([n.new_zeros(1), torch.cumsum(n, 0)]).to(cu_seqlens.dtype)
+

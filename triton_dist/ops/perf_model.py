@@ -296,3 +296,39 @@ def estimate_ep_combine_us(tokens_per_rank: int, hidden: int, topk: int, world: 
     """Combine returns bf16 rows and reduces top-k on the owner: 57.6 us (fp8 run: 110.2 - 52.6) / 70.5 us (bf16 run) measured."""
     payload = tokens_per_rank * topk * hidden * 2 * (world - 1) / max(world, 1)
     return 36.0 + payload / (NVLINK_ALLGATHER_PATTERN_GBS * 1e9) * 1e6 * (8.0 / 7.0)
+
+
+# ---- peaks computed from the machine instead of looked up (reference: gemm_perf_model.py ``get_tensorcore_tflops_by_calc`` / ``get_simd_tflops``) --
+# dense FLOP per clock per SM of the 5th-generation tensor core (tcgen05) by operand type, and of the CUDA cores
+_TC_FLOP_PER_CLK_PER_SM = {"tf32": 4096, "bf16": 8192, "fp16": 8192, "fp8": 16384, "int8": 16384, "fp4": 32768}
+_SIMD_FLOP_PER_CLK_PER_SM = {"fp64": 128, "fp32": 256, "fp16": 512, "bf16": 512}
+
+
+def _dtype_key(dtype) -> str:
+    if is_fp8_dtype(dtype):
+        return "fp8"
+    return {torch.float32: "tf32", torch.bfloat16: "bf16", torch.float16: "fp16", torch.int8: "int8", torch.uint8: "fp4"}.get(dtype, "bf16")
+
+
+def get_tensorcore_dtype_support(device=None):
+    """Operand types the tensor cores of sm_100a take (``kind::tf32 / f16 / f8f6f4 / i8 / mxf8f6f4 / mxf4``)."""
+    return sorted(_TC_FLOP_PER_CLK_PER_SM)
+
+
+def get_tensorcore_tflops_by_calc(dtype: torch.dtype, device=None, clock_rate_mhz=None) -> float:
+    """SMs x FLOP / clk / SM x clock.  Without a GPU: 148 SMs at the 1.86 GHz the nominal 2.25 PFLOP/s (bf16) corresponds to."""
+    sms = get_device_multi_processor_count(device) or 148
+    mhz = clock_rate_mhz
+    if mhz is None:
+        from ..utils.topology import get_max_gpu_clock_rate_in_khz
+        mhz = (get_max_gpu_clock_rate_in_khz(0) / 1e3) if torch.cuda.is_available() else 0.0
+    mhz = mhz or 1860.0
+    return sms * _TC_FLOP_PER_CLK_PER_SM[_dtype_key(dtype)] * mhz * 1e6 / 1e12
+
+
+def get_simd_tflops(dtype: torch.dtype = torch.float32, device=None, clock_rate_mhz=None) -> float:
+    """CUDA-core (FMA pipe) peak: what element-wise epilogues, softmax and the GEMV decode paths are bounded by when not by memory."""
+    key = {torch.float64: "fp64", torch.float32: "fp32", torch.float16: "fp16", torch.bfloat16: "bf16"}.get(dtype, "fp32")
+    sms = get_device_multi_processor_count(device) or 148
+    return sms * _SIMD_FLOP_PER_CLK_PER_SM[key] * (clock_rate_mhz or 1860.0) * 1e6 / 1e12
+

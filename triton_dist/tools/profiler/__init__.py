@@ -90,3 +90,46 @@ def summarize(pb: ProfilerBuffer) -> Dict[str, dict]:
 
 
 Profiler = ProfilerBuffer
+
+
+def decode_tag(v: int) -> dict:
+    """One 64-bit event word of ``td/profiler.cuh`` -> ``{tag, start, ns}`` (tag: 8 bits, begin / end: 1 bit, globaltimer: 55 bits)."""
+    v = int(v) & 0xFFFFFFFFFFFFFFFF
+    return dict(tag=(v >> 56) & 0xFF, start=bool((v >> 55) & 1), ns=v & ((1 << 55) - 1))
+
+
+def parse_to_tracks(pb: ProfilerBuffer, warps_per_cta: int = 8) -> Dict[str, List[dict]]:
+    """Events grouped per (CTA, warp) track and paired into intervals: ``{"cta3.w1": [{"name", "tag", "start_us", "dur_us"}, ...]}``
+    (reference: tools/profiler/viewer.py ``parse_to_tracks``).  Unmatched begins (a kernel that trapped) are kept with ``dur_us = None``."""
+    evs = pb.events()
+    t0 = min((e["ns"] for e in evs), default=0)
+    tracks: Dict[str, List[dict]] = {}
+    open_: Dict[tuple, List[dict]] = {}
+    for e in sorted(evs, key=lambda e: (e["slot"], e["ns"])):
+        track = f"cta{e['slot'] // warps_per_cta}.w{e['slot'] % warps_per_cta}"
+        key = (e["slot"], e["tag"])
+        if e["start"]:
+            rec = dict(name=pb.task_names.get(e["tag"], f"task{e['tag']}"), tag=e["tag"], start_us=(e["ns"] - t0) / 1e3, dur_us=None)
+            tracks.setdefault(track, []).append(rec)
+            open_.setdefault(key, []).append(rec)
+        elif open_.get(key):
+            rec = open_[key].pop()
+            rec["dur_us"] = (e["ns"] - t0) / 1e3 - rec["start_us"]
+    return tracks
+
+
+_EXPORT_TRACE = [False]
+
+
+def set_export_trace_on():
+    """Ops that accept ``profiler=`` export their trace on completion while this is on (reference: tools/profiler/context.py)."""
+    _EXPORT_TRACE[0] = True
+
+
+def set_export_trace_off():
+    _EXPORT_TRACE[0] = False
+
+
+def get_export_trace_on() -> bool:
+    return _EXPORT_TRACE[0]
+
