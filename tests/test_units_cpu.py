@@ -934,3 +934,32 @@ def test_double_tree_topology_schedulers_and_bookkeeping_helpers():
     tr = parse_to_tracks(pb)
     assert list(tr) == ["cta1.w1"] and tr["cta1.w1"][0]["dur_us"] == 2.5 and tr["cta1.w1"][1]["dur_us"] is None
 
+
+def test_ag_moe_tile_table_follows_arrival_order():
+    """Tiles of the grouped GEMM behind an all-gather: stage ranges match the row order ``moe_align_sort`` produces, execution order is by
+    the last shard a tile needs, every tile appears once (uniform, random and many-zero routing)."""
+    import numpy as np
+    from triton_dist.ops import moe as M
+    from triton_dist.ops import tile_swizzle as TS
+    g = torch.Generator().manual_seed(0)
+    W, E, T, topk, bm = 4, 6, 40, 2, 16
+    for kind in ("uniform", "random", "sparse"):
+        ids = torch.stack([torch.randperm(E, generator=g)[:topk] for _ in range(W * T)]).to(torch.int32)
+        if kind == "uniform":
+            ids = (torch.arange(W * T * topk) % E).view(W * T, topk).to(torch.int32)
+        if kind == "sparse":
+            ids = ids % 2                                                   # most experts receive nothing
+        cnt = np.zeros((W, E), dtype=np.int64)
+        for s_ in range(W):
+            cnt[s_] = np.bincount(ids[s_ * T:(s_ + 1) * T].reshape(-1).numpy(), minlength=E)
+        for rank in range(W):
+            tab = TS.ag_moe_tile_table(cnt, rank, bm)
+            assert TS.check_ag_moe_tile_table(tab, cnt, rank, bm), (kind, rank)
+            r = M.moe_align_sort(ids, E, bm, tokens_per_rank=T, rank=rank, world=W)
+            for e, t, first, last in tab.tolist():                            # the rows the sort put into that tile come from those stages
+                rows = r.sorted_ids[int(r.expert_offsets[e]) + t * bm:int(r.expert_offsets[e]) + (t + 1) * bm]
+                rows = rows[rows != r.pad_id]
+                stages = ((rows // topk) // T - rank) % W
+                assert int(stages.min()) == first and int(stages.max()) == last, (kind, rank, e, t)
+    assert not TS.check_swizzled(tab[::-1].copy(), cnt, rank, bm) or len(set(tab[:, 3].tolist())) == 1
+

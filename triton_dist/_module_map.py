@@ -26,18 +26,18 @@ MODULE_MAP = {
     "triton_dist.kernels.common_ops": ["triton_dist.utils", _O + "comm", "triton_dist.lk.stdlib", _O + "compat"],
     _K + "common_ops": ["triton_dist.utils", _O + "comm", "triton_dist.lk.stdlib", _O + "compat"],
     _K + "allgather_gemm": [_O + "ag_gemm"],
-    _K + "ag_gemm_threadblock_swizzle": [_O + "ag_gemm"],
+    _K + "ag_gemm_threadblock_swizzle": [_O + "tile_swizzle", _O + "ag_gemm"],
     _K + "allgather": [_O + "allgather"],
     _K + "gemm_reduce_scatter": [_O + "gemm_rs"],
-    _K + "gemm_rs_threadblock_swizzle": [_O + "gemm_rs"],
+    _K + "gemm_rs_threadblock_swizzle": [_O + "tile_swizzle", _O + "gemm_rs"],
     _K + "reduce_scatter": [_O + "comm", _O + "gemm_rs"],
     _K + "gemm_allreduce": [_O + "gemm_ar"],
     _K + "gemm": [_O + "gemm"],
     _K + "group_gemm": [_O + "moe"],
     _K + "moe_utils": [_O + "moe"],
     _K + "allgather_group_gemm": [_O + "moe"],
-    _K + "threadblock_swizzle_ag_moe": [_O + "moe"],
-    _K + "threadblock_swizzle_ag_moe_triton": [_O + "moe"],
+    _K + "threadblock_swizzle_ag_moe": [_O + "tile_swizzle", _O + "moe"],
+    _K + "threadblock_swizzle_ag_moe_triton": [_O + "tile_swizzle", _O + "moe"],
     _K + "moe_reduce_rs": [_O + "moe"],
     _K + "moe_reduce_ar": [_O + "moe"],
     _K + "low_latency_allgather": [_O + "comm"],

@@ -101,3 +101,52 @@ def tile_order_table(order: np.ndarray, device=None):
     """int32 device tensor of a tile order (what a persistent kernel indexes with its launch index)."""
     import torch
     return torch.from_numpy(np.ascontiguousarray(order)).to(device or "cpu")
+
+
+# ---- AllGather + grouped GEMM (TP-MoE up projection): tiles ordered by the arrival of the tokens they need ------------------------------
+def ag_moe_tile_table(ntokens_per_rank_per_expert, rank: int, block_m: int = 128) -> np.ndarray:
+    """Tile table of the grouped GEMM behind an all-gather of tokens, in EXECUTION order.
+
+    Reference: kernels/nvidia/threadblock_swizzle_ag_moe{.py,_triton.py,.cu,.cc} (N12): rows are sorted by (expert, arrival stage of the
+    source rank) -- stage of source s for this rank is ``(s - rank) % world``, the own shard is stage 0 -- so a 128-row tile of expert e
+    needs the shards of the sources between the first and the last row it contains; tiles whose last needed shard arrives earlier run
+    earlier.  Input: ``[world, E]`` token counts (pairs routed from every source rank to every expert).  Output: int32 ``[n_tiles, 4]``
+    rows ``(expert, tile index inside the expert, first stage, last stage)`` ordered by (last stage, expert, tile); a consumer waits for
+    the flags of stages ``first..last`` (``moe_align_sort(..., tokens_per_rank=, rank=, world=)`` produces the matching row order)."""
+    cnt = np.asarray(ntokens_per_rank_per_expert, dtype=np.int64)
+    world, E = cnt.shape
+    by_stage = np.stack([cnt[(rank + st) % world] for st in range(world)])            # [stage, E]
+    tiles = []
+    for e in range(E):
+        ends = np.cumsum(by_stage[:, e])                                               # rows of expert e up to and including every stage
+        total = int(ends[-1])
+        for t in range((total + block_m - 1) // block_m):
+            r0, r1 = t * block_m, min(total, (t + 1) * block_m) - 1
+            first = int(np.searchsorted(ends, r0, side="right"))
+            last = int(np.searchsorted(ends, r1, side="right"))
+            tiles.append((e, t, first, last))
+    tiles.sort(key=lambda x: (x[3], x[0], x[1]))
+    return np.asarray(tiles, dtype=np.int32).reshape(-1, 4)
+
+
+def check_ag_moe_tile_table(table: np.ndarray, ntokens_per_rank_per_expert, rank: int, block_m: int = 128) -> bool:
+    """Every tile of every expert appears exactly once, its stage range covers exactly the sources of its rows, and the execution order
+    never schedules a tile before one that needs strictly earlier shards only."""
+    cnt = np.asarray(ntokens_per_rank_per_expert, dtype=np.int64)
+    world, E = cnt.shape
+    want = {(e, t) for e in range(E) for t in range((int(cnt[:, e].sum()) + block_m - 1) // block_m)}
+    got = [(int(r[0]), int(r[1])) for r in table]
+    if len(got) != len(set(got)) or set(got) != want:
+        return False
+    for e, t, first, last in table.tolist():
+        stage_of_row = np.repeat(np.arange(world), [int(cnt[(rank + st) % world, e]) for st in range(world)])
+        rows = stage_of_row[t * block_m:(t + 1) * block_m]
+        if rows.size == 0 or int(rows[0]) != first or int(rows[-1]) != last:
+            return False
+    lasts = table[:, 3]
+    return bool(np.all(lasts[:-1] <= lasts[1:]))
+
+
+threadblock_swizzle_ag_moe = ag_moe_tile_table
+check_swizzled = check_ag_moe_tile_table
+
