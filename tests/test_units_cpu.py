@@ -724,6 +724,7 @@ def test_megakernel_with_a_paged_kv_cache(dist_env):
     for step in range(2):
         ids = torch.randint(0, 1000, (B, 1))
         ref = m.inference(ids, dense.kv_offset.to(torch.int64)[:, None], dense)
+        mega.builder.host_shuffle_seed = step - 1          # latest-ready-first, then a random order: only the scoreboard orders the tasks
         torch.testing.assert_close(mega.mega_forward(ids), ref, atol=1e-4, rtol=1e-4)
         dense.inc_offset(1)
         paged.inc_offset(1)
@@ -962,4 +963,64 @@ def test_ag_moe_tile_table_follows_arrival_order():
                 stages = ((rows // topk) // T - rank) % W
                 assert int(stages.min()) == first and int(stages.max()) == last, (kind, rank, e, t)
     assert not TS.check_swizzled(tab[::-1].copy(), cnt, rank, bm) or len(set(tab[:, 3].tolist())) == 1
+
+
+def test_megakernel_dependency_graph_under_out_of_order_execution(dist_env):
+    """The scoreboard is all the GPU guarantees: the host interpretation can run the tasks in random (or adversarial: latest-ready-first)
+    order subject to the counters only.  The dense model's hand-written dependencies and the inferred ones (``auto_deps=True``: storage
+    overlap, JOIN tasks for several producers) must give program-order results; a graph with a dependency removed must not."""
+    from triton_dist.mega_kernel import T_JOIN, MegaDenseModel, ModelBuilder
+    from triton_dist.models import AutoLLM, KV_Cache, ModelConfig
+    cfg = ModelConfig(model_name="tiny-dense", max_length=64, dtype=torch.float32, rank=0, world_size=1)
+    m = AutoLLM.from_pretrained(cfg)
+    for B, fuse, splits in ((2, True, 2), (12, False, 3)):
+        mk = lambda: KV_Cache(m.num_layers, B, 64, m.num_key_value_heads, m.head_dim, torch.float32, 1, "cpu")
+        kv, kv2 = mk(), mk()
+        kv.rand_fill_kv_cache(9)
+        kv2.k_cache.copy_(kv.k_cache); kv2.v_cache.copy_(kv.v_cache); kv2.kv_offset.copy_(kv.kv_offset)
+        mega = MegaDenseModel(m, B, kv2, fuse_norm=fuse, attn_splits=splits)
+        ids = torch.randint(0, 1000, (B, 1))
+        ref = m.inference(ids, kv.kv_offset.to(torch.int64)[:, None], kv)
+        for seed in (-1, 0, 1, 2):
+            mega.builder.host_shuffle_seed = seed
+            torch.testing.assert_close(mega.mega_forward(ids), ref, atol=1e-4, rtol=1e-4)
+        mega.finalize()
+
+    Bt, H, I = 4, 64, 96
+    torch.manual_seed(0)
+
+    def build(auto, break_dep=False):
+        mb = ModelBuilder(Bt, num_sms=4, auto_deps=auto)
+        x, w1, w2, nw = torch.randn(Bt, H), torch.randn(2 * I, H) * 0.1, torch.randn(H, I) * 0.1, torch.rand(H) + 0.5
+        xn, gu, act, y, z = torch.zeros(Bt, H), torch.zeros(Bt, 2 * I), torch.zeros(Bt, I), torch.zeros(Bt, H), torch.zeros(Bt, H)
+        if auto:
+            mb.make_rms_norm(x, nw, xn, 1e-6)
+            mb.make_fc1(xn, w1, gu)
+            mb.make_silu_mul_up(gu, act)
+            mb.make_fc2(act, w2, y)
+            mb.make_add(y, x, z)
+            mb.make_add(z, xn, y)                   # reads two producers' outputs and overwrites a buffer another op still reads
+        else:
+            d = mb.make_rms_norm(x, nw, xn, 1e-6)
+            d = mb.make_fc1(xn, w1, gu, d)
+            d = mb.make_silu_mul_up(gu, act, dep=d)
+            d = mb.make_fc2(act, w2, y, None if break_dep else d)
+            d = mb.make_add(y, x, z, dep=d)
+            mb.make_add(z, xn, y, dep=d)
+        mb.compile()
+        xnr = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6) * nw
+        g = xnr @ w1.t()
+        return mb, y, (torch.nn.functional.silu(g[:, :I]) * g[:, I:]) @ w2.t() + x + xnr
+
+    for auto in (False, True):
+        mb, y, want = build(auto)
+        assert (sum(t.type == T_JOIN for t in mb.tasks) > 0) == auto
+        for seed in (None, -1, 0, 1, 2, 3):
+            mb.host_shuffle_seed = seed
+            mb.run()
+            torch.testing.assert_close(y, want, atol=1e-4, rtol=1e-4)
+    bad, y, want = build(False, break_dep=True)
+    bad.host_shuffle_seed = -1
+    bad.run()
+    assert not torch.allclose(y, want, atol=1e-4)            # the missing edge is visible
 

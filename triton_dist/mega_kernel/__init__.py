@@ -25,7 +25,8 @@ T_RMSNORM, T_LINEAR, T_QKROPE, T_ATTN, T_ALLREDUCE, T_ATTN_COMBINE, T_SILU_MUL, 
 T_QKROPE_PAGED, T_ATTN_PAGED = 11, 12      # paged KV cache (block table; reference: mega_triton_kernel/models/paged_kv_cache.py)
 T_FLASH_ATTN, T_QKROPE_SPLIT = 13, 14      # prefill: tensor-core attention over [B, S, H, 128] and the qk-norm + rope that feeds it
 FLASH_BQ = 128                              # query rows per FLASH_ATTN task (8 warps x 16)
-TASK_NAMES = {1: "rms_norm", 2: "linear", 3: "qk_norm_rope_update_kvcache", 4: "flash_decode", 5: "allreduce", 7: "flash_decode_combine", 8: "silu_mul_up", 9: "add", 10: "prefetch", 11: "qk_norm_rope_update_paged_kvcache", 12: "flash_decode_paged", 13: "flash_attn", 14: "qkv_pack_qk_norm_rope_split_v"}
+T_JOIN = 15                                 # no-op: waits on its dependency, signals its counter (several producers -> one counter)
+TASK_NAMES = {1: "rms_norm", 2: "linear", 3: "qk_norm_rope_update_kvcache", 4: "flash_decode", 5: "allreduce", 7: "flash_decode_combine", 8: "silu_mul_up", 9: "add", 10: "prefetch", 11: "qk_norm_rope_update_paged_kvcache", 12: "flash_decode_paged", 13: "flash_attn", 14: "qkv_pack_qk_norm_rope_split_v", 15: "join"}
 
 
 class _MegaArgs(C.Structure):
@@ -108,13 +109,19 @@ def work_queue_list_to_device_tensor(queues: Sequence[Sequence["Task"]], device=
 class ModelBuilder:
     """Records ops of one decode step, tiles them into tasks, schedules them, launches the persistent kernel."""
 
-    def __init__(self, batch: int, num_sms: Optional[int] = None, schedule: str = "round_robin"):
+    def __init__(self, batch: int, num_sms: Optional[int] = None, schedule: str = "round_robin", auto_deps: bool = False):
         assert 1 <= batch <= 64, "megakernel decode batch: 1..8 (GEMV tasks) or 9..64 (tensor-core tasks)"
         self.B = batch
         self.device = U.current_device()
         self.is_cuda = self.device.type == "cuda"
         self.num_sms = num_sms or (torch.cuda.get_device_properties(self.device).multi_processor_count if self.is_cuda else 8)
         self.schedule_policy = schedule
+        # auto_deps: ops called WITHOUT ``dep=`` wait for whatever earlier ops wrote their inputs or still read / write their outputs
+        # (the reference derives tile dependencies from a buffer graph, mega_triton_kernel/core/graph.py; here: interval overlap of
+        # the tensors' storage, one JOIN task per extra producer when there are several)
+        self.auto_deps = auto_deps
+        self._writers: List[tuple] = []         # (lo, hi, (counter, count)) of the op that last wrote the bytes
+        self._readers: List[tuple] = []         # ops that read the bytes since
         self.tasks: List[Task] = []
         self.ptrs: List[torch.Tensor] = []
         self._ptr_idx: Dict[int, int] = {}
@@ -149,6 +156,49 @@ class ModelBuilder:
         t.layer = self.cur_layer
         self.tasks.append(t)
         self.metrics[TASK_NAMES[t.type]] = self.metrics.get(TASK_NAMES[t.type], 0) + 1
+
+    # ---- dependency inference ----
+    @staticmethod
+    def _span(t: torch.Tensor):
+        es = t.element_size()
+        n = sum((sz - 1) * st for sz, st in zip(t.shape, t.stride())) + 1 if t.numel() else 0
+        return t.data_ptr(), t.data_ptr() + n * es
+
+    def _infer_dep(self, reads, writes):
+        producers = []
+
+        def hit(entries, lo, hi):
+            for (l, h, d) in entries:
+                if l < hi and lo < h and d not in producers:
+                    producers.append(d)
+        for t in reads:
+            if t is not None:
+                hit(self._writers, *self._span(t))                      # read after write
+        for t in writes:
+            if t is not None:
+                lo, hi = self._span(t)
+                hit(self._writers, lo, hi)                               # write after write
+                hit(self._readers, lo, hi)                               # write after read
+        if not producers:
+            return (-1, 0)
+        if len(producers) == 1:
+            return producers[0]
+        j = self.counter()
+        for (sig, cnt) in producers:
+            self._add(Task(T_JOIN, sig, cnt, j, []))
+        return (j, len(producers))
+
+    def _record(self, result, reads, writes):
+        if result is None:
+            return
+        for t in writes:
+            if t is not None:
+                lo, hi = self._span(t)
+                self._writers = [(l, h, d) for (l, h, d) in self._writers if not (lo <= l and h <= hi)] + [(lo, hi, result)]
+                self._readers = [(l, h, d) for (l, h, d) in self._readers if not (l < hi and lo < h)]
+        for t in reads:
+            if t is not None:
+                self._readers.append((*self._span(t), result))
 
     # ---- ops (each returns (counter, count) that consumers wait on) ----
     def make_rms_norm(self, x, weight, out, eps: float, dep=None, residual=None, residual_out=None):
@@ -384,7 +434,7 @@ class ModelBuilder:
     def run(self, stream=None):
         assert self.compiled
         if not self.is_cuda:
-            return self._run_host()
+            return self._run_host(getattr(self, "host_shuffle_seed", None))
         a = _MegaArgs()
         a.symm = symm_args()
         a.tasks, a.queue_off, a.ptrs = self.task_tensor.data_ptr(), self.queue_off.data_ptr(), self.ptr_tensor.data_ptr()
@@ -397,150 +447,205 @@ class ModelBuilder:
         a.num_tasks = len(self.tasks)
         _C.check(_C.cuda_lib().td_mega_launch(C.byref(a), C.c_void_p((stream or torch.cuda.current_stream()).cuda_stream)), "td_mega_launch")
 
-    # emulation: interpret the task list in program order with torch ops on the same buffers
-    def _run_host(self):
+    # emulation: interpret the task list with torch ops on the same buffers -- in program order, or (``shuffle_seed``) in a random order that
+    # respects nothing but the scoreboard, which is what the GPU guarantees: a missing dependency shows up as a wrong result here
+    def _run_host(self, shuffle_seed: Optional[int] = None):
+        self.host_epoch = getattr(self, "host_epoch", 0) + 1
+        if shuffle_seed is None:
+            for t in self.tasks:
+                self._host_task(t)
+            return
+        import random
+        rng = random.Random(shuffle_seed)
+        sb = [0] * max(self.n_counters, 1)
+        pending = list(range(len(self.tasks)))
+        while pending:
+            ready = [i for i in pending if self.tasks[i].dep_idx < 0 or sb[self.tasks[i].dep_idx] >= self.tasks[i].dep_count]
+            if not ready:
+                raise RuntimeError(f"megakernel task graph deadlocks: {len(pending)} tasks wait on counters that are never reached")
+            i = ready[-1] if shuffle_seed < 0 else rng.choice(ready)       # seed < 0: always the LATEST ready task (adversarial order)
+            pending.remove(i)
+            self._host_task(self.tasks[i])
+            if self.tasks[i].sig_idx >= 0:
+                sb[self.tasks[i].sig_idx] += 1
+
+    def _host_task(self, t: Task):
         from ..ops.elementwise import rope_reference
         import ctypes
         heap = U.get_heap()
         lib = _C.host_lib()
-        self.host_epoch = getattr(self, "host_epoch", 0) + 1
         P = self.ptrs
         B = self.B
-        for t in self.tasks:
-            a = t.args
-            if t.type == T_RMSNORM:
-                x = P[a[0]].view(B, -1).float()
-                if a[1] >= 0:
-                    x = x + P[a[1]].view(B, -1).float()
-                    if a[4] >= 0:
-                        P[a[4]].view(B, -1).copy_(x.to(P[a[4]].dtype))
-                eps = struct.unpack("f", struct.pack("i", a[6]))[0]
-                y = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps) * P[a[2]].float()
-                P[a[3]].view(B, -1).copy_(y.to(P[a[3]].dtype))
-            elif t.type == T_LINEAR:
-                K, n0, nc, act = a[3], a[5], a[6], a[7]
-                x = P[a[0]].view(B, -1).float()
-                if act == 1:
-                    x = torch.nn.functional.silu(x[:, :K]) * x[:, K:2 * K]
-                elif act == 2:
-                    eps = struct.unpack("f", struct.pack("i", a[10]))[0]
-                    x = x[:, :K]
-                    x = (x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps) * P[a[9]].float()).to(P[a[0]].dtype).float()
-                else:
-                    x = x[:, :K]
-                P[a[2]].view(B, -1)[:, n0:n0 + nc] = (x @ P[a[1]][n0:n0 + nc].float().t()).to(P[a[2]].dtype)
-            elif t.type in (T_QKROPE, T_QKROPE_PAGED):
-                Hq, Hkv = a[7], a[8]
-                eps = struct.unpack("f", struct.pack("i", a[10]))[0]
-                theta = struct.unpack("f", struct.pack("i", a[11]))[0]
-                qkv = P[a[0]].view(B, Hq + 2 * Hkv, -1)
-                q, k, v = qkv[:, :Hq], qkv[:, Hq:Hq + Hkv], qkv[:, Hq + Hkv:]
-                nrm = lambda z, w: ((z.float() * torch.rsqrt(z.float().pow(2).mean(-1, keepdim=True) + eps)) * w.float()).to(z.dtype)
+        a = t.args
+        if t.type == T_RMSNORM:
+            x = P[a[0]].view(B, -1).float()
+            if a[1] >= 0:
+                x = x + P[a[1]].view(B, -1).float()
                 if a[4] >= 0:
-                    q, k = nrm(q, P[a[4]]), nrm(k, P[a[5]])
-                pos = P[a[6]].view(-1)[:B]
-                q, k = rope_reference(q, pos, theta), rope_reference(k, pos, theta)
-                P[a[1]].view(B, Hq, -1).copy_(q)
-                for b in range(B):
-                    if t.type == T_QKROPE_PAGED:
-                        ps_, bt = a[9] & 0xFFFF, P[a[3] + 1]
-                        page, slot = int(bt[b, int(pos[b]) // ps_]), int(pos[b]) % ps_
-                        P[a[2]][page, slot] = k[b]
-                        P[a[3]][page, slot] = v[b]
-                    else:
-                        P[a[2]][b, int(pos[b])] = k[b]
-                        P[a[3]][b, int(pos[b])] = v[b]
-            elif t.type in (T_ATTN, T_ATTN_PAGED):
-                b, kvh, Hq, Hkv = a[5], a[6], a[7], a[8]
-                G = Hq // Hkv
-                scale = struct.unpack("f", struct.pack("i", a[10]))[0]
-                L = int(P[a[3]].view(-1)[b]) + 1
-                q = P[a[0]].view(B, Hq, -1)[b, kvh * G:(kvh + 1) * G].float()
-                split, ns = (a[11] & 0xFFFF, max(1, a[11] >> 16)) if len(a) > 11 else (0, 1)
-                per = (L + ns - 1) // ns
-                j0, j1 = split * per, min(L, split * per + per)
-                if t.type == T_ATTN_PAGED:
-                    ps_, bt = a[9] & 0xFFFF, P[a[2] + 1]
-                    jj = torch.arange(j0, j1)
-                    pages, slots = bt[b, jj // ps_].long(), jj % ps_
-                    k, v = P[a[1]][pages, slots, kvh].float(), P[a[2]][pages, slots, kvh].float()
-                else:
-                    k, v = P[a[1]][b, j0:j1, kvh].float(), P[a[2]][b, j0:j1, kvh].float()
-                if ns == 1:
-                    pr = torch.softmax(q @ k.t() * scale, -1)
-                    P[a[4]].view(B, Hq, -1)[b, kvh * G:(kvh + 1) * G] = (pr @ v).to(P[a[4]].dtype)
-                else:
-                    part = P[a[4]].view(-1, 130)
-                    sc = q @ k.t() * scale if j1 > j0 else torch.empty(G, 0)
-                    mm = sc.max(-1).values if j1 > j0 else torch.full((G,), float("-inf"))
-                    e = torch.exp(sc - mm[:, None]) if j1 > j0 else sc
-                    base = ((b * Hkv + kvh) * ns + split) * 8
-                    part[base:base + G, 0] = mm
-                    part[base:base + G, 1] = e.sum(-1) if j1 > j0 else 0.0
-                    part[base:base + G, 2:] = (e @ v) if j1 > j0 else 0.0
-            elif t.type == T_QKROPE_SPLIT:
-                Hq, Hkv, S = a[7], a[8], a[9]
+                    P[a[4]].view(B, -1).copy_(x.to(P[a[4]].dtype))
+            eps = struct.unpack("f", struct.pack("i", a[6]))[0]
+            y = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps) * P[a[2]].float()
+            P[a[3]].view(B, -1).copy_(y.to(P[a[3]].dtype))
+        elif t.type == T_LINEAR:
+            K, n0, nc, act = a[3], a[5], a[6], a[7]
+            x = P[a[0]].view(B, -1).float()
+            if act == 1:
+                x = torch.nn.functional.silu(x[:, :K]) * x[:, K:2 * K]
+            elif act == 2:
                 eps = struct.unpack("f", struct.pack("i", a[10]))[0]
-                theta = struct.unpack("f", struct.pack("i", a[11]))[0]
-                qkv = P[a[0]].view(B, Hq + 2 * Hkv, -1)
-                q, k, v = qkv[:, :Hq], qkv[:, Hq:Hq + Hkv], qkv[:, Hq + Hkv:]
-                nrm = lambda z, w: ((z.float() * torch.rsqrt(z.float().pow(2).mean(-1, keepdim=True) + eps)) * w.float()).to(z.dtype)
-                if a[4] >= 0:
-                    q, k = nrm(q, P[a[4]]), nrm(k, P[a[5]])
-                pos = (P[a[6]].view(-1)[:B // S, None] + torch.arange(S, dtype=torch.int32)[None]).reshape(-1)
-                P[a[1]].view(B, Hq, -1).copy_(rope_reference(q, pos, theta))
-                P[a[2]].view(B, Hkv, -1).copy_(rope_reference(k, pos, theta))
-                P[a[3]].view(B, Hkv, -1).copy_(v)
-            elif t.type == T_FLASH_ATTN:
-                if a[5] or (a[6] & 0xFFFFFF):
-                    continue                                  # the (head 0, q block 0) task of a batch entry does the whole entry on the host
-                b, S, Hq, Hkv = a[4], a[7], a[8] & 0xFFFF, a[8] >> 16
-                causal = bool((a[6] >> 30) & 1)
-                scale = struct.unpack("f", struct.pack("i", a[10]))[0]
-                cap = struct.unpack("f", struct.pack("i", a[11]))[0]
-                q, k, v, out = (P[a[i]][b].float() for i in range(4))                    # [S, H, 128]
-                G = Hq // Hkv
-                sc = torch.einsum("shd,thd->hst", q, k.repeat_interleave(G, 1)) * scale
-                if cap > 0:
-                    sc = cap * torch.tanh(sc / cap)
-                if causal:
-                    sc = sc.masked_fill(torch.triu(torch.ones(S, S, dtype=torch.bool), 1), float("-inf"))
-                P[a[3]][b] = torch.einsum("hst,thd->shd", torch.softmax(sc, -1), v.repeat_interleave(G, 1)).to(P[a[3]].dtype)
-            elif t.type == T_ATTN_COMBINE:
-                b, kvh, Hq, Hkv, ns = a[2], a[3], a[4], a[5], a[6]
-                G = Hq // Hkv
-                part = P[a[0]].view(-1, 130)
-                rows = torch.stack([part[((b * Hkv + kvh) * ns + s_) * 8:((b * Hkv + kvh) * ns + s_) * 8 + G] for s_ in range(ns)])   # [ns, G, 130]
-                mm = rows[:, :, 0].max(0).values
-                c = torch.where(torch.isinf(rows[:, :, 0]), torch.zeros_like(rows[:, :, 0]), torch.exp(rows[:, :, 0] - mm[None]))
-                ll = (rows[:, :, 1] * c).sum(0)
-                o = (rows[:, :, 2:] * c[:, :, None]).sum(0) / ll[:, None]
-                P[a[1]].view(B, Hq, -1)[b, kvh * G:(kvh + 1) * G] = o.to(P[a[1]].dtype)
-            elif t.type == T_SILU_MUL:
-                inter = a[2]
-                x = P[a[0]].view(B, -1).float()
-                y = (torch.nn.functional.silu(x[:, :inter]) * x[:, inter:2 * inter]).to(P[a[1]].dtype)
-                P[a[1]].view(-1)[a[3] * 8:a[4] * 8] = y.reshape(-1)[a[3] * 8:a[4] * 8]
-            elif t.type == T_ADD:
-                v0, v1 = a[3] * 8, a[4] * 8
-                P[a[2]].view(-1)[v0:v1] = (P[a[0]].view(-1)[v0:v1].float() + P[a[1]].view(-1)[v0:v1].float()).to(P[a[2]].dtype)
-            elif t.type == T_PREFETCH:
-                pass
-            elif t.type == T_ALLREDUCE:
-                part, flags = P[a[0]], P[a[1]]
-                v0, v1, sl = a[4] * 8, a[5] * 8, a[8]
-                W, me = heap.world, heap.rank
-                fl = flags.view(-1)[sl * W:(sl + 1) * W]
-                for r in range(W):
-                    lib.tdh_notify32(ctypes.c_void_p(heap.peer_ptr(fl[me:me + 1].data_ptr(), r)), self.host_epoch, 1)
-                if lib.tdh_wait32_n(ctypes.c_void_p(fl.data_ptr()), W, self.host_epoch, 1, 60_000_000):
-                    raise TimeoutError("megakernel all-reduce flag never arrived")
-                acc = torch.zeros(v1 - v0, dtype=torch.float32)
-                for r in range(W):
-                    acc += heap.peer_view(part, (me + r) % W).view(-1)[v0:v1].float()
-                if a[2] >= 0:
-                    acc += P[a[2]].view(-1)[v0:v1].float()
-                P[a[3]].view(-1)[v0:v1] = acc.to(P[a[3]].dtype)
+                x = x[:, :K]
+                x = (x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps) * P[a[9]].float()).to(P[a[0]].dtype).float()
+            else:
+                x = x[:, :K]
+            P[a[2]].view(B, -1)[:, n0:n0 + nc] = (x @ P[a[1]][n0:n0 + nc].float().t()).to(P[a[2]].dtype)
+        elif t.type in (T_QKROPE, T_QKROPE_PAGED):
+            Hq, Hkv = a[7], a[8]
+            eps = struct.unpack("f", struct.pack("i", a[10]))[0]
+            theta = struct.unpack("f", struct.pack("i", a[11]))[0]
+            qkv = P[a[0]].view(B, Hq + 2 * Hkv, -1)
+            q, k, v = qkv[:, :Hq], qkv[:, Hq:Hq + Hkv], qkv[:, Hq + Hkv:]
+            nrm = lambda z, w: ((z.float() * torch.rsqrt(z.float().pow(2).mean(-1, keepdim=True) + eps)) * w.float()).to(z.dtype)
+            if a[4] >= 0:
+                q, k = nrm(q, P[a[4]]), nrm(k, P[a[5]])
+            pos = P[a[6]].view(-1)[:B]
+            q, k = rope_reference(q, pos, theta), rope_reference(k, pos, theta)
+            P[a[1]].view(B, Hq, -1).copy_(q)
+            for b in range(B):
+                if t.type == T_QKROPE_PAGED:
+                    ps_, bt = a[9] & 0xFFFF, P[a[3] + 1]
+                    page, slot = int(bt[b, int(pos[b]) // ps_]), int(pos[b]) % ps_
+                    P[a[2]][page, slot] = k[b]
+                    P[a[3]][page, slot] = v[b]
+                else:
+                    P[a[2]][b, int(pos[b])] = k[b]
+                    P[a[3]][b, int(pos[b])] = v[b]
+        elif t.type in (T_ATTN, T_ATTN_PAGED):
+            b, kvh, Hq, Hkv = a[5], a[6], a[7], a[8]
+            G = Hq // Hkv
+            scale = struct.unpack("f", struct.pack("i", a[10]))[0]
+            L = int(P[a[3]].view(-1)[b]) + 1
+            q = P[a[0]].view(B, Hq, -1)[b, kvh * G:(kvh + 1) * G].float()
+            split, ns = (a[11] & 0xFFFF, max(1, a[11] >> 16)) if len(a) > 11 else (0, 1)
+            per = (L + ns - 1) // ns
+            j0, j1 = split * per, min(L, split * per + per)
+            if t.type == T_ATTN_PAGED:
+                ps_, bt = a[9] & 0xFFFF, P[a[2] + 1]
+                jj = torch.arange(j0, j1)
+                pages, slots = bt[b, jj // ps_].long(), jj % ps_
+                k, v = P[a[1]][pages, slots, kvh].float(), P[a[2]][pages, slots, kvh].float()
+            else:
+                k, v = P[a[1]][b, j0:j1, kvh].float(), P[a[2]][b, j0:j1, kvh].float()
+            if ns == 1:
+                pr = torch.softmax(q @ k.t() * scale, -1)
+                P[a[4]].view(B, Hq, -1)[b, kvh * G:(kvh + 1) * G] = (pr @ v).to(P[a[4]].dtype)
+            else:
+                part = P[a[4]].view(-1, 130)
+                sc = q @ k.t() * scale if j1 > j0 else torch.empty(G, 0)
+                mm = sc.max(-1).values if j1 > j0 else torch.full((G,), float("-inf"))
+                e = torch.exp(sc - mm[:, None]) if j1 > j0 else sc
+                base = ((b * Hkv + kvh) * ns + split) * 8
+                part[base:base + G, 0] = mm
+                part[base:base + G, 1] = e.sum(-1) if j1 > j0 else 0.0
+                part[base:base + G, 2:] = (e @ v) if j1 > j0 else 0.0
+        elif t.type == T_QKROPE_SPLIT:
+            Hq, Hkv, S = a[7], a[8], a[9]
+            eps = struct.unpack("f", struct.pack("i", a[10]))[0]
+            theta = struct.unpack("f", struct.pack("i", a[11]))[0]
+            qkv = P[a[0]].view(B, Hq + 2 * Hkv, -1)
+            q, k, v = qkv[:, :Hq], qkv[:, Hq:Hq + Hkv], qkv[:, Hq + Hkv:]
+            nrm = lambda z, w: ((z.float() * torch.rsqrt(z.float().pow(2).mean(-1, keepdim=True) + eps)) * w.float()).to(z.dtype)
+            if a[4] >= 0:
+                q, k = nrm(q, P[a[4]]), nrm(k, P[a[5]])
+            pos = (P[a[6]].view(-1)[:B // S, None] + torch.arange(S, dtype=torch.int32)[None]).reshape(-1)
+            P[a[1]].view(B, Hq, -1).copy_(rope_reference(q, pos, theta))
+            P[a[2]].view(B, Hkv, -1).copy_(rope_reference(k, pos, theta))
+            P[a[3]].view(B, Hkv, -1).copy_(v)
+        elif t.type == T_FLASH_ATTN:
+            if a[5] or (a[6] & 0xFFFFFF):
+                return                                    # the (head 0, q block 0) task of a batch entry does the whole entry on the host
+            b, S, Hq, Hkv = a[4], a[7], a[8] & 0xFFFF, a[8] >> 16
+            causal = bool((a[6] >> 30) & 1)
+            scale = struct.unpack("f", struct.pack("i", a[10]))[0]
+            cap = struct.unpack("f", struct.pack("i", a[11]))[0]
+            q, k, v, out = (P[a[i]][b].float() for i in range(4))                    # [S, H, 128]
+            G = Hq // Hkv
+            sc = torch.einsum("shd,thd->hst", q, k.repeat_interleave(G, 1)) * scale
+            if cap > 0:
+                sc = cap * torch.tanh(sc / cap)
+            if causal:
+                sc = sc.masked_fill(torch.triu(torch.ones(S, S, dtype=torch.bool), 1), float("-inf"))
+            P[a[3]][b] = torch.einsum("hst,thd->shd", torch.softmax(sc, -1), v.repeat_interleave(G, 1)).to(P[a[3]].dtype)
+        elif t.type == T_ATTN_COMBINE:
+            b, kvh, Hq, Hkv, ns = a[2], a[3], a[4], a[5], a[6]
+            G = Hq // Hkv
+            part = P[a[0]].view(-1, 130)
+            rows = torch.stack([part[((b * Hkv + kvh) * ns + s_) * 8:((b * Hkv + kvh) * ns + s_) * 8 + G] for s_ in range(ns)])   # [ns, G, 130]
+            mm = rows[:, :, 0].max(0).values
+            c = torch.where(torch.isinf(rows[:, :, 0]), torch.zeros_like(rows[:, :, 0]), torch.exp(rows[:, :, 0] - mm[None]))
+            ll = (rows[:, :, 1] * c).sum(0)
+            o = (rows[:, :, 2:] * c[:, :, None]).sum(0) / ll[:, None]
+            P[a[1]].view(B, Hq, -1)[b, kvh * G:(kvh + 1) * G] = o.to(P[a[1]].dtype)
+        elif t.type == T_SILU_MUL:
+            inter = a[2]
+            x = P[a[0]].view(B, -1).float()
+            y = (torch.nn.functional.silu(x[:, :inter]) * x[:, inter:2 * inter]).to(P[a[1]].dtype)
+            P[a[1]].view(-1)[a[3] * 8:a[4] * 8] = y.reshape(-1)[a[3] * 8:a[4] * 8]
+        elif t.type == T_ADD:
+            v0, v1 = a[3] * 8, a[4] * 8
+            P[a[2]].view(-1)[v0:v1] = (P[a[0]].view(-1)[v0:v1].float() + P[a[1]].view(-1)[v0:v1].float()).to(P[a[2]].dtype)
+        elif t.type == T_PREFETCH:
+            pass
+        elif t.type == T_ALLREDUCE:
+            part, flags = P[a[0]], P[a[1]]
+            v0, v1, sl = a[4] * 8, a[5] * 8, a[8]
+            W, me = heap.world, heap.rank
+            fl = flags.view(-1)[sl * W:(sl + 1) * W]
+            for r in range(W):
+                lib.tdh_notify32(ctypes.c_void_p(heap.peer_ptr(fl[me:me + 1].data_ptr(), r)), self.host_epoch, 1)
+            if lib.tdh_wait32_n(ctypes.c_void_p(fl.data_ptr()), W, self.host_epoch, 1, 60_000_000):
+                raise TimeoutError("megakernel all-reduce flag never arrived")
+            acc = torch.zeros(v1 - v0, dtype=torch.float32)
+            for r in range(W):
+                acc += heap.peer_view(part, (me + r) % W).view(-1)[v0:v1].float()
+            if a[2] >= 0:
+                acc += P[a[2]].view(-1)[v0:v1].float()
+            P[a[3]].view(-1)[v0:v1] = acc.to(P[a[3]].dtype)
+
+
+
+def _tracked(name, reads, writes):
+    """Wrap a builder op: with ``auto_deps`` and no explicit ``dep`` the dependency is inferred from the named tensor arguments."""
+    import functools
+    import inspect
+    fn = getattr(ModelBuilder, name)
+    sig = inspect.signature(fn)
+
+    @functools.wraps(fn)
+    def op(self, *args, **kwargs):
+        ba = sig.bind_partial(self, *args, **kwargs)
+        rd = [ba.arguments.get(n) for n in reads]
+        wr = [ba.arguments.get(n) for n in writes]
+        if self.auto_deps and ba.arguments.get("dep") is None:
+            ba.arguments["dep"] = self._infer_dep(rd, wr)
+        out = fn(*ba.args, **ba.kwargs)
+        self._record(out, rd, wr)
+        return out
+    return op
+
+
+for _name, _rd, _wr in (
+        ("make_rms_norm", ("x", "weight", "residual"), ("out", "residual_out")),
+        ("make_linear", ("x", "weight", "norm_weight"), ("out",)),
+        ("make_qk_norm_rope_update_kvcache", ("qkv", "q_norm_w", "k_norm_w", "positions", "block_table"), ("q_out", "k_cache", "v_cache")),
+        ("make_flash_decode", ("q", "k_cache", "v_cache", "positions", "block_table"), ("out", "scratch")),
+        ("make_flash_attn", ("q", "k", "v"), ("output",)),
+        ("make_qkv_pack_qk_norm_rope_split_v", ("qkv", "kv_lens", "q_norm_w", "k_norm_w"), ("q_out", "k_out", "v_out")),
+        ("make_allreduce", ("part_symm", "residual"), ("residual_out",)),
+        ("make_silu_mul_up", ("fc1_out",), ("act_out",)),
+        ("make_add", ("lhs", "rhs"), ("output",)),
+        ("make_prefetch", ("weight",), ())):
+    setattr(ModelBuilder, _name, _tracked(_name, _rd, _wr))
+ModelBuilder.make_qkv_proj = ModelBuilder.make_o_proj = ModelBuilder.make_fc1 = ModelBuilder.make_fc2 = ModelBuilder.make_linear
 
 
 from .dense import MegaDenseModel  # noqa: E402,F401
