@@ -1024,3 +1024,18 @@ def test_megakernel_dependency_graph_under_out_of_order_execution(dist_env):
     bad.run()
     assert not torch.allclose(y, want, atol=1e-4)            # the missing edge is visible
 
+
+def test_tuned_entry_points_expose_their_search_spaces(dist_env):
+    from triton_dist.ops import ag_gemm as AG
+    from triton_dist.ops import gemm_rs as RS
+    space = RS.get_gemm_rs_config_space()
+    assert {(c["bn"], c["cta_group"]) for c in space} >= {(256, 2), (128, 1)} and len(AG.ag_gemm_config_space()) == len(AG.AG_GEMM_TUNE_SPACE)
+    ctx = RS.create_gemm_rs_context(max_M=256, N=384, rank=0, world_size=1, local_world_size=1, output_dtype=torch.float32)
+    A, B = torch.randn(256, 64), torch.randn(384, 64)
+    assert RS.gemm_rs_prune_fn(dict(bn=256, cta_group=2), A, B.t(), ctx) and not RS.gemm_rs_prune_fn(dict(bn=192, cta_group=2), A, torch.randn(320, 64).t(), ctx)
+    assert not RS.gemm_rs_prune_fn(dict(bn=256, cta_group=2), A[:128], B.t(), ctx) and RS.gemm_rs_prune_fn(dict(bn=256, cta_group=1), A[:128], B.t(), ctx)
+    assert "tp1" in RS.gemm_rs_key_fn(A, B.t(), ctx)
+    out = RS.gemm_rs_tuned(A, B.t(), ctx, autotune=False)
+    torch.testing.assert_close(out, A @ B.t(), atol=1e-4, rtol=1e-4)
+    ctx.finalize()
+

@@ -322,6 +322,15 @@ AG_GEMM_TUNE_SPACE = (
        dict(transport="sm", bn=128, cta_group=2, n_comm=32, kslices=0, groups=0, tail=0)])
 
 
+def ag_gemm_config_space():
+    """The search space of ``ag_gemm_tuned`` (reference: allgather_gemm.py ``ag_gemm_config_space``)."""
+    return list(AG_GEMM_TUNE_SPACE)
+
+
+def ag_gemm_key_fn(A, B, ctx, **_):
+    return f"{tuple(A.shape)}x{tuple(B.shape)}@tp{ctx.num_ranks}"
+
+
 def _ag_prune(cfg, A, B, ctx, **_):
     Ms = A.shape[0]
     if cfg["transport"] in ("sm_k", "multicast") and Ms % 128:
@@ -331,7 +340,7 @@ def _ag_prune(cfg, A, B, ctx, **_):
     return cfg["cta_group"] == 1 or Ms % 256 == 0
 
 
-@autotune(AG_GEMM_TUNE_SPACE, key_fn=lambda A, B, ctx, **kw: f"{tuple(A.shape)}x{tuple(B.shape)}@tp{ctx.num_ranks}", prune_fn=_ag_prune,
+@autotune(AG_GEMM_TUNE_SPACE, key_fn=ag_gemm_key_fn, prune_fn=_ag_prune,
           warmup=3, rep=8)
 def ag_gemm_tuned(A: torch.Tensor, B: torch.Tensor, ctx: AllGatherGEMMTensorParallelContext, out: Optional[torch.Tensor] = None,
                   config: Optional[dict] = None) -> torch.Tensor:
@@ -343,3 +352,6 @@ def ag_gemm_tuned(A: torch.Tensor, B: torch.Tensor, ctx: AllGatherGEMMTensorPara
     cfg = GemmConfig(c["bn"], c["cta_group"], max(1, Ms // (128 * c["cta_group"])), True, 0, c["n_comm"])
     return ag_gemm(A, B, ctx, gemm_config=cfg, out=out, transport=c["transport"] if A.is_cuda else "auto", kslices=c["kslices"],
                    comm_groups=c["groups"], tail_pct=c["tail"])
+
+
+ag_gemm_prune_fn = _ag_prune

@@ -253,3 +253,38 @@ def gemm_rs_mxfp8(a, b, ctx: GEMMReduceScatterTensorParallelContext, out: Option
     _C.check(_C.cuda_lib().td_gemm_launch(C.byref(args), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "td_gemm_launch(rs, mxfp8)")
     ctx.host_phase += 1
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# autotuned entry point (reference: gemm_rs is autotuned over {tile config x fuse_scatter x persistent}, gemm_reduce_scatter.py:709-741)
+# ------------------------------------------------------------------------------------------------------------
+from ..tune import autotune  # noqa: E402
+
+
+def get_gemm_rs_config_space():
+    """Tile configurations of the fused GEMM + ReduceScatter kernel worth timing: 2-CTA 256 / 192 / 128-wide tiles and the 1-CTA tile
+    (the only one for ``M / world`` that is a multiple of 128 but not of 256).  The ring runs in the epilogue of every one of them."""
+    return [dict(bn=256, cta_group=2), dict(bn=192, cta_group=2), dict(bn=128, cta_group=2), dict(bn=256, cta_group=1), dict(bn=128, cta_group=1)]
+
+
+def gemm_rs_key_fn(A, B, ctx, **_):
+    return f"{tuple(A.shape)}x{tuple(B.shape)}@tp{ctx.world_size}:{A.dtype}"
+
+
+def gemm_rs_prune_fn(cfg, A, B, ctx, **_):
+    """Keep a configuration only if the kernel accepts it for this shape."""
+    Mr = A.shape[0] // ctx.world_size
+    N = B.shape[1] if B.shape[0] == A.shape[1] else B.shape[0]
+    if Mr % (128 * cfg["cta_group"]):
+        return False
+    return N % cfg["bn"] == 0 or cfg["bn"] != 192
+
+
+@autotune(get_gemm_rs_config_space(), key_fn=gemm_rs_key_fn, prune_fn=gemm_rs_prune_fn, warmup=3, rep=8)
+def gemm_rs_tuned(A: torch.Tensor, B: torch.Tensor, ctx: GEMMReduceScatterTensorParallelContext, out: Optional[torch.Tensor] = None,
+                  config: Optional[dict] = None, **kw) -> torch.Tensor:
+    """``gemm_rs`` with the tile configuration chosen by the function-level autotuner (max over ranks decides, cached on disk per shape /
+    world size / GPU); ``autotune=False`` takes the first configuration."""
+    c = config or get_gemm_rs_config_space()[0]
+    return gemm_rs(A, B, ctx, gemm_config=GemmConfig(c["bn"], c["cta_group"], 8, True, 0, 0) if A.is_cuda else None, out=out, **kw)
+
