@@ -1203,6 +1203,26 @@ def case_lk_ep():
     ep2.finalize()
 
 
+def case_lk_rs_ring():
+    """Ring reduce-scatter written in the DSL (W - 1 hops, per-CTA flags carrying the call number, parity double-buffered slots) against
+    torch.distributed.reduce_scatter; several calls back to back and two chunk lengths reuse the same buffers."""
+    from triton_dist.lk.kernels.reduce_scatter_ring import LkRingReduceScatter
+    W, me = U.world_size(), U.rank()
+    dev = U.current_device()
+    big = dev.type == "cuda"
+    max_chunk = 1 << 16 if big else 96
+    rs = LkRingReduceScatter(max_chunk)
+    for it, chunk in enumerate((max_chunk, max_chunk // 2 + 1, max_chunk, 7)):
+        g = torch.Generator().manual_seed(17 * it + me)
+        x = torch.randn(W, chunk, generator=g).to(dev)
+        out = rs(x)
+        ref = torch.empty(chunk, device=dev)
+        dist.reduce_scatter(ref, [x[r].contiguous() for r in range(W)], group=U.get_triton_dist_world())
+        _assert_close(out, ref, 1e-5, 1e-5, f"lk ring reduce-scatter call {it} chunk {chunk}")
+    U.barrier_all_on_stream()
+    rs.finalize()
+
+
 def case_lk_ag_gemm():
     """AllGather + GEMM as ONE kernel written in the Python DSL (comm CTAs push shards + release-add flags, tcgen05 tiles acquire the
     flags of the rows they need).  GPU: the generated CUDA; emulation: the interpreter with the functional pipeline model, across ranks."""
