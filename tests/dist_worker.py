@@ -1223,6 +1223,28 @@ def case_lk_rs_ring():
     rs.finalize()
 
 
+def case_lk_ar_tree():
+    """Double-binary-tree all-reduce written in the DSL (up pass + down pass over two complementary trees, per-CTA call-numbered flags)
+    against torch.distributed.all_reduce; back-to-back calls and several message lengths on the same buffers (power-of-two worlds)."""
+    from triton_dist.lk.kernels.allreduce_tree import LkDoubleTreeAllReduce
+    W, me = U.world_size(), U.rank()
+    if W & (W - 1):
+        return
+    dev = U.current_device()
+    big = dev.type == "cuda"
+    n_max = 1 << 17 if big else 160
+    ar = LkDoubleTreeAllReduce(n_max)
+    for it, n in enumerate((n_max, n_max // 2 + 2, n_max, 6)):
+        g = torch.Generator().manual_seed(31 * it + me)
+        x = torch.randn(n, generator=g).to(dev)
+        out = ar(x)
+        ref = x.clone()
+        dist.all_reduce(ref, group=U.get_triton_dist_world())
+        _assert_close(out, ref, 1e-5, 1e-5, f"lk double-tree all-reduce call {it} n {n}")
+    U.barrier_all_on_stream()
+    ar.finalize()
+
+
 def case_lk_ag_gemm():
     """AllGather + GEMM as ONE kernel written in the Python DSL (comm CTAs push shards + release-add flags, tcgen05 tiles acquire the
     flags of the rows they need).  GPU: the generated CUDA; emulation: the interpreter with the functional pipeline model, across ranks."""

@@ -6,7 +6,7 @@ from _launch import run_dist
 CPU_ENV = {"TD_FORCE_HOST_BACKEND": "1", "CUDA_VISIBLE_DEVICES": ""}
 
 
-@pytest.mark.parametrize("case", ["primitives", "allgather", "allgather_ring", "ulysses_pack", "allgather_mc", "allreduce", "a2a", "ag_gemm", "gemm_rs", "gemm_ar", "gemm_a2a", "gemm_a2a_q8", "moe", "moe_rs", "moe_staged", "tp_e2e", "ep_ll", "ep_normal", "ep_mega", "ep_fn_api", "ep_metadata", "sp_pp", "sp_varlen", "ep_moe", "mega", "mega_paged", "engine_mega", "mega_server", "lk", "lk_shmem", "lk_ep", "lk_rs_ring", "lk_ag_gemm", "lk_gemm_rs", "shmem"])
+@pytest.mark.parametrize("case", ["primitives", "allgather", "allgather_ring", "ulysses_pack", "allgather_mc", "allreduce", "a2a", "ag_gemm", "gemm_rs", "gemm_ar", "gemm_a2a", "gemm_a2a_q8", "moe", "moe_rs", "moe_staged", "tp_e2e", "ep_ll", "ep_normal", "ep_mega", "ep_fn_api", "ep_metadata", "sp_pp", "sp_varlen", "ep_moe", "mega", "mega_paged", "engine_mega", "mega_server", "lk", "lk_shmem", "lk_ep", "lk_rs_ring", "lk_ar_tree", "lk_ag_gemm", "lk_gemm_rs", "shmem"])
 def test_cpu_world2(case):
     run_dist([case], nproc=2, env_extra=CPU_ENV)
 
@@ -21,7 +21,7 @@ def test_cpu_world3_fused_and_ep():
 
 
 def test_cpu_world4_collectives():
-    run_dist(["allreduce", "allgather", "allgather_ring", "moe", "sp_pp", "shmem"], nproc=4, env_extra=CPU_ENV)
+    run_dist(["allreduce", "allgather", "allgather_ring", "moe", "sp_pp", "shmem", "lk_ar_tree"], nproc=4, env_extra=CPU_ENV)
 
 
 def test_cpu_chaos():
