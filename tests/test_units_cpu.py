@@ -1039,3 +1039,20 @@ def test_tuned_entry_points_expose_their_search_spaces(dist_env):
     torch.testing.assert_close(out, A @ B.t(), atol=1e-4, rtol=1e-4)
     ctx.finalize()
 
+
+def test_sort_topk_ids_align_block_size_metadata():
+    from triton_dist.ops import moe as M
+    g = torch.Generator().manual_seed(1)
+    W, E, T, topk, bm, rank = 4, 5, 24, 2, 8, 2
+    ids = torch.stack([torch.randperm(E, generator=g)[:topk] for _ in range(W * T)]).to(torch.int32)
+    sorted_ids, expert_idx, tiled_m, seg0, seg1, ntiles = M.sort_topk_ids_align_block_size(ids, E, rank, W, W, bm)
+    assert int(ntiles) == expert_idx.numel() == tiled_m.numel() and torch.all(seg1[:-1] <= seg1[1:]) and len(set(tiled_m.tolist())) == tiled_m.numel()
+    for e, tm, s0, s1 in zip(expert_idx.tolist(), tiled_m.tolist(), seg0.tolist(), seg1.tolist()):
+        rows = sorted_ids[tm * bm:(tm + 1) * bm]
+        rows = rows[rows != ids.numel()]
+        assert rows.numel() > 0 and torch.all(ids.view(-1)[rows.long()] == e)                  # the row block belongs to that expert ...
+        stages = ((rows // topk) // T - rank) % W
+        assert int(stages.min()) == s0 and int(stages.max()) == s1                             # ... and needs exactly those shards
+    _, cnt, _ = M.calc_sorted_gather_index(ids, W, E, bm, rank)
+    assert cnt.shape == (W, E) and int(cnt.sum()) == ids.numel()
+

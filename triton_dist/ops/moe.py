@@ -337,6 +337,48 @@ def moe_forward_local(x: torch.Tensor, w: torch.Tensor, topk_ids: torch.Tensor, 
     return scatter_rows(ys, r, topk_ids.numel())
 
 
+def calc_sorted_gather_index(topk_ids: torch.Tensor, num_ranks: int, num_experts: int, block_size: int = 128, rank: int = 0):
+    """(sorted (token, k) indices padded per expert to ``block_size``, token counts [num_ranks, num_experts]) -- rows of every expert ordered
+    by the all-gather arrival stage of their source rank (reference: allgather_group_gemm.py ``calc_sorted_gather_index`` :86-166)."""
+    T = topk_ids.shape[0]
+    assert T % num_ranks == 0
+    r = moe_align_sort(topk_ids, num_experts, block_size, tokens_per_rank=T // num_ranks, rank=rank, world=num_ranks)
+    ids = topk_ids.view(num_ranks, -1).long()
+    valid = (ids >= 0) & (ids < num_experts)
+    cnt = torch.zeros(num_ranks, num_experts + 1, dtype=torch.int64, device=topk_ids.device)
+    cnt.scatter_add_(1, torch.where(valid, ids, torch.full_like(ids, num_experts)), torch.ones_like(ids))
+    return r.sorted_ids, cnt[:, :num_experts].to(torch.int32), r
+
+
+def sort_topk_ids_align_block_size(topk_ids: torch.Tensor, num_experts: int, rank: int, num_ranks: int, num_local_ranks: int = 0,
+                                   block_size: int = 128):
+    """The routing metadata of the fused AllGather + grouped GEMM in the reference's shape (allgather_group_gemm.py:201):
+    ``(sorted_gather_index, expert_idx, tiled_m, segment_start, segment_end, ntiles)`` -- per tile, in execution order (tiles whose
+    shards arrive first run first): its expert, its row-block index in the padded sorted layout, and the first / last all-gather stage it
+    needs.  The tile table is built on the host from the [ranks, experts] histogram (one small device-to-host copy)."""
+    from .tile_swizzle import ag_moe_tile_table
+    sorted_ids, cnt, r = calc_sorted_gather_index(topk_ids, num_ranks, num_experts, block_size, rank)
+    table = ag_moe_tile_table(cnt.cpu().numpy(), rank, block_size)
+    dev = topk_ids.device
+    t = torch.from_numpy(table).to(dev) if len(table) else torch.zeros((0, 4), dtype=torch.int32, device=dev)
+    first_block = (r.expert_offsets[:-1].to(torch.int64) // block_size).to(dev)
+    tiled_m = (first_block[t[:, 0].long()] + t[:, 1].long()).to(torch.int32)
+    return sorted_ids, t[:, 0].contiguous(), tiled_m, t[:, 2].contiguous(), t[:, 3].contiguous(), torch.tensor([t.shape[0]], dtype=torch.int32, device=dev)
+
+
+def run_moe_ag_triton_non_overlap(x_shard: torch.Tensor, weights: torch.Tensor, chosen_experts: torch.Tensor, group=None, **_hints):
+    """The NON-overlapped baseline of ``ag_group_gemm`` (reference :901): NCCL all-gather of the token shards, then the local grouped GEMM.
+    ``weights``: [E, N_local, K] -> [T * topk, N_local]."""
+    group = group or U.get_triton_dist_world()
+    W = U.world_size()
+    x = torch.empty((x_shard.shape[0] * W, x_shard.shape[1]), dtype=x_shard.dtype, device=x_shard.device)
+    torch.distributed.all_gather_into_tensor(x, x_shard.contiguous(), group=group)
+    if not x.is_cuda:
+        ids = chosen_experts.long()
+        return torch.einsum("tk,tjnk->tjn", x.float(), weights.float()[ids]).reshape(ids.numel(), -1).to(x.dtype)
+    return moe_forward_local(x, weights, chosen_experts)
+
+
 # ------------------------------------------------------------------------------------------------------------
 # AG + grouped GEMM (TP-MoE up projection)
 # ------------------------------------------------------------------------------------------------------------
