@@ -350,6 +350,11 @@ def run_moe_reduce_rs_triton_non_overlap(x, w, chosen_experts, expert_weight, ct
     return M.moe_reduce_rs_torch(x, w, chosen_experts, expert_weight, group or U.get_triton_dist_world(), W, me)
 
 
+def run_moe_reduce_ar_triton_non_overlap(x, w, chosen_experts, expert_weight, ctx=None, group=None, **_hints):
+    """(moe_reduce_ar.py) the non-overlapped baseline of ``run_moe_reduce_ar``: grouped GEMM, weighted top-k reduce, one all-reduce."""
+    return M.moe_reduce_ar_torch(x, w, chosen_experts, expert_weight, group or U.get_triton_dist_world(), U.world_size())
+
+
 def create_context(max_num_token: int, token_len_elem: int, num_expert_per_rank: int = 1, dtype: torch.dtype = torch.bfloat16, **_hints):
     """(all_to_all_vdev_2d_offset.py:528) context of the variable-size 2-D all-to-all: rows of ``token_len_elem`` elements, at most
     ``max_num_token`` rows per peer."""

@@ -692,3 +692,22 @@ def moe_reduce_rs_torch(x, w, chosen_experts, expert_weight, group, world_size, 
     if world_size > 1:
         dist.all_reduce(part, group=group)
     return part[rank * (T // world_size):(rank + 1) * (T // world_size)]
+
+
+def moe_reduce_ar_torch(x, w, chosen_experts, expert_weight, group, world_size):
+    """Golden / non-overlapped baseline of ``run_moe_reduce_ar`` (reference: moe_reduce_ar.py ``run_moe_reduce_ar_triton_non_overlap``):
+    masked per-expert matmul, weighted top-k sum, one all-reduce -> [T, N] on every rank."""
+    if w.shape[1] != x.shape[1]:
+        w = w.transpose(1, 2)
+    T, topk = chosen_experts.shape
+    ids = chosen_experts.reshape(-1).long()
+    y = torch.zeros((T * topk, w.shape[2]), dtype=torch.float32, device=x.device)
+    for e in range(w.shape[0]):
+        m = ids == e
+        if m.any():
+            y[m] = x[m].float() @ w[e].float()
+    part = (y.view(T, topk, -1) * expert_weight.float()[..., None]).sum(1)
+    if world_size > 1:
+        dist.all_reduce(part, group=group)
+    return part
+
