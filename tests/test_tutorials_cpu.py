@@ -20,3 +20,16 @@ def test_tutorial(script, expect):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert expect in r.stdout + r.stderr
+
+
+def test_stress_script_on_the_emulation_backend():
+    """The stress test of the flagship ops (random shapes on one pair of contexts, unverified back-to-back calls, then a verified one) at a
+    non-power-of-two world with random skew before every flag operation (reference: test/stress/stress_test_ag_gemm.py)."""
+    env = dict(os.environ, TD_FORCE_HOST_BACKEND="1", CUDA_VISIBLE_DEVICES="", TD_SYMM_HEAP_SIZE="256m", OMP_NUM_THREADS="2", TD_HOST_CHAOS_US="1500",
+               PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=3", "--master-addr", "127.0.0.1",
+           "--master-port", str(free_port()), os.path.join(ROOT, "triton_dist", "test", "stress", "stress_test_ag_gemm.py"),
+           "--max_M", "96", "--N", "48", "--K", "64", "--iters", "2", "--verify_hang", "4", "--verify_shapes", "3"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 0 and "stress test OK" in r.stdout + r.stderr, r.stdout[-3000:] + r.stderr[-3000:]
+
