@@ -1245,6 +1245,26 @@ def case_lk_ar_tree():
     ar.finalize()
 
 
+def case_lk_ar_push():
+    """One-shot and two-shot push all-reduce written in the DSL against torch.distributed.all_reduce: back-to-back calls, several lengths."""
+    from triton_dist.lk.kernels.allreduce_push import LkPushAllReduce
+    W, me = U.world_size(), U.rank()
+    dev = U.current_device()
+    big = dev.type == "cuda"
+    n_max = (1 << 16) * W if big else 40 * W
+    for method in ("one_shot", "two_shot"):
+        ar = LkPushAllReduce(n_max, method)
+        for it, n in enumerate((n_max, 3 * W, n_max, W)):
+            g = torch.Generator().manual_seed(13 * it + me)
+            x = torch.randn(n, generator=g).to(dev)
+            out = ar(x).clone()
+            ref = x.clone()
+            dist.all_reduce(ref, group=U.get_triton_dist_world())
+            _assert_close(out, ref, 1e-5, 1e-5, f"lk {method} push all-reduce call {it} n {n}")
+        U.barrier_all_on_stream()
+        ar.finalize()
+
+
 def case_lk_ag_gemm():
     """AllGather + GEMM as ONE kernel written in the Python DSL (comm CTAs push shards + release-add flags, tcgen05 tiles acquire the
     flags of the rows they need).  GPU: the generated CUDA; emulation: the interpreter with the functional pipeline model, across ranks."""
