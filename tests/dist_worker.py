@@ -1265,6 +1265,25 @@ def case_lk_ar_push():
         ar.finalize()
 
 
+def case_lk_ag_ll():
+    """Low-latency all-gather with the flag inside the data (8-byte atoms, no barrier, no separate flags) written in the DSL, against
+    torch.distributed.all_gather; payloads of several dtypes, back-to-back calls (parity double-buffering)."""
+    from triton_dist.lk.kernels.allgather_ll import LkLLAllGather
+    W, me = U.world_size(), U.rank()
+    dev = U.current_device()
+    big = dev.type == "cuda"
+    ag = LkLLAllGather(1 << 16 if big else 256)
+    for it, (n, dt) in enumerate(((64 if not big else 16384, torch.float32), (10, torch.bfloat16), (33, torch.int32), (64 if not big else 16384, torch.float32))):
+        g = torch.Generator().manual_seed(7 * it + me)
+        x = (torch.randn(n, generator=g) * 100).to(dt).to(dev)
+        out = ag(x)
+        ref = [torch.empty_like(x) for _ in range(W)]
+        dist.all_gather(ref, x, group=U.get_triton_dist_world())
+        assert torch.equal(out.cpu(), torch.stack(ref).cpu()), (it, n, dt)
+    U.barrier_all_on_stream()
+    ag.finalize()
+
+
 def case_lk_ag_gemm():
     """AllGather + GEMM as ONE kernel written in the Python DSL (comm CTAs push shards + release-add flags, tcgen05 tiles acquire the
     flags of the rows they need).  GPU: the generated CUDA; emulation: the interpreter with the functional pipeline model, across ranks."""

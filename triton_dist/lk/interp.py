@@ -70,9 +70,17 @@ class Ptr:
 
     def __getitem__(self, i):
         v = self.base[self.off + int(i)]
-        return v.item() if hasattr(v, "item") else v
+        v = v.item() if hasattr(v, "item") else v
+        e = self.elem
+        if e is not None and getattr(e, "kind", None) == "u" and isinstance(v, int) and v < 0:
+            v += 1 << e.bits                          # an unsigned pointer over signed storage (torch has no uint32 / uint64 arithmetic)
+        return v
 
     def __setitem__(self, i, v):
+        e = self.elem
+        if e is not None and getattr(e, "kind", None) == "u" and isinstance(v, int) and hasattr(self.base, "dtype") \
+                and getattr(self.base.dtype, "is_signed", False) and v >= 1 << (e.bits - 1):
+            v -= 1 << e.bits                          # same bits, representable in the signed storage
         self.base[self.off + int(i)] = v
 
     skey = None                                      # set for pointers into shared arrays (mbarrier identity)
