@@ -8,7 +8,7 @@ N=${1:-1}
 mkdir -p gpurun_out
 export PYTHONPATH=$PWD
 echo "== single-GPU items (xfail markers ignored: real pass / fail)"
-timeout 900 python -m pytest tests/test_zz_lk_gpu.py -q --runxfail -p no:cacheprovider 2>&1 | tail -25 | tee gpurun_out/pending_1gpu.log
+timeout 2400 python -m pytest tests/test_zz_lk_gpu.py -q --runxfail -p no:cacheprovider 2>&1 | tail -25 | tee gpurun_out/pending_1gpu.log
 echo "== DSL GEMM ladder vs the hand-written kernel (4096^3 bf16)"
 timeout 300 python - <<'PY' 2>&1 | tee gpurun_out/pending_lk_gemm_perf.log
 import torch
@@ -30,9 +30,18 @@ for name, f in (("hand-written (persistent 2-CTA)", lambda: gemm(a, b, out=c)), 
     except Exception as e:
         print(name, "FAILED", repr(e)[:200])
 PY
+echo "== DSL micro-benchmarks (numbers: gpurun_out/lk_microbench.json)"
+timeout 300 python -m triton_dist.lk.bench --json gpurun_out/lk_microbench.json 2>&1 | tail -16 | tee gpurun_out/pending_microbench.log
+echo "== DSL GEMM ladder, all nine levels"
+timeout 600 python - <<'PY' 2>&1 | tee gpurun_out/pending_lk_levels.log
+from triton_dist.lk.kernels.gemm_sm100 import LEVELS, test_all_levels
+for lv, (err, ms) in test_all_levels().items():
+    print(f"level {lv}: max|err| {err:.3f}  {ms * 1e3:8.1f} us  {2 * 4096**3 / ms / 1e9:7.0f} TFLOP/s   {LEVELS[lv][0]}")
+PY
 if [ "$N" -ge 2 ]; then
   echo "== distributed items on $N GPUs"
-  for c in shmem allgather_mc gemm_a2a_q8 sp_varlen lk lk_ag_gemm lk_gemm_rs ep_fn_api allgather; do
+  for c in shmem allgather_mc gemm_a2a_q8 sp_varlen lk lk_ag_gemm lk_gemm_rs ep_fn_api allgather allgather_ring a2a ulysses_pack \
+           lk_shmem lk_ep lk_rs_ring lk_ar_tree lk_ar_push lk_ag_ll mega_paged engine_mega mega_server ep_metadata; do
     timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port $((24000 + RANDOM % 2000)) \
       tests/dist_worker.py $c 2>&1 | grep -E "CASE|Error|rror:" | head -3 | tee -a gpurun_out/pending_dist_n$N.log
   done
