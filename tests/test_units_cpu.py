@@ -1056,3 +1056,30 @@ def test_sort_topk_ids_align_block_size_metadata():
     _, cnt, _ = M.calc_sorted_gather_index(ids, W, E, bm, rank)
     assert cnt.shape == (W, E) and int(cnt.sum()) == ids.numel()
 
+
+def test_find_topk_picks_a_covering_set_of_configurations(tmp_path):
+    """Greedy best-of-k selection over a slowdown matrix: two complementary specialists beat the single best generalist; filters; CLI."""
+    import json
+    import numpy as np
+    from triton_dist.tools.tune import find_topk as F
+    # config A wins small shapes, B wins large ones, C is second everywhere (the best SINGLE choice), D is never competitive
+    data = {}
+    for i, M in enumerate((128, 256, 512, 4096, 8192, 16384)):
+        small = M <= 512
+        data[str((M, 4096, 4096))] = [dict(cfg=["A"], ms=1.0 if small else 1.6), dict(cfg=["B"], ms=1.7 if small else 1.0),
+                                      dict(cfg=["C"], ms=1.08), dict(cfg=["D"], ms=3.0), dict(cfg=["E"], error="launch failed")]
+    cfgs, shapes, S = F.slowdown_matrix(data)
+    assert cfgs == [("A",), ("B",), ("C",), ("D",)] and S.shape == (4, 6) and np.allclose(S.min(axis=0), 1.0)
+    one, stats1 = F.find_best_topk(S, 1)
+    two, stats2 = F.find_best_topk(S, 2)
+    assert [cfgs[i] for i in one] == [("C",)] and abs(stats1[0] - 1.08) < 1e-9
+    assert {cfgs[i] for i in two} == {("A",), ("B",)} and stats2 == (1.0, 1.0, 1.0, 1.0)
+    mm, _ = F.find_best_topk(S, 1, objective="minimax")
+    assert cfgs[mm[0]] == ("C",)
+    _, shapes_small, _ = F.slowdown_matrix(data, [F.IntFilter([1, 512]), F.IntFilter(None), F.IntFilter(4096)])
+    assert len(shapes_small) == 3 and F.parse_range("128-1024-128") == (128, 1024, 128) and F.parse_int_range_args(None, "8-64-8").match(64)
+    assert not F.IntFilter(7).match(8) and F.IntFilter(7).is_int()
+    p = tmp_path / "r.json"
+    p.write_text(json.dumps(data))
+    assert F.main([str(p), "--topk", "2", "--M-range", "128-512-128"]) == 0
+
