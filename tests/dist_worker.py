@@ -1284,7 +1284,31 @@ def case_lk_ag_ll():
     ag.finalize()
 
 
-def case_lk_ag_gemm():
+def case_lk_ar_nvls():
+    """NVLS all-reduce written in the DSL (one-shot: every rank reduces the whole message with multimem.ld_reduce; two-shot: every rank reduces
+    its share and multimem.st-broadcasts it) against torch.distributed.all_reduce, bf16 and fp32.  On the emulation backend the multicast
+    alias is modelled: a multimem load sums the word over every rank's copy, a multimem store writes every copy."""
+    from triton_dist.lk.kernels.allreduce_nvls import LkNvlsAllReduce
+    W, me = U.world_size(), U.rank()
+    dev = U.current_device()
+    big = dev.type == "cuda"
+    if big and not U.is_nvshmem_multimem_supported():
+        return
+    nmax = (1 << 18) if big else 16 * 24
+    for method in ("one_shot", "two_shot"):
+        ar = LkNvlsAllReduce(nmax, method, grid=2 if not big else 4)
+        for it, (n, dt) in enumerate(((nmax // 4, torch.float32), (nmax // 2, torch.bfloat16), (8, torch.float32), (nmax // 2, torch.bfloat16))):
+            g = torch.Generator().manual_seed(11 * it + me)
+            x = (torch.randn(n, generator=g) * 0.5).to(dt).to(dev)
+            out = ar(x)
+            ref = x.float().clone()
+            dist.all_reduce(ref, group=U.get_triton_dist_world())
+            _assert_close(out.float(), ref, 5e-2 if dt == torch.bfloat16 else 1e-5, 2e-2 if dt == torch.bfloat16 else 1e-5, f"lk nvls {method} call {it}")
+        U.barrier_all_on_stream()
+        ar.finalize()
+
+
+
     """AllGather + GEMM as ONE kernel written in the Python DSL (comm CTAs push shards + release-add flags, tcgen05 tiles acquire the
     flags of the rows they need).  GPU: the generated CUDA; emulation: the interpreter with the functional pipeline model, across ranks."""
     from triton_dist.lk.kernels.ag_gemm import LkAgGemmContext, run_ag_gemm

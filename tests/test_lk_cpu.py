@@ -218,7 +218,7 @@ def test_interpreter_integer_wraparound_and_errors():
     with pytest.raises(RuntimeError, match="trap"):
         boom.interpret(1, torch.zeros(1))                    # one thread fails: the block's barrier is aborted, no hang
     with pytest.raises(NotImplementedError):
-        ll.multimem_st_v4(None, None)                        # NVLS has no CPU meaning
+        ll.ld_shared_v4(None)                                # raw shared-window addresses have no CPU meaning
 
 
 def test_gdn_chunk_kernels_in_the_interpreter_match_the_recurrence():

@@ -344,11 +344,75 @@ make_uint4 = _i("make_uint4", uint4, "make_uint4({0}, {1}, {2}, {3})", 4,
 ldg = _i("ldg", _elem, "__ldg({0})", 1, interp=_ld)
 prefetch_l2 = _i("prefetch_l2", None, "td::ptx::prefetch_l2_bulk({0}, {1})", 2)
 # NVLS multicast
-multimem_ld_reduce_bf16x8 = _i("multimem_ld_reduce_bf16x8", uint4, "td::ptx::multimem_ld_reduce_bf16x8({0})", 1)
-multimem_ld_reduce_f16x8 = _i("multimem_ld_reduce_f16x8", uint4, "td::ptx::multimem_ld_reduce_f16x8({0})", 1)
-multimem_ld_reduce_f32x4 = _i("multimem_ld_reduce_f32x4", uint4, "td::ptx::multimem_ld_reduce_f32x4({0})", 1)
-multimem_st_v4 = _i("multimem_st_v4", None, "td::ptx::multimem_st_v4({0}, {1})", 2)
-multimem_red_add_u32 = _i("multimem_red_add_u32", None, "td::ptx::multimem_red_add_u32({0}, {1})", 2)
+# NVLS in the interpreter: ``symm_mc`` returns a pointer that remembers it is the multicast alias (``McPtr``); a multimem load reads the word
+# from EVERY rank's copy on the emulation heap and adds (what the switch does), a multimem store / reduction touches every copy.
+class McPtr:
+    def __init__(self, p):
+        self.p = p
+
+    def __add__(self, n):
+        return McPtr(self.p + n)
+
+    __radd__ = __add__
+
+    def __sub__(self, n):
+        return McPtr(self.p - n)
+
+    def copies(self):
+        import triton_dist.utils as U
+        out = []
+        for r in range(U.world_size()):
+            t = U.symm_at(self.p.owner, r)
+            out.append(I.Ptr(t.view(-1), self.p.off, self.p.elem, owner=t))
+        return out
+
+
+def _need_mc(mc, what):
+    if not isinstance(mc, McPtr):
+        raise TypeError(f"ll.{what} takes the multicast alias of a symmetric pointer (ll.symm_mc(ctx, p)), got an ordinary pointer")
+    return mc
+
+
+def _interp_mm_ld_reduce(kind):
+    def f(mc):
+        import struct as _st
+        import types as _ty
+        from . import pipeline as P
+        words = [P.ld_v4(c) for c in _need_mc(mc, "multimem_ld_reduce").copies()]
+        out = []
+        for k in ("x", "y", "z", "w"):
+            ws = [getattr(w, k) for w in words]
+            if kind == "f32":
+                tot = sum(_st.unpack("f", _st.pack("I", w))[0] for w in ws)
+                out.append(_st.unpack("I", _st.pack("f", tot))[0])
+            elif kind == "bf16":
+                out.append(P.pack_bf16x2(sum(P._bf16_val(w) for w in ws), sum(P._bf16_val(w >> 16) for w in ws)))
+            else:
+                import torch
+                h = lambda b: torch.tensor([b & 0xFFFF], dtype=torch.int32).to(torch.int16).view(torch.float16).float().item()
+                lo, hi = sum(h(w) for w in ws), sum(h(w >> 16) for w in ws)
+                pk = lambda v: int(torch.tensor([v], dtype=torch.float16).view(torch.int16).item()) & 0xFFFF
+                out.append(pk(lo) | (pk(hi) << 16))
+        return _ty.SimpleNamespace(x=out[0], y=out[1], z=out[2], w=out[3])
+    return f
+
+
+def _interp_mm_st_v4(mc, v):
+    from . import pipeline as P
+    for c in _need_mc(mc, "multimem_st_v4").copies():
+        P.st_v4(c, v)
+
+
+def _interp_mm_red_add_u32(mc, v):
+    for c in _need_mc(mc, "multimem_red_add_u32").copies():
+        I.atomic_rmw(c, 0, lambda o: (o + int(v)) & 0xFFFFFFFF)
+
+
+multimem_ld_reduce_bf16x8 = _i("multimem_ld_reduce_bf16x8", uint4, "td::ptx::multimem_ld_reduce_bf16x8({0})", 1, interp=_interp_mm_ld_reduce("bf16"))
+multimem_ld_reduce_f16x8 = _i("multimem_ld_reduce_f16x8", uint4, "td::ptx::multimem_ld_reduce_f16x8({0})", 1, interp=_interp_mm_ld_reduce("f16"))
+multimem_ld_reduce_f32x4 = _i("multimem_ld_reduce_f32x4", uint4, "td::ptx::multimem_ld_reduce_f32x4({0})", 1, interp=_interp_mm_ld_reduce("f32"))
+multimem_st_v4 = _i("multimem_st_v4", None, "td::ptx::multimem_st_v4({0}, {1})", 2, interp=_interp_mm_st_v4)
+multimem_red_add_u32 = _i("multimem_red_add_u32", None, "td::ptx::multimem_red_add_u32({0}, {1})", 2, interp=_interp_mm_red_add_u32)
 red_add_bf16x8 = _i("red_add_bf16x8", None, "td::ptx::red_add_bf16x8({0}, {1})", 2)
 
 # ------------------------------------------------------------------------------------------------------------
@@ -459,7 +523,8 @@ rank = _i("rank", i32, "td::rank({0})", 1, interp=lambda ctx: ctx.rank)
 num_ranks = _i("num_ranks", i32, "td::num_ranks({0})", 1, interp=lambda ctx: ctx.world)
 symm_at = _i("symm_at", lambda a: a[1].ty if isinstance(a[1].ty, Pointer) else Pointer(a[1].ty.elem), "td::symm_at({0}, {1}, {2})", 3,
              interp=_interp_symm_at, doc="(ctx, local pointer, peer) -> the same offset in peer's heap segment")
-symm_mc = _i("symm_mc", lambda a: a[1].ty, "td::symm_mc({0}, {1})", 2, doc="(ctx, local pointer) -> NVLS multicast alias")
+symm_mc = _i("symm_mc", lambda a: a[1].ty, "td::symm_mc({0}, {1})", 2, interp=lambda ctx, p: McPtr(p),
+             doc="(ctx, local pointer) -> NVLS multicast alias (loads reduce over all ranks' copies in the switch, stores reach all of them)")
 notify = Intrinsic("notify", None, emit=_emit_notify, interp=_interp_notify,
                    doc="(ctx, flag, peer, value, op='set'|'add'): release store / add of a flag on peer; call from ONE thread")
 wait = Intrinsic("wait", None, emit=_emit_wait, interp=_interp_wait,
