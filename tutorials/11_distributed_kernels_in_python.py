@@ -113,6 +113,22 @@ ref = sum((x.float() * (ids[:, k] + 1).float()[:, None]).to(torch.bfloat16).floa
 torch.testing.assert_close(out.float().cpu(), ref.cpu(), atol=3e-2, rtol=3e-2)
 U.dist_print(f"rank {me}: dispatch -> experts -> combine ({int(cnt.sum())} rows received) OK", allowed_ranks=[0])
 
+# ---- 4. the NVSwitch as a reduction engine: multimem loads / stores from Python ------------------------------------------------------
+# ``ll.symm_mc(ctx, p)`` is the multicast alias of a symmetric pointer: ``ll.multimem_ld_reduce_*`` through it returns the SUM of the word
+# over every rank's copy (added inside the switch), ``ll.multimem_st_v4`` writes every copy.  triton_dist/lk/kernels/allreduce_nvls.py
+# builds the one-shot and two-shot all-reduce of the product from them; the interpreter models the alias on the emulation heap.
+from triton_dist.lk.kernels.allreduce_nvls import LkNvlsAllReduce  # noqa: E402
+
+if not gpu or U.is_nvshmem_multimem_supported():
+    for method in ("one_shot", "two_shot"):
+        ar = LkNvlsAllReduce(4096, method)
+        xs = torch.full((256,), float(me + 1), device=dev).bfloat16()
+        got = ar(xs)
+        assert torch.equal(got.float().cpu(), torch.full((256,), W * (W + 1) / 2.0))
+        U.barrier_all_on_stream()
+        ar.finalize()
+    U.dist_print(f"rank {me}: NVLS one-shot / two-shot all-reduce OK", allowed_ranks=[0])
+
 ep.finalize()
 for t in (total, counter, slots, sig, inbox):
     U.nvshmem_free_tensor_sync(t)
