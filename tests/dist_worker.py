@@ -1308,7 +1308,32 @@ def case_lk_ar_nvls():
         ar.finalize()
 
 
+def case_lk_gemm_ar():
+    """GEMM + AllReduce as one DSL kernel: tcgen05 tiles stage their output and flag every rank, consumer CTAs reduce finished tiles through
+    the multicast alias (multimem.ld_reduce).  Emulation: pipeline model + multicast model across processes; ragged M, three calls."""
+    from triton_dist.lk.kernels.gemm_ar import LkGemmArContext, run_gemm_ar
+    W, me = U.world_size(), U.rank()
+    dev = U.current_device()
+    gpu = dev.type == "cuda"
+    if gpu and not U.is_nvshmem_multimem_supported():
+        return
+    max_M, K, N = (512, 512, 768) if gpu else (160, 128, 136)
+    ctx = LkGemmArContext(max_M, N, BN=128, STAGES=2 if not gpu else 4, N_COMM=2 if not gpu else 8)
+    for it, M in enumerate((max_M, max_M - 27, 16)):
+        g = torch.Generator().manual_seed(50 * it + me)
+        a = (torch.randn(M, K, generator=g) * 0.3).to(torch.bfloat16).to(dev)
+        b = (torch.randn(N, K, generator=g) * 0.3).to(torch.bfloat16).to(dev)
+        out = run_gemm_ar(ctx, a, b)
+        if gpu:
+            torch.cuda.synchronize()
+        ref = (a.float() @ b.float().t()).to(torch.bfloat16).float()          # every rank's tile is rounded to bf16 before the switch adds
+        dist.all_reduce(ref, group=U.get_triton_dist_world())
+        _assert_close(out.float(), ref, 6e-2, 3e-2, f"lk gemm_ar call {it} M {M}")
+    U.barrier_all_on_stream()
+    ctx.finalize()
 
+
+def case_lk_ag_gemm():
     """AllGather + GEMM as ONE kernel written in the Python DSL (comm CTAs push shards + release-add flags, tcgen05 tiles acquire the
     flags of the rows they need).  GPU: the generated CUDA; emulation: the interpreter with the functional pipeline model, across ranks."""
     from triton_dist.lk.kernels.ag_gemm import LkAgGemmContext, run_ag_gemm

@@ -21,7 +21,7 @@ WORLD2_GROUPS = [
     ["mega_server"],
     ["lk", "lk_shmem", "lk_ep"],
     ["lk_rs_ring", "lk_ar_tree", "lk_ar_push", "lk_ag_ll", "lk_ar_nvls"],
-    ["lk_ag_gemm"],
+    ["lk_ag_gemm", "lk_gemm_ar"],
     ["lk_gemm_rs"],
 ]
 
