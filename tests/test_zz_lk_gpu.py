@@ -397,7 +397,7 @@ def test_late_host_level_cases_two_gpus(case):
         pytest.skip("needs 2 GPUs")
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from _launch import run_dist
-    run_dist([case], nproc=2, timeout=240)
+    run_dist([case], nproc=2, timeout=150)
 
 
 @pytest.mark.xfail(strict=False, reason="DSL micro-benchmark suite: kernels verified in the interpreter, first hardware run pending")
