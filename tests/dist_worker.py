@@ -1333,6 +1333,31 @@ def case_lk_gemm_ar():
     ctx.finalize()
 
 
+def case_allreduce_dsl():
+    """``TD_ALLREDUCE_DSL=1``: ``ops.comm.all_reduce`` served by the NVLS kernels written in the DSL (A/B switch against the CUDA kernels);
+    one- and two-shot methods, bf16 and fp32, a message longer than the workspace (chunked)."""
+    from triton_dist.ops import comm
+    W, me = U.world_size(), U.rank()
+    dev = U.current_device()
+    if dev.type == "cuda" and not U.is_nvshmem_multimem_supported():
+        return
+    os.environ["TD_ALLREDUCE_DSL"] = "1"
+    try:
+        ctx = comm.create_allreduce_ctx(1024, me, W, W)
+        for it, (n, dt, method) in enumerate(((128, torch.float32, comm.AllReduceMethod.OneShot_Multimem), (256, torch.bfloat16, comm.AllReduceMethod.TwoShot_Multimem),
+                                              (1000, torch.float32, comm.AllReduceMethod.Unknown))):
+            g = torch.Generator().manual_seed(5 * it + me)
+            x = (torch.randn(n, generator=g) * 0.5).to(dt).to(dev)
+            out = comm.all_reduce(x, method, ctx)
+            ref = x.float().clone()
+            dist.all_reduce(ref, group=U.get_triton_dist_world())
+            _assert_close(out.float(), ref, 5e-2 if dt == torch.bfloat16 else 1e-5, 2e-2 if dt == torch.bfloat16 else 1e-5, f"all_reduce via DSL call {it}")
+        assert set(ctx._dsl) == {"one_shot", "two_shot"}
+        ctx.finalize()
+    finally:
+        os.environ.pop("TD_ALLREDUCE_DSL", None)
+
+
 def case_lk_ag_gemm():
     """AllGather + GEMM as ONE kernel written in the Python DSL (comm CTAs push shards + release-add flags, tcgen05 tiles acquire the
     flags of the rows they need).  GPU: the generated CUDA; emulation: the interpreter with the functional pipeline model, across ranks."""

@@ -183,6 +183,8 @@ class AllReduceContext:
         if self.stage.is_cuda:
             torch.cuda.synchronize()
         U.barrier_all_host()
+        for impl in self.__dict__.pop("_dsl", {}).values():            # DSL twins created by TD_ALLREDUCE_DSL=1
+            impl.finalize()
         for t in (self.stage, self.stage2, self.slots, getattr(self, "ll_buf", None)):
             if t is not None:
                 U.get_heap().free_tensor(t)
@@ -250,6 +252,11 @@ def all_reduce(x: torch.Tensor, method=AllReduceMethod.Unknown, ctx: AllReduceCo
     nbytes = x.numel() * x.element_size()
     if nbytes % 16:
         raise ValueError("all_reduce: message size must be a multiple of 16 bytes")
+    if U.get_bool_env("TD_ALLREDUCE_DSL", False) and x.dtype in (torch.bfloat16, torch.float32) and not device_parity_input \
+            and (not x.is_cuda or U.is_nvshmem_multimem_supported()):
+        # opt-in A/B switch: the same NVLS algorithms as kernels written in the Python DSL (triton_dist/lk/kernels/allreduce_nvls.py);
+        # on the emulation backend they run in the DSL interpreter with the multicast model
+        return _all_reduce_dsl(x, method, ctx, output)
     if not x.is_cuda:
         return _all_reduce_host(x, ctx, output)
     if isinstance(method, str):
@@ -288,6 +295,28 @@ def all_reduce(x: torch.Tensor, method=AllReduceMethod.Unknown, ctx: AllReduceCo
 
 
 _LL_MAX_BYTES = 64 << 10
+
+
+def _all_reduce_dsl(x: torch.Tensor, method, ctx: "AllReduceContext", output: torch.Tensor) -> torch.Tensor:
+    from ..lk.kernels.allreduce_nvls import LkNvlsAllReduce
+    if isinstance(method, str):
+        method = to_allreduce_method(method)
+    nbytes = x.numel() * x.element_size()
+    if method in (AllReduceMethod.Unknown, None):
+        method = get_auto_allreduce_method(nbytes)
+    which = "two_shot" if method in (AllReduceMethod.TwoShot, AllReduceMethod.TwoShot_Multimem, AllReduceMethod.TwoShot_Multimem_ST,
+                                     AllReduceMethod.DoubleTree) else "one_shot"
+    cache = ctx.__dict__.setdefault("_dsl", {})
+    if which not in cache:
+        cache[which] = LkNvlsAllReduce(ctx.workspace_nbytes, which, grid=1 if not x.is_cuda else 8)
+    impl = cache[which]
+    off, xb, ob = 0, x.view(-1), output.view(-1)
+    per = impl.max_bytes // x.element_size()
+    while off < xb.numel():
+        n = min(per, xb.numel() - off)
+        impl(xb[off:off + n], out=ob[off:off + n])
+        off += n
+    return output
 
 
 class _ARLLArgs(C.Structure):
