@@ -553,3 +553,25 @@ def test_dsl_microbenchmarks_compile_and_check_out_in_the_interpreter():
     assert sass.count("HMMA") >= 4 and "MUFU.EX2" in subprocess.run(
         [shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump", "-sass", KERNELS["sfu_throughput"]._lib._name], capture_output=True, text=True).stdout
 
+
+def test_decode_attention_kernels_in_the_interpreter():
+    """Split-KV GQA decode + log-sum-exp combine written in the DSL (the megakernel's ATTN task / flash-decode algorithm): one split writes
+    the output directly, several splits go through (m, l, o) partials; ragged lengths; the returned LSE feeds a cross-rank merge."""
+    from triton_dist.lk.kernels.flash_decode import decode_combine, decode_split, gqa_decode_lk
+    torch.manual_seed(0)
+    B, Hq, Hkv = 1, 4, 2
+    q = (torch.randn(B, Hq, 128) * 0.5).bfloat16()
+    k, v = (torch.randn(B, 40, Hkv, 128) * 0.5).bfloat16(), (torch.randn(B, 40, Hkv, 128) * 0.5).bfloat16()
+    lens = torch.tensor([29], dtype=torch.int32)
+    ro, rl = torch.zeros(B, Hq, 128), torch.zeros(B, Hq)
+    for h in range(Hq):
+        s = (q[0, h].float() @ k[0, :29, h // 2].float().t()) * 128 ** -0.5
+        ro[0, h], rl[0, h] = torch.softmax(s, -1) @ v[0, :29, h // 2].float(), torch.logsumexp(s, -1)
+    o1 = gqa_decode_lk(q, k, v, lens, n_splits=1, interpret=True)
+    o2, l2 = gqa_decode_lk(q, k, v, lens, n_splits=2, interpret=True, return_lse=True)
+    torch.testing.assert_close(o1.float(), ro, atol=5e-3, rtol=5e-3)
+    torch.testing.assert_close(o2.float(), ro, atol=5e-3, rtol=5e-3)
+    torch.testing.assert_close(l2, rl, atol=1e-4, rtol=1e-4)
+    decode_split.compile()
+    decode_combine.compile()
+

@@ -408,3 +408,29 @@ def test_lk_microbenchmarks():
                        timeout=240, cwd=ROOT, env=dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", "")))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
 
+
+_DECODE_SNIPPET = r"""
+import sys, torch
+sys.path.insert(0, {root!r})
+from triton_dist.lk.kernels.flash_decode import gqa_decode_lk
+from triton_dist.ops.flash_decode import gqa_fwd_batch_decode
+torch.manual_seed(0)
+B, Hq, Hkv, L = 4, 32, 8, 1024
+q = (torch.randn(B, Hq, 128, device="cuda") * 0.5).bfloat16()
+k = (torch.randn(B, L, Hkv, 128, device="cuda") * 0.5).bfloat16()
+v = (torch.randn(B, L, Hkv, 128, device="cuda") * 0.5).bfloat16()
+lens = torch.tensor([1024, 517, 33, 900], device="cuda", dtype=torch.int32)
+ref = gqa_fwd_batch_decode(q, k, v, lens)                    # the hardware-validated CUDA kernel
+for ns in (1, 8):
+    out = gqa_decode_lk(q, k, v, lens, n_splits=ns)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out.float(), ref.float(), atol=2e-2, rtol=2e-2)
+print("DECODE_OK")
+"""
+
+
+@pytest.mark.xfail(strict=False, reason="DSL decode attention kernels: exact in the interpreter, not yet run on hardware")
+def test_lk_decode_attention():
+    r = subprocess.run([sys.executable, "-c", _DECODE_SNIPPET.format(root=ROOT)], capture_output=True, text=True, timeout=150, cwd=ROOT)
+    assert r.returncode == 0 and "DECODE_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
