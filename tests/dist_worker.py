@@ -1358,6 +1358,35 @@ def case_allreduce_dsl():
         os.environ.pop("TD_ALLREDUCE_DSL", None)
 
 
+def case_lk_sp_decode():
+    """KV-sharded decode entirely on DSL kernels: local split-KV decode, flag-in-data all-gather of the (lse, o) partials, log-sum-exp merge
+    across ranks -- against attention over the concatenated cache (one sequence has no keys on the last rank)."""
+    from triton_dist.lk.kernels.flash_decode import LkSpDecode
+    W, me = U.world_size(), U.rank()
+    dev = U.current_device()
+    big = dev.type == "cuda"
+    B, Hq, Hkv, Lmax = (4, 16, 4, 256) if big else (2, 2, 1, 12)
+    sp = LkSpDecode(B, Hq, Hkv, n_splits=2)
+    g = torch.Generator().manual_seed(77)                                     # same data on every rank, sliced per rank below
+    q = (torch.randn(B, Hq, 128, generator=g) * 0.5).to(torch.bfloat16).to(dev)
+    k_all = (torch.randn(B, W * Lmax, Hkv, 128, generator=g) * 0.5).to(torch.bfloat16)
+    v_all = (torch.randn(B, W * Lmax, Hkv, 128, generator=g) * 0.5).to(torch.bfloat16)
+    total = torch.tensor([W * Lmax - 3] + [max(1, (W - 1) * Lmax - 2)] * (B - 1))     # sequences 1.. end before the last rank's shard
+    lens_local = (total - me * Lmax).clamp(0, Lmax).to(torch.int32).to(dev)
+    for it in range(2):
+        out = sp(q, k_all[:, me * Lmax:(me + 1) * Lmax].contiguous().to(dev), v_all[:, me * Lmax:(me + 1) * Lmax].contiguous().to(dev), lens_local)
+        G = Hq // Hkv
+        ref = torch.zeros(B, Hq, 128)
+        for b in range(B):
+            n = int(total[b])
+            for h in range(Hq):
+                s_ = (q[b, h].float().cpu() @ k_all[b, :n, h // G].float().t()) * 128 ** -0.5
+                ref[b, h] = torch.softmax(s_, -1) @ v_all[b, :n, h // G].float()
+        _assert_close(out.float(), ref, 2e-2, 2e-2, f"lk sp decode call {it}")
+    U.barrier_all_on_stream()
+    sp.finalize()
+
+
 def case_lk_ag_gemm():
     """AllGather + GEMM as ONE kernel written in the Python DSL (comm CTAs push shards + release-add flags, tcgen05 tiles acquire the
     flags of the rows they need).  GPU: the generated CUDA; emulation: the interpreter with the functional pipeline model, across ranks."""

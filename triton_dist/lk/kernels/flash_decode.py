@@ -158,3 +158,43 @@ def gqa_decode_lk(q, k_cache, v_cache, kv_lens, n_splits: int = 4, sm_scale=None
     if ns > 1:
         run(decode_combine, B * Hkv, part, out, lse, Hq, Hkv, ns)
     return (out, lse) if return_lse else out
+
+
+class LkSpDecode:
+    """KV-sharded (sequence-parallel) decode entirely on DSL kernels: every rank attends to ITS shard of the KV cache (``decode_split`` +
+    ``decode_combine`` -> output and log-sum-exp), the per-head partials ``(m = lse, l = 1, o)`` are exchanged with the low-latency
+    flag-in-data all-gather (``allgather_ll``), and ``decode_combine`` merges the W partials.  Reference: layers/nvidia/
+    sp_flash_decode_layer.py ``SpGQAFlashDecodeAttention`` (local split-KV decode -> LL all-gather of (O, LSE) -> inter-rank combine)."""
+
+    def __init__(self, batch: int, num_q_heads: int, num_kv_heads: int, n_splits: int = 2):
+        import triton_dist.utils as U
+        from .allgather_ll import LkLLAllGather
+        self.B, self.Hq, self.Hkv, self.n_splits = batch, num_q_heads, num_kv_heads, n_splits
+        self.W = U.world_size()
+        self.ag = LkLLAllGather(batch * num_kv_heads * GMAX * PART * 4)
+
+    def __call__(self, q, k_shard, v_shard, local_kv_lens, sm_scale=None):
+        """q: [B, Hq, 128] (replicated); k / v shard: [B, max_len_local, Hkv, 128]; local_kv_lens: int32 [B] keys of every sequence that
+        live on THIS rank (may be 0) -> [B, Hq, 128]."""
+        import torch
+        B, Hq, Hkv, W = self.B, self.Hq, self.Hkv, self.W
+        G = Hq // Hkv
+        o, lse = gqa_decode_lk(q, k_shard, v_shard, local_kv_lens, n_splits=self.n_splits, sm_scale=sm_scale, return_lse=True)
+        empty = (local_kv_lens.to(q.device) <= 0)[:, None].expand(B, Hq)                 # a rank without keys contributes weight exp(-inf) = 0
+        mine = torch.zeros(B, Hkv, GMAX, PART, dtype=torch.float32, device=q.device)
+        mine[:, :, :G, 0] = torch.where(empty, torch.full_like(lse, -1.0e30), lse).view(B, Hkv, G)
+        mine[:, :, :G, 1] = torch.where(empty, torch.zeros_like(lse), torch.ones_like(lse)).view(B, Hkv, G)
+        mine[:, :, :G, 2:] = o.float().view(B, Hkv, G, 128)
+        allp = self.ag(mine.view(-1))                                                    # [W, B * Hkv * GMAX * PART]
+        part = allp.view(W, B, Hkv, GMAX, PART).permute(1, 2, 0, 3, 4).contiguous().view(-1)
+        out = torch.empty(B, Hq, 128, dtype=torch.bfloat16, device=q.device)
+        lse_all = torch.empty(B, Hq, dtype=torch.float32, device=q.device)
+        if q.is_cuda:
+            decode_combine[B * Hkv](part, out, lse_all, Hq, Hkv, W)
+        else:
+            decode_combine.interpret(B * Hkv, part, out, lse_all, Hq, Hkv, W)
+        return out
+
+    def finalize(self):
+        self.ag.finalize()
+
