@@ -1387,6 +1387,36 @@ def case_lk_sp_decode():
     sp.finalize()
 
 
+def case_lk_a2a():
+    """Low-latency variable-size all-to-all written with the DSL's OpenSHMEM-style API (put + put-with-signal per destination CTA, wait on the
+    source's signal) against torch.distributed.all_to_all_single with uneven splits; three calls on double-buffered slots."""
+    from triton_dist.lk.kernels.all_to_all import LkAllToAll
+    W, me = U.world_size(), U.rank()
+    dev = U.current_device()
+    big = dev.type == "cuda"
+    max_rows, H = (256, 512) if big else (6, 16)
+    a2a = LkAllToAll(max_rows, H)
+    for it in range(3):
+        g = torch.Generator().manual_seed(9 * it + me)
+        splits = torch.randint(0, max_rows + 1, (W,), generator=g).to(torch.int32)
+        send = (torch.randn(int(splits.sum()), H, generator=g)).to(torch.bfloat16).to(dev)
+        recv, cnt = a2a(send, splits.to(dev))
+        if big:
+            torch.cuda.synchronize()
+        all_splits = [torch.zeros(W, dtype=torch.int32, device=dev) for _ in range(W)]
+        dist.all_gather(all_splits, splits.to(dev), group=U.get_triton_dist_world())
+        want_cnt = [int(all_splits[s][me]) for s in range(W)]
+        assert cnt.cpu().tolist() == want_cnt, (it, cnt, want_cnt)
+        out = torch.empty(sum(want_cnt), H, dtype=torch.float32, device=dev)          # bf16 values are exact in fp32 (gloo has no bf16 / int16)
+        dist.all_to_all_single(out, send.float(), want_cnt, splits.tolist(), group=U.get_triton_dist_world())
+        off = 0
+        for s_ in range(W):
+            assert torch.equal(recv[s_, :want_cnt[s_]].float().cpu(), out[off:off + want_cnt[s_]].cpu()), (it, s_)
+            off += want_cnt[s_]
+        U.barrier_all_on_stream()
+    a2a.finalize()
+
+
 def case_lk_ag_gemm():
     """AllGather + GEMM as ONE kernel written in the Python DSL (comm CTAs push shards + release-add flags, tcgen05 tiles acquire the
     flags of the rows they need).  GPU: the generated CUDA; emulation: the interpreter with the functional pipeline model, across ranks."""
