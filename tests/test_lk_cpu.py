@@ -575,3 +575,30 @@ def test_decode_attention_kernels_in_the_interpreter():
     decode_split.compile()
     decode_combine.compile()
 
+
+def test_sass_fingerprints_of_the_dsl_communication_kernels():
+    """What the Python communication kernels become on sm_100a: switch reductions (``LDGMC...ADD.BF16x8`` = multimem.ld_reduce), tcgen05 + TMA
+    next to them in the fused GEMM + AllReduce, single 64-bit system-scope stores / loads for the flag-in-data atoms, GPU-scope atomics and
+    reductions for the EP slot counters and the grid barrier."""
+    from triton_dist.lk.kernels.all_to_all import all_to_all_ll
+    from triton_dist.lk.kernels.allgather_ll import allgather_ll
+    from triton_dist.lk.kernels.allreduce_nvls import make_allreduce_nvls
+    from triton_dist.lk.kernels.ep_a2a import ep_dispatch
+    from triton_dist.lk.kernels.gemm_ar import make_gemm_ar
+
+    def sass(k):
+        k.compile()
+        return subprocess.run([shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump", "-sass", k._lib._name], capture_output=True, text=True).stdout
+
+    one, two = make_allreduce_nvls(ll.bf16)
+    for k in (one, two):
+        s_ = sass(k)
+        assert "LDGMC.E.HPADD.BF16x8" in s_ and "MEMBAR.ALL.SYS" in s_ and "STG.E.128" in s_
+    s_ = sass(make_gemm_ar(128, 4, 8))
+    assert "UTCHMMA" in s_ and "UTMALDG.2D" in s_ and "LDGMC.E.HPADD.BF16x8" in s_
+    s_ = sass(allgather_ll)
+    assert "STG.E.64.STRONG.SYS" in s_ and "LDG.E.64.STRONG.SYS" in s_ and "MEMBAR" not in s_          # no fence, no barrier: the atom is the flag
+    assert "STG.E.64.STRONG.SYS" in sass(all_to_all_ll)
+    s_ = sass(ep_dispatch)
+    assert "ATOMG.E.ADD" in s_ and "REDG.E.ADD.STRONG.GPU" in s_
+
