@@ -41,7 +41,7 @@ PY
 if [ "$N" -ge 2 ]; then
   echo "== distributed items on $N GPUs"
   for c in shmem allgather_mc gemm_a2a_q8 sp_varlen lk lk_ag_gemm lk_gemm_rs ep_fn_api allgather allgather_ring a2a ulysses_pack \
-           lk_shmem lk_ep lk_rs_ring lk_ar_tree lk_ar_push lk_ar_nvls lk_gemm_ar allreduce_dsl lk_sp_decode lk_a2a lk_ag_ll mega_paged engine_mega mega_server ep_metadata; do
+           lk_shmem lk_ep lk_rs_ring lk_ar_tree lk_ar_push lk_ar_nvls lk_gemm_ar allreduce_dsl lk_sp_decode lk_a2a lk_nvls_collectives lk_ag_ll mega_paged engine_mega mega_server ep_metadata; do
     timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port $((24000 + RANDOM % 2000)) \
       tests/dist_worker.py $c 2>&1 | grep -E "CASE|Error|rror:" | head -3 | tee -a gpurun_out/pending_dist_n$N.log
   done

@@ -1417,6 +1417,33 @@ def case_lk_a2a():
     a2a.finalize()
 
 
+def case_lk_nvls_collectives():
+    """Reduce-scatter (multimem.ld_reduce of the own chunk) and all-gather (one multimem.st stream per rank) through the multicast alias,
+    written in the DSL, against torch.distributed; bf16 and fp32, alternating calls on one staging buffer."""
+    from triton_dist.lk.kernels.collectives_nvls import LkNvlsCollectives
+    W, me = U.world_size(), U.rank()
+    dev = U.current_device()
+    big = dev.type == "cuda"
+    if big and not U.is_nvshmem_multimem_supported():
+        return
+    unit = (1 << 14) if big else 16                        # elements per chunk / shard
+    col = LkNvlsCollectives(unit * W * 4, grid=2 if not big else 4)
+    for it, dt in enumerate((torch.float32, torch.bfloat16, torch.float32)):
+        g = torch.Generator().manual_seed(3 * it + me)
+        x = (torch.randn(W * unit, generator=g) * 0.5).to(dt).to(dev)
+        rs = col.reduce_scatter(x)
+        full = x.float().clone()
+        dist.all_reduce(full, group=U.get_triton_dist_world())
+        _assert_close(rs.float(), full[me * unit:(me + 1) * unit], 5e-2 if dt == torch.bfloat16 else 1e-5, 2e-2 if dt == torch.bfloat16 else 1e-5, f"lk nvls reduce_scatter {it}")
+        shard = x[:unit].contiguous()
+        ag = col.all_gather(shard)
+        ref = [torch.empty(unit, dtype=torch.float32, device=dev) for _ in range(W)]
+        dist.all_gather(ref, shard.float(), group=U.get_triton_dist_world())
+        assert torch.equal(ag.float().cpu(), torch.stack(ref).cpu()), it
+    U.barrier_all_on_stream()
+    col.finalize()
+
+
 def case_lk_ag_gemm():
     """AllGather + GEMM as ONE kernel written in the Python DSL (comm CTAs push shards + release-add flags, tcgen05 tiles acquire the
     flags of the rows they need).  GPU: the generated CUDA; emulation: the interpreter with the functional pipeline model, across ranks."""

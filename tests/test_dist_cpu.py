@@ -20,7 +20,7 @@ WORLD2_GROUPS = [
     ["mega", "mega_paged", "engine_mega"],
     ["mega_server"],
     ["lk", "lk_shmem", "lk_ep", "lk_sp_decode", "lk_a2a"],
-    ["lk_rs_ring", "lk_ar_tree", "lk_ar_push", "lk_ag_ll", "lk_ar_nvls", "allreduce_dsl"],
+    ["lk_rs_ring", "lk_ar_tree", "lk_ar_push", "lk_ag_ll", "lk_ar_nvls", "allreduce_dsl", "lk_nvls_collectives"],
     ["lk_ag_gemm", "lk_gemm_ar"],
     ["lk_gemm_rs"],
 ]

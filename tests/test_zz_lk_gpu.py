@@ -391,7 +391,7 @@ def test_engine_mega_backend_two_gpus():
 
 
 @pytest.mark.xfail(strict=False, reason="host-level compositions written after the last full hardware session (emulation-tested): variable all-to-all cases, ring copy-engine all-gather producers, packed Ulysses all-to-all")
-@pytest.mark.parametrize("case", ["a2a", "allgather_ring", "ulysses_pack", "lk_rs_ring", "lk_ar_tree", "lk_ar_push", "lk_ag_ll", "lk_ar_nvls", "lk_gemm_ar", "allreduce_dsl", "lk_sp_decode", "lk_a2a"])
+@pytest.mark.parametrize("case", ["a2a", "allgather_ring", "ulysses_pack", "lk_rs_ring", "lk_ar_tree", "lk_ar_push", "lk_ag_ll", "lk_ar_nvls", "lk_gemm_ar", "allreduce_dsl", "lk_sp_decode", "lk_a2a", "lk_nvls_collectives"])
 def test_late_host_level_cases_two_gpus(case):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
