@@ -55,4 +55,4 @@ def test_cpu_chaos_dsl_and_shmem():
     """The DSL's fused kernels (comm CTAs + tcgen05 tiles in the pipeline model), the NVSHMEM-style mirror and the NVLS all-gather
     names under random skew at a non-power-of-two world."""
     env = dict(CPU_ENV, TD_HOST_CHAOS_US="3000", TD_HOST_TIMEOUT_US="120000000")
-    run_dist(["lk_gemm_rs", "shmem", "allgather_mc", "lk", "lk_shmem"], nproc=3, env_extra=env, timeout=900)
+    run_dist(["lk_gemm_rs", "shmem", "allgather_mc", "lk", "lk_shmem", "lk_ar_nvls", "lk_gemm_ar", "lk_ep"], nproc=3, env_extra=env, timeout=900)
